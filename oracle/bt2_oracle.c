@@ -1,0 +1,535 @@
+/* oracle/bt2_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C CPU restatement of the bowtie2 2.5.5 alignment hot path,
+ * written from the reference's documented behaviour; every function cites the reference
+ * file:line it follows.  It exists to CHECK the CUDA product path (tests/, smoke(), the
+ * cpu_baseline "port" leg of bench.py) and is itself pinned against the real reference
+ * compiled into oracle/_ref/libbt2ref_{s,l}.so (tests/test_oracle_vs_reference.py) and
+ * against committed golden fixtures in tests/golden/.  Parity status: PINNED.
+ *
+ * Nothing under bowtie2_b200/ or include/ may include, link or call this file.
+ */
+#include "bt2_oracle.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define OFFMASK64 (~(uint64_t)0)
+
+/* ------------------------------------------------------------------------------------ */
+/* file reading helpers                                                                   */
+/* ------------------------------------------------------------------------------------ */
+static int rd_bytes(FILE *f, void *dst, size_t n) { return fread(dst, 1, n, f) == n ? 0 : -1; }
+
+static int rd_i32(FILE *f, int32_t *v) { return rd_bytes(f, v, 4); }
+
+static int rd_off(FILE *f, int off_size, uint64_t *v) {
+	if(off_size == 4) { uint32_t x; if(rd_bytes(f, &x, 4)) return -1; *v = x; return 0; }
+	return rd_bytes(f, v, 8);
+}
+
+static uint64_t *rd_off_array(FILE *f, int off_size, uint64_t n) {
+	uint64_t *a = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
+	if(!a) return NULL;
+	for(uint64_t i = 0; i < n; i++) {
+		if(rd_off(f, off_size, &a[i])) { free(a); return NULL; }
+	}
+	return a;
+}
+
+/* EbwtParams::init (bt2_idx.h:133-167) */
+static void params_init(bt2o_ebwt *e) {
+	uint64_t bwt_sz = e->len / 4 + 1;
+	e->bwt_len = e->len + 1;
+	e->side_sz = 1u << e->line_rate;
+	e->side_bwt_sz = e->side_sz - 4 * (uint32_t)e->off_size;
+	e->side_bwt_len = e->side_bwt_sz * 4;
+	e->num_sides = (bwt_sz + e->side_bwt_sz - 1) / e->side_bwt_sz;
+	e->ebwt_tot_len = e->num_sides * e->side_sz;
+	e->eftab_len = (uint64_t)e->ftab_chars * 2;
+	e->ftab_len = ((uint64_t)1 << (e->ftab_chars * 2)) + 1;
+	e->offs_len = (e->bwt_len + ((uint64_t)1 << e->off_rate) - 1) >> e->off_rate;
+}
+
+/* Ebwt::readIntoMemory (bt2_io.cpp:131-511), little-endian files only */
+static int load_ebwt(bt2o_ebwt *e, const char *base, const char *ext, int off_size, int is_fw, int load_sa) {
+	char path[4096];
+	memset(e, 0, sizeof(*e));
+	e->off_size = off_size;
+	e->is_fw = is_fw;
+	snprintf(path, sizeof(path), "%s.1.%s", base, ext);
+	FILE *f = fopen(path, "rb");
+	if(!f) return -1;
+	int32_t one, lines_per_side;
+	if(rd_i32(f, &one) || one != 1) { fclose(f); return -2; }
+	if(rd_off(f, off_size, &e->len)) { fclose(f); return -3; }
+	if(rd_i32(f, &e->line_rate) || rd_i32(f, &lines_per_side) || rd_i32(f, &e->off_rate) ||
+	   rd_i32(f, &e->ftab_chars) || rd_i32(f, &e->flags)) { fclose(f); return -3; }
+	params_init(e);
+	if(rd_off(f, off_size, &e->n_pat)) { fclose(f); return -3; }
+	e->plen = rd_off_array(f, off_size, e->n_pat);
+	if(rd_off(f, off_size, &e->n_frag)) { fclose(f); return -3; }
+	e->rstarts = rd_off_array(f, off_size, e->n_frag * 3);
+	e->ebwt = (uint8_t *)malloc(e->ebwt_tot_len);
+	if(!e->plen || !e->rstarts || !e->ebwt || rd_bytes(f, e->ebwt, e->ebwt_tot_len)) { fclose(f); return -4; }
+	if(rd_off(f, off_size, &e->z_off)) { fclose(f); return -3; }
+	for(int i = 0; i < 5; i++) if(rd_off(f, off_size, &e->fchr[i])) { fclose(f); return -3; }
+	e->ftab = rd_off_array(f, off_size, e->ftab_len);
+	e->eftab = rd_off_array(f, off_size, e->eftab_len);
+	fclose(f);
+	if(!e->ftab || !e->eftab) return -4;
+	if(load_sa) {
+		snprintf(path, sizeof(path), "%s.2.%s", base, ext);
+		f = fopen(path, "rb");
+		if(!f) return -5;
+		if(rd_i32(f, &one) || one != 1) { fclose(f); return -2; }
+		e->offs = malloc(e->offs_len * (uint64_t)off_size);
+		if(!e->offs || rd_bytes(f, e->offs, e->offs_len * (uint64_t)off_size)) { fclose(f); return -4; }
+		fclose(f);
+	}
+	return 0;
+}
+
+/* BitPairReference ctor (reference.cpp:96-200) */
+static int load_ref(bt2o_ref *r, const char *base, const char *ext, int off_size) {
+	char path[4096];
+	memset(r, 0, sizeof(*r));
+	snprintf(path, sizeof(path), "%s.3.%s", base, ext);
+	FILE *f = fopen(path, "rb");
+	if(!f) return -1;
+	int32_t one;
+	if(rd_i32(f, &one) || one != 1) { fclose(f); return -2; }
+	if(rd_off(f, off_size, &r->n_recs)) { fclose(f); return -3; }
+	uint64_t n = r->n_recs;
+	r->rec_off = (uint64_t *)malloc(n * 8); r->rec_len = (uint64_t *)malloc(n * 8);
+	r->rec_first = (uint8_t *)malloc(n);
+	r->ref_rec_offs = (uint64_t *)malloc((n + 1) * 8);
+	r->ref_offs = (uint64_t *)malloc((n + 1) * 8);
+	r->ref_lens = (uint64_t *)malloc((n + 1) * 8);
+	uint64_t cumsz = 0, cumlen = 0, nrefs = 0, nlens = 0;
+	for(uint64_t i = 0; i < n; i++) {
+		int c;
+		if(rd_off(f, off_size, &r->rec_off[i]) || rd_off(f, off_size, &r->rec_len[i]) || (c = fgetc(f)) == EOF) {
+			fclose(f); return -3;
+		}
+		r->rec_first[i] = c ? 1 : 0;
+		if(r->rec_first[i]) {
+			r->ref_rec_offs[nrefs] = i;
+			r->ref_offs[nrefs] = cumsz;
+			if(nrefs > 0) r->ref_lens[nlens++] = cumlen;
+			cumlen = 0;
+			nrefs++;
+		}
+		cumsz += r->rec_len[i];
+		cumlen += r->rec_off[i] + r->rec_len[i];
+	}
+	fclose(f);
+	r->ref_rec_offs[nrefs] = n;
+	r->ref_offs[nrefs] = cumsz;
+	r->ref_lens[nlens++] = cumlen;
+	r->n_refs = nrefs;
+	r->buf_sz = cumsz;
+	uint64_t bytes = (cumsz + 3) >> 2;
+	r->buf = (uint8_t *)malloc(bytes ? bytes : 1);
+	snprintf(path, sizeof(path), "%s.4.%s", base, ext);
+	f = fopen(path, "rb");
+	if(!f) return -1;
+	if(rd_bytes(f, r->buf, bytes)) { fclose(f); return -3; }
+	fclose(f);
+	return 0;
+}
+
+static void free_ebwt(bt2o_ebwt *e) {
+	free(e->plen); free(e->rstarts); free(e->ebwt); free(e->ftab); free(e->eftab); free(e->offs);
+}
+
+bt2o_index *bt2o_open(const char *base, int load_mirror, int load_reference) {
+	char path[4096];
+	const char *ext = "bt2";
+	int off_size = 4;
+	snprintf(path, sizeof(path), "%s.1.bt2", base);
+	FILE *f = fopen(path, "rb");
+	if(!f) {
+		snprintf(path, sizeof(path), "%s.1.bt2l", base);
+		f = fopen(path, "rb");
+		if(!f) return NULL;
+		ext = "bt2l"; off_size = 8;
+	}
+	fclose(f);
+	bt2o_index *ix = (bt2o_index *)calloc(1, sizeof(bt2o_index));
+	if(load_ebwt(&ix->fw, base, ext, off_size, 1, 1)) { free(ix); return NULL; }
+	if(load_mirror) {
+		snprintf(path, sizeof(path), "%s.rev", base);
+		if(load_ebwt(&ix->bw, path, ext, off_size, 0, 0)) { free_ebwt(&ix->fw); free(ix); return NULL; }
+		ix->has_bw = 1;
+	}
+	if(load_reference) {
+		if(load_ref(&ix->ref, base, ext, off_size)) { free_ebwt(&ix->fw); free(ix); return NULL; }
+		ix->has_ref = 1;
+	}
+	return ix;
+}
+
+void bt2o_close(bt2o_index *ix) {
+	if(!ix) return;
+	free_ebwt(&ix->fw);
+	if(ix->has_bw) free_ebwt(&ix->bw);
+	if(ix->has_ref) {
+		bt2o_ref *r = &ix->ref;
+		free(r->rec_off); free(r->rec_len); free(r->rec_first); free(r->ref_rec_offs);
+		free(r->ref_offs); free(r->ref_lens); free(r->buf);
+	}
+	free(ix);
+}
+
+uint64_t bt2o_scalar(const bt2o_index *ix, int mirror, int which) {
+	const bt2o_ebwt *e = mirror ? &ix->bw : &ix->fw;
+	switch(which) {
+		case 0: return e->len;        case 1: return e->bwt_len;
+		case 2: return (uint64_t)e->line_rate; case 3: return (uint64_t)e->off_rate;
+		case 4: return (uint64_t)e->ftab_chars; case 5: return e->num_sides;
+		case 6: return e->side_sz;    case 7: return e->side_bwt_sz;
+		case 8: return e->z_off;      case 9: return e->n_pat;
+		case 10: return e->n_frag;    case 11: return e->offs_len;
+		case 12: return e->ftab_len;  case 13: return e->eftab_len;
+		case 14: return e->ebwt_tot_len;
+	}
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* FM primitives                                                                          */
+/* ------------------------------------------------------------------------------------ */
+static inline uint64_t side_occ(const bt2o_ebwt *e, const uint8_t *side, int c) {
+	const uint8_t *p = side + e->side_bwt_sz + (size_t)c * e->off_size;
+	if(e->off_size == 4) { uint32_t v; memcpy(&v, p, 4); return v; }
+	uint64_t v; memcpy(&v, p, 8); return v;
+}
+
+/* countUpToEx (bt2_idx.h:2038): occurrences of each nucleotide in the first char_off
+ * 2-bit characters of the side.  Written as the obvious loop; the reference's word
+ * popcount + LUT tail computes the same thing. */
+static void count_upto4(const uint8_t *side, uint32_t char_off, uint64_t cnt[4]) {
+	cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
+	for(uint32_t k = 0; k < char_off; k++) {
+		cnt[(side[k >> 2] >> ((k & 3) << 1)) & 3]++;
+	}
+}
+
+/* countBt2SideEx (bt2_idx.h:1887-1919) with SideLocus::initFromRow (:369-397).
+ * The "$" is stored as an A at row z_off; an A-count taken strictly after it within
+ * the same side is decremented (:1891-1899). */
+void bt2o_rank4(const bt2o_index *ix, int mirror, uint64_t row, uint64_t out4[4]) {
+	const bt2o_ebwt *e = mirror ? &ix->bw : &ix->fw;
+	uint64_t side_num = row / e->side_bwt_len;
+	uint32_t char_off = (uint32_t)(row % e->side_bwt_len);
+	const uint8_t *side = e->ebwt + side_num * e->side_sz;
+	uint64_t cnt[4];
+	count_upto4(side, char_off, cnt);
+	uint64_t z_side = e->z_off / e->side_bwt_len;
+	uint32_t z_char = (uint32_t)(e->z_off % e->side_bwt_len);
+	if(side_num == z_side && char_off > z_char) cnt[0]--;
+	for(int c = 0; c < 4; c++) out4[c] = cnt[c] + side_occ(e, side, c) + e->fchr[c];
+}
+
+/* countBt2Side / mapLF(l,c) (bt2_idx.h:1758-1793, :2344) */
+uint64_t bt2o_rank1(const bt2o_index *ix, int mirror, uint64_t row, int c) {
+	uint64_t r[4];
+	bt2o_rank4(ix, mirror, row, r);
+	return r[c];
+}
+
+/* rowL (bt2_idx.h:2247) */
+int bt2o_rowL(const bt2o_index *ix, int mirror, uint64_t row) {
+	const bt2o_ebwt *e = mirror ? &ix->bw : &ix->fw;
+	uint64_t side_num = row / e->side_bwt_len;
+	uint32_t k = (uint32_t)(row % e->side_bwt_len);
+	const uint8_t *side = e->ebwt + side_num * e->side_sz;
+	return (side[k >> 2] >> ((k & 3) << 1)) & 3;
+}
+
+/* mapLF1(row, l, c) (bt2_idx.h:2420-2443) */
+uint64_t bt2o_maplf1(const bt2o_index *ix, int mirror, uint64_t row, int c) {
+	const bt2o_ebwt *e = mirror ? &ix->bw : &ix->fw;
+	if(bt2o_rowL(ix, mirror, row) != c || row == e->z_off) return OFFMASK64;
+	return bt2o_rank1(ix, mirror, row, c);
+}
+
+/* ftabHi / ftabLo / ftabLoHi (bt2_idx.h:1428-1554): entries > len are indirections */
+static uint64_t ftab_hi(const bt2o_ebwt *e, uint64_t i) {
+	uint64_t v = e->ftab[i];
+	if(v <= e->len) return v;
+	uint64_t mask = e->off_size == 4 ? 0xffffffffull : OFFMASK64;
+	uint64_t ef = (v ^ mask) & mask;
+	return e->eftab[ef * 2 + 1];
+}
+static uint64_t ftab_lo(const bt2o_ebwt *e, uint64_t i) {
+	uint64_t v = e->ftab[i];
+	if(v <= e->len) return v;
+	uint64_t mask = e->off_size == 4 ? 0xffffffffull : OFFMASK64;
+	uint64_t ef = (v ^ mask) & mask;
+	return e->eftab[ef * 2];
+}
+void bt2o_ftab_lohi(const bt2o_index *ix, int mirror, uint64_t i, uint64_t *top, uint64_t *bot) {
+	const bt2o_ebwt *e = mirror ? &ix->bw : &ix->fw;
+	*top = ftab_hi(e, i);
+	*bot = ftab_lo(e, i + 1);
+}
+
+static inline uint64_t offs_at(const bt2o_ebwt *e, uint64_t k) {
+	if(e->off_size == 4) return ((const uint32_t *)e->offs)[k];
+	return ((const uint64_t *)e->offs)[k];
+}
+
+/* Ebwt::getOffset(row) (bt2_idx.cpp:150-171); == GroupWalk result (group_walk.h:517-520) */
+uint64_t bt2o_get_offset(const bt2o_index *ix, uint64_t row) {
+	const bt2o_ebwt *e = &ix->fw;
+	uint64_t jumps = 0;
+	uint64_t rate_mask = ((uint64_t)1 << e->off_rate) - 1;
+	for(;;) {
+		if(row == e->z_off) return jumps;
+		if((row & rate_mask) == 0) return jumps + offs_at(e, row >> e->off_rate);
+		int c = bt2o_rowL(ix, 0, row);
+		row = bt2o_rank1(ix, 0, row, c);
+		jumps++;
+	}
+}
+
+/* Ebwt::joinedToTextOff (bt2_idx.cpp:54-124), forward index */
+int bt2o_joined_to_text(const bt2o_index *ix, uint64_t qlen, uint64_t off, int reject_straddle,
+                        uint64_t *tidx, uint64_t *textoff, uint64_t *tlen, int *straddled) {
+	const bt2o_ebwt *e = &ix->fw;
+	uint64_t top = 0, bot = e->n_frag;
+	*straddled = 0;
+	for(;;) {
+		uint64_t elt = top + ((bot - top) >> 1);
+		uint64_t lower = e->rstarts[elt * 3];
+		uint64_t upper = (elt == e->n_frag - 1) ? e->len : e->rstarts[(elt + 1) * 3];
+		if(lower <= off) {
+			if(upper > off) {
+				if(off + qlen > upper) {
+					*straddled = 1;
+					if(reject_straddle) { *tidx = OFFMASK64; *textoff = 0; *tlen = 0; return 0; }
+				}
+				*tidx = e->rstarts[elt * 3 + 1];
+				*textoff = (off - lower) + e->rstarts[elt * 3 + 2];
+				break;
+			}
+			top = elt;
+		} else {
+			bot = elt;
+		}
+	}
+	*tlen = e->plen[*tidx];
+	return 1;
+}
+
+/* BitPairReference::getBase (reference.cpp:330-358), with off-end positions read as N (4) */
+static int ref_get_base(const bt2o_ref *r, uint64_t tidx, uint64_t toff) {
+	uint64_t reci = r->ref_rec_offs[tidx], recf = r->ref_rec_offs[tidx + 1];
+	uint64_t buf_off = r->ref_offs[tidx], off = 0;
+	for(uint64_t i = reci; i < recf; i++) {
+		off += r->rec_off[i];
+		if(toff < off) return 4;
+		uint64_t rec_end = off + r->rec_len[i];
+		if(toff < rec_end) {
+			buf_off += toff - off;
+			return (r->buf[buf_off >> 2] >> ((buf_off & 3) << 1)) & 3;
+		}
+		buf_off += r->rec_len[i];
+		off = rec_end;
+	}
+	return 4;
+}
+
+int bt2o_get_stretch(const bt2o_index *ix, uint64_t tidx, int64_t off, int64_t count, uint8_t *out) {
+	const bt2o_ref *r = &ix->ref;
+	int64_t tlen = (int64_t)r->ref_lens[tidx];
+	for(int64_t i = 0; i < count; i++) {
+		int64_t p = off + i;
+		out[i] = (p < 0 || p >= tlen) ? 4 : (uint8_t)ref_get_base(r, tidx, (uint64_t)p);
+	}
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* seed search                                                                            */
+/* ------------------------------------------------------------------------------------ */
+
+/* ftabSeqToInt (bt2_idx.h:1373-1398): chars OR-ed in search order. fwex selects L->R. */
+static uint64_t ftab_seq_to_int(const uint8_t *seq, int off, int fc, int left_to_right) {
+	uint64_t v = 0;
+	for(int i = 0; i < fc; i++) {
+		int c = left_to_right ? seq[off + i] : seq[off + fc - i - 1];
+		if(c > 3) return OFFMASK64;
+		v = (v << 2) | (uint64_t)c;
+	}
+	return v;
+}
+
+/* one strand of SeedAligner::exactSweep (aligner_seed.cpp:856-970; helpers :760-850).
+ * The reference interleaves the fw and rc sweeps only for prefetching; each strand's
+ * state is independent. */
+static void exact_sweep_strand(const bt2o_index *ix, const uint8_t *seq, int len, int mine_max,
+                               uint64_t *mine, uint64_t *otop, uint64_t *obot, int *finished) {
+	const bt2o_ebwt *e = &ix->fw;
+	int ftab_len = e->ftab_chars;
+	uint64_t top = 0, bot = 0;
+	int dep = 0, nedit = 0, do_init = 1, done = 0;
+	while(dep < len && !done) {
+		if(do_init) {
+			/* exactSweepInit (:760-800) */
+			int left = len - dep;
+			int do_ftab = ftab_len > 1 && left >= ftab_len;
+			top = bot = 0;
+			if(do_ftab) {
+				for(int i = 0; i < ftab_len; i++) if(seq[left - 1 - i] > 3) { do_ftab = 0; break; }
+			}
+			if(do_ftab) {
+				uint64_t fi = ftab_seq_to_int(seq, left - ftab_len, ftab_len, 1);
+				top = ftab_hi(e, fi); bot = ftab_lo(e, fi + 1);
+				dep += ftab_len;
+			} else {
+				int c = seq[len - dep - 1];
+				if(c < 4) { top = e->fchr[c]; bot = e->fchr[c + 1]; }
+				dep++;
+			}
+			/* exactSweepStep (:826-848) */
+			if(bot <= top) {
+				nedit++;
+				if(nedit >= mine_max) { *mine = (uint64_t)nedit; done = 1; }
+				continue;
+			}
+			do_init = 0;
+		}
+		if(dep < len) {
+			/* exactSweepMapLF (:802-824) */
+			int c = seq[len - dep - 1];
+			if(c > 3) {
+				top = bot = 0;
+			} else if(bot - top > 1) {
+				uint64_t t = bt2o_rank1(ix, 0, top, c), b = bt2o_rank1(ix, 0, bot, c);
+				top = t; bot = b;
+			} else {
+				uint64_t t = bt2o_maplf1(ix, 0, top, c);
+				if(t == OFFMASK64) { top = bot = 0; } else { top = t; bot = t + 1; }
+			}
+			if(bot <= top) {
+				nedit++;
+				if(nedit >= mine_max) { *mine = (uint64_t)nedit; done = 1; }
+				do_init = 1;
+			}
+			dep++;
+		}
+	}
+	*finished = 0;
+	*otop = *obot = 0;
+	if(!done && dep >= len) {
+		*mine = (uint64_t)nedit;
+		*finished = 1;
+		if(nedit == 0 && bot > top) { *otop = top; *obot = bot; }
+	}
+}
+
+uint64_t bt2o_exact_sweep(const bt2o_index *ix, const uint8_t *codes, int len, int nofw, int norc,
+                          uint64_t mine2[2], uint64_t topbot4[4]) {
+	uint8_t *rc = (uint8_t *)malloc((size_t)len + 1);
+	for(int i = 0; i < len; i++) { int c = codes[len - 1 - i]; rc[i] = (uint8_t)(c > 3 ? 4 : 3 - c); }
+	uint64_t nelt = 0;
+	mine2[0] = mine2[1] = 0;
+	topbot4[0] = topbot4[1] = topbot4[2] = topbot4[3] = 0;
+	int fin;
+	if(!nofw) {
+		exact_sweep_strand(ix, codes, len, 2, &mine2[0], &topbot4[0], &topbot4[1], &fin);
+		nelt += topbot4[1] - topbot4[0];
+	}
+	if(!norc) {
+		exact_sweep_strand(ix, rc, len, 2, &mine2[1], &topbot4[2], &topbot4[3], &fin);
+		nelt += topbot4[3] - topbot4[2];
+	}
+	free(rc);
+	return nelt;
+}
+
+/* One exact seed: Seed::instantiate SEED_TYPE_EXACT (aligner_seed.cpp:252-259, N check
+ * :326-352), CacheAndSeed ftab indices (:88-112), startSearchSeedBi (:1637-1718, NDEBUG
+ * branch for the mirror range), searchSeedBi exact path (:1858-2037) with mapBiLFEx
+ * (bt2_idx.h:2372-2413) and mapLF1 (:2420). seq is the seed as it aligns to the Watson
+ * strand.  Returns 1 and fills r[4]=topf,botf,topb,botb if the seed occurs. */
+static int exact_seed(const bt2o_index *ix, const uint8_t *seq, int seedlen, uint64_t r[4]) {
+	const bt2o_ebwt *fw = &ix->fw;
+	const bt2o_ebwt *bw = ix->has_bw ? &ix->bw : NULL;
+	int ftab_len = fw->ftab_chars;
+	for(int i = 0; i < seedlen; i++) if(seq[i] > 3) return 0; /* exact zone cannot absorb an N */
+	uint64_t topf, botf, topb = 0, botb = 0;
+	int step;
+	if(ftab_len > 1 && ftab_len <= seedlen) {
+		int off = seedlen - ftab_len;
+		uint64_t fwi0 = ftab_seq_to_int(seq, off, ftab_len, 1);
+		topf = ftab_hi(fw, fwi0); botf = ftab_lo(fw, fwi0 + 1);
+		if(botf - topf == 0) return 0;
+		if(bw) {
+			uint64_t bwi0 = ftab_seq_to_int(seq, off, ftab_len, 0);
+			topb = ftab_hi(bw, bwi0);
+			botb = topb + (botf - topf);
+		}
+		step = ftab_len;
+	} else {
+		int c = seq[seedlen - 1];
+		topf = topb = fw->fchr[c];
+		botf = botb = fw->fchr[c + 1];
+		if(botf - topf == 0) return 0;
+		step = 1;
+	}
+	for(; step < seedlen; step++) {
+		int c = seq[seedlen - step - 1];
+		if(botf - topf > 1) {
+			uint64_t t[4], b[4];
+			bt2o_rank4(ix, 0, topf, t);
+			bt2o_rank4(ix, 0, botf, b);
+			/* mirror range by prefix sums of widths (bt2_idx.h:2404-2412) */
+			uint64_t tp = topb;
+			for(int j = 0; j < c; j++) tp += b[j] - t[j];
+			if(b[c] == t[c]) return 0;
+			topf = t[c]; botf = b[c];
+			topb = tp; botb = tp + (b[c] - t[c]);
+		} else {
+			uint64_t t = bt2o_maplf1(ix, 0, topf, c);
+			if(t == OFFMASK64) return 0;
+			topf = t; botf = t + 1;
+			/* topb/botb unchanged (tp[]/bp[] were initialised to them, :1766-1768) */
+		}
+	}
+	r[0] = topf; r[1] = botf; r[2] = topb; r[3] = botb;
+	return 1;
+}
+
+/* SeedAligner::instantiateSeeds + searchAllSeeds for exact seeds (aligner_seed.cpp:498-720);
+ * seed extraction per instantiateSeq (:471-493) / SStringExpandable windowGetDna. */
+int bt2o_seed_search(const bt2o_index *ix, const uint8_t *codes, const uint8_t *quals, int len,
+                     int seedlen, int interval, int offset, int nofw, int norc,
+                     int max_seeds, uint64_t *out_ranges) {
+	(void)quals;
+	int nseeds = 1;
+	if(len - offset > seedlen) nseeds += (len - offset - seedlen) / interval;
+	if(nseeds > max_seeds) return -1;
+	memset(out_ranges, 0, sizeof(uint64_t) * 2 * (size_t)max_seeds * 4);
+	int sl = seedlen < len ? seedlen : len;
+	uint8_t seq[1024];
+	if(sl > 1024) return -1;
+	for(int fwi = 0; fwi < 2; fwi++) {
+		if((fwi == 0 && nofw) || (fwi == 1 && norc)) continue;
+		for(int i = 0; i < nseeds; i++) {
+			int depth = i * interval + offset;
+			for(int k = 0; k < sl; k++) {
+				if(fwi == 0) seq[k] = codes[depth + k];
+				else { int c = codes[depth + sl - 1 - k]; seq[k] = (uint8_t)(c > 3 ? 4 : 3 - c); }
+			}
+			uint64_t r[4];
+			if(exact_seed(ix, seq, sl, r)) {
+				memcpy(out_ranges + ((size_t)fwi * max_seeds + i) * 4, r, sizeof(r));
+			}
+		}
+	}
+	return nseeds;
+}

@@ -1,0 +1,72 @@
+/* oracle/bt2_oracle.h -- TEST INFRASTRUCTURE ONLY (see bt2_oracle.c header). */
+#ifndef BT2_ORACLE_H_
+#define BT2_ORACLE_H_
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+	int       off_size;      /* 4 (.bt2) or 8 (.bt2l) */
+	uint64_t  len, bwt_len;
+	int32_t   line_rate, off_rate, ftab_chars, flags;
+	uint64_t  off_mask_rate; /* = off_rate */
+	uint32_t  side_sz, side_bwt_sz, side_bwt_len;
+	uint64_t  num_sides, ebwt_tot_len, offs_len, ftab_len, eftab_len;
+	uint64_t  n_pat, n_frag;
+	uint64_t *plen;          /* [n_pat] */
+	uint64_t *rstarts;       /* [3*n_frag] (NULL for mirror) */
+	uint8_t  *ebwt;          /* [ebwt_tot_len] raw sides */
+	uint64_t  z_off;
+	uint64_t  fchr[5];
+	uint64_t *ftab;          /* [ftab_len], widened */
+	uint64_t *eftab;         /* [eftab_len], widened */
+	void     *offs;          /* raw u32/u64 SA sample, NULL for mirror */
+	int       is_fw;         /* forward index? (mirror: 0) */
+} bt2o_ebwt;
+
+typedef struct {
+	uint64_t  n_recs, n_refs;
+	uint64_t *rec_off, *rec_len; uint8_t *rec_first;
+	uint64_t *ref_rec_offs;  /* [n_refs+1] */
+	uint64_t *ref_offs;      /* [n_refs+1] unambiguous chars preceding */
+	uint64_t *ref_lens;      /* [n_refs] */
+	uint8_t  *buf;           /* 2-bit packed */
+	uint64_t  buf_sz;        /* # bases */
+} bt2o_ref;
+
+typedef struct {
+	bt2o_ebwt fw, bw;
+	bt2o_ref  ref;
+	int has_bw, has_ref;
+} bt2o_index;
+
+/* loading */
+bt2o_index *bt2o_open(const char *base, int load_mirror, int load_ref);
+void        bt2o_close(bt2o_index *ix);
+uint64_t    bt2o_scalar(const bt2o_index *ix, int mirror, int which);
+
+/* FM primitives; "mirror" selects the .rev index */
+void     bt2o_rank4(const bt2o_index *ix, int mirror, uint64_t row, uint64_t out4[4]);
+uint64_t bt2o_rank1(const bt2o_index *ix, int mirror, uint64_t row, int c);
+int      bt2o_rowL(const bt2o_index *ix, int mirror, uint64_t row);
+uint64_t bt2o_maplf1(const bt2o_index *ix, int mirror, uint64_t row, int c);
+void     bt2o_ftab_lohi(const bt2o_index *ix, int mirror, uint64_t i, uint64_t *top, uint64_t *bot);
+uint64_t bt2o_get_offset(const bt2o_index *ix, uint64_t row);
+int      bt2o_joined_to_text(const bt2o_index *ix, uint64_t qlen, uint64_t off, int reject_straddle,
+                             uint64_t *tidx, uint64_t *textoff, uint64_t *tlen, int *straddled);
+int      bt2o_get_stretch(const bt2o_index *ix, uint64_t tidx, int64_t off, int64_t count, uint8_t *out);
+
+/* seed search */
+uint64_t bt2o_exact_sweep(const bt2o_index *ix, const uint8_t *codes, int len, int nofw, int norc,
+                          uint64_t mine2[2], uint64_t topbot4[4]);
+int      bt2o_seed_search(const bt2o_index *ix, const uint8_t *codes, const uint8_t *quals, int len,
+                          int seedlen, int interval, int offset, int nofw, int norc,
+                          int max_seeds, uint64_t *out_ranges);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
