@@ -1,0 +1,227 @@
+// fm_device.cuh -- device-side FM-index primitives for sm_100a.
+//
+// These are re-designs, not translations: the reference walks a side with 64-bit XOR/shift
+// popcounts plus a 4x4x256 LUT tail (bt2_idx.h:518-530, :1933-2080, ccnt_lut.cpp).  Here one
+// thread pulls the whole 64 B (.bt2) / 128 B (.bt2l) side with 128-bit loads (two / four 32 B
+// sectors of one cache line, so one rank query = one line of HBM traffic) and counts three of
+// the four nucleotides with masked __popcll on bit-plane combinations; the fourth count is
+// char_off minus the others.  No lookup table, no byte loop, no divergence on char_off.
+#pragma once
+#include "bt2g_internal.h"
+
+#define BT2G_OFFMASK (~(uint64_t)0)
+
+template <typename OFF> struct SideGeom;
+template <> struct SideGeom<uint32_t> {
+	static constexpr uint32_t SIDE_SZ = 64, BWT_SZ = 48, BWT_LEN = 192, WORDS = 6, VECS = 4;
+};
+template <> struct SideGeom<uint64_t> {
+	static constexpr uint32_t SIDE_SZ = 128, BWT_SZ = 96, BWT_LEN = 384, WORDS = 12, VECS = 8;
+};
+
+// One side in registers: WORDS 64-bit BWT words followed by the four Occ counters.
+template <typename OFF>
+struct SideRegs {
+	uint64_t w[SideGeom<OFF>::WORDS];
+	uint64_t occ[4];
+};
+
+__device__ __forceinline__ uint4 ldg_side16(const uint4 *p) {
+	// read-only path, do not pollute L1 with single-use random lines
+	uint4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+	             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+
+template <typename OFF>
+__device__ __forceinline__ void load_side(const uint8_t *ebwt, uint64_t sideNum, SideRegs<OFF> &s);
+
+template <>
+__device__ __forceinline__ void load_side<uint32_t>(const uint8_t *ebwt, uint64_t sideNum, SideRegs<uint32_t> &s) {
+	const uint4 *p = reinterpret_cast<const uint4 *>(ebwt + sideNum * 64);
+	uint4 a = ldg_side16(p), b = ldg_side16(p + 1), c = ldg_side16(p + 2), d = ldg_side16(p + 3);
+	s.w[0] = ((uint64_t)a.y << 32) | a.x; s.w[1] = ((uint64_t)a.w << 32) | a.z;
+	s.w[2] = ((uint64_t)b.y << 32) | b.x; s.w[3] = ((uint64_t)b.w << 32) | b.z;
+	s.w[4] = ((uint64_t)c.y << 32) | c.x; s.w[5] = ((uint64_t)c.w << 32) | c.z;
+	s.occ[0] = d.x; s.occ[1] = d.y; s.occ[2] = d.z; s.occ[3] = d.w;
+}
+
+template <>
+__device__ __forceinline__ void load_side<uint64_t>(const uint8_t *ebwt, uint64_t sideNum, SideRegs<uint64_t> &s) {
+	const uint4 *p = reinterpret_cast<const uint4 *>(ebwt + sideNum * 128);
+#pragma unroll
+	for(int i = 0; i < 6; i++) {
+		uint4 a = ldg_side16(p + i);
+		s.w[2 * i] = ((uint64_t)a.y << 32) | a.x; s.w[2 * i + 1] = ((uint64_t)a.w << 32) | a.z;
+	}
+	uint4 o0 = ldg_side16(p + 6), o1 = ldg_side16(p + 7);
+	s.occ[0] = ((uint64_t)o0.y << 32) | o0.x; s.occ[1] = ((uint64_t)o0.w << 32) | o0.z;
+	s.occ[2] = ((uint64_t)o1.y << 32) | o1.x; s.occ[3] = ((uint64_t)o1.w << 32) | o1.z;
+}
+
+// counts of C, G, T among the first charOff characters of the side (A = charOff - sum)
+template <typename OFF>
+__device__ __forceinline__ void count_cgt(const SideRegs<OFF> &s, uint32_t charOff,
+                                          uint32_t &nC, uint32_t &nG, uint32_t &nT) {
+	nC = nG = nT = 0;
+	const uint64_t M = 0x5555555555555555ull;
+#pragma unroll
+	for(uint32_t i = 0; i < SideGeom<OFF>::WORDS; i++) {
+		int n = (int)charOff - (int)(i * 32);           // characters of this word that count
+		n = n < 0 ? 0 : (n > 32 ? 32 : n);
+		uint64_t mask = (n == 32) ? M : (((1ull << (2 * n)) - 1) & M);
+		uint64_t lo = s.w[i] & mask, hi = (s.w[i] >> 1) & mask;
+		nC += __popcll(lo & ~hi);
+		nG += __popcll(hi & ~lo);
+		nT += __popcll(hi & lo);
+	}
+}
+
+// Ebwt::countBt2SideEx (bt2_idx.h:1887-1919): all four ranks at `row`.
+template <typename OFF>
+__device__ __forceinline__ void rank4(const DevEbwt<OFF> &e, uint64_t row, uint64_t out[4]) {
+	constexpr uint32_t BL = SideGeom<OFF>::BWT_LEN;
+	uint64_t sideNum = row / BL;
+	uint32_t charOff = (uint32_t)(row - sideNum * BL);
+	SideRegs<OFF> s;
+	load_side<OFF>(e.ebwt, sideNum, s);
+	uint32_t nC, nG, nT;
+	count_cgt<OFF>(s, charOff, nC, nG, nT);
+	uint32_t nA = charOff - nC - nG - nT;
+	// "$" is stored as an A at row zOff; do not count it (bt2_idx.h:1891-1899)
+	if(sideNum == e.zSide && charOff > e.zChar) nA--;
+	out[0] = nA + s.occ[0] + e.fchr[0];
+	out[1] = nC + s.occ[1] + e.fchr[1];
+	out[2] = nG + s.occ[2] + e.fchr[2];
+	out[3] = nT + s.occ[3] + e.fchr[3];
+}
+
+// Ebwt::countBt2Side / mapLF(l, c) (bt2_idx.h:1758-1793, :2344)
+template <typename OFF>
+__device__ __forceinline__ uint64_t rank1(const DevEbwt<OFF> &e, uint64_t row, int c) {
+	uint64_t r[4];
+	rank4<OFF>(e, row, r);
+	return c == 0 ? r[0] : (c == 1 ? r[1] : (c == 2 ? r[2] : r[3]));
+}
+
+// rowL + mapLF in one side fetch: returns LF(row) and the BWT char, for the SA walk
+// (Ebwt::mapLF(l), bt2_idx.h:2313-2338).  Caller guarantees row != zOff.
+template <typename OFF>
+__device__ __forceinline__ uint64_t lf_step(const DevEbwt<OFF> &e, uint64_t row, int &cOut) {
+	constexpr uint32_t BL = SideGeom<OFF>::BWT_LEN;
+	uint64_t sideNum = row / BL;
+	uint32_t charOff = (uint32_t)(row - sideNum * BL);
+	SideRegs<OFF> s;
+	load_side<OFF>(e.ebwt, sideNum, s);
+	// character at charOff: select the word without dynamic register indexing
+	uint64_t word = 0;
+	uint32_t wi = charOff >> 5;
+#pragma unroll
+	for(uint32_t i = 0; i < SideGeom<OFF>::WORDS; i++) word = (wi == i) ? s.w[i] : word;
+	int c = (int)((word >> ((charOff & 31) * 2)) & 3);
+	uint32_t nC, nG, nT;
+	count_cgt<OFF>(s, charOff, nC, nG, nT);
+	uint32_t nA = charOff - nC - nG - nT;
+	if(sideNum == e.zSide && charOff > e.zChar) nA--;
+	uint32_t n = c == 0 ? nA : (c == 1 ? nC : (c == 2 ? nG : nT));
+	uint64_t oc = c == 0 ? s.occ[0] : (c == 1 ? s.occ[1] : (c == 2 ? s.occ[2] : s.occ[3]));
+	cOut = c;
+	return n + oc + e.fchr[c];
+}
+
+// Ebwt::mapLF1(row, l, c) (bt2_idx.h:2420-2443)
+template <typename OFF>
+__device__ __forceinline__ uint64_t maplf1(const DevEbwt<OFF> &e, uint64_t row, int c) {
+	if(row == e.zOff) return BT2G_OFFMASK;
+	int cc;
+	uint64_t r = lf_step<OFF>(e, row, cc);
+	return cc == c ? r : BT2G_OFFMASK;
+}
+
+// Ebwt::ftabHi / ftabLo (bt2_idx.h:1428-1554)
+template <typename OFF>
+__device__ __forceinline__ uint64_t ftab_hi(const DevEbwt<OFF> &e, uint64_t i) {
+	OFF v = __ldg(e.ftab + i);
+	if((uint64_t)v <= e.len) return v;
+	OFF ef = (OFF)(v ^ (OFF)~(OFF)0);
+	return __ldg(e.eftab + (uint64_t)ef * 2 + 1);
+}
+template <typename OFF>
+__device__ __forceinline__ uint64_t ftab_lo(const DevEbwt<OFF> &e, uint64_t i) {
+	OFF v = __ldg(e.ftab + i);
+	if((uint64_t)v <= e.len) return v;
+	OFF ef = (OFF)(v ^ (OFF)~(OFF)0);
+	return __ldg(e.eftab + (uint64_t)ef * 2);
+}
+
+// Ebwt::getOffset(row) (bt2_idx.cpp:150-171) == GroupWalk2S::advanceElement result
+// (group_walk.h:517-520): LF-walk until a sampled row or the "$" row.
+template <typename OFF>
+__device__ __forceinline__ uint64_t get_offset(const DevIndex<OFF> &ix, uint64_t row) {
+	const uint64_t rateMask = (1ull << ix.offRate) - 1;
+	uint64_t jumps = 0;
+	for(;;) {
+		if(row == ix.fw.zOff) return jumps;
+		if((row & rateMask) == 0) return jumps + (uint64_t)__ldg(ix.offs + (row >> ix.offRate));
+		int c;
+		row = lf_step<OFF>(ix.fw, row, c);
+		jumps++;
+	}
+}
+
+// Ebwt::joinedToTextOff (bt2_idx.cpp:54-124), forward index.  Returns false when rejected.
+template <typename OFF>
+__device__ __forceinline__ bool joined_to_text(const DevIndex<OFF> &ix, uint64_t qlen, uint64_t off,
+                                               bool rejectStraddle, uint64_t &tidx, uint64_t &textoff,
+                                               uint64_t &tlen, bool &straddled) {
+	uint64_t top = 0, bot = ix.nFrag;
+	straddled = false;
+	for(;;) {
+		uint64_t elt = top + ((bot - top) >> 1);
+		uint64_t lower = __ldg(ix.rstarts + elt * 3);
+		uint64_t upper = (elt == ix.nFrag - 1) ? ix.fw.len : (uint64_t)__ldg(ix.rstarts + (elt + 1) * 3);
+		if(lower <= off) {
+			if(upper > off) {
+				if(off + qlen > upper) {
+					straddled = true;
+					if(rejectStraddle) { tidx = BT2G_OFFMASK; textoff = 0; tlen = 0; return false; }
+				}
+				tidx = __ldg(ix.rstarts + elt * 3 + 1);
+				textoff = (off - lower) + (uint64_t)__ldg(ix.rstarts + elt * 3 + 2);
+				break;
+			}
+			top = elt;
+		} else {
+			bot = elt;
+		}
+	}
+	tlen = __ldg(ix.plen + tidx);
+	return true;
+}
+
+// BitPairReference::getBase (reference.cpp:330-358) with a binary search over the records of
+// the target (the reference's getStretch does the same for > 16 records, reference.cpp:470-486).
+template <typename OFF>
+__device__ __forceinline__ int ref_base(const DevIndex<OFF> &ix, uint64_t tidx, int64_t toff) {
+	if(toff < 0 || (uint64_t)toff >= ix.refLens[tidx]) return 4;
+	uint64_t lo = ix.refRecOffs[tidx], hi = ix.refRecOffs[tidx + 1];
+	// last record whose N-run starts at or before toff
+	while(hi - lo > 1) {
+		uint64_t mid = lo + ((hi - lo) >> 1);
+		if(ix.recCumOff[mid] <= (uint64_t)toff) lo = mid; else hi = mid;
+	}
+	uint64_t start = ix.recCumOff[lo] + (uint64_t)ix.recOff[lo];
+	if((uint64_t)toff < start) return 4;
+	uint64_t k = (uint64_t)toff - start;
+	if(k >= (uint64_t)ix.recLen[lo]) return 4;
+	uint64_t b = ix.recCumUnamb[lo] + k;
+	return (ix.refBuf[b >> 2] >> ((b & 3) << 1)) & 3;
+}
+
+// read access helpers: strand 0 = read as given, strand 1 = reverse complement
+__device__ __forceinline__ int read_char(const uint8_t *seq, int len, int strand, int pos) {
+	if(strand == 0) return seq[pos];
+	int c = seq[len - 1 - pos];
+	return c > 3 ? 4 : 3 - c;
+}

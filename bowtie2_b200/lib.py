@@ -1,0 +1,248 @@
+"""ctypes binding of libbt2g.so (C ABI: include/bt2g.h).
+
+Names and argument meaning follow the reference calls each entry point replaces
+(SeedAligner::exactSweep / searchAllSeeds, Ebwt::getOffset + joinedToTextOff, ...); see the
+header for file:line citations.  All arrays are numpy; offsets travel as uint64.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+OFFMASK = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+class Bt2GpuError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libbt2g.so")
+
+
+class _IndexHost(C.Structure):
+    _fields_ = [
+        ("off_size", C.c_int32), ("line_rate", C.c_int32), ("off_rate", C.c_int32), ("ftab_chars", C.c_int32),
+        ("len", C.c_uint64), ("n_pat", C.c_uint64), ("n_frag", C.c_uint64),
+        ("z_off_fw", C.c_uint64), ("z_off_bw", C.c_uint64), ("fchr", C.c_uint64 * 5),
+        ("plen", C.c_void_p), ("rstarts", C.c_void_p), ("ebwt_fw", C.c_void_p), ("ebwt_bw", C.c_void_p),
+        ("ftab_fw", C.c_void_p), ("eftab_fw", C.c_void_p), ("ftab_bw", C.c_void_p), ("eftab_bw", C.c_void_p),
+        ("offs", C.c_void_p), ("n_recs", C.c_uint64), ("rec_off", C.c_void_p), ("rec_len", C.c_void_p),
+        ("rec_first", C.c_void_p), ("ref_buf", C.c_void_p),
+    ]
+
+
+class _IndexInfo(C.Structure):
+    _fields_ = [
+        ("off_size", C.c_int32), ("line_rate", C.c_int32), ("off_rate", C.c_int32), ("ftab_chars", C.c_int32),
+        ("len", C.c_uint64), ("bwt_len", C.c_uint64), ("num_sides", C.c_uint64), ("side_sz", C.c_uint64),
+        ("side_bwt_sz", C.c_uint64), ("side_bwt_len", C.c_uint64), ("ebwt_tot_len", C.c_uint64),
+        ("offs_len", C.c_uint64), ("ftab_len", C.c_uint64), ("eftab_len", C.c_uint64), ("n_pat", C.c_uint64),
+        ("n_frag", C.c_uint64), ("n_recs", C.c_uint64), ("ref_buf_bytes", C.c_uint64),
+        ("z_off_fw", C.c_uint64), ("z_off_bw", C.c_uint64), ("fchr", C.c_uint64 * 5),
+        ("has_bw", C.c_int32), ("has_ref", C.c_int32), ("device_bytes", C.c_uint64),
+    ]
+
+
+class _Reads(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("seq", C.c_void_p), ("qual", C.c_void_p), ("off", C.c_void_p)]
+
+
+class _SeedPlan(C.Structure):
+    _fields_ = [("seed_len", C.c_int32), ("max_seeds", C.c_int32), ("nofw", C.c_int32), ("norc", C.c_int32),
+                ("interval", C.c_void_p), ("offset", C.c_void_p)]
+
+
+# every symbol include/bt2g.h declares; tests assert the built library exports all of them
+EXPORTS = [
+    "bt2g_create", "bt2g_destroy", "bt2g_last_error", "bt2g_abi_version",
+    "bt2g_load_index_files", "bt2g_load_index_host", "bt2g_load_index_device",
+    "bt2g_index_info_get", "bt2g_index_array",
+    "bt2g_rank4", "bt2g_maplf1", "bt2g_ftab_lohi",
+    "bt2g_exact_sweep", "bt2g_seed_search", "bt2g_resolve", "bt2g_get_stretch",
+]
+
+
+def load_library() -> C.CDLL:
+    """Load libbt2g.so; raise (never fall back) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise Bt2GpuError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    lib.bt2g_create.argtypes = [i32, C.POINTER(vp)]
+    lib.bt2g_destroy.argtypes = [vp]
+    lib.bt2g_destroy.restype = None
+    lib.bt2g_last_error.argtypes = [vp]
+    lib.bt2g_last_error.restype = C.c_char_p
+    lib.bt2g_load_index_files.argtypes = [vp, C.c_char_p]
+    lib.bt2g_load_index_host.argtypes = [vp, C.POINTER(_IndexHost)]
+    lib.bt2g_load_index_device.argtypes = [vp, C.POINTER(_IndexHost)]
+    lib.bt2g_index_info_get.argtypes = [vp, C.POINTER(_IndexInfo)]
+    lib.bt2g_index_array.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
+    lib.bt2g_rank4.argtypes = [vp, i32, vp, u64, vp]
+    lib.bt2g_maplf1.argtypes = [vp, i32, vp, vp, u64, vp]
+    lib.bt2g_ftab_lohi.argtypes = [vp, i32, vp, u64, vp]
+    lib.bt2g_exact_sweep.argtypes = [vp, C.POINTER(_Reads), i32, i32, vp, vp]
+    lib.bt2g_seed_search.argtypes = [vp, C.POINTER(_Reads), C.POINTER(_SeedPlan), vp, vp]
+    lib.bt2g_resolve.argtypes = [vp, vp, vp, u64, i32, vp, vp, vp, vp, vp]
+    lib.bt2g_get_stretch.argtypes = [vp, vp, vp, vp, u64, C.c_int32, vp]
+    _LIB = lib
+    return lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class ReadBatch:
+    """Reads as the hot path sees them: codes 0..3 = ACGT, 4 = N; Phred+33 qualities."""
+
+    def __init__(self, seq: np.ndarray, off: np.ndarray, qual: Optional[np.ndarray] = None):
+        self.seq = _c(seq, np.uint8)
+        self.off = _c(off, np.uint64)
+        self.qual = None if qual is None else _c(qual, np.uint8)
+        self.n = len(self.off) - 1
+
+    @classmethod
+    def from_list(cls, reads, quals=None):
+        lens = np.array([len(r) for r in reads], dtype=np.uint64)
+        off = np.zeros(len(reads) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=off[1:])
+        seq = np.concatenate([np.asarray(r, dtype=np.uint8) for r in reads]) if len(reads) else np.zeros(0, np.uint8)
+        q = None
+        if quals is not None:
+            q = np.concatenate([np.asarray(x, dtype=np.uint8) for x in quals]) if len(quals) else np.zeros(0, np.uint8)
+        return cls(seq, off, q)
+
+    def lengths(self) -> np.ndarray:
+        return (self.off[1:] - self.off[:-1]).astype(np.int64)
+
+    def _struct(self) -> _Reads:
+        return _Reads(self.n, _ptr(self.seq), _ptr(self.qual), _ptr(self.off))
+
+
+class Bt2Gpu:
+    """One context per GPU (include/bt2g.h).  Raises Bt2GpuError on any failure."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.bt2g_create(device, C.byref(h))
+        if rc != 0:
+            raise Bt2GpuError(f"bt2g_create(device={device}) failed with {rc}: no usable CUDA device")
+        self._h = h
+        self.device = device
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bt2g_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self._lib.bt2g_last_error(self._h)
+            raise Bt2GpuError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # ---- index ---------------------------------------------------------------------
+    def load_index_files(self, basename: str):
+        self._check(self._lib.bt2g_load_index_files(self._h, basename.encode()), "bt2g_load_index_files")
+
+    def load_index_device(self, desc: dict, keep=None):
+        """Adopt device arrays (e.g. torch tensors filled by an NCCL broadcast). `desc` maps
+        bt2g_index_host field names to ints (scalars / raw device pointers)."""
+        ih = _IndexHost()
+        for k, v in desc.items():
+            if k == "fchr":
+                for i in range(5):
+                    ih.fchr[i] = int(v[i])
+            else:
+                setattr(ih, k, v)
+        self._keep = keep
+        self._check(self._lib.bt2g_load_index_device(self._h, C.byref(ih)), "bt2g_load_index_device")
+
+    def info(self) -> dict:
+        inf = _IndexInfo()
+        self._check(self._lib.bt2g_index_info_get(self._h, C.byref(inf)), "bt2g_index_info_get")
+        d = {k: getattr(inf, k) for k, _ in _IndexInfo._fields_ if k != "fchr"}
+        d["fchr"] = [int(x) for x in inf.fchr]
+        return d
+
+    def index_array(self, which: int):
+        p, b = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.bt2g_index_array(self._h, which, C.byref(p), C.byref(b)), "bt2g_index_array")
+        return (p.value or 0), int(b.value)
+
+    # ---- FM primitives -------------------------------------------------------------
+    def rank4(self, rows, mirror: bool = False) -> np.ndarray:
+        rows = _c(rows, np.uint64)
+        out = np.empty((len(rows), 4), dtype=np.uint64)
+        self._check(self._lib.bt2g_rank4(self._h, int(mirror), _ptr(rows), len(rows), _ptr(out)), "bt2g_rank4")
+        return out
+
+    def maplf1(self, rows, chars, mirror: bool = False) -> np.ndarray:
+        rows, chars = _c(rows, np.uint64), _c(chars, np.uint8)
+        out = np.empty(len(rows), dtype=np.uint64)
+        self._check(self._lib.bt2g_maplf1(self._h, int(mirror), _ptr(rows), _ptr(chars), len(rows), _ptr(out)), "bt2g_maplf1")
+        return out
+
+    def ftab_lohi(self, idx, mirror: bool = False) -> np.ndarray:
+        idx = _c(idx, np.uint64)
+        out = np.empty((len(idx), 2), dtype=np.uint64)
+        self._check(self._lib.bt2g_ftab_lohi(self._h, int(mirror), _ptr(idx), len(idx), _ptr(out)), "bt2g_ftab_lohi")
+        return out
+
+    # ---- K1 ------------------------------------------------------------------------
+    def exact_sweep(self, reads: ReadBatch, nofw=False, norc=False):
+        mine = np.empty((reads.n, 2), dtype=np.uint8)
+        ee = np.empty((reads.n, 4), dtype=np.uint64)
+        st = reads._struct()
+        self._check(self._lib.bt2g_exact_sweep(self._h, C.byref(st), int(nofw), int(norc), _ptr(mine), _ptr(ee)), "bt2g_exact_sweep")
+        return mine, ee
+
+    def seed_search(self, reads: ReadBatch, seed_len: int, interval, offset, max_seeds: int, nofw=False, norc=False):
+        interval = _c(np.broadcast_to(interval, (reads.n,)), np.int32)
+        offset = _c(np.broadcast_to(offset, (reads.n,)), np.int32)
+        out = np.empty((reads.n, 2, max_seeds, 4), dtype=np.uint64)
+        ns = np.empty(reads.n, dtype=np.int32)
+        plan = _SeedPlan(seed_len, max_seeds, int(nofw), int(norc), _ptr(interval), _ptr(offset))
+        st = reads._struct()
+        self._check(self._lib.bt2g_seed_search(self._h, C.byref(st), C.byref(plan), _ptr(out), _ptr(ns)), "bt2g_seed_search")
+        return out, ns
+
+    # ---- K2 ------------------------------------------------------------------------
+    def resolve(self, rows, hitlen, reject_straddle=False):
+        rows = _c(rows, np.uint64)
+        n = len(rows)
+        hitlen = _c(np.broadcast_to(hitlen, (n,)), np.uint32)
+        joined, tidx, textoff, tlen = (np.empty(n, dtype=np.uint64) for _ in range(4))
+        flags = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.bt2g_resolve(self._h, _ptr(rows), _ptr(hitlen), n, int(reject_straddle), _ptr(joined),
+                                           _ptr(tidx), _ptr(textoff), _ptr(tlen), _ptr(flags)), "bt2g_resolve")
+        return joined, tidx, textoff, tlen, flags
+
+    def get_stretch(self, tidx, off, count, stride: int) -> np.ndarray:
+        tidx, off, count = _c(tidx, np.uint64), _c(off, np.int64), _c(count, np.int32)
+        out = np.empty((len(tidx), stride), dtype=np.uint8)
+        self._check(self._lib.bt2g_get_stretch(self._h, _ptr(tidx), _ptr(off), _ptr(count), len(tidx), stride, _ptr(out)), "bt2g_get_stretch")
+        return out

@@ -1,0 +1,160 @@
+/* include/bt2g.h -- C ABI of libbt2g.so, the B200 (sm_100a) drop-in for bowtie2's alignment
+ * hot path.
+ *
+ * The reference (BenLangmead/bowtie2 2.5.5) has no FFI boundary for this path: the only
+ * extern "C" symbol is `int bowtie(int, const char**)` (bt2_search.cpp:5223-5230) and the hot
+ * path is reached through C++ member calls from multiseedSearchWorker (bt2_search.cpp:3094).
+ * This header therefore DEFINES the boundary; every entry point names the reference call(s)
+ * it replaces.  All arguments are plain pointers and sizes (no torch / C++ types).  Return
+ * value: 0 on success, negative on error (mirroring the reference's "throw 1 -> return 1"
+ * convention, bt2_search.cpp:5353-5362); bt2g_last_error() gives the message.
+ *
+ * Offsets ("OFF" = TIndexOffU, btypes.h:23-43) are 4 bytes for .bt2 and 8 bytes for .bt2l
+ * indexes.  Across this ABI every BW row / text offset travels as uint64_t regardless; the
+ * index arrays themselves stay in their on-disk width.
+ *
+ * Buffers passed to the host-pointer entry points are host memory (pinned preferred); the
+ * "_dev" twins take device pointers and an explicit cudaStream_t (passed as void*), do not
+ * copy and do not synchronise.
+ */
+#ifndef BT2G_H_
+#define BT2G_H_
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bt2g_ctx bt2g_ctx;
+
+/* ---------------------------------------------------------------- context ------------- */
+/* one context per GPU (replaces the per-process Ebwt/BitPairReference singletons that
+ * multiseedSearch() publishes to its worker threads, bt2_search.cpp:4774-4790). */
+int         bt2g_create(int device, bt2g_ctx **out);
+void        bt2g_destroy(bt2g_ctx *ctx);
+const char *bt2g_last_error(const bt2g_ctx *ctx);
+int         bt2g_abi_version(void);
+
+/* ---------------------------------------------------------------- index --------------- */
+/* Host-side description of one loaded index, arrays in their on-disk layout
+ * (Ebwt::readIntoMemory, bt2_io.cpp:131-616; BitPairReference ctor, reference.cpp:96-260).
+ * "fw" = <base>.{1,2}.bt2[l]; "bw" = mirror index <base>.rev.1.bt2[l] (needed because
+ * do1mmUpFront / SwDriver::extend use it, bt2_search.cpp:5149). */
+typedef struct {
+	int32_t  off_size;           /* 4 or 8 */
+	int32_t  line_rate, off_rate, ftab_chars;
+	uint64_t len;                /* joined text length */
+	uint64_t n_pat, n_frag;
+	uint64_t z_off_fw, z_off_bw;
+	uint64_t fchr[5];
+	const void    *plen;         /* OFF[n_pat] */
+	const void    *rstarts;      /* OFF[3*n_frag] */
+	const uint8_t *ebwt_fw;      /* num_sides * side_sz bytes */
+	const uint8_t *ebwt_bw;      /* may be NULL */
+	const void    *ftab_fw, *eftab_fw;   /* OFF[4^ftab_chars+1], OFF[2*ftab_chars] */
+	const void    *ftab_bw, *eftab_bw;   /* may be NULL */
+	const void    *offs;         /* OFF[offs_len] SA sample of the forward index */
+	/* packed reference (.3/.4) */
+	uint64_t n_recs;
+	const void    *rec_off, *rec_len;    /* OFF[n_recs] */
+	const uint8_t *rec_first;            /* u8[n_recs] */
+	const uint8_t *ref_buf;              /* 2-bit packed, ceil(sum(rec_len)/4) bytes */
+} bt2g_index_host;
+
+/* Read <base>.{1,2,3,4,rev.1}.bt2 or .bt2l from disk and upload (Ebwt ctor + loadIntoMemory,
+ * bt2_search.cpp:4986-5005,4832-4853; BitPairReference, :4789). */
+int bt2g_load_index_files(bt2g_ctx *ctx, const char *basename);
+/* Upload from host arrays (same content). */
+int bt2g_load_index_host(bt2g_ctx *ctx, const bt2g_index_host *ix);
+/* Adopt arrays that are ALREADY in this GPU's memory (pointers in bt2g_index_host are device
+ * pointers; the caller keeps ownership).  This is how a torch.distributed/NCCL broadcast
+ * receiver, or a GPU-side index builder, hands its tensors over. */
+int bt2g_load_index_device(bt2g_ctx *ctx, const bt2g_index_host *ix_dev);
+
+typedef struct {
+	int32_t  off_size, line_rate, off_rate, ftab_chars;
+	uint64_t len, bwt_len, num_sides, side_sz, side_bwt_sz, side_bwt_len;
+	uint64_t ebwt_tot_len, offs_len, ftab_len, eftab_len, n_pat, n_frag, n_recs, ref_buf_bytes;
+	uint64_t z_off_fw, z_off_bw;
+	uint64_t fchr[5];
+	int32_t  has_bw, has_ref;
+	uint64_t device_bytes;      /* total HBM held by the index */
+} bt2g_index_info;
+int bt2g_index_info_get(const bt2g_ctx *ctx, bt2g_index_info *out);
+
+/* Enumerate the device arrays of the loaded index (for one ncclBroadcast per array from the
+ * rank that read the files).  which: 0 ebwt_fw, 1 ebwt_bw, 2 offs, 3 ftab_fw,
+ * 4 eftab_fw, 5 ftab_bw, 6 eftab_bw, 7 plen, 8 rstarts, 9 rec_off, 10 rec_len, 11 rec_first,
+ * 12 ref_buf.  Returns device pointer + byte size. */
+#define BT2G_N_INDEX_ARRAYS 13
+int bt2g_index_array(const bt2g_ctx *ctx, int which, void **dev_ptr, uint64_t *bytes);
+
+/* ---------------------------------------------------------------- reads --------------- */
+/* A batch of reads as the hot path sees them (Read::patFw / Read::qual, read.h:39):
+ * seq[] = nucleotide codes 0..3 = A,C,G,T, 4 = N, all reads concatenated; qual[] = Phred+33
+ * bytes, same layout; off[i]..off[i+1] delimits read i. */
+typedef struct {
+	uint64_t        n_reads;
+	const uint8_t  *seq;
+	const uint8_t  *qual;        /* may be NULL where quality is not needed */
+	const uint64_t *off;         /* n_reads + 1 entries */
+} bt2g_reads;
+
+/* ---------------------------------------------------------------- FM primitives ------- */
+/* Ebwt::countBt2SideEx via SideLocus::initFromRow (bt2_idx.h:1887-1919, :369-397):
+ * out[4*i+c] = rank of nucleotide c at rows[i] (fchr + occ + in-side count, "$" adjusted). */
+int bt2g_rank4(bt2g_ctx *ctx, int mirror, const uint64_t *rows, uint64_t n, uint64_t *out);
+/* Ebwt::mapLF1(row, l, c) (bt2_idx.h:2420-2443): next row, or UINT64_MAX. */
+int bt2g_maplf1(bt2g_ctx *ctx, int mirror, const uint64_t *rows, const uint8_t *chars, uint64_t n, uint64_t *out);
+/* Ebwt::ftabLoHi(i, top, bot) (bt2_idx.h:1476-1485). out[2*i]=top, out[2*i+1]=bot. */
+int bt2g_ftab_lohi(bt2g_ctx *ctx, int mirror, const uint64_t *idx, uint64_t n, uint64_t *out);
+
+/* ---------------------------------------------------------------- K1: seed search ----- */
+/* SeedAligner::exactSweep (aligner_seed.cpp:856-970) with mineMax=2, repex=true, as called
+ * at bt2_search.cpp:3514.  Per read: mine[2*i+{0,1}] = min(#edits lower bound, 2) for the
+ * forward / reverse-complement read (0 for a skipped strand); ee[4*i+..] = topFw,botFw,topRc,botRc
+ * of the exact end-to-end hit ranges (0,0 when none). */
+int bt2g_exact_sweep(bt2g_ctx *ctx, const bt2g_reads *reads, int nofw, int norc,
+                     uint8_t *mine, uint64_t *ee);
+
+/* Seed layout for one seeding round (SeedAligner::instantiateSeeds, aligner_seed.cpp:498-587;
+ * round arithmetic bt2_search.cpp:3905-3945).  All seeds are exact (multiseedMms == 0,
+ * presets.cpp:37-92 => SEED_TYPE_EXACT). */
+typedef struct {
+	int32_t seed_len;            /* -L */
+	int32_t max_seeds;           /* stride of the output: per read 2*max_seeds ranges */
+	int32_t nofw, norc;
+	const int32_t *interval;     /* per read: msIval.f(len), paired boost already applied */
+	const int32_t *offset;       /* per read: (interval*roundi)/nrounds */
+} bt2g_seed_plan;
+
+/* SeedAligner::searchAllSeeds -> searchSeedBi/startSearchSeedBi for exact seeds
+ * (aligner_seed.cpp:597-720, :1637-1718, :1858-2037) using Ebwt::ftabLoHi, mapBiLFEx,
+ * mapLF1.  out[((i*2+strand)*max_seeds+k)*4 + {0,1,2,3}] = topf,botf,topb,botb of seed k
+ * (k-th offset from the 5' end) of read i, all zero when the seed does not occur.
+ * nseeds[i] receives the number of seed offsets of read i. */
+int bt2g_seed_search(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_seed_plan *plan,
+                     uint64_t *out, int32_t *nseeds);
+
+/* ---------------------------------------------------------------- K2: offset resolve -- */
+/* GroupWalk2S::advanceElement == Ebwt::getOffset(row) (group_walk.h:1160-1215,517-520;
+ * bt2_idx.cpp:150-171) followed by Ebwt::joinedToTextOff (bt2_idx.cpp:54-124) as
+ * SwDriver::extendSeeds does (aligner_sw_driver.cpp:1126-1147).
+ * For each i: joined[i] = offset in the joined text; tidx/textoff/tlen as joinedToTextOff
+ * returns them for a hit of length hitlen[i]; flags bit0 = straddled, bit1 = rejected
+ * (tidx == OFF_MASK, only when reject_straddle). Any output pointer may be NULL. */
+int bt2g_resolve(bt2g_ctx *ctx, const uint64_t *rows, const uint32_t *hitlen, uint64_t n,
+                 int reject_straddle, uint64_t *joined, uint64_t *tidx, uint64_t *textoff,
+                 uint64_t *tlen, uint8_t *flags);
+
+/* BitPairReference::getStretch (reference.cpp:420-560) with the off-end N padding of
+ * SwAligner::initRef (aligner_sw.cpp:196-245): out[i*stride + k] = code of reference tidx[i]
+ * at position off[i]+k for k < count[i] (4 = N / outside the reference). */
+int bt2g_get_stretch(bt2g_ctx *ctx, const uint64_t *tidx, const int64_t *off, const int32_t *count,
+                     uint64_t n, int32_t stride, uint8_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BT2G_H_ */

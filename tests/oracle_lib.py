@@ -1,0 +1,141 @@
+"""ctypes access to the oracle (TEST INFRASTRUCTURE):
+  * ``Oracle``    -- oracle/_ref/libbt2oracle.so, the plain-C restatement (oracle/bt2_oracle.c)
+  * ``Reference`` -- oracle/_ref/libbt2ref_{s,l}.so, the unmodified reference behind oracle/ref_glue.cpp
+Both expose the same method names so tests can run one body against either.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+OFFMASK = 0xFFFFFFFFFFFFFFFF
+
+u64, vp, ci = C.c_uint64, C.c_void_p, C.c_int
+pu64 = C.POINTER(u64)
+
+
+def ref_bin(name):
+    return os.path.join(REFDIR, name)
+
+
+def have_reference():
+    return os.path.exists(ref_bin("libbt2ref_s.so")) and os.path.exists(ref_bin("bowtie2-build-s"))
+
+
+def build_oracle():
+    """(Re)build the C restatement; also the reference objects when /root/reference is present."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle"), "ref"])
+
+
+class _Base:
+    prefix = ""
+
+    def _bind(self, lib):
+        p = self.prefix
+        g = lambda n: getattr(lib, p + n)
+        g("open").restype = vp; g("open").argtypes = [C.c_char_p, ci, ci]
+        g("close").argtypes = [vp]; g("close").restype = None
+        g("scalar").restype = u64; g("scalar").argtypes = [vp, ci, ci]
+        g("rank4").argtypes = [vp, ci, u64, pu64]; g("rank4").restype = None
+        g("rank1").restype = u64; g("rank1").argtypes = [vp, ci, u64, ci]
+        g("rowL").restype = ci; g("rowL").argtypes = [vp, ci, u64]
+        g("maplf1").restype = u64; g("maplf1").argtypes = [vp, ci, u64, ci]
+        g("ftab_lohi").argtypes = [vp, ci, u64, pu64, pu64]; g("ftab_lohi").restype = None
+        g("get_offset").restype = u64; g("get_offset").argtypes = [vp, u64]
+        g("get_stretch").argtypes = [vp, u64, C.c_int64, C.c_int64, vp]
+        g("exact_sweep").restype = u64
+        g("exact_sweep").argtypes = [vp, vp, ci, ci, ci, pu64, pu64]
+        g("seed_search").argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, pu64]
+        self._g = g
+
+    SCALARS = ["len", "bwt_len", "line_rate", "off_rate", "ftab_chars", "num_sides", "side_sz", "side_bwt_sz",
+               "z_off", "n_pat", "n_frag", "offs_len", "ftab_len", "eftab_len", "ebwt_tot_len"]
+
+    def scalars(self, mirror=False):
+        return {k: int(self._g("scalar")(self.h, int(mirror), i)) for i, k in enumerate(self.SCALARS)}
+
+    def rank4(self, rows, mirror=False):
+        out = np.empty((len(rows), 4), dtype=np.uint64)
+        buf = (u64 * 4)()
+        for i, r in enumerate(rows):
+            self._g("rank4")(self.h, int(mirror), int(r), buf)
+            out[i] = list(buf)
+        return out
+
+    def maplf1(self, rows, chars, mirror=False):
+        return np.array([self._g("maplf1")(self.h, int(mirror), int(r), int(c)) for r, c in zip(rows, chars)], dtype=np.uint64)
+
+    def ftab_lohi(self, idx, mirror=False):
+        out = np.empty((len(idx), 2), dtype=np.uint64)
+        t, b = u64(), u64()
+        for i, x in enumerate(idx):
+            self._g("ftab_lohi")(self.h, int(mirror), int(x), C.byref(t), C.byref(b))
+            out[i] = (t.value, b.value)
+        return out
+
+    def get_offset(self, rows):
+        return np.array([self._g("get_offset")(self.h, int(r)) for r in rows], dtype=np.uint64)
+
+    def joined_to_text(self, qlen, off, reject):
+        ti, to, tl, st = u64(), u64(), u64(), ci()
+        name = "joined_to_text"
+        f = self._g(name)
+        f.argtypes = [vp, u64, u64, ci, pu64, pu64, pu64, C.POINTER(ci)]
+        ok = f(self.h, int(qlen), int(off), int(reject), C.byref(ti), C.byref(to), C.byref(tl), C.byref(st))
+        return ok, ti.value, to.value, tl.value, st.value
+
+    def get_stretch(self, tidx, off, count):
+        out = np.empty(count, dtype=np.uint8)
+        self._g("get_stretch")(self.h, int(tidx), int(off), int(count), out.ctypes.data_as(vp))
+        return out
+
+    def exact_sweep(self, codes, nofw=False, norc=False):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        m, t = (u64 * 2)(), (u64 * 4)()
+        nelt = self._g("exact_sweep")(self.h, codes.ctypes.data_as(vp), len(codes), int(nofw), int(norc), m, t)
+        return int(nelt), list(m), list(t)
+
+    def seed_search(self, codes, seed_len, interval, offset, max_seeds, nofw=False, norc=False, quals=None):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        if quals is None:
+            quals = np.full(len(codes), ord("I"), dtype=np.uint8)
+        quals = np.ascontiguousarray(quals, dtype=np.uint8)
+        out = np.zeros((2, max_seeds, 4), dtype=np.uint64)
+        n = self._g("seed_search")(self.h, codes.ctypes.data_as(vp), quals.ctypes.data_as(vp), len(codes), seed_len,
+                                   interval, offset, int(nofw), int(norc), max_seeds, out.ctypes.data_as(pu64))
+        return n, out
+
+    def close(self):
+        if self.h:
+            self._g("close")(self.h)
+            self.h = None
+
+
+class Oracle(_Base):
+    prefix = "bt2o_"
+
+    def __init__(self, base, mirror=True, ref=True):
+        path = ref_bin("libbt2oracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        self.lib = C.CDLL(path)
+        self._bind(self.lib)
+        self.h = self.lib.bt2o_open(base.encode(), int(mirror), int(ref))
+        if not self.h:
+            raise RuntimeError(f"oracle: cannot open index {base}")
+
+
+class Reference(_Base):
+    prefix = "ref_"
+
+    def __init__(self, base, mirror=True, ref=True, large=False):
+        self.lib = C.CDLL(ref_bin("libbt2ref_l.so" if large else "libbt2ref_s.so"))
+        self._bind(self.lib)
+        self.h = self.lib.ref_open(base.encode(), int(mirror), int(ref))
+        if not self.h:
+            raise RuntimeError(f"reference: cannot open index {base}")

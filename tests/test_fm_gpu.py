@@ -1,0 +1,120 @@
+"""GPU parity tests for K1/K2: the CUDA path through the C ABI vs the oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from bowtie2_b200.lib import ReadBatch
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def seed_interval(ln, const=1.0, coeff=1.15):
+    return max(1, int(const + coeff * np.sqrt(ln)))
+
+
+@pytest.fixture(scope="module", params=["lambda", "synth_small", "synth_large"])
+def loaded(request, gpu, lambda_index, synth_index, synth_index_large):
+    base = {"lambda": lambda_index, "synth_small": synth_index, "synth_large": synth_index_large}[request.param]
+    gpu.load_index_files(base)
+    return gpu, Oracle(base), request.param
+
+
+def test_index_header(loaded):
+    gpu, O, _ = loaded
+    info, sc = gpu.info(), O.scalars()
+    for k in ("len", "bwt_len", "line_rate", "off_rate", "ftab_chars", "num_sides", "side_sz", "side_bwt_sz",
+              "n_pat", "n_frag", "offs_len", "ftab_len", "eftab_len", "ebwt_tot_len"):
+        assert info[k] == sc[k], k
+    assert info["z_off_fw"] == sc["z_off"] and info["z_off_bw"] == O.scalars(True)["z_off"]
+
+
+def test_rank_lf_ftab(loaded):
+    gpu, O, _ = loaded
+    n = O.scalars()["bwt_len"]
+    rng = np.random.default_rng(5)
+    for m in (False, True):
+        zo = O.scalars(m)["z_off"]
+        side = gpu.info()["side_bwt_len"]
+        edge = [0, n - 1, zo, min(zo + 1, n - 1), max(zo, 1) - 1, (zo // side) * side, min(n - 1, (zo // side + 1) * side)]
+        rows = np.concatenate([rng.integers(0, n, 4000), edge]).astype(np.uint64)
+        assert np.array_equal(gpu.rank4(rows, m), O.rank4(rows, m))
+        ch = rng.integers(0, 4, len(rows)).astype(np.uint8)
+        assert np.array_equal(gpu.maplf1(rows, ch, m), O.maplf1(rows, ch, m))
+        idx = rng.integers(0, O.scalars()["ftab_len"] - 1, 2000).astype(np.uint64)
+        assert np.array_equal(gpu.ftab_lohi(idx, m), O.ftab_lohi(idx, m))
+
+
+def test_resolve(loaded):
+    gpu, O, _ = loaded
+    sc = O.scalars()
+    rng = np.random.default_rng(6)
+    rows = np.concatenate([rng.integers(0, sc["bwt_len"], 3000), [sc["z_off"], 0, sc["bwt_len"] - 1]]).astype(np.uint64)
+    for rej in (False, True):
+        hitlen = rng.integers(1, 60, len(rows)).astype(np.uint32)
+        joined, tidx, textoff, tlen, flags = gpu.resolve(rows, hitlen, rej)
+        want = O.get_offset(rows)
+        assert np.array_equal(joined, want)
+        for i in range(0, len(rows), 3):
+            if int(want[i]) + int(hitlen[i]) > sc["len"]:
+                continue
+            ok, ti, to, tl, st = O.joined_to_text(int(hitlen[i]), int(want[i]), int(rej))
+            assert (flags[i] & 1) == st and ((flags[i] >> 1) & 1) == (0 if ok else 1)
+            if ok:
+                assert (int(tidx[i]), int(textoff[i]), int(tlen[i])) == (ti, to, tl)
+
+
+def _reads_for(name, lambda_reads, synth_genome):
+    if name == "lambda":
+        return lambda_reads[1][:600]
+    from bowtie2_b200 import synth
+    reads, _, _ = synth.make_reads(synth_genome, 600, 100, seed=9, sub_rate=0.01, indel_rate=0.001)
+    rng = np.random.default_rng(1)
+    for r in reads[:60]:
+        r[rng.integers(0, len(r))] = 4
+    reads.append(np.zeros(1, dtype=np.uint8))            # 1-base read
+    reads.append(np.full(30, 4, dtype=np.uint8))          # all-N read
+    reads.append(reads[0][:9].copy())                     # shorter than ftabChars
+    return reads
+
+
+def test_exact_sweep(loaded, lambda_reads, synth_genome):
+    gpu, O, name = loaded
+    reads = _reads_for(name, lambda_reads, synth_genome)
+    mine, ee = gpu.exact_sweep(ReadBatch.from_list(reads))
+    for i, r in enumerate(reads):
+        nelt, m, tb = O.exact_sweep(r)
+        assert list(mine[i]) == m and [int(x) for x in ee[i]] == tb, i
+    # strand switches
+    mine, ee = gpu.exact_sweep(ReadBatch.from_list(reads[:50]), nofw=True)
+    for i, r in enumerate(reads[:50]):
+        nelt, m, tb = O.exact_sweep(r, nofw=True)
+        assert list(mine[i]) == m and [int(x) for x in ee[i]] == tb
+
+
+@pytest.mark.parametrize("L,off", [(22, 0), (20, 3), (10, 1), (32, 0)])
+def test_seed_search(loaded, lambda_reads, synth_genome, L, off):
+    gpu, O, name = loaded
+    reads = [r for r in _reads_for(name, lambda_reads, synth_genome) if len(r) >= L + off]
+    batch = ReadBatch.from_list(reads)
+    interval = np.array([seed_interval(len(r)) for r in reads], dtype=np.int32)
+    MS = 32
+    out, ns = gpu.seed_search(batch, L, interval, off, MS)
+    nhit = 0
+    for i, r in enumerate(reads):
+        n, want = O.seed_search(r, L, int(interval[i]), off, MS)
+        assert n == ns[i]
+        assert np.array_equal(out[i], want), (i, L, off)
+        nhit += int((want[:, :, 1] > want[:, :, 0]).sum())
+    assert nhit > 0
+
+
+def test_get_stretch(loaded, synth_genome):
+    gpu, O, name = loaded
+    nref = 1 if name == "lambda" else len(synth_genome)
+    rng = np.random.default_rng(2)
+    tidx = rng.integers(0, nref, 200)
+    off = rng.integers(-40, 48000 if name == "lambda" else 40010, 200)
+    cnt = rng.integers(1, 300, 200)
+    out = gpu.get_stretch(tidx, off, cnt, 300)
+    for i in range(200):
+        assert np.array_equal(out[i, :cnt[i]], O.get_stretch(int(tidx[i]), int(off[i]), int(cnt[i]))), i
