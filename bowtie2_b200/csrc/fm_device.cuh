@@ -177,6 +177,9 @@ __device__ __forceinline__ bool joined_to_text(const DevIndex<OFF> &ix, uint64_t
                                                uint64_t &tlen, bool &straddled) {
 	uint64_t top = 0, bot = ix.nFrag;
 	straddled = false;
+	// the reference would spin on an offset outside the joined text (its debug build asserts
+	// progress, bt2_idx.cpp:70); a kernel must terminate, so such offsets are rejected
+	if(off >= ix.fw.len || ix.nFrag == 0) { tidx = BT2G_OFFMASK; textoff = 0; tlen = 0; return false; }
 	for(;;) {
 		uint64_t elt = top + ((bot - top) >> 1);
 		uint64_t lower = __ldg(ix.rstarts + elt * 3);

@@ -5,7 +5,7 @@ import pytest
 from bowtie2_b200.lib import ReadBatch
 from oracle_lib import Oracle
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 def seed_interval(ln, const=1.0, coeff=1.15):
