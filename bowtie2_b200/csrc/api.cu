@@ -1,6 +1,7 @@
 // api.cu -- C-ABI entry points of libbt2g.so (include/bt2g.h): context, index residency in HBM,
 // and the host-buffer wrappers around the K1/K2 kernels.
 #include "bt2g_internal.h"
+#include "dp_device.cuh"
 #include <cstring>
 #include <new>
 
@@ -400,6 +401,89 @@ int bt2g_get_stretch(bt2g_ctx *ctx, const uint64_t *tidx, const int64_t *off, co
 	              launch_get_stretch<uint64_t>(bt2g_dev_index<uint64_t>(ctx), dt.as<uint64_t>(), dof.as<int64_t>(), dc.as<int32_t>(), n, stride, dout.as<uint8_t>(), ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, n * (uint64_t)stride, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+} // extern "C"
+
+// ---- K3 ------------------------------------------------------------------------------------
+template <typename OFF> int launch_dp_e2e(const DevIndex<OFF> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);
+
+extern "C" {
+
+// Scoring::initPens (scoring.h:103-132) for COST_MODEL_QUAL mismatches, constant N penalty
+void bt2g_scoring_default(bt2g_scoring *sc, int local) {
+	memset(sc, 0, sizeof(*sc));
+	sc->match_bonus = local ? 2 : 0;
+	sc->rdgap_const = 5; sc->rdgap_linear = 3; sc->rfgap_const = 5; sc->rfgap_linear = 3;
+	sc->gapbar = 4;
+	sc->local = local ? 1 : 0;
+	for(int q = 0; q < 64; q++) {
+		int ii = q < 40 ? q : 40;
+		float frac = (float)ii / 40.0f;
+		sc->mmpen[q] = (uint8_t)(2 + (int)(frac * (6 - 2)));
+		sc->npen[q] = 1;
+	}
+}
+
+int bt2g_set_scoring(bt2g_ctx *ctx, const bt2g_scoring *sc) {
+	if(!ctx || !sc) return -1;
+	if(sc->gapbar < 1) { ctx->err = "gapbar must be >= 1"; return -1; }
+	ctx->scoring = *sc;
+	return 0;
+}
+
+int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem *probs, uint64_t n,
+                   int32_t maxCands, int32_t maxAlns, int32_t maxOps,
+                   bt2g_dp_summary *summ, bt2g_dp_cand *cands, bt2g_dp_aln *alns, uint8_t *ops) {
+	REQUIRE_LOADED(ctx);
+	if(!ctx->info.has_ref) { ctx->err = "packed reference (.3/.4) not loaded"; return -1; }
+	if(!reads || !reads->qual || !probs || !summ || !cands || !alns || !ops) { ctx->err = "null argument"; return -1; }
+	if(ctx->scoring.gapbar < 1) bt2g_scoring_default(&ctx->scoring, 0);
+	if(ctx->scoring.local) { ctx->err = "local mode DP not implemented in this build"; return -1; }
+	if(n == 0) return 0;
+	if(maxCands < 1 || maxAlns < 1 || maxOps < 1) return -1;
+	// shape of the batch
+	int maxCol = 1, maxLen = 1;
+	for(uint64_t i = 0; i < n; i++) {
+		int64_t nc = probs[i].refr - probs[i].refl + 1;
+		if(nc > maxCol) maxCol = (int)nc;
+		if(probs[i].read_idx >= reads->n_reads) { ctx->err = "read_idx out of range"; return -1; }
+		int len = (int)(reads->off[probs[i].read_idx + 1] - reads->off[probs[i].read_idx]);
+		if(len > maxLen) maxLen = len;
+	}
+	if(maxLen > 512) { ctx->err = "reads longer than 512 are not supported by the DP kernel"; return -1; }
+	if(maxCol > 8192) { ctx->err = "DP window wider than 8192 columns"; return -1; }
+	int R = maxLen <= 128 ? 4 : (maxLen <= 256 ? 8 : 16);
+	DBuf dseq, dqual, doff, dprob, dcodes, dlast, dsumm, dcand, daln, dops;
+	int rc = uploadReads(ctx, reads, dseq, dqual, doff, true);
+	if(rc) return rc;
+	DpLaunch L;
+	L.n = n; L.maxCol = maxCol; L.maxCands = maxCands; L.maxAlns = maxAlns; L.maxOps = maxOps;
+	L.codeStride = (uint64_t)(maxCol + 32) * 32 * R;
+	BT2G_CUDA_TRY(ctx, dprob.alloc(n * sizeof(bt2g_dp_problem)));
+	BT2G_CUDA_TRY(ctx, dcodes.alloc(n * L.codeStride));
+	BT2G_CUDA_TRY(ctx, dlast.alloc(n * (uint64_t)maxCol * 4));
+	BT2G_CUDA_TRY(ctx, dsumm.alloc(n * sizeof(bt2g_dp_summary)));
+	BT2G_CUDA_TRY(ctx, dcand.alloc(n * (uint64_t)maxCands * sizeof(bt2g_dp_cand)));
+	BT2G_CUDA_TRY(ctx, daln.alloc(n * (uint64_t)maxAlns * sizeof(bt2g_dp_aln)));
+	BT2G_CUDA_TRY(ctx, dops.alloc(n * (uint64_t)maxAlns * maxOps));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(dprob.p, probs, n * sizeof(bt2g_dp_problem), cudaMemcpyHostToDevice, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(dcand.p, 0, dcand.bytes, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(daln.p, 0, daln.bytes, ctx->stream));
+	L.seq = dseq.as<uint8_t>(); L.qual = dqual.as<uint8_t>(); L.roff = doff.as<uint64_t>();
+	L.probs = dprob.as<bt2g_dp_problem>(); L.codes = dcodes.as<uint8_t>(); L.lastH = dlast.as<int32_t>();
+	L.summ = dsumm.as<bt2g_dp_summary>(); L.cands = dcand.as<bt2g_dp_cand>(); L.alns = daln.as<bt2g_dp_aln>(); L.ops = dops.as<uint8_t>();
+	int lrc;
+	if(ctx->info.off_size == 4) lrc = launch_dp_e2e<uint32_t>(bt2g_dev_index<uint32_t>(ctx), ctx->scoring, L, maxLen, ctx->stream);
+	else lrc = launch_dp_e2e<uint64_t>(bt2g_dev_index<uint64_t>(ctx), ctx->scoring, L, maxLen, ctx->stream);
+	if(lrc) { ctx->err = "DP launch rejected"; return -1; }
+	BT2G_CUDA_TRY(ctx, cudaGetLastError());
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(summ, dsumm.p, dsumm.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(cands, dcand.p, dcand.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(alns, daln.p, daln.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(ops, dops.p, dops.bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	return 0;
 }

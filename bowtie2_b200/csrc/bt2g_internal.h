@@ -59,6 +59,7 @@ struct bt2g_ctx {
 	DevArray recCumOff, recCumUnamb, refRecOffs, refLens;
 	uint64_t nRefs = 0;
 	cudaStream_t stream = nullptr;
+	bt2g_scoring scoring{};
 	// scratch buffers (grown on demand)
 	std::vector<DevArray> scratch;
 };

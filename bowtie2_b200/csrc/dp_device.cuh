@@ -1,0 +1,19 @@
+// dp_device.cuh -- launch descriptor shared by api.cu and dp_kernels.cu (DP types: include/bt2g.h)
+#pragma once
+#include "bt2g_internal.h"
+
+struct DpLaunch {
+	const uint8_t  *seq, *qual;
+	const uint64_t *roff;
+	const bt2g_dp_problem *probs;
+	uint64_t        n;
+	uint8_t        *codes;        // workspace: n * codeStride bytes
+	int32_t        *lastH;        // workspace: n * maxCol ints (e2e last-row scores)
+	uint64_t        codeStride;
+	int             maxCol;
+	int             maxCands, maxAlns, maxOps;
+	bt2g_dp_summary *summ;
+	bt2g_dp_cand    *cands;
+	bt2g_dp_aln     *alns;
+	uint8_t         *ops;
+};

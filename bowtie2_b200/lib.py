@@ -246,3 +246,102 @@ class Bt2Gpu:
         out = np.empty((len(tidx), stride), dtype=np.uint8)
         self._check(self._lib.bt2g_get_stretch(self._h, _ptr(tidx), _ptr(off), _ptr(count), len(tidx), stride, _ptr(out)), "bt2g_get_stretch")
         return out
+
+
+# ---- K3: extension DP -----------------------------------------------------------------------
+class _Scoring(C.Structure):
+    _fields_ = [("match_bonus", C.c_int32), ("rdgap_const", C.c_int32), ("rdgap_linear", C.c_int32),
+                ("rfgap_const", C.c_int32), ("rfgap_linear", C.c_int32), ("gapbar", C.c_int32),
+                ("local", C.c_int32), ("mmpen", C.c_uint8 * 64), ("npen", C.c_uint8 * 64)]
+
+
+DP_PROBLEM = np.dtype([("read_idx", "<u4"), ("fw", "<u4"), ("tidx", "<u8"), ("refl", "<i8"), ("refr", "<i8"),
+                       ("triml", "<i4"), ("corel", "<i4"), ("corer", "<i4"), ("minsc", "<i4"),
+                       ("nceil", "<i4"), ("reserved", "<i4")], align=True)
+DP_SUMMARY = np.dtype([("found", "<i4"), ("best", "<i4"), ("ncand", "<i4"), ("naln", "<i4"), ("flags", "<i4")])
+DP_CAND = np.dtype([("score", "<i4"), ("row", "<i4"), ("col", "<i4"), ("fate", "<i4")])
+DP_ALN = np.dtype([("cand_idx", "<i4"), ("score", "<i4"), ("ns", "<i4"), ("gaps", "<i4"), ("refns", "<i4"),
+                   ("row0", "<i4"), ("col0", "<i4"), ("trim_beg", "<i4"), ("trim_end", "<i4"), ("nops", "<i4")])
+
+EXPORTS += ["bt2g_scoring_default", "bt2g_set_scoring", "bt2g_dp_extend"]
+
+OP_MATCH, OP_MM, OP_REFGAP, OP_READGAP = 0, 1, 2, 3
+EDIT_READ_GAP, EDIT_REF_GAP, EDIT_MM = 1, 2, 3      # edit.h:34-39
+
+
+def _bind_dp(lib):
+    if getattr(lib, "_dp_bound", False):
+        return
+    vp = C.c_void_p
+    lib.bt2g_scoring_default.argtypes = [C.POINTER(_Scoring), C.c_int]
+    lib.bt2g_scoring_default.restype = None
+    lib.bt2g_set_scoring.argtypes = [vp, C.POINTER(_Scoring)]
+    lib.bt2g_dp_extend.argtypes = [vp, C.POINTER(_Reads), vp, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp]
+    lib._dp_bound = True
+
+
+def _set_scoring(self, local: bool = False, **over):
+    """Install the scoring scheme (reference defaults, scoring.h:28-84; override by keyword)."""
+    _bind_dp(self._lib)
+    sc = _Scoring()
+    self._lib.bt2g_scoring_default(C.byref(sc), int(local))
+    for k, v in over.items():
+        setattr(sc, k, v)
+    self._check(self._lib.bt2g_set_scoring(self._h, C.byref(sc)), "bt2g_set_scoring")
+    self.scoring = sc
+
+
+def _dp_extend(self, reads: ReadBatch, probs: np.ndarray, max_cands=128, max_alns=4, max_ops=None):
+    """SwAligner::initRef + align + nextAlignment* for each problem (include/bt2g.h)."""
+    _bind_dp(self._lib)
+    assert probs.dtype == DP_PROBLEM
+    probs = np.ascontiguousarray(probs)
+    n = len(probs)
+    if max_ops is None:
+        max_ops = int(reads.lengths().max()) + 64 if reads.n else 64
+    summ = np.zeros(n, dtype=DP_SUMMARY)
+    cands = np.zeros((n, max_cands), dtype=DP_CAND)
+    alns = np.zeros((n, max_alns), dtype=DP_ALN)
+    ops = np.zeros((n, max_alns, max_ops), dtype=np.uint8)
+    st = reads._struct()
+    self._check(self._lib.bt2g_dp_extend(self._h, C.byref(st), _ptr(probs), n, max_cands, max_alns, max_ops,
+                                         _ptr(summ), _ptr(cands), _ptr(alns), _ptr(ops)), "bt2g_dp_extend")
+    return summ, cands, alns, ops
+
+
+Bt2Gpu.set_scoring = _set_scoring
+Bt2Gpu.dp_extend = _dp_extend
+
+
+def ops_to_edits(ops: np.ndarray, nops: int, read_codes: np.ndarray, fw: bool, row0: int):
+    """Rebuild the reference's Edit list (edit.h:57-) from a device op string.
+
+    The device lists columns from the last read row back to the first; the reference builds
+    `ned` in the same order and reverses it (SwResult::reverse), then inverts positions for
+    reverse-complement alignments (AlnRes::invertEdits via nextAlignment, aligner_sw.cpp:1135).
+    Returns a list of (pos, chr, qchr, type) with chr/qchr as ASCII codes, pos w.r.t. the 5'
+    end of the original read -- the representation SAM printing consumes."""
+    dna = b"ACGTN"
+    rdlen = len(read_codes)
+    seq = read_codes if fw else np.array([4 if c > 3 else 3 - c for c in read_codes[::-1]], dtype=np.uint8)
+    fwd = ops[:nops][::-1]
+    row = row0
+    out = []
+    for op in fwd:
+        typ, refc = int(op) & 3, (int(op) >> 2) & 7
+        if typ == OP_MATCH:
+            row += 1
+        elif typ == OP_MM:
+            out.append([row, dna[refc], dna[seq[row]], EDIT_MM])
+            row += 1
+        elif typ == OP_REFGAP:
+            out.append([row, ord("-"), dna[seq[row]], EDIT_REF_GAP])
+            row += 1
+        else:
+            out.append([row, dna[refc], ord("-"), EDIT_READ_GAP])
+    if not fw:
+        # AlnRes::invertEdits -> Edit::invertPoss (edit.cpp:50-78)
+        out = out[::-1]
+        for e in out:
+            e[0] = rdlen - e[0] - (0 if e[3] == EDIT_READ_GAP else 1)
+    return out

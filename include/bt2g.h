@@ -154,6 +154,78 @@ int bt2g_resolve(bt2g_ctx *ctx, const uint64_t *rows, const uint32_t *hitlen, ui
 int bt2g_get_stretch(bt2g_ctx *ctx, const uint64_t *tidx, const int64_t *off, const int32_t *count,
                      uint64_t n, int32_t stride, uint8_t *out);
 
+/* ---------------------------------------------------------------- K3: extension DP ----- */
+/* Scoring scheme (Scoring, scoring.h:96-173; defaults :28-84; built at bt2_search.cpp:5040).
+ * mmpen[q] / npen[q] are the per-quality penalty tables Scoring::initPens fills (q = Phred,
+ * clamped to 63); bt2g_scoring_default() reproduces the reference defaults for end-to-end
+ * (MA 0, MMP 6/2 by quality, NP 1, RDG/RFG 5+3, gap barrier 4) or --local (MA 2). */
+typedef struct {
+	int32_t match_bonus;
+	int32_t rdgap_const, rdgap_linear, rfgap_const, rfgap_linear;
+	int32_t gapbar;
+	int32_t local;               /* 0 end-to-end (sc.monotone), 1 local */
+	uint8_t mmpen[64];
+	uint8_t npen[64];
+} bt2g_scoring;
+void bt2g_scoring_default(bt2g_scoring *sc, int local);
+int  bt2g_set_scoring(bt2g_ctx *ctx, const bt2g_scoring *sc);
+
+/* One DP problem = one SwAligner::initRef + align + nextAlignment* session as issued by
+ * SwDriver::extendSeeds (aligner_sw_driver.cpp:1272-1376).  The rectangle comes from
+ * DynProgFramer::frameSeedExtensionRect (dp_framer.cpp:81-129; DPRect, dp_framer.h:59). */
+typedef struct {
+	uint32_t read_idx;           /* index into the bt2g_reads batch */
+	uint32_t fw;                 /* 1 = align the read, 0 = its reverse complement */
+	uint64_t tidx;               /* reference id */
+	int64_t  refl, refr;         /* DPRect.refl / refr (post-trim, inclusive) */
+	int32_t  triml;              /* DPRect.triml */
+	int32_t  corel, corer;       /* DPRect core diagonals (offsets in the untrimmed rectangle) */
+	int32_t  minsc;              /* minimum valid score */
+	int32_t  nceil;              /* SwAligner::nceil_ = nCeil.f(rdlen) (aligner_sw.cpp:43) */
+	int32_t  reserved;
+} bt2g_dp_problem;
+
+#define BT2G_DP_FLAG_BADSHAPE      1
+#define BT2G_DP_FLAG_CAND_OVERFLOW 2   /* more candidate cells than max_cands */
+#define BT2G_DP_FLAG_ALN_OVERFLOW  4   /* more successful backtraces than max_alns */
+#define BT2G_DP_FLAG_OPS_OVERFLOW  8   /* an alignment longer than max_ops */
+typedef struct {
+	int32_t found;               /* SwAligner::align return value */
+	int32_t best;                /* best score seen (aligner_sw.cpp:500 "best") */
+	int32_t ncand;               /* |btncand_| */
+	int32_t naln;                /* successful nextAlignment calls when every candidate is tried */
+	int32_t flags;
+} bt2g_dp_summary;
+
+/* candidate cell, in btncand_ order (score desc, row desc, col desc; aligner_sw_nuc.h:149-157) */
+#define BT2G_CAND_FILT_START 1   /* BT_CAND_FATE_FILT_START: start cell already reported through */
+#define BT2G_CAND_FAILED     2   /* backtrace attempted and failed (RNG was consumed) */
+#define BT2G_CAND_SUCCEEDED  3
+typedef struct { int32_t score, row, col, fate; } bt2g_dp_cand;
+
+/* one alignment: ops[] lists the alignment columns from the LAST read row back to the first
+ * (the order the backtrace discovers them).  op & 3: 0 match, 1 mismatch (or N), 2 reference
+ * gap (read char inserted), 3 read gap (reference char deleted); (op >> 2) & 7 = reference
+ * nucleotide code of the column (0..3, 4 = N) for types 0, 1, 3. */
+#define BT2G_OP_MATCH   0
+#define BT2G_OP_MM      1
+#define BT2G_OP_REFGAP  2
+#define BT2G_OP_READGAP 3
+typedef struct {
+	int32_t cand_idx;            /* index into the candidate list */
+	int32_t score, ns, gaps, refns;
+	int32_t row0, col0;          /* first aligned cell: read row (= soft trim at the upstream end) and window column */
+	int32_t trim_beg, trim_end;  /* soft-trimmed read rows upstream / downstream (local mode) */
+	int32_t nops;
+} bt2g_dp_aln;
+
+/* Fill + gather + backtrace for n problems.  Output strides: cands[n][max_cands],
+ * alns[n][max_alns], ops[n][max_alns][max_ops].  The reference offset of an alignment is
+ * problem.refl + aln.col0. */
+int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem *probs, uint64_t n,
+                   int32_t max_cands, int32_t max_alns, int32_t max_ops,
+                   bt2g_dp_summary *summ, bt2g_dp_cand *cands, bt2g_dp_aln *alns, uint8_t *ops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,135 @@
+// oracle/ref_glue_dp.cpp -- TEST INFRASTRUCTURE ONLY (see ref_glue.cpp).
+//
+// Runs ONE dynamic-programming problem through the unmodified reference SwAligner exactly as
+// SwDriver::extendSeeds does (aligner_sw_driver.cpp:1272-1376): DynProgFramer::frameSeedExtensionRect,
+// SwAligner::initRead / initRef / align, then nextAlignment until exhausted.  Returns the
+// candidate list (btncand_, aligner_sw.h:628) and every alignment produced, so the CUDA DP
+// kernel can be checked cell-for-cell on candidates and edit-for-edit on backtraces.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <memory>
+#include <iostream>
+#include <sstream>
+#include <algorithm>
+#include <limits>
+#include <map>
+#include <set>
+#include <fstream>
+#include <thread>
+#include <mutex>
+#include <atomic>
+#include <array>
+#include <utility>
+#include <stdexcept>
+
+#define private public
+#define protected public
+#include "aligner_sw.h"
+#undef private
+#undef protected
+#include "bt2_idx.h"
+#include "reference.h"
+#include "dp_framer.h"
+#include "scoring.h"
+#include "simple_func.h"
+#include "read.h"
+#include "random_source.h"
+
+struct RefHandleDp {   // must mirror RefHandle in ref_glue.cpp
+	std::unique_ptr<Ebwt> fw;
+	std::unique_ptr<Ebwt> bw;
+	std::unique_ptr<BitPairReference> ref;
+	std::unique_ptr<Scoring> sc_e2e;
+	std::unique_ptr<Scoring> sc_loc;
+};
+
+extern "C" {
+
+// DynProgFramer::frameSeedExtensionRect (dp_framer.cpp:81-129) with trimToRef = true
+// (gReportOverhangs = false).  out9: refl, refr, refl_pretrim, refr_pretrim, triml, trimr,
+// corel, corer, maxgap.  returns found.
+int ref_frame_seed_rect(int64_t off, uint64_t rdlen, int64_t reflen, uint64_t maxrdgap, uint64_t maxrfgap,
+                        int64_t maxns, uint64_t maxhalf, int64_t* out9) {
+	DynProgFramer fr(true);
+	DPRect r;
+	bool found = fr.frameSeedExtensionRect(off, rdlen, reflen, maxrdgap, maxrfgap, maxns, maxhalf, r);
+	out9[0] = r.refl; out9[1] = r.refr; out9[2] = r.refl_pretrim; out9[3] = r.refr_pretrim;
+	out9[4] = (int64_t)r.triml; out9[5] = (int64_t)r.trimr; out9[6] = (int64_t)r.corel; out9[7] = (int64_t)r.corer;
+	out9[8] = (int64_t)r.maxgap;
+	return found ? 1 : 0;
+}
+
+// Scoring::maxReadGaps / maxRefGaps (scoring.cpp:42,73), scoreMin, nCeil, perfectScore
+void ref_score_params(void* vh, int local, int64_t minsc, uint64_t rdlen, int64_t* out4) {
+	RefHandleDp* h = (RefHandleDp*)vh;
+	const Scoring& sc = local ? *h->sc_loc : *h->sc_e2e;
+	out4[0] = sc.maxReadGaps(minsc, rdlen);
+	out4[1] = sc.maxRefGaps(minsc, rdlen);
+	out4[2] = sc.perfectScore(rdlen);
+	out4[3] = sc.nCeil.f<int>((double)rdlen);
+}
+
+// One DP problem.  rect9 as above.  Outputs:
+//   summary[0]=found (align() return), [1]=best, [2]=ncand, [3]=naln
+//   cands[3*i+{0,1,2}] = row, col, score     (sorted as btncand_ is after align())
+//   alns: per alignment 8 int64: score, ns, gaps, refoff, trim5(soft), trim3(soft), nedits, fw
+//   edits: per edit 4 int32: pos, chr, qchr, type; concatenated, alignment by alignment
+int ref_dp(void* vh, int local, const uint8_t* codes, const uint8_t* quals, int len, int fw,
+           uint64_t tidx, int64_t tlen, const int64_t* rect9, int64_t minsc, uint32_t rndseed,
+           int max_cands, int max_alns, int max_edits,
+           int64_t* summary, int64_t* cands, int64_t* alns, int32_t* edits) {
+	RefHandleDp* h = (RefHandleDp*)vh;
+	const Scoring& sc = local ? *h->sc_loc : *h->sc_e2e;
+	static const char dna[] = "ACGTN";
+	std::string s(len, 'N'), q(len, 'I');
+	for(int i = 0; i < len; i++) { s[i] = dna[codes[i] > 4 ? 4 : codes[i]]; if(quals) q[i] = (char)quals[i]; }
+	Read rd; rd.init("r", s.c_str(), q.c_str());
+	DPRect rect;
+	rect.refl = rect9[0]; rect.refr = rect9[1]; rect.refl_pretrim = rect9[2]; rect.refr_pretrim = rect9[3];
+	rect.triml = (size_t)rect9[4]; rect.trimr = (size_t)rect9[5]; rect.corel = (size_t)rect9[6];
+	rect.corer = (size_t)rect9[7]; rect.maxgap = (size_t)rect9[8];
+	SwAligner sw(NULL);
+	RandomSource rnd; rnd.init(rndseed);
+	sw.initRead(rd.patFw, rd.patRc, rd.qual, rd.qualRev, 0, rd.length(), sc);
+	size_t nsLeft = 0;
+	sw.initRef(fw != 0, (TRefId)tidx, rect, *h->ref, (TRefOff)tlen, sc, (TAlScore)minsc,
+	           true /*enable8*/, 2000 /*cminlen*/, 4 /*cpow2*/, false /*doTri*/, true /*extend*/, 0, nsLeft);
+	TAlScore best = std::numeric_limits<TAlScore>::min();
+	bool found = sw.align(best);
+	summary[0] = found ? 1 : 0; summary[1] = best; summary[2] = 0; summary[3] = 0;
+	if(!found) return 0;
+	int nc = (int)sw.btncand_.size();
+	summary[2] = nc;
+	for(int i = 0; i < nc && i < max_cands; i++) {
+		cands[3 * i] = (int64_t)sw.btncand_[i].row; cands[3 * i + 1] = (int64_t)sw.btncand_[i].col;
+		cands[3 * i + 2] = sw.btncand_[i].score;
+	}
+	int naln = 0, ned = 0;
+	SwResult res;
+	while(!sw.done()) {
+		res.reset();
+		sw.nextAlignment(res, (TAlScore)minsc, rnd);
+		if(res.empty()) break;
+		if(naln < max_alns) {
+			const AlnRes& a = res.alres;
+			int64_t* o = alns + 8 * naln;
+			o[0] = a.score().score(); o[1] = a.score().ns(); o[2] = a.score().gaps();
+			o[3] = a.refoff(); o[4] = (int64_t)a.trimmed5p(true); o[5] = (int64_t)a.trimmed3p(true);
+			o[6] = (int64_t)a.ned().size(); o[7] = a.fw() ? 1 : 0;
+			for(size_t k = 0; k < a.ned().size(); k++) {
+				if(ned < max_edits) {
+					edits[4 * ned] = (int32_t)a.ned()[k].pos; edits[4 * ned + 1] = a.ned()[k].chr;
+					edits[4 * ned + 2] = a.ned()[k].qchr; edits[4 * ned + 3] = a.ned()[k].type;
+				}
+				ned++;
+			}
+		}
+		naln++;
+	}
+	summary[3] = naln;
+	return ned;
+}
+
+} // extern "C"

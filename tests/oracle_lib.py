@@ -139,3 +139,34 @@ class Reference(_Base):
         self.h = self.lib.ref_open(base.encode(), int(mirror), int(ref))
         if not self.h:
             raise RuntimeError(f"reference: cannot open index {base}")
+
+
+# ---- DP through the unmodified SwAligner (oracle/ref_glue_dp.cpp) ------------------------------
+def ref_dp(R, local, codes, quals, fw, tidx, tlen, rect, minsc, rndseed=1234, max_cands=1024, max_alns=32, max_edits=4096):
+    """Returns dict(found, best, cands[(row,col,score)], alns[dict(score,ns,gaps,refoff,trim5,trim3,fw,edits)])."""
+    i64 = C.c_int64
+    L = R.lib
+    L.ref_dp.argtypes = [vp, ci, vp, vp, ci, ci, u64, i64, C.POINTER(i64), i64, C.c_uint32, ci, ci, ci, vp, vp, vp, vp]
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    quals = np.ascontiguousarray(quals, dtype=np.uint8)
+    r9 = (i64 * 9)(rect.refl, rect.refr, rect.refl_pretrim, rect.refr_pretrim, rect.triml, rect.trimr,
+                   rect.corel, rect.corer, rect.maxgap)
+    summ = np.zeros(4, np.int64)
+    cands = np.zeros(3 * max_cands, np.int64)
+    alns = np.zeros(8 * max_alns, np.int64)
+    eds = np.zeros(4 * max_edits, np.int32)
+    L.ref_dp(R.h, int(local), codes.ctypes.data_as(vp), quals.ctypes.data_as(vp), len(codes), int(fw), int(tidx),
+             int(tlen), r9, int(minsc), rndseed, max_cands, max_alns, max_edits, summ.ctypes.data_as(vp),
+             cands.ctypes.data_as(vp), alns.ctypes.data_as(vp), eds.ctypes.data_as(vp))
+    out = {"found": int(summ[0]), "best": int(summ[1]), "ncand": int(summ[2]), "naln": int(summ[3])}
+    out["cands"] = [tuple(int(x) for x in cands[3 * i:3 * i + 3]) for i in range(min(out["ncand"], max_cands))]
+    al, e0 = [], 0
+    for i in range(min(out["naln"], max_alns)):
+        a = alns[8 * i:8 * i + 8]
+        ne = int(a[6])
+        al.append({"score": int(a[0]), "ns": int(a[1]), "gaps": int(a[2]), "refoff": int(a[3]), "trim5": int(a[4]),
+                   "trim3": int(a[5]), "fw": int(a[7]),
+                   "edits": [[int(x) for x in eds[4 * k:4 * k + 4]] for k in range(e0, e0 + ne)]})
+        e0 += ne
+    out["alns"] = al
+    return out

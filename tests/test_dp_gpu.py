@@ -1,0 +1,112 @@
+"""GPU parity for K3: the CUDA DP (fill + gather + backtrace) through the C ABI vs the unmodified
+reference SwAligner (oracle/_ref glue): found/best, the full candidate list, every alignment's
+score / offset / gaps / Ns and its edit list."""
+import numpy as np
+import pytest
+
+from bowtie2_b200 import policy, synth
+from bowtie2_b200.lib import DP_PROBLEM, ReadBatch, ops_to_edits
+from oracle_lib import Reference, have_reference, ref_dp
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+def _problems(genome, reads, truth, sc, jitter_rng, minsc_bump=0):
+    """One seed-extension DP per alignable read, framed as SwDriver::extendSeeds would
+    (aligner_sw_driver.cpp:1185-1283), with the seed diagonal jittered by a few bases."""
+    probs, meta = [], []
+    for i, (r, (c, p, strand)) in enumerate(zip(reads, truth)):
+        if c < 0:
+            c, p, strand = 0, int(jitter_rng.integers(0, len(genome[0]) - len(r))), 1
+        rdlen = len(r)
+        minsc = sc.min_score(rdlen) + minsc_bump
+        if minsc > sc.perfect_score(rdlen):
+            continue
+        off = p + int(jitter_rng.integers(-3, 4))
+        tlen = len(genome[c])
+        found, rect = policy.frame_seed_extension_rect(off, rdlen, tlen, sc.max_read_gaps(minsc, rdlen),
+                                                       sc.max_ref_gaps(minsc, rdlen), sc.n_ceil(rdlen))
+        if not found:
+            continue
+        probs.append((i, 1 if strand > 0 else 0, c, rect.refl, rect.refr, rect.triml, rect.corel, rect.corer,
+                      minsc, sc.n_ceil_raw(rdlen), 0))
+        meta.append((tlen, rect, minsc))
+    return np.array(probs, dtype=DP_PROBLEM), meta
+
+
+def _check(gpu, R, genome, reads, quals, probs, meta, local=False):
+    batch = ReadBatch.from_list(reads, quals)
+    summ, cands, alns, ops = gpu.dp_extend(batch, probs, max_cands=256, max_alns=8, max_ops=int(batch.lengths().max()) + 80)
+    nfound = naln = ngap = 0
+    for k, pr in enumerate(probs):
+        tlen, rect, minsc = meta[k]
+        i = int(pr["read_idx"])
+        want = ref_dp(R, local, reads[i], quals[i], int(pr["fw"]), int(pr["tidx"]), tlen, rect, minsc)
+        s = summ[k]
+        assert s["flags"] == 0, (k, s)
+        assert bool(s["found"]) == bool(want["found"]), (k, s, want["found"], want["best"])
+        if not want["found"]:
+            # the reference returns the best score even when below minsc (aligner_sw.cpp:1130-1136)
+            if want["best"] > -(1 << 62):
+                assert s["best"] == want["best"], (k, s["best"], want["best"])
+            continue
+        nfound += 1
+        assert s["best"] == want["best"]
+        assert s["ncand"] == want["ncand"]
+        got_c = [(int(c["row"]), int(c["col"]), int(c["score"])) for c in cands[k][:s["ncand"]]]
+        assert got_c == want["cands"], (k, got_c[:5], want["cands"][:5])
+        assert s["naln"] == want["naln"], (k, s["naln"], want["naln"])
+        for a_i, wa in enumerate(want["alns"]):
+            a = alns[k][a_i]
+            assert (int(a["score"]), int(a["ns"]), int(a["gaps"])) == (wa["score"], wa["ns"], wa["gaps"]), (k, a, wa)
+            assert int(pr["refl"]) + int(a["col0"]) == wa["refoff"], (k, a, wa)
+            ed = ops_to_edits(ops[k][a_i], int(a["nops"]), reads[i], bool(pr["fw"]), int(a["row0"]))
+            assert ed == wa["edits"], (k, a_i, ed, wa["edits"])
+            naln += 1
+            ngap += wa["gaps"] > 0
+    return nfound, naln, ngap
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("rdlen,sub,indel", [(100, 0.01, 0.002), (150, 0.02, 0.004), (50, 0.01, 0.0), (250, 0.01, 0.003), (33, 0.03, 0.01)])
+def test_dp_e2e_matches_reference(gpu, synth_index, synth_genome, rdlen, sub, indel):
+    gpu.load_index_files(synth_index)
+    gpu.set_scoring(local=False)
+    R = Reference(synth_index)
+    sc = policy.Scoring.default(False)
+    reads, quals, truth = synth.make_reads(synth_genome, 250, rdlen, seed=rdlen, sub_rate=sub, indel_rate=indel, random_frac=0.05)
+    rng = np.random.default_rng(rdlen)
+    for r in reads[:25]:
+        r[rng.integers(0, len(r))] = 4                       # Ns in reads
+    probs, meta = _problems(synth_genome, reads, truth, sc, rng)
+    nfound, naln, ngap = _check(gpu, R, synth_genome, reads, quals, probs, meta)
+    assert nfound > 100 and naln > 100
+    if indel > 0:
+        assert ngap > 0
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_dp_e2e_edges(gpu, synth_index, synth_genome):
+    """Windows hanging off either reference end, spanning the N gap, repeats (many candidates),
+    and a tightened minimum score."""
+    gpu.load_index_files(synth_index)
+    gpu.set_scoring(local=False)
+    R = Reference(synth_index)
+    sc = policy.Scoring.default(False)
+    g = synth_genome
+    rng = np.random.default_rng(3)
+    reads, quals, truth = [], [], []
+    L = 100
+    glen = len(g[0])
+    for p in [0, 1, 5, 29, 31, glen - L, glen - L - 1, glen - L - 31, glen // 2 - 60, glen // 2 - 20, glen // 2 + 10]:
+        for strand in (1, -1):
+            r = g[1][p:p + L].copy()
+            r[r > 3] = 0
+            r[rng.integers(0, L)] ^= 1
+            reads.append(r if strand > 0 else synth.revcomp(r))
+            quals.append(rng.integers(35, 74, L).astype(np.uint8))
+            truth.append((1, p, strand))
+    probs, meta = _problems(g, reads, truth, sc, rng)
+    _check(gpu, R, g, reads, quals, probs, meta)
+    probs, meta = _problems(g, reads, truth, sc, rng, minsc_bump=40)
+    _check(gpu, R, g, reads, quals, probs, meta)
