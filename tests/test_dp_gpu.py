@@ -46,9 +46,9 @@ def _check(gpu, R, genome, reads, quals, probs, meta, local=False):
         assert s["flags"] == 0, (k, s)
         assert bool(s["found"]) == bool(want["found"]), (k, s, want["found"], want["best"])
         if not want["found"]:
-            # the reference returns the best score even when below minsc (aligner_sw.cpp:1130-1136)
-            if want["best"] > -(1 << 62):
-                assert s["best"] == want["best"], (k, s["best"], want["best"])
+            # below minsc the reference's number is a saturated 8/16-bit value (0xff-biased u8 clamps
+            # at -255, aligner_swsse_ee_u8.cpp:1119-1131); only "not found" is comparable
+            assert s["best"] < minsc
             continue
         nfound += 1
         assert s["best"] == want["best"]
