@@ -9,9 +9,9 @@
 template <typename OFF> void launch_rank4(const DevEbwt<OFF> &, const uint64_t *, uint64_t, uint64_t *, cudaStream_t);
 template <typename OFF> void launch_maplf1(const DevEbwt<OFF> &, const uint64_t *, const uint8_t *, uint64_t, uint64_t *, cudaStream_t);
 template <typename OFF> void launch_ftab(const DevEbwt<OFF> &, const uint64_t *, uint64_t, uint64_t *, cudaStream_t);
-template <typename OFF> void launch_exact_sweep(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, cudaStream_t);
-template <typename OFF> void launch_seed_search(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, cudaStream_t);
-template <typename OFF> void launch_resolve(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t);
+template <typename OFF> void launch_exact_sweep(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, cudaStream_t, unsigned long long * = nullptr);
+template <typename OFF> void launch_seed_search(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, cudaStream_t, unsigned long long * = nullptr);
+template <typename OFF> void launch_resolve(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t, unsigned long long * = nullptr);
 template <typename OFF> void launch_get_stretch(const DevIndex<OFF> &, const uint64_t *, const int64_t *, const int32_t *, uint64_t, int, uint8_t *, cudaStream_t);
 
 namespace {
@@ -460,11 +460,16 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 	int rc = uploadReads(ctx, reads, dseq, dqual, doff, true);
 	if(rc) return rc;
 	DpLaunch L;
-	L.n = n; L.maxCol = maxCol; L.maxCands = maxCands; L.maxAlns = maxAlns; L.maxOps = maxOps;
+	L.n = n; L.nDev = nullptr; L.maxCol = maxCol;
+	{
+		int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+		uint64_t want = (uint64_t)sms * 16;      // 16 resident warps per SM
+		L.numSlots = ((n < want ? n : want) + 3) / 4 * 4;
+	} L.maxCands = maxCands; L.maxAlns = maxAlns; L.maxOps = maxOps;
 	L.codeStride = (uint64_t)(maxCol + 32) * 32 * R;
 	BT2G_CUDA_TRY(ctx, dprob.alloc(n * sizeof(bt2g_dp_problem)));
-	BT2G_CUDA_TRY(ctx, dcodes.alloc(n * L.codeStride));
-	BT2G_CUDA_TRY(ctx, dlast.alloc(n * (uint64_t)maxCol * 4));
+	BT2G_CUDA_TRY(ctx, dcodes.alloc(L.numSlots * L.codeStride));
+	BT2G_CUDA_TRY(ctx, dlast.alloc(L.numSlots * (uint64_t)maxCol * 4));
 	BT2G_CUDA_TRY(ctx, dsumm.alloc(n * sizeof(bt2g_dp_summary)));
 	BT2G_CUDA_TRY(ctx, dcand.alloc(n * (uint64_t)maxCands * sizeof(bt2g_dp_cand)));
 	BT2G_CUDA_TRY(ctx, daln.alloc(n * (uint64_t)maxAlns * sizeof(bt2g_dp_aln)));

@@ -7,6 +7,8 @@ struct DpLaunch {
 	const uint64_t *roff;
 	const bt2g_dp_problem *probs;
 	uint64_t        n;
+	const uint32_t *nDev;         // optional: problem count produced on the device
+	uint64_t        numSlots;     // persistent warp slots (multiple of 4)
 	uint8_t        *codes;        // workspace: n * codeStride bytes
 	int32_t        *lastH;        // workspace: n * maxCol ints (e2e last-row scores)
 	uint64_t        codeStride;

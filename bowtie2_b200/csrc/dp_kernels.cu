@@ -35,18 +35,25 @@ template <typename OFF, int R>
 __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L) {
 	extern __shared__ uint8_t smem[];
 	const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint64_t w = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock;
-	if(w >= L.n) return;
+	const uint64_t slot = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock;
+	const uint64_t nSlots = (uint64_t)gridDim.x * (blockDim.x >> 5);
+	const uint64_t nProb = L.nDev ? (uint64_t)*L.nDev : L.n;
 	uint8_t *refw = smem + (size_t)warpInBlock * (L.maxCol + 16);
+	// persistent warps: the move-byte workspace belongs to the warp SLOT, not to the problem, so
+	// it is (#SMs x resident warps) x codeStride bytes and stays L2-resident across problems
+	uint8_t *codes = L.codes + slot * L.codeStride;
+	int32_t *lastH = L.lastH + slot * (uint64_t)L.maxCol;
+	for(uint64_t w = slot; w < nProb; w += nSlots) {
 	const bt2g_dp_problem p = L.probs[w];
 	const uint8_t *rs = L.seq + L.roff[p.read_idx];
 	const uint8_t *rq = L.qual + L.roff[p.read_idx];
 	const int rdlen = (int)(L.roff[p.read_idx + 1] - L.roff[p.read_idx]);
 	const int ncol = (int)(p.refr - p.refl + 1);
 	bt2g_dp_summary *summ = L.summ + w;
+	__syncwarp();
 	if(ncol <= 0 || ncol > L.maxCol || rdlen > 32 * R || rdlen <= 0) {
 		if(lane == 0) { summ->found = 0; summ->best = DP_NEG; summ->ncand = 0; summ->naln = 0; summ->flags = BT2G_DP_FLAG_BADSHAPE; }
-		return;
+		continue;
 	}
 	// reference window (SwAligner::initRef, aligner_sw.cpp:155-271): codes 0..3, 4 = N / off-end
 	for(int k = lane; k < ncol; k += 32) refw[k] = (uint8_t)ref_base<OFF>(ix, p.tidx, p.refl + k);
@@ -76,8 +83,6 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 #pragma unroll
 	for(int r = 0; r < R; r++) { Hleft[r] = DP_NEG; Earr[r] = DP_NEG; Eprev[r] = DP_NEG; }
 	int botH = DP_NEG, botF = DP_NEG, prevInH = DP_NEG;
-	uint8_t *codes = L.codes + w * L.codeStride;
-	int32_t *lastH = L.lastH + w * (uint64_t)L.maxCol;
 	const int nsteps = ncol + lastLane;   // lanes beyond lastLane hold no rows
 	int best = DP_NEG;
 	for(int t = 0; t < nsteps; t++) {
@@ -137,11 +142,11 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 	}
 	best = __shfl_sync(0xffffffffu, best, lastLane);
 	__syncwarp();
-	if(lane != 0) return;
+	if(lane != 0) continue;
 
 	// ---- SwAligner::align tail (aligner_sw.cpp:679-729) + gatherCellsNucleotidesEnd2End (:1176-1208)
 	summ->best = best; summ->flags = 0; summ->naln = 0; summ->ncand = 0;
-	if(best < p.minsc) { summ->found = 0; return; }
+	if(best < p.minsc) { summ->found = 0; continue; }
 	bt2g_dp_cand *cands = L.cands + w * (uint64_t)L.maxCands;
 	int ncand = 0, totalCand = 0;
 	for(int j = 0; j < ncol; j++) {
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 		naln++;
 	}
 	summ->naln = naln;
+	} // persistent loop over problems
 }
 
 // ----------------------------------------------------------------------------------------
@@ -260,7 +266,7 @@ int launch_dp_e2e(const DevIndex<OFF> &ix, const bt2g_scoring &sc, const DpLaunc
 	if(L.n == 0) return 0;
 	const int warpsPerBlock = 4;
 	size_t smem = (size_t)warpsPerBlock * (L.maxCol + 16);
-	unsigned grid = (unsigned)((L.n + warpsPerBlock - 1) / warpsPerBlock);
+	unsigned grid = (unsigned)(L.numSlots / warpsPerBlock);
 	if(maxRdLen <= 128) {
 		if(smem > 48 * 1024) cudaFuncSetAttribute(k_dp_e2e<OFF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		k_dp_e2e<OFF, 4><<<grid, warpsPerBlock * 32, smem, st>>>(ix, sc, L);

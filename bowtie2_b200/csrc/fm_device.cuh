@@ -158,7 +158,7 @@ __device__ __forceinline__ uint64_t ftab_lo(const DevEbwt<OFF> &e, uint64_t i) {
 // Ebwt::getOffset(row) (bt2_idx.cpp:150-171) == GroupWalk2S::advanceElement result
 // (group_walk.h:517-520): LF-walk until a sampled row or the "$" row.
 template <typename OFF>
-__device__ __forceinline__ uint64_t get_offset(const DevIndex<OFF> &ix, uint64_t row) {
+__device__ __forceinline__ uint64_t get_offset(const DevIndex<OFF> &ix, uint64_t row, unsigned &nside) {
 	const uint64_t rateMask = (1ull << ix.offRate) - 1;
 	uint64_t jumps = 0;
 	for(;;) {
@@ -166,7 +166,7 @@ __device__ __forceinline__ uint64_t get_offset(const DevIndex<OFF> &ix, uint64_t
 		if((row & rateMask) == 0) return jumps + (uint64_t)__ldg(ix.offs + (row >> ix.offRate));
 		int c;
 		row = lf_step<OFF>(ix.fw, row, c);
-		jumps++;
+		jumps++; nside++;
 	}
 }
 

@@ -43,7 +43,7 @@ __global__ void k_ftab(DevEbwt<OFF> e, const uint64_t *idx, uint64_t n, uint64_t
 // ----------------------------------------------------------------------------------------
 template <typename OFF>
 __global__ void k_exact_sweep(DevIndex<OFF> ix, const uint8_t *seq, const uint64_t *roff, uint64_t nReads,
-                              int nofw, int norc, uint8_t *mine, uint64_t *ee) {
+                              int nofw, int norc, uint8_t *mine, uint64_t *ee, unsigned long long *cnt) {
 	uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(t >= nReads * 2) return;
 	uint64_t rd = t >> 1;
@@ -57,6 +57,7 @@ __global__ void k_exact_sweep(DevIndex<OFF> ix, const uint8_t *seq, const uint64
 	const int mineMax = 2;
 	uint64_t top = 0, bot = 0;
 	int dep = 0, nedit = 0;
+	unsigned nside = 0;
 	bool doInit = true, done = false;
 	while(dep < len && !done) {
 		if(doInit) {
@@ -95,9 +96,9 @@ __global__ void k_exact_sweep(DevIndex<OFF> ix, const uint8_t *seq, const uint64
 				// two independent side fetches in flight
 				uint64_t nt = rank1<OFF>(e, top, c);
 				uint64_t nb = rank1<OFF>(e, bot, c);
-				top = nt; bot = nb;
+				top = nt; bot = nb; nside += 2;
 			} else {
-				uint64_t nt = maplf1<OFF>(e, top, c);
+				uint64_t nt = maplf1<OFF>(e, top, c); nside++;
 				if(nt == BT2G_OFFMASK) { top = bot = 0; } else { top = nt; bot = nt + 1; }
 			}
 			if(bot <= top) {
@@ -108,6 +109,7 @@ __global__ void k_exact_sweep(DevIndex<OFF> ix, const uint8_t *seq, const uint64
 			dep++;
 		}
 	}
+	if(cnt) atomicAdd(cnt, (unsigned long long)nside);
 	mine[t] = (uint8_t)nedit;
 	if(!done && nedit == 0 && bot > top) { eo[0] = top; eo[1] = bot; } else { eo[0] = eo[1] = 0; }
 }
@@ -123,7 +125,7 @@ template <typename OFF>
 __global__ void k_seed_search(DevIndex<OFF> ix, const uint8_t *seq, const uint64_t *roff, uint64_t nReads,
                               int seedLen, int maxSeeds, int nofw, int norc,
                               const int32_t *interval, const int32_t *offset,
-                              uint64_t *out, int32_t *nseedsOut) {
+                              uint64_t *out, int32_t *nseedsOut, unsigned long long *cnt) {
 	uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	uint64_t perRead = 2ull * maxSeeds;
 	if(t >= nReads * perRead) return;
@@ -156,6 +158,7 @@ __global__ void k_seed_search(DevIndex<OFF> ix, const uint8_t *seq, const uint64
 	const int ftabLen = fw.ftabChars;
 	uint64_t topf, botf, topb = 0, botb = 0;
 	int step;
+	unsigned nside = 0;
 	if(ftabLen > 1 && ftabLen <= sl) {
 		uint64_t fwi = 0, bwi = 0;
 		for(int i = 0; i < ftabLen; i++) {
@@ -178,18 +181,21 @@ __global__ void k_seed_search(DevIndex<OFF> ix, const uint8_t *seq, const uint64
 			uint64_t tt[4], bb[4];
 			rank4<OFF>(fw, topf, tt);
 			rank4<OFF>(fw, botf, bb);
+			nside += 2;
 			uint64_t w0 = bb[0] - tt[0], w1 = bb[1] - tt[1], w2 = bb[2] - tt[2];
 			uint64_t tp = topb + (c > 0 ? w0 : 0) + (c > 1 ? w1 : 0) + (c > 2 ? w2 : 0);
 			uint64_t nt = c == 0 ? tt[0] : (c == 1 ? tt[1] : (c == 2 ? tt[2] : tt[3]));
 			uint64_t nb = c == 0 ? bb[0] : (c == 1 ? bb[1] : (c == 2 ? bb[2] : bb[3]));
-			if(nb <= nt) return;
+			if(nb <= nt) break;
 			topf = nt; botf = nb; topb = tp; botb = tp + (nb - nt);
 		} else {
-			uint64_t nt = maplf1<OFF>(fw, topf, c);
-			if(nt == BT2G_OFFMASK) return;
+			uint64_t nt = maplf1<OFF>(fw, topf, c); nside++;
+			if(nt == BT2G_OFFMASK) break;
 			topf = nt; botf = nt + 1;
 		}
 	}
+	if(cnt) atomicAdd(cnt, (unsigned long long)nside);
+	if(step < sl) return;   // died before the last step
 	o[0] = topf; o[1] = botf; o[2] = topb; o[3] = botb;
 }
 
@@ -199,10 +205,13 @@ __global__ void k_seed_search(DevIndex<OFF> ix, const uint8_t *seq, const uint64
 template <typename OFF>
 __global__ void k_resolve(DevIndex<OFF> ix, const uint64_t *rows, const uint32_t *hitlen, uint64_t n,
                           int rejectStraddle, uint64_t *joined, uint64_t *tidx, uint64_t *textoff,
-                          uint64_t *tlen, uint8_t *flags) {
+                          uint64_t *tlen, uint8_t *flags, unsigned long long *cnt) {
 	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(i >= n) return;
-	uint64_t off = get_offset<OFF>(ix, rows[i]);
+	if(rows[i] == BT2G_OFFMASK) { if(flags) flags[i] = 4; return; }   // empty slot
+	unsigned nside = 0;
+	uint64_t off = get_offset<OFF>(ix, rows[i], nside);
+	if(cnt) atomicAdd(cnt, (unsigned long long)nside);
 	if(joined) joined[i] = off;
 	if(tidx || textoff || tlen || flags) {
 		uint64_t ti, to, tl; bool st;
@@ -243,21 +252,21 @@ void launch_ftab(const DevEbwt<OFF> &e, const uint64_t *idx, uint64_t n, uint64_
 }
 template <typename OFF>
 void launch_exact_sweep(const DevIndex<OFF> &ix, const uint8_t *seq, const uint64_t *roff, uint64_t nReads,
-                        int nofw, int norc, uint8_t *mine, uint64_t *ee, cudaStream_t st) {
-	if(nReads) k_exact_sweep<OFF><<<gridFor(nReads * 2, 128), 128, 0, st>>>(ix, seq, roff, nReads, nofw, norc, mine, ee);
+                        int nofw, int norc, uint8_t *mine, uint64_t *ee, cudaStream_t st, unsigned long long *cnt) {
+	if(nReads) k_exact_sweep<OFF><<<gridFor(nReads * 2, 128), 128, 0, st>>>(ix, seq, roff, nReads, nofw, norc, mine, ee, cnt);
 }
 template <typename OFF>
 void launch_seed_search(const DevIndex<OFF> &ix, const uint8_t *seq, const uint64_t *roff, uint64_t nReads,
                         int seedLen, int maxSeeds, int nofw, int norc, const int32_t *interval,
-                        const int32_t *offset, uint64_t *out, int32_t *nseeds, cudaStream_t st) {
+                        const int32_t *offset, uint64_t *out, int32_t *nseeds, cudaStream_t st, unsigned long long *cnt) {
 	uint64_t n = nReads * 2ull * maxSeeds;
 	if(n) k_seed_search<OFF><<<gridFor(n, 128), 128, 0, st>>>(ix, seq, roff, nReads, seedLen, maxSeeds, nofw, norc,
-	                                                        interval, offset, out, nseeds);
+	                                                        interval, offset, out, nseeds, cnt);
 }
 template <typename OFF>
 void launch_resolve(const DevIndex<OFF> &ix, const uint64_t *rows, const uint32_t *hitlen, uint64_t n, int rej,
-                    uint64_t *joined, uint64_t *tidx, uint64_t *textoff, uint64_t *tlen, uint8_t *flags, cudaStream_t st) {
-	if(n) k_resolve<OFF><<<gridFor(n, 128), 128, 0, st>>>(ix, rows, hitlen, n, rej, joined, tidx, textoff, tlen, flags);
+                    uint64_t *joined, uint64_t *tidx, uint64_t *textoff, uint64_t *tlen, uint8_t *flags, cudaStream_t st, unsigned long long *cnt) {
+	if(n) k_resolve<OFF><<<gridFor(n, 128), 128, 0, st>>>(ix, rows, hitlen, n, rej, joined, tidx, textoff, tlen, flags, cnt);
 }
 template <typename OFF>
 void launch_get_stretch(const DevIndex<OFF> &ix, const uint64_t *tidx, const int64_t *off, const int32_t *count,
@@ -269,9 +278,9 @@ void launch_get_stretch(const DevIndex<OFF> &ix, const uint64_t *tidx, const int
 	template void launch_rank4<OFF>(const DevEbwt<OFF> &, const uint64_t *, uint64_t, uint64_t *, cudaStream_t);  \
 	template void launch_maplf1<OFF>(const DevEbwt<OFF> &, const uint64_t *, const uint8_t *, uint64_t, uint64_t *, cudaStream_t); \
 	template void launch_ftab<OFF>(const DevEbwt<OFF> &, const uint64_t *, uint64_t, uint64_t *, cudaStream_t);   \
-	template void launch_exact_sweep<OFF>(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, cudaStream_t); \
-	template void launch_seed_search<OFF>(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, cudaStream_t); \
-	template void launch_resolve<OFF>(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t); \
+	template void launch_exact_sweep<OFF>(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, cudaStream_t, unsigned long long *); \
+	template void launch_seed_search<OFF>(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, cudaStream_t, unsigned long long *); \
+	template void launch_resolve<OFF>(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t, unsigned long long *); \
 	template void launch_get_stretch<OFF>(const DevIndex<OFF> &, const uint64_t *, const int64_t *, const int32_t *, uint64_t, int, uint8_t *, cudaStream_t);
 INSTANTIATE(uint32_t)
 INSTANTIATE(uint64_t)

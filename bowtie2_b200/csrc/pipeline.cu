@@ -1,0 +1,370 @@
+// pipeline.cu -- the batched hot path: one pass of  exactSweep -> multiseed search -> SA-offset
+// resolution -> seed-extension DP (fill + backtrace)  over a batch of reads, entirely on the
+// device (seven launches, no host round trip between stages).
+//
+// This is the data-parallel core the reference runs one read at a time inside
+// multiseedSearchWorker (bt2_search.cpp:3094-4254; stages [A] :3514, [C] :3931-3955,
+// SwDriver::extendSeeds aligner_sw_driver.cpp:921-1494).  Each stage is the same kernel the
+// stand-alone entry points expose (parity-tested one by one against the oracle); what this
+// file adds is the glue that the reference interleaves per read:
+//   collect : which BW rows to resolve.  Exact end-to-end hits first (eeSaTups, :66-291);
+//             otherwise seed ranges smallest-first (SATuple::operator<, aligner_cache.h:397-405),
+//             every row of ranges up to `range_max` until `row_cap` rows (the reference instead
+//             samples rows with its per-read RNG and stops early by policy -- see DESIGN.md
+//             "speculative pipeline vs sequential policy").
+//   frame   : refoff = textoff - rdoff, duplicate diagonals dropped (seenDiags1_, :1162-1170),
+//             DynProgFramer::frameSeedExtensionRect (dp_framer.cpp:81-129).
+//   pick    : best-scoring alignment per read (+ runner-up score).
+#include "fm_device.cuh"
+#include "dp_device.cuh"
+#include <new>
+#include <cstring>
+
+template <typename OFF> void launch_exact_sweep(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, cudaStream_t, unsigned long long *);
+template <typename OFF> void launch_seed_search(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, cudaStream_t, unsigned long long *);
+template <typename OFF> void launch_resolve(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t, unsigned long long *);
+template <typename OFF> int launch_dp_e2e(const DevIndex<OFF> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);
+
+struct PipeBufs {
+	// inputs (device copies for the host-buffer entry point)
+	uint8_t *seq, *qual; uint64_t *roff;
+	// per-length policy tables
+	int32_t *minscByLen, *nceilByLen, *nceilRawByLen, *ivalByLen, *rdgapsByLen, *rfgapsByLen;
+	int32_t *interval, *offset;               // per read
+	uint8_t *mine; uint64_t *ee;              // exact sweep
+	uint64_t *ranges; int32_t *nseeds;        // seed search
+	uint64_t *rows; uint32_t *hitlen, *meta;  // collect
+	uint64_t *tidx, *textoff, *tlen; uint8_t *rflags;   // resolve
+	bt2g_dp_problem *probs; uint32_t *nProb; int32_t *readProb; int32_t *readNProb;
+	uint8_t *codes; int32_t *lastH;
+	bt2g_dp_summary *summ; bt2g_dp_cand *cands; bt2g_dp_aln *alns; uint8_t *ops;
+	bt2g_read_result *res; uint8_t *resOps;
+	unsigned long long *counters;             // [4]: sweep sides, seed sides, resolve sides, dp cells
+};
+
+struct bt2g_pipeline {
+	bt2g_ctx *ctx;
+	bt2g_pipeline_params prm;
+	uint64_t maxReads, maxBases;
+	PipeBufs b;
+	std::vector<void *> allocs;
+	uint64_t numSlots, codeStride;
+	int maxCol, R;
+	// pinned staging for the host entry point
+	uint8_t *hSeq = nullptr, *hQual = nullptr; uint64_t *hOff = nullptr;
+	bt2g_read_result *hRes = nullptr; uint8_t *hOps = nullptr;
+	uint64_t lastN = 0;
+};
+
+#define META_STRAND(m) (((m) >> 31) & 1u)
+#define META_EE(m)     (((m) >> 30) & 1u)
+#define META_SEED(m)   (((m) >> 16) & 0x3fffu)
+
+// per-read seed plan from the per-length tables
+__global__ void k_plan(const uint64_t *roff, uint64_t n, const int32_t *ivalByLen, int maxLen, int32_t *interval, int32_t *offset) {
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	int len = (int)(roff[i + 1] - roff[i]);
+	interval[i] = ivalByLen[len > maxLen ? maxLen : len];
+	offset[i] = 0;
+}
+
+// collect: one thread per read
+__global__ void k_collect(uint64_t n, const uint64_t *roff, const uint64_t *ee, const uint64_t *ranges, const int32_t *nseeds,
+                          int maxSeeds, int seedLen, int rowCap, int rangeMax,
+                          uint64_t *rows, uint32_t *hitlen, uint32_t *meta) {
+	uint64_t rd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(rd >= n) return;
+	uint64_t *ro = rows + rd * rowCap;
+	uint32_t *ho = hitlen + rd * rowCap, *mo = meta + rd * rowCap;
+	const int len = (int)(roff[rd + 1] - roff[rd]);
+	int cnt = 0;
+	const uint64_t *e = ee + rd * 4;
+	for(int strand = 0; strand < 2; strand++) {
+		for(uint64_t r = e[2 * strand]; r < e[2 * strand + 1] && cnt < rowCap; r++) {
+			ro[cnt] = r; ho[cnt] = (uint32_t)len; mo[cnt] = ((uint32_t)strand << 31) | (1u << 30); cnt++;
+		}
+	}
+	if(cnt == 0) {
+		const int ns = nseeds[rd];
+		const int sl = seedLen < len ? seedLen : len;
+		const uint64_t *rg = ranges + rd * 2ull * maxSeeds * 4;
+		for(int sz = 1; sz <= rangeMax && cnt < rowCap; sz++) {
+			for(int strand = 0; strand < 2 && cnt < rowCap; strand++) {
+				for(int k = 0; k < ns && cnt < rowCap; k++) {
+					const uint64_t *q = rg + ((size_t)strand * maxSeeds + k) * 4;
+					if((int)(q[1] - q[0]) != sz) continue;
+					for(uint64_t r = q[0]; r < q[1] && cnt < rowCap; r++) {
+						ro[cnt] = r; ho[cnt] = (uint32_t)sl; mo[cnt] = ((uint32_t)strand << 31) | ((uint32_t)k << 16); cnt++;
+					}
+				}
+			}
+		}
+	}
+	for(; cnt < rowCap; cnt++) { ro[cnt] = BT2G_OFFMASK; ho[cnt] = 0; mo[cnt] = 0; }
+}
+
+// frame: one thread per read
+__global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interval, const int32_t *offset,
+                        const uint64_t *rows, const uint32_t *hitlen, const uint32_t *meta,
+                        const uint64_t *tidx, const uint64_t *textoff, const uint64_t *tlen, const uint8_t *rflags,
+                        int rowCap, int maxLen, int maxhalf, int matchBonus,
+                        const int32_t *minscByLen, const int32_t *nceilRawByLen, const int32_t *rdgapsByLen, const int32_t *rfgapsByLen,
+                        bt2g_dp_problem *probs, uint32_t *nProb, int32_t *readProb, int32_t *readNProb, bt2g_read_result *res) {
+	uint64_t rd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(rd >= n) return;
+	const int len = (int)(roff[rd + 1] - roff[rd]);
+	const int li = len > maxLen ? maxLen : len;
+	bt2g_read_result r;
+	r.found = 0; r.score = 0; r.score2 = INT32_MIN; r.fw = 0; r.tidx = 0; r.refoff = 0; r.nops = 0; r.ndp = 0;
+	int np = 0;
+	uint64_t seenT[32]; int64_t seenO[32]; uint8_t seenS[32]; int nseen = 0;
+	const int minsc = minscByLen[li];
+	for(int i = 0; i < rowCap; i++) {
+		uint64_t s = rd * rowCap + i;
+		if(rows[s] == BT2G_OFFMASK) break;
+		uint32_t m = meta[s];
+		const bool isEE = META_EE(m) != 0;
+		const uint8_t fl = rflags[s];
+		if(fl & 2) continue;
+		if(isEE && (fl & 1)) continue;                     // eeMode rejects straddlers (aligner_sw_driver.cpp:1141)
+		const int strand = (int)META_STRAND(m);
+		int rdoff = 0;
+		if(!isEE) {
+			int depth = (int)META_SEED(m) * interval[rd] + offset[rd];
+			rdoff = strand == 0 ? depth : len - depth - (int)hitlen[s];
+		}
+		const int64_t refoff = (int64_t)textoff[s] - rdoff;
+		bool dup = false;
+		for(int k = 0; k < nseen; k++) if(seenT[k] == tidx[s] && seenO[k] == refoff && seenS[k] == strand) { dup = true; break; }
+		if(dup) continue;
+		if(nseen < 32) { seenT[nseen] = tidx[s]; seenO[nseen] = refoff; seenS[nseen] = (uint8_t)strand; nseen++; }
+		if(isEE) {
+			if(r.found == 0) { r.found = 2; r.score = len * matchBonus; r.fw = strand == 0; r.tidx = tidx[s]; r.refoff = refoff; }
+			else if(r.score2 == INT32_MIN) r.score2 = len * matchBonus;
+			continue;
+		}
+		// DynProgFramer::frameSeedExtensionRect (dp_framer.cpp:81-129), trimToRef
+		int maxgap = rdgapsByLen[li] > rfgapsByLen[li] ? rdgapsByLen[li] : rfgapsByLen[li];
+		if(maxgap < 0 || maxgap > maxhalf) maxgap = maxhalf;
+		int64_t refl = refoff - 2 * maxgap, refr = refoff + (len - 1) + 2 * maxgap;
+		const int64_t reflen = (int64_t)tlen[s];
+		int64_t triml = 0, trimr = 0;
+		if(refr >= reflen) trimr = refr - (reflen - 1);
+		if(refl < 0) triml = -refl;
+		if(refr - trimr < refl + triml) continue;
+		uint32_t pi = atomicAdd(nProb, 1u);
+		bt2g_dp_problem &p = probs[pi];
+		p.read_idx = (uint32_t)rd; p.fw = strand == 0; p.tidx = tidx[s];
+		p.refl = refl + triml; p.refr = refr - trimr; p.triml = (int32_t)triml;
+		p.corel = maxgap; p.corer = 3 * maxgap; p.minsc = minsc; p.nceil = nceilRawByLen[li]; p.reserved = 0;
+		readProb[rd * rowCap + np] = (int32_t)pi;
+		np++;
+	}
+	readNProb[rd] = np;
+	r.ndp = np;
+	res[rd] = r;
+}
+
+// pick: one thread per read
+__global__ void k_pick(uint64_t n, int rowCap, int maxAlns, int maxOps, const int32_t *readProb, const int32_t *readNProb,
+                       const bt2g_dp_problem *probs, const bt2g_dp_summary *summ, const bt2g_dp_aln *alns, const uint8_t *ops,
+                       bt2g_read_result *res, uint8_t *resOps, unsigned long long *cellCnt, const uint64_t *roff) {
+	uint64_t rd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(rd >= n) return;
+	bt2g_read_result r = res[rd];
+	const int np = readNProb[rd];
+	int bestP = -1, bestA = 0;
+	unsigned long long cells = 0;
+	const int len = (int)(roff[rd + 1] - roff[rd]);
+	for(int k = 0; k < np; k++) {
+		const int pi = readProb[rd * rowCap + k];
+		cells += (unsigned long long)len * (unsigned long long)(probs[pi].refr - probs[pi].refl + 1);
+		const int na = summ[pi].naln < maxAlns ? summ[pi].naln : maxAlns;
+		for(int a = 0; a < na; a++) {
+			const bt2g_dp_aln &al = alns[(size_t)pi * maxAlns + a];
+			if(r.found == 0 || al.score > r.score) {
+				if(r.found) r.score2 = r.score2 > r.score ? r.score2 : r.score;
+				r.found = 1; r.score = al.score; bestP = pi; bestA = a;
+			} else if(al.score > r.score2) r.score2 = al.score;
+		}
+	}
+	if(bestP >= 0 && r.found == 1) {
+		const bt2g_dp_aln &al = alns[(size_t)bestP * maxAlns + bestA];
+		r.fw = probs[bestP].fw; r.tidx = probs[bestP].tidx; r.refoff = probs[bestP].refl + al.col0;
+		r.nops = al.nops < maxOps ? al.nops : maxOps;
+		const uint8_t *src = ops + ((size_t)bestP * maxAlns + bestA) * maxOps;
+		uint8_t *dst = resOps + rd * (size_t)maxOps;
+		for(int k = 0; k < r.nops; k++) dst[k] = src[k];
+	}
+	res[rd] = r;
+	if(cellCnt && cells) atomicAdd(cellCnt, cells);
+}
+
+template <typename T> static int pipeAlloc(bt2g_pipeline *p, T *&ptr, uint64_t count) {
+	void *v = nullptr;
+	cudaError_t e = cudaMalloc(&v, (count ? count : 1) * sizeof(T));
+	if(e != cudaSuccess) { p->ctx->err = std::string("pipeline cudaMalloc: ") + cudaGetErrorString(e); return -2; }
+	p->allocs.push_back(v);
+	ptr = (T *)v;
+	return 0;
+}
+
+template <typename OFF>
+static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, const uint64_t *roff, uint64_t n, cudaStream_t st, bool count) {
+	bt2g_ctx *ctx = p->ctx;
+	PipeBufs &b = p->b;
+	const bt2g_pipeline_params &q = p->prm;
+	DevIndex<OFF> ix = bt2g_dev_index<OFF>(ctx);
+	unsigned long long *c = count ? b.counters : nullptr;
+	const unsigned T = 128;
+	auto grid = [&](uint64_t m) { return (unsigned)((m + T - 1) / T); };
+	if(count) BT2G_CUDA_TRY(ctx, cudaMemsetAsync(b.counters, 0, 4 * sizeof(unsigned long long), st));
+	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(b.nProb, 0, sizeof(uint32_t), st));
+	k_plan<<<grid(n), T, 0, st>>>(roff, n, b.ivalByLen, q.max_len, b.interval, b.offset);
+	launch_exact_sweep<OFF>(ix, seq, roff, n, 0, 0, b.mine, b.ee, st, c ? c + 0 : nullptr);
+	launch_seed_search<OFF>(ix, seq, roff, n, q.seed_len, q.max_seeds, 0, 0, b.interval, b.offset, b.ranges, b.nseeds, st, c ? c + 1 : nullptr);
+	k_collect<<<grid(n), T, 0, st>>>(n, roff, b.ee, b.ranges, b.nseeds, q.max_seeds, q.seed_len, q.row_cap, q.range_max, b.rows, b.hitlen, b.meta);
+	launch_resolve<OFF>(ix, b.rows, b.hitlen, n * (uint64_t)q.row_cap, 0, nullptr, b.tidx, b.textoff, b.tlen, b.rflags, st, c ? c + 2 : nullptr);
+	k_frame<<<grid(n), T, 0, st>>>(n, roff, b.interval, b.offset, b.rows, b.hitlen, b.meta, b.tidx, b.textoff, b.tlen, b.rflags,
+	                               q.row_cap, q.max_len, q.maxhalf, ctx->scoring.match_bonus,
+	                               b.minscByLen, b.nceilRawByLen, b.rdgapsByLen, b.rfgapsByLen,
+	                               b.probs, b.nProb, b.readProb, b.readNProb, b.res);
+	DpLaunch L;
+	L.seq = seq; L.qual = qual; L.roff = roff; L.probs = b.probs; L.n = n * (uint64_t)q.row_cap; L.nDev = b.nProb;
+	L.numSlots = p->numSlots; L.codes = b.codes; L.lastH = b.lastH; L.codeStride = p->codeStride; L.maxCol = p->maxCol;
+	L.maxCands = q.max_cands; L.maxAlns = q.max_alns; L.maxOps = q.max_ops;
+	L.summ = b.summ; L.cands = b.cands; L.alns = b.alns; L.ops = b.ops;
+	if(launch_dp_e2e<OFF>(ix, ctx->scoring, L, q.max_len, st)) { ctx->err = "pipeline: DP launch rejected"; return -1; }
+	k_pick<<<grid(n), T, 0, st>>>(n, q.row_cap, q.max_alns, q.max_ops, b.readProb, b.readNProb, b.probs, b.summ, b.alns, b.ops,
+	                              b.res, b.resOps, c ? c + 3 : nullptr, roff);
+	BT2G_CUDA_TRY(ctx, cudaGetLastError());
+	p->lastN = n;
+	return 0;
+}
+
+extern "C" {
+
+int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_t maxReads, uint64_t maxBases, bt2g_pipeline **out) {
+	if(!ctx || !prm || !out) return -1;
+	if(!ctx->loaded) { ctx->err = "no index loaded"; return -1; }
+	if(ctx->scoring.gapbar < 1) bt2g_scoring_default(&ctx->scoring, 0);
+	if(ctx->scoring.local) { ctx->err = "pipeline: local mode not implemented in this build"; return -1; }
+	if(prm->max_len < 1 || prm->max_len > 512 || prm->row_cap < 1 || prm->row_cap > 32 || prm->max_seeds < 1 || prm->max_seeds > 16383) {
+		ctx->err = "pipeline: bad parameters"; return -1;
+	}
+	cudaSetDevice(ctx->device);
+	bt2g_pipeline *p = new(std::nothrow) bt2g_pipeline();
+	if(!p) return -4;
+	p->ctx = ctx; p->prm = *prm; p->maxReads = maxReads; p->maxBases = maxBases;
+	PipeBufs &b = p->b;
+	memset(&b, 0, sizeof(b));
+	const uint64_t n = maxReads, cap = prm->row_cap, nprobMax = n * cap;
+	int rc = 0;
+	const int L1 = prm->max_len + 1;
+	rc |= pipeAlloc(p, b.seq, maxBases); rc |= pipeAlloc(p, b.qual, maxBases); rc |= pipeAlloc(p, b.roff, n + 1);
+	rc |= pipeAlloc(p, b.minscByLen, L1); rc |= pipeAlloc(p, b.nceilByLen, L1); rc |= pipeAlloc(p, b.nceilRawByLen, L1);
+	rc |= pipeAlloc(p, b.ivalByLen, L1); rc |= pipeAlloc(p, b.rdgapsByLen, L1); rc |= pipeAlloc(p, b.rfgapsByLen, L1);
+	rc |= pipeAlloc(p, b.interval, n); rc |= pipeAlloc(p, b.offset, n);
+	rc |= pipeAlloc(p, b.mine, n * 2); rc |= pipeAlloc(p, b.ee, n * 4);
+	rc |= pipeAlloc(p, b.ranges, n * 2ull * prm->max_seeds * 4); rc |= pipeAlloc(p, b.nseeds, n);
+	rc |= pipeAlloc(p, b.rows, nprobMax); rc |= pipeAlloc(p, b.hitlen, nprobMax); rc |= pipeAlloc(p, b.meta, nprobMax);
+	rc |= pipeAlloc(p, b.tidx, nprobMax); rc |= pipeAlloc(p, b.textoff, nprobMax); rc |= pipeAlloc(p, b.tlen, nprobMax); rc |= pipeAlloc(p, b.rflags, nprobMax);
+	rc |= pipeAlloc(p, b.probs, nprobMax); rc |= pipeAlloc(p, b.nProb, 1); rc |= pipeAlloc(p, b.readProb, nprobMax); rc |= pipeAlloc(p, b.readNProb, n);
+	p->maxCol = prm->max_len + 4 * prm->maxhalf + 4;
+	p->R = prm->max_len <= 128 ? 4 : (prm->max_len <= 256 ? 8 : 16);
+	p->codeStride = (uint64_t)(p->maxCol + 32) * 32 * p->R;
+	int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	p->numSlots = (uint64_t)sms * 16;
+	rc |= pipeAlloc(p, b.codes, p->numSlots * p->codeStride); rc |= pipeAlloc(p, b.lastH, p->numSlots * (uint64_t)p->maxCol);
+	rc |= pipeAlloc(p, b.summ, nprobMax); rc |= pipeAlloc(p, b.cands, nprobMax * prm->max_cands);
+	rc |= pipeAlloc(p, b.alns, nprobMax * prm->max_alns); rc |= pipeAlloc(p, b.ops, nprobMax * prm->max_alns * (uint64_t)prm->max_ops);
+	rc |= pipeAlloc(p, b.res, n); rc |= pipeAlloc(p, b.resOps, n * (uint64_t)prm->max_ops);
+	rc |= pipeAlloc(p, b.counters, 4);
+	if(rc) { bt2g_pipeline_destroy(p); return -2; }
+	cudaError_t e = cudaSuccess;
+	auto up = [&](int32_t *dst, const int32_t *src) { if(e == cudaSuccess) e = cudaMemcpy(dst, src, L1 * sizeof(int32_t), cudaMemcpyHostToDevice); };
+	up(b.minscByLen, prm->minsc_by_len); up(b.nceilByLen, prm->nceil_by_len); up(b.nceilRawByLen, prm->nceil_raw_by_len);
+	up(b.ivalByLen, prm->interval_by_len); up(b.rdgapsByLen, prm->rdgaps_by_len); up(b.rfgapsByLen, prm->rfgaps_by_len);
+	if(e == cudaSuccess) e = cudaMemset(b.alns, 0, nprobMax * prm->max_alns * sizeof(bt2g_dp_aln));
+	if(e == cudaSuccess) e = cudaMemset(b.cands, 0, nprobMax * prm->max_cands * sizeof(bt2g_dp_cand));
+	// pinned staging
+	if(e == cudaSuccess) e = cudaHostAlloc((void **)&p->hSeq, maxBases, cudaHostAllocDefault);
+	if(e == cudaSuccess) e = cudaHostAlloc((void **)&p->hQual, maxBases, cudaHostAllocDefault);
+	if(e == cudaSuccess) e = cudaHostAlloc((void **)&p->hOff, (n + 1) * 8, cudaHostAllocDefault);
+	if(e == cudaSuccess) e = cudaHostAlloc((void **)&p->hRes, n * sizeof(bt2g_read_result), cudaHostAllocDefault);
+	if(e == cudaSuccess) e = cudaHostAlloc((void **)&p->hOps, n * (uint64_t)prm->max_ops, cudaHostAllocDefault);
+	if(e != cudaSuccess) { ctx->err = std::string("pipeline setup: ") + cudaGetErrorString(e); bt2g_pipeline_destroy(p); return -2; }
+	// the params struct keeps host pointers that may die; null them
+	p->prm.minsc_by_len = p->prm.nceil_by_len = p->prm.nceil_raw_by_len = p->prm.interval_by_len = p->prm.rdgaps_by_len = p->prm.rfgaps_by_len = nullptr;
+	*out = p;
+	return 0;
+}
+
+void bt2g_pipeline_destroy(bt2g_pipeline *p) {
+	if(!p) return;
+	cudaSetDevice(p->ctx->device);
+	for(void *v : p->allocs) cudaFree(v);
+	if(p->hSeq) cudaFreeHost(p->hSeq);
+	if(p->hQual) cudaFreeHost(p->hQual);
+	if(p->hOff) cudaFreeHost(p->hOff);
+	if(p->hRes) cudaFreeHost(p->hRes);
+	if(p->hOps) cudaFreeHost(p->hOps);
+	delete p;
+}
+
+int bt2g_pipeline_run_dev(bt2g_pipeline *p, const uint8_t *dSeq, const uint8_t *dQual, const uint64_t *dOff,
+                          uint64_t nReads, void *stream, int count) {
+	if(!p || !dSeq || !dQual || !dOff) return -1;
+	if(nReads > p->maxReads) { p->ctx->err = "pipeline: batch larger than max_reads"; return -1; }
+	if(nReads == 0) return 0;
+	BT2G_CUDA_TRY(p->ctx, cudaSetDevice(p->ctx->device));
+	cudaStream_t st = stream ? (cudaStream_t)stream : p->ctx->stream;
+	if(p->ctx->info.off_size == 4) return runStages<uint32_t>(p, dSeq, dQual, dOff, nReads, st, count != 0);
+	return runStages<uint64_t>(p, dSeq, dQual, dOff, nReads, st, count != 0);
+}
+
+int bt2g_pipeline_run_host(bt2g_pipeline *p, const bt2g_reads *reads, bt2g_read_result *res, uint8_t *ops) {
+	if(!p || !reads || !reads->qual || !res) return -1;
+	bt2g_ctx *ctx = p->ctx;
+	const uint64_t n = reads->n_reads;
+	if(n > p->maxReads || reads->off[n] > p->maxBases) { ctx->err = "pipeline: batch larger than the pipeline was created for"; return -1; }
+	if(n == 0) return 0;
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const uint64_t nb = reads->off[n];
+	// caller buffers may be pageable: the copies below are then staged by the driver
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.seq, reads->seq, nb, cudaMemcpyHostToDevice, st));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.qual, reads->qual, nb, cudaMemcpyHostToDevice, st));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.roff, reads->off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	int rc = bt2g_pipeline_run_dev(p, p->b.seq, p->b.qual, p->b.roff, n, st, 0);
+	if(rc) return rc;
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(res, p->b.res, n * sizeof(bt2g_read_result), cudaMemcpyDeviceToHost, st));
+	if(ops) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(ops, p->b.resOps, n * (uint64_t)p->prm.max_ops, cudaMemcpyDeviceToHost, st));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	return 0;
+}
+
+int bt2g_pipeline_results_dev(bt2g_pipeline *p, bt2g_read_result **res, uint8_t **ops) {
+	if(!p) return -1;
+	if(res) *res = p->b.res;
+	if(ops) *ops = p->b.resOps;
+	return 0;
+}
+
+// counters of the last run made with count=1: [0] exact-sweep side fetches, [1] seed-search side
+// fetches, [2] resolve side fetches, [3] DP cells, [4] DP problems, [5] reads
+int bt2g_pipeline_counters(bt2g_pipeline *p, uint64_t *out6) {
+	if(!p || !out6) return -1;
+	bt2g_ctx *ctx = p->ctx;
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	unsigned long long c[4]; uint32_t np = 0;
+	BT2G_CUDA_TRY(ctx, cudaMemcpy(c, p->b.counters, sizeof(c), cudaMemcpyDeviceToHost));
+	BT2G_CUDA_TRY(ctx, cudaMemcpy(&np, p->b.nProb, sizeof(np), cudaMemcpyDeviceToHost));
+	for(int i = 0; i < 4; i++) out6[i] = c[i];
+	out6[4] = np; out6[5] = p->lastN;
+	return 0;
+}
+
+} // extern "C"

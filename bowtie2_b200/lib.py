@@ -345,3 +345,109 @@ def ops_to_edits(ops: np.ndarray, nops: int, read_codes: np.ndarray, fw: bool, r
         for e in out:
             e[0] = rdlen - e[0] - (0 if e[3] == EDIT_READ_GAP else 1)
     return out
+
+
+# ---- batched hot path ------------------------------------------------------------------------
+class _PipeParams(C.Structure):
+    _fields_ = [("seed_len", C.c_int32), ("max_seeds", C.c_int32), ("row_cap", C.c_int32), ("range_max", C.c_int32),
+                ("max_len", C.c_int32), ("maxhalf", C.c_int32), ("max_cands", C.c_int32), ("max_alns", C.c_int32),
+                ("max_ops", C.c_int32), ("minsc_by_len", C.c_void_p), ("nceil_by_len", C.c_void_p),
+                ("nceil_raw_by_len", C.c_void_p), ("interval_by_len", C.c_void_p), ("rdgaps_by_len", C.c_void_p),
+                ("rfgaps_by_len", C.c_void_p)]
+
+
+READ_RESULT = np.dtype([("found", "<i4"), ("score", "<i4"), ("score2", "<i4"), ("fw", "<u4"), ("tidx", "<u8"),
+                        ("refoff", "<i8"), ("nops", "<i4"), ("ndp", "<i4")], align=True)
+
+EXPORTS += ["bt2g_pipeline_create", "bt2g_pipeline_destroy", "bt2g_pipeline_run_dev", "bt2g_pipeline_run_host",
+            "bt2g_pipeline_results_dev", "bt2g_pipeline_counters"]
+
+
+class Pipeline:
+    """bt2g_pipeline: the batched hot path for one preset / scoring scheme (include/bt2g.h)."""
+
+    def __init__(self, gpu: "Bt2Gpu", preset_name: str = "sensitive", max_len: int = 100, max_reads: int = 1 << 20,
+                 row_cap: int = 16, range_max: int = 8, max_cands: int = 64, max_alns: int = 2, local: bool = False,
+                 both_mates: bool = False):
+        from . import policy
+        self.gpu = gpu
+        lib = gpu._lib
+        _bind_dp(lib)
+        vp = C.c_void_p
+        lib.bt2g_pipeline_create.argtypes = [vp, C.POINTER(_PipeParams), C.c_uint64, C.c_uint64, C.POINTER(vp)]
+        lib.bt2g_pipeline_destroy.argtypes = [vp]
+        lib.bt2g_pipeline_destroy.restype = None
+        lib.bt2g_pipeline_run_dev.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, C.c_int]
+        lib.bt2g_pipeline_run_host.argtypes = [vp, C.POINTER(_Reads), vp, vp]
+        lib.bt2g_pipeline_results_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        lib.bt2g_pipeline_counters.argtypes = [vp, vp]
+        gpu.set_scoring(local=local)
+        sc = policy.Scoring.default(local)
+        pre = policy.preset(preset_name, local)
+        L1 = max_len + 1
+        lens = np.arange(L1)
+        tab = lambda f: np.array([f(int(x)) if x > 0 else 0 for x in lens], dtype=np.int32)
+        self._tabs = [tab(sc.min_score), tab(sc.n_ceil), tab(sc.n_ceil_raw),
+                      tab(lambda x: policy.seed_interval(pre.ival, x, both_mates)),
+                      tab(lambda x: sc.max_read_gaps(sc.min_score(x), x)), tab(lambda x: sc.max_ref_gaps(sc.min_score(x), x))]
+        self.max_ops = max_len + 64
+        self.seed_len = pre.seed_len
+        min_ival = int(self._tabs[3][1:].min()) if max_len >= 1 else 1
+        self.max_seeds = max(1, policy.n_seeds(max_len, pre.seed_len, max(min_ival, 1)))
+        prm = _PipeParams(pre.seed_len, self.max_seeds, row_cap, range_max, max_len, 15, max_cands, max_alns, self.max_ops,
+                          *[_ptr(t) for t in self._tabs])
+        h = vp()
+        gpu._check(lib.bt2g_pipeline_create(gpu._h, C.byref(prm), max_reads, max_reads * max_len, C.byref(h)), "bt2g_pipeline_create")
+        self._h = h
+        self.max_reads, self.max_len = max_reads, max_len
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.gpu._lib.bt2g_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_host(self, reads: ReadBatch, want_ops: bool = True):
+        res = np.zeros(reads.n, dtype=READ_RESULT)
+        ops = np.zeros((reads.n, self.max_ops), dtype=np.uint8) if want_ops else None
+        st = reads._struct()
+        self.gpu._check(self.gpu._lib.bt2g_pipeline_run_host(self._h, C.byref(st), _ptr(res), _ptr(ops)), "bt2g_pipeline_run_host")
+        return res, ops
+
+    def run_dev(self, d_seq: int, d_qual: int, d_off: int, n_reads: int, stream: int = 0, count: bool = False):
+        self.gpu._check(self.gpu._lib.bt2g_pipeline_run_dev(self._h, d_seq, d_qual, d_off, n_reads, stream or None, int(count)),
+                        "bt2g_pipeline_run_dev")
+
+    def counters(self) -> dict:
+        out = np.zeros(6, dtype=np.uint64)
+        self.gpu._check(self.gpu._lib.bt2g_pipeline_counters(self._h, _ptr(out)), "bt2g_pipeline_counters")
+        k = ["sweep_sides", "seed_sides", "resolve_sides", "dp_cells", "dp_problems", "reads"]
+        return {a: int(b) for a, b in zip(k, out)}
+
+    def results_dev(self):
+        r, o = C.c_void_p(), C.c_void_p()
+        self.gpu._check(self.gpu._lib.bt2g_pipeline_results_dev(self._h, C.byref(r), C.byref(o)), "bt2g_pipeline_results_dev")
+        return r.value, o.value
+
+
+def ops_to_cigar(ops: np.ndarray, nops: int) -> str:
+    """SAM CIGAR of a device op string (reference: AlnRes::printCigar via StackedAln,
+    aligner_result.cpp): M for match/mismatch, I for a reference gap, D for a read gap."""
+    sym = {OP_MATCH: "M", OP_MM: "M", OP_REFGAP: "I", OP_READGAP: "D"}
+    out, run, last = [], 0, None
+    for op in ops[:nops][::-1]:
+        s = sym[int(op) & 3]
+        if s == last:
+            run += 1
+        else:
+            if last is not None:
+                out.append(f"{run}{last}")
+            last, run = s, 1
+    if last is not None:
+        out.append(f"{run}{last}")
+    return "".join(out)

@@ -226,6 +226,48 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
                    int32_t max_cands, int32_t max_alns, int32_t max_ops,
                    bt2g_dp_summary *summ, bt2g_dp_cand *cands, bt2g_dp_aln *alns, uint8_t *ops);
 
+/* ---------------------------------------------------------------- batched hot path ----- */
+/* One pass of the hot path over a batch: exactSweep -> searchAllSeeds (round 0) -> offset
+ * resolution -> extension DP + backtrace -> best alignment per read.  This is the unit the
+ * caller (the restated multiseedSearchWorker loop, bt2_search.cpp:3253-4199) schedules; the
+ * per-length tables carry the policy arithmetic the caller owns (scoreMin.f :3352-3372, nCeil.f
+ * :3427, msIval.f :3443-3450, Scoring::maxReadGaps/maxRefGaps scoring.cpp:42,73). */
+typedef struct {
+	int32_t seed_len;            /* -L */
+	int32_t max_seeds;           /* seeds per strand the buffers are sized for */
+	int32_t row_cap;             /* BW rows resolved per read (<= 32) */
+	int32_t range_max;           /* seed ranges wider than this are skipped by the collect stage */
+	int32_t max_len;             /* longest read (<= 512) */
+	int32_t maxhalf;             /* DP half-width cap (bt2_search.cpp maxhalf = 15) */
+	int32_t max_cands, max_alns, max_ops;
+	const int32_t *minsc_by_len, *nceil_by_len, *nceil_raw_by_len, *interval_by_len;   /* [max_len+1] */
+	const int32_t *rdgaps_by_len, *rfgaps_by_len;                                     /* [max_len+1] */
+} bt2g_pipeline_params;
+
+typedef struct {
+	int32_t  found;              /* 0 none, 1 gapped DP alignment, 2 exact end-to-end hit */
+	int32_t  score, score2;      /* best and runner-up score (INT32_MIN when none) */
+	uint32_t fw;
+	uint64_t tidx;
+	int64_t  refoff;             /* 0-based offset of the leftmost aligned reference base */
+	int32_t  nops;               /* ops (bt2g_dp_aln encoding) in the per-read op buffer */
+	int32_t  ndp;                /* DP problems issued for this read */
+} bt2g_read_result;
+
+typedef struct bt2g_pipeline bt2g_pipeline;
+int  bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_t max_reads, uint64_t max_bases,
+                          bt2g_pipeline **out);
+void bt2g_pipeline_destroy(bt2g_pipeline *p);
+/* inputs already in HBM; asynchronous on `stream` (a cudaStream_t, NULL = the context stream);
+ * count != 0 additionally tallies side fetches / DP cells (see bt2g_pipeline_counters) */
+int  bt2g_pipeline_run_dev(bt2g_pipeline *p, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_off,
+                           uint64_t n_reads, void *stream, int count);
+/* host buffers in, host results out (copies + kernels + synchronise): ops may be NULL,
+ * else n_reads * max_ops bytes */
+int  bt2g_pipeline_run_host(bt2g_pipeline *p, const bt2g_reads *reads, bt2g_read_result *res, uint8_t *ops);
+int  bt2g_pipeline_results_dev(bt2g_pipeline *p, bt2g_read_result **res, uint8_t **ops);
+int  bt2g_pipeline_counters(bt2g_pipeline *p, uint64_t *out6);
+
 #ifdef __cplusplus
 }
 #endif

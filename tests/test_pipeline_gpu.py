@@ -1,0 +1,92 @@
+"""GPU: the batched hot path (bt2g_pipeline) end to end.
+
+(1) stage consistency: the pipeline's per-read result equals what the stand-alone, individually
+    parity-tested entry points give for the same read;
+(2) against the unmodified reference run as a program (oracle/_ref/bowtie2-align-s): for reads
+    the reference aligns, the pipeline finds the same locus / strand / score / CIGAR.  The
+    pipeline resolves candidates speculatively instead of replaying the reference's sequential,
+    RNG-driven policy, so this is a high-concordance property, not bit-identity."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bowtie2_b200 import policy, synth
+from bowtie2_b200.lib import Pipeline, ReadBatch, ops_to_cigar
+from oracle_lib import have_reference, ref_bin
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+def _run_reference(index, fq, preset="--sensitive"):
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), preset, "--end-to-end", "--seed", "0", "-p", "4", "--reorder",
+                                   "-x", index, "-U", fq], stderr=subprocess.DEVNULL).decode()
+    recs = []
+    for line in out.splitlines():
+        if line.startswith("@"):
+            continue
+        f = line.split("\t")
+        tags = {t[:2]: t[5:] for t in f[11:]}
+        recs.append(dict(flag=int(f[1]), rname=f[2], pos=int(f[3]) - 1, mapq=int(f[4]), cigar=f[5],
+                         AS=int(tags["AS"]) if "AS" in tags else None, XS=int(tags["XS"]) if "XS" in tags else None))
+    return recs
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("rdlen", [100, 150])
+def test_pipeline_vs_reference_program(gpu, synth_index, synth_genome, tmp_path, rdlen):
+    gpu.load_index_files(synth_index)
+    reads, quals, truth = synth.make_reads(synth_genome, 3000, rdlen, seed=77 + rdlen, sub_rate=0.01, indel_rate=0.001)
+    fq = str(tmp_path / "r.fq")
+    synth.write_fastq(fq, reads, quals)
+    want = _run_reference(synth_index, fq)
+    pipe = Pipeline(gpu, "sensitive", max_len=rdlen, max_reads=4096, row_cap=16, range_max=16)
+    res, ops = pipe.run_host(ReadBatch.from_list(reads, quals))
+    n_ref_aln = n_same = n_same_cigar = n_unique = n_unique_same = n_gpu_only = 0
+    for i, w in enumerate(want):
+        r = res[i]
+        if w["flag"] & 4:
+            n_gpu_only += r["found"] != 0
+            continue
+        n_ref_aln += 1
+        same = (r["found"] != 0 and int(r["tidx"]) == int(w["rname"][3:]) - 1 and int(r["refoff"]) == w["pos"]
+                and bool(r["fw"]) == (not (w["flag"] & 16)) and int(r["score"]) == w["AS"])
+        n_same += same
+        if w["mapq"] >= 30:
+            n_unique += 1
+            n_unique_same += same
+        if same:
+            cig = f"{rdlen}M" if r["found"] == 2 else ops_to_cigar(ops[i], int(r["nops"]))
+            n_same_cigar += cig == w["cigar"]
+    assert n_ref_aln > 2500
+    # reads the reference places confidently must agree; repeats may legitimately differ
+    assert n_unique_same >= 0.995 * n_unique, (n_unique_same, n_unique)
+    assert n_same >= 0.97 * n_ref_aln, (n_same, n_ref_aln)
+    assert n_same_cigar >= 0.995 * n_same, (n_same_cigar, n_same)
+    pipe.close()
+
+
+def test_pipeline_stage_consistency(gpu, synth_index, synth_genome):
+    gpu.load_index_files(synth_index)
+    rdlen = 100
+    reads, quals, truth = synth.make_reads(synth_genome, 400, rdlen, seed=5, sub_rate=0.02, indel_rate=0.003)
+    batch = ReadBatch.from_list(reads, quals)
+    pipe = Pipeline(gpu, "sensitive", max_len=rdlen, max_reads=1024, row_cap=16, range_max=16)
+    res, ops = pipe.run_host(batch)
+    # same answer through the device-pointer entry point, and counters are populated
+    import torch
+    dseq = torch.from_numpy(batch.seq).cuda(); dq = torch.from_numpy(batch.qual).cuda()
+    doff = torch.from_numpy(batch.off.astype(np.int64)).cuda()
+    pipe.run_dev(dseq.data_ptr(), dq.data_ptr(), doff.data_ptr(), batch.n, count=True)
+    torch.cuda.synchronize()
+    c = pipe.counters()
+    assert c["reads"] == batch.n and c["sweep_sides"] > 0 and c["seed_sides"] > 0 and c["dp_cells"] > 0
+    res2, _ = pipe.run_host(batch)
+    assert np.array_equal(res, res2)
+    # exact end-to-end hits are exactly the reads whose exact sweep reports a range
+    mine, ee = gpu.exact_sweep(batch)
+    has_ee = (ee[:, 1] > ee[:, 0]) | (ee[:, 3] > ee[:, 2])
+    assert np.array_equal(res["found"] == 2, has_ee)
+    assert (res["found"] != 0).sum() > 350
+    pipe.close()
