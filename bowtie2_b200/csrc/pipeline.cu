@@ -48,8 +48,10 @@ struct bt2g_pipeline {
 	uint64_t maxReads, maxBases;
 	PipeBufs b;
 	std::vector<void *> allocs;
-	uint64_t numSlots, codeStride;
+	uint64_t numSlots, codeStride, maxProbs;
 	int maxCol, R;
+	cudaEvent_t ev[9];
+	bool evOk = false;
 	// pinned staging for the host entry point
 	uint8_t *hSeq = nullptr, *hQual = nullptr; uint64_t *hOff = nullptr;
 	bt2g_read_result *hRes = nullptr; uint8_t *hOps = nullptr;
@@ -110,7 +112,7 @@ __global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interva
                         const uint64_t *tidx, const uint64_t *textoff, const uint64_t *tlen, const uint8_t *rflags,
                         int rowCap, int maxLen, int maxhalf, int matchBonus,
                         const int32_t *minscByLen, const int32_t *nceilRawByLen, const int32_t *rdgapsByLen, const int32_t *rfgapsByLen,
-                        bt2g_dp_problem *probs, uint32_t *nProb, int32_t *readProb, int32_t *readNProb, bt2g_read_result *res) {
+                        bt2g_dp_problem *probs, uint32_t *nProb, uint32_t maxProbs, int32_t *readProb, int32_t *readNProb, bt2g_read_result *res) {
 	uint64_t rd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(rd >= n) return;
 	const int len = (int)(roff[rd + 1] - roff[rd]);
@@ -154,6 +156,7 @@ __global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interva
 		if(refl < 0) triml = -refl;
 		if(refr - trimr < refl + triml) continue;
 		uint32_t pi = atomicAdd(nProb, 1u);
+		if(pi >= maxProbs) { atomicSub(nProb, 1u); r.found |= 0x100; break; }   // workspace full: flagged, never silent
 		bt2g_dp_problem &p = probs[pi];
 		p.read_idx = (uint32_t)rd; p.fw = strand == 0; p.tidx = tidx[s];
 		p.refl = refl + triml; p.refr = refr - trimr; p.triml = (int32_t)triml;
@@ -219,25 +222,35 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 	unsigned long long *c = count ? b.counters : nullptr;
 	const unsigned T = 128;
 	auto grid = [&](uint64_t m) { return (unsigned)((m + T - 1) / T); };
+	auto mark = [&](int i) { if(p->evOk) cudaEventRecord(p->ev[i], st); };
 	if(count) BT2G_CUDA_TRY(ctx, cudaMemsetAsync(b.counters, 0, 4 * sizeof(unsigned long long), st));
 	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(b.nProb, 0, sizeof(uint32_t), st));
+	mark(0);
 	k_plan<<<grid(n), T, 0, st>>>(roff, n, b.ivalByLen, q.max_len, b.interval, b.offset);
+	mark(1);
 	launch_exact_sweep<OFF>(ix, seq, roff, n, 0, 0, b.mine, b.ee, st, c ? c + 0 : nullptr);
+	mark(2);
 	launch_seed_search<OFF>(ix, seq, roff, n, q.seed_len, q.max_seeds, 0, 0, b.interval, b.offset, b.ranges, b.nseeds, st, c ? c + 1 : nullptr);
+	mark(3);
 	k_collect<<<grid(n), T, 0, st>>>(n, roff, b.ee, b.ranges, b.nseeds, q.max_seeds, q.seed_len, q.row_cap, q.range_max, b.rows, b.hitlen, b.meta);
+	mark(4);
 	launch_resolve<OFF>(ix, b.rows, b.hitlen, n * (uint64_t)q.row_cap, 0, nullptr, b.tidx, b.textoff, b.tlen, b.rflags, st, c ? c + 2 : nullptr);
+	mark(5);
 	k_frame<<<grid(n), T, 0, st>>>(n, roff, b.interval, b.offset, b.rows, b.hitlen, b.meta, b.tidx, b.textoff, b.tlen, b.rflags,
 	                               q.row_cap, q.max_len, q.maxhalf, ctx->scoring.match_bonus,
 	                               b.minscByLen, b.nceilRawByLen, b.rdgapsByLen, b.rfgapsByLen,
-	                               b.probs, b.nProb, b.readProb, b.readNProb, b.res);
+	                               b.probs, b.nProb, (uint32_t)p->maxProbs, b.readProb, b.readNProb, b.res);
 	DpLaunch L;
-	L.seq = seq; L.qual = qual; L.roff = roff; L.probs = b.probs; L.n = n * (uint64_t)q.row_cap; L.nDev = b.nProb;
+	L.seq = seq; L.qual = qual; L.roff = roff; L.probs = b.probs; L.n = p->maxProbs; L.nDev = b.nProb;
 	L.numSlots = p->numSlots; L.codes = b.codes; L.lastH = b.lastH; L.codeStride = p->codeStride; L.maxCol = p->maxCol;
 	L.maxCands = q.max_cands; L.maxAlns = q.max_alns; L.maxOps = q.max_ops;
 	L.summ = b.summ; L.cands = b.cands; L.alns = b.alns; L.ops = b.ops;
+	mark(6);
 	if(launch_dp_e2e<OFF>(ix, ctx->scoring, L, q.max_len, st)) { ctx->err = "pipeline: DP launch rejected"; return -1; }
+	mark(7);
 	k_pick<<<grid(n), T, 0, st>>>(n, q.row_cap, q.max_alns, q.max_ops, b.readProb, b.readNProb, b.probs, b.summ, b.alns, b.ops,
 	                              b.res, b.resOps, c ? c + 3 : nullptr, roff);
+	mark(8);
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	p->lastN = n;
 	return 0;
@@ -259,7 +272,9 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	p->ctx = ctx; p->prm = *prm; p->maxReads = maxReads; p->maxBases = maxBases;
 	PipeBufs &b = p->b;
 	memset(&b, 0, sizeof(b));
-	const uint64_t n = maxReads, cap = prm->row_cap, nprobMax = n * cap;
+	const uint64_t n = maxReads, cap = prm->row_cap, nrowMax = n * cap;
+	const uint64_t nprobMax = (prm->max_probs > 0 && (uint64_t)prm->max_probs < nrowMax) ? (uint64_t)prm->max_probs : nrowMax;
+	p->maxProbs = nprobMax;
 	int rc = 0;
 	const int L1 = prm->max_len + 1;
 	rc |= pipeAlloc(p, b.seq, maxBases); rc |= pipeAlloc(p, b.qual, maxBases); rc |= pipeAlloc(p, b.roff, n + 1);
@@ -268,9 +283,9 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	rc |= pipeAlloc(p, b.interval, n); rc |= pipeAlloc(p, b.offset, n);
 	rc |= pipeAlloc(p, b.mine, n * 2); rc |= pipeAlloc(p, b.ee, n * 4);
 	rc |= pipeAlloc(p, b.ranges, n * 2ull * prm->max_seeds * 4); rc |= pipeAlloc(p, b.nseeds, n);
-	rc |= pipeAlloc(p, b.rows, nprobMax); rc |= pipeAlloc(p, b.hitlen, nprobMax); rc |= pipeAlloc(p, b.meta, nprobMax);
-	rc |= pipeAlloc(p, b.tidx, nprobMax); rc |= pipeAlloc(p, b.textoff, nprobMax); rc |= pipeAlloc(p, b.tlen, nprobMax); rc |= pipeAlloc(p, b.rflags, nprobMax);
-	rc |= pipeAlloc(p, b.probs, nprobMax); rc |= pipeAlloc(p, b.nProb, 1); rc |= pipeAlloc(p, b.readProb, nprobMax); rc |= pipeAlloc(p, b.readNProb, n);
+	rc |= pipeAlloc(p, b.rows, nrowMax); rc |= pipeAlloc(p, b.hitlen, nrowMax); rc |= pipeAlloc(p, b.meta, nrowMax);
+	rc |= pipeAlloc(p, b.tidx, nrowMax); rc |= pipeAlloc(p, b.textoff, nrowMax); rc |= pipeAlloc(p, b.tlen, nrowMax); rc |= pipeAlloc(p, b.rflags, nrowMax);
+	rc |= pipeAlloc(p, b.probs, nprobMax); rc |= pipeAlloc(p, b.nProb, 1); rc |= pipeAlloc(p, b.readProb, nrowMax); rc |= pipeAlloc(p, b.readNProb, n);
 	p->maxCol = prm->max_len + 4 * prm->maxhalf + 4;
 	p->R = prm->max_len <= 128 ? 4 : (prm->max_len <= 256 ? 8 : 16);
 	p->codeStride = (uint64_t)(p->maxCol + 32) * 32 * p->R;
@@ -295,6 +310,8 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	if(e == cudaSuccess) e = cudaHostAlloc((void **)&p->hRes, n * sizeof(bt2g_read_result), cudaHostAllocDefault);
 	if(e == cudaSuccess) e = cudaHostAlloc((void **)&p->hOps, n * (uint64_t)prm->max_ops, cudaHostAllocDefault);
 	if(e != cudaSuccess) { ctx->err = std::string("pipeline setup: ") + cudaGetErrorString(e); bt2g_pipeline_destroy(p); return -2; }
+	p->evOk = true;
+	for(int i = 0; i < 9; i++) if(cudaEventCreate(&p->ev[i]) != cudaSuccess) p->evOk = false;
 	// the params struct keeps host pointers that may die; null them
 	p->prm.minsc_by_len = p->prm.nceil_by_len = p->prm.nceil_raw_by_len = p->prm.interval_by_len = p->prm.rdgaps_by_len = p->prm.rfgaps_by_len = nullptr;
 	*out = p;
@@ -305,6 +322,7 @@ void bt2g_pipeline_destroy(bt2g_pipeline *p) {
 	if(!p) return;
 	cudaSetDevice(p->ctx->device);
 	for(void *v : p->allocs) cudaFree(v);
+	if(p->evOk) for(int i = 0; i < 9; i++) cudaEventDestroy(p->ev[i]);
 	if(p->hSeq) cudaFreeHost(p->hSeq);
 	if(p->hQual) cudaFreeHost(p->hQual);
 	if(p->hOff) cudaFreeHost(p->hOff);
@@ -349,6 +367,17 @@ int bt2g_pipeline_results_dev(bt2g_pipeline *p, bt2g_read_result **res, uint8_t 
 	if(!p) return -1;
 	if(res) *res = p->b.res;
 	if(ops) *ops = p->b.resOps;
+	return 0;
+}
+
+// device time of each stage of the LAST run, measured with CUDA events on the launching stream:
+// [0] plan, [1] exact sweep, [2] seed search, [3] collect, [4] resolve, [5] frame, [6] DP, [7] pick
+int bt2g_pipeline_stage_ms(bt2g_pipeline *p, float *out8) {
+	if(!p || !out8 || !p->evOk) return -1;
+	bt2g_ctx *ctx = p->ctx;
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	BT2G_CUDA_TRY(ctx, cudaEventSynchronize(p->ev[8]));
+	for(int i = 0; i < 8; i++) BT2G_CUDA_TRY(ctx, cudaEventElapsedTime(&out8[i], p->ev[i], p->ev[i + 1]));
 	return 0;
 }
 

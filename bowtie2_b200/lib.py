@@ -351,7 +351,7 @@ def ops_to_edits(ops: np.ndarray, nops: int, read_codes: np.ndarray, fw: bool, r
 class _PipeParams(C.Structure):
     _fields_ = [("seed_len", C.c_int32), ("max_seeds", C.c_int32), ("row_cap", C.c_int32), ("range_max", C.c_int32),
                 ("max_len", C.c_int32), ("maxhalf", C.c_int32), ("max_cands", C.c_int32), ("max_alns", C.c_int32),
-                ("max_ops", C.c_int32), ("minsc_by_len", C.c_void_p), ("nceil_by_len", C.c_void_p),
+                ("max_ops", C.c_int32), ("max_probs", C.c_int32), ("minsc_by_len", C.c_void_p), ("nceil_by_len", C.c_void_p),
                 ("nceil_raw_by_len", C.c_void_p), ("interval_by_len", C.c_void_p), ("rdgaps_by_len", C.c_void_p),
                 ("rfgaps_by_len", C.c_void_p)]
 
@@ -360,7 +360,7 @@ READ_RESULT = np.dtype([("found", "<i4"), ("score", "<i4"), ("score2", "<i4"), (
                         ("refoff", "<i8"), ("nops", "<i4"), ("ndp", "<i4")], align=True)
 
 EXPORTS += ["bt2g_pipeline_create", "bt2g_pipeline_destroy", "bt2g_pipeline_run_dev", "bt2g_pipeline_run_host",
-            "bt2g_pipeline_results_dev", "bt2g_pipeline_counters"]
+            "bt2g_pipeline_results_dev", "bt2g_pipeline_counters", "bt2g_pipeline_stage_ms"]
 
 
 class Pipeline:
@@ -368,7 +368,7 @@ class Pipeline:
 
     def __init__(self, gpu: "Bt2Gpu", preset_name: str = "sensitive", max_len: int = 100, max_reads: int = 1 << 20,
                  row_cap: int = 16, range_max: int = 8, max_cands: int = 64, max_alns: int = 2, local: bool = False,
-                 both_mates: bool = False):
+                 both_mates: bool = False, max_probs: int = 0):
         from . import policy
         self.gpu = gpu
         lib = gpu._lib
@@ -381,6 +381,7 @@ class Pipeline:
         lib.bt2g_pipeline_run_host.argtypes = [vp, C.POINTER(_Reads), vp, vp]
         lib.bt2g_pipeline_results_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         lib.bt2g_pipeline_counters.argtypes = [vp, vp]
+        lib.bt2g_pipeline_stage_ms.argtypes = [vp, vp]
         gpu.set_scoring(local=local)
         sc = policy.Scoring.default(local)
         pre = policy.preset(preset_name, local)
@@ -394,7 +395,7 @@ class Pipeline:
         self.seed_len = pre.seed_len
         min_ival = int(self._tabs[3][1:].min()) if max_len >= 1 else 1
         self.max_seeds = max(1, policy.n_seeds(max_len, pre.seed_len, max(min_ival, 1)))
-        prm = _PipeParams(pre.seed_len, self.max_seeds, row_cap, range_max, max_len, 15, max_cands, max_alns, self.max_ops,
+        prm = _PipeParams(pre.seed_len, self.max_seeds, row_cap, range_max, max_len, 15, max_cands, max_alns, self.max_ops, max_probs,
                           *[_ptr(t) for t in self._tabs])
         h = vp()
         gpu._check(lib.bt2g_pipeline_create(gpu._h, C.byref(prm), max_reads, max_reads * max_len, C.byref(h)), "bt2g_pipeline_create")
@@ -428,6 +429,13 @@ class Pipeline:
         self.gpu._check(self.gpu._lib.bt2g_pipeline_counters(self._h, _ptr(out)), "bt2g_pipeline_counters")
         k = ["sweep_sides", "seed_sides", "resolve_sides", "dp_cells", "dp_problems", "reads"]
         return {a: int(b) for a, b in zip(k, out)}
+
+    STAGES = ["plan", "exact_sweep", "seed_search", "collect", "resolve", "frame", "dp", "pick"]
+
+    def stage_ms(self) -> dict:
+        out = np.zeros(8, dtype=np.float32)
+        self.gpu._check(self.gpu._lib.bt2g_pipeline_stage_ms(self._h, _ptr(out)), "bt2g_pipeline_stage_ms")
+        return {k: float(v) for k, v in zip(self.STAGES, out)}
 
     def results_dev(self):
         r, o = C.c_void_p(), C.c_void_p()

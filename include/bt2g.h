@@ -240,6 +240,7 @@ typedef struct {
 	int32_t max_len;             /* longest read (<= 512) */
 	int32_t maxhalf;             /* DP half-width cap (bt2_search.cpp maxhalf = 15) */
 	int32_t max_cands, max_alns, max_ops;
+	int32_t max_probs;           /* DP problems the workspace holds per batch (0 = max_reads*row_cap) */
 	const int32_t *minsc_by_len, *nceil_by_len, *nceil_raw_by_len, *interval_by_len;   /* [max_len+1] */
 	const int32_t *rdgaps_by_len, *rfgaps_by_len;                                     /* [max_len+1] */
 } bt2g_pipeline_params;
@@ -267,6 +268,8 @@ int  bt2g_pipeline_run_dev(bt2g_pipeline *p, const uint8_t *d_seq, const uint8_t
 int  bt2g_pipeline_run_host(bt2g_pipeline *p, const bt2g_reads *reads, bt2g_read_result *res, uint8_t *ops);
 int  bt2g_pipeline_results_dev(bt2g_pipeline *p, bt2g_read_result **res, uint8_t **ops);
 int  bt2g_pipeline_counters(bt2g_pipeline *p, uint64_t *out6);
+/* device milliseconds of the 8 stages of the last run (CUDA events on the launching stream) */
+int  bt2g_pipeline_stage_ms(bt2g_pipeline *p, float *out8);
 
 #ifdef __cplusplus
 }
