@@ -463,7 +463,7 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 	L.n = n; L.nDev = nullptr; L.maxCol = maxCol;
 	{
 		int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-		uint64_t want = (uint64_t)sms * 16;      // 16 resident warps per SM
+		uint64_t want = (uint64_t)sms * 24;      // 24 resident warps per SM
 		L.numSlots = ((n < want ? n : want) + 3) / 4 * 4;
 	} L.maxCands = maxCands; L.maxAlns = maxAlns; L.maxOps = maxOps;
 	L.codeStride = (uint64_t)(maxCol + 32) * 32 * R;

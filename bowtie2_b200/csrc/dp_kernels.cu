@@ -5,9 +5,10 @@
 // kernel that stores E, F and H for every cell and then repairs the vertical-gap dependency
 // in a "lazy F" fix-up loop (aligner_swsse_ee_u8.cpp:775-1146; the fix-up loop dominates its
 // run time).  This kernel is a different design:
-//   * one warp per DP problem; lane k owns R consecutive read rows; at step t lane k computes
-//     column t-k, so the 32 lanes sweep an anti-diagonal wavefront and the vertical (F) and
-//     diagonal dependencies cross lanes through one __shfl_up per step -- no fix-up loop;
+//   * persistent warps, one DP problem at a time per warp; lane k owns R consecutive read rows;
+//     at step t lane k computes column t-k, so the 32 lanes sweep an anti-diagonal wavefront and
+//     the vertical (F) and diagonal dependencies cross lanes through one __shfl_up per step --
+//     no fix-up loop;
 //   * exact 32-bit arithmetic with DPX max/add-max (no saturating 8/16-bit lanes, so the
 //     reference's u8 -> i16 fallback (aligner_sw.cpp:518,569-605) has no equivalent here;
 //     the two paths produce identical scores by the reference's own debug asserts :622-677);
@@ -15,18 +16,21 @@
 //     reference's backtrace would take from the H, E and F states of that cell under its fixed
 //     preference order diag > ref-gap open > ref-gap extend > read-gap open > read-gap extend
 //     (aligner_swsse_ee_u8.cpp:1509-1520, E: :1376-1380, F: :1434-1438).  Bytes are laid out
-//     wavefront-major ([step][lane][R]) so every step's store is one coalesced line per warp;
-//   * the backtrace (lane 0) replays SwAligner::nextAlignment (aligner_sw.cpp:737-1146) for ALL
+//     wavefront-major ([step][lane][R]) so every step's store is one coalesced line per warp,
+//     in a per-warp-slot workspace that is reused problem after problem and stays in L2;
+//   * the backtrace replays SwAligner::nextAlignment (aligner_sw.cpp:737-1146) for ALL
 //     candidates in their sorted order, marking visited cells in bit 7 of the move byte.  In
 //     the reference a backtrace that reaches an already reported-through cell unwinds its whole
 //     branch stack (every stacked cell is itself already marked, :1336-1340,:1561-1585) and
 //     fails, so the remaining-option masks never matter and the walk is a pure function of the
-//     move bytes + visited bits.
+//     move bytes + visited bits.  The walk is warp-cooperative: the 32 lanes prefetch the next
+//     32 cells of the current diagonal in one load, every lane then steps through them in
+//     lock-step (uniform control flow), so the latency chain is one L2 round trip per diagonal
+//     run instead of one per cell.
 #include "fm_device.cuh"
 #include "dp_device.cuh"
 
 #define DP_NEG (-(1 << 28))
-
 
 __device__ __forceinline__ int dp_max(int a, int b) { return a > b ? a : b; }
 
@@ -38,225 +42,249 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 	const uint64_t slot = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock;
 	const uint64_t nSlots = (uint64_t)gridDim.x * (blockDim.x >> 5);
 	const uint64_t nProb = L.nDev ? (uint64_t)*L.nDev : L.n;
-	uint8_t *refw = smem + (size_t)warpInBlock * (L.maxCol + 16);
+	// per-warp shared memory: last-row scores (ints) then the reference window (bytes)
+	const size_t perWarp = ((size_t)L.maxCol * 5 + 16 + 15) & ~(size_t)15;
+	int32_t *lastH = reinterpret_cast<int32_t *>(smem + (size_t)warpInBlock * perWarp);
+	uint8_t *refw = reinterpret_cast<uint8_t *>(lastH + L.maxCol);
 	// persistent warps: the move-byte workspace belongs to the warp SLOT, not to the problem, so
 	// it is (#SMs x resident warps) x codeStride bytes and stays L2-resident across problems
 	uint8_t *codes = L.codes + slot * L.codeStride;
-	int32_t *lastH = L.lastH + slot * (uint64_t)L.maxCol;
-	for(uint64_t w = slot; w < nProb; w += nSlots) {
-	const bt2g_dp_problem p = L.probs[w];
-	const uint8_t *rs = L.seq + L.roff[p.read_idx];
-	const uint8_t *rq = L.qual + L.roff[p.read_idx];
-	const int rdlen = (int)(L.roff[p.read_idx + 1] - L.roff[p.read_idx]);
-	const int ncol = (int)(p.refr - p.refl + 1);
-	bt2g_dp_summary *summ = L.summ + w;
-	__syncwarp();
-	if(ncol <= 0 || ncol > L.maxCol || rdlen > 32 * R || rdlen <= 0) {
-		if(lane == 0) { summ->found = 0; summ->best = DP_NEG; summ->ncand = 0; summ->naln = 0; summ->flags = BT2G_DP_FLAG_BADSHAPE; }
-		continue;
-	}
-	// reference window (SwAligner::initRef, aligner_sw.cpp:155-271): codes 0..3, 4 = N / off-end
-	for(int k = lane; k < ncol; k += 32) refw[k] = (uint8_t)ref_base<OFF>(ix, p.tidx, p.refl + k);
-	__syncwarp();
-
-	// per-row constants (buildQueryProfileEnd2EndSseU8, aligner_swsse_ee_u8.cpp:75-142)
-	int rc[R], mmp[R], npn[R];
-	bool bar[R];
-#pragma unroll
-	for(int r = 0; r < R; r++) {
-		int i = lane * R + r;
-		if(i < rdlen) {
-			int pos = p.fw ? i : rdlen - 1 - i;
-			int c = rs[pos];
-			rc[r] = p.fw ? c : (c > 3 ? 4 : 3 - c);
-			int q = (int)rq[pos] - 33;
-			q = q < 0 ? 0 : (q > 63 ? 63 : q);
-			mmp[r] = sc.mmpen[q]; npn[r] = sc.npen[q];
-			bar[r] = (i < sc.gapbar) || (rdlen - 1 - i < sc.gapbar);
-		} else { rc[r] = 5; mmp[r] = 0; npn[r] = 0; bar[r] = true; }
-	}
 	const int rdgapo = sc.rdgap_const + sc.rdgap_linear, rdgape = sc.rdgap_linear;
 	const int rfgapo = sc.rfgap_const + sc.rfgap_linear, rfgape = sc.rfgap_linear;
-	const int lastLane = (rdlen - 1) / R, lastR = (rdlen - 1) % R;
 
-	int Hleft[R], Earr[R], Eprev[R];
-#pragma unroll
-	for(int r = 0; r < R; r++) { Hleft[r] = DP_NEG; Earr[r] = DP_NEG; Eprev[r] = DP_NEG; }
-	int botH = DP_NEG, botF = DP_NEG, prevInH = DP_NEG;
-	const int nsteps = ncol + lastLane;   // lanes beyond lastLane hold no rows
-	int best = DP_NEG;
-	for(int t = 0; t < nsteps; t++) {
-		int inH = __shfl_up_sync(0xffffffffu, botH, 1);
-		int inF = __shfl_up_sync(0xffffffffu, botF, 1);
-		if(lane == 0) { inH = DP_NEG; inF = DP_NEG; }
-		const int j = t - lane;
-		if(j >= 0 && j < ncol && lane <= lastLane) {
-			const int refc = refw[j];
-			// H[i0-1][j-1]: row -1 is the free start row of end-to-end mode (vhilsw, :853,923-927)
-			int diag = (lane == 0) ? 0 : prevInH;
-			int upH = inH, upF = inF;
-			uint32_t packed[(R + 3) / 4];
-#pragma unroll
-			for(int q4 = 0; q4 < (R + 3) / 4; q4++) packed[q4] = 0;
-#pragma unroll
-			for(int r = 0; r < R; r++) {
-				// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo), vetoed in gap-barrier rows (:944-945,:983-985)
-				int F = __viaddmax_s32(upF, -rfgape, upH - rfgapo);
-				F = bar[r] ? DP_NEG : F;
-				int s;
-				if(rc[r] > 3 || refc > 3) s = -npn[r];
-				else s = (rc[r] == refc) ? sc.match_bonus : -mmp[r];
-				int Hd = diag + s;
-				int E = Earr[r];
-				int H = __vimax3_s32(Hd, E, F);
-				// move byte: what the backtrace would do from each state of this cell
-				int hsel = 0;
-				const bool gaps = !bar[r];
-				if(H == Hd && diag > DP_NEG / 2) hsel = 1;
-				else if(gaps && H == upH - rfgapo) hsel = 2;
-				else if(gaps && H == upF - rfgape) hsel = 3;
-				else if(gaps && H == Hleft[r] - rdgapo) hsel = 4;
-				else if(gaps && H == Eprev[r] - rdgape) hsel = 5;
-				int esel = (E == Hleft[r] - rdgapo) ? 1 : ((E == Eprev[r] - rdgape) ? 2 : 0);
-				int fsel = (F == upH - rfgapo) ? 1 : ((F == upF - rfgape) ? 2 : 0);
-				uint32_t code = (uint32_t)(hsel | (esel << 3) | (fsel << 5));
-				packed[r >> 2] |= code << ((r & 3) * 8);
-				// E[i][j+1] = max(E[i][j]-rdgape, H[i][j]-rdgapo [vetoed in barrier rows]) (:966-969)
-				int En = __viaddmax_s32(E, -rdgape, bar[r] ? DP_NEG : H - rdgapo);
-				diag = Hleft[r]; Hleft[r] = H; Eprev[r] = E; Earr[r] = En;
-				upH = H; upF = F;
-				if(lane == lastLane && r == lastR) { lastH[j] = H; best = dp_max(best, H); }
-			}
-			botH = upH; botF = upF;
-			prevInH = inH;
-			uint8_t *dst = codes + ((size_t)t * 32 + lane) * R;
-			if(R == 4) *reinterpret_cast<uint32_t *>(dst) = packed[0];
-			else if(R == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(packed[0], packed[1]);
-			else {
-#pragma unroll
-				for(int q4 = 0; q4 < (R + 3) / 4; q4++) reinterpret_cast<uint32_t *>(dst)[q4] = packed[q4];
-			}
-		} else if(j >= ncol) {
-			botH = DP_NEG; botF = DP_NEG;
+	for(uint64_t w = slot; w < nProb; w += nSlots) {
+		const bt2g_dp_problem p = L.probs[w];
+		const uint8_t *rs = L.seq + L.roff[p.read_idx];
+		const uint8_t *rq = L.qual + L.roff[p.read_idx];
+		const int rdlen = (int)(L.roff[p.read_idx + 1] - L.roff[p.read_idx]);
+		const int ncol = (int)(p.refr - p.refl + 1);
+		bt2g_dp_summary *summ = L.summ + w;
+		__syncwarp();
+		if(ncol <= 0 || ncol > L.maxCol || rdlen > 32 * R || rdlen <= 0) {
+			if(lane == 0) { summ->found = 0; summ->best = DP_NEG; summ->ncand = 0; summ->naln = 0; summ->flags = BT2G_DP_FLAG_BADSHAPE; }
+			continue;
 		}
-	}
-	best = __shfl_sync(0xffffffffu, best, lastLane);
-	__syncwarp();
-	if(lane != 0) continue;
+		// reference window (SwAligner::initRef, aligner_sw.cpp:155-271): codes 0..3, 4 = N / off-end
+		for(int k = lane; k < ncol; k += 32) refw[k] = (uint8_t)ref_base<OFF>(ix, p.tidx, p.refl + k);
+		__syncwarp();
 
-	// ---- SwAligner::align tail (aligner_sw.cpp:679-729) + gatherCellsNucleotidesEnd2End (:1176-1208)
-	summ->best = best; summ->flags = 0; summ->naln = 0; summ->ncand = 0;
-	if(best < p.minsc) { summ->found = 0; continue; }
-	bt2g_dp_cand *cands = L.cands + w * (uint64_t)L.maxCands;
-	int ncand = 0, totalCand = 0;
-	for(int j = 0; j < ncol; j++) {
-		int s = lastH[j];
-		if(s >= p.minsc) {
-			totalCand++;
-			// insertion sort: score desc, (row equal), col desc (DpBtCandidate::operator<, aligner_sw_nuc.h:149-157)
-			int pos = ncand < L.maxCands ? ncand : L.maxCands - 1;
-			if(ncand >= L.maxCands) {
-				// full: only keep if better than the current worst
-				const bt2g_dp_cand &wc = cands[L.maxCands - 1];
-				if(!(s > wc.score || (s == wc.score && j > wc.col))) continue;
-			}
-			while(pos > 0 && (cands[pos - 1].score < s || (cands[pos - 1].score == s && cands[pos - 1].col < j))) {
-				cands[pos] = cands[pos - 1]; pos--;
-			}
-			cands[pos].score = s; cands[pos].col = j; cands[pos].row = rdlen - 1; cands[pos].fate = 0;
-			if(ncand < L.maxCands) ncand++;
+		// per-row constants (buildQueryProfileEnd2EndSseU8, aligner_swsse_ee_u8.cpp:75-142)
+		int rc[R], mmp[R], npn[R];
+		bool bar[R];
+#pragma unroll
+		for(int r = 0; r < R; r++) {
+			int i = lane * R + r;
+			if(i < rdlen) {
+				int pos = p.fw ? i : rdlen - 1 - i;
+				int c = rs[pos];
+				rc[r] = p.fw ? c : (c > 3 ? 4 : 3 - c);
+				int q = (int)rq[pos] - 33;
+				q = q < 0 ? 0 : (q > 63 ? 63 : q);
+				mmp[r] = sc.mmpen[q]; npn[r] = sc.npen[q];
+				bar[r] = (i < sc.gapbar) || (rdlen - 1 - i < sc.gapbar);
+			} else { rc[r] = 5; mmp[r] = 0; npn[r] = 0; bar[r] = true; }
 		}
-	}
-	summ->ncand = totalCand;
-	summ->found = totalCand > 0;
-	if(totalCand > L.maxCands) summ->flags |= BT2G_DP_FLAG_CAND_OVERFLOW;
+		const int lastLane = (rdlen - 1) / R, lastR = (rdlen - 1) % R;
 
-	// ---- SwAligner::nextAlignment over every candidate (aligner_sw.cpp:737-1146) ------------
-	bt2g_dp_aln *alns = L.alns + w * (uint64_t)L.maxAlns;
-	uint8_t *ops = L.ops + w * (uint64_t)L.maxAlns * L.maxOps;
-	int naln = 0;
-	for(int ci = 0; ci < ncand; ci++) {
-		int row = cands[ci].row, col = cands[ci].col;
+		int Hleft[R], Earr[R], Eprev[R];
+#pragma unroll
+		for(int r = 0; r < R; r++) { Hleft[r] = DP_NEG; Earr[r] = DP_NEG; Eprev[r] = DP_NEG; }
+		int botH = DP_NEG, botF = DP_NEG, prevInH = DP_NEG;
+		const int nsteps = ncol + lastLane;   // lanes beyond lastLane hold no rows
+		int best = DP_NEG;
+		for(int t = 0; t < nsteps; t++) {
+			int inH = __shfl_up_sync(0xffffffffu, botH, 1);
+			int inF = __shfl_up_sync(0xffffffffu, botF, 1);
+			if(lane == 0) { inH = DP_NEG; inF = DP_NEG; }
+			const int j = t - lane;
+			if(j >= 0 && j < ncol && lane <= lastLane) {
+				const int refc = refw[j];
+				// H[i0-1][j-1]: row -1 is the free start row of end-to-end mode (vhilsw, :853,923-927)
+				int diag = (lane == 0) ? 0 : prevInH;
+				int upH = inH, upF = inF;
+				uint32_t packed[(R + 3) / 4];
+#pragma unroll
+				for(int q4 = 0; q4 < (R + 3) / 4; q4++) packed[q4] = 0;
+#pragma unroll
+				for(int r = 0; r < R; r++) {
+					// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo), vetoed in gap-barrier rows (:944-945,:983-985)
+					int F = __viaddmax_s32(upF, -rfgape, upH - rfgapo);
+					F = bar[r] ? DP_NEG : F;
+					int s;
+					if(rc[r] > 3 || refc > 3) s = -npn[r];
+					else s = (rc[r] == refc) ? sc.match_bonus : -mmp[r];
+					int Hd = diag + s;
+					int E = Earr[r];
+					int H = __vimax3_s32(Hd, E, F);
+					// move byte: what the backtrace would do from each state of this cell
+					int hsel = 0;
+					const bool gaps = !bar[r];
+					if(H == Hd && diag > DP_NEG / 2) hsel = 1;
+					else if(gaps && H == upH - rfgapo) hsel = 2;
+					else if(gaps && H == upF - rfgape) hsel = 3;
+					else if(gaps && H == Hleft[r] - rdgapo) hsel = 4;
+					else if(gaps && H == Eprev[r] - rdgape) hsel = 5;
+					int esel = (E == Hleft[r] - rdgapo) ? 1 : ((E == Eprev[r] - rdgape) ? 2 : 0);
+					int fsel = (F == upH - rfgapo) ? 1 : ((F == upF - rfgape) ? 2 : 0);
+					uint32_t code = (uint32_t)(hsel | (esel << 3) | (fsel << 5));
+					packed[r >> 2] |= code << ((r & 3) * 8);
+					// E[i][j+1] = max(E[i][j]-rdgape, H[i][j]-rdgapo [vetoed in barrier rows]) (:966-969)
+					int En = __viaddmax_s32(E, -rdgape, bar[r] ? DP_NEG : H - rdgapo);
+					diag = Hleft[r]; Hleft[r] = H; Eprev[r] = E; Earr[r] = En;
+					upH = H; upF = F;
+					if(lane == lastLane && r == lastR) { lastH[j] = H; best = dp_max(best, H); }
+				}
+				botH = upH; botF = upF;
+				prevInH = inH;
+				uint8_t *dst = codes + ((size_t)t * 32 + lane) * R;
+				if(R == 4) *reinterpret_cast<uint32_t *>(dst) = packed[0];
+				else if(R == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(packed[0], packed[1]);
+				else {
+#pragma unroll
+					for(int q4 = 0; q4 < (R + 3) / 4; q4++) reinterpret_cast<uint32_t *>(dst)[q4] = packed[q4];
+				}
+			} else if(j >= ncol) {
+				botH = DP_NEG; botF = DP_NEG;
+			}
+		}
+		best = __shfl_sync(0xffffffffu, best, lastLane);
+		__syncwarp();
+
+		// ---- SwAligner::align tail (aligner_sw.cpp:679-729) + gatherCellsNucleotidesEnd2End (:1176-1208)
+		if(lane == 0) { summ->best = best; summ->flags = 0; summ->naln = 0; summ->ncand = 0; summ->found = 0; }
+		if(best < p.minsc) continue;
+		bt2g_dp_cand *cands = L.cands + w * (uint64_t)L.maxCands;
+		// rank of each candidate under DpBtCandidate::operator< (score desc, row equal, col desc;
+		// aligner_sw_nuc.h:149-157) computed directly: every lane ranks the columns it owns
+		int totalCand = 0;
+		for(int j0 = 0; j0 < ncol; j0 += 32) {
+			const int j = j0 + lane;
+			const int s = j < ncol ? lastH[j] : DP_NEG;
+			const bool isC = j < ncol && s >= p.minsc;
+			if(isC) {
+				int rank = 0;
+				for(int k = 0; k < ncol; k++) {
+					const int sk = lastH[k];
+					rank += (sk >= p.minsc) && (sk > s || (sk == s && k > j));
+				}
+				if(rank < L.maxCands) { cands[rank].score = s; cands[rank].col = j; cands[rank].row = rdlen - 1; cands[rank].fate = 0; }
+			}
+			totalCand += __popc(__ballot_sync(0xffffffffu, isC));
+		}
+		const int ncand = totalCand < L.maxCands ? totalCand : L.maxCands;
+		if(lane == 0) {
+			summ->ncand = totalCand; summ->found = totalCand > 0;
+			if(totalCand > L.maxCands) summ->flags |= BT2G_DP_FLAG_CAND_OVERFLOW;
+		}
+		__syncwarp();
+
+		// ---- SwAligner::nextAlignment over every candidate (aligner_sw.cpp:737-1146) ------------
+		bt2g_dp_aln *alns = L.alns + w * (uint64_t)L.maxAlns;
+		uint8_t *ops = L.ops + w * (uint64_t)L.maxAlns * L.maxOps;
+		int naln = 0, flags = 0;
 		auto cell = [&](int rr, int cc) -> uint8_t * { int k = rr / R; return codes + ((size_t)(cc + k) * 32 + k) * R + (rr - k * R); };
-		if(*cell(row, col) & 0x80) { cands[ci].fate = BT2G_CAND_FILT_START; continue; }   // :771-789
-		// backtraceNucleotidesEnd2EndSseU8 (aligner_swsse_ee_u8.cpp:1283-1877)
-		uint8_t *o = ops + (size_t)naln * L.maxOps;
-		const bool room = naln < L.maxAlns;
-		int nops = 0, score = 0, ns = 0, gaps = 0, ct = 0;   // ct: 0 H, 1 E, 2 F
-		bool fail = false, core = false, opOverflow = false;
-		const int origCol = col;
-		int trimBeg = 0;
-		for(;;) {
-			uint8_t *cp = cell(row, col);
-			uint8_t code = *cp;
-			if(code & 0x80) { fail = true; break; }
-			*cp = code | 0x80;
-			{
-				int diagi = col - row + p.triml;
-				if(diagi >= p.corel && diagi <= p.corer) core = true;
+		for(int ci = 0; ci < ncand; ci++) {
+			int row = cands[ci].row, col = cands[ci].col;      // same address in every lane: one broadcast load
+			// backtraceNucleotidesEnd2EndSseU8 (aligner_swsse_ee_u8.cpp:1283-1877); all lanes run the
+			// same scalar walk, lane k additionally owns cell k of the current diagonal prefetch
+			uint8_t *o = ops + (size_t)naln * L.maxOps;
+			const bool room = naln < L.maxAlns;
+			int nops = 0, score = 0, ns = 0, gaps = 0, ct = 0;   // ct: 0 H, 1 E, 2 F
+			bool fail = false, core = false, opOverflow = false, done = false, first = true, filtStart = false;
+			const int origCol = col;
+			int trimBeg = 0;
+			while(!done && !fail) {
+				// prefetch the diagonal (row-k, col-k), k = lane
+				const int rk = row - lane, ck = col - lane;
+				uint8_t *cp = (rk >= 0 && ck >= 0) ? cell(rk, ck) : nullptr;
+				const uint8_t mine = cp ? *cp : 0xff;
+				uint32_t consumed = 0;
+				for(int k = 0; k < 32; k++) {
+					const uint8_t code = (uint8_t)__shfl_sync(0xffffffffu, (int)mine, k);
+					if(code & 0x80) {
+						// start cell already reported through -> BT_CAND_FATE_FILT_START (:771-789);
+						// anywhere else the backtrace fails
+						if(first) filtStart = true;
+						fail = true; break;
+					}
+					first = false;
+					consumed |= 1u << k;
+					{
+						int diagi = col - row + p.triml;
+						if(diagi >= p.corel && diagi <= p.corer) core = true;
+					}
+					if(row == 0) { done = true; break; }
+					int mv;   // 1 diag, 2 refopen, 3 rfext, 4 rdopen, 5 rdext
+					if(ct == 0) { mv = code & 7; if(mv == 0) { trimBeg = row; done = true; break; } }
+					else if(ct == 1) { int e = (code >> 3) & 3; if(e == 0) { fail = true; break; } mv = e == 1 ? 4 : 5; }
+					else { int f = (code >> 5) & 3; if(f == 0) { fail = true; break; } mv = f == 1 ? 2 : 3; }
+					const int pos = p.fw ? row : rdlen - 1 - row;
+					int c = rs[pos]; c = p.fw ? c : (c > 3 ? 4 : 3 - c);
+					int q = (int)rq[pos] - 33; q = q < 0 ? 0 : (q > 63 ? 63 : q);
+					const int refc = refw[col];
+					uint8_t op;
+					bool stay = false;
+					if(mv == 1) {
+						if(c > 3 || refc > 3) { score -= sc.npen[q]; ns++; op = BT2G_OP_MM; }
+						else if(c == refc) { score += sc.match_bonus; op = BT2G_OP_MATCH; }
+						else { score -= sc.mmpen[q]; op = BT2G_OP_MM; }
+						op |= (uint8_t)(refc << 2);
+						row--; col--; ct = 0; stay = true;
+					} else if(mv == 2 || mv == 3) {
+						score -= (mv == 2) ? rfgapo : rfgape; gaps++;
+						op = BT2G_OP_REFGAP;
+						row--; ct = (mv == 2) ? 0 : 2;
+					} else {
+						score -= (mv == 4) ? rdgapo : rdgape; gaps++;
+						op = BT2G_OP_READGAP | (uint8_t)(refc << 2);
+						col--; ct = (mv == 4) ? 0 : 1;
+					}
+					if(room && lane == 0) { if(nops < L.maxOps) o[nops] = op; }
+					if(nops >= L.maxOps) opOverflow = true;
+					nops++;
+					if(!stay) break;            // left the prefetched diagonal
+				}
+				if(cp && ((consumed >> lane) & 1u)) *cp = mine | 0x80;     // setReportedThrough (:1555)
+				__syncwarp();
 			}
-			if(row == 0) break;
-			int mv;   // 1 diag, 2 refopen, 3 rfext, 4 rdopen, 5 rdext
-			if(ct == 0) { mv = code & 7; if(mv == 0) { trimBeg = row; break; } }
-			else if(ct == 1) { int e = (code >> 3) & 3; if(e == 0) { fail = true; break; } mv = e == 1 ? 4 : 5; }
-			else { int f = (code >> 5) & 3; if(f == 0) { fail = true; break; } mv = f == 1 ? 2 : 3; }
-			int pos = p.fw ? row : rdlen - 1 - row;
-			int c = rs[pos]; c = p.fw ? c : (c > 3 ? 4 : 3 - c);
-			int q = (int)rq[pos] - 33; q = q < 0 ? 0 : (q > 63 ? 63 : q);
-			int refc = refw[col];
-			uint8_t op;
-			if(mv == 1) {
+			if(filtStart) { if(lane == 0) cands[ci].fate = BT2G_CAND_FILT_START; continue; }
+			if(!fail) {
+				// the alignment's first cell (row, col) (:1797-1813)
+				const int pos = p.fw ? row : rdlen - 1 - row;
+				int c = rs[pos]; c = p.fw ? c : (c > 3 ? 4 : 3 - c);
+				int q = (int)rq[pos] - 33; q = q < 0 ? 0 : (q > 63 ? 63 : q);
+				const int refc = refw[col];
+				uint8_t op;
 				if(c > 3 || refc > 3) { score -= sc.npen[q]; ns++; op = BT2G_OP_MM; }
 				else if(c == refc) { score += sc.match_bonus; op = BT2G_OP_MATCH; }
 				else { score -= sc.mmpen[q]; op = BT2G_OP_MM; }
 				op |= (uint8_t)(refc << 2);
-				row--; col--; ct = 0;
-			} else if(mv == 2 || mv == 3) {
-				score -= (mv == 2) ? rfgapo : rfgape; gaps++;
-				op = BT2G_OP_REFGAP;
-				row--; ct = (mv == 2) ? 0 : 2;
+				if(!core) fail = true;                   // core-diagonal rejection (:1764-1795)
+				else if(ns > p.nceil) fail = true;       // N ceiling (:1813-1818)
+				else {
+					if(room && lane == 0) { if(nops < L.maxOps) o[nops] = op; }
+					if(nops >= L.maxOps) opOverflow = true;
+					nops++;
+				}
+			}
+			if(fail) { if(lane == 0) cands[ci].fate = BT2G_CAND_FAILED; continue; }
+			if(lane == 0) cands[ci].fate = BT2G_CAND_SUCCEEDED;
+			if(room) {
+				if(lane == 0) {
+					bt2g_dp_aln &a = alns[naln];
+					a.cand_idx = ci; a.score = score; a.ns = ns; a.gaps = gaps; a.col0 = col; a.row0 = row;
+					a.trim_beg = trimBeg; a.trim_end = 0; a.nops = nops;
+					int refns = 0;
+					for(int k = col; k <= origCol; k++) refns += refw[k] > 3;
+					a.refns = refns;
+				}
+				if(opOverflow) flags |= BT2G_DP_FLAG_OPS_OVERFLOW;
 			} else {
-				score -= (mv == 4) ? rdgapo : rdgape; gaps++;
-				op = BT2G_OP_READGAP | (uint8_t)(refc << 2);
-				col--; ct = (mv == 4) ? 0 : 1;
+				flags |= BT2G_DP_FLAG_ALN_OVERFLOW;
 			}
-			if(room) { if(nops < L.maxOps) o[nops] = op; else opOverflow = true; }
-			nops++;
+			naln++;
 		}
-		if(!fail) {
-			// the alignment's first cell (row, col) (:1797-1813)
-			int pos = p.fw ? row : rdlen - 1 - row;
-			int c = rs[pos]; c = p.fw ? c : (c > 3 ? 4 : 3 - c);
-			int q = (int)rq[pos] - 33; q = q < 0 ? 0 : (q > 63 ? 63 : q);
-			int refc = refw[col];
-			uint8_t op;
-			if(c > 3 || refc > 3) { score -= sc.npen[q]; ns++; op = BT2G_OP_MM; }
-			else if(c == refc) { score += sc.match_bonus; op = BT2G_OP_MATCH; }
-			else { score -= sc.mmpen[q]; op = BT2G_OP_MM; }
-			op |= (uint8_t)(refc << 2);
-			if(!core) fail = true;                   // core-diagonal rejection (:1764-1795)
-			else if(ns > p.nceil) fail = true;       // N ceiling (:1813-1818)
-			else {
-				if(room) { if(nops < L.maxOps) o[nops] = op; else opOverflow = true; }
-				nops++;
-			}
-		}
-		if(fail) { cands[ci].fate = BT2G_CAND_FAILED; continue; }
-		cands[ci].fate = BT2G_CAND_SUCCEEDED;
-		if(room) {
-			bt2g_dp_aln &a = alns[naln];
-			a.cand_idx = ci; a.score = score; a.ns = ns; a.gaps = gaps; a.col0 = col; a.row0 = row;
-			a.trim_beg = trimBeg; a.trim_end = 0; a.nops = nops;
-			int refns = 0;
-			for(int k = col; k <= origCol; k++) refns += refw[k] > 3;
-			a.refns = refns;
-			if(opOverflow) summ->flags |= BT2G_DP_FLAG_OPS_OVERFLOW;
-		} else {
-			summ->flags |= BT2G_DP_FLAG_ALN_OVERFLOW;
-		}
-		naln++;
-	}
-	summ->naln = naln;
+		if(lane == 0) { summ->naln = naln; summ->flags |= flags; }
 	} // persistent loop over problems
 }
 
@@ -265,7 +293,8 @@ template <typename OFF>
 int launch_dp_e2e(const DevIndex<OFF> &ix, const bt2g_scoring &sc, const DpLaunch &L, int maxRdLen, cudaStream_t st) {
 	if(L.n == 0) return 0;
 	const int warpsPerBlock = 4;
-	size_t smem = (size_t)warpsPerBlock * (L.maxCol + 16);
+	const size_t perWarp = ((size_t)L.maxCol * 5 + 16 + 15) & ~(size_t)15;
+	size_t smem = (size_t)warpsPerBlock * perWarp;
 	unsigned grid = (unsigned)(L.numSlots / warpsPerBlock);
 	if(maxRdLen <= 128) {
 		if(smem > 48 * 1024) cudaFuncSetAttribute(k_dp_e2e<OFF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

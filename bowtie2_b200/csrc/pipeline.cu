@@ -290,7 +290,7 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	p->R = prm->max_len <= 128 ? 4 : (prm->max_len <= 256 ? 8 : 16);
 	p->codeStride = (uint64_t)(p->maxCol + 32) * 32 * p->R;
 	int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-	p->numSlots = (uint64_t)sms * 16;
+	p->numSlots = (uint64_t)sms * 24;
 	rc |= pipeAlloc(p, b.codes, p->numSlots * p->codeStride); rc |= pipeAlloc(p, b.lastH, p->numSlots * (uint64_t)p->maxCol);
 	rc |= pipeAlloc(p, b.summ, nprobMax); rc |= pipeAlloc(p, b.cands, nprobMax * prm->max_cands);
 	rc |= pipeAlloc(p, b.alns, nprobMax * prm->max_alns); rc |= pipeAlloc(p, b.ops, nprobMax * prm->max_alns * (uint64_t)prm->max_ops);
