@@ -66,6 +66,17 @@ int      bt2o_seed_search(const bt2o_index *ix, const uint8_t *codes, const uint
                           int seedlen, int interval, int offset, int nofw, int norc,
                           int max_seeds, uint64_t *out_ranges);
 
+/* seed-extension DP (end-to-end) */
+typedef struct {
+	int match_bonus, mmp_max, mmp_min, n_pen;
+	int rdgap_const, rdgap_linear, rfgap_const, rfgap_linear, gapbar, local;
+} bt2o_scoring;
+void bt2o_scoring_default(bt2o_scoring *sc, int local);
+int  bt2o_dp(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, const uint8_t *quals, int len, int fw,
+             uint64_t tidx, int64_t refl, int64_t refr, int triml, int corel, int corer, int64_t minsc, int nceil,
+             int max_cands, int max_alns, int max_edits,
+             int64_t *summary, int64_t *cands, int64_t *alns, int32_t *edits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,3 +170,40 @@ def ref_dp(R, local, codes, quals, fw, tidx, tlen, rect, minsc, rndseed=1234, ma
         e0 += ne
     out["alns"] = al
     return out
+
+
+class _OScoring(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("match_bonus", "mmp_max", "mmp_min", "n_pen", "rdgap_const", "rdgap_linear",
+                                       "rfgap_const", "rfgap_linear", "gapbar", "local")]
+
+
+def oracle_dp(O, local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=1024, max_alns=32, max_edits=4096):
+    """Same outputs as ref_dp(), from the plain-C restatement (oracle/bt2_oracle.c: bt2o_dp)."""
+    i64 = C.c_int64
+    L = O.lib
+    L.bt2o_scoring_default.argtypes = [C.POINTER(_OScoring), ci]
+    L.bt2o_dp.argtypes = [vp, C.POINTER(_OScoring), vp, vp, ci, ci, u64, i64, i64, ci, ci, ci, i64, ci, ci, ci, ci, vp, vp, vp, vp]
+    sc = _OScoring()
+    L.bt2o_scoring_default(C.byref(sc), int(local))
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    quals = np.ascontiguousarray(quals, dtype=np.uint8)
+    summ = np.zeros(4, np.int64)
+    cands = np.zeros(3 * max_cands, np.int64)
+    alns = np.zeros(8 * max_alns, np.int64)
+    eds = np.zeros(4 * max_edits, np.int32)
+    L.bt2o_dp(O.h, C.byref(sc), codes.ctypes.data_as(vp), quals.ctypes.data_as(vp), len(codes), int(fw), int(tidx),
+              int(rect.refl), int(rect.refr), int(rect.triml), int(rect.corel), int(rect.corer), int(minsc), int(nceil),
+              max_cands, max_alns, max_edits, summ.ctypes.data_as(vp), cands.ctypes.data_as(vp), alns.ctypes.data_as(vp),
+              eds.ctypes.data_as(vp))
+    out = {"found": int(summ[0]), "best": int(summ[1]), "ncand": int(summ[2]), "naln": int(summ[3])}
+    out["cands"] = [tuple(int(x) for x in cands[3 * i:3 * i + 3]) for i in range(min(out["ncand"], max_cands))]
+    al, e0 = [], 0
+    for i in range(min(out["naln"], max_alns)):
+        a = alns[8 * i:8 * i + 8]
+        ne = int(a[6])
+        al.append({"score": int(a[0]), "ns": int(a[1]), "gaps": int(a[2]), "refoff": int(a[3]), "trim5": int(a[4]),
+                   "trim3": int(a[5]), "fw": int(a[7]),
+                   "edits": [[int(x) for x in eds[4 * k:4 * k + 4]] for k in range(e0, e0 + ne)]})
+        e0 += ne
+    out["alns"] = al
+    return out
