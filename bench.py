@@ -274,27 +274,13 @@ def main():
     gpu = Bt2Gpu(local_rank)
     bcast_s = 0.0
     if distributed:
-        # single broadcast of every index array from rank 0: scalars as an object,
-        # arrays as byte tensors over NCCL / NVLink
-        meta = [None]
-        if rank == 0:
-            desc = built.device_desc(dev)
-            meta[0] = {k: v for k, v in desc.items() if not isinstance(v, int) or k in (
-                "off_size", "line_rate", "off_rate", "ftab_chars", "len", "n_pat", "n_frag", "z_off_fw", "z_off_bw", "n_recs")}
-            meta[0]["shapes"] = {k: (tuple(t.shape), str(t.dtype)) for k, t in built.tensors.items()}
-        dist.broadcast_object_list(meta, src=0)
+        # single broadcast of every index array from rank 0 over NCCL / NVLink
+        from bowtie2_b200.dist import broadcast_index
         torch.cuda.synchronize(); dist.barrier()
         tb = time.time()
-        tensors = {}
-        for k, (shape, dt) in meta[0]["shapes"].items():
-            t = built.tensors[k] if rank == 0 else torch.empty(shape, dtype=getattr(torch, dt.split(".")[1]), device=dev)
-            dist.broadcast(t, src=0)
-            tensors[k] = t
+        desc, tensors = broadcast_index(built, 0, dev)
         torch.cuda.synchronize(); dist.barrier()
         bcast_s = time.time() - tb
-        desc = {k: v for k, v in meta[0].items() if k != "shapes"}
-        for k, t in tensors.items():
-            desc[k] = t.data_ptr()
         gpu.load_index_device(desc, keep=tensors)
     else:
         gpu.load_index_device(built.device_desc(dev), keep=built)

@@ -13,6 +13,7 @@ template <typename OFF> void launch_exact_sweep(const DevIndex<OFF> &, const uin
 template <typename OFF> void launch_seed_search(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, cudaStream_t, unsigned long long * = nullptr);
 template <typename OFF> void launch_resolve(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t, unsigned long long * = nullptr);
 template <typename OFF> void launch_get_stretch(const DevIndex<OFF> &, const uint64_t *, const int64_t *, const int32_t *, uint64_t, int, uint8_t *, cudaStream_t);
+template <typename OFF> void launch_extend(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint64_t *, uint8_t *, cudaStream_t);
 
 namespace {
 
@@ -354,6 +355,28 @@ int bt2g_seed_search(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_seed_pla
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
 	if(nseeds) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(nseeds, dns.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int bt2g_extend_exact(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_seed_plan *plan, const uint64_t *ranges, uint8_t *out) {
+	REQUIRE_LOADED(ctx);
+	if(!reads || !plan || !ranges || !out || plan->max_seeds <= 0 || plan->seed_len <= 0) return -1;
+	uint64_t n = reads->n_reads;
+	if(n == 0) return 0;
+	DBuf dseq, dqual, doff, dint, doffs, drng, dout;
+	int rc = uploadReads(ctx, reads, dseq, dqual, doff, false);
+	if(rc) return rc;
+	const uint64_t nr = n * 2ull * plan->max_seeds;
+	BT2G_CUDA_TRY(ctx, dint.alloc(n * 4)); BT2G_CUDA_TRY(ctx, doffs.alloc(n * 4));
+	BT2G_CUDA_TRY(ctx, drng.alloc(nr * 32)); BT2G_CUDA_TRY(ctx, dout.alloc(nr * 2));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(dint.p, plan->interval, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(doffs.p, plan->offset, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(drng.p, ranges, nr * 32, cudaMemcpyHostToDevice, ctx->stream));
+	DISPATCH(ctx, launch_extend<uint32_t>(bt2g_dev_index<uint32_t>(ctx), dseq.as<uint8_t>(), doff.as<uint64_t>(), n, plan->seed_len, plan->max_seeds, dint.as<int32_t>(), doffs.as<int32_t>(), drng.as<uint64_t>(), dout.as<uint8_t>(), ctx->stream),
+	              launch_extend<uint64_t>(bt2g_dev_index<uint64_t>(ctx), dseq.as<uint8_t>(), doff.as<uint64_t>(), n, plan->seed_len, plan->max_seeds, dint.as<int32_t>(), doffs.as<int32_t>(), drng.as<uint64_t>(), dout.as<uint8_t>(), ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaGetLastError());
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, nr * 2, cudaMemcpyDeviceToHost, ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	return 0;
 }

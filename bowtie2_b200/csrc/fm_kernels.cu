@@ -223,6 +223,80 @@ __global__ void k_resolve(DevIndex<OFF> ix, const uint64_t *rows, const uint32_t
 	}
 }
 
+// ----------------------------------------------------------------------------------------
+// SwDriver::extend (aligner_sw_driver.cpp:299-484): how far each seed hit extends without an
+// edit, to the left with the forward index and to the right with the mirror index (<= 255).
+// Two threads per seed hit (one per direction) so both walks run concurrently.
+// ----------------------------------------------------------------------------------------
+template <typename OFF>
+__device__ __forceinline__ uint32_t extend_one(const DevEbwt<OFF> &e, uint64_t top, uint64_t bot, const uint8_t *s, int len,
+                                               int strand, int i0, int step, int lim) {
+	uint32_t n = 0;
+	for(int ii = 0; ii < lim; ii++) {
+		const int rdc = read_char(s, len, strand, i0 + ii * step);
+		if(bot - top > 1) {
+			uint64_t t[4], b[4];
+			rank4<OFF>(e, top, t);
+			rank4<OFF>(e, bot, b);
+			const uint64_t orig = bot - top;
+			int nonz = -1; bool abort = false;
+#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				if(!abort && b[j] > t[j]) {
+					if(nonz >= 0) abort = true;
+					else { nonz = j; top = t[j]; bot = b[j]; }
+				}
+			}
+			if(abort || (nonz != rdc && rdc <= 3) || bot - top < orig) break;
+		} else {
+			int c = -1;
+			if(top != e.zOff) top = lf_step<OFF>(e, top, c);
+			if(c != rdc && rdc <= 3) break;
+			bot = top + 1;
+		}
+		if(++n == 255) break;
+	}
+	return n;
+}
+
+template <typename OFF>
+__global__ void k_extend(DevIndex<OFF> ix, const uint8_t *seq, const uint64_t *roff, uint64_t nReads,
+                         int seedLen, int maxSeeds, const int32_t *interval, const int32_t *offset,
+                         const uint64_t *ranges, uint8_t *out) {
+	uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	const uint64_t perRead = 4ull * maxSeeds;     // [strand][seed][direction]
+	if(t >= nReads * perRead) return;
+	const uint64_t rd = t / perRead;
+	int rem = (int)(t - rd * perRead);
+	const int dir = rem & 1; rem >>= 1;
+	const int strand = rem / maxSeeds, k = rem - strand * maxSeeds;
+	out[t] = 0;
+	const uint64_t *q = ranges + ((rd * 2 + strand) * maxSeeds + k) * 4;
+	if(q[1] <= q[0]) return;
+	const uint8_t *s = seq + roff[rd];
+	const int len = (int)(roff[rd + 1] - roff[rd]);
+	const int sl = seedLen < len ? seedLen : len;
+	const int off = k * interval[rd] + offset[rd];
+	const bool fw = strand == 0;
+	if(dir == 0) {
+		const int lim = fw ? off : len - sl - off;
+		if(lim > 0) out[t] = (uint8_t)extend_one<OFF>(ix.fw, q[0], q[1], s, len, strand, fw ? off - 1 : len - off - sl - 1, -1, lim);
+	} else {
+		const int lim = fw ? len - sl - off : off;
+		if(lim > 0 && ix.bw.ebwt != nullptr)
+			out[t] = (uint8_t)extend_one<OFF>(ix.bw, q[2], q[3], s, len, strand, fw ? sl + off : len - off, +1, lim);
+	}
+}
+
+template <typename OFF>
+void launch_extend(const DevIndex<OFF> &ix, const uint8_t *seq, const uint64_t *roff, uint64_t nReads, int seedLen, int maxSeeds,
+                   const int32_t *interval, const int32_t *offset, const uint64_t *ranges, uint8_t *out, cudaStream_t st) {
+	uint64_t n = nReads * 4ull * maxSeeds;
+	if(n) k_extend<OFF><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ix, seq, roff, nReads, seedLen, maxSeeds, interval, offset, ranges, out);
+}
+template void launch_extend<uint32_t>(const DevIndex<uint32_t> &, const uint8_t *, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint64_t *, uint8_t *, cudaStream_t);
+template void launch_extend<uint64_t>(const DevIndex<uint64_t> &, const uint8_t *, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint64_t *, uint8_t *, cudaStream_t);
+
 template <typename OFF>
 __global__ void k_get_stretch(DevIndex<OFF> ix, const uint64_t *tidx, const int64_t *off, const int32_t *count,
                               uint64_t n, int stride, uint8_t *out) {

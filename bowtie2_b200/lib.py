@@ -459,3 +459,24 @@ def ops_to_cigar(ops: np.ndarray, nops: int) -> str:
     if last is not None:
         out.append(f"{run}{last}")
     return "".join(out)
+
+
+# ---- SwDriver::extend ------------------------------------------------------------------------
+EXPORTS += ["bt2g_extend_exact"]
+
+
+def _extend_exact(self, reads: ReadBatch, seed_len: int, interval, offset, max_seeds: int, ranges: np.ndarray) -> np.ndarray:
+    """nlex/nrex of every seed hit (include/bt2g.h: bt2g_extend_exact) -> uint8 [n, 2, max_seeds, 2]."""
+    lib = self._lib
+    lib.bt2g_extend_exact.argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_SeedPlan), C.c_void_p, C.c_void_p]
+    interval = _c(np.broadcast_to(interval, (reads.n,)), np.int32)
+    offset = _c(np.broadcast_to(offset, (reads.n,)), np.int32)
+    ranges = _c(ranges, np.uint64)
+    out = np.zeros((reads.n, 2, max_seeds, 2), dtype=np.uint8)
+    plan = _SeedPlan(seed_len, max_seeds, 0, 0, _ptr(interval), _ptr(offset))
+    st = reads._struct()
+    self._check(lib.bt2g_extend_exact(self._h, C.byref(st), C.byref(plan), _ptr(ranges), _ptr(out)), "bt2g_extend_exact")
+    return out
+
+
+Bt2Gpu.extend_exact = _extend_exact

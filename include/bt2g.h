@@ -137,6 +137,13 @@ typedef struct {
 int bt2g_seed_search(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_seed_plan *plan,
                      uint64_t *out, int32_t *nseeds);
 
+/* SwDriver::extend (aligner_sw_driver.cpp:299-484): for every seed hit of bt2g_seed_search
+ * (same plan, `ranges` = its output) the number of read positions the hit extends without an
+ * edit to the left (forward index) and to the right (mirror index), each capped at 255.
+ * out[(((i*2+strand)*max_seeds+k)*2 + {0,1}] = nlex, nrex. */
+int bt2g_extend_exact(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_seed_plan *plan,
+                      const uint64_t *ranges, uint8_t *out);
+
 /* ---------------------------------------------------------------- K2: offset resolve -- */
 /* GroupWalk2S::advanceElement == Ebwt::getOffset(row) (group_walk.h:1160-1215,517-520;
  * bt2_idx.cpp:150-171) followed by Ebwt::joinedToTextOff (bt2_idx.cpp:54-124) as

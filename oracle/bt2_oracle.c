@@ -534,6 +534,61 @@ int bt2o_seed_search(const bt2o_index *ix, const uint8_t *codes, const uint8_t *
 	return nseeds;
 }
 
+/* SwDriver::extend (aligner_sw_driver.cpp:299-484): extend a seed hit to the left with the
+ * forward index and to the right with the mirror index while the BW range keeps its size and
+ * the (single) extending character equals the read character; at most 255 each way.
+ * One direction; `mirror` selects the index, seq/i0/step address the read characters. */
+static uint64_t extend_one(const bt2o_index *ix, int mirror, uint64_t top, uint64_t bot,
+                           const uint8_t *seq, int64_t i0, int step, uint64_t lim) {
+	const bt2o_ebwt *e = mirror ? &ix->bw : &ix->fw;
+	uint64_t n = 0;
+	for(uint64_t ii = 0; ii < lim; ii++) {
+		int rdc = seq[i0 + (int64_t)ii * step];
+		if(bot - top > 1) {
+			uint64_t t[4], b[4];
+			bt2o_rank4(ix, mirror, top, t);
+			bt2o_rank4(ix, mirror, bot, b);
+			int nonz = -1, abort = 0;
+			uint64_t orig = bot - top;
+			for(int j = 0; j < 4; j++) {
+				if(b[j] > t[j]) {
+					if(nonz >= 0) { abort = 1; break; }
+					nonz = j; top = t[j]; bot = b[j];
+				}
+			}
+			if(abort || (nonz != rdc && rdc <= 3) || bot - top < orig) break;
+		} else {
+			/* int Ebwt::mapLF1(row&, l) (bt2_idx.h:2451-2473): -1 and row unchanged at the "$" row */
+			int c = -1;
+			if(top != e->z_off) { c = bt2o_rowL(ix, mirror, top); top = bt2o_rank1(ix, mirror, top, c); }
+			if(c != rdc && rdc <= 3) break;
+			bot = top + 1;
+		}
+		if(++n == 255) break;
+	}
+	return n;
+}
+
+void bt2o_extend(const bt2o_index *ix, const uint8_t *codes, int len, int fw, uint64_t off, uint64_t seedlen,
+                 uint64_t topf, uint64_t botf, uint64_t topb, uint64_t botb, uint64_t nlex_nrex[2]) {
+	uint8_t *rc = (uint8_t *)malloc((size_t)len + 1);
+	for(int i = 0; i < len; i++) { int c = codes[len - 1 - i]; rc[i] = (uint8_t)(c > 3 ? 4 : 3 - c); }
+	const uint8_t *seq = fw ? codes : rc;
+	uint64_t rdlen = (uint64_t)len;
+	uint64_t lim = fw ? off : rdlen - seedlen - off;
+	nlex_nrex[0] = nlex_nrex[1] = 0;
+	if(lim > 0) {
+		int64_t i0 = fw ? (int64_t)off - 1 : (int64_t)(rdlen - off - seedlen) - 1;
+		nlex_nrex[0] = extend_one(ix, 0, topf, botf, seq, i0, -1, lim);
+	}
+	lim = fw ? rdlen - seedlen - off : off;
+	if(lim > 0 && ix->has_bw) {
+		int64_t i0 = fw ? (int64_t)(seedlen + off) : (int64_t)(rdlen - off);
+		nlex_nrex[1] = extend_one(ix, 1, topb, botb, seq, i0, +1, lim);
+	}
+	free(rc);
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* seed-extension DP: end-to-end fill, candidate gather, backtrace                       */
 /* ------------------------------------------------------------------------------------ */

@@ -66,6 +66,9 @@ int      bt2o_seed_search(const bt2o_index *ix, const uint8_t *codes, const uint
                           int seedlen, int interval, int offset, int nofw, int norc,
                           int max_seeds, uint64_t *out_ranges);
 
+void     bt2o_extend(const bt2o_index *ix, const uint8_t *codes, int len, int fw, uint64_t off, uint64_t seedlen,
+                     uint64_t topf, uint64_t botf, uint64_t topb, uint64_t botb, uint64_t nlex_nrex[2]);
+
 /* seed-extension DP (end-to-end) */
 typedef struct {
 	int match_bonus, mmp_max, mmp_min, n_pen;

@@ -207,3 +207,14 @@ def oracle_dp(O, local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=10
         e0 += ne
     out["alns"] = al
     return out
+
+
+def extend_both(X, codes, fw, off, seedlen, rng4):
+    """SwDriver::extend through the reference glue (X = Reference) or the C restatement (X = Oracle)."""
+    out = (u64 * 2)()
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    f = X._g("extend")
+    f.argtypes = [vp, vp, ci, ci, u64, u64, u64, u64, u64, u64, pu64]
+    f.restype = None
+    f(X.h, codes.ctypes.data_as(vp), len(codes), int(fw), int(off), int(seedlen), int(rng4[0]), int(rng4[1]), int(rng4[2]), int(rng4[3]), out)
+    return int(out[0]), int(out[1])
