@@ -25,6 +25,30 @@ import torch
 
 OFF_DT = {4: (torch.int64, np.uint32), 8: (torch.int64, np.uint64)}
 
+_T0 = [None]
+
+
+def _tick(msg, dev=None):
+    """phase timing on stderr when BT2G_VERBOSE=1 (synchronises the device)"""
+    if not os.environ.get("BT2G_VERBOSE"):
+        return
+    import sys, time
+    if dev is not None and dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    now = time.time()
+    if _T0[0] is None:
+        _T0[0] = now
+    print(f"[index_build +{now - _T0[0]:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def _group_rank(start: torch.Tensor, rows_base: torch.Tensor = None) -> torch.Tensor:
+    """For a bool vector marking group starts (start[0] is True): for every position the
+    position of its group's first element.  cumsum + gather (torch.cummax over a single
+    multi-billion-element row runs in one thread block)."""
+    gid = torch.cumsum(start, 0, dtype=torch.int64) - 1
+    firsts = torch.nonzero(start).flatten()
+    return firsts[gid]
+
 
 def _records(contigs: List[torch.Tensor]):
     """RefRecord list (ref_read.h:60-100): per unambiguous stretch (off = #Ns preceding it
@@ -81,6 +105,7 @@ def suffix_array(s: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     c = torch.cat([s, torch.full((64 + 1,), 4, dtype=torch.uint8, device=dev)])   # position n = empty suffix
     key = _pack_k(c, K, BITS)                                  # n+1 keys
     del c
+    _tick("keys packed", dev)
     bucket = (key >> (BITS * (K - 2))).to(torch.uint8)
     sa = torch.empty(n + 1, dtype=torch.int64, device=dev)
     start = torch.zeros(n + 2, dtype=torch.bool, device=dev)  # start[row] = row begins a key group
@@ -99,15 +124,19 @@ def suffix_array(s: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         ofs += m
         del idx, kb, perm, st
     del key, bucket
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
     # rank of a row = first row of its group
-    rows = torch.arange(n + 1, device=dev, dtype=torch.int64)
-    rank_of_row = torch.cummax(torch.where(start[: n + 1], rows, torch.zeros_like(rows)), 0).values
+    _tick("bucket sorts done", dev)
+    rank_of_row = _group_rank(start[: n + 1])
+    _tick("group ranks", dev)
     isa = torch.empty(n + 1, dtype=torch.int64, device=dev)
     isa[sa] = rank_of_row
     single = start[: n + 1] & start[1:]
     act = torch.nonzero(~single).flatten()                     # active rows (ascending)
     grp = rank_of_row[act]
-    del rows, rank_of_row, single, start
+    del rank_of_row, single, start
+    _tick(f"isa scattered, {act.numel()} tied suffixes", dev)
     h = K
     while act.numel() > 0:
         pos = sa[act]
@@ -122,8 +151,7 @@ def suffix_array(s: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         sa[act] = pos_s
         ns = torch.ones_like(gstart)
         ns[1:] = comp_s[1:] != comp_s[:-1]
-        ar = torch.arange(act.numel(), device=dev, dtype=torch.int64)
-        first_idx = torch.cummax(torch.where(ns, ar, torch.zeros_like(ar)), 0).values
+        first_idx = _group_rank(ns)
         new_rank = act[first_idx]
         isa[pos_s] = new_rank
         nxt_start = torch.ones_like(ns)
@@ -132,6 +160,7 @@ def suffix_array(s: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         act = act[keep]
         grp = new_rank[keep]
         h *= 2
+        _tick(f"refined to h={h}, {act.numel()} still tied", dev)
     return sa, isa
 
 
@@ -148,13 +177,34 @@ class EbwtArrays:
 def _build_ebwt(s: torch.Tensor, off_size: int, off_rate: int, ftab_chars: int, want_offs: bool) -> EbwtArrays:
     dev = s.device
     n = s.numel()
+    _tick(f"suffix array of {n} symbols", dev)
     sa, isa = suffix_array(s)
     z_off = int(isa[0])
+    _tick("suffix array done", dev)
+    # everything that needs sa / isa first, so both can be released before the k-mer pass
+    # (each is 8 bytes per base: 24 GB at 3 Gbp)
+    short_pos = torch.arange(max(n - ftab_chars + 1, 0), n + 1, device=dev)
+    short_rows = sorted(isa[short_pos].tolist())
+    del isa
+    short_set = set(short_rows)
+    absorb_at = []                                   # (text position of the next long suffix | None, run length)
+    run = 0
+    for r in short_rows:
+        run += 1
+        nxt = r + 1
+        if nxt in short_set:
+            continue
+        absorb_at.append((None if nxt > n else int(sa[nxt]), run))
+        run = 0
+    offs = sa[:: (1 << off_rate)].clone() if want_offs else None
     # BWT: char preceding each suffix; "$" (SA == 0) stored as A and not counted (bt2_idx.h:2958-2971)
-    prev = torch.clamp(sa - 1, min=0)
-    bwt = s[prev]
+    sa -= 1
+    sa.clamp_(min=0)
+    bwt = s[sa]
+    del sa
     bwt[z_off] = 0
-    del prev
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
     side_sz = 16 * off_size
     side_bwt_sz = side_sz - 4 * off_size
     side_bwt_len = side_bwt_sz * 4
@@ -176,34 +226,28 @@ def _build_ebwt(s: torch.Tensor, off_size: int, off_rate: int, ftab_chars: int, 
     else:
         occ_b = occ.contiguous().view(torch.uint8).view(num_sides, 32)
     ebwt = torch.cat([packed, occ_b], dim=1).contiguous().view(-1)
+    _tick("sides packed", dev)
     del packed, occ_b, occ, cnt
     # fchr (bt2_idx.h:3089-3105)
-    cc = torch.bincount(s.to(torch.int64), minlength=4)[:4].tolist() if n < (1 << 31) else \
-        [int((s == ch).sum()) for ch in range(4)]
+    cc = [int((s == ch).sum()) for ch in range(4)]
     fchr = [0, cc[0], cc[0] + cc[1], cc[0] + cc[1] + cc[2], n]
     # ftab / eftab (bt2_idx.h:2973-3006, :3107-3160)
     ftab_len = (1 << (2 * ftab_chars)) + 1
+
+    def kmer_at(p):
+        v_ = 0
+        for c_ in s[p:p + ftab_chars].tolist():
+            v_ = (v_ << 2) | c_
+        return v_
+
+    absorb = np.zeros(ftab_len, dtype=np.int64)
+    for p_, run_ in absorb_at:
+        absorb[ftab_len - 1 if p_ is None else kmer_at(p_)] = run_
     cpad = torch.cat([s, torch.zeros(64, dtype=torch.uint8, device=dev)])
     kmer = _pack_k(cpad, ftab_chars, 2)[: max(n - ftab_chars + 1, 0)]
     del cpad
     cnt10 = torch.bincount(kmer, minlength=ftab_len - 1).to(torch.int64) if kmer.numel() else \
         torch.zeros(ftab_len - 1, dtype=torch.int64, device=dev)
-    absorb = np.zeros(ftab_len, dtype=np.int64)
-    short_pos = torch.arange(max(n - ftab_chars + 1, 0), n + 1, device=dev)
-    short_rows = sorted(isa[short_pos].tolist())
-    short_set = set(short_rows)
-    run = 0
-    for i, r in enumerate(short_rows):
-        run += 1
-        nxt = r + 1
-        if nxt in short_set:
-            continue
-        if nxt > n:
-            absorb[ftab_len - 1] = run
-        else:
-            p = int(sa[nxt])
-            absorb[int(kmer[p])] = run
-        run = 0
     del kmer
     cnt_np = cnt10.cpu().numpy()
     csum = np.concatenate([[0], np.cumsum(cnt_np)])            # sum_{k<i} cnt[k]
@@ -219,10 +263,9 @@ def _build_ebwt(s: torch.Tensor, off_size: int, off_rate: int, ftab_chars: int, 
         eftab[2 * e] = lo[i]; eftab[2 * e + 1] = hi[i]
         ftab[i] = (e ^ mask) & mask
         e += 1
-    offs = None
-    if want_offs:
-        offs = sa[:: (1 << off_rate)].clone()
-    del sa, isa
+    _tick("ftab done", dev)
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
     return EbwtArrays(ebwt, z_off, fchr, torch.from_numpy(ftab.astype(np.int64)), torch.from_numpy(eftab.astype(np.int64)), offs)
 
 
