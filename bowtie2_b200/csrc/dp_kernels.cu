@@ -80,18 +80,27 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 				rc[r] = p.fw ? c : (c > 3 ? 4 : 3 - c);
 				int q = (int)rq[pos] - 33;
 				q = q < 0 ? 0 : (q > 63 ? 63 : q);
-				mmp[r] = sc.mmpen[q]; npn[r] = sc.npen[q];
+				npn[r] = sc.npen[q];
+				// a read N never "equals" a reference base and is charged the N penalty (Scoring::score, scoring.h:241-251)
+				mmp[r] = rc[r] > 3 ? npn[r] : sc.mmpen[q];
+				if(rc[r] > 3) rc[r] = 5;
 				bar[r] = (i < sc.gapbar) || (rdlen - 1 - i < sc.gapbar);
 			} else { rc[r] = 5; mmp[r] = 0; npn[r] = 0; bar[r] = true; }
 		}
 		const int lastLane = (rdlen - 1) / R, lastR = (rdlen - 1) % R;
 
-		int Hleft[R], Earr[R], Eprev[R];
+		// Branch-free move codes.  With E = max(E'-rdgape, H'-rdgapo) and F = max(F^-rfgape, H^-rfgapo),
+		// "which term is the max (open wins ties)" IS the E/F move, and the H move is
+		//   diag if H == Hd, else the F move if H == F, else the E move
+		// -- the same choice the reference makes from its five equality tests in preference order
+		// (aligner_swsse_ee_u8.cpp:1468-1520): H==F with F==open implies H==H^-rfgapo (bit 0), H==F with
+		// F==extend only implies bit 2, and likewise for E (bits 1, 3).  Cells below the minimum score
+		// may get arbitrary codes; no backtrace visits them (scores are monotone along a path).
+		int Hleft[R], Earr[R], Esel[R];
 #pragma unroll
-		for(int r = 0; r < R; r++) { Hleft[r] = DP_NEG; Earr[r] = DP_NEG; Eprev[r] = DP_NEG; }
+		for(int r = 0; r < R; r++) { Hleft[r] = DP_NEG; Earr[r] = DP_NEG; Esel[r] = 1; }
 		int botH = DP_NEG, botF = DP_NEG, prevInH = DP_NEG;
 		const int nsteps = ncol + lastLane;   // lanes beyond lastLane hold no rows
-		int best = DP_NEG;
 		for(int t = 0; t < nsteps; t++) {
 			int inH = __shfl_up_sync(0xffffffffu, botH, 1);
 			int inF = __shfl_up_sync(0xffffffffu, botF, 1);
@@ -99,6 +108,7 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 			const int j = t - lane;
 			if(j >= 0 && j < ncol && lane <= lastLane) {
 				const int refc = refw[j];
+				const bool refN = refc > 3;
 				// H[i0-1][j-1]: row -1 is the free start row of end-to-end mode (vhilsw, :853,923-927)
 				int diag = (lane == 0) ? 0 : prevInH;
 				int upH = inH, upF = inF;
@@ -108,31 +118,28 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 #pragma unroll
 				for(int r = 0; r < R; r++) {
 					// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo), vetoed in gap-barrier rows (:944-945,:983-985)
-					int F = __viaddmax_s32(upF, -rfgape, upH - rfgapo);
-					F = bar[r] ? DP_NEG : F;
-					int s;
-					if(rc[r] > 3 || refc > 3) s = -npn[r];
-					else s = (rc[r] == refc) ? sc.match_bonus : -mmp[r];
-					int Hd = diag + s;
-					int E = Earr[r];
-					int H = __vimax3_s32(Hd, E, F);
-					// move byte: what the backtrace would do from each state of this cell
-					int hsel = 0;
-					const bool gaps = !bar[r];
-					if(H == Hd && diag > DP_NEG / 2) hsel = 1;
-					else if(gaps && H == upH - rfgapo) hsel = 2;
-					else if(gaps && H == upF - rfgape) hsel = 3;
-					else if(gaps && H == Hleft[r] - rdgapo) hsel = 4;
-					else if(gaps && H == Eprev[r] - rdgape) hsel = 5;
-					int esel = (E == Hleft[r] - rdgapo) ? 1 : ((E == Eprev[r] - rdgape) ? 2 : 0);
-					int fsel = (F == upH - rfgapo) ? 1 : ((F == upF - rfgape) ? 2 : 0);
-					uint32_t code = (uint32_t)(hsel | (esel << 3) | (fsel << 5));
+					const int fo = upH - rfgapo, fe = upF - rfgape;
+					const int fsel = fo >= fe ? 1 : 2;
+					int F = bar[r] ? DP_NEG : dp_max(fo, fe);
+					int s = (rc[r] == refc) ? sc.match_bonus : -mmp[r];
+					s = refN ? -npn[r] : s;
+					const int Hd = diag + s;
+					const int E = Earr[r];
+					const int H = __vimax3_s32(Hd, E, F);
+					const int hsel = (H == Hd) ? 1 : ((H == F) ? 1 + fsel : (bar[r] ? 0 : 3 + Esel[r]));
+					const uint32_t code = (uint32_t)(hsel | (Esel[r] << 3) | (fsel << 5));
 					packed[r >> 2] |= code << ((r & 3) * 8);
 					// E[i][j+1] = max(E[i][j]-rdgape, H[i][j]-rdgapo [vetoed in barrier rows]) (:966-969)
-					int En = __viaddmax_s32(E, -rdgape, bar[r] ? DP_NEG : H - rdgapo);
-					diag = Hleft[r]; Hleft[r] = H; Eprev[r] = E; Earr[r] = En;
+					const int eo = bar[r] ? DP_NEG : H - rdgapo, ee = E - rdgape;
+					Esel[r] = eo >= ee ? 1 : 2;
+					diag = Hleft[r]; Hleft[r] = H; Earr[r] = dp_max(eo, ee);
 					upH = H; upF = F;
-					if(lane == lastLane && r == lastR) { lastH[j] = H; best = dp_max(best, H); }
+				}
+				if(lane == lastLane) {
+					int hl = Hleft[0];
+#pragma unroll
+					for(int r = 1; r < R; r++) hl = (lastR == r) ? Hleft[r] : hl;
+					lastH[j] = hl;
 				}
 				botH = upH; botF = upF;
 				prevInH = inH;
@@ -147,8 +154,12 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 				botH = DP_NEG; botF = DP_NEG;
 			}
 		}
-		best = __shfl_sync(0xffffffffu, best, lastLane);
 		__syncwarp();
+		// best = max of the last row (aligner_swsse_ee_u8.cpp:1095-1100)
+		int best = DP_NEG;
+		for(int k = lane; k < ncol; k += 32) best = dp_max(best, lastH[k]);
+#pragma unroll
+		for(int o = 16; o > 0; o >>= 1) best = dp_max(best, __shfl_xor_sync(0xffffffffu, best, o));
 
 		// ---- SwAligner::align tail (aligner_sw.cpp:679-729) + gatherCellsNucleotidesEnd2End (:1176-1208)
 		if(lane == 0) { summ->best = best; summ->flags = 0; summ->naln = 0; summ->ncand = 0; summ->found = 0; }
