@@ -11,6 +11,9 @@ template <typename OFF> void launch_maplf1(const DevEbwt<OFF> &, const uint64_t 
 template <typename OFF> void launch_ftab(const DevEbwt<OFF> &, const uint64_t *, uint64_t, uint64_t *, cudaStream_t);
 template <typename OFF> void launch_exact_sweep(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, cudaStream_t, unsigned long long * = nullptr);
 template <typename OFF> void launch_seed_search(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, cudaStream_t, unsigned long long * = nullptr);
+template <typename OFF> void launch_seed_search2(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+template <typename OFF> void launch_exact_sweep2(const DevIndex<OFF> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+void launch_pack_reads(const uint8_t *, const uint64_t *, uint64_t, int, uint64_t *, uint32_t *, cudaStream_t);
 template <typename OFF> void launch_resolve(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t, unsigned long long * = nullptr);
 template <typename OFF> void launch_get_stretch(const DevIndex<OFF> &, const uint64_t *, const int64_t *, const int32_t *, uint64_t, int, uint8_t *, cudaStream_t);
 template <typename OFF> void launch_extend(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint64_t *, uint8_t *, cudaStream_t);
@@ -328,8 +331,15 @@ int bt2g_exact_sweep(bt2g_ctx *ctx, const bt2g_reads *reads, int nofw, int norc,
 	int rc = uploadReads(ctx, reads, dseq, dqual, doff, false);
 	if(rc) return rc;
 	BT2G_CUDA_TRY(ctx, dmine.alloc(n * 2)); BT2G_CUDA_TRY(ctx, dee.alloc(n * 32));
-	DISPATCH(ctx, launch_exact_sweep<uint32_t>(bt2g_dev_index<uint32_t>(ctx), dseq.as<uint8_t>(), doff.as<uint64_t>(), n, nofw, norc, dmine.as<uint8_t>(), dee.as<uint64_t>(), ctx->stream),
-	              launch_exact_sweep<uint64_t>(bt2g_dev_index<uint64_t>(ctx), dseq.as<uint8_t>(), doff.as<uint64_t>(), n, nofw, norc, dmine.as<uint8_t>(), dee.as<uint64_t>(), ctx->stream));
+	int maxLen = 1;
+	for(uint64_t i = 0; i < n; i++) { int l = (int)(reads->off[i + 1] - reads->off[i]); if(l > maxLen) maxLen = l; }
+	DBuf dpack, dnm, dnext;
+	const uint64_t nWords = (reads->off[n] >> 5) + n + 2;
+	BT2G_CUDA_TRY(ctx, dpack.alloc(nWords * 8)); BT2G_CUDA_TRY(ctx, dnm.alloc(nWords * 4)); BT2G_CUDA_TRY(ctx, dnext.alloc(8));
+	int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	launch_pack_reads(dseq.as<uint8_t>(), doff.as<uint64_t>(), n, maxLen, dpack.as<uint64_t>(), dnm.as<uint32_t>(), ctx->stream);
+	DISPATCH(ctx, launch_exact_sweep2<uint32_t>(bt2g_dev_index<uint32_t>(ctx), doff.as<uint64_t>(), n, nofw, norc, dmine.as<uint8_t>(), dee.as<uint64_t>(), dpack.as<uint64_t>(), dnm.as<uint32_t>(), dnext.as<unsigned long long>(), sms, ctx->stream, nullptr),
+	              launch_exact_sweep2<uint64_t>(bt2g_dev_index<uint64_t>(ctx), doff.as<uint64_t>(), n, nofw, norc, dmine.as<uint8_t>(), dee.as<uint64_t>(), dpack.as<uint64_t>(), dnm.as<uint32_t>(), dnext.as<unsigned long long>(), sms, ctx->stream, nullptr));
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(mine, dmine.p, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(ee, dee.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -350,8 +360,16 @@ int bt2g_seed_search(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_seed_pla
 	BT2G_CUDA_TRY(ctx, dout.alloc(outBytes)); BT2G_CUDA_TRY(ctx, dns.alloc(n * 4));
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(dint.p, plan->interval, n * 4, cudaMemcpyHostToDevice, ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(doffs.p, plan->offset, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-	DISPATCH(ctx, launch_seed_search<uint32_t>(bt2g_dev_index<uint32_t>(ctx), dseq.as<uint8_t>(), doff.as<uint64_t>(), n, plan->seed_len, plan->max_seeds, plan->nofw, plan->norc, dint.as<int32_t>(), doffs.as<int32_t>(), dout.as<uint64_t>(), dns.as<int32_t>(), ctx->stream),
-	              launch_seed_search<uint64_t>(bt2g_dev_index<uint64_t>(ctx), dseq.as<uint8_t>(), doff.as<uint64_t>(), n, plan->seed_len, plan->max_seeds, plan->nofw, plan->norc, dint.as<int32_t>(), doffs.as<int32_t>(), dout.as<uint64_t>(), dns.as<int32_t>(), ctx->stream));
+	if(plan->seed_len > 32) { ctx->err = "seed length must be <= 32 (as in bowtie2 -L)"; return -1; }
+	int maxLen = 1;
+	for(uint64_t i = 0; i < n; i++) { int l = (int)(reads->off[i + 1] - reads->off[i]); if(l > maxLen) maxLen = l; }
+	DBuf dpack, dnm, dnext;
+	const uint64_t nWords = (reads->off[n] >> 5) + n + 2;
+	BT2G_CUDA_TRY(ctx, dpack.alloc(nWords * 8)); BT2G_CUDA_TRY(ctx, dnm.alloc(nWords * 4)); BT2G_CUDA_TRY(ctx, dnext.alloc(8));
+	int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	launch_pack_reads(dseq.as<uint8_t>(), doff.as<uint64_t>(), n, maxLen, dpack.as<uint64_t>(), dnm.as<uint32_t>(), ctx->stream);
+	DISPATCH(ctx, launch_seed_search2<uint32_t>(bt2g_dev_index<uint32_t>(ctx), dseq.as<uint8_t>(), doff.as<uint64_t>(), n, maxLen, plan->seed_len, plan->max_seeds, plan->nofw, plan->norc, dint.as<int32_t>(), doffs.as<int32_t>(), dout.as<uint64_t>(), dns.as<int32_t>(), dpack.as<uint64_t>(), dnm.as<uint32_t>(), dnext.as<unsigned long long>(), sms, ctx->stream, nullptr),
+	              launch_seed_search2<uint64_t>(bt2g_dev_index<uint64_t>(ctx), dseq.as<uint8_t>(), doff.as<uint64_t>(), n, maxLen, plan->seed_len, plan->max_seeds, plan->nofw, plan->norc, dint.as<int32_t>(), doffs.as<int32_t>(), dout.as<uint64_t>(), dns.as<int32_t>(), dpack.as<uint64_t>(), dnm.as<uint32_t>(), dnext.as<unsigned long long>(), sms, ctx->stream, nullptr));
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
 	if(nseeds) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(nseeds, dns.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));

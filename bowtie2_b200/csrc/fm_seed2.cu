@@ -1,0 +1,354 @@
+// fm_seed2.cu -- K1 v2: exact multiseed search with full lanes.
+//
+// The first version gave every (read, strand, seed) its own thread and let it run to
+// completion; ncu showed 6.5 of 32 lanes active per instruction (seeds die at different steps,
+// reverse-strand seeds of a forward read die after ~6 steps, and the range>1 / range==1 paths
+// serialised), so the kernel was issue-bound at 20 % of HBM bandwidth (profiles/r01_*).
+// This version keeps lanes full:
+//   * reads are first packed to 2 bits/base (+ an N bit mask) by k_pack_reads, so a whole seed
+//     (<= 32 bases) lives in one 64-bit register: no byte loads or strand branches per step;
+//   * ONE uniform step for every range size: ranks are taken at top and bot whatever the width.
+//     For a width-1 range this equals Ebwt::mapLF1 (bt2_idx.h:2420): rank_c(top+1)-rank_c(top) is
+//     1 exactly when BWT[top] == c and top is not the "$" row (the "$" adjustment of
+//     countBt2Side removes it), and the mirror range is unchanged because every other width is 0;
+//     when top and bot fall in the same side the side is fetched once;
+//   * persistent lanes: a lane whose seed finished or died pulls the next task from a global
+//     counter (one warp-aggregated atomic per refill), so a warp keeps 32 searches in flight.
+#include "fm_device.cuh"
+
+// 2-bit packing of a read batch.  Word w of read r holds bases 32w..32w+31 (base i at bits 2(i&31)),
+// nmask has the same word structure with one bit per base.  Word offset of read r is
+// (roff[r] >> 5) + r, which needs no extra offset array and never overlaps the next read.
+__global__ void k_pack_reads(const uint8_t *seq, const uint64_t *roff, uint64_t nReads, int maxWords,
+                             uint64_t *packed, uint32_t *nmask) {
+	uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(t >= nReads * (uint64_t)maxWords) return;
+	const uint64_t rd = t / maxWords;
+	const int w = (int)(t - rd * maxWords);
+	const int len = (int)(roff[rd + 1] - roff[rd]);
+	if(w * 32 >= len) return;
+	const uint8_t *s = seq + roff[rd] + (uint64_t)w * 32;
+	const int n = len - w * 32 < 32 ? len - w * 32 : 32;
+	uint64_t p = 0; uint32_t m = 0;
+	for(int i = 0; i < n; i++) {
+		const uint32_t c = s[i];
+		if(c > 3) m |= 1u << i; else p |= (uint64_t)c << (2 * i);
+	}
+	const uint64_t wb = (roff[rd] >> 5) + rd + (uint64_t)w;
+	packed[wb] = p; nmask[wb] = m;
+}
+
+// reverse the order of the n 2-bit groups held in the low 2n bits of x
+__device__ __forceinline__ uint64_t rev_pairs(uint64_t x, int n) {
+	uint64_t r = __brevll(x);
+	r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+	return r >> (64 - 2 * n);
+}
+
+template <typename OFF>
+__device__ __forceinline__ void rank4_loaded(const DevEbwt<OFF> &e, const SideRegs<OFF> &s, uint64_t sideNum, uint32_t charOff, uint64_t out[4]) {
+	uint32_t nC, nG, nT;
+	count_cgt<OFF>(s, charOff, nC, nG, nT);
+	uint32_t nA = charOff - nC - nG - nT;
+	if(sideNum == e.zSide && charOff > e.zChar) nA--;
+	out[0] = nA + s.occ[0] + e.fchr[0];
+	out[1] = nC + s.occ[1] + e.fchr[1];
+	out[2] = nG + s.occ[2] + e.fchr[2];
+	out[3] = nT + s.occ[3] + e.fchr[3];
+}
+
+template <typename OFF>
+__global__ void __launch_bounds__(256) k_seed_search2(DevIndex<OFF> ix, const uint64_t *packed, const uint32_t *nmask,
+                                                      const uint64_t *roff, uint64_t nReads, int seedLen, int maxSeeds,
+                                                      int nofw, int norc, const int32_t *interval, const int32_t *offset,
+                                                      uint64_t *out, int32_t *nseedsOut, unsigned long long *next,
+                                                      unsigned long long *cnt) {
+	constexpr uint32_t BL = SideGeom<OFF>::BWT_LEN;
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const uint64_t perRead = 2ull * maxSeeds, total = nReads * perRead;
+	const DevEbwt<OFF> &fw = ix.fw;
+	const DevEbwt<OFF> &bw = ix.bw;
+	const int ftabLen = fw.ftabChars;
+	bool active = false, exhausted = false;
+	uint64_t topf = 0, botf = 0, topb = 0, botb = 0, bits = 0;
+	uint64_t *o = nullptr;
+	int sl = 0, step = 0;
+	unsigned nside = 0;
+	for(;;) {
+		const unsigned need = __ballot_sync(FULL, !active && !exhausted);
+		if(need) {
+			unsigned long long base = 0;
+			const int leader = __ffs(need) - 1;
+			if(lane == leader) base = atomicAdd(next, (unsigned long long)__popc(need));
+			base = __shfl_sync(FULL, base, leader);
+			if(!active && !exhausted) {
+				const uint64_t t = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+				if(t >= total) {
+					exhausted = true;
+				} else {
+					const uint64_t rd = t / perRead;
+					const int rem = (int)(t - rd * perRead);
+					const int strand = rem / maxSeeds, k = rem - strand * maxSeeds;
+					o = out + t * 4;
+					reinterpret_cast<uint4 *>(o)[0] = make_uint4(0, 0, 0, 0);
+					reinterpret_cast<uint4 *>(o)[1] = make_uint4(0, 0, 0, 0);
+					const uint64_t r0 = roff[rd];
+					const int len = (int)(roff[rd + 1] - r0);
+					const int per = interval[rd], off0 = offset[rd];
+					int nseeds = 1;                                   // instantiateSeeds (aligner_seed.cpp:523-526)
+					if(len - off0 > seedLen) nseeds += (len - off0 - seedLen) / per;
+					if(rem == 0 && nseedsOut) nseedsOut[rd] = nseeds;
+					sl = seedLen < len ? seedLen : len;
+					const int depth = k * per + off0;
+					bool ok = k < nseeds && !((strand == 0 && nofw) || (strand == 1 && norc)) && depth + sl <= len && sl >= 1;
+					if(ok) {
+						const uint64_t wb = (r0 >> 5) + rd;
+						const int w = depth >> 5, sh = depth & 31;
+						const bool two = sh + sl > 32;
+						const uint64_t p0 = packed[wb + w], p1 = two ? packed[wb + w + 1] : 0;
+						const uint64_t n0 = nmask[wb + w], n1 = two ? nmask[wb + w + 1] : 0;
+						const uint64_t m2 = sl == 32 ? ~0ull : ((1ull << (2 * sl)) - 1);
+						bits = (sh ? ((p0 >> (2 * sh)) | (p1 << (64 - 2 * sh))) : p0) & m2;
+						const uint64_t nb = ((n0 | (n1 << 32)) >> sh) & (sl == 32 ? 0xffffffffull : ((1ull << sl) - 1));
+						if(nb) ok = false;                           // exact seeds cannot absorb an N (aligner_seed.cpp:326-352)
+						if(strand == 1) bits = rev_pairs(bits, sl) ^ m2;   // reverse complement of the window
+					}
+					if(ok) {
+						if(ftabLen > 1 && ftabLen <= sl) {
+							const uint64_t top20 = bits >> (2 * (sl - ftabLen));
+							const uint64_t fwi = rev_pairs(top20, ftabLen), bwi = top20;
+							topf = ftab_hi<OFF>(fw, fwi); botf = ftab_lo<OFF>(fw, fwi + 1);
+							if(botf <= topf) ok = false;
+							else if(bw.ebwt != nullptr) { topb = ftab_hi<OFF>(bw, bwi); botb = topb + (botf - topf); }
+							else { topb = botb = 0; }
+							step = ftabLen;
+						} else {
+							const int c = (int)((bits >> (2 * (sl - 1))) & 3);
+							topf = topb = fw.fchr[c]; botf = botb = fw.fchr[c + 1];
+							if(botf <= topf) ok = false;
+							step = 1;
+						}
+					}
+					if(ok) {
+						if(step >= sl) { o[0] = topf; o[1] = botf; o[2] = topb; o[3] = botb; }
+						else active = true;
+					}
+				}
+			}
+		}
+		if(__ballot_sync(FULL, active) == 0) {
+			if(__all_sync(FULL, exhausted)) break;
+			continue;
+		}
+		if(active) {
+			const int c = (int)((bits >> (2 * (sl - step - 1))) & 3);
+			const uint64_t sideT = topf / BL, sideB = botf / BL;
+			const uint32_t offT = (uint32_t)(topf - sideT * BL), offB = (uint32_t)(botf - sideB * BL);
+			nside += (botf - topf > 1) ? 2 : 1;                     // algorithmic count (mapBiLFEx = 2, mapLF1 = 1)
+			uint64_t tt[4], bb[4];
+			SideRegs<OFF> s;
+			load_side<OFF>(fw.ebwt, sideT, s);
+			rank4_loaded<OFF>(fw, s, sideT, offT, tt);
+			if(sideB != sideT) load_side<OFF>(fw.ebwt, sideB, s);
+			rank4_loaded<OFF>(fw, s, sideB, offB, bb);
+			const uint64_t w0 = bb[0] - tt[0], w1 = bb[1] - tt[1], w2 = bb[2] - tt[2];
+			const uint64_t tp = topb + (c > 0 ? w0 : 0) + (c > 1 ? w1 : 0) + (c > 2 ? w2 : 0);
+			const uint64_t nt = c == 0 ? tt[0] : (c == 1 ? tt[1] : (c == 2 ? tt[2] : tt[3]));
+			const uint64_t nb = c == 0 ? bb[0] : (c == 1 ? bb[1] : (c == 2 ? bb[2] : bb[3]));
+			if(nb <= nt) {
+				active = false;
+			} else {
+				topf = nt; botf = nb; topb = tp; botb = tp + (nb - nt);
+				if(++step == sl) { o[0] = topf; o[1] = botf; o[2] = topb; o[3] = botb; active = false; }
+			}
+		}
+	}
+	if(cnt && nside) atomicAdd(cnt, (unsigned long long)nside);
+}
+
+template <typename OFF>
+void launch_seed_search2(const DevIndex<OFF> &ix, const uint8_t *seq, const uint64_t *roff, uint64_t nReads, int maxLen,
+                         int seedLen, int maxSeeds, int nofw, int norc, const int32_t *interval, const int32_t *offset,
+                         uint64_t *out, int32_t *nseeds, uint64_t *packed, uint32_t *nmask, unsigned long long *next,
+                         int numSMs, cudaStream_t st, unsigned long long *cnt) {
+	if(nReads == 0) return;
+	(void)seq; (void)maxLen;          // reads arrive packed (launch_pack_reads)
+	cudaMemsetAsync(next, 0, sizeof(unsigned long long), st);
+	// persistent grid: exactly as many blocks as can be resident (no second wave, no tail)
+	int perSM = 4;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_seed_search2<OFF>, 256, 0);
+	if(perSM < 1) perSM = 1;
+	const unsigned blocks = (unsigned)(numSMs * perSM);
+	k_seed_search2<OFF><<<blocks, 256, 0, st>>>(ix, packed, nmask, roff, nReads, seedLen, maxSeeds, nofw, norc, interval, offset,
+	                                            out, nseeds, next, cnt);
+}
+template void launch_seed_search2<uint32_t>(const DevIndex<uint32_t> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+template void launch_seed_search2<uint64_t>(const DevIndex<uint64_t> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+
+// ----------------------------------------------------------------------------------------
+// K1' v2: exact end-to-end sweep (SeedAligner::exactSweep, aligner_seed.cpp:856-970) with packed
+// reads, single-character ranks, one uniform LF step and persistent lanes.  Task = (read, strand).
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ int packed_char(const uint64_t *pk, const uint32_t *nm, uint64_t wb, int pos) {
+	const int w = pos >> 5, b = pos & 31;
+	if((nm[wb + w] >> b) & 1u) return 4;
+	return (int)((pk[wb + w] >> (2 * b)) & 3);
+}
+
+// occurrences of nucleotide c among the first charOff characters of a loaded side
+template <typename OFF>
+__device__ __forceinline__ uint32_t count_one(const SideRegs<OFF> &s, uint32_t charOff, int c) {
+	const uint64_t M = 0x5555555555555555ull, pat = (uint64_t)c * M;
+	uint32_t n = 0;
+#pragma unroll
+	for(uint32_t i = 0; i < SideGeom<OFF>::WORDS; i++) {
+		int k = (int)charOff - (int)(i * 32);
+		k = k < 0 ? 0 : (k > 32 ? 32 : k);
+		const uint64_t mask = (k == 32) ? M : (((1ull << (2 * k)) - 1) & M);
+		const uint64_t z = ~(s.w[i] ^ pat);
+		n += __popcll(z & (z >> 1) & mask);
+	}
+	return n;
+}
+
+template <typename OFF>
+__device__ __forceinline__ uint64_t rank1_loaded(const DevEbwt<OFF> &e, const SideRegs<OFF> &s, uint64_t sideNum, uint32_t charOff, int c) {
+	uint32_t n = count_one<OFF>(s, charOff, c);
+	if(c == 0 && sideNum == e.zSide && charOff > e.zChar) n--;
+	const uint64_t oc = c == 0 ? s.occ[0] : (c == 1 ? s.occ[1] : (c == 2 ? s.occ[2] : s.occ[3]));
+	return n + oc + e.fchr[c];
+}
+
+template <typename OFF>
+__global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const uint64_t *packed, const uint32_t *nmask,
+                                                      const uint64_t *roff, uint64_t nReads, int nofw, int norc,
+                                                      uint8_t *mine, uint64_t *ee, unsigned long long *next, unsigned long long *cnt) {
+	constexpr uint32_t BL = SideGeom<OFF>::BWT_LEN;
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const uint64_t total = nReads * 2;
+	const DevEbwt<OFF> &e = ix.fw;
+	const int ftabLen = e.ftabChars;
+	const int mineMax = 2;
+	bool active = false, exhausted = false, doInit = true;
+	uint64_t top = 0, bot = 0, wb = 0, task = 0;
+	int len = 0, dep = 0, nedit = 0, strand = 0;
+	unsigned nside = 0;
+	for(;;) {
+		const unsigned need = __ballot_sync(FULL, !active && !exhausted);
+		if(need) {
+			unsigned long long base = 0;
+			const int leader = __ffs(need) - 1;
+			if(lane == leader) base = atomicAdd(next, (unsigned long long)__popc(need));
+			base = __shfl_sync(FULL, base, leader);
+			if(!active && !exhausted) {
+				task = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+				if(task >= total) exhausted = true;
+				else {
+					const uint64_t rd = task >> 1;
+					strand = (int)(task & 1);
+					if((strand == 0 && nofw) || (strand == 1 && norc)) {
+						mine[task] = 0; ee[rd * 4 + strand * 2] = 0; ee[rd * 4 + strand * 2 + 1] = 0;
+					} else {
+						const uint64_t r0 = roff[rd];
+						len = (int)(roff[rd + 1] - r0);
+						wb = (r0 >> 5) + rd;
+						dep = 0; nedit = 0; doInit = true; top = bot = 0;
+						active = true;
+						if(len <= 0) { mine[task] = 0; ee[rd * 4 + strand * 2] = 0; ee[rd * 4 + strand * 2 + 1] = 0; active = false; }
+					}
+				}
+			}
+		}
+		if(__ballot_sync(FULL, active) == 0) {
+			if(__all_sync(FULL, exhausted)) break;
+			continue;
+		}
+		if(active) {
+			bool done = false;
+			// character of the strand-oriented read at position p: fw -> read[p]; rc -> comp(read[len-1-p])
+			auto chr = [&](int p) -> int {
+				if(strand == 0) return packed_char(packed, nmask, wb, p);
+				const int c = packed_char(packed, nmask, wb, len - 1 - p);
+				return c > 3 ? 4 : 3 - c;
+			};
+			bool stepNow = true;
+			if(doInit) {
+				// exactSweepInit (aligner_seed.cpp:760-800)
+				const int left = len - dep;
+				bool doFtab = ftabLen > 1 && left >= ftabLen;
+				uint64_t fi = 0;
+				if(doFtab) {
+					for(int i = 0; i < ftabLen; i++) {
+						const int c = chr(left - ftabLen + i);
+						if(c > 3) { doFtab = false; break; }
+						fi = (fi << 2) | (uint64_t)c;
+					}
+				}
+				top = bot = 0;
+				if(doFtab) { top = ftab_hi<OFF>(e, fi); bot = ftab_lo<OFF>(e, fi + 1); dep += ftabLen; }
+				else {
+					const int c = chr(len - dep - 1);
+					if(c < 4) { top = e.fchr[c]; bot = e.fchr[c + 1]; }
+					dep++;
+				}
+				if(bot <= top) {
+					nedit++;
+					if(nedit >= mineMax) done = true;
+					stepNow = false;                    // the reference `continue`s: re-init from the new depth
+				} else doInit = false;
+			}
+			if(stepNow && !done && dep < len) {
+				const int c = chr(len - dep - 1);
+				if(c > 3) { top = bot = 0; }
+				else {
+					nside += (bot - top > 1) ? 2 : 1;
+					const uint64_t sideT = top / BL, sideB = bot / BL;
+					SideRegs<OFF> s;
+					load_side<OFF>(e.ebwt, sideT, s);
+					const uint64_t nt = rank1_loaded<OFF>(e, s, sideT, (uint32_t)(top - sideT * BL), c);
+					if(sideB != sideT) load_side<OFF>(e.ebwt, sideB, s);
+					const uint64_t nb = rank1_loaded<OFF>(e, s, sideB, (uint32_t)(bot - sideB * BL), c);
+					top = nt; bot = nb;
+					if(bot <= top) { top = bot = 0; }
+				}
+				if(bot <= top) {
+					nedit++;
+					if(nedit >= mineMax) done = true;
+					doInit = true;
+				}
+				dep++;
+			}
+			if(done || dep >= len) {
+				const uint64_t rd = task >> 1;
+				mine[task] = (uint8_t)nedit;
+				uint64_t *eo = ee + rd * 4 + strand * 2;
+				if(!done && nedit == 0 && bot > top) { eo[0] = top; eo[1] = bot; } else { eo[0] = eo[1] = 0; }
+				active = false;
+			}
+		}
+	}
+	if(cnt && nside) atomicAdd(cnt, (unsigned long long)nside);
+}
+
+template <typename OFF>
+void launch_exact_sweep2(const DevIndex<OFF> &ix, const uint64_t *roff, uint64_t nReads, int nofw, int norc,
+                         uint8_t *mine, uint64_t *ee, const uint64_t *packed, const uint32_t *nmask, unsigned long long *next,
+                         int numSMs, cudaStream_t st, unsigned long long *cnt) {
+	if(nReads == 0) return;
+	cudaMemsetAsync(next, 0, sizeof(unsigned long long), st);
+	int perSM = 4;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_exact_sweep2<OFF>, 256, 0);
+	if(perSM < 1) perSM = 1;
+	k_exact_sweep2<OFF><<<(unsigned)(numSMs * perSM), 256, 0, st>>>(ix, packed, nmask, roff, nReads, nofw, norc, mine, ee, next, cnt);
+}
+template void launch_exact_sweep2<uint32_t>(const DevIndex<uint32_t> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+template void launch_exact_sweep2<uint64_t>(const DevIndex<uint64_t> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+
+void launch_pack_reads(const uint8_t *seq, const uint64_t *roff, uint64_t nReads, int maxLen, uint64_t *packed, uint32_t *nmask, cudaStream_t st) {
+	if(nReads == 0) return;
+	const int maxWords = (maxLen + 31) / 32;
+	const uint64_t nw = nReads * (uint64_t)maxWords;
+	k_pack_reads<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(seq, roff, nReads, maxWords, packed, nmask);
+}

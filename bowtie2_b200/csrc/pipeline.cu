@@ -22,6 +22,9 @@
 
 template <typename OFF> void launch_exact_sweep(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, cudaStream_t, unsigned long long *);
 template <typename OFF> void launch_seed_search(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, cudaStream_t, unsigned long long *);
+template <typename OFF> void launch_seed_search2(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+template <typename OFF> void launch_exact_sweep2(const DevIndex<OFF> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+void launch_pack_reads(const uint8_t *, const uint64_t *, uint64_t, int, uint64_t *, uint32_t *, cudaStream_t);
 template <typename OFF> void launch_resolve(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t, unsigned long long *);
 template <typename OFF> int launch_dp_e2e(const DevIndex<OFF> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);
 
@@ -33,6 +36,7 @@ struct PipeBufs {
 	int32_t *interval, *offset;               // per read
 	uint8_t *mine; uint64_t *ee;              // exact sweep
 	uint64_t *ranges; int32_t *nseeds;        // seed search
+	uint64_t *packed; uint32_t *nmask; unsigned long long *nextTask;   // 2-bit reads + task counter
 	uint64_t *rows; uint32_t *hitlen, *meta;  // collect
 	uint64_t *tidx, *textoff, *tlen; uint8_t *rflags;   // resolve
 	bt2g_dp_problem *probs; uint32_t *nProb; int32_t *readProb; int32_t *readNProb;
@@ -49,7 +53,7 @@ struct bt2g_pipeline {
 	PipeBufs b;
 	std::vector<void *> allocs;
 	uint64_t numSlots, codeStride, maxProbs;
-	int maxCol, R;
+	int maxCol, R, sms = 148;
 	cudaEvent_t ev[9];
 	bool evOk = false;
 	// pinned staging for the host entry point
@@ -228,9 +232,11 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 	mark(0);
 	k_plan<<<grid(n), T, 0, st>>>(roff, n, b.ivalByLen, q.max_len, b.interval, b.offset);
 	mark(1);
-	launch_exact_sweep<OFF>(ix, seq, roff, n, 0, 0, b.mine, b.ee, st, c ? c + 0 : nullptr);
+	launch_pack_reads(seq, roff, n, q.max_len, b.packed, b.nmask, st);
+	launch_exact_sweep2<OFF>(ix, roff, n, 0, 0, b.mine, b.ee, b.packed, b.nmask, b.nextTask, p->sms, st, c ? c + 0 : nullptr);
 	mark(2);
-	launch_seed_search<OFF>(ix, seq, roff, n, q.seed_len, q.max_seeds, 0, 0, b.interval, b.offset, b.ranges, b.nseeds, st, c ? c + 1 : nullptr);
+	launch_seed_search2<OFF>(ix, seq, roff, n, q.max_len, q.seed_len, q.max_seeds, 0, 0, b.interval, b.offset, b.ranges, b.nseeds,
+	                         b.packed, b.nmask, b.nextTask, p->sms, st, c ? c + 1 : nullptr);
 	mark(3);
 	k_collect<<<grid(n), T, 0, st>>>(n, roff, b.ee, b.ranges, b.nseeds, q.max_seeds, q.seed_len, q.row_cap, q.range_max, b.rows, b.hitlen, b.meta);
 	mark(4);
@@ -263,6 +269,7 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	if(!ctx->loaded) { ctx->err = "no index loaded"; return -1; }
 	if(ctx->scoring.gapbar < 1) bt2g_scoring_default(&ctx->scoring, 0);
 	if(ctx->scoring.local) { ctx->err = "pipeline: local mode not implemented in this build"; return -1; }
+	if(prm->seed_len > 32) { ctx->err = "pipeline: seed length must be <= 32"; return -1; }
 	if(prm->max_len < 1 || prm->max_len > 512 || prm->row_cap < 1 || prm->row_cap > 32 || prm->max_seeds < 1 || prm->max_seeds > 16383) {
 		ctx->err = "pipeline: bad parameters"; return -1;
 	}
@@ -283,6 +290,7 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	rc |= pipeAlloc(p, b.interval, n); rc |= pipeAlloc(p, b.offset, n);
 	rc |= pipeAlloc(p, b.mine, n * 2); rc |= pipeAlloc(p, b.ee, n * 4);
 	rc |= pipeAlloc(p, b.ranges, n * 2ull * prm->max_seeds * 4); rc |= pipeAlloc(p, b.nseeds, n);
+	rc |= pipeAlloc(p, b.packed, (maxBases >> 5) + n + 2); rc |= pipeAlloc(p, b.nmask, (maxBases >> 5) + n + 2); rc |= pipeAlloc(p, b.nextTask, 1);
 	rc |= pipeAlloc(p, b.rows, nrowMax); rc |= pipeAlloc(p, b.hitlen, nrowMax); rc |= pipeAlloc(p, b.meta, nrowMax);
 	rc |= pipeAlloc(p, b.tidx, nrowMax); rc |= pipeAlloc(p, b.textoff, nrowMax); rc |= pipeAlloc(p, b.tlen, nrowMax); rc |= pipeAlloc(p, b.rflags, nrowMax);
 	rc |= pipeAlloc(p, b.probs, nprobMax); rc |= pipeAlloc(p, b.nProb, 1); rc |= pipeAlloc(p, b.readProb, nrowMax); rc |= pipeAlloc(p, b.readNProb, n);
@@ -290,6 +298,7 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	p->R = prm->max_len <= 128 ? 4 : (prm->max_len <= 256 ? 8 : 16);
 	p->codeStride = (uint64_t)(p->maxCol + 32) * 32 * p->R;
 	int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	p->sms = sms;
 	p->numSlots = (uint64_t)sms * 24;
 	rc |= pipeAlloc(p, b.codes, p->numSlots * p->codeStride); rc |= pipeAlloc(p, b.lastH, p->numSlots * (uint64_t)p->maxCol);
 	rc |= pipeAlloc(p, b.summ, nprobMax); rc |= pipeAlloc(p, b.cands, nprobMax * prm->max_cands);
