@@ -3,6 +3,7 @@
 #include "bt2g_internal.h"
 #include "dp_device.cuh"
 #include <cstring>
+#include <cstdlib>
 #include <new>
 
 // launchers from fm_kernels.cu
@@ -15,6 +16,7 @@ template <typename OFF> void launch_seed_search2(const DevIndex<OFF> &, const ui
 template <typename OFF> void launch_exact_sweep2(const DevIndex<OFF> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
 void launch_pack_reads(const uint8_t *, const uint64_t *, uint64_t, int, uint64_t *, uint32_t *, cudaStream_t);
 template <typename OFF> void launch_resolve(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t, unsigned long long * = nullptr);
+template <typename OFF> void launch_resolve2(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, const uint32_t *, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
 template <typename OFF> void launch_get_stretch(const DevIndex<OFF> &, const uint64_t *, const int64_t *, const int32_t *, uint64_t, int, uint8_t *, cudaStream_t);
 template <typename OFF> void launch_extend(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint64_t *, uint8_t *, cudaStream_t);
 
@@ -227,6 +229,8 @@ int bt2g_create(int device, bt2g_ctx **out) {
 	if(cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
 		delete ctx; return -2;
 	}
+	// experiment knob: L2 -> HBM fetch granularity hint for the random 64 B side gathers
+	if(const char *g = getenv("BT2G_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
 	*out = ctx;
 	return 0;
 }
@@ -414,8 +418,11 @@ int bt2g_resolve(bt2g_ctx *ctx, const uint64_t *rows, const uint32_t *hitlen, ui
 	if(textoff) BT2G_CUDA_TRY(ctx, dto.alloc(n * 8));
 	if(tlen) BT2G_CUDA_TRY(ctx, dtl.alloc(n * 8));
 	if(flags) BT2G_CUDA_TRY(ctx, dfl.alloc(n));
-	DISPATCH(ctx, launch_resolve<uint32_t>(bt2g_dev_index<uint32_t>(ctx), dr.as<uint64_t>(), dh.as<uint32_t>(), n, rejectStraddle, dj.as<uint64_t>(), dti.as<uint64_t>(), dto.as<uint64_t>(), dtl.as<uint64_t>(), dfl.as<uint8_t>(), ctx->stream),
-	              launch_resolve<uint64_t>(bt2g_dev_index<uint64_t>(ctx), dr.as<uint64_t>(), dh.as<uint32_t>(), n, rejectStraddle, dj.as<uint64_t>(), dti.as<uint64_t>(), dto.as<uint64_t>(), dtl.as<uint64_t>(), dfl.as<uint8_t>(), ctx->stream));
+	DBuf dnext;
+	BT2G_CUDA_TRY(ctx, dnext.alloc(8));
+	int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	DISPATCH(ctx, launch_resolve2<uint32_t>(bt2g_dev_index<uint32_t>(ctx), dr.as<uint64_t>(), dh.as<uint32_t>(), n, nullptr, rejectStraddle, dj.as<uint64_t>(), dti.as<uint64_t>(), dto.as<uint64_t>(), dtl.as<uint64_t>(), dfl.as<uint8_t>(), dnext.as<unsigned long long>(), sms, ctx->stream, nullptr),
+	              launch_resolve2<uint64_t>(bt2g_dev_index<uint64_t>(ctx), dr.as<uint64_t>(), dh.as<uint32_t>(), n, nullptr, rejectStraddle, dj.as<uint64_t>(), dti.as<uint64_t>(), dto.as<uint64_t>(), dtl.as<uint64_t>(), dfl.as<uint8_t>(), dnext.as<unsigned long long>(), sms, ctx->stream, nullptr));
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	if(joined) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(joined, dj.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	if(tidx) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(tidx, dti.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));

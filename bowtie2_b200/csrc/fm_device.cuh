@@ -26,12 +26,17 @@ struct SideRegs {
 	uint64_t occ[4];
 };
 
-__device__ __forceinline__ uint4 ldg_side16(const uint4 *p) {
-	// read-only path, do not pollute L1 with single-use random lines
-	uint4 v;
-	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-	             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-	return v;
+// One 32-byte sector per instruction (sm_100 256-bit loads), read-only path, and an explicit
+// L2 fetch granule equal to the side: tools/gather_bench.cu measured on B200 (random gathers over
+// 1 GB) 4 x LDG.128 nc/no_allocate = 0.70 TB/s with 128 B of DRAM traffic per 64 B side, while
+// 2 x LDG.256 with .L2::64B = 1.39 TB/s with 64 B of DRAM traffic per side.
+__device__ __forceinline__ void ldg_sector(const uint8_t *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+	asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
+	             : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+__device__ __forceinline__ void ldg_sector128(const uint8_t *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+	asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u64 {%0,%1,%2,%3}, [%4];"
+	             : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 
 template <typename OFF>
@@ -39,25 +44,20 @@ __device__ __forceinline__ void load_side(const uint8_t *ebwt, uint64_t sideNum,
 
 template <>
 __device__ __forceinline__ void load_side<uint32_t>(const uint8_t *ebwt, uint64_t sideNum, SideRegs<uint32_t> &s) {
-	const uint4 *p = reinterpret_cast<const uint4 *>(ebwt + sideNum * 64);
-	uint4 a = ldg_side16(p), b = ldg_side16(p + 1), c = ldg_side16(p + 2), d = ldg_side16(p + 3);
-	s.w[0] = ((uint64_t)a.y << 32) | a.x; s.w[1] = ((uint64_t)a.w << 32) | a.z;
-	s.w[2] = ((uint64_t)b.y << 32) | b.x; s.w[3] = ((uint64_t)b.w << 32) | b.z;
-	s.w[4] = ((uint64_t)c.y << 32) | c.x; s.w[5] = ((uint64_t)c.w << 32) | c.z;
-	s.occ[0] = d.x; s.occ[1] = d.y; s.occ[2] = d.z; s.occ[3] = d.w;
+	const uint8_t *p = ebwt + sideNum * 64;
+	uint64_t o0, o1;
+	ldg_sector(p, s.w[0], s.w[1], s.w[2], s.w[3]);
+	ldg_sector(p + 32, s.w[4], s.w[5], o0, o1);
+	s.occ[0] = (uint32_t)o0; s.occ[1] = o0 >> 32; s.occ[2] = (uint32_t)o1; s.occ[3] = o1 >> 32;
 }
 
 template <>
 __device__ __forceinline__ void load_side<uint64_t>(const uint8_t *ebwt, uint64_t sideNum, SideRegs<uint64_t> &s) {
-	const uint4 *p = reinterpret_cast<const uint4 *>(ebwt + sideNum * 128);
-#pragma unroll
-	for(int i = 0; i < 6; i++) {
-		uint4 a = ldg_side16(p + i);
-		s.w[2 * i] = ((uint64_t)a.y << 32) | a.x; s.w[2 * i + 1] = ((uint64_t)a.w << 32) | a.z;
-	}
-	uint4 o0 = ldg_side16(p + 6), o1 = ldg_side16(p + 7);
-	s.occ[0] = ((uint64_t)o0.y << 32) | o0.x; s.occ[1] = ((uint64_t)o0.w << 32) | o0.z;
-	s.occ[2] = ((uint64_t)o1.y << 32) | o1.x; s.occ[3] = ((uint64_t)o1.w << 32) | o1.z;
+	const uint8_t *p = ebwt + sideNum * 128;
+	ldg_sector128(p, s.w[0], s.w[1], s.w[2], s.w[3]);
+	ldg_sector128(p + 32, s.w[4], s.w[5], s.w[6], s.w[7]);
+	ldg_sector128(p + 64, s.w[8], s.w[9], s.w[10], s.w[11]);
+	ldg_sector128(p + 96, s.occ[0], s.occ[1], s.occ[2], s.occ[3]);
 }
 
 // counts of C, G, T among the first charOff characters of the side (A = charOff - sum)

@@ -16,6 +16,8 @@
 //     counter (one warp-aggregated atomic per refill), so a warp keeps 32 searches in flight.
 #include "fm_device.cuh"
 
+#define REFILL_MIN 8
+
 // 2-bit packing of a read batch.  Word w of read r holds bases 32w..32w+31 (base i at bits 2(i&31)),
 // nmask has the same word structure with one bit per base.  Word offset of read r is
 // (roff[r] >> 5) + r, which needs no extra offset array and never overlaps the next read.
@@ -77,7 +79,8 @@ __global__ void __launch_bounds__(256) k_seed_search2(DevIndex<OFF> ix, const ui
 	unsigned nside = 0;
 	for(;;) {
 		const unsigned need = __ballot_sync(FULL, !active && !exhausted);
-		if(need) {
+		// refill in batches: the refill path is a chain of dependent loads that stalls the whole warp
+		if(need && (__popc(need) >= REFILL_MIN || __ballot_sync(FULL, active) == 0)) {
 			unsigned long long base = 0;
 			const int leader = __ffs(need) - 1;
 			if(lane == leader) base = atomicAdd(next, (unsigned long long)__popc(need));
@@ -237,7 +240,8 @@ __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const ui
 	unsigned nside = 0;
 	for(;;) {
 		const unsigned need = __ballot_sync(FULL, !active && !exhausted);
-		if(need) {
+		// refill in batches: the refill path is a chain of dependent loads that stalls the whole warp
+		if(need && (__popc(need) >= REFILL_MIN || __ballot_sync(FULL, active) == 0)) {
 			unsigned long long base = 0;
 			const int leader = __ffs(need) - 1;
 			if(lane == leader) base = atomicAdd(next, (unsigned long long)__popc(need));
@@ -352,3 +356,78 @@ void launch_pack_reads(const uint8_t *seq, const uint64_t *roff, uint64_t nReads
 	const uint64_t nw = nReads * (uint64_t)maxWords;
 	k_pack_reads<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(seq, roff, nReads, maxWords, packed, nmask);
 }
+
+// ----------------------------------------------------------------------------------------
+// K2 v2: SA-offset resolution over a DENSE row list with persistent lanes (v1 ran one thread per
+// padded slot: 2.8 of 32 lanes active).  The row count lives on the device (written by the
+// collect stage), so no host round trip is needed to size the launch.
+// ----------------------------------------------------------------------------------------
+template <typename OFF>
+__global__ void __launch_bounds__(256) k_resolve2(DevIndex<OFF> ix, const uint64_t *rows, const uint32_t *hitlen, uint64_t nHost,
+                                                  const uint32_t *nDev, int rejectStraddle, uint64_t *joined, uint64_t *tidx,
+                                                  uint64_t *textoff, uint64_t *tlen, uint8_t *flags, unsigned long long *next,
+                                                  unsigned long long *cnt) {
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const uint64_t total = nDev ? (uint64_t)*nDev : nHost;
+	const uint64_t rateMask = (1ull << ix.offRate) - 1;
+	bool active = false, exhausted = false;
+	uint64_t row = 0, jumps = 0, task = 0;
+	unsigned nside = 0;
+	for(;;) {
+		const unsigned need = __ballot_sync(FULL, !active && !exhausted);
+		if(need && (__popc(need) >= REFILL_MIN || __ballot_sync(FULL, active) == 0)) {
+			unsigned long long base = 0;
+			const int leader = __ffs(need) - 1;
+			if(lane == leader) base = atomicAdd(next, (unsigned long long)__popc(need));
+			base = __shfl_sync(FULL, base, leader);
+			if(!active && !exhausted) {
+				task = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+				if(task >= total) exhausted = true;
+				else {
+					row = rows[task]; jumps = 0;
+					if(row == BT2G_OFFMASK) { if(flags) flags[task] = 4; }
+					else active = true;
+				}
+			}
+		}
+		if(__ballot_sync(FULL, active) == 0) {
+			if(__all_sync(FULL, exhausted)) break;
+			continue;
+		}
+		if(active) {
+			// Ebwt::getOffset (bt2_idx.cpp:150-171), one LF step per iteration
+			bool fin = false; uint64_t off = 0;
+			if(row == ix.fw.zOff) { fin = true; off = jumps; }
+			else if((row & rateMask) == 0) { fin = true; off = jumps + (uint64_t)__ldg(ix.offs + (row >> ix.offRate)); }
+			else { int c; row = lf_step<OFF>(ix.fw, row, c); jumps++; nside++; }
+			if(fin) {
+				if(joined) joined[task] = off;
+				if(tidx || textoff || tlen || flags) {
+					uint64_t ti, to, tl; bool st;
+					const bool ok = joined_to_text<OFF>(ix, hitlen ? hitlen[task] : 1, off, rejectStraddle != 0, ti, to, tl, st);
+					if(tidx) tidx[task] = ti;
+					if(textoff) textoff[task] = to;
+					if(tlen) tlen[task] = tl;
+					if(flags) flags[task] = (uint8_t)((st ? 1 : 0) | (ok ? 0 : 2));
+				}
+				active = false;
+			}
+		}
+	}
+	if(cnt && nside) atomicAdd(cnt, (unsigned long long)nside);
+}
+
+template <typename OFF>
+void launch_resolve2(const DevIndex<OFF> &ix, const uint64_t *rows, const uint32_t *hitlen, uint64_t nHost, const uint32_t *nDev,
+                     int rej, uint64_t *joined, uint64_t *tidx, uint64_t *textoff, uint64_t *tlen, uint8_t *flags,
+                     unsigned long long *next, int numSMs, cudaStream_t st, unsigned long long *cnt) {
+	if(nHost == 0 && nDev == nullptr) return;
+	cudaMemsetAsync(next, 0, sizeof(unsigned long long), st);
+	int perSM = 4;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_resolve2<OFF>, 256, 0);
+	if(perSM < 1) perSM = 1;
+	k_resolve2<OFF><<<(unsigned)(numSMs * perSM), 256, 0, st>>>(ix, rows, hitlen, nHost, nDev, rej, joined, tidx, textoff, tlen, flags, next, cnt);
+}
+template void launch_resolve2<uint32_t>(const DevIndex<uint32_t> &, const uint64_t *, const uint32_t *, uint64_t, const uint32_t *, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+template void launch_resolve2<uint64_t>(const DevIndex<uint64_t> &, const uint64_t *, const uint32_t *, uint64_t, const uint32_t *, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);

@@ -25,6 +25,7 @@ template <typename OFF> void launch_seed_search(const DevIndex<OFF> &, const uin
 template <typename OFF> void launch_seed_search2(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
 template <typename OFF> void launch_exact_sweep2(const DevIndex<OFF> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
 void launch_pack_reads(const uint8_t *, const uint64_t *, uint64_t, int, uint64_t *, uint32_t *, cudaStream_t);
+template <typename OFF> void launch_resolve2(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, const uint32_t *, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
 template <typename OFF> void launch_resolve(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t, unsigned long long *);
 template <typename OFF> int launch_dp_e2e(const DevIndex<OFF> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);
 
@@ -37,7 +38,8 @@ struct PipeBufs {
 	uint8_t *mine; uint64_t *ee;              // exact sweep
 	uint64_t *ranges; int32_t *nseeds;        // seed search
 	uint64_t *packed; uint32_t *nmask; unsigned long long *nextTask;   // 2-bit reads + task counter
-	uint64_t *rows; uint32_t *hitlen, *meta;  // collect
+	uint64_t *rows; uint32_t *hitlen, *meta;  // collect (dense: rows of read r at [rowBase[r], +rowCnt[r]))
+	uint32_t *nRows, *rowBase, *rowCnt;
 	uint64_t *tidx, *textoff, *tlen; uint8_t *rflags;   // resolve
 	bt2g_dp_problem *probs; uint32_t *nProb; int32_t *readProb; int32_t *readNProb;
 	uint8_t *codes; int32_t *lastH;
@@ -75,45 +77,59 @@ __global__ void k_plan(const uint64_t *roff, uint64_t n, const int32_t *ivalByLe
 	offset[i] = 0;
 }
 
-// collect: one thread per read
+// collect: one thread per read; rows are appended to one dense list (a contiguous block per read)
 __global__ void k_collect(uint64_t n, const uint64_t *roff, const uint64_t *ee, const uint64_t *ranges, const int32_t *nseeds,
                           int maxSeeds, int seedLen, int rowCap, int rangeMax,
-                          uint64_t *rows, uint32_t *hitlen, uint32_t *meta) {
+                          uint64_t *rows, uint32_t *hitlen, uint32_t *meta, uint32_t *nRows, uint32_t *rowBase, uint32_t *rowCnt) {
 	uint64_t rd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(rd >= n) return;
-	uint64_t *ro = rows + rd * rowCap;
-	uint32_t *ho = hitlen + rd * rowCap, *mo = meta + rd * rowCap;
 	const int len = (int)(roff[rd + 1] - roff[rd]);
-	int cnt = 0;
 	const uint64_t *e = ee + rd * 4;
-	for(int strand = 0; strand < 2; strand++) {
-		for(uint64_t r = e[2 * strand]; r < e[2 * strand + 1] && cnt < rowCap; r++) {
-			ro[cnt] = r; ho[cnt] = (uint32_t)len; mo[cnt] = ((uint32_t)strand << 31) | (1u << 30); cnt++;
-		}
+	const int ns = nseeds[rd];
+	const int sl = seedLen < len ? seedLen : len;
+	const uint64_t *rg = ranges + rd * 2ull * maxSeeds * 4;
+	uint64_t eeTot = (e[1] - e[0]) + (e[3] - e[2]);
+	// pass 1: count
+	int cnt = 0;
+	if(eeTot > 0) cnt = eeTot < (uint64_t)rowCap ? (int)eeTot : rowCap;
+	else {
+		for(int strand = 0; strand < 2; strand++)
+			for(int k = 0; k < ns; k++) {
+				const uint64_t *q = rg + ((size_t)strand * maxSeeds + k) * 4;
+				const uint64_t sz = q[1] - q[0];
+				if(sz >= 1 && sz <= (uint64_t)rangeMax) cnt += (int)sz;
+			}
+		if(cnt > rowCap) cnt = rowCap;
 	}
-	if(cnt == 0) {
-		const int ns = nseeds[rd];
-		const int sl = seedLen < len ? seedLen : len;
-		const uint64_t *rg = ranges + rd * 2ull * maxSeeds * 4;
-		for(int sz = 1; sz <= rangeMax && cnt < rowCap; sz++) {
-			for(int strand = 0; strand < 2 && cnt < rowCap; strand++) {
-				for(int k = 0; k < ns && cnt < rowCap; k++) {
+	const uint32_t base = cnt ? atomicAdd(nRows, (uint32_t)cnt) : 0;
+	rowBase[rd] = base; rowCnt[rd] = (uint32_t)cnt;
+	uint64_t *ro = rows + base;
+	uint32_t *ho = hitlen + base, *mo = meta + base;
+	// pass 2: write (exact end-to-end hits first, else seed ranges smallest first)
+	int w = 0;
+	if(eeTot > 0) {
+		for(int strand = 0; strand < 2; strand++)
+			for(uint64_t r = e[2 * strand]; r < e[2 * strand + 1] && w < cnt; r++) {
+				ro[w] = r; ho[w] = (uint32_t)len; mo[w] = ((uint32_t)strand << 31) | (1u << 30); w++;
+			}
+	} else {
+		for(int sz = 1; sz <= rangeMax && w < cnt; sz++)
+			for(int strand = 0; strand < 2 && w < cnt; strand++)
+				for(int k = 0; k < ns && w < cnt; k++) {
 					const uint64_t *q = rg + ((size_t)strand * maxSeeds + k) * 4;
 					if((int)(q[1] - q[0]) != sz) continue;
-					for(uint64_t r = q[0]; r < q[1] && cnt < rowCap; r++) {
-						ro[cnt] = r; ho[cnt] = (uint32_t)sl; mo[cnt] = ((uint32_t)strand << 31) | ((uint32_t)k << 16); cnt++;
+					for(uint64_t r = q[0]; r < q[1] && w < cnt; r++) {
+						ro[w] = r; ho[w] = (uint32_t)sl; mo[w] = ((uint32_t)strand << 31) | ((uint32_t)k << 16); w++;
 					}
 				}
-			}
-		}
 	}
-	for(; cnt < rowCap; cnt++) { ro[cnt] = BT2G_OFFMASK; ho[cnt] = 0; mo[cnt] = 0; }
 }
 
 // frame: one thread per read
 __global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interval, const int32_t *offset,
                         const uint64_t *rows, const uint32_t *hitlen, const uint32_t *meta,
                         const uint64_t *tidx, const uint64_t *textoff, const uint64_t *tlen, const uint8_t *rflags,
+                        const uint32_t *rowBase, const uint32_t *rowCnt,
                         int rowCap, int maxLen, int maxhalf, int matchBonus,
                         const int32_t *minscByLen, const int32_t *nceilRawByLen, const int32_t *rdgapsByLen, const int32_t *rfgapsByLen,
                         bt2g_dp_problem *probs, uint32_t *nProb, uint32_t maxProbs, int32_t *readProb, int32_t *readNProb, bt2g_read_result *res) {
@@ -126,9 +142,9 @@ __global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interva
 	int np = 0;
 	uint64_t seenT[32]; int64_t seenO[32]; uint8_t seenS[32]; int nseen = 0;
 	const int minsc = minscByLen[li];
-	for(int i = 0; i < rowCap; i++) {
-		uint64_t s = rd * rowCap + i;
-		if(rows[s] == BT2G_OFFMASK) break;
+	const uint32_t rb = rowBase[rd], rcnt = rowCnt[rd];
+	for(uint32_t i = 0; i < rcnt; i++) {
+		uint64_t s = (uint64_t)rb + i;
 		uint32_t m = meta[s];
 		const bool isEE = META_EE(m) != 0;
 		const uint8_t fl = rflags[s];
@@ -229,6 +245,7 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 	auto mark = [&](int i) { if(p->evOk) cudaEventRecord(p->ev[i], st); };
 	if(count) BT2G_CUDA_TRY(ctx, cudaMemsetAsync(b.counters, 0, 4 * sizeof(unsigned long long), st));
 	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(b.nProb, 0, sizeof(uint32_t), st));
+	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(b.nRows, 0, sizeof(uint32_t), st));
 	mark(0);
 	k_plan<<<grid(n), T, 0, st>>>(roff, n, b.ivalByLen, q.max_len, b.interval, b.offset);
 	mark(1);
@@ -238,12 +255,13 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 	launch_seed_search2<OFF>(ix, seq, roff, n, q.max_len, q.seed_len, q.max_seeds, 0, 0, b.interval, b.offset, b.ranges, b.nseeds,
 	                         b.packed, b.nmask, b.nextTask, p->sms, st, c ? c + 1 : nullptr);
 	mark(3);
-	k_collect<<<grid(n), T, 0, st>>>(n, roff, b.ee, b.ranges, b.nseeds, q.max_seeds, q.seed_len, q.row_cap, q.range_max, b.rows, b.hitlen, b.meta);
+	k_collect<<<grid(n), T, 0, st>>>(n, roff, b.ee, b.ranges, b.nseeds, q.max_seeds, q.seed_len, q.row_cap, q.range_max, b.rows, b.hitlen, b.meta,
+	                                 b.nRows, b.rowBase, b.rowCnt);
 	mark(4);
-	launch_resolve<OFF>(ix, b.rows, b.hitlen, n * (uint64_t)q.row_cap, 0, nullptr, b.tidx, b.textoff, b.tlen, b.rflags, st, c ? c + 2 : nullptr);
+	launch_resolve2<OFF>(ix, b.rows, b.hitlen, 0, b.nRows, 0, nullptr, b.tidx, b.textoff, b.tlen, b.rflags, b.nextTask, p->sms, st, c ? c + 2 : nullptr);
 	mark(5);
 	k_frame<<<grid(n), T, 0, st>>>(n, roff, b.interval, b.offset, b.rows, b.hitlen, b.meta, b.tidx, b.textoff, b.tlen, b.rflags,
-	                               q.row_cap, q.max_len, q.maxhalf, ctx->scoring.match_bonus,
+	                               b.rowBase, b.rowCnt, q.row_cap, q.max_len, q.maxhalf, ctx->scoring.match_bonus,
 	                               b.minscByLen, b.nceilRawByLen, b.rdgapsByLen, b.rfgapsByLen,
 	                               b.probs, b.nProb, (uint32_t)p->maxProbs, b.readProb, b.readNProb, b.res);
 	DpLaunch L;
@@ -291,6 +309,7 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	rc |= pipeAlloc(p, b.mine, n * 2); rc |= pipeAlloc(p, b.ee, n * 4);
 	rc |= pipeAlloc(p, b.ranges, n * 2ull * prm->max_seeds * 4); rc |= pipeAlloc(p, b.nseeds, n);
 	rc |= pipeAlloc(p, b.packed, (maxBases >> 5) + n + 2); rc |= pipeAlloc(p, b.nmask, (maxBases >> 5) + n + 2); rc |= pipeAlloc(p, b.nextTask, 1);
+	rc |= pipeAlloc(p, b.nRows, 1); rc |= pipeAlloc(p, b.rowBase, n); rc |= pipeAlloc(p, b.rowCnt, n);
 	rc |= pipeAlloc(p, b.rows, nrowMax); rc |= pipeAlloc(p, b.hitlen, nrowMax); rc |= pipeAlloc(p, b.meta, nrowMax);
 	rc |= pipeAlloc(p, b.tidx, nrowMax); rc |= pipeAlloc(p, b.textoff, nrowMax); rc |= pipeAlloc(p, b.tlen, nrowMax); rc |= pipeAlloc(p, b.rflags, nrowMax);
 	rc |= pipeAlloc(p, b.probs, nprobMax); rc |= pipeAlloc(p, b.nProb, 1); rc |= pipeAlloc(p, b.readProb, nrowMax); rc |= pipeAlloc(p, b.readNProb, n);
