@@ -250,6 +250,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     distributed = world > 1 and args.impl == "ours"
     if distributed:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from bowtie2_b200 import Bt2Gpu
@@ -261,6 +263,11 @@ def main():
     workload = (f"synthetic {GENOME_CONTIGS * contig_len / 1e9:.2f} Gbp genome .bt2 index, {args.reads / 1e6:g}M 1x{READ_LEN} bp reads, "
                 "--end-to-end --sensitive")
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:                                   # container CPU quota, if any (explains where the reference stops scaling)
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        cpu_quota = None if q == "max" else float(q) / float(per)
+    except Exception:
+        cpu_quota = None
 
     # ---- setup (untimed): genome, index (built once on rank 0, NCCL-broadcast to the others), reads
     t0 = time.time()
@@ -329,7 +336,7 @@ def main():
             line = {"metric": "Mreads/s", "value": val, "unit": "Mreads/s", "n_gpus": 0, "steps": len(per), "warmup": args.warmup,
                     "ms_per_step": 1e3 * (n_big - n_small) / rps, "higher_is_better": True, "scaling": "weak",
                     "vs_baseline": None, "dtype": "u8/i16 (SSE/AVX2 striped DP), u64 popcount FM", "data": "synthetic",
-                    "impl": "reference", "config": {"workload": workload, "full_size": full},
+                    "impl": "reference", "config": {"workload": workload, "full_size": full, "host_threads": cores, "cgroup_cpu_quota": cpu_quota},
                     "cpu_baseline": {"value": val, "unit": "Mreads/s", "cores": threads, "kind": "reference",
                                      "sample": f"{n_big - n_small} reads (difference of a {n_big}- and a {n_small}-read run of "
                                                f"{per[0]['binary']} -p {threads} (fastest of the thread counts tried on {cores} "
@@ -458,7 +465,7 @@ def main():
                 "config": {"workload": workload, "full_size": full, "batch_reads": B, "preset": "--end-to-end --sensitive",
                            "l2": "inputs larger than L2 (random access over a %.1f GB index; a different 1M-read batch each step)" % (info["device_bytes"] / 1e9),
                            "pipeline": "exactSweep + multiseed round 0 + resolve(all rows of ranges<=8, cap 16) + DP/backtrace per distinct diagonal",
-                           "index_bcast_s": bcast_s, "aligned_frac": found, "dp_workspace_overflows": overflow},
+                           "index_bcast_s": bcast_s, "aligned_frac": found, "host_threads": cores, "cgroup_cpu_quota": cpu_quota, "dp_workspace_overflows": overflow},
                 "clocks": clk, "gpu_launches": 8 * args.steps,
                 "e2e": {"value": e2e_val, "unit": "Mreads/s", "h2d_bytes_per_step": 2 * B * READ_LEN + (B + 1) * 8,
                         "d2h_bytes_per_step": B * READ_RESULT.itemsize + B * pipe.max_ops},
