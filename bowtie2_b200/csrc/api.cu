@@ -457,6 +457,7 @@ int bt2g_get_stretch(bt2g_ctx *ctx, const uint64_t *tidx, const int64_t *off, co
 
 // ---- K3 ------------------------------------------------------------------------------------
 template <typename OFF> int launch_dp_e2e(const DevIndex<OFF> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);
+template <typename OFF> int launch_dp_local(const DevIndex<OFF> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);
 
 extern "C" {
 
@@ -489,7 +490,6 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 	if(!ctx->info.has_ref) { ctx->err = "packed reference (.3/.4) not loaded"; return -1; }
 	if(!reads || !reads->qual || !probs || !summ || !cands || !alns || !ops) { ctx->err = "null argument"; return -1; }
 	if(ctx->scoring.gapbar < 1) bt2g_scoring_default(&ctx->scoring, 0);
-	if(ctx->scoring.local) { ctx->err = "local mode DP not implemented in this build"; return -1; }
 	if(n == 0) return 0;
 	if(maxCands < 1 || maxAlns < 1 || maxOps < 1) return -1;
 	// shape of the batch
@@ -502,9 +502,10 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 		if(len > maxLen) maxLen = len;
 	}
 	if(maxLen > 512) { ctx->err = "reads longer than 512 are not supported by the DP kernel"; return -1; }
+	maxCol += 1;                              // local mode keeps one extra reference character
 	if(maxCol > 8192) { ctx->err = "DP window wider than 8192 columns"; return -1; }
 	int R = maxLen <= 128 ? 4 : (maxLen <= 256 ? 8 : 16);
-	DBuf dseq, dqual, doff, dprob, dcodes, dlast, dsumm, dcand, daln, dops;
+	DBuf dseq, dqual, doff, dprob, dcodes, dlast, dsumm, dcand, daln, dops, draw;
 	int rc = uploadReads(ctx, reads, dseq, dqual, doff, true);
 	if(rc) return rc;
 	DpLaunch L;
@@ -518,6 +519,9 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 	BT2G_CUDA_TRY(ctx, dprob.alloc(n * sizeof(bt2g_dp_problem)));
 	BT2G_CUDA_TRY(ctx, dcodes.alloc(L.numSlots * L.codeStride));
 	BT2G_CUDA_TRY(ctx, dlast.alloc(L.numSlots * (uint64_t)maxCol * 4));
+	L.maxRaw = maxCands * 4 < 1024 ? 1024 : maxCands * 4;
+	BT2G_CUDA_TRY(ctx, draw.alloc(L.numSlots * (uint64_t)L.maxRaw * 8));
+	L.rawKeys = draw.as<uint64_t>();
 	BT2G_CUDA_TRY(ctx, dsumm.alloc(n * sizeof(bt2g_dp_summary)));
 	BT2G_CUDA_TRY(ctx, dcand.alloc(n * (uint64_t)maxCands * sizeof(bt2g_dp_cand)));
 	BT2G_CUDA_TRY(ctx, daln.alloc(n * (uint64_t)maxAlns * sizeof(bt2g_dp_aln)));
@@ -529,8 +533,13 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 	L.probs = dprob.as<bt2g_dp_problem>(); L.codes = dcodes.as<uint8_t>(); L.lastH = dlast.as<int32_t>();
 	L.summ = dsumm.as<bt2g_dp_summary>(); L.cands = dcand.as<bt2g_dp_cand>(); L.alns = daln.as<bt2g_dp_aln>(); L.ops = dops.as<uint8_t>();
 	int lrc;
-	if(ctx->info.off_size == 4) lrc = launch_dp_e2e<uint32_t>(bt2g_dev_index<uint32_t>(ctx), ctx->scoring, L, maxLen, ctx->stream);
-	else lrc = launch_dp_e2e<uint64_t>(bt2g_dev_index<uint64_t>(ctx), ctx->scoring, L, maxLen, ctx->stream);
+	if(ctx->scoring.local) {
+		if(ctx->info.off_size == 4) lrc = launch_dp_local<uint32_t>(bt2g_dev_index<uint32_t>(ctx), ctx->scoring, L, maxLen, ctx->stream);
+		else lrc = launch_dp_local<uint64_t>(bt2g_dev_index<uint64_t>(ctx), ctx->scoring, L, maxLen, ctx->stream);
+	} else {
+		if(ctx->info.off_size == 4) lrc = launch_dp_e2e<uint32_t>(bt2g_dev_index<uint32_t>(ctx), ctx->scoring, L, maxLen, ctx->stream);
+		else lrc = launch_dp_e2e<uint64_t>(bt2g_dev_index<uint64_t>(ctx), ctx->scoring, L, maxLen, ctx->stream);
+	}
 	if(lrc) { ctx->err = "DP launch rejected"; return -1; }
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(summ, dsumm.p, dsumm.bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -10,7 +10,9 @@ struct DpLaunch {
 	const uint32_t *nDev;         // optional: problem count produced on the device
 	uint64_t        numSlots;     // persistent warp slots (multiple of 4)
 	uint8_t        *codes;        // workspace: n * codeStride bytes
-	int32_t        *lastH;        // workspace: n * maxCol ints (e2e last-row scores)
+	int32_t        *lastH;
+	uint64_t       *rawKeys;      // local mode: per-slot candidate keys (score<<32 | row<<16 | col)
+	int             maxRaw;        // workspace: n * maxCol ints (e2e last-row scores)
 	uint64_t        codeStride;
 	int             maxCol;
 	int             maxCands, maxAlns, maxOps;

@@ -313,7 +313,7 @@ Bt2Gpu.set_scoring = _set_scoring
 Bt2Gpu.dp_extend = _dp_extend
 
 
-def ops_to_edits(ops: np.ndarray, nops: int, read_codes: np.ndarray, fw: bool, row0: int):
+def ops_to_edits(ops: np.ndarray, nops: int, read_codes: np.ndarray, fw: bool, row0: int, trim_end: int = 0):
     """Rebuild the reference's Edit list (edit.h:57-) from a device op string.
 
     The device lists columns from the last read row back to the first; the reference builds
@@ -332,18 +332,20 @@ def ops_to_edits(ops: np.ndarray, nops: int, read_codes: np.ndarray, fw: bool, r
         if typ == OP_MATCH:
             row += 1
         elif typ == OP_MM:
-            out.append([row, dna[refc], dna[seq[row]], EDIT_MM])
+            out.append([row - row0, dna[refc], dna[seq[row]], EDIT_MM])
             row += 1
         elif typ == OP_REFGAP:
-            out.append([row, ord("-"), dna[seq[row]], EDIT_REF_GAP])
+            out.append([row - row0, ord("-"), dna[seq[row]], EDIT_REF_GAP])
             row += 1
         else:
-            out.append([row, dna[refc], ord("-"), EDIT_READ_GAP])
+            out.append([row - row0, dna[refc], ord("-"), EDIT_READ_GAP])
     if not fw:
         # AlnRes::invertEdits -> Edit::invertPoss (edit.cpp:50-78)
+        # positions are relative to the soft-trimmed extent (AlnRes::setShape, aligner_result.cpp:101-117)
+        ext = rdlen - row0 - trim_end
         out = out[::-1]
         for e in out:
-            e[0] = rdlen - e[0] - (0 if e[3] == EDIT_READ_GAP else 1)
+            e[0] = ext - e[0] - (0 if e[3] == EDIT_READ_GAP else 1)
     return out
 
 

@@ -208,6 +208,7 @@ typedef struct {
 #define BT2G_CAND_FILT_START 1   /* BT_CAND_FATE_FILT_START: start cell already reported through */
 #define BT2G_CAND_FAILED     2   /* backtrace attempted and failed (RNG was consumed) */
 #define BT2G_CAND_SUCCEEDED  3
+#define BT2G_CAND_FILT_DOMINATED 4  /* local mode: within rows/16 of an attempted candidate (aligner_sw.cpp:946-971) */
 typedef struct { int32_t score, row, col, fate; } bt2g_dp_cand;
 
 /* one alignment: ops[] lists the alignment columns from the LAST read row back to the first

@@ -36,12 +36,13 @@ def _problems(genome, reads, truth, sc, jitter_rng, minsc_bump=0):
 
 def _check(gpu, R, genome, reads, quals, probs, meta, local=False):
     batch = ReadBatch.from_list(reads, quals)
-    summ, cands, alns, ops = gpu.dp_extend(batch, probs, max_cands=256, max_alns=8, max_ops=int(batch.lengths().max()) + 80)
+    summ, cands, alns, ops = gpu.dp_extend(batch, probs, max_cands=1024 if local else 256, max_alns=16 if local else 8,
+                                           max_ops=int(batch.lengths().max()) + 80)
     nfound = naln = ngap = 0
     for k, pr in enumerate(probs):
         tlen, rect, minsc = meta[k]
         i = int(pr["read_idx"])
-        want = ref_dp(R, local, reads[i], quals[i], int(pr["fw"]), int(pr["tidx"]), tlen, rect, minsc)
+        want = ref_dp(R, local, reads[i], quals[i], int(pr["fw"]), int(pr["tidx"]), tlen, rect, minsc, max_cands=4096, max_alns=64, max_edits=16384)
         s = summ[k]
         assert s["flags"] == 0, (k, s)
         assert bool(s["found"]) == bool(want["found"]), (k, s, want["found"], want["best"])
@@ -60,7 +61,9 @@ def _check(gpu, R, genome, reads, quals, probs, meta, local=False):
             a = alns[k][a_i]
             assert (int(a["score"]), int(a["ns"]), int(a["gaps"])) == (wa["score"], wa["ns"], wa["gaps"]), (k, a, wa)
             assert int(pr["refl"]) + int(a["col0"]) == wa["refoff"], (k, a, wa)
-            ed = ops_to_edits(ops[k][a_i], int(a["nops"]), reads[i], bool(pr["fw"]), int(a["row0"]))
+            ed = ops_to_edits(ops[k][a_i], int(a["nops"]), reads[i], bool(pr["fw"]), int(a["row0"]), int(a["trim_end"]))
+            t5, t3 = (int(a["trim_beg"]), int(a["trim_end"])) if pr["fw"] else (int(a["trim_end"]), int(a["trim_beg"]))
+            assert (t5, t3) == (wa["trim5"], wa["trim3"]), (k, a, wa)
             assert ed == wa["edits"], (k, a_i, ed, wa["edits"])
             naln += 1
             ngap += wa["gaps"] > 0
@@ -110,3 +113,28 @@ def test_dp_e2e_edges(gpu, synth_index, synth_genome):
     _check(gpu, R, g, reads, quals, probs, meta)
     probs, meta = _problems(g, reads, truth, sc, rng, minsc_bump=40)
     _check(gpu, R, g, reads, quals, probs, meta)
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("rdlen,sub,indel", [(100, 0.02, 0.003), (150, 0.03, 0.005), (300, 0.02, 0.004), (60, 0.02, 0.0)])
+def test_dp_local_matches_reference(gpu, synth_index, synth_genome, rdlen, sub, indel):
+    """--local: floors at 0, candidates anywhere in the rectangle, soft trimming, domination filter."""
+    gpu.load_index_files(synth_index)
+    gpu.set_scoring(local=True)
+    R = Reference(synth_index)
+    sc = policy.Scoring.default(True)
+    reads, quals, truth = synth.make_reads(synth_genome, 160, rdlen, seed=7 * rdlen, sub_rate=sub, indel_rate=indel, random_frac=0.05)
+    rng = np.random.default_rng(rdlen + 1)
+    for i, r in enumerate(reads):
+        if i % 3 == 0:                                   # junk ends -> soft clipping
+            k = int(rng.integers(3, max(4, rdlen // 5)))
+            r[:k] = rng.integers(0, 4, k)
+        if i % 4 == 0:
+            k = int(rng.integers(3, max(4, rdlen // 5)))
+            r[-k:] = rng.integers(0, 4, k)
+        if i % 11 == 0:
+            r[rng.integers(0, rdlen)] = 4
+    probs, meta = _problems(synth_genome, reads, truth, sc, rng)
+    nfound, naln, ngap = _check(gpu, R, synth_genome, reads, quals, probs, meta, local=True)
+    assert nfound > 100 and naln > 100
+    gpu.set_scoring(local=False)
