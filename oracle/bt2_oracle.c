@@ -619,200 +619,239 @@ static int cell_score(const bt2o_scoring *sc, int rdc, int refc, int q) {
 typedef struct { int nedsz, celsz, row, col, gaps, score, ns, ct; } bt_frame;
 
 /* One SwAligner session (aligner_sw.cpp:155-271 initRef, :500-729 align, :737-1146
- * nextAlignment; fill recurrences aligner_swsse_ee_u8.cpp:931-993; gather :1176-1208;
- * backtrace :1283-1877 INCLUDING its reported-through marks, remaining-option masks and branch
- * stack, restated literally so that the device kernel's shortcut can be checked against it).
+ * nextAlignment).  End-to-end: fill recurrences aligner_swsse_ee_u8.cpp:931-993, gather :1176-1208,
+ * backtrace :1283-1877.  Local: fill aligner_swsse_loc_i16.cpp:938-1367 (scores floored at 0 by
+ * signed saturation), gather :1420-1535, backtrace :1615-2218 (moves only from cells with score
+ * > 0), domination filter aligner_sw.cpp:946-971.  The backtrace is restated literally INCLUDING
+ * its reported-through marks, remaining-option masks and branch stack, so that the device
+ * kernel's shortcut can be checked against it.
  * Outputs use the same layout as oracle/ref_glue_dp.cpp:ref_dp(). */
 int bt2o_dp(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, const uint8_t *quals, int len, int fw,
             uint64_t tidx, int64_t refl, int64_t refr, int triml, int corel, int corer, int64_t minsc, int nceil,
             int max_cands, int max_alns, int max_edits,
             int64_t *summary, int64_t *cands, int64_t *alns, int32_t *edits) {
 	const int nrow = len, ncol = (int)(refr - refl + 1);
+	const int local = sc->local;
 	const int rdo = sc->rdgap_const + sc->rdgap_linear, rde = sc->rdgap_linear;
 	const int rfo = sc->rfgap_const + sc->rfgap_linear, rfe = sc->rfgap_linear;
+	const int NEGV = local ? 0 : DPNEG;          /* "minus infinity" of the mode */
+	const int FLOOR = local ? 0 : DPNEG;         /* a source must be > FLOOR to be moved from */
 	summary[0] = 0; summary[1] = DPNEG; summary[2] = 0; summary[3] = 0;
-	if(ncol <= 0 || nrow <= 0 || sc->local) return -1;
+	if(ncol <= 0 || nrow <= 0) return -1;
 	uint8_t *rd = (uint8_t *)malloc((size_t)nrow), *qu = (uint8_t *)malloc((size_t)nrow);
-	uint8_t *rf = (uint8_t *)malloc((size_t)ncol + 1);
+	uint8_t *rf = (uint8_t *)malloc((size_t)ncol + 2);
 	for(int i = 0; i < nrow; i++) {
 		if(fw) { rd[i] = codes[i]; qu[i] = quals[i]; }
 		else { int c = codes[nrow - 1 - i]; rd[i] = (uint8_t)(c > 3 ? 4 : 3 - c); qu[i] = quals[nrow - 1 - i]; }
 	}
-	bt2o_get_stretch(ix, tidx, refl, ncol, rf);
+	bt2o_get_stretch(ix, tidx, refl, ncol + 1, rf);   /* one extra character (aligner_sw.cpp:170-173) */
 	size_t ncell = (size_t)nrow * (size_t)ncol;
 	int *H = (int *)malloc(ncell * sizeof(int)), *E = (int *)malloc(ncell * sizeof(int)), *F = (int *)malloc(ncell * sizeof(int));
 	uint16_t *mask = (uint16_t *)calloc(ncell, sizeof(uint16_t));
 #define AT(M, i, j) M[(size_t)(i) * (size_t)ncol + (size_t)(j)]
+#define MAX2(a, b) ((a) > (b) ? (a) : (b))
+	int best = DPNEG;
 	for(int j = 0; j < ncol; j++) {
 		for(int i = 0; i < nrow; i++) {
 			int bar = (i < sc->gapbar) || (nrow - 1 - i < sc->gapbar);
-			int f = DPNEG;
-			if(i > 0 && !bar) {
-				int a = AT(F, i - 1, j) - rfe, b = AT(H, i - 1, j) - rfo;
-				f = a > b ? a : b;
-			}
-			int diag = (i == 0) ? 0 : (j == 0 ? DPNEG : AT(H, i - 1, j - 1));
+			int upH = i > 0 ? AT(H, i - 1, j) : NEGV, upF = i > 0 ? AT(F, i - 1, j) : NEGV;
+			int f = bar ? NEGV : MAX2(upF - rfe, upH - rfo);
+			int diag = (i == 0) ? 0 : (j == 0 ? NEGV : AT(H, i - 1, j - 1));
 			int hd = diag + cell_score(sc, rd[i], rf[j], (int)qu[i] - 33);
-			int e = DPNEG;
-			if(j > 0) {
-				int a = AT(E, i, j - 1) - rde, b = bar ? DPNEG : AT(H, i, j - 1) - rdo;
-				e = a > b ? a : b;
-			}
+			int lH = j > 0 ? AT(H, i, j - 1) : NEGV, lE = j > 0 ? AT(E, i, j - 1) : NEGV;
+			int e = MAX2(lE - rde, bar ? NEGV : lH - rdo);
+			if(local) { if(f < 0) f = 0; if(e < 0) e = 0; }
 			int h = hd; if(e > h) h = e; if(f > h) h = f;
+			if(local && h < 0) h = 0;
 			AT(H, i, j) = h; AT(E, i, j) = e; AT(F, i, j) = f;
+			if(local && h > best) best = h;
 		}
 	}
-	int best = DPNEG;
-	for(int j = 0; j < ncol; j++) if(AT(H, nrow - 1, j) > best) best = AT(H, nrow - 1, j);
+	if(!local) for(int j = 0; j < ncol; j++) if(AT(H, nrow - 1, j) > best) best = AT(H, nrow - 1, j);
 	summary[1] = best;
 	if(best < minsc) goto done;
+	{
 	/* gather + sort (score desc, row desc, col desc) */
 	int ncand = 0;
-	int *ccol = (int *)malloc((size_t)ncol * sizeof(int));
-	for(int j = 0; j < ncol; j++) if(AT(H, nrow - 1, j) >= minsc) ccol[ncand++] = j;
-	for(int a = 1; a < ncand; a++) {
-		int cj = ccol[a], cs = AT(H, nrow - 1, cj), b = a - 1;
-		while(b >= 0 && (AT(H, nrow - 1, ccol[b]) < cs || (AT(H, nrow - 1, ccol[b]) == cs && ccol[b] < cj))) { ccol[b + 1] = ccol[b]; b--; }
-		ccol[b + 1] = cj;
+	int *crow = (int *)malloc(ncell * sizeof(int)), *ccol = (int *)malloc(ncell * sizeof(int));
+	if(!local) {
+		for(int j = 0; j < ncol; j++) if(AT(H, nrow - 1, j) >= minsc) { crow[ncand] = nrow - 1; ccol[ncand++] = j; }
+	} else {
+		int bonus = sc->match_bonus;
+		int minrow = (int)((minsc + bonus - 1) / bonus) - 1;
+		for(int j = 0; j < ncol; j++)
+			for(int i = (minrow > 0 ? minrow : 0); i < nrow; i++) {
+				if(AT(H, i, j) < minsc) continue;
+				int match = rd[i] == rf[j];                    /* mask test: N(16) & (1<<4) also "matches" */
+				int match_succ = (i < nrow - 1) && rd[i + 1] == rf[j + 1];
+				if(match && !match_succ) { crow[ncand] = i; ccol[ncand++] = j; }
+			}
+	}
+	/* simple O(n^2) insertion sort on (score desc, row desc, col desc) */
+	for(int a2 = 1; a2 < ncand; a2++) {
+		int cr = crow[a2], cj = ccol[a2], cs = AT(H, cr, cj), b2 = a2 - 1;
+		while(b2 >= 0) {
+			int bs = AT(H, crow[b2], ccol[b2]);
+			int less = bs < cs || (bs == cs && (crow[b2] < cr || (crow[b2] == cr && ccol[b2] < cj)));
+			if(!less) break;
+			crow[b2 + 1] = crow[b2]; ccol[b2 + 1] = ccol[b2]; b2--;
+		}
+		crow[b2 + 1] = cr; ccol[b2 + 1] = cj;
 	}
 	summary[0] = ncand > 0; summary[2] = ncand;
-	for(int a = 0; a < ncand && a < max_cands; a++) {
-		cands[3 * a] = nrow - 1; cands[3 * a + 1] = ccol[a]; cands[3 * a + 2] = AT(H, nrow - 1, ccol[a]);
+	for(int a2 = 0; a2 < ncand && a2 < max_cands; a2++) {
+		cands[3 * a2] = crow[a2]; cands[3 * a2 + 1] = ccol[a2]; cands[3 * a2 + 2] = AT(H, crow[a2], ccol[a2]);
 	}
-	{
-		int naln = 0, ned_total = 0;
-		int32_t *ned = (int32_t *)malloc(4 * sizeof(int32_t) * (size_t)(nrow + ncol + 4));
-		int *btcells = (int *)malloc(2 * sizeof(int) * (size_t)(nrow + ncol + 4));
-		bt_frame *stack = (bt_frame *)malloc(sizeof(bt_frame) * (size_t)(nrow + ncol + 4));
-		static const char dna[] = "ACGTN";
-		for(int ci = 0; ci < ncand; ci++) {
-			int row = nrow - 1, col = ccol[ci];
-			if(AT(mask, row, col) & 1) continue;                       /* BT_CAND_FATE_FILT_START */
-			int nned = 0, ncells = 0, nstack = 0, gaps = 0, score = 0, ns = 0, ct = 0 /*0 H,1 E,2 F*/;
-			int ok = 1, trim_beg = 0;
-			const int orig_col = col;
-			for(;;) {
-				int reported = AT(mask, row, col) & 1;
-				int can_move = !reported, empty = 0, branch = 0, cur = -1;
-				if(!reported && row > 0) {
-					int gaps_allowed = !((row < sc->gapbar) || (nrow - 1 - row < sc->gapbar));
-					uint16_t *mk = &AT(mask, row, col);
-					if(ct == 1) {
-						int sc_cur = AT(E, row, col), m = 0;
-						if(AT(H, row, col - 1) - rdo == sc_cur) m |= 1;
-						if(AT(E, row, col - 1) - rde == sc_cur) m |= 2;
-						int orig = m;
-						if(*mk & (1 << 7)) m = (*mk >> 8) & 3;
-						if(m == 3) { cur = 4; *mk = (uint16_t)((*mk & ~(7 << 7)) | (1 << 7) | (2 << 8)); branch = 1; }
-						else if(m == 2) { cur = 5; *mk = (uint16_t)((*mk & ~(7 << 7)) | (1 << 7)); }
-						else if(m == 1) { cur = 4; *mk = (uint16_t)((*mk & ~(7 << 7)) | (1 << 7)); }
-						else { empty = 1; can_move = (orig == 0); }
-					} else if(ct == 2) {
-						int sc_cur = AT(F, row, col), m = 0;
-						if(AT(H, row - 1, col) - rfo == sc_cur) m |= 1;
-						if(AT(F, row - 1, col) - rfe == sc_cur) m |= 2;
-						int orig = m;
-						if(*mk & (1 << 10)) m = (*mk >> 11) & 3;
-						if(m == 3) { cur = 2; *mk = (uint16_t)((*mk & ~(7 << 10)) | (1 << 10) | (2 << 11)); branch = 1; }
-						else if(m == 2) { cur = 3; *mk = (uint16_t)((*mk & ~(7 << 10)) | (1 << 10)); }
-						else if(m == 1) { cur = 2; *mk = (uint16_t)((*mk & ~(7 << 10)) | (1 << 10)); }
-						else { empty = 1; can_move = (orig == 0); }
-					} else {
-						int sc_cur = AT(H, row, col), m = 0;
-						int sdiag = cell_score(sc, rd[row], rf[col], (int)qu[row] - 33);
-						if(gaps_allowed) {
-							if(sc_cur == AT(H, row - 1, col) - rfo) m |= 1;
-							if(col > 0 && sc_cur == AT(H, row, col - 1) - rdo) m |= 2;
-							if(sc_cur == AT(F, row - 1, col) - rfe) m |= 4;
-							if(col > 0 && sc_cur == AT(E, row, col - 1) - rde) m |= 8;
-						}
-						if(col > 0 && sc_cur == AT(H, row - 1, col - 1) + sdiag) m |= 16;
-						int orig = m;
-						if(*mk & (1 << 1)) m = (*mk >> 2) & 31;
-						int opts = 0, sel = -1;
-						for(int b = 0; b < 5; b++) opts += (m >> b) & 1;
-						if(opts >= 1) {
-							if(m & 16) sel = 4; else if(m & 1) sel = 0; else if(m & 4) sel = 2; else if(m & 2) sel = 1; else sel = 3;
-							int rem = opts > 1 ? (m & ~(1 << sel)) : 0;
-							*mk = (uint16_t)((*mk & ~(31 << 1)) | (1 << 1) | (rem << 2));
-							if(opts > 1) branch = 1;
-							cur = sel == 4 ? 1 : (sel == 0 ? 2 : (sel == 1 ? 4 : (sel == 2 ? 3 : 5)));
-						} else { empty = 1; can_move = (orig == 0); }
-					}
-				}
-				AT(mask, row, col) |= 1;                                  /* setReportedThrough */
-				if(!can_move) {
-					if(nstack > 0) {
-						bt_frame *fr = &stack[--nstack];
-						ncells = fr->celsz; nned = fr->nedsz; row = fr->row; col = fr->col; gaps = fr->gaps;
-						score = fr->score; ns = fr->ns; ct = fr->ct;
-						continue;
-					}
-					ok = 0; break;
-				}
-				if(empty || row == 0) { btcells[2 * ncells] = row; btcells[2 * ncells + 1] = col; ncells++; trim_beg = row; break; }
-				if(branch) {
-					bt_frame *fr = &stack[nstack++];
-					fr->nedsz = nned; fr->celsz = ncells; fr->row = row; fr->col = col; fr->gaps = gaps; fr->score = score; fr->ns = ns; fr->ct = ct;
-				}
-				btcells[2 * ncells] = row; btcells[2 * ncells + 1] = col; ncells++;
-				int32_t *e4 = ned + 4 * nned;
-				if(cur == 1) {
-					int rdc = rd[row], rfc = rf[col];
-					if(rdc > 3 || rfc > 3 || rdc != rfc) {
-						e4[0] = row; e4[1] = dna[rfc]; e4[2] = dna[rdc]; e4[3] = 3; nned++;
-						score -= (rdc > 3 || rfc > 3) ? sc->n_pen : mm_pen(sc, (int)qu[row] - 33);
-					} else score += sc->match_bonus;
-					if(rdc > 3 || rfc > 3) ns++;
-					row--; col--; ct = 0;
-				} else if(cur == 2 || cur == 3) {
-					e4[0] = row; e4[1] = '-'; e4[2] = dna[rd[row]]; e4[3] = 2; nned++;
-					score -= cur == 2 ? rfo : rfe; gaps++; row--; ct = cur == 2 ? 0 : 2;
+	int naln = 0, ned_total = 0, ndone = 0;
+	int32_t *ned = (int32_t *)malloc(4 * sizeof(int32_t) * (size_t)(nrow + ncol + 4));
+	int *btcells = (int *)malloc(2 * sizeof(int) * (size_t)(nrow + ncol + 4));
+	bt_frame *stack = (bt_frame *)malloc(sizeof(bt_frame) * (size_t)(nrow + ncol + 4));
+	int *donerow = (int *)malloc(sizeof(int) * (size_t)(ncand + 1)), *donecol = (int *)malloc(sizeof(int) * (size_t)(ncand + 1));
+	int SQ = nrow >> 4; if(SQ == 0) SQ = 1;
+	static const char dna[] = "ACGTN";
+	for(int ci = 0; ci < ncand; ci++) {
+		int row = crow[ci], col = ccol[ci];
+		if(AT(mask, row, col) & 1) continue;                       /* BT_CAND_FATE_FILT_START */
+		if(local) {
+			int dom = 0;
+			for(int k = 0; k < ndone && !dom; k++) {
+				int dr = donerow[k] - row, dc = donecol[k] - col;
+				if(dr < 0) dr = -dr;
+				if(dc < 0) dc = -dc;
+				if(dr <= SQ && dc <= SQ) dom = 1;
+			}
+			if(dom) continue;
+			donerow[ndone] = row; donecol[ndone] = col; ndone++;
+		}
+		const int start_row = row;
+		int nned = 0, ncells = 0, nstack = 0, gaps = 0, score = 0, ns = 0, ct = 0 /*0 H,1 E,2 F*/;
+		int ok = 1, trim_beg = 0;
+		for(;;) {
+			int reported = AT(mask, row, col) & 1;
+			int can_move = !reported, empty = 0, branch = 0, cur = -1;
+			if(!reported && row > 0) {
+				int gaps_allowed = !((row < sc->gapbar) || (nrow - 1 - row < sc->gapbar));
+				uint16_t *mk = &AT(mask, row, col);
+				if(ct == 1) {
+					int sc_cur = AT(E, row, col), m = 0;
+					if(AT(H, row, col - 1) > FLOOR && AT(H, row, col - 1) - rdo == sc_cur) m |= 1;
+					if(AT(E, row, col - 1) > FLOOR && AT(E, row, col - 1) - rde == sc_cur) m |= 2;
+					int orig = m;
+					if(*mk & (1 << 7)) m = (*mk >> 8) & 3;
+					if(m == 3) { cur = 4; *mk = (uint16_t)((*mk & ~(7 << 7)) | (1 << 7) | (2 << 8)); branch = 1; }
+					else if(m == 2) { cur = 5; *mk = (uint16_t)((*mk & ~(7 << 7)) | (1 << 7)); }
+					else if(m == 1) { cur = 4; *mk = (uint16_t)((*mk & ~(7 << 7)) | (1 << 7)); }
+					else { empty = 1; can_move = (orig == 0); }
+				} else if(ct == 2) {
+					int sc_cur = AT(F, row, col), m = 0;
+					if(AT(H, row - 1, col) > FLOOR && AT(H, row - 1, col) - rfo == sc_cur) m |= 1;
+					if(AT(F, row - 1, col) > FLOOR && AT(F, row - 1, col) - rfe == sc_cur) m |= 2;
+					int orig = m;
+					if(*mk & (1 << 10)) m = (*mk >> 11) & 3;
+					if(m == 3) { cur = 2; *mk = (uint16_t)((*mk & ~(7 << 10)) | (1 << 10) | (2 << 11)); branch = 1; }
+					else if(m == 2) { cur = 3; *mk = (uint16_t)((*mk & ~(7 << 10)) | (1 << 10)); }
+					else if(m == 1) { cur = 2; *mk = (uint16_t)((*mk & ~(7 << 10)) | (1 << 10)); }
+					else { empty = 1; can_move = (orig == 0); }
 				} else {
-					e4[0] = row + 1; e4[1] = dna[rf[col]]; e4[2] = '-'; e4[3] = 1; nned++;
-					score -= cur == 4 ? rdo : rde; gaps++; col--; ct = cur == 4 ? 0 : 1;
+					int sc_cur = AT(H, row, col), m = 0;
+					int sdiag = cell_score(sc, rd[row], rf[col], (int)qu[row] - 33);
+					if(gaps_allowed) {
+						if(AT(H, row - 1, col) > FLOOR && sc_cur == AT(H, row - 1, col) - rfo) m |= 1;
+						if(col > 0 && AT(H, row, col - 1) > FLOOR && sc_cur == AT(H, row, col - 1) - rdo) m |= 2;
+						if(AT(F, row - 1, col) > FLOOR && sc_cur == AT(F, row - 1, col) - rfe) m |= 4;
+						if(col > 0 && AT(E, row, col - 1) > FLOOR && sc_cur == AT(E, row, col - 1) - rde) m |= 8;
+					}
+					if(col > 0 && AT(H, row - 1, col - 1) > FLOOR && sc_cur == AT(H, row - 1, col - 1) + sdiag) m |= 16;
+					int orig = m;
+					if(*mk & (1 << 1)) m = (*mk >> 2) & 31;
+					int opts = 0, sel = -1;
+					for(int b = 0; b < 5; b++) opts += (m >> b) & 1;
+					if(opts >= 1) {
+						if(m & 16) sel = 4; else if(m & 1) sel = 0; else if(m & 4) sel = 2; else if(m & 2) sel = 1; else sel = 3;
+						int rem = opts > 1 ? (m & ~(1 << sel)) : 0;
+						*mk = (uint16_t)((*mk & ~(31 << 1)) | (1 << 1) | (rem << 2));
+						if(opts > 1) branch = 1;
+						cur = sel == 4 ? 1 : (sel == 0 ? 2 : (sel == 1 ? 4 : (sel == 2 ? 3 : 5)));
+					} else { empty = 1; can_move = (orig == 0); }
 				}
 			}
-			if(!ok) continue;
-			int core = 0;
-			for(int k = 0; k < ncells; k++) {
-				int d = btcells[2 * k + 1] - btcells[2 * k] + triml;
-				if(d >= corel && d <= corer) { core = 1; break; }
+			AT(mask, row, col) |= 1;                                  /* setReportedThrough */
+			if(!can_move) {
+				if(nstack > 0) {
+					bt_frame *fr = &stack[--nstack];
+					ncells = fr->celsz; nned = fr->nedsz; row = fr->row; col = fr->col; gaps = fr->gaps;
+					score = fr->score; ns = fr->ns; ct = fr->ct;
+					continue;
+				}
+				ok = 0; break;
 			}
-			if(!core) continue;
-			{
+			if(empty || row == 0) { btcells[2 * ncells] = row; btcells[2 * ncells + 1] = col; ncells++; trim_beg = row; break; }
+			if(branch) {
+				bt_frame *fr = &stack[nstack++];
+				fr->nedsz = nned; fr->celsz = ncells; fr->row = row; fr->col = col; fr->gaps = gaps; fr->score = score; fr->ns = ns; fr->ct = ct;
+			}
+			btcells[2 * ncells] = row; btcells[2 * ncells + 1] = col; ncells++;
+			int32_t *e4 = ned + 4 * nned;
+			if(cur == 1) {
 				int rdc = rd[row], rfc = rf[col];
-				int32_t *e4 = ned + 4 * nned;
 				if(rdc > 3 || rfc > 3 || rdc != rfc) {
 					e4[0] = row; e4[1] = dna[rfc]; e4[2] = dna[rdc]; e4[3] = 3; nned++;
 					score -= (rdc > 3 || rfc > 3) ? sc->n_pen : mm_pen(sc, (int)qu[row] - 33);
 				} else score += sc->match_bonus;
 				if(rdc > 3 || rfc > 3) ns++;
+				row--; col--; ct = 0;
+			} else if(cur == 2 || cur == 3) {
+				e4[0] = row; e4[1] = '-'; e4[2] = dna[rd[row]]; e4[3] = 2; nned++;
+				score -= cur == 2 ? rfo : rfe; gaps++; row--; ct = cur == 2 ? 0 : 2;
+			} else {
+				e4[0] = row + 1; e4[1] = dna[rf[col]]; e4[2] = '-'; e4[3] = 1; nned++;
+				score -= cur == 4 ? rdo : rde; gaps++; col--; ct = cur == 4 ? 0 : 1;
 			}
-			if(ns > nceil) continue;
-			if(naln < max_alns) {
-				int64_t *o = alns + 8 * naln;
-				o[0] = score; o[1] = ns; o[2] = gaps; o[3] = refl + col; o[4] = 0; o[5] = 0; o[6] = nned; o[7] = fw ? 1 : 0;
-				(void)trim_beg; (void)orig_col;
-				/* SwResult::reverse, then AlnRes::invertEdits for reverse-complement alignments (edit.cpp:50-78) */
-				for(int k = 0; k < nned; k++) {
-					const int32_t *src = fw ? ned + 4 * (nned - 1 - k) : ned + 4 * k;
-					if(ned_total < max_edits) {
-						int32_t *dst = edits + 4 * ned_total;
-						dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-						if(!fw) dst[0] = nrow - src[0] - (src[3] == 1 ? 0 : 1);
-					}
-					ned_total++;
-				}
-			}
-			naln++;
 		}
-		summary[3] = naln;
-		free(ned); free(btcells); free(stack);
+		if(!ok) continue;
+		int core = 0;
+		for(int k = 0; k < ncells; k++) {
+			int d = btcells[2 * k + 1] - btcells[2 * k] + triml;
+			if(d >= corel && d <= corer) { core = 1; break; }
+		}
+		if(!core) continue;
+		{
+			int rdc = rd[row], rfc = rf[col];
+			int32_t *e4 = ned + 4 * nned;
+			if(rdc > 3 || rfc > 3 || rdc != rfc) {
+				e4[0] = row; e4[1] = dna[rfc]; e4[2] = dna[rdc]; e4[3] = 3; nned++;
+				score -= (rdc > 3 || rfc > 3) ? sc->n_pen : mm_pen(sc, (int)qu[row] - 33);
+			} else score += sc->match_bonus;
+			if(rdc > 3 || rfc > 3) ns++;
+		}
+		if(ns > nceil) continue;
+		if(naln < max_alns) {
+			const int trim_end = nrow - 1 - start_row;
+			const int ext = nrow - trim_beg - trim_end;
+			int64_t *o = alns + 8 * naln;
+			o[0] = score; o[1] = ns; o[2] = gaps; o[3] = refl + col;
+			o[4] = fw ? trim_beg : trim_end; o[5] = fw ? trim_end : trim_beg; o[6] = nned; o[7] = fw ? 1 : 0;
+			/* SwResult::reverse; AlnRes::setShape shifts positions by the upstream trim (aligner_result.cpp:101-109);
+			 * AlnRes::invertEdits for reverse-complement alignments (edit.cpp:50-78) */
+			for(int k = 0; k < nned; k++) {
+				const int32_t *src = fw ? ned + 4 * (nned - 1 - k) : ned + 4 * k;
+				if(ned_total < max_edits) {
+					int32_t *dst = edits + 4 * ned_total;
+					dst[0] = src[0] - trim_beg; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+					if(!fw) dst[0] = ext - dst[0] - (src[3] == 1 ? 0 : 1);
+				}
+				ned_total++;
+			}
+		}
+		naln++;
 	}
-	free(ccol);
+	summary[3] = naln;
+	free(ned); free(btcells); free(stack); free(donerow); free(donecol);
+	free(crow); free(ccol);
+	}
 done:
 	free(rd); free(qu); free(rf); free(H); free(E); free(F); free(mask);
 	return 0;
 #undef AT
+#undef MAX2
 }
