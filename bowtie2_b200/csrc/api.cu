@@ -17,6 +17,7 @@ template <typename OFF> void launch_exact_sweep2(const DevIndex<OFF> &, const ui
 void launch_pack_reads(const uint8_t *, const uint64_t *, uint64_t, int, uint64_t *, uint32_t *, cudaStream_t);
 template <typename OFF> void launch_resolve(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t, unsigned long long * = nullptr);
 template <typename OFF> void launch_resolve2(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, const uint32_t *, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+template <typename OFF> void launch_one_mm(const DevIndex<OFF> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t);
 template <typename OFF> void launch_get_stretch(const DevIndex<OFF> &, const uint64_t *, const int64_t *, const int32_t *, uint64_t, int, uint8_t *, cudaStream_t);
 template <typename OFF> void launch_extend(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint64_t *, uint8_t *, cudaStream_t);
 
@@ -381,6 +382,31 @@ int bt2g_seed_search(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_seed_pla
 	return 0;
 }
 
+int bt2g_one_mm(bt2g_ctx *ctx, const bt2g_reads *reads, const int32_t *minsc, const uint8_t *strandMask, int32_t maxHits,
+                bt2g_mm_hit *hits, int32_t *counts) {
+	REQUIRE_LOADED(ctx);
+	if(!reads || !reads->qual || !minsc || !strandMask || !hits || !counts || maxHits < 1) return -1;
+	if(!ctx->info.has_bw) { ctx->err = "mirror index not loaded"; return -1; }
+	if(ctx->scoring.gapbar < 1) bt2g_scoring_default(&ctx->scoring, 0);
+	uint64_t n = reads->n_reads;
+	if(n == 0) return 0;
+	DBuf dseq, dqual, doff, dms, dmask, dhits, dcnt;
+	int rc = uploadReads(ctx, reads, dseq, dqual, doff, true);
+	if(rc) return rc;
+	BT2G_CUDA_TRY(ctx, dms.alloc(n * 4)); BT2G_CUDA_TRY(ctx, dmask.alloc(n));
+	BT2G_CUDA_TRY(ctx, dhits.alloc(n * 4 * (uint64_t)maxHits * sizeof(bt2g_mm_hit))); BT2G_CUDA_TRY(ctx, dcnt.alloc(n * 16));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(dms.p, minsc, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(dmask.p, strandMask, n, cudaMemcpyHostToDevice, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(dhits.p, 0, dhits.bytes, ctx->stream));
+	DISPATCH(ctx, launch_one_mm<uint32_t>(bt2g_dev_index<uint32_t>(ctx), dseq.as<uint8_t>(), dqual.as<uint8_t>(), doff.as<uint64_t>(), n, dms.as<int32_t>(), dmask.as<uint8_t>(), ctx->scoring, maxHits, dhits.as<bt2g_mm_hit>(), dcnt.as<int32_t>(), ctx->stream),
+	              launch_one_mm<uint64_t>(bt2g_dev_index<uint64_t>(ctx), dseq.as<uint8_t>(), dqual.as<uint8_t>(), doff.as<uint64_t>(), n, dms.as<int32_t>(), dmask.as<uint8_t>(), ctx->scoring, maxHits, dhits.as<bt2g_mm_hit>(), dcnt.as<int32_t>(), ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaGetLastError());
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(hits, dhits.p, dhits.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(counts, dcnt.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
 int bt2g_extend_exact(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_seed_plan *plan, const uint64_t *ranges, uint8_t *out) {
 	REQUIRE_LOADED(ctx);
 	if(!reads || !plan || !ranges || !out || plan->max_seeds <= 0 || plan->seed_len <= 0) return -1;
@@ -474,6 +500,7 @@ void bt2g_scoring_default(bt2g_scoring *sc, int local) {
 		sc->mmpen[q] = (uint8_t)(2 + (int)(frac * (6 - 2)));
 		sc->npen[q] = 1;
 	}
+	sc->nceil_const = 0.0; sc->nceil_linear = (double)0.15f;
 }
 
 int bt2g_set_scoring(bt2g_ctx *ctx, const bt2g_scoring *sc) {

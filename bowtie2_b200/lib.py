@@ -252,7 +252,8 @@ class Bt2Gpu:
 class _Scoring(C.Structure):
     _fields_ = [("match_bonus", C.c_int32), ("rdgap_const", C.c_int32), ("rdgap_linear", C.c_int32),
                 ("rfgap_const", C.c_int32), ("rfgap_linear", C.c_int32), ("gapbar", C.c_int32),
-                ("local", C.c_int32), ("mmpen", C.c_uint8 * 64), ("npen", C.c_uint8 * 64)]
+                ("local", C.c_int32), ("mmpen", C.c_uint8 * 64), ("npen", C.c_uint8 * 64),
+                ("nceil_const", C.c_double), ("nceil_linear", C.c_double)]
 
 
 DP_PROBLEM = np.dtype([("read_idx", "<u4"), ("fw", "<u4"), ("tidx", "<u8"), ("refl", "<i8"), ("refr", "<i8"),
@@ -482,3 +483,24 @@ def _extend_exact(self, reads: ReadBatch, seed_len: int, interval, offset, max_s
 
 
 Bt2Gpu.extend_exact = _extend_exact
+
+
+# ---- SeedAligner::oneMmSearch ------------------------------------------------------------------
+EXPORTS += ["bt2g_one_mm"]
+MM_HIT = np.dtype([("top", "<u8"), ("bot", "<u8"), ("pos", "<i4"), ("chr", "<i4"), ("qchr", "<i4"), ("score", "<i4")])
+
+
+def _one_mm(self, reads: ReadBatch, minsc, strand_mask=3, max_hits: int = 16):
+    """1-mismatch end-to-end hits (include/bt2g.h: bt2g_one_mm) -> (hits [n,4,max_hits], counts [n,4])."""
+    lib = self._lib
+    lib.bt2g_one_mm.argtypes = [C.c_void_p, C.POINTER(_Reads), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    minsc = _c(np.broadcast_to(minsc, (reads.n,)), np.int32)
+    mask = _c(np.broadcast_to(strand_mask, (reads.n,)), np.uint8)
+    hits = np.zeros((reads.n, 4, max_hits), dtype=MM_HIT)
+    counts = np.zeros((reads.n, 4), dtype=np.int32)
+    st = reads._struct()
+    self._check(lib.bt2g_one_mm(self._h, C.byref(st), _ptr(minsc), _ptr(mask), max_hits, _ptr(hits), _ptr(counts)), "bt2g_one_mm")
+    return hits, counts
+
+
+Bt2Gpu.one_mm = _one_mm

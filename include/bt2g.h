@@ -137,6 +137,22 @@ typedef struct {
 int bt2g_seed_search(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_seed_plan *plan,
                      uint64_t *out, int32_t *nseeds);
 
+/* SeedAligner::oneMmSearch (aligner_seed.cpp:975-1325) as called from bt2_search.cpp:3709
+ * (repex = false, rep1mm = true; scoring / local flag from bt2g_set_scoring): end-to-end hits
+ * with exactly one mismatch.  strand_mask[i] bit0 = search the read (yfw), bit1 = search its
+ * reverse complement (yrc) (bt2_search.cpp:3704-3706).  Task order per read = the reference's
+ * loop order: (fw, forward index), (fw, mirror index), (rc, forward), (rc, mirror); within a task
+ * hits appear by increasing depth then substituted nucleotide, i.e. the order of
+ * SeedResults::add1mmEe calls.  counts[4*i+task] hits are stored at hits[(4*i+task)*max_hits ..]. */
+typedef struct {
+	uint64_t top, bot;           /* BW range in the FORWARD index */
+	int32_t  pos;                /* mismatch offset from the 5' end of the read (Edit::pos) */
+	int32_t  chr, qchr;          /* reference / read nucleotide codes (Edit::chr, qchr) */
+	int32_t  score;
+} bt2g_mm_hit;
+int bt2g_one_mm(bt2g_ctx *ctx, const bt2g_reads *reads, const int32_t *minsc, const uint8_t *strand_mask,
+                int32_t max_hits, bt2g_mm_hit *hits, int32_t *counts);
+
 /* SwDriver::extend (aligner_sw_driver.cpp:299-484): for every seed hit of bt2g_seed_search
  * (same plan, `ranges` = its output) the number of read positions the hit extends without an
  * edit to the left (forward index) and to the right (mirror index), each capped at 255.
@@ -173,6 +189,7 @@ typedef struct {
 	int32_t local;               /* 0 end-to-end (sc.monotone), 1 local */
 	uint8_t mmpen[64];
 	uint8_t npen[64];
+	double  nceil_const, nceil_linear;   /* N ceiling function L,const,linear (scoring.h:58-62; (double)0.15f) */
 } bt2g_scoring;
 void bt2g_scoring_default(bt2g_scoring *sc, int local);
 int  bt2g_set_scoring(bt2g_ctx *ctx, const bt2g_scoring *sc);

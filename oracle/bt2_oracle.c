@@ -534,6 +534,123 @@ int bt2o_seed_search(const bt2o_index *ix, const uint8_t *codes, const uint8_t *
 	return nseeds;
 }
 
+static int mm_pen(const bt2o_scoring *sc, int q);
+
+/* SeedAligner::oneMmSearch (aligner_seed.cpp:975-1325) with repex = false, rep1mm = true.
+ * Hits are appended in the reference's loop order.  out: 6 x int64 per hit (top, bot, pos, chr,
+ * qchr as ASCII, score); out_fw per hit. */
+static void bi_step_o(const bt2o_index *ix, int mirror, uint64_t top, uint64_t bot, uint64_t topp,
+                      uint64_t t[4], uint64_t b[4], uint64_t tp[4], uint64_t bp[4]) {
+	bt2o_rank4(ix, mirror, top, t);
+	bt2o_rank4(ix, mirror, bot, b);
+	uint64_t acc = topp;
+	for(int j = 0; j < 4; j++) { tp[j] = acc; acc += b[j] - t[j]; bp[j] = acc; }
+}
+
+int bt2o_one_mm(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, const uint8_t *quals, int len,
+                int64_t minsc, int nofw, int norc, int max_hits, int64_t *out, int *out_fw) {
+	static const char dna[] = "ACGTN";
+	int nh = 0, ns = 0;
+	for(int i = 0; i < len; i++) ns += codes[i] > 3;
+	if(ns > 1 || len < 2 || !ix->has_bw) return 0;
+	const int nceil = (int)(0.0 + (double)0.15f * (double)len);
+	uint8_t *pat[2][2];                          /* [fw?0:1][ebwtfw?0:1] = patFw, patFwRev, patRc, patRcRev */
+	uint8_t *qu[2];                              /* qual, qualRev */
+	for(int a = 0; a < 2; a++) for(int b = 0; b < 2; b++) pat[a][b] = (uint8_t *)malloc((size_t)len);
+	qu[0] = (uint8_t *)malloc((size_t)len); qu[1] = (uint8_t *)malloc((size_t)len);
+	for(int i = 0; i < len; i++) {
+		int c = codes[i], rc = codes[len - 1 - i]; rc = rc > 3 ? 4 : 3 - rc;
+		pat[0][0][i] = (uint8_t)c; pat[0][1][len - 1 - i] = (uint8_t)c;
+		pat[1][0][i] = (uint8_t)rc; pat[1][1][len - 1 - i] = (uint8_t)rc;
+		qu[0][i] = quals[i]; qu[1][len - 1 - i] = quals[i];
+	}
+	const int ftab_len = ix->fw.ftab_chars;
+	for(int fwi = 0; fwi < 2; fwi++) {
+		const int fw = fwi == 0;
+		if((fw && nofw) || (!fw && norc)) continue;
+		for(int pass = 0; pass < 2; pass++) {
+			const int ebwtfw = pass == 0, mir = ebwtfw ? 0 : 1;
+			const bt2o_ebwt *e = mir ? &ix->bw : &ix->fw, *ep = mir ? &ix->fw : &ix->bw;
+			const uint8_t *seq = pat[fw ? 0 : 1][ebwtfw ? 0 : 1];
+			const uint8_t *qual = fw ? (ebwtfw ? qu[0] : qu[1]) : (ebwtfw ? qu[1] : qu[0]);
+			const int nea = ebwtfw ? (len >> 1) : ((len >> 1) + (len & 1));
+			int skip = 0;
+			for(int dep = 0; dep < nea; dep++) if(seq[len - dep - 1] > 3) { skip = 1; break; }
+			if(skip) continue;
+			uint64_t top, bot, topp, botp, t[4], b[4], tp[4], bp[4];
+			int dep;
+			if(ftab_len > 1 && ftab_len <= nea) {
+				uint64_t fi = ftab_seq_to_int(seq, len - ftab_len, ftab_len, 1), fip = ftab_seq_to_int(seq, len - ftab_len, ftab_len, 0);
+				top = ftab_hi(e, fi); bot = ftab_lo(e, fi + 1);
+				topp = ftab_hi(ep, fip); botp = ftab_lo(ep, fip + 1);
+				if(bot <= top) continue;
+				dep = ftab_len;
+			} else {
+				int c = seq[len - 1];
+				top = topp = e->fchr[c]; bot = botp = e->fchr[c + 1];
+				if(bot <= top) continue;
+				dep = 1;
+			}
+			int dead = 0;
+			for(; dep < nea; dep++) {
+				int rdc = seq[len - dep - 1];
+				bi_step_o(ix, mir, top, bot, topp, t, b, tp, bp);
+				if(b[rdc] <= t[rdc]) { dead = 1; break; }
+				topp = tp[rdc]; botp = bp[rdc]; top = t[rdc]; bot = b[rdc];
+			}
+			if(dead) continue;
+			for(; dep < len; dep++) {
+				int rdc = seq[len - dep - 1], quc = qual[len - dep - 1];
+				if(rdc > 3 && nceil == 0) break;
+				if(bot - top == 1 && top == e->z_off) break;
+				bi_step_o(ix, mir, top, bot, topp, t, b, tp, bp);
+				if(ns == 0 || rdc > 3) {
+					for(int j = 0; j < 4; j++) {
+						if(j == rdc || b[j] == t[j]) continue;
+						uint64_t topm = t[j], botm = b[j], topmp = tp[j], botmp = bp[j];
+						int depm = dep + 1;
+						for(; depm < len; depm++) {
+							int rdcm = seq[len - depm - 1];
+							if(rdcm > 3) break;
+							uint64_t tm[4], bm[4], tmp[4], bmp[4];
+							bi_step_o(ix, mir, topm, botm, topmp, tm, bm, tmp, bmp);
+							if(bm[rdcm] <= tm[rdcm]) break;
+							topmp = tmp[rdcm]; botmp = bmp[rdcm]; topm = tm[rdcm]; botm = bm[rdcm];
+						}
+						if(depm != len) continue;
+						int off5p = dep;
+						if(fw == ebwtfw) off5p = len - off5p - 1;
+						int pen = rdc > 3 ? -sc->n_pen : -mm_pen(sc, quc - 33);
+						int64_t score = (int64_t)(len - 1) * sc->match_bonus + pen;
+						int valid = 1;
+						if(sc->local) {
+							int64_t lf = 0, lb = 0;
+							for(int i = 0; i < len && valid; i++) {
+								if(i == dep) { if(lf + pen <= 0) valid = 0; lf += pen; } else lf += sc->match_bonus;
+								if(len - i - 1 == dep) { if(lb + pen <= 0) valid = 0; lb += pen; } else lb += sc->match_bonus;
+							}
+						}
+						if(valid && score >= minsc) {
+							if(nh < max_hits) {
+								int64_t *o = out + 6 * nh;
+								o[0] = ebwtfw ? topm : topmp; o[1] = ebwtfw ? botm : botmp; o[2] = off5p;
+								o[3] = dna[j]; o[4] = dna[rdc]; o[5] = score;
+								out_fw[nh] = fw;
+							}
+							nh++;
+						}
+					}
+				}
+				if(rdc > 3 || b[rdc] <= t[rdc] || dep == len - 1) break;
+				topp = tp[rdc]; botp = bp[rdc]; top = t[rdc]; bot = b[rdc];
+			}
+		}
+	}
+	for(int a = 0; a < 2; a++) for(int b2 = 0; b2 < 2; b2++) free(pat[a][b2]);
+	free(qu[0]); free(qu[1]);
+	return nh;
+}
+
 /* SwDriver::extend (aligner_sw_driver.cpp:299-484): extend a seed hit to the left with the
  * forward index and to the right with the mirror index while the BW range keeps its size and
  * the (single) extending character equals the read character; at most 255 each way.

@@ -271,6 +271,33 @@ int ref_seed_search(void* vh, const uint8_t* codes, const uint8_t* quals, int le
 	return nseeds;
 }
 
+// SeedAligner::oneMmSearch (aligner_seed.cpp:975-1325) as called at bt2_search.cpp:3709.
+// out: per hit 6 x int64: top, bot, pos, chr, qchr, score (in the order the reference stored
+// them in SeedResults::mm1Hit_), plus fw flag in out_fw.  returns the number of hits.
+int ref_one_mm(void* vh, int local, const uint8_t* codes, const uint8_t* quals, int len, int64_t minsc,
+               int nofw, int norc, int max_hits, int64_t* out, int* out_fw) {
+	RefHandle* h = (RefHandle*)vh;
+	const Scoring& sc = local ? *h->sc_loc : *h->sc_e2e;
+	Read rd; fillRead(rd, codes, quals, len, "r");
+	SeedAligner al;
+	SeedResults shs;
+	SeedSearchMetrics sdm;
+	shs.clear();
+	shs.nextRead(rd);
+	al.oneMmSearch(h->fw.get(), h->bw.get(), rd, sc, minsc, nofw != 0, norc != 0, local != 0, false, true, shs, sdm);
+	const EList<EEHit>& hs = shs.mm1EEHits();
+	int n = 0;
+	for(size_t i = 0; i < hs.size(); i++) {
+		if(n < max_hits) {
+			int64_t* o = out + 6 * n;
+			o[0] = hs[i].top; o[1] = hs[i].bot; o[2] = hs[i].e1.pos; o[3] = hs[i].e1.chr; o[4] = hs[i].e1.qchr; o[5] = hs[i].score;
+			out_fw[n] = hs[i].fw ? 1 : 0;
+		}
+		n++;
+	}
+	return n;
+}
+
 // whole program entry, for completeness (bt2_search.cpp:5230)
 int ref_bowtie_main(int argc, const char** argv) { return bowtie(argc, argv); }
 

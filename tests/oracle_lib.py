@@ -177,6 +177,13 @@ class _OScoring(C.Structure):
                                        "rfgap_const", "rfgap_linear", "gapbar", "local")]
 
 
+def oracle_scoring(O, local):
+    O.lib.bt2o_scoring_default.argtypes = [C.POINTER(_OScoring), ci]
+    sc = _OScoring()
+    O.lib.bt2o_scoring_default(C.byref(sc), int(local))
+    return sc
+
+
 def oracle_dp(O, local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=1024, max_alns=32, max_edits=4096):
     """Same outputs as ref_dp(), from the plain-C restatement (oracle/bt2_oracle.c: bt2o_dp)."""
     i64 = C.c_int64
@@ -218,3 +225,28 @@ def extend_both(X, codes, fw, off, seedlen, rng4):
     f.restype = None
     f(X.h, codes.ctypes.data_as(vp), len(codes), int(fw), int(off), int(seedlen), int(rng4[0]), int(rng4[1]), int(rng4[2]), int(rng4[3]), out)
     return int(out[0]), int(out[1])
+
+
+# ---- SeedAligner::oneMmSearch (oracle/ref_glue.cpp: ref_one_mm, oracle/bt2_oracle.c: bt2o_one_mm) ----
+def _one_mm_call(fn, first, codes, quals, minsc, nofw, norc, max_hits):
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    if quals is None:
+        quals = np.full(len(codes), ord("I"), dtype=np.uint8)
+    quals = np.ascontiguousarray(quals, dtype=np.uint8)
+    out = np.zeros((max_hits, 6), dtype=np.int64)
+    fws = np.zeros(max_hits, dtype=np.int32)
+    fn.restype = ci
+    n = fn(*first, codes.ctypes.data_as(vp), quals.ctypes.data_as(vp), ci(len(codes)), C.c_int64(int(minsc)),
+           ci(int(nofw)), ci(int(norc)), ci(max_hits), out.ctypes.data_as(vp), fws.ctypes.data_as(vp))
+    assert n <= max_hits
+    return [tuple(int(x) for x in out[i]) + (int(fws[i]),) for i in range(n)]
+
+
+def ref_one_mm(R, local, codes, quals, minsc, nofw=False, norc=False, max_hits=256):
+    """-> list of (top, bot, pos, chr, qchr, score, fw) in SeedResults::mm1EEHits() order."""
+    return _one_mm_call(R.lib.ref_one_mm, (vp(R.h), ci(int(local))), codes, quals, minsc, nofw, norc, max_hits)
+
+
+def oracle_one_mm(O, local, codes, quals, minsc, nofw=False, norc=False, max_hits=256):
+    sc = oracle_scoring(O, local)
+    return _one_mm_call(O.lib.bt2o_one_mm, (vp(O.h), C.byref(sc)), codes, quals, minsc, nofw, norc, max_hits)
