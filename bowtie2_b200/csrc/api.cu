@@ -21,6 +21,8 @@ template <typename OFF> void launch_one_mm(const DevIndex<OFF> &, const uint8_t 
 template <typename OFF> void launch_get_stretch(const DevIndex<OFF> &, const uint64_t *, const int64_t *, const int32_t *, uint64_t, int, uint8_t *, cudaStream_t);
 template <typename OFF> void launch_extend(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint64_t *, uint8_t *, cudaStream_t);
 
+void launch_frame_mate(const bt2g_pe_policy &, const bt2g_mate_anchor *, uint64_t, bt2g_mate_frame *, cudaStream_t);
+void launch_pe_classify(const bt2g_pe_policy &, const int64_t *, uint64_t, int32_t *, cudaStream_t);
 namespace {
 
 // RAII device buffer for the host-pointer wrappers
@@ -403,6 +405,36 @@ int bt2g_one_mm(bt2g_ctx *ctx, const bt2g_reads *reads, const int32_t *minsc, co
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(hits, dhits.p, dhits.bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(counts, dcnt.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int bt2g_frame_mate(bt2g_ctx *ctx, const bt2g_pe_policy *pol, const bt2g_mate_anchor *anchors, uint64_t n, bt2g_mate_frame *out) {
+	if(!ctx) return -1;
+	if(!pol || !anchors || !out || pol->pol < 1 || pol->pol > 4) { ctx->err = "bt2g_frame_mate: bad argument"; return -1; }
+	if(n == 0) return 0;
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	DBuf da, dout;
+	BT2G_CUDA_TRY(ctx, da.alloc(n * sizeof(bt2g_mate_anchor))); BT2G_CUDA_TRY(ctx, dout.alloc(n * sizeof(bt2g_mate_frame)));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(da.p, anchors, da.bytes, cudaMemcpyHostToDevice, ctx->stream));
+	launch_frame_mate(*pol, da.as<bt2g_mate_anchor>(), n, dout.as<bt2g_mate_frame>(), ctx->stream);
+	BT2G_CUDA_TRY(ctx, cudaGetLastError());
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, dout.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int bt2g_pe_classify(bt2g_ctx *ctx, const bt2g_pe_policy *pol, const int64_t *pairs, uint64_t n, int32_t *out) {
+	if(!ctx) return -1;
+	if(!pol || !pairs || !out || pol->pol < 1 || pol->pol > 4) { ctx->err = "bt2g_pe_classify: bad argument"; return -1; }
+	if(n == 0) return 0;
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	DBuf dp, dout;
+	BT2G_CUDA_TRY(ctx, dp.alloc(n * 48)); BT2G_CUDA_TRY(ctx, dout.alloc(n * 4));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(dp.p, pairs, n * 48, cudaMemcpyHostToDevice, ctx->stream));
+	launch_pe_classify(*pol, dp.as<int64_t>(), n, dout.as<int32_t>(), ctx->stream);
+	BT2G_CUDA_TRY(ctx, cudaGetLastError());
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	return 0;
 }

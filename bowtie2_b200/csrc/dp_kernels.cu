@@ -31,6 +31,10 @@
 #include "dp_device.cuh"
 
 #define DP_NEG (-(1 << 28))
+#define DP_BIG (1 << 20)
+
+// per-warp shared memory: maxCol ints (last-row scores), maxCol u16 (candidate columns), the reference window
+__host__ __device__ __forceinline__ size_t dp_smem_per_warp(int maxCol) { return ((size_t)maxCol * 7 + 16 + 15) & ~(size_t)15; }
 
 __device__ __forceinline__ int dp_max(int a, int b) { return a > b ? a : b; }
 
@@ -67,97 +71,104 @@ __device__ __forceinline__ void dp_backtrace_all(const DpLaunch &L, const bt2g_s
 			}
 			if(__any_sync(0xffffffffu, dom)) { if(lane == 0) cands[ci].fate = BT2G_CAND_FILT_DOMINATED; __syncwarp(); continue; }
 		}
-		// backtraceNucleotidesEnd2EndSseU8 (aligner_swsse_ee_u8.cpp:1283-1877); all lanes run the
-		// same scalar walk, lane k additionally owns cell k of the current diagonal prefetch
+		// backtraceNucleotidesEnd2EndSseU8 (aligner_swsse_ee_u8.cpp:1283-1877).  Lane k holds cell k of the
+		// current diagonal (row-k, col-k).  In the H state the walk follows the diagonal as long as the
+		// cells say "diagonal move" and are not yet reported through, so the length of that run is one
+		// ballot, and the run's cells are processed by their own lanes in parallel (edit op, N count,
+		// reported-through mark); only the cell that ends a run (gap move, row 0, visited cell, soft trim)
+		// is handled by uniform scalar code.  The alignment score is the candidate cell's score: the
+		// walk follows exact equalities of the recurrences (the reference asserts the same, :1842-1846).
 		uint8_t *o = ops + (size_t)naln * L.maxOps;
 		const bool room = naln < L.maxAlns;
-		int nops = 0, score = 0, ns = 0, gaps = 0, ct = 0;   // ct: 0 H, 1 E, 2 F
-		bool fail = false, core = false, opOverflow = false, done = false, first = true, filtStart = false;
+		int nops = 0, ns = 0, gaps = 0, ct = 0;              // ct: 0 H, 1 E, 2 F
+		bool fail = false, core = false, done = false, first = true, filtStart = false;
 		const int origCol = col;
 		int trimBeg = 0;
+		auto rdchar = [&](int rr) -> int { const int pos = p.fw ? rr : rdlen - 1 - rr; int c = rs[pos]; return p.fw ? c : (c > 3 ? 4 : 3 - c); };
 		while(!done && !fail) {
-			// prefetch the diagonal (row-k, col-k), k = lane
 			const int rk = row - lane, ck = col - lane;
 			uint8_t *cp = (rk >= 0 && ck >= 0) ? cell(rk, ck) : nullptr;
 			const uint8_t mine = cp ? *cp : 0xff;
-			uint32_t consumed = 0;
-			for(int k = 0; k < 32; k++) {
-				const uint8_t code = (uint8_t)__shfl_sync(0xffffffffu, (int)mine, k);
-				if(code & 0x80) {
-					// start cell already reported through -> BT_CAND_FATE_FILT_START (:771-789);
-					// anywhere else the backtrace fails
-					if(first) filtStart = true;
-					fail = true; break;
-				}
-				first = false;
-				consumed |= 1u << k;
-				{
-					int diagi = col - row + p.triml;
+			int stop = 0;                                     // lane holding the cell that ends this round
+			if(ct == 0) {
+				const bool cont = !(mine & 0x80) && ((mine & 7) == 1) && rk > 0;
+				const uint32_t m = __ballot_sync(0xffffffffu, cont);
+				const int run = (m == 0xffffffffu) ? 32 : __ffs(~m) - 1;
+				if(run > 0) {
+					first = false;
+					const int diagi = col - row + p.triml;
 					if(diagi >= p.corel && diagi <= p.corer) core = true;
+					bool isN = false;
+					if(lane < run) {
+						const int c = rdchar(rk), refc = refw[ck];
+						isN = c > 3 || refc > 3;
+						const uint8_t op = (uint8_t)(((!isN && c == refc) ? BT2G_OP_MATCH : BT2G_OP_MM) | (refc << 2));
+						if(room && nops + lane < L.maxOps) o[nops + lane] = op;
+						*cp = mine | 0x80;                        // setReportedThrough (:1555)
+					}
+					ns += __popc(__ballot_sync(0xffffffffu, isN));
+					nops += run; row -= run; col -= run;
 				}
-				if(row == 0) { done = true; break; }
-				int mv;   // 1 diag, 2 refopen, 3 rfext, 4 rdopen, 5 rdext
-				if(ct == 0) { mv = code & 7; if(mv == 0) { trimBeg = row; done = true; break; } }
-				else if(ct == 1) { int e = (code >> 3) & 3; if(e == 0) { fail = true; break; } mv = e == 1 ? 4 : 5; }
-				else { int f = (code >> 5) & 3; if(f == 0) { fail = true; break; } mv = f == 1 ? 2 : 3; }
-				const int pos = p.fw ? row : rdlen - 1 - row;
-				int c = rs[pos]; c = p.fw ? c : (c > 3 ? 4 : 3 - c);
-				int q = (int)rq[pos] - 33; q = q < 0 ? 0 : (q > 63 ? 63 : q);
-				const int refc = refw[col];
-				uint8_t op;
-				bool stay = false;
-				if(mv == 1) {
-					if(c > 3 || refc > 3) { score -= sc.npen[q]; ns++; op = BT2G_OP_MM; }
-					else if(c == refc) { score += sc.match_bonus; op = BT2G_OP_MATCH; }
-					else { score -= sc.mmpen[q]; op = BT2G_OP_MM; }
-					op |= (uint8_t)(refc << 2);
-					row--; col--; ct = 0; stay = true;
-				} else if(mv == 2 || mv == 3) {
-					score -= (mv == 2) ? rfgapo : rfgape; gaps++;
-					op = BT2G_OP_REFGAP;
-					row--; ct = (mv == 2) ? 0 : 2;
-				} else {
-					score -= (mv == 4) ? rdgapo : rdgape; gaps++;
-					op = BT2G_OP_READGAP | (uint8_t)(refc << 2);
-					col--; ct = (mv == 4) ? 0 : 1;
-				}
-				if(room && lane == 0) { if(nops < L.maxOps) o[nops] = op; }
-				if(nops >= L.maxOps) opOverflow = true;
-				nops++;
-				if(!stay) break;            // left the prefetched diagonal
+				if(run == 32) { __syncwarp(); continue; }
+				stop = run;
 			}
-			if(cp && ((consumed >> lane) & 1u)) *cp = mine | 0x80;     // setReportedThrough (:1555)
+			// the cell at (row, col), held by lane `stop`
+			const uint8_t code = (uint8_t)__shfl_sync(0xffffffffu, (int)mine, stop);
+			if(code & 0x80) {
+				// start cell already reported through -> BT_CAND_FATE_FILT_START (:771-789);
+				// anywhere else the backtrace fails
+				if(first) filtStart = true;
+				fail = true; break;
+			}
+			first = false;
+			if(lane == stop) *cp = mine | 0x80;
+			{
+				const int diagi = col - row + p.triml;
+				if(diagi >= p.corel && diagi <= p.corer) core = true;
+			}
+			if(row == 0) { done = true; break; }
+			int mv;   // 2 refopen, 3 rfext, 4 rdopen, 5 rdext (a diagonal move never ends a run above row 0)
+			if(ct == 0) { mv = code & 7; if(mv == 0) { trimBeg = row; done = true; break; } }
+			else if(ct == 1) { int e = (code >> 3) & 3; if(e == 0) { fail = true; break; } mv = e == 1 ? 4 : 5; }
+			else { int f = (code >> 5) & 3; if(f == 0) { fail = true; break; } mv = f == 1 ? 2 : 3; }
+			uint8_t op;
+			gaps++;
+			if(mv == 2 || mv == 3) {
+				op = BT2G_OP_REFGAP;
+				row--; ct = (mv == 2) ? 0 : 2;
+			} else {
+				op = (uint8_t)(BT2G_OP_READGAP | (refw[col] << 2));
+				col--; ct = (mv == 4) ? 0 : 1;
+			}
+			if(room && lane == 0 && nops < L.maxOps) o[nops] = op;
+			nops++;
 			__syncwarp();
 		}
 		if(filtStart) { if(lane == 0) cands[ci].fate = BT2G_CAND_FILT_START; continue; }
 		if(!fail) {
 			// the alignment's first cell (row, col) (:1797-1813)
-			const int pos = p.fw ? row : rdlen - 1 - row;
-			int c = rs[pos]; c = p.fw ? c : (c > 3 ? 4 : 3 - c);
-			int q = (int)rq[pos] - 33; q = q < 0 ? 0 : (q > 63 ? 63 : q);
-			const int refc = refw[col];
-			uint8_t op;
-			if(c > 3 || refc > 3) { score -= sc.npen[q]; ns++; op = BT2G_OP_MM; }
-			else if(c == refc) { score += sc.match_bonus; op = BT2G_OP_MATCH; }
-			else { score -= sc.mmpen[q]; op = BT2G_OP_MM; }
-			op |= (uint8_t)(refc << 2);
+			const int c = rdchar(row), refc = refw[col];
+			const bool isN = c > 3 || refc > 3;
+			ns += isN;
+			const uint8_t op = (uint8_t)(((!isN && c == refc) ? BT2G_OP_MATCH : BT2G_OP_MM) | (refc << 2));
 			if(!core) fail = true;                   // core-diagonal rejection (:1764-1795)
 			else if(ns > p.nceil) fail = true;       // N ceiling (:1813-1818)
 			else {
-				if(room && lane == 0) { if(nops < L.maxOps) o[nops] = op; }
-				if(nops >= L.maxOps) opOverflow = true;
+				if(room && lane == 0 && nops < L.maxOps) o[nops] = op;
 				nops++;
 			}
 		}
+		const bool opOverflow = nops > L.maxOps;
 		if(fail) { if(lane == 0) cands[ci].fate = BT2G_CAND_FAILED; continue; }
 		if(lane == 0) cands[ci].fate = BT2G_CAND_SUCCEEDED;
 		if(room) {
+			int refns = 0;
+			for(int k = col + lane; k <= origCol; k += 32) refns += refw[k] > 3;
+			refns = __reduce_add_sync(0xffffffffu, refns);
 			if(lane == 0) {
 				bt2g_dp_aln &a = alns[naln];
-				a.cand_idx = ci; a.score = score; a.ns = ns; a.gaps = gaps; a.col0 = col; a.row0 = row;
+				a.cand_idx = ci; a.score = cands[ci].score; a.ns = ns; a.gaps = gaps; a.col0 = col; a.row0 = row;
 				a.trim_beg = trimBeg; a.trim_end = rdlen - 1 - startRow; a.nops = nops;
-				int refns = 0;
-				for(int k = col; k <= origCol; k++) refns += refw[k] > 3;
 				a.refns = refns;
 			}
 			if(opOverflow) flags |= BT2G_DP_FLAG_OPS_OVERFLOW;
@@ -178,9 +189,10 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 	const uint64_t nSlots = (uint64_t)gridDim.x * (blockDim.x >> 5);
 	const uint64_t nProb = L.nDev ? (uint64_t)*L.nDev : L.n;
 	// per-warp shared memory: last-row scores (ints) then the reference window (bytes)
-	const size_t perWarp = ((size_t)L.maxCol * 5 + 16 + 15) & ~(size_t)15;
+	const size_t perWarp = dp_smem_per_warp(L.maxCol);
 	int32_t *lastH = reinterpret_cast<int32_t *>(smem + (size_t)warpInBlock * perWarp);
-	uint8_t *refw = reinterpret_cast<uint8_t *>(lastH + L.maxCol);
+	uint16_t *candCol = reinterpret_cast<uint16_t *>(lastH + L.maxCol);
+	uint8_t *refw = reinterpret_cast<uint8_t *>(candCol + L.maxCol);
 	// persistent warps: the move-byte workspace belongs to the warp SLOT, not to the problem, so
 	// it is (#SMs x resident warps) x codeStride bytes and stays L2-resident across problems
 	uint8_t *codes = L.codes + slot * L.codeStride;
@@ -203,26 +215,30 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 		for(int k = lane; k < ncol; k += 32) refw[k] = (uint8_t)ref_base<OFF>(ix, p.tidx, p.refl + k);
 		__syncwarp();
 
-		// per-row constants (buildQueryProfileEnd2EndSseU8, aligner_swsse_ee_u8.cpp:75-142)
-		int rc[R], mmp[R], npn[R];
-		bool bar[R];
+		// per-row constants (buildQueryProfileEnd2EndSseU8, aligner_swsse_ee_u8.cpp:75-142).  Penalties are
+		// kept negated; the gap barrier (:944-945,:966-969,:983-985) is folded into per-row gap-open/extend
+		// costs: in a barrier row they are DP_BIG, which puts E and F far below any minimum score.
+		int rc[R], mmpN[R], npnN[R], rfo[R], rfe[R], rdo[R];
 #pragma unroll
 		for(int r = 0; r < R; r++) {
 			int i = lane * R + r;
+			bool bar = true;
 			if(i < rdlen) {
 				int pos = p.fw ? i : rdlen - 1 - i;
 				int c = rs[pos];
 				rc[r] = p.fw ? c : (c > 3 ? 4 : 3 - c);
 				int q = (int)rq[pos] - 33;
 				q = q < 0 ? 0 : (q > 63 ? 63 : q);
-				npn[r] = sc.npen[q];
+				npnN[r] = -sc.npen[q];
 				// a read N never "equals" a reference base and is charged the N penalty (Scoring::score, scoring.h:241-251)
-				mmp[r] = rc[r] > 3 ? npn[r] : sc.mmpen[q];
+				mmpN[r] = rc[r] > 3 ? npnN[r] : -sc.mmpen[q];
 				if(rc[r] > 3) rc[r] = 5;
-				bar[r] = (i < sc.gapbar) || (rdlen - 1 - i < sc.gapbar);
-			} else { rc[r] = 5; mmp[r] = 0; npn[r] = 0; bar[r] = true; }
+				bar = (i < sc.gapbar) || (rdlen - 1 - i < sc.gapbar);
+			} else { rc[r] = 5; mmpN[r] = 0; npnN[r] = 0; }
+			rfo[r] = bar ? DP_BIG : rfgapo; rfe[r] = bar ? DP_BIG : rfgape; rdo[r] = bar ? DP_BIG : rdgapo;
 		}
 		const int lastLane = (rdlen - 1) / R, lastR = (rdlen - 1) % R;
+		const int bonus = sc.match_bonus;
 
 		// Branch-free move codes.  With E = max(E'-rdgape, H'-rdgapo) and F = max(F^-rfgape, H^-rfgapo),
 		// "which term is the max (open wins ties)" IS the E/F move, and the H move is
@@ -230,13 +246,18 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 		// -- the same choice the reference makes from its five equality tests in preference order
 		// (aligner_swsse_ee_u8.cpp:1468-1520): H==F with F==open implies H==H^-rfgapo (bit 0), H==F with
 		// F==extend only implies bit 2, and likewise for E (bits 1, 3).  Cells below the minimum score
-		// may get arbitrary codes; no backtrace visits them (scores are monotone along a path).
-		int Hleft[R], Earr[R], Esel[R];
+		// (all of E and F in barrier rows included) may get arbitrary codes; no backtrace visits them
+		// (scores are monotone along a path).  Byte = hsel | (esel << 3) | (fsel << 5) with esel, fsel in
+		// {1 open, 2 extend}; the state kept per row is ev = 3 + esel so that ev is also the H code of an
+		// E move, and fv = 1 + fsel is the H code of an F move; the constant (3 << 3) + (1 << 5) comes off
+		// once per packed word.
+		int Hleft[R], Earr[R], ev[R];
 #pragma unroll
-		for(int r = 0; r < R; r++) { Hleft[r] = DP_NEG; Earr[r] = DP_NEG; Esel[r] = 1; }
+		for(int r = 0; r < R; r++) { Hleft[r] = DP_NEG; Earr[r] = DP_NEG; ev[r] = 4; }
 		int botH = DP_NEG, botF = DP_NEG, prevInH = DP_NEG;
 		const int nsteps = ncol + lastLane;   // lanes beyond lastLane hold no rows
-		for(int t = 0; t < nsteps; t++) {
+		uint8_t *dst = codes + (size_t)lane * R;
+		for(int t = 0; t < nsteps; t++, dst += 32 * R) {
 			int inH = __shfl_up_sync(0xffffffffu, botH, 1);
 			int inF = __shfl_up_sync(0xffffffffu, botF, 1);
 			if(lane == 0) { inH = DP_NEG; inF = DP_NEG; }
@@ -249,25 +270,27 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 				int upH = inH, upF = inF;
 				uint32_t packed[(R + 3) / 4];
 #pragma unroll
-				for(int q4 = 0; q4 < (R + 3) / 4; q4++) packed[q4] = 0;
+				for(int q4 = 0; q4 < (R + 3) / 4; q4++) packed[q4] = 0u - 0x38383838u;
 #pragma unroll
 				for(int r = 0; r < R; r++) {
-					// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo), vetoed in gap-barrier rows (:944-945,:983-985)
-					const int fo = upH - rfgapo, fe = upF - rfgape;
-					const int fsel = fo >= fe ? 1 : 2;
-					int F = bar[r] ? DP_NEG : dp_max(fo, fe);
-					int s = (rc[r] == refc) ? sc.match_bonus : -mmp[r];
-					s = refN ? -npn[r] : s;
-					const int Hd = diag + s;
+					// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo)
+					const int fo = upH - rfo[r], fe = upF - rfe[r];
+					const bool fopen = fo >= fe;
+					const int F = fopen ? fo : fe;
+					const int fv = fopen ? 2 : 3;
+					const int pen = refN ? npnN[r] : mmpN[r];
+					const int Hd = diag + ((rc[r] == refc) ? bonus : pen);
 					const int E = Earr[r];
 					const int H = __vimax3_s32(Hd, E, F);
-					const int hsel = (H == Hd) ? 1 : ((H == F) ? 1 + fsel : (bar[r] ? 0 : 3 + Esel[r]));
-					const uint32_t code = (uint32_t)(hsel | (Esel[r] << 3) | (fsel << 5));
-					packed[r >> 2] |= code << ((r & 3) * 8);
-					// E[i][j+1] = max(E[i][j]-rdgape, H[i][j]-rdgapo [vetoed in barrier rows]) (:966-969)
-					const int eo = bar[r] ? DP_NEG : H - rdgapo, ee = E - rdgape;
-					Esel[r] = eo >= ee ? 1 : 2;
-					diag = Hleft[r]; Hleft[r] = H; Earr[r] = dp_max(eo, ee);
+					const int x = (H != F) ? ev[r] : fv;
+					const int hsel = (H != Hd) ? x : 1;
+					packed[r >> 2] += (uint32_t)(hsel + ev[r] * 8 + fv * 32) << ((r & 3) * 8);
+					// E[i][j+1] = max(E[i][j]-rdgape, H[i][j]-rdgapo)
+					const int eo = H - rdo[r], ee = E - rdgape;
+					const bool eopen = eo >= ee;
+					Earr[r] = eopen ? eo : ee;
+					ev[r] = eopen ? 4 : 5;
+					diag = Hleft[r]; Hleft[r] = H;
 					upH = H; upF = F;
 				}
 				if(lane == lastLane) {
@@ -278,7 +301,6 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 				}
 				botH = upH; botF = upF;
 				prevInH = inH;
-				uint8_t *dst = codes + ((size_t)t * 32 + lane) * R;
 				if(R == 4) *reinterpret_cast<uint32_t *>(dst) = packed[0];
 				else if(R == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(packed[0], packed[1]);
 				else {
@@ -300,22 +322,32 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 		if(lane == 0) { summ->best = best; summ->flags = 0; summ->naln = 0; summ->ncand = 0; summ->found = 0; }
 		if(best < p.minsc) continue;
 		bt2g_dp_cand *cands = L.cands + w * (uint64_t)L.maxCands;
-		// rank of each candidate under DpBtCandidate::operator< (score desc, row equal, col desc;
-		// aligner_sw_nuc.h:149-157) computed directly: every lane ranks the columns it owns
+		// compact the last-row cells with score >= minsc (in place: slot k <= column j), then rank them
+		// under DpBtCandidate::operator< (score desc, row equal, col desc; aligner_sw_nuc.h:149-157)
 		int totalCand = 0;
 		for(int j0 = 0; j0 < ncol; j0 += 32) {
 			const int j = j0 + lane;
 			const int s = j < ncol ? lastH[j] : DP_NEG;
 			const bool isC = j < ncol && s >= p.minsc;
+			const uint32_t m = __ballot_sync(0xffffffffu, isC);
 			if(isC) {
-				int rank = 0;
-				for(int k = 0; k < ncol; k++) {
-					const int sk = lastH[k];
-					rank += (sk >= p.minsc) && (sk > s || (sk == s && k > j));
-				}
-				if(rank < L.maxCands) { cands[rank].score = s; cands[rank].col = j; cands[rank].row = rdlen - 1; cands[rank].fate = 0; }
+				const int k = totalCand + __popc(m & ((1u << lane) - 1u));
+				lastH[k] = s; candCol[k] = (uint16_t)j;
 			}
-			totalCand += __popc(__ballot_sync(0xffffffffu, isC));
+			totalCand += __popc(m);
+			__syncwarp();
+		}
+		for(int a0 = 0; a0 < totalCand; a0 += 32) {
+			const int a = a0 + lane;
+			if(a < totalCand) {
+				const int s = lastH[a];
+				int rank = 0;
+				for(int k = 0; k < totalCand; k++) {
+					const int sk = lastH[k];
+					rank += (sk > s) || (sk == s && k > a);
+				}
+				if(rank < L.maxCands) { cands[rank].score = s; cands[rank].col = candCol[a]; cands[rank].row = rdlen - 1; cands[rank].fate = 0; }
+			}
 		}
 		const int ncand = totalCand < L.maxCands ? totalCand : L.maxCands;
 		if(lane == 0) {
@@ -333,7 +365,7 @@ template <typename OFF>
 int launch_dp_e2e(const DevIndex<OFF> &ix, const bt2g_scoring &sc, const DpLaunch &L, int maxRdLen, cudaStream_t st) {
 	if(L.n == 0) return 0;
 	const int warpsPerBlock = 4;
-	const size_t perWarp = ((size_t)L.maxCol * 5 + 16 + 15) & ~(size_t)15;
+	const size_t perWarp = dp_smem_per_warp(L.maxCol);
 	size_t smem = (size_t)warpsPerBlock * perWarp;
 	unsigned grid = (unsigned)(L.numSlots / warpsPerBlock);
 	if(maxRdLen <= 128) {
@@ -372,9 +404,9 @@ __global__ void __launch_bounds__(128) k_dp_local(DevIndex<OFF> ix, bt2g_scoring
 	const uint64_t slot = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock;
 	const uint64_t nSlots = (uint64_t)gridDim.x * (blockDim.x >> 5);
 	const uint64_t nProb = L.nDev ? (uint64_t)*L.nDev : L.n;
-	const size_t perWarp = ((size_t)L.maxCol * 5 + 16 + 15) & ~(size_t)15;
+	const size_t perWarp = dp_smem_per_warp(L.maxCol);
 	int32_t *wsm = reinterpret_cast<int32_t *>(smem + (size_t)warpInBlock * perWarp);   // [0] = raw candidate counter
-	uint8_t *refw = reinterpret_cast<uint8_t *>(wsm + L.maxCol);
+	uint8_t *refw = reinterpret_cast<uint8_t *>(wsm + L.maxCol) + 2 * (size_t)L.maxCol;
 	uint8_t *codes = L.codes + slot * L.codeStride;
 	uint64_t *raw = L.rawKeys + slot * (uint64_t)L.maxRaw;
 	const int rdgapo = sc.rdgap_const + sc.rdgap_linear, rdgape = sc.rdgap_linear;
@@ -520,7 +552,7 @@ template <typename OFF>
 int launch_dp_local(const DevIndex<OFF> &ix, const bt2g_scoring &sc, const DpLaunch &L, int maxRdLen, cudaStream_t st) {
 	if(L.n == 0) return 0;
 	const int warpsPerBlock = 4;
-	const size_t perWarp = ((size_t)L.maxCol * 5 + 16 + 15) & ~(size_t)15;
+	const size_t perWarp = dp_smem_per_warp(L.maxCol);
 	size_t smem = (size_t)warpsPerBlock * perWarp;
 	unsigned grid = (unsigned)(L.numSlots / warpsPerBlock);
 	if(maxRdLen <= 128) {

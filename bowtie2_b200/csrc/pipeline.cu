@@ -28,6 +28,7 @@ void launch_pack_reads(const uint8_t *, const uint64_t *, uint64_t, int, uint64_
 template <typename OFF> void launch_resolve2(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, const uint32_t *, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
 template <typename OFF> void launch_resolve(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t, unsigned long long *);
 template <typename OFF> int launch_dp_e2e(const DevIndex<OFF> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);
+template <typename OFF> int launch_dp_local(const DevIndex<OFF> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);
 
 struct PipeBufs {
 	// inputs (device copies for the host-buffer entry point)
@@ -42,7 +43,7 @@ struct PipeBufs {
 	uint32_t *nRows, *rowBase, *rowCnt;
 	uint64_t *tidx, *textoff, *tlen; uint8_t *rflags;   // resolve
 	bt2g_dp_problem *probs; uint32_t *nProb; int32_t *readProb; int32_t *readNProb;
-	uint8_t *codes; int32_t *lastH;
+	uint8_t *codes; int32_t *lastH; uint64_t *rawKeys;
 	bt2g_dp_summary *summ; bt2g_dp_cand *cands; bt2g_dp_aln *alns; uint8_t *ops;
 	bt2g_read_result *res; uint8_t *resOps;
 	unsigned long long *counters;             // [4]: sweep sides, seed sides, resolve sides, dp cells
@@ -51,6 +52,7 @@ struct PipeBufs {
 struct bt2g_pipeline {
 	bt2g_ctx *ctx;
 	bt2g_pipeline_params prm;
+	bt2g_scoring sc;                          // scoring scheme at creation time
 	uint64_t maxReads, maxBases;
 	PipeBufs b;
 	std::vector<void *> allocs;
@@ -64,6 +66,7 @@ struct bt2g_pipeline {
 	uint64_t lastN = 0;
 };
 
+#define PIPE_MAX_RAW 8192
 #define META_STRAND(m) (((m) >> 31) & 1u)
 #define META_EE(m)     (((m) >> 30) & 1u)
 #define META_SEED(m)   (((m) >> 16) & 0x3fffu)
@@ -138,7 +141,7 @@ __global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interva
 	const int len = (int)(roff[rd + 1] - roff[rd]);
 	const int li = len > maxLen ? maxLen : len;
 	bt2g_read_result r;
-	r.found = 0; r.score = 0; r.score2 = INT32_MIN; r.fw = 0; r.tidx = 0; r.refoff = 0; r.nops = 0; r.ndp = 0;
+	r.found = 0; r.score = 0; r.score2 = INT32_MIN; r.fw = 0; r.tidx = 0; r.refoff = 0; r.nops = 0; r.ndp = 0; r.trim_left = 0; r.trim_right = 0;
 	int np = 0;
 	uint64_t seenT[32]; int64_t seenO[32]; uint8_t seenS[32]; int nseen = 0;
 	const int minsc = minscByLen[li];
@@ -216,6 +219,7 @@ __global__ void k_pick(uint64_t n, int rowCap, int maxAlns, int maxOps, const in
 		const bt2g_dp_aln &al = alns[(size_t)bestP * maxAlns + bestA];
 		r.fw = probs[bestP].fw; r.tidx = probs[bestP].tidx; r.refoff = probs[bestP].refl + al.col0;
 		r.nops = al.nops < maxOps ? al.nops : maxOps;
+		r.trim_left = al.trim_beg; r.trim_right = al.trim_end;
 		const uint8_t *src = ops + ((size_t)bestP * maxAlns + bestA) * maxOps;
 		uint8_t *dst = resOps + rd * (size_t)maxOps;
 		for(int k = 0; k < r.nops; k++) dst[k] = src[k];
@@ -261,17 +265,18 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 	launch_resolve2<OFF>(ix, b.rows, b.hitlen, 0, b.nRows, 0, nullptr, b.tidx, b.textoff, b.tlen, b.rflags, b.nextTask, p->sms, st, c ? c + 2 : nullptr);
 	mark(5);
 	k_frame<<<grid(n), T, 0, st>>>(n, roff, b.interval, b.offset, b.rows, b.hitlen, b.meta, b.tidx, b.textoff, b.tlen, b.rflags,
-	                               b.rowBase, b.rowCnt, q.row_cap, q.max_len, q.maxhalf, ctx->scoring.match_bonus,
+	                               b.rowBase, b.rowCnt, q.row_cap, q.max_len, q.maxhalf, p->sc.match_bonus,
 	                               b.minscByLen, b.nceilRawByLen, b.rdgapsByLen, b.rfgapsByLen,
 	                               b.probs, b.nProb, (uint32_t)p->maxProbs, b.readProb, b.readNProb, b.res);
 	DpLaunch L;
 	L.seq = seq; L.qual = qual; L.roff = roff; L.probs = b.probs; L.n = p->maxProbs; L.nDev = b.nProb;
-	L.rawKeys = nullptr; L.maxRaw = 0;
+	L.rawKeys = b.rawKeys; L.maxRaw = b.rawKeys ? PIPE_MAX_RAW : 0;
 	L.numSlots = p->numSlots; L.codes = b.codes; L.lastH = b.lastH; L.codeStride = p->codeStride; L.maxCol = p->maxCol;
 	L.maxCands = q.max_cands; L.maxAlns = q.max_alns; L.maxOps = q.max_ops;
 	L.summ = b.summ; L.cands = b.cands; L.alns = b.alns; L.ops = b.ops;
 	mark(6);
-	if(launch_dp_e2e<OFF>(ix, ctx->scoring, L, q.max_len, st)) { ctx->err = "pipeline: DP launch rejected"; return -1; }
+	const int drc = p->sc.local ? launch_dp_local<OFF>(ix, p->sc, L, q.max_len, st) : launch_dp_e2e<OFF>(ix, p->sc, L, q.max_len, st);
+	if(drc) { ctx->err = "pipeline: DP launch rejected"; return -1; }
 	mark(7);
 	k_pick<<<grid(n), T, 0, st>>>(n, q.row_cap, q.max_alns, q.max_ops, b.readProb, b.readNProb, b.probs, b.summ, b.alns, b.ops,
 	                              b.res, b.resOps, c ? c + 3 : nullptr, roff);
@@ -287,7 +292,6 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	if(!ctx || !prm || !out) return -1;
 	if(!ctx->loaded) { ctx->err = "no index loaded"; return -1; }
 	if(ctx->scoring.gapbar < 1) bt2g_scoring_default(&ctx->scoring, 0);
-	if(ctx->scoring.local) { ctx->err = "pipeline: local mode not implemented in this build"; return -1; }
 	if(prm->seed_len > 32) { ctx->err = "pipeline: seed length must be <= 32"; return -1; }
 	if(prm->max_len < 1 || prm->max_len > 512 || prm->row_cap < 1 || prm->row_cap > 32 || prm->max_seeds < 1 || prm->max_seeds > 16383) {
 		ctx->err = "pipeline: bad parameters"; return -1;
@@ -295,7 +299,7 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	cudaSetDevice(ctx->device);
 	bt2g_pipeline *p = new(std::nothrow) bt2g_pipeline();
 	if(!p) return -4;
-	p->ctx = ctx; p->prm = *prm; p->maxReads = maxReads; p->maxBases = maxBases;
+	p->ctx = ctx; p->prm = *prm; p->sc = ctx->scoring; p->maxReads = maxReads; p->maxBases = maxBases;
 	PipeBufs &b = p->b;
 	memset(&b, 0, sizeof(b));
 	const uint64_t n = maxReads, cap = prm->row_cap, nrowMax = n * cap;
@@ -321,6 +325,8 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	p->sms = sms;
 	p->numSlots = (uint64_t)sms * 24;
 	rc |= pipeAlloc(p, b.codes, p->numSlots * p->codeStride); rc |= pipeAlloc(p, b.lastH, p->numSlots * (uint64_t)p->maxCol);
+	// local mode gathers candidate cells during the fill (k_dp_local): a raw key list per warp slot
+	if(ctx->scoring.local) rc |= pipeAlloc(p, b.rawKeys, p->numSlots * (uint64_t)PIPE_MAX_RAW);
 	rc |= pipeAlloc(p, b.summ, nprobMax); rc |= pipeAlloc(p, b.cands, nprobMax * prm->max_cands);
 	rc |= pipeAlloc(p, b.alns, nprobMax * prm->max_alns); rc |= pipeAlloc(p, b.ops, nprobMax * prm->max_alns * (uint64_t)prm->max_ops);
 	rc |= pipeAlloc(p, b.res, n); rc |= pipeAlloc(p, b.resOps, n * (uint64_t)prm->max_ops);

@@ -360,7 +360,8 @@ class _PipeParams(C.Structure):
 
 
 READ_RESULT = np.dtype([("found", "<i4"), ("score", "<i4"), ("score2", "<i4"), ("fw", "<u4"), ("tidx", "<u8"),
-                        ("refoff", "<i8"), ("nops", "<i4"), ("ndp", "<i4")], align=True)
+                        ("refoff", "<i8"), ("nops", "<i4"), ("ndp", "<i4"), ("trim_left", "<i4"), ("trim_right", "<i4")],
+                       align=True)
 
 EXPORTS += ["bt2g_pipeline_create", "bt2g_pipeline_destroy", "bt2g_pipeline_run_dev", "bt2g_pipeline_run_host",
             "bt2g_pipeline_results_dev", "bt2g_pipeline_counters", "bt2g_pipeline_stage_ms"]
@@ -446,11 +447,14 @@ class Pipeline:
         return r.value, o.value
 
 
-def ops_to_cigar(ops: np.ndarray, nops: int) -> str:
+def ops_to_cigar(ops: np.ndarray, nops: int, trim_left: int = 0, trim_right: int = 0) -> str:
     """SAM CIGAR of a device op string (reference: AlnRes::printCigar via StackedAln,
-    aligner_result.cpp): M for match/mismatch, I for a reference gap, D for a read gap."""
+    aligner_result.cpp): M for match/mismatch, I for a reference gap, D for a read gap, S for
+    the soft-trimmed ends of a local alignment."""
     sym = {OP_MATCH: "M", OP_MM: "M", OP_REFGAP: "I", OP_READGAP: "D"}
     out, run, last = [], 0, None
+    if trim_left:
+        out.append(f"{trim_left}S")
     for op in ops[:nops][::-1]:
         s = sym[int(op) & 3]
         if s == last:
@@ -461,6 +465,8 @@ def ops_to_cigar(ops: np.ndarray, nops: int) -> str:
             last, run = s, 1
     if last is not None:
         out.append(f"{run}{last}")
+    if trim_right:
+        out.append(f"{trim_right}S")
     return "".join(out)
 
 
@@ -504,3 +510,49 @@ def _one_mm(self, reads: ReadBatch, minsc, strand_mask=3, max_hits: int = 16):
 
 
 Bt2Gpu.one_mm = _one_mm
+
+
+# ---- paired-end framing (PairedEndPolicy::otherMate + DynProgFramer::frameFindMateRect, peClassifyPair) ----
+EXPORTS += ["bt2g_frame_mate", "bt2g_pe_classify"]
+MATE_ANCHOR = np.dtype([("off", "<i8"), ("reflen", "<u8"), ("len1", "<u4"), ("len2", "<u4"), ("maxalcols", "<i4"),
+                        ("maxrdgap", "<i4"), ("maxrfgap", "<i4"), ("maxns", "<i4"), ("maxhalf", "<i4"),
+                        ("is1", "u1"), ("fw", "u1"), ("pad", "u1", (2,))], align=True)
+MATE_FRAME = np.dtype([("status", "<i4"), ("oleft", "u1"), ("ofw", "u1"), ("pad", "u1", (2,)),
+                       ("oll", "<i8"), ("olr", "<i8"), ("orl", "<i8"), ("orr", "<i8"),
+                       ("refl", "<i8"), ("refr", "<i8"), ("refl_pretrim", "<i8"), ("refr_pretrim", "<i8"),
+                       ("triml", "<i8"), ("trimr", "<i8"), ("corel", "<i8"), ("corer", "<i8"), ("maxgap", "<i8")], align=True)
+
+
+class _PePolicy(C.Structure):
+    _fields_ = [("pol", C.c_int32), ("flags", C.c_int32), ("maxfrag", C.c_uint64), ("minfrag", C.c_uint64)]
+
+
+def _pe_struct(pe) -> _PePolicy:
+    """policy.PairedEndPolicy -> bt2g_pe_policy (the local flag does not enter this arithmetic)."""
+    return _PePolicy(int(pe.pol), int(pe.flags()) & 31, int(pe.maxfrag), int(pe.minfrag))
+
+
+def _frame_mate(self, pe, anchors: np.ndarray) -> np.ndarray:
+    """include/bt2g.h: bt2g_frame_mate.  anchors: MATE_ANCHOR array -> MATE_FRAME array."""
+    lib = self._lib
+    lib.bt2g_frame_mate.argtypes = [C.c_void_p, C.POINTER(_PePolicy), C.c_void_p, C.c_uint64, C.c_void_p]
+    anchors = np.ascontiguousarray(anchors, dtype=MATE_ANCHOR)
+    out = np.zeros(len(anchors), dtype=MATE_FRAME)
+    pp = _pe_struct(pe)
+    self._check(lib.bt2g_frame_mate(self._h, C.byref(pp), _ptr(anchors), len(anchors), _ptr(out)), "bt2g_frame_mate")
+    return out
+
+
+def _pe_classify(self, pe, pairs: np.ndarray) -> np.ndarray:
+    """include/bt2g.h: bt2g_pe_classify.  pairs: int64 [n, 6] = off1, len1, fw1, off2, len2, fw2."""
+    lib = self._lib
+    lib.bt2g_pe_classify.argtypes = [C.c_void_p, C.POINTER(_PePolicy), C.c_void_p, C.c_uint64, C.c_void_p]
+    pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 6)
+    out = np.zeros(len(pairs), dtype=np.int32)
+    pp = _pe_struct(pe)
+    self._check(lib.bt2g_pe_classify(self._h, C.byref(pp), _ptr(pairs), len(pairs), _ptr(out)), "bt2g_pe_classify")
+    return out
+
+
+Bt2Gpu.frame_mate = _frame_mate
+Bt2Gpu.pe_classify = _pe_classify

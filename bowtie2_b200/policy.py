@@ -180,3 +180,139 @@ def frame_seed_extension_rect(off: int, rdlen: int, reflen: int, maxrdgap: int, 
         triml = (-refl) - maxns
     r = DPRect(refl + triml, refr - trimr, refl, refr, triml, trimr, maxgap, maxgap + 2 * maxgap, maxgap)
     return (not r.entirely_trimmed()), r
+
+
+# ---- paired-end policy (pe.h / pe.cpp) and mate-finding rectangles (dp_framer.cpp:177-361) ------
+PE_POLICY_FF, PE_POLICY_RR, PE_POLICY_FR, PE_POLICY_RF = 1, 2, 3, 4
+PE_ALS_NORMAL, PE_ALS_OVERLAP, PE_ALS_CONTAIN, PE_ALS_DOVETAIL, PE_ALS_DISCORD = 1, 2, 3, 4, 5
+
+
+@dataclass
+class PairedEndPolicy:
+    """PairedEndPolicy (pe.h:169-330) with the program defaults of bt2_search.cpp:350-358
+    (-I 0 -X 500 --fr, no flipping, no dovetail, containment and overlap allowed, expand to fit)."""
+    pol: int = PE_POLICY_FR
+    maxfrag: int = 500
+    minfrag: int = 0
+    local: bool = False
+    flipping_ok: bool = False
+    dovetail_ok: bool = False
+    contain_ok: bool = True
+    olap_ok: bool = True
+    expand_to_fit: bool = True
+
+    def flags(self) -> int:
+        return (int(self.flipping_ok) | int(self.dovetail_ok) << 1 | int(self.contain_ok) << 2 | int(self.olap_ok) << 3
+                | int(self.expand_to_fit) << 4 | int(self.local) << 5)
+
+    def mate_dir(self, is1: bool, fw: bool):
+        """pePolicyMateDir (pe.h:130-164) -> (left, mfw)."""
+        if self.pol == PE_POLICY_FF:
+            return is1 != fw, fw
+        if self.pol == PE_POLICY_RR:
+            return is1 == fw, fw
+        if self.pol == PE_POLICY_FR:
+            return (not fw), (not fw)
+        return fw, (not fw)
+
+    def other_mate(self, is1: bool, fw: bool, off: int, maxalcols: int, reflen: int, len1: int, len2: int):
+        """PairedEndPolicy::otherMate (pe.cpp:161-355) -> None or (oleft, oll, olr, orl, orr, ofw)."""
+        oleft, ofw = self.mate_dir(is1, fw)
+        alen = len1 if is1 else len2
+        maxfrag, minfrag = self.maxfrag, max(self.minfrag, 1)
+        if self.expand_to_fit:
+            maxfrag = max(maxfrag, len1, len2)
+        elif len1 > maxfrag or len2 > maxfrag:
+            return None
+        if oleft:
+            oll = off + alen - maxfrag
+            olr = off + alen - minfrag
+            orl = oll
+            orr = off + maxfrag - 1
+            if not self.olap_ok:
+                orr = min(orr, off - 1)
+                if orr < olr:
+                    olr = orr
+            elif not self.dovetail_ok:
+                orr = min(orr, off + alen - 1)
+            elif not self.flipping_ok and maxalcols != -1:
+                orr = min(orr, off + alen - 1 + (maxalcols - 1))
+        else:
+            orr = off + (maxfrag - 1)
+            orl = off + (minfrag - 1)
+            oll = off + alen - maxfrag
+            olr = orr
+            if not self.olap_ok:
+                oll = max(oll, off + alen)
+                if oll > orl:
+                    orl = oll
+            elif not self.dovetail_ok:
+                oll = max(oll, off)
+            elif not self.flipping_ok and maxalcols != -1:
+                oll = max(oll, off - maxalcols + 1)
+        return oleft, oll, olr, orl, orr, ofw
+
+    def classify_pair(self, off1: int, len1: int, fw1: bool, off2: int, len2: int, fw2: bool) -> int:
+        """PairedEndPolicy::peClassifyPair (pe.cpp:37-137)."""
+        maxfrag = self.maxfrag
+        if self.expand_to_fit:
+            maxfrag = max(maxfrag, len1, len2)
+        minfrag = max(self.minfrag, 1)
+        if self.pol in (PE_POLICY_FF, PE_POLICY_RR):
+            if fw1 != fw2:
+                return PE_ALS_DISCORD
+            one_left = fw1 if self.pol == PE_POLICY_FF else not fw1
+        else:
+            if fw1 == fw2:
+                return PE_ALS_DISCORD
+            one_left = fw1 if self.pol == PE_POLICY_FR else not fw1
+        frag = max(off1 + len1, off2 + len2) - min(off1, off2)
+        if frag > maxfrag or frag < minfrag:
+            return PE_ALS_DISCORD
+        lo1, hi1, lo2, hi2 = off1, off1 + len1 - 1, off2, off2 + len2 - 1
+        containment = (lo1 >= lo2 and hi1 <= hi2) or (lo2 >= lo1 and hi2 <= hi1)
+        typ = PE_ALS_NORMAL
+        olap = False
+        if (lo1 <= lo2 and hi1 >= lo2) or (lo1 <= hi2 and hi1 >= hi2) or containment:
+            olap = True
+            if not self.olap_ok:
+                return PE_ALS_DISCORD
+            typ = PE_ALS_OVERLAP
+        if not olap:
+            if (one_left and lo2 < lo1) or (not one_left and lo1 < lo2):
+                return PE_ALS_DISCORD
+        if containment:
+            if not self.contain_ok:
+                return PE_ALS_DISCORD
+            typ = PE_ALS_CONTAIN
+        if (one_left and (hi1 > hi2 or lo2 < lo1)) or (not one_left and (hi2 > hi1 or lo1 < lo2)):
+            if not self.dovetail_ok:
+                return PE_ALS_DISCORD
+            typ = PE_ALS_DOVETAIL
+        return typ
+
+
+def frame_find_mate_rect(anchor_left: bool, ll: int, lr: int, rl: int, rr: int, rdlen: int, reflen: int,
+                         maxrdgap: int, maxrfgap: int, maxns: int, maxhalf: int = 15, trim_to_ref: bool = True):
+    """DynProgFramer::frameFindMateRect (dp_framer.h:155-197 -> dp_framer.cpp:177-361).  Returns (found, DPRect).
+    NB the mate rectangles take maxgap = max(gaps, maxhalf) (dp_framer.cpp:197-198, :310-311), not min."""
+    m64 = (1 << 64) - 1
+    maxgap = max(maxrdgap & m64, maxrfgap & m64, maxhalf)
+    if anchor_left:
+        refl = (rl - (rdlen - 1)) - maxgap
+        refr = rr + maxgap
+    else:
+        refl = ll - maxgap
+        refr = (lr + (rdlen - 1)) + maxgap
+    triml = trimr = 0
+    if trim_to_ref:
+        maxns = 0
+    elif maxns == rdlen:
+        maxns -= 1
+    if refr >= reflen + maxns:
+        trimr = refr - (reflen + maxns - 1)
+    if refl < -maxns:
+        triml = (-refl) - maxns
+    width = refr - refl + 1
+    r = DPRect(refl + triml, refr - trimr, refl, refr, triml, trimr, maxgap, width - maxgap - 1, maxgap)
+    return (not r.entirely_trimmed()), r

@@ -251,6 +251,53 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
                    int32_t max_cands, int32_t max_alns, int32_t max_ops,
                    bt2g_dp_summary *summ, bt2g_dp_cand *cands, bt2g_dp_aln *alns, uint8_t *ops);
 
+/* ------------------------------------------------------------- paired-end framing ----- */
+/* PairedEndPolicy (pe.h:169-330): pol = PE_POLICY_FF 1 / RR 2 / FR 3 / RF 4 (pe.h:43-55);
+ * defaults of the program (bt2_search.cpp:350-358): FR, maxfrag 500, minfrag 0, flags
+ * BT2G_PE_CONTAIN_OK | BT2G_PE_OLAP_OK | BT2G_PE_EXPAND_TO_FIT. */
+#define BT2G_PE_FLIPPING_OK   1
+#define BT2G_PE_DOVETAIL_OK   2
+#define BT2G_PE_CONTAIN_OK    4
+#define BT2G_PE_OLAP_OK       8
+#define BT2G_PE_EXPAND_TO_FIT 16
+typedef struct {
+	int32_t  pol;
+	int32_t  flags;
+	uint64_t maxfrag, minfrag;
+} bt2g_pe_policy;
+
+/* one anchor alignment for which the opposite mate is sought (aligner_sw_driver.cpp:2157-2256) */
+typedef struct {
+	int64_t  off;                /* reference offset of the anchor alignment (AlnRes::refoff) */
+	uint64_t reflen;             /* length of the reference sequence (tlen) */
+	uint32_t len1, len2;         /* mate lengths */
+	int32_t  maxalcols;          /* orows + oreadGaps, or -1 */
+	int32_t  maxrdgap, maxrfgap; /* Scoring::maxReadGaps / maxRefGaps of the opposite mate */
+	int32_t  maxns;              /* nCeil of the opposite mate */
+	int32_t  maxhalf;            /* maxhalf (bt2_search.cpp: 15) */
+	uint8_t  is1, fw;            /* anchor is mate 1?  anchor aligned to Watson? */
+	uint8_t  pad[2];
+} bt2g_mate_anchor;
+
+/* PairedEndPolicy::otherMate (pe.cpp:161-355) followed by DynProgFramer::frameFindMateRect
+ * (dp_framer.h:155-197; dp_framer.cpp:177-361; trimToRef = !gReportOverhangs = true):
+ * status 0 = no concordant placement possible, 1 = window found but the rectangle is entirely
+ * trimmed, 2 = rectangle valid. */
+typedef struct {
+	int32_t status;
+	uint8_t oleft, ofw;          /* opposite mate lies to the left?  must align to Watson? */
+	uint8_t pad[2];
+	int64_t oll, olr, orl, orr;  /* windows for the LHS / RHS extreme of the opposite mate */
+	int64_t refl, refr, refl_pretrim, refr_pretrim;
+	int64_t triml, trimr, corel, corer, maxgap;   /* DPRect (dp_framer.h:33-73) */
+} bt2g_mate_frame;
+int bt2g_frame_mate(bt2g_ctx *ctx, const bt2g_pe_policy *pol, const bt2g_mate_anchor *anchors, uint64_t n,
+                    bt2g_mate_frame *out);
+
+/* PairedEndPolicy::peClassifyPair (pe.cpp:37-137) for n pairs: pairs[6*i] = off1, len1, fw1,
+ * off2, len2, fw2; out[i] = PE_ALS_NORMAL 1 / OVERLAP 2 / CONTAIN 3 / DOVETAIL 4 / DISCORD 5. */
+int bt2g_pe_classify(bt2g_ctx *ctx, const bt2g_pe_policy *pol, const int64_t *pairs, uint64_t n, int32_t *out);
+
 /* ---------------------------------------------------------------- batched hot path ----- */
 /* One pass of the hot path over a batch: exactSweep -> searchAllSeeds (round 0) -> offset
  * resolution -> extension DP + backtrace -> best alignment per read.  This is the unit the
@@ -278,6 +325,8 @@ typedef struct {
 	int64_t  refoff;             /* 0-based offset of the leftmost aligned reference base */
 	int32_t  nops;               /* ops (bt2g_dp_aln encoding) in the per-read op buffer */
 	int32_t  ndp;                /* DP problems issued for this read */
+	int32_t  trim_left, trim_right; /* read positions soft-trimmed left / right of the alignment in reference
+	                                 * orientation (local mode; SwResult alres softTrimmed 5'/3' per strand) */
 } bt2g_read_result;
 
 typedef struct bt2g_pipeline bt2g_pipeline;

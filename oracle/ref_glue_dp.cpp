@@ -27,6 +27,7 @@
 #define private public
 #define protected public
 #include "aligner_sw.h"
+#include "pe.h"
 #undef private
 #undef protected
 #include "bt2_idx.h"
@@ -59,6 +60,40 @@ int ref_frame_seed_rect(int64_t off, uint64_t rdlen, int64_t reflen, uint64_t ma
 	out9[4] = (int64_t)r.triml; out9[5] = (int64_t)r.trimr; out9[6] = (int64_t)r.corel; out9[7] = (int64_t)r.corer;
 	out9[8] = (int64_t)r.maxgap;
 	return found ? 1 : 0;
+}
+
+// PairedEndPolicy::otherMate (pe.cpp:161-355) + DynProgFramer::frameFindMateRect (dp_framer.h:155-197,
+// dp_framer.cpp:177-361) as chained in SwDriver::extendSeedsPaired (aligner_sw_driver.cpp:2226-2256).
+// pol: PE_POLICY_FF=1, RR=2, FR=3, RF=4; flags bit0 flippingOk, bit1 dovetailOk, bit2 containOk,
+// bit3 olapOk, bit4 expandToFit, bit5 local.  out15: oleft, ofw, oll, olr, orl, orr, then rect9.
+// returns 0 none, 1 otherMate ok but rectangle entirely trimmed, 2 found.
+int ref_frame_mate(int pol, uint64_t maxfrag, uint64_t minfrag, int flags,
+                   int is1, int fw, int64_t off, int64_t maxalcols, uint64_t reflen, uint64_t len1, uint64_t len2,
+                   uint64_t maxrdgap, uint64_t maxrfgap, int64_t maxns, uint64_t maxhalf, int64_t* out15) {
+	PairedEndPolicy pe(pol, maxfrag, minfrag, (flags & 32) != 0, (flags & 1) != 0, (flags & 2) != 0,
+	                   (flags & 4) != 0, (flags & 8) != 0, (flags & 16) != 0);
+	bool oleft = false, ofw = false;
+	int64_t oll = 0, olr = 0, orl = 0, orr = 0;
+	for(int i = 0; i < 15; i++) out15[i] = 0;
+	if(!pe.otherMate(is1 != 0, fw != 0, off, maxalcols, reflen, len1, len2, oleft, oll, olr, orl, orr, ofw)) return 0;
+	out15[0] = oleft; out15[1] = ofw; out15[2] = oll; out15[3] = olr; out15[4] = orl; out15[5] = orr;
+	DynProgFramer fr(true);
+	DPRect r;
+	const uint64_t orows = is1 ? len2 : len1;
+	bool found = fr.frameFindMateRect(!oleft, oll, olr, orl, orr, orows, (int64_t)reflen, maxrdgap, maxrfgap, maxns, maxhalf, r);
+	int64_t* o = out15 + 6;
+	o[0] = r.refl; o[1] = r.refr; o[2] = r.refl_pretrim; o[3] = r.refr_pretrim;
+	o[4] = (int64_t)r.triml; o[5] = (int64_t)r.trimr; o[6] = (int64_t)r.corel; o[7] = (int64_t)r.corer;
+	o[8] = (int64_t)r.maxgap;
+	return found ? 2 : 1;
+}
+
+// PairedEndPolicy::peClassifyPair (pe.cpp:37-137): PE_ALS_NORMAL=1, OVERLAP, CONTAIN, DOVETAIL, DISCORD=5
+int ref_pe_classify(int pol, uint64_t maxfrag, uint64_t minfrag, int flags,
+                    int64_t off1, uint64_t len1, int fw1, int64_t off2, uint64_t len2, int fw2) {
+	PairedEndPolicy pe(pol, maxfrag, minfrag, (flags & 32) != 0, (flags & 1) != 0, (flags & 2) != 0,
+	                   (flags & 4) != 0, (flags & 8) != 0, (flags & 16) != 0);
+	return pe.peClassifyPair(off1, len1, fw1 != 0, off2, len2, fw2 != 0);
 }
 
 // Scoring::maxReadGaps / maxRefGaps (scoring.cpp:42,73), scoreMin, nCeil, perfectScore

@@ -19,8 +19,8 @@ from oracle_lib import have_reference, ref_bin
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
-def _run_reference(index, fq, preset="--sensitive"):
-    out = subprocess.check_output([ref_bin("bowtie2-align-s"), preset, "--end-to-end", "--seed", "0", "-p", "4", "--reorder",
+def _run_reference(index, fq, preset="--sensitive", mode="--end-to-end"):
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), preset, mode, "--seed", "0", "-p", "4", "--reorder",
                                    "-x", index, "-U", fq], stderr=subprocess.DEVNULL).decode()
     recs = []
     for line in out.splitlines():
@@ -65,6 +65,50 @@ def test_pipeline_vs_reference_program(gpu, synth_index, synth_genome, tmp_path,
     assert n_same >= 0.97 * n_ref_aln, (n_same, n_ref_aln)
     assert n_same_cigar >= 0.995 * n_same, (n_same_cigar, n_same)
     pipe.close()
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_pipeline_local_vs_reference_program(gpu, synth_index, synth_genome, tmp_path):
+    """--local --sensitive-local: soft-clipped alignments (reads carry 12 random bases at one end)."""
+    gpu.load_index_files(synth_index)
+    rdlen = 120
+    reads, quals, truth = synth.make_reads(synth_genome, 2000, rdlen, seed=311, sub_rate=0.01, indel_rate=0.001)
+    rng = np.random.default_rng(9)
+    for k, r in enumerate(reads):
+        if k % 2 == 0:
+            junk = rng.integers(0, 4, size=12)
+            if k % 4 == 0:
+                r[:12] = junk
+            else:
+                r[-12:] = junk
+    fq = str(tmp_path / "r.fq")
+    synth.write_fastq(fq, reads, quals)
+    want = _run_reference(synth_index, fq, preset="--sensitive-local", mode="--local")
+    pipe = Pipeline(gpu, "sensitive", max_len=rdlen, max_reads=2048, row_cap=16, range_max=16, local=True, max_cands=256)
+    res, ops = pipe.run_host(ReadBatch.from_list(reads, quals))
+    n_ref_aln = n_same = n_same_cigar = n_unique = n_unique_same = n_clipped = 0
+    for i, w in enumerate(want):
+        r = res[i]
+        if w["flag"] & 4:
+            continue
+        n_ref_aln += 1
+        same = (r["found"] != 0 and int(r["tidx"]) == int(w["rname"][3:]) - 1 and int(r["refoff"]) == w["pos"]
+                and bool(r["fw"]) == (not (w["flag"] & 16)) and int(r["score"]) == w["AS"])
+        n_same += same
+        if w["mapq"] >= 30:
+            n_unique += 1
+            n_unique_same += same
+        if same:
+            cig = f"{rdlen}M" if r["found"] == 2 else ops_to_cigar(ops[i], int(r["nops"]), int(r["trim_left"]), int(r["trim_right"]))
+            n_same_cigar += cig == w["cigar"]
+            n_clipped += "S" in cig
+    assert n_ref_aln > 1800
+    assert n_clipped > 500
+    assert n_unique_same >= 0.99 * n_unique, (n_unique_same, n_unique)
+    assert n_same >= 0.97 * n_ref_aln, (n_same, n_ref_aln)
+    assert n_same_cigar >= 0.99 * n_same, (n_same_cigar, n_same)
+    pipe.close()
+    gpu.set_scoring(local=False)
 
 
 def test_pipeline_stage_consistency(gpu, synth_index, synth_genome):

@@ -46,3 +46,68 @@ def test_min_scores_and_intervals():
     assert policy.seed_interval(policy.preset("very-sensitive", True).ival, 300) == 9
     assert policy.seed_interval(policy.preset("sensitive").ival, 150, True) == 18
     assert policy.n_seeds(100, 22, 12) == 7
+
+
+def _pe_cases(n=4000, seed=5):
+    rng = np.random.default_rng(seed)
+    for k in range(n):
+        pol = int(rng.integers(1, 5))
+        maxfrag = int(rng.choice([50, 200, 500, 800]))
+        minfrag = int(rng.choice([0, 0, 30, 150]))
+        if minfrag > maxfrag:
+            minfrag = 0
+        flags = int(rng.integers(0, 32))
+        if k % 3 == 0:
+            flags = 4 | 8 | 16          # program defaults
+        pe = policy.PairedEndPolicy(pol, maxfrag, minfrag, False, bool(flags & 1), bool(flags & 2), bool(flags & 4),
+                                    bool(flags & 8), bool(flags & 16))
+        len1, len2 = int(rng.integers(20, 260)), int(rng.integers(20, 260))
+        reflen = int(rng.choice([300, 2000, 48502]))
+        off = int(rng.integers(-40, reflen + 40))
+        yield pe, flags, len1, len2, reflen, off, rng
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_other_mate_and_mate_rect_match_reference(lambda_index):
+    R = Reference(lambda_index, mirror=False, ref=False)
+    L = R.lib
+    i64, u64 = C.c_int64, C.c_uint64
+    L.ref_frame_mate.argtypes = [C.c_int, u64, u64, C.c_int, C.c_int, C.c_int, i64, i64, u64, u64, u64, u64, u64, i64, u64, C.POINTER(i64)]
+    out = (i64 * 15)()
+    nfound = 0
+    for pe, flags, len1, len2, reflen, off, rng in _pe_cases():
+        is1, fw = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        olen = len2 if is1 else len1
+        rg, fg = int(rng.integers(0, 25)), int(rng.integers(0, 25))
+        maxalcols = olen + rg if rng.integers(0, 4) else -1
+        maxns = int(0.15 * olen)
+        st = L.ref_frame_mate(pe.pol, pe.maxfrag, pe.minfrag, flags, int(is1), int(fw), off, maxalcols, reflen, len1, len2,
+                              rg, fg, maxns, 15, out)
+        om = pe.other_mate(is1, fw, off, maxalcols, reflen, len1, len2)
+        assert (st != 0) == (om is not None)
+        if om is None:
+            continue
+        oleft, oll, olr, orl, orr, ofw = om
+        assert [int(oleft), int(ofw), oll, olr, orl, orr] == list(out[:6])
+        found, r = policy.frame_find_mate_rect(not oleft, oll, olr, orl, orr, olen, reflen, rg, fg, maxns, 15)
+        assert found == (st == 2)
+        assert [r.refl, r.refr, r.refl_pretrim, r.refr_pretrim, r.triml, r.trimr, r.corel, r.corer, r.maxgap] == list(out[6:15])
+        nfound += found
+    assert nfound > 1000
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_pe_classify_matches_reference(lambda_index):
+    R = Reference(lambda_index, mirror=False, ref=False)
+    L = R.lib
+    i64, u64 = C.c_int64, C.c_uint64
+    L.ref_pe_classify.argtypes = [C.c_int, u64, u64, C.c_int, i64, u64, C.c_int, i64, u64, C.c_int]
+    seen = set()
+    for pe, flags, len1, len2, reflen, off, rng in _pe_cases(6000, seed=8):
+        off2 = off + int(rng.integers(-300, 600))
+        fw1, fw2 = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        want = L.ref_pe_classify(pe.pol, pe.maxfrag, pe.minfrag, flags, off, len1, int(fw1), off2, len2, int(fw2))
+        got = pe.classify_pair(off, len1, fw1, off2, len2, fw2)
+        assert got == want
+        seen.add(got)
+    assert seen == {1, 2, 3, 4, 5}

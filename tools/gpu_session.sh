@@ -1,0 +1,24 @@
+#!/bin/bash
+# One gpurun session: GPU parity tests, a bench line, the ncu launch list and full captures of the top kernels.
+# usage: tools/gpu_session.sh <tag> [tests|bench|ncu ...]
+set -u
+TAG=${1:-rXX}; shift || true
+WHAT=${*:-tests bench ncu}
+OUT=gpurun_out; mkdir -p $OUT
+for w in $WHAT; do
+case $w in
+tests)
+  timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -5 $OUT/${TAG}_pytest.log ;;
+bench)
+  timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"; tail -c 1500 $OUT/${TAG}_bench.json ;;
+benchfull)
+  timeout 1500 python bench.py > $OUT/${TAG}_bench_full.json 2> $OUT/${TAG}_bench_full.err; echo "bench exit $?"; tail -c 1500 $OUT/${TAG}_bench_full.json ;;
+ncu)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
+     python bench.py --steps 2 --warmup 1 --reads 2000000 --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1; echo "ncu launches exit $?"
+  for k in k_dp_e2e k_seed_search2 k_exact_sweep2; do
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:^$k -s 1 -c 1 -f -o $OUT/${TAG}_$k \
+       python bench.py --steps 2 --warmup 1 --reads 2000000 --no-cpu-baseline > $OUT/${TAG}_ncu_$k.log 2>&1; echo "ncu $k exit $?"
+  done ;;
+esac
+done
