@@ -553,7 +553,9 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 	if(maxCands < 1 || maxAlns < 1 || maxOps < 1) return -1;
 	// shape of the batch
 	int maxCol = 1, maxLen = 1;
+	int64_t minMinsc = 0;
 	for(uint64_t i = 0; i < n; i++) {
+		if(probs[i].minsc < minMinsc) minMinsc = probs[i].minsc;
 		int64_t nc = probs[i].refr - probs[i].refl + 1;
 		if(nc > maxCol) maxCol = (int)nc;
 		if(probs[i].read_idx >= reads->n_reads) { ctx->err = "read_idx out of range"; return -1; }
@@ -575,8 +577,9 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 		L.numSlots = ((n < want ? n : want) + 3) / 4 * 4;
 	} L.maxCands = maxCands; L.maxAlns = maxAlns; L.maxOps = maxOps;
 	L.codeStride = (uint64_t)(maxCol + 32) * 32 * R;
+	L.packed = dp_packed_ok(ctx->scoring, minMinsc, maxLen) ? 1 : 0;
 	BT2G_CUDA_TRY(ctx, dprob.alloc(n * sizeof(bt2g_dp_problem)));
-	BT2G_CUDA_TRY(ctx, dcodes.alloc(L.numSlots * L.codeStride));
+	BT2G_CUDA_TRY(ctx, dcodes.alloc(L.numSlots * L.codeStride * (L.packed ? 2 : 1)));
 	BT2G_CUDA_TRY(ctx, dlast.alloc(L.numSlots * (uint64_t)maxCol * 4));
 	L.maxRaw = maxCands * 4 < 1024 ? 1024 : maxCands * 4;
 	BT2G_CUDA_TRY(ctx, draw.alloc(L.numSlots * (uint64_t)L.maxRaw * 8));

@@ -1,6 +1,15 @@
 // dp_device.cuh -- launch descriptor shared by api.cu and dp_kernels.cu (DP types: include/bt2g.h)
 #pragma once
 #include "bt2g_internal.h"
+#include <cstdlib>
+
+// the s16x2 kernel needs every reachable score within +-DPX_LIMIT (dp_kernels.cu): end-to-end mode,
+// minimum score >= -8000 and perfect score <= 8000; BT2G_DP_PACKED=0 in the environment disables it
+static inline bool dp_packed_ok(const bt2g_scoring &sc, int64_t minMinsc, int maxLen) {
+	const char *e = getenv("BT2G_DP_PACKED");
+	if(e && e[0] == '0') return false;
+	return !sc.local && minMinsc >= -8000 && (int64_t)sc.match_bonus * maxLen <= 8000 && sc.match_bonus >= 0;
+}
 
 struct DpLaunch {
 	const uint8_t  *seq, *qual;
@@ -16,6 +25,7 @@ struct DpLaunch {
 	uint64_t        codeStride;
 	int             maxCol;
 	int             maxCands, maxAlns, maxOps;
+	int             packed = 0;   // e2e: two problems per warp as s16x2 pairs (codes workspace: 2 * codeStride per slot)
 	bt2g_dp_summary *summ;
 	bt2g_dp_cand    *cands;
 	bt2g_dp_aln     *alns;

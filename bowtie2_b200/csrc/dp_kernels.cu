@@ -180,6 +180,59 @@ __device__ __forceinline__ void dp_backtrace_all(const DpLaunch &L, const bt2g_s
 	if(lane == 0) { summ->naln = naln; summ->flags |= flags; }
 }
 
+// ---- end-to-end tail: best of the last row, candidate list (gatherCellsNucleotidesEnd2End), backtraces
+template <int R>
+__device__ __forceinline__ void dp_e2e_tail(const DpLaunch &L, const bt2g_scoring &sc, const bt2g_dp_problem &p, uint64_t w,
+                                            const uint8_t *rs, const uint8_t *rq, int rdlen, int ncol, int32_t *lastH,
+                                            uint16_t *candCol, const uint8_t *refw, uint8_t *codes, bt2g_dp_summary *summ, int lane) {
+	__syncwarp();
+	// best = max of the last row (aligner_swsse_ee_u8.cpp:1095-1100)
+	int best = DP_NEG;
+	for(int k = lane; k < ncol; k += 32) best = dp_max(best, lastH[k]);
+#pragma unroll
+	for(int o = 16; o > 0; o >>= 1) best = dp_max(best, __shfl_xor_sync(0xffffffffu, best, o));
+
+	// ---- SwAligner::align tail (aligner_sw.cpp:679-729) + gatherCellsNucleotidesEnd2End (:1176-1208)
+	if(lane == 0) { summ->best = best; summ->flags = 0; summ->naln = 0; summ->ncand = 0; summ->found = 0; }
+	if(best < p.minsc) return;
+	bt2g_dp_cand *cands = L.cands + w * (uint64_t)L.maxCands;
+	// compact the last-row cells with score >= minsc (in place: slot k <= column j), then rank them
+	// under DpBtCandidate::operator< (score desc, row equal, col desc; aligner_sw_nuc.h:149-157)
+	int totalCand = 0;
+	for(int j0 = 0; j0 < ncol; j0 += 32) {
+		const int j = j0 + lane;
+		const int s = j < ncol ? lastH[j] : DP_NEG;
+		const bool isC = j < ncol && s >= p.minsc;
+		const uint32_t m = __ballot_sync(0xffffffffu, isC);
+		if(isC) {
+			const int k = totalCand + __popc(m & ((1u << lane) - 1u));
+			lastH[k] = s; candCol[k] = (uint16_t)j;
+		}
+		totalCand += __popc(m);
+		__syncwarp();
+	}
+	for(int a0 = 0; a0 < totalCand; a0 += 32) {
+		const int a = a0 + lane;
+		if(a < totalCand) {
+			const int s = lastH[a];
+			int rank = 0;
+			for(int k = 0; k < totalCand; k++) {
+				const int sk = lastH[k];
+				rank += (sk > s) || (sk == s && k > a);
+			}
+			if(rank < L.maxCands) { cands[rank].score = s; cands[rank].col = candCol[a]; cands[rank].row = rdlen - 1; cands[rank].fate = 0; }
+		}
+	}
+	const int ncand = totalCand < L.maxCands ? totalCand : L.maxCands;
+	if(lane == 0) {
+		summ->ncand = totalCand; summ->found = totalCand > 0;
+		if(totalCand > L.maxCands) summ->flags |= BT2G_DP_FLAG_CAND_OVERFLOW;
+	}
+	__syncwarp();
+
+	dp_backtrace_all<R>(L, sc, p, w, rs, rq, rdlen, refw, codes, cands, ncand, summ, lane, false);
+}
+
 // R = rows per lane (rdlen <= 32*R)
 template <typename OFF, int R>
 __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L) {
@@ -311,75 +364,226 @@ __global__ void __launch_bounds__(128) k_dp_e2e(DevIndex<OFF> ix, bt2g_scoring s
 				botH = DP_NEG; botF = DP_NEG;
 			}
 		}
-		__syncwarp();
-		// best = max of the last row (aligner_swsse_ee_u8.cpp:1095-1100)
-		int best = DP_NEG;
-		for(int k = lane; k < ncol; k += 32) best = dp_max(best, lastH[k]);
-#pragma unroll
-		for(int o = 16; o > 0; o >>= 1) best = dp_max(best, __shfl_xor_sync(0xffffffffu, best, o));
-
-		// ---- SwAligner::align tail (aligner_sw.cpp:679-729) + gatherCellsNucleotidesEnd2End (:1176-1208)
-		if(lane == 0) { summ->best = best; summ->flags = 0; summ->naln = 0; summ->ncand = 0; summ->found = 0; }
-		if(best < p.minsc) continue;
-		bt2g_dp_cand *cands = L.cands + w * (uint64_t)L.maxCands;
-		// compact the last-row cells with score >= minsc (in place: slot k <= column j), then rank them
-		// under DpBtCandidate::operator< (score desc, row equal, col desc; aligner_sw_nuc.h:149-157)
-		int totalCand = 0;
-		for(int j0 = 0; j0 < ncol; j0 += 32) {
-			const int j = j0 + lane;
-			const int s = j < ncol ? lastH[j] : DP_NEG;
-			const bool isC = j < ncol && s >= p.minsc;
-			const uint32_t m = __ballot_sync(0xffffffffu, isC);
-			if(isC) {
-				const int k = totalCand + __popc(m & ((1u << lane) - 1u));
-				lastH[k] = s; candCol[k] = (uint16_t)j;
-			}
-			totalCand += __popc(m);
-			__syncwarp();
-		}
-		for(int a0 = 0; a0 < totalCand; a0 += 32) {
-			const int a = a0 + lane;
-			if(a < totalCand) {
-				const int s = lastH[a];
-				int rank = 0;
-				for(int k = 0; k < totalCand; k++) {
-					const int sk = lastH[k];
-					rank += (sk > s) || (sk == s && k > a);
-				}
-				if(rank < L.maxCands) { cands[rank].score = s; cands[rank].col = candCol[a]; cands[rank].row = rdlen - 1; cands[rank].fate = 0; }
-			}
-		}
-		const int ncand = totalCand < L.maxCands ? totalCand : L.maxCands;
-		if(lane == 0) {
-			summ->ncand = totalCand; summ->found = totalCand > 0;
-			if(totalCand > L.maxCands) summ->flags |= BT2G_DP_FLAG_CAND_OVERFLOW;
-		}
-		__syncwarp();
-
-		dp_backtrace_all<R>(L, sc, p, w, rs, rq, rdlen, refw, codes, cands, ncand, summ, lane, false);
+		dp_e2e_tail<R>(L, sc, p, w, rs, rq, rdlen, ncol, lastH, candCol, refw, codes, summ, lane);
 	} // persistent loop over problems
 }
 
 // ----------------------------------------------------------------------------------------
+// Two problems per warp, packed as signed 16-bit pairs (DPX s16x2): the low half of every value
+// belongs to problem A, the high half to problem B; lane k holds rows kR..kR+R-1 of both.
+// Same recurrences and the same move bytes as k_dp_e2e, with
+//   * add+max fused (VIADDMNMX.S16x2), every sum clamped at DPX_FLOOR so nothing wraps
+//     (|gap cost| <= DPX_BIG, so a + b >= DPX_FLOOR - DPX_BIG > -32768);
+//   * "which operand won" taken from XOR + unsigned min instead of predicates: (F != fo) is 1 exactly
+//     when the extension beat the open (open wins ties), (H != Hd) / (H != F) select the H move;
+//     0/1 halves times 0xffff give half-word masks for LOP3 selects;
+//   * small non-negative code arithmetic done with plain 32-bit adds (no half can borrow).
+// The host only selects this kernel when every score fits (|minsc|, perfect score <= DPX_LIMIT).
+#define DPX_FLOOR (-16384)
+#define DPX_BIG   16000
+#define DPX_LIMIT 8000
+
+__device__ __forceinline__ uint32_t dpx_pack(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ uint32_t dpx_both(int v) { return dpx_pack(v, v); }
+__device__ __forceinline__ uint32_t dpx_ne01(uint32_t a, uint32_t b) { return __vminu2(a ^ b, 0x00010001u); }   // per half: a != b
+__device__ __forceinline__ uint32_t dpx_sel(uint32_t mask, uint32_t a, uint32_t b) { return (a & mask) | (b & ~mask); }
+
+template <typename OFF, int R>
+__global__ void __launch_bounds__(128) k_dp_e2e_x2(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L) {
+	extern __shared__ uint8_t smem[];
+	const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint64_t slot = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock;
+	const uint64_t nSlots = (uint64_t)gridDim.x * (blockDim.x >> 5);
+	const uint64_t nProb = L.nDev ? (uint64_t)*L.nDev : L.n;
+	const uint64_t nPairs = (nProb + 1) >> 1;
+	const size_t perProb = dp_smem_per_warp(L.maxCol);
+	uint8_t *sm0 = smem + (size_t)warpInBlock * 2 * perProb;
+	int32_t *lastH[2]; uint16_t *candCol[2]; uint8_t *refw[2]; uint8_t *codes[2];
+#pragma unroll
+	for(int x = 0; x < 2; x++) {
+		lastH[x] = reinterpret_cast<int32_t *>(sm0 + x * perProb);
+		candCol[x] = reinterpret_cast<uint16_t *>(lastH[x] + L.maxCol);
+		refw[x] = reinterpret_cast<uint8_t *>(candCol[x] + L.maxCol);
+		codes[x] = L.codes + (slot * 2 + x) * L.codeStride;
+	}
+	const int rdgapo = sc.rdgap_const + sc.rdgap_linear, rdgape = sc.rdgap_linear;
+	const int rfgapo = sc.rfgap_const + sc.rfgap_linear, rfgape = sc.rfgap_linear;
+	const uint32_t FLOORP = dpx_both(DPX_FLOOR), ONEP = 0x00010001u;
+	const uint32_t bonusP = dpx_both(sc.match_bonus), nrdeP = dpx_both(-rdgape);
+
+	for(uint64_t pw = slot; pw < nPairs; pw += nSlots) {
+		uint64_t w[2] = {2 * pw, 2 * pw + 1};
+		bool live[2] = {true, w[1] < nProb};
+		if(!live[1]) w[1] = w[0];
+		bt2g_dp_problem p[2] = {L.probs[w[0]], L.probs[w[1]]};
+		const uint8_t *rs[2], *rq[2]; int rdlen[2], ncol[2];
+		__syncwarp();
+#pragma unroll
+		for(int x = 0; x < 2; x++) {
+			rs[x] = L.seq + L.roff[p[x].read_idx]; rq[x] = L.qual + L.roff[p[x].read_idx];
+			rdlen[x] = (int)(L.roff[p[x].read_idx + 1] - L.roff[p[x].read_idx]);
+			ncol[x] = (int)(p[x].refr - p[x].refl + 1);
+			if(ncol[x] <= 0 || ncol[x] > L.maxCol || rdlen[x] > 32 * R || rdlen[x] <= 0) {
+				if(live[x] && lane == 0) {
+					bt2g_dp_summary *sm = L.summ + w[x];
+					sm->found = 0; sm->best = DP_NEG; sm->ncand = 0; sm->naln = 0; sm->flags = BT2G_DP_FLAG_BADSHAPE;
+				}
+				live[x] = false;
+			}
+		}
+		if(!live[0] && !live[1]) continue;
+		// a dead half mirrors the live one (its results are discarded)
+		if(!live[0]) { p[0] = p[1]; rs[0] = rs[1]; rq[0] = rq[1]; rdlen[0] = rdlen[1]; ncol[0] = ncol[1]; w[0] = w[1]; }
+		if(!live[1]) { p[1] = p[0]; rs[1] = rs[0]; rq[1] = rq[0]; rdlen[1] = rdlen[0]; ncol[1] = ncol[0]; w[1] = w[0]; }
+		// reference windows (SwAligner::initRef, aligner_sw.cpp:155-271): codes 0..3, 4 = N / off-end
+#pragma unroll
+		for(int x = 0; x < 2; x++)
+			for(int k = lane; k < ncol[x]; k += 32) refw[x][k] = (uint8_t)ref_base<OFF>(ix, p[x].tidx, p[x].refl + k);
+		const int ncolMax = ncol[0] > ncol[1] ? ncol[0] : ncol[1], ncolMin = ncol[0] < ncol[1] ? ncol[0] : ncol[1];
+		// pad the shorter window so that the packed loop may read it (values are never used)
+		for(int x = 0; x < 2; x++) for(int k = ncol[x] + lane; k < ncolMax; k += 32) refw[x][k] = 4;
+		(void)ncolMin;
+		__syncwarp();
+
+		// per-row constants of both problems (buildQueryProfileEnd2EndSseU8, aligner_swsse_ee_u8.cpp:75-142)
+		uint32_t rcP[R], mmpP[R], npnP[R], nrfoP[R], nrfeP[R], nrdoP[R];
+#pragma unroll
+		for(int r = 0; r < R; r++) {
+			int v[2][6];
+#pragma unroll
+			for(int x = 0; x < 2; x++) {
+				const int i = lane * R + r;
+				bool bar = true;
+				int c = 5, mm = 0, np = 0;
+				if(i < rdlen[x]) {
+					const int pos = p[x].fw ? i : rdlen[x] - 1 - i;
+					c = rs[x][pos];
+					c = p[x].fw ? c : (c > 3 ? 4 : 3 - c);
+					int q = (int)rq[x][pos] - 33;
+					q = q < 0 ? 0 : (q > 63 ? 63 : q);
+					np = -(int)sc.npen[q];
+					mm = c > 3 ? np : -(int)sc.mmpen[q];
+					if(c > 3) c = 5;
+					bar = (i < sc.gapbar) || (rdlen[x] - 1 - i < sc.gapbar);
+				}
+				v[x][0] = c; v[x][1] = mm; v[x][2] = np;
+				v[x][3] = bar ? -DPX_BIG : -rfgapo; v[x][4] = bar ? -DPX_BIG : -rfgape; v[x][5] = bar ? -DPX_BIG : -rdgapo;
+			}
+			rcP[r] = dpx_pack(v[0][0], v[1][0]); mmpP[r] = dpx_pack(v[0][1], v[1][1]); npnP[r] = dpx_pack(v[0][2], v[1][2]);
+			nrfoP[r] = dpx_pack(v[0][3], v[1][3]); nrfeP[r] = dpx_pack(v[0][4], v[1][4]); nrdoP[r] = dpx_pack(v[0][5], v[1][5]);
+		}
+		int lastLane[2], lastR[2];
+#pragma unroll
+		for(int x = 0; x < 2; x++) { lastLane[x] = (rdlen[x] - 1) / R; lastR[x] = (rdlen[x] - 1) % R; }
+		const int lastLaneMax = lastLane[0] > lastLane[1] ? lastLane[0] : lastLane[1];
+
+		uint32_t Hleft[R], Earr[R], ev[R];
+#pragma unroll
+		for(int r = 0; r < R; r++) { Hleft[r] = FLOORP; Earr[r] = FLOORP; ev[r] = 0x00040004u; }
+		uint32_t botH = FLOORP, botF = FLOORP, prevInH = FLOORP;
+		const int nsteps = ncolMax + lastLaneMax;
+		uint8_t *dstA = codes[0] + (size_t)lane * R, *dstB = codes[1] + (size_t)lane * R;
+		for(int t = 0; t < nsteps; t++, dstA += 32 * R, dstB += 32 * R) {
+			uint32_t inH = __shfl_up_sync(0xffffffffu, botH, 1);
+			uint32_t inF = __shfl_up_sync(0xffffffffu, botF, 1);
+			if(lane == 0) { inH = FLOORP; inF = FLOORP; }
+			const int j = t - lane;
+			if(j >= 0 && j < ncolMax && lane <= lastLaneMax) {
+				const uint32_t refcP = (uint32_t)refw[0][j] | ((uint32_t)refw[1][j] << 16);
+				const uint32_t refNm = ((refcP >> 2) & ONEP) * 0xffffu;      // half mask: reference N
+				// H[i0-1][j-1]: row -1 is the free start row of end-to-end mode (vhilsw, :853,923-927)
+				uint32_t diag = (lane == 0) ? 0u : prevInH;
+				uint32_t upH = inH, upF = inF;
+				uint32_t cw[R];
+#pragma unroll
+				for(int r = 0; r < R; r++) {
+					// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo)
+					const uint32_t fo = __viaddmax_s16x2(upH, nrfoP[r], FLOORP);
+					const uint32_t F = __viaddmax_s16x2(upF, nrfeP[r], fo);
+					const uint32_t fv = 0x00020002u + dpx_ne01(F, fo);
+					const uint32_t pen = dpx_sel(refNm, npnP[r], mmpP[r]);
+					const uint32_t mmask = dpx_ne01(rcP[r], refcP) * 0xffffu;
+					const uint32_t Hd = __viaddmax_s16x2(diag, dpx_sel(mmask, pen, bonusP), FLOORP);
+					const uint32_t E = Earr[r];
+					const uint32_t H = __vimax3_s16x2(Hd, E, F);
+					const uint32_t m0 = dpx_ne01(H, Hd) * 0xffffu, m1 = dpx_ne01(H, F) * 0xffffu;
+					const uint32_t hsel = dpx_sel(m0, dpx_sel(m1, ev[r], fv), ONEP);
+					cw[r] = hsel + ev[r] * 8u + fv * 32u;
+					// E[i][j+1] = max(E[i][j]-rdgape, H[i][j]-rdgapo)
+					const uint32_t eo = __viaddmax_s16x2(H, nrdoP[r], FLOORP);
+					const uint32_t En = __viaddmax_s16x2(E, nrdeP, eo);
+					ev[r] = 0x00040004u + dpx_ne01(En, eo);
+					Earr[r] = En;
+					diag = Hleft[r]; Hleft[r] = H;
+					upH = H; upF = F;
+				}
+#pragma unroll
+				for(int x = 0; x < 2; x++) {
+					if(lane == lastLane[x] && j < ncol[x]) {
+						uint32_t hl = Hleft[0];
+#pragma unroll
+						for(int r = 1; r < R; r++) hl = (lastR[x] == r) ? Hleft[r] : hl;
+						lastH[x][j] = x == 0 ? (int)(int16_t)(hl & 0xffffu) : (int)(int16_t)(hl >> 16);
+					}
+				}
+				botH = upH; botF = upF;
+				prevInH = inH;
+				// move bytes: byte 0 of every code word is problem A's, byte 2 problem B's
+#pragma unroll
+				for(int q4 = 0; q4 < R / 4; q4++) {
+					const uint32_t t01 = __byte_perm(cw[4 * q4], cw[4 * q4 + 1], 0x6240), t23 = __byte_perm(cw[4 * q4 + 2], cw[4 * q4 + 3], 0x6240);
+					reinterpret_cast<uint32_t *>(dstA)[q4] = __byte_perm(t01, t23, 0x5410) - 0x38383838u;
+					reinterpret_cast<uint32_t *>(dstB)[q4] = __byte_perm(t01, t23, 0x7632) - 0x38383838u;
+				}
+			} else if(j >= ncolMax) {
+				botH = FLOORP; botF = FLOORP;
+			}
+		}
+#pragma unroll
+		for(int x = 0; x < 2; x++) {
+			if(!live[x]) continue;
+			dp_e2e_tail<R>(L, sc, p[x], w[x], rs[x], rq[x], rdlen[x], ncol[x], lastH[x], candCol[x], refw[x], codes[x], L.summ + w[x], lane);
+		}
+	} // persistent loop over problem pairs
+}
+
+// ----------------------------------------------------------------------------------------
+// persistent grid = resident blocks only (a second, partial wave would double the makespan)
+template <typename K>
+static unsigned dp_resident_grid(K kernel, int threads, size_t smem, uint64_t numSlots, int warpsPerBlock) {
+	int dev = 0, sms = 148, nb = 1;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+	uint64_t g = (uint64_t)nb * sms, cap = numSlots / warpsPerBlock;
+	return (unsigned)(g < cap ? g : cap);
+}
+
+template <typename OFF, int R>
+static void launch_dp_e2e_r(const DevIndex<OFF> &ix, const bt2g_scoring &sc, const DpLaunch &L, cudaStream_t st) {
+	const int warpsPerBlock = 4;
+	if(L.packed) {
+		const size_t smem = (size_t)warpsPerBlock * 2 * dp_smem_per_warp(L.maxCol);
+		if(smem > 48 * 1024) cudaFuncSetAttribute(k_dp_e2e_x2<OFF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		const unsigned grid = dp_resident_grid(k_dp_e2e_x2<OFF, R>, warpsPerBlock * 32, smem, L.numSlots, warpsPerBlock);
+		k_dp_e2e_x2<OFF, R><<<grid, warpsPerBlock * 32, smem, st>>>(ix, sc, L);
+	} else {
+		const size_t smem = (size_t)warpsPerBlock * dp_smem_per_warp(L.maxCol);
+		if(smem > 48 * 1024) cudaFuncSetAttribute(k_dp_e2e<OFF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		const unsigned grid = dp_resident_grid(k_dp_e2e<OFF, R>, warpsPerBlock * 32, smem, L.numSlots, warpsPerBlock);
+		k_dp_e2e<OFF, R><<<grid, warpsPerBlock * 32, smem, st>>>(ix, sc, L);
+	}
+}
+
+// L.packed selects the two-problems-per-warp s16x2 kernel; the caller guarantees the score range
+// (dp_packed_ok) and a workspace of 2 * codeStride bytes per slot.
 template <typename OFF>
 int launch_dp_e2e(const DevIndex<OFF> &ix, const bt2g_scoring &sc, const DpLaunch &L, int maxRdLen, cudaStream_t st) {
 	if(L.n == 0) return 0;
-	const int warpsPerBlock = 4;
-	const size_t perWarp = dp_smem_per_warp(L.maxCol);
-	size_t smem = (size_t)warpsPerBlock * perWarp;
-	unsigned grid = (unsigned)(L.numSlots / warpsPerBlock);
-	if(maxRdLen <= 128) {
-		if(smem > 48 * 1024) cudaFuncSetAttribute(k_dp_e2e<OFF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_dp_e2e<OFF, 4><<<grid, warpsPerBlock * 32, smem, st>>>(ix, sc, L);
-	} else if(maxRdLen <= 256) {
-		if(smem > 48 * 1024) cudaFuncSetAttribute(k_dp_e2e<OFF, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_dp_e2e<OFF, 8><<<grid, warpsPerBlock * 32, smem, st>>>(ix, sc, L);
-	} else if(maxRdLen <= 512) {
-		if(smem > 48 * 1024) cudaFuncSetAttribute(k_dp_e2e<OFF, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_dp_e2e<OFF, 16><<<grid, warpsPerBlock * 32, smem, st>>>(ix, sc, L);
-	} else {
-		return -1;
-	}
+	if(maxRdLen <= 128) launch_dp_e2e_r<OFF, 4>(ix, sc, L, st);
+	else if(maxRdLen <= 256) launch_dp_e2e_r<OFF, 8>(ix, sc, L, st);
+	else if(maxRdLen <= 512) launch_dp_e2e_r<OFF, 16>(ix, sc, L, st);
+	else return -1;
 	return 0;
 }
 template int launch_dp_e2e<uint32_t>(const DevIndex<uint32_t> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);

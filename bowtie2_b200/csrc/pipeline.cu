@@ -17,6 +17,7 @@
 //   pick    : best-scoring alignment per read (+ runner-up score).
 #include "fm_device.cuh"
 #include "dp_device.cuh"
+#include "pe_device.cuh"
 #include <new>
 #include <cstring>
 
@@ -47,6 +48,11 @@ struct PipeBufs {
 	bt2g_dp_summary *summ; bt2g_dp_cand *cands; bt2g_dp_aln *alns; uint8_t *ops;
 	bt2g_read_result *res; uint8_t *resOps;
 	unsigned long long *counters;             // [4]: sweep sides, seed sides, resolve sides, dp cells
+	uint64_t *probTlen, *resTlen;             // reference length per DP problem / per read result
+	// paired-end tail
+	bt2g_dp_problem *mProbs; uint32_t *nMateProb; int32_t *mateOfRead;
+	bt2g_dp_summary *mSumm; bt2g_dp_cand *mCands; bt2g_dp_aln *mAlns; uint8_t *mOps;
+	bt2g_pair_result *pairs; unsigned long long *mateCells;
 };
 
 struct bt2g_pipeline {
@@ -57,8 +63,11 @@ struct bt2g_pipeline {
 	PipeBufs b;
 	std::vector<void *> allocs;
 	uint64_t numSlots, codeStride, maxProbs;
+	int packed = 0;                           // DP: s16x2 two-problem kernel (dp_packed_ok)
 	int maxCol, R, sms = 148;
-	cudaEvent_t ev[9];
+	cudaEvent_t ev[9], pev[4];
+	bool pairsOn = false; bt2g_pe_policy pe{}; int mateMaxCol = 0; uint64_t mateCodeStride = 0;
+	bt2g_pair_result *hPairs = nullptr;
 	bool evOk = false;
 	// pinned staging for the host entry point
 	uint8_t *hSeq = nullptr, *hQual = nullptr; uint64_t *hOff = nullptr;
@@ -135,7 +144,8 @@ __global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interva
                         const uint32_t *rowBase, const uint32_t *rowCnt,
                         int rowCap, int maxLen, int maxhalf, int matchBonus,
                         const int32_t *minscByLen, const int32_t *nceilRawByLen, const int32_t *rdgapsByLen, const int32_t *rfgapsByLen,
-                        bt2g_dp_problem *probs, uint32_t *nProb, uint32_t maxProbs, int32_t *readProb, int32_t *readNProb, bt2g_read_result *res) {
+                        bt2g_dp_problem *probs, uint32_t *nProb, uint32_t maxProbs, int32_t *readProb, int32_t *readNProb, bt2g_read_result *res,
+                        uint64_t *probTlen, uint64_t *resTlen) {
 	uint64_t rd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(rd >= n) return;
 	const int len = (int)(roff[rd + 1] - roff[rd]);
@@ -165,7 +175,7 @@ __global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interva
 		if(dup) continue;
 		if(nseen < 32) { seenT[nseen] = tidx[s]; seenO[nseen] = refoff; seenS[nseen] = (uint8_t)strand; nseen++; }
 		if(isEE) {
-			if(r.found == 0) { r.found = 2; r.score = len * matchBonus; r.fw = strand == 0; r.tidx = tidx[s]; r.refoff = refoff; }
+			if(r.found == 0) { r.found = 2; r.score = len * matchBonus; r.fw = strand == 0; r.tidx = tidx[s]; r.refoff = refoff; resTlen[rd] = tlen[s]; }
 			else if(r.score2 == INT32_MIN) r.score2 = len * matchBonus;
 			continue;
 		}
@@ -185,6 +195,7 @@ __global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interva
 		p.refl = refl + triml; p.refr = refr - trimr; p.triml = (int32_t)triml;
 		p.corel = maxgap; p.corer = 3 * maxgap; p.minsc = minsc; p.nceil = nceilRawByLen[li]; p.reserved = 0;
 		readProb[rd * rowCap + np] = (int32_t)pi;
+		probTlen[pi] = tlen[s];
 		np++;
 	}
 	readNProb[rd] = np;
@@ -195,7 +206,8 @@ __global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interva
 // pick: one thread per read
 __global__ void k_pick(uint64_t n, int rowCap, int maxAlns, int maxOps, const int32_t *readProb, const int32_t *readNProb,
                        const bt2g_dp_problem *probs, const bt2g_dp_summary *summ, const bt2g_dp_aln *alns, const uint8_t *ops,
-                       bt2g_read_result *res, uint8_t *resOps, unsigned long long *cellCnt, const uint64_t *roff) {
+                       bt2g_read_result *res, uint8_t *resOps, unsigned long long *cellCnt, const uint64_t *roff,
+                       const uint64_t *probTlen, uint64_t *resTlen) {
 	uint64_t rd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(rd >= n) return;
 	bt2g_read_result r = res[rd];
@@ -218,6 +230,7 @@ __global__ void k_pick(uint64_t n, int rowCap, int maxAlns, int maxOps, const in
 	if(bestP >= 0 && r.found == 1) {
 		const bt2g_dp_aln &al = alns[(size_t)bestP * maxAlns + bestA];
 		r.fw = probs[bestP].fw; r.tidx = probs[bestP].tidx; r.refoff = probs[bestP].refl + al.col0;
+		resTlen[rd] = probTlen[bestP];
 		r.nops = al.nops < maxOps ? al.nops : maxOps;
 		r.trim_left = al.trim_beg; r.trim_right = al.trim_end;
 		const uint8_t *src = ops + ((size_t)bestP * maxAlns + bestA) * maxOps;
@@ -226,6 +239,131 @@ __global__ void k_pick(uint64_t n, int rowCap, int maxAlns, int maxOps, const in
 	}
 	res[rd] = r;
 	if(cellCnt && cells) atomicAdd(cellCnt, cells);
+}
+
+
+// ---- paired-end tail ------------------------------------------------------------------------
+// number of reference positions an alignment covers: ops are M/MM (read+ref), READGAP (ref only), REFGAP (read only)
+__device__ __forceinline__ int pe_ref_extent(const bt2g_read_result &r, const uint8_t *ops, int len) {
+	if(r.found == 2) return len;
+	int e = 0;
+	for(int k = 0; k < r.nops; k++) e += (ops[k] & 3) != BT2G_OP_REFGAP;
+	return e;
+}
+
+// frame: one thread per read (the anchor); emits at most one mate-finding DP problem for the opposite mate
+__global__ void k_frame_mates(uint64_t nReads, const uint64_t *roff, const bt2g_read_result *res, const uint8_t *resOps, int maxOps,
+                              const uint64_t *resTlen, bt2g_pe_policy pp, int maxLen, int maxhalf, int mateMaxCol,
+                              const int32_t *minscByLen, const int32_t *nceilRawByLen, const int32_t *rdgapsByLen, const int32_t *rfgapsByLen,
+                              bt2g_dp_problem *mProbs, uint32_t *nMateProb, int32_t *mateOfRead) {
+	const uint64_t rd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(rd >= nReads) return;
+	mateOfRead[rd] = -1;
+	const bt2g_read_result a = res[rd];
+	if((a.found & 0xff) == 0) return;
+	const uint64_t od = rd ^ 1ull;
+	const bt2g_read_result o = res[od];
+	const int alen = (int)(roff[rd + 1] - roff[rd]), olen = (int)(roff[od + 1] - roff[od]);
+	const bool anchor1 = (rd & 1ull) == 0;
+	if((o.found & 0xff) != 0 && o.tidx == a.tidx) {
+		// the two independent alignments may already be a concordant pair
+		const int ea = pe_ref_extent(a, resOps + rd * (size_t)maxOps, alen), eo = pe_ref_extent(o, resOps + od * (size_t)maxOps, olen);
+		const int k = anchor1 ? pe_classify(pp, a.refoff, (uint64_t)ea, a.fw != 0, o.refoff, (uint64_t)eo, o.fw != 0)
+		                      : pe_classify(pp, o.refoff, (uint64_t)eo, o.fw != 0, a.refoff, (uint64_t)ea, a.fw != 0);
+		if(k != 5) return;
+	}
+	const int li = olen > maxLen ? maxLen : olen;
+	bt2g_mate_anchor an;
+	an.off = a.refoff; an.reflen = resTlen[rd];
+	an.len1 = (uint32_t)(anchor1 ? alen : olen); an.len2 = (uint32_t)(anchor1 ? olen : alen);
+	an.maxrdgap = rdgapsByLen[li]; an.maxrfgap = rfgapsByLen[li];
+	an.maxalcols = olen + an.maxrdgap;
+	an.maxns = nceilRawByLen[li]; an.maxhalf = maxhalf;
+	an.is1 = anchor1; an.fw = a.fw != 0; an.pad[0] = an.pad[1] = 0;
+	bt2g_mate_frame f;
+	pe_frame_anchor(pp, an, f);
+	if(f.status != 2) return;
+	if(f.refr - f.refl + 1 > mateMaxCol) return;           // wider than the workspace: not attempted
+	const uint32_t pi = atomicAdd(nMateProb, 1u);
+	bt2g_dp_problem &q = mProbs[pi];
+	q.read_idx = (uint32_t)od; q.fw = f.ofw; q.tidx = a.tidx;
+	q.refl = f.refl; q.refr = f.refr; q.triml = (int32_t)f.triml;
+	q.corel = (int32_t)f.corel; q.corer = (int32_t)f.corer;
+	q.minsc = minscByLen[li]; q.nceil = nceilRawByLen[li]; q.reserved = 0;
+	mateOfRead[rd] = (int32_t)pi;
+}
+
+// pick: one thread per pair
+__global__ void k_pick_pairs(uint64_t nPairs, const uint64_t *roff, bt2g_read_result *res, uint8_t *resOps, int maxOps, int maxAlns,
+                             bt2g_pe_policy pp, const int32_t *mateOfRead, const bt2g_dp_problem *mProbs, const bt2g_dp_summary *mSumm,
+                             const bt2g_dp_aln *mAlns, const uint8_t *mOps, bt2g_pair_result *pairs, unsigned long long *mateCells) {
+	const uint64_t pr = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(pr >= nPairs) return;
+	const uint64_t r1 = 2 * pr, r2 = 2 * pr + 1;
+	bt2g_read_result a1 = res[r1], a2 = res[r2];
+	const int len1 = (int)(roff[r1 + 1] - roff[r1]), len2 = (int)(roff[r2 + 1] - roff[r2]);
+	const bool f1 = (a1.found & 0xff) != 0, f2 = (a2.found & 0xff) != 0;
+	bt2g_pair_result out;
+	out.pair_type = (f1 && f2) ? 2 : ((f1 || f2) ? 3 : 0); out.kind = 5; out.source = 0; out.score_sum = 0; out.fraglen = 0;
+	int bestSum = INT32_MIN, bestSrc = -1, bestKind = 5, bestAln = 0;
+	const int e1 = f1 ? pe_ref_extent(a1, resOps + r1 * (size_t)maxOps, len1) : 0;
+	const int e2 = f2 ? pe_ref_extent(a2, resOps + r2 * (size_t)maxOps, len2) : 0;
+	if(f1 && f2 && a1.tidx == a2.tidx) {
+		const int k = pe_classify(pp, a1.refoff, (uint64_t)e1, a1.fw != 0, a2.refoff, (uint64_t)e2, a2.fw != 0);
+		if(k != 5) { bestSum = a1.score + a2.score; bestSrc = 0; bestKind = k; }
+	}
+	unsigned long long cells = 0;
+	// anchor = mate 1 (source 1: mate 2 from the mate DP), anchor = mate 2 (source 2)
+	for(int src = 1; src <= 2; src++) {
+		const uint64_t ra = src == 1 ? r1 : r2;
+		const bool fa = src == 1 ? f1 : f2;
+		if(!fa) continue;
+		const int pi = mateOfRead[ra];
+		if(pi < 0) continue;
+		const bt2g_dp_problem &q = mProbs[pi];
+		cells += (unsigned long long)(src == 1 ? len2 : len1) * (unsigned long long)(q.refr - q.refl + 1);
+		const int na = mSumm[pi].naln < maxAlns ? mSumm[pi].naln : maxAlns;
+		const bt2g_read_result &an = src == 1 ? a1 : a2;
+		const int ea = src == 1 ? e1 : e2;
+		for(int k = 0; k < na; k++) {
+			const bt2g_dp_aln &al = mAlns[(size_t)pi * maxAlns + k];
+			const uint8_t *o = mOps + ((size_t)pi * maxAlns + k) * maxOps;
+			int em = 0;
+			const int no = al.nops < maxOps ? al.nops : maxOps;
+			for(int x = 0; x < no; x++) em += (o[x] & 3) != BT2G_OP_REFGAP;
+			const int64_t moff = q.refl + al.col0;
+			const int kind = src == 1 ? pe_classify(pp, an.refoff, (uint64_t)ea, an.fw != 0, moff, (uint64_t)em, q.fw != 0)
+			                          : pe_classify(pp, moff, (uint64_t)em, q.fw != 0, an.refoff, (uint64_t)ea, an.fw != 0);
+			if(kind == 5) continue;
+			const int sum = an.score + al.score;
+			if(sum > bestSum) { bestSum = sum; bestSrc = src; bestKind = kind; bestAln = k; }
+		}
+	}
+	if(bestSrc > 0) {
+		// replace the opposite mate's result by the mate-DP alignment
+		const uint64_t ra = bestSrc == 1 ? r1 : r2, ro = bestSrc == 1 ? r2 : r1;
+		const int pi = mateOfRead[ra];
+		const bt2g_dp_problem &q = mProbs[pi];
+		const bt2g_dp_aln &al = mAlns[(size_t)pi * maxAlns + bestAln];
+		bt2g_read_result m = res[ro];
+		if((m.found & 0xff) != 0 && m.score > m.score2) m.score2 = m.score;   // the displaced alignment becomes the runner-up
+		m.found = (m.found & ~0xff) | 1; m.score = al.score; m.fw = q.fw; m.tidx = q.tidx; m.refoff = q.refl + al.col0;
+		m.nops = al.nops < maxOps ? al.nops : maxOps; m.trim_left = al.trim_beg; m.trim_right = al.trim_end;
+		const uint8_t *src = mOps + ((size_t)pi * maxAlns + bestAln) * maxOps;
+		uint8_t *dst = resOps + ro * (size_t)maxOps;
+		for(int k = 0; k < m.nops; k++) dst[k] = src[k];
+		res[ro] = m;
+		if(bestSrc == 1) a2 = m; else a1 = m;
+	}
+	if(bestSrc >= 0) {
+		out.pair_type = 1; out.kind = bestKind; out.source = bestSrc; out.score_sum = bestSum;
+		const int ee1 = pe_ref_extent(a1, resOps + r1 * (size_t)maxOps, len1), ee2 = pe_ref_extent(a2, resOps + r2 * (size_t)maxOps, len2);
+		const int64_t lo = a1.refoff < a2.refoff ? a1.refoff : a2.refoff;
+		const int64_t h1 = a1.refoff + ee1, h2 = a2.refoff + ee2;
+		out.fraglen = (h1 > h2 ? h1 : h2) - lo;
+	}
+	pairs[pr] = out;
+	if(mateCells && cells) atomicAdd(mateCells, cells);
 }
 
 template <typename T> static int pipeAlloc(bt2g_pipeline *p, T *&ptr, uint64_t count) {
@@ -267,22 +405,51 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 	k_frame<<<grid(n), T, 0, st>>>(n, roff, b.interval, b.offset, b.rows, b.hitlen, b.meta, b.tidx, b.textoff, b.tlen, b.rflags,
 	                               b.rowBase, b.rowCnt, q.row_cap, q.max_len, q.maxhalf, p->sc.match_bonus,
 	                               b.minscByLen, b.nceilRawByLen, b.rdgapsByLen, b.rfgapsByLen,
-	                               b.probs, b.nProb, (uint32_t)p->maxProbs, b.readProb, b.readNProb, b.res);
+	                               b.probs, b.nProb, (uint32_t)p->maxProbs, b.readProb, b.readNProb, b.res, b.probTlen, b.resTlen);
 	DpLaunch L;
 	L.seq = seq; L.qual = qual; L.roff = roff; L.probs = b.probs; L.n = p->maxProbs; L.nDev = b.nProb;
 	L.rawKeys = b.rawKeys; L.maxRaw = b.rawKeys ? PIPE_MAX_RAW : 0;
 	L.numSlots = p->numSlots; L.codes = b.codes; L.lastH = b.lastH; L.codeStride = p->codeStride; L.maxCol = p->maxCol;
-	L.maxCands = q.max_cands; L.maxAlns = q.max_alns; L.maxOps = q.max_ops;
+	L.maxCands = q.max_cands; L.maxAlns = q.max_alns; L.maxOps = q.max_ops; L.packed = p->packed;
 	L.summ = b.summ; L.cands = b.cands; L.alns = b.alns; L.ops = b.ops;
 	mark(6);
 	const int drc = p->sc.local ? launch_dp_local<OFF>(ix, p->sc, L, q.max_len, st) : launch_dp_e2e<OFF>(ix, p->sc, L, q.max_len, st);
 	if(drc) { ctx->err = "pipeline: DP launch rejected"; return -1; }
 	mark(7);
 	k_pick<<<grid(n), T, 0, st>>>(n, q.row_cap, q.max_alns, q.max_ops, b.readProb, b.readNProb, b.probs, b.summ, b.alns, b.ops,
-	                              b.res, b.resOps, c ? c + 3 : nullptr, roff);
+	                              b.res, b.resOps, c ? c + 3 : nullptr, roff, b.probTlen, b.resTlen);
 	mark(8);
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	p->lastN = n;
+	return 0;
+}
+
+template <typename OFF>
+static int runPairTail(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, const uint64_t *roff, uint64_t nPairs, cudaStream_t st, bool count) {
+	bt2g_ctx *ctx = p->ctx;
+	PipeBufs &b = p->b;
+	const bt2g_pipeline_params &q = p->prm;
+	DevIndex<OFF> ix = bt2g_dev_index<OFF>(ctx);
+	const uint64_t n = 2 * nPairs;
+	const unsigned T = 128;
+	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(b.nMateProb, 0, sizeof(uint32_t), st));
+	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(b.mateCells, 0, sizeof(unsigned long long), st));
+	cudaEventRecord(p->pev[0], st);
+	k_frame_mates<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(n, roff, b.res, b.resOps, q.max_ops, b.resTlen, p->pe, q.max_len, q.maxhalf, p->mateMaxCol,
+	                                                         b.minscByLen, b.nceilRawByLen, b.rdgapsByLen, b.rfgapsByLen, b.mProbs, b.nMateProb, b.mateOfRead);
+	cudaEventRecord(p->pev[1], st);
+	DpLaunch L;
+	L.seq = seq; L.qual = qual; L.roff = roff; L.probs = b.mProbs; L.n = p->maxReads; L.nDev = b.nMateProb;
+	L.rawKeys = nullptr; L.maxRaw = 0;
+	L.numSlots = p->numSlots; L.codes = b.codes; L.lastH = nullptr; L.codeStride = p->mateCodeStride; L.maxCol = p->mateMaxCol;
+	L.maxCands = q.max_cands; L.maxAlns = q.max_alns; L.maxOps = q.max_ops; L.packed = p->packed;
+	L.summ = b.mSumm; L.cands = b.mCands; L.alns = b.mAlns; L.ops = b.mOps;
+	if(launch_dp_e2e<OFF>(ix, p->sc, L, q.max_len, st)) { ctx->err = "pipeline: mate DP launch rejected"; return -1; }
+	cudaEventRecord(p->pev[2], st);
+	k_pick_pairs<<<(unsigned)((nPairs + T - 1) / T), T, 0, st>>>(nPairs, roff, b.res, b.resOps, q.max_ops, q.max_alns, p->pe, b.mateOfRead, b.mProbs,
+	                                                             b.mSumm, b.mAlns, b.mOps, b.pairs, count ? b.mateCells : nullptr);
+	cudaEventRecord(p->pev[3], st);
+	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	return 0;
 }
 
@@ -324,13 +491,19 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
 	p->sms = sms;
 	p->numSlots = (uint64_t)sms * 24;
-	rc |= pipeAlloc(p, b.codes, p->numSlots * p->codeStride); rc |= pipeAlloc(p, b.lastH, p->numSlots * (uint64_t)p->maxCol);
+	{
+		int64_t mn = 0;
+		for(int l = 1; l <= prm->max_len; l++) if(prm->minsc_by_len[l] < mn) mn = prm->minsc_by_len[l];
+		p->packed = dp_packed_ok(p->sc, mn, prm->max_len) ? 1 : 0;
+	}
+	rc |= pipeAlloc(p, b.codes, p->numSlots * p->codeStride * (p->packed ? 2 : 1)); rc |= pipeAlloc(p, b.lastH, p->numSlots * (uint64_t)p->maxCol);
 	// local mode gathers candidate cells during the fill (k_dp_local): a raw key list per warp slot
 	if(ctx->scoring.local) rc |= pipeAlloc(p, b.rawKeys, p->numSlots * (uint64_t)PIPE_MAX_RAW);
 	rc |= pipeAlloc(p, b.summ, nprobMax); rc |= pipeAlloc(p, b.cands, nprobMax * prm->max_cands);
 	rc |= pipeAlloc(p, b.alns, nprobMax * prm->max_alns); rc |= pipeAlloc(p, b.ops, nprobMax * prm->max_alns * (uint64_t)prm->max_ops);
 	rc |= pipeAlloc(p, b.res, n); rc |= pipeAlloc(p, b.resOps, n * (uint64_t)prm->max_ops);
 	rc |= pipeAlloc(p, b.counters, 4);
+	rc |= pipeAlloc(p, b.probTlen, nprobMax); rc |= pipeAlloc(p, b.resTlen, n);
 	if(rc) { bt2g_pipeline_destroy(p); return -2; }
 	cudaError_t e = cudaSuccess;
 	auto up = [&](int32_t *dst, const int32_t *src) { if(e == cudaSuccess) e = cudaMemcpy(dst, src, L1 * sizeof(int32_t), cudaMemcpyHostToDevice); };
@@ -363,6 +536,8 @@ void bt2g_pipeline_destroy(bt2g_pipeline *p) {
 	if(p->hOff) cudaFreeHost(p->hOff);
 	if(p->hRes) cudaFreeHost(p->hRes);
 	if(p->hOps) cudaFreeHost(p->hOps);
+	if(p->hPairs) cudaFreeHost(p->hPairs);
+	if(p->pairsOn) for(int i = 0; i < 4; i++) cudaEventDestroy(p->pev[i]);
 	delete p;
 }
 
@@ -395,6 +570,104 @@ int bt2g_pipeline_run_host(bt2g_pipeline *p, const bt2g_reads *reads, bt2g_read_
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(res, p->b.res, n * sizeof(bt2g_read_result), cudaMemcpyDeviceToHost, st));
 	if(ops) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(ops, p->b.resOps, n * (uint64_t)p->prm.max_ops, cudaMemcpyDeviceToHost, st));
 	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	return 0;
+}
+
+
+int bt2g_pipeline_enable_pairs(bt2g_pipeline *p, const bt2g_pe_policy *pol) {
+	if(!p || !pol) return -1;
+	bt2g_ctx *ctx = p->ctx;
+	if(pol->pol < 1 || pol->pol > 4) { ctx->err = "pipeline: bad paired-end policy"; return -1; }
+	if(p->sc.local) { ctx->err = "pipeline: paired-end pass is end-to-end only in this build"; return -1; }
+	if(p->pairsOn) { p->pe = *pol; return 0; }
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	PipeBufs &b = p->b;
+	const bt2g_pipeline_params &q = p->prm;
+	const uint64_t n = p->maxReads;
+	// widest mate rectangle: (maxfrag [expanded to the longer mate]) + rdlen - 1 + 2 * maxgap columns
+	uint64_t maxfrag = pol->maxfrag > (uint64_t)q.max_len ? pol->maxfrag : (uint64_t)q.max_len;
+	const int maxgap = q.maxhalf > 32 ? q.maxhalf : 32;
+	p->mateMaxCol = (int)(maxfrag + q.max_len + 2 * maxgap + 8);
+	if(p->mateMaxCol > 8192) { ctx->err = "pipeline: -X too large for the mate-finding workspace"; return -1; }
+	p->mateCodeStride = (uint64_t)(p->mateMaxCol + 32) * 32 * p->R;
+	int rc = 0;
+	uint8_t *codes2 = nullptr;
+	rc |= pipeAlloc(p, codes2, p->numSlots * p->mateCodeStride * (p->packed ? 2 : 1));
+	rc |= pipeAlloc(p, b.mProbs, n); rc |= pipeAlloc(p, b.nMateProb, 1); rc |= pipeAlloc(p, b.mateOfRead, n);
+	rc |= pipeAlloc(p, b.mSumm, n); rc |= pipeAlloc(p, b.mCands, n * q.max_cands);
+	rc |= pipeAlloc(p, b.mAlns, n * q.max_alns); rc |= pipeAlloc(p, b.mOps, n * q.max_alns * (uint64_t)q.max_ops);
+	rc |= pipeAlloc(p, b.pairs, n / 2 + 1); rc |= pipeAlloc(p, b.mateCells, 1);
+	if(rc) return -2;
+	b.codes = codes2;        // the wider workspace serves both DP passes
+	p->codeStride = p->mateCodeStride;
+	cudaError_t e = cudaMemset(b.mAlns, 0, n * q.max_alns * sizeof(bt2g_dp_aln));
+	if(e == cudaSuccess) e = cudaMemset(b.mCands, 0, n * q.max_cands * sizeof(bt2g_dp_cand));
+	if(e == cudaSuccess) e = cudaHostAlloc((void **)&p->hPairs, (n / 2 + 1) * sizeof(bt2g_pair_result), cudaHostAllocDefault);
+	for(int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&p->pev[i]);
+	if(e != cudaSuccess) { ctx->err = std::string("pipeline pairs setup: ") + cudaGetErrorString(e); return -2; }
+	p->pe = *pol; p->pairsOn = true;
+	return 0;
+}
+
+int bt2g_pipeline_run_paired_dev(bt2g_pipeline *p, const uint8_t *dSeq, const uint8_t *dQual, const uint64_t *dOff,
+                                 uint64_t nPairs, void *stream, int count) {
+	if(!p || !dSeq || !dQual || !dOff) return -1;
+	if(!p->pairsOn) { p->ctx->err = "pipeline: call bt2g_pipeline_enable_pairs first"; return -1; }
+	if(2 * nPairs > p->maxReads) { p->ctx->err = "pipeline: batch larger than max_reads"; return -1; }
+	if(nPairs == 0) return 0;
+	int rc = bt2g_pipeline_run_dev(p, dSeq, dQual, dOff, 2 * nPairs, stream, count);
+	if(rc) return rc;
+	cudaStream_t st = stream ? (cudaStream_t)stream : p->ctx->stream;
+	if(p->ctx->info.off_size == 4) return runPairTail<uint32_t>(p, dSeq, dQual, dOff, nPairs, st, count != 0);
+	return runPairTail<uint64_t>(p, dSeq, dQual, dOff, nPairs, st, count != 0);
+}
+
+int bt2g_pipeline_run_paired_host(bt2g_pipeline *p, const bt2g_reads *reads, bt2g_read_result *res, uint8_t *ops, bt2g_pair_result *pairs) {
+	if(!p || !reads || !reads->qual || !res || !pairs) return -1;
+	bt2g_ctx *ctx = p->ctx;
+	const uint64_t n = reads->n_reads;
+	if(n & 1ull) { ctx->err = "pipeline: paired input needs an even number of reads (mate 1, mate 2 interleaved)"; return -1; }
+	if(n > p->maxReads || reads->off[n] > p->maxBases) { ctx->err = "pipeline: batch larger than the pipeline was created for"; return -1; }
+	if(n == 0) return 0;
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const uint64_t nb = reads->off[n];
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.seq, reads->seq, nb, cudaMemcpyHostToDevice, st));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.qual, reads->qual, nb, cudaMemcpyHostToDevice, st));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.roff, reads->off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	int rc = bt2g_pipeline_run_paired_dev(p, p->b.seq, p->b.qual, p->b.roff, n / 2, st, 0);
+	if(rc) return rc;
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(res, p->b.res, n * sizeof(bt2g_read_result), cudaMemcpyDeviceToHost, st));
+	if(ops) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(ops, p->b.resOps, n * (uint64_t)p->prm.max_ops, cudaMemcpyDeviceToHost, st));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(pairs, p->b.pairs, (n / 2) * sizeof(bt2g_pair_result), cudaMemcpyDeviceToHost, st));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	return 0;
+}
+
+int bt2g_pipeline_pairs_dev(bt2g_pipeline *p, bt2g_pair_result **pairs) {
+	if(!p || !pairs || !p->pairsOn) return -1;
+	*pairs = p->b.pairs;
+	return 0;
+}
+
+int bt2g_pipeline_pair_counters(bt2g_pipeline *p, uint64_t *out2) {
+	if(!p || !out2 || !p->pairsOn) return -1;
+	bt2g_ctx *ctx = p->ctx;
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	uint32_t np = 0; unsigned long long cells = 0;
+	BT2G_CUDA_TRY(ctx, cudaMemcpy(&np, p->b.nMateProb, sizeof(np), cudaMemcpyDeviceToHost));
+	BT2G_CUDA_TRY(ctx, cudaMemcpy(&cells, p->b.mateCells, sizeof(cells), cudaMemcpyDeviceToHost));
+	out2[0] = np; out2[1] = cells;
+	return 0;
+}
+
+int bt2g_pipeline_pair_stage_ms(bt2g_pipeline *p, float *out3) {
+	if(!p || !out3 || !p->pairsOn) return -1;
+	bt2g_ctx *ctx = p->ctx;
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	BT2G_CUDA_TRY(ctx, cudaEventSynchronize(p->pev[3]));
+	for(int i = 0; i < 3; i++) BT2G_CUDA_TRY(ctx, cudaEventElapsedTime(&out3[i], p->pev[i], p->pev[i + 1]));
 	return 0;
 }
 

@@ -364,7 +364,10 @@ READ_RESULT = np.dtype([("found", "<i4"), ("score", "<i4"), ("score2", "<i4"), (
                        align=True)
 
 EXPORTS += ["bt2g_pipeline_create", "bt2g_pipeline_destroy", "bt2g_pipeline_run_dev", "bt2g_pipeline_run_host",
-            "bt2g_pipeline_results_dev", "bt2g_pipeline_counters", "bt2g_pipeline_stage_ms"]
+            "bt2g_pipeline_results_dev", "bt2g_pipeline_counters", "bt2g_pipeline_stage_ms",
+            "bt2g_pipeline_enable_pairs", "bt2g_pipeline_run_paired_dev", "bt2g_pipeline_run_paired_host",
+            "bt2g_pipeline_pairs_dev", "bt2g_pipeline_pair_counters", "bt2g_pipeline_pair_stage_ms"]
+PAIR_RESULT = np.dtype([("pair_type", "<i4"), ("kind", "<i4"), ("source", "<i4"), ("score_sum", "<i4"), ("fraglen", "<i8")], align=True)
 
 
 class Pipeline:
@@ -416,6 +419,45 @@ class Pipeline:
             self.close()
         except Exception:
             pass
+
+    # ---- paired-end pass (include/bt2g.h: bt2g_pipeline_enable_pairs ...) ----
+    def enable_pairs(self, pe=None):
+        from . import policy
+        lib = self.gpu._lib
+        vp = C.c_void_p
+        lib.bt2g_pipeline_enable_pairs.argtypes = [vp, vp]
+        lib.bt2g_pipeline_run_paired_dev.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, C.c_int]
+        lib.bt2g_pipeline_run_paired_host.argtypes = [vp, C.POINTER(_Reads), vp, vp, vp]
+        lib.bt2g_pipeline_pairs_dev.argtypes = [vp, C.POINTER(vp)]
+        lib.bt2g_pipeline_pair_counters.argtypes = [vp, vp]
+        lib.bt2g_pipeline_pair_stage_ms.argtypes = [vp, vp]
+        self.pe = pe if pe is not None else policy.PairedEndPolicy()
+        pp = _pe_struct(self.pe)
+        self.gpu._check(lib.bt2g_pipeline_enable_pairs(self._h, C.byref(pp)), "bt2g_pipeline_enable_pairs")
+
+    def run_paired_host(self, reads: ReadBatch, want_ops: bool = True):
+        """reads: mate 1 / mate 2 interleaved -> (per-read results, ops, per-pair results)."""
+        res = np.zeros(reads.n, dtype=READ_RESULT)
+        ops = np.zeros((reads.n, self.max_ops), dtype=np.uint8) if want_ops else None
+        pairs = np.zeros(reads.n // 2, dtype=PAIR_RESULT)
+        st = reads._struct()
+        self.gpu._check(self.gpu._lib.bt2g_pipeline_run_paired_host(self._h, C.byref(st), _ptr(res), _ptr(ops), _ptr(pairs)),
+                        "bt2g_pipeline_run_paired_host")
+        return res, ops, pairs
+
+    def run_paired_dev(self, d_seq: int, d_qual: int, d_off: int, n_pairs: int, stream: int = 0, count: bool = False):
+        self.gpu._check(self.gpu._lib.bt2g_pipeline_run_paired_dev(self._h, d_seq, d_qual, d_off, n_pairs, stream, int(count)),
+                        "bt2g_pipeline_run_paired_dev")
+
+    def pair_counters(self) -> dict:
+        out = np.zeros(2, dtype=np.uint64)
+        self.gpu._check(self.gpu._lib.bt2g_pipeline_pair_counters(self._h, _ptr(out)), "bt2g_pipeline_pair_counters")
+        return {"mate_problems": int(out[0]), "mate_cells": int(out[1])}
+
+    def pair_stage_ms(self) -> dict:
+        out = np.zeros(3, dtype=np.float32)
+        self.gpu._check(self.gpu._lib.bt2g_pipeline_pair_stage_ms(self._h, _ptr(out)), "bt2g_pipeline_pair_stage_ms")
+        return dict(zip(("frame_mates", "mate_dp", "pick_pairs"), (float(x) for x in out)))
 
     def run_host(self, reads: ReadBatch, want_ops: bool = True):
         res = np.zeros(reads.n, dtype=READ_RESULT)

@@ -101,3 +101,55 @@ def write_fastq(path: str, reads, quals, prefix: str = "r"):
         for i, (r, q) in enumerate(zip(reads, quals)):
             f.write(f"@{prefix}{i}\n".encode())
             f.write(DNA[r].tobytes() + b"\n+\n" + q.tobytes() + b"\n")
+
+
+def make_pairs(contigs, n_pairs: int, read_len: int, seed: int = 1, sub_rate: float = 0.005, indel_rate: float = 0.0005,
+               ins_mean: float = 350.0, ins_sd: float = 30.0, hard_frac: float = 0.0, hard_period: int = 14):
+    """FR pairs (SURVEY.md section 8d): fragment length ~ N(ins_mean, ins_sd) clipped to [read_len + 20, 500];
+    mate 1 is the fragment's left end on a random strand of the fragment, mate 2 the reverse complement of its
+    right end.  A `hard_frac` share of pairs gets a substitution every `hard_period` bases in one mate, which
+    leaves no exact seed there so that only the mate-finding DP can place it.
+    Returns (reads interleaved m1, m2, ..., quals, truth [(contig, fragment start, fragment length, flipped)])."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    reads, quals, truth = [], [], []
+    base_q = np.linspace(40, 20, read_len)
+
+    def mutate(src):
+        out, k = [], 0
+        while len(out) < read_len and k < len(src):
+            u = rng.random()
+            if u < indel_rate / 2:
+                k += 1
+                continue
+            if u < indel_rate:
+                out.append(int(rng.integers(0, 4)))
+                continue
+            b = int(src[k])
+            if b < 4 and rng.random() < sub_rate:
+                b = (b + 1 + int(rng.integers(0, 3))) % 4
+            out.append(b)
+            k += 1
+        r = np.array(out[:read_len], dtype=np.uint8)
+        if len(r) < read_len:
+            r = np.concatenate([r, rng.integers(0, 4, size=read_len - len(r), dtype=np.uint8)])
+        return r
+
+    for i in range(n_pairs):
+        c = int(rng.integers(0, len(contigs)))
+        g = contigs[c]
+        frag = int(np.clip(rng.normal(ins_mean, ins_sd), read_len + 20, 500))
+        p = int(rng.integers(0, max(1, len(g) - frag - 16)))
+        left = mutate(g[p:p + read_len + 8])
+        right = mutate(revcomp(g[p + frag - read_len - 8:p + frag]))     # reads the fragment's right end inwards
+        flipped = rng.random() < 0.5                                      # fragment from the reverse strand
+        m1, m2 = (right, left) if flipped else (left, right)
+        if rng.random() < hard_frac:
+            tgt = m2 if rng.random() < 0.5 else m1
+            for k in range(int(rng.integers(0, hard_period)), read_len, hard_period):
+                if tgt[k] < 4:
+                    tgt[k] = (tgt[k] + 1 + int(rng.integers(0, 3))) % 4
+        for m in (m1, m2):
+            reads.append(m)
+            quals.append(np.clip(base_q + rng.normal(0, 3, read_len), 2, 41).astype(np.uint8) + 33)
+        truth.append((c, p, frag, flipped))
+    return reads, quals, truth

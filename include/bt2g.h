@@ -342,6 +342,33 @@ int  bt2g_pipeline_run_dev(bt2g_pipeline *p, const uint8_t *d_seq, const uint8_t
 int  bt2g_pipeline_run_host(bt2g_pipeline *p, const bt2g_reads *reads, bt2g_read_result *res, uint8_t *ops);
 int  bt2g_pipeline_results_dev(bt2g_pipeline *p, bt2g_read_result **res, uint8_t **ops);
 int  bt2g_pipeline_counters(bt2g_pipeline *p, uint64_t *out6);
+/* ---- paired-end pass (SwDriver::extendSeedsPaired's mate finding, aligner_sw_driver.cpp:2157-2440) ----
+ * Reads are interleaved: mate 1 of pair i is read 2i, mate 2 is read 2i+1.  The pass runs the
+ * single-end stages on all 2n reads, then for every aligned mate (the anchor) whose opposite mate has
+ * no alignment concordant with it, frames the mate-finding rectangle (bt2g_frame_mate arithmetic) and
+ * runs the same DP kernel on the opposite mate inside that window; finally the best concordant
+ * combination per pair is chosen (peClassifyPair) and the per-read results are updated with it.
+ * The reference runs the mate DP for EVERY anchor alignment as it goes; skipping it when the two
+ * independent alignments already form a concordant pair is this pipeline's speculation. */
+typedef struct {
+	int32_t pair_type;           /* 0 neither mate aligned, 1 concordant pair, 2 both aligned but not concordant,
+	                              * 3 only one mate aligned */
+	int32_t kind;                /* peClassifyPair of the reported pair (1..4) or 5 */
+	int32_t source;              /* 0 independent alignments, 1 mate 2 found by mate DP, 2 mate 1 found by mate DP */
+	int32_t score_sum;           /* sum of the two alignment scores when pair_type == 1 */
+	int64_t fraglen;             /* fragment length (pe.cpp:89-92) when pair_type == 1 */
+} bt2g_pair_result;
+int  bt2g_pipeline_enable_pairs(bt2g_pipeline *p, const bt2g_pe_policy *pol);
+int  bt2g_pipeline_run_paired_dev(bt2g_pipeline *p, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_off,
+                                  uint64_t n_pairs, void *stream, int count);
+int  bt2g_pipeline_run_paired_host(bt2g_pipeline *p, const bt2g_reads *reads, bt2g_read_result *res, uint8_t *ops,
+                                   bt2g_pair_result *pairs);
+int  bt2g_pipeline_pairs_dev(bt2g_pipeline *p, bt2g_pair_result **pairs);
+/* [0] mate DP problems, [1] mate DP cells of the last paired run made with count != 0 */
+int  bt2g_pipeline_pair_counters(bt2g_pipeline *p, uint64_t *out2);
+/* device milliseconds of the paired tail of the last run: [0] mate framing, [1] mate DP, [2] pair pick */
+int  bt2g_pipeline_pair_stage_ms(bt2g_pipeline *p, float *out3);
+
 /* device milliseconds of the 8 stages of the last run (CUDA events on the launching stream) */
 int  bt2g_pipeline_stage_ms(bt2g_pipeline *p, float *out8);
 

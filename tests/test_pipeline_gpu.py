@@ -134,3 +134,67 @@ def test_pipeline_stage_consistency(gpu, synth_index, synth_genome):
     assert np.array_equal(res["found"] == 2, has_ee)
     assert (res["found"] != 0).sum() > 350
     pipe.close()
+
+
+def _write_pair_fastq(tmp_path, reads, quals):
+    f1, f2 = str(tmp_path / "r_1.fq"), str(tmp_path / "r_2.fq")
+    synth.write_fastq(f1, reads[0::2], quals[0::2])
+    synth.write_fastq(f2, reads[1::2], quals[1::2])
+    return f1, f2
+
+
+def _run_reference_paired(index, f1, f2, preset="--sensitive"):
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), preset, "--end-to-end", "--seed", "0", "-p", "4", "--reorder",
+                                   "-x", index, "-1", f1, "-2", f2], stderr=subprocess.DEVNULL).decode()
+    recs = []
+    for line in out.splitlines():
+        if line.startswith("@"):
+            continue
+        f = line.split("\t")
+        tags = {t[:2]: t[5:] for t in f[11:]}
+        recs.append(dict(flag=int(f[1]), rname=f[2], pos=int(f[3]) - 1, mapq=int(f[4]), cigar=f[5], tlen=int(f[8]),
+                         AS=int(tags["AS"]) if "AS" in tags else None, YT=tags.get("YT")))
+    return recs
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_paired_pipeline_vs_reference_program(gpu, synth_index, synth_genome, tmp_path):
+    """FR pairs, -I 0 -X 500: concordant pairs of the reference are found with the same placement,
+    including pairs where one mate has no exact seed and only the mate-finding DP can place it."""
+    gpu.load_index_files(synth_index)
+    rdlen, npairs = 100, 1500
+    reads, quals, truth = synth.make_pairs(synth_genome, npairs, rdlen, seed=4242, sub_rate=0.01, indel_rate=0.001,
+                                           hard_frac=0.25, hard_period=12)
+    f1, f2 = _write_pair_fastq(tmp_path, reads, quals)
+    want = _run_reference_paired(synth_index, f1, f2)
+    assert len(want) == 2 * npairs
+    pipe = Pipeline(gpu, "sensitive", max_len=rdlen, max_reads=4096, row_cap=16, range_max=16, both_mates=True)
+    pipe.enable_pairs()
+    res, ops, pairs = pipe.run_paired_host(ReadBatch.from_list(reads, quals))
+    n_cp = n_cp_same = n_rescued = n_rescued_same = n_cigar = 0
+    for i in range(npairs):
+        w1, w2 = want[2 * i], want[2 * i + 1]
+        if w1["YT"] != "CP" or w2["YT"] != "CP":
+            continue
+        n_cp += 1
+        ok = pairs[i]["pair_type"] == 1
+        for k, w in ((2 * i, w1), (2 * i + 1, w2)):
+            r = res[k]
+            ok = ok and (r["found"] & 0xff) != 0 and int(r["tidx"]) == int(w["rname"][3:]) - 1 and int(r["refoff"]) == w["pos"] \
+                and bool(r["fw"]) == (not (w["flag"] & 16)) and int(r["score"]) == w["AS"]
+        n_cp_same += ok
+        if ok:
+            assert int(pairs[i]["fraglen"]) == abs(w1["tlen"])
+            for k, w in ((2 * i, w1), (2 * i + 1, w2)):
+                cig = f"{rdlen}M" if (res[k]["found"] & 0xff) == 2 else ops_to_cigar(ops[k], int(res[k]["nops"]))
+                n_cigar += cig == w["cigar"]
+        if pairs[i]["source"] != 0:
+            n_rescued += 1
+            n_rescued_same += ok
+    assert n_cp > 0.9 * npairs
+    assert n_cp_same >= 0.97 * n_cp, (n_cp_same, n_cp)
+    assert n_cigar >= 0.99 * 2 * n_cp_same, (n_cigar, n_cp_same)
+    assert n_rescued > 100, n_rescued                      # the mate DP really ran and decided pairs
+    assert n_rescued_same >= 0.9 * n_rescued, (n_rescued_same, n_rescued)
+    c = pipe.pair_counters()
+    pipe.close()

@@ -11,6 +11,11 @@ tests)
   timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -5 $OUT/${TAG}_pytest.log ;;
 bench)
   timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"; tail -c 1500 $OUT/${TAG}_bench.json ;;
+bench0)
+  BT2G_DP_PACKED=0 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench0.json 2> $OUT/${TAG}_bench0.err; echo "bench0 exit $?"; tail -c 700 $OUT/${TAG}_bench0.json ;;
+ncudp)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:^k_dp_e2e -s 1 -c 1 -f -o $OUT/${TAG}_k_dp_e2e \
+     python bench.py --steps 2 --warmup 1 --reads 2000000 --no-cpu-baseline > $OUT/${TAG}_ncu_k_dp_e2e.log 2>&1; echo "ncu dp exit $?" ;;
 benchfull)
   timeout 1500 python bench.py > $OUT/${TAG}_bench_full.json 2> $OUT/${TAG}_bench_full.err; echo "bench exit $?"; tail -c 1500 $OUT/${TAG}_bench_full.json ;;
 ncu)
