@@ -577,7 +577,7 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 		L.numSlots = ((n < want ? n : want) + 3) / 4 * 4;
 	} L.maxCands = maxCands; L.maxAlns = maxAlns; L.maxOps = maxOps;
 	L.codeStride = (uint64_t)(maxCol + 32) * 32 * R;
-	L.packed = dp_packed_ok(ctx->scoring, minMinsc, maxLen) ? 1 : 0;
+	L.packed = dp_kernel_mode(ctx->scoring, minMinsc, maxLen);
 	BT2G_CUDA_TRY(ctx, dprob.alloc(n * sizeof(bt2g_dp_problem)));
 	BT2G_CUDA_TRY(ctx, dcodes.alloc(L.numSlots * L.codeStride * (L.packed ? 2 : 1)));
 	BT2G_CUDA_TRY(ctx, dlast.alloc(L.numSlots * (uint64_t)maxCol * 4));

@@ -6,9 +6,19 @@
 // the s16x2 kernel needs every reachable score within +-DPX_LIMIT (dp_kernels.cu): end-to-end mode,
 // minimum score >= -8000 and perfect score <= 8000; BT2G_DP_PACKED=0 in the environment disables it
 static inline bool dp_packed_ok(const bt2g_scoring &sc, int64_t minMinsc, int maxLen) {
-	const char *e = getenv("BT2G_DP_PACKED");
-	if(e && e[0] == '0') return false;
 	return !sc.local && minMinsc >= -8000 && (int64_t)sc.match_bonus * maxLen <= 8000 && sc.match_bonus >= 0;
+}
+
+// DpLaunch.packed: 0 = k_dp_e2e (32-bit, move codes), 1 = k_dp_e2e_x2 (s16x2, move codes),
+// 2 = k_dp_e2e_h (s16x2, H bytes: needs perfect - (minsc - bonus - 1) <= 127 for every problem).
+// BT2G_DP_PACKED in the environment caps the mode (0, 1 or 2).
+static inline int dp_kernel_mode(const bt2g_scoring &sc, int64_t minMinsc, int maxLen) {
+	int cap = 2;
+	const char *e = getenv("BT2G_DP_PACKED");
+	if(e && e[0] >= '0' && e[0] <= '2') cap = e[0] - '0';
+	if(cap == 0 || !dp_packed_ok(sc, minMinsc, maxLen)) return 0;
+	const int64_t range = (int64_t)sc.match_bonus * maxLen - (minMinsc - sc.match_bonus - 1);
+	return (cap >= 2 && range <= 127) ? 2 : 1;
 }
 
 struct DpLaunch {

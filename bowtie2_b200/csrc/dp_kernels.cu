@@ -180,8 +180,14 @@ __device__ __forceinline__ void dp_backtrace_all(const DpLaunch &L, const bt2g_s
 	if(lane == 0) { summ->naln = naln; summ->flags |= flags; }
 }
 
-// ---- end-to-end tail: best of the last row, candidate list (gatherCellsNucleotidesEnd2End), backtraces
 template <int R>
+__device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_scoring &sc, const bt2g_dp_problem &p, uint64_t w,
+                                               const uint8_t *rs, const uint8_t *rq, int rdlen, const uint8_t *refw,
+                                               uint8_t *hb, bt2g_dp_cand *cands, int ncand, bt2g_dp_summary *summ, int lane);
+
+// ---- end-to-end tail: best of the last row, candidate list (gatherCellsNucleotidesEnd2End), backtraces.
+// HB: the workspace holds H bytes (k_dp_e2e_h) instead of move codes.
+template <int R, bool HB = false>
 __device__ __forceinline__ void dp_e2e_tail(const DpLaunch &L, const bt2g_scoring &sc, const bt2g_dp_problem &p, uint64_t w,
                                             const uint8_t *rs, const uint8_t *rq, int rdlen, int ncol, int32_t *lastH,
                                             uint16_t *candCol, const uint8_t *refw, uint8_t *codes, bt2g_dp_summary *summ, int lane) {
@@ -230,7 +236,8 @@ __device__ __forceinline__ void dp_e2e_tail(const DpLaunch &L, const bt2g_scorin
 	}
 	__syncwarp();
 
-	dp_backtrace_all<R>(L, sc, p, w, rs, rq, rdlen, refw, codes, cands, ncand, summ, lane, false);
+	if(HB) dp_backtrace_h<R>(L, sc, p, w, rs, rq, rdlen, refw, codes, cands, ncand, summ, lane);
+	else dp_backtrace_all<R>(L, sc, p, w, rs, rq, rdlen, refw, codes, cands, ncand, summ, lane, false);
 }
 
 // R = rows per lane (rdlen <= 32*R)
@@ -548,6 +555,326 @@ __global__ void __launch_bounds__(128) k_dp_e2e_x2(DevIndex<OFF> ix, bt2g_scorin
 }
 
 // ----------------------------------------------------------------------------------------
+// ----------------------------------------------------------------------------------------
+// Fill of the H-byte kernel (two problems per warp, s16x2; see the description below).
+template <typename OFF, int R>
+__global__ void __launch_bounds__(128) k_dp_e2e_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L) {
+	extern __shared__ uint8_t smem[];
+	const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint64_t slot = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock;
+	const uint64_t nSlots = (uint64_t)gridDim.x * (blockDim.x >> 5);
+	const uint64_t nProb = L.nDev ? (uint64_t)*L.nDev : L.n;
+	const uint64_t nPairs = (nProb + 1) >> 1;
+	const size_t perProb = dp_smem_per_warp(L.maxCol);
+	uint8_t *sm0 = smem + (size_t)warpInBlock * 2 * perProb;
+	int32_t *lastH[2]; uint16_t *candCol[2]; uint8_t *refw[2]; uint8_t *hb[2];
+#pragma unroll
+	for(int x = 0; x < 2; x++) {
+		lastH[x] = reinterpret_cast<int32_t *>(sm0 + x * perProb);
+		candCol[x] = reinterpret_cast<uint16_t *>(lastH[x] + L.maxCol);
+		refw[x] = reinterpret_cast<uint8_t *>(candCol[x] + L.maxCol);
+		hb[x] = L.codes + (slot * 2 + x) * L.codeStride;
+	}
+	const int rdgapo = sc.rdgap_const + sc.rdgap_linear, rdgape = sc.rdgap_linear;
+	const int rfgapo = sc.rfgap_const + sc.rfgap_linear, rfgape = sc.rfgap_linear;
+	const int bonus = sc.match_bonus;
+	const uint32_t FLOORP = dpx_both(DPX_FLOOR), ONEP = 0x00010001u;
+	const uint32_t bonusP = dpx_both(bonus), nrdeP = dpx_both(-rdgape);
+
+	for(uint64_t pw = slot; pw < nPairs; pw += nSlots) {
+		uint64_t w[2] = {2 * pw, 2 * pw + 1};
+		bool live[2] = {true, w[1] < nProb};
+		if(!live[1]) w[1] = w[0];
+		bt2g_dp_problem p[2] = {L.probs[w[0]], L.probs[w[1]]};
+		const uint8_t *rs[2], *rq[2]; int rdlen[2], ncol[2], floorv[2];
+		__syncwarp();
+#pragma unroll
+		for(int x = 0; x < 2; x++) {
+			rs[x] = L.seq + L.roff[p[x].read_idx]; rq[x] = L.qual + L.roff[p[x].read_idx];
+			rdlen[x] = (int)(L.roff[p[x].read_idx + 1] - L.roff[p[x].read_idx]);
+			ncol[x] = (int)(p[x].refr - p[x].refl + 1);
+			floorv[x] = p[x].minsc - bonus - 1;
+			// shape, and the score range the byte encoding can hold (perfect - floor <= 127)
+			if(ncol[x] <= 0 || ncol[x] > L.maxCol || rdlen[x] > 32 * R || rdlen[x] <= 0 ||
+			   (int64_t)bonus * rdlen[x] - floorv[x] > 127 || floorv[x] < -DPX_LIMIT) {
+				if(live[x] && lane == 0) {
+					bt2g_dp_summary *sm = L.summ + w[x];
+					sm->found = 0; sm->best = DP_NEG; sm->ncand = 0; sm->naln = 0; sm->flags = BT2G_DP_FLAG_BADSHAPE;
+				}
+				live[x] = false;
+			}
+		}
+		if(!live[0] && !live[1]) continue;
+		// a dead half mirrors the live one (its results are discarded)
+		if(!live[0]) { p[0] = p[1]; rs[0] = rs[1]; rq[0] = rq[1]; rdlen[0] = rdlen[1]; ncol[0] = ncol[1]; floorv[0] = floorv[1]; w[0] = w[1]; }
+		if(!live[1]) { p[1] = p[0]; rs[1] = rs[0]; rq[1] = rq[0]; rdlen[1] = rdlen[0]; ncol[1] = ncol[0]; floorv[1] = floorv[0]; w[1] = w[0]; }
+		// reference windows (SwAligner::initRef, aligner_sw.cpp:155-271): codes 0..3, 4 = N / off-end
+		const int ncolMax = ncol[0] > ncol[1] ? ncol[0] : ncol[1];
+#pragma unroll
+		for(int x = 0; x < 2; x++)
+			for(int k = lane; k < ncolMax; k += 32) refw[x][k] = k < ncol[x] ? (uint8_t)ref_base<OFF>(ix, p[x].tidx, p[x].refl + k) : (uint8_t)4;
+		__syncwarp();
+
+		// per-row constants of both problems (buildQueryProfileEnd2EndSseU8, aligner_swsse_ee_u8.cpp:75-142)
+		uint32_t rcP[R], mmpP[R], npnP[R], nrfoP[R], nrfeP[R], nrdoP[R];
+#pragma unroll
+		for(int r = 0; r < R; r++) {
+			int v[2][6];
+#pragma unroll
+			for(int x = 0; x < 2; x++) {
+				const int i = lane * R + r;
+				bool bar = true;
+				int c = 5, mm = 0, np = 0;
+				if(i < rdlen[x]) {
+					const int pos = p[x].fw ? i : rdlen[x] - 1 - i;
+					c = rs[x][pos];
+					c = p[x].fw ? c : (c > 3 ? 4 : 3 - c);
+					int q = (int)rq[x][pos] - 33;
+					q = q < 0 ? 0 : (q > 63 ? 63 : q);
+					np = -(int)sc.npen[q];
+					mm = c > 3 ? np : -(int)sc.mmpen[q];
+					if(c > 3) c = 5;
+					bar = (i < sc.gapbar) || (rdlen[x] - 1 - i < sc.gapbar);
+				}
+				v[x][0] = c; v[x][1] = mm; v[x][2] = np;
+				v[x][3] = bar ? -DPX_BIG : -rfgapo; v[x][4] = bar ? -DPX_BIG : -rfgape; v[x][5] = bar ? -DPX_BIG : -rdgapo;
+			}
+			rcP[r] = dpx_pack(v[0][0], v[1][0]); mmpP[r] = dpx_pack(v[0][1], v[1][1]); npnP[r] = dpx_pack(v[0][2], v[1][2]);
+			nrfoP[r] = dpx_pack(v[0][3], v[1][3]); nrfeP[r] = dpx_pack(v[0][4], v[1][4]); nrdoP[r] = dpx_pack(v[0][5], v[1][5]);
+		}
+		const int lastLane0 = (rdlen[0] - 1) / R, lastLane1 = (rdlen[1] - 1) / R;
+		const int lastLaneMax = lastLane0 > lastLane1 ? lastLane0 : lastLane1;
+		const uint32_t nfloorP = dpx_pack(-floorv[0], -floorv[1]);
+
+		uint32_t Hleft[R], Earr[R];
+#pragma unroll
+		for(int r = 0; r < R; r++) { Hleft[r] = FLOORP; Earr[r] = FLOORP; }
+		uint32_t botH = FLOORP, botF = FLOORP, prevInH = FLOORP;
+		const int nsteps = ncolMax + lastLaneMax;
+		uint8_t *dstA = hb[0] + (size_t)lane * R, *dstB = hb[1] + (size_t)lane * R;
+		for(int t = 0; t < nsteps; t++, dstA += 32 * R, dstB += 32 * R) {
+			uint32_t inH = __shfl_up_sync(0xffffffffu, botH, 1);
+			uint32_t inF = __shfl_up_sync(0xffffffffu, botF, 1);
+			if(lane == 0) { inH = FLOORP; inF = FLOORP; }
+			const int j = t - lane;
+			if(j >= 0 && j < ncolMax && lane <= lastLaneMax) {
+				const uint32_t refcP = (uint32_t)refw[0][j] | ((uint32_t)refw[1][j] << 16);
+				const uint32_t refNm = ((refcP >> 2) & ONEP) * 0xffffu;      // half mask: reference N
+				// H[i0-1][j-1]: row -1 is the free start row of end-to-end mode (vhilsw, :853,923-927)
+				uint32_t diag = (lane == 0) ? 0u : prevInH;
+				uint32_t upH = inH, upF = inF;
+				uint32_t hs[R];
+#pragma unroll
+				for(int r = 0; r < R; r++) {
+					// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo)
+					const uint32_t F = __viaddmax_s16x2(upF, nrfeP[r], __viaddmax_s16x2(upH, nrfoP[r], FLOORP));
+					const uint32_t pen = dpx_sel(refNm, npnP[r], mmpP[r]);
+					const uint32_t mmask = dpx_ne01(rcP[r], refcP) * 0xffffu;
+					const uint32_t Hd = __viaddmax_s16x2(diag, dpx_sel(mmask, pen, bonusP), FLOORP);
+					const uint32_t E = Earr[r];
+					const uint32_t H = __vimax3_s16x2(Hd, E, F);
+					// E[i][j+1] = max(E[i][j]-rdgape, H[i][j]-rdgapo)
+					Earr[r] = __viaddmax_s16x2(E, nrdeP, __viaddmax_s16x2(H, nrdoP[r], FLOORP));
+					hs[r] = __viaddmax_s16x2(H, nfloorP, 0u);              // max(H - floor, 0): the stored byte
+					diag = Hleft[r]; Hleft[r] = H;
+					upH = H; upF = F;
+				}
+				botH = upH; botF = upF;
+				prevInH = inH;
+				// byte 0 of every word is problem A's cell, byte 2 problem B's
+#pragma unroll
+				for(int q4 = 0; q4 < R / 4; q4++) {
+					const uint32_t t01 = __byte_perm(hs[4 * q4], hs[4 * q4 + 1], 0x6240), t23 = __byte_perm(hs[4 * q4 + 2], hs[4 * q4 + 3], 0x6240);
+					reinterpret_cast<uint32_t *>(dstA)[q4] = __byte_perm(t01, t23, 0x5410);
+					reinterpret_cast<uint32_t *>(dstB)[q4] = __byte_perm(t01, t23, 0x7632);
+				}
+			} else if(j >= ncolMax) {
+				botH = FLOORP; botF = FLOORP;
+			}
+		}
+		__syncwarp();
+#pragma unroll
+		for(int x = 0; x < 2; x++) {
+			if(!live[x]) continue;
+			// last row -> scores (candidates are the cells >= minsc; a clamped byte reads as floor < minsc)
+			const int lr = rdlen[x] - 1, kk = lr / R;
+			for(int j = lane; j < ncol[x]; j += 32)
+				lastH[x][j] = (int)hb[x][((size_t)(j + kk) * 32 + kk) * R + (lr - kk * R)] + floorv[x];
+			dp_e2e_tail<R, true>(L, sc, p[x], w[x], rs[x], rq[x], rdlen[x], ncol[x], lastH[x], candCol[x], refw[x], hb[x], L.summ + w[x], lane);
+		}
+	} // persistent loop over problem pairs
+}
+
+// ----------------------------------------------------------------------------------------
+// "H-byte" end-to-end kernel: the fill stores ONE byte per cell that is the cell's H score itself
+// (offset by floor = minsc - bonus - 1, clamped to [0,127]; bit 7 = reported-through mark), not a
+// move code.  The fill then is just the three recurrences (13 DPX/logic instructions per row for two
+// problems).  The backtrace re-derives each move from the stored scores, in the reference's
+// preference order (aligner_swsse_ee_u8.cpp:1468-1520):
+//   diag      H[i][j] == H[i-1][j-1] + score(i,j)          tested for a whole diagonal run at once;
+//   ref gap   H[i][j] == H[i-k][j] - rfgapo - (k-1) rfgape  smallest k  (open first, then extensions:
+//             exactly the F-state walk of the reference, because F[i][j] is the max of those terms);
+//   read gap  H[i][j] == H[i][j-k] - rdgapo - (k-1) rdgape  smallest k,
+// with the gap barrier of the recurrences (no F in barrier rows, no E opened from a barrier row).
+// A clamped (zero) byte is a cell below floor: floor + bonus < minsc, so it can never satisfy an
+// equality with a cell on a valid path.  Usable when perfect - floor <= 127 (dp_hbyte_ok).
+template <int R>
+__device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_scoring &sc, const bt2g_dp_problem &p, uint64_t w,
+                                               const uint8_t *rs, const uint8_t *rq, int rdlen, const uint8_t *refw,
+                                               uint8_t *hb, bt2g_dp_cand *cands, int ncand, bt2g_dp_summary *summ, int lane) {
+	const int rdgapo = sc.rdgap_const + sc.rdgap_linear, rdgape = sc.rdgap_linear;
+	const int rfgapo = sc.rfgap_const + sc.rfgap_linear, rfgape = sc.rfgap_linear;
+	const int bonus = sc.match_bonus, gapbar = sc.gapbar;
+	bt2g_dp_aln *alns = L.alns + w * (uint64_t)L.maxAlns;
+	uint8_t *ops = L.ops + w * (uint64_t)L.maxAlns * L.maxOps;
+	int naln = 0, flags = 0;
+	auto cell = [&](int rr, int cc) -> uint8_t * { int k = rr / R; return hb + ((size_t)(cc + k) * 32 + k) * R + (rr - k * R); };
+	auto rdchar = [&](int rr) -> int { const int pos = p.fw ? rr : rdlen - 1 - rr; int c = rs[pos]; return p.fw ? c : (c > 3 ? 4 : 3 - c); };
+	auto rdqual = [&](int rr) -> int { const int pos = p.fw ? rr : rdlen - 1 - rr; int q = (int)rq[pos] - 33; return q < 0 ? 0 : (q > 63 ? 63 : q); };
+	auto inCore = [&](int dlo, int dhi) -> bool { return dhi >= p.corel && dlo <= p.corer; };   // some diagonal of [dlo,dhi] is a core diagonal
+	for(int ci = 0; ci < ncand; ci++) {
+		int row = cands[ci].row, col = cands[ci].col;
+		const int startRow = row, origCol = col;
+		uint8_t *o = ops + (size_t)naln * L.maxOps;
+		const bool room = naln < L.maxAlns;
+		int nops = 0, ns = 0, gaps = 0;
+		bool fail = false, core = false, done = false, first = true, filtStart = false;
+		while(!done && !fail) {
+			// ---- H state at (row, col): the diagonal run.  Lane k holds cell (row-k, col-k).
+			const int rk = row - lane, ck = col - lane;
+			uint8_t *cp = (rk >= 0 && ck >= 0) ? cell(rk, ck) : nullptr;
+			const int mine = cp ? (int)*cp : 0x80;
+			const int v = mine & 0x7f;
+			const int vn = __shfl_down_sync(0xffffffffu, v, 1);       // H of my diagonal predecessor (lane 31: not loaded)
+			int sck = 0, refc = 4; bool isN = false, isMatch = false;
+			if(cp) {
+				const int c = rdchar(rk), q = rdqual(rk);
+				refc = refw[ck];
+				isN = c > 3 || refc > 3;
+				isMatch = !isN && c == refc;
+				sck = isN ? -(int)sc.npen[q] : (isMatch ? bonus : -(int)sc.mmpen[q]);
+			}
+			const bool cont = lane < 31 && !(mine & 0x80) && rk > 0 && ck > 0 && vn > 0 && v == vn + sck;
+			const int run = __ffs(~__ballot_sync(0xffffffffu, cont)) - 1;   // 0..31
+			if(run > 0) {
+				first = false;
+				const int diagi = col - row + p.triml;
+				if(inCore(diagi, diagi)) core = true;
+				if(lane < run) {
+					const uint8_t op = (uint8_t)((isMatch ? BT2G_OP_MATCH : BT2G_OP_MM) | (refc << 2));
+					if(room && nops + lane < L.maxOps) o[nops + lane] = op;
+					*cp = (uint8_t)(mine | 0x80);                      // setReportedThrough (:1555)
+				}
+				ns += __popc(__ballot_sync(0xffffffffu, lane < run && isN));
+				nops += run; row -= run; col -= run;
+			}
+			const int endBits = __shfl_sync(0xffffffffu, mine, run);   // the cell at (row, col) now
+			if(run == 31 && !(endBits & 0x80) && row > 0 && col > 0) { __syncwarp(); continue; }   // lane 31: decide next round
+			// ---- the cell that ends the run
+			if(endBits & 0x80) {
+				// start cell already reported through -> BT_CAND_FATE_FILT_START (:771-789); elsewhere the backtrace fails
+				if(first) filtStart = true;
+				fail = true; break;
+			}
+			first = false;
+			if(lane == run) *cp = (uint8_t)(mine | 0x80);
+			{
+				const int diagi = col - row + p.triml;
+				if(inCore(diagi, diagi)) core = true;
+			}
+			if(row == 0) { done = true; break; }
+			const int cur = endBits & 0x7f;
+			__syncwarp();
+			// ---- which gap?  decided from scores only; reference gap (vertical) before read gap (horizontal)
+			int klen = 0, gapKind = 0;                                 // 1 ref gap (rows), 2 read gap (columns)
+			if(row >= gapbar && rdlen - 1 - row >= gapbar) {
+				for(int k0 = 0; k0 < row; k0 += 32) {
+					if(127 - rfgapo - k0 * rfgape < cur) break;        // longer gaps cannot reach cur any more
+					const int k = k0 + lane + 1, r2 = row - k;
+					bool ok = false;
+					if(r2 >= 0 && row - k + 1 >= gapbar) {             // the gap's rows row-k+1..row lie outside the barrier
+						const int u = *cell(r2, col) & 0x7f;
+						ok = u > 0 && u - rfgapo - (k - 1) * rfgape == cur;
+					}
+					const uint32_t mk = __ballot_sync(0xffffffffu, ok);
+					if(mk) { klen = k0 + __ffs(mk); gapKind = 1; break; }
+				}
+				if(gapKind == 0) {
+					for(int k0 = 0; k0 < col; k0 += 32) {
+						if(127 - rdgapo - k0 * rdgape < cur) break;
+						const int k = k0 + lane + 1, c2 = col - k;
+						bool ok = false;
+						if(c2 >= 0) {
+							const int u = *cell(row, c2) & 0x7f;
+							ok = u > 0 && u - rdgapo - (k - 1) * rdgape == cur;
+						}
+						const uint32_t mk = __ballot_sync(0xffffffffu, ok);
+						if(mk) { klen = k0 + __ffs(mk); gapKind = 2; break; }
+					}
+				}
+			}
+			if(gapKind == 0) { fail = true; break; }                   // no legal move (cannot happen for a cell >= minsc)
+			// ---- the klen-1 gap-state cells in between: reported-through check in walking order, then mark
+			for(int m0 = 1; m0 < klen && !fail; m0 += 32) {
+				const int mth = m0 + lane;
+				uint8_t *q2 = nullptr; int b = 0;
+				if(mth < klen) { q2 = gapKind == 1 ? cell(row - mth, col) : cell(row, col - mth); b = *q2; }
+				const uint32_t vm = __ballot_sync(0xffffffffu, (b & 0x80) != 0);
+				const int lim = vm ? __ffs(vm) - 1 : 32;
+				if(q2 && lane < lim) *q2 = (uint8_t)(b | 0x80);
+				if(vm) fail = true;
+			}
+			if(fail) break;
+			{
+				const int d0 = col - row + p.triml, ni = klen - 1;
+				if(ni > 0 && (gapKind == 1 ? inCore(d0 + 1, d0 + ni) : inCore(d0 - ni, d0 - 1))) core = true;
+			}
+			if(room) {
+				for(int k = lane; k < klen; k += 32) {
+					const int idx = nops + k;
+					if(idx < L.maxOps) o[idx] = gapKind == 1 ? (uint8_t)BT2G_OP_REFGAP : (uint8_t)(BT2G_OP_READGAP | (refw[col - k] << 2));
+				}
+			}
+			nops += klen; gaps += klen;
+			if(gapKind == 1) row -= klen; else col -= klen;
+			__syncwarp();
+		}
+		if(filtStart) { if(lane == 0) cands[ci].fate = BT2G_CAND_FILT_START; continue; }
+		if(!fail) {
+			// the alignment's first cell (row, col) (:1797-1813)
+			const int c = rdchar(row), refc = refw[col];
+			const bool isN = c > 3 || refc > 3;
+			ns += isN;
+			const uint8_t op = (uint8_t)(((!isN && c == refc) ? BT2G_OP_MATCH : BT2G_OP_MM) | (refc << 2));
+			if(!core) fail = true;                   // core-diagonal rejection (:1764-1795)
+			else if(ns > p.nceil) fail = true;       // N ceiling (:1813-1818)
+			else {
+				if(room && lane == 0 && nops < L.maxOps) o[nops] = op;
+				nops++;
+			}
+		}
+		const bool opOverflow = nops > L.maxOps;
+		if(fail) { if(lane == 0) cands[ci].fate = BT2G_CAND_FAILED; continue; }
+		if(lane == 0) cands[ci].fate = BT2G_CAND_SUCCEEDED;
+		if(room) {
+			int refns = 0;
+			for(int k = col + lane; k <= origCol; k += 32) refns += refw[k] > 3;
+			refns = __reduce_add_sync(0xffffffffu, refns);
+			if(lane == 0) {
+				bt2g_dp_aln &a = alns[naln];
+				a.cand_idx = ci; a.score = cands[ci].score; a.ns = ns; a.gaps = gaps; a.col0 = col; a.row0 = row;
+				a.trim_beg = 0; a.trim_end = rdlen - 1 - startRow; a.nops = nops;
+				a.refns = refns;
+			}
+			if(opOverflow) flags |= BT2G_DP_FLAG_OPS_OVERFLOW;
+		} else {
+			flags |= BT2G_DP_FLAG_ALN_OVERFLOW;
+		}
+		naln++;
+	}
+	if(lane == 0) { summ->naln = naln; summ->flags |= flags; }
+}
+
 // persistent grid = resident blocks only (a second, partial wave would double the makespan)
 template <typename K>
 static unsigned dp_resident_grid(K kernel, int threads, size_t smem, uint64_t numSlots, int warpsPerBlock) {
@@ -562,7 +889,12 @@ static unsigned dp_resident_grid(K kernel, int threads, size_t smem, uint64_t nu
 template <typename OFF, int R>
 static void launch_dp_e2e_r(const DevIndex<OFF> &ix, const bt2g_scoring &sc, const DpLaunch &L, cudaStream_t st) {
 	const int warpsPerBlock = 4;
-	if(L.packed) {
+	if(L.packed == 2) {
+		const size_t smem = (size_t)warpsPerBlock * 2 * dp_smem_per_warp(L.maxCol);
+		if(smem > 48 * 1024) cudaFuncSetAttribute(k_dp_e2e_h<OFF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		const unsigned grid = dp_resident_grid(k_dp_e2e_h<OFF, R>, warpsPerBlock * 32, smem, L.numSlots, warpsPerBlock);
+		k_dp_e2e_h<OFF, R><<<grid, warpsPerBlock * 32, smem, st>>>(ix, sc, L);
+	} else if(L.packed) {
 		const size_t smem = (size_t)warpsPerBlock * 2 * dp_smem_per_warp(L.maxCol);
 		if(smem > 48 * 1024) cudaFuncSetAttribute(k_dp_e2e_x2<OFF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		const unsigned grid = dp_resident_grid(k_dp_e2e_x2<OFF, R>, warpsPerBlock * 32, smem, L.numSlots, warpsPerBlock);

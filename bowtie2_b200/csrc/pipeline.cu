@@ -73,6 +73,10 @@ struct bt2g_pipeline {
 	uint8_t *hSeq = nullptr, *hQual = nullptr; uint64_t *hOff = nullptr;
 	bt2g_read_result *hRes = nullptr; uint8_t *hOps = nullptr;
 	uint64_t lastN = 0;
+	// copy streams / events of the chunked host entry point
+	cudaStream_t sIn = nullptr, sOut = nullptr;
+	cudaEvent_t evIn[8], evDone[8];
+	bool chunkOk = false;
 };
 
 #define PIPE_MAX_RAW 8192
@@ -376,7 +380,8 @@ template <typename T> static int pipeAlloc(bt2g_pipeline *p, T *&ptr, uint64_t c
 }
 
 template <typename OFF>
-static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, const uint64_t *roff, uint64_t n, cudaStream_t st, bool count) {
+static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, const uint64_t *roff, uint64_t n, cudaStream_t st, bool count,
+                     uint64_t resBase = 0) {
 	bt2g_ctx *ctx = p->ctx;
 	PipeBufs &b = p->b;
 	const bt2g_pipeline_params &q = p->prm;
@@ -405,7 +410,7 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 	k_frame<<<grid(n), T, 0, st>>>(n, roff, b.interval, b.offset, b.rows, b.hitlen, b.meta, b.tidx, b.textoff, b.tlen, b.rflags,
 	                               b.rowBase, b.rowCnt, q.row_cap, q.max_len, q.maxhalf, p->sc.match_bonus,
 	                               b.minscByLen, b.nceilRawByLen, b.rdgapsByLen, b.rfgapsByLen,
-	                               b.probs, b.nProb, (uint32_t)p->maxProbs, b.readProb, b.readNProb, b.res, b.probTlen, b.resTlen);
+	                               b.probs, b.nProb, (uint32_t)p->maxProbs, b.readProb, b.readNProb, b.res + resBase, b.probTlen, b.resTlen + resBase);
 	DpLaunch L;
 	L.seq = seq; L.qual = qual; L.roff = roff; L.probs = b.probs; L.n = p->maxProbs; L.nDev = b.nProb;
 	L.rawKeys = b.rawKeys; L.maxRaw = b.rawKeys ? PIPE_MAX_RAW : 0;
@@ -417,7 +422,7 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 	if(drc) { ctx->err = "pipeline: DP launch rejected"; return -1; }
 	mark(7);
 	k_pick<<<grid(n), T, 0, st>>>(n, q.row_cap, q.max_alns, q.max_ops, b.readProb, b.readNProb, b.probs, b.summ, b.alns, b.ops,
-	                              b.res, b.resOps, c ? c + 3 : nullptr, roff, b.probTlen, b.resTlen);
+	                              b.res + resBase, b.resOps + resBase * (uint64_t)q.max_ops, c ? c + 3 : nullptr, roff, b.probTlen, b.resTlen + resBase);
 	mark(8);
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	p->lastN = n;
@@ -494,7 +499,7 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	{
 		int64_t mn = 0;
 		for(int l = 1; l <= prm->max_len; l++) if(prm->minsc_by_len[l] < mn) mn = prm->minsc_by_len[l];
-		p->packed = dp_packed_ok(p->sc, mn, prm->max_len) ? 1 : 0;
+		p->packed = dp_kernel_mode(p->sc, mn, prm->max_len);
 	}
 	rc |= pipeAlloc(p, b.codes, p->numSlots * p->codeStride * (p->packed ? 2 : 1)); rc |= pipeAlloc(p, b.lastH, p->numSlots * (uint64_t)p->maxCol);
 	// local mode gathers candidate cells during the fill (k_dp_local): a raw key list per warp slot
@@ -520,6 +525,11 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	if(e != cudaSuccess) { ctx->err = std::string("pipeline setup: ") + cudaGetErrorString(e); bt2g_pipeline_destroy(p); return -2; }
 	p->evOk = true;
 	for(int i = 0; i < 9; i++) if(cudaEventCreate(&p->ev[i]) != cudaSuccess) p->evOk = false;
+	p->chunkOk = cudaStreamCreateWithFlags(&p->sIn, cudaStreamNonBlocking) == cudaSuccess &&
+	             cudaStreamCreateWithFlags(&p->sOut, cudaStreamNonBlocking) == cudaSuccess;
+	for(int i = 0; i < 8 && p->chunkOk; i++)
+		p->chunkOk = cudaEventCreateWithFlags(&p->evIn[i], cudaEventDisableTiming) == cudaSuccess &&
+		             cudaEventCreateWithFlags(&p->evDone[i], cudaEventDisableTiming) == cudaSuccess;
 	// the params struct keeps host pointers that may die; null them
 	p->prm.minsc_by_len = p->prm.nceil_by_len = p->prm.nceil_raw_by_len = p->prm.interval_by_len = p->prm.rdgaps_by_len = p->prm.rfgaps_by_len = nullptr;
 	*out = p;
@@ -531,6 +541,9 @@ void bt2g_pipeline_destroy(bt2g_pipeline *p) {
 	cudaSetDevice(p->ctx->device);
 	for(void *v : p->allocs) cudaFree(v);
 	if(p->evOk) for(int i = 0; i < 9; i++) cudaEventDestroy(p->ev[i]);
+	if(p->chunkOk) { for(int i = 0; i < 8; i++) { cudaEventDestroy(p->evIn[i]); cudaEventDestroy(p->evDone[i]); } }
+	if(p->sIn) cudaStreamDestroy(p->sIn);
+	if(p->sOut) cudaStreamDestroy(p->sOut);
 	if(p->hSeq) cudaFreeHost(p->hSeq);
 	if(p->hQual) cudaFreeHost(p->hQual);
 	if(p->hOff) cudaFreeHost(p->hOff);
@@ -561,18 +574,51 @@ int bt2g_pipeline_run_host(bt2g_pipeline *p, const bt2g_reads *reads, bt2g_read_
 	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
 	const uint64_t nb = reads->off[n];
-	// caller buffers may be pageable: the copies below are then staged by the driver
-	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.seq, reads->seq, nb, cudaMemcpyHostToDevice, st));
-	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.qual, reads->qual, nb, cudaMemcpyHostToDevice, st));
-	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.roff, reads->off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-	int rc = bt2g_pipeline_run_dev(p, p->b.seq, p->b.qual, p->b.roff, n, st, 0);
-	if(rc) return rc;
-	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(res, p->b.res, n * sizeof(bt2g_read_result), cudaMemcpyDeviceToHost, st));
-	if(ops) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(ops, p->b.resOps, n * (uint64_t)p->prm.max_ops, cudaMemcpyDeviceToHost, st));
+	const uint64_t maxOps = (uint64_t)p->prm.max_ops;
+	// Large batches go through in chunks: the upload of chunk c+1 and the download of chunk c-1 run on
+	// their own streams (both copy engines) while chunk c computes.  Caller buffers may be pageable:
+	// the copies are then staged by the driver and overlap less.
+	uint64_t chunkMin = 1u << 18;
+	if(const char *e = getenv("BT2G_HOST_CHUNK_MIN")) chunkMin = strtoull(e, nullptr, 10);
+	const int nChunks = (p->chunkOk && n >= chunkMin && n >= 4) ? 4 : 1;
+	if(nChunks == 1) {
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.seq, reads->seq, nb, cudaMemcpyHostToDevice, st));
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.qual, reads->qual, nb, cudaMemcpyHostToDevice, st));
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.roff, reads->off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+		int rc = bt2g_pipeline_run_dev(p, p->b.seq, p->b.qual, p->b.roff, n, st, 0);
+		if(rc) return rc;
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(res, p->b.res, n * sizeof(bt2g_read_result), cudaMemcpyDeviceToHost, st));
+		if(ops) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(ops, p->b.resOps, n * maxOps, cudaMemcpyDeviceToHost, st));
+		BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		return 0;
+	}
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));                 // earlier work on the compute stream owns the buffers
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.roff, reads->off, (n + 1) * 8, cudaMemcpyHostToDevice, p->sIn));
+	const uint64_t per = (n + nChunks - 1) / nChunks;
+	for(int c = 0; c < nChunks; c++) {
+		const uint64_t s0 = c * per, s1 = (s0 + per < n) ? s0 + per : n;
+		const uint64_t b0 = reads->off[s0], b1 = reads->off[s1];
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.seq + b0, reads->seq + b0, b1 - b0, cudaMemcpyHostToDevice, p->sIn));
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.qual + b0, reads->qual + b0, b1 - b0, cudaMemcpyHostToDevice, p->sIn));
+		BT2G_CUDA_TRY(ctx, cudaEventRecord(p->evIn[c], p->sIn));
+	}
+	for(int c = 0; c < nChunks; c++) {
+		const uint64_t s0 = c * per, s1 = (s0 + per < n) ? s0 + per : n;
+		BT2G_CUDA_TRY(ctx, cudaStreamWaitEvent(st, p->evIn[c], 0));
+		int rc;
+		if(ctx->info.off_size == 4) rc = runStages<uint32_t>(p, p->b.seq, p->b.qual, p->b.roff + s0, s1 - s0, st, false, s0);
+		else rc = runStages<uint64_t>(p, p->b.seq, p->b.qual, p->b.roff + s0, s1 - s0, st, false, s0);
+		if(rc) return rc;
+		BT2G_CUDA_TRY(ctx, cudaEventRecord(p->evDone[c], st));
+		BT2G_CUDA_TRY(ctx, cudaStreamWaitEvent(p->sOut, p->evDone[c], 0));
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(res + s0, p->b.res + s0, (s1 - s0) * sizeof(bt2g_read_result), cudaMemcpyDeviceToHost, p->sOut));
+		if(ops) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(ops + s0 * maxOps, p->b.resOps + s0 * maxOps, (s1 - s0) * maxOps, cudaMemcpyDeviceToHost, p->sOut));
+	}
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(p->sOut));
 	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	p->lastN = n;
 	return 0;
 }
-
 
 int bt2g_pipeline_enable_pairs(bt2g_pipeline *p, const bt2g_pe_policy *pol) {
 	if(!p || !pol) return -1;

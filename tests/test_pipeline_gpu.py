@@ -128,6 +128,15 @@ def test_pipeline_stage_consistency(gpu, synth_index, synth_genome):
     assert c["reads"] == batch.n and c["sweep_sides"] > 0 and c["seed_sides"] > 0 and c["dp_cells"] > 0
     res2, _ = pipe.run_host(batch)
     assert np.array_equal(res, res2)
+    # the chunked host path (copies overlapped with compute) gives the same answers
+    os.environ["BT2G_HOST_CHUNK_MIN"] = "64"
+    try:
+        res3, ops3 = pipe.run_host(batch)
+    finally:
+        del os.environ["BT2G_HOST_CHUNK_MIN"]
+    assert np.array_equal(res, res3)
+    for i in range(batch.n):
+        assert np.array_equal(ops[i, :res[i]["nops"]], ops3[i, :res3[i]["nops"]])
     # exact end-to-end hits are exactly the reads whose exact sweep reports a range
     mine, ee = gpu.exact_sweep(batch)
     has_ee = (ee[:, 1] > ee[:, 0]) | (ee[:, 3] > ee[:, 2])
