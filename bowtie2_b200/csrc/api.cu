@@ -21,6 +21,7 @@ template <typename OFF> void launch_one_mm(const DevIndex<OFF> &, const uint8_t 
 template <typename OFF> void launch_get_stretch(const DevIndex<OFF> &, const uint64_t *, const int64_t *, const int32_t *, uint64_t, int, uint8_t *, cudaStream_t);
 template <typename OFF> void launch_extend(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint64_t *, uint8_t *, cudaStream_t);
 
+template <typename OFF> void launch_ungapped(const DevIndex<OFF> &, const bt2g_scoring &, const uint8_t *, const uint8_t *, const uint64_t *, const bt2g_ungapped_problem *, uint64_t, bt2g_ungapped_result *, uint8_t *, uint32_t, cudaStream_t);
 void launch_frame_mate(const bt2g_pe_policy &, const bt2g_mate_anchor *, uint64_t, bt2g_mate_frame *, cudaStream_t);
 void launch_pe_classify(const bt2g_pe_policy &, const int64_t *, uint64_t, int32_t *, cudaStream_t);
 namespace {
@@ -405,6 +406,29 @@ int bt2g_one_mm(bt2g_ctx *ctx, const bt2g_reads *reads, const int32_t *minsc, co
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(hits, dhits.p, dhits.bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(counts, dcnt.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int bt2g_ungapped(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_ungapped_problem *probs, uint64_t n,
+                  bt2g_ungapped_result *out, uint8_t *editMask, uint32_t maskStride) {
+	REQUIRE_LOADED(ctx);
+	if(!ctx->info.has_ref) { ctx->err = "packed reference (.3/.4) not loaded"; return -1; }
+	if(!reads || !reads->qual || !probs || !out) { ctx->err = "null argument"; return -1; }
+	if(ctx->scoring.gapbar < 1) bt2g_scoring_default(&ctx->scoring, 0);
+	if(n == 0) return 0;
+	for(uint64_t i = 0; i < n; i++) if(probs[i].read_idx >= reads->n_reads) { ctx->err = "read_idx out of range"; return -1; }
+	DBuf dseq, dqual, doff, dprob, dout, dmask;
+	int rc = uploadReads(ctx, reads, dseq, dqual, doff, true);
+	if(rc) return rc;
+	BT2G_CUDA_TRY(ctx, dprob.alloc(n * sizeof(bt2g_ungapped_problem))); BT2G_CUDA_TRY(ctx, dout.alloc(n * sizeof(bt2g_ungapped_result)));
+	if(editMask) { BT2G_CUDA_TRY(ctx, dmask.alloc(n * (uint64_t)maskStride)); BT2G_CUDA_TRY(ctx, cudaMemsetAsync(dmask.p, 0, dmask.bytes, ctx->stream)); }
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(dprob.p, probs, dprob.bytes, cudaMemcpyHostToDevice, ctx->stream));
+	DISPATCH(ctx, launch_ungapped<uint32_t>(bt2g_dev_index<uint32_t>(ctx), ctx->scoring, dseq.as<uint8_t>(), dqual.as<uint8_t>(), doff.as<uint64_t>(), dprob.as<bt2g_ungapped_problem>(), n, dout.as<bt2g_ungapped_result>(), editMask ? dmask.as<uint8_t>() : nullptr, maskStride, ctx->stream),
+	              launch_ungapped<uint64_t>(bt2g_dev_index<uint64_t>(ctx), ctx->scoring, dseq.as<uint8_t>(), dqual.as<uint8_t>(), doff.as<uint64_t>(), dprob.as<bt2g_ungapped_problem>(), n, dout.as<bt2g_ungapped_result>(), editMask ? dmask.as<uint8_t>() : nullptr, maskStride, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaGetLastError());
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, dout.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	if(editMask) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(editMask, dmask.p, dmask.bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	return 0;
 }

@@ -598,3 +598,27 @@ def _pe_classify(self, pe, pairs: np.ndarray) -> np.ndarray:
 
 Bt2Gpu.frame_mate = _frame_mate
 Bt2Gpu.pe_classify = _pe_classify
+
+
+# ---- SwAligner::ungappedAlign ---------------------------------------------------------------------
+EXPORTS += ["bt2g_ungapped"]
+UNGAPPED_PROBLEM = np.dtype([("read_idx", "<u4"), ("fw", "<u4"), ("tidx", "<u8"), ("refoff", "<i8"), ("reflen", "<u8"),
+                             ("minsc", "<i4"), ("ohang", "<i4")], align=True)
+UNGAPPED_RESULT = np.dtype([("status", "<i4"), ("score", "<i4"), ("rowi", "<i4"), ("rowf", "<i4"), ("ns", "<i4"),
+                            ("refns", "<i4"), ("nedits", "<i4"), ("pad", "<i4")], align=True)
+
+
+def _ungapped(self, reads: ReadBatch, probs: np.ndarray, want_mask: bool = True):
+    """include/bt2g.h: bt2g_ungapped -> (results, edit mask [n, max_len] or None)."""
+    lib = self._lib
+    lib.bt2g_ungapped.argtypes = [C.c_void_p, C.POINTER(_Reads), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
+    probs = np.ascontiguousarray(probs, dtype=UNGAPPED_PROBLEM)
+    out = np.zeros(len(probs), dtype=UNGAPPED_RESULT)
+    stride = int(reads.lengths().max()) if reads.n else 1
+    mask = np.zeros((len(probs), stride), dtype=np.uint8) if want_mask else None
+    st = reads._struct()
+    self._check(lib.bt2g_ungapped(self._h, C.byref(st), _ptr(probs), len(probs), _ptr(out), _ptr(mask), stride), "bt2g_ungapped")
+    return out, mask
+
+
+Bt2Gpu.ungapped = _ungapped

@@ -251,6 +251,30 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
                    int32_t max_cands, int32_t max_alns, int32_t max_ops,
                    bt2g_dp_summary *summ, bt2g_dp_cand *cands, bt2g_dp_aln *alns, uint8_t *ops);
 
+/* ------------------------------------------------------------------- ungapped alignment ----- */
+/* SwAligner::ungappedAlign (aligner_sw.cpp:286-487): the single-diagonal alignment the driver takes when
+ * neither read nor reference gaps fit under the minimum score (aligner_sw_driver.cpp:1189-1253).
+ * status: 0 no alignment, -1 more than one local solution on the diagonal (defer to the DP), 1 found.
+ * Rows are in strand orientation (row 0 = leftmost aligned read position on the reference); the
+ * reference offset of the alignment is refoff + rowi; edit_mask (optional, n * mask_stride bytes) gets a
+ * 1 for every row in [rowi, rowf] whose base differs from the reference or faces an N. */
+typedef struct {
+	uint32_t read_idx;
+	uint32_t fw;
+	uint64_t tidx;
+	int64_t  refoff;             /* Coord::off(): may be negative / run past the end (overhang) */
+	uint64_t reflen;             /* length of the reference sequence */
+	int32_t  minsc;
+	int32_t  ohang;              /* gReportOverhangs */
+} bt2g_ungapped_problem;
+typedef struct {
+	int32_t status, score;
+	int32_t rowi, rowf;
+	int32_t ns, refns, nedits, pad;
+} bt2g_ungapped_result;
+int bt2g_ungapped(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_ungapped_problem *probs, uint64_t n,
+                  bt2g_ungapped_result *out, uint8_t *edit_mask, uint32_t mask_stride);
+
 /* ------------------------------------------------------------- paired-end framing ----- */
 /* PairedEndPolicy (pe.h:169-330): pol = PE_POLICY_FF 1 / RR 2 / FR 3 / RF 4 (pe.h:43-55);
  * defaults of the program (bt2_search.cpp:350-358): FR, maxfrag 500, minfrag 0, flags

@@ -733,6 +733,66 @@ static int cell_score(const bt2o_scoring *sc, int rdc, int refc, int q) {
 	return -mm_pen(sc, q);
 }
 
+/* SwAligner::ungappedAlign (aligner_sw.cpp:286-487).  out6: score, rowi, rowf, ns, refns, nedits;
+ * editmask[i] = 1 where row i (strand orientation) carries an edit.  Returns 0 / -1 / 1. */
+int bt2o_ungapped(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, const uint8_t *quals, int len, int fw,
+                  uint64_t tidx, int64_t off, int64_t tlen, int ohang, int64_t minsc, int64_t *out6, uint8_t *editmask) {
+	const int nceil = (int)(0.0 + (double)0.15f * (double)len);
+	int ns = 0;
+	const int64_t rfi = off, rff = off + len;
+	int64_t leftNs = 0, rightNs = 0;
+	for(int k = 0; k < 6; k++) out6[k] = 0;
+	if(len <= 0) return 0;
+	if(rfi < 0) { if(ohang) leftNs = -rfi; else return 0; }
+	if(rff > tlen) { if(ohang) rightNs = rff - tlen; else return 0; }
+	if(leftNs + rightNs > nceil) return 0;
+	uint8_t *rf = (uint8_t *)malloc((size_t)len);
+	bt2o_get_stretch(ix, tidx, off, len, rf);                   /* off-end positions come back as 4 (N) */
+	for(int i = 0; i < len; i++) if((int64_t)i < leftNs || (int64_t)i >= (int64_t)len - rightNs) rf[i] = 4;
+	int64_t score = 0;
+	int rowi = 0, rowf = len - 1, rc = 1;
+	const int monotone = sc->match_bonus == 0;                  /* Scoring::monotone (scoring.h) */
+#define RD(i) (fw ? (int)codes[i] : ((int)codes[len - 1 - (i)] > 3 ? 4 : 3 - (int)codes[len - 1 - (i)]))
+#define QU(i) ((int)(fw ? quals[i] : quals[len - 1 - (i)]) - 33)
+	if(monotone) {
+		for(int i = 0; i < len && rc == 1; i++) {
+			int rdc = RD(i);
+			if(rdc > 3 || rf[i] > 3) ns++;
+			score += cell_score(sc, rdc, rf[i], QU(i));
+			if(score < minsc || ns > nceil) rc = 0;
+		}
+	} else {
+		int64_t scoreMax = 0;
+		int lastfloor = 0, sols = 0;
+		rowi = -1;
+		for(int i = 0; i < len; i++) {
+			int rdc = RD(i);
+			if(rdc > 3 || rf[i] > 3) ns++;
+			score += cell_score(sc, rdc, rf[i], QU(i));
+			if(score >= minsc && score >= scoreMax) {
+				scoreMax = score; rowf = i;
+				if(rowi != lastfloor) { rowi = lastfloor; sols++; }
+			}
+			if(score <= 0) { score = 0; lastfloor = i + 1; }
+		}
+		if(ns > nceil || scoreMax < minsc) rc = 0;
+		else if(sols > 1) rc = -1;
+		score = scoreMax;
+	}
+	if(rc == 1) {
+		int refns = 0, ned = 0;
+		memset(editmask, 0, (size_t)len);
+		for(int i = rowi; i <= rowf; i++) {
+			if(rf[i] > 3 || RD(i) != rf[i]) { editmask[i] = 1; ned++; if(rf[i] > 3) refns++; }
+		}
+		out6[0] = score; out6[1] = rowi; out6[2] = rowf; out6[3] = ns; out6[4] = refns; out6[5] = ned;
+	}
+#undef RD
+#undef QU
+	free(rf);
+	return rc;
+}
+
 typedef struct { int nedsz, celsz, row, col, gaps, score, ns, ct; } bt_frame;
 
 /* One SwAligner session (aligner_sw.cpp:155-271 initRef, :500-729 align, :737-1146

@@ -62,6 +62,37 @@ int ref_frame_seed_rect(int64_t off, uint64_t rdlen, int64_t reflen, uint64_t ma
 	return found ? 1 : 0;
 }
 
+// SwAligner::ungappedAlign (aligner_sw.cpp:286-487).  out8: score, refoff, trim5, trim3, ns, refns, nedits, -;
+// edits (pos, chr, qchr, type) as for ref_dp.  returns the function's return value (0, -1, 1).
+int ref_ungapped(void* vh, int local, const uint8_t* codes, const uint8_t* quals, int len, int fw,
+                 uint64_t tidx, int64_t off, int64_t tlen, int ohang, int64_t minsc, int max_edits,
+                 int64_t* out8, int32_t* edits) {
+	RefHandleDp* h = (RefHandleDp*)vh;
+	const Scoring& sc = local ? *h->sc_loc : *h->sc_e2e;
+	static const char dna[] = "ACGTN";
+	std::string s(len, 'N'), q(len, 'I');
+	for(int i = 0; i < len; i++) { s[i] = dna[codes[i] > 4 ? 4 : codes[i]]; if(quals) q[i] = (char)quals[i]; }
+	Read rd; rd.init("r", s.c_str(), q.c_str());
+	SwAligner sw(NULL);
+	SwResult res;
+	Coord coord((TRefId)tidx, (TRefOff)off, fw != 0);
+	for(int i = 0; i < 8; i++) out8[i] = 0;
+	int al = sw.ungappedAlign(fw ? rd.patFw : rd.patRc, fw ? rd.qual : rd.qualRev, coord, *h->ref, (size_t)tlen, sc,
+	                          ohang != 0, (TAlScore)minsc, res);
+	if(al == 1) {
+		const AlnRes& a = res.alres;
+		out8[0] = a.score().score(); out8[1] = a.refoff();
+		out8[2] = (int64_t)a.trimmed5p(true); out8[3] = (int64_t)a.trimmed3p(true);
+		out8[4] = a.score().ns(); out8[5] = (int64_t)a.refNs();
+		const EList<Edit>& ned = a.ned();
+		out8[6] = (int64_t)ned.size();
+		for(size_t k = 0; k < ned.size() && (int)k < max_edits; k++) {
+			edits[4 * k] = (int32_t)ned[k].pos; edits[4 * k + 1] = ned[k].chr; edits[4 * k + 2] = ned[k].qchr; edits[4 * k + 3] = ned[k].type;
+		}
+	}
+	return al;
+}
+
 // PairedEndPolicy::otherMate (pe.cpp:161-355) + DynProgFramer::frameFindMateRect (dp_framer.h:155-197,
 // dp_framer.cpp:177-361) as chained in SwDriver::extendSeedsPaired (aligner_sw_driver.cpp:2226-2256).
 // pol: PE_POLICY_FF=1, RR=2, FR=3, RF=4; flags bit0 flippingOk, bit1 dovetailOk, bit2 containOk,

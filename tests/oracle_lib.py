@@ -250,3 +250,36 @@ def ref_one_mm(R, local, codes, quals, minsc, nofw=False, norc=False, max_hits=2
 def oracle_one_mm(O, local, codes, quals, minsc, nofw=False, norc=False, max_hits=256):
     sc = oracle_scoring(O, local)
     return _one_mm_call(O.lib.bt2o_one_mm, (vp(O.h), C.byref(sc)), codes, quals, minsc, nofw, norc, max_hits)
+
+
+# ---- SwAligner::ungappedAlign (oracle/ref_glue_dp.cpp: ref_ungapped, oracle/bt2_oracle.c: bt2o_ungapped) ----
+def ref_ungapped(R, local, codes, quals, fw, tidx, off, tlen, ohang, minsc, max_edits=1024):
+    """-> (rc, dict(score, refoff, trim5, trim3, ns, refns, edits=[(pos, chr, qchr, type)]))"""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    quals = np.ascontiguousarray(quals, dtype=np.uint8)
+    out8 = np.zeros(8, np.int64)
+    ed = np.zeros(4 * max_edits, np.int32)
+    f = R.lib.ref_ungapped
+    f.restype = ci
+    i64 = C.c_int64
+    rc = f(vp(R.h), ci(int(local)), codes.ctypes.data_as(vp), quals.ctypes.data_as(vp), ci(len(codes)), ci(int(fw)), u64(int(tidx)),
+           i64(int(off)), i64(int(tlen)), ci(int(ohang)), i64(int(minsc)), ci(max_edits), out8.ctypes.data_as(vp), ed.ctypes.data_as(vp))
+    n = int(out8[6])
+    return rc, dict(score=int(out8[0]), refoff=int(out8[1]), trim5=int(out8[2]), trim3=int(out8[3]), ns=int(out8[4]),
+                    refns=int(out8[5]), edits=[tuple(int(x) for x in ed[4 * k:4 * k + 4]) for k in range(n)])
+
+
+def oracle_ungapped(O, local, codes, quals, fw, tidx, off, tlen, ohang, minsc):
+    """-> (rc, dict(score, rowi, rowf, ns, refns, nedits, mask))"""
+    sc = oracle_scoring(O, local)
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    quals = np.ascontiguousarray(quals, dtype=np.uint8)
+    out6 = np.zeros(6, np.int64)
+    mask = np.zeros(len(codes), np.uint8)
+    f = O.lib.bt2o_ungapped
+    f.restype = ci
+    i64 = C.c_int64
+    rc = f(vp(O.h), C.byref(sc), codes.ctypes.data_as(vp), quals.ctypes.data_as(vp), ci(len(codes)), ci(int(fw)), u64(int(tidx)),
+           i64(int(off)), i64(int(tlen)), ci(int(ohang)), i64(int(minsc)), out6.ctypes.data_as(vp), mask.ctypes.data_as(vp))
+    return rc, dict(score=int(out6[0]), rowi=int(out6[1]), rowf=int(out6[2]), ns=int(out6[3]), refns=int(out6[4]),
+                    nedits=int(out6[5]), mask=mask)
