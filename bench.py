@@ -466,7 +466,7 @@ def main():
                            "l2": "inputs larger than L2 (random access over a %.1f GB index; a different 1M-read batch each step)" % (info["device_bytes"] / 1e9),
                            "pipeline": "exactSweep + multiseed round 0 + resolve(all rows of ranges<=8, cap 16) + DP/backtrace per distinct diagonal",
                            "index_bcast_s": bcast_s, "aligned_frac": found, "host_threads": cores, "cgroup_cpu_quota": cpu_quota, "dp_workspace_overflows": overflow},
-                "clocks": clk, "gpu_launches": 9 * args.steps,   # k_plan, k_pack_reads, k_exact_sweep2, k_seed_search2, k_collect, k_resolve2, k_frame, k_dp_e2e[_x2], k_pick
+                "clocks": clk, "gpu_launches": pipe.kernel_launches() * args.steps,
                 "e2e": {"value": e2e_val, "unit": "Mreads/s", "h2d_bytes_per_step": 2 * B * READ_LEN + (B + 1) * 8,
                         "d2h_bytes_per_step": B * READ_RESULT.itemsize + B * pipe.max_ops},
                 "roofline": roof, "stage_ms": stage_ms, "work_per_step": cnt, "cpu_baseline": cpu_baseline}

@@ -603,7 +603,12 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 	L.codeStride = (uint64_t)(maxCol + 32) * 32 * R;
 	L.packed = dp_kernel_mode(ctx->scoring, minMinsc, maxLen);
 	BT2G_CUDA_TRY(ctx, dprob.alloc(n * sizeof(bt2g_dp_problem)));
-	BT2G_CUDA_TRY(ctx, dcodes.alloc(L.numSlots * L.codeStride * (L.packed ? 2 : 1)));
+	if(L.packed == 3) {
+		L.chunk = dp_chunk_problems(L.codeStride, n);
+		BT2G_CUDA_TRY(ctx, dcodes.alloc(L.chunk * L.codeStride));
+	} else {
+		BT2G_CUDA_TRY(ctx, dcodes.alloc(L.numSlots * L.codeStride * (L.packed ? 2 : 1)));
+	}
 	BT2G_CUDA_TRY(ctx, dlast.alloc(L.numSlots * (uint64_t)maxCol * 4));
 	L.maxRaw = maxCands * 4 < 1024 ? 1024 : maxCands * 4;
 	BT2G_CUDA_TRY(ctx, draw.alloc(L.numSlots * (uint64_t)L.maxRaw * 8));

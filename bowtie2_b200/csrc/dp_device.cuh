@@ -10,15 +10,27 @@ static inline bool dp_packed_ok(const bt2g_scoring &sc, int64_t minMinsc, int ma
 }
 
 // DpLaunch.packed: 0 = k_dp_e2e (32-bit, move codes), 1 = k_dp_e2e_x2 (s16x2, move codes),
-// 2 = k_dp_e2e_h (s16x2, H bytes: needs perfect - (minsc - bonus - 1) <= 127 for every problem).
+// 2 = k_dp_e2e_h (s16x2, H bytes: needs perfect - (minsc - bonus - 1) <= 127 for every problem),
+// 3 = the same split into k_dp_fill_h + k_dp_tail_h over chunks of DpLaunch.chunk problems
+//     (workspace: chunk * codeStride bytes).
 // BT2G_DP_PACKED in the environment caps the mode (0, 1 or 2).
 static inline int dp_kernel_mode(const bt2g_scoring &sc, int64_t minMinsc, int maxLen) {
-	int cap = 2;
+	int cap = 3;
 	const char *e = getenv("BT2G_DP_PACKED");
-	if(e && e[0] >= '0' && e[0] <= '2') cap = e[0] - '0';
+	if(e && e[0] >= '0' && e[0] <= '3') cap = e[0] - '0';
 	if(cap == 0 || !dp_packed_ok(sc, minMinsc, maxLen)) return 0;
 	const int64_t range = (int64_t)sc.match_bonus * maxLen - (minMinsc - sc.match_bonus - 1);
-	return (cap >= 2 && range <= 127) ? 2 : 1;
+	return (cap >= 2 && range <= 127) ? (cap >= 3 ? 3 : 2) : 1;
+}
+
+// mode 3 workspace: as many problems per chunk as fit a byte budget (default 6 GiB; BT2G_DP_CHUNK_MB overrides)
+static inline uint64_t dp_chunk_problems(uint64_t codeStride, uint64_t nMax) {
+	uint64_t budget = 6ull << 30;
+	if(const char *e = getenv("BT2G_DP_CHUNK_MB")) { uint64_t v = strtoull(e, nullptr, 10); if(v) budget = v << 20; }
+	uint64_t c = budget / (codeStride ? codeStride : 1);
+	if(c < 1024) c = 1024;
+	if(c > nMax) c = nMax;
+	return c ? c : 1;
 }
 
 struct DpLaunch {
@@ -35,6 +47,7 @@ struct DpLaunch {
 	uint64_t        codeStride;
 	int             maxCol;
 	int             maxCands, maxAlns, maxOps;
+	uint64_t        chunk = 0;    // mode 3: problems per fill/tail chunk
 	int             packed = 0;   // e2e: two problems per warp as s16x2 pairs (codes workspace: 2 * codeStride per slot)
 	bt2g_dp_summary *summ;
 	bt2g_dp_cand    *cands;

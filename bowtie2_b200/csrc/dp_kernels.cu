@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(128) k_dp_e2e_x2(DevIndex<OFF> ix, bt2g_scorin
 // ----------------------------------------------------------------------------------------
 // Fill of the H-byte kernel (two problems per warp, s16x2; see the description below).
 template <typename OFF, int R>
-__global__ void __launch_bounds__(128) k_dp_e2e_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L) {
+__global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L) {
 	extern __shared__ uint8_t smem[];
 	const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint64_t slot = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock;
@@ -611,8 +611,10 @@ __global__ void __launch_bounds__(128) k_dp_e2e_h(DevIndex<OFF> ix, bt2g_scoring
 		// reference windows (SwAligner::initRef, aligner_sw.cpp:155-271): codes 0..3, 4 = N / off-end
 		const int ncolMax = ncol[0] > ncol[1] ? ncol[0] : ncol[1];
 #pragma unroll
-		for(int x = 0; x < 2; x++)
-			for(int k = lane; k < ncolMax; k += 32) refw[x][k] = k < ncol[x] ? (uint8_t)ref_base<OFF>(ix, p[x].tidx, p[x].refl + k) : (uint8_t)4;
+		for(int x = 0; x < 2; x++) {
+			ref_window<OFF>(ix, p[x].tidx, p[x].refl, ncol[x], refw[x], lane);
+			for(int k = ncol[x] + lane; k < ncolMax; k += 32) refw[x][k] = 4;      // padding read by the packed loop, never used
+		}
 		__syncwarp();
 
 		// per-row constants of both problems (buildQueryProfileEnd2EndSseU8, aligner_swsse_ee_u8.cpp:75-142)
@@ -703,6 +705,178 @@ __global__ void __launch_bounds__(128) k_dp_e2e_h(DevIndex<OFF> ix, bt2g_scoring
 			dp_e2e_tail<R, true>(L, sc, p[x], w[x], rs[x], rq[x], rdlen[x], ncol[x], lastH[x], candCol[x], refw[x], hb[x], L.summ + w[x], lane);
 		}
 	} // persistent loop over problem pairs
+}
+
+// ----------------------------------------------------------------------------------------
+// Split form of the H-byte kernel: k_dp_fill_h writes the H bytes of a CHUNK of problems to a problem-indexed
+// workspace (pure DPX compute, high occupancy), k_dp_tail_h then runs candidates + backtraces with one warp per
+// problem (latency-bound on workspace reads, hidden by far more resident warps than the fused kernel can hold).
+template <typename OFF, int R>
+__global__ void __launch_bounds__(128, R == 4 ? 7 : 4) k_dp_fill_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L, uint64_t chunkStart, uint64_t chunkMax) {
+	extern __shared__ uint8_t smem[];
+	const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint64_t slot = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock;
+	const uint64_t nSlots = (uint64_t)gridDim.x * (blockDim.x >> 5);
+	const uint64_t nAll = L.nDev ? (uint64_t)*L.nDev : L.n;
+	if(chunkStart >= nAll) return;
+	const uint64_t nProb = (nAll - chunkStart < chunkMax) ? nAll - chunkStart : chunkMax;   // problems of this chunk
+	const uint64_t nPairs = (nProb + 1) >> 1;
+	const size_t perProb = ((size_t)L.maxCol + 15) & ~(size_t)15;
+	uint8_t *sm0 = smem + (size_t)warpInBlock * 2 * perProb;
+	uint8_t *refw[2] = {sm0, sm0 + perProb}; uint8_t *hb[2];
+	const int rdgapo = sc.rdgap_const + sc.rdgap_linear, rdgape = sc.rdgap_linear;
+	const int rfgapo = sc.rfgap_const + sc.rfgap_linear, rfgape = sc.rfgap_linear;
+	const int bonus = sc.match_bonus;
+	const uint32_t FLOORP = dpx_both(DPX_FLOOR), ONEP = 0x00010001u;
+	const uint32_t bonusP = dpx_both(bonus), nrdeP = dpx_both(-rdgape);
+
+	for(uint64_t pw = slot; pw < nPairs; pw += nSlots) {
+		uint64_t w[2] = {2 * pw, 2 * pw + 1};
+		bool live[2] = {true, w[1] < nProb};
+		if(!live[1]) w[1] = w[0];
+		bt2g_dp_problem p[2] = {L.probs[chunkStart + w[0]], L.probs[chunkStart + w[1]]};
+		hb[0] = L.codes + w[0] * L.codeStride; hb[1] = L.codes + w[1] * L.codeStride;
+		const uint8_t *rs[2], *rq[2]; int rdlen[2], ncol[2], floorv[2];
+		__syncwarp();
+#pragma unroll
+		for(int x = 0; x < 2; x++) {
+			rs[x] = L.seq + L.roff[p[x].read_idx]; rq[x] = L.qual + L.roff[p[x].read_idx];
+			rdlen[x] = (int)(L.roff[p[x].read_idx + 1] - L.roff[p[x].read_idx]);
+			ncol[x] = (int)(p[x].refr - p[x].refl + 1);
+			floorv[x] = p[x].minsc - bonus - 1;
+			// shape, and the score range the byte encoding can hold (perfect - floor <= 127)
+			if(ncol[x] <= 0 || ncol[x] > L.maxCol || rdlen[x] > 32 * R || rdlen[x] <= 0 ||
+			   (int64_t)bonus * rdlen[x] - floorv[x] > 127 || floorv[x] < -DPX_LIMIT) {
+				if(live[x] && lane == 0) {
+					bt2g_dp_summary *sm = L.summ + chunkStart + w[x];
+					sm->found = 0; sm->best = DP_NEG; sm->ncand = 0; sm->naln = 0; sm->flags = BT2G_DP_FLAG_BADSHAPE;
+				}
+				live[x] = false;
+			}
+		}
+		if(!live[0] && !live[1]) continue;
+		// a dead half mirrors the live one (its results are discarded)
+		if(!live[0]) { p[0] = p[1]; rs[0] = rs[1]; rq[0] = rq[1]; rdlen[0] = rdlen[1]; ncol[0] = ncol[1]; floorv[0] = floorv[1]; }
+		if(!live[1]) { p[1] = p[0]; rs[1] = rs[0]; rq[1] = rq[0]; rdlen[1] = rdlen[0]; ncol[1] = ncol[0]; floorv[1] = floorv[0]; }
+		// reference windows (SwAligner::initRef, aligner_sw.cpp:155-271): codes 0..3, 4 = N / off-end
+		const int ncolMax = ncol[0] > ncol[1] ? ncol[0] : ncol[1];
+#pragma unroll
+		for(int x = 0; x < 2; x++) {
+			ref_window<OFF>(ix, p[x].tidx, p[x].refl, ncol[x], refw[x], lane);
+			for(int k = ncol[x] + lane; k < ncolMax; k += 32) refw[x][k] = 4;      // padding read by the packed loop, never used
+		}
+		__syncwarp();
+
+		// per-row constants of both problems (buildQueryProfileEnd2EndSseU8, aligner_swsse_ee_u8.cpp:75-142)
+		uint32_t rcP[R], mmpP[R], npnP[R], nrfoP[R], nrfeP[R], nrdoP[R];
+#pragma unroll
+		for(int r = 0; r < R; r++) {
+			int v[2][6];
+#pragma unroll
+			for(int x = 0; x < 2; x++) {
+				const int i = lane * R + r;
+				bool bar = true;
+				int c = 5, mm = 0, np = 0;
+				if(i < rdlen[x]) {
+					const int pos = p[x].fw ? i : rdlen[x] - 1 - i;
+					c = rs[x][pos];
+					c = p[x].fw ? c : (c > 3 ? 4 : 3 - c);
+					int q = (int)rq[x][pos] - 33;
+					q = q < 0 ? 0 : (q > 63 ? 63 : q);
+					np = -(int)sc.npen[q];
+					mm = c > 3 ? np : -(int)sc.mmpen[q];
+					if(c > 3) c = 5;
+					bar = (i < sc.gapbar) || (rdlen[x] - 1 - i < sc.gapbar);
+				}
+				v[x][0] = c; v[x][1] = mm; v[x][2] = np;
+				v[x][3] = bar ? -DPX_BIG : -rfgapo; v[x][4] = bar ? -DPX_BIG : -rfgape; v[x][5] = bar ? -DPX_BIG : -rdgapo;
+			}
+			rcP[r] = dpx_pack(v[0][0], v[1][0]); mmpP[r] = dpx_pack(v[0][1], v[1][1]); npnP[r] = dpx_pack(v[0][2], v[1][2]);
+			nrfoP[r] = dpx_pack(v[0][3], v[1][3]); nrfeP[r] = dpx_pack(v[0][4], v[1][4]); nrdoP[r] = dpx_pack(v[0][5], v[1][5]);
+		}
+		const int lastLane0 = (rdlen[0] - 1) / R, lastLane1 = (rdlen[1] - 1) / R;
+		const int lastLaneMax = lastLane0 > lastLane1 ? lastLane0 : lastLane1;
+		const uint32_t nfloorP = dpx_pack(-floorv[0], -floorv[1]);
+
+		uint32_t Hleft[R], Earr[R];
+#pragma unroll
+		for(int r = 0; r < R; r++) { Hleft[r] = FLOORP; Earr[r] = FLOORP; }
+		uint32_t botH = FLOORP, botF = FLOORP, prevInH = FLOORP;
+		const int nsteps = ncolMax + lastLaneMax;
+		uint8_t *dstA = hb[0] + (size_t)lane * R, *dstB = hb[1] + (size_t)lane * R;
+		for(int t = 0; t < nsteps; t++, dstA += 32 * R, dstB += 32 * R) {
+			uint32_t inH = __shfl_up_sync(0xffffffffu, botH, 1);
+			uint32_t inF = __shfl_up_sync(0xffffffffu, botF, 1);
+			if(lane == 0) { inH = FLOORP; inF = FLOORP; }
+			const int j = t - lane;
+			if(j >= 0 && j < ncolMax && lane <= lastLaneMax) {
+				const uint32_t refcP = (uint32_t)refw[0][j] | ((uint32_t)refw[1][j] << 16);
+				const uint32_t refNm = ((refcP >> 2) & ONEP) * 0xffffu;      // half mask: reference N
+				// H[i0-1][j-1]: row -1 is the free start row of end-to-end mode (vhilsw, :853,923-927)
+				uint32_t diag = (lane == 0) ? 0u : prevInH;
+				uint32_t upH = inH, upF = inF;
+				uint32_t hs[R];
+#pragma unroll
+				for(int r = 0; r < R; r++) {
+					// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo)
+					const uint32_t F = __viaddmax_s16x2(upF, nrfeP[r], __viaddmax_s16x2(upH, nrfoP[r], FLOORP));
+					const uint32_t pen = dpx_sel(refNm, npnP[r], mmpP[r]);
+					const uint32_t mmask = dpx_ne01(rcP[r], refcP) * 0xffffu;
+					const uint32_t Hd = __viaddmax_s16x2(diag, dpx_sel(mmask, pen, bonusP), FLOORP);
+					const uint32_t E = Earr[r];
+					const uint32_t H = __vimax3_s16x2(Hd, E, F);
+					// E[i][j+1] = max(E[i][j]-rdgape, H[i][j]-rdgapo)
+					Earr[r] = __viaddmax_s16x2(E, nrdeP, __viaddmax_s16x2(H, nrdoP[r], FLOORP));
+					hs[r] = __viaddmax_s16x2(H, nfloorP, 0u);              // max(H - floor, 0): the stored byte
+					diag = Hleft[r]; Hleft[r] = H;
+					upH = H; upF = F;
+				}
+				botH = upH; botF = upF;
+				prevInH = inH;
+				// byte 0 of every word is problem A's cell, byte 2 problem B's
+#pragma unroll
+				for(int q4 = 0; q4 < R / 4; q4++) {
+					const uint32_t t01 = __byte_perm(hs[4 * q4], hs[4 * q4 + 1], 0x6240), t23 = __byte_perm(hs[4 * q4 + 2], hs[4 * q4 + 3], 0x6240);
+					reinterpret_cast<uint32_t *>(dstA)[q4] = __byte_perm(t01, t23, 0x5410);
+					reinterpret_cast<uint32_t *>(dstB)[q4] = __byte_perm(t01, t23, 0x7632);
+				}
+			} else if(j >= ncolMax) {
+				botH = FLOORP; botF = FLOORP;
+			}
+		}
+	} // persistent loop over problem pairs
+}
+
+template <typename OFF, int R>
+__global__ void __launch_bounds__(256) k_dp_tail_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L, uint64_t chunkStart, uint64_t chunkMax) {
+	extern __shared__ uint8_t smem[];
+	const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint64_t nAll = L.nDev ? (uint64_t)*L.nDev : L.n;
+	if(chunkStart >= nAll) return;
+	const uint64_t nProb = (nAll - chunkStart < chunkMax) ? nAll - chunkStart : chunkMax;
+	const size_t perWarp = dp_smem_per_warp(L.maxCol);
+	int32_t *lastH = reinterpret_cast<int32_t *>(smem + (size_t)warpInBlock * perWarp);
+	uint16_t *candCol = reinterpret_cast<uint16_t *>(lastH + L.maxCol);
+	uint8_t *refw = reinterpret_cast<uint8_t *>(candCol + L.maxCol);
+	const int bonus = sc.match_bonus;
+	const uint64_t nWarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+	for(uint64_t wl = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock; wl < nProb; wl += nWarps) {
+		const uint64_t w = chunkStart + wl;
+		const bt2g_dp_problem p = L.probs[w];
+		const uint8_t *rs = L.seq + L.roff[p.read_idx], *rq = L.qual + L.roff[p.read_idx];
+		const int rdlen = (int)(L.roff[p.read_idx + 1] - L.roff[p.read_idx]);
+		const int ncol = (int)(p.refr - p.refl + 1);
+		const int floorv = p.minsc - bonus - 1;
+		__syncwarp();
+		// the fill kernel flagged the same shapes as BADSHAPE
+		if(ncol <= 0 || ncol > L.maxCol || rdlen > 32 * R || rdlen <= 0 || (int64_t)bonus * rdlen - floorv > 127 || floorv < -DPX_LIMIT) continue;
+		uint8_t *hb = L.codes + wl * L.codeStride;
+		ref_window<OFF>(ix, p.tidx, p.refl, ncol, refw, lane);
+		// last row -> scores (candidates are the cells >= minsc; a clamped byte reads as floor < minsc)
+		const int lr = rdlen - 1, kk = lr / R;
+		for(int j = lane; j < ncol; j += 32) lastH[j] = (int)hb[((size_t)(j + kk) * 32 + kk) * R + (lr - kk * R)] + floorv;
+		dp_e2e_tail<R, true>(L, sc, p, w, rs, rq, rdlen, ncol, lastH, candCol, refw, hb, L.summ + w, lane);
+	}
 }
 
 // ----------------------------------------------------------------------------------------
@@ -889,7 +1063,21 @@ static unsigned dp_resident_grid(K kernel, int threads, size_t smem, uint64_t nu
 template <typename OFF, int R>
 static void launch_dp_e2e_r(const DevIndex<OFF> &ix, const bt2g_scoring &sc, const DpLaunch &L, cudaStream_t st) {
 	const int warpsPerBlock = 4;
-	if(L.packed == 2) {
+	if(L.packed == 3) {
+		// split: chunks of L.chunk problems through fill then tail (workspace = L.chunk * codeStride bytes)
+		int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		const size_t smF = (size_t)warpsPerBlock * 2 * (((size_t)L.maxCol + 15) & ~(size_t)15);
+		const size_t smT = (size_t)8 * dp_smem_per_warp(L.maxCol);
+		if(smF > 48 * 1024) cudaFuncSetAttribute(k_dp_fill_h<OFF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smF);
+		if(smT > 48 * 1024) cudaFuncSetAttribute(k_dp_tail_h<OFF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
+		int nbF = 1, nbT = 1;
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbF, k_dp_fill_h<OFF, R>, warpsPerBlock * 32, smF) != cudaSuccess || nbF < 1) nbF = 1;
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbT, k_dp_tail_h<OFF, R>, 256, smT) != cudaSuccess || nbT < 1) nbT = 1;
+		for(uint64_t c0 = 0; c0 < L.n; c0 += L.chunk) {
+			k_dp_fill_h<OFF, R><<<(unsigned)(nbF * sms), warpsPerBlock * 32, smF, st>>>(ix, sc, L, c0, L.chunk);
+			k_dp_tail_h<OFF, R><<<(unsigned)(nbT * sms), 256, smT, st>>>(ix, sc, L, c0, L.chunk);
+		}
+	} else if(L.packed == 2) {
 		const size_t smem = (size_t)warpsPerBlock * 2 * dp_smem_per_warp(L.maxCol);
 		if(smem > 48 * 1024) cudaFuncSetAttribute(k_dp_e2e_h<OFF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		const unsigned grid = dp_resident_grid(k_dp_e2e_h<OFF, R>, warpsPerBlock * 32, smem, L.numSlots, warpsPerBlock);

@@ -222,6 +222,35 @@ __device__ __forceinline__ int ref_base(const DevIndex<OFF> &ix, uint64_t tidx, 
 	return (ix.refBuf[b >> 2] >> ((b & 3) << 1)) & 3;
 }
 
+// A whole reference window [refl, refl+ncol) into out[] (one warp; lane k fills columns k, k+32, ...).
+// Fast path: the window lies inside one unambiguous stretch, found once per window instead of once
+// per column; otherwise every column goes through ref_base (N runs, reference ends).
+template <typename OFF>
+__device__ __forceinline__ void ref_window(const DevIndex<OFF> &ix, uint64_t tidx, int64_t refl, int ncol, uint8_t *out, int lane) {
+	bool fast = false;
+	uint64_t b0 = 0;
+	if(refl >= 0 && (uint64_t)(refl + ncol) <= ix.refLens[tidx]) {
+		uint64_t lo = ix.refRecOffs[tidx], hi = ix.refRecOffs[tidx + 1];
+		while(hi - lo > 1) {
+			const uint64_t mid = lo + ((hi - lo) >> 1);
+			if(ix.recCumOff[mid] <= (uint64_t)refl) lo = mid; else hi = mid;
+		}
+		const uint64_t start = ix.recCumOff[lo] + (uint64_t)ix.recOff[lo];
+		if((uint64_t)refl >= start && (uint64_t)(refl + ncol) <= start + (uint64_t)ix.recLen[lo]) {
+			fast = true;
+			b0 = ix.recCumUnamb[lo] + ((uint64_t)refl - start);
+		}
+	}
+	if(fast) {
+		for(int k = lane; k < ncol; k += 32) {
+			const uint64_t b = b0 + (uint64_t)k;
+			out[k] = (uint8_t)((ix.refBuf[b >> 2] >> ((b & 3) << 1)) & 3);
+		}
+	} else {
+		for(int k = lane; k < ncol; k += 32) out[k] = (uint8_t)ref_base<OFF>(ix, tidx, refl + k);
+	}
+}
+
 // read access helpers: strand 0 = read as given, strand 1 = reverse complement
 __device__ __forceinline__ int read_char(const uint8_t *seq, int len, int strand, int pos) {
 	if(strand == 0) return seq[pos];

@@ -63,7 +63,8 @@ struct bt2g_pipeline {
 	PipeBufs b;
 	std::vector<void *> allocs;
 	uint64_t numSlots, codeStride, maxProbs;
-	int packed = 0;                           // DP: s16x2 two-problem kernel (dp_packed_ok)
+	int packed = 0;                           // DP kernel mode (dp_kernel_mode)
+	uint64_t dpChunk = 0, mateChunk = 0;      // mode 3: problems per fill/tail chunk
 	int maxCol, R, sms = 148;
 	cudaEvent_t ev[9], pev[4];
 	bool pairsOn = false; bt2g_pe_policy pe{}; int mateMaxCol = 0; uint64_t mateCodeStride = 0;
@@ -415,7 +416,7 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 	L.seq = seq; L.qual = qual; L.roff = roff; L.probs = b.probs; L.n = p->maxProbs; L.nDev = b.nProb;
 	L.rawKeys = b.rawKeys; L.maxRaw = b.rawKeys ? PIPE_MAX_RAW : 0;
 	L.numSlots = p->numSlots; L.codes = b.codes; L.lastH = b.lastH; L.codeStride = p->codeStride; L.maxCol = p->maxCol;
-	L.maxCands = q.max_cands; L.maxAlns = q.max_alns; L.maxOps = q.max_ops; L.packed = p->packed;
+	L.maxCands = q.max_cands; L.maxAlns = q.max_alns; L.maxOps = q.max_ops; L.packed = p->packed; L.chunk = p->dpChunk;
 	L.summ = b.summ; L.cands = b.cands; L.alns = b.alns; L.ops = b.ops;
 	mark(6);
 	const int drc = p->sc.local ? launch_dp_local<OFF>(ix, p->sc, L, q.max_len, st) : launch_dp_e2e<OFF>(ix, p->sc, L, q.max_len, st);
@@ -447,7 +448,7 @@ static int runPairTail(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual
 	L.seq = seq; L.qual = qual; L.roff = roff; L.probs = b.mProbs; L.n = p->maxReads; L.nDev = b.nMateProb;
 	L.rawKeys = nullptr; L.maxRaw = 0;
 	L.numSlots = p->numSlots; L.codes = b.codes; L.lastH = nullptr; L.codeStride = p->mateCodeStride; L.maxCol = p->mateMaxCol;
-	L.maxCands = q.max_cands; L.maxAlns = q.max_alns; L.maxOps = q.max_ops; L.packed = p->packed;
+	L.maxCands = q.max_cands; L.maxAlns = q.max_alns; L.maxOps = q.max_ops; L.packed = p->packed; L.chunk = p->mateChunk;
 	L.summ = b.mSumm; L.cands = b.mCands; L.alns = b.mAlns; L.ops = b.mOps;
 	if(launch_dp_e2e<OFF>(ix, p->sc, L, q.max_len, st)) { ctx->err = "pipeline: mate DP launch rejected"; return -1; }
 	cudaEventRecord(p->pev[2], st);
@@ -501,7 +502,12 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 		for(int l = 1; l <= prm->max_len; l++) if(prm->minsc_by_len[l] < mn) mn = prm->minsc_by_len[l];
 		p->packed = dp_kernel_mode(p->sc, mn, prm->max_len);
 	}
-	rc |= pipeAlloc(p, b.codes, p->numSlots * p->codeStride * (p->packed ? 2 : 1)); rc |= pipeAlloc(p, b.lastH, p->numSlots * (uint64_t)p->maxCol);
+	if(p->packed == 3) {
+		p->dpChunk = dp_chunk_problems(p->codeStride, nprobMax);
+		rc |= pipeAlloc(p, b.codes, p->dpChunk * p->codeStride);
+	} else {
+		rc |= pipeAlloc(p, b.codes, p->numSlots * p->codeStride * (p->packed ? 2 : 1));
+	} rc |= pipeAlloc(p, b.lastH, p->numSlots * (uint64_t)p->maxCol);
 	// local mode gathers candidate cells during the fill (k_dp_local): a raw key list per warp slot
 	if(ctx->scoring.local) rc |= pipeAlloc(p, b.rawKeys, p->numSlots * (uint64_t)PIPE_MAX_RAW);
 	rc |= pipeAlloc(p, b.summ, nprobMax); rc |= pipeAlloc(p, b.cands, nprobMax * prm->max_cands);
@@ -638,14 +644,20 @@ int bt2g_pipeline_enable_pairs(bt2g_pipeline *p, const bt2g_pe_policy *pol) {
 	p->mateCodeStride = (uint64_t)(p->mateMaxCol + 32) * 32 * p->R;
 	int rc = 0;
 	uint8_t *codes2 = nullptr;
-	rc |= pipeAlloc(p, codes2, p->numSlots * p->mateCodeStride * (p->packed ? 2 : 1));
+	if(p->packed == 3) {
+		p->mateChunk = dp_chunk_problems(p->mateCodeStride, n);
+		const uint64_t need = p->mateChunk * p->mateCodeStride, have = p->dpChunk * p->codeStride;
+		rc |= pipeAlloc(p, codes2, need > have ? need : have);
+	} else {
+		rc |= pipeAlloc(p, codes2, p->numSlots * p->mateCodeStride * (p->packed ? 2 : 1));
+	}
 	rc |= pipeAlloc(p, b.mProbs, n); rc |= pipeAlloc(p, b.nMateProb, 1); rc |= pipeAlloc(p, b.mateOfRead, n);
 	rc |= pipeAlloc(p, b.mSumm, n); rc |= pipeAlloc(p, b.mCands, n * q.max_cands);
 	rc |= pipeAlloc(p, b.mAlns, n * q.max_alns); rc |= pipeAlloc(p, b.mOps, n * q.max_alns * (uint64_t)q.max_ops);
 	rc |= pipeAlloc(p, b.pairs, n / 2 + 1); rc |= pipeAlloc(p, b.mateCells, 1);
 	if(rc) return -2;
 	b.codes = codes2;        // the wider workspace serves both DP passes
-	p->codeStride = p->mateCodeStride;
+	if(p->packed != 3) p->codeStride = p->mateCodeStride;
 	cudaError_t e = cudaMemset(b.mAlns, 0, n * q.max_alns * sizeof(bt2g_dp_aln));
 	if(e == cudaSuccess) e = cudaMemset(b.mCands, 0, n * q.max_cands * sizeof(bt2g_dp_cand));
 	if(e == cudaSuccess) e = cudaHostAlloc((void **)&p->hPairs, (n / 2 + 1) * sizeof(bt2g_pair_result), cudaHostAllocDefault);
@@ -715,6 +727,16 @@ int bt2g_pipeline_pair_stage_ms(bt2g_pipeline *p, float *out3) {
 	BT2G_CUDA_TRY(ctx, cudaEventSynchronize(p->pev[3]));
 	for(int i = 0; i < 3; i++) BT2G_CUDA_TRY(ctx, cudaEventElapsedTime(&out3[i], p->pev[i], p->pev[i + 1]));
 	return 0;
+}
+
+// kernels launched by one bt2g_pipeline_run_dev call (k_plan, k_pack_reads, k_exact_sweep2, k_seed_search2,
+// k_collect, k_resolve2, k_frame, the DP kernel(s), k_pick); the split DP mode launches a fill and a tail
+// kernel per workspace chunk
+int bt2g_pipeline_kernel_launches(bt2g_pipeline *p) {
+	if(!p) return -1;
+	int dp = 1;
+	if(p->packed == 3 && p->dpChunk) dp = 2 * (int)((p->maxProbs + p->dpChunk - 1) / p->dpChunk);
+	return 8 + dp;
 }
 
 int bt2g_pipeline_results_dev(bt2g_pipeline *p, bt2g_read_result **res, uint8_t **ops) {

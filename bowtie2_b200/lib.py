@@ -364,7 +364,7 @@ READ_RESULT = np.dtype([("found", "<i4"), ("score", "<i4"), ("score2", "<i4"), (
                        align=True)
 
 EXPORTS += ["bt2g_pipeline_create", "bt2g_pipeline_destroy", "bt2g_pipeline_run_dev", "bt2g_pipeline_run_host",
-            "bt2g_pipeline_results_dev", "bt2g_pipeline_counters", "bt2g_pipeline_stage_ms",
+            "bt2g_pipeline_results_dev", "bt2g_pipeline_counters", "bt2g_pipeline_stage_ms", "bt2g_pipeline_kernel_launches",
             "bt2g_pipeline_enable_pairs", "bt2g_pipeline_run_paired_dev", "bt2g_pipeline_run_paired_host",
             "bt2g_pipeline_pairs_dev", "bt2g_pipeline_pair_counters", "bt2g_pipeline_pair_stage_ms"]
 PAIR_RESULT = np.dtype([("pair_type", "<i4"), ("kind", "<i4"), ("source", "<i4"), ("score_sum", "<i4"), ("fraglen", "<i8")], align=True)
@@ -458,6 +458,10 @@ class Pipeline:
         out = np.zeros(3, dtype=np.float32)
         self.gpu._check(self.gpu._lib.bt2g_pipeline_pair_stage_ms(self._h, _ptr(out)), "bt2g_pipeline_pair_stage_ms")
         return dict(zip(("frame_mates", "mate_dp", "pick_pairs"), (float(x) for x in out)))
+
+    def kernel_launches(self) -> int:
+        self.gpu._lib.bt2g_pipeline_kernel_launches.argtypes = [C.c_void_p]
+        return int(self.gpu._lib.bt2g_pipeline_kernel_launches(self._h))
 
     def run_host(self, reads: ReadBatch, want_ops: bool = True):
         res = np.zeros(reads.n, dtype=READ_RESULT)

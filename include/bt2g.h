@@ -366,6 +366,8 @@ int  bt2g_pipeline_run_dev(bt2g_pipeline *p, const uint8_t *d_seq, const uint8_t
 int  bt2g_pipeline_run_host(bt2g_pipeline *p, const bt2g_reads *reads, bt2g_read_result *res, uint8_t *ops);
 int  bt2g_pipeline_results_dev(bt2g_pipeline *p, bt2g_read_result **res, uint8_t **ops);
 int  bt2g_pipeline_counters(bt2g_pipeline *p, uint64_t *out6);
+/* kernels launched by one bt2g_pipeline_run_dev call */
+int  bt2g_pipeline_kernel_launches(bt2g_pipeline *p);
 /* ---- paired-end pass (SwDriver::extendSeedsPaired's mate finding, aligner_sw_driver.cpp:2157-2440) ----
  * Reads are interleaved: mate 1 of pair i is read 2i, mate 2 is read 2i+1.  The pass runs the
  * single-end stages on all 2n reads, then for every aligned mate (the anchor) whose opposite mate has

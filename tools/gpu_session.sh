@@ -11,6 +11,8 @@ tests)
   timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -5 $OUT/${TAG}_pytest.log ;;
 bench)
   timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"; tail -c 1500 $OUT/${TAG}_bench.json ;;
+bench2)
+  BT2G_DP_PACKED=2 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench2.json 2> $OUT/${TAG}_bench2.err; echo "bench2 exit $?"; tail -c 700 $OUT/${TAG}_bench2.json ;;
 bench0)
   BT2G_DP_PACKED=0 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench0.json 2> $OUT/${TAG}_bench0.err; echo "bench0 exit $?"; tail -c 700 $OUT/${TAG}_bench0.json ;;
 ncudp)
