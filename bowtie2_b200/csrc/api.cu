@@ -589,7 +589,6 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 	if(maxLen > 512) { ctx->err = "reads longer than 512 are not supported by the DP kernel"; return -1; }
 	maxCol += 1;                              // local mode keeps one extra reference character
 	if(maxCol > 8192) { ctx->err = "DP window wider than 8192 columns"; return -1; }
-	int R = maxLen <= 128 ? 4 : (maxLen <= 256 ? 8 : 16);
 	DBuf dseq, dqual, doff, dprob, dcodes, dlast, dsumm, dcand, daln, dops, draw;
 	int rc = uploadReads(ctx, reads, dseq, dqual, doff, true);
 	if(rc) return rc;
@@ -600,8 +599,8 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 		uint64_t want = (uint64_t)sms * 24;      // 24 resident warps per SM
 		L.numSlots = ((n < want ? n : want) + 3) / 4 * 4;
 	} L.maxCands = maxCands; L.maxAlns = maxAlns; L.maxOps = maxOps;
-	L.codeStride = (uint64_t)(maxCol + 32) * 32 * R;
-	L.packed = dp_kernel_mode(ctx->scoring, minMinsc, maxLen);
+	L.packed = ctx->scoring.local ? 0 : dp_kernel_mode(ctx->scoring, minMinsc, maxLen);
+	L.codeStride = dp_code_stride(maxCol, maxLen, L.packed);
 	BT2G_CUDA_TRY(ctx, dprob.alloc(n * sizeof(bt2g_dp_problem)));
 	if(L.packed == 3) {
 		L.chunk = dp_chunk_problems(L.codeStride, n);

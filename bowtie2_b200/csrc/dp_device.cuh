@@ -23,6 +23,22 @@ static inline int dp_kernel_mode(const bt2g_scoring &sc, int64_t minMinsc, int m
 	return (cap >= 2 && range <= 127) ? (cap >= 3 ? 3 : 2) : 1;
 }
 
+// rows per lane: the H-byte kernels (modes 2, 3) take the smallest R of {4,5,6,8,10,12,16} with 32 R >= rdlen
+// (a 150 bp read fills 30 lanes at R = 5 instead of 19 at R = 8); the move-code kernels use 4 / 8 / 16.
+static inline int dp_rows_per_lane(int maxLen, int mode) {
+	if(mode >= 2) {
+		const int rs[7] = {4, 5, 6, 8, 10, 12, 16};
+		for(int i = 0; i < 7; i++) if(32 * rs[i] >= maxLen) return rs[i];
+		return 0;
+	}
+	return maxLen <= 128 ? 4 : (maxLen <= 256 ? 8 : (maxLen <= 512 ? 16 : 0));
+}
+// bytes of workspace per problem (per warp slot in modes 0-2): (maxCol + 32) steps x 32 lanes x R rounded up to 4
+static inline uint64_t dp_code_stride(int maxCol, int maxLen, int mode) {
+	const int R = dp_rows_per_lane(maxLen, mode);
+	return (uint64_t)(maxCol + 32) * 32 * (uint64_t)(((R + 3) / 4) * 4);
+}
+
 // mode 3 workspace: as many problems per chunk as fit a byte budget (default 6 GiB; BT2G_DP_CHUNK_MB overrides)
 static inline uint64_t dp_chunk_problems(uint64_t codeStride, uint64_t nMax) {
 	uint64_t budget = 6ull << 30;

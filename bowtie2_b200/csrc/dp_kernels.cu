@@ -557,6 +557,9 @@ __global__ void __launch_bounds__(128) k_dp_e2e_x2(DevIndex<OFF> ix, bt2g_scorin
 // ----------------------------------------------------------------------------------------
 // ----------------------------------------------------------------------------------------
 // Fill of the H-byte kernel (two problems per warp, s16x2; see the description below).
+// H-byte kernels take any R (rows per lane) and store RP = R rounded up to 4 bytes per lane and step
+#define DP_RP(R) ((((R) + 3) / 4) * 4)
+
 template <typename OFF, int R>
 __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L) {
 	extern __shared__ uint8_t smem[];
@@ -653,8 +656,8 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 		for(int r = 0; r < R; r++) { Hleft[r] = FLOORP; Earr[r] = FLOORP; }
 		uint32_t botH = FLOORP, botF = FLOORP, prevInH = FLOORP;
 		const int nsteps = ncolMax + lastLaneMax;
-		uint8_t *dstA = hb[0] + (size_t)lane * R, *dstB = hb[1] + (size_t)lane * R;
-		for(int t = 0; t < nsteps; t++, dstA += 32 * R, dstB += 32 * R) {
+		uint8_t *dstA = hb[0] + (size_t)lane * DP_RP(R), *dstB = hb[1] + (size_t)lane * DP_RP(R);
+		for(int t = 0; t < nsteps; t++, dstA += 32 * DP_RP(R), dstB += 32 * DP_RP(R)) {
 			uint32_t inH = __shfl_up_sync(0xffffffffu, botH, 1);
 			uint32_t inF = __shfl_up_sync(0xffffffffu, botF, 1);
 			if(lane == 0) { inH = FLOORP; inF = FLOORP; }
@@ -665,7 +668,9 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 				// H[i0-1][j-1]: row -1 is the free start row of end-to-end mode (vhilsw, :853,923-927)
 				uint32_t diag = (lane == 0) ? 0u : prevInH;
 				uint32_t upH = inH, upF = inF;
-				uint32_t hs[R];
+				uint32_t hs[DP_RP(R)];
+#pragma unroll
+				for(int r = R; r < DP_RP(R); r++) hs[r] = 0u;
 #pragma unroll
 				for(int r = 0; r < R; r++) {
 					// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo)
@@ -685,7 +690,7 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 				prevInH = inH;
 				// byte 0 of every word is problem A's cell, byte 2 problem B's
 #pragma unroll
-				for(int q4 = 0; q4 < R / 4; q4++) {
+				for(int q4 = 0; q4 < DP_RP(R) / 4; q4++) {
 					const uint32_t t01 = __byte_perm(hs[4 * q4], hs[4 * q4 + 1], 0x6240), t23 = __byte_perm(hs[4 * q4 + 2], hs[4 * q4 + 3], 0x6240);
 					reinterpret_cast<uint32_t *>(dstA)[q4] = __byte_perm(t01, t23, 0x5410);
 					reinterpret_cast<uint32_t *>(dstB)[q4] = __byte_perm(t01, t23, 0x7632);
@@ -701,7 +706,7 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 			// last row -> scores (candidates are the cells >= minsc; a clamped byte reads as floor < minsc)
 			const int lr = rdlen[x] - 1, kk = lr / R;
 			for(int j = lane; j < ncol[x]; j += 32)
-				lastH[x][j] = (int)hb[x][((size_t)(j + kk) * 32 + kk) * R + (lr - kk * R)] + floorv[x];
+				lastH[x][j] = (int)hb[x][((size_t)(j + kk) * 32 + kk) * DP_RP(R) + (lr - kk * R)] + floorv[x];
 			dp_e2e_tail<R, true>(L, sc, p[x], w[x], rs[x], rq[x], rdlen[x], ncol[x], lastH[x], candCol[x], refw[x], hb[x], L.summ + w[x], lane);
 		}
 	} // persistent loop over problem pairs
@@ -712,7 +717,7 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 // workspace (pure DPX compute, high occupancy), k_dp_tail_h then runs candidates + backtraces with one warp per
 // problem (latency-bound on workspace reads, hidden by far more resident warps than the fused kernel can hold).
 template <typename OFF, int R>
-__global__ void __launch_bounds__(128, R == 4 ? 7 : 4) k_dp_fill_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L, uint64_t chunkStart, uint64_t chunkMax) {
+__global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L, uint64_t chunkStart, uint64_t chunkMax) {
 	extern __shared__ uint8_t smem[];
 	const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint64_t slot = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock;
@@ -803,8 +808,8 @@ __global__ void __launch_bounds__(128, R == 4 ? 7 : 4) k_dp_fill_h(DevIndex<OFF>
 		for(int r = 0; r < R; r++) { Hleft[r] = FLOORP; Earr[r] = FLOORP; }
 		uint32_t botH = FLOORP, botF = FLOORP, prevInH = FLOORP;
 		const int nsteps = ncolMax + lastLaneMax;
-		uint8_t *dstA = hb[0] + (size_t)lane * R, *dstB = hb[1] + (size_t)lane * R;
-		for(int t = 0; t < nsteps; t++, dstA += 32 * R, dstB += 32 * R) {
+		uint8_t *dstA = hb[0] + (size_t)lane * DP_RP(R), *dstB = hb[1] + (size_t)lane * DP_RP(R);
+		for(int t = 0; t < nsteps; t++, dstA += 32 * DP_RP(R), dstB += 32 * DP_RP(R)) {
 			uint32_t inH = __shfl_up_sync(0xffffffffu, botH, 1);
 			uint32_t inF = __shfl_up_sync(0xffffffffu, botF, 1);
 			if(lane == 0) { inH = FLOORP; inF = FLOORP; }
@@ -815,7 +820,9 @@ __global__ void __launch_bounds__(128, R == 4 ? 7 : 4) k_dp_fill_h(DevIndex<OFF>
 				// H[i0-1][j-1]: row -1 is the free start row of end-to-end mode (vhilsw, :853,923-927)
 				uint32_t diag = (lane == 0) ? 0u : prevInH;
 				uint32_t upH = inH, upF = inF;
-				uint32_t hs[R];
+				uint32_t hs[DP_RP(R)];
+#pragma unroll
+				for(int r = R; r < DP_RP(R); r++) hs[r] = 0u;
 #pragma unroll
 				for(int r = 0; r < R; r++) {
 					// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo)
@@ -835,7 +842,7 @@ __global__ void __launch_bounds__(128, R == 4 ? 7 : 4) k_dp_fill_h(DevIndex<OFF>
 				prevInH = inH;
 				// byte 0 of every word is problem A's cell, byte 2 problem B's
 #pragma unroll
-				for(int q4 = 0; q4 < R / 4; q4++) {
+				for(int q4 = 0; q4 < DP_RP(R) / 4; q4++) {
 					const uint32_t t01 = __byte_perm(hs[4 * q4], hs[4 * q4 + 1], 0x6240), t23 = __byte_perm(hs[4 * q4 + 2], hs[4 * q4 + 3], 0x6240);
 					reinterpret_cast<uint32_t *>(dstA)[q4] = __byte_perm(t01, t23, 0x5410);
 					reinterpret_cast<uint32_t *>(dstB)[q4] = __byte_perm(t01, t23, 0x7632);
@@ -874,7 +881,7 @@ __global__ void __launch_bounds__(256) k_dp_tail_h(DevIndex<OFF> ix, bt2g_scorin
 		ref_window<OFF>(ix, p.tidx, p.refl, ncol, refw, lane);
 		// last row -> scores (candidates are the cells >= minsc; a clamped byte reads as floor < minsc)
 		const int lr = rdlen - 1, kk = lr / R;
-		for(int j = lane; j < ncol; j += 32) lastH[j] = (int)hb[((size_t)(j + kk) * 32 + kk) * R + (lr - kk * R)] + floorv;
+		for(int j = lane; j < ncol; j += 32) lastH[j] = (int)hb[((size_t)(j + kk) * 32 + kk) * DP_RP(R) + (lr - kk * R)] + floorv;
 		dp_e2e_tail<R, true>(L, sc, p, w, rs, rq, rdlen, ncol, lastH, candCol, refw, hb, L.summ + w, lane);
 	}
 }
@@ -899,10 +906,11 @@ __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_sco
 	const int rdgapo = sc.rdgap_const + sc.rdgap_linear, rdgape = sc.rdgap_linear;
 	const int rfgapo = sc.rfgap_const + sc.rfgap_linear, rfgape = sc.rfgap_linear;
 	const int bonus = sc.match_bonus, gapbar = sc.gapbar;
+	const int vmax = bonus * rdlen - (p.minsc - bonus - 1);   // the largest byte a cell can hold: perfect score - floor
 	bt2g_dp_aln *alns = L.alns + w * (uint64_t)L.maxAlns;
 	uint8_t *ops = L.ops + w * (uint64_t)L.maxAlns * L.maxOps;
 	int naln = 0, flags = 0;
-	auto cell = [&](int rr, int cc) -> uint8_t * { int k = rr / R; return hb + ((size_t)(cc + k) * 32 + k) * R + (rr - k * R); };
+	auto cell = [&](int rr, int cc) -> uint8_t * { int k = rr / R; return hb + ((size_t)(cc + k) * 32 + k) * DP_RP(R) + (rr - k * R); };
 	auto rdchar = [&](int rr) -> int { const int pos = p.fw ? rr : rdlen - 1 - rr; int c = rs[pos]; return p.fw ? c : (c > 3 ? 4 : 3 - c); };
 	auto rdqual = [&](int rr) -> int { const int pos = p.fw ? rr : rdlen - 1 - rr; int q = (int)rq[pos] - 33; return q < 0 ? 0 : (q > 63 ? 63 : q); };
 	auto inCore = [&](int dlo, int dhi) -> bool { return dhi >= p.corel && dlo <= p.corer; };   // some diagonal of [dlo,dhi] is a core diagonal
@@ -915,11 +923,15 @@ __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_sco
 		bool fail = false, core = false, done = false, first = true, filtStart = false;
 		while(!done && !fail) {
 			// ---- H state at (row, col): the diagonal run.  Lane k holds cell (row-k, col-k).
+			// Every lane's byte sits in a different 32 B sector of the wavefront-major workspace, so a round costs as many
+			// sectors as lanes that load.  Candidates after the best one usually leave their diagonal (and die on a
+			// reported-through cell) within a few cells: their first round looks at 8 cells only.
+			const int wd = (ci > 0 && first) ? 8 : 32;
 			const int rk = row - lane, ck = col - lane;
-			uint8_t *cp = (rk >= 0 && ck >= 0) ? cell(rk, ck) : nullptr;
+			uint8_t *cp = (lane < wd && rk >= 0 && ck >= 0) ? cell(rk, ck) : nullptr;
 			const int mine = cp ? (int)*cp : 0x80;
 			const int v = mine & 0x7f;
-			const int vn = __shfl_down_sync(0xffffffffu, v, 1);       // H of my diagonal predecessor (lane 31: not loaded)
+			const int vn = __shfl_down_sync(0xffffffffu, v, 1);       // H of my diagonal predecessor (last loading lane: not loaded)
 			int sck = 0, refc = 4; bool isN = false, isMatch = false;
 			if(cp) {
 				const int c = rdchar(rk), q = rdqual(rk);
@@ -928,8 +940,8 @@ __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_sco
 				isMatch = !isN && c == refc;
 				sck = isN ? -(int)sc.npen[q] : (isMatch ? bonus : -(int)sc.mmpen[q]);
 			}
-			const bool cont = lane < 31 && !(mine & 0x80) && rk > 0 && ck > 0 && vn > 0 && v == vn + sck;
-			const int run = __ffs(~__ballot_sync(0xffffffffu, cont)) - 1;   // 0..31
+			const bool cont = lane < wd - 1 && !(mine & 0x80) && rk > 0 && ck > 0 && vn > 0 && v == vn + sck;
+			const int run = __ffs(~__ballot_sync(0xffffffffu, cont)) - 1;   // 0..wd-1
 			if(run > 0) {
 				first = false;
 				const int diagi = col - row + p.triml;
@@ -943,7 +955,7 @@ __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_sco
 				nops += run; row -= run; col -= run;
 			}
 			const int endBits = __shfl_sync(0xffffffffu, mine, run);   // the cell at (row, col) now
-			if(run == 31 && !(endBits & 0x80) && row > 0 && col > 0) { __syncwarp(); continue; }   // lane 31: decide next round
+			if(run == wd - 1 && !(endBits & 0x80) && row > 0 && col > 0) { __syncwarp(); continue; }   // last loaded cell: decide next round
 			// ---- the cell that ends the run
 			if(endBits & 0x80) {
 				// start cell already reported through -> BT_CAND_FATE_FILT_START (:771-789); elsewhere the backtrace fails
@@ -963,10 +975,10 @@ __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_sco
 			int klen = 0, gapKind = 0;                                 // 1 ref gap (rows), 2 read gap (columns)
 			if(row >= gapbar && rdlen - 1 - row >= gapbar) {
 				for(int k0 = 0; k0 < row; k0 += 32) {
-					if(127 - rfgapo - k0 * rfgape < cur) break;        // longer gaps cannot reach cur any more
+					if(vmax - rfgapo - k0 * rfgape < cur) break;       // longer gaps cannot reach cur any more
 					const int k = k0 + lane + 1, r2 = row - k;
 					bool ok = false;
-					if(r2 >= 0 && row - k + 1 >= gapbar) {             // the gap's rows row-k+1..row lie outside the barrier
+					if(r2 >= 0 && row - k + 1 >= gapbar && vmax - rfgapo - (k - 1) * rfgape >= cur) {   // rows row-k+1..row outside the barrier
 						const int u = *cell(r2, col) & 0x7f;
 						ok = u > 0 && u - rfgapo - (k - 1) * rfgape == cur;
 					}
@@ -975,10 +987,10 @@ __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_sco
 				}
 				if(gapKind == 0) {
 					for(int k0 = 0; k0 < col; k0 += 32) {
-						if(127 - rdgapo - k0 * rdgape < cur) break;
+						if(vmax - rdgapo - k0 * rdgape < cur) break;
 						const int k = k0 + lane + 1, c2 = col - k;
 						bool ok = false;
-						if(c2 >= 0) {
+						if(c2 >= 0 && vmax - rdgapo - (k - 1) * rdgape >= cur) {
 							const int u = *cell(row, c2) & 0x7f;
 							ok = u > 0 && u - rdgapo - (k - 1) * rdgape == cur;
 						}
@@ -1100,10 +1112,16 @@ static void launch_dp_e2e_r(const DevIndex<OFF> &ix, const bt2g_scoring &sc, con
 template <typename OFF>
 int launch_dp_e2e(const DevIndex<OFF> &ix, const bt2g_scoring &sc, const DpLaunch &L, int maxRdLen, cudaStream_t st) {
 	if(L.n == 0) return 0;
-	if(maxRdLen <= 128) launch_dp_e2e_r<OFF, 4>(ix, sc, L, st);
-	else if(maxRdLen <= 256) launch_dp_e2e_r<OFF, 8>(ix, sc, L, st);
-	else if(maxRdLen <= 512) launch_dp_e2e_r<OFF, 16>(ix, sc, L, st);
-	else return -1;
+	switch(dp_rows_per_lane(maxRdLen, L.packed)) {
+		case 4: launch_dp_e2e_r<OFF, 4>(ix, sc, L, st); break;
+		case 5: launch_dp_e2e_r<OFF, 5>(ix, sc, L, st); break;
+		case 6: launch_dp_e2e_r<OFF, 6>(ix, sc, L, st); break;
+		case 8: launch_dp_e2e_r<OFF, 8>(ix, sc, L, st); break;
+		case 10: launch_dp_e2e_r<OFF, 10>(ix, sc, L, st); break;
+		case 12: launch_dp_e2e_r<OFF, 12>(ix, sc, L, st); break;
+		case 16: launch_dp_e2e_r<OFF, 16>(ix, sc, L, st); break;
+		default: return -1;
+	}
 	return 0;
 }
 template int launch_dp_e2e<uint32_t>(const DevIndex<uint32_t> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);

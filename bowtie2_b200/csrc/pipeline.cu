@@ -431,17 +431,20 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 }
 
 template <typename OFF>
-static int runPairTail(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, const uint64_t *roff, uint64_t nPairs, cudaStream_t st, bool count) {
+static int runPairTail(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, const uint64_t *roff, uint64_t nPairs, cudaStream_t st, bool count,
+                       uint64_t resBase = 0) {
 	bt2g_ctx *ctx = p->ctx;
 	PipeBufs &b = p->b;
 	const bt2g_pipeline_params &q = p->prm;
 	DevIndex<OFF> ix = bt2g_dev_index<OFF>(ctx);
 	const uint64_t n = 2 * nPairs;
 	const unsigned T = 128;
+	bt2g_read_result *res = b.res + resBase; uint8_t *resOps = b.resOps + resBase * (uint64_t)q.max_ops;
+	const uint64_t *resTlen = b.resTlen + resBase; bt2g_pair_result *pairs = b.pairs + resBase / 2;
 	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(b.nMateProb, 0, sizeof(uint32_t), st));
 	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(b.mateCells, 0, sizeof(unsigned long long), st));
 	cudaEventRecord(p->pev[0], st);
-	k_frame_mates<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(n, roff, b.res, b.resOps, q.max_ops, b.resTlen, p->pe, q.max_len, q.maxhalf, p->mateMaxCol,
+	k_frame_mates<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(n, roff, res, resOps, q.max_ops, resTlen, p->pe, q.max_len, q.maxhalf, p->mateMaxCol,
 	                                                         b.minscByLen, b.nceilRawByLen, b.rdgapsByLen, b.rfgapsByLen, b.mProbs, b.nMateProb, b.mateOfRead);
 	cudaEventRecord(p->pev[1], st);
 	DpLaunch L;
@@ -452,8 +455,8 @@ static int runPairTail(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual
 	L.summ = b.mSumm; L.cands = b.mCands; L.alns = b.mAlns; L.ops = b.mOps;
 	if(launch_dp_e2e<OFF>(ix, p->sc, L, q.max_len, st)) { ctx->err = "pipeline: mate DP launch rejected"; return -1; }
 	cudaEventRecord(p->pev[2], st);
-	k_pick_pairs<<<(unsigned)((nPairs + T - 1) / T), T, 0, st>>>(nPairs, roff, b.res, b.resOps, q.max_ops, q.max_alns, p->pe, b.mateOfRead, b.mProbs,
-	                                                             b.mSumm, b.mAlns, b.mOps, b.pairs, count ? b.mateCells : nullptr);
+	k_pick_pairs<<<(unsigned)((nPairs + T - 1) / T), T, 0, st>>>(nPairs, roff, res, resOps, q.max_ops, q.max_alns, p->pe, b.mateOfRead, b.mProbs,
+	                                                             b.mSumm, b.mAlns, b.mOps, pairs, count ? b.mateCells : nullptr);
 	cudaEventRecord(p->pev[3], st);
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	return 0;
@@ -492,16 +495,16 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	rc |= pipeAlloc(p, b.tidx, nrowMax); rc |= pipeAlloc(p, b.textoff, nrowMax); rc |= pipeAlloc(p, b.tlen, nrowMax); rc |= pipeAlloc(p, b.rflags, nrowMax);
 	rc |= pipeAlloc(p, b.probs, nprobMax); rc |= pipeAlloc(p, b.nProb, 1); rc |= pipeAlloc(p, b.readProb, nrowMax); rc |= pipeAlloc(p, b.readNProb, n);
 	p->maxCol = prm->max_len + 4 * prm->maxhalf + 4;
-	p->R = prm->max_len <= 128 ? 4 : (prm->max_len <= 256 ? 8 : 16);
-	p->codeStride = (uint64_t)(p->maxCol + 32) * 32 * p->R;
 	int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
 	p->sms = sms;
 	p->numSlots = (uint64_t)sms * 24;
 	{
 		int64_t mn = 0;
 		for(int l = 1; l <= prm->max_len; l++) if(prm->minsc_by_len[l] < mn) mn = prm->minsc_by_len[l];
-		p->packed = dp_kernel_mode(p->sc, mn, prm->max_len);
+		p->packed = p->sc.local ? 0 : dp_kernel_mode(p->sc, mn, prm->max_len);
 	}
+	p->R = dp_rows_per_lane(prm->max_len, p->packed);
+	p->codeStride = dp_code_stride(p->maxCol, prm->max_len, p->packed);
 	if(p->packed == 3) {
 		p->dpChunk = dp_chunk_problems(p->codeStride, nprobMax);
 		rc |= pipeAlloc(p, b.codes, p->dpChunk * p->codeStride);
@@ -641,7 +644,7 @@ int bt2g_pipeline_enable_pairs(bt2g_pipeline *p, const bt2g_pe_policy *pol) {
 	const int maxgap = q.maxhalf > 32 ? q.maxhalf : 32;
 	p->mateMaxCol = (int)(maxfrag + q.max_len + 2 * maxgap + 8);
 	if(p->mateMaxCol > 8192) { ctx->err = "pipeline: -X too large for the mate-finding workspace"; return -1; }
-	p->mateCodeStride = (uint64_t)(p->mateMaxCol + 32) * 32 * p->R;
+	p->mateCodeStride = dp_code_stride(p->mateMaxCol, q.max_len, p->packed);
 	int rc = 0;
 	uint8_t *codes2 = nullptr;
 	if(p->packed == 3) {
@@ -683,22 +686,52 @@ int bt2g_pipeline_run_paired_dev(bt2g_pipeline *p, const uint8_t *dSeq, const ui
 int bt2g_pipeline_run_paired_host(bt2g_pipeline *p, const bt2g_reads *reads, bt2g_read_result *res, uint8_t *ops, bt2g_pair_result *pairs) {
 	if(!p || !reads || !reads->qual || !res || !pairs) return -1;
 	bt2g_ctx *ctx = p->ctx;
+	if(!p->pairsOn) { ctx->err = "pipeline: call bt2g_pipeline_enable_pairs first"; return -1; }
 	const uint64_t n = reads->n_reads;
 	if(n & 1ull) { ctx->err = "pipeline: paired input needs an even number of reads (mate 1, mate 2 interleaved)"; return -1; }
 	if(n > p->maxReads || reads->off[n] > p->maxBases) { ctx->err = "pipeline: batch larger than the pipeline was created for"; return -1; }
 	if(n == 0) return 0;
 	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
-	const uint64_t nb = reads->off[n];
-	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.seq, reads->seq, nb, cudaMemcpyHostToDevice, st));
-	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.qual, reads->qual, nb, cudaMemcpyHostToDevice, st));
-	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.roff, reads->off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-	int rc = bt2g_pipeline_run_paired_dev(p, p->b.seq, p->b.qual, p->b.roff, n / 2, st, 0);
-	if(rc) return rc;
-	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(res, p->b.res, n * sizeof(bt2g_read_result), cudaMemcpyDeviceToHost, st));
-	if(ops) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(ops, p->b.resOps, n * (uint64_t)p->prm.max_ops, cudaMemcpyDeviceToHost, st));
-	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(pairs, p->b.pairs, (n / 2) * sizeof(bt2g_pair_result), cudaMemcpyDeviceToHost, st));
+	const uint64_t maxOps = (uint64_t)p->prm.max_ops;
+	uint64_t chunkMin = 1u << 18;
+	if(const char *e = getenv("BT2G_HOST_CHUNK_MIN")) chunkMin = strtoull(e, nullptr, 10);
+	const int nChunks = (p->chunkOk && n >= chunkMin && n >= 8) ? 4 : 1;
+	// same overlap scheme as bt2g_pipeline_run_host; chunks hold whole pairs
 	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.roff, reads->off, (n + 1) * 8, cudaMemcpyHostToDevice, p->sIn));
+	const uint64_t per = (((n / 2) + nChunks - 1) / nChunks) * 2;
+	for(int c = 0; c < nChunks; c++) {
+		const uint64_t s0 = (uint64_t)c * per < n ? (uint64_t)c * per : n, s1 = (s0 + per < n) ? s0 + per : n;
+		const uint64_t b0 = reads->off[s0], b1 = reads->off[s1];
+		if(b1 > b0) {
+			BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.seq + b0, reads->seq + b0, b1 - b0, cudaMemcpyHostToDevice, p->sIn));
+			BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(p->b.qual + b0, reads->qual + b0, b1 - b0, cudaMemcpyHostToDevice, p->sIn));
+		}
+		BT2G_CUDA_TRY(ctx, cudaEventRecord(p->evIn[c], p->sIn));
+	}
+	for(int c = 0; c < nChunks; c++) {
+		const uint64_t s0 = (uint64_t)c * per < n ? (uint64_t)c * per : n, s1 = (s0 + per < n) ? s0 + per : n;
+		BT2G_CUDA_TRY(ctx, cudaStreamWaitEvent(st, p->evIn[c], 0));
+		if(s1 == s0) continue;
+		int rc;
+		if(ctx->info.off_size == 4) {
+			rc = runStages<uint32_t>(p, p->b.seq, p->b.qual, p->b.roff + s0, s1 - s0, st, false, s0);
+			if(!rc) rc = runPairTail<uint32_t>(p, p->b.seq, p->b.qual, p->b.roff + s0, (s1 - s0) / 2, st, false, s0);
+		} else {
+			rc = runStages<uint64_t>(p, p->b.seq, p->b.qual, p->b.roff + s0, s1 - s0, st, false, s0);
+			if(!rc) rc = runPairTail<uint64_t>(p, p->b.seq, p->b.qual, p->b.roff + s0, (s1 - s0) / 2, st, false, s0);
+		}
+		if(rc) return rc;
+		BT2G_CUDA_TRY(ctx, cudaEventRecord(p->evDone[c], st));
+		BT2G_CUDA_TRY(ctx, cudaStreamWaitEvent(p->sOut, p->evDone[c], 0));
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(res + s0, p->b.res + s0, (s1 - s0) * sizeof(bt2g_read_result), cudaMemcpyDeviceToHost, p->sOut));
+		if(ops) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(ops + s0 * maxOps, p->b.resOps + s0 * maxOps, (s1 - s0) * maxOps, cudaMemcpyDeviceToHost, p->sOut));
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(pairs + s0 / 2, p->b.pairs + s0 / 2, ((s1 - s0) / 2) * sizeof(bt2g_pair_result), cudaMemcpyDeviceToHost, p->sOut));
+	}
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(p->sOut));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	p->lastN = n;
 	return 0;
 }
 
@@ -729,14 +762,21 @@ int bt2g_pipeline_pair_stage_ms(bt2g_pipeline *p, float *out3) {
 	return 0;
 }
 
-// kernels launched by one bt2g_pipeline_run_dev call (k_plan, k_pack_reads, k_exact_sweep2, k_seed_search2,
+// kernels launched by one bt2g_pipeline_run_dev (after bt2g_pipeline_enable_pairs: run_paired_dev) call (k_plan, k_pack_reads, k_exact_sweep2, k_seed_search2,
 // k_collect, k_resolve2, k_frame, the DP kernel(s), k_pick); the split DP mode launches a fill and a tail
 // kernel per workspace chunk
 int bt2g_pipeline_kernel_launches(bt2g_pipeline *p) {
 	if(!p) return -1;
 	int dp = 1;
 	if(p->packed == 3 && p->dpChunk) dp = 2 * (int)((p->maxProbs + p->dpChunk - 1) / p->dpChunk);
-	return 8 + dp;
+	int pe = 0;
+	if(p->pairsOn) {
+		// k_frame_mates, the mate DP kernel(s), k_pick_pairs
+		int mdp = 1;
+		if(p->packed == 3 && p->mateChunk) mdp = 2 * (int)((p->maxReads + p->mateChunk - 1) / p->mateChunk);
+		pe = 2 + mdp;
+	}
+	return 8 + dp + pe;
 }
 
 int bt2g_pipeline_results_dev(bt2g_pipeline *p, bt2g_read_result **res, uint8_t **ops) {

@@ -205,5 +205,11 @@ def test_paired_pipeline_vs_reference_program(gpu, synth_index, synth_genome, tm
     assert n_cigar >= 0.99 * 2 * n_cp_same, (n_cigar, n_cp_same)
     assert n_rescued > 100, n_rescued                      # the mate DP really ran and decided pairs
     assert n_rescued_same >= 0.9 * n_rescued, (n_rescued_same, n_rescued)
-    c = pipe.pair_counters()
+    # chunked host path (copies overlapped with compute): identical answers
+    os.environ["BT2G_HOST_CHUNK_MIN"] = "64"
+    try:
+        res3, ops3, pairs3 = pipe.run_paired_host(ReadBatch.from_list(reads, quals))
+    finally:
+        del os.environ["BT2G_HOST_CHUNK_MIN"]
+    assert np.array_equal(res, res3) and np.array_equal(pairs, pairs3)
     pipe.close()

@@ -11,6 +11,17 @@ tests)
   timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -5 $OUT/${TAG}_pytest.log ;;
 bench)
   timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"; tail -c 1500 $OUT/${TAG}_bench.json ;;
+ncusplit)
+  timeout 900 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:^k_dp_ -c 8 --csv --log-file $OUT/${TAG}_dp_split.csv \
+     python bench.py --steps 1 --warmup 1 --reads 2000000 --no-cpu-baseline > $OUT/${TAG}_ncu_split.log 2>&1; echo "ncu split exit $?"
+  for k in k_dp_fill_h k_dp_tail_h; do
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:^$k -c 1 -f -o $OUT/${TAG}_$k \
+       python bench.py --steps 1 --warmup 1 --reads 2000000 --no-cpu-baseline > $OUT/${TAG}_ncu_$k.log 2>&1; echo "ncu $k exit $?"
+  done ;;
+benchsmall)
+  timeout 600 python bench.py --genome-mbp 240 --reads 400000 --batch 200000 --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_benchsmall.json 2> $OUT/${TAG}_benchsmall.err; echo "benchsmall exit $?"; tail -c 1200 $OUT/${TAG}_benchsmall.json; tail -5 $OUT/${TAG}_benchsmall.err ;;
+benchse)
+  timeout 900 python bench.py --workload se100 --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_benchse.json 2> $OUT/${TAG}_benchse.err; echo "benchse exit $?"; tail -c 900 $OUT/${TAG}_benchse.json ;;
 bench2)
   BT2G_DP_PACKED=2 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench2.json 2> $OUT/${TAG}_bench2.err; echo "bench2 exit $?"; tail -c 700 $OUT/${TAG}_bench2.json ;;
 bench0)
