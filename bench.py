@@ -301,6 +301,8 @@ def main():
     ap.add_argument("--genome-mbp", type=float, default=GENOME_CONTIGS * CONTIG_LEN / 1e6,
                     help="debug only: smaller genome (any value other than the default is NOT the BASELINE config)")
     ap.add_argument("--reads", type=int, default=0, help="reads (pairs) resident in HBM (0 = the workload's default)")
+    ap.add_argument("--seed-table", type=int, default=15,
+                    help="k of the extended seed table derived from the index at load time (0 = off; results are identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads (pairs) in the CPU baseline sample (0 = auto)")
     args = ap.parse_args()
@@ -368,6 +370,12 @@ def main():
     else:
         gpu.load_index_device(built.device_desc(dev), keep=built)
     info = gpu.info()
+    ktab_s = 0.0
+    if args.seed_table > info["ftab_chars"]:
+        torch.cuda.synchronize(); tk = time.time()
+        gpu.build_seed_table(args.seed_table)
+        ktab_s = time.time() - tk
+        log(f"rank {rank}: {args.seed_table}-mer seed table built in {ktab_s:.2f}s")
     if paired:
         reads, quals = make_pairs_gpu(torch, dev, contigs, args.reads, READ_LEN, seed=1 + rank)
     else:
@@ -574,7 +582,7 @@ def main():
                 "config": {"workload": workload, "full_size": full, "read_unit": unit[:-1], "mates_per_s_M": value * mates,
                            "batch": B, "preset": " ".join(ref_preset),
                            "l2": "inputs larger than L2 (random access over a %.1f GB index; a different batch each step)" % (info["device_bytes"] / 1e9),
-                           "pipeline": pipeline_desc, "index_bcast_s": bcast_s, "aligned_frac": found, "pairs": conc,
+                           "pipeline": pipeline_desc, "seed_table_k": args.seed_table, "seed_table_build_s": ktab_s, "index_bcast_s": bcast_s, "aligned_frac": found, "pairs": conc,
                            "host_threads": cores, "cgroup_cpu_quota": cpu_quota, "dp_workspace_overflows": overflow},
                 "clocks": clk, "gpu_launches": pipe.kernel_launches() * args.steps,
                 "e2e": {"value": e2e_val, "unit": "Mreads/s", "h2d_bytes_per_step": 2 * BR * READ_LEN + (BR + 1) * 8,

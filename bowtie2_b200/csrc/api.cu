@@ -22,6 +22,7 @@ template <typename OFF> void launch_get_stretch(const DevIndex<OFF> &, const uin
 template <typename OFF> void launch_extend(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint64_t *, uint8_t *, cudaStream_t);
 
 template <typename OFF> void launch_ungapped(const DevIndex<OFF> &, const bt2g_scoring &, const uint8_t *, const uint8_t *, const uint64_t *, const bt2g_ungapped_problem *, uint64_t, bt2g_ungapped_result *, uint8_t *, uint32_t, cudaStream_t);
+template <typename OFF> void launch_build_ktab(const DevIndex<OFF> &, int, OFF *, cudaStream_t);
 void launch_frame_mate(const bt2g_pe_policy &, const bt2g_mate_anchor *, uint64_t, bt2g_mate_frame *, cudaStream_t);
 void launch_pe_classify(const bt2g_pe_policy &, const int64_t *, uint64_t, int32_t *, cudaStream_t);
 namespace {
@@ -43,6 +44,7 @@ void freeArr(DevArray &a) {
 void freeIndex(bt2g_ctx *ctx) {
 	for(int i = 0; i < BT2G_N_INDEX_ARRAYS; i++) freeArr(ctx->arr[i]);
 	freeArr(ctx->recCumOff); freeArr(ctx->recCumUnamb); freeArr(ctx->refRecOffs); freeArr(ctx->refLens);
+	freeArr(ctx->ktab); ctx->ktabChars = 0;
 	ctx->loaded = false;
 }
 
@@ -189,6 +191,7 @@ DevIndex<OFF> bt2g_dev_index(const bt2g_ctx *ctx) {
 	ix.fw = devEbwt<OFF>(ctx, false);
 	ix.bw = devEbwt<OFF>(ctx, true);
 	ix.offs = (const OFF *)ctx->arr[2].ptr;
+	ix.ktab = (const OFF *)ctx->ktab.ptr; ix.ktabChars = ctx->ktab.ptr ? ctx->ktabChars : 0;
 	ix.offRate = ctx->info.off_rate;
 	ix.rstarts = (const OFF *)ctx->arr[8].ptr;
 	ix.nFrag = ctx->info.n_frag;
@@ -430,6 +433,28 @@ int bt2g_ungapped(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_ungapped_pr
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, dout.bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	if(editMask) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(editMask, dmask.p, dmask.bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int bt2g_build_seed_table(bt2g_ctx *ctx, int k) {
+	REQUIRE_LOADED(ctx);
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	freeArr(ctx->ktab); ctx->ktabChars = 0;
+	if(k == 0) return 0;
+	const int F = ctx->info.ftab_chars;
+	if(k <= F || k > 16 || F < 1) { ctx->err = "seed table: k must be in (ftab_chars, 16]"; return -1; }
+	if(!ctx->info.has_bw) { ctx->err = "seed table: mirror index not loaded"; return -1; }
+	const uint64_t entries = 1ull << (2 * k), bytes = entries * 3ull * (uint64_t)ctx->info.off_size;
+	void *p = nullptr;
+	cudaError_t e = cudaMalloc(&p, bytes);
+	if(e != cudaSuccess) { ctx->err = std::string("seed table cudaMalloc: ") + cudaGetErrorString(e); return -2; }
+	if(ctx->info.off_size == 4) launch_build_ktab<uint32_t>(bt2g_dev_index<uint32_t>(ctx), k, (uint32_t *)p, ctx->stream);
+	else launch_build_ktab<uint64_t>(bt2g_dev_index<uint64_t>(ctx), k, (uint64_t *)p, ctx->stream);
+	e = cudaStreamSynchronize(ctx->stream);
+	if(e == cudaSuccess) e = cudaGetLastError();
+	if(e != cudaSuccess) { cudaFree(p); ctx->err = std::string("seed table build: ") + cudaGetErrorString(e); return -2; }
+	ctx->ktab.ptr = p; ctx->ktab.bytes = bytes; ctx->ktab.owned = true; ctx->ktabChars = k;
 	return 0;
 }
 

@@ -41,6 +41,10 @@ struct DevIndex {
 	const uint64_t *refLens;      // [nRefs]
 	const uint8_t  *refBuf;
 	uint64_t       nRecs, nRefs;
+	// optional extended seed table (bt2g_build_seed_table): for every K-mer the state of the bidirectional
+	// search after its K characters: 3 OFF per entry = topf, botf, topb (all 0 = empty range)
+	const OFF     *ktab;
+	int            ktabChars;
 };
 
 struct DevArray {
@@ -58,6 +62,7 @@ struct bt2g_ctx {
 	// derived reference tables (always owned)
 	DevArray recCumOff, recCumUnamb, refRecOffs, refLens;
 	uint64_t nRefs = 0;
+	DevArray ktab; int ktabChars = 0;
 	cudaStream_t stream = nullptr;
 	bt2g_scoring scoring{};
 	// scratch buffers (grown on demand)

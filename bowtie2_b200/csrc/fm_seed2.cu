@@ -118,7 +118,13 @@ __global__ void __launch_bounds__(256) k_seed_search2(DevIndex<OFF> ix, const ui
 						if(strand == 1) bits = rev_pairs(bits, sl) ^ m2;   // reverse complement of the window
 					}
 					if(ok) {
-						if(ftabLen > 1 && ftabLen <= sl) {
+						if(ix.ktab != nullptr && ix.ktabChars <= sl) {
+							// extended seed table: the search state after the first ktabChars characters
+							const OFF *e3 = ix.ktab + 3ull * (bits >> (2 * (sl - ix.ktabChars)));
+							topf = e3[0]; botf = e3[1]; topb = e3[2]; botb = topb + (botf - topf);
+							if(botf <= topf) ok = false;
+							step = ix.ktabChars;
+						} else if(ftabLen > 1 && ftabLen <= sl) {
 							const uint64_t top20 = bits >> (2 * (sl - ftabLen));
 							const uint64_t fwi = rev_pairs(top20, ftabLen), bwi = top20;
 							topf = ftab_hi<OFF>(fw, fwi); botf = ftab_lo<OFF>(fw, fwi + 1);
@@ -188,6 +194,54 @@ void launch_seed_search2(const DevIndex<OFF> &ix, const uint8_t *seq, const uint
 }
 template void launch_seed_search2<uint32_t>(const DevIndex<uint32_t> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
 template void launch_seed_search2<uint64_t>(const DevIndex<uint64_t> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+
+// ----------------------------------------------------------------------------------------
+// Extended seed table (include/bt2g.h: bt2g_build_seed_table): one thread per K-mer replays the first K
+// characters of k_seed_search2's chain: ftab lookup for the first ftabChars, then K - ftabChars
+// bidirectional LF steps.  Entry index = the K characters in the order the search consumes them,
+// first character in the most significant pair.
+template <typename OFF>
+__global__ void k_build_ktab(DevIndex<OFF> ix, int K, OFF *out) {
+	constexpr uint32_t BL = SideGeom<OFF>::BWT_LEN;
+	const uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(x >> (2 * K)) return;
+	const DevEbwt<OFF> &fw = ix.fw;
+	const DevEbwt<OFF> &bw = ix.bw;
+	const int F = fw.ftabChars;
+	OFF *o = out + 3ull * x;
+	o[0] = 0; o[1] = 0; o[2] = 0;
+	const uint64_t top20 = x >> (2 * (K - F));
+	const uint64_t fwi = rev_pairs(top20, F), bwi = top20;
+	uint64_t topf = ftab_hi<OFF>(fw, fwi), botf = ftab_lo<OFF>(fw, fwi + 1);
+	if(botf <= topf) return;
+	uint64_t topb = ftab_hi<OFF>(bw, bwi);
+	for(int step = F; step < K; step++) {
+		const int c = (int)((x >> (2 * (K - step - 1))) & 3);
+		const uint64_t sideT = topf / BL, sideB = botf / BL;
+		const uint32_t offT = (uint32_t)(topf - sideT * BL), offB = (uint32_t)(botf - sideB * BL);
+		uint64_t tt[4], bb[4];
+		SideRegs<OFF> s;
+		load_side<OFF>(fw.ebwt, sideT, s);
+		rank4_loaded<OFF>(fw, s, sideT, offT, tt);
+		if(sideB != sideT) load_side<OFF>(fw.ebwt, sideB, s);
+		rank4_loaded<OFF>(fw, s, sideB, offB, bb);
+		const uint64_t w0 = bb[0] - tt[0], w1 = bb[1] - tt[1], w2 = bb[2] - tt[2];
+		const uint64_t tp = topb + (c > 0 ? w0 : 0) + (c > 1 ? w1 : 0) + (c > 2 ? w2 : 0);
+		const uint64_t nt = c == 0 ? tt[0] : (c == 1 ? tt[1] : (c == 2 ? tt[2] : tt[3]));
+		const uint64_t nb = c == 0 ? bb[0] : (c == 1 ? bb[1] : (c == 2 ? bb[2] : bb[3]));
+		if(nb <= nt) return;
+		topf = nt; botf = nb; topb = tp;
+	}
+	o[0] = (OFF)topf; o[1] = (OFF)botf; o[2] = (OFF)topb;
+}
+
+template <typename OFF>
+void launch_build_ktab(const DevIndex<OFF> &ix, int K, OFF *out, cudaStream_t st) {
+	const uint64_t n = 1ull << (2 * K);
+	k_build_ktab<OFF><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ix, K, out);
+}
+template void launch_build_ktab<uint32_t>(const DevIndex<uint32_t> &, int, uint32_t *, cudaStream_t);
+template void launch_build_ktab<uint64_t>(const DevIndex<uint64_t> &, int, uint64_t *, cudaStream_t);
 
 // ----------------------------------------------------------------------------------------
 // K1' v2: exact end-to-end sweep (SeedAligner::exactSweep, aligner_seed.cpp:856-970) with packed

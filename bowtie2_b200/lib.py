@@ -626,3 +626,16 @@ def _ungapped(self, reads: ReadBatch, probs: np.ndarray, want_mask: bool = True)
 
 
 Bt2Gpu.ungapped = _ungapped
+
+
+# ---- extended seed table (include/bt2g.h: bt2g_build_seed_table) -----------------------------------
+EXPORTS += ["bt2g_build_seed_table"]
+
+
+def _build_seed_table(self, k: int):
+    """Derive the k-mer start table of the seed search from the loaded index (k = 0 drops it)."""
+    self._lib.bt2g_build_seed_table.argtypes = [C.c_void_p, C.c_int]
+    self._check(self._lib.bt2g_build_seed_table(self._h, int(k)), "bt2g_build_seed_table")
+
+
+Bt2Gpu.build_seed_table = _build_seed_table

@@ -251,6 +251,16 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
                    int32_t max_cands, int32_t max_alns, int32_t max_ops,
                    bt2g_dp_summary *summ, bt2g_dp_cand *cands, bt2g_dp_aln *alns, uint8_t *ops);
 
+/* ------------------------------------------------------------------ extended seed table ----- */
+/* An acceleration structure derived from the loaded index, in the spirit of ftab (bt2_idx.h:1373-1554)
+ * but for k-mers of k > ftab_chars characters (k <= 16): for every k-mer, the state (topf, botf, topb)
+ * of the bidirectional backward search after its k characters, i.e. exactly what ftabLoHi + (k -
+ * ftab_chars) mapBiLFEx steps of SeedAligner::searchSeedBi would produce.  The seed-search kernel then
+ * starts at depth k instead of ftab_chars; its results are bit-identical with and without the table.
+ * Costs 3 * off_size * 4^k bytes of HBM (k = 14: 3.2 GB for .bt2) and one pass of (k - ftab_chars)
+ * LF steps per entry at build time.  k = 0 drops the table. */
+int bt2g_build_seed_table(bt2g_ctx *ctx, int k);
+
 /* ------------------------------------------------------------------- ungapped alignment ----- */
 /* SwAligner::ungappedAlign (aligner_sw.cpp:286-487): the single-diagonal alignment the driver takes when
  * neither read nor reference gaps fit under the minimum score (aligner_sw_driver.cpp:1189-1253).

@@ -108,6 +108,29 @@ def test_seed_search(loaded, lambda_reads, synth_genome, L, off):
     assert nhit > 0
 
 
+@pytest.mark.parametrize("k", [11, 12, 13])
+def test_seed_search_with_extended_table(loaded, lambda_reads, synth_genome, k):
+    """bt2g_build_seed_table: the k-mer start table changes where the search starts, never what it returns."""
+    gpu, O, name = loaded
+    reads = _reads_for(name, lambda_reads, synth_genome)
+    gpu.build_seed_table(k)
+    try:
+        for L, off in ((22, 0), (20, 3), (13, 1), (12, 0), (32, 2)):
+            rr = [r for r in reads if len(r) >= L + off]
+            batch = ReadBatch.from_list(rr)
+            interval = np.array([seed_interval(len(r)) for r in rr], dtype=np.int32)
+            out, ns = gpu.seed_search(batch, L, interval, off, 32)
+            nhit = 0
+            for i, r in enumerate(rr):
+                n, want = O.seed_search(r, L, int(interval[i]), off, 32)
+                assert n == ns[i]
+                assert np.array_equal(out[i], want), (i, L, off, k)
+                nhit += int((want[:, :, 1] > want[:, :, 0]).sum())
+            assert nhit > 0
+    finally:
+        gpu.build_seed_table(0)
+
+
 def test_get_stretch(loaded, synth_genome):
     gpu, O, name = loaded
     nref = 1 if name == "lambda" else len(synth_genome)

@@ -22,6 +22,11 @@ benchsmall)
   timeout 600 python bench.py --genome-mbp 240 --reads 400000 --batch 200000 --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_benchsmall.json 2> $OUT/${TAG}_benchsmall.err; echo "benchsmall exit $?"; tail -c 1200 $OUT/${TAG}_benchsmall.json; tail -5 $OUT/${TAG}_benchsmall.err ;;
 benchse)
   timeout 900 python bench.py --workload se100 --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_benchse.json 2> $OUT/${TAG}_benchse.err; echo "benchse exit $?"; tail -c 900 $OUT/${TAG}_benchse.json ;;
+benchk)
+  for k in 0 14 16; do
+    timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --seed-table $k > $OUT/${TAG}_benchk$k.json 2> $OUT/${TAG}_benchk$k.err; echo "benchk$k exit $?"
+    python -c "import json; d=json.loads(open('$OUT/${TAG}_benchk$k.json').read().strip().splitlines()[-1]); print('k=$k', round(d['value'],2), round(d['e2e']['value'],2), {a:round(b,1) for a,b in d['stage_ms'].items()}, d['work_per_step']['seed_sides'], d['config']['seed_table_build_s'])"
+  done ;;
 bench2)
   BT2G_DP_PACKED=2 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench2.json 2> $OUT/${TAG}_bench2.err; echo "bench2 exit $?"; tail -c 700 $OUT/${TAG}_bench2.json ;;
 bench0)
