@@ -301,7 +301,7 @@ def main():
     ap.add_argument("--genome-mbp", type=float, default=GENOME_CONTIGS * CONTIG_LEN / 1e6,
                     help="debug only: smaller genome (any value other than the default is NOT the BASELINE config)")
     ap.add_argument("--reads", type=int, default=0, help="reads (pairs) resident in HBM (0 = the workload's default)")
-    ap.add_argument("--seed-table", type=int, default=15,
+    ap.add_argument("--seed-table", type=int, default=16,
                     help="k of the extended seed table derived from the index at load time (0 = off; results are identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads (pairs) in the CPU baseline sample (0 = auto)")

@@ -33,10 +33,10 @@ static inline int dp_rows_per_lane(int maxLen, int mode) {
 	}
 	return maxLen <= 128 ? 4 : (maxLen <= 256 ? 8 : (maxLen <= 512 ? 16 : 0));
 }
-// bytes of workspace per problem (per warp slot in modes 0-2): (maxCol + 32) steps x 32 lanes x R rounded up to 4
+// bytes of workspace per problem (per warp slot in modes 0-2): (maxCol + 32) steps x 32 lanes x R rows
 static inline uint64_t dp_code_stride(int maxCol, int maxLen, int mode) {
 	const int R = dp_rows_per_lane(maxLen, mode);
-	return (uint64_t)(maxCol + 32) * 32 * (uint64_t)(((R + 3) / 4) * 4);
+	return (((uint64_t)(maxCol + 32) * 32 * (uint64_t)R) + 255) & ~(uint64_t)255;   // planes of hb_index, 256 B aligned
 }
 
 // mode 3 workspace: as many problems per chunk as fit a byte budget (default 6 GiB; BT2G_DP_CHUNK_MB overrides)

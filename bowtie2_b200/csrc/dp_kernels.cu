@@ -559,6 +559,16 @@ __global__ void __launch_bounds__(128) k_dp_e2e_x2(DevIndex<OFF> ix, bt2g_scorin
 // Fill of the H-byte kernel (two problems per warp, s16x2; see the description below).
 // H-byte kernels take any R (rows per lane) and store RP = R rounded up to 4 bytes per lane and step
 #define DP_RP(R) ((((R) + 3) / 4) * 4)
+// Workspace layout of one problem with S = maxCol + 32 step slots: R / 4 word planes [S][32] x 4 B holding rows
+// 4g..4g+3 of each lane, then one byte plane [S][32] per remaining row, so that every store of a warp is one
+// contiguous, fully written run of sectors and nothing but real cells reaches HBM (S * 32 * R bytes in all).
+template <int R>
+__device__ __forceinline__ size_t hb_index(int S, int rr, int cc) {
+	const int k = rr / R, r = rr - k * R, st = cc + k;
+	constexpr int G4 = R / 4;
+	if(r < 4 * G4) return (size_t)(r >> 2) * ((size_t)S * 128) + ((size_t)st * 32 + k) * 4 + (r & 3);
+	return (size_t)G4 * ((size_t)S * 128) + (size_t)(r - 4 * G4) * ((size_t)S * 32) + (size_t)st * 32 + k;
+}
 
 template <typename OFF, int R>
 __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L) {
@@ -656,8 +666,8 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 		for(int r = 0; r < R; r++) { Hleft[r] = FLOORP; Earr[r] = FLOORP; }
 		uint32_t botH = FLOORP, botF = FLOORP, prevInH = FLOORP;
 		const int nsteps = ncolMax + lastLaneMax;
-		uint8_t *dstA = hb[0] + (size_t)lane * DP_RP(R), *dstB = hb[1] + (size_t)lane * DP_RP(R);
-		for(int t = 0; t < nsteps; t++, dstA += 32 * DP_RP(R), dstB += 32 * DP_RP(R)) {
+		const size_t P4 = (size_t)(L.maxCol + 32) * 128, P1 = (size_t)(L.maxCol + 32) * 32;
+		for(int t = 0; t < nsteps; t++) {
 			uint32_t inH = __shfl_up_sync(0xffffffffu, botH, 1);
 			uint32_t inF = __shfl_up_sync(0xffffffffu, botF, 1);
 			if(lane == 0) { inH = FLOORP; inF = FLOORP; }
@@ -689,11 +699,17 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 				botH = upH; botF = upF;
 				prevInH = inH;
 				// byte 0 of every word is problem A's cell, byte 2 problem B's
+				const size_t sl4 = ((size_t)t * 32 + lane) * 4, sl1 = (size_t)t * 32 + lane;
 #pragma unroll
-				for(int q4 = 0; q4 < DP_RP(R) / 4; q4++) {
+				for(int q4 = 0; q4 < R / 4; q4++) {
 					const uint32_t t01 = __byte_perm(hs[4 * q4], hs[4 * q4 + 1], 0x6240), t23 = __byte_perm(hs[4 * q4 + 2], hs[4 * q4 + 3], 0x6240);
-					reinterpret_cast<uint32_t *>(dstA)[q4] = __byte_perm(t01, t23, 0x5410);
-					reinterpret_cast<uint32_t *>(dstB)[q4] = __byte_perm(t01, t23, 0x7632);
+					*reinterpret_cast<uint32_t *>(hb[0] + q4 * P4 + sl4) = __byte_perm(t01, t23, 0x5410);
+					*reinterpret_cast<uint32_t *>(hb[1] + q4 * P4 + sl4) = __byte_perm(t01, t23, 0x7632);
+				}
+#pragma unroll
+				for(int r = (R / 4) * 4; r < R; r++) {
+					hb[0][(R / 4) * P4 + (r - (R / 4) * 4) * P1 + sl1] = (uint8_t)(hs[r] & 0xffu);
+					hb[1][(R / 4) * P4 + (r - (R / 4) * 4) * P1 + sl1] = (uint8_t)((hs[r] >> 16) & 0xffu);
 				}
 			} else if(j >= ncolMax) {
 				botH = FLOORP; botF = FLOORP;
@@ -706,7 +722,7 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 			// last row -> scores (candidates are the cells >= minsc; a clamped byte reads as floor < minsc)
 			const int lr = rdlen[x] - 1, kk = lr / R;
 			for(int j = lane; j < ncol[x]; j += 32)
-				lastH[x][j] = (int)hb[x][((size_t)(j + kk) * 32 + kk) * DP_RP(R) + (lr - kk * R)] + floorv[x];
+				lastH[x][j] = (int)hb[x][hb_index<R>(L.maxCol + 32, lr, j)] + floorv[x];
 			dp_e2e_tail<R, true>(L, sc, p[x], w[x], rs[x], rq[x], rdlen[x], ncol[x], lastH[x], candCol[x], refw[x], hb[x], L.summ + w[x], lane);
 		}
 	} // persistent loop over problem pairs
@@ -808,8 +824,8 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 		for(int r = 0; r < R; r++) { Hleft[r] = FLOORP; Earr[r] = FLOORP; }
 		uint32_t botH = FLOORP, botF = FLOORP, prevInH = FLOORP;
 		const int nsteps = ncolMax + lastLaneMax;
-		uint8_t *dstA = hb[0] + (size_t)lane * DP_RP(R), *dstB = hb[1] + (size_t)lane * DP_RP(R);
-		for(int t = 0; t < nsteps; t++, dstA += 32 * DP_RP(R), dstB += 32 * DP_RP(R)) {
+		const size_t P4 = (size_t)(L.maxCol + 32) * 128, P1 = (size_t)(L.maxCol + 32) * 32;
+		for(int t = 0; t < nsteps; t++) {
 			uint32_t inH = __shfl_up_sync(0xffffffffu, botH, 1);
 			uint32_t inF = __shfl_up_sync(0xffffffffu, botF, 1);
 			if(lane == 0) { inH = FLOORP; inF = FLOORP; }
@@ -841,11 +857,17 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 				botH = upH; botF = upF;
 				prevInH = inH;
 				// byte 0 of every word is problem A's cell, byte 2 problem B's
+				const size_t sl4 = ((size_t)t * 32 + lane) * 4, sl1 = (size_t)t * 32 + lane;
 #pragma unroll
-				for(int q4 = 0; q4 < DP_RP(R) / 4; q4++) {
+				for(int q4 = 0; q4 < R / 4; q4++) {
 					const uint32_t t01 = __byte_perm(hs[4 * q4], hs[4 * q4 + 1], 0x6240), t23 = __byte_perm(hs[4 * q4 + 2], hs[4 * q4 + 3], 0x6240);
-					reinterpret_cast<uint32_t *>(dstA)[q4] = __byte_perm(t01, t23, 0x5410);
-					reinterpret_cast<uint32_t *>(dstB)[q4] = __byte_perm(t01, t23, 0x7632);
+					*reinterpret_cast<uint32_t *>(hb[0] + q4 * P4 + sl4) = __byte_perm(t01, t23, 0x5410);
+					*reinterpret_cast<uint32_t *>(hb[1] + q4 * P4 + sl4) = __byte_perm(t01, t23, 0x7632);
+				}
+#pragma unroll
+				for(int r = (R / 4) * 4; r < R; r++) {
+					hb[0][(R / 4) * P4 + (r - (R / 4) * 4) * P1 + sl1] = (uint8_t)(hs[r] & 0xffu);
+					hb[1][(R / 4) * P4 + (r - (R / 4) * 4) * P1 + sl1] = (uint8_t)((hs[r] >> 16) & 0xffu);
 				}
 			} else if(j >= ncolMax) {
 				botH = FLOORP; botF = FLOORP;
@@ -881,7 +903,7 @@ __global__ void __launch_bounds__(256) k_dp_tail_h(DevIndex<OFF> ix, bt2g_scorin
 		ref_window<OFF>(ix, p.tidx, p.refl, ncol, refw, lane);
 		// last row -> scores (candidates are the cells >= minsc; a clamped byte reads as floor < minsc)
 		const int lr = rdlen - 1, kk = lr / R;
-		for(int j = lane; j < ncol; j += 32) lastH[j] = (int)hb[((size_t)(j + kk) * 32 + kk) * DP_RP(R) + (lr - kk * R)] + floorv;
+		for(int j = lane; j < ncol; j += 32) lastH[j] = (int)hb[hb_index<R>(L.maxCol + 32, lr, j)] + floorv;
 		dp_e2e_tail<R, true>(L, sc, p, w, rs, rq, rdlen, ncol, lastH, candCol, refw, hb, L.summ + w, lane);
 	}
 }
@@ -910,7 +932,8 @@ __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_sco
 	bt2g_dp_aln *alns = L.alns + w * (uint64_t)L.maxAlns;
 	uint8_t *ops = L.ops + w * (uint64_t)L.maxAlns * L.maxOps;
 	int naln = 0, flags = 0;
-	auto cell = [&](int rr, int cc) -> uint8_t * { int k = rr / R; return hb + ((size_t)(cc + k) * 32 + k) * DP_RP(R) + (rr - k * R); };
+	const int S = L.maxCol + 32;
+	auto cell = [&](int rr, int cc) -> uint8_t * { return hb + hb_index<R>(S, rr, cc); };
 	auto rdchar = [&](int rr) -> int { const int pos = p.fw ? rr : rdlen - 1 - rr; int c = rs[pos]; return p.fw ? c : (c > 3 ? 4 : 3 - c); };
 	auto rdqual = [&](int rr) -> int { const int pos = p.fw ? rr : rdlen - 1 - rr; int q = (int)rq[pos] - 33; return q < 0 ? 0 : (q > 63 ? 63 : q); };
 	auto inCore = [&](int dlo, int dhi) -> bool { return dhi >= p.corel && dlo <= p.corer; };   // some diagonal of [dlo,dhi] is a core diagonal
