@@ -183,14 +183,16 @@ __device__ __forceinline__ void dp_backtrace_all(const DpLaunch &L, const bt2g_s
 template <int R>
 __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_scoring &sc, const bt2g_dp_problem &p, uint64_t w,
                                                const uint8_t *rs, const uint8_t *rq, int rdlen, const uint8_t *refw,
-                                               uint8_t *hb, bt2g_dp_cand *cands, int ncand, bt2g_dp_summary *summ, int lane);
+                                               uint8_t *hb, bt2g_dp_cand *cands, int ncand, bt2g_dp_summary *summ, int lane,
+                                               const uint8_t *prof);
 
 // ---- end-to-end tail: best of the last row, candidate list (gatherCellsNucleotidesEnd2End), backtraces.
 // HB: the workspace holds H bytes (k_dp_e2e_h) instead of move codes.
 template <int R, bool HB = false>
 __device__ __forceinline__ void dp_e2e_tail(const DpLaunch &L, const bt2g_scoring &sc, const bt2g_dp_problem &p, uint64_t w,
                                             const uint8_t *rs, const uint8_t *rq, int rdlen, int ncol, int32_t *lastH,
-                                            uint16_t *candCol, const uint8_t *refw, uint8_t *codes, bt2g_dp_summary *summ, int lane) {
+                                            uint16_t *candCol, const uint8_t *refw, uint8_t *codes, bt2g_dp_summary *summ, int lane,
+                                            const uint8_t *prof = nullptr) {
 	__syncwarp();
 	// best = max of the last row (aligner_swsse_ee_u8.cpp:1095-1100)
 	int best = DP_NEG;
@@ -236,7 +238,7 @@ __device__ __forceinline__ void dp_e2e_tail(const DpLaunch &L, const bt2g_scorin
 	}
 	__syncwarp();
 
-	if(HB) dp_backtrace_h<R>(L, sc, p, w, rs, rq, rdlen, refw, codes, cands, ncand, summ, lane);
+	if(HB) dp_backtrace_h<R>(L, sc, p, w, rs, rq, rdlen, refw, codes, cands, ncand, summ, lane, prof);
 	else dp_backtrace_all<R>(L, sc, p, w, rs, rq, rdlen, refw, codes, cands, ncand, summ, lane, false);
 }
 
@@ -559,6 +561,7 @@ __global__ void __launch_bounds__(128) k_dp_e2e_x2(DevIndex<OFF> ix, bt2g_scorin
 // Fill of the H-byte kernel (two problems per warp, s16x2; see the description below).
 // H-byte kernels take any R (rows per lane) and store RP = R rounded up to 4 bytes per lane and step
 #define DP_RP(R) ((((R) + 3) / 4) * 4)
+#define DP_PROF_BYTES(R) ((size_t)(3 * 32 * (R) + 15) & ~(size_t)15)      // per-row profile of the tail kernel: 3 bytes x 32 R rows
 // Workspace layout of one problem with S = maxCol + 32 step slots: R / 4 word planes [S][32] x 4 B holding rows
 // 4g..4g+3 of each lane, then one byte plane [S][32] per remaining row, so that every store of a warp is one
 // contiguous, fully written run of sectors and nothing but real cells reaches HBM (S * 32 * R bytes in all).
@@ -666,7 +669,13 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 		for(int r = 0; r < R; r++) { Hleft[r] = FLOORP; Earr[r] = FLOORP; }
 		uint32_t botH = FLOORP, botF = FLOORP, prevInH = FLOORP;
 		const int nsteps = ncolMax + lastLaneMax;
+		// running store pointers: one per word plane and per byte plane of either problem
 		const size_t P4 = (size_t)(L.maxCol + 32) * 128, P1 = (size_t)(L.maxCol + 32) * 32;
+		uint8_t *w4A[R / 4 + 1], *w4B[R / 4 + 1], *w1A[R % 4 + 1], *w1B[R % 4 + 1];
+#pragma unroll
+		for(int g = 0; g < R / 4; g++) { w4A[g] = hb[0] + g * P4 + (size_t)lane * 4; w4B[g] = hb[1] + g * P4 + (size_t)lane * 4; }
+#pragma unroll
+		for(int g = 0; g < R % 4; g++) { w1A[g] = hb[0] + (R / 4) * P4 + g * P1 + lane; w1B[g] = hb[1] + (R / 4) * P4 + g * P1 + lane; }
 		for(int t = 0; t < nsteps; t++) {
 			uint32_t inH = __shfl_up_sync(0xffffffffu, botH, 1);
 			uint32_t inF = __shfl_up_sync(0xffffffffu, botF, 1);
@@ -699,21 +708,24 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 				botH = upH; botF = upF;
 				prevInH = inH;
 				// byte 0 of every word is problem A's cell, byte 2 problem B's
-				const size_t sl4 = ((size_t)t * 32 + lane) * 4, sl1 = (size_t)t * 32 + lane;
 #pragma unroll
 				for(int q4 = 0; q4 < R / 4; q4++) {
 					const uint32_t t01 = __byte_perm(hs[4 * q4], hs[4 * q4 + 1], 0x6240), t23 = __byte_perm(hs[4 * q4 + 2], hs[4 * q4 + 3], 0x6240);
-					*reinterpret_cast<uint32_t *>(hb[0] + q4 * P4 + sl4) = __byte_perm(t01, t23, 0x5410);
-					*reinterpret_cast<uint32_t *>(hb[1] + q4 * P4 + sl4) = __byte_perm(t01, t23, 0x7632);
+					*reinterpret_cast<uint32_t *>(w4A[q4]) = __byte_perm(t01, t23, 0x5410);
+					*reinterpret_cast<uint32_t *>(w4B[q4]) = __byte_perm(t01, t23, 0x7632);
 				}
 #pragma unroll
-				for(int r = (R / 4) * 4; r < R; r++) {
-					hb[0][(R / 4) * P4 + (r - (R / 4) * 4) * P1 + sl1] = (uint8_t)(hs[r] & 0xffu);
-					hb[1][(R / 4) * P4 + (r - (R / 4) * 4) * P1 + sl1] = (uint8_t)((hs[r] >> 16) & 0xffu);
+				for(int g = 0; g < R % 4; g++) {
+					*w1A[g] = (uint8_t)(hs[(R / 4) * 4 + g] & 0xffu);
+					*w1B[g] = (uint8_t)((hs[(R / 4) * 4 + g] >> 16) & 0xffu);
 				}
 			} else if(j >= ncolMax) {
 				botH = FLOORP; botF = FLOORP;
 			}
+#pragma unroll
+			for(int g = 0; g < R / 4; g++) { w4A[g] += 128; w4B[g] += 128; }
+#pragma unroll
+			for(int g = 0; g < R % 4; g++) { w1A[g] += 32; w1B[g] += 32; }
 		}
 		__syncwarp();
 #pragma unroll
@@ -824,7 +836,13 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 		for(int r = 0; r < R; r++) { Hleft[r] = FLOORP; Earr[r] = FLOORP; }
 		uint32_t botH = FLOORP, botF = FLOORP, prevInH = FLOORP;
 		const int nsteps = ncolMax + lastLaneMax;
+		// running store pointers: one per word plane and per byte plane of either problem
 		const size_t P4 = (size_t)(L.maxCol + 32) * 128, P1 = (size_t)(L.maxCol + 32) * 32;
+		uint8_t *w4A[R / 4 + 1], *w4B[R / 4 + 1], *w1A[R % 4 + 1], *w1B[R % 4 + 1];
+#pragma unroll
+		for(int g = 0; g < R / 4; g++) { w4A[g] = hb[0] + g * P4 + (size_t)lane * 4; w4B[g] = hb[1] + g * P4 + (size_t)lane * 4; }
+#pragma unroll
+		for(int g = 0; g < R % 4; g++) { w1A[g] = hb[0] + (R / 4) * P4 + g * P1 + lane; w1B[g] = hb[1] + (R / 4) * P4 + g * P1 + lane; }
 		for(int t = 0; t < nsteps; t++) {
 			uint32_t inH = __shfl_up_sync(0xffffffffu, botH, 1);
 			uint32_t inF = __shfl_up_sync(0xffffffffu, botF, 1);
@@ -857,21 +875,24 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 				botH = upH; botF = upF;
 				prevInH = inH;
 				// byte 0 of every word is problem A's cell, byte 2 problem B's
-				const size_t sl4 = ((size_t)t * 32 + lane) * 4, sl1 = (size_t)t * 32 + lane;
 #pragma unroll
 				for(int q4 = 0; q4 < R / 4; q4++) {
 					const uint32_t t01 = __byte_perm(hs[4 * q4], hs[4 * q4 + 1], 0x6240), t23 = __byte_perm(hs[4 * q4 + 2], hs[4 * q4 + 3], 0x6240);
-					*reinterpret_cast<uint32_t *>(hb[0] + q4 * P4 + sl4) = __byte_perm(t01, t23, 0x5410);
-					*reinterpret_cast<uint32_t *>(hb[1] + q4 * P4 + sl4) = __byte_perm(t01, t23, 0x7632);
+					*reinterpret_cast<uint32_t *>(w4A[q4]) = __byte_perm(t01, t23, 0x5410);
+					*reinterpret_cast<uint32_t *>(w4B[q4]) = __byte_perm(t01, t23, 0x7632);
 				}
 #pragma unroll
-				for(int r = (R / 4) * 4; r < R; r++) {
-					hb[0][(R / 4) * P4 + (r - (R / 4) * 4) * P1 + sl1] = (uint8_t)(hs[r] & 0xffu);
-					hb[1][(R / 4) * P4 + (r - (R / 4) * 4) * P1 + sl1] = (uint8_t)((hs[r] >> 16) & 0xffu);
+				for(int g = 0; g < R % 4; g++) {
+					*w1A[g] = (uint8_t)(hs[(R / 4) * 4 + g] & 0xffu);
+					*w1B[g] = (uint8_t)((hs[(R / 4) * 4 + g] >> 16) & 0xffu);
 				}
 			} else if(j >= ncolMax) {
 				botH = FLOORP; botF = FLOORP;
 			}
+#pragma unroll
+			for(int g = 0; g < R / 4; g++) { w4A[g] += 128; w4B[g] += 128; }
+#pragma unroll
+			for(int g = 0; g < R % 4; g++) { w1A[g] += 32; w1B[g] += 32; }
 		}
 	} // persistent loop over problem pairs
 }
@@ -883,10 +904,11 @@ __global__ void __launch_bounds__(256) k_dp_tail_h(DevIndex<OFF> ix, bt2g_scorin
 	const uint64_t nAll = L.nDev ? (uint64_t)*L.nDev : L.n;
 	if(chunkStart >= nAll) return;
 	const uint64_t nProb = (nAll - chunkStart < chunkMax) ? nAll - chunkStart : chunkMax;
-	const size_t perWarp = dp_smem_per_warp(L.maxCol);
+	const size_t perWarp = dp_smem_per_warp(L.maxCol) + DP_PROF_BYTES(R);
 	int32_t *lastH = reinterpret_cast<int32_t *>(smem + (size_t)warpInBlock * perWarp);
 	uint16_t *candCol = reinterpret_cast<uint16_t *>(lastH + L.maxCol);
 	uint8_t *refw = reinterpret_cast<uint8_t *>(candCol + L.maxCol);
+	uint8_t *prof = smem + (size_t)warpInBlock * perWarp + dp_smem_per_warp(L.maxCol);
 	const int bonus = sc.match_bonus;
 	const uint64_t nWarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
 	for(uint64_t wl = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock; wl < nProb; wl += nWarps) {
@@ -901,10 +923,16 @@ __global__ void __launch_bounds__(256) k_dp_tail_h(DevIndex<OFF> ix, bt2g_scorin
 		if(ncol <= 0 || ncol > L.maxCol || rdlen > 32 * R || rdlen <= 0 || (int64_t)bonus * rdlen - floorv > 127 || floorv < -DPX_LIMIT) continue;
 		uint8_t *hb = L.codes + wl * L.codeStride;
 		ref_window<OFF>(ix, p.tidx, p.refl, ncol, refw, lane);
+		for(int i = lane; i < rdlen; i += 32) {
+			const int pos = p.fw ? i : rdlen - 1 - i;
+			int c = rs[pos]; c = p.fw ? c : (c > 3 ? 4 : 3 - c);
+			int q = (int)rq[pos] - 33; q = q < 0 ? 0 : (q > 63 ? 63 : q);
+			prof[i] = (uint8_t)c; prof[rdlen + i] = sc.mmpen[q]; prof[2 * rdlen + i] = sc.npen[q];
+		}
 		// last row -> scores (candidates are the cells >= minsc; a clamped byte reads as floor < minsc)
 		const int lr = rdlen - 1, kk = lr / R;
 		for(int j = lane; j < ncol; j += 32) lastH[j] = (int)hb[hb_index<R>(L.maxCol + 32, lr, j)] + floorv;
-		dp_e2e_tail<R, true>(L, sc, p, w, rs, rq, rdlen, ncol, lastH, candCol, refw, hb, L.summ + w, lane);
+		dp_e2e_tail<R, true>(L, sc, p, w, rs, rq, rdlen, ncol, lastH, candCol, refw, hb, L.summ + w, lane, prof);
 	}
 }
 
@@ -924,7 +952,9 @@ __global__ void __launch_bounds__(256) k_dp_tail_h(DevIndex<OFF> ix, bt2g_scorin
 template <int R>
 __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_scoring &sc, const bt2g_dp_problem &p, uint64_t w,
                                                const uint8_t *rs, const uint8_t *rq, int rdlen, const uint8_t *refw,
-                                               uint8_t *hb, bt2g_dp_cand *cands, int ncand, bt2g_dp_summary *summ, int lane) {
+                                               uint8_t *hb, bt2g_dp_cand *cands, int ncand, bt2g_dp_summary *summ, int lane,
+                                               const uint8_t *prof) {
+	// prof (optional, shared memory): per read row the strand-adjusted base code, its mismatch and its N penalty
 	const int rdgapo = sc.rdgap_const + sc.rdgap_linear, rdgape = sc.rdgap_linear;
 	const int rfgapo = sc.rfgap_const + sc.rfgap_linear, rfgape = sc.rfgap_linear;
 	const int bonus = sc.match_bonus, gapbar = sc.gapbar;
@@ -932,6 +962,7 @@ __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_sco
 	bt2g_dp_aln *alns = L.alns + w * (uint64_t)L.maxAlns;
 	uint8_t *ops = L.ops + w * (uint64_t)L.maxAlns * L.maxOps;
 	int naln = 0, flags = 0;
+	bool screened = false;
 	const int S = L.maxCol + 32;
 	auto cell = [&](int rr, int cc) -> uint8_t * { return hb + hb_index<R>(S, rr, cc); };
 	auto rdchar = [&](int rr) -> int { const int pos = p.fw ? rr : rdlen - 1 - rr; int c = rs[pos]; return p.fw ? c : (c > 3 ? 4 : 3 - c); };
@@ -957,11 +988,18 @@ __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_sco
 			const int vn = __shfl_down_sync(0xffffffffu, v, 1);       // H of my diagonal predecessor (last loading lane: not loaded)
 			int sck = 0, refc = 4; bool isN = false, isMatch = false;
 			if(cp) {
-				const int c = rdchar(rk), q = rdqual(rk);
 				refc = refw[ck];
-				isN = c > 3 || refc > 3;
-				isMatch = !isN && c == refc;
-				sck = isN ? -(int)sc.npen[q] : (isMatch ? bonus : -(int)sc.mmpen[q]);
+				if(prof) {
+					const int c = prof[rk];
+					isN = c > 3 || refc > 3;
+					isMatch = !isN && c == refc;
+					sck = isN ? -(int)prof[2 * rdlen + rk] : (isMatch ? bonus : -(int)prof[rdlen + rk]);
+				} else {
+					const int c = rdchar(rk), q = rdqual(rk);
+					isN = c > 3 || refc > 3;
+					isMatch = !isN && c == refc;
+					sck = isN ? -(int)sc.npen[q] : (isMatch ? bonus : -(int)sc.mmpen[q]);
+				}
 			}
 			const bool cont = lane < wd - 1 && !(mine & 0x80) && rk > 0 && ck > 0 && vn > 0 && v == vn + sck;
 			const int run = __ffs(~__ballot_sync(0xffffffffu, cont)) - 1;   // 0..wd-1
@@ -1080,6 +1118,71 @@ __device__ __forceinline__ void dp_backtrace_h(const DpLaunch &L, const bt2g_sco
 			flags |= BT2G_DP_FLAG_ALN_OVERFLOW;
 		}
 		naln++;
+		// ---- screening of the remaining candidates, one per lane.  After the first alignment almost every other
+		// candidate is a shifted variant that runs into its reported-through cells within a few moves.  A read-only
+		// walk against the marks that exist NOW decides each of them independently: marks added later (by other
+		// failing candidates) can only make a walk stop earlier, so "fails now" implies "fails in sequence", and a
+		// failing candidate changes nothing but marks.  Only if some walk gets through to row 0 is the sequential
+		// procedure above needed for the rest (it then runs unchanged, from the next candidate).
+		if(naln == 1 && !screened && ci + 1 < ncand) {
+			screened = true;
+			bool needSeq = false;
+			for(int base = ci + 1; base < ncand; base += 32) {
+				const int cj = base + lane;
+				int verdict = 0;                               // 0 fails, 1 start cell already reported through, 2 might succeed
+				if(cj < ncand) {
+					int r2 = cands[cj].row, c2 = cands[cj].col;
+					int b = *cell(r2, c2);
+					if(b & 0x80) verdict = 1;
+					else {
+						for(int guard = 0; guard < 4 * rdlen + 8; guard++) {
+							const int curv = b & 0x7f;
+							if(r2 == 0) { verdict = 2; break; }
+							if(c2 > 0) {
+								const int pb = *cell(r2 - 1, c2 - 1), pv = pb & 0x7f;
+								const int rf = refw[c2];
+								int c, mm, np;
+								if(prof) { c = prof[r2]; mm = prof[rdlen + r2]; np = prof[2 * rdlen + r2]; }
+								else { c = rdchar(r2); const int q = rdqual(r2); mm = sc.mmpen[q]; np = sc.npen[q]; }
+								const int sc2 = (c > 3 || rf > 3) ? -np : (c == rf ? bonus : -mm);
+								if(pv > 0 && curv == pv + sc2) {
+									if(pb & 0x80) break;              // runs into a reported-through cell
+									r2--; c2--; b = pb;
+									continue;
+								}
+							}
+							if(r2 < gapbar || rdlen - 1 - r2 < gapbar) break;         // no legal move
+							bool moved = false, dead = false, marked = false;
+							for(int k = 1; k <= r2 && r2 - k + 1 >= gapbar && vmax - rfgapo - (k - 1) * rfgape >= curv; k++) {
+								const int ub = *cell(r2 - k, c2), u = ub & 0x7f;
+								if(u > 0 && u - rfgapo - (k - 1) * rfgape == curv) {
+									if(marked || (ub & 0x80)) dead = true; else { r2 -= k; b = ub; moved = true; }
+									break;
+								}
+								marked = marked || (ub & 0x80);
+							}
+							if(!moved && !dead) {
+								marked = false;
+								for(int k = 1; k <= c2 && vmax - rdgapo - (k - 1) * rdgape >= curv; k++) {
+									const int ub = *cell(r2, c2 - k), u = ub & 0x7f;
+									if(u > 0 && u - rdgapo - (k - 1) * rdgape == curv) {
+										if(marked || (ub & 0x80)) dead = true; else { c2 -= k; b = ub; moved = true; }
+										break;
+									}
+									marked = marked || (ub & 0x80);
+								}
+							}
+							if(!moved) break;                      // dead end or no legal move: fails
+						}
+					}
+				}
+				if(__any_sync(0xffffffffu, verdict == 2)) { needSeq = true; break; }
+				if(cj < ncand) cands[cj].fate = verdict == 1 ? BT2G_CAND_FILT_START : BT2G_CAND_FAILED;
+			}
+			__syncwarp();
+			if(!needSeq) break;
+			// some fates were written by lanes of completed groups; the sequential pass below rewrites all of them
+		}
 	}
 	if(lane == 0) { summ->naln = naln; summ->flags |= flags; }
 }
@@ -1102,7 +1205,7 @@ static void launch_dp_e2e_r(const DevIndex<OFF> &ix, const bt2g_scoring &sc, con
 		// split: chunks of L.chunk problems through fill then tail (workspace = L.chunk * codeStride bytes)
 		int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 		const size_t smF = (size_t)warpsPerBlock * 2 * (((size_t)L.maxCol + 15) & ~(size_t)15);
-		const size_t smT = (size_t)8 * dp_smem_per_warp(L.maxCol);
+		const size_t smT = (size_t)8 * (dp_smem_per_warp(L.maxCol) + DP_PROF_BYTES(R));
 		if(smF > 48 * 1024) cudaFuncSetAttribute(k_dp_fill_h<OFF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smF);
 		if(smT > 48 * 1024) cudaFuncSetAttribute(k_dp_tail_h<OFF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
 		int nbF = 1, nbT = 1;
