@@ -303,6 +303,8 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="reads (pairs) resident in HBM (0 = the workload's default)")
     ap.add_argument("--seed-table", type=int, default=16,
                     help="k of the extended seed table derived from the index at load time (0 = off; results are identical)")
+    ap.add_argument("--dense-sa", type=int, default=0,
+                    help="rate of the denser SA sample derived from the index at load time (0 = full suffix array, -1 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads (pairs) in the CPU baseline sample (0 = auto)")
     args = ap.parse_args()
@@ -376,6 +378,12 @@ def main():
         gpu.build_seed_table(args.seed_table)
         ktab_s = time.time() - tk
         log(f"rank {rank}: {args.seed_table}-mer seed table built in {ktab_s:.2f}s")
+    sa_s = 0.0
+    if 0 <= args.dense_sa < info["off_rate"]:
+        torch.cuda.synchronize(); tk = time.time()
+        gpu.build_dense_sa(args.dense_sa)
+        sa_s = time.time() - tk
+        log(f"rank {rank}: SA sample of rate {args.dense_sa} built in {sa_s:.2f}s")
     if paired:
         reads, quals = make_pairs_gpu(torch, dev, contigs, args.reads, READ_LEN, seed=1 + rank)
     else:
@@ -582,7 +590,7 @@ def main():
                 "config": {"workload": workload, "full_size": full, "read_unit": unit[:-1], "mates_per_s_M": value * mates,
                            "batch": B, "preset": " ".join(ref_preset),
                            "l2": "inputs larger than L2 (random access over a %.1f GB index; a different batch each step)" % (info["device_bytes"] / 1e9),
-                           "pipeline": pipeline_desc, "seed_table_k": args.seed_table, "seed_table_build_s": ktab_s, "index_bcast_s": bcast_s, "aligned_frac": found, "pairs": conc,
+                           "pipeline": pipeline_desc, "seed_table_k": args.seed_table, "seed_table_build_s": ktab_s, "dense_sa_rate": args.dense_sa, "dense_sa_build_s": sa_s, "index_bcast_s": bcast_s, "aligned_frac": found, "pairs": conc,
                            "host_threads": cores, "cgroup_cpu_quota": cpu_quota, "dp_workspace_overflows": overflow},
                 "clocks": clk, "gpu_launches": pipe.kernel_launches() * args.steps,
                 "e2e": {"value": e2e_val, "unit": "Mreads/s", "h2d_bytes_per_step": 2 * BR * READ_LEN + (BR + 1) * 8,

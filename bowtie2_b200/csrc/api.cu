@@ -23,6 +23,7 @@ template <typename OFF> void launch_extend(const DevIndex<OFF> &, const uint8_t 
 
 template <typename OFF> void launch_ungapped(const DevIndex<OFF> &, const bt2g_scoring &, const uint8_t *, const uint8_t *, const uint64_t *, const bt2g_ungapped_problem *, uint64_t, bt2g_ungapped_result *, uint8_t *, uint32_t, cudaStream_t);
 template <typename OFF> void launch_build_ktab(const DevIndex<OFF> &, int, OFF *, cudaStream_t);
+template <typename OFF> void launch_build_dense_sa(const DevIndex<OFF> &, int, OFF *, cudaStream_t);
 void launch_frame_mate(const bt2g_pe_policy &, const bt2g_mate_anchor *, uint64_t, bt2g_mate_frame *, cudaStream_t);
 void launch_pe_classify(const bt2g_pe_policy &, const int64_t *, uint64_t, int32_t *, cudaStream_t);
 namespace {
@@ -45,6 +46,7 @@ void freeIndex(bt2g_ctx *ctx) {
 	for(int i = 0; i < BT2G_N_INDEX_ARRAYS; i++) freeArr(ctx->arr[i]);
 	freeArr(ctx->recCumOff); freeArr(ctx->recCumUnamb); freeArr(ctx->refRecOffs); freeArr(ctx->refLens);
 	freeArr(ctx->ktab); ctx->ktabChars = 0;
+	freeArr(ctx->denseSa); ctx->denseRate = -1;
 	ctx->loaded = false;
 }
 
@@ -192,6 +194,8 @@ DevIndex<OFF> bt2g_dev_index(const bt2g_ctx *ctx) {
 	ix.bw = devEbwt<OFF>(ctx, true);
 	ix.offs = (const OFF *)ctx->arr[2].ptr;
 	ix.ktab = (const OFF *)ctx->ktab.ptr; ix.ktabChars = ctx->ktab.ptr ? ctx->ktabChars : 0;
+	if(ctx->denseSa.ptr) { ix.saOffs = (const OFF *)ctx->denseSa.ptr; ix.saRate = ctx->denseRate; }
+	else { ix.saOffs = ix.offs; ix.saRate = ctx->info.off_rate; }
 	ix.offRate = ctx->info.off_rate;
 	ix.rstarts = (const OFF *)ctx->arr[8].ptr;
 	ix.nFrag = ctx->info.n_frag;
@@ -455,6 +459,26 @@ int bt2g_build_seed_table(bt2g_ctx *ctx, int k) {
 	if(e == cudaSuccess) e = cudaGetLastError();
 	if(e != cudaSuccess) { cudaFree(p); ctx->err = std::string("seed table build: ") + cudaGetErrorString(e); return -2; }
 	ctx->ktab.ptr = p; ctx->ktab.bytes = bytes; ctx->ktab.owned = true; ctx->ktabChars = k;
+	return 0;
+}
+
+int bt2g_build_dense_sa(bt2g_ctx *ctx, int rate) {
+	REQUIRE_LOADED(ctx);
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	freeArr(ctx->denseSa); ctx->denseRate = -1;
+	if(rate < 0) return 0;
+	if(rate >= ctx->info.off_rate) { ctx->err = "dense SA: rate must be below the index's offRate"; return -1; }
+	const uint64_t entries = (ctx->info.bwt_len + ((1ull << rate) - 1)) >> rate, bytes = entries * (uint64_t)ctx->info.off_size;
+	void *p = nullptr;
+	cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+	if(e != cudaSuccess) { ctx->err = std::string("dense SA cudaMalloc: ") + cudaGetErrorString(e); return -2; }
+	if(ctx->info.off_size == 4) launch_build_dense_sa<uint32_t>(bt2g_dev_index<uint32_t>(ctx), rate, (uint32_t *)p, ctx->stream);
+	else launch_build_dense_sa<uint64_t>(bt2g_dev_index<uint64_t>(ctx), rate, (uint64_t *)p, ctx->stream);
+	e = cudaStreamSynchronize(ctx->stream);
+	if(e == cudaSuccess) e = cudaGetLastError();
+	if(e != cudaSuccess) { cudaFree(p); ctx->err = std::string("dense SA build: ") + cudaGetErrorString(e); return -2; }
+	ctx->denseSa.ptr = p; ctx->denseSa.bytes = bytes; ctx->denseSa.owned = true; ctx->denseRate = rate;
 	return 0;
 }
 

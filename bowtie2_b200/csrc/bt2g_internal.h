@@ -45,6 +45,9 @@ struct DevIndex {
 	// search after its K characters: 3 OFF per entry = topf, botf, topb (all 0 = empty range)
 	const OFF     *ktab;
 	int            ktabChars;
+	// SA sample in effect: the index's own offs[] / offRate, or the denser one of bt2g_build_dense_sa
+	const OFF     *saOffs;
+	int            saRate;
 };
 
 struct DevArray {
@@ -63,6 +66,7 @@ struct bt2g_ctx {
 	DevArray recCumOff, recCumUnamb, refRecOffs, refLens;
 	uint64_t nRefs = 0;
 	DevArray ktab; int ktabChars = 0;
+	DevArray denseSa; int denseRate = -1;
 	cudaStream_t stream = nullptr;
 	bt2g_scoring scoring{};
 	// scratch buffers (grown on demand)

@@ -159,11 +159,11 @@ __device__ __forceinline__ uint64_t ftab_lo(const DevEbwt<OFF> &e, uint64_t i) {
 // (group_walk.h:517-520): LF-walk until a sampled row or the "$" row.
 template <typename OFF>
 __device__ __forceinline__ uint64_t get_offset(const DevIndex<OFF> &ix, uint64_t row, unsigned &nside) {
-	const uint64_t rateMask = (1ull << ix.offRate) - 1;
+	const uint64_t rateMask = (1ull << ix.saRate) - 1;
 	uint64_t jumps = 0;
 	for(;;) {
 		if(row == ix.fw.zOff) return jumps;
-		if((row & rateMask) == 0) return jumps + (uint64_t)__ldg(ix.offs + (row >> ix.offRate));
+		if((row & rateMask) == 0) return jumps + (uint64_t)__ldg(ix.saOffs + (row >> ix.saRate));
 		int c;
 		row = lf_step<OFF>(ix.fw, row, c);
 		jumps++; nside++;

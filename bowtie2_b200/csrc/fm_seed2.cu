@@ -244,6 +244,29 @@ template void launch_build_ktab<uint32_t>(const DevIndex<uint32_t> &, int, uint3
 template void launch_build_ktab<uint64_t>(const DevIndex<uint64_t> &, int, uint64_t *, cudaStream_t);
 
 // ----------------------------------------------------------------------------------------
+// Denser SA sample (include/bt2g.h: bt2g_build_dense_sa): one thread per sampled row walks to the index's own
+// sample (Ebwt::getOffset) and records the offset.
+template <typename OFF>
+__global__ void k_build_dense_sa(DevIndex<OFF> ix, int rate, uint64_t entries, OFF *out) {
+	const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(i >= entries) return;
+	DevIndex<OFF> base = ix;
+	base.saOffs = ix.offs; base.saRate = ix.offRate;            // always walk against the index's own sample
+	unsigned nside = 0;
+	const uint64_t row = i << rate;
+	out[i] = row < ix.fw.len + 1 ? (OFF)get_offset<OFF>(base, row, nside) : (OFF)0;
+}
+
+template <typename OFF>
+void launch_build_dense_sa(const DevIndex<OFF> &ix, int rate, OFF *out, cudaStream_t st) {
+	const uint64_t entries = ((ix.fw.len + 1) + ((1ull << rate) - 1)) >> rate;
+	if(entries == 0) return;
+	k_build_dense_sa<OFF><<<(unsigned)((entries + 255) / 256), 256, 0, st>>>(ix, rate, entries, out);
+}
+template void launch_build_dense_sa<uint32_t>(const DevIndex<uint32_t> &, int, uint32_t *, cudaStream_t);
+template void launch_build_dense_sa<uint64_t>(const DevIndex<uint64_t> &, int, uint64_t *, cudaStream_t);
+
+// ----------------------------------------------------------------------------------------
 // K1' v2: exact end-to-end sweep (SeedAligner::exactSweep, aligner_seed.cpp:856-970) with packed
 // reads, single-character ranks, one uniform LF step and persistent lanes.  Task = (read, strand).
 // ----------------------------------------------------------------------------------------
@@ -424,7 +447,7 @@ __global__ void __launch_bounds__(256) k_resolve2(DevIndex<OFF> ix, const uint64
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	const uint64_t total = nDev ? (uint64_t)*nDev : nHost;
-	const uint64_t rateMask = (1ull << ix.offRate) - 1;
+	const uint64_t rateMask = (1ull << ix.saRate) - 1;
 	bool active = false, exhausted = false;
 	uint64_t row = 0, jumps = 0, task = 0;
 	unsigned nside = 0;
@@ -453,7 +476,7 @@ __global__ void __launch_bounds__(256) k_resolve2(DevIndex<OFF> ix, const uint64
 			// Ebwt::getOffset (bt2_idx.cpp:150-171), one LF step per iteration
 			bool fin = false; uint64_t off = 0;
 			if(row == ix.fw.zOff) { fin = true; off = jumps; }
-			else if((row & rateMask) == 0) { fin = true; off = jumps + (uint64_t)__ldg(ix.offs + (row >> ix.offRate)); }
+			else if((row & rateMask) == 0) { fin = true; off = jumps + (uint64_t)__ldg(ix.saOffs + (row >> ix.saRate)); }
 			else { int c; row = lf_step<OFF>(ix.fw, row, c); jumps++; nside++; }
 			if(fin) {
 				if(joined) joined[task] = off;

@@ -639,3 +639,16 @@ def _build_seed_table(self, k: int):
 
 
 Bt2Gpu.build_seed_table = _build_seed_table
+
+
+# ---- denser SA sample (include/bt2g.h: bt2g_build_dense_sa) ------------------------------------------
+EXPORTS += ["bt2g_build_dense_sa"]
+
+
+def _build_dense_sa(self, rate: int):
+    """Derive offs2[row >> rate] for rows divisible by 2^rate from the loaded index (rate < 0 drops it)."""
+    self._lib.bt2g_build_dense_sa.argtypes = [C.c_void_p, C.c_int]
+    self._check(self._lib.bt2g_build_dense_sa(self._h, int(rate)), "bt2g_build_dense_sa")
+
+
+Bt2Gpu.build_dense_sa = _build_dense_sa

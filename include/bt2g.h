@@ -261,6 +261,13 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
  * LF steps per entry at build time.  k = 0 drops the table. */
 int bt2g_build_seed_table(bt2g_ctx *ctx, int k);
 
+/* A denser suffix-array sample derived from the loaded index: offs2[row >> rate] for every row with
+ * row % 2^rate == 0 (rate < offRate; rate = 0 is the full suffix array, 4 bytes x bwt_len for .bt2), each
+ * value obtained with the index's own Ebwt::getOffset walk (bt2_idx.cpp:150-171).  bt2g_resolve and the
+ * pipeline then stop their LF walk after < 2^rate steps instead of < 2^offRate; the offsets they return are
+ * the same numbers.  rate < 0 drops it. */
+int bt2g_build_dense_sa(bt2g_ctx *ctx, int rate);
+
 /* ------------------------------------------------------------------- ungapped alignment ----- */
 /* SwAligner::ungappedAlign (aligner_sw.cpp:286-487): the single-diagonal alignment the driver takes when
  * neither read nor reference gaps fit under the minimum score (aligner_sw_driver.cpp:1189-1253).

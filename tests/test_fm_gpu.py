@@ -63,6 +63,27 @@ def test_resolve(loaded):
                 assert (int(tidx[i]), int(textoff[i]), int(tlen[i])) == (ti, to, tl)
 
 
+@pytest.mark.parametrize("rate", [0, 1, 2])
+def test_resolve_with_dense_sa(loaded, rate):
+    """bt2g_build_dense_sa: a denser sample shortens the walk, never changes the offsets."""
+    gpu, O, _ = loaded
+    sc = O.scalars()
+    if rate >= sc["off_rate"]:
+        pytest.skip("index already at least this dense")
+    rng = np.random.default_rng(16)
+    rows = np.concatenate([rng.integers(0, sc["bwt_len"], 3000), [sc["z_off"], 0, sc["bwt_len"] - 1]]).astype(np.uint64)
+    hitlen = rng.integers(1, 60, len(rows)).astype(np.uint32)
+    base = gpu.resolve(rows, hitlen, False)
+    gpu.build_dense_sa(rate)
+    try:
+        got = gpu.resolve(rows, hitlen, False)
+    finally:
+        gpu.build_dense_sa(-1)
+    assert np.array_equal(got[0], O.get_offset(rows))
+    for a, b in zip(base, got):
+        assert np.array_equal(a, b)
+
+
 def _reads_for(name, lambda_reads, synth_genome):
     if name == "lambda":
         return lambda_reads[1][:600]
