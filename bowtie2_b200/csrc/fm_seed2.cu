@@ -15,6 +15,7 @@
 //   * persistent lanes: a lane whose seed finished or died pulls the next task from a global
 //     counter (one warp-aggregated atomic per refill), so a warp keeps 32 searches in flight.
 #include "fm_device.cuh"
+#include <cstdlib>
 
 #define REFILL_MIN 8
 
@@ -176,6 +177,142 @@ __global__ void __launch_bounds__(256) k_seed_search2(DevIndex<OFF> ix, const ui
 	if(cnt && nside) atomicAdd(cnt, (unsigned long long)nside);
 }
 
+// v3: task = (read, strand); the lane walks through that strand's seeds one after another, so the per-read
+// loads (offsets, interval, packed words) are paid once per strand instead of once per seed.  With the extended
+// seed table a seed is only a table lookup plus L - K steps, and v2's per-seed refill chain (task id -> offsets ->
+// packed words -> table -> first side) had become the bulk of the kernel.  Same outputs as v2.
+template <typename OFF>
+__global__ void __launch_bounds__(256) k_seed_search3(DevIndex<OFF> ix, const uint64_t *packed, const uint32_t *nmask,
+                                                      const uint64_t *roff, uint64_t nReads, int seedLen, int maxSeeds,
+                                                      int nofw, int norc, const int32_t *interval, const int32_t *offset,
+                                                      uint64_t *out, int32_t *nseedsOut, unsigned long long *next,
+                                                      unsigned long long *cnt) {
+	constexpr uint32_t BL = SideGeom<OFF>::BWT_LEN;
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const uint64_t total = nReads * 2;
+	const DevEbwt<OFF> &fw = ix.fw;
+	const DevEbwt<OFF> &bw = ix.bw;
+	const int ftabLen = fw.ftabChars;
+	bool haveTask = false, exhausted = false, active = false;
+	uint64_t topf = 0, botf = 0, topb = 0, botb = 0, bits = 0, wb = 0;
+	uint64_t *o = nullptr, *obase = nullptr;
+	int sl = 0, step = 0, k = 0, nseeds = 0, per = 1, off0 = 0, len = 0, strand = 0;
+	unsigned nside = 0;
+	for(;;) {
+		const unsigned need = __ballot_sync(FULL, !haveTask && !exhausted);
+		if(need && (__popc(need) >= REFILL_MIN || __ballot_sync(FULL, haveTask) == 0)) {
+			unsigned long long base = 0;
+			const int leader = __ffs(need) - 1;
+			if(lane == leader) base = atomicAdd(next, (unsigned long long)__popc(need));
+			base = __shfl_sync(FULL, base, leader);
+			if(!haveTask && !exhausted) {
+				const uint64_t t = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+				if(t >= total) exhausted = true;
+				else {
+					const uint64_t rd = t >> 1;
+					strand = (int)(t & 1);
+					const uint64_t r0 = roff[rd];
+					len = (int)(roff[rd + 1] - r0);
+					per = interval[rd]; off0 = offset[rd];
+					nseeds = 1;                                       // instantiateSeeds (aligner_seed.cpp:523-526)
+					if(len - off0 > seedLen) nseeds += (len - off0 - seedLen) / per;
+					if(strand == 0 && nseedsOut) nseedsOut[rd] = nseeds;
+					sl = seedLen < len ? seedLen : len;
+					wb = (r0 >> 5) + rd;
+					obase = out + (rd * 2ull + strand) * (uint64_t)maxSeeds * 4;
+					k = 0; haveTask = true; active = false;
+				}
+			}
+		}
+		if(__ballot_sync(FULL, haveTask) == 0) {
+			if(__all_sync(FULL, exhausted)) break;
+			continue;
+		}
+		// ---- seed set-up for the lanes between seeds
+		if(haveTask && !active) {
+			if(k >= maxSeeds) haveTask = false;
+			else {
+				o = obase + (uint64_t)k * 4;
+				reinterpret_cast<uint4 *>(o)[0] = make_uint4(0, 0, 0, 0);
+				reinterpret_cast<uint4 *>(o)[1] = make_uint4(0, 0, 0, 0);
+				const int depth = k * per + off0;
+				bool ok = k < nseeds && !((strand == 0 && nofw) || (strand == 1 && norc)) && depth + sl <= len && sl >= 1;
+				if(ok) {
+					const int w = depth >> 5, sh = depth & 31;
+					const bool two = sh + sl > 32;
+					const uint64_t p0 = packed[wb + w], p1 = two ? packed[wb + w + 1] : 0;
+					const uint64_t n0 = nmask[wb + w], n1 = two ? nmask[wb + w + 1] : 0;
+					const uint64_t m2 = sl == 32 ? ~0ull : ((1ull << (2 * sl)) - 1);
+					bits = (sh ? ((p0 >> (2 * sh)) | (p1 << (64 - 2 * sh))) : p0) & m2;
+					const uint64_t nb = ((n0 | (n1 << 32)) >> sh) & (sl == 32 ? 0xffffffffull : ((1ull << sl) - 1));
+					if(nb) ok = false;                               // exact seeds cannot absorb an N (aligner_seed.cpp:326-352)
+					if(strand == 1) bits = rev_pairs(bits, sl) ^ m2;   // reverse complement of the window
+				}
+				if(ok) {
+					if(ix.ktab != nullptr && ix.ktabChars <= sl) {
+						const OFF *e3 = ix.ktab + 3ull * (bits >> (2 * (sl - ix.ktabChars)));
+						topf = e3[0]; botf = e3[1]; topb = e3[2]; botb = topb + (botf - topf);
+						if(botf <= topf) ok = false;
+						step = ix.ktabChars;
+					} else if(ftabLen > 1 && ftabLen <= sl) {
+						const uint64_t top20 = bits >> (2 * (sl - ftabLen));
+						const uint64_t fwi = rev_pairs(top20, ftabLen), bwi = top20;
+						topf = ftab_hi<OFF>(fw, fwi); botf = ftab_lo<OFF>(fw, fwi + 1);
+						if(botf <= topf) ok = false;
+						else if(bw.ebwt != nullptr) { topb = ftab_hi<OFF>(bw, bwi); botb = topb + (botf - topf); }
+						else { topb = botb = 0; }
+						step = ftabLen;
+					} else {
+						const int c = (int)((bits >> (2 * (sl - 1))) & 3);
+						topf = topb = fw.fchr[c]; botf = botb = fw.fchr[c + 1];
+						if(botf <= topf) ok = false;
+						step = 1;
+					}
+				}
+				if(ok) {
+					if(step >= sl) { o[0] = topf; o[1] = botf; o[2] = topb; o[3] = botb; }
+					else active = true;
+				}
+				k++;
+				// the remaining slots of this strand (k >= nseeds) only need their zero fill: finish them in this pass
+				if(!active && k >= nseeds) {
+					for(; k < maxSeeds; k++) {
+						uint64_t *z = obase + (uint64_t)k * 4;
+						reinterpret_cast<uint4 *>(z)[0] = make_uint4(0, 0, 0, 0);
+						reinterpret_cast<uint4 *>(z)[1] = make_uint4(0, 0, 0, 0);
+					}
+					haveTask = false;
+				}
+			}
+		}
+		// ---- one LF step for the lanes inside a seed
+		if(active) {
+			const int c = (int)((bits >> (2 * (sl - step - 1))) & 3);
+			const uint64_t sideT = topf / BL, sideB = botf / BL;
+			const uint32_t offT = (uint32_t)(topf - sideT * BL), offB = (uint32_t)(botf - sideB * BL);
+			nside += (botf - topf > 1) ? 2 : 1;                     // algorithmic count (mapBiLFEx = 2, mapLF1 = 1)
+			uint64_t tt[4], bb[4];
+			SideRegs<OFF> s;
+			load_side<OFF>(fw.ebwt, sideT, s);
+			rank4_loaded<OFF>(fw, s, sideT, offT, tt);
+			if(sideB != sideT) load_side<OFF>(fw.ebwt, sideB, s);
+			rank4_loaded<OFF>(fw, s, sideB, offB, bb);
+			const uint64_t w0 = bb[0] - tt[0], w1 = bb[1] - tt[1], w2 = bb[2] - tt[2];
+			const uint64_t tp = topb + (c > 0 ? w0 : 0) + (c > 1 ? w1 : 0) + (c > 2 ? w2 : 0);
+			const uint64_t nt = c == 0 ? tt[0] : (c == 1 ? tt[1] : (c == 2 ? tt[2] : tt[3]));
+			const uint64_t nb = c == 0 ? bb[0] : (c == 1 ? bb[1] : (c == 2 ? bb[2] : bb[3]));
+			if(nb <= nt) {
+				active = false;
+			} else {
+				topf = nt; botf = nb; topb = tp; botb = tp + (nb - nt);
+				if(++step == sl) { o[0] = topf; o[1] = botf; o[2] = topb; o[3] = botb; active = false; }
+			}
+		}
+	}
+	if(cnt && nside) atomicAdd(cnt, (unsigned long long)nside);
+}
+
 template <typename OFF>
 void launch_seed_search2(const DevIndex<OFF> &ix, const uint8_t *seq, const uint64_t *roff, uint64_t nReads, int maxLen,
                          int seedLen, int maxSeeds, int nofw, int norc, const int32_t *interval, const int32_t *offset,
@@ -186,11 +323,18 @@ void launch_seed_search2(const DevIndex<OFF> &ix, const uint8_t *seq, const uint
 	cudaMemsetAsync(next, 0, sizeof(unsigned long long), st);
 	// persistent grid: exactly as many blocks as can be resident (no second wave, no tail)
 	int perSM = 4;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_seed_search2<OFF>, 256, 0);
+	const char *v2 = getenv("BT2G_SEED_V2");
+	if(v2 && v2[0] == '1') {
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_seed_search2<OFF>, 256, 0);
+		if(perSM < 1) perSM = 1;
+		k_seed_search2<OFF><<<(unsigned)(numSMs * perSM), 256, 0, st>>>(ix, packed, nmask, roff, nReads, seedLen, maxSeeds, nofw, norc,
+		                                                              interval, offset, out, nseeds, next, cnt);
+		return;
+	}
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_seed_search3<OFF>, 256, 0);
 	if(perSM < 1) perSM = 1;
-	const unsigned blocks = (unsigned)(numSMs * perSM);
-	k_seed_search2<OFF><<<blocks, 256, 0, st>>>(ix, packed, nmask, roff, nReads, seedLen, maxSeeds, nofw, norc, interval, offset,
-	                                            out, nseeds, next, cnt);
+	k_seed_search3<OFF><<<(unsigned)(numSMs * perSM), 256, 0, st>>>(ix, packed, nmask, roff, nReads, seedLen, maxSeeds, nofw, norc,
+	                                                              interval, offset, out, nseeds, next, cnt);
 }
 template void launch_seed_search2<uint32_t>(const DevIndex<uint32_t> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
 template void launch_seed_search2<uint64_t>(const DevIndex<uint64_t> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
