@@ -561,6 +561,7 @@ __global__ void __launch_bounds__(128) k_dp_e2e_x2(DevIndex<OFF> ix, bt2g_scorin
 // Fill of the H-byte kernel (two problems per warp, s16x2; see the description below).
 // H-byte kernels take any R (rows per lane) and store RP = R rounded up to 4 bytes per lane and step
 #define DP_RP(R) ((((R) + 3) / 4) * 4)
+#define DP_QPROF_BYTES(R) ((size_t)(5 * (R) * 32 * 2))                      // fill kernel: query profile of one problem
 #define DP_PROF_BYTES(R) ((size_t)(3 * 32 * (R) + 15) & ~(size_t)15)      // per-row profile of the tail kernel: 3 bytes x 32 R rows
 // Workspace layout of one problem with S = maxCol + 32 step slots: R / 4 word planes [S][32] x 4 B holding rows
 // 4g..4g+3 of each lane, then one byte plane [S][32] per remaining row, so that every store of a warp is one
@@ -744,7 +745,7 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 // Split form of the H-byte kernel: k_dp_fill_h writes the H bytes of a CHUNK of problems to a problem-indexed
 // workspace (pure DPX compute, high occupancy), k_dp_tail_h then runs candidates + backtraces with one warp per
 // problem (latency-bound on workspace reads, hidden by far more resident warps than the fused kernel can hold).
-template <typename OFF, int R>
+template <typename OFF, int R, bool OFFDOM>
 __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L, uint64_t chunkStart, uint64_t chunkMax) {
 	extern __shared__ uint8_t smem[];
 	const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -754,13 +755,20 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 	if(chunkStart >= nAll) return;
 	const uint64_t nProb = (nAll - chunkStart < chunkMax) ? nAll - chunkStart : chunkMax;   // problems of this chunk
 	const uint64_t nPairs = (nProb + 1) >> 1;
+	// per warp: two reference windows, then the two query profiles [refc 0..4][row-in-lane][lane] as 16-bit scores
+	// (buildQueryProfileEnd2EndSseU8, aligner_swsse_ee_u8.cpp:75-142): the substitution score of a cell is then two
+	// shared-memory loads and one IMAD instead of five ALU-pipe instructions -- the ALU pipe is what bounds this kernel
 	const size_t perProb = ((size_t)L.maxCol + 15) & ~(size_t)15;
-	uint8_t *sm0 = smem + (size_t)warpInBlock * 2 * perProb;
+	uint8_t *sm0 = smem + (size_t)warpInBlock * (2 * perProb + 2 * DP_QPROF_BYTES(R));
 	uint8_t *refw[2] = {sm0, sm0 + perProb}; uint8_t *hb[2];
+	uint16_t *qprof[2] = {reinterpret_cast<uint16_t *>(sm0 + 2 * perProb), reinterpret_cast<uint16_t *>(sm0 + 2 * perProb + DP_QPROF_BYTES(R))};
 	const int rdgapo = sc.rdgap_const + sc.rdgap_linear, rdgape = sc.rdgap_linear;
 	const int rfgapo = sc.rfgap_const + sc.rfgap_linear, rfgape = sc.rfgap_linear;
 	const int bonus = sc.match_bonus;
-	const uint32_t FLOORP = dpx_both(DPX_FLOOR), ONEP = 0x00010001u;
+	// OFFDOM (match bonus 0, the end-to-end default): every increment is <= 0, so clamping each intermediate value
+	// at floor commutes with the recurrences (clamp(x) + s clamps to the same value as clamp(x + s) for s <= 0) and the
+	// whole fill can run in the stored domain H - floor with 0 as its lower clamp: the H register IS the byte to store.
+	const uint32_t FLOORP = OFFDOM ? 0u : dpx_both(DPX_FLOOR);
 	const uint32_t bonusP = dpx_both(bonus), nrdeP = dpx_both(-rdgape);
 
 	for(uint64_t pw = slot; pw < nPairs; pw += nSlots) {
@@ -801,7 +809,7 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 		__syncwarp();
 
 		// per-row constants of both problems (buildQueryProfileEnd2EndSseU8, aligner_swsse_ee_u8.cpp:75-142)
-		uint32_t rcP[R], mmpP[R], npnP[R], nrfoP[R], nrfeP[R], nrdoP[R];
+		uint32_t nrfoP[R], nrfeP[R], nrdoP[R];
 #pragma unroll
 		for(int r = 0; r < R; r++) {
 			int v[2][6];
@@ -821,10 +829,12 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 					if(c > 3) c = 5;
 					bar = (i < sc.gapbar) || (rdlen[x] - 1 - i < sc.gapbar);
 				}
-				v[x][0] = c; v[x][1] = mm; v[x][2] = np;
+				// profile entries of this row: score against reference A, C, G, T and N
+#pragma unroll
+				for(int rf = 0; rf < 5; rf++)
+					qprof[x][(rf * R + r) * 32 + lane] = (uint16_t)(int16_t)(rf > 3 ? np : (c == rf ? bonus : mm));
 				v[x][3] = bar ? -DPX_BIG : -rfgapo; v[x][4] = bar ? -DPX_BIG : -rfgape; v[x][5] = bar ? -DPX_BIG : -rdgapo;
 			}
-			rcP[r] = dpx_pack(v[0][0], v[1][0]); mmpP[r] = dpx_pack(v[0][1], v[1][1]); npnP[r] = dpx_pack(v[0][2], v[1][2]);
 			nrfoP[r] = dpx_pack(v[0][3], v[1][3]); nrfeP[r] = dpx_pack(v[0][4], v[1][4]); nrdoP[r] = dpx_pack(v[0][5], v[1][5]);
 		}
 		const int lastLane0 = (rdlen[0] - 1) / R, lastLane1 = (rdlen[1] - 1) / R;
@@ -849,10 +859,9 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 			if(lane == 0) { inH = FLOORP; inF = FLOORP; }
 			const int j = t - lane;
 			if(j >= 0 && j < ncolMax && lane <= lastLaneMax) {
-				const uint32_t refcP = (uint32_t)refw[0][j] | ((uint32_t)refw[1][j] << 16);
-				const uint32_t refNm = ((refcP >> 2) & ONEP) * 0xffffu;      // half mask: reference N
+				const uint16_t *qa = qprof[0] + (int)refw[0][j] * (R * 32) + lane, *qb = qprof[1] + (int)refw[1][j] * (R * 32) + lane;
 				// H[i0-1][j-1]: row -1 is the free start row of end-to-end mode (vhilsw, :853,923-927)
-				uint32_t diag = (lane == 0) ? 0u : prevInH;
+				uint32_t diag = (lane == 0) ? (OFFDOM ? nfloorP : 0u) : prevInH;
 				uint32_t upH = inH, upF = inF;
 				uint32_t hs[DP_RP(R)];
 #pragma unroll
@@ -861,14 +870,13 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 				for(int r = 0; r < R; r++) {
 					// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo)
 					const uint32_t F = __viaddmax_s16x2(upF, nrfeP[r], __viaddmax_s16x2(upH, nrfoP[r], FLOORP));
-					const uint32_t pen = dpx_sel(refNm, npnP[r], mmpP[r]);
-					const uint32_t mmask = dpx_ne01(rcP[r], refcP) * 0xffffu;
-					const uint32_t Hd = __viaddmax_s16x2(diag, dpx_sel(mmask, pen, bonusP), FLOORP);
+					const uint32_t sP = (uint32_t)qb[r * 32] * 65536u + (uint32_t)qa[r * 32];
+					const uint32_t Hd = __viaddmax_s16x2(diag, sP, FLOORP);
 					const uint32_t E = Earr[r];
 					const uint32_t H = __vimax3_s16x2(Hd, E, F);
 					// E[i][j+1] = max(E[i][j]-rdgape, H[i][j]-rdgapo)
 					Earr[r] = __viaddmax_s16x2(E, nrdeP, __viaddmax_s16x2(H, nrdoP[r], FLOORP));
-					hs[r] = __viaddmax_s16x2(H, nfloorP, 0u);              // max(H - floor, 0): the stored byte
+					hs[r] = OFFDOM ? H : __viaddmax_s16x2(H, nfloorP, 0u);  // max(H - floor, 0): the stored byte
 					diag = Hleft[r]; Hleft[r] = H;
 					upH = H; upF = F;
 				}
@@ -1204,15 +1212,16 @@ static void launch_dp_e2e_r(const DevIndex<OFF> &ix, const bt2g_scoring &sc, con
 	if(L.packed == 3) {
 		// split: chunks of L.chunk problems through fill then tail (workspace = L.chunk * codeStride bytes)
 		int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		const size_t smF = (size_t)warpsPerBlock * 2 * (((size_t)L.maxCol + 15) & ~(size_t)15);
+		const size_t smF = (size_t)warpsPerBlock * (2 * (((size_t)L.maxCol + 15) & ~(size_t)15) + 2 * DP_QPROF_BYTES(R));
 		const size_t smT = (size_t)8 * (dp_smem_per_warp(L.maxCol) + DP_PROF_BYTES(R));
-		if(smF > 48 * 1024) cudaFuncSetAttribute(k_dp_fill_h<OFF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smF);
+		auto kfill = sc.match_bonus == 0 ? k_dp_fill_h<OFF, R, true> : k_dp_fill_h<OFF, R, false>;
+		if(smF > 48 * 1024) cudaFuncSetAttribute(kfill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smF);
 		if(smT > 48 * 1024) cudaFuncSetAttribute(k_dp_tail_h<OFF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smT);
 		int nbF = 1, nbT = 1;
-		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbF, k_dp_fill_h<OFF, R>, warpsPerBlock * 32, smF) != cudaSuccess || nbF < 1) nbF = 1;
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbF, kfill, warpsPerBlock * 32, smF) != cudaSuccess || nbF < 1) nbF = 1;
 		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbT, k_dp_tail_h<OFF, R>, 256, smT) != cudaSuccess || nbT < 1) nbT = 1;
 		for(uint64_t c0 = 0; c0 < L.n; c0 += L.chunk) {
-			k_dp_fill_h<OFF, R><<<(unsigned)(nbF * sms), warpsPerBlock * 32, smF, st>>>(ix, sc, L, c0, L.chunk);
+			kfill<<<(unsigned)(nbF * sms), warpsPerBlock * 32, smF, st>>>(ix, sc, L, c0, L.chunk);
 			k_dp_tail_h<OFF, R><<<(unsigned)(nbT * sms), 256, smT, st>>>(ix, sc, L, c0, L.chunk);
 		}
 	} else if(L.packed == 2) {

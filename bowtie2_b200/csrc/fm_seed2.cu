@@ -447,7 +447,10 @@ __device__ __forceinline__ uint64_t rank1_loaded(const DevEbwt<OFF> &e, const Si
 template <typename OFF>
 __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const uint64_t *packed, const uint32_t *nmask,
                                                       const uint64_t *roff, uint64_t nReads, int nofw, int norc,
-                                                      uint8_t *mine, uint64_t *ee, unsigned long long *next, unsigned long long *cnt) {
+                                                      uint8_t *mine, uint64_t *ee, unsigned long long *next, unsigned long long *cnt,
+                                                      int eeOnly) {
+	// eeOnly (the pipeline): only the exact end-to-end range is wanted, so the search stops at the first failed
+	// extension (mine = 1 then means "at least one edit") and may start from the extended seed table.
 	constexpr uint32_t BL = SideGeom<OFF>::BWT_LEN;
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
@@ -504,15 +507,33 @@ __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const ui
 				const int left = len - dep;
 				bool doFtab = ftabLen > 1 && left >= ftabLen;
 				uint64_t fi = 0;
-				if(doFtab) {
+				bool viaTable = false;
+				if(eeOnly && ix.ktab != nullptr && left >= ix.ktabChars) {
+					const int K = ix.ktabChars;
+					uint64_t x = 0;
+					bool clean = true;
+					for(int i = 0; i < K; i++) {
+						const int c = chr(left - 1 - i);
+						if(c > 3) { clean = false; break; }
+						x = (x << 2) | (uint64_t)c;
+					}
+					if(clean) {
+						const OFF *e3 = ix.ktab + 3ull * x;
+						top = e3[0]; bot = e3[1]; dep += K;
+						viaTable = true; doFtab = false;
+					}
+				}
+				if(viaTable) {
+				} else if(doFtab) {
 					for(int i = 0; i < ftabLen; i++) {
 						const int c = chr(left - ftabLen + i);
 						if(c > 3) { doFtab = false; break; }
 						fi = (fi << 2) | (uint64_t)c;
 					}
 				}
-				top = bot = 0;
-				if(doFtab) { top = ftab_hi<OFF>(e, fi); bot = ftab_lo<OFF>(e, fi + 1); dep += ftabLen; }
+				if(!viaTable) top = bot = 0;
+				if(viaTable) {
+				} else if(doFtab) { top = ftab_hi<OFF>(e, fi); bot = ftab_lo<OFF>(e, fi + 1); dep += ftabLen; }
 				else {
 					const int c = chr(len - dep - 1);
 					if(c < 4) { top = e.fchr[c]; bot = e.fchr[c + 1]; }
@@ -520,7 +541,7 @@ __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const ui
 				}
 				if(bot <= top) {
 					nedit++;
-					if(nedit >= mineMax) done = true;
+					if(nedit >= mineMax || eeOnly) done = true;
 					stepNow = false;                    // the reference `continue`s: re-init from the new depth
 				} else doInit = false;
 			}
@@ -540,7 +561,7 @@ __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const ui
 				}
 				if(bot <= top) {
 					nedit++;
-					if(nedit >= mineMax) done = true;
+					if(nedit >= mineMax || eeOnly) done = true;
 					doInit = true;
 				}
 				dep++;
@@ -560,16 +581,16 @@ __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const ui
 template <typename OFF>
 void launch_exact_sweep2(const DevIndex<OFF> &ix, const uint64_t *roff, uint64_t nReads, int nofw, int norc,
                          uint8_t *mine, uint64_t *ee, const uint64_t *packed, const uint32_t *nmask, unsigned long long *next,
-                         int numSMs, cudaStream_t st, unsigned long long *cnt) {
+                         int numSMs, cudaStream_t st, unsigned long long *cnt, int eeOnly) {
 	if(nReads == 0) return;
 	cudaMemsetAsync(next, 0, sizeof(unsigned long long), st);
 	int perSM = 4;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_exact_sweep2<OFF>, 256, 0);
 	if(perSM < 1) perSM = 1;
-	k_exact_sweep2<OFF><<<(unsigned)(numSMs * perSM), 256, 0, st>>>(ix, packed, nmask, roff, nReads, nofw, norc, mine, ee, next, cnt);
+	k_exact_sweep2<OFF><<<(unsigned)(numSMs * perSM), 256, 0, st>>>(ix, packed, nmask, roff, nReads, nofw, norc, mine, ee, next, cnt, eeOnly);
 }
-template void launch_exact_sweep2<uint32_t>(const DevIndex<uint32_t> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
-template void launch_exact_sweep2<uint64_t>(const DevIndex<uint64_t> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+template void launch_exact_sweep2<uint32_t>(const DevIndex<uint32_t> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *, int);
+template void launch_exact_sweep2<uint64_t>(const DevIndex<uint64_t> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *, int);
 
 void launch_pack_reads(const uint8_t *seq, const uint64_t *roff, uint64_t nReads, int maxLen, uint64_t *packed, uint32_t *nmask, cudaStream_t st) {
 	if(nReads == 0) return;

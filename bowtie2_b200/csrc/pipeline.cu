@@ -24,7 +24,7 @@
 template <typename OFF> void launch_exact_sweep(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, cudaStream_t, unsigned long long *);
 template <typename OFF> void launch_seed_search(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, cudaStream_t, unsigned long long *);
 template <typename OFF> void launch_seed_search2(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
-template <typename OFF> void launch_exact_sweep2(const DevIndex<OFF> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
+template <typename OFF> void launch_exact_sweep2(const DevIndex<OFF> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *, int = 0);
 void launch_pack_reads(const uint8_t *, const uint64_t *, uint64_t, int, uint64_t *, uint32_t *, cudaStream_t);
 template <typename OFF> void launch_resolve2(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, const uint32_t *, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
 template <typename OFF> void launch_resolve(const DevIndex<OFF> &, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *, cudaStream_t, unsigned long long *);
@@ -398,7 +398,7 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 	k_plan<<<grid(n), T, 0, st>>>(roff, n, b.ivalByLen, q.max_len, b.interval, b.offset);
 	mark(1);
 	launch_pack_reads(seq, roff, n, q.max_len, b.packed, b.nmask, st);
-	launch_exact_sweep2<OFF>(ix, roff, n, 0, 0, b.mine, b.ee, b.packed, b.nmask, b.nextTask, p->sms, st, c ? c + 0 : nullptr);
+	launch_exact_sweep2<OFF>(ix, roff, n, 0, 0, b.mine, b.ee, b.packed, b.nmask, b.nextTask, p->sms, st, c ? c + 0 : nullptr, 1 /* ee ranges only */);
 	mark(2);
 	launch_seed_search2<OFF>(ix, seq, roff, n, q.max_len, q.seed_len, q.max_seeds, 0, 0, b.interval, b.offset, b.ranges, b.nseeds,
 	                         b.packed, b.nmask, b.nextTask, p->sms, st, c ? c + 1 : nullptr);

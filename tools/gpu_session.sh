@@ -27,6 +27,8 @@ benchk)
     timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --seed-table $k > $OUT/${TAG}_benchk$k.json 2> $OUT/${TAG}_benchk$k.err; echo "benchk$k exit $?"
     python -c "import json; d=json.loads(open('$OUT/${TAG}_benchk$k.json').read().strip().splitlines()[-1]); print('k=$k', round(d['value'],2), round(d['e2e']['value'],2), {a:round(b,1) for a,b in d['stage_ms'].items()}, d['work_per_step']['seed_sides'], d['config']['seed_table_build_s'])"
   done ;;
+smoke)
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -3 $OUT/${TAG}_smoke.log ;;
 bench2)
   BT2G_DP_PACKED=2 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench2.json 2> $OUT/${TAG}_bench2.err; echo "bench2 exit $?"; tail -c 700 $OUT/${TAG}_bench2.json ;;
 bench0)
