@@ -18,6 +18,7 @@
 #include "fm_device.cuh"
 #include "dp_device.cuh"
 #include "pe_device.cuh"
+#include "mapq_device.cuh"
 #include <new>
 #include <cstring>
 
@@ -156,7 +157,7 @@ __global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interva
 	const int len = (int)(roff[rd + 1] - roff[rd]);
 	const int li = len > maxLen ? maxLen : len;
 	bt2g_read_result r;
-	r.found = 0; r.score = 0; r.score2 = INT32_MIN; r.fw = 0; r.tidx = 0; r.refoff = 0; r.nops = 0; r.ndp = 0; r.trim_left = 0; r.trim_right = 0;
+	r.found = 0; r.score = 0; r.score2 = INT32_MIN; r.fw = 0; r.tidx = 0; r.refoff = 0; r.nops = 0; r.ndp = 0; r.trim_left = 0; r.trim_right = 0; r.mapq = 0; r.pad = 0;
 	int np = 0;
 	uint64_t seenT[32]; int64_t seenO[32]; uint8_t seenS[32]; int nseen = 0;
 	const int minsc = minscByLen[li];
@@ -212,7 +213,7 @@ __global__ void k_frame(uint64_t n, const uint64_t *roff, const int32_t *interva
 __global__ void k_pick(uint64_t n, int rowCap, int maxAlns, int maxOps, const int32_t *readProb, const int32_t *readNProb,
                        const bt2g_dp_problem *probs, const bt2g_dp_summary *summ, const bt2g_dp_aln *alns, const uint8_t *ops,
                        bt2g_read_result *res, uint8_t *resOps, unsigned long long *cellCnt, const uint64_t *roff,
-                       const uint64_t *probTlen, uint64_t *resTlen) {
+                       const uint64_t *probTlen, uint64_t *resTlen, const int32_t *minscByLen, int maxLen, int matchBonus, int monotone) {
 	uint64_t rd = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(rd >= n) return;
 	bt2g_read_result r = res[rd];
@@ -241,6 +242,10 @@ __global__ void k_pick(uint64_t n, int rowCap, int maxAlns, int maxOps, const in
 		const uint8_t *src = ops + ((size_t)bestP * maxAlns + bestA) * maxOps;
 		uint8_t *dst = resOps + rd * (size_t)maxOps;
 		for(int k = 0; k < r.nops; k++) dst[k] = src[k];
+	}
+	if((r.found & 0xff) != 0) {
+		const int li = len > maxLen ? maxLen : len;
+		r.mapq = mapq_v2(r.score, r.score2 != INT32_MIN, r.score2, minscByLen[li], (long long)len * matchBonus, monotone != 0);
 	}
 	res[rd] = r;
 	if(cellCnt && cells) atomicAdd(cellCnt, cells);
@@ -301,7 +306,8 @@ __global__ void k_frame_mates(uint64_t nReads, const uint64_t *roff, const bt2g_
 // pick: one thread per pair
 __global__ void k_pick_pairs(uint64_t nPairs, const uint64_t *roff, bt2g_read_result *res, uint8_t *resOps, int maxOps, int maxAlns,
                              bt2g_pe_policy pp, const int32_t *mateOfRead, const bt2g_dp_problem *mProbs, const bt2g_dp_summary *mSumm,
-                             const bt2g_dp_aln *mAlns, const uint8_t *mOps, bt2g_pair_result *pairs, unsigned long long *mateCells) {
+                             const bt2g_dp_aln *mAlns, const uint8_t *mOps, bt2g_pair_result *pairs, unsigned long long *mateCells,
+                             const int32_t *minscByLen, int maxLen, int matchBonus, int monotone) {
 	const uint64_t pr = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(pr >= nPairs) return;
 	const uint64_t r1 = 2 * pr, r2 = 2 * pr + 1;
@@ -366,6 +372,10 @@ __global__ void k_pick_pairs(uint64_t nPairs, const uint64_t *roff, bt2g_read_re
 		const int64_t lo = a1.refoff < a2.refoff ? a1.refoff : a2.refoff;
 		const int64_t h1 = a1.refoff + ee1, h2 = a2.refoff + ee2;
 		out.fraglen = (h1 > h2 ? h1 : h2) - lo;
+		// MAPQ of a concordant pair: both mates from the pair's sums (unique.h:205-222)
+		const int l1 = len1 > maxLen ? maxLen : len1, l2 = len2 > maxLen ? maxLen : len2;
+		const int mq = mapq_v2(bestSum, false, 0, (long long)minscByLen[l1] + minscByLen[l2], (long long)(len1 + len2) * matchBonus, monotone != 0);
+		res[r1].mapq = mq; res[r2].mapq = mq;
 	}
 	pairs[pr] = out;
 	if(mateCells && cells) atomicAdd(mateCells, cells);
@@ -423,7 +433,7 @@ static int runStages(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual, 
 	if(drc) { ctx->err = "pipeline: DP launch rejected"; return -1; }
 	mark(7);
 	k_pick<<<grid(n), T, 0, st>>>(n, q.row_cap, q.max_alns, q.max_ops, b.readProb, b.readNProb, b.probs, b.summ, b.alns, b.ops,
-	                              b.res + resBase, b.resOps + resBase * (uint64_t)q.max_ops, c ? c + 3 : nullptr, roff, b.probTlen, b.resTlen + resBase);
+	                              b.res + resBase, b.resOps + resBase * (uint64_t)q.max_ops, c ? c + 3 : nullptr, roff, b.probTlen, b.resTlen + resBase, b.minscByLen, q.max_len, p->sc.match_bonus, p->sc.match_bonus == 0);
 	mark(8);
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	p->lastN = n;
@@ -456,7 +466,7 @@ static int runPairTail(bt2g_pipeline *p, const uint8_t *seq, const uint8_t *qual
 	if(launch_dp_e2e<OFF>(ix, p->sc, L, q.max_len, st)) { ctx->err = "pipeline: mate DP launch rejected"; return -1; }
 	cudaEventRecord(p->pev[2], st);
 	k_pick_pairs<<<(unsigned)((nPairs + T - 1) / T), T, 0, st>>>(nPairs, roff, res, resOps, q.max_ops, q.max_alns, p->pe, b.mateOfRead, b.mProbs,
-	                                                             b.mSumm, b.mAlns, b.mOps, pairs, count ? b.mateCells : nullptr);
+	                                                             b.mSumm, b.mAlns, b.mOps, pairs, count ? b.mateCells : nullptr, b.minscByLen, q.max_len, p->sc.match_bonus, p->sc.match_bonus == 0);
 	cudaEventRecord(p->pev[3], st);
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	return 0;

@@ -360,8 +360,8 @@ class _PipeParams(C.Structure):
 
 
 READ_RESULT = np.dtype([("found", "<i4"), ("score", "<i4"), ("score2", "<i4"), ("fw", "<u4"), ("tidx", "<u8"),
-                        ("refoff", "<i8"), ("nops", "<i4"), ("ndp", "<i4"), ("trim_left", "<i4"), ("trim_right", "<i4")],
-                       align=True)
+                        ("refoff", "<i8"), ("nops", "<i4"), ("ndp", "<i4"), ("trim_left", "<i4"), ("trim_right", "<i4"),
+                        ("mapq", "<i4"), ("pad", "<i4")], align=True)
 
 EXPORTS += ["bt2g_pipeline_create", "bt2g_pipeline_destroy", "bt2g_pipeline_run_dev", "bt2g_pipeline_run_host",
             "bt2g_pipeline_results_dev", "bt2g_pipeline_counters", "bt2g_pipeline_stage_ms", "bt2g_pipeline_kernel_launches",

@@ -316,3 +316,54 @@ def frame_find_mate_rect(anchor_left: bool, ll: int, lr: int, rl: int, rr: int, 
     width = refr - refl + 1
     r = DPRect(refl + triml, refr - trimr, refl, refr, triml, trimr, maxgap, width - maxgap - 1, maxgap)
     return (not r.entirely_trimmed()), r
+
+
+# ---- MAPQ (unique.h:170-392, BowtieMapq2 = the default model) ---------------------------------------
+def mapq_v2(best: int, secbest, sc_min: int, sc_perfect: int, monotone: bool) -> int:
+    """BowtieMapq2::mapq for a primary alignment whose search was exhaustive or capped (not the 255 case).
+    `secbest` is None when there is no second-best score.  For pairs pass the concordant sums and the summed
+    minimum / perfect scores.  Thresholds are float literals widened to double, as in the reference."""
+    import struct
+
+    def f(x):                      # (double)0.8f
+        return struct.unpack("f", struct.pack("f", x))[0]
+
+    diff = max(1, sc_perfect - sc_min)
+    best_over = best - sc_min
+    if secbest is None:
+        table = ((0.8, 42), (0.7, 40), (0.6, 24), (0.5, 23), (0.4, 8), (0.3, 3)) if monotone else \
+                ((0.8, 44), (0.7, 42), (0.6, 41), (0.5, 36), (0.4, 28), (0.3, 24))
+        for th, v in table:
+            if best_over >= diff * f(th):
+                return v
+        return 0 if monotone else 22
+    bestdiff = abs(abs(best) - abs(secbest))
+    if monotone:
+        for th, hi, lo in ((0.9, 39, 33), (0.8, 38, 27), (0.7, 37, 26), (0.6, 36, 22)):
+            if bestdiff >= diff * f(th):
+                return hi if best_over == diff else lo
+        for th, top, a, va, b, vb, rest in ((0.5, 35, 0.84, 25, 0.68, 16, 5), (0.4, 34, 0.84, 21, 0.68, 14, 4),
+                                             (0.3, 32, 0.88, 18, 0.67, 15, 3), (0.2, 31, 0.88, 17, 0.67, 11, 0),
+                                             (0.1, 30, 0.88, 12, 0.67, 7, 0)):
+            if bestdiff >= diff * f(th):
+                if best_over == diff:
+                    return top
+                if best_over >= diff * f(a):
+                    return va
+                if best_over >= diff * f(b):
+                    return vb
+                return rest
+        if bestdiff > 0:
+            return 6 if best_over >= diff * f(0.67) else 2
+        return 1 if best_over >= diff * f(0.67) else 0
+    for th, v in ((0.9, 40), (0.8, 39), (0.7, 38), (0.6, 37)):
+        if bestdiff >= diff * f(th):
+            return v
+    for th, top, va, rest in ((0.5, 35, 25, 20), (0.4, 34, 21, 19), (0.3, 33, 18, 16), (0.2, 32, 17, 12), (0.1, 31, 14, 9)):
+        if bestdiff >= diff * f(th):
+            if best_over == diff:
+                return top
+            return va if best_over >= diff * f(0.5) else rest
+    if bestdiff > 0:
+        return 11 if best_over >= diff * f(0.5) else 2
+    return 1 if best_over >= diff * f(0.5) else 0

@@ -368,6 +368,10 @@ typedef struct {
 	int32_t  ndp;                /* DP problems issued for this read */
 	int32_t  trim_left, trim_right; /* read positions soft-trimmed left / right of the alignment in reference
 	                                 * orientation (local mode; SwResult alres softTrimmed 5'/3' per strand) */
+	int32_t  mapq;               /* BowtieMapq2::mapq (unique.h:170-392) from score / score2 and the read's minimum and
+	                              * perfect scores; for a concordant pair from the pair's score sums (no second-best pair
+	                              * is tracked: the "no second best" branch) */
+	int32_t  pad;
 } bt2g_read_result;
 
 typedef struct bt2g_pipeline bt2g_pipeline;

@@ -28,6 +28,7 @@
 #define protected public
 #include "aligner_sw.h"
 #include "pe.h"
+#include "unique.h"
 #undef private
 #undef protected
 #include "bt2_idx.h"
@@ -60,6 +61,30 @@ int ref_frame_seed_rect(int64_t off, uint64_t rdlen, int64_t reflen, uint64_t ma
 	out9[4] = (int64_t)r.triml; out9[5] = (int64_t)r.trimr; out9[6] = (int64_t)r.corel; out9[7] = (int64_t)r.corer;
 	out9[8] = (int64_t)r.maxgap;
 	return found ? 1 : 0;
+}
+
+// BowtieMapq2::mapq (unique.h:170-392), the default MAPQ model.  Unpaired: best / secbest are the read's best and
+// best-unchosen alignment scores; paired (ordlen > 0): the concordant-pair sums.  The summary object is filled
+// directly (this glue is built with private members exposed, as for SwAligner).
+int ref_mapq_v2(void* vh, int local, int64_t rdlen, int64_t ordlen, int64_t best, int has_sec, int64_t secbest) {
+	RefHandleDp* h = (RefHandleDp*)vh;
+	const Scoring& sc = local ? *h->sc_loc : *h->sc_e2e;
+	SimpleFunc scoreMin;
+	if(local) scoreMin.init(SIMPLE_FUNC_LOG, DEFAULT_MIN_CONST_LOCAL, DEFAULT_MIN_LINEAR_LOCAL);
+	else      scoreMin.init(SIMPLE_FUNC_LINEAR, DEFAULT_MIN_CONST, DEFAULT_MIN_LINEAR);
+	BowtieMapq2 mq(scoreMin, sc);
+	AlnSetSumm s;
+	s.reset();
+	const bool paired = ordlen > 0;
+	s.paired_ = paired;
+	s.exhausted1_ = s.exhausted2_ = true;
+	AlnScore b; b.score_ = best; b.ns_ = 0; b.gaps_ = 0; b.basesAligned_ = 0; b.edits_ = 0;
+	AlnScore u; u.score_ = secbest; u.ns_ = 0; u.gaps_ = 0; u.basesAligned_ = 0; u.edits_ = 0;
+	if(paired) { s.bestCScore_ = b; s.bestP1Score_ = b; if(has_sec) s.bestUnchosenCScore_ = u; }
+	else       { s.bestUScore_ = b; if(has_sec) s.bestUnchosenUScore_ = u; }
+	AlnFlags flags(paired ? ALN_FLAG_PAIR_CONCORD_MATE1 : ALN_FLAG_PAIR_UNPAIRED, true /*canMax*/, false, false, false, false, false, false,
+	               false, true /*primary*/, paired, false, false, false);
+	return (int)mq.mapq(s, flags, true, (size_t)rdlen, (size_t)ordlen, NULL);
 }
 
 // SwAligner::ungappedAlign (aligner_sw.cpp:286-487).  out8: score, refoff, trim5, trim3, ns, refns, nedits, -;

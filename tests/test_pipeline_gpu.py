@@ -43,7 +43,7 @@ def test_pipeline_vs_reference_program(gpu, synth_index, synth_genome, tmp_path,
     want = _run_reference(synth_index, fq)
     pipe = Pipeline(gpu, "sensitive", max_len=rdlen, max_reads=4096, row_cap=16, range_max=16)
     res, ops = pipe.run_host(ReadBatch.from_list(reads, quals))
-    n_ref_aln = n_same = n_same_cigar = n_unique = n_unique_same = n_gpu_only = 0
+    n_ref_aln = n_same = n_same_cigar = n_unique = n_unique_same = n_gpu_only = n_same_mapq = 0
     for i, w in enumerate(want):
         r = res[i]
         if w["flag"] & 4:
@@ -59,7 +59,10 @@ def test_pipeline_vs_reference_program(gpu, synth_index, synth_genome, tmp_path,
         if same:
             cig = f"{rdlen}M" if r["found"] == 2 else ops_to_cigar(ops[i], int(r["nops"]))
             n_same_cigar += cig == w["cigar"]
+            n_same_mapq += int(r["mapq"]) == w["mapq"]
     assert n_ref_aln > 2500
+    # the MAPQ formula is the reference's; the runner-up score feeding it comes from the speculative pipeline
+    assert n_same_mapq >= 0.9 * n_same, (n_same_mapq, n_same)
     # reads the reference places confidently must agree; repeats may legitimately differ
     assert n_unique_same >= 0.995 * n_unique, (n_unique_same, n_unique)
     assert n_same >= 0.97 * n_ref_aln, (n_same, n_ref_aln)
@@ -142,6 +145,15 @@ def test_pipeline_stage_consistency(gpu, synth_index, synth_genome):
     has_ee = (ee[:, 1] > ee[:, 0]) | (ee[:, 3] > ee[:, 2])
     assert np.array_equal(res["found"] == 2, has_ee)
     assert (res["found"] != 0).sum() > 350
+    # MAPQ = BowtieMapq2 on (best, runner-up) with the read's minimum and perfect scores
+    sc = policy.Scoring.default(False)
+    INT_MIN = -(1 << 31)
+    for i in range(batch.n):
+        r = res[i]
+        if r["found"] == 0:
+            continue
+        sec = None if int(r["score2"]) == INT_MIN else int(r["score2"])
+        assert int(r["mapq"]) == policy.mapq_v2(int(r["score"]), sec, sc.min_score(rdlen), sc.perfect_score(rdlen), True), i
     pipe.close()
 
 

@@ -111,3 +111,30 @@ def test_pe_classify_matches_reference(lambda_index):
         assert got == want
         seen.add(got)
     assert seen == {1, 2, 3, 4, 5}
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("local", [False, True])
+def test_mapq_v2_matches_reference(lambda_index, local):
+    R = Reference(lambda_index, mirror=False, ref=False)
+    L = R.lib
+    i64 = C.c_int64
+    L.ref_mapq_v2.argtypes = [C.c_void_p, C.c_int, i64, i64, i64, C.c_int, i64]
+    sc = policy.Scoring.default(local)
+    rng = np.random.default_rng(31)
+    seen = set()
+    for k in range(6000):
+        rdlen = int(rng.choice([50, 100, 150, 250]))
+        ordlen = int(rng.choice([0, 0, 100, 150]))
+        mn = sc.min_score(rdlen) + (sc.min_score(ordlen) if ordlen else 0)
+        pf = sc.perfect_score(rdlen) + (sc.perfect_score(ordlen) if ordlen else 0)
+        best = int(rng.integers(mn, pf + 1))
+        if k % 5 == 0:
+            best = pf
+        has_sec = bool(rng.integers(0, 2))
+        sec = int(rng.integers(mn, best + 1)) if has_sec else 0
+        want = L.ref_mapq_v2(R.h, int(local), rdlen, ordlen, best, int(has_sec), sec)
+        got = policy.mapq_v2(best, sec if has_sec else None, mn, pf, monotone=not local)
+        assert got == want, (k, rdlen, ordlen, best, has_sec, sec, got, want)
+        seen.add(want)
+    assert len(seen) > 25
