@@ -29,6 +29,8 @@ benchk)
   done ;;
 smoke)
   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -3 $OUT/${TAG}_smoke.log ;;
+benchref)
+  timeout 1200 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "benchref exit $?"; tail -c 1200 $OUT/${TAG}_bench_ref.json; tail -8 $OUT/${TAG}_bench_ref.err ;;
 bench2)
   BT2G_DP_PACKED=2 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench2.json 2> $OUT/${TAG}_bench2.err; echo "bench2 exit $?"; tail -c 700 $OUT/${TAG}_bench2.json ;;
 bench0)
