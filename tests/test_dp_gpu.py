@@ -71,7 +71,8 @@ def _check(gpu, R, genome, reads, quals, probs, meta, local=False):
 
 
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("rdlen,sub,indel", [(100, 0.01, 0.002), (150, 0.02, 0.004), (50, 0.01, 0.0), (250, 0.01, 0.003), (33, 0.03, 0.01)])
+@pytest.mark.parametrize("rdlen,sub,indel", [(100, 0.01, 0.002), (150, 0.02, 0.004), (50, 0.01, 0.0), (250, 0.01, 0.003), (33, 0.03, 0.01),
+                                             (128, 0.01, 0.003), (129, 0.02, 0.003), (180, 0.01, 0.004), (200, 0.015, 0.003)])
 def test_dp_e2e_matches_reference(gpu, synth_index, synth_genome, rdlen, sub, indel):
     gpu.load_index_files(synth_index)
     gpu.set_scoring(local=False)
@@ -86,6 +87,23 @@ def test_dp_e2e_matches_reference(gpu, synth_index, synth_genome, rdlen, sub, in
     assert nfound > 100 and naln > 100
     if indel > 0:
         assert ngap > 0
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_dp_e2e_kernel_generations(gpu, synth_index, synth_genome, mode, monkeypatch):
+    """The older end-to-end DP kernels (move codes 32-bit, move codes s16x2, fused H bytes) stay correct: they are the
+    fallbacks when a batch does not fit the split H-byte kernels (BT2G_DP_PACKED caps the mode)."""
+    import os
+    monkeypatch.setenv("BT2G_DP_PACKED", mode)
+    gpu.load_index_files(synth_index)
+    gpu.set_scoring(local=False)
+    R = Reference(synth_index)
+    sc = policy.Scoring.default(False)
+    reads, quals, truth = synth.make_reads(synth_genome, 120, 100, seed=900 + int(mode), sub_rate=0.02, indel_rate=0.004)
+    probs, meta = _problems(synth_genome, reads, truth, sc, np.random.default_rng(5))
+    nfound, naln, ngap = _check(gpu, R, synth_genome, reads, quals, probs, meta)
+    assert nfound > 80 and ngap > 3
 
 
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
