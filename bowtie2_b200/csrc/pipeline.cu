@@ -238,7 +238,7 @@ __global__ void k_pick(uint64_t n, int rowCap, int maxAlns, int maxOps, const in
 		r.fw = probs[bestP].fw; r.tidx = probs[bestP].tidx; r.refoff = probs[bestP].refl + al.col0;
 		resTlen[rd] = probTlen[bestP];
 		r.nops = al.nops < maxOps ? al.nops : maxOps;
-		r.trim_left = al.trim_beg; r.trim_right = al.trim_end;
+		r.trim_left = al.trim_beg; r.trim_right = al.trim_end; r.pad = al.refns;
 		const uint8_t *src = ops + ((size_t)bestP * maxAlns + bestA) * maxOps;
 		uint8_t *dst = resOps + rd * (size_t)maxOps;
 		for(int k = 0; k < r.nops; k++) dst[k] = src[k];
@@ -359,7 +359,7 @@ __global__ void k_pick_pairs(uint64_t nPairs, const uint64_t *roff, bt2g_read_re
 		bt2g_read_result m = res[ro];
 		if((m.found & 0xff) != 0 && m.score > m.score2) m.score2 = m.score;   // the displaced alignment becomes the runner-up
 		m.found = (m.found & ~0xff) | 1; m.score = al.score; m.fw = q.fw; m.tidx = q.tidx; m.refoff = q.refl + al.col0;
-		m.nops = al.nops < maxOps ? al.nops : maxOps; m.trim_left = al.trim_beg; m.trim_right = al.trim_end;
+		m.nops = al.nops < maxOps ? al.nops : maxOps; m.trim_left = al.trim_beg; m.trim_right = al.trim_end; m.pad = al.refns;
 		const uint8_t *src = mOps + ((size_t)pi * maxAlns + bestAln) * maxOps;
 		uint8_t *dst = resOps + ro * (size_t)maxOps;
 		for(int k = 0; k < m.nops; k++) dst[k] = src[k];

@@ -1,0 +1,246 @@
+// sam_host.cpp -- SAM records from pipeline results (host only; no CUDA).
+//
+// The reporting tail of the reference for one alignment per read: AlnSinkSam::appendMate (aln_sink.cpp:1889-2060)
+// with StackedAln (aligner_result.cpp:520-880: stacked alignment, leftAlign(false), CIGAR, MD:Z) and
+// SamConfig::printAlignedOptFlags (sam.cpp:121-330: AS, XS, XN, XM, XO, XG, NM, MD, YS, YT in that order).
+// Inputs are what bt2g_pipeline_run_*_host returns: bt2g_read_result + the op string of the reported alignment
+// (ops list the alignment from its last read position back to its first, in reference orientation; every op
+// that consumes a reference character carries its code in bits 2..4).
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <thread>
+#include "../../include/bt2g.h"
+
+namespace {
+
+struct Stacked {
+	std::vector<char> ref, rel, rd;          // reference char / relation (= X I D) / read char per alignment column
+	void leftAlign() {                       // StackedAln::leftAlign(false) (aligner_result.cpp:629-675)
+		const size_t ln = ref.size();
+		for(size_t i = 0; i < ln; i++) {
+			const char r = rel[i];
+			if(r == '=' || r == 'X') continue;
+			size_t glen = 1;
+			for(size_t j = i + 1; j < ln; j++) { if(rel[j] != r) break; glen++; }
+			if(i == 0) { i += glen - 1; continue; }
+			size_t l = i - 1, rr = l + glen;
+			std::vector<char> &gp = (r == 'I') ? ref : rd;
+			const std::vector<char> &ngp = (r == 'I') ? rd : ref;
+			while(l > 0 && ngp[l] == ngp[rr]) {
+				if(rel[l] == 'X') break;
+				std::swap(gp[l], gp[rr]);
+				std::swap(rel[l], rel[rr]);
+				l--; rr--;
+			}
+			i += glen - 1;
+		}
+	}
+};
+
+void appendInt(std::string &o, long long v) {
+	char b[24]; int k = 24;
+	unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+	do { b[--k] = (char)('0' + u % 10); u /= 10; } while(u);
+	if(v < 0) b[--k] = '-';
+	o.append(b + k, (size_t)(24 - k));
+}
+
+} // namespace
+
+static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const bt2g_read_result *res, const uint8_t *ops,
+                       uint32_t maxOps, const bt2g_pair_result *pairs, uint64_t i0, uint64_t i1, std::string &o) {
+	static const char dna[] = "ACGTN";
+	static const char comp[] = "TGCAN";
+	const bool paired = pairs != nullptr;
+	o.reserve((size_t)(i1 - i0) * 400);
+	std::string cigar, mdz, line, held;
+	Stacked st;                                                        // buffers reused from record to record
+	for(uint64_t i = i0; i < i1; i++) {
+		const bt2g_read_result &r = res[i];
+		const uint8_t *seq = reads->seq + reads->off[i];
+		const uint8_t *qual = reads->qual ? reads->qual + reads->off[i] : nullptr;
+		const int len = (int)(reads->off[i + 1] - reads->off[i]);
+		const bool aligned = (r.found & 0xff) != 0;
+		const bool fw = r.fw != 0;
+		// ---- mate bookkeeping
+		const bt2g_read_result *m = paired ? &res[i ^ 1ull] : nullptr;
+		const bool mateAligned = m && (m->found & 0xff) != 0;
+		const bt2g_pair_result *pr = paired ? &pairs[i >> 1] : nullptr;
+		const bool concordant = pr && pr->pair_type == 1;
+		int flag = 0;
+		if(paired) {
+			flag |= 1;
+			if(concordant) flag |= 2;
+			if(!aligned) flag |= 4;
+			if(!mateAligned) flag |= 8;
+			if(aligned && !fw) flag |= 16;
+			if(mateAligned && m->fw == 0) flag |= 32;
+			flag |= (i & 1) ? 128 : 64;
+		} else {
+			if(!aligned) flag |= 4; else if(!fw) flag |= 16;
+		}
+		// ---- stacked alignment, CIGAR, MD:Z, edit counts
+		cigar.clear(); mdz.clear();
+		long long refExtent = 0;
+		int nmm = 0, ngo = 0, ngx = 0, nedits = 0;
+		if(aligned) {
+			st.ref.clear(); st.rel.clear(); st.rd.clear();
+			const int nops = (r.found & 0xff) == 2 ? 0 : r.nops;
+			const uint8_t *op = ops ? ops + i * (uint64_t)maxOps : nullptr;
+			// read characters in reference orientation
+			auto rdch = [&](int row) -> char { return fw ? dna[seq[row] > 4 ? 4 : seq[row]] : comp[seq[len - 1 - row] > 4 ? 4 : seq[len - 1 - row]]; };
+			int row = r.trim_left;
+			if((r.found & 0xff) == 2) {
+				for(int k = 0; k < len; k++) { st.ref.push_back(rdch(k)); st.rel.push_back('='); st.rd.push_back(rdch(k)); }
+			} else {
+				if(!op) return -1;
+				int prevGap = -1;                                  // 2 read gap, 1 ref gap run tracking for XO/XG
+				for(int k = nops - 1; k >= 0; k--) {
+					const int typ = op[k] & 3, rc = (op[k] >> 2) & 7;
+					if(typ == BT2G_OP_MATCH) { st.ref.push_back(dna[rc > 4 ? 4 : rc]); st.rel.push_back('='); st.rd.push_back(rdch(row)); row++; prevGap = -1; }
+					else if(typ == BT2G_OP_MM) { st.ref.push_back(dna[rc > 4 ? 4 : rc]); st.rel.push_back('X'); st.rd.push_back(rdch(row)); row++; nmm++; nedits++; prevGap = -1; }
+					else if(typ == BT2G_OP_REFGAP) { st.ref.push_back('-'); st.rel.push_back('I'); st.rd.push_back(rdch(row)); row++; nedits++; ngx++; if(prevGap != 1) ngo++; prevGap = 1; }
+					else { st.ref.push_back(dna[rc > 4 ? 4 : rc]); st.rel.push_back('D'); st.rd.push_back('-'); nedits++; ngx++; if(prevGap != 2) ngo++; prevGap = 2; }
+				}
+			}
+			st.leftAlign();
+			// CIGAR (StackedAln::buildCigar, xeq = false)
+			if(r.trim_left > 0) { appendInt(cigar, r.trim_left); cigar += 'S'; }
+			const size_t ln = st.rel.size();
+			for(size_t k = 0; k < ln;) {
+				char c = st.rel[k]; if(c == 'X' || c == '=') c = 'M';
+				size_t run = 1;
+				while(k + run < ln) { char c2 = st.rel[k + run]; if(c2 == 'X' || c2 == '=') c2 = 'M'; if(c2 != c) break; run++; }
+				appendInt(cigar, (long long)run); cigar += c;
+				k += run;
+			}
+			if(r.trim_right > 0) { appendInt(cigar, r.trim_right); cigar += 'S'; }
+			// MD:Z (StackedAln::buildMdz + writeMdz)
+			bool mmLast = false, gapLast = false, first = true;
+			for(size_t k = 0; k < ln; k++) {
+				const char c = st.rel[k];
+				if(c == '=') {
+					size_t run = 1, nins = 0;
+					for(; k + run < ln; run++) { if(st.rel[k + run] == '=') {} else if(st.rel[k + run] == 'I') nins++; else break; }
+					k += run - 1;
+					if(run - nins > 0) { appendInt(mdz, (long long)(run - nins)); first = false; mmLast = false; gapLast = false; }
+				} else if(c == 'X') {
+					if(gapLast || mmLast || first) mdz += '0';
+					mdz += st.ref[k]; first = false; mmLast = true; gapLast = false;
+				} else if(c == 'D') {
+					if(mmLast || first) mdz += '0';
+					if(!gapLast) mdz += '^';
+					mdz += st.ref[k]; first = false; mmLast = false; gapLast = true;
+				}
+			}
+			if(mmLast || gapLast) mdz += '0';
+			for(size_t k = 0; k < ln; k++) refExtent += st.rel[k] != 'I';
+		}
+		// ---- the record
+		line.clear();
+		if(opt->read_names && opt->read_names[i]) line += opt->read_names[i];
+		else { line += 'r'; appendInt(line, (long long)(paired ? (i >> 1) : i)); }
+		line += '\t'; appendInt(line, flag); line += '\t';
+		auto refName = [&](uint64_t t) -> const char * { return (opt->ref_names && t < opt->n_refs && opt->ref_names[t]) ? opt->ref_names[t] : "*"; };
+		if(aligned) { line += refName(r.tidx); line += '\t'; appendInt(line, r.refoff + 1); line += '\t'; appendInt(line, r.mapq); line += '\t'; line += cigar; }
+		else if(paired && mateAligned) { line += refName(m->tidx); line += '\t'; appendInt(line, m->refoff + 1); line += "\t0\t*"; }   // unaligned mate takes its mate's coordinates
+		else line += "*\t0\t0\t*";
+		line += '\t';
+		// RNEXT PNEXT TLEN
+		if(paired && mateAligned) {
+			if(aligned && m->tidx == r.tidx) line += '='; else if(!aligned) line += '='; else line += refName(m->tidx);
+			line += '\t'; appendInt(line, m->refoff + 1); line += '\t';
+			long long tlen = 0;
+			if(aligned && m->tidx == r.tidx) {
+				// AlnRes::setFragmentLength (aligner_result.h:1311-1343); extents include soft-trimmed ends
+				long long st0 = r.refoff - r.trim_left, en0 = r.refoff + refExtent - 1 + r.trim_right;
+				// the mate's extent needs its own ops
+				long long mExt = 0;
+				const int mlen = (int)(reads->off[(i ^ 1ull) + 1] - reads->off[i ^ 1ull]);
+				if((m->found & 0xff) == 2) mExt = mlen;
+				else if(ops) { const uint8_t *mo = ops + (i ^ 1ull) * (uint64_t)maxOps; for(int k = 0; k < m->nops; k++) mExt += (mo[k] & 3) != BT2G_OP_REFGAP; }
+				long long st1 = m->refoff - m->trim_left, en1 = m->refoff + mExt - 1 + m->trim_right;
+				bool up;
+				const bool mfw = m->fw != 0, mate1 = (i & 1) == 0;
+				if(st0 == st1) up = (fw && mfw && mate1) || (fw && !mfw);
+				else up = st0 < st1;
+				tlen = 1 + (en0 > en1 ? en0 : en1) - (st0 < st1 ? st0 : st1);
+				if(!up) tlen = -tlen;
+			}
+			appendInt(line, tlen);
+		} else if(paired && aligned) { line += "=\t"; appendInt(line, r.refoff + 1); line += "\t0"; }       // mate unaligned: points at this mate
+		else line += "*\t0\t0";
+		line += '\t';
+		// SEQ QUAL (reverse-complemented / reversed for the reverse strand)
+		const bool rev = aligned && !fw;
+		for(int k = 0; k < len; k++) { const int c = rev ? seq[len - 1 - k] : seq[k]; line += rev ? comp[c > 4 ? 4 : c] : dna[c > 4 ? 4 : c]; }
+		line += '\t';
+		if(qual) for(int k = 0; k < len; k++) line += (char)(rev ? qual[len - 1 - k] : qual[k]); else line += '*';
+		// optional fields
+		if(aligned) {
+			line += "\tAS:i:"; appendInt(line, r.score);
+			if(r.score2 != INT32_MIN) { line += "\tXS:i:"; appendInt(line, r.score2); }
+			line += "\tXN:i:"; appendInt(line, r.pad);
+			line += "\tXM:i:"; appendInt(line, nmm);
+			line += "\tXO:i:"; appendInt(line, ngo);
+			line += "\tXG:i:"; appendInt(line, ngx);
+			line += "\tNM:i:"; appendInt(line, nedits);
+			line += "\tMD:Z:"; line += mdz;
+			// YS:i only for mates reported as a pair (summ.paired(), sam.cpp:250)
+			if(paired && mateAligned && (pr->pair_type == 1 || pr->pair_type == 2)) { line += "\tYS:i:"; appendInt(line, m->score); }
+		}
+		line += "\tYT:Z:";
+		line += !paired ? "UU" : (concordant ? "CP" : ((aligned && mateAligned && pr->pair_type == 2) ? "DP" : "UP"));
+		if(!aligned) {
+			// YF:Z: why the read was filtered out (sam.cpp:331-345; filters at bt2_search.cpp:3405-3431)
+			int ns = 0;
+			for(int k = 0; k < len; k++) ns += seq[k] > 3;
+			const double nc = (opt->nceil_const == 0.0 && opt->nceil_linear == 0.0) ? 0.0 : opt->nceil_const;
+			const double nl = (opt->nceil_const == 0.0 && opt->nceil_linear == 0.0) ? (double)0.15f : opt->nceil_linear;
+			int nceil = (int)(nc + nl * (double)len); if(nceil > len) nceil = len;
+			if(len < 2) line += "\tYF:Z:LN";
+			else if(ns > nceil) line += "\tYF:Z:NS";
+		}
+		line += '\n';
+		// a pair with only mate 2 aligned is printed aligned mate first (AlnSinkWrap::finishRead reports the
+		// unpaired alignment of mate 2, then the unaligned mate 1, aln_sink.cpp:930-1010)
+		if(paired && (i & 1) == 0 && !aligned && mateAligned) { held = line; continue; }
+		o += line;
+		if(!held.empty()) { o += held; held.clear(); }
+	}
+	return 0;
+}
+
+extern "C" int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads, const bt2g_read_result *res, const uint8_t *ops,
+                               uint32_t maxOps, const bt2g_pair_result *pairs, char *out, uint64_t cap, uint64_t *written) {
+	if(!opt || !reads || !res || !written) return -1;
+	const uint64_t n = reads->n_reads;
+	const bool paired = pairs != nullptr;
+	if(paired && (n & 1)) return -1;
+	// records are independent (pairs stay together): format contiguous ranges on opt->threads host threads
+	int T = opt->threads > 0 ? opt->threads : 1;
+	const uint64_t units = paired ? n / 2 : n;
+	if((uint64_t)T > units) T = units ? (int)units : 1;
+	std::vector<std::string> parts((size_t)T);
+	std::vector<int> rcs((size_t)T, 0);
+	auto work = [&](int t) {
+		const uint64_t u0 = units * (uint64_t)t / T, u1 = units * (uint64_t)(t + 1) / T;
+		rcs[t] = formatRange(opt, reads, res, ops, maxOps, pairs, paired ? 2 * u0 : u0, paired ? 2 * u1 : u1, parts[t]);
+	};
+	if(T == 1) work(0);
+	else {
+		std::vector<std::thread> th;
+		for(int t = 0; t < T; t++) th.emplace_back(work, t);
+		for(auto &x : th) x.join();
+	}
+	uint64_t total = 0;
+	for(int t = 0; t < T; t++) { if(rcs[t]) return rcs[t]; total += parts[t].size(); }
+	*written = total;
+	if(!out || total > cap) return -3;                             // buffer too small: *written holds the size needed
+	uint64_t at = 0;
+	for(int t = 0; t < T; t++) { memcpy(out + at, parts[t].data(), parts[t].size()); at += parts[t].size(); }
+	return 0;
+}

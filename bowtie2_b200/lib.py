@@ -253,7 +253,7 @@ class _Scoring(C.Structure):
     _fields_ = [("match_bonus", C.c_int32), ("rdgap_const", C.c_int32), ("rdgap_linear", C.c_int32),
                 ("rfgap_const", C.c_int32), ("rfgap_linear", C.c_int32), ("gapbar", C.c_int32),
                 ("local", C.c_int32), ("mmpen", C.c_uint8 * 64), ("npen", C.c_uint8 * 64),
-                ("nceil_const", C.c_double), ("nceil_linear", C.c_double)]
+                ("threads", C.c_int32), ("reserved", C.c_int32), ("nceil_const", C.c_double), ("nceil_linear", C.c_double)]
 
 
 DP_PROBLEM = np.dtype([("read_idx", "<u4"), ("fw", "<u4"), ("tidx", "<u8"), ("refl", "<i8"), ("refr", "<i8"),
@@ -652,3 +652,35 @@ def _build_dense_sa(self, rate: int):
 
 
 Bt2Gpu.build_dense_sa = _build_dense_sa
+
+
+# ---- SAM records (include/bt2g.h: bt2g_sam_format; host code) ----------------------------------------
+EXPORTS += ["bt2g_sam_format"]
+
+
+class _SamOpts(C.Structure):
+    _fields_ = [("ref_names", C.POINTER(C.c_char_p)), ("n_refs", C.c_uint64), ("read_names", C.POINTER(C.c_char_p)),
+                ("threads", C.c_int32), ("reserved", C.c_int32), ("nceil_const", C.c_double), ("nceil_linear", C.c_double)]
+
+
+def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_names=None, pairs=None, threads: int = 1) -> str:
+    """SAM text for pipeline results (one record per read).  `lib` is the loaded libbt2g (load_library())."""
+    lib.bt2g_sam_format.argtypes = [C.POINTER(_SamOpts), C.POINTER(_Reads), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                    C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    rn = (C.c_char_p * len(ref_names))(*[x.encode() for x in ref_names])
+    qn = (C.c_char_p * reads.n)(*[x.encode() for x in read_names]) if read_names is not None else None
+    opt = _SamOpts(rn, len(ref_names), qn, int(threads), 0, 0.0, 0.0)
+    res = np.ascontiguousarray(res, dtype=READ_RESULT)
+    max_ops = 0 if ops is None else ops.shape[1]
+    if ops is not None:
+        ops = np.ascontiguousarray(ops, dtype=np.uint8)
+    if pairs is not None:
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_RESULT)
+    st = reads._struct()
+    need = C.c_uint64(0)
+    lib.bt2g_sam_format(C.byref(opt), C.byref(st), _ptr(res), _ptr(ops), max_ops, _ptr(pairs), None, 0, C.byref(need))
+    buf = C.create_string_buffer(int(need.value) + 1)
+    rc = lib.bt2g_sam_format(C.byref(opt), C.byref(st), _ptr(res), _ptr(ops), max_ops, _ptr(pairs), buf, need.value, C.byref(need))
+    if rc:
+        raise RuntimeError(f"bt2g_sam_format failed ({rc})")
+    return buf.raw[:need.value].decode()

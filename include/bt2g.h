@@ -371,7 +371,7 @@ typedef struct {
 	int32_t  mapq;               /* BowtieMapq2::mapq (unique.h:170-392) from score / score2 and the read's minimum and
 	                              * perfect scores; for a concordant pair from the pair's score sums (no second-best pair
 	                              * is tracked: the "no second best" branch) */
-	int32_t  pad;
+	int32_t  pad;                /* reference Ns spanned by the alignment (AlnRes::refNs, the XN:i field) */
 } bt2g_read_result;
 
 typedef struct bt2g_pipeline bt2g_pipeline;
@@ -418,6 +418,25 @@ int  bt2g_pipeline_pair_stage_ms(bt2g_pipeline *p, float *out3);
 
 /* device milliseconds of the 8 stages of the last run (CUDA events on the launching stream) */
 int  bt2g_pipeline_stage_ms(bt2g_pipeline *p, float *out8);
+
+/* ---------------------------------------------------------------------- SAM records ----- */
+/* The reporting tail for the pipeline's one-alignment-per-read results (host code, no GPU work):
+ * AlnSinkSam::appendMate (aln_sink.cpp:1889-2060), StackedAln with leftAlign(false) -> CIGAR / MD:Z
+ * (aligner_result.cpp:520-880), optional fields in the order of SamConfig::printAlignedOptFlags
+ * (sam.cpp:121-330): AS XS XN XM XO XG NM MD YS YT.  `ops` / `max_ops` as returned by
+ * bt2g_pipeline_run_*_host; `pairs` NULL for unpaired reads.  Returns 0, or -3 with *written = bytes
+ * needed when `cap` is too small. */
+typedef struct {
+	const char *const *ref_names;   /* [n_refs] reference names as they should appear in RNAME */
+	uint64_t           n_refs;
+	const char *const *read_names;  /* [n_reads] or NULL: "r<index>" (pair index for paired input) */
+	int32_t            threads;     /* host threads formatting disjoint ranges of records (0 or 1 = the calling thread) */
+	int32_t            reserved;
+	double             nceil_const, nceil_linear;   /* --n-ceil (0, 0.15): unaligned reads with more Ns carry YF:Z:NS
+	                                                * (bt2_search.cpp:3427-3431, sam.cpp:331-345); both 0 = defaults */
+} bt2g_sam_opts;
+int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads, const bt2g_read_result *res, const uint8_t *ops,
+                    uint32_t max_ops, const bt2g_pair_result *pairs, char *out, uint64_t cap, uint64_t *written);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,167 @@
+"""bt2g_sam_format (host code): SAM records rebuilt from alignments and compared, whole line, with the committed
+output of the reference program (tests/golden/lambda_U_sensitive.sam: bowtie2 --sensitive -U lambda_reads_1.fq).
+
+The alignment fed to the formatter is the oracle DP's (C restatement of SwAligner) for the window around the
+reference's reported position, converted from the reference's Edit representation to the device op string;
+MAPQ and XS:i depend on the sequential search policy and are taken from the golden record."""
+import os
+
+import numpy as np
+import pytest
+
+from bowtie2_b200 import policy
+from bowtie2_b200.lib import (OP_MATCH, OP_MM, OP_READGAP, OP_REFGAP, READ_RESULT, ReadBatch, load_library, sam_format)
+from conftest import GOLDEN, read_fastq_codes
+from oracle_lib import Oracle, oracle_dp
+
+
+
+def _edits_to_ops(edits, read, fw):
+    """Inverse of lib.ops_to_edits for an untrimmed end-to-end alignment: reference Edit list -> op string
+    (last read row first), every op that consumes a reference base carrying its code."""
+    code = {ord(c): i for i, c in enumerate("ACGTN")}
+    rdlen = len(read)
+    seq = read if fw else np.array([4 if c > 3 else 3 - c for c in read[::-1]], dtype=np.uint8)
+    ed = [list(e) for e in edits]
+    gap = ord("-")
+    if not fw:
+        ed = ed[::-1]
+        for e in ed:
+            e[0] = rdlen - e[0] - (0 if e[2] == gap else 1)          # read gap: qchr == '-'
+    fwd = []
+    k = 0
+    for row in range(rdlen):
+        while k < len(ed) and ed[k][0] == row and ed[k][2] == gap:     # read gaps before this row
+            fwd.append(OP_READGAP | (code[ed[k][1]] << 2)); k += 1
+        if k < len(ed) and ed[k][0] == row:
+            if ed[k][1] == gap:
+                fwd.append(OP_REFGAP)
+            else:
+                fwd.append(OP_MM | (code[ed[k][1]] << 2))
+            k += 1
+        else:
+            fwd.append(OP_MATCH | (int(seq[row]) << 2))
+    assert k == len(ed)
+    return fwd[::-1]
+
+
+def test_sam_records_match_reference_program(lambda_index):
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "lambda_U_sensitive.sam")) if not l.startswith("@")]
+    n = 300
+    names, reads, quals = read_fastq_codes(os.path.join(GOLDEN, "lambda_reads_1.fq"), n)
+    O = Oracle(lambda_index)
+    sc = policy.Scoring.default(False)
+    tlen = 48502
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    maxops = max(len(r) for r in reads) + 64
+    ops = np.zeros((n, maxops), dtype=np.uint8)
+    use = []
+    for i in range(n):
+        f = golden[i].split("\t")
+        flag = int(f[1])
+        if flag & 4:
+            use.append(i)
+            continue
+        tags = {t[:2]: t[5:] for t in f[11:]}
+        pos, fw, AS = int(f[3]) - 1, not (flag & 16), int(tags["AS"])
+        r = reads[i]
+        rdlen = len(r)
+        minsc = sc.min_score(rdlen)
+        found, rect = policy.frame_seed_extension_rect(pos, rdlen, tlen, sc.max_read_gaps(minsc, rdlen), sc.max_ref_gaps(minsc, rdlen),
+                                                       sc.n_ceil(rdlen))
+        d = oracle_dp(O, False, r, quals[i], fw, 0, rect, minsc, sc.n_ceil_raw(rdlen), max_alns=8)
+        al = [a for a in d["alns"] if a["refoff"] == pos and a["score"] == AS]
+        if not al:
+            continue                                       # the reference reported an alignment from another window
+        a = al[0]
+        o = _edits_to_ops(a["edits"], r, fw)
+        res[i]["found"] = 2 if (not a["edits"]) else 1
+        res[i]["score"] = AS
+        res[i]["score2"] = int(tags["XS"]) if "XS" in tags else -(1 << 31)
+        res[i]["fw"] = int(fw); res[i]["tidx"] = 0; res[i]["refoff"] = pos; res[i]["nops"] = len(o)
+        res[i]["mapq"] = int(f[4]); res[i]["pad"] = int(tags["XN"])
+        ops[i, :len(o)] = o
+        use.append(i)
+    assert len(use) > 0.9 * n
+    lib = load_library()
+    text = sam_format(lib, ReadBatch.from_list(reads, quals), res, ops, ["gi|9626243|ref|NC_001416.1|"], read_names=names)
+    lines = text.rstrip("\n").split("\n")
+    assert len(lines) == n
+    ngap = 0
+    for i in use:
+        assert lines[i] == golden[i], (i, lines[i], golden[i])
+        ngap += ("I" in golden[i].split("\t")[5]) or ("D" in golden[i].split("\t")[5])
+    assert ngap > 3
+
+
+def test_sam_paired_records_match_reference_program(lambda_index):
+    """Paired records (flags, RNEXT/PNEXT/TLEN, YS, YT, mate of an unaligned read) against the golden output for the
+    first 200 pairs; alignments of each mate rebuilt through the oracle DP as above."""
+    from bowtie2_b200.lib import PAIR_RESULT
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "lambda_P_sensitive.sam")) if not l.startswith("@")]
+    npairs = len(golden) // 2
+    n1, r1, q1 = read_fastq_codes(os.path.join(GOLDEN, "lambda_reads_1.fq"), npairs)
+    n2, r2, q2 = read_fastq_codes(os.path.join(GOLDEN, "lambda_reads_2.fq"), npairs)
+    O = Oracle(lambda_index)
+    sc = policy.Scoring.default(False)
+    tlen = 48502
+    n = 2 * npairs
+    reads = [x for p in zip(r1, r2) for x in p]
+    quals = [x for p in zip(q1, q2) for x in p]
+    names = [x for p in zip(n1, n2) for x in p]
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    maxops = max(len(r) for r in reads) + 64
+    ops = np.zeros((n, maxops), dtype=np.uint8)
+    pairs = np.zeros(npairs, dtype=PAIR_RESULT)
+    # golden lines by (pair, mate): the reference prints the aligned mate first when only mate 2 aligned
+    by = {}
+    for l in golden:
+        f = l.split("\t")
+        by[(f[0], 1 if int(f[1]) & 128 else 0)] = l
+    ok_pair = []
+    for pi in range(npairs):
+        good = True
+        for mate in range(2):
+            i = 2 * pi + mate
+            f = by[(names[i], mate)].split("\t")
+            flag = int(f[1])
+            if flag & 4:
+                continue
+            tags = {t[:2]: t[5:] for t in f[11:]}
+            pos, fw, AS = int(f[3]) - 1, not (flag & 16), int(tags["AS"])
+            r = reads[i]
+            rdlen = len(r)
+            minsc = sc.min_score(rdlen)
+            found, rect = policy.frame_seed_extension_rect(pos, rdlen, tlen, sc.max_read_gaps(minsc, rdlen), sc.max_ref_gaps(minsc, rdlen),
+                                                           sc.n_ceil(rdlen))
+            d = oracle_dp(O, False, r, quals[i], fw, 0, rect, minsc, sc.n_ceil_raw(rdlen), max_alns=8)
+            al = [a for a in d["alns"] if a["refoff"] == pos and a["score"] == AS]
+            if not al:
+                good = False
+                continue
+            o = _edits_to_ops(al[0]["edits"], r, fw)
+            res[i]["found"] = 2 if not al[0]["edits"] else 1
+            res[i]["score"] = AS
+            res[i]["score2"] = int(tags["XS"]) if "XS" in tags else -(1 << 31)
+            res[i]["fw"] = int(fw); res[i]["refoff"] = pos; res[i]["nops"] = len(o)
+            res[i]["mapq"] = int(f[4]); res[i]["pad"] = int(tags["XN"])
+            ops[i, :len(o)] = o
+        yt = by[(names[2 * pi], 0)].split("YT:Z:")[1][:2]
+        a1, a2 = res[2 * pi]["found"] != 0, res[2 * pi + 1]["found"] != 0
+        pairs[pi]["pair_type"] = 1 if yt == "CP" else (2 if yt == "DP" else (3 if (a1 or a2) else 0))
+        if good:
+            ok_pair.append(pi)
+    assert len(ok_pair) > 0.9 * npairs
+    lib = load_library()
+    text = sam_format(lib, ReadBatch.from_list(reads, quals), res, ops, ["gi|9626243|ref|NC_001416.1|"], read_names=names, pairs=pairs)
+    assert text == sam_format(lib, ReadBatch.from_list(reads, quals), res, ops, ["gi|9626243|ref|NC_001416.1|"], read_names=names, pairs=pairs, threads=5)
+    lines = text.rstrip("\n").split("\n")
+    assert len(lines) == n
+    kinds = set()
+    for pi in ok_pair:
+        for k in (2 * pi, 2 * pi + 1):
+            assert lines[k] == golden[k], (pi, lines[k], golden[k])
+            kinds.add(int(golden[k].split("\t")[1]))
+    assert {99, 147, 83, 163}.issubset(kinds) and (69 in kinds or 137 in kinds)
