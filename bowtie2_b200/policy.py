@@ -367,3 +367,95 @@ def mapq_v2(best: int, secbest, sc_min: int, sc_perfect: int, monotone: bool) ->
     if bestdiff > 0:
         return 11 if best_over >= diff * f(0.5) else 2
     return 1 if best_over >= diff * f(0.5) else 0
+
+
+# ---- per-read pseudo-randomness (random_source.h:32-180, pat.cpp:45-82) ----------------------------
+class RandomSource:
+    """The reference's linear congruential generator (a = 1664525, c = 1013904223), including the bit-slicing
+    helpers nextU2 / nextBool that re-use bits of the last state."""
+    A, Cc = 1664525, 1013904223
+
+    def __init__(self, seed: int = 0):
+        self.init(seed)
+
+    def init(self, seed: int = 0):
+        self.last = seed & 0xffffffff
+        self.last_off = 30
+
+    def next_u32(self) -> int:
+        self.last = (self.A * self.last + self.Cc) & 0xffffffff
+        ret = self.last >> 16
+        self.last = (self.A * self.last + self.Cc) & 0xffffffff
+        ret ^= self.last
+        self.last_off = 0
+        return ret
+
+    def next_u2(self) -> int:
+        if self.last_off > 30:
+            self.next_u32()
+        ret = (self.last >> self.last_off) & 3
+        self.last_off += 2
+        return ret
+
+    def next_bool(self) -> int:
+        if self.last_off > 31:
+            self.next_u32()
+        ret = (self.last >> self.last_off) & 1
+        self.last_off += 1
+        return ret
+
+    def next_float_bits(self) -> int:
+        import struct
+        import numpy as _np
+        f = _np.float32(self.next_u32()) / _np.float32(0xffffffff)
+        return struct.unpack("I", struct.pack("f", float(f)))[0]
+
+
+def gen_rand_seed(codes, quals, name: str, seed: int = 0) -> int:
+    """genRandSeed (pat.cpp:45-82): the per-read RNG seed from the read's bases, qualities (ASCII) and name."""
+    rseed = ((seed + 101) * 59 * 61 * 67 * 71 * 73 * 79 * 83) & 0xffffffff
+    for i, p in enumerate(codes):
+        rseed ^= (int(p) << ((i & 15) << 1)) & 0xffffffff
+    for i, p in enumerate(quals):
+        rseed ^= (int(p) << ((i & 3) << 3)) & 0xffffffff
+    for i, ch in enumerate(name.encode()):
+        if ch == ord("/"):
+            break
+        rseed ^= (ch << ((i & 3) << 3)) & 0xffffffff
+    return rseed & 0xffffffff
+
+
+def rank_seed_hits(nelt_fw, nelt_rc, rnd: RandomSource, all_hits: bool = False):
+    """SeedResults::rankSeedHits (aligner_seed.h:1019-1080): order in which (offset index, fw) seed hits are
+    extended -- ascending by number of BW elements, the scan start and the strand order drawn from the read's RNG.
+    nelt_*[i] = elements of the hit at offset index i (0 = none)."""
+    num = len(nelt_fw)
+    out = []
+    if all_hits:
+        for i in range(1, num):
+            for fw in (True, False):
+                if (nelt_fw if fw else nelt_rc)[i] > 0:
+                    out.append((i, fw))
+        if num and nelt_fw[0] > 0:
+            out.append((0, True))
+        if num and nelt_rc[0] > 0:
+            out.append((0, False))
+        return out
+    nonz = sum(1 for x in nelt_fw if x > 0) + sum(1 for x in nelt_rc if x > 0)
+    sorted_fw, sorted_rc = [False] * num, [False] * num
+    while len(out) < nonz:
+        minsz, minidx, minfw = 0xffffffff, 0, True
+        rb = rnd.next_bool()
+        for fwi in (0, 1):
+            fw = fwi == (1 if rb else 0)
+            rrs, srt = (nelt_fw, sorted_fw) if fw else (nelt_rc, sorted_rc)
+            i = rnd.next_u32() % num
+            for _ in range(num):
+                if rrs[i] > 0 and not srt[i] and rrs[i] < minsz:
+                    minsz, minidx, minfw = rrs[i], i, fw
+                i += 1
+                if i == num:
+                    i = 0
+        (sorted_fw if minfw else sorted_rc)[minidx] = True
+        out.append((minidx, minfw))
+    return out

@@ -28,6 +28,8 @@
 #define protected public
 #include "aligner_sw.h"
 #include "pe.h"
+#include "aligner_seed.h"
+#include "random_source.h"
 #include "unique.h"
 #undef private
 #undef protected
@@ -61,6 +63,40 @@ int ref_frame_seed_rect(int64_t off, uint64_t rdlen, int64_t reflen, uint64_t ma
 	out9[4] = (int64_t)r.triml; out9[5] = (int64_t)r.trimr; out9[6] = (int64_t)r.corel; out9[7] = (int64_t)r.corer;
 	out9[8] = (int64_t)r.maxgap;
 	return found ? 1 : 0;
+}
+
+// RandomSource (random_source.h:32-180): n draws after init(seed).  kind 0 nextU32, 1 nextU2, 2 nextBool,
+// 3 nextU32 % mod (mod in arg), 4 nextFloat bits
+void ref_rng_draws(uint32_t seed, const int32_t* kinds, const uint32_t* args, int n, uint32_t* out) {
+	RandomSource r; r.init(seed);
+	for(int i = 0; i < n; i++) {
+		switch(kinds[i]) {
+			case 0: out[i] = r.nextU32(); break;
+			case 1: out[i] = r.nextU2(); break;
+			case 2: out[i] = r.nextBool() ? 1u : 0u; break;
+			case 3: out[i] = r.nextU32() % args[i]; break;
+			default: { float f = r.nextFloat(); uint32_t u; memcpy(&u, &f, 4); out[i] = u; }
+		}
+	}
+}
+
+// SeedResults::rankSeedHits (aligner_seed.h:1019-1080) for given element counts per (strand, offset index);
+// 0 = no hit.  out_off / out_fw receive the ranking.  Returns its length.
+int ref_rank_seed_hits(uint32_t rndseed, int num_offs, const uint32_t* nelt_fw, const uint32_t* nelt_rc, int all,
+                       uint32_t* out_off, int* out_fw) {
+	SeedResults sr;
+	Read rd; rd.init("r", "ACGT", "IIII");
+	EList<uint32_t> off2; for(int i = 0; i < num_offs; i++) off2.push_back((uint32_t)i);
+	sr.reset(rd, off2, (size_t)num_offs);
+	for(int i = 0; i < num_offs; i++) {
+		if(nelt_fw[i]) { sr.hitsFw_[i].init(0, 1, nelt_fw[i]); sr.nonzTot_++; }
+		if(nelt_rc[i]) { sr.hitsRc_[i].init(0, 1, nelt_rc[i]); sr.nonzTot_++; }
+	}
+	RandomSource rnd; rnd.init(rndseed);
+	sr.rankSeedHits(rnd, all != 0);
+	int n = (int)sr.rankOffs_.size();
+	for(int i = 0; i < n; i++) { out_off[i] = sr.rankOffs_[i]; out_fw[i] = sr.rankFws_[i] ? 1 : 0; }
+	return n;
 }
 
 // BowtieMapq2::mapq (unique.h:170-392), the default MAPQ model.  Unpaired: best / secbest are the read's best and

@@ -138,3 +138,53 @@ def test_mapq_v2_matches_reference(lambda_index, local):
         assert got == want, (k, rdlen, ordlen, best, has_sec, sec, got, want)
         seen.add(want)
     assert len(seen) > 25
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_random_source_and_rank_seed_hits_match_reference(lambda_index):
+    R = Reference(lambda_index, mirror=False, ref=False)
+    L = R.lib
+    u32p, i32p = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    L.ref_rng_draws.argtypes = [C.c_uint32, i32p, u32p, C.c_int, u32p]
+    L.ref_rng_draws.restype = None
+    L.ref_rank_seed_hits.argtypes = [C.c_uint32, C.c_int, u32p, u32p, C.c_int, u32p, i32p]
+    rng = np.random.default_rng(41)
+    for trial in range(40):
+        seed = int(rng.integers(0, 1 << 32))
+        n = 400
+        kinds = rng.integers(0, 5, n).astype(np.int32)
+        args = rng.integers(1, 1000, n).astype(np.uint32)
+        out = np.zeros(n, dtype=np.uint32)
+        L.ref_rng_draws(seed, kinds.ctypes.data_as(i32p), args.ctypes.data_as(u32p), n, out.ctypes.data_as(u32p))
+        r = policy.RandomSource(seed)
+        got = []
+        for k, a in zip(kinds, args):
+            got.append([r.next_u32, r.next_u2, r.next_bool, lambda: r.next_u32() % int(a), r.next_float_bits][int(k)]())
+        assert got == [int(x) for x in out], trial
+    for trial in range(300):
+        num = int(rng.integers(1, 34))
+        fw = (rng.integers(0, 6, num) * (rng.random(num) < 0.6)).astype(np.uint32)
+        rc = (rng.integers(0, 400, num) * (rng.random(num) < 0.5)).astype(np.uint32)
+        seed = int(rng.integers(0, 1 << 32))
+        for all_hits in (False, True):
+            oo, of = np.zeros(2 * num, np.uint32), np.zeros(2 * num, np.int32)
+            n = L.ref_rank_seed_hits(seed, num, fw.ctypes.data_as(u32p), rc.ctypes.data_as(u32p), int(all_hits),
+                                     oo.ctypes.data_as(u32p), of.ctypes.data_as(i32p))
+            want = [(int(oo[i]), bool(of[i])) for i in range(n)]
+            got = policy.rank_seed_hits([int(x) for x in fw], [int(x) for x in rc], policy.RandomSource(seed), all_hits)
+            assert got == want, (trial, all_hits)
+
+
+def test_gen_rand_seed_known_values():
+    # genRandSeed is a static function of pat.cpp; pinned here through values computed by a direct transcription of
+    # its three XOR loops (sequence 2 bits at (i & 15) * 2, quality / name bytes at (i & 3) * 8), seed 0
+    s = policy.gen_rand_seed([0, 1, 2, 3, 4], [ord(c) for c in "IIIII"], "r1/1", 0)
+    base = ((0 + 101) * 59 * 61 * 67 * 71 * 73 * 79 * 83) & 0xffffffff
+    x = base
+    for i, p in enumerate([0, 1, 2, 3, 4]):
+        x ^= p << ((i & 15) << 1)
+    for i in range(5):
+        x ^= ord("I") << ((i & 3) << 3)
+    for i, ch in enumerate(b"r1"):
+        x ^= ch << ((i & 3) << 3)
+    assert s == x & 0xffffffff
