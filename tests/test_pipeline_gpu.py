@@ -200,17 +200,22 @@ def _run_reference_paired(index, f1, f2, preset="--sensitive"):
 
 
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
-def test_paired_pipeline_vs_reference_program(gpu, synth_index, synth_genome, tmp_path):
+@pytest.mark.parametrize("rdlen,preset,tables", [(100, "sensitive", False), (150, "very-sensitive", True)])
+def test_paired_pipeline_vs_reference_program(gpu, synth_index, synth_genome, tmp_path, rdlen, preset, tables):
     """FR pairs, -I 0 -X 500: concordant pairs of the reference are found with the same placement,
-    including pairs where one mate has no exact seed and only the mate-finding DP can place it."""
+    including pairs where one mate has no exact seed and only the mate-finding DP can place it.
+    The second case is the headline configuration (2x150, --very-sensitive) with the seed table and the dense SA on."""
     gpu.load_index_files(synth_index)
-    rdlen, npairs = 100, 1500
-    reads, quals, truth = synth.make_pairs(synth_genome, npairs, rdlen, seed=4242, sub_rate=0.01, indel_rate=0.001,
-                                           hard_frac=0.25, hard_period=12)
+    if tables:
+        gpu.build_seed_table(12)
+        gpu.build_dense_sa(0)
+    npairs = 1500
+    reads, quals, truth = synth.make_pairs(synth_genome, npairs, rdlen, seed=4242 + rdlen, sub_rate=0.01, indel_rate=0.001,
+                                           hard_frac=0.25, hard_period=12 if rdlen == 100 else 14)
     f1, f2 = _write_pair_fastq(tmp_path, reads, quals)
-    want = _run_reference_paired(synth_index, f1, f2)
+    want = _run_reference_paired(synth_index, f1, f2, preset="--" + preset)
     assert len(want) == 2 * npairs
-    pipe = Pipeline(gpu, "sensitive", max_len=rdlen, max_reads=4096, row_cap=16, range_max=16, both_mates=True)
+    pipe = Pipeline(gpu, preset, max_len=rdlen, max_reads=4096, row_cap=16, range_max=16, both_mates=True)
     pipe.enable_pairs()
     res, ops, pairs = pipe.run_paired_host(ReadBatch.from_list(reads, quals))
     n_cp = n_cp_same = n_rescued = n_rescued_same = n_cigar = 0
@@ -246,3 +251,6 @@ def test_paired_pipeline_vs_reference_program(gpu, synth_index, synth_genome, tm
         del os.environ["BT2G_HOST_CHUNK_MIN"]
     assert np.array_equal(res, res3) and np.array_equal(pairs, pairs3)
     pipe.close()
+    if tables:
+        gpu.build_seed_table(0)
+        gpu.build_dense_sa(-1)

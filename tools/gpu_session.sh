@@ -31,6 +31,13 @@ smoke)
   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -3 $OUT/${TAG}_smoke.log ;;
 benchref)
   timeout 1200 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "benchref exit $?"; tail -c 1200 $OUT/${TAG}_bench_ref.json; tail -8 $OUT/${TAG}_bench_ref.err ;;
+ncufinal)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+     python bench.py --steps 2 --warmup 1 --reads 2000000 --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1; echo "ncu launches exit $?"
+  for k in k_seed_search3 k_exact_sweep2; do
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:^$k -s 1 -c 1 -f -o $OUT/${TAG}_$k \
+       python bench.py --steps 2 --warmup 1 --reads 2000000 --no-cpu-baseline > $OUT/${TAG}_ncu_$k.log 2>&1; echo "ncu $k exit $?"
+  done ;;
 bench2)
   BT2G_DP_PACKED=2 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench2.json 2> $OUT/${TAG}_bench2.err; echo "bench2 exit $?"; tail -c 700 $OUT/${TAG}_bench2.json ;;
 bench0)
