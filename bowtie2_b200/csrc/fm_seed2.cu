@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const ui
 	bool active = false, exhausted = false, doInit = true;
 	uint64_t top = 0, bot = 0, wb = 0, task = 0;
 	int len = 0, dep = 0, nedit = 0, strand = 0;
+	int cacheW = -1; uint64_t cacheP = 0; uint32_t cacheM = 0;
 	unsigned nside = 0;
 	for(;;) {
 		const unsigned need = __ballot_sync(FULL, !active && !exhausted);
@@ -471,6 +472,7 @@ __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const ui
 			if(lane == leader) base = atomicAdd(next, (unsigned long long)__popc(need));
 			base = __shfl_sync(FULL, base, leader);
 			if(!active && !exhausted) {
+				cacheW = -1;
 				task = base + (unsigned)__popc(need & ((1u << lane) - 1u));
 				if(task >= total) exhausted = true;
 				else {
@@ -496,9 +498,17 @@ __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const ui
 		if(active) {
 			bool done = false;
 			// character of the strand-oriented read at position p: fw -> read[p]; rc -> comp(read[len-1-p])
+			// the packed word holding the character is kept in registers: the sweep walks the read monotonically, so it
+			// changes once every 32 characters
+			auto rawchr = [&](int pos) -> int {
+				const int w = pos >> 5, b = pos & 31;
+				if(w != cacheW) { cacheW = w; cacheP = packed[wb + w]; cacheM = nmask[wb + w]; }
+				if((cacheM >> b) & 1u) return 4;
+				return (int)((cacheP >> (2 * b)) & 3);
+			};
 			auto chr = [&](int p) -> int {
-				if(strand == 0) return packed_char(packed, nmask, wb, p);
-				const int c = packed_char(packed, nmask, wb, len - 1 - p);
+				if(strand == 0) return rawchr(p);
+				const int c = rawchr(len - 1 - p);
 				return c > 3 ? 4 : 3 - c;
 			};
 			bool stepNow = true;

@@ -400,8 +400,9 @@ class Pipeline:
                       tab(lambda x: sc.max_read_gaps(sc.min_score(x), x)), tab(lambda x: sc.max_ref_gaps(sc.min_score(x), x))]
         self.max_ops = max_len + 64
         self.seed_len = pre.seed_len
-        min_ival = int(self._tabs[3][1:].min()) if max_len >= 1 else 1
-        self.max_seeds = max(1, policy.n_seeds(max_len, pre.seed_len, max(min_ival, 1)))
+        # seeds per strand the buffers must hold: the largest count any read length up to max_len produces with ITS
+        # OWN interval (the smallest interval belongs to the shortest reads, which have the fewest positions)
+        self.max_seeds = max(1, max(policy.n_seeds(l, pre.seed_len, max(int(self._tabs[3][l]), 1)) for l in range(1, L1)))
         prm = _PipeParams(pre.seed_len, self.max_seeds, row_cap, range_max, max_len, 15, max_cands, max_alns, self.max_ops, max_probs,
                           *[_ptr(t) for t in self._tabs])
         h = vp()
