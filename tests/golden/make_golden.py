@@ -10,6 +10,7 @@ Outputs (all small, committed):
                                  joinedToTextOff answers of the reference for seeded queries,
                                  plus exactSweep and searchAllSeeds results for the first 300 reads
     lambda_U_sensitive.sam       bowtie2-align-s --sensitive -U lambda_reads_1.fq --seed 0 (config 1)
+    lambda_U_local.sam           --local --sensitive-local for the first 300 reads
     lambda_P_sensitive.sam       the same for the first 200 pairs of lambda_reads_{1,2}.fq (-1/-2)
 The index itself is rebuilt at test time with oracle/_ref/bowtie2-build-s (default parameters);
 the generating command is recorded in the npz.
@@ -103,6 +104,12 @@ def main():
     subprocess.check_call([ref_bin("bowtie2-align-s"), "--sensitive", "--seed", "0", "-p", "1", "-x", base,
                            "-U", os.path.join(HERE, "lambda_reads_1.fq"), "-S", sam], stderr=subprocess.DEVNULL)
     # drop the @PG line (contains paths)
+    lines = [l for l in open(sam) if not l.startswith("@PG")]
+    open(sam, "w").writelines(lines)
+    # local mode: the first 300 reads
+    sam = os.path.join(HERE, "lambda_U_local.sam")
+    subprocess.check_call([ref_bin("bowtie2-align-s"), "--local", "--sensitive-local", "--seed", "0", "-p", "1", "-x", base, "-u", "300",
+                           "-U", os.path.join(HERE, "lambda_reads_1.fq"), "-S", sam], stderr=subprocess.DEVNULL)
     lines = [l for l in open(sam) if not l.startswith("@PG")]
     open(sam, "w").writelines(lines)
     # paired: the first 200 pairs (config 3 flags: FR, -I 0 -X 500)

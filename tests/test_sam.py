@@ -16,31 +16,34 @@ from oracle_lib import Oracle, oracle_dp
 
 
 
-def _edits_to_ops(edits, read, fw):
-    """Inverse of lib.ops_to_edits for an untrimmed end-to-end alignment: reference Edit list -> op string
-    (last read row first), every op that consumes a reference base carrying its code."""
+def _edits_to_ops(edits, read, fw, trim5=0, trim3=0):
+    """Inverse of lib.ops_to_edits: reference Edit list (positions relative to the soft-trimmed extent, from the 5'
+    end of the read) -> op string (last aligned read row first), every op that consumes a reference base carrying
+    its code."""
     code = {ord(c): i for i, c in enumerate("ACGTN")}
     rdlen = len(read)
     seq = read if fw else np.array([4 if c > 3 else 3 - c for c in read[::-1]], dtype=np.uint8)
+    row0 = trim5 if fw else trim3                      # rows soft-trimmed on the left, in reference orientation
+    ext = rdlen - trim5 - trim3
     ed = [list(e) for e in edits]
     gap = ord("-")
     if not fw:
         ed = ed[::-1]
         for e in ed:
-            e[0] = rdlen - e[0] - (0 if e[2] == gap else 1)          # read gap: qchr == '-'
+            e[0] = ext - e[0] - (0 if e[2] == gap else 1)            # read gap: qchr == '-'
     fwd = []
     k = 0
-    for row in range(rdlen):
-        while k < len(ed) and ed[k][0] == row and ed[k][2] == gap:     # read gaps before this row
+    for rel in range(ext):
+        while k < len(ed) and ed[k][0] == rel and ed[k][2] == gap:     # read gaps before this row
             fwd.append(OP_READGAP | (code[ed[k][1]] << 2)); k += 1
-        if k < len(ed) and ed[k][0] == row:
+        if k < len(ed) and ed[k][0] == rel:
             if ed[k][1] == gap:
                 fwd.append(OP_REFGAP)
             else:
                 fwd.append(OP_MM | (code[ed[k][1]] << 2))
             k += 1
         else:
-            fwd.append(OP_MATCH | (int(seq[row]) << 2))
+            fwd.append(OP_MATCH | (int(seq[row0 + rel]) << 2))
     assert k == len(ed)
     return fwd[::-1]
 
@@ -165,3 +168,53 @@ def test_sam_paired_records_match_reference_program(lambda_index):
             assert lines[k] == golden[k], (pi, lines[k], golden[k])
             kinds.add(int(golden[k].split("\t")[1]))
     assert {99, 147, 83, 163}.issubset(kinds) and (69 in kinds or 137 in kinds)
+
+
+def test_sam_local_records_match_reference_program(lambda_index):
+    """--local --sensitive-local: soft-clipped records (S in CIGAR, POS at the first aligned base)."""
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "lambda_U_local.sam")) if not l.startswith("@")]
+    n = len(golden)
+    names, reads, quals = read_fastq_codes(os.path.join(GOLDEN, "lambda_reads_1.fq"), n)
+    O = Oracle(lambda_index)
+    sc = policy.Scoring.default(True)
+    tlen = 48502
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    maxops = max(len(r) for r in reads) + 64
+    ops = np.zeros((n, maxops), dtype=np.uint8)
+    use, nclip = [], 0
+    for i in range(n):
+        f = golden[i].split("\t")
+        flag = int(f[1])
+        if flag & 4:
+            use.append(i)
+            continue
+        tags = {t[:2]: t[5:] for t in f[11:]}
+        pos, fw, AS, cig = int(f[3]) - 1, not (flag & 16), int(tags["AS"]), f[5]
+        lead = int(cig[:cig.index("S")]) if "S" in cig and cig.index("S") < cig.index("M") else 0
+        r = reads[i]
+        rdlen = len(r)
+        minsc = sc.min_score(rdlen)
+        found, rect = policy.frame_seed_extension_rect(pos - lead, rdlen, tlen, sc.max_read_gaps(minsc, rdlen),
+                                                       sc.max_ref_gaps(minsc, rdlen), sc.n_ceil(rdlen))
+        d = oracle_dp(O, True, r, quals[i], fw, 0, rect, minsc, sc.n_ceil_raw(rdlen), max_cands=16384, max_alns=16)
+        al = [a for a in d["alns"] if a["refoff"] == pos and a["score"] == AS]
+        if not al:
+            continue
+        a = al[0]
+        o = _edits_to_ops(a["edits"], r, fw, a["trim5"], a["trim3"])
+        res[i]["found"] = 1
+        res[i]["score"] = AS
+        res[i]["score2"] = int(tags["XS"]) if "XS" in tags else -(1 << 31)
+        res[i]["fw"] = int(fw); res[i]["refoff"] = pos; res[i]["nops"] = len(o)
+        res[i]["trim_left"] = a["trim5"] if fw else a["trim3"]
+        res[i]["trim_right"] = a["trim3"] if fw else a["trim5"]
+        res[i]["mapq"] = int(f[4]); res[i]["pad"] = int(tags["XN"])
+        ops[i, :len(o)] = o
+        use.append(i)
+        nclip += "S" in cig
+    assert len(use) > 0.9 * n and nclip > 30
+    text = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ["gi|9626243|ref|NC_001416.1|"], read_names=names)
+    lines = text.rstrip("\n").split("\n")
+    for i in use:
+        assert lines[i] == golden[i], (i, lines[i], golden[i])
