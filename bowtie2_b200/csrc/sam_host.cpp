@@ -141,7 +141,14 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		}
 		// ---- the record
 		line.clear();
-		if(opt->read_names && opt->read_names[i]) line += opt->read_names[i];
+		if(opt->read_names && opt->read_names[i]) {
+			// QNAME = the name up to the first whitespace (sam.h printReadName), without a /1 or /2 mate suffix
+			const char *nm = opt->read_names[i];
+			size_t l = 0;
+			while(nm[l] && nm[l] != ' ' && nm[l] != '\t') l++;
+			if(paired && l >= 2 && nm[l - 2] == '/' && (nm[l - 1] == '1' || nm[l - 1] == '2')) l -= 2;
+			line.append(nm, l);
+		}
 		else { line += 'r'; appendInt(line, (long long)(paired ? (i >> 1) : i)); }
 		line += '\t'; appendInt(line, flag); line += '\t';
 		auto refName = [&](uint64_t t) -> const char * { return (opt->ref_names && t < opt->n_refs && opt->ref_names[t]) ? opt->ref_names[t] : "*"; };
@@ -242,5 +249,69 @@ extern "C" int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads
 	if(!out || total > cap) return -3;                             // buffer too small: *written holds the size needed
 	uint64_t at = 0;
 	for(int t = 0; t < T; t++) { memcpy(out + at, parts[t].data(), parts[t].size()); at += parts[t].size(); }
+	return 0;
+}
+
+// ---- FASTQ text -> bt2g_reads buffers (host) ----------------------------------------------------------------
+// FastqPatternSource::parse (pat.cpp:1130-1245) for plain 4-line records without trimming: the name is the header
+// line after '@'; sequence characters are letters ('.' = N), A/C/G/T in either case map to 0..3 and every other
+// letter to 4 (alphabet.cpp asc2dna); the '+' line is skipped; qualities are kept as raw Phred+33 bytes and must
+// number exactly the bases (tooFewQualities / tooManyQualities, pat.cpp:1226-1232).
+extern "C" int bt2g_fastq_parse(const char *text, uint64_t len, uint64_t maxReads, uint64_t maxBases, uint8_t *seq, uint8_t *qual,
+                                uint64_t *off, char *names, uint32_t nameStride, uint64_t *nReads, uint64_t *consumed) {
+	if(!text || !seq || !qual || !off || !nReads || !consumed) return -1;
+	uint64_t cur = 0, n = 0, nb = 0;
+	off[0] = 0;
+	*nReads = 0; *consumed = 0;
+	while(cur < len && n < maxReads) {
+		while(cur < len && (text[cur] == '\n' || text[cur] == '\r')) cur++;
+		if(cur >= len) break;
+		const uint64_t recStart = cur;
+		if(text[cur] != '@') return -4;                           // not a FASTQ record
+		cur++;
+		const uint64_t nameBeg = cur;
+		while(cur < len && text[cur] != '\n' && text[cur] != '\r') cur++;
+		const uint64_t nameEnd = cur;
+		while(cur < len && (text[cur] == '\n' || text[cur] == '\r')) cur++;
+		// sequence up to the '+' line
+		const uint64_t b0 = nb;
+		bool full = false;
+		while(cur < len && text[cur] != '+') {
+			int c = (unsigned char)text[cur++];
+			if(c == '.') c = 'N';
+			if((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z')) {
+				if(nb >= maxBases) { full = true; break; }
+				const int u = c & ~0x20;
+				seq[nb++] = (uint8_t)(u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : 4);
+			}
+		}
+		if(full) { nb = b0; cur = recStart; break; }              // out of room: stop before this record
+		if(cur >= len) { nb = b0; cur = recStart; break; }        // truncated record: leave it for the next call
+		while(cur < len && text[cur] != '\n' && text[cur] != '\r') cur++;   // the '+' line
+		while(cur < len && (text[cur] == '\n' || text[cur] == '\r')) cur++;
+		const uint64_t nbases = nb - b0;
+		uint64_t nq = 0;
+		while(cur < len && text[cur] != '\n' && text[cur] != '\r') {
+			const unsigned char c = (unsigned char)text[cur++];
+			if(c == ' ') return -5;                                // integer qualities are not supported
+			if(nq < nbases) qual[b0 + nq] = c;
+			nq++;
+		}
+		if(nq < nbases) {
+			if(cur >= len) { nb = b0; cur = recStart; break; }    // truncated quality line
+			return -6;                                             // fewer qualities than bases
+		}
+		if(nq > nbases) return -7;                                 // more qualities than bases
+		if(names && nameStride) {
+			uint64_t l = nameEnd - nameBeg;
+			if(l >= nameStride) l = nameStride - 1;
+			memcpy(names + n * (uint64_t)nameStride, text + nameBeg, l);
+			names[n * (uint64_t)nameStride + l] = 0;
+		}
+		n++;
+		off[n] = nb;
+		while(cur < len && (text[cur] == '\n' || text[cur] == '\r')) cur++;
+	}
+	*nReads = n; *consumed = cur;
 	return 0;
 }

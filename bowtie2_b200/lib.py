@@ -685,3 +685,26 @@ def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_name
     if rc:
         raise RuntimeError(f"bt2g_sam_format failed ({rc})")
     return buf.raw[:need.value].decode()
+
+
+EXPORTS += ["bt2g_fastq_parse"]
+
+
+def fastq_parse(lib, text: bytes, max_reads: int = 1 << 30, name_stride: int = 64):
+    """include/bt2g.h: bt2g_fastq_parse -> (ReadBatch, names, bytes consumed)."""
+    lib.bt2g_fastq_parse.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    cap_reads = min(max_reads, text.count(b"\n") // 4 + 1)
+    seq = np.zeros(len(text), dtype=np.uint8)
+    qual = np.zeros(len(text), dtype=np.uint8)
+    off = np.zeros(cap_reads + 1, dtype=np.uint64)
+    names = np.zeros((cap_reads, name_stride), dtype=np.uint8)
+    n, used = C.c_uint64(0), C.c_uint64(0)
+    rc = lib.bt2g_fastq_parse(text, len(text), cap_reads, len(text), _ptr(seq), _ptr(qual), _ptr(off), _ptr(names), name_stride,
+                              C.byref(n), C.byref(used))
+    if rc:
+        raise RuntimeError(f"bt2g_fastq_parse failed ({rc})")
+    n = int(n.value)
+    nb = int(off[n])
+    nm = [bytes(names[i]).split(b"\0", 1)[0].decode() for i in range(n)]
+    return ReadBatch(seq[:nb].copy(), off[:n + 1].copy(), qual[:nb].copy()), nm, int(used.value)

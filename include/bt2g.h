@@ -438,6 +438,14 @@ typedef struct {
 int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads, const bt2g_read_result *res, const uint8_t *ops,
                     uint32_t max_ops, const bt2g_pair_result *pairs, char *out, uint64_t cap, uint64_t *written);
 
+/* FASTQ text -> read buffers (host code; FastqPatternSource::parse, pat.cpp:1130-1245, plain 4-line records,
+ * Phred+33, no trimming).  Parses whole records until max_reads / max_bases / the end of `text`; *consumed is the
+ * offset of the first unparsed byte (a truncated last record is left for the next call).  names: n * name_stride
+ * bytes, NUL-terminated header lines (may be NULL).  Errors: -4 not FASTQ, -5 integer qualities, -6 / -7 fewer /
+ * more qualities than bases. */
+int bt2g_fastq_parse(const char *text, uint64_t len, uint64_t max_reads, uint64_t max_bases, uint8_t *seq, uint8_t *qual,
+                     uint64_t *off, char *names, uint32_t name_stride, uint64_t *n_reads, uint64_t *consumed);
+
 #ifdef __cplusplus
 }
 #endif

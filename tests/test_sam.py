@@ -218,3 +218,31 @@ def test_sam_local_records_match_reference_program(lambda_index):
     lines = text.rstrip("\n").split("\n")
     for i in use:
         assert lines[i] == golden[i], (i, lines[i], golden[i])
+
+
+def test_fastq_parse_matches_test_reader():
+    """bt2g_fastq_parse against the tests' own FASTQ reader on the golden reads, plus chunked parsing and the
+    error paths."""
+    from bowtie2_b200.lib import fastq_parse
+    lib = load_library()
+    path = os.path.join(GOLDEN, "lambda_reads_1.fq")
+    text = open(path, "rb").read()
+    names, reads, quals = read_fastq_codes(path, 10 ** 9)
+    batch, nm, used = fastq_parse(lib, text)
+    assert used == len(text) and batch.n == len(reads) and nm == names
+    for i in (0, 1, 17, len(reads) - 1):
+        a, b = int(batch.off[i]), int(batch.off[i + 1])
+        assert np.array_equal(batch.seq[a:b], reads[i]) and np.array_equal(batch.qual[a:b], quals[i])
+    assert np.array_equal(batch.seq, np.concatenate(reads)) and np.array_equal(batch.qual, np.concatenate(quals))
+    # a buffer cut in the middle of a record: whole records only, the rest is left for the next call
+    cut = len(text) // 2 + 7
+    b1, n1, u1 = fastq_parse(lib, text[:cut])
+    b2, n2, u2 = fastq_parse(lib, text[u1:])
+    assert u1 <= cut and n1 + n2 == names and b1.n + b2.n == batch.n
+    # lower case, '.', IUPAC codes, CRLF
+    b3, n3, _ = fastq_parse(lib, b"@x y\r\nacgtN.Rn\r\n+\r\nIIIIIIII\r\n")
+    assert n3 == ["x y"] and b3.seq.tolist() == [0, 1, 2, 3, 4, 4, 4, 4]
+    with pytest.raises(RuntimeError):
+        fastq_parse(lib, b">x\nACGT\n")
+    with pytest.raises(RuntimeError):
+        fastq_parse(lib, b"@x\nACGT\n+\nII\n@y\nAC\n+\nII\n")
