@@ -315,3 +315,31 @@ extern "C" int bt2g_fastq_parse(const char *text, uint64_t len, uint64_t maxRead
 	*nReads = n; *consumed = cur;
 	return 0;
 }
+
+
+// ---- host entry points over the __host__ __device__ policy arithmetic the kernels use -------------------------
+// (same source as the device code: mapq_device.cuh, pe_device.cuh; lets the CPU test suite pin it against the reference)
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#include "mapq_device.cuh"
+#include "pe_device.cuh"
+
+extern "C" int bt2g_mapq(int64_t best, int hasSecbest, int64_t secbest, int64_t scMin, int64_t scPerfect, int monotone) {
+	return mapq_v2(best, hasSecbest != 0, secbest, scMin, scPerfect, monotone != 0);
+}
+
+extern "C" int bt2g_frame_mate_host(const bt2g_pe_policy *pol, const bt2g_mate_anchor *anchors, uint64_t n, bt2g_mate_frame *out) {
+	if(!pol || !anchors || !out || pol->pol < 1 || pol->pol > 4) return -1;
+	for(uint64_t i = 0; i < n; i++) pe_frame_anchor(*pol, anchors[i], out[i]);
+	return 0;
+}
+
+extern "C" int bt2g_pe_classify_host(const bt2g_pe_policy *pol, const int64_t *pairs, uint64_t n, int32_t *out) {
+	if(!pol || !pairs || !out || pol->pol < 1 || pol->pol > 4) return -1;
+	for(uint64_t i = 0; i < n; i++) {
+		const int64_t *q = pairs + 6 * i;
+		out[i] = pe_classify(*pol, q[0], (uint64_t)q[1], q[2] != 0, q[3], (uint64_t)q[4], q[5] != 0);
+	}
+	return 0;
+}

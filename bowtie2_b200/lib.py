@@ -708,3 +708,5 @@ def fastq_parse(lib, text: bytes, max_reads: int = 1 << 30, name_stride: int = 6
     nb = int(off[n])
     nm = [bytes(names[i]).split(b"\0", 1)[0].decode() for i in range(n)]
     return ReadBatch(seq[:nb].copy(), off[:n + 1].copy(), qual[:nb].copy()), nm, int(used.value)
+
+EXPORTS += ["bt2g_mapq", "bt2g_frame_mate_host", "bt2g_pe_classify_host"]

@@ -438,6 +438,14 @@ typedef struct {
 int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads, const bt2g_read_result *res, const uint8_t *ops,
                     uint32_t max_ops, const bt2g_pair_result *pairs, char *out, uint64_t cap, uint64_t *written);
 
+/* Host evaluations of the policy arithmetic that the kernels run on the device (one source for both: the
+ * __host__ __device__ functions of mapq_device.cuh / pe_device.cuh), for callers that need a single value and for
+ * the CPU test suite: BowtieMapq2::mapq (unique.h:170-392), PairedEndPolicy::otherMate + frameFindMateRect,
+ * PairedEndPolicy::peClassifyPair. */
+int bt2g_mapq(int64_t best, int has_secbest, int64_t secbest, int64_t sc_min, int64_t sc_perfect, int monotone);
+int bt2g_frame_mate_host(const bt2g_pe_policy *pol, const bt2g_mate_anchor *anchors, uint64_t n, bt2g_mate_frame *out);
+int bt2g_pe_classify_host(const bt2g_pe_policy *pol, const int64_t *pairs, uint64_t n, int32_t *out);
+
 /* FASTQ text -> read buffers (host code; FastqPatternSource::parse, pat.cpp:1130-1245, plain 4-line records,
  * Phred+33, no trimming).  Parses whole records until max_reads / max_bases / the end of `text`; *consumed is the
  * offset of the first unparsed byte (a truncated last record is left for the next call).  names: n * name_stride

@@ -188,3 +188,62 @@ def test_gen_rand_seed_known_values():
     for i, ch in enumerate(b"r1"):
         x ^= ch << ((i & 3) << 3)
     assert s == x & 0xffffffff
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_device_policy_sources_match_reference_on_host(lambda_index):
+    """The __host__ __device__ functions the kernels run (mapq_device.cuh, pe_device.cuh), evaluated on the host through
+    bt2g_mapq / bt2g_frame_mate_host / bt2g_pe_classify_host, against the unmodified reference."""
+    from bowtie2_b200.lib import MATE_ANCHOR, MATE_FRAME, _PePolicy, _pe_struct, load_library
+    lib = load_library()
+    R = Reference(lambda_index, mirror=False, ref=False)
+    L = R.lib
+    i64, u64 = C.c_int64, C.c_uint64
+    # MAPQ
+    L.ref_mapq_v2.argtypes = [C.c_void_p, C.c_int, i64, i64, i64, C.c_int, i64]
+    lib.bt2g_mapq.argtypes = [i64, C.c_int, i64, i64, i64, C.c_int]
+    rng = np.random.default_rng(77)
+    for local in (False, True):
+        sc = policy.Scoring.default(local)
+        for k in range(3000):
+            rdlen = int(rng.choice([50, 100, 150, 250]))
+            ordlen = int(rng.choice([0, 0, 100, 150]))
+            mn = sc.min_score(rdlen) + (sc.min_score(ordlen) if ordlen else 0)
+            pf = sc.perfect_score(rdlen) + (sc.perfect_score(ordlen) if ordlen else 0)
+            best = pf if k % 5 == 0 else int(rng.integers(mn, pf + 1))
+            has_sec = bool(rng.integers(0, 2))
+            sec = int(rng.integers(mn, best + 1)) if has_sec else 0
+            want = L.ref_mapq_v2(R.h, int(local), rdlen, ordlen, best, int(has_sec), sec)
+            assert lib.bt2g_mapq(best, int(has_sec), sec, mn, pf, int(not local)) == want
+    # mate windows / rectangles and pair classes
+    L.ref_frame_mate.argtypes = [C.c_int, u64, u64, C.c_int, C.c_int, C.c_int, i64, i64, u64, u64, u64, u64, u64, i64, u64, C.POINTER(i64)]
+    L.ref_pe_classify.argtypes = [C.c_int, u64, u64, C.c_int, i64, u64, C.c_int, i64, u64, C.c_int]
+    lib.bt2g_frame_mate_host.argtypes = [C.POINTER(_PePolicy), C.c_void_p, u64, C.c_void_p]
+    lib.bt2g_pe_classify_host.argtypes = [C.POINTER(_PePolicy), C.c_void_p, u64, C.c_void_p]
+    out15 = (i64 * 15)()
+    nfound = 0
+    for pe, flags, len1, len2, reflen, off, r2 in _pe_cases(3000, seed=19):
+        is1, fw = bool(r2.integers(0, 2)), bool(r2.integers(0, 2))
+        olen = len2 if is1 else len1
+        rg, fg = int(r2.integers(0, 25)), int(r2.integers(0, 25))
+        maxalcols = olen + rg if r2.integers(0, 4) else -1
+        a = np.zeros(1, dtype=MATE_ANCHOR)
+        a[0] = (off, reflen, len1, len2, maxalcols, rg, fg, int(0.15 * olen), 15, int(is1), int(fw), (0, 0))
+        f = np.zeros(1, dtype=MATE_FRAME)
+        pp = _pe_struct(pe)
+        assert lib.bt2g_frame_mate_host(C.byref(pp), a.ctypes.data_as(C.c_void_p), 1, f.ctypes.data_as(C.c_void_p)) == 0
+        st = L.ref_frame_mate(pe.pol, pe.maxfrag, pe.minfrag, flags, int(is1), int(fw), off, maxalcols, reflen, len1, len2, rg, fg,
+                              int(0.15 * olen), 15, out15)
+        g = f[0]
+        assert int(g["status"]) == st
+        if st:
+            assert [int(g["oleft"]), int(g["ofw"]), int(g["oll"]), int(g["olr"]), int(g["orl"]), int(g["orr"])] == list(out15[:6])
+            assert [int(g[k]) for k in ("refl", "refr", "refl_pretrim", "refr_pretrim", "triml", "trimr", "corel", "corer", "maxgap")] == list(out15[6:15])
+            nfound += st == 2
+        off2 = off + int(r2.integers(-300, 600))
+        fw1, fw2 = bool(r2.integers(0, 2)), bool(r2.integers(0, 2))
+        pr = np.array([off, len1, int(fw1), off2, len2, int(fw2)], dtype=np.int64)
+        cls = np.zeros(1, dtype=np.int32)
+        assert lib.bt2g_pe_classify_host(C.byref(pp), pr.ctypes.data_as(C.c_void_p), 1, cls.ctypes.data_as(C.c_void_p)) == 0
+        assert int(cls[0]) == L.ref_pe_classify(pe.pol, pe.maxfrag, pe.minfrag, flags, off, len1, int(fw1), off2, len2, int(fw2))
+    assert nfound > 800
