@@ -546,6 +546,26 @@ def main():
         pr = np.frombuffer(hpairs.numpy().tobytes(), dtype=PAIR_RESULT)
         conc = {"concordant_frac": float((pr["pair_type"] == 1).mean()), "by_mate_dp_frac": float((pr["source"] != 0).mean())}
     clk = clocks.stop() if rank == 0 else None
+    # informational: host-side SAM formatting rate of the last batch's results (bt2g_sam_format on the host threads the
+    # container may use); not part of `value` or `e2e` -- the records/s it sustains is the next bottleneck
+    sam_info = None
+    if rank == 0:
+        try:
+            from bowtie2_b200.lib import ReadBatch, sam_format
+            nfmt = min(BR, 200_000) // mates * mates
+            kl = (args.steps - 1) % nbuf                    # the host buffers of the last timed step
+            rb = ReadBatch(hseq[kl].numpy()[:nfmt * READ_LEN], hoff[:nfmt + 1], hqual[kl].numpy()[:nfmt * READ_LEN])
+            res_f = np.frombuffer(hres.numpy().tobytes(), dtype=READ_RESULT)[:nfmt]
+            ops_f = hops.numpy()[:nfmt * pipe.max_ops].reshape(nfmt, pipe.max_ops)
+            prs_f = np.frombuffer(hpairs.numpy().tobytes(), dtype=PAIR_RESULT)[:nfmt // 2] if paired else None
+            thr = int(cpu_quota) if cpu_quota else min(cores, 16)
+            t_f = time.perf_counter()
+            txt = sam_format(gpu._lib, rb, res_f, ops_f, [f"chr{k + 1}" for k in range(GENOME_CONTIGS)], pairs=prs_f, threads=max(thr, 1))
+            dt_f = time.perf_counter() - t_f
+            sam_info = {"records": nfmt, "threads": max(thr, 1), "Mrecords_per_s": nfmt / dt_f / 1e6, "bytes_per_record": len(txt) / max(nfmt, 1),
+                        "note": "includes the python wrapper's sizing pass; host formatter, device-side formatting is next"}
+        except Exception as e:                      # never let the informational extra break the bench line
+            sam_info = {"error": repr(e)[:200]}
 
     # max over ranks
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -595,7 +615,7 @@ def main():
                 "clocks": clk, "gpu_launches": pipe.kernel_launches() * args.steps,
                 "e2e": {"value": e2e_val, "unit": "Mreads/s", "h2d_bytes_per_step": 2 * BR * READ_LEN + (BR + 1) * 8,
                         "d2h_bytes_per_step": BR * READ_RESULT.itemsize + BR * pipe.max_ops + (B * PAIR_RESULT.itemsize if paired else 0)},
-                "roofline": roof, "stage_ms": stage_ms, "work_per_step": cnt, "cpu_baseline": cpu_baseline}
+                "roofline": roof, "stage_ms": stage_ms, "work_per_step": cnt, "sam_format_host": sam_info, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     if distributed:
         dist.barrier()

@@ -87,9 +87,35 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		long long refExtent = 0;
 		int nmm = 0, ngo = 0, ngx = 0, nedits = 0;
 		if(aligned) {
-			st.ref.clear(); st.rel.clear(); st.rd.clear();
 			const int nops = (r.found & 0xff) == 2 ? 0 : r.nops;
 			const uint8_t *op = ops ? ops + i * (uint64_t)maxOps : nullptr;
+			bool gapless = true;
+			if((r.found & 0xff) != 2) {
+				if(!op) return -1;
+				for(int k = 0; k < nops; k++) if((op[k] & 3) >= BT2G_OP_REFGAP) { gapless = false; break; }
+			}
+			if(gapless) {
+				// no gaps: nothing to left-align; CIGAR is one M run and MD:Z a scan of the mismatches
+				const int nrow = (r.found & 0xff) == 2 ? len : nops;
+				if(r.trim_left > 0) { appendInt(cigar, r.trim_left); cigar += 'S'; }
+				appendInt(cigar, nrow); cigar += 'M';
+				if(r.trim_right > 0) { appendInt(cigar, r.trim_right); cigar += 'S'; }
+				int run = 0; bool mmLast = false, first = true;
+				for(int k = nops - 1; k >= 0; k--) {
+					if((op[k] & 3) == BT2G_OP_MM) {
+						if(run > 0) { appendInt(mdz, run); first = false; mmLast = false; run = 0; }
+						if(mmLast || first) mdz += '0';
+						const int rc = (op[k] >> 2) & 7;
+						mdz += dna[rc > 4 ? 4 : rc]; first = false; mmLast = true;
+						nmm++; nedits++;
+					} else run++;
+				}
+				if((r.found & 0xff) == 2) run = len;
+				if(run > 0) { appendInt(mdz, run); mmLast = false; }
+				if(mmLast) mdz += '0';
+				refExtent = nrow;
+			} else {
+			st.ref.clear(); st.rel.clear(); st.rd.clear();
 			// read characters in reference orientation
 			auto rdch = [&](int row) -> char { return fw ? dna[seq[row] > 4 ? 4 : seq[row]] : comp[seq[len - 1 - row] > 4 ? 4 : seq[len - 1 - row]]; };
 			int row = r.trim_left;
@@ -138,6 +164,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 			}
 			if(mmLast || gapLast) mdz += '0';
 			for(size_t k = 0; k < ln; k++) refExtent += st.rel[k] != 'I';
+			}
 		}
 		// ---- the record
 		line.clear();
@@ -183,9 +210,18 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		line += '\t';
 		// SEQ QUAL (reverse-complemented / reversed for the reverse strand)
 		const bool rev = aligned && !fw;
-		for(int k = 0; k < len; k++) { const int c = rev ? seq[len - 1 - k] : seq[k]; line += rev ? comp[c > 4 ? 4 : c] : dna[c > 4 ? 4 : c]; }
-		line += '\t';
-		if(qual) for(int k = 0; k < len; k++) line += (char)(rev ? qual[len - 1 - k] : qual[k]); else line += '*';
+		{
+			const size_t at = line.size();
+			line.resize(at + (size_t)len + 1 + (qual ? (size_t)len : 1));
+			char *d = &line[at];
+			if(rev) for(int k = 0; k < len; k++) { const int c = seq[len - 1 - k]; d[k] = comp[c > 4 ? 4 : c]; }
+			else    for(int k = 0; k < len; k++) { const int c = seq[k]; d[k] = dna[c > 4 ? 4 : c]; }
+			d[len] = '\t';
+			char *e = d + len + 1;
+			if(!qual) e[0] = '*';
+			else if(rev) for(int k = 0; k < len; k++) e[k] = (char)qual[len - 1 - k];
+			else memcpy(e, qual, (size_t)len);
+		}
 		// optional fields
 		if(aligned) {
 			line += "\tAS:i:"; appendInt(line, r.score);
