@@ -87,7 +87,10 @@ struct HostIndex {
 	bt2g_index_host d{};
 	std::vector<uint8_t> plen, rstarts, ebwt_fw, ebwt_bw, ftab_fw, eftab_fw, ftab_bw, eftab_bw, offs;
 	std::vector<uint8_t> rec_off, rec_len, rec_first, ref_buf;
+	std::vector<std::string> names;                 // reference names stored in the .1 file
 };
 int bt2g_read_index_files(const char *basename, HostIndex &out, std::string &err);
+// offRateOverride < 0: none (Ebwt's _overrideOffRate, bt2_io.cpp:217-230)
+int bt2g_read_index_files_ex(const char *basename, int offRateOverride, HostIndex &out, std::string &err);
 
 template <typename OFF> DevIndex<OFF> bt2g_dev_index(const bt2g_ctx *ctx);

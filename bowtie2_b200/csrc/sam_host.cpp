@@ -70,6 +70,10 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		const bool mateAligned = m && (m->found & 0xff) != 0;
 		const bt2g_pair_result *pr = paired ? &pairs[i >> 1] : nullptr;
 		const bool concordant = pr && pr->pair_type == 1;
+		// discordant = no concordant pair and exactly one alignment for each mate (AlnSinkWrap::getReport,
+		// aln_sink.cpp:240-256); with more, the mates are reported as unpaired alignments of a paired read
+		const bool discordant = pr && pr->pair_type == 2 && r.score2 == INT32_MIN && m->score2 == INT32_MIN;
+		const bool asPair = concordant || discordant;
 		int flag = 0;
 		if(paired) {
 			flag |= 1;
@@ -188,7 +192,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 			if(aligned && m->tidx == r.tidx) line += '='; else if(!aligned) line += '='; else line += refName(m->tidx);
 			line += '\t'; appendInt(line, m->refoff + 1); line += '\t';
 			long long tlen = 0;
-			if(aligned && m->tidx == r.tidx) {
+			if(aligned && asPair && m->tidx == r.tidx) {
 				// AlnRes::setFragmentLength (aligner_result.h:1311-1343); extents include soft-trimmed ends
 				long long st0 = r.refoff - r.trim_left, en0 = r.refoff + refExtent - 1 + r.trim_right;
 				// the mate's extent needs its own ops
@@ -225,7 +229,9 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		// optional fields
 		if(aligned) {
 			line += "\tAS:i:"; appendInt(line, r.score);
-			if(r.score2 != INT32_MIN) { line += "\tXS:i:"; appendInt(line, r.score2); }
+			// XS:i of a paired read is the best unchosen PAIRED score of this mate (sam.cpp:146-158): never set for
+			// mates reported as unpaired alignments
+			if(r.score2 != INT32_MIN && (!paired || concordant)) { line += "\tXS:i:"; appendInt(line, r.score2); }
 			line += "\tXN:i:"; appendInt(line, r.pad);
 			line += "\tXM:i:"; appendInt(line, nmm);
 			line += "\tXO:i:"; appendInt(line, ngo);
@@ -233,10 +239,10 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 			line += "\tNM:i:"; appendInt(line, nedits);
 			line += "\tMD:Z:"; line += mdz;
 			// YS:i only for mates reported as a pair (summ.paired(), sam.cpp:250)
-			if(paired && mateAligned && (pr->pair_type == 1 || pr->pair_type == 2)) { line += "\tYS:i:"; appendInt(line, m->score); }
+			if(paired && mateAligned && asPair) { line += "\tYS:i:"; appendInt(line, m->score); }
 		}
 		line += "\tYT:Z:";
-		line += !paired ? "UU" : (concordant ? "CP" : ((aligned && mateAligned && pr->pair_type == 2) ? "DP" : "UP"));
+		line += !paired ? "UU" : (concordant ? "CP" : (discordant ? "DP" : "UP"));
 		if(!aligned) {
 			// YF:Z: why the read was filtered out (sam.cpp:331-345; filters at bt2_search.cpp:3405-3431)
 			int ns = 0;
@@ -377,5 +383,106 @@ extern "C" int bt2g_pe_classify_host(const bt2g_pe_policy *pol, const int64_t *p
 		const int64_t *q = pairs + 6 * i;
 		out[i] = pe_classify(*pol, q[0], (uint64_t)q[1], q[2] != 0, q[3], (uint64_t)q[4], q[5] != 0);
 	}
+	return 0;
+}
+
+// ---- SAM header (SamConfig::printHeader, sam.cpp:54-111) -----------------------------------------
+extern "C" int bt2g_sam_header(const char *const *names, const uint64_t *lens, uint64_t n, const char *pgCl,
+                               char *out, uint64_t cap, uint64_t *written) {
+	if(!written || (n && (!names || !lens))) return -1;
+	std::string o = "@HD\tVN:1.5\tSO:unsorted\tGO:query\n";
+	for(uint64_t i = 0; i < n; i++) {
+		o += "@SQ\tSN:";
+		for(const char *c = names[i]; c && *c && !isspace((unsigned char)*c); c++) o += *c;     // printRefName: up to the first whitespace
+		o += "\tLN:"; appendInt(o, (long long)lens[i]); o += '\n';
+	}
+	if(pgCl) { o += "@PG\tID:bowtie2\tPN:bowtie2\tVN:2.5.5\tCL:\""; o += pgCl; o += "\"\n"; }
+	*written = o.size();
+	if(!out || cap < o.size()) return -3;
+	memcpy(out, o.data(), o.size());
+	return 0;
+}
+
+// ---- alignment summary (ReportingMetrics updates of AlnSinkWrap::finishRead, aln_sink.cpp:708-1046;
+//      text of AlnSink::printAlSumm, aln_sink.cpp:349-528) ---------------------------------------------
+extern "C" int bt2g_align_counts_add(bt2g_align_counts *c, const bt2g_read_result *res, uint64_t nReads, const bt2g_pair_result *pairs) {
+	if(!c || (nReads && !res)) return -1;
+	auto aligned = [](const bt2g_read_result &r) { return (r.found & 0xff) != 0; };
+	auto multi = [](const bt2g_read_result &r) { return r.score2 != INT32_MIN; };
+	if(!pairs) {
+		for(uint64_t i = 0; i < nReads; i++) {
+			c->nread++; c->nunpaired++;
+			if(!aligned(res[i])) c->nunp_0++;
+			else if(multi(res[i])) c->nunp_gt1++;
+			else c->nunp_uni1++;
+		}
+		return 0;
+	}
+	if(nReads & 1) return -1;
+	for(uint64_t p = 0; p < nReads / 2; p++) {
+		const bt2g_read_result &a = res[2 * p], &b = res[2 * p + 1];
+		const bt2g_pair_result &pr = pairs[p];
+		c->nread++; c->npaired++;
+		if(pr.pair_type == 1) {
+			// ">1" in the reference = a second concordant PAIR was found; the pipeline keeps one pair per read, so this
+			// takes "both mates have a second alignment" as the indicator (an approximation)
+			if(multi(a) && multi(b)) c->nconcord_gt1++; else c->nconcord_uni1++;
+			continue;
+		}
+		c->nconcord_0++;
+		if(pr.pair_type == 2 && !multi(a) && !multi(b)) { c->ndiscord++; continue; }
+		for(const bt2g_read_result *m : {&a, &b}) {
+			if(!aligned(*m)) c->nunp_0_0++;
+			else if(multi(*m)) c->nunp_0_gt1++;
+			else c->nunp_0_uni1++;
+		}
+	}
+	return 0;
+}
+
+extern "C" int bt2g_align_summary(const bt2g_align_counts *c, int discord, int mixed, char *out, uint64_t cap, uint64_t *written) {
+	if(!c || !written) return -1;
+	std::string o;
+	char buf[64];
+	auto num = [&](uint64_t v) { appendInt(o, (long long)v); };
+	auto pct = [&](uint64_t nu, uint64_t de) {
+		double p = 0.0;
+		if(de != 0) p = 100.0 * (double)nu / (double)de;
+		snprintf(buf, sizeof(buf), "%.2f%%", p);
+		o += buf;
+	};
+	auto line = [&](const char *indent, uint64_t v, uint64_t de, const char *tail) { o += indent; num(v); o += " ("; pct(v, de); o += ") "; o += tail; o += '\n'; };
+	if(c->nread > 0) { num(c->nread); o += " reads; of these:\n"; }
+	else { num(c->nread); o += " reads\n"; }
+	if(c->npaired > 0) {
+		line("  ", c->npaired, c->nread, "were paired; of these:");
+		line("    ", c->nconcord_0, c->npaired, "aligned concordantly 0 times");
+		line("    ", c->nconcord_uni1, c->npaired, "aligned concordantly exactly 1 time");
+		line("    ", c->nconcord_gt1, c->npaired, "aligned concordantly >1 times");
+		if(discord) {
+			o += "    ----\n    "; num(c->nconcord_0); o += " pairs aligned concordantly 0 times; of these:\n";
+			line("      ", c->ndiscord, c->nconcord_0, "aligned discordantly 1 time");
+		}
+		const uint64_t nc0 = c->nconcord_0 - c->ndiscord;
+		if(mixed) {
+			o += "    ----\n    "; num(nc0); o += " pairs aligned 0 times concordantly or discordantly; of these:\n";
+			o += "      "; num(nc0 * 2); o += " mates make up the pairs; of these:\n";
+			line("        ", c->nunp_0_0, nc0 * 2, "aligned 0 times");
+			line("        ", c->nunp_0_uni1, nc0 * 2, "aligned exactly 1 time");
+			line("        ", c->nunp_0_gt1, nc0 * 2, "aligned >1 times");
+		}
+	}
+	if(c->nunpaired > 0) {
+		line("  ", c->nunpaired, c->nread, "were unpaired; of these:");
+		line("    ", c->nunp_0, c->nunpaired, "aligned 0 times");
+		line("    ", c->nunp_uni1, c->nunpaired, "aligned exactly 1 time");
+		line("    ", c->nunp_gt1, c->nunpaired, "aligned >1 times");
+	}
+	const uint64_t cand = c->nunpaired + c->npaired * 2;
+	const uint64_t al = (c->nconcord_uni1 + c->nconcord_gt1) * 2 + c->ndiscord * 2 + c->nunp_0_uni1 + c->nunp_0_gt1 + c->nunp_uni1 + c->nunp_gt1;
+	pct(al, cand); o += " overall alignment rate\n";
+	*written = o.size();
+	if(!out || cap < o.size()) return -3;
+	memcpy(out, o.data(), o.size());
 	return 0;
 }

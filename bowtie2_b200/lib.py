@@ -85,6 +85,7 @@ def load_library() -> C.CDLL:
     lib.bt2g_last_error.argtypes = [vp]
     lib.bt2g_last_error.restype = C.c_char_p
     lib.bt2g_load_index_files.argtypes = [vp, C.c_char_p]
+    lib.bt2g_load_index_files_ex.argtypes = [vp, C.c_char_p, i32]
     lib.bt2g_load_index_host.argtypes = [vp, C.POINTER(_IndexHost)]
     lib.bt2g_load_index_device.argtypes = [vp, C.POINTER(_IndexHost)]
     lib.bt2g_index_info_get.argtypes = [vp, C.POINTER(_IndexInfo)]
@@ -165,8 +166,12 @@ class Bt2Gpu:
             raise Bt2GpuError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
 
     # ---- index ---------------------------------------------------------------------
-    def load_index_files(self, basename: str):
-        self._check(self._lib.bt2g_load_index_files(self._h, basename.encode()), "bt2g_load_index_files")
+    def load_index_files(self, basename: str, offrate: int = -1):
+        """offrate > the index's own offRate keeps every 2^diff-th SA sample (bowtie2 --offrate, bt2_io.cpp:217-230)."""
+        if offrate >= 0:
+            self._check(self._lib.bt2g_load_index_files_ex(self._h, basename.encode(), int(offrate)), "bt2g_load_index_files_ex")
+        else:
+            self._check(self._lib.bt2g_load_index_files(self._h, basename.encode()), "bt2g_load_index_files")
 
     def load_index_device(self, desc: dict, keep=None):
         """Adopt device arrays (e.g. torch tensors filled by an NCCL broadcast). `desc` maps
@@ -710,3 +715,135 @@ def fastq_parse(lib, text: bytes, max_reads: int = 1 << 30, name_stride: int = 6
     return ReadBatch(seq[:nb].copy(), off[:n + 1].copy(), qual[:nb].copy()), nm, int(used.value)
 
 EXPORTS += ["bt2g_mapq", "bt2g_frame_mate_host", "bt2g_pe_classify_host"]
+
+
+EXPORTS += ["bt2g_sam_header", "bt2g_align_counts_add", "bt2g_align_summary", "bt2g_index_file_open", "bt2g_index_file_desc",
+            "bt2g_index_file_n_refs", "bt2g_index_file_ref_names", "bt2g_index_file_ref_lens", "bt2g_index_file_close",
+            "bt2g_load_index_files_ex"]
+
+
+def sam_header(lib, names, lens, pg_cl=None) -> str:
+    """include/bt2g.h: bt2g_sam_header."""
+    lib.bt2g_sam_header.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    rn = (C.c_char_p * len(names))(*[x.encode() for x in names])
+    ln = np.ascontiguousarray(lens, dtype=np.uint64)
+    cl = pg_cl.encode() if pg_cl is not None else None
+    need = C.c_uint64(0)
+    lib.bt2g_sam_header(rn, _ptr(ln), len(names), cl, None, 0, C.byref(need))
+    buf = C.create_string_buffer(int(need.value) + 1)
+    rc = lib.bt2g_sam_header(rn, _ptr(ln), len(names), cl, buf, need.value, C.byref(need))
+    if rc:
+        raise RuntimeError(f"bt2g_sam_header failed ({rc})")
+    return buf.raw[:need.value].decode()
+
+
+ALIGN_COUNTS = np.dtype([(k, np.uint64) for k in ("nread", "npaired", "nunpaired", "nconcord_0", "nconcord_uni1", "nconcord_gt1",
+                                                  "ndiscord", "nunp_0_0", "nunp_0_uni1", "nunp_0_gt1", "nunp_0", "nunp_uni1", "nunp_gt1")])
+
+
+def align_counts_add(lib, counts, res, pairs=None):
+    """include/bt2g.h: bt2g_align_counts_add; `counts` is a 1-element ALIGN_COUNTS array (None starts a new one)."""
+    if counts is None:
+        counts = np.zeros(1, dtype=ALIGN_COUNTS)
+    lib.bt2g_align_counts_add.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    res = np.ascontiguousarray(res, dtype=READ_RESULT)
+    if pairs is not None:
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_RESULT)
+    rc = lib.bt2g_align_counts_add(_ptr(counts), _ptr(res), len(res), _ptr(pairs))
+    if rc:
+        raise RuntimeError(f"bt2g_align_counts_add failed ({rc})")
+    return counts
+
+
+def align_summary(lib, counts, discord: bool = True, mixed: bool = True) -> str:
+    """include/bt2g.h: bt2g_align_summary: the text bowtie2 prints on stderr at the end of a run."""
+    lib.bt2g_align_summary.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    counts = np.ascontiguousarray(counts, dtype=ALIGN_COUNTS)
+    need = C.c_uint64(0)
+    lib.bt2g_align_summary(_ptr(counts), int(discord), int(mixed), None, 0, C.byref(need))
+    buf = C.create_string_buffer(int(need.value) + 1)
+    rc = lib.bt2g_align_summary(_ptr(counts), int(discord), int(mixed), buf, need.value, C.byref(need))
+    if rc:
+        raise RuntimeError(f"bt2g_align_summary failed ({rc})")
+    return buf.raw[:need.value].decode()
+
+
+class IndexFile:
+    """Host image of an index on disk (include/bt2g.h: bt2g_index_file_*); no GPU involved."""
+
+    _ARRAYS = ("plen", "rstarts", "ebwt_fw", "ebwt_bw", "ftab_fw", "eftab_fw", "ftab_bw", "eftab_bw", "offs",
+               "rec_off", "rec_len", "rec_first", "ref_buf")
+
+    def __init__(self, basename: str, offrate: int = -1):
+        lib = load_library()
+        self._lib = lib
+        lib.bt2g_index_file_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_uint32]
+        lib.bt2g_index_file_desc.argtypes = [C.c_void_p]
+        lib.bt2g_index_file_desc.restype = C.POINTER(_IndexHost)
+        lib.bt2g_index_file_n_refs.argtypes = [C.c_void_p]
+        lib.bt2g_index_file_n_refs.restype = C.c_uint64
+        lib.bt2g_index_file_ref_names.argtypes = [C.c_void_p]
+        lib.bt2g_index_file_ref_names.restype = C.POINTER(C.c_char_p)
+        lib.bt2g_index_file_ref_lens.argtypes = [C.c_void_p]
+        lib.bt2g_index_file_ref_lens.restype = C.POINTER(C.c_uint64)
+        lib.bt2g_index_file_close.argtypes = [C.c_void_p]
+        lib.bt2g_index_file_close.restype = None
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        if lib.bt2g_index_file_open(basename.encode(), int(offrate), C.byref(h), err, 512):
+            raise RuntimeError(f"bt2g_index_file_open({basename}): {err.value.decode()}")
+        self._h = h
+        self.desc = lib.bt2g_index_file_desc(h).contents
+        n = int(lib.bt2g_index_file_n_refs(h))
+        names = lib.bt2g_index_file_ref_names(h)
+        self.ref_names = [names[i].decode() for i in range(n)]
+        lens = lib.bt2g_index_file_ref_lens(h)
+        self.ref_lens = [int(lens[i]) for i in range(int(self.desc.n_pat))]
+
+    def scalars(self) -> dict:
+        d = self.desc
+        out = {k: int(getattr(d, k)) for k in ("off_size", "line_rate", "off_rate", "ftab_chars", "len", "n_pat", "n_frag",
+                                               "z_off_fw", "z_off_bw", "n_recs")}
+        out["fchr"] = [int(x) for x in d.fchr]
+        return out
+
+    def array(self, name: str) -> np.ndarray:
+        """Copy of one array of the image, typed (OFF arrays as u32/u64, byte arrays as u8)."""
+        d = self.desc
+        osz = int(d.off_size)
+        side = 1 << int(d.line_rate)
+        nsides = ((int(d.len) // 4 + 1) + (side - 4 * osz) - 1) // (side - 4 * osz)
+        ftab_len = (1 << (2 * int(d.ftab_chars))) + 1
+        offs_len = (int(d.len) + 1 + (1 << int(d.off_rate)) - 1) >> int(d.off_rate)
+        counts = {"plen": int(d.n_pat), "rstarts": 3 * int(d.n_frag), "ftab_fw": ftab_len, "ftab_bw": ftab_len,
+                  "eftab_fw": 2 * int(d.ftab_chars), "eftab_bw": 2 * int(d.ftab_chars), "offs": offs_len,
+                  "rec_off": int(d.n_recs), "rec_len": int(d.n_recs)}
+        p = getattr(d, name)
+        p = p if isinstance(p, int) else C.cast(p, C.c_void_p).value
+        if not p:
+            return None
+        if name in counts:
+            dt = np.uint32 if osz == 4 else np.uint64
+            nbytes = counts[name] * osz
+        else:
+            dt = np.uint8
+            if name in ("ebwt_fw", "ebwt_bw"):
+                nbytes = nsides * side
+            elif name == "rec_first":
+                nbytes = int(d.n_recs)
+            else:
+                rl = self.array("rec_len")
+                nbytes = (int(rl.sum()) + 3) >> 2
+        buf = (C.c_uint8 * nbytes).from_address(p)
+        return np.frombuffer(buf, dtype=dt).copy()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bt2g_index_file_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -454,6 +454,42 @@ int bt2g_pe_classify_host(const bt2g_pe_policy *pol, const int64_t *pairs, uint6
 int bt2g_fastq_parse(const char *text, uint64_t len, uint64_t max_reads, uint64_t max_bases, uint8_t *seq, uint8_t *qual,
                      uint64_t *off, char *names, uint32_t name_stride, uint64_t *n_reads, uint64_t *consumed);
 
+/* SAM header: @HD, one @SQ per reference (name up to the first whitespace), and @PG with the given command line
+ * when pg_cl != NULL (SamConfig::printHeader, sam.cpp:54-111).  -3 with *written = bytes needed when cap is short. */
+int bt2g_sam_header(const char *const *names, const uint64_t *lens, uint64_t n, const char *pg_cl,
+                    char *out, uint64_t cap, uint64_t *written);
+
+/* Alignment summary = what the reference prints on stderr at the end of a run (AlnSink::printAlSumm,
+ * aln_sink.cpp:349-528), from the counters AlnSinkWrap::finishRead keeps (aln_sink.cpp:708-1046).  The ">1 times"
+ * lines print uni2 + rep of the reference's ReportingMetrics (the -M mode both presets use).  counts_add derives
+ * the counters from pipeline results: a read "aligned >1 times" when a second alignment was found (score2 valid);
+ * a pair is discordant when both mates aligned exactly once without forming a concordant pair; a concordant pair
+ * counts ">1" when both mates have a second alignment (the pipeline does not keep the second-best PAIR: an
+ * approximation of the reference's bestUnchosenCScore test, aln_sink.cpp:838-842). */
+typedef struct {
+	uint64_t nread, npaired, nunpaired;
+	uint64_t nconcord_0, nconcord_uni1, nconcord_gt1, ndiscord;
+	uint64_t nunp_0_0, nunp_0_uni1, nunp_0_gt1;       /* mates of pairs that aligned neither concordantly nor discordantly */
+	uint64_t nunp_0, nunp_uni1, nunp_gt1;             /* unpaired reads */
+} bt2g_align_counts;
+int bt2g_align_counts_add(bt2g_align_counts *c, const bt2g_read_result *res, uint64_t n_reads, const bt2g_pair_result *pairs);
+int bt2g_align_summary(const bt2g_align_counts *c, int discord, int mixed, char *out, uint64_t cap, uint64_t *written);
+
+/* ---------------------------------------------------------------------- index files on the host ----- */
+/* Host image of <basename>.{1,2,3,4,rev.1}.bt2[l] (no GPU involved): Ebwt::readIntoMemory (bt2_io.cpp:131-616) incl.
+ * its endian switch and --offrate override (offrate_override < 0: none; <= the stored offRate: ignored), the
+ * reference names stored after eftab, BitPairReference's .3/.4 (reference.cpp:30-260).  The descriptor points
+ * into the image and stays valid until close; hand it to bt2g_load_index_host (or broadcast its arrays first). */
+typedef struct bt2g_index_file bt2g_index_file;
+int  bt2g_index_file_open(const char *basename, int offrate_override, bt2g_index_file **out, char *err, uint32_t err_cap);
+const bt2g_index_host *bt2g_index_file_desc(const bt2g_index_file *f);
+uint64_t bt2g_index_file_n_refs(const bt2g_index_file *f);
+const char *const *bt2g_index_file_ref_names(const bt2g_index_file *f);
+const uint64_t *bt2g_index_file_ref_lens(const bt2g_index_file *f);      /* plen[]: the @SQ LN values */
+void bt2g_index_file_close(bt2g_index_file *f);
+/* bt2g_load_index_files with an --offrate override */
+int  bt2g_load_index_files_ex(bt2g_ctx *ctx, const char *basename, int offrate_override);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,15 @@ def lambda_index(tmp_path_factory):
 
 
 @pytest.fixture(scope="session")
+def rep_index(tmp_path_factory):
+    """index of the repeat-rich golden genome (tests/golden/rep_genome.fa: ctg1 14000 bp, ctg2 10000 bp)"""
+    d = tmp_path_factory.mktemp("rep")
+    base = str(d / "rep")
+    _build_index("bowtie2-build-s", os.path.join(GOLDEN, "rep_genome.fa"), base)
+    return base
+
+
+@pytest.fixture(scope="session")
 def synth_genome():
     from bowtie2_b200 import synth
     return synth.make_genome(n_contigs=3, contig_len=40000, seed=11, repeat_frac=0.05, repeat_len=300,

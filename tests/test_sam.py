@@ -246,3 +246,175 @@ def test_fastq_parse_matches_test_reader():
         fastq_parse(lib, b">x\nACGT\n")
     with pytest.raises(RuntimeError):
         fastq_parse(lib, b"@x\nACGT\n+\nII\n@y\nAC\n+\nII\n")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# repeat-rich fixture (tests/golden/rep_*): XS:i, low MAPQ, two contigs, discordant pairs, mates reported as
+# unpaired alignments of a paired read, and the ">1 times" lines of the summary
+
+REP_NAMES, REP_LENS = ["ctg1", "ctg2"], [14000, 10000]
+
+
+def _rebuild(golden, names, reads, quals, O, paired):
+    """Per-read results and op strings for the formatter from the reference's own records: the alignment through the
+    oracle DP around the reported position; the policy-dependent fields (MAPQ, XS:i and, for mates of a paired read
+    reported as unpaired, whether a second alignment existed) from the record."""
+    from bowtie2_b200.lib import PAIR_RESULT, load_library
+    lib = load_library()
+    sc = policy.Scoring.default(False)
+    n = len(reads)
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    maxops = max(len(r) for r in reads) + 64
+    ops = np.zeros((n, maxops), dtype=np.uint8)
+    by = {}
+    for l in golden:
+        f = l.split("\t")
+        by[(f[0], 1 if int(f[1]) & 128 else 0)] = l
+    good = np.ones(n, dtype=bool)
+    order = []
+    for i in range(n):
+        l = by[(names[i], (i & 1) if paired else 0)]
+        order.append(l)
+        f = l.split("\t")
+        flag = int(f[1])
+        if flag & 4:
+            continue
+        tags = {t[:2]: t[5:] for t in f[11:]}
+        pos, fw, AS = int(f[3]) - 1, not (flag & 16), int(tags["AS"])
+        tidx = REP_NAMES.index(f[2])
+        r = reads[i]
+        rdlen = len(r)
+        minsc = sc.min_score(rdlen)
+        found, rect = policy.frame_seed_extension_rect(pos, rdlen, REP_LENS[tidx], sc.max_read_gaps(minsc, rdlen),
+                                                       sc.max_ref_gaps(minsc, rdlen), sc.n_ceil(rdlen))
+        d = oracle_dp(O, False, r, quals[i], fw, tidx, rect, minsc, sc.n_ceil_raw(rdlen), max_alns=8)
+        al = [a for a in d["alns"] if a["refoff"] == pos and a["score"] == AS]
+        if not al:
+            good[i] = False
+            continue
+        o = _edits_to_ops(al[0]["edits"], r, fw)
+        res[i]["found"] = 2 if not al[0]["edits"] else 1
+        res[i]["score"] = AS
+        res[i]["fw"] = int(fw); res[i]["tidx"] = tidx; res[i]["refoff"] = pos; res[i]["nops"] = len(o)
+        res[i]["mapq"] = int(f[4]); res[i]["pad"] = int(tags["XN"])
+        if "XS" in tags:
+            res[i]["score2"] = int(tags["XS"])
+        elif paired and "YT:Z:UP" in l:
+            # XS:i is never printed for these; a MAPQ different from the unique-alignment value means a second alignment
+            # (discordant mates are unique by definition, and their MAPQ is computed from the pair's score sum)
+            uniq = lib.bt2g_mapq(AS, 0, 0, minsc, 0, 1)
+            if int(f[4]) != uniq:
+                res[i]["score2"] = AS                           # any valid value: only its presence matters
+        ops[i, :len(o)] = o
+    pairs = None
+    if paired:
+        pairs = np.zeros(n // 2, dtype=PAIR_RESULT)
+        for pi in range(n // 2):
+            yt = order[2 * pi].split("YT:Z:")[1][:2]
+            a1, a2 = res[2 * pi]["found"] != 0, res[2 * pi + 1]["found"] != 0
+            pairs[pi]["pair_type"] = 1 if yt == "CP" else (2 if (a1 and a2) else (3 if (a1 or a2) else 0))
+    return res, ops, pairs, good, order
+
+
+def _load_rep(paired):
+    tag = "P" if paired else "U"
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, f"rep_{tag}_sensitive.sam")) if not l.startswith("@")]
+    n1, r1, q1 = read_fastq_codes(os.path.join(GOLDEN, "rep_reads_1.fq"), 10 ** 9)
+    if not paired:
+        return golden, n1, r1, q1
+    n2, r2, q2 = read_fastq_codes(os.path.join(GOLDEN, "rep_reads_2.fq"), 10 ** 9)
+    return (golden, [x for p in zip(n1, n2) for x in p], [x for p in zip(r1, r2) for x in p], [x for p in zip(q1, q2) for x in p])
+
+
+def test_sam_repeat_genome_unpaired(rep_index):
+    golden, names, reads, quals = _load_rep(False)
+    res, ops, _, good, order = _rebuild(golden, names, reads, quals, Oracle(rep_index), False)
+    assert good.mean() > 0.9
+    lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, REP_NAMES, read_names=names).rstrip("\n").split("\n")
+    nxs = nlow = 0
+    for i in np.nonzero(good)[0]:
+        assert lines[i] == golden[i], (i, lines[i], golden[i])
+        nxs += "XS:i:" in golden[i]
+        nlow += (not int(golden[i].split("\t")[1]) & 4) and int(golden[i].split("\t")[4]) <= 1
+    assert nxs > 80 and nlow > 40
+
+
+def test_sam_repeat_genome_paired(rep_index):
+    golden, names, reads, quals = _load_rep(True)
+    res, ops, pairs, good, order = _rebuild(golden, names, reads, quals, Oracle(rep_index), True)
+    assert good.mean() > 0.9
+    lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, REP_NAMES, read_names=names, pairs=pairs,
+                       threads=3).rstrip("\n").split("\n")
+    assert len(lines) == len(golden)
+    seen = set()
+    for pi in range(len(reads) // 2):
+        if not (good[2 * pi] and good[2 * pi + 1]):
+            continue
+        # the reference prints the aligned mate first when only mate 2 aligned: compare by (name, mate)
+        got = {bool(int(l.split("\t")[1]) & 128): l for l in lines[2 * pi:2 * pi + 2]}
+        for k in (0, 1):
+            assert got[bool(k)] == order[2 * pi + k], (pi, got[bool(k)], order[2 * pi + k])
+            f = order[2 * pi + k].split("\t")
+            seen.add((f[-1] if f[-1].startswith("YT") else [t for t in f if t.startswith("YT")][0], int(f[1])))
+        assert lines[2 * pi:2 * pi + 2] == golden[2 * pi:2 * pi + 2]              # and in the same order
+    kinds = {k for k, _ in seen}
+    flags = {v for _, v in seen}
+    assert kinds == {"YT:Z:CP", "YT:Z:DP", "YT:Z:UP"}
+    assert {99, 147, 83, 163, 65, 129, 81, 161, 97, 145, 73, 133, 89, 165, 77, 141, 137, 69}.issubset(flags)
+
+
+@pytest.mark.parametrize("fixture", ["lambda_U_sensitive", "lambda_U_local", "lambda_P_sensitive", "rep_U_sensitive", "rep_P_sensitive"])
+def test_alignment_summary_matches_reference_stderr(fixture):
+    """bt2g_align_counts_add + bt2g_align_summary against what the reference printed for the same run; the records of
+    the run supply found / second-alignment / pair type, as the pipeline's result arrays would."""
+    from bowtie2_b200.lib import PAIR_RESULT, align_counts_add, align_summary
+    lib = load_library()
+    want = open(os.path.join(GOLDEN, fixture + ".summary.txt")).read()
+    golden = [l.rstrip("\n").split("\t") for l in open(os.path.join(GOLDEN, fixture + ".sam")) if not l.startswith("@")]
+    paired = "_P_" in fixture
+    local = "local" in fixture
+    sc = policy.Scoring.default(local)
+    n = len(golden)
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    # order records as (pair, mate)
+    if paired:
+        golden = [x for i in range(0, n, 2) for x in sorted(golden[i:i + 2], key=lambda f: int(f[1]) & 128)]
+    for i, f in enumerate(golden):
+        flag = int(f[1])
+        if flag & 4:
+            continue
+        tags = {t[:2]: t[5:] for t in f[11:]}
+        res[i]["found"] = 1
+        res[i]["score"] = int(tags["AS"])
+        rdlen = len(f[9])
+        uniq = lib.bt2g_mapq(int(tags["AS"]), 0, 0, sc.min_score(rdlen), sc.perfect_score(rdlen) if local else 0, 1)
+        if "XS" in tags or (int(f[4]) != uniq and paired and "YT:Z:UP" in f):
+            res[i]["score2"] = int(tags["AS"])
+    pairs = None
+    if paired:
+        pairs = np.zeros(n // 2, dtype=PAIR_RESULT)
+        for pi in range(n // 2):
+            yt = [t for t in golden[2 * pi] if t.startswith("YT:Z:")][0][5:]
+            a1, a2 = res[2 * pi]["found"] != 0, res[2 * pi + 1]["found"] != 0
+            pairs[pi]["pair_type"] = 1 if yt == "CP" else (2 if (a1 and a2) else (3 if (a1 or a2) else 0))
+    counts = align_counts_add(lib, None, res, pairs)
+    # counters add up over batches
+    if n > 10:
+        k = (n // 4) * 2
+        c2 = align_counts_add(lib, None, res[:k], None if pairs is None else pairs[:k // 2])
+        c2 = align_counts_add(lib, c2, res[k:], None if pairs is None else pairs[k // 2:])
+        assert c2.tobytes() == counts.tobytes()
+    got = align_summary(lib, counts)
+    if paired:
+        # the second-best concordant PAIR is not part of the pipeline's results (include/bt2g.h): take the reference's
+        # split of the concordant pairs into "exactly 1" / ">1", check the total, and compare the rest of the text
+        wl = want.split("\n")
+        uni1, gt1 = int(wl[3].split()[0]), int(wl[4].split()[0])
+        assert int(counts["nconcord_uni1"][0] + counts["nconcord_gt1"][0]) == uni1 + gt1
+        counts["nconcord_uni1"], counts["nconcord_gt1"] = uni1, gt1
+        got = align_summary(lib, counts)
+    assert got == want
+    if not paired:
+        assert align_summary(lib, counts, discord=False, mixed=False) == want
