@@ -1,0 +1,131 @@
+"""Reads in -> SAM out: the caller of the hot path for whole files (host plumbing around include/bt2g.h).
+
+FASTQ text (optionally gzip) is parsed in batches (bt2g_fastq_parse), each batch goes through the pipeline
+(bt2g_pipeline_run_host / _run_paired_host: copies and kernels overlapped inside), the records are formatted by
+bt2g_sam_format on host threads and written behind the header (bt2g_sam_header); the alignment summary
+(bt2g_align_summary) is what the reference prints on stderr.  This is the part of multiseedSearchWorker
+(bt2_search.cpp:3101-4100) that surrounds the search: read a batch, align, report, in input order.
+Nothing here computes alignments; without a GPU `Bt2Gpu` raises before any file is opened for writing."""
+import gzip
+import io
+import sys
+
+import numpy as np
+
+from .lib import (ALIGN_COUNTS, Bt2Gpu, IndexFile, Pipeline, ReadBatch, align_counts_add, align_summary, fastq_parse,
+                  load_library, sam_format, sam_header)
+
+
+class FastqStream:
+    """Batches of whole FASTQ records from a file (plain or .gz)."""
+
+    def __init__(self, path: str, chunk_bytes: int = 32 << 20, name_stride: int = 96):
+        self._f = gzip.open(path, "rb") if path.endswith(".gz") else open(path, "rb")
+        self._buf = b""
+        self._eof = False
+        self._chunk = chunk_bytes
+        self._stride = name_stride
+        self._lib = load_library()
+
+    def next_batch(self, max_reads: int):
+        """-> (ReadBatch, names) with up to max_reads records; an empty batch at the end of the file."""
+        while not self._eof and self._buf.count(b"\n") < 4 * max_reads + 4:
+            more = self._f.read(self._chunk)
+            if not more:
+                self._eof = True
+                break
+            self._buf += more
+        if self._eof and self._buf and not self._buf.endswith(b"\n"):
+            self._buf += b"\n"                                   # last record without a final newline
+        if not self._buf.strip():
+            return ReadBatch(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(0, np.uint8)), []
+        batch, names, used = fastq_parse(self._lib, self._buf, max_reads=max_reads, name_stride=self._stride)
+        if batch.n == 0 and self._eof:
+            raise RuntimeError("truncated FASTQ record at the end of the input")
+        self._buf = self._buf[used:]
+        return batch, names
+
+    def close(self):
+        self._f.close()
+
+
+def interleave(b1: ReadBatch, b2: ReadBatch) -> ReadBatch:
+    """mate 1 of pair i -> read 2i, mate 2 -> read 2i+1 (the layout bt2g_pipeline_run_paired_* takes)"""
+    if b1.n != b2.n:
+        raise ValueError(f"mate files differ in length within a batch ({b1.n} vs {b2.n} records)")
+    n = b1.n
+    l1, l2 = b1.lengths(), b2.lengths()
+    lens = np.empty(2 * n, dtype=np.uint64)
+    lens[0::2], lens[1::2] = l1, l2
+    off = np.zeros(2 * n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    total = int(off[-1])
+    seq = np.empty(total, dtype=np.uint8)
+    qual = np.empty(total, dtype=np.uint8)
+    for b, l, start in ((b1, l1, off[0:2 * n:2]), (b2, l2, off[1:2 * n:2])):
+        src0 = b.off[:-1].astype(np.int64)
+        dst = np.repeat(start.astype(np.int64) - src0, l) + np.arange(int(b.off[-1]), dtype=np.int64)
+        seq[dst] = b.seq[:int(b.off[-1])]
+        qual[dst] = b.qual[:int(b.off[-1])]
+    return ReadBatch(seq, off, qual)
+
+
+def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None, preset: str = "sensitive", local: bool = False,
+                device: int = 0, batch_reads: int = 1 << 20, threads: int = 8, seed_table: int = 0, dense_sa: int = -1,
+                offrate: int = -1, pg_cl: str = None, summary=sys.stderr, gpu: Bt2Gpu = None):
+    """bowtie2 -x index_base (-U reads1 | -1 reads1 -2 reads2) -S out_path.  Returns the ALIGN_COUNTS record."""
+    own = gpu is None
+    gpu = gpu or Bt2Gpu(device)                                  # raises without a GPU: nothing below runs on the CPU
+    lib = gpu._lib
+    image = IndexFile(index_base, offrate)
+    gpu.load_index_host(image)
+    ref_names, ref_lens = image.ref_names, image.ref_lens
+    image.close()
+    if seed_table:
+        gpu.build_seed_table(seed_table)
+    if dense_sa >= 0:
+        gpu.build_dense_sa(dense_sa)
+    paired = reads2 is not None
+    s1 = FastqStream(reads1)
+    s2 = FastqStream(reads2) if paired else None
+    per_batch = batch_reads // 2 if paired else batch_reads
+    counts = np.zeros(1, dtype=ALIGN_COUNTS)
+    pipe, pipe_len = None, 0
+    sam_names = [n.split()[0] if n.split() else n for n in ref_names]
+    with open(out_path, "w") as out:
+        out.write(sam_header(lib, ref_names, ref_lens, pg_cl))
+        while True:
+            b1, n1 = s1.next_batch(per_batch)
+            if paired:
+                b2, n2 = s2.next_batch(per_batch)
+                if b1.n != b2.n:
+                    raise RuntimeError("fewer reads in one mate file than in the other")
+            if b1.n == 0:
+                break
+            batch = interleave(b1, b2) if paired else b1
+            names = [x for p in zip(n1, n2) for x in p] if paired else n1
+            need = int(batch.lengths().max())
+            if pipe is None or need > pipe_len:
+                if pipe is not None:
+                    pipe.close()
+                pipe_len = max(need, 32)
+                pipe = Pipeline(gpu, preset, max_len=pipe_len, max_reads=max(batch_reads, 2), row_cap=16, range_max=16, local=local,
+                                both_mates=paired)
+                if paired:
+                    pipe.enable_pairs()
+            if paired:
+                res, ops, pairs = pipe.run_paired_host(batch)
+            else:
+                (res, ops), pairs = pipe.run_host(batch), None
+            out.write(sam_format(lib, batch, res, ops, sam_names, read_names=names, pairs=pairs, threads=threads))
+            align_counts_add(lib, counts, res, pairs)
+    if pipe is not None:
+        pipe.close()
+    s1.close()
+    if s2 is not None:
+        s2.close()
+    if summary is not None:
+        summary.write(align_summary(lib, counts))
+    if own:
+        gpu.close()
+    return counts

@@ -173,6 +173,10 @@ class Bt2Gpu:
         else:
             self._check(self._lib.bt2g_load_index_files(self._h, basename.encode()), "bt2g_load_index_files")
 
+    def load_index_host(self, index_file: "IndexFile"):
+        """Upload a host image read with IndexFile (bt2g_load_index_host copies; the image may be closed afterwards)."""
+        self._check(self._lib.bt2g_load_index_host(self._h, C.byref(index_file.desc)), "bt2g_load_index_host")
+
     def load_index_device(self, desc: dict, keep=None):
         """Adopt device arrays (e.g. torch tensors filled by an NCCL broadcast). `desc` maps
         bt2g_index_host field names to ints (scalars / raw device pointers)."""

