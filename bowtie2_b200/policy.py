@@ -36,6 +36,12 @@ class SimpleFunc:
         return int(self.f(x))        # C cast: truncation toward zero
 
 
+def _F32(x: float) -> float:
+    """a float literal of the reference widened to double"""
+    import struct
+    return struct.unpack("f", struct.pack("f", x))[0]
+
+
 @dataclass
 class Preset:
     """presets.cpp:37-92 ("%LOCAL%" variants) -> policy string fields."""
@@ -80,10 +86,12 @@ class Scoring:
         return cls(match_bonus=2 if local else 0, local=local)
 
     def score_min(self) -> SimpleFunc:
-        return SimpleFunc(SIMPLE_FUNC_LOG, 20.0, 8.0) if self.local else SimpleFunc(SIMPLE_FUNC_LINEAR, -0.6, -0.6)
+        # the defaults are FLOAT literals widened to double (scoring.h:50-55: -0.6f = -0.60000002384...), which moves the
+        # truncation point for read lengths where 0.6 * (len + 1) is an integer: 109 bp -> -66, not -65
+        return SimpleFunc(SIMPLE_FUNC_LOG, 20.0, 8.0) if self.local else SimpleFunc(SIMPLE_FUNC_LINEAR, _F32(-0.6), _F32(-0.6))
 
     def n_ceil_func(self) -> SimpleFunc:
-        return SimpleFunc(SIMPLE_FUNC_LINEAR, 0.0, 0.15, 0.0, float("inf"))
+        return SimpleFunc(SIMPLE_FUNC_LINEAR, 0.0, _F32(0.15), 0.0, float("inf"))      # scoring.h:61-63: 0.0f, 0.15f
 
     def read_gap_open(self): return self.rdgap_const + self.rdgap_linear
     def read_gap_extend(self): return self.rdgap_linear

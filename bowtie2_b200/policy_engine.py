@@ -1,0 +1,727 @@
+"""Sequential search policy of the reference for ONE unpaired end-to-end read, replayed exactly.
+
+The batched pipeline (pipeline.cu) speculates: it extends every plausible seed hit at once and keeps the best
+result.  The reference instead walks a per-read, RNG-driven sequence (multiseedSearchWorker, bt2_search.cpp:3101-4250;
+SwDriver::extendSeeds, aligner_sw_driver.cpp:921-1500) whose decisions -- which BW rows get resolved, when the
+-M ceiling or a failure streak stops the search, how ties are broken -- decide MAPQ, XS:i and, in repeats, the
+reported locus.  This module restates that control flow over an abstract `backend` that supplies the hot-path
+primitives (exact sweep, 1-mismatch search, seed search, seed extension, offset resolution, ungapped and gapped
+DP), so that records can be made byte-identical to the reference program's.  The test-suite plugs in the CPU oracle
+to pin the control flow against the reference's SAM; a product backend issues the same calls through include/bt2g.h.
+
+Scope: unpaired reads, end-to-end mode, default reporting (-M, no -k/-a), no --local, no mates.  Everything
+numeric that the reference does in float/double is done in the same type here.
+
+Every RNG draw of the reference on this path is reproduced, in order:
+  rnd.init(genRandSeed)                         bt2_search.cpp:3437-3440, pat.cpp:45-82
+  eeSaTups: strand order, range trimming        aligner_sw_driver.cpp:101-131, 205-221 (sort1mmEe)
+  rankSeedHits                                   aligner_seed.h:1019-1080
+  prioritizeSATupsRands: RowSampler, Random1toN  aligner_sw_driver.cpp:690-706
+  extendSeeds: Random1toN per range              aligner_sw_driver.cpp:1120
+  nextAlignment: reseed per backtrace attempt    aligner_sw.cpp:794-795, 877 (8-bit) / 879, 932 (16-bit)
+  finishRead: selectByScore tie shuffles         aln_sink.cpp:1552-1568
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import policy
+from .policy import RandomSource
+
+MIN_I64 = -(1 << 63)
+EXHAUSTED, FULFILLED, PERFECT, SOFT_LIMIT, HARD_LIMIT = 1, 2, 3, 4, 5
+
+
+def _next_u64(rnd):
+    hi = rnd.next_u32()
+    return (hi << 32) | rnd.next_u32()
+
+
+def _next_float(rnd):
+    """RandomSource::nextFloat (random_source.h:137-140): float32 division, widened to double by the callers"""
+    return float(np.float32(rnd.next_u32()) / np.float32(0xffffffff))
+
+
+def shuffle_portion(lst, begin, num, rnd):
+    """EList::shufflePortion (ds.h:804-815) with 64-bit size_t"""
+    if num < 2:
+        return
+    left = num
+    for i in range(begin, begin + num - 1):
+        r = _next_u64(rnd) % left
+        if r > 0:
+            lst[i], lst[i + r] = lst[i + r], lst[i]
+        left -= 1
+
+
+def shuffle_equal_streaks(lst, key, rnd):
+    """the streak loop shared by selectByScore (aln_sink.cpp:1552-1568) and sort1mmEe (aligner_seed.h:1223-1245)"""
+    streak = 0
+    for i in range(1, len(lst)):
+        if key(lst[i]) == key(lst[i - 1]):
+            if streak == 0:
+                streak = 1
+            streak += 1
+        else:
+            if streak > 1:
+                shuffle_portion(lst, i - streak, streak, rnd)
+            streak = 0
+    if streak > 1:
+        shuffle_portion(lst, len(lst) - streak, streak, rnd)
+
+
+class Random1toN:
+    """random_util.h:32-160: pseudo-randoms from [0, n) without replacement"""
+    SWAPLIST_THRESH, CONVERSION_THRESH = 128, 16
+
+    def __init__(self):
+        self.n = self.cur = 0
+        self.swaplist = self.converted = False
+        self.list, self.seen, self.thresh = [], [], 0
+
+    def init(self, n, without_replacement):
+        self.n, self.cur = n, 0
+        self.converted = False
+        self.swaplist = n < self.SWAPLIST_THRESH or without_replacement
+        self.list, self.seen = [], []
+        self.thresh = max(self.CONVERSION_THRESH, int(np.float32(0.10) * np.float32(n)))
+
+    def inited(self):
+        return self.n > 0
+
+    def done(self):
+        return self.inited() and self.cur >= self.n
+
+    def next(self, rnd):
+        if self.cur == 0 and not self.converted:
+            if self.n == 1:
+                self.cur = 1
+                return 0
+            if self.swaplist:
+                self.list = list(range(self.n))
+        if self.swaplist:
+            r = self.cur + (rnd.next_u32() % (self.n - self.cur))
+            if r != self.cur:
+                self.list[self.cur], self.list[r] = self.list[r], self.list[self.cur]
+            self.cur += 1
+            return self.list[self.cur - 1]
+        seen_sz = len(self.seen)
+        while True:
+            rn = rnd.next_u32() % self.n
+            if rn not in self.seen[:seen_sz]:
+                break
+        self.seen.append(rn)
+        self.cur += 1
+        if len(self.seen) >= self.thresh and self.cur < self.n:
+            s = set(self.seen)
+            self.list = [j for j in range(self.n) if j not in s]
+            self.seen = []
+            self.cur = 0
+            self.n = len(self.list)
+            self.converted = True
+            self.swaplist = True
+        return rn
+
+
+class RowSampler:
+    """aligner_sw_driver.h:179-256: weighted choice of the next non-small range (double arithmetic)"""
+
+    def __init__(self, sats, lensq=True, szsq=True):
+        self.masses, self.elim, self.mass = [], [False] * len(sats), 0.0
+        for s in sats:
+            num = float(s.nlex + s.nrex + 1)
+            if lensq:
+                num *= num
+            den = float(s.size)
+            if szsq:
+                den *= den
+            self.masses.append(num / den)
+            self.mass += self.masses[-1]
+
+    def finished(self, i):
+        self.elim[i] = True
+        self.mass -= self.masses[i]
+
+    def next(self, rnd):
+        rd = _next_float(rnd) * self.mass
+        sofar, last = 0.0, None
+        for i, m in enumerate(self.masses):
+            if not self.elim[i]:
+                last = i
+                sofar += m
+                if rd < sofar:
+                    return i
+        return last
+
+
+class IntervalSet:
+    """EIvalMergeListBinned as used by SwDriver (seenDiags1_): membership of (ref, strand, offset) in a union of intervals"""
+
+    def __init__(self):
+        self.iv = {}
+
+    def add(self, tidx, fw, off, length):
+        self.iv.setdefault((tidx, fw), []).append((off, off + length))
+
+    def present(self, tidx, fw, off):
+        return any(a <= off < b for a, b in self.iv.get((tidx, fw), ()))
+
+
+@dataclass
+class Aln:
+    """what the engine needs of an AlnRes"""
+    tidx: int
+    refoff: int
+    fw: bool
+    score: int
+    rdlen: int
+    edits: list            # reference Edit convention: (pos from the 5' end, chr, qchr, type 1 read gap / 2 ref gap / 3 mismatch)
+    ns: int = 0
+    refns: int = 0
+    exact: bool = False     # came from the end-to-end exact / 1-mismatch search
+
+
+def edits_left_to_right(a: Aln):
+    """AlnRes::invertEdits for reverse-strand alignments (edit.cpp:50-78): positions from the left end in reference orientation"""
+    if a.fw:
+        return [tuple(e) for e in a.edits]
+    out = []
+    for pos, ch, qch, typ in reversed(a.edits):
+        out.append((a.rdlen - pos - (0 if typ == 1 else 1), ch, qch, typ))
+    return out
+
+
+class RedundantAlns:
+    """aligner_result.cpp:929-1030: cells (row, ref column) already covered by a reported alignment"""
+
+    def __init__(self):
+        self.cells = set()
+
+    def _walk(self, a: Aln):
+        ned = edits_left_to_right(a)
+        left = a.refoff
+        k = 0
+        n = a.rdlen
+        for i in range(n):
+            diff = 1
+            right = left + 1
+            while k < len(ned) and ned[k][0] == i:
+                if ned[k][3] == 2:
+                    diff = 0
+                k += 1
+            if i < n - 1:
+                k2 = k
+                while k2 < len(ned) and ned[k2][0] == i + 1:
+                    if ned[k2][3] == 1:
+                        right += 1
+                    k2 += 1
+            for j in range(left, right):
+                yield (a.tidx, a.fw, j, i)
+            left = right + diff - 1
+
+    def overlap(self, a: Aln):
+        return any(c in self.cells for c in self._walk(a))
+
+    def add(self, a: Aln):
+        self.cells.update(self._walk(a))
+
+
+class UnpairedSink:
+    """AlnSinkWrap + ReportingState for an unpaired read in -M mode (aln_sink.cpp:60-330, 1395-1452)"""
+
+    def __init__(self, khits=1, mhits=50):
+        self.khits, self.mhits = khits, mhits
+        self.alns = []
+        self.done = False
+        self.exit_m = False
+        self.best = self.best2 = MIN_I64
+
+    def report(self, a: Aln):
+        self.alns.append(a)
+        if not self.done and len(self.alns) > self.mhits:
+            self.done = True
+            self.exit_m = True
+        if a.score > self.best:
+            self.best2, self.best = self.best, a.score
+        elif a.score > self.best2:
+            self.best2 = a.score
+        return self.done
+
+    def done_with_mate(self):
+        return self.done
+
+
+@dataclass
+class SatPos:
+    topf: int
+    topb: int
+    size: int
+    key_len: int
+    fw: bool
+    offidx: int
+    rdoff: int
+    seedlen: int
+    nlex: int = 0
+    nrex: int = 0
+    orig_size: int = 0
+
+    def sort_key(self):
+        # SATuple::operator< (aligner_cache.h:399-407) then SeedPos::operator< (aligner_sw_driver.h:118-128)
+        return (self.size, self.topf, self.offidx, self.rdoff, self.seedlen, 0 if self.fw else 1)
+
+
+@dataclass
+class EEHit:
+    top: int
+    bot: int
+    fw: bool
+    score: int
+    edit: tuple = None      # (pos, chr, qchr) of the single mismatch, reference Edit convention
+
+    def mms(self):
+        return 0 if self.edit is None else 1
+
+    def ns(self):
+        return int(self.edit is not None and (self.edit[1] == ord("N") or self.edit[2] == ord("N")))
+
+    def refns(self):
+        return int(self.edit is not None and self.edit[1] == ord("N"))
+
+
+@dataclass
+class ReadResult:
+    aligned: bool = False
+    aln: Aln = None
+    xs: int = None
+    mapq: int = 0
+    filtered: str = None         # "NS" / "LN" when the read never entered the search
+    n_alns: int = 0
+    maxed: bool = False
+    counters: dict = None        # nExIters / nExDps / nExUgs / nRedundants of the reference's per-read metrics (ZI XD XU YR)
+
+
+class PolicyEngine:
+    def __init__(self, backend, preset="sensitive", seed=0, sc=None):
+        self.b = backend
+        self.pre = policy.preset(preset, False)
+        self.sc = sc or policy.Scoring.default(False)
+        self.seed = seed
+        # bt2_search.cpp:342-343, 459-492 and the preset's -D / -R
+        self.khits, self.mhits = 1, 50
+        self.maxhalf = 15
+        self.max_iters, self.max_ug, self.max_dp = 400, 300, 300
+        self.streak = self.pre.dp_fail_streak
+        self.n_seed_rounds = self.pre.seed_rounds
+        self.tighten = 3
+        self.seed_boost_thresh = 300
+        self.nsm = 5
+
+    # ------------------------------------------------------------------------------------------------- one read
+    def align_read(self, codes, quals, name) -> ReadResult:
+        sc = self.sc
+        rdlen = len(codes)
+        res = ReadResult()
+        codes = np.asarray(codes, dtype=np.uint8)
+        quals = np.asarray(quals, dtype=np.uint8)
+        ns_in_read = int((codes > 3).sum())
+        if rdlen < 2 or rdlen <= 0:
+            res.filtered = "LN"
+            return res
+        if ns_in_read > sc.n_ceil(rdlen):
+            res.filtered = "NS"
+            return res
+        self.codes, self.quals, self.rdlen = codes, quals, rdlen
+        self.minsc = sc.min_score(rdlen)
+        self.perfect = sc.perfect_score(rdlen)
+        self.nceil = sc.n_ceil(rdlen)
+        rnd = self.rnd = RandomSource(policy.gen_rand_seed(codes, quals, name, self.seed))
+        interval = policy.seed_interval(self.pre.ival, rdlen, False)
+        # per-read state of SwDriver (nextRead) and of the sink
+        self.seen = IntervalSet()
+        self.red = RedundantAlns()
+        self.ex_ranges = {True: [], False: []}
+        self.sink = UnpairedSink(self.khits, self.mhits)
+        self.n_iters = self.n_dps = self.n_ugs = self.n_red = 0
+        self.mm1 = []                 # SeedResults::mm1Hit_
+        done = False
+        # ---- exact end-to-end (bt2_search.cpp:3493-3690)
+        nelt, mined, tb = self.b.exact_sweep(codes)
+        minedfw, minedrc = int(mined[0]), int(mined[1])
+        if nelt > 0:
+            ee = []
+            if tb[1] > tb[0]:
+                ee.append(EEHit(int(tb[0]), int(tb[1]), True, self.perfect))
+            if tb[3] > tb[2]:
+                ee.append(EEHit(int(tb[2]), int(tb[3]), False, self.perfect))
+            ret = self.extend_seeds(None, ee)
+            done = self._after_extend(ret, done)
+        # ---- 1-mismatch end-to-end (bt2_search.cpp:3692-3875)
+        if not done:
+            yfw, yrc = minedfw <= 1, minedrc <= 1
+            if yfw or yrc:
+                hits = self.b.one_mm(codes, quals, self.minsc, not yfw, not yrc)
+                self.mm1 = [EEHit(int(h[0]), int(h[1]), bool(h[6]), int(h[5]), (int(h[2]), int(h[3]), int(h[4]))) for h in hits]
+                if self.mm1 and not self.sink.done_with_mate():
+                    ret = self.extend_seeds(None, [])
+                    self.mm1 = []                           # clear1mmE2eHits (bt2_search.cpp:3839)
+                    done = self._after_extend(ret, done)
+                elif self.mm1:
+                    done = True
+        # ---- seed rounds (bt2_search.cpp:3876-4150)
+        nrounds = min(self.n_seed_rounds, interval)
+        L = self.pre.seed_len
+        for roundi in range(self.n_seed_rounds):
+            if done or self.sink.done_with_mate():
+                done = True
+                break
+            if roundi >= nrounds or interval <= roundi:
+                continue
+            offset = (interval * roundi) // nrounds
+            if offset > 0 and L + offset > rdlen:
+                continue
+            hits = self.b.seed_search(codes, quals, min(L, rdlen), interval, offset)
+            if hits is None:                                   # no seed could be instantiated
+                done = True
+                break
+            nelt_fw = [max(0, int(h[1]) - int(h[0])) for h in hits[0]]
+            nelt_rc = [max(0, int(h[1]) - int(h[0])) for h in hits[1]]
+            nonz = sum(x > 0 for x in nelt_fw) + sum(x > 0 for x in nelt_rc)
+            if nonz == 0:
+                done = True
+                break
+            ranks = policy.rank_seed_hits(nelt_fw, nelt_rc, rnd, False)
+            sh = dict(hits=hits, ranks=ranks, interval=interval, offset=offset, seedlen=min(L, rdlen), nonz=nonz,
+                      nelt=sum(nelt_fw) + sum(nelt_rc))
+            ret = self.extend_seeds(sh, [])
+            done = self._after_extend(ret, done, check_perfect=False)
+            if not done and sh["nelt"] // nonz < self.seed_boost_thresh:
+                done = True
+        return self.finish_read(res)
+
+    def _after_extend(self, ret, done, check_perfect=True):
+        if ret == FULFILLED:
+            if self.sink.done_with_mate():
+                done = True
+        elif ret in (PERFECT, HARD_LIMIT):
+            done = True
+        if check_perfect and not done and self.minsc == self.perfect:
+            done = True
+        return done
+
+    # ------------------------------------------------------------------------------------------- eeSaTups
+    def _ee_sa_tups(self, ee_exact, maxelt):
+        """aligner_sw_driver.cpp:66-290 -> list of (SatPos, EEHit, Random1toN)"""
+        rnd = self.rnd
+        out = []
+        nelt = 0
+        done = False
+        tot = sum(h.bot - h.top for h in ee_exact)
+        if tot > 0:
+            fw_first = True
+            fwsz = sum(h.bot - h.top for h in ee_exact if h.fw)
+            rn = (rnd.next_u32() if self.b.off_size == 4 else _next_u64(rnd)) % tot
+            if rn >= fwsz:
+                fw_first = False
+            for fwi in range(2):
+                if done:
+                    break
+                fw = (fwi == 0) == fw_first
+                hit = next((h for h in ee_exact if h.fw == fw), None)
+                if hit is None:
+                    continue
+                nelt, done = self._ee_add(out, hit, nelt, maxelt, done)
+        if not done and self.mm1:
+            # EList::sort = std::sort; the lists here are short enough for its insertion-sort (stable) regime
+            self.mm1.sort(key=lambda h: -h.score)
+            shuffle_equal_streaks(self.mm1, lambda h: h.score, rnd)
+            for hit in self.mm1:
+                if done:
+                    break
+                nelt, done = self._ee_add(out, hit, nelt, maxelt, done)
+        return out, nelt
+
+    def _ee_add(self, out, hit, nelt, maxelt, done):
+        rnd = self.rnd
+        tops, bots = [hit.top, 0], [hit.bot, 0]
+        width = hit.bot - hit.top
+        if width <= 0:
+            return nelt, done
+        if nelt + width > maxelt:
+            trim = (nelt + width) - maxelt
+            rn = (rnd.next_u32() if self.b.off_size == 4 else _next_u64(rnd)) % width
+            newwidth = width - trim
+            if hit.top + rn + newwidth > hit.bot:
+                tops[0], bots[0] = hit.top + rn, hit.bot
+                tops[1], bots[1] = hit.top, hit.top + newwidth - (bots[0] - tops[0])
+            else:
+                tops[0] = hit.top + rn
+                bots[0] = tops[0] + newwidth
+        for i in range(2):
+            if done or bots[i] <= tops[i]:
+                break
+            w = bots[i] - tops[i]
+            sp = SatPos(tops[i], 0, w, self.rdlen, hit.fw, 0, 0, self.rdlen, orig_size=w)
+            r = Random1toN()
+            r.init(w, False)
+            out.append((sp, hit, r))
+            nelt += w
+            if nelt >= maxelt:
+                done = True
+        return nelt, done
+
+    # ------------------------------------------------------------------------------- prioritizeSATupsRands
+    def _prioritize(self, sh, maxelt):
+        """aligner_sw_driver.cpp:490-725 -> (list of (SatPos, None, Random1toN), nelt)"""
+        rnd = self.rnd
+        sats = []
+        nelt = 0
+        for offidx, fw in sh["ranks"]:
+            h = sh["hits"][0 if fw else 1][offidx]
+            topf, botf, topb, botb = (int(x) for x in h)
+            sz = botf - topf
+            rdoff = sh["offset"] + offidx * sh["interval"]
+            seedlen = sh["seedlen"]
+            nelt += sz
+            rng = self.ex_ranges[fw]
+            if any(p5 <= rdoff and p5 + ln >= rdoff + seedlen and sz <= rsz for p5, ln, rsz in rng):
+                nelt -= sz
+                continue
+            sp = SatPos(topf, topb, sz, seedlen, fw, offidx, rdoff, seedlen, orig_size=sz)
+            sp.nlex, sp.nrex = self.b.extend(self.codes, fw, rdoff, seedlen, (topf, botf, topb, botb))
+            if sp.nlex > 0 or sp.nrex > 0:
+                rng.append((rdoff - (sp.nlex if fw else sp.nrex), seedlen + sp.nlex + sp.nrex, sz))
+            sats.append(sp)
+        nsmall = sum(s.size <= self.nsm for s in sats)
+        sats.sort(key=SatPos.sort_key)
+        out = []
+        added = 0
+        j = 0
+        while j < nsmall and added < maxelt:
+            s = sats[j]
+            r = Random1toN()
+            r.init(s.size, False)
+            out.append((s, None, r))
+            added += s.size
+            j += 1
+        if added >= maxelt or nsmall == len(sats):
+            return out, added
+        sampler = RowSampler(sats[nsmall:])
+        rands2 = [Random1toN() for _ in sats]
+        while added < maxelt and added < nelt:
+            ri = sampler.next(rnd) + nsmall
+            if not rands2[ri].inited():
+                rands2[ri].init(sats[ri].size, False)
+            r = rands2[ri].next(rnd)
+            if rands2[ri].done():
+                sampler.finished(ri - nsmall)
+            src = sats[ri]
+            s = SatPos(src.topf + r, 0, 1, src.key_len, src.fw, src.offidx, src.rdoff, src.seedlen, src.nlex, src.nrex, src.orig_size)
+            one = Random1toN()
+            one.init(1, False)
+            out.append((s, None, one))
+            added += 1
+        return out, added
+
+    # --------------------------------------------------------------------------------------- extendSeeds
+    def extend_seeds(self, sh, ee_exact):
+        sc, rnd, rdlen = self.sc, self.rnd, self.rdlen
+        nonz = sh["nonz"] if sh else 0
+        ee_mode = bool(ee_exact or self.mm1)
+        first_ee = first_extend = True
+        n_ug_fail = n_dp_fail = 0
+        nelt_left = 0
+        satpos = []
+        while True:
+            if ee_mode:
+                if first_ee:
+                    first_ee = False
+                    satpos, _ = self._ee_sa_tups(ee_exact, self.max_iters)
+                else:
+                    ee_mode = False
+            if not ee_mode:
+                if nonz == 0:
+                    return EXHAUSTED
+                if self.minsc == self.perfect:
+                    return PERFECT
+                if first_extend:
+                    satpos, nelt = self._prioritize(sh, self.max_iters)
+                    nelt_left = nelt
+                    first_extend = False
+                if nelt_left == 0:
+                    break
+            for sp, eehit, rands in satpos:
+                if ee_mode and eehit.score < self.minsc:
+                    return PERFECT
+                is_small = sp.size < self.nsm
+                fw = sp.fw
+                rdoff = sp.rdoff
+                if not fw:
+                    rdoff = rdlen - rdoff - sp.seedlen
+                first = True
+                while (not rands.done()) and (first or is_small or ee_mode):
+                    if self.minsc == self.perfect:
+                        if not ee_mode or eehit.score < self.perfect:
+                            return PERFECT
+                    elif ee_mode and eehit.score < self.minsc:
+                        break
+                    if self.n_dps >= self.max_dp or self.n_ugs >= self.max_ug or self.n_iters >= self.max_iters:
+                        return HARD_LIMIT
+                    self.n_iters += 1
+                    first = False
+                    elt = rands.next(rnd)
+                    joined = self.b.resolve(sp.topf + elt)
+                    if not ee_mode:
+                        nelt_left -= 1
+                    ok, tidx, toff, tlen, straddled = self.b.joined_to_text(sp.key_len, joined, ee_mode)
+                    if not ok:
+                        continue
+                    refoff = toff - rdoff
+                    if self.seen.present(tidx, fw, refoff):
+                        self.n_red += 1
+                        continue
+                    read_gaps = ref_gaps = 0
+                    ungapped = False
+                    if not ee_mode:
+                        read_gaps = sc.max_read_gaps(self.minsc, rdlen)
+                        ref_gaps = sc.max_ref_gaps(self.minsc, rdlen)
+                        ungapped = read_gaps == 0 and ref_gaps == 0
+                    found_alns = None                 # list of Aln for EE / ungapped, or a DP attempt iterator
+                    state = 0
+                    if ee_mode:
+                        ed = [] if eehit.edit is None else [(eehit.edit[0], eehit.edit[1], eehit.edit[2], 3)]
+                        a = Aln(tidx, refoff, fw, eehit.score, rdlen, ed, eehit.ns(), eehit.refns(), True)
+                        found_alns = [a]
+                        state = 1
+                        self.seen.add(tidx, fw, refoff, 1)
+                    elif ungapped:
+                        rc, a = self.b.ungapped(self.codes, self.quals, fw, tidx, refoff, tlen, self.minsc)
+                        self.seen.add(tidx, fw, refoff, 1)
+                        self.n_ugs += 1
+                        if rc == 0:
+                            n_ug_fail += 1
+                            if n_ug_fail >= self.streak:
+                                return SOFT_LIMIT
+                            continue
+                        elif rc == -1:
+                            n_ug_fail += 1
+                            if n_ug_fail >= self.streak:
+                                return SOFT_LIMIT
+                        else:
+                            n_ug_fail = 0
+                            found_alns = [a]
+                            state = 2
+                    dp = None
+                    if state == 0:
+                        found, rect = policy.frame_seed_extension_rect(refoff, rdlen, tlen, read_gaps, ref_gaps, self.nceil, self.maxhalf)
+                        self.seen.add(tidx, fw, refoff, 1)
+                        if not found:
+                            continue
+                        self.seen.add(tidx, fw, rect.refl_pretrim + rect.corel, rect.corer - rect.corel + 1)
+                        dp = self.b.dp(self.codes, self.quals, fw, tidx, rect, self.minsc, sc.n_ceil_raw(rdlen))
+                        self.n_dps += 1
+                        if not dp["found"]:
+                            n_dp_fail += 1
+                            if n_dp_fail >= self.streak:
+                                return SOFT_LIMIT
+                            continue
+                        n_dp_fail = 0
+                        dp["cursor"] = 0
+                        dp["u8"] = self.minsc >= -254
+                    first_inner = True
+                    while True:
+                        if state != 0:
+                            if not first_inner:
+                                break
+                            a = found_alns[0]
+                        else:
+                            a = self._next_alignment(dp, tidx)
+                            if a is None:
+                                break
+                        first_inner = False
+                        # (alignments falling off the reference are clipped only with --local / overhangs enabled)
+                        if self.red.overlap(a):
+                            continue
+                        self.red.add(a)
+                        if self.sink.report(a):
+                            return FULFILLED
+                        if self.tighten > 0 and self.sink.best2 != MIN_I64:
+                            best, best2 = self.sink.best, self.sink.best2
+                            if self.tighten == 1:
+                                if best >= self.minsc:
+                                    self.minsc = best
+                                    if self.minsc < self.perfect and best == best2:
+                                        self.minsc += 1
+                            elif self.tighten == 2:
+                                if best2 >= self.minsc:
+                                    self.minsc = best2
+                                    if self.minsc < self.perfect:
+                                        self.minsc += 1
+                            else:
+                                diff = best - best2
+                                bot = best2 + (diff * 3) // 4              # diff >= 0
+                                if bot >= self.minsc:
+                                    self.minsc = bot
+                                    if self.minsc < self.perfect:
+                                        self.minsc += 1
+        return EXHAUSTED
+
+    def _next_alignment(self, dp, tidx):
+        """SwAligner::nextAlignment (aligner_sw.cpp:737-1146) over the backend's attempt list: candidates below the
+        current minimum score are skipped without touching the RNG, every backtrace attempt reseeds it."""
+        rnd = self.rnd
+        att = dp["attempts"]
+        while dp["cursor"] < len(att):
+            cand_score, ai = att[dp["cursor"]]
+            dp["cursor"] += 1
+            if cand_score < self.minsc:
+                continue
+            reseed = (rnd.next_u32() + 1) & 0xffffffff
+            rnd.init((reseed + 1) & 0xffffffff if dp["u8"] else reseed)
+            if ai >= 0:
+                al = dp["alns"][ai]
+                ed = [tuple(e) for e in al["edits"]]
+                # AlnRes::refNs: ambiguous reference characters under the alignment (XN:i)
+                extent = self.rdlen + sum(e[3] == 1 for e in ed) - sum(e[3] == 2 for e in ed)
+                return Aln(tidx, al["refoff"], bool(al["fw"]), al["score"], self.rdlen, ed, al["ns"],
+                           self.b.count_ref_ns(tidx, al["refoff"], extent))
+        return None
+
+    # ---------------------------------------------------------------------------------------- finishRead
+    def finish_read(self, res: ReadResult) -> ReadResult:
+        rnd = self.rnd
+        alns = self.sink.alns
+        res.n_alns = len(alns)
+        res.maxed = self.sink.exit_m
+        res.counters = dict(ZI=self.n_iters, XD=self.n_dps, XU=self.n_ugs, YR=self.n_red)
+        if not alns:
+            return res
+        # selectByScore (aln_sink.cpp:1477-1628): descending by score, index descending within ties, tie streaks shuffled
+        buf = sorted(((a.score, i) for i, a in enumerate(alns)), reverse=True)
+        shuffle_equal_streaks(buf, lambda t: t[0], rnd)
+        best = alns[buf[0][1]]
+        res.aligned, res.aln = True, best
+        res.xs = buf[1][0] if len(buf) > 1 else None
+        res.mapq = policy.mapq_v2(best.score, res.xs, self.sc.min_score(self.rdlen), self.perfect, True)
+        return res
+
+
+def aln_to_ops(a: Aln, codes):
+    """op string of include/bt2g.h (last aligned read row first; every op that consumes a reference base carries its
+    code) from an alignment in the reference's Edit representation."""
+    from .lib import OP_MATCH, OP_MM, OP_READGAP, OP_REFGAP
+    code = {ord(c): i for i, c in enumerate("ACGTN")}
+    rdlen = len(codes)
+    seq = codes if a.fw else np.array([4 if c > 3 else 3 - c for c in codes[::-1]], dtype=np.uint8)
+    ed = edits_left_to_right(a)
+    fwd, k = [], 0
+    for rel in range(rdlen):
+        while k < len(ed) and ed[k][0] == rel and ed[k][3] == 1:
+            fwd.append(OP_READGAP | (code[ed[k][1]] << 2))
+            k += 1
+        if k < len(ed) and ed[k][0] == rel:
+            fwd.append(OP_REFGAP if ed[k][3] == 2 else (OP_MM | (code[ed[k][1]] << 2)))
+            k += 1
+        else:
+            fwd.append(OP_MATCH | (int(seq[rel]) << 2))
+    assert k == len(ed)
+    return fwd[::-1]

@@ -795,6 +795,15 @@ int bt2o_ungapped(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *c
 
 typedef struct { int nedsz, celsz, row, col, gaps, score, ns, ct; } bt_frame;
 
+/* Optional log of the backtrace attempts of the next bt2o_dp call, in the order SwAligner::nextAlignment makes them
+ * (aligner_sw.cpp:757-1120): one pair per candidate that passed the start filter (and, local mode, the domination
+ * filter) = per RNG reseed of the reference: [candidate score, index of the alignment it produced or -1].  Used by the
+ * tests that replay the reference's sequential policy, where the per-read RNG state depends on the attempt count. */
+static int64_t *g_attempt_log = NULL;
+static int g_attempt_cap = 0, g_attempt_n = 0;
+void bt2o_dp_attempt_log(int64_t *buf, int cap) { g_attempt_log = buf; g_attempt_cap = cap; g_attempt_n = 0; }
+int bt2o_dp_attempt_count(void) { return g_attempt_n; }
+
 /* One SwAligner session (aligner_sw.cpp:155-271 initRef, :500-729 align, :737-1146
  * nextAlignment).  End-to-end: fill recurrences aligner_swsse_ee_u8.cpp:931-993, gather :1176-1208,
  * backtrace :1283-1877.  Local: fill aligner_swsse_loc_i16.cpp:938-1367 (scores floored at 0 by
@@ -901,6 +910,9 @@ int bt2o_dp(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, 
 			donerow[ndone] = row; donecol[ndone] = col; ndone++;
 		}
 		const int start_row = row;
+		const int attempt = g_attempt_n;
+		if(g_attempt_log && g_attempt_n < g_attempt_cap) { g_attempt_log[2 * g_attempt_n] = AT(H, row, col); g_attempt_log[2 * g_attempt_n + 1] = -1; }
+		g_attempt_n++;
 		int nned = 0, ncells = 0, nstack = 0, gaps = 0, score = 0, ns = 0, ct = 0 /*0 H,1 E,2 F*/;
 		int ok = 1, trim_beg = 0;
 		for(;;) {
@@ -1002,6 +1014,7 @@ int bt2o_dp(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, 
 			if(rdc > 3 || rfc > 3) ns++;
 		}
 		if(ns > nceil) continue;
+		if(g_attempt_log && attempt < g_attempt_cap) g_attempt_log[2 * attempt + 1] = naln;
 		if(naln < max_alns) {
 			const int trim_end = nrow - 1 - start_row;
 			const int ext = nrow - trim_beg - trim_end;

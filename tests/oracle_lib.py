@@ -184,10 +184,18 @@ def oracle_scoring(O, local):
     return sc
 
 
-def oracle_dp(O, local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=1024, max_alns=32, max_edits=4096):
-    """Same outputs as ref_dp(), from the plain-C restatement (oracle/bt2_oracle.c: bt2o_dp)."""
+def oracle_dp(O, local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=1024, max_alns=32, max_edits=4096, attempts=False):
+    """Same outputs as ref_dp(), from the plain-C restatement (oracle/bt2_oracle.c: bt2o_dp).  attempts=True adds
+    out["attempts"] = [(candidate score, alignment index or -1)], one entry per backtrace the reference would start."""
     i64 = C.c_int64
     L = O.lib
+    att = None
+    if attempts:
+        att = np.full(2 * 4096, -1, np.int64)
+        L.bt2o_dp_attempt_log.argtypes = [vp, ci]
+        L.bt2o_dp_attempt_log.restype = None
+        L.bt2o_dp_attempt_count.restype = ci
+        L.bt2o_dp_attempt_log(att.ctypes.data_as(vp), 4096)
     L.bt2o_scoring_default.argtypes = [C.POINTER(_OScoring), ci]
     L.bt2o_dp.argtypes = [vp, C.POINTER(_OScoring), vp, vp, ci, ci, u64, i64, i64, ci, ci, ci, i64, ci, ci, ci, ci, vp, vp, vp, vp]
     sc = _OScoring()
@@ -213,6 +221,11 @@ def oracle_dp(O, local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=10
                    "edits": [[int(x) for x in eds[4 * k:4 * k + 4]] for k in range(e0, e0 + ne)]})
         e0 += ne
     out["alns"] = al
+    if attempts:
+        n = int(L.bt2o_dp_attempt_count())
+        assert n <= 4096
+        out["attempts"] = [(int(att[2 * k]), int(att[2 * k + 1])) for k in range(n)]
+        L.bt2o_dp_attempt_log(None, 0)
     return out
 
 

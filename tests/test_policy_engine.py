@@ -1,0 +1,117 @@
+"""bowtie2_b200.policy_engine: the reference's sequential, RNG-driven search policy for unpaired end-to-end reads,
+replayed over the CPU oracle's primitives, must reproduce the reference PROGRAM byte for byte -- every SAM field
+including MAPQ and XS:i, the locus chosen among equal repeats -- and its per-read work counters (--read-times:
+ZI extend-loop iterations, XD gapped DPs, XU ungapped extensions, YR redundant seed hits), which pins the order and
+number of RNG draws."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bowtie2_b200 import synth
+from bowtie2_b200.lib import READ_RESULT, ReadBatch, load_library, sam_format
+from bowtie2_b200.policy_engine import PolicyEngine, Random1toN, aln_to_ops
+from bowtie2_b200.policy import RandomSource
+from conftest import GOLDEN, read_fastq_codes
+from oracle_lib import Oracle, have_reference, ref_bin
+from policy_backend import OracleBackend
+
+KEEP = ("AS", "XS", "XN", "XM", "XO", "XG", "NM", "MD", "YS", "YT", "YF")
+
+
+def _run_engine(index, reads, quals, names, ref_names, preset):
+    O = Oracle(index)
+    eng = PolicyEngine(OracleBackend(O), preset)
+    n = len(reads)
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    ops = np.zeros((n, max(len(r) for r in reads) + 64), dtype=np.uint8)
+    outs = []
+    for i in range(n):
+        r = eng.align_read(reads[i], quals[i], names[i])
+        outs.append(r)
+        if r.aligned:
+            a = r.aln
+            o = aln_to_ops(a, reads[i])
+            res[i]["found"] = 2 if not a.edits else 1
+            res[i]["score"] = a.score
+            if r.xs is not None:
+                res[i]["score2"] = r.xs
+            res[i]["fw"] = int(a.fw); res[i]["tidx"] = a.tidx; res[i]["refoff"] = a.refoff; res[i]["nops"] = len(o)
+            res[i]["mapq"] = r.mapq; res[i]["pad"] = a.refns
+            ops[i, :len(o)] = o
+    lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ref_names, read_names=names).rstrip("\n").split("\n")
+    return lines, outs
+
+
+@pytest.mark.parametrize("fixture,index,ref_names", [
+    ("lambda", "lambda_index", ["gi|9626243|ref|NC_001416.1|"]),
+    ("rep", "rep_index", ["ctg1", "ctg2"]),
+])
+def test_sam_identical_to_golden(fixture, index, ref_names, request):
+    base = request.getfixturevalue(index)
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, f"{fixture}_U_sensitive.sam")) if not l.startswith("@")]
+    names, reads, quals = read_fastq_codes(os.path.join(GOLDEN, f"{fixture}_reads_1.fq"), len(golden))
+    lines, outs = _run_engine(base, reads, quals, names, ref_names, "sensitive")
+    bad = [i for i in range(len(golden)) if lines[i] != golden[i]]
+    assert not bad, (len(bad), lines[bad[0]], golden[bad[0]])
+    if fixture == "rep":
+        assert sum(o.n_alns >= 2 for o in outs) > 80          # ties in repeats were decided by the replayed RNG
+
+
+def _reference_run(index, fq, preset):
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), "--" + preset, "--seed", "0", "-p", "1", "--read-times", "-x", index, "-U", fq],
+                                  stderr=subprocess.DEVNULL).decode()
+    full = [l for l in out.split("\n") if l and not l.startswith("@")]
+    recs, counters = [], []
+    for l in full:
+        f = l.split("\t")
+        recs.append("\t".join(f[:11] + [x for x in f[11:] if x[:2] in KEEP]))
+        tags = {t[:2]: t[5:] for t in f[11:]}
+        counters.append(tuple(int(tags[k]) for k in ("ZI", "XD", "XU", "YR")) if "ZI" in tags else None)
+    return recs, counters
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("preset,rdlen,n,genome_kw", [
+    ("sensitive", 100, 500, {}),
+    ("very-sensitive", 150, 300, {}),
+    ("fast", 50, 400, {}),
+    ("very-fast", 250, 200, {}),
+    ("sensitive", 36, 400, {}),
+    # half of the genome in 400-copy repeat families: -M ceiling, weighted range sampling, re-seeding rounds
+    ("sensitive", 100, 400, dict(contig_len=120000, repeat_frac=0.6, repeat_len=250, repeat_copies=400)),
+])
+def test_sam_and_work_counters_identical_to_reference_program(tmp_path, preset, rdlen, n, genome_kw):
+    kw = dict(n_contigs=3, contig_len=40000, seed=11, repeat_frac=0.05, repeat_len=300, repeat_copies=12, n_gap=37)
+    kw.update(genome_kw)
+    genome = synth.make_genome(**kw)
+    fa, base, fq = str(tmp_path / "g.fa"), str(tmp_path / "g"), str(tmp_path / "r.fq")
+    synth.write_fasta(fa, genome)
+    subprocess.check_call([ref_bin("bowtie2-build-s"), "--seed", "0", "--quiet", fa, base])
+    reads, quals, _ = synth.make_reads(genome, n, rdlen, seed=5 + rdlen, sub_rate=0.02, indel_rate=0.003)
+    synth.write_fastq(fq, reads, quals)
+    want, counters = _reference_run(base, fq, preset)
+    names = [f"r{i}" for i in range(len(reads))]
+    lines, outs = _run_engine(base, reads, quals, names, [f"chr{k + 1}" for k in range(len(genome))], preset)
+    bad = [i for i in range(len(want)) if lines[i] != want[i]]
+    assert not bad, (len(bad), lines[bad[0]], want[bad[0]])
+    for i, o in enumerate(outs):
+        if o.counters is not None and counters[i] is not None:
+            c = o.counters
+            assert (c["ZI"], c["XD"], c["XU"], c["YR"]) == counters[i], (i, c, counters[i])
+    if genome_kw:
+        assert any(o.maxed for o in outs) and max(o.counters["ZI"] for o in outs if o.counters) > 50
+
+
+def test_random_1_to_n_is_a_permutation_in_every_mode():
+    """seen-list mode (n >= 128), its conversion to the swap list, and the small-set swap list"""
+    for n in (1, 2, 5, 127, 128, 200, 1000):
+        r = Random1toN()
+        r.init(n, False)
+        rnd = RandomSource(n)
+        got = []
+        while not r.done():
+            got.append(r.next(rnd))
+        assert sorted(got) == list(range(n)), n
