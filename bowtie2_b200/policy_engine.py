@@ -300,6 +300,25 @@ class ReadResult:
     counters: dict = None        # nExIters / nExDps / nExUgs / nRedundants of the reference's per-read metrics (ZI XD XU YR)
 
 
+@dataclass
+class MateCtx:
+    """per-mate state of the worker loop and of SwDriver (one of these is the "anchor" during extendSeeds*)"""
+    codes: np.ndarray
+    quals: np.ndarray
+    name: str
+    rdlen: int = 0
+    minsc: int = 0
+    perfect: int = 0
+    nceil: int = 0
+    filt: bool = True
+    filtered: str = None
+    mm1: list = field(default_factory=list)            # SeedResults::mm1Hit_
+    ee: list = field(default_factory=list)             # exact end-to-end hits
+    ex_ranges: dict = field(default_factory=lambda: {True: [], False: []})   # seedExRangeFw_/Rc_
+    seen: "IntervalSet" = field(default_factory=lambda: IntervalSet())           # seenDiags1_/2_
+    sh: dict = None                                    # seed hits of the current round
+
+
 class PolicyEngine:
     def __init__(self, backend, preset="sensitive", seed=0, sc=None):
         self.b = backend
@@ -330,19 +349,13 @@ class PolicyEngine:
         if ns_in_read > sc.n_ceil(rdlen):
             res.filtered = "NS"
             return res
-        self.codes, self.quals, self.rdlen = codes, quals, rdlen
-        self.minsc = sc.min_score(rdlen)
-        self.perfect = sc.perfect_score(rdlen)
-        self.nceil = sc.n_ceil(rdlen)
+        self.cur = MateCtx(codes, quals, name, rdlen, sc.min_score(rdlen), sc.perfect_score(rdlen), sc.n_ceil(rdlen))
         rnd = self.rnd = RandomSource(policy.gen_rand_seed(codes, quals, name, self.seed))
         interval = policy.seed_interval(self.pre.ival, rdlen, False)
         # per-read state of SwDriver (nextRead) and of the sink
-        self.seen = IntervalSet()
         self.red = RedundantAlns()
-        self.ex_ranges = {True: [], False: []}
         self.sink = UnpairedSink(self.khits, self.mhits)
         self.n_iters = self.n_dps = self.n_ugs = self.n_red = 0
-        self.mm1 = []                 # SeedResults::mm1Hit_
         done = False
         # ---- exact end-to-end (bt2_search.cpp:3493-3690)
         nelt, mined, tb = self.b.exact_sweep(codes)
@@ -350,22 +363,22 @@ class PolicyEngine:
         if nelt > 0:
             ee = []
             if tb[1] > tb[0]:
-                ee.append(EEHit(int(tb[0]), int(tb[1]), True, self.perfect))
+                ee.append(EEHit(int(tb[0]), int(tb[1]), True, self.cur.perfect))
             if tb[3] > tb[2]:
-                ee.append(EEHit(int(tb[2]), int(tb[3]), False, self.perfect))
+                ee.append(EEHit(int(tb[2]), int(tb[3]), False, self.cur.perfect))
             ret = self.extend_seeds(None, ee)
             done = self._after_extend(ret, done)
         # ---- 1-mismatch end-to-end (bt2_search.cpp:3692-3875)
         if not done:
             yfw, yrc = minedfw <= 1, minedrc <= 1
             if yfw or yrc:
-                hits = self.b.one_mm(codes, quals, self.minsc, not yfw, not yrc)
-                self.mm1 = [EEHit(int(h[0]), int(h[1]), bool(h[6]), int(h[5]), (int(h[2]), int(h[3]), int(h[4]))) for h in hits]
-                if self.mm1 and not self.sink.done_with_mate():
+                hits = self.b.one_mm(codes, quals, self.cur.minsc, not yfw, not yrc)
+                self.cur.mm1 = [EEHit(int(h[0]), int(h[1]), bool(h[6]), int(h[5]), (int(h[2]), int(h[3]), int(h[4]))) for h in hits]
+                if self.cur.mm1 and not self.sink.done_with_mate():
                     ret = self.extend_seeds(None, [])
-                    self.mm1 = []                           # clear1mmE2eHits (bt2_search.cpp:3839)
+                    self.cur.mm1 = []                           # clear1mmE2eHits (bt2_search.cpp:3839)
                     done = self._after_extend(ret, done)
-                elif self.mm1:
+                elif self.cur.mm1:
                     done = True
         # ---- seed rounds (bt2_search.cpp:3876-4150)
         nrounds = min(self.n_seed_rounds, interval)
@@ -404,7 +417,7 @@ class PolicyEngine:
                 done = True
         elif ret in (PERFECT, HARD_LIMIT):
             done = True
-        if check_perfect and not done and self.minsc == self.perfect:
+        if check_perfect and not done and self.cur.minsc == self.cur.perfect:
             done = True
         return done
 
@@ -430,11 +443,11 @@ class PolicyEngine:
                 if hit is None:
                     continue
                 nelt, done = self._ee_add(out, hit, nelt, maxelt, done)
-        if not done and self.mm1:
+        if not done and self.cur.mm1:
             # EList::sort = std::sort; the lists here are short enough for its insertion-sort (stable) regime
-            self.mm1.sort(key=lambda h: -h.score)
-            shuffle_equal_streaks(self.mm1, lambda h: h.score, rnd)
-            for hit in self.mm1:
+            self.cur.mm1.sort(key=lambda h: -h.score)
+            shuffle_equal_streaks(self.cur.mm1, lambda h: h.score, rnd)
+            for hit in self.cur.mm1:
                 if done:
                     break
                 nelt, done = self._ee_add(out, hit, nelt, maxelt, done)
@@ -460,7 +473,7 @@ class PolicyEngine:
             if done or bots[i] <= tops[i]:
                 break
             w = bots[i] - tops[i]
-            sp = SatPos(tops[i], 0, w, self.rdlen, hit.fw, 0, 0, self.rdlen, orig_size=w)
+            sp = SatPos(tops[i], 0, w, self.cur.rdlen, hit.fw, 0, 0, self.cur.rdlen, orig_size=w)
             r = Random1toN()
             r.init(w, False)
             out.append((sp, hit, r))
@@ -482,12 +495,12 @@ class PolicyEngine:
             rdoff = sh["offset"] + offidx * sh["interval"]
             seedlen = sh["seedlen"]
             nelt += sz
-            rng = self.ex_ranges[fw]
+            rng = self.cur.ex_ranges[fw]
             if any(p5 <= rdoff and p5 + ln >= rdoff + seedlen and sz <= rsz for p5, ln, rsz in rng):
                 nelt -= sz
                 continue
             sp = SatPos(topf, topb, sz, seedlen, fw, offidx, rdoff, seedlen, orig_size=sz)
-            sp.nlex, sp.nrex = self.b.extend(self.codes, fw, rdoff, seedlen, (topf, botf, topb, botb))
+            sp.nlex, sp.nrex = self.b.extend(self.cur.codes, fw, rdoff, seedlen, (topf, botf, topb, botb))
             if sp.nlex > 0 or sp.nrex > 0:
                 rng.append((rdoff - (sp.nlex if fw else sp.nrex), seedlen + sp.nlex + sp.nrex, sz))
             sats.append(sp)
@@ -524,9 +537,9 @@ class PolicyEngine:
 
     # --------------------------------------------------------------------------------------- extendSeeds
     def extend_seeds(self, sh, ee_exact):
-        sc, rnd, rdlen = self.sc, self.rnd, self.rdlen
+        sc, rnd, rdlen = self.sc, self.rnd, self.cur.rdlen
         nonz = sh["nonz"] if sh else 0
-        ee_mode = bool(ee_exact or self.mm1)
+        ee_mode = bool(ee_exact or self.cur.mm1)
         first_ee = first_extend = True
         n_ug_fail = n_dp_fail = 0
         nelt_left = 0
@@ -541,7 +554,7 @@ class PolicyEngine:
             if not ee_mode:
                 if nonz == 0:
                     return EXHAUSTED
-                if self.minsc == self.perfect:
+                if self.cur.minsc == self.cur.perfect:
                     return PERFECT
                 if first_extend:
                     satpos, nelt = self._prioritize(sh, self.max_iters)
@@ -550,7 +563,7 @@ class PolicyEngine:
                 if nelt_left == 0:
                     break
             for sp, eehit, rands in satpos:
-                if ee_mode and eehit.score < self.minsc:
+                if ee_mode and eehit.score < self.cur.minsc:
                     return PERFECT
                 is_small = sp.size < self.nsm
                 fw = sp.fw
@@ -559,10 +572,10 @@ class PolicyEngine:
                     rdoff = rdlen - rdoff - sp.seedlen
                 first = True
                 while (not rands.done()) and (first or is_small or ee_mode):
-                    if self.minsc == self.perfect:
-                        if not ee_mode or eehit.score < self.perfect:
+                    if self.cur.minsc == self.cur.perfect:
+                        if not ee_mode or eehit.score < self.cur.perfect:
                             return PERFECT
-                    elif ee_mode and eehit.score < self.minsc:
+                    elif ee_mode and eehit.score < self.cur.minsc:
                         break
                     if self.n_dps >= self.max_dp or self.n_ugs >= self.max_ug or self.n_iters >= self.max_iters:
                         return HARD_LIMIT
@@ -576,14 +589,14 @@ class PolicyEngine:
                     if not ok:
                         continue
                     refoff = toff - rdoff
-                    if self.seen.present(tidx, fw, refoff):
+                    if self.cur.seen.present(tidx, fw, refoff):
                         self.n_red += 1
                         continue
                     read_gaps = ref_gaps = 0
                     ungapped = False
                     if not ee_mode:
-                        read_gaps = sc.max_read_gaps(self.minsc, rdlen)
-                        ref_gaps = sc.max_ref_gaps(self.minsc, rdlen)
+                        read_gaps = sc.max_read_gaps(self.cur.minsc, rdlen)
+                        ref_gaps = sc.max_ref_gaps(self.cur.minsc, rdlen)
                         ungapped = read_gaps == 0 and ref_gaps == 0
                     found_alns = None                 # list of Aln for EE / ungapped, or a DP attempt iterator
                     state = 0
@@ -592,10 +605,10 @@ class PolicyEngine:
                         a = Aln(tidx, refoff, fw, eehit.score, rdlen, ed, eehit.ns(), eehit.refns(), True)
                         found_alns = [a]
                         state = 1
-                        self.seen.add(tidx, fw, refoff, 1)
+                        self.cur.seen.add(tidx, fw, refoff, 1)
                     elif ungapped:
-                        rc, a = self.b.ungapped(self.codes, self.quals, fw, tidx, refoff, tlen, self.minsc)
-                        self.seen.add(tidx, fw, refoff, 1)
+                        rc, a = self.b.ungapped(self.cur.codes, self.cur.quals, fw, tidx, refoff, tlen, self.cur.minsc)
+                        self.cur.seen.add(tidx, fw, refoff, 1)
                         self.n_ugs += 1
                         if rc == 0:
                             n_ug_fail += 1
@@ -612,12 +625,12 @@ class PolicyEngine:
                             state = 2
                     dp = None
                     if state == 0:
-                        found, rect = policy.frame_seed_extension_rect(refoff, rdlen, tlen, read_gaps, ref_gaps, self.nceil, self.maxhalf)
-                        self.seen.add(tidx, fw, refoff, 1)
+                        found, rect = policy.frame_seed_extension_rect(refoff, rdlen, tlen, read_gaps, ref_gaps, self.cur.nceil, self.maxhalf)
+                        self.cur.seen.add(tidx, fw, refoff, 1)
                         if not found:
                             continue
-                        self.seen.add(tidx, fw, rect.refl_pretrim + rect.corel, rect.corer - rect.corel + 1)
-                        dp = self.b.dp(self.codes, self.quals, fw, tidx, rect, self.minsc, sc.n_ceil_raw(rdlen))
+                        self.cur.seen.add(tidx, fw, rect.refl_pretrim + rect.corel, rect.corer - rect.corel + 1)
+                        dp = self.b.dp(self.cur.codes, self.cur.quals, fw, tidx, rect, self.cur.minsc, sc.n_ceil_raw(rdlen))
                         self.n_dps += 1
                         if not dp["found"]:
                             n_dp_fail += 1
@@ -626,7 +639,7 @@ class PolicyEngine:
                             continue
                         n_dp_fail = 0
                         dp["cursor"] = 0
-                        dp["u8"] = self.minsc >= -254
+                        dp["u8"] = self.cur.minsc >= -254
                     first_inner = True
                     while True:
                         if state != 0:
@@ -634,7 +647,7 @@ class PolicyEngine:
                                 break
                             a = found_alns[0]
                         else:
-                            a = self._next_alignment(dp, tidx)
+                            a = self._next_alignment(dp, tidx, self.cur.minsc, rdlen)
                             if a is None:
                                 break
                         first_inner = False
@@ -647,25 +660,25 @@ class PolicyEngine:
                         if self.tighten > 0 and self.sink.best2 != MIN_I64:
                             best, best2 = self.sink.best, self.sink.best2
                             if self.tighten == 1:
-                                if best >= self.minsc:
-                                    self.minsc = best
-                                    if self.minsc < self.perfect and best == best2:
-                                        self.minsc += 1
+                                if best >= self.cur.minsc:
+                                    self.cur.minsc = best
+                                    if self.cur.minsc < self.cur.perfect and best == best2:
+                                        self.cur.minsc += 1
                             elif self.tighten == 2:
-                                if best2 >= self.minsc:
-                                    self.minsc = best2
-                                    if self.minsc < self.perfect:
-                                        self.minsc += 1
+                                if best2 >= self.cur.minsc:
+                                    self.cur.minsc = best2
+                                    if self.cur.minsc < self.cur.perfect:
+                                        self.cur.minsc += 1
                             else:
                                 diff = best - best2
                                 bot = best2 + (diff * 3) // 4              # diff >= 0
-                                if bot >= self.minsc:
-                                    self.minsc = bot
-                                    if self.minsc < self.perfect:
-                                        self.minsc += 1
+                                if bot >= self.cur.minsc:
+                                    self.cur.minsc = bot
+                                    if self.cur.minsc < self.cur.perfect:
+                                        self.cur.minsc += 1
         return EXHAUSTED
 
-    def _next_alignment(self, dp, tidx):
+    def _next_alignment(self, dp, tidx, minsc, rdlen):
         """SwAligner::nextAlignment (aligner_sw.cpp:737-1146) over the backend's attempt list: candidates below the
         current minimum score are skipped without touching the RNG, every backtrace attempt reseeds it."""
         rnd = self.rnd
@@ -673,7 +686,7 @@ class PolicyEngine:
         while dp["cursor"] < len(att):
             cand_score, ai = att[dp["cursor"]]
             dp["cursor"] += 1
-            if cand_score < self.minsc:
+            if cand_score < minsc:
                 continue
             reseed = (rnd.next_u32() + 1) & 0xffffffff
             rnd.init((reseed + 1) & 0xffffffff if dp["u8"] else reseed)
@@ -681,8 +694,8 @@ class PolicyEngine:
                 al = dp["alns"][ai]
                 ed = [tuple(e) for e in al["edits"]]
                 # AlnRes::refNs: ambiguous reference characters under the alignment (XN:i)
-                extent = self.rdlen + sum(e[3] == 1 for e in ed) - sum(e[3] == 2 for e in ed)
-                return Aln(tidx, al["refoff"], bool(al["fw"]), al["score"], self.rdlen, ed, al["ns"],
+                extent = rdlen + sum(e[3] == 1 for e in ed) - sum(e[3] == 2 for e in ed)
+                return Aln(tidx, al["refoff"], bool(al["fw"]), al["score"], rdlen, ed, al["ns"],
                            self.b.count_ref_ns(tidx, al["refoff"], extent))
         return None
 
@@ -701,7 +714,7 @@ class PolicyEngine:
         best = alns[buf[0][1]]
         res.aligned, res.aln = True, best
         res.xs = buf[1][0] if len(buf) > 1 else None
-        res.mapq = policy.mapq_v2(best.score, res.xs, self.sc.min_score(self.rdlen), self.perfect, True)
+        res.mapq = policy.mapq_v2(best.score, res.xs, self.sc.min_score(self.cur.rdlen), self.cur.perfect, True)
         return res
 
 
