@@ -738,3 +738,557 @@ def aln_to_ops(a: Aln, codes):
             fwd.append(OP_MATCH | (int(seq[rel]) << 2))
     assert k == len(ed)
     return fwd[::-1]
+
+
+# =====================================================================================================================
+# Paired-end reads: multiseedSearchWorker's two-mate flow (bt2_search.cpp:3400-4250), SwDriver::extendSeedsPaired
+# (aligner_sw_driver.cpp:1582-2615), ReportingState / AlnSinkWrap for pairs (aln_sink.cpp:26-330, 643-1070).
+# Program defaults: --fr, -I 0 -X 500, discordant and mixed (unpaired) alignments reported.
+
+class PairedSink:
+    def __init__(self, khits=1, mhits=50, discord=True, mixed=True):
+        self.khits, self.mhits = khits, mhits
+        self.rs1, self.rs2, self.rs1u, self.rs2u = [], [], [], []
+        self.done_concord = False
+        self.done_discord = not discord
+        self.done_unp = [not mixed, not mixed]
+        self.exit_concord_m = False
+        self.exit_unp_m = [False, False]
+        self.discord_exit_noaln = False
+        self.nconcord = 0
+        self.nunp = [0, 0]
+        self.done = False
+        self.best_pair = self.best2_pair = MIN_I64
+        self.best_unp = [MIN_I64, MIN_I64]
+        self.best2_unp = [MIN_I64, MIN_I64]
+
+    def _update_done(self):
+        self.done = self.done_unp[0] and self.done_unp[1] and self.done_discord and self.done_concord
+
+    def report(self, a1, a2):
+        """AlnSinkWrap::report: a pair when both are given, else an unpaired alignment of the given mate"""
+        if a1 is not None and a2 is not None:
+            self.nconcord += 1
+            if self.nconcord > self.mhits:
+                self.done_concord, self.exit_concord_m = True, True
+            self.done_discord = True
+            # (a concordant category closed by -M does not trump the unpaired ones)
+            self._update_done()
+            self.rs1.append(a1)
+            self.rs2.append(a2)
+            score = a1.score + a2.score
+            if score > self.best_pair:
+                self.best2_pair, self.best_pair = self.best_pair, score
+            elif score > self.best2_pair:
+                self.best2_pair = score
+        else:
+            m = 0 if a1 is not None else 1
+            a = a1 if a1 is not None else a2
+            self.nunp[m] += 1
+            if not self.done_unp[m]:
+                if self.nunp[m] > self.mhits:
+                    self.done_unp[m], self.exit_unp_m[m] = True, True
+                    self._update_done()
+            if self.nunp[m] > 1:
+                self.done_discord = True
+            (self.rs1u if m == 0 else self.rs2u).append(a)
+            if a.score > self.best_unp[m]:
+                self.best2_unp[m], self.best_unp[m] = self.best_unp[m], a.score
+            elif a.score > self.best2_unp[m]:
+                self.best2_unp[m] = a.score
+        return self.done
+
+    def done_with_mate(self, mate1):
+        m = 0 if mate1 else 1
+        if not self.done_unp[m] or not self.done_concord:
+            return False
+        if not self.done_discord and self.nunp[m] == 0:
+            return False
+        return True
+
+    def done_unpaired(self, mate1):
+        return self.done_unp[0 if mate1 else 1]
+
+
+@dataclass
+class PairResult:
+    pair_type: int = 0             # include/bt2g.h: 0 none, 1 concordant, 2 both aligned (discordant or unpaired), 3 one mate
+    mates: list = None             # two ReadResult
+    counters: dict = None
+    n_concord: int = 0
+
+
+class PairedPolicyEngine(PolicyEngine):
+    def __init__(self, backend, preset="sensitive", seed=0, sc=None, pe=None):
+        super().__init__(backend, preset, seed, sc)
+        self.pe = pe or policy.PairedEndPolicy()
+        self.max_mate_streak = 10
+
+    def align_pair(self, codes1, quals1, name1, codes2, quals2, name2) -> PairResult:
+        sc = self.sc
+        m = []
+        for codes, quals, name in ((codes1, quals1, name1), (codes2, quals2, name2)):
+            codes = np.asarray(codes, dtype=np.uint8)
+            quals = np.asarray(quals, dtype=np.uint8)
+            rdlen = len(codes)
+            c = MateCtx(codes, quals, name, rdlen, sc.min_score(rdlen) if rdlen else 0, sc.perfect_score(rdlen), sc.n_ceil(rdlen) if rdlen else 0)
+            if rdlen < 2:
+                c.filt, c.filtered = False, "LN"
+            elif int((codes > 3).sum()) > sc.n_ceil(rdlen):
+                c.filt, c.filtered = False, "NS"
+            m.append(c)
+        self.m = m
+        both = m[0].filt and m[1].filt
+        s1 = policy.gen_rand_seed(m[0].codes, m[0].quals, name1, self.seed)
+        s2 = policy.gen_rand_seed(m[1].codes, m[1].quals, name2, self.seed)
+        rnd = self.rnd = RandomSource((s1 ^ s2) if both else s1)
+        interval = [policy.seed_interval(self.pre.ival, c.rdlen, both) if c.rdlen else 1 for c in m]
+        streak = self.pre.dp_fail_streak
+        nrounds_all = self.n_seed_rounds
+        if both:
+            streak = -(-streak // 2)
+            nrounds_all = -(-nrounds_all // 2)
+        self.streak_cur = streak
+        self.red = RedundantAlns()
+        self.red_mate = [RedundantAlns(), RedundantAlns()]
+        self.sink = PairedSink(self.khits, self.mhits)
+        self.n_iters = self.n_dps = self.n_ugs = self.n_red = self.n_mate_dps = 0
+        done = [not m[0].filt, not m[1].filt]
+        sink = self.sink
+        matemap = [0, 1]
+        nelt = [0, 0]
+        mined = [[0, 0], [0, 0]]
+
+        def after(ret, mate):
+            if ret == FULFILLED:
+                if sink.done_with_mate(mate == 0):
+                    done[mate] = True
+                if sink.done_with_mate(mate == 1):
+                    done[mate ^ 1] = True
+            elif ret in (PERFECT, HARD_LIMIT):
+                done[mate] = True
+
+        # ---- exact end-to-end
+        for mate in matemap:
+            c = m[mate]
+            if not c.filt or done[mate] or sink.done_with_mate(mate == 0):
+                continue
+            ne, mi, tb = self.b.exact_sweep(c.codes)
+            nelt[mate] = ne
+            mined[mate] = [int(mi[0]), int(mi[1])]
+            c.ee = []
+            if tb[1] > tb[0]:
+                c.ee.append(EEHit(int(tb[0]), int(tb[1]), True, c.perfect))
+            if tb[3] > tb[2]:
+                c.ee.append(EEHit(int(tb[2]), int(tb[3]), False, c.perfect))
+        matemap = [1, 0] if (nelt[0] > 0 and nelt[1] > 0 and nelt[0] > nelt[1]) else [0, 1]
+        for mate in matemap:
+            c = m[mate]
+            if nelt[mate] == 0:
+                c.ee = []
+                continue
+            if sink.done_with_mate(mate == 0):
+                c.ee = []
+                done[mate] = True
+                continue
+            ret = self.extend_seeds_paired(mate, None, c.ee)
+            c.ee = []
+            after(ret, mate)
+            if not done[mate] and c.minsc == c.perfect:
+                done[mate] = True
+        # ---- 1-mismatch end-to-end
+        for mate in matemap:
+            c = m[mate]
+            if not c.filt or done[mate]:
+                c.mm1 = []
+                nelt[mate] = 0
+                continue
+            nelt[mate] = 0
+            yfw, yrc = mined[mate][0] <= 1, mined[mate][1] <= 1
+            if yfw or yrc:
+                hits = self.b.one_mm(c.codes, c.quals, c.minsc, not yfw, not yrc)
+                c.mm1 = [EEHit(int(h[0]), int(h[1]), bool(h[6]), int(h[5]), (int(h[2]), int(h[3]), int(h[4]))) for h in hits]
+                nelt[mate] = sum(h.bot - h.top for h in c.mm1)
+        matemap = [1, 0] if (nelt[0] > 0 and nelt[1] > 0 and nelt[0] > nelt[1]) else [0, 1]
+        for mate in matemap:
+            c = m[mate]
+            if nelt[mate] == 0:
+                continue
+            if sink.done_with_mate(mate == 0):
+                done[mate] = True
+                continue
+            ret = self.extend_seeds_paired(mate, None, [])
+            c.mm1 = []
+            after(ret, mate)
+            if not done[mate] and c.minsc == c.perfect:
+                done[mate] = True
+        # ---- seed rounds
+        nrounds = [min(nrounds_all, interval[0]), min(nrounds_all, interval[1])]
+        L = self.pre.seed_len
+        for roundi in range(self.n_seed_rounds):
+            for c in m:
+                c.sh = None
+            for mate in matemap:
+                c = m[mate]
+                if done[mate] or sink.done_with_mate(mate == 0):
+                    done[mate] = True
+                    continue
+                if roundi >= nrounds[mate] or interval[mate] <= roundi:
+                    continue
+                offset = (interval[mate] * roundi) // nrounds[mate]
+                if offset > 0 and min(L, c.rdlen) + offset > c.rdlen:
+                    continue
+                hits = self.b.seed_search(c.codes, c.quals, L, interval[mate], offset)
+                nfw = [max(0, int(h[1]) - int(h[0])) for h in hits[0]]
+                nrc = [max(0, int(h[1]) - int(h[0])) for h in hits[1]]
+                nonz = sum(x > 0 for x in nfw) + sum(x > 0 for x in nrc)
+                if nonz == 0:
+                    done[mate] = True
+                    break
+                c.sh = dict(hits=hits, interval=interval[mate], offset=offset, seedlen=min(L, c.rdlen), nonz=nonz,
+                            nelt=sum(nfw) + sum(nrc), nfw=nfw, nrc=nrc)
+            uniq = [0.0, 0.0]
+            for i, c in enumerate(m):
+                if c.sh:
+                    uniq[i] = sum(1.0 / float(x * x) for x in c.sh["nfw"] + c.sh["nrc"] if x > 0)
+            matemap = [1, 0] if (m[0].sh and m[1].sh and uniq[1] > uniq[0]) else [0, 1]
+            for mate in matemap:
+                c = m[mate]
+                if done[mate] or sink.done_with_mate(mate == 0):
+                    done[mate] = True
+                    continue
+                if not c.sh:
+                    continue
+                c.sh["ranks"] = policy.rank_seed_hits(c.sh["nfw"], c.sh["nrc"], rnd, False)
+                ret = self.extend_seeds_paired(mate, c.sh, [])
+                after(ret, mate)
+            for mate in (0, 1):
+                c = m[mate]
+                if not done[mate] and c.sh and c.sh["nelt"] // c.sh["nonz"] < self.seed_boost_thresh:
+                    done[mate] = True
+        return self.finish_pair()
+
+    # ------------------------------------------------------------------------------------ extendSeedsPaired
+    def _tightened_pair_score(self, best_pair_score):
+        sink = self.sink
+        if self.tighten == 1:
+            ps = sink.best_pair
+        elif self.tighten == 2:
+            ps = sink.best2_pair
+        else:
+            ps = sink.best2_pair + ((sink.best_pair - sink.best2_pair) * 3) // 4
+        if self.tighten == 1 and ps < best_pair_score and sink.best_pair == sink.best2_pair:
+            ps += 1
+        if self.tighten >= 2 and ps < best_pair_score:
+            ps += 1
+        return ps
+
+    def extend_seeds_paired(self, ai, sh, ee_exact):
+        sc, rnd, sink, pe = self.sc, self.rnd, self.sink, self.pe
+        anchor1 = ai == 0
+        c = self.cur = self.m[ai]
+        o = self.m[ai ^ 1]
+        rdlen, ordlen = c.rdlen, o.rdlen
+        opp_filt = not o.filt
+        operfect = o.perfect
+        best_pair_score = c.perfect + operfect
+        if self.tighten > 0 and sink.best2_pair != MIN_I64:
+            nc = self._tightened_pair_score(best_pair_score) - operfect
+            if nc > c.minsc:
+                c.minsc = nc
+        nonz = sh["nonz"] if sh else 0
+        ee_mode = bool(ee_exact or c.mm1)
+        first_ee = first_extend = True
+        n_ee_fail = n_ug_fail = n_dp_fail = 0
+        nelt_left = 0
+        satpos = []
+        mate_streaks = []
+        sw_mate_immediately = True
+        streak = self.streak_cur
+        while True:
+            if ee_mode:
+                if first_ee:
+                    first_ee = False
+                    satpos, _ = self._ee_sa_tups(ee_exact, self.max_iters)
+                    mate_streaks = [0] * len(satpos)
+                else:
+                    ee_mode = False
+            if not ee_mode:
+                if nonz == 0:
+                    return EXHAUSTED
+                if c.minsc == c.perfect:
+                    return PERFECT
+                if first_extend:
+                    satpos, nelt = self._prioritize(sh, self.max_iters)
+                    nelt_left = nelt
+                    first_extend = False
+                    mate_streaks = [0] * len(satpos)
+                if nelt_left == 0:
+                    break
+            for si, (sp, eehit, rands) in enumerate(satpos):
+                if ee_mode and eehit.score < c.minsc:
+                    return PERFECT
+                is_small = sp.size < self.nsm
+                fw = sp.fw
+                rdoff = sp.rdoff
+                if not fw:
+                    rdoff = rdlen - rdoff - sp.seedlen
+                first = True
+                while (not rands.done()) and (first or is_small or ee_mode):
+                    if c.minsc == c.perfect:
+                        if not ee_mode or eehit.score < c.perfect:
+                            return PERFECT
+                    elif ee_mode and eehit.score < c.minsc:
+                        break
+                    if self.n_dps >= self.max_dp or self.n_mate_dps >= self.max_dp or self.n_ugs >= self.max_ug or self.n_iters >= self.max_iters:
+                        return HARD_LIMIT
+                    if ee_mode and n_ee_fail >= streak:
+                        return SOFT_LIMIT
+                    if not ee_mode and (n_dp_fail >= streak or n_ug_fail >= streak):
+                        return SOFT_LIMIT
+                    if mate_streaks[si] >= self.max_mate_streak:
+                        rands.cur = rands.n                    # Random1toN::setDone
+                        break
+                    self.n_iters += 1
+                    first = False
+                    elt = rands.next(rnd)
+                    joined = self.b.resolve(sp.topf + elt)
+                    nelt_left -= 1
+                    ok, tidx, toff, tlen, straddled = self.b.joined_to_text(sp.key_len, joined, ee_mode)
+                    if not ok:
+                        continue
+                    refoff = toff - rdoff
+                    if c.seen.present(tidx, fw, refoff):
+                        self.n_red += 1
+                        continue
+                    read_gaps = ref_gaps = 0
+                    ungapped = False
+                    if not ee_mode:
+                        read_gaps = sc.max_read_gaps(c.minsc, rdlen)
+                        ref_gaps = sc.max_ref_gaps(c.minsc, rdlen)
+                        ungapped = read_gaps == 0 and ref_gaps == 0
+                    state = 0
+                    fixed = None
+                    if ee_mode:
+                        ed = [] if eehit.edit is None else [(eehit.edit[0], eehit.edit[1], eehit.edit[2], 3)]
+                        fixed = Aln(tidx, refoff, fw, eehit.score, rdlen, ed, eehit.ns(), eehit.refns(), True)
+                        state = 1
+                        c.seen.add(tidx, fw, refoff, 1)
+                        n_ee_fail += 1
+                    elif ungapped:
+                        rc, a = self.b.ungapped(c.codes, c.quals, fw, tidx, refoff, tlen, c.minsc)
+                        c.seen.add(tidx, fw, refoff, 1)
+                        self.n_ugs += 1
+                        n_ug_fail += 1
+                        if rc == 0:
+                            continue
+                        if rc == 1:
+                            fixed = a
+                            state = 2
+                    dp = None
+                    if state == 0:
+                        found, rect = policy.frame_seed_extension_rect(refoff, rdlen, tlen, read_gaps, ref_gaps, c.nceil, self.maxhalf)
+                        c.seen.add(tidx, fw, refoff, 1)
+                        if not found:
+                            continue
+                        c.seen.add(tidx, fw, rect.refl_pretrim + rect.corel, rect.corer - rect.corel + 1)
+                        dp = self.b.dp(c.codes, c.quals, fw, tidx, rect, c.minsc, sc.n_ceil_raw(rdlen))
+                        self.n_dps += 1
+                        n_dp_fail += 1
+                        if not dp["found"]:
+                            continue
+                        dp["cursor"] = 0
+                        dp["u8"] = c.minsc >= -254
+                    first_inner = True
+                    found_concordant = False
+                    while True:
+                        if state != 0:
+                            if not first_inner:
+                                break
+                            a = fixed
+                        else:
+                            a = self._next_alignment(dp, tidx, c.minsc, rdlen)
+                            if a is None:
+                                break
+                        first_inner = False
+                        if self.red.overlap(a):
+                            continue
+                        self.red.add(a)
+                        if sink.done_with_mate(not anchor1) and not sink.done_with_mate(anchor1):
+                            sw_mate_immediately = False
+                        if sw_mate_immediately:
+                            found_mate = not opp_filt
+                            ominsc_cur = o.minsc
+                            odp = None
+                            if found_mate:
+                                if self.tighten > 0 and sink.best2_pair != MIN_I64:
+                                    nc = self._tightened_pair_score(best_pair_score) - a.score
+                                    if nc > ominsc_cur:
+                                        ominsc_cur = nc
+                                ordgaps = sc.max_read_gaps(ominsc_cur, ordlen)
+                                orfgaps = sc.max_ref_gaps(ominsc_cur, ordlen)
+                                om = pe.other_mate(anchor1, fw, a.refoff, ordlen + ordgaps, tlen,
+                                                   rdlen if anchor1 else ordlen, ordlen if anchor1 else rdlen)
+                                found_mate = om is not None
+                            if found_mate:
+                                oleft, oll, olr, orl, orr, ofw = om
+                                found_mate, orect = policy.frame_find_mate_rect(not oleft, oll, olr, orl, orr, ordlen, tlen, ordgaps, orfgaps,
+                                                                                o.nceil, self.maxhalf)
+                            if found_mate:
+                                odp = self.b.dp(o.codes, o.quals, ofw, tidx, orect, ominsc_cur, sc.n_ceil_raw(ordlen))
+                                self.n_mate_dps += 1
+                                found_mate = bool(odp["found"])
+                                if found_mate:
+                                    odp["cursor"] = 0
+                                    odp["u8"] = ominsc_cur >= -254
+                            did_anchor = False
+                            brk = False
+                            while True:
+                                oa = None
+                                if found_mate:
+                                    oa = self._next_alignment(odp, tidx, ominsc_cur, ordlen)
+                                    found_mate = oa is not None
+                                if found_mate:
+                                    if not self.red.overlap(oa):
+                                        self.red.add(oa)
+                                    oext = ordlen + sum(e[3] == 1 for e in oa.edits) - sum(e[3] == 2 for e in oa.edits)
+                                    if oa.refoff < 0 or oa.refoff + oext > tlen:
+                                        found_mate = False          # falls off the reference (no overhangs)
+                                pair_cl = policy.PE_ALS_DISCORD
+                                if found_mate:
+                                    aext = rdlen + sum(e[3] == 1 for e in a.edits) - sum(e[3] == 2 for e in a.edits)
+                                    a1, a2 = (a, oa) if anchor1 else (oa, a)
+                                    l1, l2 = (aext, oext) if anchor1 else (oext, aext)
+                                    pair_cl = pe.classify_pair(a1.refoff, l1, a1.fw, a2.refoff, l2, a2.fw)
+                                if sink.done_concord:
+                                    found_mate = False
+                                if found_mate:
+                                    done_unpaired = False
+                                    if not anchor1 or not did_anchor:
+                                        if anchor1:
+                                            did_anchor = True
+                                        r1 = a if anchor1 else oa
+                                        if not self.red_mate[0].overlap(r1):
+                                            self.red_mate[0].add(r1)
+                                            if sink.report(r1, None):
+                                                done_unpaired = True
+                                    if anchor1 or not did_anchor:
+                                        if not anchor1:
+                                            did_anchor = True
+                                        r2 = oa if anchor1 else a
+                                        if not self.red_mate[1].overlap(r2):
+                                            self.red_mate[1].add(r2)
+                                            if sink.report(None, r2):
+                                                done_unpaired = True
+                                    done_paired = False
+                                    if pair_cl != policy.PE_ALS_DISCORD:
+                                        found_concordant = True
+                                        if sink.report(a if anchor1 else oa, oa if anchor1 else a):
+                                            done_paired = True
+                                        elif self.tighten > 0 and sink.best2_pair != MIN_I64:
+                                            nc = self._tightened_pair_score(best_pair_score) - operfect
+                                            if nc > c.minsc:
+                                                c.minsc = nc
+                                                if c.minsc > a.score:
+                                                    brk = True
+                                    if brk:
+                                        break
+                                    if done_paired or done_unpaired:
+                                        return FULFILLED
+                                    if sink.done_with_mate(anchor1):
+                                        return FULFILLED
+                                elif not did_anchor:
+                                    did_anchor = True
+                                    if not sink.done_unpaired(anchor1):
+                                        red = self.red_mate[0 if anchor1 else 1]
+                                        if not red.overlap(a):
+                                            red.add(a)
+                                            if sink.report(a if anchor1 else None, None if anchor1 else a):
+                                                return FULFILLED
+                                    if sink.done_with_mate(anchor1):
+                                        return FULFILLED
+                                if oa is None:
+                                    break
+                        else:
+                            if not sink.done_unpaired(anchor1):
+                                red = self.red_mate[0 if anchor1 else 1]
+                                if not red.overlap(a):
+                                    red.add(a)
+                                    if sink.report(a if anchor1 else None, None if anchor1 else a):
+                                        return FULFILLED
+                            if sink.done_with_mate(anchor1):
+                                return FULFILLED
+                    if found_concordant:
+                        mate_streaks[si] = 0
+                        if state == 2:
+                            n_ug_fail = 0
+                        elif state == 1:
+                            n_ee_fail = 0
+                        else:
+                            n_dp_fail = 0
+                    else:
+                        mate_streaks[si] += 1
+        return EXHAUSTED
+
+    # ------------------------------------------------------------------------------------------ finishRead
+    def _select(self, rs1, rs2, rs1u, rs2u):
+        """selectByScore for a list of pairs (rs2 given) or of unpaired alignments: -> (index, best-unchosen info)"""
+        rnd = self.rnd
+        buf = sorted(((a.score + (rs2[i].score if rs2 is not None else 0), i) for i, a in enumerate(rs1)), reverse=True)
+        shuffle_equal_streaks(buf, lambda t: t[0], rnd)
+        sel = buf[0][1]
+        out = dict(sel=sel, unchosen_u=None, unchosen_p=[None, None], unchosen_c=None)
+        if rs2 is not None:
+            for k, (rsu, chosen) in enumerate(((rs1u, rs1[sel]), (rs2u, rs2[sel]))):
+                best = None
+                for a in rsu:
+                    if (a.tidx, a.refoff, a.fw) == (chosen.tidx, chosen.refoff, chosen.fw):
+                        continue
+                    if best is None or a.score > best:
+                        best = a.score
+                out["unchosen_p"][k] = best
+            if len(buf) > 1:
+                out["unchosen_c"] = buf[1][0]
+        elif len(buf) > 1:
+            out["unchosen_u"] = rs1[buf[1][1]].score
+        return out
+
+    def finish_pair(self) -> PairResult:
+        sink, m, sc = self.sink, self.m, self.sc
+        res = PairResult(mates=[ReadResult(filtered=m[0].filtered), ReadResult(filtered=m[1].filtered)])
+        res.counters = dict(ZI=self.n_iters, XD=self.n_dps, XU=self.n_ugs, YR=self.n_red)
+        res.n_concord = sink.nconcord
+        mn = [sc.min_score(c.rdlen) if c.rdlen else 0 for c in m]
+        # ReportingState::finish + getReport (aln_sink.cpp:131-260)
+        if sink.nconcord > 0:
+            s = self._select(sink.rs1, sink.rs2, sink.rs1u, sink.rs2u)
+            a1, a2 = sink.rs1[s["sel"]], sink.rs2[s["sel"]]
+            mq = policy.mapq_v2(a1.score + a2.score, s["unchosen_c"], mn[0] + mn[1], m[0].perfect + m[1].perfect, True)
+            for k, a in enumerate((a1, a2)):
+                r = res.mates[k]
+                r.aligned, r.aln, r.xs, r.mapq = True, a, s["unchosen_p"][k], mq
+            res.pair_type = 1
+            return res
+        discord = (not sink.done_discord) and sink.nunp[0] == 1 and sink.nunp[1] == 1
+        if discord:
+            # prepareDiscordants + selectByScore over the single pair
+            s = self._select([sink.rs1u[0]], [sink.rs2u[0]], sink.rs1u, sink.rs2u)
+            a1, a2 = sink.rs1u[0], sink.rs2u[0]
+            mq = policy.mapq_v2(a1.score + a2.score, None, mn[0] + mn[1], m[0].perfect + m[1].perfect, True)
+            for k, a in enumerate((a1, a2)):
+                r = res.mates[k]
+                r.aligned, r.aln, r.xs, r.mapq = True, a, None, mq
+            res.pair_type = 2
+            return res
+        for k, rsu in enumerate((sink.rs1u, sink.rs2u)):
+            if not rsu:
+                continue
+            s = self._select(rsu, None, None, None)
+            a = rsu[s["sel"]]
+            r = res.mates[k]
+            r.aligned, r.aln, r.xs = True, a, s["unchosen_u"]
+            r.mapq = policy.mapq_v2(a.score, s["unchosen_u"], mn[k], m[k].perfect, True)
+            r.n_alns = len(rsu)
+        n_al = sum(r.aligned for r in res.mates)
+        res.pair_type = 2 if n_al == 2 else (3 if n_al == 1 else 0)
+        return res

@@ -115,3 +115,89 @@ def test_random_1_to_n_is_a_permutation_in_every_mode():
         while not r.done():
             got.append(r.next(rnd))
         assert sorted(got) == list(range(n)), n
+
+
+# ---------------------------------------------------------------------------------------------------------- pairs
+def _run_paired_engine(index, reads, quals, names, ref_names, preset):
+    """reads / quals / names interleaved (mate 1, mate 2, ...) -> (SAM lines, per-pair results)"""
+    from bowtie2_b200.lib import PAIR_RESULT
+    from bowtie2_b200.policy_engine import PairedPolicyEngine
+    eng = PairedPolicyEngine(OracleBackend(Oracle(index)), preset)
+    n = len(reads)
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    ops = np.zeros((n, max(len(r) for r in reads) + 64), dtype=np.uint8)
+    pairs = np.zeros(n // 2, dtype=PAIR_RESULT)
+    outs = []
+    for i in range(n // 2):
+        pr = eng.align_pair(reads[2 * i], quals[2 * i], names[2 * i], reads[2 * i + 1], quals[2 * i + 1], names[2 * i + 1])
+        outs.append(pr)
+        pairs[i]["pair_type"] = pr.pair_type
+        for k in range(2):
+            r, j = pr.mates[k], 2 * i + k
+            if r.aligned:
+                a = r.aln
+                o = aln_to_ops(a, reads[j])
+                res[j]["found"] = 2 if not a.edits else 1
+                res[j]["score"] = a.score
+                if r.xs is not None:
+                    res[j]["score2"] = r.xs
+                res[j]["fw"] = int(a.fw); res[j]["tidx"] = a.tidx; res[j]["refoff"] = a.refoff; res[j]["nops"] = len(o)
+                res[j]["mapq"] = r.mapq; res[j]["pad"] = a.refns
+                ops[j, :len(o)] = o
+    lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ref_names, read_names=names, pairs=pairs)
+    return lines.rstrip("\n").split("\n"), outs
+
+
+@pytest.mark.parametrize("fixture,index,ref_names", [
+    ("lambda", "lambda_index", ["gi|9626243|ref|NC_001416.1|"]),
+    ("rep", "rep_index", ["ctg1", "ctg2"]),
+])
+def test_paired_sam_identical_to_golden(fixture, index, ref_names, request):
+    """concordant, discordant and unpaired-mate records, the locus among equal repeats, MAPQ, XS:i, YS:i, TLEN: every line"""
+    base = request.getfixturevalue(index)
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, f"{fixture}_P_sensitive.sam")) if not l.startswith("@")]
+    npairs = len(golden) // 2
+    n1, r1, q1 = read_fastq_codes(os.path.join(GOLDEN, f"{fixture}_reads_1.fq"), npairs)
+    n2, r2, q2 = read_fastq_codes(os.path.join(GOLDEN, f"{fixture}_reads_2.fq"), npairs)
+    il = lambda a, b: [x for p in zip(a, b) for x in p]
+    lines, outs = _run_paired_engine(base, il(r1, r2), il(q1, q2), il(n1, n2), ref_names, "sensitive")
+    assert lines == golden
+    if fixture == "rep":
+        types = np.bincount([o.pair_type for o in outs], minlength=4)
+        assert types[1] > 300 and types[2] > 20 and types[3] > 10
+        assert sum(o.n_concord >= 2 for o in outs) > 20
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("preset,rdlen,n,ins_sd,genome_kw", [
+    ("sensitive", 100, 250, 60, {}),
+    ("very-sensitive", 150, 200, 60, {}),                  # the headline configuration's preset and read length
+    ("fast", 50, 250, 150, {}),
+    ("sensitive", 100, 150, 120, dict(contig_len=120000, repeat_frac=0.6, repeat_len=250, repeat_copies=400)),
+])
+def test_paired_sam_and_work_counters_identical_to_reference_program(tmp_path, preset, rdlen, n, ins_sd, genome_kw):
+    kw = dict(n_contigs=3, contig_len=40000, seed=11, repeat_frac=0.05, repeat_len=300, repeat_copies=12, n_gap=37)
+    kw.update(genome_kw)
+    genome = synth.make_genome(**kw)
+    fa, base = str(tmp_path / "g.fa"), str(tmp_path / "g")
+    synth.write_fasta(fa, genome)
+    subprocess.check_call([ref_bin("bowtie2-build-s"), "--seed", "0", "--quiet", fa, base])
+    reads, quals, _ = synth.make_pairs(genome, n, rdlen, seed=7 + rdlen, sub_rate=0.02, indel_rate=0.003, hard_frac=0.2, hard_period=12,
+                                       ins_sd=ins_sd)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    synth.write_fastq(f1, reads[0::2], quals[0::2])
+    synth.write_fastq(f2, reads[1::2], quals[1::2])
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), "--" + preset, "--seed", "0", "-p", "1", "--read-times", "-x", base,
+                                   "-1", f1, "-2", f2], stderr=subprocess.DEVNULL).decode()
+    full = [l for l in out.split("\n") if l and not l.startswith("@")]
+    want = ["\t".join(l.split("\t")[:11] + [x for x in l.split("\t")[11:] if x[:2] in KEEP]) for l in full]
+    names = [f"r{i // 2}" for i in range(2 * n)]
+    lines, outs = _run_paired_engine(base, reads, quals, names, [f"chr{k + 1}" for k in range(len(genome))], preset)
+    bad = [i for i in range(n) if lines[2 * i:2 * i + 2] != want[2 * i:2 * i + 2]]
+    assert not bad, (len(bad), lines[2 * bad[0]], want[2 * bad[0]])
+    for i, o in enumerate(outs):
+        tags = {t[:2]: t[5:] for t in full[2 * i].split("\t")[11:]}
+        if "ZI" in tags:
+            c = o.counters
+            assert (c["ZI"], c["XD"], c["XU"], c["YR"]) == tuple(int(tags[k]) for k in ("ZI", "XD", "XU", "YR")), (i, c)
