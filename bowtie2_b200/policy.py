@@ -137,6 +137,14 @@ class Scoring:
         return num - 1
 
 
+def mm_penalty(q: int, mmp_max: int = 6, mmp_min: int = 2) -> int:
+    """Scoring::mm for the default quality-aware model (scoring.h: COST_MODEL_QUAL; float arithmetic)"""
+    import numpy as _np
+    ii = min(max(q, 0), 40)
+    frac = _np.float32(ii) / _np.float32(40.0)
+    return mmp_min + int(frac * _np.float32(mmp_max - mmp_min))
+
+
 def seed_interval(ival: SimpleFunc, rdlen: int, both_mates: bool = False) -> int:
     """bt2_search.cpp:3443-3450"""
     v = ival.fi(float(rdlen))

@@ -179,15 +179,30 @@ class Aln:
     ns: int = 0
     refns: int = 0
     exact: bool = False     # came from the end-to-end exact / 1-mismatch search
+    trim5: int = 0          # soft-trimmed read characters at the 5' / 3' end (local mode)
+    trim3: int = 0
+
+    @property
+    def ext(self):          # AlnRes::readExtentRows
+        return self.rdlen - self.trim5 - self.trim3
+
+    @property
+    def trim_left(self):    # AlnRes::trimmedLeft(true): in reference orientation
+        return self.trim5 if self.fw else self.trim3
+
+    @property
+    def ref_extent(self):
+        return self.ext + sum(e[3] == 1 for e in self.edits) - sum(e[3] == 2 for e in self.edits)
 
 
 def edits_left_to_right(a: Aln):
-    """AlnRes::invertEdits for reverse-strand alignments (edit.cpp:50-78): positions from the left end in reference orientation"""
+    """AlnRes::invertEdits for reverse-strand alignments (edit.cpp:50-78): positions from the left end of the aligned
+    extent in reference orientation"""
     if a.fw:
         return [tuple(e) for e in a.edits]
     out = []
     for pos, ch, qch, typ in reversed(a.edits):
-        out.append((a.rdlen - pos - (0 if typ == 1 else 1), ch, qch, typ))
+        out.append((a.ext - pos - (0 if typ == 1 else 1), ch, qch, typ))
     return out
 
 
@@ -201,8 +216,9 @@ class RedundantAlns:
         ned = edits_left_to_right(a)
         left = a.refoff
         k = 0
-        n = a.rdlen
-        for i in range(n):
+        start = a.trim_left          # the reference compares edit positions (relative to the extent) with rows counted
+        n = start + a.ext            # from the untrimmed read start: restated as written
+        for i in range(start, n):
             diff = 1
             right = left + 1
             while k < len(ned) and ned[k][0] == i:
@@ -320,10 +336,11 @@ class MateCtx:
 
 
 class PolicyEngine:
-    def __init__(self, backend, preset="sensitive", seed=0, sc=None):
+    def __init__(self, backend, preset="sensitive", seed=0, sc=None, local=False):
         self.b = backend
-        self.pre = policy.preset(preset, False)
-        self.sc = sc or policy.Scoring.default(False)
+        self.local = local
+        self.pre = policy.preset(preset, local)
+        self.sc = sc or policy.Scoring.default(local)
         self.seed = seed
         # bt2_search.cpp:342-343, 459-492 and the preset's -D / -R
         self.khits, self.mhits = 1, 50
@@ -639,7 +656,7 @@ class PolicyEngine:
                             continue
                         n_dp_fail = 0
                         dp["cursor"] = 0
-                        dp["u8"] = self.cur.minsc >= -254
+                        dp["u8"] = self._dp_u8(dp, self.cur.minsc, self.cur.quals)
                     first_inner = True
                     while True:
                         if state != 0:
@@ -678,6 +695,14 @@ class PolicyEngine:
                                         self.cur.minsc += 1
         return EXHAUSTED
 
+    def _dp_u8(self, dp, minsc, quals):
+        """did SwAligner::align stay on the 8-bit matrices (aligner_sw.cpp:514-600)?  End-to-end: the minimum score must
+        fit; local: no cell may reach 255 - bias, bias = the largest penalty of the query profile (aligner_swsse_loc_u8.cpp:97-110)"""
+        if not self.local:
+            return minsc >= -254
+        bias = max([policy.mm_penalty(int(q) - 33) for q in quals] + [1])
+        return dp["best"] + bias < 255
+
     def _next_alignment(self, dp, tidx, minsc, rdlen):
         """SwAligner::nextAlignment (aligner_sw.cpp:737-1146) over the backend's attempt list: candidates below the
         current minimum score are skipped without touching the RNG, every backtrace attempt reseeds it."""
@@ -694,9 +719,9 @@ class PolicyEngine:
                 al = dp["alns"][ai]
                 ed = [tuple(e) for e in al["edits"]]
                 # AlnRes::refNs: ambiguous reference characters under the alignment (XN:i)
-                extent = rdlen + sum(e[3] == 1 for e in ed) - sum(e[3] == 2 for e in ed)
-                return Aln(tidx, al["refoff"], bool(al["fw"]), al["score"], rdlen, ed, al["ns"],
-                           self.b.count_ref_ns(tidx, al["refoff"], extent))
+                a = Aln(tidx, al["refoff"], bool(al["fw"]), al["score"], rdlen, ed, al["ns"], 0, False, al["trim5"], al["trim3"])
+                a.refns = self.b.count_ref_ns(tidx, a.refoff, a.ref_extent)
+                return a
         return None
 
     # ---------------------------------------------------------------------------------------- finishRead
@@ -714,7 +739,7 @@ class PolicyEngine:
         best = alns[buf[0][1]]
         res.aligned, res.aln = True, best
         res.xs = buf[1][0] if len(buf) > 1 else None
-        res.mapq = policy.mapq_v2(best.score, res.xs, self.sc.min_score(self.cur.rdlen), self.cur.perfect, True)
+        res.mapq = policy.mapq_v2(best.score, res.xs, self.sc.min_score(self.cur.rdlen), self.cur.perfect, not self.local)
         return res
 
 
@@ -723,11 +748,11 @@ def aln_to_ops(a: Aln, codes):
     code) from an alignment in the reference's Edit representation."""
     from .lib import OP_MATCH, OP_MM, OP_READGAP, OP_REFGAP
     code = {ord(c): i for i, c in enumerate("ACGTN")}
-    rdlen = len(codes)
     seq = codes if a.fw else np.array([4 if c > 3 else 3 - c for c in codes[::-1]], dtype=np.uint8)
     ed = edits_left_to_right(a)
     fwd, k = [], 0
-    for rel in range(rdlen):
+    row0 = a.trim_left
+    for rel in range(a.ext):
         while k < len(ed) and ed[k][0] == rel and ed[k][3] == 1:
             fwd.append(OP_READGAP | (code[ed[k][1]] << 2))
             k += 1
@@ -735,7 +760,7 @@ def aln_to_ops(a: Aln, codes):
             fwd.append(OP_REFGAP if ed[k][3] == 2 else (OP_MM | (code[ed[k][1]] << 2)))
             k += 1
         else:
-            fwd.append(OP_MATCH | (int(seq[rel]) << 2))
+            fwd.append(OP_MATCH | (int(seq[row0 + rel]) << 2))
     assert k == len(ed)
     return fwd[::-1]
 
@@ -819,9 +844,9 @@ class PairResult:
 
 
 class PairedPolicyEngine(PolicyEngine):
-    def __init__(self, backend, preset="sensitive", seed=0, sc=None, pe=None):
-        super().__init__(backend, preset, seed, sc)
-        self.pe = pe or policy.PairedEndPolicy()
+    def __init__(self, backend, preset="sensitive", seed=0, sc=None, pe=None, local=False):
+        super().__init__(backend, preset, seed, sc, local)
+        self.pe = pe or policy.PairedEndPolicy(local=local)
         self.max_mate_streak = 10
 
     def align_pair(self, codes1, quals1, name1, codes2, quals2, name2) -> PairResult:
@@ -1098,7 +1123,7 @@ class PairedPolicyEngine(PolicyEngine):
                         if not dp["found"]:
                             continue
                         dp["cursor"] = 0
-                        dp["u8"] = c.minsc >= -254
+                        dp["u8"] = self._dp_u8(dp, c.minsc, c.quals)
                     first_inner = True
                     found_concordant = False
                     while True:
@@ -1140,7 +1165,7 @@ class PairedPolicyEngine(PolicyEngine):
                                 found_mate = bool(odp["found"])
                                 if found_mate:
                                     odp["cursor"] = 0
-                                    odp["u8"] = ominsc_cur >= -254
+                                    odp["u8"] = self._dp_u8(odp, ominsc_cur, o.quals)
                             did_anchor = False
                             brk = False
                             while True:
@@ -1151,12 +1176,12 @@ class PairedPolicyEngine(PolicyEngine):
                                 if found_mate:
                                     if not self.red.overlap(oa):
                                         self.red.add(oa)
-                                    oext = ordlen + sum(e[3] == 1 for e in oa.edits) - sum(e[3] == 2 for e in oa.edits)
+                                    oext = oa.ref_extent
                                     if oa.refoff < 0 or oa.refoff + oext > tlen:
                                         found_mate = False          # falls off the reference (no overhangs)
                                 pair_cl = policy.PE_ALS_DISCORD
                                 if found_mate:
-                                    aext = rdlen + sum(e[3] == 1 for e in a.edits) - sum(e[3] == 2 for e in a.edits)
+                                    aext = a.ref_extent
                                     a1, a2 = (a, oa) if anchor1 else (oa, a)
                                     l1, l2 = (aext, oext) if anchor1 else (oext, aext)
                                     pair_cl = pe.classify_pair(a1.refoff, l1, a1.fw, a2.refoff, l2, a2.fw)
@@ -1263,7 +1288,7 @@ class PairedPolicyEngine(PolicyEngine):
         if sink.nconcord > 0:
             s = self._select(sink.rs1, sink.rs2, sink.rs1u, sink.rs2u)
             a1, a2 = sink.rs1[s["sel"]], sink.rs2[s["sel"]]
-            mq = policy.mapq_v2(a1.score + a2.score, s["unchosen_c"], mn[0] + mn[1], m[0].perfect + m[1].perfect, True)
+            mq = policy.mapq_v2(a1.score + a2.score, s["unchosen_c"], mn[0] + mn[1], m[0].perfect + m[1].perfect, not self.local)
             for k, a in enumerate((a1, a2)):
                 r = res.mates[k]
                 r.aligned, r.aln, r.xs, r.mapq = True, a, s["unchosen_p"][k], mq
@@ -1274,7 +1299,7 @@ class PairedPolicyEngine(PolicyEngine):
             # prepareDiscordants + selectByScore over the single pair
             s = self._select([sink.rs1u[0]], [sink.rs2u[0]], sink.rs1u, sink.rs2u)
             a1, a2 = sink.rs1u[0], sink.rs2u[0]
-            mq = policy.mapq_v2(a1.score + a2.score, None, mn[0] + mn[1], m[0].perfect + m[1].perfect, True)
+            mq = policy.mapq_v2(a1.score + a2.score, None, mn[0] + mn[1], m[0].perfect + m[1].perfect, not self.local)
             for k, a in enumerate((a1, a2)):
                 r = res.mates[k]
                 r.aligned, r.aln, r.xs, r.mapq = True, a, None, mq
@@ -1287,7 +1312,7 @@ class PairedPolicyEngine(PolicyEngine):
             a = rsu[s["sel"]]
             r = res.mates[k]
             r.aligned, r.aln, r.xs = True, a, s["unchosen_u"]
-            r.mapq = policy.mapq_v2(a.score, s["unchosen_u"], mn[k], m[k].perfect, True)
+            r.mapq = policy.mapq_v2(a.score, s["unchosen_u"], mn[k], m[k].perfect, not self.local)
             r.n_alns = len(rsu)
         n_al = sum(r.aligned for r in res.mates)
         res.pair_type = 2 if n_al == 2 else (3 if n_al == 1 else 0)

@@ -8,15 +8,16 @@ from oracle_lib import extend_both, oracle_dp, oracle_one_mm, oracle_ungapped
 
 
 class OracleBackend:
-    def __init__(self, O, off_size=4):
+    def __init__(self, O, off_size=4, local=False):
         self.O = O
         self.off_size = off_size
+        self.local = local
 
     def exact_sweep(self, codes):
         return self.O.exact_sweep(codes)
 
     def one_mm(self, codes, quals, minsc, nofw, norc):
-        return oracle_one_mm(self.O, False, codes, quals, minsc, nofw, norc)
+        return oracle_one_mm(self.O, self.local, codes, quals, minsc, nofw, norc)
 
     def seed_search(self, codes, quals, seed_len, interval, offset):
         n = max(1, policy.n_seeds(len(codes), seed_len, interval, offset))
@@ -36,19 +37,26 @@ class OracleBackend:
         return int((self.O.get_stretch(tidx, off, extent) > 3).sum())
 
     def ungapped(self, codes, quals, fw, tidx, refoff, tlen, minsc):
-        rc, d = oracle_ungapped(self.O, False, codes, quals, fw, tidx, refoff, tlen, 0, minsc)
+        rc, d = oracle_ungapped(self.O, self.local, codes, quals, fw, tidx, refoff, tlen, 0, minsc)
         if rc != 1:
             return rc, None
         rdlen = len(codes)
         ref = self.O.get_stretch(tidx, refoff, rdlen)
         seq = codes if fw else np.array([4 if c > 3 else 3 - c for c in codes[::-1]], dtype=np.uint8)
+        rowi, rowf = d["rowi"], d["rowf"]                     # aligned rows in reference orientation (local mode trims)
+        ext = rowf - rowi + 1
         ed = []
         for i in np.nonzero(d["mask"])[0]:
-            pos = int(i) if fw else rdlen - 1 - int(i)
+            i = int(i)
+            if i < rowi or i > rowf:
+                continue
+            rel = i - rowi
+            pos = rel if fw else ext - 1 - rel
             ed.append((pos, ord("ACGTN"[min(int(ref[i]), 4)]), ord("ACGTN"[min(int(seq[i]), 4)]), 3))
         if not fw:
             ed = ed[::-1]
-        return rc, Aln(tidx, refoff, fw, d["score"], rdlen, ed, d["ns"], d["refns"])
+        tl, tr = rowi, rdlen - 1 - rowf
+        return rc, Aln(tidx, refoff + rowi, fw, d["score"], rdlen, ed, d["ns"], d["refns"], False, tl if fw else tr, tr if fw else tl)
 
     def dp(self, codes, quals, fw, tidx, rect, minsc, nceil):
-        return oracle_dp(self.O, False, codes, quals, fw, tidx, rect, minsc, nceil, max_alns=64, max_edits=16384, attempts=True)
+        return oracle_dp(self.O, self.local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=65536, max_alns=64, max_edits=16384, attempts=True)

@@ -20,9 +20,22 @@ from policy_backend import OracleBackend
 KEEP = ("AS", "XS", "XN", "XM", "XO", "XG", "NM", "MD", "YS", "YT", "YF")
 
 
-def _run_engine(index, reads, quals, names, ref_names, preset):
+def _fill(res, ops, j, r, read):
+    a = r.aln
+    o = aln_to_ops(a, read)
+    res[j]["found"] = 2 if (not a.edits and a.ext == a.rdlen) else 1
+    res[j]["score"] = a.score
+    if r.xs is not None:
+        res[j]["score2"] = r.xs
+    res[j]["fw"] = int(a.fw); res[j]["tidx"] = a.tidx; res[j]["refoff"] = a.refoff; res[j]["nops"] = len(o)
+    res[j]["trim_left"] = a.trim_left; res[j]["trim_right"] = a.rdlen - a.ext - a.trim_left
+    res[j]["mapq"] = r.mapq; res[j]["pad"] = a.refns
+    ops[j, :len(o)] = o
+
+
+def _run_engine(index, reads, quals, names, ref_names, preset, local=False):
     O = Oracle(index)
-    eng = PolicyEngine(OracleBackend(O), preset)
+    eng = PolicyEngine(OracleBackend(O, local=local), preset, local=local)
     n = len(reads)
     res = np.zeros(n, dtype=READ_RESULT)
     res["score2"] = -(1 << 31)
@@ -32,15 +45,7 @@ def _run_engine(index, reads, quals, names, ref_names, preset):
         r = eng.align_read(reads[i], quals[i], names[i])
         outs.append(r)
         if r.aligned:
-            a = r.aln
-            o = aln_to_ops(a, reads[i])
-            res[i]["found"] = 2 if not a.edits else 1
-            res[i]["score"] = a.score
-            if r.xs is not None:
-                res[i]["score2"] = r.xs
-            res[i]["fw"] = int(a.fw); res[i]["tidx"] = a.tidx; res[i]["refoff"] = a.refoff; res[i]["nops"] = len(o)
-            res[i]["mapq"] = r.mapq; res[i]["pad"] = a.refns
-            ops[i, :len(o)] = o
+            _fill(res, ops, i, r, reads[i])
     lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ref_names, read_names=names).rstrip("\n").split("\n")
     return lines, outs
 
@@ -48,20 +53,23 @@ def _run_engine(index, reads, quals, names, ref_names, preset):
 @pytest.mark.parametrize("fixture,index,ref_names", [
     ("lambda", "lambda_index", ["gi|9626243|ref|NC_001416.1|"]),
     ("rep", "rep_index", ["ctg1", "ctg2"]),
+    ("lambda:local", "lambda_index", ["gi|9626243|ref|NC_001416.1|"]),
 ])
 def test_sam_identical_to_golden(fixture, index, ref_names, request):
     base = request.getfixturevalue(index)
-    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, f"{fixture}_U_sensitive.sam")) if not l.startswith("@")]
+    local = fixture.endswith(":local")
+    fixture = fixture.split(":")[0]
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, f"{fixture}_U_{'local' if local else 'sensitive'}.sam")) if not l.startswith("@")]
     names, reads, quals = read_fastq_codes(os.path.join(GOLDEN, f"{fixture}_reads_1.fq"), len(golden))
-    lines, outs = _run_engine(base, reads, quals, names, ref_names, "sensitive")
+    lines, outs = _run_engine(base, reads, quals, names, ref_names, "sensitive", local)
     bad = [i for i in range(len(golden)) if lines[i] != golden[i]]
     assert not bad, (len(bad), lines[bad[0]], golden[bad[0]])
     if fixture == "rep":
         assert sum(o.n_alns >= 2 for o in outs) > 80          # ties in repeats were decided by the replayed RNG
 
 
-def _reference_run(index, fq, preset):
-    out = subprocess.check_output([ref_bin("bowtie2-align-s"), "--" + preset, "--seed", "0", "-p", "1", "--read-times", "-x", index, "-U", fq],
+def _reference_run(index, fq, preset, local=False):
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), *(["--local"] if local else []), "--" + preset, "--seed", "0", "-p", "1", "--read-times", "-x", index, "-U", fq],
                                   stderr=subprocess.DEVNULL).decode()
     full = [l for l in out.split("\n") if l and not l.startswith("@")]
     recs, counters = [], []
@@ -75,6 +83,9 @@ def _reference_run(index, fq, preset):
 
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("preset,rdlen,n,genome_kw", [
+    ("local:sensitive", 100, 300, {}),
+    ("local:very-sensitive", 300, 100, {}),               # configuration 4's preset and read length (--local)
+    ("local:sensitive", 100, 200, dict(contig_len=120000, repeat_frac=0.6, repeat_len=250, repeat_copies=400)),
     ("sensitive", 100, 500, {}),
     ("very-sensitive", 150, 300, {}),
     ("fast", 50, 400, {}),
@@ -84,6 +95,8 @@ def _reference_run(index, fq, preset):
     ("sensitive", 100, 400, dict(contig_len=120000, repeat_frac=0.6, repeat_len=250, repeat_copies=400)),
 ])
 def test_sam_and_work_counters_identical_to_reference_program(tmp_path, preset, rdlen, n, genome_kw):
+    local = preset.startswith("local:")
+    preset = preset.split(":")[-1]
     kw = dict(n_contigs=3, contig_len=40000, seed=11, repeat_frac=0.05, repeat_len=300, repeat_copies=12, n_gap=37)
     kw.update(genome_kw)
     genome = synth.make_genome(**kw)
@@ -92,16 +105,18 @@ def test_sam_and_work_counters_identical_to_reference_program(tmp_path, preset, 
     subprocess.check_call([ref_bin("bowtie2-build-s"), "--seed", "0", "--quiet", fa, base])
     reads, quals, _ = synth.make_reads(genome, n, rdlen, seed=5 + rdlen, sub_rate=0.02, indel_rate=0.003)
     synth.write_fastq(fq, reads, quals)
-    want, counters = _reference_run(base, fq, preset)
+    want, counters = _reference_run(base, fq, preset, local)
     names = [f"r{i}" for i in range(len(reads))]
-    lines, outs = _run_engine(base, reads, quals, names, [f"chr{k + 1}" for k in range(len(genome))], preset)
+    lines, outs = _run_engine(base, reads, quals, names, [f"chr{k + 1}" for k in range(len(genome))], preset, local)
     bad = [i for i in range(len(want)) if lines[i] != want[i]]
     assert not bad, (len(bad), lines[bad[0]], want[bad[0]])
     for i, o in enumerate(outs):
         if o.counters is not None and counters[i] is not None:
             c = o.counters
             assert (c["ZI"], c["XD"], c["XU"], c["YR"]) == counters[i], (i, c, counters[i])
-    if genome_kw:
+    if local:
+        assert sum("S" in l.split("\t")[5] for l in want) > 10          # soft-clipped records were compared
+    if genome_kw and not local:
         assert any(o.maxed for o in outs) and max(o.counters["ZI"] for o in outs if o.counters) > 50
 
 
@@ -118,11 +133,11 @@ def test_random_1_to_n_is_a_permutation_in_every_mode():
 
 
 # ---------------------------------------------------------------------------------------------------------- pairs
-def _run_paired_engine(index, reads, quals, names, ref_names, preset):
+def _run_paired_engine(index, reads, quals, names, ref_names, preset, local=False):
     """reads / quals / names interleaved (mate 1, mate 2, ...) -> (SAM lines, per-pair results)"""
     from bowtie2_b200.lib import PAIR_RESULT
     from bowtie2_b200.policy_engine import PairedPolicyEngine
-    eng = PairedPolicyEngine(OracleBackend(Oracle(index)), preset)
+    eng = PairedPolicyEngine(OracleBackend(Oracle(index), local=local), preset, local=local)
     n = len(reads)
     res = np.zeros(n, dtype=READ_RESULT)
     res["score2"] = -(1 << 31)
@@ -136,15 +151,7 @@ def _run_paired_engine(index, reads, quals, names, ref_names, preset):
         for k in range(2):
             r, j = pr.mates[k], 2 * i + k
             if r.aligned:
-                a = r.aln
-                o = aln_to_ops(a, reads[j])
-                res[j]["found"] = 2 if not a.edits else 1
-                res[j]["score"] = a.score
-                if r.xs is not None:
-                    res[j]["score2"] = r.xs
-                res[j]["fw"] = int(a.fw); res[j]["tidx"] = a.tidx; res[j]["refoff"] = a.refoff; res[j]["nops"] = len(o)
-                res[j]["mapq"] = r.mapq; res[j]["pad"] = a.refns
-                ops[j, :len(o)] = o
+                _fill(res, ops, j, r, reads[j])
     lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ref_names, read_names=names, pairs=pairs)
     return lines.rstrip("\n").split("\n"), outs
 
@@ -171,12 +178,16 @@ def test_paired_sam_identical_to_golden(fixture, index, ref_names, request):
 
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("preset,rdlen,n,ins_sd,genome_kw", [
+    ("local:sensitive", 100, 200, 60, {}),
+    ("local:very-sensitive", 150, 100, 120, dict(contig_len=120000, repeat_frac=0.6, repeat_len=250, repeat_copies=400)),
     ("sensitive", 100, 250, 60, {}),
     ("very-sensitive", 150, 200, 60, {}),                  # the headline configuration's preset and read length
     ("fast", 50, 250, 150, {}),
     ("sensitive", 100, 150, 120, dict(contig_len=120000, repeat_frac=0.6, repeat_len=250, repeat_copies=400)),
 ])
 def test_paired_sam_and_work_counters_identical_to_reference_program(tmp_path, preset, rdlen, n, ins_sd, genome_kw):
+    local = preset.startswith("local:")
+    preset = preset.split(":")[-1]
     kw = dict(n_contigs=3, contig_len=40000, seed=11, repeat_frac=0.05, repeat_len=300, repeat_copies=12, n_gap=37)
     kw.update(genome_kw)
     genome = synth.make_genome(**kw)
@@ -188,12 +199,12 @@ def test_paired_sam_and_work_counters_identical_to_reference_program(tmp_path, p
     f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
     synth.write_fastq(f1, reads[0::2], quals[0::2])
     synth.write_fastq(f2, reads[1::2], quals[1::2])
-    out = subprocess.check_output([ref_bin("bowtie2-align-s"), "--" + preset, "--seed", "0", "-p", "1", "--read-times", "-x", base,
-                                   "-1", f1, "-2", f2], stderr=subprocess.DEVNULL).decode()
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), *(["--local"] if local else []), "--" + preset, "--seed", "0", "-p", "1",
+                                   "--read-times", "-x", base, "-1", f1, "-2", f2], stderr=subprocess.DEVNULL).decode()
     full = [l for l in out.split("\n") if l and not l.startswith("@")]
     want = ["\t".join(l.split("\t")[:11] + [x for x in l.split("\t")[11:] if x[:2] in KEEP]) for l in full]
     names = [f"r{i // 2}" for i in range(2 * n)]
-    lines, outs = _run_paired_engine(base, reads, quals, names, [f"chr{k + 1}" for k in range(len(genome))], preset)
+    lines, outs = _run_paired_engine(base, reads, quals, names, [f"chr{k + 1}" for k in range(len(genome))], preset, local)
     bad = [i for i in range(n) if lines[2 * i:2 * i + 2] != want[2 * i:2 * i + 2]]
     assert not bad, (len(bad), lines[2 * bad[0]], want[2 * bad[0]])
     for i, o in enumerate(outs):
