@@ -133,11 +133,11 @@ def test_random_1_to_n_is_a_permutation_in_every_mode():
 
 
 # ---------------------------------------------------------------------------------------------------------- pairs
-def _run_paired_engine(index, reads, quals, names, ref_names, preset, local=False):
+def _run_paired_engine(index, reads, quals, names, ref_names, preset, local=False, off_size=4):
     """reads / quals / names interleaved (mate 1, mate 2, ...) -> (SAM lines, per-pair results)"""
     from bowtie2_b200.lib import PAIR_RESULT
     from bowtie2_b200.policy_engine import PairedPolicyEngine
-    eng = PairedPolicyEngine(OracleBackend(Oracle(index), local=local), preset, local=local)
+    eng = PairedPolicyEngine(OracleBackend(Oracle(index), off_size=off_size, local=local), preset, local=local)
     n = len(reads)
     res = np.zeros(n, dtype=READ_RESULT)
     res["score2"] = -(1 << 31)
@@ -178,6 +178,8 @@ def test_paired_sam_identical_to_golden(fixture, index, ref_names, request):
 
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("preset,rdlen,n,ins_sd,genome_kw", [
+    # configuration 5: .bt2l index (64-bit offsets: the RNG draws of eeSaTups widen to 64 bits), 2x150, --sensitive
+    ("large:sensitive", 150, 150, 120, dict(contig_len=120000, repeat_frac=0.6, repeat_len=250, repeat_copies=400)),
     ("local:sensitive", 100, 200, 60, {}),
     ("local:very-sensitive", 150, 100, 120, dict(contig_len=120000, repeat_frac=0.6, repeat_len=250, repeat_copies=400)),
     ("sensitive", 100, 250, 60, {}),
@@ -187,24 +189,26 @@ def test_paired_sam_identical_to_golden(fixture, index, ref_names, request):
 ])
 def test_paired_sam_and_work_counters_identical_to_reference_program(tmp_path, preset, rdlen, n, ins_sd, genome_kw):
     local = preset.startswith("local:")
+    large = preset.startswith("large:")
+    sfx = "l" if large else "s"
     preset = preset.split(":")[-1]
     kw = dict(n_contigs=3, contig_len=40000, seed=11, repeat_frac=0.05, repeat_len=300, repeat_copies=12, n_gap=37)
     kw.update(genome_kw)
     genome = synth.make_genome(**kw)
     fa, base = str(tmp_path / "g.fa"), str(tmp_path / "g")
     synth.write_fasta(fa, genome)
-    subprocess.check_call([ref_bin("bowtie2-build-s"), "--seed", "0", "--quiet", fa, base])
+    subprocess.check_call([ref_bin("bowtie2-build-" + sfx), "--seed", "0", "--quiet", fa, base])
     reads, quals, _ = synth.make_pairs(genome, n, rdlen, seed=7 + rdlen, sub_rate=0.02, indel_rate=0.003, hard_frac=0.2, hard_period=12,
                                        ins_sd=ins_sd)
     f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
     synth.write_fastq(f1, reads[0::2], quals[0::2])
     synth.write_fastq(f2, reads[1::2], quals[1::2])
-    out = subprocess.check_output([ref_bin("bowtie2-align-s"), *(["--local"] if local else []), "--" + preset, "--seed", "0", "-p", "1",
+    out = subprocess.check_output([ref_bin("bowtie2-align-" + sfx), *(["--local"] if local else []), "--" + preset, "--seed", "0", "-p", "1",
                                    "--read-times", "-x", base, "-1", f1, "-2", f2], stderr=subprocess.DEVNULL).decode()
     full = [l for l in out.split("\n") if l and not l.startswith("@")]
     want = ["\t".join(l.split("\t")[:11] + [x for x in l.split("\t")[11:] if x[:2] in KEEP]) for l in full]
     names = [f"r{i // 2}" for i in range(2 * n)]
-    lines, outs = _run_paired_engine(base, reads, quals, names, [f"chr{k + 1}" for k in range(len(genome))], preset, local)
+    lines, outs = _run_paired_engine(base, reads, quals, names, [f"chr{k + 1}" for k in range(len(genome))], preset, local, 8 if large else 4)
     bad = [i for i in range(n) if lines[2 * i:2 * i + 2] != want[2 * i:2 * i + 2]]
     assert not bad, (len(bad), lines[2 * bad[0]], want[2 * bad[0]])
     for i, o in enumerate(outs):
