@@ -336,12 +336,21 @@ class MateCtx:
 
 
 class PolicyEngine:
-    def __init__(self, backend, preset="sensitive", seed=0, sc=None, local=False):
+    def __init__(self, backend, preset="sensitive", seed=0, sc=None, local=False, nofw=False, norc=False,
+                 dp_fail_streak=None, seed_rounds=None, seed_len=None):
+        """seed = --seed; nofw / norc = --nofw / --norc; dp_fail_streak / seed_rounds / seed_len = -D / -R / -L on top of the preset"""
         self.b = backend
         self.local = local
         self.pre = policy.preset(preset, local)
+        if dp_fail_streak is not None:
+            self.pre.dp_fail_streak = dp_fail_streak
+        if seed_rounds is not None:
+            self.pre.seed_rounds = seed_rounds
+        if seed_len is not None:
+            self.pre.seed_len = seed_len
         self.sc = sc or policy.Scoring.default(local)
         self.seed = seed
+        self.gnofw, self.gnorc = nofw, norc
         # bt2_search.cpp:342-343, 459-492 and the preset's -D / -R
         self.khits, self.mhits = 1, 50
         self.maxhalf = 15
@@ -375,7 +384,8 @@ class PolicyEngine:
         self.n_iters = self.n_dps = self.n_ugs = self.n_red = 0
         done = False
         # ---- exact end-to-end (bt2_search.cpp:3493-3690)
-        nelt, mined, tb = self.b.exact_sweep(codes)
+        nofw, norc = self.gnofw, self.gnorc
+        nelt, mined, tb = self.b.exact_sweep(codes, nofw, norc)
         minedfw, minedrc = int(mined[0]), int(mined[1])
         if nelt > 0:
             ee = []
@@ -387,7 +397,7 @@ class PolicyEngine:
             done = self._after_extend(ret, done)
         # ---- 1-mismatch end-to-end (bt2_search.cpp:3692-3875)
         if not done:
-            yfw, yrc = minedfw <= 1, minedrc <= 1
+            yfw, yrc = minedfw <= 1 and not nofw, minedrc <= 1 and not norc
             if yfw or yrc:
                 hits = self.b.one_mm(codes, quals, self.cur.minsc, not yfw, not yrc)
                 self.cur.mm1 = [EEHit(int(h[0]), int(h[1]), bool(h[6]), int(h[5]), (int(h[2]), int(h[3]), int(h[4]))) for h in hits]
@@ -409,7 +419,7 @@ class PolicyEngine:
             offset = (interval * roundi) // nrounds
             if offset > 0 and L + offset > rdlen:
                 continue
-            hits = self.b.seed_search(codes, quals, min(L, rdlen), interval, offset)
+            hits = self.b.seed_search(codes, quals, min(L, rdlen), interval, offset, nofw, norc)
             if hits is None:                                   # no seed could be instantiated
                 done = True
                 break
@@ -844,9 +854,12 @@ class PairResult:
 
 
 class PairedPolicyEngine(PolicyEngine):
-    def __init__(self, backend, preset="sensitive", seed=0, sc=None, pe=None, local=False):
-        super().__init__(backend, preset, seed, sc, local)
+    def __init__(self, backend, preset="sensitive", seed=0, sc=None, pe=None, local=False, discord=True, mixed=True, **kw):
+        """pe = PairedEndPolicy (-I / -X / --fr --rf --ff / --dovetail / --no-contain / --no-overlap);
+        discord / mixed = not --no-discordant / not --no-mixed"""
+        super().__init__(backend, preset, seed, sc, local, **kw)
         self.pe = pe or policy.PairedEndPolicy(local=local)
+        self.discord, self.mixed = discord, mixed
         self.max_mate_streak = 10
 
     def align_pair(self, codes1, quals1, name1, codes2, quals2, name2) -> PairResult:
@@ -876,8 +889,13 @@ class PairedPolicyEngine(PolicyEngine):
         self.streak_cur = streak
         self.red = RedundantAlns()
         self.red_mate = [RedundantAlns(), RedundantAlns()]
-        self.sink = PairedSink(self.khits, self.mhits)
+        self.sink = PairedSink(self.khits, self.mhits, self.discord, self.mixed)
         self.n_iters = self.n_dps = self.n_ugs = self.n_red = self.n_mate_dps = 0
+        # bt2_search.cpp:3419-3426: --nofw / --norc refer to the fragment; which strand of a mate that is depends on --fr/--rf/--ff
+        m1fw = self.pe.pol in (policy.PE_POLICY_FF, policy.PE_POLICY_FR)
+        m2fw = self.pe.pol in (policy.PE_POLICY_FF, policy.PE_POLICY_RF)
+        nofw = [self.gnofw if m1fw else self.gnorc, self.gnofw if m2fw else self.gnorc]
+        norc = [self.gnorc if m1fw else self.gnofw, self.gnorc if m2fw else self.gnofw]
         done = [not m[0].filt, not m[1].filt]
         sink = self.sink
         matemap = [0, 1]
@@ -898,7 +916,7 @@ class PairedPolicyEngine(PolicyEngine):
             c = m[mate]
             if not c.filt or done[mate] or sink.done_with_mate(mate == 0):
                 continue
-            ne, mi, tb = self.b.exact_sweep(c.codes)
+            ne, mi, tb = self.b.exact_sweep(c.codes, nofw[mate], norc[mate])
             nelt[mate] = ne
             mined[mate] = [int(mi[0]), int(mi[1])]
             c.ee = []
@@ -929,7 +947,7 @@ class PairedPolicyEngine(PolicyEngine):
                 nelt[mate] = 0
                 continue
             nelt[mate] = 0
-            yfw, yrc = mined[mate][0] <= 1, mined[mate][1] <= 1
+            yfw, yrc = mined[mate][0] <= 1 and not nofw[mate], mined[mate][1] <= 1 and not norc[mate]
             if yfw or yrc:
                 hits = self.b.one_mm(c.codes, c.quals, c.minsc, not yfw, not yrc)
                 c.mm1 = [EEHit(int(h[0]), int(h[1]), bool(h[6]), int(h[5]), (int(h[2]), int(h[3]), int(h[4]))) for h in hits]
@@ -963,7 +981,7 @@ class PairedPolicyEngine(PolicyEngine):
                 offset = (interval[mate] * roundi) // nrounds[mate]
                 if offset > 0 and min(L, c.rdlen) + offset > c.rdlen:
                     continue
-                hits = self.b.seed_search(c.codes, c.quals, L, interval[mate], offset)
+                hits = self.b.seed_search(c.codes, c.quals, L, interval[mate], offset, nofw[mate], norc[mate])
                 nfw = [max(0, int(h[1]) - int(h[0])) for h in hits[0]]
                 nrc = [max(0, int(h[1]) - int(h[0])) for h in hits[1]]
                 nonz = sum(x > 0 for x in nfw) + sum(x > 0 for x in nrc)
@@ -1222,7 +1240,7 @@ class PairedPolicyEngine(PolicyEngine):
                                         return FULFILLED
                                     if sink.done_with_mate(anchor1):
                                         return FULFILLED
-                                elif not did_anchor:
+                                elif (self.mixed or self.discord) and not did_anchor:
                                     did_anchor = True
                                     if not sink.done_unpaired(anchor1):
                                         red = self.red_mate[0 if anchor1 else 1]
@@ -1234,7 +1252,7 @@ class PairedPolicyEngine(PolicyEngine):
                                         return FULFILLED
                                 if oa is None:
                                     break
-                        else:
+                        elif self.mixed or self.discord:
                             if not sink.done_unpaired(anchor1):
                                 red = self.red_mate[0 if anchor1 else 1]
                                 if not red.overlap(a):
@@ -1306,7 +1324,7 @@ class PairedPolicyEngine(PolicyEngine):
             res.pair_type = 2
             return res
         for k, rsu in enumerate((sink.rs1u, sink.rs2u)):
-            if not rsu:
+            if not rsu or not self.mixed:              # --no-mixed: ReportingState::getReport returns before the unpaired counts
                 continue
             s = self._select(rsu, None, None, None)
             a = rsu[s["sel"]]

@@ -13,15 +13,15 @@ class OracleBackend:
         self.off_size = off_size
         self.local = local
 
-    def exact_sweep(self, codes):
-        return self.O.exact_sweep(codes)
+    def exact_sweep(self, codes, nofw=False, norc=False):
+        return self.O.exact_sweep(codes, nofw, norc)
 
     def one_mm(self, codes, quals, minsc, nofw, norc):
         return oracle_one_mm(self.O, self.local, codes, quals, minsc, nofw, norc)
 
-    def seed_search(self, codes, quals, seed_len, interval, offset):
+    def seed_search(self, codes, quals, seed_len, interval, offset, nofw=False, norc=False):
         n = max(1, policy.n_seeds(len(codes), seed_len, interval, offset))
-        cnt, out = self.O.seed_search(codes, seed_len, interval, offset, n + 2, quals=quals)
+        cnt, out = self.O.seed_search(codes, seed_len, interval, offset, n + 2, nofw, norc, quals=quals)
         return out[:, :cnt, :]
 
     def extend(self, codes, fw, rdoff, seedlen, rng4):

@@ -216,3 +216,88 @@ def test_paired_sam_and_work_counters_identical_to_reference_program(tmp_path, p
         if "ZI" in tags:
             c = o.counters
             assert (c["ZI"], c["XD"], c["XU"], c["YR"]) == tuple(int(tags[k]) for k in ("ZI", "XD", "XU", "YR")), (i, c)
+
+
+# ------------------------------------------------------------------------------------------------- options
+def _synth_index(tmp_path):
+    genome = synth.make_genome(n_contigs=3, contig_len=40000, seed=11, repeat_frac=0.15, repeat_len=300, repeat_copies=12, n_gap=37)
+    fa, base = str(tmp_path / "g.fa"), str(tmp_path / "g")
+    synth.write_fasta(fa, genome)
+    subprocess.check_call([ref_bin("bowtie2-build-s"), "--seed", "0", "--quiet", fa, base])
+    return genome, base
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args,kw", [
+    (["--nofw"], dict(nofw=True)),
+    (["--norc"], dict(norc=True)),
+    (["--seed", "7"], dict(seed=7)),
+    (["-D", "5", "-R", "1", "-L", "20"], dict(dp_fail_streak=5, seed_rounds=1, seed_len=20)),
+])
+def test_unpaired_options(tmp_path, args, kw):
+    genome, base = _synth_index(tmp_path)
+    reads, quals, _ = synth.make_reads(genome, 300, 100, seed=77, sub_rate=0.02, indel_rate=0.003)
+    fq = str(tmp_path / "r.fq")
+    synth.write_fastq(fq, reads, quals)
+    cmd = [ref_bin("bowtie2-align-s"), "--sensitive", "-p", "1", "-x", base, "-U", fq] + args
+    if "--seed" not in args:
+        cmd += ["--seed", "0"]
+    out = subprocess.check_output(cmd, stderr=subprocess.DEVNULL).decode()
+    want = [l for l in out.split("\n") if l and not l.startswith("@")]
+    O = Oracle(base)
+    eng = PolicyEngine(OracleBackend(O), "sensitive", **kw)
+    n = len(reads)
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    ops = np.zeros((n, 164), dtype=np.uint8)
+    for i in range(n):
+        r = eng.align_read(reads[i], quals[i], f"r{i}")
+        if r.aligned:
+            _fill(res, ops, i, r, reads[i])
+    names = [f"r{i}" for i in range(n)]
+    lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ["chr1", "chr2", "chr3"], read_names=names).rstrip("\n").split("\n")
+    assert lines == want
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args,pe_kw,eng_kw", [
+    (["--no-mixed"], {}, dict(mixed=False)),
+    (["--no-discordant"], {}, dict(discord=False)),
+    (["--no-mixed", "--no-discordant"], {}, dict(mixed=False, discord=False)),
+    (["-I", "250", "-X", "380"], dict(minfrag=250, maxfrag=380), {}),
+    (["--ff"], dict(pol=1), {}),
+    (["--rf"], dict(pol=4), {}),
+    (["--no-contain", "--no-overlap"], dict(contain_ok=False, olap_ok=False), {}),
+    (["--dovetail"], dict(dovetail_ok=True), {}),
+    (["--nofw"], {}, dict(nofw=True)),
+])
+def test_paired_options(tmp_path, args, pe_kw, eng_kw):
+    from bowtie2_b200 import policy
+    from bowtie2_b200.lib import PAIR_RESULT
+    from bowtie2_b200.policy_engine import PairedPolicyEngine
+    genome, base = _synth_index(tmp_path)
+    n = 200
+    reads, quals, _ = synth.make_pairs(genome, n, 100, seed=31, sub_rate=0.02, indel_rate=0.003, hard_frac=0.2, hard_period=12,
+                                       ins_mean=300, ins_sd=90)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    synth.write_fastq(f1, reads[0::2], quals[0::2])
+    synth.write_fastq(f2, reads[1::2], quals[1::2])
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), "--sensitive", "--seed", "0", "-p", "1", "-x", base, "-1", f1, "-2", f2] + args,
+                                  stderr=subprocess.DEVNULL).decode()
+    want = [l for l in out.split("\n") if l and not l.startswith("@")]
+    eng = PairedPolicyEngine(OracleBackend(Oracle(base)), "sensitive", pe=policy.PairedEndPolicy(**pe_kw), **eng_kw)
+    res = np.zeros(2 * n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    ops = np.zeros((2 * n, 164), dtype=np.uint8)
+    pairs = np.zeros(n, dtype=PAIR_RESULT)
+    names = [f"r{i // 2}" for i in range(2 * n)]
+    for i in range(n):
+        pr = eng.align_pair(reads[2 * i], quals[2 * i], names[2 * i], reads[2 * i + 1], quals[2 * i + 1], names[2 * i + 1])
+        pairs[i]["pair_type"] = pr.pair_type
+        for k in range(2):
+            if pr.mates[k].aligned:
+                _fill(res, ops, 2 * i + k, pr.mates[k], reads[2 * i + k])
+    lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ["chr1", "chr2", "chr3"], read_names=names,
+                       pairs=pairs).rstrip("\n").split("\n")
+    bad = [i for i in range(n) if lines[2 * i:2 * i + 2] != want[2 * i:2 * i + 2]]
+    assert not bad, (len(bad), lines[2 * bad[0]:2 * bad[0] + 2], want[2 * bad[0]:2 * bad[0] + 2])

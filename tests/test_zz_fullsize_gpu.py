@@ -160,6 +160,7 @@ def _norm(line):
     return "\t".join(x for x in f if not x.startswith("XS:i:"))
 
 
+@pytest.mark.xfail(reason="written after the round's GPU minutes were spent: staged, not yet run on hardware", strict=False)
 @pytest.mark.parametrize("paired", [False, True])
 def test_files_in_sam_out(paired, lambda_index, tmp_path):
     """bowtie2_b200.align.align_files on the golden lambda reads: header identical to the reference program's, records in
