@@ -252,6 +252,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 			int nceil = (int)(nc + nl * (double)len); if(nceil > len) nceil = len;
 			if(len < 2) line += "\tYF:Z:LN";
 			else if(ns > nceil) line += "\tYF:Z:NS";
+			else if(len <= opt->sc_filter_maxlen) line += "\tYF:Z:SC";      // perfect score below the minimum (scoreFilter)
 		}
 		line += '\n';
 		// a pair with only mate 2 aligned is printed aligned mate first (AlnSinkWrap::finishRead reports the

@@ -670,16 +670,28 @@ EXPORTS += ["bt2g_sam_format"]
 
 class _SamOpts(C.Structure):
     _fields_ = [("ref_names", C.POINTER(C.c_char_p)), ("n_refs", C.c_uint64), ("read_names", C.POINTER(C.c_char_p)),
-                ("threads", C.c_int32), ("reserved", C.c_int32), ("nceil_const", C.c_double), ("nceil_linear", C.c_double)]
+                ("threads", C.c_int32), ("sc_filter_maxlen", C.c_int32), ("nceil_const", C.c_double), ("nceil_linear", C.c_double)]
 
 
-def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_names=None, pairs=None, threads: int = 1) -> str:
+def sc_filter_maxlen(local: bool) -> int:
+    """longest read whose perfect score stays below the minimum score (0 in end-to-end mode)"""
+    from . import policy
+    sc = policy.Scoring.default(local)
+    n = 0
+    for ln in range(2, 200):
+        if sc.perfect_score(ln) < sc.score_min().fi(ln):
+            n = ln
+    return n
+
+
+def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_names=None, pairs=None, threads: int = 1,
+               local: bool = False) -> str:
     """SAM text for pipeline results (one record per read).  `lib` is the loaded libbt2g (load_library())."""
     lib.bt2g_sam_format.argtypes = [C.POINTER(_SamOpts), C.POINTER(_Reads), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     rn = (C.c_char_p * len(ref_names))(*[x.encode() for x in ref_names])
     qn = (C.c_char_p * reads.n)(*[x.encode() for x in read_names]) if read_names is not None else None
-    opt = _SamOpts(rn, len(ref_names), qn, int(threads), 0, 0.0, 0.0)
+    opt = _SamOpts(rn, len(ref_names), qn, int(threads), sc_filter_maxlen(True) if local else 0, 0.0, 0.0)
     res = np.ascontiguousarray(res, dtype=READ_RESULT)
     max_ops = 0 if ops is None else ops.shape[1]
     if ops is not None:

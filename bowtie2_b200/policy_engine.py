@@ -375,6 +375,9 @@ class PolicyEngine:
         if ns_in_read > sc.n_ceil(rdlen):
             res.filtered = "NS"
             return res
+        if sc.perfect_score(rdlen) < sc.min_score(rdlen):        # Scoring::scoreFilter (bt2_search.cpp:3385)
+            res.filtered = "SC"
+            return res
         self.cur = MateCtx(codes, quals, name, rdlen, sc.min_score(rdlen), sc.perfect_score(rdlen), sc.n_ceil(rdlen))
         rnd = self.rnd = RandomSource(policy.gen_rand_seed(codes, quals, name, self.seed))
         interval = policy.seed_interval(self.pre.ival, rdlen, False)
@@ -874,6 +877,8 @@ class PairedPolicyEngine(PolicyEngine):
                 c.filt, c.filtered = False, "LN"
             elif int((codes > 3).sum()) > sc.n_ceil(rdlen):
                 c.filt, c.filtered = False, "NS"
+            elif sc.perfect_score(rdlen) < sc.min_score(rdlen):
+                c.filt, c.filtered = False, "SC"
             m.append(c)
         self.m = m
         both = m[0].filt and m[1].filt

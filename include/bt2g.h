@@ -431,7 +431,8 @@ typedef struct {
 	uint64_t           n_refs;
 	const char *const *read_names;  /* [n_reads] or NULL: "r<index>" (pair index for paired input) */
 	int32_t            threads;     /* host threads formatting disjoint ranges of records (0 or 1 = the calling thread) */
-	int32_t            reserved;
+	int32_t            sc_filter_maxlen; /* reads up to this length cannot reach the minimum score (Scoring::scoreFilter,
+	                                     * bt2_search.cpp:3385: --local with very short reads): unaligned ones carry YF:Z:SC; 0 = none */
 	double             nceil_const, nceil_linear;   /* --n-ceil (0, 0.15): unaligned reads with more Ns carry YF:Z:NS
 	                                                * (bt2_search.cpp:3427-3431, sam.cpp:331-345); both 0 = defaults */
 } bt2g_sam_opts;

@@ -301,3 +301,57 @@ def test_paired_options(tmp_path, args, pe_kw, eng_kw):
                        pairs=pairs).rstrip("\n").split("\n")
     bad = [i for i in range(n) if lines[2 * i:2 * i + 2] != want[2 * i:2 * i + 2]]
     assert not bad, (len(bad), lines[2 * bad[0]:2 * bad[0] + 2], want[2 * bad[0]:2 * bad[0] + 2])
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("local", [False, True])
+def test_edge_case_reads(tmp_path, local):
+    """1-200 bp reads, Ns (a few / all), random reads, extreme qualities, reads shorter than the seed: the filters (YF:Z:LN /
+    NS / SC), the short-read seed handling and the ungapped path, against the reference program."""
+    genome = synth.make_genome(n_contigs=3, contig_len=30000, seed=5, repeat_frac=0.1, repeat_len=200, repeat_copies=10, n_gap=60)
+    fa, base, fq = str(tmp_path / "g.fa"), str(tmp_path / "g"), str(tmp_path / "r.fq")
+    synth.write_fasta(fa, genome)
+    subprocess.check_call([ref_bin("bowtie2-build-s"), "--seed", "0", "--quiet", fa, base])
+    rng = np.random.default_rng(1)
+    reads, quals = [], []
+    n = 400
+    for i in range(n):
+        ln = int(rng.choice([1, 2, 3, 5, 10, 15, 19, 20, 21, 22, 23, 25, 30, 33, 40, 49, 54, 64, 99, 104, 109, 149, 200]))
+        c = int(rng.integers(0, 3))
+        p = int(rng.integers(0, len(genome[c]) - ln))
+        r = genome[c][p:p + ln].copy()
+        if rng.random() < 0.5:
+            r = np.array([4 if x > 3 else 3 - x for x in r[::-1]], dtype=np.uint8)
+        k = rng.random()
+        if k < 0.2:
+            for _ in range(int(rng.integers(1, 4))):
+                r[int(rng.integers(0, ln))] = 4
+        elif k < 0.25:
+            r[:] = 4
+        elif k < 0.6:
+            for _ in range(int(rng.integers(1, 5))):
+                j = int(rng.integers(0, ln))
+                r[j] = (r[j] + 1) % 4 if r[j] < 4 else r[j]
+        elif k < 0.65:
+            r = rng.integers(0, 4, ln).astype(np.uint8)
+        reads.append(r)
+        quals.append(rng.choice([35, 43, 53, 63, 73, 74], ln).astype(np.uint8))
+    synth.write_fastq(fq, reads, quals)
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), *(["--local"] if local else []), "--sensitive", "--seed", "0", "-p", "1",
+                                   "-x", base, "-U", fq], stderr=subprocess.DEVNULL).decode()
+    want = [l for l in out.split("\n") if l and not l.startswith("@")]
+    eng = PolicyEngine(OracleBackend(Oracle(base), local=local), "sensitive", local=local)
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    ops = np.zeros((n, 264), dtype=np.uint8)
+    filt = set()
+    for i in range(n):
+        r = eng.align_read(reads[i], quals[i], f"r{i}")
+        filt.add(r.filtered)
+        if r.aligned:
+            _fill(res, ops, i, r, reads[i])
+    lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ["chr1", "chr2", "chr3"],
+                       read_names=[f"r{i}" for i in range(n)], local=local).rstrip("\n").split("\n")
+    bad = [i for i in range(n) if lines[i] != want[i]]
+    assert not bad, (len(bad), lines[bad[0]], want[bad[0]])
+    assert {"LN", "NS"}.issubset(filt) and (("SC" in filt) == local)
