@@ -206,3 +206,55 @@ def test_files_in_sam_out(paired, lambda_index, tmp_path):
     text = summ.getvalue()
     assert text.startswith(f"{len(want) // (2 if paired else 1)} reads; of these:\n") and text.endswith("overall alignment rate\n")
     assert int(counts["nread"][0]) == len(want) // (2 if paired else 1)
+
+
+@pytest.mark.xfail(reason="written after the round's GPU minutes were spent: staged, not yet run on hardware", strict=False)
+@pytest.mark.parametrize("paired", [False, True])
+def test_exact_policy_over_gpu_primitives(paired, lambda_index):
+    """policy_engine over the GPU entry points (policy_backend_gpu.GpuBackend): byte-identical golden SAM, i.e. the
+    reference's sequential policy with every hot-path primitive computed on the device."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from bowtie2_b200 import Bt2Gpu
+    from bowtie2_b200.lib import PAIR_RESULT, READ_RESULT, ReadBatch, load_library, sam_format
+    from bowtie2_b200.policy_backend_gpu import GpuBackend
+    from bowtie2_b200.policy_engine import PairedPolicyEngine, PolicyEngine
+    from conftest import GOLDEN, read_fastq_codes
+    from test_policy_engine import _fill
+    g = Bt2Gpu(0)
+    g.load_index_files(lambda_index)
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "lambda_P_sensitive.sam" if paired else "lambda_U_sensitive.sam"))
+              if not l.startswith("@")]
+    n = 100 if paired else 300
+    n1, r1, q1 = read_fastq_codes(os.path.join(GOLDEN, "lambda_reads_1.fq"), n)
+    ref = ["gi|9626243|ref|NC_001416.1|"]
+    if not paired:
+        eng = PolicyEngine(GpuBackend(g), "sensitive")
+        res = np.zeros(n, dtype=READ_RESULT)
+        res["score2"] = -(1 << 31)
+        ops = np.zeros((n, max(len(r) for r in r1) + 64), dtype=np.uint8)
+        for i in range(n):
+            r = eng.align_read(r1[i], q1[i], n1[i])
+            if r.aligned:
+                _fill(res, ops, i, r, r1[i])
+        lines = sam_format(load_library(), ReadBatch.from_list(r1, q1), res, ops, ref, read_names=n1).rstrip("\n").split("\n")
+        assert lines == golden[:n]
+    else:
+        n2, r2, q2 = read_fastq_codes(os.path.join(GOLDEN, "lambda_reads_2.fq"), n)
+        il = lambda a, b: [x for p in zip(a, b) for x in p]
+        reads, quals, names = il(r1, r2), il(q1, q2), il(n1, n2)
+        eng = PairedPolicyEngine(GpuBackend(g), "sensitive")
+        res = np.zeros(2 * n, dtype=READ_RESULT)
+        res["score2"] = -(1 << 31)
+        ops = np.zeros((2 * n, max(len(r) for r in reads) + 64), dtype=np.uint8)
+        pairs = np.zeros(n, dtype=PAIR_RESULT)
+        for i in range(n):
+            pr = eng.align_pair(r1[i], q1[i], n1[i], r2[i], q2[i], n2[i])
+            pairs[i]["pair_type"] = pr.pair_type
+            for k in range(2):
+                if pr.mates[k].aligned:
+                    _fill(res, ops, 2 * i + k, pr.mates[k], reads[2 * i + k])
+        lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ref, read_names=names, pairs=pairs).rstrip("\n").split("\n")
+        assert lines == golden[:2 * n]
+    g.close()
