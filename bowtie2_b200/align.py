@@ -70,10 +70,58 @@ def interleave(b1: ReadBatch, b2: ReadBatch) -> ReadBatch:
     return ReadBatch(seq, off, qual)
 
 
+def _exact_batch(gpu, batch, names, paired, preset, local, seed):
+    """one batch through the sequential policy engine over the GPU primitives -> the pipeline's result arrays"""
+    from .lib import PAIR_RESULT, READ_RESULT
+    from .policy_backend_gpu import GpuBackend
+    from .policy_engine import PairedPolicyEngine, PolicyEngine, aln_to_ops
+    backend = GpuBackend(gpu, local)
+    n = batch.n
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    ops = np.zeros((n, int(batch.lengths().max()) + 64), dtype=np.uint8)
+    rd = lambda i: (batch.seq[int(batch.off[i]):int(batch.off[i + 1])], batch.qual[int(batch.off[i]):int(batch.off[i + 1])])
+
+    def fill(j, r, codes):
+        a = r.aln
+        o = aln_to_ops(a, codes)
+        res[j]["found"] = 2 if (not a.edits and a.ext == a.rdlen) else 1
+        res[j]["score"] = a.score
+        if r.xs is not None:
+            res[j]["score2"] = r.xs
+        res[j]["fw"], res[j]["tidx"], res[j]["refoff"], res[j]["nops"] = int(a.fw), a.tidx, a.refoff, len(o)
+        res[j]["trim_left"], res[j]["trim_right"] = a.trim_left, a.rdlen - a.ext - a.trim_left
+        res[j]["mapq"], res[j]["pad"] = r.mapq, a.refns
+        ops[j, :len(o)] = o
+    if not paired:
+        eng = PolicyEngine(backend, preset, seed=seed, local=local)
+        for i in range(n):
+            c, q = rd(i)
+            r = eng.align_read(c, q, names[i])
+            if r.aligned:
+                fill(i, r, c)
+        return res, ops, None
+    eng = PairedPolicyEngine(backend, preset, seed=seed, local=local)
+    pairs = np.zeros(n // 2, dtype=PAIR_RESULT)
+    for i in range(n // 2):
+        (c1, q1), (c2, q2) = rd(2 * i), rd(2 * i + 1)
+        pr = eng.align_pair(c1, q1, names[2 * i], c2, q2, names[2 * i + 1])
+        pairs[i]["pair_type"] = pr.pair_type
+        for k, c in enumerate((c1, c2)):
+            if pr.mates[k].aligned:
+                fill(2 * i + k, pr.mates[k], c)
+    return res, ops, pairs
+
+
 def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None, preset: str = "sensitive", local: bool = False,
                 device: int = 0, batch_reads: int = 1 << 20, threads: int = 8, seed_table: int = 0, dense_sa: int = -1,
-                offrate: int = -1, pg_cl: str = None, summary=sys.stderr, gpu: Bt2Gpu = None):
-    """bowtie2 -x index_base (-U reads1 | -1 reads1 -2 reads2) -S out_path.  Returns the ALIGN_COUNTS record."""
+                offrate: int = -1, pg_cl: str = None, summary=sys.stderr, gpu: Bt2Gpu = None, exact: bool = False, seed: int = 0):
+    """bowtie2 -x index_base (-U reads1 | -1 reads1 -2 reads2) -S out_path.  Returns the ALIGN_COUNTS record.
+
+    exact=False: the batched speculative pipeline (fast; agrees with the reference on the confidently placed reads).
+    exact=True: the reference's sequential search policy (policy_engine) with every primitive computed on the GPU through
+    policy_backend_gpu.GpuBackend, read by read: records identical to the reference program's, at a small fraction of the
+    pipeline's speed (intended for parity subsets until the policy runs as a device-side state machine)."""
     own = gpu is None
     gpu = gpu or Bt2Gpu(device)                                  # raises without a GPU: nothing below runs on the CPU
     lib = gpu._lib
@@ -105,7 +153,7 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
             batch = interleave(b1, b2) if paired else b1
             names = [x for p in zip(n1, n2) for x in p] if paired else n1
             need = int(batch.lengths().max())
-            if pipe is None or need > pipe_len:
+            if not exact and (pipe is None or need > pipe_len):
                 if pipe is not None:
                     pipe.close()
                 pipe_len = max(need, 32)
@@ -113,11 +161,13 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
                                 both_mates=paired)
                 if paired:
                     pipe.enable_pairs()
-            if paired:
+            if exact:
+                res, ops, pairs = _exact_batch(gpu, batch, names, paired, preset, local, seed)
+            elif paired:
                 res, ops, pairs = pipe.run_paired_host(batch)
             else:
                 (res, ops), pairs = pipe.run_host(batch), None
-            out.write(sam_format(lib, batch, res, ops, sam_names, read_names=names, pairs=pairs, threads=threads))
+            out.write(sam_format(lib, batch, res, ops, sam_names, read_names=names, pairs=pairs, threads=threads, local=local))
             align_counts_add(lib, counts, res, pairs)
     if pipe is not None:
         pipe.close()
