@@ -340,6 +340,7 @@ class PolicyEngine:
                  dp_fail_streak=None, seed_rounds=None, seed_len=None):
         """seed = --seed; nofw / norc = --nofw / --norc; dp_fail_streak / seed_rounds / seed_len = -D / -R / -L on top of the preset"""
         self.b = backend
+        self.off_size = backend.off_size if backend is not None else 4
         self.local = local
         self.pre = policy.preset(preset, local)
         if dp_fail_streak is not None:
@@ -362,7 +363,22 @@ class PolicyEngine:
         self.nsm = 5
 
     # ------------------------------------------------------------------------------------------------- one read
+    def _drive(self, gen):
+        """run a step generator to completion against self.b (one backend call per request)"""
+        try:
+            req = next(gen)
+            while True:
+                req = gen.send(getattr(self.b, req[0])(*req[1]))
+        except StopIteration as e:
+            return e.value
+
     def align_read(self, codes, quals, name) -> ReadResult:
+        return self._drive(self.read_steps(codes, quals, name))
+
+    def read_steps(self, codes, quals, name):
+        """generator form of the policy: yields (primitive name, argument tuple) requests, receives their results, and
+        returns the ReadResult.  The wave scheduler (policy_waves.py) interleaves many of these so that each primitive
+        runs as one batched call per wave."""
         sc = self.sc
         rdlen = len(codes)
         res = ReadResult()
@@ -388,7 +404,7 @@ class PolicyEngine:
         done = False
         # ---- exact end-to-end (bt2_search.cpp:3493-3690)
         nofw, norc = self.gnofw, self.gnorc
-        nelt, mined, tb = self.b.exact_sweep(codes, nofw, norc)
+        nelt, mined, tb = yield ("exact_sweep", (codes, nofw, norc,))
         minedfw, minedrc = int(mined[0]), int(mined[1])
         if nelt > 0:
             ee = []
@@ -396,16 +412,16 @@ class PolicyEngine:
                 ee.append(EEHit(int(tb[0]), int(tb[1]), True, self.cur.perfect))
             if tb[3] > tb[2]:
                 ee.append(EEHit(int(tb[2]), int(tb[3]), False, self.cur.perfect))
-            ret = self.extend_seeds(None, ee)
+            ret = yield from self.extend_seeds(None, ee)
             done = self._after_extend(ret, done)
         # ---- 1-mismatch end-to-end (bt2_search.cpp:3692-3875)
         if not done:
             yfw, yrc = minedfw <= 1 and not nofw, minedrc <= 1 and not norc
             if yfw or yrc:
-                hits = self.b.one_mm(codes, quals, self.cur.minsc, not yfw, not yrc)
+                hits = yield ("one_mm", (codes, quals, self.cur.minsc, not yfw, not yrc,))
                 self.cur.mm1 = [EEHit(int(h[0]), int(h[1]), bool(h[6]), int(h[5]), (int(h[2]), int(h[3]), int(h[4]))) for h in hits]
                 if self.cur.mm1 and not self.sink.done_with_mate():
-                    ret = self.extend_seeds(None, [])
+                    ret = yield from self.extend_seeds(None, [])
                     self.cur.mm1 = []                           # clear1mmE2eHits (bt2_search.cpp:3839)
                     done = self._after_extend(ret, done)
                 elif self.cur.mm1:
@@ -422,7 +438,7 @@ class PolicyEngine:
             offset = (interval * roundi) // nrounds
             if offset > 0 and L + offset > rdlen:
                 continue
-            hits = self.b.seed_search(codes, quals, min(L, rdlen), interval, offset, nofw, norc)
+            hits = yield ("seed_search", (codes, quals, min(L, rdlen), interval, offset, nofw, norc,))
             if hits is None:                                   # no seed could be instantiated
                 done = True
                 break
@@ -435,7 +451,7 @@ class PolicyEngine:
             ranks = policy.rank_seed_hits(nelt_fw, nelt_rc, rnd, False)
             sh = dict(hits=hits, ranks=ranks, interval=interval, offset=offset, seedlen=min(L, rdlen), nonz=nonz,
                       nelt=sum(nelt_fw) + sum(nelt_rc))
-            ret = self.extend_seeds(sh, [])
+            ret = yield from self.extend_seeds(sh, [])
             done = self._after_extend(ret, done, check_perfect=False)
             if not done and sh["nelt"] // nonz < self.seed_boost_thresh:
                 done = True
@@ -462,7 +478,7 @@ class PolicyEngine:
         if tot > 0:
             fw_first = True
             fwsz = sum(h.bot - h.top for h in ee_exact if h.fw)
-            rn = (rnd.next_u32() if self.b.off_size == 4 else _next_u64(rnd)) % tot
+            rn = (rnd.next_u32() if self.off_size == 4 else _next_u64(rnd)) % tot
             if rn >= fwsz:
                 fw_first = False
             for fwi in range(2):
@@ -491,7 +507,7 @@ class PolicyEngine:
             return nelt, done
         if nelt + width > maxelt:
             trim = (nelt + width) - maxelt
-            rn = (rnd.next_u32() if self.b.off_size == 4 else _next_u64(rnd)) % width
+            rn = (rnd.next_u32() if self.off_size == 4 else _next_u64(rnd)) % width
             newwidth = width - trim
             if hit.top + rn + newwidth > hit.bot:
                 tops[0], bots[0] = hit.top + rn, hit.bot
@@ -530,7 +546,7 @@ class PolicyEngine:
                 nelt -= sz
                 continue
             sp = SatPos(topf, topb, sz, seedlen, fw, offidx, rdoff, seedlen, orig_size=sz)
-            sp.nlex, sp.nrex = self.b.extend(self.cur.codes, fw, rdoff, seedlen, (topf, botf, topb, botb))
+            sp.nlex, sp.nrex = yield ("extend", (self.cur.codes, fw, rdoff, seedlen, (topf, botf, topb, botb),))
             if sp.nlex > 0 or sp.nrex > 0:
                 rng.append((rdoff - (sp.nlex if fw else sp.nrex), seedlen + sp.nlex + sp.nrex, sz))
             sats.append(sp)
@@ -587,7 +603,7 @@ class PolicyEngine:
                 if self.cur.minsc == self.cur.perfect:
                     return PERFECT
                 if first_extend:
-                    satpos, nelt = self._prioritize(sh, self.max_iters)
+                    satpos, nelt = yield from self._prioritize(sh, self.max_iters)
                     nelt_left = nelt
                     first_extend = False
                 if nelt_left == 0:
@@ -612,10 +628,10 @@ class PolicyEngine:
                     self.n_iters += 1
                     first = False
                     elt = rands.next(rnd)
-                    joined = self.b.resolve(sp.topf + elt)
+                    joined = yield ("resolve", (sp.topf + elt,))
                     if not ee_mode:
                         nelt_left -= 1
-                    ok, tidx, toff, tlen, straddled = self.b.joined_to_text(sp.key_len, joined, ee_mode)
+                    ok, tidx, toff, tlen, straddled = yield ("joined_to_text", (sp.key_len, joined, ee_mode,))
                     if not ok:
                         continue
                     refoff = toff - rdoff
@@ -637,7 +653,7 @@ class PolicyEngine:
                         state = 1
                         self.cur.seen.add(tidx, fw, refoff, 1)
                     elif ungapped:
-                        rc, a = self.b.ungapped(self.cur.codes, self.cur.quals, fw, tidx, refoff, tlen, self.cur.minsc)
+                        rc, a = yield ("ungapped", (self.cur.codes, self.cur.quals, fw, tidx, refoff, tlen, self.cur.minsc,))
                         self.cur.seen.add(tidx, fw, refoff, 1)
                         self.n_ugs += 1
                         if rc == 0:
@@ -660,7 +676,7 @@ class PolicyEngine:
                         if not found:
                             continue
                         self.cur.seen.add(tidx, fw, rect.refl_pretrim + rect.corel, rect.corer - rect.corel + 1)
-                        dp = self.b.dp(self.cur.codes, self.cur.quals, fw, tidx, rect, self.cur.minsc, sc.n_ceil_raw(rdlen))
+                        dp = yield ("dp", (self.cur.codes, self.cur.quals, fw, tidx, rect, self.cur.minsc, sc.n_ceil_raw(rdlen),))
                         self.n_dps += 1
                         if not dp["found"]:
                             n_dp_fail += 1
@@ -677,7 +693,7 @@ class PolicyEngine:
                                 break
                             a = found_alns[0]
                         else:
-                            a = self._next_alignment(dp, tidx, self.cur.minsc, rdlen)
+                            a = yield from self._next_alignment(dp, tidx, self.cur.minsc, rdlen)
                             if a is None:
                                 break
                         first_inner = False
@@ -733,7 +749,7 @@ class PolicyEngine:
                 ed = [tuple(e) for e in al["edits"]]
                 # AlnRes::refNs: ambiguous reference characters under the alignment (XN:i)
                 a = Aln(tidx, al["refoff"], bool(al["fw"]), al["score"], rdlen, ed, al["ns"], 0, False, al["trim5"], al["trim3"])
-                a.refns = self.b.count_ref_ns(tidx, a.refoff, a.ref_extent)
+                a.refns = yield ("count_ref_ns", (tidx, a.refoff, a.ref_extent,))
                 return a
         return None
 
@@ -866,6 +882,9 @@ class PairedPolicyEngine(PolicyEngine):
         self.max_mate_streak = 10
 
     def align_pair(self, codes1, quals1, name1, codes2, quals2, name2) -> PairResult:
+        return self._drive(self.pair_steps(codes1, quals1, name1, codes2, quals2, name2))
+
+    def pair_steps(self, codes1, quals1, name1, codes2, quals2, name2):
         sc = self.sc
         m = []
         for codes, quals, name in ((codes1, quals1, name1), (codes2, quals2, name2)):
@@ -921,7 +940,7 @@ class PairedPolicyEngine(PolicyEngine):
             c = m[mate]
             if not c.filt or done[mate] or sink.done_with_mate(mate == 0):
                 continue
-            ne, mi, tb = self.b.exact_sweep(c.codes, nofw[mate], norc[mate])
+            ne, mi, tb = yield ("exact_sweep", (c.codes, nofw[mate], norc[mate],))
             nelt[mate] = ne
             mined[mate] = [int(mi[0]), int(mi[1])]
             c.ee = []
@@ -939,7 +958,7 @@ class PairedPolicyEngine(PolicyEngine):
                 c.ee = []
                 done[mate] = True
                 continue
-            ret = self.extend_seeds_paired(mate, None, c.ee)
+            ret = yield from self.extend_seeds_paired(mate, None, c.ee)
             c.ee = []
             after(ret, mate)
             if not done[mate] and c.minsc == c.perfect:
@@ -954,7 +973,7 @@ class PairedPolicyEngine(PolicyEngine):
             nelt[mate] = 0
             yfw, yrc = mined[mate][0] <= 1 and not nofw[mate], mined[mate][1] <= 1 and not norc[mate]
             if yfw or yrc:
-                hits = self.b.one_mm(c.codes, c.quals, c.minsc, not yfw, not yrc)
+                hits = yield ("one_mm", (c.codes, c.quals, c.minsc, not yfw, not yrc,))
                 c.mm1 = [EEHit(int(h[0]), int(h[1]), bool(h[6]), int(h[5]), (int(h[2]), int(h[3]), int(h[4]))) for h in hits]
                 nelt[mate] = sum(h.bot - h.top for h in c.mm1)
         matemap = [1, 0] if (nelt[0] > 0 and nelt[1] > 0 and nelt[0] > nelt[1]) else [0, 1]
@@ -965,7 +984,7 @@ class PairedPolicyEngine(PolicyEngine):
             if sink.done_with_mate(mate == 0):
                 done[mate] = True
                 continue
-            ret = self.extend_seeds_paired(mate, None, [])
+            ret = yield from self.extend_seeds_paired(mate, None, [])
             c.mm1 = []
             after(ret, mate)
             if not done[mate] and c.minsc == c.perfect:
@@ -986,7 +1005,7 @@ class PairedPolicyEngine(PolicyEngine):
                 offset = (interval[mate] * roundi) // nrounds[mate]
                 if offset > 0 and min(L, c.rdlen) + offset > c.rdlen:
                     continue
-                hits = self.b.seed_search(c.codes, c.quals, L, interval[mate], offset, nofw[mate], norc[mate])
+                hits = yield ("seed_search", (c.codes, c.quals, L, interval[mate], offset, nofw[mate], norc[mate],))
                 nfw = [max(0, int(h[1]) - int(h[0])) for h in hits[0]]
                 nrc = [max(0, int(h[1]) - int(h[0])) for h in hits[1]]
                 nonz = sum(x > 0 for x in nfw) + sum(x > 0 for x in nrc)
@@ -1008,7 +1027,7 @@ class PairedPolicyEngine(PolicyEngine):
                 if not c.sh:
                     continue
                 c.sh["ranks"] = policy.rank_seed_hits(c.sh["nfw"], c.sh["nrc"], rnd, False)
-                ret = self.extend_seeds_paired(mate, c.sh, [])
+                ret = yield from self.extend_seeds_paired(mate, c.sh, [])
                 after(ret, mate)
             for mate in (0, 1):
                 c = m[mate]
@@ -1067,7 +1086,7 @@ class PairedPolicyEngine(PolicyEngine):
                 if c.minsc == c.perfect:
                     return PERFECT
                 if first_extend:
-                    satpos, nelt = self._prioritize(sh, self.max_iters)
+                    satpos, nelt = yield from self._prioritize(sh, self.max_iters)
                     nelt_left = nelt
                     first_extend = False
                     mate_streaks = [0] * len(satpos)
@@ -1100,9 +1119,9 @@ class PairedPolicyEngine(PolicyEngine):
                     self.n_iters += 1
                     first = False
                     elt = rands.next(rnd)
-                    joined = self.b.resolve(sp.topf + elt)
+                    joined = yield ("resolve", (sp.topf + elt,))
                     nelt_left -= 1
-                    ok, tidx, toff, tlen, straddled = self.b.joined_to_text(sp.key_len, joined, ee_mode)
+                    ok, tidx, toff, tlen, straddled = yield ("joined_to_text", (sp.key_len, joined, ee_mode,))
                     if not ok:
                         continue
                     refoff = toff - rdoff
@@ -1124,7 +1143,7 @@ class PairedPolicyEngine(PolicyEngine):
                         c.seen.add(tidx, fw, refoff, 1)
                         n_ee_fail += 1
                     elif ungapped:
-                        rc, a = self.b.ungapped(c.codes, c.quals, fw, tidx, refoff, tlen, c.minsc)
+                        rc, a = yield ("ungapped", (c.codes, c.quals, fw, tidx, refoff, tlen, c.minsc,))
                         c.seen.add(tidx, fw, refoff, 1)
                         self.n_ugs += 1
                         n_ug_fail += 1
@@ -1140,7 +1159,7 @@ class PairedPolicyEngine(PolicyEngine):
                         if not found:
                             continue
                         c.seen.add(tidx, fw, rect.refl_pretrim + rect.corel, rect.corer - rect.corel + 1)
-                        dp = self.b.dp(c.codes, c.quals, fw, tidx, rect, c.minsc, sc.n_ceil_raw(rdlen))
+                        dp = yield ("dp", (c.codes, c.quals, fw, tidx, rect, c.minsc, sc.n_ceil_raw(rdlen),))
                         self.n_dps += 1
                         n_dp_fail += 1
                         if not dp["found"]:
@@ -1155,7 +1174,7 @@ class PairedPolicyEngine(PolicyEngine):
                                 break
                             a = fixed
                         else:
-                            a = self._next_alignment(dp, tidx, c.minsc, rdlen)
+                            a = yield from self._next_alignment(dp, tidx, c.minsc, rdlen)
                             if a is None:
                                 break
                         first_inner = False
@@ -1183,7 +1202,7 @@ class PairedPolicyEngine(PolicyEngine):
                                 found_mate, orect = policy.frame_find_mate_rect(not oleft, oll, olr, orl, orr, ordlen, tlen, ordgaps, orfgaps,
                                                                                 o.nceil, self.maxhalf)
                             if found_mate:
-                                odp = self.b.dp(o.codes, o.quals, ofw, tidx, orect, ominsc_cur, sc.n_ceil_raw(ordlen))
+                                odp = yield ("dp", (o.codes, o.quals, ofw, tidx, orect, ominsc_cur, sc.n_ceil_raw(ordlen),))
                                 self.n_mate_dps += 1
                                 found_mate = bool(odp["found"])
                                 if found_mate:
@@ -1194,7 +1213,7 @@ class PairedPolicyEngine(PolicyEngine):
                             while True:
                                 oa = None
                                 if found_mate:
-                                    oa = self._next_alignment(odp, tidx, ominsc_cur, ordlen)
+                                    oa = yield from self._next_alignment(odp, tidx, ominsc_cur, ordlen)
                                     found_mate = oa is not None
                                 if found_mate:
                                     if not self.red.overlap(oa):
