@@ -71,20 +71,22 @@ def interleave(b1: ReadBatch, b2: ReadBatch) -> ReadBatch:
 
 
 def _exact_batch(gpu, batch, names, paired, preset, local, seed):
-    """one batch through the sequential policy engine over the GPU primitives -> the pipeline's result arrays"""
+    """one batch through the sequential policy (policy_engine) in waves over the GPU primitives (policy_backend_gpu):
+    every read's state machine advances together, each primitive runs as one batched entry-point call per wave"""
     from .lib import PAIR_RESULT, READ_RESULT
-    from .policy_backend_gpu import GpuBackend
+    from .policy_backend_gpu import GpuBatchBackend
     from .policy_engine import PairedPolicyEngine, PolicyEngine, aln_to_ops
-    backend = GpuBackend(gpu, local)
+    from .policy_waves import WaveScheduler
     n = batch.n
     res = np.zeros(n, dtype=READ_RESULT)
     res["score2"] = -(1 << 31)
     ops = np.zeros((n, int(batch.lengths().max()) + 64), dtype=np.uint8)
-    rd = lambda i: (batch.seq[int(batch.off[i]):int(batch.off[i + 1])], batch.qual[int(batch.off[i]):int(batch.off[i + 1])])
+    reads = [batch.seq[int(batch.off[i]):int(batch.off[i + 1])] for i in range(n)]
+    quals = [batch.qual[int(batch.off[i]):int(batch.off[i + 1])] for i in range(n)]
 
-    def fill(j, r, codes):
+    def fill(j, r):
         a = r.aln
-        o = aln_to_ops(a, codes)
+        o = aln_to_ops(a, reads[j])
         res[j]["found"] = 2 if (not a.edits and a.ext == a.rdlen) else 1
         res[j]["score"] = a.score
         if r.xs is not None:
@@ -93,23 +95,20 @@ def _exact_batch(gpu, batch, names, paired, preset, local, seed):
         res[j]["trim_left"], res[j]["trim_right"] = a.trim_left, a.rdlen - a.ext - a.trim_left
         res[j]["mapq"], res[j]["pad"] = r.mapq, a.refns
         ops[j, :len(o)] = o
+    bb = GpuBatchBackend(gpu, local)
     if not paired:
-        eng = PolicyEngine(backend, preset, seed=seed, local=local)
-        for i in range(n):
-            c, q = rd(i)
-            r = eng.align_read(c, q, names[i])
+        ws = WaveScheduler(bb, lambda: PolicyEngine(None, preset, seed=seed, local=local))
+        for j, r in enumerate(ws.run_reads(reads, quals, names)):
             if r.aligned:
-                fill(i, r, c)
+                fill(j, r)
         return res, ops, None
-    eng = PairedPolicyEngine(backend, preset, seed=seed, local=local)
+    ws = WaveScheduler(bb, lambda: PairedPolicyEngine(None, preset, seed=seed, local=local))
     pairs = np.zeros(n // 2, dtype=PAIR_RESULT)
-    for i in range(n // 2):
-        (c1, q1), (c2, q2) = rd(2 * i), rd(2 * i + 1)
-        pr = eng.align_pair(c1, q1, names[2 * i], c2, q2, names[2 * i + 1])
+    for i, pr in enumerate(ws.run_pairs(reads, quals, names)):
         pairs[i]["pair_type"] = pr.pair_type
-        for k, c in enumerate((c1, c2)):
+        for k in range(2):
             if pr.mates[k].aligned:
-                fill(2 * i + k, pr.mates[k], c)
+                fill(2 * i + k, pr.mates[k])
     return res, ops, pairs
 
 

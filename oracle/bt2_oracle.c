@@ -797,7 +797,8 @@ typedef struct { int nedsz, celsz, row, col, gaps, score, ns, ct; } bt_frame;
 
 /* Optional log of the backtrace attempts of the next bt2o_dp call, in the order SwAligner::nextAlignment makes them
  * (aligner_sw.cpp:757-1120): one pair per candidate that passed the start filter (and, local mode, the domination
- * filter) = per RNG reseed of the reference: [candidate score, index of the alignment it produced or -1].  Used by the
+ * filter) = per RNG reseed of the reference: [candidate score, index of the alignment it produced or -1, index of
+ * the candidate in the sorted list].  Used by the
  * tests that replay the reference's sequential policy, where the per-read RNG state depends on the attempt count. */
 static int64_t *g_attempt_log = NULL;
 static int g_attempt_cap = 0, g_attempt_n = 0;
@@ -911,7 +912,7 @@ int bt2o_dp(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, 
 		}
 		const int start_row = row;
 		const int attempt = g_attempt_n;
-		if(g_attempt_log && g_attempt_n < g_attempt_cap) { g_attempt_log[2 * g_attempt_n] = AT(H, row, col); g_attempt_log[2 * g_attempt_n + 1] = -1; }
+		if(g_attempt_log && g_attempt_n < g_attempt_cap) { g_attempt_log[3 * g_attempt_n] = AT(H, row, col); g_attempt_log[3 * g_attempt_n + 1] = -1; g_attempt_log[3 * g_attempt_n + 2] = ci; }
 		g_attempt_n++;
 		int nned = 0, ncells = 0, nstack = 0, gaps = 0, score = 0, ns = 0, ct = 0 /*0 H,1 E,2 F*/;
 		int ok = 1, trim_beg = 0;
@@ -1014,7 +1015,7 @@ int bt2o_dp(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, 
 			if(rdc > 3 || rfc > 3) ns++;
 		}
 		if(ns > nceil) continue;
-		if(g_attempt_log && attempt < g_attempt_cap) g_attempt_log[2 * attempt + 1] = naln;
+		if(g_attempt_log && attempt < g_attempt_cap) g_attempt_log[3 * attempt + 1] = naln;
 		if(naln < max_alns) {
 			const int trim_end = nrow - 1 - start_row;
 			const int ext = nrow - trim_beg - trim_end;

@@ -79,7 +79,7 @@ int  bt2o_one_mm(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *co
                  int64_t minsc, int nofw, int norc, int max_hits, int64_t *out, int *out_fw);
 int  bt2o_ungapped(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, const uint8_t *quals, int len, int fw,
                    uint64_t tidx, int64_t off, int64_t tlen, int ohang, int64_t minsc, int64_t *out6, uint8_t *editmask);
-/* log of backtrace attempts of the following bt2o_dp calls: pairs [candidate score, alignment index or -1] */
+/* log of backtrace attempts of the following bt2o_dp calls: triples [candidate score, alignment index or -1, candidate index] */
 void bt2o_dp_attempt_log(int64_t *buf, int cap);
 int  bt2o_dp_attempt_count(void);
 int  bt2o_dp(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, const uint8_t *quals, int len, int fw,

@@ -191,7 +191,7 @@ def oracle_dp(O, local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=10
     L = O.lib
     att = None
     if attempts:
-        att = np.full(2 * 4096, -1, np.int64)
+        att = np.full(3 * 4096, -1, np.int64)
         L.bt2o_dp_attempt_log.argtypes = [vp, ci]
         L.bt2o_dp_attempt_log.restype = None
         L.bt2o_dp_attempt_count.restype = ci
@@ -224,7 +224,8 @@ def oracle_dp(O, local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=10
     if attempts:
         n = int(L.bt2o_dp_attempt_count())
         assert n <= 4096
-        out["attempts"] = [(int(att[2 * k]), int(att[2 * k + 1])) for k in range(n)]
+        out["attempts"] = [(int(att[3 * k]), int(att[3 * k + 1])) for k in range(n)]
+        out["attempt_cands"] = [int(att[3 * k + 2]) for k in range(n)]
         L.bt2o_dp_attempt_log(None, 0)
     return out
 

@@ -383,3 +383,37 @@ def test_wave_scheduler_gives_the_sequential_answers(lambda_index, rep_index):
     gotp = ws2.run_pairs(R, Q, N)
     pkey = lambda p: (p.pair_type, [key(m) for m in p.mates])
     assert [pkey(p) for p in gotp] == [pkey(p) for p in seqp]
+
+
+@pytest.mark.parametrize("local", [False, True])
+def test_gpu_batch_backend_logic_over_a_fake_device(rep_index, local):
+    """policy_backend_gpu.GpuBatchBackend (grouping, DP chunking, array conversions) with the oracle answering behind the
+    entry-point conventions: waves over it == the engine over the plain oracle backend, for reads and pairs."""
+    from bowtie2_b200.policy_backend_gpu import GpuBackend, GpuBatchBackend
+    from bowtie2_b200.policy_engine import PairedPolicyEngine
+    from bowtie2_b200.policy_waves import WaveScheduler
+    from fake_gpu import FakeGpu
+    O = Oracle(rep_index)
+    n1, r1, q1 = read_fastq_codes(os.path.join(GOLDEN, "rep_reads_1.fq"), 120)
+    n2, r2, q2 = read_fastq_codes(os.path.join(GOLDEN, "rep_reads_2.fq"), 120)
+    key = lambda r: (r.aligned, r.filtered, r.xs, r.mapq, None if r.aln is None else (r.aln.tidx, r.aln.refoff, r.aln.fw, r.aln.score,
+                                                                                   r.aln.trim5, r.aln.trim3, r.aln.refns, tuple(r.aln.edits)))
+    ref_eng = PolicyEngine(OracleBackend(O, local=local), "sensitive", local=local)
+    want = [key(ref_eng.align_read(r1[i], q1[i], n1[i])) for i in range(len(r1))]
+    fake = FakeGpu(O)
+    bb = GpuBatchBackend(fake, local)
+    bb.DP_CHUNK = 16                                              # several chunks per wave
+    ws = WaveScheduler(bb, lambda: PolicyEngine(None, "sensitive", local=local), max_inflight=64)
+    assert [key(r) for r in ws.run_reads(r1, q1, n1)] == want
+    assert fake.calls < 400                                        # batched: far fewer entry-point calls than the ~2000 requests
+    # per-item view
+    eng1 = PolicyEngine(GpuBackend(FakeGpu(O), local), "sensitive", local=local)
+    assert [key(eng1.align_read(r1[i], q1[i], n1[i])) for i in range(30)] == want[:30]
+    # pairs
+    il = lambda a, b: [x for p in zip(a, b) for x in p]
+    R, Q, N = il(r1, r2), il(q1, q2), il(n1, n2)
+    pe = PairedPolicyEngine(OracleBackend(O, local=local), "sensitive", local=local)
+    wantp = [(p.pair_type, [key(m) for m in p.mates]) for p in
+             (pe.align_pair(R[2 * i], Q[2 * i], N[2 * i], R[2 * i + 1], Q[2 * i + 1], N[2 * i + 1]) for i in range(len(r1)))]
+    ws2 = WaveScheduler(GpuBatchBackend(FakeGpu(O), local), lambda: PairedPolicyEngine(None, "sensitive", local=local))
+    assert [(p.pair_type, [key(m) for m in p.mates]) for p in ws2.run_pairs(R, Q, N)] == wantp

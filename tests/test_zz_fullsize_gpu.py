@@ -240,6 +240,13 @@ def test_exact_policy_over_gpu_primitives(paired, lambda_index):
                 _fill(res, ops, i, r, r1[i])
         lines = sam_format(load_library(), ReadBatch.from_list(r1, q1), res, ops, ref, read_names=n1).rstrip("\n").split("\n")
         assert lines == golden[:n]
+        # and in waves (one batched entry-point call per primitive and wave), through the whole-file driver
+        import tempfile
+        from bowtie2_b200.align import align_files
+        out = os.path.join(tempfile.mkdtemp(), "exact.sam")
+        align_files(lambda_index, out, os.path.join(GOLDEN, "lambda_reads_1.fq"), exact=True, batch_reads=1024, summary=None, gpu=g)
+        got = [l.rstrip("\n") for l in open(out) if not l.startswith("@")]
+        assert got == golden
     else:
         n2, r2, q2 = read_fastq_codes(os.path.join(GOLDEN, "lambda_reads_2.fq"), n)
         il = lambda a, b: [x for p in zip(a, b) for x in p]
