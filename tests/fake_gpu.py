@@ -15,6 +15,14 @@ class FakeGpu:
         self.local = False
         self._off_size = off_size
         self.calls = 0
+        from bowtie2_b200.lib import load_library
+        self._lib = load_library()               # host-side formatting / parsing entry points are real
+
+    def load_index_host(self, image):
+        pass
+
+    def close(self):
+        pass
 
     def set_scoring(self, local=False):
         self.local = local

@@ -74,3 +74,33 @@ def test_align_files_fails_loudly_without_gpu(tmp_path, lambda_index):
     with pytest.raises(Bt2GpuError):
         align_files(lambda_index, str(out), os.path.join(GOLDEN, "lambda_reads_1.fq"))
     assert not out.exists()
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_exact_mode_whole_files_over_a_fake_device(tmp_path, lambda_index, paired):
+    """align_files(exact=True): FASTQ in -> policy engine in waves -> SAM out, with the CPU oracle answering behind the GPU
+    entry-point conventions (tests/fake_gpu.py): header, records and order identical to the reference program's file."""
+    from fake_gpu import FakeGpu
+    from oracle_lib import Oracle
+    golden_path = os.path.join(GOLDEN, "lambda_P_sensitive.sam" if paired else "lambda_U_sensitive.sam")
+    r1, r2 = os.path.join(GOLDEN, "lambda_reads_1.fq"), os.path.join(GOLDEN, "lambda_reads_2.fq")
+    out = str(tmp_path / "o.sam")
+    import io
+    summ = io.StringIO()
+    if paired:
+        for src, dst in ((r1, "a.fq"), (r2, "b.fq")):
+            with open(src) as f, open(tmp_path / dst, "w") as g:
+                g.writelines(f.readlines()[:800])                 # the golden holds the first 200 pairs
+        align_files(lambda_index, out, str(tmp_path / "a.fq"), str(tmp_path / "b.fq"), exact=True, batch_reads=150, summary=summ,
+                    gpu=FakeGpu(Oracle(lambda_index)))
+    else:
+        with open(r1) as f, open(tmp_path / "a.fq", "w") as g:
+            g.writelines(f.readlines()[:4 * 500])
+        align_files(lambda_index, out, str(tmp_path / "a.fq"), exact=True, batch_reads=128, summary=summ, gpu=FakeGpu(Oracle(lambda_index)))
+    want = [l for l in open(golden_path)]
+    got = [l for l in open(out)]
+    n = len(got)
+    assert got == want[:n] and n == (402 if paired else 502)        # 2 header lines + the records
+    if paired:
+        # the summary text equals the reference's except for the documented concordant ">1" split (0 here either way)
+        assert summ.getvalue() == open(os.path.join(GOLDEN, "lambda_P_sensitive.summary.txt")).read()
