@@ -55,6 +55,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 	static const char dna[] = "ACGTN";
 	static const char comp[] = "TGCAN";
 	const bool paired = pairs != nullptr;
+	const bool xeq = (opt->flags & BT2G_SAM_XEQ) != 0, noUnal = (opt->flags & BT2G_SAM_NO_UNAL) != 0;
 	o.reserve((size_t)(i1 - i0) * 400);
 	std::string cigar, mdz, line, held;
 	Stacked st;                                                        // buffers reused from record to record
@@ -102,7 +103,17 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 				// no gaps: nothing to left-align; CIGAR is one M run and MD:Z a scan of the mismatches
 				const int nrow = (r.found & 0xff) == 2 ? len : nops;
 				if(r.trim_left > 0) { appendInt(cigar, r.trim_left); cigar += 'S'; }
-				appendInt(cigar, nrow); cigar += 'M';
+				if(!xeq || nops == 0) { appendInt(cigar, nrow); cigar += xeq ? '=' : 'M'; }
+				else {
+					// --xeq: runs of = / X (StackedAln::buildCigar(true))
+					for(int k = nops - 1; k >= 0;) {
+						const bool mm = (op[k] & 3) == BT2G_OP_MM;
+						int run = 1;
+						while(k - run >= 0 && (((op[k - run] & 3) == BT2G_OP_MM) == mm)) run++;
+						appendInt(cigar, run); cigar += mm ? 'X' : '=';
+						k -= run;
+					}
+				}
 				if(r.trim_right > 0) { appendInt(cigar, r.trim_right); cigar += 'S'; }
 				int run = 0; bool mmLast = false, first = true;
 				for(int k = nops - 1; k >= 0; k--) {
@@ -141,9 +152,9 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 			if(r.trim_left > 0) { appendInt(cigar, r.trim_left); cigar += 'S'; }
 			const size_t ln = st.rel.size();
 			for(size_t k = 0; k < ln;) {
-				char c = st.rel[k]; if(c == 'X' || c == '=') c = 'M';
+				char c = st.rel[k]; if(!xeq && (c == 'X' || c == '=')) c = 'M';
 				size_t run = 1;
-				while(k + run < ln) { char c2 = st.rel[k + run]; if(c2 == 'X' || c2 == '=') c2 = 'M'; if(c2 != c) break; run++; }
+				while(k + run < ln) { char c2 = st.rel[k + run]; if(!xeq && (c2 == 'X' || c2 == '=')) c2 = 'M'; if(c2 != c) break; run++; }
 				appendInt(cigar, (long long)run); cigar += c;
 				k += run;
 			}
@@ -254,7 +265,9 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 			else if(ns > nceil) line += "\tYF:Z:NS";
 			else if(len <= opt->sc_filter_maxlen) line += "\tYF:Z:SC";      // perfect score below the minimum (scoreFilter)
 		}
+		if(opt->rg_optflag && opt->rg_optflag[0]) { line += '\t'; line += opt->rg_optflag; }     // RG:Z:<id> (sam.cpp:384-387)
 		line += '\n';
+		if(noUnal && !aligned) continue;                              // --no-unal (AlnSinkSam::appendMate, aln_sink.cpp:1905)
 		// a pair with only mate 2 aligned is printed aligned mate first (AlnSinkWrap::finishRead reports the
 		// unpaired alignment of mate 2, then the unaligned mate 1, aln_sink.cpp:930-1010)
 		if(paired && (i & 1) == 0 && !aligned && mateAligned) { held = line; continue; }
@@ -388,8 +401,15 @@ extern "C" int bt2g_pe_classify_host(const bt2g_pe_policy *pol, const int64_t *p
 }
 
 // ---- SAM header (SamConfig::printHeader, sam.cpp:54-111) -----------------------------------------
+extern "C" int bt2g_sam_header_rg(const char *const *names, const uint64_t *lens, uint64_t n, const char *rgLine, const char *pgCl,
+                                  char *out, uint64_t cap, uint64_t *written);
 extern "C" int bt2g_sam_header(const char *const *names, const uint64_t *lens, uint64_t n, const char *pgCl,
                                char *out, uint64_t cap, uint64_t *written) {
+	return bt2g_sam_header_rg(names, lens, n, nullptr, pgCl, out, cap, written);
+}
+
+extern "C" int bt2g_sam_header_rg(const char *const *names, const uint64_t *lens, uint64_t n, const char *rgLine, const char *pgCl,
+                                  char *out, uint64_t cap, uint64_t *written) {
 	if(!written || (n && (!names || !lens))) return -1;
 	std::string o = "@HD\tVN:1.5\tSO:unsorted\tGO:query\n";
 	for(uint64_t i = 0; i < n; i++) {
@@ -397,6 +417,7 @@ extern "C" int bt2g_sam_header(const char *const *names, const uint64_t *lens, u
 		for(const char *c = names[i]; c && *c && !isspace((unsigned char)*c); c++) o += *c;     // printRefName: up to the first whitespace
 		o += "\tLN:"; appendInt(o, (long long)lens[i]); o += '\n';
 	}
+	if(rgLine && rgLine[0]) { o += "@RG\t"; o += rgLine; o += '\n'; }
 	if(pgCl) { o += "@PG\tID:bowtie2\tPN:bowtie2\tVN:2.5.5\tCL:\""; o += pgCl; o += "\"\n"; }
 	*written = o.size();
 	if(!out || cap < o.size()) return -3;

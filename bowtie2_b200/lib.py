@@ -670,7 +670,8 @@ EXPORTS += ["bt2g_sam_format"]
 
 class _SamOpts(C.Structure):
     _fields_ = [("ref_names", C.POINTER(C.c_char_p)), ("n_refs", C.c_uint64), ("read_names", C.POINTER(C.c_char_p)),
-                ("threads", C.c_int32), ("sc_filter_maxlen", C.c_int32), ("nceil_const", C.c_double), ("nceil_linear", C.c_double)]
+                ("threads", C.c_int32), ("sc_filter_maxlen", C.c_int32), ("nceil_const", C.c_double), ("nceil_linear", C.c_double),
+                ("flags", C.c_uint32), ("reserved2", C.c_uint32), ("rg_optflag", C.c_char_p)]
 
 
 def sc_filter_maxlen(local: bool) -> int:
@@ -685,13 +686,14 @@ def sc_filter_maxlen(local: bool) -> int:
 
 
 def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_names=None, pairs=None, threads: int = 1,
-               local: bool = False) -> str:
+               local: bool = False, xeq: bool = False, no_unal: bool = False, rg_id: str = None) -> str:
     """SAM text for pipeline results (one record per read).  `lib` is the loaded libbt2g (load_library())."""
     lib.bt2g_sam_format.argtypes = [C.POINTER(_SamOpts), C.POINTER(_Reads), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     rn = (C.c_char_p * len(ref_names))(*[x.encode() for x in ref_names])
     qn = (C.c_char_p * reads.n)(*[x.encode() for x in read_names]) if read_names is not None else None
-    opt = _SamOpts(rn, len(ref_names), qn, int(threads), sc_filter_maxlen(True) if local else 0, 0.0, 0.0)
+    opt = _SamOpts(rn, len(ref_names), qn, int(threads), sc_filter_maxlen(True) if local else 0, 0.0, 0.0,
+                   (1 if xeq else 0) | (2 if no_unal else 0), 0, ("RG:Z:" + rg_id).encode() if rg_id else None)
     res = np.ascontiguousarray(res, dtype=READ_RESULT)
     max_ops = 0 if ops is None else ops.shape[1]
     if ops is not None:
@@ -733,13 +735,26 @@ def fastq_parse(lib, text: bytes, max_reads: int = 1 << 30, name_stride: int = 6
 EXPORTS += ["bt2g_mapq", "bt2g_frame_mate_host", "bt2g_pe_classify_host"]
 
 
-EXPORTS += ["bt2g_sam_header", "bt2g_align_counts_add", "bt2g_align_summary", "bt2g_index_file_open", "bt2g_index_file_desc",
+EXPORTS += ["bt2g_sam_header", "bt2g_sam_header_rg", "bt2g_align_counts_add", "bt2g_align_summary", "bt2g_index_file_open", "bt2g_index_file_desc",
             "bt2g_index_file_n_refs", "bt2g_index_file_ref_names", "bt2g_index_file_ref_lens", "bt2g_index_file_close",
             "bt2g_load_index_files_ex"]
 
 
-def sam_header(lib, names, lens, pg_cl=None) -> str:
-    """include/bt2g.h: bt2g_sam_header."""
+def sam_header(lib, names, lens, pg_cl=None, rg_id=None, rg_fields=()) -> str:
+    """include/bt2g.h: bt2g_sam_header / bt2g_sam_header_rg (--rg-id <id>, --rg <field> ...)."""
+    if rg_id:
+        lib.bt2g_sam_header_rg.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint64,
+                                           C.POINTER(C.c_uint64)]
+        rn = (C.c_char_p * len(names))(*[x.encode() for x in names])
+        ln = np.ascontiguousarray(lens, dtype=np.uint64)
+        rg = "\t".join(["ID:" + rg_id] + list(rg_fields)).encode()
+        cl = pg_cl.encode() if pg_cl is not None else None
+        need = C.c_uint64(0)
+        lib.bt2g_sam_header_rg(rn, _ptr(ln), len(names), rg, cl, None, 0, C.byref(need))
+        buf = C.create_string_buffer(int(need.value) + 1)
+        if lib.bt2g_sam_header_rg(rn, _ptr(ln), len(names), rg, cl, buf, need.value, C.byref(need)):
+            raise RuntimeError("bt2g_sam_header_rg failed")
+        return buf.raw[:need.value].decode()
     lib.bt2g_sam_header.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     rn = (C.c_char_p * len(names))(*[x.encode() for x in names])
     ln = np.ascontiguousarray(lens, dtype=np.uint64)

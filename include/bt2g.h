@@ -435,7 +435,12 @@ typedef struct {
 	                                     * bt2_search.cpp:3385: --local with very short reads): unaligned ones carry YF:Z:SC; 0 = none */
 	double             nceil_const, nceil_linear;   /* --n-ceil (0, 0.15): unaligned reads with more Ns carry YF:Z:NS
 	                                                * (bt2_search.cpp:3427-3431, sam.cpp:331-345); both 0 = defaults */
+	uint32_t           flags;       /* BT2G_SAM_XEQ: --xeq (=/X instead of M); BT2G_SAM_NO_UNAL: --no-unal */
+	uint32_t           reserved2;
+	const char        *rg_optflag;  /* "RG:Z:<id>" of --rg-id, appended to every record (sam.cpp:384-387), or NULL */
 } bt2g_sam_opts;
+#define BT2G_SAM_XEQ     1u
+#define BT2G_SAM_NO_UNAL 2u
 int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads, const bt2g_read_result *res, const uint8_t *ops,
                     uint32_t max_ops, const bt2g_pair_result *pairs, char *out, uint64_t cap, uint64_t *written);
 
@@ -459,6 +464,9 @@ int bt2g_fastq_parse(const char *text, uint64_t len, uint64_t max_reads, uint64_
  * when pg_cl != NULL (SamConfig::printHeader, sam.cpp:54-111).  -3 with *written = bytes needed when cap is short. */
 int bt2g_sam_header(const char *const *names, const uint64_t *lens, uint64_t n, const char *pg_cl,
                     char *out, uint64_t cap, uint64_t *written);
+/* the same with the @RG line of --rg-id / --rg between @SQ and @PG: rg_line = "ID:<id>\t<field>..." or NULL */
+int bt2g_sam_header_rg(const char *const *names, const uint64_t *lens, uint64_t n, const char *rg_line, const char *pg_cl,
+                       char *out, uint64_t cap, uint64_t *written);
 
 /* Alignment summary = what the reference prints on stderr at the end of a run (AlnSink::printAlSumm,
  * aln_sink.cpp:349-528), from the counters AlnSinkWrap::finishRead keeps (aln_sink.cpp:708-1046).  The ">1 times"

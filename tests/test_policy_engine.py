@@ -417,3 +417,36 @@ def test_gpu_batch_backend_logic_over_a_fake_device(rep_index, local):
              (pe.align_pair(R[2 * i], Q[2 * i], N[2 * i], R[2 * i + 1], Q[2 * i + 1], N[2 * i + 1]) for i in range(len(r1)))]
     ws2 = WaveScheduler(GpuBatchBackend(FakeGpu(O), local), lambda: PairedPolicyEngine(None, "sensitive", local=local))
     assert [(p.pair_type, [key(m) for m in p.mates]) for p in ws2.run_pairs(R, Q, N)] == wantp
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_sam_output_options(tmp_path):
+    """--xeq, --no-unal, --rg-id / --rg: records and header against the reference program"""
+    from bowtie2_b200.lib import IndexFile, sam_header
+    genome, base = _synth_index(tmp_path)
+    reads, quals, _ = synth.make_reads(genome, 300, 100, seed=78, sub_rate=0.02, indel_rate=0.004)
+    rng = np.random.default_rng(3)
+    for i in range(0, 300, 9):
+        reads[i] = rng.integers(0, 4, 100).astype(np.uint8)          # unalignable
+    fq = str(tmp_path / "r.fq")
+    synth.write_fastq(fq, reads, quals)
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), "--sensitive", "--seed", "0", "-p", "1", "-x", base, "-U", fq, "--xeq",
+                                   "--no-unal", "--rg-id", "grp1", "--rg", "SM:sample7", "--rg", "PL:synthetic"],
+                                  stderr=subprocess.DEVNULL).decode()
+    want_hdr = [l for l in out.split("\n") if l.startswith("@") and not l.startswith("@PG")]
+    want = [l for l in out.split("\n") if l and not l.startswith("@")]
+    eng = PolicyEngine(OracleBackend(Oracle(base)), "sensitive")
+    n = len(reads)
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    ops = np.zeros((n, 164), dtype=np.uint8)
+    for i in range(n):
+        r = eng.align_read(reads[i], quals[i], f"r{i}")
+        if r.aligned:
+            _fill(res, ops, i, r, reads[i])
+    lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ["chr1", "chr2", "chr3"],
+                       read_names=[f"r{i}" for i in range(n)], xeq=True, no_unal=True, rg_id="grp1", threads=3).rstrip("\n").split("\n")
+    assert lines == want and len(want) < n and any("X" in l.split("\t")[5] for l in want) and any("D" in l.split("\t")[5] or "I" in l.split("\t")[5] for l in want)
+    f = IndexFile(base)
+    hdr = sam_header(load_library(), f.ref_names, f.ref_lens, rg_id="grp1", rg_fields=["SM:sample7", "PL:synthetic"])
+    assert hdr.rstrip("\n").split("\n") == want_hdr
