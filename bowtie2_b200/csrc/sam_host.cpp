@@ -75,7 +75,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		// aln_sink.cpp:240-256); with more, the mates are reported as unpaired alignments of a paired read
 		const bool discordant = pr && pr->pair_type == 2 && r.score2 == INT32_MIN && m->score2 == INT32_MIN;
 		const bool asPair = concordant || discordant;
-		int flag = 0;
+		int flag = (r.found & 0x100) ? 256 : 0;                   // caller-marked secondary alignment (-k / -a records)
 		if(paired) {
 			flag |= 1;
 			if(concordant) flag |= 2;

@@ -245,18 +245,21 @@ class RedundantAlns:
 class UnpairedSink:
     """AlnSinkWrap + ReportingState for an unpaired read in -M mode (aln_sink.cpp:60-330, 1395-1452)"""
 
-    def __init__(self, khits=1, mhits=50):
-        self.khits, self.mhits = khits, mhits
+    def __init__(self, khits=1, mhits=50, mmode=True):
+        self.khits, self.mhits, self.mmode = khits, mhits, mmode
         self.alns = []
         self.done = False
         self.exit_m = False
+        self.exit_k = False
         self.best = self.best2 = MIN_I64
 
     def report(self, a: Aln):
         self.alns.append(a)
-        if not self.done and len(self.alns) > self.mhits:
-            self.done = True
-            self.exit_m = True
+        if not self.done:                                  # ReportingState::areDone (aln_sink.cpp:305-318)
+            if not self.mmode and len(self.alns) >= self.khits:
+                self.done = self.exit_k = True
+            elif self.mmode and len(self.alns) > self.mhits:
+                self.done = self.exit_m = True
         if a.score > self.best:
             self.best2, self.best = self.best, a.score
         elif a.score > self.best2:
@@ -313,6 +316,7 @@ class ReadResult:
     filtered: str = None         # "NS" / "LN" when the read never entered the search
     n_alns: int = 0
     maxed: bool = False
+    secondary: list = None       # -k / -a: the further selected alignments, in report order (FLAG 256, MAPQ 255)
     counters: dict = None        # nExIters / nExDps / nExUgs / nRedundants of the reference's per-read metrics (ZI XD XU YR)
 
 
@@ -337,8 +341,9 @@ class MateCtx:
 
 class PolicyEngine:
     def __init__(self, backend, preset="sensitive", seed=0, sc=None, local=False, nofw=False, norc=False,
-                 dp_fail_streak=None, seed_rounds=None, seed_len=None):
-        """seed = --seed; nofw / norc = --nofw / --norc; dp_fail_streak / seed_rounds / seed_len = -D / -R / -L on top of the preset"""
+                 dp_fail_streak=None, seed_rounds=None, seed_len=None, k=None, all_hits=False):
+        """seed = --seed; nofw / norc = --nofw / --norc; dp_fail_streak / seed_rounds / seed_len = -D / -R / -L on top of the
+        preset; k = -k <int> (up to k alignments per read, no -M sampling); all_hits = -a"""
         self.b = backend
         self.off_size = backend.off_size if backend is not None else 4
         self.local = local
@@ -353,10 +358,23 @@ class PolicyEngine:
         self.seed = seed
         self.gnofw, self.gnorc = nofw, norc
         # bt2_search.cpp:342-343, 459-492 and the preset's -D / -R
-        self.khits, self.mhits = 1, 50
+        # default: -M mode (khits 1, mhits 50, bt2_search.cpp:342-343); -k / -a switch -M off (:1772-1774)
+        self.all = all_hits
+        self.mmode = not (all_hits or k is not None)
+        self.khits = (1 << 62) if all_hits else (k if k is not None else 1)
+        self.mhits = 50 if self.mmode else (1 << 62)
         self.maxhalf = 15
         self.max_iters, self.max_ug, self.max_dp = 400, 300, 300
         self.streak = self.pre.dp_fail_streak
+        self.max_mate_streak = 10
+        if all_hits:                                   # bt2_search.cpp:3459-3473
+            self.max_iters = self.max_ug = self.max_dp = self.streak = self.max_mate_streak = 1 << 62
+        elif self.khits > 1:
+            self.streak += (self.khits - 1) * 10
+            self.max_mate_streak += (self.khits - 1) * 10
+            self.max_iters += (self.khits - 1) * 20
+            self.max_ug += (self.khits - 1) * 20
+            self.max_dp += (self.khits - 1) * 20
         self.n_seed_rounds = self.pre.seed_rounds
         self.tighten = 3
         self.seed_boost_thresh = 300
@@ -399,7 +417,7 @@ class PolicyEngine:
         interval = policy.seed_interval(self.pre.ival, rdlen, False)
         # per-read state of SwDriver (nextRead) and of the sink
         self.red = RedundantAlns()
-        self.sink = UnpairedSink(self.khits, self.mhits)
+        self.sink = UnpairedSink(self.khits, self.mhits, self.mmode)
         self.n_iters = self.n_dps = self.n_ugs = self.n_red = 0
         done = False
         # ---- exact end-to-end (bt2_search.cpp:3493-3690)
@@ -448,7 +466,7 @@ class PolicyEngine:
             if nonz == 0:
                 done = True
                 break
-            ranks = policy.rank_seed_hits(nelt_fw, nelt_rc, rnd, False)
+            ranks = policy.rank_seed_hits(nelt_fw, nelt_rc, rnd, self.all)
             sh = dict(hits=hits, ranks=ranks, interval=interval, offset=offset, seedlen=min(L, rdlen), nonz=nonz,
                       nelt=sum(nelt_fw) + sum(nelt_rc))
             ret = yield from self.extend_seeds(sh, [])
@@ -521,7 +539,7 @@ class PolicyEngine:
             w = bots[i] - tops[i]
             sp = SatPos(tops[i], 0, w, self.cur.rdlen, hit.fw, 0, 0, self.cur.rdlen, orig_size=w)
             r = Random1toN()
-            r.init(w, False)
+            r.init(w, self.all)
             out.append((sp, hit, r))
             nelt += w
             if nelt >= maxelt:
@@ -558,7 +576,7 @@ class PolicyEngine:
         while j < nsmall and added < maxelt:
             s = sats[j]
             r = Random1toN()
-            r.init(s.size, False)
+            r.init(s.size, self.all)
             out.append((s, None, r))
             added += s.size
             j += 1
@@ -569,14 +587,14 @@ class PolicyEngine:
         while added < maxelt and added < nelt:
             ri = sampler.next(rnd) + nsmall
             if not rands2[ri].inited():
-                rands2[ri].init(sats[ri].size, False)
+                rands2[ri].init(sats[ri].size, self.all)
             r = rands2[ri].next(rnd)
             if rands2[ri].done():
                 sampler.finished(ri - nsmall)
             src = sats[ri]
             s = SatPos(src.topf + r, 0, 1, src.key_len, src.fw, src.offidx, src.rdoff, src.seedlen, src.nlex, src.nrex, src.orig_size)
             one = Random1toN()
-            one.init(1, False)
+            one.init(1, self.all)
             out.append((s, None, one))
             added += 1
         return out, added
@@ -703,7 +721,7 @@ class PolicyEngine:
                         self.red.add(a)
                         if self.sink.report(a):
                             return FULFILLED
-                        if self.tighten > 0 and self.sink.best2 != MIN_I64:
+                        if self.tighten > 0 and self.mmode and self.sink.best2 != MIN_I64:
                             best, best2 = self.sink.best, self.sink.best2
                             if self.tighten == 1:
                                 if best >= self.cur.minsc:
@@ -768,8 +786,18 @@ class PolicyEngine:
         best = alns[buf[0][1]]
         res.aligned, res.aln = True, best
         res.xs = buf[1][0] if len(buf) > 1 else None
-        res.mapq = policy.mapq_v2(best.score, res.xs, self.sc.min_score(self.cur.rdlen), self.cur.perfect, not self.local)
+        res.mapq = self._mapq(best.score, res.xs, self.sc.min_score(self.cur.rdlen), self.cur.perfect)
+        # ReportingState::getReport: -k short circuit -> khits alignments, else min(found, khits)
+        num = self.khits if self.sink.exit_k else min(len(alns), self.khits)
+        res.secondary = [alns[buf[i][1]] for i in range(1, min(num, len(buf)))]
         return res
+
+    def _mapq(self, best, secbest, sc_min, perfect):
+        """BowtieMapq2::mapq incl. its 255 case: without -M (no "canMax") and no second-best score the search says nothing
+        about uniqueness (unique.h:201-205; the search is never flagged exhaustive)"""
+        if not self.mmode and secbest is None:
+            return 255
+        return policy.mapq_v2(best, secbest, sc_min, perfect, not self.local)
 
 
 def aln_to_ops(a: Aln, codes):
@@ -800,8 +828,10 @@ def aln_to_ops(a: Aln, codes):
 # Program defaults: --fr, -I 0 -X 500, discordant and mixed (unpaired) alignments reported.
 
 class PairedSink:
-    def __init__(self, khits=1, mhits=50, discord=True, mixed=True):
-        self.khits, self.mhits = khits, mhits
+    def __init__(self, khits=1, mhits=50, discord=True, mixed=True, mmode=True):
+        self.khits, self.mhits, self.mmode = khits, mhits, mmode
+        self.exit_concord_k = False
+        self.exit_unp_k = [False, False]
         self.rs1, self.rs2, self.rs1u, self.rs2u = [], [], [], []
         self.done_concord = False
         self.done_discord = not discord
@@ -823,10 +853,14 @@ class PairedSink:
         """AlnSinkWrap::report: a pair when both are given, else an unpaired alignment of the given mate"""
         if a1 is not None and a2 is not None:
             self.nconcord += 1
-            if self.nconcord > self.mhits:
+            if not self.mmode and self.nconcord >= self.khits:
+                self.done_concord, self.exit_concord_k = True, True
+            elif self.mmode and self.nconcord > self.mhits:
                 self.done_concord, self.exit_concord_m = True, True
             self.done_discord = True
-            # (a concordant category closed by -M does not trump the unpaired ones)
+            if self.done_concord and not self.exit_concord_m:
+                # closed by -k: the unpaired categories are trumped (a category closed by -M does not trump them)
+                self.done_unp = [True, True]
             self._update_done()
             self.rs1.append(a1)
             self.rs2.append(a2)
@@ -840,7 +874,10 @@ class PairedSink:
             a = a1 if a1 is not None else a2
             self.nunp[m] += 1
             if not self.done_unp[m]:
-                if self.nunp[m] > self.mhits:
+                if not self.mmode and self.nunp[m] >= self.khits:
+                    self.done_unp[m], self.exit_unp_k[m] = True, True
+                    self._update_done()
+                elif self.mmode and self.nunp[m] > self.mhits:
                     self.done_unp[m], self.exit_unp_m[m] = True, True
                     self._update_done()
             if self.nunp[m] > 1:
@@ -870,6 +907,7 @@ class PairResult:
     mates: list = None             # two ReadResult
     counters: dict = None
     n_concord: int = 0
+    secondary_pairs: list = None   # -k / -a: the further selected concordant pairs, in report order
 
 
 class PairedPolicyEngine(PolicyEngine):
@@ -879,7 +917,6 @@ class PairedPolicyEngine(PolicyEngine):
         super().__init__(backend, preset, seed, sc, local, **kw)
         self.pe = pe or policy.PairedEndPolicy(local=local)
         self.discord, self.mixed = discord, mixed
-        self.max_mate_streak = 10
 
     def align_pair(self, codes1, quals1, name1, codes2, quals2, name2) -> PairResult:
         return self._drive(self.pair_steps(codes1, quals1, name1, codes2, quals2, name2))
@@ -905,7 +942,7 @@ class PairedPolicyEngine(PolicyEngine):
         s2 = policy.gen_rand_seed(m[1].codes, m[1].quals, name2, self.seed)
         rnd = self.rnd = RandomSource((s1 ^ s2) if both else s1)
         interval = [policy.seed_interval(self.pre.ival, c.rdlen, both) if c.rdlen else 1 for c in m]
-        streak = self.pre.dp_fail_streak
+        streak = self.streak                             # -D, raised by -k / unbounded with -a (set in __init__)
         nrounds_all = self.n_seed_rounds
         if both:
             streak = -(-streak // 2)
@@ -913,7 +950,7 @@ class PairedPolicyEngine(PolicyEngine):
         self.streak_cur = streak
         self.red = RedundantAlns()
         self.red_mate = [RedundantAlns(), RedundantAlns()]
-        self.sink = PairedSink(self.khits, self.mhits, self.discord, self.mixed)
+        self.sink = PairedSink(self.khits, self.mhits, self.discord, self.mixed, self.mmode)
         self.n_iters = self.n_dps = self.n_ugs = self.n_red = self.n_mate_dps = 0
         # bt2_search.cpp:3419-3426: --nofw / --norc refer to the fragment; which strand of a mate that is depends on --fr/--rf/--ff
         m1fw = self.pe.pol in (policy.PE_POLICY_FF, policy.PE_POLICY_FR)
@@ -1026,7 +1063,7 @@ class PairedPolicyEngine(PolicyEngine):
                     continue
                 if not c.sh:
                     continue
-                c.sh["ranks"] = policy.rank_seed_hits(c.sh["nfw"], c.sh["nrc"], rnd, False)
+                c.sh["ranks"] = policy.rank_seed_hits(c.sh["nfw"], c.sh["nrc"], rnd, self.all)
                 ret = yield from self.extend_seeds_paired(mate, c.sh, [])
                 after(ret, mate)
             for mate in (0, 1):
@@ -1059,7 +1096,7 @@ class PairedPolicyEngine(PolicyEngine):
         opp_filt = not o.filt
         operfect = o.perfect
         best_pair_score = c.perfect + operfect
-        if self.tighten > 0 and sink.best2_pair != MIN_I64:
+        if self.tighten > 0 and self.mmode and sink.best2_pair != MIN_I64:
             nc = self._tightened_pair_score(best_pair_score) - operfect
             if nc > c.minsc:
                 c.minsc = nc
@@ -1083,7 +1120,7 @@ class PairedPolicyEngine(PolicyEngine):
             if not ee_mode:
                 if nonz == 0:
                     return EXHAUSTED
-                if c.minsc == c.perfect:
+                if self.mmode and c.minsc == c.perfect:
                     return PERFECT
                 if first_extend:
                     satpos, nelt = yield from self._prioritize(sh, self.max_iters)
@@ -1188,7 +1225,7 @@ class PairedPolicyEngine(PolicyEngine):
                             ominsc_cur = o.minsc
                             odp = None
                             if found_mate:
-                                if self.tighten > 0 and sink.best2_pair != MIN_I64:
+                                if self.tighten > 0 and self.mmode and sink.best2_pair != MIN_I64:
                                     nc = self._tightened_pair_score(best_pair_score) - a.score
                                     if nc > ominsc_cur:
                                         ominsc_cur = nc
@@ -1252,7 +1289,7 @@ class PairedPolicyEngine(PolicyEngine):
                                         found_concordant = True
                                         if sink.report(a if anchor1 else oa, oa if anchor1 else a):
                                             done_paired = True
-                                        elif self.tighten > 0 and sink.best2_pair != MIN_I64:
+                                        elif self.tighten > 0 and self.mmode and sink.best2_pair != MIN_I64:
                                             nc = self._tightened_pair_score(best_pair_score) - operfect
                                             if nc > c.minsc:
                                                 c.minsc = nc
@@ -1304,7 +1341,7 @@ class PairedPolicyEngine(PolicyEngine):
         buf = sorted(((a.score + (rs2[i].score if rs2 is not None else 0), i) for i, a in enumerate(rs1)), reverse=True)
         shuffle_equal_streaks(buf, lambda t: t[0], rnd)
         sel = buf[0][1]
-        out = dict(sel=sel, unchosen_u=None, unchosen_p=[None, None], unchosen_c=None)
+        out = dict(sel=sel, order=[t[1] for t in buf], unchosen_u=None, unchosen_p=[None, None], unchosen_c=None)
         if rs2 is not None:
             for k, (rsu, chosen) in enumerate(((rs1u, rs1[sel]), (rs2u, rs2[sel]))):
                 best = None
@@ -1330,18 +1367,20 @@ class PairedPolicyEngine(PolicyEngine):
         if sink.nconcord > 0:
             s = self._select(sink.rs1, sink.rs2, sink.rs1u, sink.rs2u)
             a1, a2 = sink.rs1[s["sel"]], sink.rs2[s["sel"]]
-            mq = policy.mapq_v2(a1.score + a2.score, s["unchosen_c"], mn[0] + mn[1], m[0].perfect + m[1].perfect, not self.local)
+            mq = self._mapq(a1.score + a2.score, s["unchosen_c"], mn[0] + mn[1], m[0].perfect + m[1].perfect)
             for k, a in enumerate((a1, a2)):
                 r = res.mates[k]
                 r.aligned, r.aln, r.xs, r.mapq = True, a, s["unchosen_p"][k], mq
             res.pair_type = 1
+            num = self.khits if sink.exit_concord_k else min(sink.nconcord, self.khits)
+            res.secondary_pairs = [(sink.rs1[j], sink.rs2[j]) for j in s["order"][1:num]]
             return res
         discord = (not sink.done_discord) and sink.nunp[0] == 1 and sink.nunp[1] == 1
         if discord:
             # prepareDiscordants + selectByScore over the single pair
             s = self._select([sink.rs1u[0]], [sink.rs2u[0]], sink.rs1u, sink.rs2u)
             a1, a2 = sink.rs1u[0], sink.rs2u[0]
-            mq = policy.mapq_v2(a1.score + a2.score, None, mn[0] + mn[1], m[0].perfect + m[1].perfect, not self.local)
+            mq = self._mapq(a1.score + a2.score, None, mn[0] + mn[1], m[0].perfect + m[1].perfect)
             for k, a in enumerate((a1, a2)):
                 r = res.mates[k]
                 r.aligned, r.aln, r.xs, r.mapq = True, a, None, mq
@@ -1354,8 +1393,10 @@ class PairedPolicyEngine(PolicyEngine):
             a = rsu[s["sel"]]
             r = res.mates[k]
             r.aligned, r.aln, r.xs = True, a, s["unchosen_u"]
-            r.mapq = policy.mapq_v2(a.score, s["unchosen_u"], mn[k], m[k].perfect, not self.local)
+            r.mapq = self._mapq(a.score, s["unchosen_u"], mn[k], m[k].perfect)
             r.n_alns = len(rsu)
+            num = self.khits if sink.exit_unp_k[k] else min(len(rsu), self.khits)
+            r.secondary = [rsu[j] for j in s["order"][1:num]]
         n_al = sum(r.aligned for r in res.mates)
         res.pair_type = 2 if n_al == 2 else (3 if n_al == 1 else 0)
         return res

@@ -450,3 +450,118 @@ def test_sam_output_options(tmp_path):
     f = IndexFile(base)
     hdr = sam_header(load_library(), f.ref_names, f.ref_lens, rg_id="grp1", rg_fields=["SM:sample7", "PL:synthetic"])
     assert hdr.rstrip("\n").split("\n") == want_hdr
+
+
+# ------------------------------------------------------------------------------------------------ -k / -a
+def _multi_sam(outs, reads, quals, names, ref_names):
+    """SAM for results that carry secondary alignments: one formatter record per reported alignment (the read repeated),
+    secondaries marked in found's bit 8 (FLAG 256) with MAPQ 255; all records of a read share its XS:i"""
+    R, Q, N, rows = [], [], [], []
+    for i, r in enumerate(outs):
+        alns = [None] if not r.aligned else [r.aln] + (r.secondary or [])
+        for j, a in enumerate(alns):
+            R.append(reads[i]); Q.append(quals[i]); N.append(names[i])
+            rows.append((r, a, j > 0))
+    res = np.zeros(len(R), dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    ops = np.zeros((len(R), max(len(x) for x in R) + 64), dtype=np.uint8)
+    from bowtie2_b200.policy_engine import ReadResult
+    for j, (r, a, sec) in enumerate(rows):
+        if a is None:
+            continue
+        _fill(res, ops, j, ReadResult(aligned=True, aln=a, xs=r.xs, mapq=255 if sec else r.mapq), R[j])
+        if sec:
+            res[j]["found"] |= 0x100
+    return sam_format(load_library(), ReadBatch.from_list(R, Q), res, ops, ref_names, read_names=N).rstrip("\n").split("\n")
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args,kw", [(["-k", "3"], dict(k=3)), (["-k", "12"], dict(k=12)), (["-a"], dict(all_hits=True)), (["-k", "1"], dict(k=1))])
+def test_k_and_all_modes_unpaired(tmp_path, args, kw):
+    genome, base = _synth_index(tmp_path)
+    reads, quals, _ = synth.make_reads(genome, 250, 100, seed=79, sub_rate=0.02, indel_rate=0.003)
+    fq = str(tmp_path / "r.fq")
+    synth.write_fastq(fq, reads, quals)
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), "--sensitive", "--seed", "0", "-p", "1", "-x", base, "-U", fq] + args,
+                                  stderr=subprocess.DEVNULL).decode()
+    want = [l for l in out.split("\n") if l and not l.startswith("@")]
+    eng = PolicyEngine(OracleBackend(Oracle(base)), "sensitive", **kw)
+    names = [f"r{i}" for i in range(len(reads))]
+    outs = [eng.align_read(reads[i], quals[i], names[i]) for i in range(len(reads))]
+    lines = _multi_sam(outs, reads, quals, names, ["chr1", "chr2", "chr3"])
+    assert lines == want, next((a, b) for a, b in zip(lines, want) if a != b)
+    if kw.get("k", 2) > 1:
+        assert sum(int(l.split("\t")[1]) & 256 != 0 for l in want) > 20
+
+
+def _multi_sam_pairs(outs, reads, quals, names, ref_names):
+    """records of pairs that carry secondary alignments, in the reference's order (AlnSink::reportHits, aln_sink.h:640-735):
+    concordant pairs one after the other; otherwise both primaries, then mate 1's secondaries, then mate 2's (each printed
+    with the opposite mate's primary as its mate).  Every record comes from a formatter pair entry; `keep` picks its lines."""
+    from bowtie2_b200.lib import PAIR_RESULT
+    from bowtie2_b200.policy_engine import ReadResult
+    R, Q, N, ent, keep = [], [], [], [], []
+    for i, pr in enumerate(outs):
+        m1, m2 = pr.mates
+        rq = (reads[2 * i], reads[2 * i + 1], quals[2 * i], quals[2 * i + 1], names[2 * i], names[2 * i + 1])
+
+        def add(a1, a2, sec1, sec2, lines):
+            R.extend(rq[0:2]); Q.extend(rq[2:4]); N.extend(rq[4:6])
+            ent.append((pr, a1, a2, sec1, sec2))
+            keep.append(lines)
+        a1 = m1.aln if m1.aligned else None
+        a2 = m2.aln if m2.aligned else None
+        add(a1, a2, False, False, (0, 1))
+        if pr.pair_type == 1:
+            for (b1, b2) in pr.secondary_pairs or []:
+                add(b1, b2, True, True, (0, 1))
+        else:
+            for b1 in (m1.secondary or []):
+                add(b1, a2, True, False, (0,))
+            for b2 in (m2.secondary or []):
+                add(a1, b2, False, True, (1,))
+    n = len(R)
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    ops = np.zeros((n, max(len(x) for x in R) + 64), dtype=np.uint8)
+    pairs = np.zeros(n // 2, dtype=PAIR_RESULT)
+    for e, (pr, a1, a2, sec1, sec2) in enumerate(ent):
+        pairs[e]["pair_type"] = pr.pair_type
+        for k, (a, sec, m) in enumerate(((a1, sec1, pr.mates[0]), (a2, sec2, pr.mates[1]))):
+            if a is None:
+                continue
+            _fill(res, ops, 2 * e + k, ReadResult(aligned=True, aln=a, xs=m.xs, mapq=255 if sec else m.mapq), R[2 * e + k])
+            if sec:
+                res[2 * e + k]["found"] |= 0x100
+    lines = sam_format(load_library(), ReadBatch.from_list(R, Q), res, ops, ref_names, read_names=N, pairs=pairs).rstrip("\n").split("\n")
+    out = []
+    for e, k in enumerate(keep):
+        pair_lines = lines[2 * e:2 * e + 2]
+        by_mate = {bool(int(l.split("\t")[1]) & 128): l for l in pair_lines}
+        if k == (0, 1):
+            out.extend(pair_lines)
+        else:
+            out.append(by_mate[k[0] == 1])
+    return out
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args,kw", [(["-k", "3"], dict(k=3)), (["-a"], dict(all_hits=True))])
+def test_k_and_all_modes_paired(tmp_path, args, kw):
+    from bowtie2_b200.policy_engine import PairedPolicyEngine
+    genome, base = _synth_index(tmp_path)
+    n = 150
+    reads, quals, _ = synth.make_pairs(genome, n, 100, seed=32, sub_rate=0.02, indel_rate=0.003, hard_frac=0.2, hard_period=12,
+                                       ins_mean=300, ins_sd=90)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    synth.write_fastq(f1, reads[0::2], quals[0::2])
+    synth.write_fastq(f2, reads[1::2], quals[1::2])
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), "--sensitive", "--seed", "0", "-p", "1", "-x", base, "-1", f1, "-2", f2] + args,
+                                  stderr=subprocess.DEVNULL).decode()
+    want = [l for l in out.split("\n") if l and not l.startswith("@")]
+    eng = PairedPolicyEngine(OracleBackend(Oracle(base)), "sensitive", **kw)
+    names = [f"r{i // 2}" for i in range(2 * n)]
+    outs = [eng.align_pair(reads[2 * i], quals[2 * i], names[2 * i], reads[2 * i + 1], quals[2 * i + 1], names[2 * i + 1]) for i in range(n)]
+    lines = _multi_sam_pairs(outs, reads, quals, names, ["chr1", "chr2", "chr3"])
+    diff = [(a, b) for a, b in zip(lines, want) if a != b]
+    assert len(lines) == len(want) and not diff, (len(lines), len(want), diff[:1])
