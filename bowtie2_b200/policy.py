@@ -80,17 +80,29 @@ class Scoring:
     rfgap_linear: int = 3
     gapbar: int = 4
     local: bool = False
+    mmp_max: int = 6              # --mp MX,MN
+    mmp_min: int = 2
+    n_pen: int = 1                # --np
+    score_min_func: "SimpleFunc" = None   # --score-min
+    n_ceil_over: "SimpleFunc" = None      # --n-ceil
 
     @classmethod
     def default(cls, local=False):
         return cls(match_bonus=2 if local else 0, local=local)
 
+    def mm_penalty(self, q: int) -> int:
+        return mm_penalty(q, self.mmp_max, self.mmp_min)
+
     def score_min(self) -> SimpleFunc:
+        if self.score_min_func is not None:
+            return self.score_min_func
         # the defaults are FLOAT literals widened to double (scoring.h:50-55: -0.6f = -0.60000002384...), which moves the
         # truncation point for read lengths where 0.6 * (len + 1) is an integer: 109 bp -> -66, not -65
         return SimpleFunc(SIMPLE_FUNC_LOG, 20.0, 8.0) if self.local else SimpleFunc(SIMPLE_FUNC_LINEAR, _F32(-0.6), _F32(-0.6))
 
     def n_ceil_func(self) -> SimpleFunc:
+        if self.n_ceil_over is not None:
+            return self.n_ceil_over
         return SimpleFunc(SIMPLE_FUNC_LINEAR, 0.0, _F32(0.15), 0.0, float("inf"))      # scoring.h:61-63: 0.0f, 0.15f
 
     def read_gap_open(self): return self.rdgap_const + self.rdgap_linear

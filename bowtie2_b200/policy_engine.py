@@ -341,7 +341,7 @@ class MateCtx:
 
 class PolicyEngine:
     def __init__(self, backend, preset="sensitive", seed=0, sc=None, local=False, nofw=False, norc=False,
-                 dp_fail_streak=None, seed_rounds=None, seed_len=None, k=None, all_hits=False):
+                 dp_fail_streak=None, seed_rounds=None, seed_len=None, k=None, all_hits=False, mhits=None, ival=None):
         """seed = --seed; nofw / norc = --nofw / --norc; dp_fail_streak / seed_rounds / seed_len = -D / -R / -L on top of the
         preset; k = -k <int> (up to k alignments per read, no -M sampling); all_hits = -a"""
         self.b = backend
@@ -362,7 +362,9 @@ class PolicyEngine:
         self.all = all_hits
         self.mmode = not (all_hits or k is not None)
         self.khits = (1 << 62) if all_hits else (k if k is not None else 1)
-        self.mhits = 50 if self.mmode else (1 << 62)
+        self.mhits = (mhits if mhits is not None else 50) if self.mmode else (1 << 62)     # -M <n>
+        if ival is not None:                           # -i <func>
+            self.pre.ival = ival
         self.maxhalf = 15
         self.max_iters, self.max_ug, self.max_dp = 400, 300, 300
         self.streak = self.pre.dp_fail_streak
@@ -747,7 +749,7 @@ class PolicyEngine:
         fit; local: no cell may reach 255 - bias, bias = the largest penalty of the query profile (aligner_swsse_loc_u8.cpp:97-110)"""
         if not self.local:
             return minsc >= -254
-        bias = max([policy.mm_penalty(int(q) - 33) for q in quals] + [1])
+        bias = max([self.sc.mm_penalty(int(q) - 33) for q in quals] + [self.sc.n_pen])
         return dp["best"] + bias < 255
 
     def _next_alignment(self, dp, tidx, minsc, rdlen):

@@ -177,10 +177,18 @@ class _OScoring(C.Structure):
                                        "rfgap_const", "rfgap_linear", "gapbar", "local")]
 
 
+SCORING_OVERRIDE = None      # a bowtie2_b200.policy.Scoring: non-default penalties for the oracle calls that follow
+
+
 def oracle_scoring(O, local):
     O.lib.bt2o_scoring_default.argtypes = [C.POINTER(_OScoring), ci]
     sc = _OScoring()
     O.lib.bt2o_scoring_default(C.byref(sc), int(local))
+    p = SCORING_OVERRIDE
+    if p is not None:
+        sc.match_bonus, sc.mmp_max, sc.mmp_min, sc.n_pen = p.match_bonus, p.mmp_max, p.mmp_min, p.n_pen
+        sc.rdgap_const, sc.rdgap_linear, sc.rfgap_const, sc.rfgap_linear, sc.gapbar = (p.rdgap_const, p.rdgap_linear, p.rfgap_const,
+                                                                                        p.rfgap_linear, p.gapbar)
     return sc
 
 

@@ -8,15 +8,21 @@ from oracle_lib import extend_both, oracle_dp, oracle_one_mm, oracle_ungapped
 
 
 class OracleBackend:
-    def __init__(self, O, off_size=4, local=False):
+    def __init__(self, O, off_size=4, local=False, scoring=None):
         self.O = O
         self.off_size = off_size
         self.local = local
+        self.scoring = scoring                     # policy.Scoring with non-default penalties, or None
+
+    def _sc(self):
+        import oracle_lib
+        oracle_lib.SCORING_OVERRIDE = self.scoring
 
     def exact_sweep(self, codes, nofw=False, norc=False):
         return self.O.exact_sweep(codes, nofw, norc)
 
     def one_mm(self, codes, quals, minsc, nofw, norc):
+        self._sc()
         return oracle_one_mm(self.O, self.local, codes, quals, minsc, nofw, norc)
 
     def seed_search(self, codes, quals, seed_len, interval, offset, nofw=False, norc=False):
@@ -37,6 +43,7 @@ class OracleBackend:
         return int((self.O.get_stretch(tidx, off, extent) > 3).sum())
 
     def ungapped(self, codes, quals, fw, tidx, refoff, tlen, minsc):
+        self._sc()
         rc, d = oracle_ungapped(self.O, self.local, codes, quals, fw, tidx, refoff, tlen, 0, minsc)
         if rc != 1:
             return rc, None
@@ -59,4 +66,5 @@ class OracleBackend:
         return rc, Aln(tidx, refoff + rowi, fw, d["score"], rdlen, ed, d["ns"], d["refns"], False, tl if fw else tr, tr if fw else tl)
 
     def dp(self, codes, quals, fw, tidx, rect, minsc, nceil):
+        self._sc()
         return oracle_dp(self.O, self.local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=65536, max_alns=64, max_edits=16384, attempts=True)

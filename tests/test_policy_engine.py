@@ -453,7 +453,7 @@ def test_sam_output_options(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------ -k / -a
-def _multi_sam(outs, reads, quals, names, ref_names):
+def _multi_sam(outs, reads, quals, names, ref_names, local=False):
     """SAM for results that carry secondary alignments: one formatter record per reported alignment (the read repeated),
     secondaries marked in found's bit 8 (FLAG 256) with MAPQ 255; all records of a read share its XS:i"""
     R, Q, N, rows = [], [], [], []
@@ -472,7 +472,7 @@ def _multi_sam(outs, reads, quals, names, ref_names):
         _fill(res, ops, j, ReadResult(aligned=True, aln=a, xs=r.xs, mapq=255 if sec else r.mapq), R[j])
         if sec:
             res[j]["found"] |= 0x100
-    return sam_format(load_library(), ReadBatch.from_list(R, Q), res, ops, ref_names, read_names=N).rstrip("\n").split("\n")
+    return sam_format(load_library(), ReadBatch.from_list(R, Q), res, ops, ref_names, read_names=N, local=local).rstrip("\n").split("\n")
 
 
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
@@ -494,7 +494,7 @@ def test_k_and_all_modes_unpaired(tmp_path, args, kw):
         assert sum(int(l.split("\t")[1]) & 256 != 0 for l in want) > 20
 
 
-def _multi_sam_pairs(outs, reads, quals, names, ref_names):
+def _multi_sam_pairs(outs, reads, quals, names, ref_names, local=False):
     """records of pairs that carry secondary alignments, in the reference's order (AlnSink::reportHits, aln_sink.h:640-735):
     concordant pairs one after the other; otherwise both primaries, then mate 1's secondaries, then mate 2's (each printed
     with the opposite mate's primary as its mate).  Every record comes from a formatter pair entry; `keep` picks its lines."""
@@ -533,7 +533,7 @@ def _multi_sam_pairs(outs, reads, quals, names, ref_names):
             _fill(res, ops, 2 * e + k, ReadResult(aligned=True, aln=a, xs=m.xs, mapq=255 if sec else m.mapq), R[2 * e + k])
             if sec:
                 res[2 * e + k]["found"] |= 0x100
-    lines = sam_format(load_library(), ReadBatch.from_list(R, Q), res, ops, ref_names, read_names=N, pairs=pairs).rstrip("\n").split("\n")
+    lines = sam_format(load_library(), ReadBatch.from_list(R, Q), res, ops, ref_names, read_names=N, pairs=pairs, local=local).rstrip("\n").split("\n")
     out = []
     for e, k in enumerate(keep):
         pair_lines = lines[2 * e:2 * e + 2]

@@ -1,0 +1,215 @@
+"""The reference's own regression corpus (scripts/test/simple_tests.pl, 272 cases: tiny references, hand-made reads with
+gaps at the ends, Ns, overlapping / containing / dovetailing mates, repeats ...) as inputs: every case whose options the
+policy engine models is run through the reference PROGRAM and through the engine (oracle backend) and the two SAM files
+must be identical, record for record.  Cases with options outside the engine's scope (raw --policy strings, read
+trimming, --overhang, -N 1, non-FASTQ input formats) are counted and skipped."""
+import json
+import os
+import re
+import shlex
+import subprocess
+
+import numpy as np
+import pytest
+
+from bowtie2_b200 import policy
+from bowtie2_b200.policy_engine import PairedPolicyEngine, PolicyEngine
+from conftest import GOLDEN
+from oracle_lib import Oracle, have_reference, ref_bin
+from policy_backend import OracleBackend
+from test_policy_engine import _multi_sam, _multi_sam_pairs
+
+CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
+FUNC = {"C": policy.SIMPLE_FUNC_CONST, "L": policy.SIMPLE_FUNC_LINEAR, "S": policy.SIMPLE_FUNC_SQRT, "G": policy.SIMPLE_FUNC_LOG}
+FORMATS = ("fastq", "tabbed", "fasta", "qseq", "raw", "cline_reads", "cont_fasta_reads", "fastq1", "fasta1", "raw1", "qseq1",
+           "cline_reads1", "should_abort", "lines")
+
+
+def _func(text, dflt_min=0.0, dflt_max=float("inf")):
+    t = text.split(",")
+    return policy.SimpleFunc(FUNC[t[0]], float(t[1]), float(t[2]) if len(t) > 2 else 0.0)
+
+
+def _options(case):
+    """-> (reference arguments, engine kwargs, scoring, pe policy kwargs) or None when an option is out of scope"""
+    toks = shlex.split((case.get("args") or "") + " " + (case.get("report") if case.get("report") is not None else "-a"))
+    local = "--local" in toks
+    sc = policy.Scoring.default(local)
+    kw, pe = {}, {}
+    i = 0
+    while i < len(toks):
+        t = toks[i]
+        val = None
+        if "=" in t and t.startswith("--"):
+            t, val = t.split("=", 1)
+
+        def arg():
+            nonlocal i
+            if val is not None:
+                return val
+            i += 1
+            return toks[i]
+        if t in ("--local", "--quiet"):
+            pass
+        elif t == "-a":
+            kw["all_hits"] = True
+        elif t == "-k":
+            kw["k"] = int(arg())
+        elif t == "-M":
+            kw["mhits"] = int(arg())
+        elif t == "-L":
+            kw["seed_len"] = int(arg())
+        elif t == "-i":
+            kw["ival"] = _func(arg())
+        elif t == "-D":
+            kw["dp_fail_streak"] = int(arg())
+        elif t == "-R":
+            kw["seed_rounds"] = int(arg())
+        elif t == "--seed":
+            kw["seed"] = int(arg())
+        elif t == "--multiseed":
+            f = arg().split(",")                       # mms, length, interval function...
+            if int(f[0]) != 0:
+                return None
+            kw["seed_len"] = int(f[1])
+            if len(f) >= 4:
+                kw["ival"] = policy.SimpleFunc(FUNC[f[2]], float(f[3]), float(f[4]) if len(f) > 4 else 0.0)
+        elif t == "--score-min":
+            sc.score_min_func = _func(arg())
+        elif t == "--ignore-quals":
+            sc.mmp_min = sc.mmp_max
+        elif t == "--mp":
+            f = arg().split(",")
+            sc.mmp_max = int(f[0])
+            if len(f) > 1:
+                sc.mmp_min = int(f[1])
+        elif t == "--nofw":
+            kw["nofw"] = True
+        elif t == "--norc":
+            kw["norc"] = True
+        elif t == "-I":
+            pe["minfrag"] = int(arg())
+        elif t == "-X":
+            pe["maxfrag"] = int(arg())
+        elif t in ("--ff", "--fr", "--rf"):
+            pe["pol"] = {"--ff": 1, "--fr": 3, "--rf": 4}[t]
+        elif t == "--no-mixed":
+            kw["mixed"] = False
+        elif t == "--no-discordant":
+            kw["discord"] = False
+        elif t == "--no-contain":
+            pe["contain_ok"] = False
+        elif t == "--no-overlap":
+            pe["olap_ok"] = False
+        elif t == "--dovetail":
+            pe["dovetail_ok"] = True
+        elif t == "--no-dovetail":
+            pe["dovetail_ok"] = False
+        else:
+            return None
+        i += 1
+    if "all_hits" in kw and "k" in kw:
+        del kw["all_hits"]
+    if ("all_hits" in kw or "k" in kw) and "mhits" in kw:
+        del kw["mhits"]                                 # -k / -a switch -M off (bt2_search.cpp:1772-1774)
+    return toks, kw, sc, pe, local
+
+
+def _usable(case):
+    if any(k in case for k in FORMATS) or not ("reads" in case or "mate1s" in case):
+        return False
+    seqs = (case.get("reads") or []) + (case.get("mate1s") or []) + (case.get("mate2s") or [])
+    if any((not s) or re.search(r"[^ACGTN]", s) for s in seqs) or any(re.search(r"[^ACGTN]", r.upper()) for r in case["ref"]):
+        return False
+    return _options(case) is not None
+
+
+def _cases():
+    return json.load(open(os.path.join(GOLDEN, "simple_tests_cases.json")))
+
+
+def _codes(s):
+    return np.array([CODE.get(c, 4) for c in s], dtype=np.uint8)
+
+
+def _write_fq(path, seqs, quals, names, suffix=""):
+    with open(path, "w") as f:
+        for s, q, n in zip(seqs, quals, names):
+            f.write(f"@{n}{suffix}\n{s}\n+\n{q}\n")
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_reference_regression_corpus(tmp_path):
+    cases = _cases()
+    assert len(cases) == 272
+    n_run = n_pairs = n_reads = 0
+    skipped = 0
+    for ci, case in enumerate(cases):
+        if not _usable(case):
+            skipped += 1
+            continue
+        toks, kw, sc, pe_kw, local = _options(case)
+        d = tmp_path / f"c{ci}"
+        d.mkdir()
+        fa, base = str(d / "ref.fa"), str(d / "ref")
+        with open(fa, "w") as f:
+            for k, r in enumerate(case["ref"]):
+                f.write(f">{k}\n{r}\n")
+        subprocess.check_call([ref_bin("bowtie2-build-s"), "--quiet", fa, base])
+        ref_names = [str(k) for k in range(len(case["ref"]))]
+        paired = "mate1s" in case
+        if paired and ("mate1fw" in case or "mate2fw" in case) and "pol" not in pe_kw:
+            m1, m2 = case.get("mate1fw", 1), case.get("mate2fw", 0)
+            if m1 == m2:
+                toks, pe_kw["pol"] = toks + ["--ff"], 1
+            elif not m1:
+                toks, pe_kw["pol"] = toks + ["--rf"], 4
+        if case.get("norc"):
+            pass                                         # harness-side: do not also test the reverse complements
+        cmd = [ref_bin("bowtie2-align-s"), "--quiet", "-p", "1", "-x", base] + [t for t in toks if t != "--quiet"]
+        if "--seed" not in " ".join(toks):
+            cmd += ["--seed", "0"]
+        kw.setdefault("seed", 0)
+        backend = OracleBackend(Oracle(base), local=local, scoring=sc)
+        if not paired:
+            seqs = case["reads"]
+            quals = [(case.get("quals") or [None] * len(seqs))[k] or "I" * len(s) for k, s in enumerate(seqs)]
+            names = [(case.get("names") or [None] * len(seqs))[k] or f"r{k}" for k in range(len(seqs))]
+            fq = str(d / "r.fq")
+            _write_fq(fq, seqs, quals, names)
+            out = subprocess.run(cmd + ["-U", fq], capture_output=True, text=True)
+            if out.returncode != 0:
+                skipped += 1
+                continue
+            want = [l for l in out.stdout.split("\n") if l and not l.startswith("@")]
+            eng = PolicyEngine(backend, "sensitive", sc=sc, local=local, **{k: v for k, v in kw.items() if k not in ("mixed", "discord")})
+            R = [_codes(s) for s in seqs]
+            Q = [np.frombuffer(q.encode(), dtype=np.uint8) for q in quals]
+            outs = [eng.align_read(R[k], Q[k], names[k]) for k in range(len(R))]
+            lines = _multi_sam(outs, R, Q, names, ref_names, local=local)
+            n_reads += len(R)
+        else:
+            s1, s2 = case["mate1s"], case["mate2s"]
+            q1 = [(case.get("qual1s") or [None] * len(s1))[k] or "I" * len(s) for k, s in enumerate(s1)]
+            q2 = [(case.get("qual2s") or [None] * len(s2))[k] or "I" * len(s) for k, s in enumerate(s2)]
+            names = [(case.get("names") or [None] * len(s1))[k] or f"r{k}" for k in range(len(s1))]
+            f1, f2 = str(d / "r1.fq"), str(d / "r2.fq")
+            _write_fq(f1, s1, q1, names, "/1")
+            _write_fq(f2, s2, q2, names, "/2")
+            out = subprocess.run(cmd + ["-1", f1, "-2", f2], capture_output=True, text=True)
+            if out.returncode != 0:
+                skipped += 1
+                continue
+            want = [l for l in out.stdout.split("\n") if l and not l.startswith("@")]
+            eng = PairedPolicyEngine(backend, "sensitive", sc=sc, local=local, pe=policy.PairedEndPolicy(local=local, **pe_kw), **kw)
+            R = [x for p in zip((_codes(s) for s in s1), (_codes(s) for s in s2)) for x in p]
+            Q = [np.frombuffer(x.encode(), dtype=np.uint8) for p in zip(q1, q2) for x in p]
+            N = [x for k in range(len(s1)) for x in (names[k] + "/1", names[k] + "/2")]
+            outs = [eng.align_pair(R[2 * k], Q[2 * k], N[2 * k], R[2 * k + 1], Q[2 * k + 1], N[2 * k + 1]) for k in range(len(s1))]
+            lines = _multi_sam_pairs(outs, R, Q, N, ref_names, local=local)
+            n_pairs += len(s1)
+        assert lines == want, (ci, case.get("name"), case.get("args"), case.get("report"),
+                               next(((a, b) for a, b in zip(lines, want) if a != b), (len(lines), len(want))))
+        n_run += 1
+    assert n_run >= 90, (n_run, skipped)
+    print(f"simple_tests.pl corpus: {n_run} cases identical ({n_reads} reads, {n_pairs} pairs), {skipped} outside the engine's options")
