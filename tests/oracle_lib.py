@@ -206,8 +206,7 @@ def oracle_dp(O, local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=10
         L.bt2o_dp_attempt_log(att.ctypes.data_as(vp), 4096)
     L.bt2o_scoring_default.argtypes = [C.POINTER(_OScoring), ci]
     L.bt2o_dp.argtypes = [vp, C.POINTER(_OScoring), vp, vp, ci, ci, u64, i64, i64, ci, ci, ci, i64, ci, ci, ci, ci, vp, vp, vp, vp]
-    sc = _OScoring()
-    L.bt2o_scoring_default(C.byref(sc), int(local))
+    sc = oracle_scoring(O, local)
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
     quals = np.ascontiguousarray(quals, dtype=np.uint8)
     summ = np.zeros(4, np.int64)

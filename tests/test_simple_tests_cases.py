@@ -105,6 +105,68 @@ def _options(case):
             pe["dovetail_ok"] = True
         elif t == "--no-dovetail":
             pe["dovetail_ok"] = False
+        elif t in ("-3", "-5", "--trim3", "--trim5"):
+            kw["_trim3" if t in ("-3", "--trim3") else "_trim5"] = int(arg())
+        elif t in ("-u", "-s"):
+            kw["_upto" if t == "-u" else "_skip"] = int(arg())
+        elif t == "--rdg":
+            f = arg().split(",")
+            sc.rdgap_const = int(f[0])
+            if len(f) > 1:
+                sc.rdgap_linear = int(f[1])
+        elif t == "--rfg":
+            f = arg().split(",")
+            sc.rfgap_const = int(f[0])
+            if len(f) > 1:
+                sc.rfgap_linear = int(f[1])
+        elif t == "--np":
+            sc.n_pen = int(arg())
+        elif t == "--ma":
+            sc.match_bonus = int(arg())
+        elif t == "--n-ceil":
+            sc.n_ceil_over = _func(arg())
+        elif t == "--policy":
+            # SeedAlignmentPolicy::parseString (aligner_seed_policy.cpp): integer-valued settings only
+            for kv in arg().replace("\\;", ";").replace("\\", "").split(";"):
+                if not kv:
+                    continue
+                key, v = kv.split("=", 1)
+                try:
+                    if key == "SEED":
+                        if int(v.split(",")[0]) != 0:
+                            return None
+                        if "," in v:
+                            kw["seed_len"] = int(v.split(",")[1])
+                    elif key == "SEEDLEN":
+                        kw["seed_len"] = int(v)
+                    elif key == "IVAL":
+                        kw["ival"] = _func(v)
+                    elif key == "MIN":
+                        sc.score_min_func = _func(v)
+                    elif key == "NCEIL":
+                        sc.n_ceil_over = _func(v)
+                    elif key == "MMP":
+                        if v.startswith("C"):
+                            sc.mmp_max = sc.mmp_min = int(v[1:])
+                        elif v != "Q":
+                            return None
+                    elif key == "NP":
+                        if not v.startswith("C"):
+                            return None
+                        sc.n_pen = int(v[1:])
+                    elif key in ("RDG", "RFG"):
+                        f = v.split(",")
+                        a, b = int(f[0]), (int(f[1]) if len(f) > 1 else None)
+                        if key == "RDG":
+                            sc.rdgap_const = a
+                            sc.rdgap_linear = b if b is not None else sc.rdgap_linear
+                        else:
+                            sc.rfgap_const = a
+                            sc.rfgap_linear = b if b is not None else sc.rfgap_linear
+                    else:
+                        return None
+                except ValueError:
+                    return None
         else:
             return None
         i += 1
@@ -149,6 +211,9 @@ def test_reference_regression_corpus(tmp_path):
             skipped += 1
             continue
         toks, kw, sc, pe_kw, local = _options(case)
+        skip, upto = kw.pop("_skip", 0), kw.pop("_upto", None)
+        t5, t3 = kw.pop("_trim5", 0), kw.pop("_trim3", 0)
+        trim = lambda x: x[t5:len(x) - t3] if t3 else x[t5:]       # -5 / -3: bases removed before alignment (and from SEQ / QUAL)
         d = tmp_path / f"c{ci}"
         d.mkdir()
         fa, base = str(d / "ref.fa"), str(d / "ref")
@@ -183,8 +248,10 @@ def test_reference_regression_corpus(tmp_path):
                 continue
             want = [l for l in out.stdout.split("\n") if l and not l.startswith("@")]
             eng = PolicyEngine(backend, "sensitive", sc=sc, local=local, **{k: v for k, v in kw.items() if k not in ("mixed", "discord")})
-            R = [_codes(s) for s in seqs]
-            Q = [np.frombuffer(q.encode(), dtype=np.uint8) for q in quals]
+            R = [trim(_codes(s)) for s in seqs]
+            Q = [trim(np.frombuffer(q.encode(), dtype=np.uint8)) for q in quals]
+            sel = range(len(R))[skip:][:upto] if upto is not None else range(len(R))[skip:]     # -s / -u
+            R, Q, names = [R[k] for k in sel], [Q[k] for k in sel], [names[k] for k in sel]
             outs = [eng.align_read(R[k], Q[k], names[k]) for k in range(len(R))]
             lines = _multi_sam(outs, R, Q, names, ref_names, local=local)
             n_reads += len(R)
@@ -202,14 +269,18 @@ def test_reference_regression_corpus(tmp_path):
                 continue
             want = [l for l in out.stdout.split("\n") if l and not l.startswith("@")]
             eng = PairedPolicyEngine(backend, "sensitive", sc=sc, local=local, pe=policy.PairedEndPolicy(local=local, **pe_kw), **kw)
-            R = [x for p in zip((_codes(s) for s in s1), (_codes(s) for s in s2)) for x in p]
-            Q = [np.frombuffer(x.encode(), dtype=np.uint8) for p in zip(q1, q2) for x in p]
+            R = [trim(x) for p in zip((_codes(s) for s in s1), (_codes(s) for s in s2)) for x in p]
+            Q = [trim(np.frombuffer(x.encode(), dtype=np.uint8)) for p in zip(q1, q2) for x in p]
             N = [x for k in range(len(s1)) for x in (names[k] + "/1", names[k] + "/2")]
-            outs = [eng.align_pair(R[2 * k], Q[2 * k], N[2 * k], R[2 * k + 1], Q[2 * k + 1], N[2 * k + 1]) for k in range(len(s1))]
+            sel = range(len(s1))[skip:][:upto] if upto is not None else range(len(s1))[skip:]
+            R = [R[2 * k + j] for k in sel for j in (0, 1)]
+            Q = [Q[2 * k + j] for k in sel for j in (0, 1)]
+            N = [N[2 * k + j] for k in sel for j in (0, 1)]
+            outs = [eng.align_pair(R[2 * k], Q[2 * k], N[2 * k], R[2 * k + 1], Q[2 * k + 1], N[2 * k + 1]) for k in range(len(R) // 2)]
             lines = _multi_sam_pairs(outs, R, Q, N, ref_names, local=local)
             n_pairs += len(s1)
         assert lines == want, (ci, case.get("name"), case.get("args"), case.get("report"),
                                next(((a, b) for a, b in zip(lines, want) if a != b), (len(lines), len(want))))
         n_run += 1
-    assert n_run >= 90, (n_run, skipped)
+    assert n_run >= 130, (n_run, skipped)
     print(f"simple_tests.pl corpus: {n_run} cases identical ({n_reads} reads, {n_pairs} pairs), {skipped} outside the engine's options")
