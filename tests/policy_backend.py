@@ -14,16 +14,20 @@ class OracleBackend:
         self.local = local
         self.scoring = scoring                     # policy.Scoring with non-default penalties, or None
 
-    def _sc(self):
+    def _sc(self, fn, *args, **kw):
+        """run one oracle call under this backend's scoring scheme (the override is module state: always restored)"""
         import oracle_lib
         oracle_lib.SCORING_OVERRIDE = self.scoring
+        try:
+            return fn(*args, **kw)
+        finally:
+            oracle_lib.SCORING_OVERRIDE = None
 
     def exact_sweep(self, codes, nofw=False, norc=False):
         return self.O.exact_sweep(codes, nofw, norc)
 
     def one_mm(self, codes, quals, minsc, nofw, norc):
-        self._sc()
-        return oracle_one_mm(self.O, self.local, codes, quals, minsc, nofw, norc)
+        return self._sc(oracle_one_mm, self.O, self.local, codes, quals, minsc, nofw, norc)
 
     def seed_search(self, codes, quals, seed_len, interval, offset, nofw=False, norc=False):
         n = max(1, policy.n_seeds(len(codes), seed_len, interval, offset))
@@ -43,8 +47,7 @@ class OracleBackend:
         return int((self.O.get_stretch(tidx, off, extent) > 3).sum())
 
     def ungapped(self, codes, quals, fw, tidx, refoff, tlen, minsc):
-        self._sc()
-        rc, d = oracle_ungapped(self.O, self.local, codes, quals, fw, tidx, refoff, tlen, 0, minsc)
+        rc, d = self._sc(oracle_ungapped, self.O, self.local, codes, quals, fw, tidx, refoff, tlen, 0, minsc)
         if rc != 1:
             return rc, None
         rdlen = len(codes)
@@ -66,5 +69,5 @@ class OracleBackend:
         return rc, Aln(tidx, refoff + rowi, fw, d["score"], rdlen, ed, d["ns"], d["refns"], False, tl if fw else tr, tr if fw else tl)
 
     def dp(self, codes, quals, fw, tidx, rect, minsc, nceil):
-        self._sc()
-        return oracle_dp(self.O, self.local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=65536, max_alns=64, max_edits=16384, attempts=True)
+        return self._sc(oracle_dp, self.O, self.local, codes, quals, fw, tidx, rect, minsc, nceil, max_cands=65536, max_alns=64,
+                        max_edits=16384, attempts=True)
