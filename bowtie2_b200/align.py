@@ -19,12 +19,13 @@ from .lib import (ALIGN_COUNTS, Bt2Gpu, IndexFile, Pipeline, ReadBatch, align_co
 class FastqStream:
     """Batches of whole FASTQ records from a file (plain or .gz)."""
 
-    def __init__(self, path: str, chunk_bytes: int = 32 << 20, name_stride: int = 96):
+    def __init__(self, path: str, chunk_bytes: int = 32 << 20, name_stride: int = 96, threads: int = 1):
         self._f = gzip.open(path, "rb") if path.endswith(".gz") else open(path, "rb")
         self._buf = b""
         self._eof = False
         self._chunk = chunk_bytes
         self._stride = name_stride
+        self._threads = threads
         self._lib = load_library()
 
     def next_batch(self, max_reads: int):
@@ -38,8 +39,9 @@ class FastqStream:
         if self._eof and self._buf and not self._buf.endswith(b"\n"):
             self._buf += b"\n"                                   # last record without a final newline
         if not self._buf.strip():
-            return ReadBatch(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(0, np.uint8)), []
-        batch, names, used = fastq_parse(self._lib, self._buf, max_reads=max_reads, name_stride=self._stride)
+            from .lib import NameTable
+            return ReadBatch(np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros(0, np.uint8)), NameTable(np.zeros((0, self._stride), np.uint8))
+        batch, names, used = fastq_parse(self._lib, self._buf, max_reads=max_reads, name_stride=self._stride, threads=self._threads)
         if batch.n == 0 and self._eof:
             raise RuntimeError("truncated FASTQ record at the end of the input")
         self._buf = self._buf[used:]
@@ -68,6 +70,14 @@ def interleave(b1: ReadBatch, b2: ReadBatch) -> ReadBatch:
         seq[dst] = b.seq[:int(b.off[-1])]
         qual[dst] = b.qual[:int(b.off[-1])]
     return ReadBatch(seq, off, qual)
+
+
+def interleave_names(n1, n2):
+    """names of mate 1 / mate 2 interleaved, as a NameTable (no per-name Python work)"""
+    from .lib import NameTable
+    rows = np.empty((2 * len(n1), n1.rows.shape[1]), dtype=np.uint8)
+    rows[0::2], rows[1::2] = n1.rows, n2.rows
+    return NameTable(rows)
 
 
 def _exact_batch(gpu, batch, names, paired, preset, local, seed):
@@ -133,14 +143,14 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
     if dense_sa >= 0:
         gpu.build_dense_sa(dense_sa)
     paired = reads2 is not None
-    s1 = FastqStream(reads1)
-    s2 = FastqStream(reads2) if paired else None
+    s1 = FastqStream(reads1, threads=max(1, threads // (2 if paired else 1)))
+    s2 = FastqStream(reads2, threads=max(1, threads // 2)) if paired else None
     per_batch = batch_reads // 2 if paired else batch_reads
     counts = np.zeros(1, dtype=ALIGN_COUNTS)
     pipe, pipe_len = None, 0
     sam_names = [n.split()[0] if n.split() else n for n in ref_names]
-    with open(out_path, "w") as out:
-        out.write(sam_header(lib, ref_names, ref_lens, pg_cl))
+    with open(out_path, "wb") as out:
+        out.write(sam_header(lib, ref_names, ref_lens, pg_cl).encode())
         while True:
             b1, n1 = s1.next_batch(per_batch)
             if paired:
@@ -150,7 +160,7 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
             if b1.n == 0:
                 break
             batch = interleave(b1, b2) if paired else b1
-            names = [x for p in zip(n1, n2) for x in p] if paired else n1
+            names = interleave_names(n1, n2) if paired else n1
             need = int(batch.lengths().max())
             if not exact and (pipe is None or need > pipe_len):
                 if pipe is not None:
@@ -166,7 +176,7 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
                 res, ops, pairs = pipe.run_paired_host(batch)
             else:
                 (res, ops), pairs = pipe.run_host(batch), None
-            out.write(sam_format(lib, batch, res, ops, sam_names, read_names=names, pairs=pairs, threads=threads, local=local))
+            out.write(sam_format(lib, batch, res, ops, sam_names, read_names=names, pairs=pairs, threads=threads, local=local, as_bytes=True))
             align_counts_add(lib, counts, res, pairs)
     if pipe is not None:
         pipe.close()

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include <thread>
+#include <memory>
 #include "../../include/bt2g.h"
 
 namespace {
@@ -303,8 +304,14 @@ extern "C" int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads
 	for(int t = 0; t < T; t++) { if(rcs[t]) return rcs[t]; total += parts[t].size(); }
 	*written = total;
 	if(!out || total > cap) return -3;                             // buffer too small: *written holds the size needed
-	uint64_t at = 0;
-	for(int t = 0; t < T; t++) { memcpy(out + at, parts[t].data(), parts[t].size()); at += parts[t].size(); }
+	std::vector<uint64_t> at((size_t)T + 1, 0);
+	for(int t = 0; t < T; t++) at[t + 1] = at[t] + parts[t].size();
+	if(T == 1) memcpy(out, parts[0].data(), parts[0].size());
+	else {
+		std::vector<std::thread> th;
+		for(int t = 0; t < T; t++) th.emplace_back([&, t]() { memcpy(out + at[t], parts[t].data(), parts[t].size()); });
+		for(auto &x : th) x.join();
+	}
 	return 0;
 }
 
@@ -313,8 +320,9 @@ extern "C" int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads
 // line after '@'; sequence characters are letters ('.' = N), A/C/G/T in either case map to 0..3 and every other
 // letter to 4 (alphabet.cpp asc2dna); the '+' line is skipped; qualities are kept as raw Phred+33 bytes and must
 // number exactly the bases (tooFewQualities / tooManyQualities, pat.cpp:1226-1232).
-extern "C" int bt2g_fastq_parse(const char *text, uint64_t len, uint64_t maxReads, uint64_t maxBases, uint8_t *seq, uint8_t *qual,
-                                uint64_t *off, char *names, uint32_t nameStride, uint64_t *nReads, uint64_t *consumed) {
+// recStart (optional, maxReads + 1 entries): text offset at which each parsed record starts, then the end offset
+static int fastqParseCore(const char *text, uint64_t len, uint64_t maxReads, uint64_t maxBases, uint8_t *seq, uint8_t *qual,
+                          uint64_t *off, char *names, uint32_t nameStride, uint64_t *nReads, uint64_t *consumed, uint64_t *recStarts) {
 	if(!text || !seq || !qual || !off || !nReads || !consumed) return -1;
 	uint64_t cur = 0, n = 0, nb = 0;
 	off[0] = 0;
@@ -323,6 +331,7 @@ extern "C" int bt2g_fastq_parse(const char *text, uint64_t len, uint64_t maxRead
 		while(cur < len && (text[cur] == '\n' || text[cur] == '\r')) cur++;
 		if(cur >= len) break;
 		const uint64_t recStart = cur;
+		if(recStarts) recStarts[n] = recStart;
 		if(text[cur] != '@') return -4;                           // not a FASTQ record
 		cur++;
 		const uint64_t nameBeg = cur;
@@ -367,6 +376,79 @@ extern "C" int bt2g_fastq_parse(const char *text, uint64_t len, uint64_t maxRead
 		n++;
 		off[n] = nb;
 		while(cur < len && (text[cur] == '\n' || text[cur] == '\r')) cur++;
+	}
+	*nReads = n; *consumed = cur;
+	if(recStarts) recStarts[n] = cur;
+	return 0;
+}
+
+extern "C" int bt2g_fastq_parse(const char *text, uint64_t len, uint64_t maxReads, uint64_t maxBases, uint8_t *seq, uint8_t *qual,
+                                uint64_t *off, char *names, uint32_t nameStride, uint64_t *nReads, uint64_t *consumed) {
+	return fastqParseCore(text, len, maxReads, maxBases, seq, qual, off, names, nameStride, nReads, consumed, nullptr);
+}
+
+// Multi-threaded variant: the text is cut at record boundaries (a line starting with '@' whose second-next line starts with
+// '+'), the pieces are parsed concurrently into private buffers and concatenated in order.  Same outputs and error codes as
+// bt2g_fastq_parse for 4-line FASTQ (multi-line sequences fall back to the serial parser).
+extern "C" int bt2g_fastq_parse_mt(const char *text, uint64_t len, uint64_t maxReads, uint64_t maxBases, uint8_t *seq, uint8_t *qual,
+                                   uint64_t *off, char *names, uint32_t nameStride, uint64_t *nReads, uint64_t *consumed, int threads) {
+	if(threads <= 1 || len < (1u << 20))
+		return fastqParseCore(text, len, maxReads, maxBases, seq, qual, off, names, nameStride, nReads, consumed, nullptr);
+	if(!text || !seq || !qual || !off || !nReads || !consumed) return -1;
+	// ---- cut points
+	auto lineEnd = [&](uint64_t p) { while(p < len && text[p] != '\n') p++; return p < len ? p + 1 : len; };
+	std::vector<uint64_t> cuts{0};
+	for(int k = 1; k < threads; k++) {
+		uint64_t p = len / (uint64_t)threads * (uint64_t)k;
+		if(p <= cuts.back()) continue;
+		p = lineEnd(p);                                            // first full line after the target
+		bool found = false;
+		for(int tries = 0; tries < 8 && p < len; tries++) {
+			if(text[p] == '@') {
+				const uint64_t l1 = lineEnd(p), l2 = lineEnd(l1);
+				if(l2 < len && text[l2] == '+') { found = true; break; }
+			}
+			p = lineEnd(p);
+		}
+		if(found && p > cuts.back()) cuts.push_back(p);
+	}
+	cuts.push_back(len);
+	const size_t nc = cuts.size() - 1;
+	if(nc < 2) return fastqParseCore(text, len, maxReads, maxBases, seq, qual, off, names, nameStride, nReads, consumed, nullptr);
+	// private buffers are left uninitialised (new[]): zero-filling them would cost more than the parse
+	struct Piece { std::unique_ptr<uint8_t[]> seq, qual; std::unique_ptr<uint64_t[]> off, starts; std::unique_ptr<char[]> names;
+	               uint64_t n = 0, used = 0; int rc = 0; };
+	std::vector<Piece> pc(nc);
+	std::vector<std::thread> th;
+	for(size_t k = 0; k < nc; k++) th.emplace_back([&, k]() {
+		Piece &q = pc[k];
+		const uint64_t l = cuts[k + 1] - cuts[k];
+		uint64_t nl = 0;
+		for(const char *p = text + cuts[k], *e = p + l; (p = (const char *)memchr(p, '\n', (size_t)(e - p))) != nullptr; p++) nl++;
+		const uint64_t cap = nl / 4 + 2;                           // >= records: each has at least four lines
+		q.seq.reset(new uint8_t[l]); q.qual.reset(new uint8_t[l]); q.off.reset(new uint64_t[cap + 1]); q.starts.reset(new uint64_t[cap + 1]);
+		if(names && nameStride) q.names.reset(new char[cap * (uint64_t)nameStride]());      // zeroed rows (copied whole)
+		q.rc = fastqParseCore(text + cuts[k], l, cap, l, q.seq.get(), q.qual.get(), q.off.get(), q.names.get(),
+		                      nameStride, &q.n, &q.used, q.starts.get());
+	});
+	for(auto &t : th) t.join();
+	// ---- concatenate while the limits allow; a piece that did not end on its boundary (a truncated last record) ends the parse
+	uint64_t n = 0, nb = 0, cur = 0;
+	off[0] = 0;
+	for(size_t k = 0; k < nc; k++) {
+		Piece &q = pc[k];
+		if(q.rc) { if(n == 0 || true) { *nReads = 0; *consumed = 0; return q.rc; } }
+		uint64_t take = q.n;
+		if(n + take > maxReads) take = maxReads - n;
+		while(take > 0 && nb + q.off[take] > maxBases) take--;
+		const uint64_t bases = q.off[take];
+		memcpy(seq + nb, q.seq.get(), bases);
+		memcpy(qual + nb, q.qual.get(), bases);
+		for(uint64_t i = 1; i <= take; i++) off[n + i] = nb + q.off[i];
+		if(names && nameStride && take) memcpy(names + n * (uint64_t)nameStride, q.names.get(), take * (uint64_t)nameStride);
+		n += take; nb += bases;
+		cur = cuts[k] + (take == q.n ? q.used : q.starts[take]);
+		if(take < q.n || cuts[k] + q.used < cuts[k + 1]) break;   // limit reached, or a truncated record at the end of the piece
 	}
 	*nReads = n; *consumed = cur;
 	return 0;

@@ -686,12 +686,16 @@ def sc_filter_maxlen(local: bool) -> int:
 
 
 def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_names=None, pairs=None, threads: int = 1,
-               local: bool = False, xeq: bool = False, no_unal: bool = False, rg_id: str = None) -> str:
+               local: bool = False, xeq: bool = False, no_unal: bool = False, rg_id: str = None, as_bytes: bool = False):
     """SAM text for pipeline results (one record per read).  `lib` is the loaded libbt2g (load_library())."""
     lib.bt2g_sam_format.argtypes = [C.POINTER(_SamOpts), C.POINTER(_Reads), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     rn = (C.c_char_p * len(ref_names))(*[x.encode() for x in ref_names])
-    qn = (C.c_char_p * reads.n)(*[x.encode() for x in read_names]) if read_names is not None else None
+    if isinstance(read_names, NameTable):
+        ptrs = read_names.pointers()                       # no per-name Python work
+        qn = C.cast(ptrs.ctypes.data, C.POINTER(C.c_char_p))
+    else:
+        qn = (C.c_char_p * reads.n)(*[x.encode() for x in read_names]) if read_names is not None else None
     opt = _SamOpts(rn, len(ref_names), qn, int(threads), sc_filter_maxlen(True) if local else 0, 0.0, 0.0,
                    (1 if xeq else 0) | (2 if no_unal else 0), 0, ("RG:Z:" + rg_id).encode() if rg_id else None)
     res = np.ascontiguousarray(res, dtype=READ_RESULT)
@@ -702,35 +706,78 @@ def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_name
         pairs = np.ascontiguousarray(pairs, dtype=PAIR_RESULT)
     st = reads._struct()
     need = C.c_uint64(0)
-    lib.bt2g_sam_format(C.byref(opt), C.byref(st), _ptr(res), _ptr(ops), max_ops, _ptr(pairs), None, 0, C.byref(need))
-    buf = C.create_string_buffer(int(need.value) + 1)
-    rc = lib.bt2g_sam_format(C.byref(opt), C.byref(st), _ptr(res), _ptr(ops), max_ops, _ptr(pairs), buf, need.value, C.byref(need))
+    # one formatting pass in the common case: a buffer sized from the batch (SEQ + QUAL + ~220 bytes of fields per record);
+    # the call reports the size it needs (-3) when that estimate is short
+    cap = int(reads.off[-1]) * 2 + reads.n * 260 + 4096 if reads.n else 4096
+    out = np.empty(cap, dtype=np.uint8)
+    rc = lib.bt2g_sam_format(C.byref(opt), C.byref(st), _ptr(res), _ptr(ops), max_ops, _ptr(pairs), _ptr(out), cap, C.byref(need))
+    if rc == -3:
+        cap = int(need.value)
+        out = np.empty(cap, dtype=np.uint8)
+        rc = lib.bt2g_sam_format(C.byref(opt), C.byref(st), _ptr(res), _ptr(ops), max_ops, _ptr(pairs), _ptr(out), cap, C.byref(need))
     if rc:
         raise RuntimeError(f"bt2g_sam_format failed ({rc})")
-    return buf.raw[:need.value].decode()
+    data = out[:int(need.value)]
+    return data.tobytes() if as_bytes else data.tobytes().decode()
 
 
-EXPORTS += ["bt2g_fastq_parse"]
+EXPORTS += ["bt2g_fastq_parse", "bt2g_fastq_parse_mt"]
 
 
-def fastq_parse(lib, text: bytes, max_reads: int = 1 << 30, name_stride: int = 64):
-    """include/bt2g.h: bt2g_fastq_parse -> (ReadBatch, names, bytes consumed)."""
-    lib.bt2g_fastq_parse.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+class NameTable:
+    """read names as the parser leaves them: one NUL-terminated row of `stride` bytes per read.  Behaves like a list of str
+    (decoded on access); sam_format takes it without touching the individual names."""
+
+    def __init__(self, rows: np.ndarray):
+        self.rows = np.ascontiguousarray(rows, dtype=np.uint8)
+
+    def __len__(self):
+        return self.rows.shape[0]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return NameTable(self.rows[i])
+        return bytes(self.rows[i]).split(b"\0", 1)[0].decode()
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __add__(self, other):
+        return NameTable(np.concatenate([self.rows, other.rows]))
+
+    def pointers(self):
+        """array of char* (one per read) into the table"""
+        n, stride = self.rows.shape
+        return (self.rows.ctypes.data + stride * np.arange(n, dtype=np.uint64)).astype(np.uint64)
+
+
+def fastq_parse(lib, text: bytes, max_reads: int = 1 << 30, name_stride: int = 64, threads: int = 1):
+    """include/bt2g.h: bt2g_fastq_parse[_mt] -> (ReadBatch, names (NameTable), bytes consumed)."""
+    args = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.bt2g_fastq_parse.argtypes = args
+    lib.bt2g_fastq_parse_mt.argtypes = args + [C.c_int]
     cap_reads = min(max_reads, text.count(b"\n") // 4 + 1)
-    seq = np.zeros(len(text), dtype=np.uint8)
-    qual = np.zeros(len(text), dtype=np.uint8)
-    off = np.zeros(cap_reads + 1, dtype=np.uint64)
+    seq = np.empty(len(text), dtype=np.uint8)
+    qual = np.empty(len(text), dtype=np.uint8)
+    off = np.empty(cap_reads + 1, dtype=np.uint64)
+    off[0] = 0
     names = np.zeros((cap_reads, name_stride), dtype=np.uint8)
     n, used = C.c_uint64(0), C.c_uint64(0)
-    rc = lib.bt2g_fastq_parse(text, len(text), cap_reads, len(text), _ptr(seq), _ptr(qual), _ptr(off), _ptr(names), name_stride,
-                              C.byref(n), C.byref(used))
+    if threads > 1:
+        rc = lib.bt2g_fastq_parse_mt(text, len(text), cap_reads, len(text), _ptr(seq), _ptr(qual), _ptr(off), _ptr(names), name_stride,
+                                     C.byref(n), C.byref(used), int(threads))
+    else:
+        rc = lib.bt2g_fastq_parse(text, len(text), cap_reads, len(text), _ptr(seq), _ptr(qual), _ptr(off), _ptr(names), name_stride,
+                                  C.byref(n), C.byref(used))
     if rc:
         raise RuntimeError(f"bt2g_fastq_parse failed ({rc})")
     n = int(n.value)
     nb = int(off[n])
-    nm = [bytes(names[i]).split(b"\0", 1)[0].decode() for i in range(n)]
-    return ReadBatch(seq[:nb].copy(), off[:n + 1].copy(), qual[:nb].copy()), nm, int(used.value)
+    return ReadBatch(seq[:nb], off[:n + 1], qual[:nb]), NameTable(names[:n]), int(used.value)
 
 EXPORTS += ["bt2g_mapq", "bt2g_frame_mate_host", "bt2g_pe_classify_host"]
 

@@ -499,6 +499,11 @@ void bt2g_index_file_close(bt2g_index_file *f);
 /* bt2g_load_index_files with an --offrate override */
 int  bt2g_load_index_files_ex(bt2g_ctx *ctx, const char *basename, int offrate_override);
 
+/* bt2g_fastq_parse on `threads` host threads: the text is cut at record boundaries, the pieces parsed concurrently and
+ * concatenated in input order; outputs, limits and error codes as bt2g_fastq_parse */
+int bt2g_fastq_parse_mt(const char *text, uint64_t len, uint64_t max_reads, uint64_t max_bases, uint8_t *seq, uint8_t *qual,
+                        uint64_t *off, char *names, uint32_t name_stride, uint64_t *n_reads, uint64_t *consumed, int threads);
+
 #ifdef __cplusplus
 }
 #endif

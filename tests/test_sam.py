@@ -418,3 +418,44 @@ def test_alignment_summary_matches_reference_stderr(fixture):
     assert got == want
     if not paired:
         assert align_summary(lib, counts, discord=False, mixed=False) == want
+
+
+def test_fastq_parse_multithreaded_equals_serial():
+    """bt2g_fastq_parse_mt: pieces cut at record boundaries, parsed concurrently, concatenated in order: same arrays, same
+    stopping points under the read limit and with a truncated tail; quality lines starting with '@' do not fool the cutter"""
+    from bowtie2_b200.lib import fastq_parse
+    lib = load_library()
+    rng = np.random.default_rng(4)
+    parts = []
+    n = 30000
+    for i in range(n):
+        ln = int(rng.integers(30, 150))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), ln, p=[0.245, 0.245, 0.245, 0.245, 0.02]))
+        q = bytearray(rng.integers(33, 74, ln).astype(np.uint8).tobytes())
+        if i % 7 == 0:
+            q[0] = ord("@")                                  # a quality string that looks like a header
+        if i % 11 == 0:
+            q[0] = ord("+")
+        parts.append(b"@read%d some comment\n%s\n+\n%s\n" % (i, seq, bytes(q)))
+    text = b"".join(parts)
+    assert len(text) > (1 << 21)
+    b1, n1, u1 = fastq_parse(lib, text, threads=1)
+    for th in (2, 5, 16):
+        b2, n2, u2 = fastq_parse(lib, text, threads=th)
+        assert u2 == u1 == len(text) and b2.n == b1.n == n
+        assert np.array_equal(b1.seq, b2.seq) and np.array_equal(b1.qual, b2.qual) and np.array_equal(b1.off, b2.off)
+        assert np.array_equal(n1.rows, n2.rows)
+    # read limit: stops at the same record as the serial parser
+    b3, n3, u3 = fastq_parse(lib, text, max_reads=12345, threads=1)
+    b4, n4, u4 = fastq_parse(lib, text, max_reads=12345, threads=6)
+    assert b3.n == b4.n == 12345 and u3 == u4 and np.array_equal(b3.seq, b4.seq) and np.array_equal(n3.rows, n4.rows)
+    assert fastq_parse(lib, text[u3:], threads=4)[0].n == n - 12345
+    # truncated tail: whole records only
+    cut = len(text) - 37
+    b5, _, u5 = fastq_parse(lib, text[:cut], threads=1)
+    b6, _, u6 = fastq_parse(lib, text[:cut], threads=8)
+    assert b5.n == b6.n == n - 1 and u5 == u6 and np.array_equal(b5.off, b6.off)
+    # errors surface
+    bad = text[:len(text) // 2] + b"@x\nACGT\n+\nII\n" + text[len(text) // 2:]
+    with pytest.raises(RuntimeError):
+        fastq_parse(lib, bad, threads=4)
