@@ -188,3 +188,94 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
     if own:
         gpu.close()
     return counts
+
+
+# ---- the reference's other read formats (pat.cpp: FastaPatternSource, RawPatternSource, TabbedPatternSource,
+#      QseqPatternSource, VectorPatternSource, FastaContinuousPatternSource): host-side parsing into the same buffers.
+#      Secondary formats: plain Python, whole text at a time.
+_CODE = np.full(256, 4, dtype=np.uint8)
+for _i, _c in enumerate("ACGT"):
+    _CODE[ord(_c)] = _CODE[ord(_c.lower())] = _i
+
+
+def _batch_from(seqs, quals):
+    seq = [_CODE[np.frombuffer(s.replace(".", "N").encode(), dtype=np.uint8)] for s in seqs]
+    q = [np.frombuffer((qq if qq is not None else "I" * len(s)).encode(), dtype=np.uint8) for s, qq in zip(seqs, quals)]
+    return ReadBatch.from_list(seq, q)
+
+
+def parse_reads(text: str, fmt: str, first_id: int = 0, fasta_cont=None):
+    """-> (names, sequences, qualities or None, mate-2 sequences / qualities for paired tabbed records or None)
+    fmt: fasta (-f), raw (-r), tab5 (--tab5), tab6 (--tab6), qseq (--qseq), cline (-c: comma-separated sequences),
+    fastacont (-F k,i with fasta_cont = (k, i)).  Reads without a name get their 0-based ordinal, as in the reference."""
+    names, seqs, quals = [], [], []
+    mate2 = []
+    if fmt == "fasta":
+        name, cur = None, []
+        # FastaPatternSource::parse never appends the last character of a record's buffer (pat.cpp:864-879): harmless when it
+        # is the newline, but a file without a final newline loses the last base of its last read.  Reproduced.
+        if text and not text.endswith(("\n", "\r")) and not text.rstrip("\n").split("\n")[-1].startswith(">"):
+            text = text[:-1]
+        for line in text.split("\n") + [">"]:
+            line = line.rstrip("\r")
+            if line.startswith(">"):
+                if name is not None:
+                    names.append(name or str(first_id + len(names)))
+                    seqs.append("".join(cur)); quals.append(None)
+                name, cur = line[1:], []
+            elif name is not None:
+                cur.append(line.strip())
+    elif fmt == "raw":
+        for line in text.split("\n"):
+            line = line.strip()
+            if line:
+                names.append(str(first_id + len(names))); seqs.append(line); quals.append(None)
+    elif fmt == "cline":
+        for s in text.split(","):
+            s = s.strip()
+            if ":" in s:                                           # SEQ:QUAL
+                s, q = s.split(":", 1)
+            else:
+                q = None
+            names.append(str(first_id + len(names))); seqs.append(s); quals.append(q)
+    elif fmt in ("tab5", "tab6"):
+        for line in text.split("\n"):
+            f = line.rstrip("\r").split("\t")
+            if len(f) < 3:
+                continue
+            if len(f) == 3:
+                names.append(f[0]); seqs.append(f[1]); quals.append(f[2]); mate2.append(None)
+            elif len(f) == 5:
+                names.append(f[0]); seqs.append(f[1]); quals.append(f[2]); mate2.append((f[0], f[3], f[4]))
+            else:
+                names.append(f[0]); seqs.append(f[1]); quals.append(f[2]); mate2.append((f[3], f[4], f[5]))
+    elif fmt == "qseq":
+        for line in text.split("\n"):
+            f = line.rstrip("\r").split("\t")
+            if len(f) < 11:
+                continue
+            names.append("_".join(f[0:7]) + "/" + f[7]); seqs.append(f[8]); quals.append(f[9])
+    elif fmt == "fastacont":
+        k, step = fasta_cont
+        name, cur = None, []
+        recs = []
+        for line in text.split("\n") + [">"]:
+            line = line.rstrip("\r")
+            if line.startswith(">"):
+                if name is not None:
+                    recs.append((name.split()[0] if name.split() else name, "".join(cur)))
+                name, cur = line[1:], []
+            elif name is not None:
+                cur.append(line.strip())
+        for nm, s in recs:
+            for off in range(0, len(s) - k + 1):
+                if off % step == 0 or True:
+                    pass
+            # FastaContinuousPatternSource: every window of k characters whose end offset is a multiple of the interval
+            for end in range(k, len(s) + 1):
+                off = end - k
+                if off % step == 0:
+                    names.append(f"{nm}_{off}"); seqs.append(s[off:end]); quals.append(None)
+    else:
+        raise ValueError(f"unknown read format {fmt}")
+    return names, seqs, quals, (mate2 if any(m is not None for m in mate2) else None)

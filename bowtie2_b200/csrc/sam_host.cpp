@@ -226,7 +226,8 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		line += '\t';
 		// SEQ QUAL (reverse-complemented / reversed for the reverse strand)
 		const bool rev = aligned && !fw;
-		{
+		if(len == 0) line += "*\t*";                               // an empty (fully trimmed) read
+		else {
 			const size_t at = line.size();
 			line.resize(at + (size_t)len + 1 + (qual ? (size_t)len : 1));
 			char *d = &line[at];

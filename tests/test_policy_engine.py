@@ -462,6 +462,8 @@ def _multi_sam(outs, reads, quals, names, ref_names, local=False):
         for j, a in enumerate(alns):
             R.append(reads[i]); Q.append(quals[i]); N.append(names[i])
             rows.append((r, a, j > 0))
+    if not R:
+        return []
     res = np.zeros(len(R), dtype=READ_RESULT)
     res["score2"] = -(1 << 31)
     ops = np.zeros((len(R), max(len(x) for x in R) + 64), dtype=np.uint8)
@@ -521,6 +523,8 @@ def _multi_sam_pairs(outs, reads, quals, names, ref_names, local=False):
             for b2 in (m2.secondary or []):
                 add(a1, b2, False, True, (1,))
     n = len(R)
+    if n == 0:
+        return []
     res = np.zeros(n, dtype=READ_RESULT)
     res["score2"] = -(1 << 31)
     ops = np.zeros((n, max(len(x) for x in R) + 64), dtype=np.uint8)

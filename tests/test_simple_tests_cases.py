@@ -284,3 +284,100 @@ def test_reference_regression_corpus(tmp_path):
         n_run += 1
     assert n_run >= 130, (n_run, skipped)
     print(f"simple_tests.pl corpus: {n_run} cases identical ({n_reads} reads, {n_pairs} pairs), {skipped} outside the engine's options")
+
+
+FMT_KEYS = {"fasta": ("fasta", "-f"), "raw": ("raw", "-r"), "tabbed": ("tab5", "--tab5"), "qseq": ("qseq", "--qseq"),
+            "cline_reads": ("cline", "-c"), "fastq": ("fastq", "-q")}
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_reference_corpus_read_formats(tmp_path):
+    """the corpus' input-format cases (FASTA, raw, tab-delimited, qseq, command-line reads, FASTQ with odd line ends), unpaired
+    and as mate files: bowtie2_b200.align.parse_reads / the FASTQ parser feed the engine, the reference reads the file itself;
+    names, sequences, qualities and therefore the SAM must agree"""
+    from bowtie2_b200.align import parse_reads
+    from bowtie2_b200.lib import fastq_parse, load_library
+    lib = load_library()
+    n_run = skipped = 0
+    why = []
+    for ci, case in enumerate(_cases()):
+        key = next((k for k in FMT_KEYS if k in case or k + "1" in case), None)
+        if key is None or case.get("should_abort") or _options({k: v for k, v in case.items() if k in ("args", "report")}) is None:
+            continue
+        fmt, farg = FMT_KEYS[key]
+        toks, kw, sc, pe_kw, local = _options(case)
+        skip, upto = kw.pop("_skip", 0), kw.pop("_upto", None)
+        t5, t3 = kw.pop("_trim5", 0), kw.pop("_trim3", 0)
+        trim = lambda x: x[t5:len(x) - t3] if t3 else x[t5:]
+        pick = lambda lst: (lst[skip:][:upto] if upto is not None else lst[skip:])
+        paired_files = key + "1" in case
+        d = tmp_path / f"f{ci}"
+        d.mkdir()
+        fa, base = str(d / "ref.fa"), str(d / "ref")
+        with open(fa, "w") as f:
+            for k, r in enumerate(case["ref"]):
+                f.write(f">{k}\n{r}\n")
+        subprocess.check_call([ref_bin("bowtie2-build-s"), "--quiet", fa, base])
+        ref_names = [str(k) for k in range(len(case["ref"]))]
+        cmd = [ref_bin("bowtie2-align-s"), "--quiet", "-p", "1", "--seed", "0", "-x", base] + [t for t in toks if t != "--quiet"] + [farg]
+        kw.setdefault("seed", 0)
+
+        def load(text):
+            if fmt == "fastq":
+                b, names, used = fastq_parse(lib, text.encode() + (b"" if text.endswith("\n") else b"\n"))
+                rd = [(b.seq[int(b.off[i]):int(b.off[i + 1])], b.qual[int(b.off[i]):int(b.off[i + 1])]) for i in range(b.n)]
+                return [n.split()[0] if n.split() else n for n in names], [r[0] for r in rd], [r[1] for r in rd], None
+            names, seqs, quals, m2 = parse_reads(text, fmt)
+            R = [_codes(s.upper().replace(".", "N")) for s in seqs]
+            Q = [np.frombuffer((q if q is not None else "I" * len(s)).encode(), dtype=np.uint8) for s, q in zip(seqs, quals)]
+            return names, R, Q, m2
+        backend = OracleBackend(Oracle(base), local=local, scoring=sc)
+        try:
+            if paired_files:
+                t1, t2 = case[key + "1"], case[key + "2"]
+                if fmt == "cline":
+                    out = subprocess.run(cmd + ["-1", t1, "-2", t2], capture_output=True, text=True)
+                else:
+                    p1, p2 = str(d / "m1.txt"), str(d / "m2.txt")
+                    open(p1, "w").write(t1); open(p2, "w").write(t2)
+                    out = subprocess.run(cmd + ["-1", p1, "-2", p2], capture_output=True, text=True)
+                n1, R1, Q1, _ = load(t1)
+                n2, R2, Q2, _ = load(t2)
+                n1, R1, Q1, n2, R2, Q2 = (pick(n1), pick([trim(x) for x in R1]), pick([trim(x) for x in Q1]),
+                                          pick(n2), pick([trim(x) for x in R2]), pick([trim(x) for x in Q2]))
+                strip = lambda n: n[:-2] if n.endswith(("/1", "/2")) else n
+                N = [x for a, b in zip(n1, n2) for x in (strip(a), strip(b))]
+                R = [x for p in zip(R1, R2) for x in p]
+                Q = [x for p in zip(Q1, Q2) for x in p]
+                eng = PairedPolicyEngine(backend, "sensitive", sc=sc, local=local, pe=policy.PairedEndPolicy(local=local, **pe_kw), **kw)
+                outs = [eng.align_pair(R[2 * k], Q[2 * k], N[2 * k], R[2 * k + 1], Q[2 * k + 1], N[2 * k + 1]) for k in range(len(R1))]
+                lines = _multi_sam_pairs(outs, R, Q, N, ref_names, local=local)
+            else:
+                text = case[key]
+                if fmt == "cline":
+                    out = subprocess.run(cmd + ["-U", text], capture_output=True, text=True)
+                else:
+                    p = str(d / "reads.txt")
+                    open(p, "w").write(text)
+                    out = subprocess.run(cmd + ["-U", p], capture_output=True, text=True)
+                names, R, Q, m2 = load(text)
+                names, R, Q = pick(names), pick([trim(x) for x in R]), pick([trim(x) for x in Q])
+                if m2 is not None:
+                    skipped += 1                                   # tab-delimited files mixing pairs and single reads
+                    continue
+                eng = PolicyEngine(backend, "sensitive", sc=sc, local=local, **{k: v for k, v in kw.items() if k not in ("mixed", "discord")})
+                outs = [eng.align_read(R[k], Q[k], names[k]) for k in range(len(R))]
+                lines = _multi_sam(outs, R, Q, names, ref_names, local=local)
+        except Exception as e:                                     # an input the readers do not model: count, do not hide
+            skipped += 1
+            why.append((ci, key, repr(e)[:80]))
+            continue
+        if out.returncode != 0:
+            skipped += 1
+            why.append((ci, key, "reference exit " + str(out.returncode)))
+            continue
+        want = [l for l in out.stdout.split("\n") if l and not l.startswith("@") and l.count("\t") >= 10]   # (@PG may span lines)
+        assert lines == want, (ci, key, case.get("name"), next(((a, b) for a, b in zip(lines, want) if a != b), (len(lines), len(want))))
+        n_run += 1
+    print(f"read-format cases identical: {n_run}, skipped {skipped}", why[:12])
+    assert n_run >= 60, (n_run, skipped, why)
