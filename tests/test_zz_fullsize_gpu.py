@@ -265,3 +265,46 @@ def test_exact_policy_over_gpu_primitives(paired, lambda_index):
         lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ref, read_names=names, pairs=pairs).rstrip("\n").split("\n")
         assert lines == golden[:2 * n]
     g.close()
+
+
+@pytest.mark.xfail(reason="written after the round's GPU minutes were spent: staged, not yet run on hardware", strict=False)
+@pytest.mark.parametrize("local", [False, True])
+def test_dp_candidate_fates_match_the_oracle_attempt_log(local, synth_index, synth_genome):
+    """bt2g_dp_extend's per-candidate fates: FAILED / SUCCEEDED exactly at the candidates the reference would start a backtrace
+    from (= consume an RNG reseed), in order: what the exact policy needs from the DP kernel beyond the alignments."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from bowtie2_b200 import Bt2Gpu, policy, synth
+    from bowtie2_b200.lib import DP_PROBLEM, ReadBatch
+    from oracle_lib import Oracle, oracle_dp
+    g = Bt2Gpu(0)
+    g.load_index_files(synth_index)
+    g.set_scoring(local=local)
+    O = Oracle(synth_index)
+    sc = policy.Scoring.default(local)
+    reads, quals, truth = synth.make_reads(synth_genome, 300, 100, seed=91, sub_rate=0.03, indel_rate=0.01)
+    probs = np.zeros(len(reads), dtype=DP_PROBLEM)
+    meta = []
+    for i, r in enumerate(reads):
+        c, pos, fw = int(truth[i][0]), int(truth[i][1]), bool(truth[i][2])
+        rdlen = len(r)
+        minsc = sc.min_score(rdlen)
+        tlen = len(synth_genome[c])
+        found, rect = policy.frame_seed_extension_rect(pos, rdlen, tlen, sc.max_read_gaps(minsc, rdlen), sc.max_ref_gaps(minsc, rdlen),
+                                                       sc.n_ceil(rdlen))
+        probs[i] = (i, int(fw), c, rect.refl, rect.refr, rect.triml, rect.corel, rect.corer, minsc, sc.n_ceil_raw(rdlen), 0)
+        meta.append(rect)
+    summ, cands, alns, ops = g.dp_extend(ReadBatch.from_list(reads, quals), probs, max_cands=16384 if local else 512, max_alns=32)
+    n_att = 0
+    for i, r in enumerate(reads):
+        d = oracle_dp(O, local, r, quals[i], bool(probs[i]["fw"]), int(probs[i]["tidx"]), meta[i], int(probs[i]["minsc"]),
+                      int(probs[i]["nceil"]), max_cands=65536, max_alns=64, max_edits=16384, attempts=True)
+        if not d["found"]:
+            continue
+        got = [(ci, int(cands[i][ci]["fate"])) for ci in range(int(summ[i]["ncand"])) if int(cands[i][ci]["fate"]) in (2, 3)]
+        want = [(ci, 3 if ai >= 0 else 2) for (s, ai), ci in zip(d["attempts"], d["attempt_cands"])]
+        assert got == want, (i, got[:6], want[:6])
+        n_att += len(want)
+    assert n_att > 100
+    g.close()
