@@ -287,7 +287,9 @@ def test_dp_candidate_fates_match_the_oracle_attempt_log(local, synth_index, syn
     probs = np.zeros(len(reads), dtype=DP_PROBLEM)
     meta = []
     for i, r in enumerate(reads):
-        c, pos, fw = int(truth[i][0]), int(truth[i][1]), bool(truth[i][2])
+        c, pos, fw = int(truth[i][0]), int(truth[i][1]), int(truth[i][2]) > 0
+        if c < 0:                                           # a random read: frame it anywhere
+            c, pos, fw = 0, 1000 + i, True
         rdlen = len(r)
         minsc = sc.min_score(rdlen)
         tlen = len(synth_genome[c])
