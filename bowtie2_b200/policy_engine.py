@@ -1044,7 +1044,7 @@ class PairedPolicyEngine(PolicyEngine):
                 offset = (interval[mate] * roundi) // nrounds[mate]
                 if offset > 0 and min(L, c.rdlen) + offset > c.rdlen:
                     continue
-                hits = yield ("seed_search", (c.codes, c.quals, L, interval[mate], offset, nofw[mate], norc[mate],))
+                hits = yield ("seed_search", (c.codes, c.quals, min(L, c.rdlen), interval[mate], offset, nofw[mate], norc[mate],))
                 nfw = [max(0, int(h[1]) - int(h[0])) for h in hits[0]]
                 nrc = [max(0, int(h[1]) - int(h[0])) for h in hits[1]]
                 nonz = sum(x > 0 for x in nfw) + sum(x > 0 for x in nrc)

@@ -569,3 +569,42 @@ def test_k_and_all_modes_paired(tmp_path, args, kw):
     lines = _multi_sam_pairs(outs, reads, quals, names, ["chr1", "chr2", "chr3"])
     diff = [(a, b) for a, b in zip(lines, want) if a != b]
     assert len(lines) == len(want) and not diff, (len(lines), len(want), diff[:1])
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("local", [False, True])
+def test_edge_case_pairs(tmp_path, local):
+    """mates of 1-60 bp (shorter than the seed, filtered by length / Ns / minimum score), fragments barely longer than a mate"""
+    from bowtie2_b200.policy_engine import PairedPolicyEngine
+    genome = synth.make_genome(n_contigs=3, contig_len=30000, seed=5, repeat_frac=0.1, repeat_len=200, repeat_copies=10, n_gap=60)
+    fa, base = str(tmp_path / "g.fa"), str(tmp_path / "g")
+    synth.write_fasta(fa, genome)
+    subprocess.check_call([ref_bin("bowtie2-build-s"), "--seed", "0", "--quiet", fa, base])
+    rng = np.random.default_rng(3)
+    R, Q = [], []
+    n = 200
+    for i in range(n):
+        c = int(rng.integers(0, 3)); frag = int(rng.integers(60, 400)); st = int(rng.integers(0, len(genome[c]) - frag))
+        l1 = min(int(rng.choice([1, 5, 12, 18, 21, 22, 25, 40, 60])), frag)
+        l2 = min(int(rng.choice([1, 8, 15, 20, 23, 30, 50, 60])), frag)
+        f = genome[c][st:st + frag]
+        a = f[:l1].copy()
+        b = np.array([4 if x > 3 else 3 - x for x in f[-l2:][::-1]], dtype=np.uint8)
+        if rng.random() < 0.3 and l1 > 3:
+            a[int(rng.integers(0, l1))] = 4
+        if rng.random() < 0.5:
+            a, b = b, a
+        R += [a, b]
+        Q += [np.full(len(a), 73, np.uint8), np.full(len(b), 53, np.uint8)]
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    synth.write_fastq(f1, R[0::2], Q[0::2])
+    synth.write_fastq(f2, R[1::2], Q[1::2])
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), *(["--local"] if local else []), "--sensitive", "--seed", "0", "-p", "1",
+                                   "-x", base, "-1", f1, "-2", f2], stderr=subprocess.DEVNULL).decode()
+    want = [l for l in out.split("\n") if l and not l.startswith("@")]
+    eng = PairedPolicyEngine(OracleBackend(Oracle(base), local=local), "sensitive", local=local)
+    names = [f"r{i // 2}" for i in range(2 * n)]
+    outs = [eng.align_pair(R[2 * i], Q[2 * i], names[2 * i], R[2 * i + 1], Q[2 * i + 1], names[2 * i + 1]) for i in range(n)]
+    lines = _multi_sam_pairs(outs, R, Q, names, ["chr1", "chr2", "chr3"], local=local)
+    bad = [i for i in range(n) if lines[2 * i:2 * i + 2] != want[2 * i:2 * i + 2]]
+    assert not bad, (len(bad), lines[2 * bad[0]:2 * bad[0] + 2], want[2 * bad[0]:2 * bad[0] + 2])
