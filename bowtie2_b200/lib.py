@@ -925,3 +925,89 @@ class IndexFile:
             self.close()
         except Exception:
             pass
+
+
+# ---- the exact search policy in waves (include/bt2g.h: bt2g_policy_align; csrc/policy_engine.cpp) ----------------------
+EXPORTS += ["bt2g_policy_align", "bt2g_policy_backend_gpu"]
+_CB = C.CFUNCTYPE
+_vp = C.c_void_p
+
+
+class _PolicyBackend(C.Structure):
+    _fields_ = [("ctx", _vp),
+                ("exact_sweep", _CB(C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp)),
+                ("seed_search", _CB(C.c_int, _vp, _vp, _vp, _vp, _vp)),
+                ("one_mm", _CB(C.c_int, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp)),
+                ("extend_exact", _CB(C.c_int, _vp, _vp, _vp, _vp, _vp)),
+                ("resolve", _CB(C.c_int, _vp, _vp, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp, _vp, _vp)),
+                ("get_stretch", _CB(C.c_int, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int32, _vp)),
+                ("ungapped", _CB(C.c_int, _vp, _vp, _vp, C.c_uint64, _vp, _vp, C.c_uint32)),
+                ("dp_extend", _CB(C.c_int, _vp, _vp, _vp, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp)),
+                ("off_size", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _PePolicyS(C.Structure):
+    _fields_ = [("pol", C.c_int32), ("flags", C.c_int32), ("maxfrag", C.c_uint64), ("minfrag", C.c_uint64)]
+
+
+class _PolicyParams(C.Structure):
+    _fields_ = [("local", C.c_int32), ("paired", C.c_int32), ("seed_len", C.c_int32), ("seed_rounds", C.c_int32), ("dp_fail_streak", C.c_int32),
+                ("ival_type", C.c_int32), ("ival_const", C.c_double), ("ival_coeff", C.c_double),
+                ("smin_type", C.c_int32), ("smin_const", C.c_double), ("smin_coeff", C.c_double),
+                ("nceil_const", C.c_double), ("nceil_coeff", C.c_double), ("khits", C.c_int64), ("mhits", C.c_int64),
+                ("mmode", C.c_int32), ("all_hits", C.c_int32), ("nofw", C.c_int32), ("norc", C.c_int32), ("discord", C.c_int32),
+                ("mixed", C.c_int32), ("seed", C.c_uint32), ("max_inflight", C.c_int32),
+                ("match_bonus", C.c_int32), ("mmp_max", C.c_int32), ("mmp_min", C.c_int32), ("n_pen", C.c_int32),
+                ("rdgap_const", C.c_int32), ("rdgap_linear", C.c_int32), ("rfgap_const", C.c_int32), ("rfgap_linear", C.c_int32),
+                ("pe", _PePolicyS)]
+
+
+def policy_params(preset="sensitive", local=False, paired=False, seed=0, k=None, all_hits=False, mhits=50, nofw=False, norc=False,
+                  discord=True, mixed=True, pe=None, sc=None, max_inflight=0):
+    from . import policy
+    pre = policy.preset(preset, local)
+    sc = sc or policy.Scoring.default(local)
+    pe = pe or policy.PairedEndPolicy(local=local)
+    smin, nce = sc.score_min(), sc.n_ceil_func()
+    p = _PolicyParams()
+    p.local, p.paired, p.seed_len, p.seed_rounds, p.dp_fail_streak = int(local), int(paired), pre.seed_len, pre.seed_rounds, pre.dp_fail_streak
+    p.ival_type, p.ival_const, p.ival_coeff = pre.ival.type, pre.ival.C, pre.ival.L
+    p.smin_type, p.smin_const, p.smin_coeff = smin.type, smin.C, smin.L
+    p.nceil_const, p.nceil_coeff = nce.C, nce.L
+    p.khits, p.mhits = (k or 0), mhits
+    p.mmode, p.all_hits = int(not (all_hits or k is not None)), int(all_hits)
+    p.nofw, p.norc, p.discord, p.mixed, p.seed, p.max_inflight = int(nofw), int(norc), int(discord), int(mixed), seed, max_inflight
+    p.match_bonus, p.mmp_max, p.mmp_min, p.n_pen = sc.match_bonus, sc.mmp_max, sc.mmp_min, sc.n_pen
+    p.rdgap_const, p.rdgap_linear, p.rfgap_const, p.rfgap_linear = sc.rdgap_const, sc.rdgap_linear, sc.rfgap_const, sc.rfgap_linear
+    p.pe.pol, p.pe.flags, p.pe.maxfrag, p.pe.minfrag = pe.pol, pe.flags(), pe.maxfrag, pe.minfrag
+    return p
+
+
+def policy_align(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads: ReadBatch, names):
+    """include/bt2g.h: bt2g_policy_align -> (results, ops, pairs or None, (waves, backend calls, requests))"""
+    lib.bt2g_policy_align.argtypes = [C.POINTER(_PolicyBackend), C.POINTER(_PolicyParams), C.POINTER(_Reads), _vp, _vp, _vp, C.c_uint32, _vp, _vp]
+    n = reads.n
+    max_ops = int(reads.lengths().max()) + 64 if n else 64
+    res = np.zeros(n, dtype=READ_RESULT)
+    ops = np.zeros((max(n, 1), max_ops), dtype=np.uint8)
+    pairs = np.zeros(n // 2, dtype=PAIR_RESULT) if params.paired else None
+    stats = np.zeros(3, dtype=np.uint64)
+    if isinstance(names, NameTable):
+        qn = C.cast(names.pointers().ctypes.data, _vp)
+        keep = names
+    else:
+        keep = (C.c_char_p * n)(*[x.encode() for x in names])
+        qn = C.cast(keep, _vp)
+    st = reads._struct()
+    rc = lib.bt2g_policy_align(C.byref(backend), C.byref(params), C.byref(st), qn, _ptr(res), _ptr(ops), max_ops, _ptr(pairs), _ptr(stats))
+    if rc:
+        raise RuntimeError(f"bt2g_policy_align failed ({rc})")
+    return res, ops, pairs, tuple(int(x) for x in stats)
+
+
+def policy_backend_gpu(gpu: "Bt2Gpu") -> "_PolicyBackend":
+    be = _PolicyBackend()
+    gpu._lib.bt2g_policy_backend_gpu.argtypes = [_vp, C.POINTER(_PolicyBackend)]
+    gpu._lib.bt2g_policy_backend_gpu.restype = None
+    gpu._lib.bt2g_policy_backend_gpu(gpu._h, C.byref(be))
+    return be

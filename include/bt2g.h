@@ -499,6 +499,50 @@ void bt2g_index_file_close(bt2g_index_file *f);
 /* bt2g_load_index_files with an --offrate override */
 int  bt2g_load_index_files_ex(bt2g_ctx *ctx, const char *basename, int offrate_override);
 
+
+/* ------------------------------------------------------------- the exact search policy, in waves ----- */
+/* The reference's sequential, RNG-driven policy (multiseedSearchWorker + SwDriver::extendSeeds[Paired] + AlnSinkWrap) for a
+ * whole batch: every read (pair) is a coroutine blocked on one hot-path request at a time; per wave the pending requests
+ * are grouped by primitive and answered by ONE call of the entry point below (csrc/policy_engine.cpp; specification and
+ * CPU pinning: bowtie2_b200/policy_engine.py).  The backend table holds those entry points; bt2g_policy_backend_gpu fills it
+ * with this library's own (ctx = the bt2g_ctx), the CPU test-suite fills it with callbacks that answer from the oracle. */
+typedef struct {
+	void *ctx;
+	int (*exact_sweep)(void *, const bt2g_reads *, int, int, uint8_t *, uint64_t *);
+	int (*seed_search)(void *, const bt2g_reads *, const bt2g_seed_plan *, uint64_t *, int32_t *);
+	int (*one_mm)(void *, const bt2g_reads *, const int32_t *, const uint8_t *, int32_t, bt2g_mm_hit *, int32_t *);
+	int (*extend_exact)(void *, const bt2g_reads *, const bt2g_seed_plan *, const uint64_t *, uint8_t *);
+	int (*resolve)(void *, const uint64_t *, const uint32_t *, uint64_t, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *, uint8_t *);
+	int (*get_stretch)(void *, const uint64_t *, const int64_t *, const int32_t *, uint64_t, int32_t, uint8_t *);
+	int (*ungapped)(void *, const bt2g_reads *, const bt2g_ungapped_problem *, uint64_t, bt2g_ungapped_result *, uint8_t *, uint32_t);
+	int (*dp_extend)(void *, const bt2g_reads *, const bt2g_dp_problem *, uint64_t, int32_t, int32_t, int32_t, bt2g_dp_summary *,
+	                 bt2g_dp_cand *, bt2g_dp_aln *, uint8_t *);
+	int32_t off_size;            /* 4 (.bt2) or 8 (.bt2l): width of the RNG draws of eeSaTups */
+	int32_t reserved;
+} bt2g_policy_backend;
+void bt2g_policy_backend_gpu(bt2g_ctx *ctx, bt2g_policy_backend *be);
+
+typedef struct {
+	int32_t local, paired;
+	int32_t seed_len, seed_rounds, dp_fail_streak;          /* -L -R -D (the preset's values) */
+	int32_t ival_type; double ival_const, ival_coeff;       /* -i: 1 const, 2 linear, 3 sqrt, 4 log (simple_func.h) */
+	int32_t smin_type; double smin_const, smin_coeff;       /* --score-min (defaults are FLOAT literals: pass (double)-0.6f) */
+	double  nceil_const, nceil_coeff;                       /* --n-ceil L,const,coeff */
+	int64_t khits;                                          /* -k; 0 with all_hits = -a */
+	int64_t mhits;                                          /* -M (default 50) */
+	int32_t mmode, all_hits;                                /* mmode = no -k / -a given */
+	int32_t nofw, norc, discord, mixed;
+	uint32_t seed; int32_t max_inflight;                    /* --seed; reads (pairs) advanced together (0 = 65536) */
+	int32_t match_bonus, mmp_max, mmp_min, n_pen, rdgap_const, rdgap_linear, rfgap_const, rfgap_linear;
+	bt2g_pe_policy pe;
+} bt2g_policy_params;
+
+/* reads: the batch (mates interleaved when prm->paired); names[i]: read names (the RNG seed depends on them).  Outputs as
+ * bt2g_pipeline_run_[paired_]host: res[n_reads], ops[n_reads * max_ops], pairs[n_reads / 2] (NULL if unpaired).
+ * stats (optional, 3 entries): waves, backend calls, requests.  The primary alignment per read / pair is reported. */
+int bt2g_policy_align(const bt2g_policy_backend *be, const bt2g_policy_params *prm, const bt2g_reads *reads, const char *const *names,
+                      bt2g_read_result *res, uint8_t *ops, uint32_t max_ops, bt2g_pair_result *pairs, uint64_t *stats);
+
 /* bt2g_fastq_parse on `threads` host threads: the text is cut at record boundaries, the pieces parsed concurrently and
  * concatenated in input order; outputs, limits and error codes as bt2g_fastq_parse */
 int bt2g_fastq_parse_mt(const char *text, uint64_t len, uint64_t max_reads, uint64_t max_bases, uint8_t *seq, uint8_t *qual,

@@ -164,3 +164,105 @@ class FakeGpu:
                                len(c) - a.ext - tl, len(o))
                 ops[k, ai, :len(o)] = o
         return summ, cands, alns, ops
+
+
+# ---- FakeGpu behind the C function-pointer table of bt2g_policy_align (bt2g_policy_backend) ---------------------------------
+import ctypes as C
+
+from bowtie2_b200.lib import DP_PROBLEM, UNGAPPED_PROBLEM, ReadBatch, _PolicyBackend, _Reads
+
+
+def _arr(ptr, dtype, n):
+    if not ptr or n == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype)
+
+
+class _SeedPlanS(C.Structure):
+    _fields_ = [("seed_len", C.c_int32), ("max_seeds", C.c_int32), ("nofw", C.c_int32), ("norc", C.c_int32), ("interval", C.c_void_p),
+                ("offset", C.c_void_p)]
+
+
+def _batch(ptr):
+    r = C.cast(ptr, C.POINTER(_Reads)).contents
+    n = int(r.n_reads)
+    off = _arr(r.off, np.uint64, n + 1).copy()
+    nb = int(off[-1]) if n else 0
+    return ReadBatch(_arr(r.seq, np.uint8, nb).copy(), off, _arr(r.qual, np.uint8, nb).copy() if r.qual else None)
+
+
+def backend_table(fake: "FakeGpu"):
+    """-> (_PolicyBackend, keep-alive list): every entry point of the table answered by `fake` in place of the device"""
+    F = dict(_PolicyBackend._fields_)
+
+    def exact_sweep(ctx, reads, nofw, norc, mine, ee):
+        b = _batch(reads)
+        m, e = fake.exact_sweep(b, bool(nofw), bool(norc))
+        _arr(mine, np.uint8, 2 * b.n)[:] = m.reshape(-1)
+        _arr(ee, np.uint64, 4 * b.n)[:] = e.reshape(-1)
+        return 0
+
+    def seed_search(ctx, reads, plan, out, nseeds):
+        b = _batch(reads)
+        p = C.cast(plan, C.POINTER(_SeedPlanS)).contents
+        o, ns = fake.seed_search(b, p.seed_len, _arr(p.interval, np.int32, b.n), _arr(p.offset, np.int32, b.n), p.max_seeds, bool(p.nofw), bool(p.norc))
+        _arr(out, np.uint64, b.n * 2 * p.max_seeds * 4)[:] = o.reshape(-1)
+        _arr(nseeds, np.int32, b.n)[:] = ns
+        return 0
+
+    def one_mm(ctx, reads, minsc, mask, max_hits, hits, counts):
+        from bowtie2_b200.lib import MM_HIT
+        b = _batch(reads)
+        h, c = fake.one_mm(b, _arr(minsc, np.int32, b.n), _arr(mask, np.uint8, b.n), max_hits)
+        _arr(hits, MM_HIT, b.n * 4 * max_hits)[:] = h.reshape(-1)
+        _arr(counts, np.int32, b.n * 4)[:] = c.reshape(-1)
+        return 0
+
+    def extend_exact(ctx, reads, plan, ranges, out):
+        b = _batch(reads)
+        p = C.cast(plan, C.POINTER(_SeedPlanS)).contents
+        rg = _arr(ranges, np.uint64, b.n * 2 * p.max_seeds * 4).reshape(b.n, 2, p.max_seeds, 4)
+        o = fake.extend_exact(b, p.seed_len, _arr(p.interval, np.int32, b.n), _arr(p.offset, np.int32, b.n), p.max_seeds, rg)
+        _arr(out, np.uint8, b.n * 2 * p.max_seeds * 2)[:] = o.reshape(-1)
+        return 0
+
+    def resolve(ctx, rows, hitlen, n, reject, joined, tidx, textoff, tlen, flags):
+        j, t, o, l, f = fake.resolve(_arr(rows, np.uint64, n).copy(), _arr(hitlen, np.uint32, n).copy(), bool(reject))
+        _arr(joined, np.uint64, n)[:] = j; _arr(tidx, np.uint64, n)[:] = t; _arr(textoff, np.uint64, n)[:] = o
+        _arr(tlen, np.uint64, n)[:] = l; _arr(flags, np.uint8, n)[:] = f
+        return 0
+
+    def get_stretch(ctx, tidx, off, count, n, stride, out):
+        s = fake.get_stretch(_arr(tidx, np.uint64, n), _arr(off, np.int64, n), _arr(count, np.int32, n), stride)
+        _arr(out, np.uint8, n * stride)[:] = s.reshape(-1)
+        return 0
+
+    def ungapped(ctx, reads, probs, n, out, mask, stride):
+        from bowtie2_b200.lib import UNGAPPED_RESULT
+        b = _batch(reads)
+        o, m = fake.ungapped(b, _arr(probs, UNGAPPED_PROBLEM, n).copy())
+        _arr(out, UNGAPPED_RESULT, n)[:] = o
+        mm = _arr(mask, np.uint8, n * stride).reshape(n, stride)
+        mm[:, :m.shape[1]] = m[:, :stride]
+        return 0
+
+    def dp_extend(ctx, reads, probs, n, max_cands, max_alns, max_ops, summ, cands, alns, ops):
+        from bowtie2_b200.lib import DP_ALN, DP_CAND, DP_SUMMARY
+        b = _batch(reads)
+        s, c, a, o = fake.dp_extend(b, _arr(probs, DP_PROBLEM, n).copy(), max_cands, max_alns, max_ops)
+        _arr(summ, DP_SUMMARY, n)[:] = s
+        _arr(cands, DP_CAND, n * max_cands)[:] = c.reshape(-1)
+        _arr(alns, DP_ALN, n * max_alns)[:] = a.reshape(-1)
+        _arr(ops, np.uint8, n * max_alns * max_ops)[:] = o.reshape(-1)
+        return 0
+
+    be = _PolicyBackend()
+    keep = []
+    for name, fn in (("exact_sweep", exact_sweep), ("seed_search", seed_search), ("one_mm", one_mm), ("extend_exact", extend_exact),
+                     ("resolve", resolve), ("get_stretch", get_stretch), ("ungapped", ungapped), ("dp_extend", dp_extend)):
+        cb = F[name](fn)
+        keep.append(cb)
+        setattr(be, name, cb)
+    be.off_size = fake.info()["off_size"]
+    return be, keep
