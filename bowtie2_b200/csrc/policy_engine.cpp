@@ -708,11 +708,352 @@ Result Engine::finishRead() {
 
 
 // ---------------------------------------------------------------------------------------------- pairs
-//PAIRS_BEGIN
-Task<int> Engine::extendSeedsPaired(int, SeedHits *, std::vector<EEHit>) { co_return EXHAUSTED; }
-Task<PairOut> Engine::pairSteps(int, const uint8_t *, const uint8_t *, int, std::string, const uint8_t *, const uint8_t *, int, std::string) { co_return PairOut{}; }
-PairOut Engine::finishPair() { return PairOut{}; }
-//PAIRS_END
+static bool frameMateRect(bool anchorLeft, int64_t ll, int64_t lr, int64_t rl, int64_t rr, int rdlen, int64_t reflen, int maxrdgap, int maxrfgap,
+                          int maxhalf, DPRect &r) {
+	// DynProgFramer::frameFindMateRect (dp_framer.cpp:177-361): maxgap = max(gaps, maxhalf)
+	const uint64_t a = (uint64_t)(int64_t)maxrdgap, b = (uint64_t)(int64_t)maxrfgap;
+	const int64_t maxgap = (int64_t)std::max<uint64_t>(std::max(a, b), (uint64_t)maxhalf);
+	int64_t refl, refr;
+	if(anchorLeft) { refl = (rl - (rdlen - 1)) - maxgap; refr = rr + maxgap; }
+	else { refl = ll - maxgap; refr = (lr + (rdlen - 1)) + maxgap; }
+	int64_t triml = 0, trimr = 0;
+	if(refr >= reflen) trimr = refr - (reflen - 1);
+	if(refl < 0) triml = -refl;
+	const int64_t width = refr - refl + 1;
+	r = DPRect{refl + triml, refr - trimr, refl, refr, triml, trimr, maxgap, width - maxgap - 1, maxgap};
+	return !r.trimmedAway();
+}
+
+Task<int> Engine::extendSeedsPaired(int ai, SeedHits *sh, std::vector<EEHit> eeExact) {
+	const bool anchor1 = ai == 0;
+	Mate &c = m[ai], &o = m[ai ^ 1]; cur = &c;
+	const int rdlen = c.rdlen, ordlen = o.rdlen;
+	const bool oppFilt = !o.filt;
+	const int64_t operfect = o.perfect, bestPairScore = c.perfect + operfect;
+	auto tightened = [&]() {
+		int64_t ps = psink.best2Pair + ((psink.bestPair - psink.best2Pair) * 3) / 4;     // tighten == 3
+		if(ps < bestPairScore) ps++;
+		return ps;
+	};
+	const bool canTighten = P.mmode;
+	if(canTighten && psink.best2Pair != MIN_I64) { const int64_t nc = tightened() - operfect; if(nc > c.minsc) c.minsc = nc; }
+	const int64_t nonz = sh ? sh->nonz : 0;
+	bool eeMode = !eeExact.empty() || !c.mm1.empty(), firstEe = true, firstExtend = true, swMateImmediately = true;
+	int64_t nEeFail = 0, nUgFail = 0, nDpFail = 0, neltLeft = 0;
+	const int64_t streak = streakCur;
+	std::vector<SatEntry> satpos; std::vector<EEHit> hitList; std::vector<int64_t> mateStreaks;
+	for(;;) {
+		if(eeMode) { if(firstEe) { firstEe = false; eeSaTups(eeExact, satpos, hitList); mateStreaks.assign(satpos.size(), 0); } else eeMode = false; }
+		if(!eeMode) {
+			if(nonz == 0) co_return EXHAUSTED;
+			if(P.mmode && c.minsc == c.perfect) co_return PERFECT;
+			if(firstExtend) { neltLeft = co_await prioritize(*sh, satpos); firstExtend = false; mateStreaks.assign(satpos.size(), 0); }
+			if(neltLeft == 0) break;
+		}
+		for(size_t si = 0; si < satpos.size(); si++) {
+			SatEntry &se = satpos[si];
+			const EEHit *eh = eeMode ? &hitList[se.ee] : nullptr;
+			if(eeMode && eh->score < c.minsc) co_return PERFECT;
+			const bool isSmall = se.sp.size < 5, fw = se.sp.fw;
+			int rdoff = se.sp.rdoff;
+			if(!fw) rdoff = rdlen - rdoff - se.sp.seedlen;
+			bool first = true;
+			while(!se.rands.done() && (first || isSmall || eeMode)) {
+				if(c.minsc == c.perfect) { if(!eeMode || eh->score < c.perfect) co_return PERFECT; }
+				else if(eeMode && eh->score < c.minsc) break;
+				if(nDps >= P.maxDp || nMateDps >= P.maxDp || nUgs >= P.maxUg || nIters >= P.maxIters) co_return HARD_LIMIT;
+				if(eeMode && nEeFail >= streak) co_return SOFT_LIMIT;
+				if(!eeMode && (nDpFail >= streak || nUgFail >= streak)) co_return SOFT_LIMIT;
+				if(mateStreaks[si] >= P.maxMateStreak) { se.rands.setDone(); break; }
+				nIters++; first = false;
+				const size_t elt = se.rands.next(rnd);
+				Req rq; rq.kind = RQ_RESOLVE; rq.row = se.sp.topf + elt; rq.qlen = se.sp.keyLen; rq.reject = eeMode;
+				co_await AwaitReq{slot, &rq};
+				neltLeft--;
+				if(!rq.ok) continue;
+				const int64_t tidx = rq.rtidx, toff = rq.rtoff, tlen = rq.rtlen, refoff = toff - rdoff;
+				if(c.seen.present(tidx, fw, refoff)) continue;
+				int readGaps = 0, refGaps = 0; bool ungapped = false;
+				if(!eeMode) { readGaps = P.maxReadGaps(c.minsc, rdlen); refGaps = P.maxRefGaps(c.minsc, rdlen); ungapped = readGaps == 0 && refGaps == 0; }
+				int state = 0; Aln fixed; Req dq;
+				if(eeMode) { fixed = eeAln(*eh, tidx, refoff, fw, rdlen); state = 1; c.seen.add(tidx, fw, refoff, 1); nEeFail++; }
+				else if(ungapped) {
+					Req uq; uq.kind = RQ_UNGAPPED; uq.read = c.idx; uq.fw = fw; uq.tidx = tidx; uq.refoff = refoff; uq.tlen = tlen; uq.minsc = c.minsc;
+					co_await AwaitReq{slot, &uq};
+					c.seen.add(tidx, fw, refoff, 1);
+					nUgs++; nUgFail++;
+					if(uq.ugStatus == 0) continue;
+					if(uq.ugStatus == 1) { fixed = uq.ugAln; state = 2; }
+				}
+				if(state == 0) {
+					DPRect rect;
+					const bool found = frameSeedRect(refoff, rdlen, tlen, readGaps, refGaps, 15, rect);
+					c.seen.add(tidx, fw, refoff, 1);
+					if(!found) continue;
+					c.seen.add(tidx, fw, rect.reflPre + rect.corel, rect.corer - rect.corel + 1);
+					dq.kind = RQ_DP; dq.read = c.idx;
+					dq.prob = bt2g_dp_problem{}; dq.prob.fw = fw; dq.prob.tidx = (uint64_t)tidx; dq.prob.refl = rect.refl; dq.prob.refr = rect.refr;
+					dq.prob.triml = (int32_t)rect.triml; dq.prob.corel = (int32_t)rect.corel; dq.prob.corer = (int32_t)rect.corer;
+					dq.prob.minsc = (int32_t)c.minsc; dq.prob.nceil = P.nCeilRaw(rdlen);
+					co_await AwaitReq{slot, &dq};
+					nDps++; nDpFail++;
+					if(!dq.dp.found) continue;
+					dq.dp.cursor = 0; dq.dp.u8 = dpU8(dq.dp, c.minsc, c);
+				}
+				bool firstInner = true, foundConcordant = false;
+				for(;;) {
+					Aln a;
+					if(state != 0) { if(!firstInner) break; a = fixed; }
+					else if(!nextAlignment(dq.dp, c.minsc, a)) break;
+					firstInner = false;
+					if(red.overlap(a)) continue;
+					red.add(a);
+					if(psink.doneWithMate(!anchor1) && !psink.doneWithMate(anchor1)) swMateImmediately = false;
+					if(swMateImmediately) {
+						bool foundMate = !oppFilt;
+						int64_t ominscCur = o.minsc;
+						Req oq; bool oleft = false, ofw = false; int64_t oll = 0, olr = 0, orl = 0, orr = 0; int ordgaps = 0, orfgaps = 0;
+						if(foundMate) {
+							if(canTighten && psink.best2Pair != MIN_I64) { const int64_t nc = tightened() - a.score; if(nc > ominscCur) ominscCur = nc; }
+							ordgaps = P.maxReadGaps(ominscCur, ordlen); orfgaps = P.maxRefGaps(ominscCur, ordlen);
+							foundMate = pe_other_mate(P.pe, anchor1, fw, a.refoff, (int64_t)ordlen + ordgaps, (uint64_t)(anchor1 ? rdlen : ordlen),
+							                          (uint64_t)(anchor1 ? ordlen : rdlen), oleft, oll, olr, orl, orr, ofw);
+						}
+						DPRect orect{};
+						if(foundMate) foundMate = frameMateRect(!oleft, oll, olr, orl, orr, ordlen, tlen, ordgaps, orfgaps, 15, orect);
+						if(foundMate) {
+							oq.kind = RQ_DP; oq.read = o.idx;
+							oq.prob = bt2g_dp_problem{}; oq.prob.fw = ofw; oq.prob.tidx = (uint64_t)tidx; oq.prob.refl = orect.refl; oq.prob.refr = orect.refr;
+							oq.prob.triml = (int32_t)orect.triml; oq.prob.corel = (int32_t)orect.corel; oq.prob.corer = (int32_t)orect.corer;
+							oq.prob.minsc = (int32_t)ominscCur; oq.prob.nceil = P.nCeilRaw(ordlen);
+							co_await AwaitReq{slot, &oq};
+							nMateDps++;
+							foundMate = oq.dp.found;
+							if(foundMate) { oq.dp.cursor = 0; oq.dp.u8 = dpU8(oq.dp, ominscCur, o); }
+						}
+						bool didAnchor = false, brk = false;
+						for(;;) {
+							Aln oa; bool haveOa = false;
+							if(foundMate) { haveOa = nextAlignment(oq.dp, ominscCur, oa); foundMate = haveOa; }
+							int64_t oext = 0;
+							if(foundMate) {
+								if(!red.overlap(oa)) red.add(oa);
+								oext = oa.refExtent();
+								if(oa.refoff < 0 || oa.refoff + oext > tlen) foundMate = false;
+							}
+							int pairCl = 5;
+							if(foundMate) {
+								const int64_t aext = a.refExtent();
+								const Aln &a1 = anchor1 ? a : oa, &a2 = anchor1 ? oa : a;
+								pairCl = pe_classify(P.pe, a1.refoff, (uint64_t)(anchor1 ? aext : oext), a1.fw, a2.refoff, (uint64_t)(anchor1 ? oext : aext), a2.fw);
+							}
+							if(psink.doneConcord) foundMate = false;
+							if(foundMate) {
+								bool doneUnpaired = false;
+								if(!anchor1 || !didAnchor) {
+									if(anchor1) didAnchor = true;
+									const Aln &r1 = anchor1 ? a : oa;
+									if(!redMate[0].overlap(r1)) { redMate[0].add(r1); if(psink.report(&r1, nullptr)) doneUnpaired = true; }
+								}
+								if(anchor1 || !didAnchor) {
+									if(!anchor1) didAnchor = true;
+									const Aln &r2 = anchor1 ? oa : a;
+									if(!redMate[1].overlap(r2)) { redMate[1].add(r2); if(psink.report(nullptr, &r2)) doneUnpaired = true; }
+								}
+								bool donePaired = false;
+								if(pairCl != 5) {
+									foundConcordant = true;
+									if(psink.report(anchor1 ? &a : &oa, anchor1 ? &oa : &a)) donePaired = true;
+									else if(canTighten && psink.best2Pair != MIN_I64) {
+										const int64_t nc = tightened() - operfect;
+										if(nc > c.minsc) { c.minsc = nc; if(c.minsc > a.score) brk = true; }
+									}
+								}
+								if(brk) break;
+								if(donePaired || doneUnpaired) co_return FULFILLED;
+								if(psink.doneWithMate(anchor1)) co_return FULFILLED;
+							} else if((P.mixed || P.discord) && !didAnchor) {
+								didAnchor = true;
+								if(!psink.doneUnp[anchor1 ? 0 : 1]) {
+									RedundantAlns &rm = redMate[anchor1 ? 0 : 1];
+									if(!rm.overlap(a)) { rm.add(a); if(psink.report(anchor1 ? &a : nullptr, anchor1 ? nullptr : &a)) co_return FULFILLED; }
+								}
+								if(psink.doneWithMate(anchor1)) co_return FULFILLED;
+							}
+							if(!haveOa) break;
+						}
+					} else if(P.mixed || P.discord) {
+						if(!psink.doneUnp[anchor1 ? 0 : 1]) {
+							RedundantAlns &rm = redMate[anchor1 ? 0 : 1];
+							if(!rm.overlap(a)) { rm.add(a); if(psink.report(anchor1 ? &a : nullptr, anchor1 ? nullptr : &a)) co_return FULFILLED; }
+						}
+						if(psink.doneWithMate(anchor1)) co_return FULFILLED;
+					}
+				}
+				if(foundConcordant) { mateStreaks[si] = 0; if(state == 2) nUgFail = 0; else if(state == 1) nEeFail = 0; else nDpFail = 0; }
+				else mateStreaks[si]++;
+			}
+		}
+	}
+	co_return EXHAUSTED;
+}
+
+Task<PairOut> Engine::pairSteps(int idx1, const uint8_t *c1, const uint8_t *q1, int l1, std::string n1, const uint8_t *c2, const uint8_t *q2, int l2, std::string n2) {
+	const uint8_t *cs[2] = {c1, c2}, *qs[2] = {q1, q2}; const int ls[2] = {l1, l2}; const std::string ns[2] = {n1, n2};
+	for(int k = 0; k < 2; k++) {
+		Mate &c = m[k];
+		c.codes = cs[k]; c.quals = qs[k]; c.name = ns[k]; c.idx = idx1 + k; c.rdlen = ls[k];
+		c.minsc = ls[k] ? P.minScore(ls[k]) : 0; c.perfect = P.perfect(ls[k]); c.nceil = ls[k] ? P.nCeil(ls[k]) : 0;
+		int nn = 0; for(int i = 0; i < ls[k]; i++) nn += cs[k][i] > 3;
+		c.filt = !(ls[k] < 2 || nn > P.nCeil(ls[k]) || P.perfect(ls[k]) < P.minScore(ls[k]));
+	}
+	const bool both = m[0].filt && m[1].filt;
+	const uint32_t s1 = genRandSeed(c1, q1, l1, n1, P.seed), s2 = genRandSeed(c2, q2, l2, n2, P.seed);
+	rnd.init(both ? (s1 ^ s2) : s1);
+	int interval[2];
+	for(int k = 0; k < 2; k++) interval[k] = ls[k] ? P.seedInterval(ls[k], both) : 1;
+	int64_t streak = P.streak; int nroundsAll = P.seedRounds;
+	if(both) { streak = (streak + 1) / 2; nroundsAll = (nroundsAll + 1) / 2; }
+	streakCur = streak;
+	psink = PairedSink{P.khits, P.mhits, P.mmode};
+	psink.doneDiscord = !P.discord; psink.doneUnp[0] = psink.doneUnp[1] = !P.mixed;
+	const bool m1fw = P.pe.pol == 1 || P.pe.pol == 3, m2fw = P.pe.pol == 1 || P.pe.pol == 4;
+	const bool nofw[2] = {m1fw ? P.nofw : P.norc, m2fw ? P.nofw : P.norc}, norc[2] = {m1fw ? P.norc : P.nofw, m2fw ? P.norc : P.nofw};
+	bool done[2] = {!m[0].filt, !m[1].filt};
+	int matemap[2] = {0, 1}; int64_t nelt[2] = {0, 0}; int mined[2][2] = {{0, 0}, {0, 0}};
+	auto after = [&](int ret, int mate) {
+		if(ret == FULFILLED) { if(psink.doneWithMate(mate == 0)) done[mate] = true; if(psink.doneWithMate(mate == 1)) done[mate ^ 1] = true; }
+		else if(ret == PERFECT || ret == HARD_LIMIT) done[mate] = true;
+	};
+	// ---- exact end-to-end
+	for(int mi = 0; mi < 2; mi++) {
+		const int mate = matemap[mi]; Mate &c = m[mate];
+		if(!c.filt || done[mate] || psink.doneWithMate(mate == 0)) continue;
+		Req sw; sw.kind = RQ_EXACT_SWEEP; sw.read = c.idx; sw.nofw = nofw[mate]; sw.norc = norc[mate];
+		co_await AwaitReq{slot, &sw};
+		nelt[mate] = (int64_t)sw.nelt; mined[mate][0] = sw.mined[0]; mined[mate][1] = sw.mined[1];
+		c.ee.clear();
+		if(sw.tb[1] > sw.tb[0]) c.ee.push_back(EEHit{sw.tb[0], sw.tb[1], true, c.perfect});
+		if(sw.tb[3] > sw.tb[2]) c.ee.push_back(EEHit{sw.tb[2], sw.tb[3], false, c.perfect});
+	}
+	if(nelt[0] > 0 && nelt[1] > 0 && nelt[0] > nelt[1]) { matemap[0] = 1; matemap[1] = 0; } else { matemap[0] = 0; matemap[1] = 1; }
+	for(int mi = 0; mi < 2; mi++) {
+		const int mate = matemap[mi]; Mate &c = m[mate];
+		if(nelt[mate] == 0) { c.ee.clear(); continue; }
+		if(psink.doneWithMate(mate == 0)) { c.ee.clear(); done[mate] = true; continue; }
+		std::vector<EEHit> ee = c.ee;
+		const int ret = co_await extendSeedsPaired(mate, nullptr, ee);
+		c.ee.clear();
+		after(ret, mate);
+		if(!done[mate] && c.minsc == c.perfect) done[mate] = true;
+	}
+	// ---- 1-mismatch end-to-end
+	for(int mi = 0; mi < 2; mi++) {
+		const int mate = matemap[mi]; Mate &c = m[mate];
+		if(!c.filt || done[mate]) { c.mm1.clear(); nelt[mate] = 0; continue; }
+		nelt[mate] = 0;
+		const bool yfw = mined[mate][0] <= 1 && !nofw[mate], yrc = mined[mate][1] <= 1 && !norc[mate];
+		if(yfw || yrc) {
+			Req mq; mq.kind = RQ_ONE_MM; mq.read = c.idx; mq.minsc = c.minsc; mq.nofw = !yfw; mq.norc = !yrc;
+			co_await AwaitReq{slot, &mq};
+			c.mm1.clear();
+			for(const Req::MmHit &h : mq.mm) { c.mm1.push_back(EEHit{h.top, h.bot, h.fw, h.score, true, Edit{h.pos, h.chr, h.qchr, 3}}); nelt[mate] += (int64_t)(h.bot - h.top); }
+		}
+	}
+	if(nelt[0] > 0 && nelt[1] > 0 && nelt[0] > nelt[1]) { matemap[0] = 1; matemap[1] = 0; } else { matemap[0] = 0; matemap[1] = 1; }
+	for(int mi = 0; mi < 2; mi++) {
+		const int mate = matemap[mi]; Mate &c = m[mate];
+		if(nelt[mate] == 0) continue;
+		if(psink.doneWithMate(mate == 0)) { done[mate] = true; continue; }
+		const int ret = co_await extendSeedsPaired(mate, nullptr, {});
+		c.mm1.clear();
+		after(ret, mate);
+		if(!done[mate] && c.minsc == c.perfect) done[mate] = true;
+	}
+	// ---- seed rounds
+	const int nrounds[2] = {std::min(nroundsAll, interval[0]), std::min(nroundsAll, interval[1])};
+	const int L = P.seedLen;
+	for(int roundi = 0; roundi < P.seedRounds; roundi++) {
+		m[0].hasSh = m[1].hasSh = false;
+		for(int mi = 0; mi < 2; mi++) {
+			const int mate = matemap[mi]; Mate &c = m[mate];
+			if(done[mate] || psink.doneWithMate(mate == 0)) { done[mate] = true; continue; }
+			if(roundi >= nrounds[mate] || interval[mate] <= roundi) continue;
+			const int offset = (interval[mate] * roundi) / nrounds[mate];
+			if(offset > 0 && std::min(L, c.rdlen) + offset > c.rdlen) continue;
+			Req sq; sq.kind = RQ_SEED_SEARCH; sq.read = c.idx; sq.L = std::min(L, c.rdlen); sq.interval = interval[mate]; sq.offset = offset; sq.nofw = nofw[mate]; sq.norc = norc[mate];
+			co_await AwaitReq{slot, &sq};
+			fillSeedHits(c.sh, sq, interval[mate], offset, std::min(L, c.rdlen));
+			if(c.sh.nonz == 0) { done[mate] = true; break; }
+			c.hasSh = true;
+		}
+		double uniq[2] = {0.0, 0.0};
+		for(int k = 0; k < 2; k++) if(m[k].hasSh) {
+			for(int64_t x : m[k].sh.nfw) if(x > 0) uniq[k] += 1.0 / (double)(x * x);
+			for(int64_t x : m[k].sh.nrc) if(x > 0) uniq[k] += 1.0 / (double)(x * x);
+		}
+		if(m[0].hasSh && m[1].hasSh && uniq[1] > uniq[0]) { matemap[0] = 1; matemap[1] = 0; } else { matemap[0] = 0; matemap[1] = 1; }
+		for(int mi = 0; mi < 2; mi++) {
+			const int mate = matemap[mi]; Mate &c = m[mate];
+			if(done[mate] || psink.doneWithMate(mate == 0)) { done[mate] = true; continue; }
+			if(!c.hasSh) continue;
+			cur = &c;
+			rankSeedHits(c.sh);
+			after(co_await extendSeedsPaired(mate, &c.sh, {}), mate);
+		}
+		for(int k = 0; k < 2; k++) if(!done[k] && m[k].hasSh && m[k].sh.nelt / m[k].sh.nonz < 300) done[k] = true;
+	}
+	co_return finishPair();
+}
+
+PairOut Engine::finishPair() {
+	PairOut po;
+	const int64_t mn[2] = {m[0].rdlen ? P.minScore(m[0].rdlen) : 0, m[1].rdlen ? P.minScore(m[1].rdlen) : 0};
+	// selectByScore over pairs / unpaired lists (aln_sink.cpp:1477-1628)
+	auto select = [&](const std::vector<Aln> &r1, const std::vector<Aln> *r2, std::vector<std::pair<int64_t, int>> &buf) {
+		buf.clear();
+		for(size_t i = 0; i < r1.size(); i++) buf.push_back({r1[i].score + (r2 ? (*r2)[i].score : 0), (int)i});
+		std::sort(buf.begin(), buf.end(), [](auto &a, auto &b) { return a > b; });
+		shuffleEqualStreaks(buf, [](const std::pair<int64_t, int> &t) { return t.first; }, rnd);
+	};
+	std::vector<std::pair<int64_t, int>> buf;
+	auto unchosenP = [&](const std::vector<Aln> &rsu, const Aln &chosen, bool &has, int64_t &best) {
+		has = false; best = 0;
+		for(const Aln &a : rsu) { if(a.tidx == chosen.tidx && a.refoff == chosen.refoff && a.fw == chosen.fw) continue; if(!has || a.score > best) { has = true; best = a.score; } }
+	};
+	if(psink.nconcord > 0) {
+		select(psink.rs1, &psink.rs2, buf);
+		const Aln &a1 = psink.rs1[buf[0].second], &a2 = psink.rs2[buf[0].second];
+		const bool hasC = buf.size() > 1;
+		const int mq = (int)mapq(a1.score + a2.score, hasC, hasC ? buf[1].first : 0, mn[0] + mn[1], m[0].perfect + m[1].perfect);
+		for(int k = 0; k < 2; k++) {
+			Result &r = po.m[k]; r.aligned = true; r.aln = k == 0 ? a1 : a2; r.mapq = mq;
+			unchosenP(k == 0 ? psink.rs1u : psink.rs2u, r.aln, r.hasXs, r.xs);
+		}
+		po.pairType = 1;
+		return po;
+	}
+	if(!psink.doneDiscord && psink.nunp[0] == 1 && psink.nunp[1] == 1) {
+		const Aln &a1 = psink.rs1u[0], &a2 = psink.rs2u[0];
+		const int mq = (int)mapq(a1.score + a2.score, false, 0, mn[0] + mn[1], m[0].perfect + m[1].perfect);
+		for(int k = 0; k < 2; k++) { Result &r = po.m[k]; r.aligned = true; r.aln = k == 0 ? a1 : a2; r.mapq = mq; }
+		po.pairType = 2;
+		return po;
+	}
+	int nal = 0;
+	for(int k = 0; k < 2; k++) {
+		const std::vector<Aln> &rsu = k == 0 ? psink.rs1u : psink.rs2u;
+		if(rsu.empty() || !P.mixed) continue;
+		select(rsu, nullptr, buf);
+		Result &r = po.m[k]; r.aligned = true; r.aln = rsu[buf[0].second];
+		r.hasXs = buf.size() > 1; r.xs = r.hasXs ? rsu[buf[1].second].score : 0;
+		r.mapq = (int)mapq(r.aln.score, r.hasXs, r.xs, mn[k], m[k].perfect);
+		nal++;
+	}
+	po.pairType = nal == 2 ? 2 : (nal == 1 ? 3 : 0);
+	return po;
+}
+
 
 // ---------------------------------------------------------------------------------------------- waves
 struct Batch {                                        // a sub-batch of reads for one entry-point call

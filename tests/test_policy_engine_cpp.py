@@ -1,0 +1,129 @@
+"""csrc/policy_engine.cpp (bt2g_policy_align): the exact search policy as C++20 coroutines scheduled in waves over the
+entry-point table.  With the table answered by the CPU oracle behind the entry points' own array conventions
+(tests/fake_gpu.py) the SAM must be identical to the reference program's golden files, and the result arrays identical to
+the Python engine's (the pinned specification) across modes and options."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bowtie2_b200 import policy, synth
+from bowtie2_b200.lib import PAIR_RESULT, READ_RESULT, ReadBatch, load_library, policy_align, policy_params, sam_format
+from bowtie2_b200.policy_engine import PairedPolicyEngine, PolicyEngine
+from conftest import GOLDEN, read_fastq_codes
+from fake_gpu import FakeGpu, backend_table
+from oracle_lib import Oracle, have_reference, ref_bin
+from policy_backend import OracleBackend
+from test_policy_engine import _fill
+
+
+def _table(index, local=False, off_size=4):
+    fake = FakeGpu(Oracle(index), off_size)
+    fake.set_scoring(local)
+    be, keep = backend_table(fake)
+    return be, keep, fake
+
+
+@pytest.mark.parametrize("fixture,index,ref_names,local", [
+    ("lambda_U_sensitive", "lambda_index", ["gi|9626243|ref|NC_001416.1|"], False),
+    ("lambda_U_local", "lambda_index", ["gi|9626243|ref|NC_001416.1|"], True),
+    ("rep_U_sensitive", "rep_index", ["ctg1", "ctg2"], False),
+])
+def test_unpaired_sam_identical_to_golden(fixture, index, ref_names, local, request):
+    base = request.getfixturevalue(index)
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, fixture + ".sam")) if not l.startswith("@")]
+    names, reads, quals = read_fastq_codes(os.path.join(GOLDEN, fixture.split("_")[0] + "_reads_1.fq"), len(golden))
+    be, keep, fake = _table(base, local)
+    lib = load_library()
+    batch = ReadBatch.from_list(reads, quals)
+    res, ops, _, (waves, calls, requests) = policy_align(lib, be, policy_params("sensitive", local=local), batch, names)
+    lines = sam_format(lib, batch, res, ops, ref_names, read_names=names, local=local).rstrip("\n").split("\n")
+    assert lines == golden
+    assert waves < 80 and calls * 20 < requests          # batched: one entry-point call per primitive and wave
+
+
+@pytest.mark.parametrize("fixture,index,ref_names", [
+    ("lambda", "lambda_index", ["gi|9626243|ref|NC_001416.1|"]),
+    ("rep", "rep_index", ["ctg1", "ctg2"]),
+])
+def test_paired_sam_identical_to_golden(fixture, index, ref_names, request):
+    base = request.getfixturevalue(index)
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, f"{fixture}_P_sensitive.sam")) if not l.startswith("@")]
+    n = len(golden) // 2
+    n1, r1, q1 = read_fastq_codes(os.path.join(GOLDEN, f"{fixture}_reads_1.fq"), n)
+    n2, r2, q2 = read_fastq_codes(os.path.join(GOLDEN, f"{fixture}_reads_2.fq"), n)
+    il = lambda a, b: [x for p in zip(a, b) for x in p]
+    R, Q, N = il(r1, r2), il(q1, q2), il(n1, n2)
+    be, keep, fake = _table(base)
+    lib = load_library()
+    batch = ReadBatch.from_list(R, Q)
+    res, ops, pairs, stats = policy_align(lib, be, policy_params("sensitive", paired=True, max_inflight=64), batch, N)
+    lines = sam_format(lib, batch, res, ops, ref_names, read_names=N, pairs=pairs).rstrip("\n").split("\n")
+    assert lines == golden
+
+
+def _python_results(index, reads, quals, names, paired, local, off_size, **kw):
+    n = len(reads)
+    res = np.zeros(n, dtype=READ_RESULT)
+    res["score2"] = -(1 << 31)
+    ops = np.zeros((n, max(len(r) for r in reads) + 64), dtype=np.uint8)
+    backend = OracleBackend(Oracle(index), off_size=off_size, local=local)
+    if not paired:
+        eng = PolicyEngine(backend, "sensitive", local=local, **kw)
+        for i in range(n):
+            r = eng.align_read(reads[i], quals[i], names[i])
+            if r.aligned:
+                _fill(res, ops, i, r, reads[i])
+        return res, ops, None
+    eng = PairedPolicyEngine(backend, "sensitive", local=local, **kw)
+    pairs = np.zeros(n // 2, dtype=PAIR_RESULT)
+    for i in range(n // 2):
+        pr = eng.align_pair(reads[2 * i], quals[2 * i], names[2 * i], reads[2 * i + 1], quals[2 * i + 1], names[2 * i + 1])
+        pairs[i]["pair_type"] = pr.pair_type
+        for k in range(2):
+            if pr.mates[k].aligned:
+                _fill(res, ops, 2 * i + k, pr.mates[k], reads[2 * i + k])
+    return res, ops, pairs
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("paired,local,large,kw", [
+    (False, False, False, {}),
+    (False, True, False, {}),
+    (True, False, False, {}),
+    (True, True, False, {}),
+    (True, False, True, {}),                                   # .bt2l: 64-bit RNG draws
+    (False, False, False, dict(k=4)),                          # -k: primary records (the secondaries are the Python engine's)
+    (True, False, False, dict(all_hits=True)),
+    (True, False, False, dict(mixed=False, discord=False)),
+    (False, False, False, dict(nofw=True, seed=9)),
+])
+def test_same_results_as_the_python_engine(tmp_path, paired, local, large, kw):
+    """repeat-rich synthetic genome; results (locus, strand, scores, MAPQ, trims, op strings, pair types) equal to the pinned
+    Python engine's, through the same oracle"""
+    genome = synth.make_genome(n_contigs=3, contig_len=60000, seed=11, repeat_frac=0.5, repeat_len=250, repeat_copies=150, n_gap=37)
+    fa, base = str(tmp_path / "g.fa"), str(tmp_path / "g")
+    synth.write_fasta(fa, genome)
+    subprocess.check_call([ref_bin("bowtie2-build-" + ("l" if large else "s")), "--seed", "0", "--quiet", fa, base])
+    if paired:
+        reads, quals, _ = synth.make_pairs(genome, 120, 100, seed=41, sub_rate=0.02, indel_rate=0.003, hard_frac=0.2, hard_period=12, ins_sd=100)
+        names = [f"r{i // 2}" for i in range(len(reads))]
+    else:
+        reads, quals, _ = synth.make_reads(genome, 250, 100, seed=42, sub_rate=0.02, indel_rate=0.003)
+        names = [f"r{i}" for i in range(len(reads))]
+    off_size = 8 if large else 4
+    want_res, want_ops, want_pairs = _python_results(base, reads, quals, names, paired, local, off_size, **kw)
+    be, keep, fake = _table(base, local, off_size)
+    pk = dict(kw)
+    prm = policy_params("sensitive", local=local, paired=paired, k=pk.pop("k", None), all_hits=pk.pop("all_hits", False),
+                        nofw=pk.pop("nofw", False), seed=pk.pop("seed", 0), mixed=pk.pop("mixed", True), discord=pk.pop("discord", True))
+    assert not pk
+    res, ops, pairs, stats = policy_align(load_library(), be, prm, ReadBatch.from_list(reads, quals), names)
+    for f in ("found", "score", "score2", "fw", "tidx", "refoff", "nops", "trim_left", "trim_right", "mapq", "pad"):
+        assert np.array_equal(res[f], want_res[f]), (f, np.nonzero(res[f] != want_res[f])[0][:5])
+    w = want_ops.shape[1]
+    assert np.array_equal(ops[:, :w], want_ops)
+    if paired:
+        assert np.array_equal(pairs["pair_type"], want_pairs["pair_type"])
+    assert (res["found"] != 0).mean() > 0.3
