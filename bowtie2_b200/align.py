@@ -81,44 +81,15 @@ def interleave_names(n1, n2):
 
 
 def _exact_batch(gpu, batch, names, paired, preset, local, seed):
-    """one batch through the sequential policy (policy_engine) in waves over the GPU primitives (policy_backend_gpu):
-    every read's state machine advances together, each primitive runs as one batched entry-point call per wave"""
-    from .lib import PAIR_RESULT, READ_RESULT
-    from .policy_backend_gpu import GpuBatchBackend
-    from .policy_engine import PairedPolicyEngine, PolicyEngine, aln_to_ops
-    from .policy_waves import WaveScheduler
-    n = batch.n
-    res = np.zeros(n, dtype=READ_RESULT)
-    res["score2"] = -(1 << 31)
-    ops = np.zeros((n, int(batch.lengths().max()) + 64), dtype=np.uint8)
-    reads = [batch.seq[int(batch.off[i]):int(batch.off[i + 1])] for i in range(n)]
-    quals = [batch.qual[int(batch.off[i]):int(batch.off[i + 1])] for i in range(n)]
-
-    def fill(j, r):
-        a = r.aln
-        o = aln_to_ops(a, reads[j])
-        res[j]["found"] = 2 if (not a.edits and a.ext == a.rdlen) else 1
-        res[j]["score"] = a.score
-        if r.xs is not None:
-            res[j]["score2"] = r.xs
-        res[j]["fw"], res[j]["tidx"], res[j]["refoff"], res[j]["nops"] = int(a.fw), a.tidx, a.refoff, len(o)
-        res[j]["trim_left"], res[j]["trim_right"] = a.trim_left, a.rdlen - a.ext - a.trim_left
-        res[j]["mapq"], res[j]["pad"] = r.mapq, a.refns
-        ops[j, :len(o)] = o
-    bb = GpuBatchBackend(gpu, local)
-    if not paired:
-        ws = WaveScheduler(bb, lambda: PolicyEngine(None, preset, seed=seed, local=local))
-        for j, r in enumerate(ws.run_reads(reads, quals, names)):
-            if r.aligned:
-                fill(j, r)
-        return res, ops, None
-    ws = WaveScheduler(bb, lambda: PairedPolicyEngine(None, preset, seed=seed, local=local))
-    pairs = np.zeros(n // 2, dtype=PAIR_RESULT)
-    for i, pr in enumerate(ws.run_pairs(reads, quals, names)):
-        pairs[i]["pair_type"] = pr.pair_type
-        for k in range(2):
-            if pr.mates[k].aligned:
-                fill(2 * i + k, pr.mates[k])
+    """one batch through the exact search policy in waves (csrc/policy_engine.cpp: bt2g_policy_align) over the entry points of
+    this library: every read's state machine advances together, each primitive runs as one batched call per wave"""
+    from .lib import policy_align, policy_backend_gpu, policy_params
+    if hasattr(gpu, "policy_backend_table"):                    # a stand-in device (tests): its own table
+        be, keep = gpu.policy_backend_table()
+    else:
+        be, keep = policy_backend_gpu(gpu), None
+    gpu.set_scoring(local=local)
+    res, ops, pairs, stats = policy_align(gpu._lib, be, policy_params(preset, local=local, paired=paired, seed=seed), batch, names)
     return res, ops, pairs
 
 

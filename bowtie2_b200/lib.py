@@ -993,8 +993,8 @@ def policy_align(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads:
     pairs = np.zeros(n // 2, dtype=PAIR_RESULT) if params.paired else None
     stats = np.zeros(3, dtype=np.uint64)
     if isinstance(names, NameTable):
-        qn = C.cast(names.pointers().ctypes.data, _vp)
-        keep = names
+        keep = names.pointers()                                # (kept alive across the call)
+        qn = C.cast(keep.ctypes.data, _vp)
     else:
         keep = (C.c_char_p * n)(*[x.encode() for x in names])
         qn = C.cast(keep, _vp)

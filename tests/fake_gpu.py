@@ -21,6 +21,9 @@ class FakeGpu:
     def load_index_host(self, image):
         pass
 
+    def policy_backend_table(self):
+        return backend_table(self)
+
     def close(self):
         pass
 
