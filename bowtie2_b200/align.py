@@ -80,7 +80,7 @@ def interleave_names(n1, n2):
     return NameTable(rows)
 
 
-def _exact_batch(gpu, batch, names, paired, preset, local, seed):
+def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1):
     """one batch through the exact search policy in waves (csrc/policy_engine.cpp: bt2g_policy_align) over the entry points of
     this library: every read's state machine advances together, each primitive runs as one batched call per wave"""
     from .lib import policy_align, policy_backend_gpu, policy_params
@@ -89,7 +89,7 @@ def _exact_batch(gpu, batch, names, paired, preset, local, seed):
     else:
         be, keep = policy_backend_gpu(gpu), None
     gpu.set_scoring(local=local)
-    res, ops, pairs, stats = policy_align(gpu._lib, be, policy_params(preset, local=local, paired=paired, seed=seed), batch, names)
+    res, ops, pairs, stats = policy_align(gpu._lib, be, policy_params(preset, local=local, paired=paired, seed=seed, host_threads=threads), batch, names)
     return res, ops, pairs
 
 
@@ -142,7 +142,7 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
                 if paired:
                     pipe.enable_pairs()
             if exact:
-                res, ops, pairs = _exact_batch(gpu, batch, names, paired, preset, local, seed)
+                res, ops, pairs = _exact_batch(gpu, batch, names, paired, preset, local, seed, threads)
             elif paired:
                 res, ops, pairs = pipe.run_paired_host(batch)
             else:

@@ -16,6 +16,7 @@
 #include <limits>
 #include <memory>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <utility>
 #include <vector>
@@ -1376,11 +1377,15 @@ extern "C" int bt2g_policy_align(const bt2g_policy_backend *be, const bt2g_polic
 		for(auto &u : active) groups[u->pend.req->kind].push_back(u->pend.req);
 		for(int k = 0; k < RQ_NKINDS; k++) if(!groups[k].empty()) S.answer(k, groups[k]);
 		if(S.rc) return -2;
-		std::vector<std::unique_ptr<Unit>> still;
-		for(auto &u : active) {
-			u->pend.leaf.resume();
-			if(isDone(*u)) finish(*u); else still.push_back(std::move(u));
+		// resume every unit (they are independent: own engine, own RNG), on the host threads the caller allows
+		{
+			const size_t T = std::min<size_t>(std::max(1, pp->host_threads), std::max<size_t>(1, active.size() / 64));
+			auto run = [&](size_t t) { for(size_t i = t; i < active.size(); i += T) active[i]->pend.leaf.resume(); };
+			if(T == 1) run(0);
+			else { std::vector<std::thread> th; for(size_t t = 0; t < T; t++) th.emplace_back(run, t); for(auto &x : th) x.join(); }
 		}
+		std::vector<std::unique_ptr<Unit>> still;
+		for(auto &u : active) { if(isDone(*u)) finish(*u); else still.push_back(std::move(u)); }
 		active.swap(still);
 	}
 	if(stats) { stats[0] = S.nWaves; stats[1] = S.nCalls; stats[2] = S.nRequests; }

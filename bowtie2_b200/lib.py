@@ -959,11 +959,11 @@ class _PolicyParams(C.Structure):
                 ("mixed", C.c_int32), ("seed", C.c_uint32), ("max_inflight", C.c_int32),
                 ("match_bonus", C.c_int32), ("mmp_max", C.c_int32), ("mmp_min", C.c_int32), ("n_pen", C.c_int32),
                 ("rdgap_const", C.c_int32), ("rdgap_linear", C.c_int32), ("rfgap_const", C.c_int32), ("rfgap_linear", C.c_int32),
-                ("pe", _PePolicyS)]
+                ("pe", _PePolicyS), ("host_threads", C.c_int32), ("reserved", C.c_int32)]
 
 
 def policy_params(preset="sensitive", local=False, paired=False, seed=0, k=None, all_hits=False, mhits=50, nofw=False, norc=False,
-                  discord=True, mixed=True, pe=None, sc=None, max_inflight=0):
+                  discord=True, mixed=True, pe=None, sc=None, max_inflight=0, host_threads=1):
     from . import policy
     pre = policy.preset(preset, local)
     sc = sc or policy.Scoring.default(local)
@@ -980,6 +980,7 @@ def policy_params(preset="sensitive", local=False, paired=False, seed=0, k=None,
     p.match_bonus, p.mmp_max, p.mmp_min, p.n_pen = sc.match_bonus, sc.mmp_max, sc.mmp_min, sc.n_pen
     p.rdgap_const, p.rdgap_linear, p.rfgap_const, p.rfgap_linear = sc.rdgap_const, sc.rdgap_linear, sc.rfgap_const, sc.rfgap_linear
     p.pe.pol, p.pe.flags, p.pe.maxfrag, p.pe.minfrag = pe.pol, pe.flags(), pe.maxfrag, pe.minfrag
+    p.host_threads = host_threads
     return p
 
 

@@ -535,6 +535,8 @@ typedef struct {
 	uint32_t seed; int32_t max_inflight;                    /* --seed; reads (pairs) advanced together (0 = 65536) */
 	int32_t match_bonus, mmp_max, mmp_min, n_pen, rdgap_const, rdgap_linear, rfgap_const, rfgap_linear;
 	bt2g_pe_policy pe;
+	int32_t host_threads;                                   /* threads resuming the per-read state machines between waves (0 / 1 = caller) */
+	int32_t reserved;
 } bt2g_policy_params;
 
 /* reads: the batch (mates interleaved when prm->paired); names[i]: read names (the RNG seed depends on them).  Outputs as
