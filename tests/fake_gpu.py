@@ -163,7 +163,8 @@ class FakeGpu:
                         al["trim5"], al["trim3"])
                 o = aln_to_ops(a, c)
                 tl = a.trim_left
-                alns[k][ai] = (cand_of[ai], al["score"], al["ns"], al["gaps"], 0, tl, al["refoff"] - int(p["refl"]), tl,
+                refns = int((self.O.get_stretch(int(p["tidx"]), al["refoff"], a.ref_extent) > 3).sum())       # AlnRes::refNs, as the kernel reports it
+                alns[k][ai] = (cand_of[ai], al["score"], al["ns"], al["gaps"], refns, tl, al["refoff"] - int(p["refl"]), tl,
                                len(c) - a.ext - tl, len(o))
                 ops[k, ai, :len(o)] = o
         return summ, cands, alns, ops
