@@ -264,6 +264,13 @@ def test_exact_policy_over_gpu_primitives(paired, lambda_index):
                     _fill(res, ops, 2 * i + k, pr.mates[k], reads[2 * i + k])
         lines = sam_format(load_library(), ReadBatch.from_list(reads, quals), res, ops, ref, read_names=names, pairs=pairs).rstrip("\n").split("\n")
         assert lines == golden[:2 * n]
+        # the compiled engine in waves over the library's own entry points
+        from bowtie2_b200.lib import policy_align, policy_backend_gpu, policy_params
+        batch = ReadBatch.from_list(reads, quals)
+        res2, ops2, pairs2, stats = policy_align(load_library(), policy_backend_gpu(g), policy_params("sensitive", paired=True, host_threads=4),
+                                                 batch, names)
+        lines2 = sam_format(load_library(), batch, res2, ops2, ref, read_names=names, pairs=pairs2).rstrip("\n").split("\n")
+        assert lines2 == golden[:2 * n]
     g.close()
 
 
