@@ -351,7 +351,7 @@ struct PairedSink {
 };
 
 struct Result { bool aligned = false; Aln aln; bool hasXs = false; int64_t xs = 0; int mapq = 0; };
-struct PairOut { int pairType = 0; Result m[2]; };
+struct PairOut { int pairType = 0; Result m[2]; int kind = 5; int64_t scoreSum = 0, fraglen = 0; };
 
 struct Engine {
 	const Params &P; Pending *slot;
@@ -1032,6 +1032,13 @@ PairOut Engine::finishPair() {
 			unchosenP(k == 0 ? psink.rs1u : psink.rs2u, r.aln, r.hasXs, r.xs);
 		}
 		po.pairType = 1;
+		po.scoreSum = a1.score + a2.score;
+		po.kind = pe_classify(P.pe, a1.refoff, (uint64_t)a1.refExtent(), a1.fw, a2.refoff, (uint64_t)a2.refExtent(), a2.fw);
+		{   // fragment length (pe.cpp:89-92): the span of the two alignments, soft-trimmed ends included
+			const int64_t s1 = a1.refoff - a1.trimLeft(), e1 = a1.refoff + a1.refExtent() + (a1.rdlen - a1.ext() - a1.trimLeft());
+			const int64_t s2 = a2.refoff - a2.trimLeft(), e2 = a2.refoff + a2.refExtent() + (a2.rdlen - a2.ext() - a2.trimLeft());
+			po.fraglen = std::max(e1, e2) - std::min(s1, s2);
+		}
 		return po;
 	}
 	if(!psink.doneDiscord && psink.nunp[0] == 1 && psink.nunp[1] == 1) {
@@ -1347,7 +1354,8 @@ extern "C" int bt2g_policy_align(const bt2g_policy_backend *be, const bt2g_polic
 	auto finish = [&](Unit &u) {
 		if(P.paired) {
 			PairOut po = std::move(u.tp->h.promise().value);
-			pairs[u.id] = bt2g_pair_result{}; pairs[u.id].pair_type = po.pairType; pairs[u.id].kind = 5;
+			pairs[u.id] = bt2g_pair_result{}; pairs[u.id].pair_type = po.pairType; pairs[u.id].kind = po.kind;
+			pairs[u.id].score_sum = (int32_t)po.scoreSum; pairs[u.id].fraglen = po.fraglen;
 			for(int k = 0; k < 2; k++) fillResult(po.m[k], S.codes((int)(2 * u.id + k)), res[2 * u.id + k], ops + (2 * u.id + k) * (size_t)maxOps, maxOps);
 		} else {
 			fillResult(u.tr->h.promise().value, S.codes((int)u.id), res[u.id], ops + u.id * (size_t)maxOps, maxOps);
