@@ -19,7 +19,7 @@ from .lib import (ALIGN_COUNTS, Bt2Gpu, IndexFile, Pipeline, ReadBatch, align_co
 class FastqStream:
     """Batches of whole FASTQ records from a file (plain or .gz)."""
 
-    def __init__(self, path: str, chunk_bytes: int = 32 << 20, name_stride: int = 96, threads: int = 1):
+    def __init__(self, path: str, chunk_bytes: int = 32 << 20, name_stride: int = 256, threads: int = 1):
         self._f = gzip.open(path, "rb") if path.endswith(".gz") else open(path, "rb")
         self._buf = b""
         self._eof = False
