@@ -80,7 +80,7 @@ def interleave_names(n1, n2):
     return NameTable(rows)
 
 
-def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1):
+def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1, options=None):
     """one batch through the exact search policy in waves (csrc/policy_engine.cpp: bt2g_policy_align) over the entry points of
     this library: every read's state machine advances together, each primitive runs as one batched call per wave"""
     from .lib import policy_align, policy_backend_gpu, policy_params
@@ -89,19 +89,22 @@ def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1):
     else:
         be, keep = policy_backend_gpu(gpu), None
     gpu.set_scoring(local=local)
-    res, ops, pairs, stats = policy_align(gpu._lib, be, policy_params(preset, local=local, paired=paired, seed=seed, host_threads=threads), batch, names)
+    res, ops, pairs, stats = policy_align(gpu._lib, be, policy_params(preset, local=local, paired=paired, seed=seed, host_threads=threads, **(options or {})), batch, names)
     return res, ops, pairs
 
 
 def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None, preset: str = "sensitive", local: bool = False,
                 device: int = 0, batch_reads: int = 1 << 20, threads: int = 8, seed_table: int = 0, dense_sa: int = -1,
-                offrate: int = -1, pg_cl: str = None, summary=sys.stderr, gpu: Bt2Gpu = None, exact: bool = False, seed: int = 0):
+                offrate: int = -1, pg_cl: str = None, summary=sys.stderr, gpu: Bt2Gpu = None, exact: bool = False, seed: int = 0,
+                policy_options: dict = None):
     """bowtie2 -x index_base (-U reads1 | -1 reads1 -2 reads2) -S out_path.  Returns the ALIGN_COUNTS record.
 
     exact=False: the batched speculative pipeline (fast; agrees with the reference on the confidently placed reads).
     exact=True: the reference's sequential search policy (policy_engine) with every primitive computed on the GPU through
     policy_backend_gpu.GpuBackend, read by read: records identical to the reference program's, at a small fraction of the
-    pipeline's speed (intended for parity subsets until the policy runs as a device-side state machine)."""
+    pipeline's speed (intended for parity subsets until the policy runs as a device-side state machine).
+    policy_options (exact mode): keyword arguments of lib.policy_params -- nofw, norc, mixed, discord, pe (a
+    policy.PairedEndPolicy: -I / -X / --ff ...), mhits (-M), sc (a policy.Scoring: --mp / --rdg / --score-min ...)."""
     own = gpu is None
     gpu = gpu or Bt2Gpu(device)                                  # raises without a GPU: nothing below runs on the CPU
     lib = gpu._lib
@@ -142,7 +145,7 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
                 if paired:
                     pipe.enable_pairs()
             if exact:
-                res, ops, pairs = _exact_batch(gpu, batch, names, paired, preset, local, seed, threads)
+                res, ops, pairs = _exact_batch(gpu, batch, names, paired, preset, local, seed, threads, policy_options)
             elif paired:
                 res, ops, pairs = pipe.run_paired_host(batch)
             else:
