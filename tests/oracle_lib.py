@@ -304,3 +304,14 @@ def oracle_ungapped(O, local, codes, quals, fw, tidx, off, tlen, ohang, minsc):
            i64(int(off)), i64(int(tlen)), ci(int(ohang)), i64(int(minsc)), out6.ctypes.data_as(vp), mask.ctypes.data_as(vp))
     return rc, dict(score=int(out6[0]), rowi=int(out6[1]), rowf=int(out6[2]), ns=int(out6[3]), refns=int(out6[4]),
                     nedits=int(out6[5]), mask=mask)
+
+
+def oracle_policy_table(O, local=False, off_size=4):
+    """bt2g_policy_backend filled with the C oracle's functions (oracle/bt2_oracle_table.c): the exact-policy engine driven on the
+    CPU at C speed.  Returns (table, handle to keep alive)."""
+    from bowtie2_b200.lib import _PolicyBackend
+    be = _PolicyBackend()
+    O.lib.bt2o_policy_table.argtypes = [vp, ci, ci, C.POINTER(_PolicyBackend)]
+    O.lib.bt2o_policy_table.restype = vp
+    h = O.lib.bt2o_policy_table(O.h, int(local), int(off_size), C.byref(be))
+    return be, (O, h)

@@ -4,12 +4,13 @@
   python tools/parity_subset.py P 50000 very-sensitive 150     # configs[2]: 2x150, --very-sensitive
   python tools/parity_subset.py U 20000 very-sensitive 300 local
 Builds a 5 Mbp four-contig genome with repeats and N gaps, runs the reference PROGRAM (oracle/_ref) and bt2g_policy_align over
-the oracle-backed entry-point table (tests/fake_gpu.py), and diffs every SAM record.  CPU only; minutes, not part of pytest."""
+the oracle-backed entry-point table (oracle/bt2_oracle_table.c; TABLE=python: tests/fake_gpu.py), and diffs every SAM record.  CPU only; minutes, not part of pytest."""
 import os, sys, time, subprocess, tempfile
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import numpy as np
 from oracle_lib import Oracle, ref_bin
 from fake_gpu import FakeGpu, backend_table
+from oracle_lib import oracle_policy_table
 from bowtie2_b200 import synth
 from bowtie2_b200.lib import ReadBatch, load_library, sam_format, policy_align, policy_params
 paired = sys.argv[1] == 'P'; N = int(sys.argv[2]); preset = sys.argv[3]; rdlen = int(sys.argv[4]); LOCAL = len(sys.argv) > 5 and sys.argv[5] == 'local'
@@ -31,7 +32,11 @@ t0 = time.time()
 out = subprocess.check_output([ref_bin('bowtie2-align-s'), *(['--local'] if LOCAL else []), '--' + preset, '--seed', '0', '-p', '8', '--reorder', '-x', base] + io, stderr=subprocess.DEVNULL).decode()
 print('reference program: %.1f s on 8 threads' % (time.time() - t0))
 want = [l for l in out.split('\n') if l and not l.startswith('@')]
-fake = FakeGpu(Oracle(base)); fake.set_scoring(LOCAL); be, keep = backend_table(fake); lib = load_library()
+lib = load_library()
+if os.environ.get('TABLE') == 'python':      # the Python stand-in device (tests/fake_gpu.py)
+    fake = FakeGpu(Oracle(base)); fake.set_scoring(LOCAL); be, keep = backend_table(fake)
+else:                                         # the C table over the oracle (oracle/bt2_oracle_table.c)
+    be, keep = oracle_policy_table(Oracle(base), LOCAL)
 batch = ReadBatch.from_list(reads, quals)
 t0 = time.time()
 res, ops, pairs, stats = policy_align(lib, be, policy_params(preset, local=LOCAL, paired=paired, host_threads=8), batch, names)
