@@ -127,3 +127,36 @@ def test_same_results_as_the_python_engine(tmp_path, paired, local, large, kw):
     if paired:
         assert np.array_equal(pairs["pair_type"], want_pairs["pair_type"])
     assert (res["found"] != 0).mean() > 0.3
+
+
+@pytest.mark.parametrize("fixture,index,ref_names,local,paired", [
+    ("lambda_U_sensitive", "lambda_index", ["gi|9626243|ref|NC_001416.1|"], False, False),
+    ("lambda_U_local", "lambda_index", ["gi|9626243|ref|NC_001416.1|"], True, False),
+    ("rep_P_sensitive", "rep_index", ["ctg1", "ctg2"], False, True),
+])
+def test_whole_path_in_c_over_the_oracle_table(fixture, index, ref_names, local, paired, request):
+    """the compiled engine over oracle/bt2_oracle_table.c (the entry points answered by the plain-C restatement): the whole path
+    in C / C++ on the CPU, byte-identical to the reference program; also pins the stand-in device of tests/fake_gpu.py, which
+    implements the same conventions in Python"""
+    from oracle_lib import oracle_policy_table
+    base = request.getfixturevalue(index)
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, fixture + ".sam")) if not l.startswith("@")]
+    pre = fixture.split("_")[0]
+    n = len(golden) // (2 if paired else 1)
+    n1, r1, q1 = read_fastq_codes(os.path.join(GOLDEN, pre + "_reads_1.fq"), n)
+    if paired:
+        n2, r2, q2 = read_fastq_codes(os.path.join(GOLDEN, pre + "_reads_2.fq"), n)
+        il = lambda a, b: [x for p in zip(a, b) for x in p]
+        R, Q, N = il(r1, r2), il(q1, q2), il(n1, n2)
+    else:
+        R, Q, N = r1, q1, n1
+    be, keep = oracle_policy_table(Oracle(base), local)
+    lib = load_library()
+    batch = ReadBatch.from_list(R, Q)
+    res, ops, pairs, stats = policy_align(lib, be, policy_params("sensitive", local=local, paired=paired, host_threads=3), batch, N)
+    lines = sam_format(lib, batch, res, ops, ref_names, read_names=N, pairs=pairs, local=local).rstrip("\n").split("\n")
+    assert lines == golden
+    # the Python stand-in device gives the same arrays
+    be2, keep2, fake = _table(base, local)
+    res2, ops2, pairs2, _ = policy_align(lib, be2, policy_params("sensitive", local=local, paired=paired), batch, N)
+    assert res.tobytes() == res2.tobytes() and ops.tobytes() == ops2.tobytes()
