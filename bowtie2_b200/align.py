@@ -7,6 +7,7 @@ bt2g_sam_format on host threads and written behind the header (bt2g_sam_header);
 (bt2_search.cpp:3101-4100) that surrounds the search: read a batch, align, report, in input order.
 Nothing here computes alignments; without a GPU `Bt2Gpu` raises before any file is opened for writing."""
 import gzip
+import os
 import io
 import sys
 
@@ -89,7 +90,19 @@ def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1, opti
     else:
         be, keep = policy_backend_gpu(gpu), None
     gpu.set_scoring(local=local)
-    res, ops, pairs, stats = policy_align(gpu._lib, be, policy_params(preset, local=local, paired=paired, seed=seed, host_threads=threads, **(options or {})), batch, names)
+    # the exact policy counts the reference's backtrace attempts (one RNG reseed each): take them from the move-code DP kernels,
+    # whose candidate loop is sequential; the H-byte tail screens candidates in parallel and can label a candidate FAILED that
+    # the sequential order would have skipped ("Known gap")
+    prev = os.environ.get("BT2G_DP_PACKED")
+    os.environ["BT2G_DP_PACKED"] = "1"
+    try:
+        res, ops, pairs, stats = policy_align(gpu._lib, be, policy_params(preset, local=local, paired=paired, seed=seed, host_threads=threads,
+                                                                          **(options or {})), batch, names)
+    finally:
+        if prev is None:
+            del os.environ["BT2G_DP_PACKED"]
+        else:
+            os.environ["BT2G_DP_PACKED"] = prev
     return res, ops, pairs
 
 

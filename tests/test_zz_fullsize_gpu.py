@@ -210,7 +210,7 @@ def test_files_in_sam_out(paired, lambda_index, tmp_path):
 
 @pytest.mark.xfail(reason="written after the round's GPU minutes were spent: staged, not yet run on hardware", strict=False)
 @pytest.mark.parametrize("paired", [False, True])
-def test_exact_policy_over_gpu_primitives(paired, lambda_index):
+def test_exact_policy_over_gpu_primitives(paired, lambda_index, monkeypatch):
     """policy_engine over the GPU entry points (policy_backend_gpu.GpuBackend): byte-identical golden SAM, i.e. the
     reference's sequential policy with every hot-path primitive computed on the device."""
     import torch
@@ -222,6 +222,7 @@ def test_exact_policy_over_gpu_primitives(paired, lambda_index):
     from bowtie2_b200.policy_engine import PairedPolicyEngine, PolicyEngine
     from conftest import GOLDEN, read_fastq_codes
     from test_policy_engine import _fill
+    monkeypatch.setenv("BT2G_DP_PACKED", "1")               # sequential candidate loop: exact attempt counts
     g = Bt2Gpu(0)
     g.load_index_files(lambda_index)
     golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "lambda_P_sensitive.sam" if paired else "lambda_U_sensitive.sam"))
@@ -275,8 +276,8 @@ def test_exact_policy_over_gpu_primitives(paired, lambda_index):
 
 
 @pytest.mark.xfail(reason="written after the round's GPU minutes were spent: staged, not yet run on hardware", strict=False)
-@pytest.mark.parametrize("local", [False, True])
-def test_dp_candidate_fates_match_the_oracle_attempt_log(local, synth_index, synth_genome):
+@pytest.mark.parametrize("local,cap", [(False, "1"), (True, "1"), (False, None)])
+def test_dp_candidate_fates_match_the_oracle_attempt_log(local, cap, synth_index, synth_genome, monkeypatch):
     """bt2g_dp_extend's per-candidate fates: FAILED / SUCCEEDED exactly at the candidates the reference would start a backtrace
     from (= consume an RNG reseed), in order: what the exact policy needs from the DP kernel beyond the alignments."""
     import torch
@@ -285,6 +286,10 @@ def test_dp_candidate_fates_match_the_oracle_attempt_log(local, synth_index, syn
     from bowtie2_b200 import Bt2Gpu, policy, synth
     from bowtie2_b200.lib import DP_PROBLEM, ReadBatch
     from oracle_lib import Oracle, oracle_dp
+    # cap "1": the move-code kernels (sequential candidate loop), which exact mode selects; None: the default H-byte tail, whose
+    # parallel screening is the known gap
+    if cap is not None:
+        monkeypatch.setenv("BT2G_DP_PACKED", cap)
     g = Bt2Gpu(0)
     g.load_index_files(synth_index)
     g.set_scoring(local=local)
