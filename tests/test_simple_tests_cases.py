@@ -186,6 +186,24 @@ def _usable(case):
     return _options(case) is not None
 
 
+_INDEX_CACHE = {}
+
+
+def _index_for(tmp_path, refs):
+    """bowtie2-build once per distinct reference set"""
+    key = tuple(refs)
+    if key not in _INDEX_CACHE:
+        d = tmp_path / f"ix{len(_INDEX_CACHE)}"
+        d.mkdir()
+        fa, base = str(d / "ref.fa"), str(d / "ref")
+        with open(fa, "w") as f:
+            for k, r in enumerate(refs):
+                f.write(f">{k}\n{r}\n")
+        subprocess.check_call([ref_bin("bowtie2-build-s"), "--quiet", fa, base])
+        _INDEX_CACHE[key] = base
+    return _INDEX_CACHE[key]
+
+
 def _cases():
     return json.load(open(os.path.join(GOLDEN, "simple_tests_cases.json")))
 
@@ -216,11 +234,7 @@ def test_reference_regression_corpus(tmp_path):
         trim = lambda x: x[t5:len(x) - t3] if t3 else x[t5:]       # -5 / -3: bases removed before alignment (and from SEQ / QUAL)
         d = tmp_path / f"c{ci}"
         d.mkdir()
-        fa, base = str(d / "ref.fa"), str(d / "ref")
-        with open(fa, "w") as f:
-            for k, r in enumerate(case["ref"]):
-                f.write(f">{k}\n{r}\n")
-        subprocess.check_call([ref_bin("bowtie2-build-s"), "--quiet", fa, base])
+        base = _index_for(tmp_path, case["ref"])
         ref_names = [str(k) for k in range(len(case["ref"]))]
         paired = "mate1s" in case
         if paired and ("mate1fw" in case or "mate2fw" in case) and "pol" not in pe_kw:
@@ -313,11 +327,7 @@ def test_reference_corpus_read_formats(tmp_path):
         paired_files = key + "1" in case
         d = tmp_path / f"f{ci}"
         d.mkdir()
-        fa, base = str(d / "ref.fa"), str(d / "ref")
-        with open(fa, "w") as f:
-            for k, r in enumerate(case["ref"]):
-                f.write(f">{k}\n{r}\n")
-        subprocess.check_call([ref_bin("bowtie2-build-s"), "--quiet", fa, base])
+        base = _index_for(tmp_path, case["ref"])
         ref_names = [str(k) for k in range(len(case["ref"]))]
         cmd = [ref_bin("bowtie2-align-s"), "--quiet", "-p", "1", "--seed", "0", "-x", base] + [t for t in toks if t != "--quiet"] + [farg]
         kw.setdefault("seed", 0)
