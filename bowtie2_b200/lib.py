@@ -963,9 +963,18 @@ class _PolicyParams(C.Structure):
 
 
 def policy_params(preset="sensitive", local=False, paired=False, seed=0, k=None, all_hits=False, mhits=50, nofw=False, norc=False,
-                  discord=True, mixed=True, pe=None, sc=None, max_inflight=0, host_threads=1):
+                  discord=True, mixed=True, pe=None, sc=None, max_inflight=0, host_threads=1, seed_len=None, seed_rounds=None,
+                  dp_fail_streak=None, ival=None):
     from . import policy
     pre = policy.preset(preset, local)
+    if seed_len is not None:
+        pre.seed_len = seed_len                    # -L
+    if seed_rounds is not None:
+        pre.seed_rounds = seed_rounds              # -R
+    if dp_fail_streak is not None:
+        pre.dp_fail_streak = dp_fail_streak        # -D
+    if ival is not None:
+        pre.ival = ival                            # -i
     sc = sc or policy.Scoring.default(local)
     pe = pe or policy.PairedEndPolicy(local=local)
     smin, nce = sc.score_min(), sc.n_ceil_func()

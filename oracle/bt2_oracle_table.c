@@ -220,4 +220,11 @@ void *bt2o_policy_table(bt2o_index *ix, int local, int off_size, bt2g_policy_bac
 	be->off_size = off_size; be->reserved = 0;
 	return t;
 }
+/* non-default penalties for the table's calls (--mp / --np / --rdg / --rfg / --ma) */
+void bt2o_policy_table_scoring(void *tv, int match_bonus, int mmp_max, int mmp_min, int n_pen, int rdgap_const, int rdgap_linear,
+                               int rfgap_const, int rfgap_linear) {
+	table_ctx *t = (table_ctx *)tv;
+	t->sc.match_bonus = match_bonus; t->sc.mmp_max = mmp_max; t->sc.mmp_min = mmp_min; t->sc.n_pen = n_pen;
+	t->sc.rdgap_const = rdgap_const; t->sc.rdgap_linear = rdgap_linear; t->sc.rfgap_const = rfgap_const; t->sc.rfgap_linear = rfgap_linear;
+}
 void bt2o_policy_table_free(void *t) { free(t); }

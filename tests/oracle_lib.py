@@ -306,7 +306,7 @@ def oracle_ungapped(O, local, codes, quals, fw, tidx, off, tlen, ohang, minsc):
                     nedits=int(out6[5]), mask=mask)
 
 
-def oracle_policy_table(O, local=False, off_size=4):
+def oracle_policy_table(O, local=False, off_size=4, scoring=None):
     """bt2g_policy_backend filled with the C oracle's functions (oracle/bt2_oracle_table.c): the exact-policy engine driven on the
     CPU at C speed.  Returns (table, handle to keep alive)."""
     from bowtie2_b200.lib import _PolicyBackend
@@ -314,4 +314,9 @@ def oracle_policy_table(O, local=False, off_size=4):
     O.lib.bt2o_policy_table.argtypes = [vp, ci, ci, C.POINTER(_PolicyBackend)]
     O.lib.bt2o_policy_table.restype = vp
     h = O.lib.bt2o_policy_table(O.h, int(local), int(off_size), C.byref(be))
+    if scoring is not None:
+        O.lib.bt2o_policy_table_scoring.argtypes = [vp] + [ci] * 8
+        O.lib.bt2o_policy_table_scoring.restype = None
+        O.lib.bt2o_policy_table_scoring(h, scoring.match_bonus, scoring.mmp_max, scoring.mmp_min, scoring.n_pen, scoring.rdgap_const,
+                                        scoring.rdgap_linear, scoring.rfgap_const, scoring.rfgap_linear)
     return be, (O, h)

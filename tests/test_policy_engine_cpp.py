@@ -63,12 +63,12 @@ def test_paired_sam_identical_to_golden(fixture, index, ref_names, request):
     assert lines == golden
 
 
-def _python_results(index, reads, quals, names, paired, local, off_size, **kw):
+def _python_results(index, reads, quals, names, paired, local, off_size, scoring=None, **kw):
     n = len(reads)
     res = np.zeros(n, dtype=READ_RESULT)
     res["score2"] = -(1 << 31)
     ops = np.zeros((n, max(len(r) for r in reads) + 64), dtype=np.uint8)
-    backend = OracleBackend(Oracle(index), off_size=off_size, local=local)
+    backend = OracleBackend(Oracle(index), off_size=off_size, local=local, scoring=scoring)
     if not paired:
         eng = PolicyEngine(backend, "sensitive", local=local, **kw)
         for i in range(n):
