@@ -85,6 +85,9 @@ def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1, opti
     """one batch through the exact search policy in waves (csrc/policy_engine.cpp: bt2g_policy_align) over the entry points of
     this library: every read's state machine advances together, each primitive runs as one batched call per wave"""
     from .lib import policy_align, policy_backend_gpu, policy_params
+    if options and (options.get("k") is not None or options.get("all_hits")):
+        # the compiled engine reports the primary alignment; the secondary records of -k / -a exist in policy_engine.py only
+        raise NotImplementedError("-k / -a output needs the secondary records: use bowtie2_b200.policy_engine (PolicyEngine(..., k=...))")
     if hasattr(gpu, "policy_backend_table"):                    # a stand-in device (tests): its own table
         be, keep = gpu.policy_backend_table()
     else:
