@@ -107,6 +107,10 @@ def _options(case):
             pe["dovetail_ok"] = False
         elif t in ("-3", "-5", "--trim3", "--trim5"):
             kw["_trim3" if t in ("-3", "--trim3") else "_trim5"] = int(arg())
+        elif t == "--trim-to":
+            v = arg()                                  # [3:|5:]N: trim the 3' (default) or 5' end so that N bases remain
+            end, num = ("3", v) if ":" not in v else tuple(v.split(":"))
+            kw["_trimto"] = (end, int(num))
         elif t in ("-u", "-s"):
             kw["_upto" if t == "-u" else "_skip"] = int(arg())
         elif t == "--rdg":
@@ -231,7 +235,12 @@ def test_reference_regression_corpus(tmp_path):
         toks, kw, sc, pe_kw, local = _options(case)
         skip, upto = kw.pop("_skip", 0), kw.pop("_upto", None)
         t5, t3 = kw.pop("_trim5", 0), kw.pop("_trim3", 0)
-        trim = lambda x: x[t5:len(x) - t3] if t3 else x[t5:]       # -5 / -3: bases removed before alignment (and from SEQ / QUAL)
+        tt = kw.pop("_trimto", None)
+
+        def trim(x):                                       # -5 / -3 / --trim-to: bases removed before alignment (and from SEQ / QUAL)
+            if tt is not None:
+                return x if len(x) <= tt[1] else (x[:tt[1]] if tt[0] == "3" else x[len(x) - tt[1]:])
+            return x[t5:len(x) - t3] if t3 else x[t5:]
         d = tmp_path / f"c{ci}"
         d.mkdir()
         base = _index_for(tmp_path, case["ref"])
@@ -322,7 +331,12 @@ def test_reference_corpus_read_formats(tmp_path):
         toks, kw, sc, pe_kw, local = _options(case)
         skip, upto = kw.pop("_skip", 0), kw.pop("_upto", None)
         t5, t3 = kw.pop("_trim5", 0), kw.pop("_trim3", 0)
-        trim = lambda x: x[t5:len(x) - t3] if t3 else x[t5:]
+        tt = kw.pop("_trimto", None)
+
+        def trim(x, t5=t5, t3=t3, tt=tt):
+            if tt is not None:
+                return x if len(x) <= tt[1] else (x[:tt[1]] if tt[0] == "3" else x[len(x) - tt[1]:])
+            return x[t5:len(x) - t3] if t3 else x[t5:]
         pick = lambda lst: (lst[skip:][:upto] if upto is not None else lst[skip:])
         paired_files = key + "1" in case
         d = tmp_path / f"f{ci}"
@@ -369,12 +383,33 @@ def test_reference_corpus_read_formats(tmp_path):
                 else:
                     p = str(d / "reads.txt")
                     open(p, "w").write(text)
-                    out = subprocess.run(cmd + ["-U", p], capture_output=True, text=True)
+                    # --tab5 / --tab6 take the file themselves (and may hold pairs); the other formats go through -U
+                    out = subprocess.run(cmd + ([p] if fmt == "tab5" else ["-U", p]), capture_output=True, text=True)
                 names, R, Q, m2 = load(text)
-                names, R, Q = pick(names), pick([trim(x) for x in R]), pick([trim(x) for x in Q])
                 if m2 is not None:
-                    skipped += 1                                   # tab-delimited files mixing pairs and single reads
+                    if any(x is None for x in m2):
+                        skipped += 1                               # a file mixing pairs and single reads
+                        why.append((ci, key, "mixed paired / unpaired records"))
+                        continue
+                    R2 = [_codes(x[1].upper().replace(".", "N")) for x in m2]
+                    Q2 = [np.frombuffer(x[2].encode(), dtype=np.uint8) for x in m2]
+                    N = [x for k in range(len(names)) for x in (names[k], m2[k][0])]
+                    N = [x[:-2] if x.endswith(("/1", "/2")) else x for x in N]
+                    Rp = [x for pp in zip(pick([trim(x) for x in R]), pick([trim(x) for x in R2])) for x in pp]
+                    Qp = [x for pp in zip(pick([trim(x) for x in Q]), pick([trim(x) for x in Q2])) for x in pp]
+                    Np = [x for k in (range(len(names))[skip:][:upto] if upto is not None else range(len(names))[skip:]) for x in N[2 * k:2 * k + 2]]
+                    eng = PairedPolicyEngine(backend, "sensitive", sc=sc, local=local, pe=policy.PairedEndPolicy(local=local, **pe_kw), **kw)
+                    outs = [eng.align_pair(Rp[2 * k], Qp[2 * k], Np[2 * k], Rp[2 * k + 1], Qp[2 * k + 1], Np[2 * k + 1]) for k in range(len(Rp) // 2)]
+                    lines = _multi_sam_pairs(outs, Rp, Qp, Np, ref_names, local=local)
+                    if out.returncode != 0:
+                        skipped += 1
+                        why.append((ci, key, "reference exit " + str(out.returncode)))
+                        continue
+                    want = [l for l in out.stdout.split("\n") if l and not l.startswith("@") and l.count("\t") >= 10]
+                    assert lines == want, (ci, key, case.get("name"), next(((a, b) for a, b in zip(lines, want) if a != b), (len(lines), len(want))))
+                    n_run += 1
                     continue
+                names, R, Q = pick(names), pick([trim(x) for x in R]), pick([trim(x) for x in Q])
                 eng = PolicyEngine(backend, "sensitive", sc=sc, local=local, **{k: v for k, v in kw.items() if k not in ("mixed", "discord")})
                 outs = [eng.align_read(R[k], Q[k], names[k]) for k in range(len(R))]
                 lines = _multi_sam(outs, R, Q, names, ref_names, local=local)
