@@ -81,13 +81,17 @@ def interleave_names(n1, n2):
     return NameTable(rows)
 
 
+ALL_HITS_CAP = 1024            # records per read kept for -a in exact mode (a warning is printed when a read had more)
+
+
 def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1, options=None):
     """one batch through the exact search policy in waves (csrc/policy_engine.cpp: bt2g_policy_align) over the entry points of
     this library: every read's state machine advances together, each primitive runs as one batched call per wave"""
-    from .lib import policy_align, policy_backend_gpu, policy_params
-    if options and (options.get("k") is not None or options.get("all_hits")):
-        # the compiled engine reports the primary alignment; the secondary records of -k / -a exist in policy_engine.py only
-        raise NotImplementedError("-k / -a output needs the secondary records: use bowtie2_b200.policy_engine (PolicyEngine(..., k=...))")
+    from .lib import policy_align, policy_align_k, policy_backend_gpu, policy_params
+    multi = bool(options and (options.get("k") is not None or options.get("all_hits")))
+    if multi and paired:
+        # the compiled engine reports the primary pair; the secondary records of paired -k / -a exist in policy_engine.py only
+        raise NotImplementedError("paired -k / -a output needs the secondary records: use bowtie2_b200.policy_engine (PairedPolicyEngine(..., k=...))")
     if hasattr(gpu, "policy_backend_table"):                    # a stand-in device (tests): its own table
         be, keep = gpu.policy_backend_table()
     else:
@@ -99,8 +103,23 @@ def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1, opti
     prev = os.environ.get("BT2G_DP_PACKED")
     os.environ["BT2G_DP_PACKED"] = "1"
     try:
-        res, ops, pairs, stats = policy_align(gpu._lib, be, policy_params(preset, local=local, paired=paired, seed=seed, host_threads=threads,
-                                                                          **(options or {})), batch, names)
+        prm = policy_params(preset, local=local, paired=paired, seed=seed, host_threads=threads, **(options or {}))
+        if multi:
+            # unpaired -k N / -a (bt2g_policy_align_k): one record per reported alignment, the read repeated; -a is capped per read
+            cap = int(options["k"]) if options.get("k") is not None else ALL_HITS_CAP
+            res_k, ops_k, cnt, truncated, stats = policy_align_k(gpu._lib, be, prm, batch, names, cap)
+            if truncated:
+                sys.stderr.write(f"Warning: -a: reads with more than {cap} alignments were cut to {cap} records\n")
+            per = np.maximum(cnt.astype(np.int64), 1)           # an unaligned read still prints one record
+            rows = np.repeat(np.arange(batch.n), per)
+            sub = np.arange(len(rows)) - np.repeat(np.cumsum(per) - per, per)
+            o = batch.off.astype(np.int64)
+            seqs = [batch.seq[o[i]:o[i + 1]] for i in rows]
+            quals = [batch.qual[o[i]:o[i + 1]] for i in rows]
+            nm = list(names)
+            return ReadBatch.from_list(seqs, quals), [nm[i] for i in rows], np.ascontiguousarray(res_k[rows, sub]), np.ascontiguousarray(ops_k[rows, sub]), \
+                np.ascontiguousarray(res_k[:, 0])
+        res, ops, pairs, stats = policy_align(gpu._lib, be, prm, batch, names)
     finally:
         if prev is None:
             del os.environ["BT2G_DP_PACKED"]
@@ -160,6 +179,11 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
                                 both_mates=paired)
                 if paired:
                     pipe.enable_pairs()
+            if exact and not paired and policy_options and (policy_options.get("k") is not None or policy_options.get("all_hits")):
+                batch_k, names_k, res, ops, primary = _exact_batch(gpu, batch, names, paired, preset, local, seed, threads, policy_options)
+                out.write(sam_format(lib, batch_k, res, ops, sam_names, read_names=names_k, threads=threads, local=local, as_bytes=True))
+                align_counts_add(lib, counts, primary, None)
+                continue
             if exact:
                 res, ops, pairs = _exact_batch(gpu, batch, names, paired, preset, local, seed, threads, policy_options)
             elif paired:

@@ -350,7 +350,7 @@ struct PairedSink {
 	}
 };
 
-struct Result { bool aligned = false; Aln aln; bool hasXs = false; int64_t xs = 0; int mapq = 0; };
+struct Result { bool aligned = false; Aln aln; bool hasXs = false; int64_t xs = 0; int mapq = 0; std::vector<Aln> secondary; };
 struct PairOut { int pairType = 0; Result m[2]; int kind = 5; int64_t scoreSum = 0, fraglen = 0; };
 
 struct Engine {
@@ -704,6 +704,9 @@ Result Engine::finishRead() {
 	r.aligned = true; r.aln = alns[buf[0].second];
 	r.hasXs = buf.size() > 1; r.xs = r.hasXs ? buf[1].first : 0;
 	r.mapq = (int)mapq(r.aln.score, r.hasXs, r.xs, P.minScore(cur->rdlen), cur->perfect);
+	// ReportingState::getReport (aln_sink.cpp:300-330): after a -k short circuit khits alignments, else min(found, khits)
+	const int64_t num = usink.exitK ? P.khits : std::min<int64_t>((int64_t)alns.size(), P.khits);
+	for(int64_t i = 1; i < std::min<int64_t>(num, (int64_t)buf.size()); i++) r.secondary.push_back(alns[buf[(size_t)i].second]);
 	return r;
 }
 
@@ -1325,9 +1328,11 @@ static void fillResult(const Result &r, const uint8_t *codes, bt2g_read_result &
 	out.mapq = r.mapq; out.pad = a.refns;
 }
 
-extern "C" int bt2g_policy_align(const bt2g_policy_backend *be, const bt2g_policy_params *pp, const bt2g_reads *reads, const char *const *names,
-                                 bt2g_read_result *res, uint8_t *ops, uint32_t maxOps, bt2g_pair_result *pairs, uint64_t *stats) {
+static int policyAlign(const bt2g_policy_backend *be, const bt2g_policy_params *pp, const bt2g_reads *reads, const char *const *names,
+                       bt2g_read_result *res, uint8_t *ops, uint32_t maxOps, bt2g_pair_result *pairs, uint64_t *stats,
+                       uint32_t maxPerRead, uint32_t *nReported) {
 	if(!be || !pp || !reads || !res || !ops || (pp->paired && (!pairs || (reads->n_reads & 1)))) return -1;
+	bool truncated = false;
 	Params P{};
 	P.local = pp->local; P.paired = pp->paired; P.all = pp->all_hits; P.mmode = pp->mmode; P.nofw = pp->nofw; P.norc = pp->norc;
 	P.discord = pp->discord; P.mixed = pp->mixed;
@@ -1358,7 +1363,19 @@ extern "C" int bt2g_policy_align(const bt2g_policy_backend *be, const bt2g_polic
 			pairs[u.id].score_sum = (int32_t)po.scoreSum; pairs[u.id].fraglen = po.fraglen;
 			for(int k = 0; k < 2; k++) fillResult(po.m[k], S.codes((int)(2 * u.id + k)), res[2 * u.id + k], ops + (2 * u.id + k) * (size_t)maxOps, maxOps);
 		} else {
-			fillResult(u.tr->h.promise().value, S.codes((int)u.id), res[u.id], ops + u.id * (size_t)maxOps, maxOps);
+			// one row per reported alignment: the primary, then the secondaries (found bit 8 -> FLAG 256, MAPQ 255, the read's XS:i)
+			Result &r = u.tr->h.promise().value;
+			const size_t row0 = u.id * (size_t)maxPerRead;
+			fillResult(r, S.codes((int)u.id), res[row0], ops + row0 * (size_t)maxOps, maxOps);
+			size_t n = r.aligned ? 1 : 0;
+			for(size_t j = 0; r.aligned && j < r.secondary.size(); j++) {
+				if(n >= maxPerRead) { truncated = truncated || maxPerRead > 1; break; }
+				Result s2; s2.aligned = true; s2.aln = r.secondary[j]; s2.hasXs = r.hasXs; s2.xs = r.xs; s2.mapq = 255;
+				fillResult(s2, S.codes((int)u.id), res[row0 + n], ops + (row0 + n) * (size_t)maxOps, maxOps);
+				res[row0 + n].found |= 0x100;
+				n++;
+			}
+			if(nReported) nReported[u.id] = (uint32_t)n;
 		}
 	};
 	auto isDone = [&](Unit &u) { return P.paired ? u.tp->h.done() : u.tr->h.done(); };
@@ -1397,5 +1414,16 @@ extern "C" int bt2g_policy_align(const bt2g_policy_backend *be, const bt2g_polic
 		active.swap(still);
 	}
 	if(stats) { stats[0] = S.nWaves; stats[1] = S.nCalls; stats[2] = S.nRequests; }
-	return 0;
+	return truncated ? 1 : 0;
+}
+
+extern "C" int bt2g_policy_align(const bt2g_policy_backend *be, const bt2g_policy_params *pp, const bt2g_reads *reads, const char *const *names,
+                                 bt2g_read_result *res, uint8_t *ops, uint32_t maxOps, bt2g_pair_result *pairs, uint64_t *stats) {
+	return policyAlign(be, pp, reads, names, res, ops, maxOps, pairs, stats, 1, nullptr);
+}
+
+extern "C" int bt2g_policy_align_k(const bt2g_policy_backend *be, const bt2g_policy_params *pp, const bt2g_reads *reads, const char *const *names,
+                                   uint32_t maxPerRead, bt2g_read_result *res, uint8_t *ops, uint32_t maxOps, uint32_t *nReported, uint64_t *stats) {
+	if(!pp || pp->paired || maxPerRead == 0 || !nReported) return -1;
+	return policyAlign(be, pp, reads, names, res, ops, maxOps, nullptr, stats, maxPerRead, nReported);
 }

@@ -1015,6 +1015,30 @@ def policy_align(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads:
     return res, ops, pairs, tuple(int(x) for x in stats)
 
 
+def policy_align_k(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads: ReadBatch, names, max_per_read: int):
+    """include/bt2g.h: bt2g_policy_align_k (unpaired -k / -a) -> (results [n, max_per_read], ops [n, max_per_read, max_ops],
+    n_reported [n], truncated, (waves, backend calls, requests))"""
+    lib.bt2g_policy_align_k.argtypes = [C.POINTER(_PolicyBackend), C.POINTER(_PolicyParams), C.POINTER(_Reads), _vp, C.c_uint32, _vp, _vp, C.c_uint32,
+                                        _vp, _vp]
+    n = reads.n
+    max_ops = int(reads.lengths().max()) + 64 if n else 64
+    res = np.zeros((max(n, 1), max_per_read), dtype=READ_RESULT)
+    ops = np.zeros((max(n, 1), max_per_read, max_ops), dtype=np.uint8)
+    cnt = np.zeros(max(n, 1), dtype=np.uint32)
+    stats = np.zeros(3, dtype=np.uint64)
+    if isinstance(names, NameTable):
+        keep = names.pointers()                                # (kept alive across the call)
+        qn = C.cast(keep.ctypes.data, _vp)
+    else:
+        keep = (C.c_char_p * n)(*[x.encode() for x in names])
+        qn = C.cast(keep, _vp)
+    st = reads._struct()
+    rc = lib.bt2g_policy_align_k(C.byref(backend), C.byref(params), C.byref(st), qn, max_per_read, _ptr(res), _ptr(ops), max_ops, _ptr(cnt), _ptr(stats))
+    if rc < 0:
+        raise RuntimeError(f"bt2g_policy_align_k failed ({rc})")
+    return res[:n], ops[:n], cnt[:n], bool(rc), tuple(int(x) for x in stats)
+
+
 def policy_backend_gpu(gpu: "Bt2Gpu") -> "_PolicyBackend":
     be = _PolicyBackend()
     gpu._lib.bt2g_policy_backend_gpu.argtypes = [_vp, C.POINTER(_PolicyBackend)]

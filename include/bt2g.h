@@ -545,6 +545,15 @@ typedef struct {
 int bt2g_policy_align(const bt2g_policy_backend *be, const bt2g_policy_params *prm, const bt2g_reads *reads, const char *const *names,
                       bt2g_read_result *res, uint8_t *ops, uint32_t max_ops, bt2g_pair_result *pairs, uint64_t *stats);
 
+/* -k N / -a for unpaired reads (AlnSinkWrap::finishRead with khits > 1, aln_sink.cpp:643-1070; ReportingState::getReport,
+ * aln_sink.cpp:300-330): up to max_per_read records per read, rows [i * max_per_read, i * max_per_read + n_reported[i]) of res / ops:
+ * the primary first, then the secondaries in the reference's order (found bit 8 set -> FLAG 256, MAPQ 255, the read's XS:i).
+ * An unaligned read has n_reported[i] = 0 and an unaligned row at i * max_per_read.  Returns 1 when a read had more alignments
+ * than max_per_read (the extra ones are dropped), 0 otherwise, < 0 on error (paired parameters are an error). */
+int bt2g_policy_align_k(const bt2g_policy_backend *be, const bt2g_policy_params *prm, const bt2g_reads *reads, const char *const *names,
+                        uint32_t max_per_read, bt2g_read_result *res, uint8_t *ops, uint32_t max_ops, uint32_t *n_reported,
+                        uint64_t *stats);
+
 /* bt2g_fastq_parse on `threads` host threads: the text is cut at record boundaries, the pieces parsed concurrently and
  * concatenated in input order; outputs, limits and error codes as bt2g_fastq_parse */
 int bt2g_fastq_parse_mt(const char *text, uint64_t len, uint64_t max_reads, uint64_t max_bases, uint8_t *seq, uint8_t *qual,

@@ -104,3 +104,27 @@ def test_exact_mode_whole_files_over_a_fake_device(tmp_path, lambda_index, paire
     if paired:
         # the summary text equals the reference's except for the documented concordant ">1" split (0 here either way)
         assert summ.getvalue() == open(os.path.join(GOLDEN, "lambda_P_sensitive.summary.txt")).read()
+
+
+def test_exact_mode_k_hits_whole_files_over_a_fake_device(tmp_path, rep_index):
+    """align_files(exact=True, policy_options={"k": 3}) on the repeat-rich fixture: every record of -k 3 (FLAG 256 secondaries
+    included) and the alignment summary identical to the reference program's"""
+    import io
+    import subprocess
+    from fake_gpu import FakeGpu
+    from oracle_lib import Oracle, have_reference, ref_bin
+    if not have_reference():
+        pytest.skip("oracle/_ref not built")
+    fq = os.path.join(GOLDEN, "rep_reads_1.fq")
+    with open(fq) as f, open(tmp_path / "a.fq", "w") as g:
+        g.writelines(f.readlines()[:4 * 300])
+    p = subprocess.run([ref_bin("bowtie2-align-s"), "--sensitive", "--seed", "0", "-p", "1", "-k", "3", "-x", rep_index, "-U", str(tmp_path / "a.fq")],
+                       capture_output=True, text=True, check=True)
+    want = [l for l in p.stdout.split("\n") if l and not l.startswith("@")]
+    out, summ = str(tmp_path / "o.sam"), io.StringIO()
+    align_files(rep_index, out, str(tmp_path / "a.fq"), exact=True, batch_reads=128, summary=summ, gpu=FakeGpu(Oracle(rep_index)),
+                policy_options={"k": 3})
+    got = [l.rstrip("\n") for l in open(out) if not l.startswith("@")]
+    assert got == want, next((a, b) for a, b in zip(got, want) if a != b)
+    assert sum(int(l.split("\t")[1]) & 256 != 0 for l in want) > 50
+    assert summ.getvalue() == p.stderr

@@ -160,3 +160,37 @@ def test_whole_path_in_c_over_the_oracle_table(fixture, index, ref_names, local,
     be2, keep2, fake = _table(base, local)
     res2, ops2, pairs2, _ = policy_align(lib, be2, policy_params("sensitive", local=local, paired=paired), batch, N)
     assert res.tobytes() == res2.tobytes() and ops.tobytes() == ops2.tobytes()
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args,kw,cap", [(["-k", "3"], dict(k=3), 3), (["-k", "12"], dict(k=12), 12), (["-a"], dict(all_hits=True), 400)])
+def test_k_and_all_modes_unpaired_compiled(tmp_path, args, kw, cap):
+    """bt2g_policy_align_k: every reported alignment of -k N / -a (primary, then the secondaries in the reference's order):
+    SAM identical to the reference program's"""
+    from bowtie2_b200.lib import policy_align_k
+    genome = synth.make_genome(n_contigs=3, contig_len=60000, seed=11, repeat_frac=0.5, repeat_len=250, repeat_copies=150, n_gap=37)
+    fa, base = str(tmp_path / "g.fa"), str(tmp_path / "g")
+    synth.write_fasta(fa, genome)
+    subprocess.check_call([ref_bin("bowtie2-build-s"), "--seed", "0", "--quiet", fa, base])
+    reads, quals, _ = synth.make_reads(genome, 250, 100, seed=79, sub_rate=0.02, indel_rate=0.003)
+    fq = str(tmp_path / "r.fq")
+    synth.write_fastq(fq, reads, quals)
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), "--sensitive", "--seed", "0", "-p", "1", "-x", base, "-U", fq] + args,
+                                  stderr=subprocess.DEVNULL).decode()
+    want = [l for l in out.split("\n") if l and not l.startswith("@")]
+    names = [f"r{i}" for i in range(len(reads))]
+    be, keep, fake = _table(base)
+    prm = policy_params("sensitive", k=kw.get("k"), all_hits=kw.get("all_hits", False))
+    res, ops, cnt, truncated, stats = policy_align_k(load_library(), be, prm, ReadBatch.from_list(reads, quals), names, cap)
+    assert not truncated
+    rows = [(i, j) for i in range(len(reads)) for j in range(max(int(cnt[i]), 1))]        # an unaligned read still prints one record
+    R, Q, N = [reads[i] for i, _ in rows], [quals[i] for i, _ in rows], [names[i] for i, _ in rows]
+    res_f = np.array([res[i, j] for i, j in rows], dtype=READ_RESULT)
+    ops_f = np.stack([ops[i, j] for i, j in rows])
+    ref_names = [l.split("\t")[1][3:] for l in out.split("\n") if l.startswith("@SQ")]
+    lines = sam_format(load_library(), ReadBatch.from_list(R, Q), res_f, ops_f, ref_names, read_names=N).rstrip("\n").split("\n")
+    assert lines == want, next((a, b) for a, b in zip(lines, want) if a != b)
+    assert sum(int(l.split("\t")[1]) & 256 != 0 for l in want) > 20
+    # a cap below the number of alignments drops the extra ones and says so
+    res2, ops2, cnt2, truncated2, _ = policy_align_k(load_library(), be, prm, ReadBatch.from_list(reads, quals), names, 2)
+    assert truncated2 and int(cnt2.max()) == 2 and np.array_equal(res2[:, 0], res[:, 0])
