@@ -928,7 +928,7 @@ class IndexFile:
 
 
 # ---- the exact search policy in waves (include/bt2g.h: bt2g_policy_align; csrc/policy_engine.cpp) ----------------------
-EXPORTS += ["bt2g_policy_align", "bt2g_policy_backend_gpu"]
+EXPORTS += ["bt2g_policy_align", "bt2g_policy_align_k", "bt2g_policy_backend_gpu"]
 _CB = C.CFUNCTYPE
 _vp = C.c_void_p
 
