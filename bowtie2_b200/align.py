@@ -96,12 +96,12 @@ def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1, opti
         be, keep = gpu.policy_backend_table()
     else:
         be, keep = policy_backend_gpu(gpu), None
-    gpu.set_scoring(local=local)
-    # the exact policy counts the reference's backtrace attempts (one RNG reseed each): take them from the move-code DP kernels,
-    # whose candidate loop is sequential; the H-byte tail screens candidates in parallel and can label a candidate FAILED that
-    # the sequential order would have skipped ("Known gap")
-    prev = os.environ.get("BT2G_DP_PACKED")
-    os.environ["BT2G_DP_PACKED"] = "1"
+    from . import policy
+    sc = (options or {}).get("sc") or policy.Scoring.default(local)
+    if hasattr(gpu, "set_scoring_policy"):
+        gpu.set_scoring_policy(sc, local)                       # kernels score with the same scheme the policy reasons about
+    else:
+        gpu.set_scoring(local=local)
     try:
         prm = policy_params(preset, local=local, paired=paired, seed=seed, host_threads=threads, **(options or {}))
         if multi:
@@ -121,10 +121,7 @@ def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1, opti
                 np.ascontiguousarray(res_k[:, 0])
         res, ops, pairs, stats = policy_align(gpu._lib, be, prm, batch, names)
     finally:
-        if prev is None:
-            del os.environ["BT2G_DP_PACKED"]
-        else:
-            os.environ["BT2G_DP_PACKED"] = prev
+        pass
     return res, ops, pairs
 
 

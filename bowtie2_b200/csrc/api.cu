@@ -241,6 +241,7 @@ int bt2g_create(int device, bt2g_ctx **out) {
 		delete ctx; return -2;
 	}
 	// experiment knob: L2 -> HBM fetch granularity hint for the random 64 B side gathers
+	if(const char *m = getenv("BT2G_DP_PACKED")) if(m[0] >= '0' && m[0] <= '3') ctx->dpModeCap = m[0] - '0';   // experiment knob, read once
 	if(const char *g = getenv("BT2G_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
 	*out = ctx;
 	return 0;
@@ -615,6 +616,12 @@ int bt2g_set_scoring(bt2g_ctx *ctx, const bt2g_scoring *sc) {
 	return 0;
 }
 
+int bt2g_set_dp_mode(bt2g_ctx *ctx, int cap) {
+	if(!ctx || cap < 0 || cap > 3) return -1;
+	ctx->dpModeCap = cap;
+	return 0;
+}
+
 int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem *probs, uint64_t n,
                    int32_t maxCands, int32_t maxAlns, int32_t maxOps,
                    bt2g_dp_summary *summ, bt2g_dp_cand *cands, bt2g_dp_aln *alns, uint8_t *ops) {
@@ -648,7 +655,7 @@ int bt2g_dp_extend(bt2g_ctx *ctx, const bt2g_reads *reads, const bt2g_dp_problem
 		uint64_t want = (uint64_t)sms * 24;      // 24 resident warps per SM
 		L.numSlots = ((n < want ? n : want) + 3) / 4 * 4;
 	} L.maxCands = maxCands; L.maxAlns = maxAlns; L.maxOps = maxOps;
-	L.packed = ctx->scoring.local ? 0 : dp_kernel_mode(ctx->scoring, minMinsc, maxLen);
+	L.packed = ctx->scoring.local ? 0 : dp_kernel_mode(ctx->scoring, minMinsc, maxLen, ctx->dpModeCap);
 	L.codeStride = dp_code_stride(maxCol, maxLen, L.packed);
 	BT2G_CUDA_TRY(ctx, dprob.alloc(n * sizeof(bt2g_dp_problem)));
 	if(L.packed == 3) {

@@ -69,6 +69,7 @@ struct bt2g_ctx {
 	DevArray denseSa; int denseRate = -1;
 	cudaStream_t stream = nullptr;
 	bt2g_scoring scoring{};
+	int dpModeCap = 3;             // highest end-to-end DP kernel generation the launchers may pick (dp_device.cuh)
 	// scratch buffers (grown on demand)
 	std::vector<DevArray> scratch;
 };

@@ -13,11 +13,9 @@ static inline bool dp_packed_ok(const bt2g_scoring &sc, int64_t minMinsc, int ma
 // 2 = k_dp_e2e_h (s16x2, H bytes: needs perfect - (minsc - bonus - 1) <= 127 for every problem),
 // 3 = the same split into k_dp_fill_h + k_dp_tail_h over chunks of DpLaunch.chunk problems
 //     (workspace: chunk * codeStride bytes).
-// BT2G_DP_PACKED in the environment caps the mode (0, 1 or 2).
-static inline int dp_kernel_mode(const bt2g_scoring &sc, int64_t minMinsc, int maxLen) {
-	int cap = 3;
-	const char *e = getenv("BT2G_DP_PACKED");
-	if(e && e[0] >= '0' && e[0] <= '3') cap = e[0] - '0';
+// `cap` (bt2g_ctx::dpModeCap, set by bt2g_set_dp_mode; initialised once from BT2G_DP_PACKED at bt2g_create) caps the mode.
+static inline int dp_kernel_mode(const bt2g_scoring &sc, int64_t minMinsc, int maxLen, int cap = 3) {
+	if(cap < 0 || cap > 3) cap = 3;
 	if(cap == 0 || !dp_packed_ok(sc, minMinsc, maxLen)) return 0;
 	const int64_t range = (int64_t)sc.match_bonus * maxLen - (minMinsc - sc.match_bonus - 1);
 	return (cap >= 2 && range <= 127) ? (cap >= 3 ? 3 : 2) : 1;

@@ -511,7 +511,7 @@ int bt2g_pipeline_create(bt2g_ctx *ctx, const bt2g_pipeline_params *prm, uint64_
 	{
 		int64_t mn = 0;
 		for(int l = 1; l <= prm->max_len; l++) if(prm->minsc_by_len[l] < mn) mn = prm->minsc_by_len[l];
-		p->packed = p->sc.local ? 0 : dp_kernel_mode(p->sc, mn, prm->max_len);
+		p->packed = p->sc.local ? 0 : dp_kernel_mode(p->sc, mn, prm->max_len, ctx->dpModeCap);
 	}
 	p->R = dp_rows_per_lane(prm->max_len, p->packed);
 	p->codeStride = dp_code_stride(p->maxCol, prm->max_len, p->packed);

@@ -262,7 +262,7 @@ class _Scoring(C.Structure):
     _fields_ = [("match_bonus", C.c_int32), ("rdgap_const", C.c_int32), ("rdgap_linear", C.c_int32),
                 ("rfgap_const", C.c_int32), ("rfgap_linear", C.c_int32), ("gapbar", C.c_int32),
                 ("local", C.c_int32), ("mmpen", C.c_uint8 * 64), ("npen", C.c_uint8 * 64),
-                ("threads", C.c_int32), ("reserved", C.c_int32), ("nceil_const", C.c_double), ("nceil_linear", C.c_double)]
+                ("nceil_const", C.c_double), ("nceil_linear", C.c_double)]      # = bt2g_scoring (include/bt2g.h), 176 bytes
 
 
 DP_PROBLEM = np.dtype([("read_idx", "<u4"), ("fw", "<u4"), ("tidx", "<u8"), ("refl", "<i8"), ("refr", "<i8"),
@@ -273,7 +273,7 @@ DP_CAND = np.dtype([("score", "<i4"), ("row", "<i4"), ("col", "<i4"), ("fate", "
 DP_ALN = np.dtype([("cand_idx", "<i4"), ("score", "<i4"), ("ns", "<i4"), ("gaps", "<i4"), ("refns", "<i4"),
                    ("row0", "<i4"), ("col0", "<i4"), ("trim_beg", "<i4"), ("trim_end", "<i4"), ("nops", "<i4")])
 
-EXPORTS += ["bt2g_scoring_default", "bt2g_set_scoring", "bt2g_dp_extend"]
+EXPORTS += ["bt2g_scoring_default", "bt2g_set_scoring", "bt2g_set_dp_mode", "bt2g_dp_extend"]
 
 OP_MATCH, OP_MM, OP_REFGAP, OP_READGAP = 0, 1, 2, 3
 EDIT_READ_GAP, EDIT_REF_GAP, EDIT_MM = 1, 2, 3      # edit.h:34-39
@@ -301,6 +301,25 @@ def _set_scoring(self, local: bool = False, **over):
     self.scoring = sc
 
 
+def _set_scoring_policy(self, sc, local: bool = None):
+    """Install the device scoring that corresponds to a policy.Scoring (--ma / --mp / --np / --rdg / --rfg / --n-ceil): the
+    same object the exact policy derives minsc / perfect / MAPQ from, so kernels and policy cannot disagree."""
+    from . import policy
+    local = bool(sc.local if local is None else local)
+    nce = sc.n_ceil_func()
+    mm = (C.c_uint8 * 64)(*[policy.mm_penalty(min(q, 40), sc.mmp_max, sc.mmp_min) for q in range(64)])
+    np_ = (C.c_uint8 * 64)(*[sc.n_pen] * 64)
+    self.set_scoring(local=local, match_bonus=sc.match_bonus, rdgap_const=sc.rdgap_const, rdgap_linear=sc.rdgap_linear,
+                     rfgap_const=sc.rfgap_const, rfgap_linear=sc.rfgap_linear, gapbar=sc.gapbar, mmpen=mm, npen=np_,
+                     nceil_const=float(nce.C), nceil_linear=float(nce.L))
+
+
+def _set_dp_mode(self, cap: int):
+    """bt2g_set_dp_mode: cap the end-to-end DP kernel generation (0..3) of this context"""
+    self._lib.bt2g_set_dp_mode.argtypes = [C.c_void_p, C.c_int]
+    self._check(self._lib.bt2g_set_dp_mode(self._h, int(cap)), "bt2g_set_dp_mode")
+
+
 def _dp_extend(self, reads: ReadBatch, probs: np.ndarray, max_cands=128, max_alns=4, max_ops=None):
     """SwAligner::initRef + align + nextAlignment* for each problem (include/bt2g.h)."""
     _bind_dp(self._lib)
@@ -320,6 +339,8 @@ def _dp_extend(self, reads: ReadBatch, probs: np.ndarray, max_cands=128, max_aln
 
 
 Bt2Gpu.set_scoring = _set_scoring
+Bt2Gpu.set_scoring_policy = _set_scoring_policy
+Bt2Gpu.set_dp_mode = _set_dp_mode
 Bt2Gpu.dp_extend = _dp_extend
 
 

@@ -6,8 +6,7 @@ of the same code.  Conventions are those the -m gpu parity tests establish for e
 test_onemm, test_extend, test_ungapped, test_dp_gpu), where the results are pinned bit-exact against the CPU oracle.
 The DP's backtrace attempts come from the per-candidate fates bt2g_dp_extend returns (BT2G_CAND_FAILED / _SUCCEEDED).
 
-NOT YET RUN ON HARDWARE (written after the round's GPU minutes were spent): tests/test_zz_fullsize_gpu.py holds the
-staged checks (engine over this backend == golden SAM, per item and in waves)."""
+tests/test_exact_gpu.py: engine over this backend == golden SAM, per item and in waves."""
 import numpy as np
 
 from . import policy
@@ -25,10 +24,13 @@ def _u8(x):
 class GpuBatchBackend:
     DP_CHUNK = 4096
 
-    def __init__(self, gpu: Bt2Gpu, local: bool = False):
+    def __init__(self, gpu: Bt2Gpu, local: bool = False, sc: "policy.Scoring" = None):
         self.gpu = gpu
         self.local = local
-        gpu.set_scoring(local=local)
+        if hasattr(gpu, "set_scoring_policy"):
+            gpu.set_scoring_policy(sc or policy.Scoring.default(local), local)
+        else:                                        # the stand-in device of the CPU test-suite
+            gpu.set_scoring(local=local)
         self.off_size = int(gpu.info()["off_size"])
         self._rows = {}                              # id -> BW row of the read's last resolve request
 
@@ -216,8 +218,8 @@ class GpuBatchBackend:
 class GpuBackend:
     """per-item view (one entry-point call per request): policy_engine.PolicyEngine(GpuBackend(gpu), ...)"""
 
-    def __init__(self, gpu: Bt2Gpu, local: bool = False):
-        self.bb = GpuBatchBackend(gpu, local)
+    def __init__(self, gpu: Bt2Gpu, local: bool = False, sc: "policy.Scoring" = None):
+        self.bb = GpuBatchBackend(gpu, local, sc)
         self.off_size = self.bb.off_size
         self.local = local
 

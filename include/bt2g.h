@@ -194,6 +194,11 @@ typedef struct {
 void bt2g_scoring_default(bt2g_scoring *sc, int local);
 int  bt2g_set_scoring(bt2g_ctx *ctx, const bt2g_scoring *sc);
 
+/* Highest generation of the end-to-end DP kernels the launchers may select (0 32-bit move codes, 1 s16x2 move codes,
+ * 2 fused H-byte, 3 split H-byte fill + tail = default); all generations return identical results (tests/test_dp_gpu.py).
+ * A per-context setting: no process-global state. */
+int  bt2g_set_dp_mode(bt2g_ctx *ctx, int cap);
+
 /* One DP problem = one SwAligner::initRef + align + nextAlignment* session as issued by
  * SwDriver::extendSeeds (aligner_sw_driver.cpp:1272-1376).  The rectangle comes from
  * DynProgFramer::frameSeedExtensionRect (dp_framer.cpp:81-129; DPRect, dp_framer.h:59). */
