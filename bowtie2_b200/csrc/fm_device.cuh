@@ -257,3 +257,37 @@ __device__ __forceinline__ int read_char(const uint8_t *seq, int len, int strand
 	int c = seq[len - 1 - pos];
 	return c > 3 ? 4 : 3 - c;
 }
+
+// SwDriver::extend (aligner_sw_driver.cpp:299-484), one direction: how many read positions the range [top, bot) extends
+// without an edit and without shrinking (<= 255).  Used by k_extend (fm_kernels.cu) and inline by the exact engine.
+template <typename OFF>
+__device__ __forceinline__ uint32_t extend_one(const DevEbwt<OFF> &e, uint64_t top, uint64_t bot, const uint8_t *s, int len,
+                                               int strand, int i0, int step, int lim) {
+	uint32_t n = 0;
+	for(int ii = 0; ii < lim; ii++) {
+		const int rdc = read_char(s, len, strand, i0 + ii * step);
+		if(bot - top > 1) {
+			uint64_t t[4], b[4];
+			rank4<OFF>(e, top, t);
+			rank4<OFF>(e, bot, b);
+			const uint64_t orig = bot - top;
+			int nonz = -1; bool abort = false;
+#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				if(!abort && b[j] > t[j]) {
+					if(nonz >= 0) abort = true;
+					else { nonz = j; top = t[j]; bot = b[j]; }
+				}
+			}
+			if(abort || (nonz != rdc && rdc <= 3) || bot - top < orig) break;
+		} else {
+			int c = -1;
+			if(top != e.zOff) top = lf_step<OFF>(e, top, c);
+			if(c != rdc && rdc <= 3) break;
+			bot = top + 1;
+		}
+		if(++n == 255) break;
+	}
+	return n;
+}
+

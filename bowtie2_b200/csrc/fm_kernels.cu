@@ -229,37 +229,6 @@ __global__ void k_resolve(DevIndex<OFF> ix, const uint64_t *rows, const uint32_t
 // Two threads per seed hit (one per direction) so both walks run concurrently.
 // ----------------------------------------------------------------------------------------
 template <typename OFF>
-__device__ __forceinline__ uint32_t extend_one(const DevEbwt<OFF> &e, uint64_t top, uint64_t bot, const uint8_t *s, int len,
-                                               int strand, int i0, int step, int lim) {
-	uint32_t n = 0;
-	for(int ii = 0; ii < lim; ii++) {
-		const int rdc = read_char(s, len, strand, i0 + ii * step);
-		if(bot - top > 1) {
-			uint64_t t[4], b[4];
-			rank4<OFF>(e, top, t);
-			rank4<OFF>(e, bot, b);
-			const uint64_t orig = bot - top;
-			int nonz = -1; bool abort = false;
-#pragma unroll
-			for(int j = 0; j < 4; j++) {
-				if(!abort && b[j] > t[j]) {
-					if(nonz >= 0) abort = true;
-					else { nonz = j; top = t[j]; bot = b[j]; }
-				}
-			}
-			if(abort || (nonz != rdc && rdc <= 3) || bot - top < orig) break;
-		} else {
-			int c = -1;
-			if(top != e.zOff) top = lf_step<OFF>(e, top, c);
-			if(c != rdc && rdc <= 3) break;
-			bot = top + 1;
-		}
-		if(++n == 255) break;
-	}
-	return n;
-}
-
-template <typename OFF>
 __global__ void k_extend(DevIndex<OFF> ix, const uint8_t *seq, const uint64_t *roff, uint64_t nReads,
                          int seedLen, int maxSeeds, const int32_t *interval, const int32_t *offset,
                          const uint64_t *ranges, uint8_t *out) {

@@ -39,13 +39,17 @@ __device__ __forceinline__ void bi_step(const DevEbwt<OFF> &e, uint64_t top, uin
 template <typename OFF>
 __global__ void k_one_mm(DevIndex<OFF> ix, const uint8_t *seq, const uint8_t *qual, const uint64_t *roff, uint64_t nReads,
                          const int32_t *minsc, const uint8_t *strandMask, bt2g_scoring sc, int maxHits,
-                         bt2g_mm_hit *hits, int32_t *counts) {
+                         bt2g_mm_hit *hits, int32_t *counts, const uint32_t *sel, const uint32_t *nDev) {
+	// sel != nullptr: request slot s searches read sel[s] (minsc / strandMask / hits / counts are indexed by slot);
+	// nDev != nullptr: the number of slots is a device-side count
 	uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(nDev) nReads = *nDev;
 	if(t >= nReads * 4) return;
-	const uint64_t rd = t >> 2;
+	const uint64_t slot = t >> 2;
+	const uint64_t rd = sel ? sel[slot] : slot;
 	const int fwi = (int)((t >> 1) & 1), pass = (int)(t & 1);
 	counts[t] = 0;
-	if(!((strandMask[rd] >> fwi) & 1)) return;
+	if(!((strandMask[slot] >> fwi) & 1)) return;
 	OneMmCtx c;
 	c.s = seq + roff[rd]; c.q = qual + roff[rd];
 	c.len = (int)(roff[rd + 1] - roff[rd]); c.fw = fwi == 0; c.ebwtfw = pass == 0;
@@ -131,7 +135,7 @@ __global__ void k_one_mm(DevIndex<OFF> ix, const uint8_t *seq, const uint8_t *qu
 							if(len - i - 1 == dep) { if(lb + pen <= 0) valid = false; lb += pen; } else lb += sc.match_bonus;
 						}
 					}
-					if(valid && score >= minsc[rd]) {
+					if(valid && score >= minsc[slot]) {
 						if(nh < maxHits) {
 							bt2g_mm_hit &h = out[nh];
 							h.top = c.ebwtfw ? topm : topmp; h.bot = c.ebwtfw ? botm : botmp;
@@ -159,7 +163,17 @@ void launch_one_mm(const DevIndex<OFF> &ix, const uint8_t *seq, const uint8_t *q
                    const int32_t *minsc, const uint8_t *strandMask, const bt2g_scoring &sc, int maxHits, bt2g_mm_hit *hits,
                    int32_t *counts, cudaStream_t st) {
 	const uint64_t n = nReads * 4;
-	if(n) k_one_mm<OFF><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ix, seq, qual, roff, nReads, minsc, strandMask, sc, maxHits, hits, counts);
+	if(n) k_one_mm<OFF><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ix, seq, qual, roff, nReads, minsc, strandMask, sc, maxHits, hits, counts, nullptr, nullptr);
 }
+// request-queue form: nSlots requests, slot s = read sel[s]
+template <typename OFF>
+void launch_one_mm_sel(const DevIndex<OFF> &ix, const uint8_t *seq, const uint8_t *qual, const uint64_t *roff, uint64_t nSlots, const uint32_t *sel,
+                       const int32_t *minsc, const uint8_t *strandMask, const bt2g_scoring &sc, int maxHits, bt2g_mm_hit *hits,
+                       int32_t *counts, cudaStream_t st) {
+	const uint64_t n = nSlots * 4;
+	if(n) k_one_mm<OFF><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ix, seq, qual, roff, nSlots, minsc, strandMask, sc, maxHits, hits, counts, sel, nullptr);
+}
+template void launch_one_mm_sel<uint32_t>(const DevIndex<uint32_t> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const uint32_t *, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t);
+template void launch_one_mm_sel<uint64_t>(const DevIndex<uint64_t> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const uint32_t *, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t);
 template void launch_one_mm<uint32_t>(const DevIndex<uint32_t> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t);
 template void launch_one_mm<uint64_t>(const DevIndex<uint64_t> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t);

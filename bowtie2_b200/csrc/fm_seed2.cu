@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(256) k_seed_search3(DevIndex<OFF> ix, const ui
                                                       const uint64_t *roff, uint64_t nReads, int seedLen, int maxSeeds,
                                                       int nofw, int norc, const int32_t *interval, const int32_t *offset,
                                                       uint64_t *out, int32_t *nseedsOut, unsigned long long *next,
-                                                      unsigned long long *cnt) {
+                                                      unsigned long long *cnt, const uint8_t *actv) {
+	// actv != nullptr: only reads with actv[rd] != 0 are searched (their output slots are rewritten; the others stay untouched)
 	constexpr uint32_t BL = SideGeom<OFF>::BWT_LEN;
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(256) k_seed_search3(DevIndex<OFF> ix, const ui
 			if(!haveTask && !exhausted) {
 				const uint64_t t = base + (unsigned)__popc(need & ((1u << lane) - 1u));
 				if(t >= total) exhausted = true;
+				else if(actv && !actv[t >> 1]) { }               // not requested: take another task next round
 				else {
 					const uint64_t rd = t >> 1;
 					strand = (int)(t & 1);
@@ -334,8 +336,24 @@ void launch_seed_search2(const DevIndex<OFF> &ix, const uint8_t *seq, const uint
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_seed_search3<OFF>, 256, 0);
 	if(perSM < 1) perSM = 1;
 	k_seed_search3<OFF><<<(unsigned)(numSMs * perSM), 256, 0, st>>>(ix, packed, nmask, roff, nReads, seedLen, maxSeeds, nofw, norc,
-	                                                              interval, offset, out, nseeds, next, cnt);
+	                                                              interval, offset, out, nseeds, next, cnt, nullptr);
 }
+// the same over the reads flagged in actv[] (re-seeding rounds of the exact engine, csrc/xengine.cu)
+template <typename OFF>
+void launch_seed_search_active(const DevIndex<OFF> &ix, const uint64_t *roff, uint64_t nReads, int seedLen, int maxSeeds,
+                               const int32_t *interval, const int32_t *offset, const uint8_t *actv, uint64_t *out, int32_t *nseeds,
+                               const uint64_t *packed, const uint32_t *nmask, unsigned long long *next, int numSMs, cudaStream_t st) {
+	if(nReads == 0) return;
+	cudaMemsetAsync(next, 0, sizeof(unsigned long long), st);
+	int perSM = 4;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_seed_search3<OFF>, 256, 0);
+	if(perSM < 1) perSM = 1;
+	uint64_t blocks = (uint64_t)numSMs * perSM, want = (nReads * 2 + 255) / 256;
+	if(want < blocks) blocks = want ? want : 1;
+	k_seed_search3<OFF><<<(unsigned)blocks, 256, 0, st>>>(ix, packed, nmask, roff, nReads, seedLen, maxSeeds, 0, 0, interval, offset, out, nseeds, next, nullptr, actv);
+}
+template void launch_seed_search_active<uint32_t>(const DevIndex<uint32_t> &, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint8_t *, uint64_t *, int32_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t);
+template void launch_seed_search_active<uint64_t>(const DevIndex<uint64_t> &, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint8_t *, uint64_t *, int32_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t);
 template void launch_seed_search2<uint32_t>(const DevIndex<uint32_t> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
 template void launch_seed_search2<uint64_t>(const DevIndex<uint64_t> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, uint64_t *, uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *);
 

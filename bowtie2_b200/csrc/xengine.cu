@@ -1,0 +1,489 @@
+// xengine.cu -- the exact search policy ON THE DEVICE: the state machine of xengine.cuh as a kernel (one thread per read pair /
+// read, state resident in HBM), advanced in WAVES.  A wave = k_xe_step (every unfinished unit runs until it needs a batched
+// primitive and appends that request to a device queue; SA-offset resolution, SwDriver::extend and ungapped alignment happen
+// inline in the thread) followed by one launch per non-empty queue: seed-extension DP, mate-finding DP (both = the fill + tail
+// kernels of dp_kernels.cu over the queued bt2g_dp_problem arrays), 1-mismatch search, (re-)seeding.  exactSweep for every read
+// runs once at admission.  The host only reads five queue counters per wave to size the launches.
+//
+// This replaces the reference's per-thread control loop (multiseedSearchWorker, bt2_search.cpp:3094-4254, driving
+// SwDriver::extendSeedsPaired, aligner_sw_driver.cpp:1582-2637) with the same decisions, RNG draws included, made by up to
+// hundreds of thousands of reads at once; results are the reference program's (tests/test_xengine_gpu.py, bench.py's parity gate).
+#include <new>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "dp_ungapped_device.cuh"
+#include "dp_device.cuh"
+#define XE_HD __device__           // the host twin of the state machine is compiled in xengine_host.cpp
+#include "xengine.cuh"
+#include "xengine_shared.h"
+
+template <typename OFF> int launch_dp_e2e(const DevIndex<OFF> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);
+template <typename OFF> int launch_dp_local(const DevIndex<OFF> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);
+template <typename OFF> void launch_exact_sweep2(const DevIndex<OFF> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *, int);
+void launch_pack_reads(const uint8_t *, const uint64_t *, uint64_t, int, uint64_t *, uint32_t *, cudaStream_t);
+template <typename OFF> void launch_one_mm_sel(const DevIndex<OFF> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const uint32_t *, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t);
+template <typename OFF> void launch_seed_search_active(const DevIndex<OFF> &, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint8_t *, uint64_t *, int32_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t);
+
+extern "C" int bt2g_policy_align(const bt2g_policy_backend *, const bt2g_policy_params *, const bt2g_reads *, const char *const *,
+                                 bt2g_read_result *, uint8_t *, uint32_t, bt2g_pair_result *, uint64_t *);
+
+namespace {
+using namespace xe;
+
+#define XE_MM_MAXHITS 16
+
+struct XQueues {                     // per wave, reset before k_xe_step
+	uint32_t nDpA, nDpM, nMm, nSeed, nDone, nFallback, pad0, pad1;
+	unsigned long long cellsA, cellsM;
+};
+
+struct DpOut { bt2g_dp_problem *probs; bt2g_dp_summary *summ; bt2g_dp_cand *cands; bt2g_dp_aln *alns; uint8_t *ops; int maxCands, maxAlns, maxOps; };
+
+struct XDev {                        // everything the step kernel needs (passed by value)
+	const uint8_t *seq, *qual; const uint64_t *roff;
+	const uint32_t *seeds;
+	const uint8_t *mine; const uint64_t *ee;
+	const bt2g_mm_hit *mmHits; const int32_t *mmCounts;
+	uint32_t *mmSel; int32_t *mmMinsc; uint8_t *mmMask;
+	const uint64_t *ranges; const int32_t *nseeds; int maxSeeds;
+	int32_t *seedInterval, *seedOffset; uint8_t *seedActive;
+	DpOut A, M;
+	XQueues *q;
+	XUnit *units; uint8_t *status; uint64_t nUnits;
+	bt2g_read_result *res; uint8_t *resOps; bt2g_pair_result *pairs; uint32_t resMaxOps;
+};
+
+template <typename OFF>
+struct DevSvc {
+	const DevIndex<OFF> &ix; const bt2g_scoring &sc; const XDev &d;
+	__device__ DevSvc(const DevIndex<OFF> &i, const bt2g_scoring &s, const XDev &dd) : ix(i), sc(s), d(dd) {}
+	__device__ const uint8_t *codes(int read) const { return d.seq + d.roff[read]; }
+	__device__ const uint8_t *quals(int read) const { return d.qual + d.roff[read]; }
+	__device__ int rdlen(int read) const { return (int)(d.roff[read + 1] - d.roff[read]); }
+	__device__ uint32_t randSeed(int read) const { return d.seeds[read]; }
+	__device__ void sweep(int read, int mined[2], uint64_t tb[4]) const {
+		mined[0] = d.mine[2 * (size_t)read]; mined[1] = d.mine[2 * (size_t)read + 1];
+		for(int j = 0; j < 4; j++) tb[j] = d.ee[4 * (size_t)read + j];
+	}
+	__device__ int mmMax() const { return XE_MM_MAXHITS; }
+	__device__ int mmCount(int slot, int task) const { return d.mmCounts[4 * (size_t)slot + task]; }
+	__device__ const bt2g_mm_hit *mmHits(int slot, int task) const { return d.mmHits + (4 * (size_t)slot + task) * XE_MM_MAXHITS; }
+	__device__ int nSeeds(int read) const { return d.nseeds[read]; }
+	__device__ const uint64_t *seedRange(int read, int strand, int i) const { return d.ranges + (((size_t)read * 2 + strand) * d.maxSeeds + i) * 4; }
+	__device__ const DpOut &dq(bool mate) const { return mate ? d.M : d.A; }
+	__device__ const bt2g_dp_summary *dpSumm(int slot, bool mate) const { return dq(mate).summ + slot; }
+	__device__ const bt2g_dp_cand *dpCands(int slot, bool mate) const { return dq(mate).cands + (size_t)slot * dq(mate).maxCands; }
+	__device__ const bt2g_dp_aln *dpAlns(int slot, bool mate) const { return dq(mate).alns + (size_t)slot * dq(mate).maxAlns; }
+	__device__ const uint8_t *dpOps(int slot, bool mate, int k) const { const DpOut &o = dq(mate); return o.ops + ((size_t)slot * o.maxAlns + k) * o.maxOps; }
+	__device__ int dpMaxAlns() const { return d.A.maxAlns; }
+	// GroupWalk2S::advanceElement == Ebwt::getOffset, then Ebwt::joinedToTextOff (k_resolve2, fm_seed2.cu)
+	__device__ bool resolve(uint64_t row, int qlen, bool reject, int64_t &tidx, int64_t &toff, int64_t &tlen) const {
+		unsigned nside = 0;
+		const uint64_t off = get_offset<OFF>(ix, row, nside);
+		uint64_t ti, to, tl; bool st;
+		const bool ok = joined_to_text<OFF>(ix, (uint64_t)qlen, off, reject, ti, to, tl, st);
+		tidx = (int64_t)ti; toff = (int64_t)to; tlen = (int64_t)tl;
+		return ok;
+	}
+	// SwDriver::extend (k_extend, fm_kernels.cu): left with the forward index, right with the mirror index
+	__device__ void extend(int read, bool fw, int rdoff, int seedlen, const uint64_t rng[4], int &nlex, int &nrex) const {
+		const uint8_t *s = codes(read); const int len = rdlen(read);
+		const int sl = seedlen < len ? seedlen : len, off = rdoff, strand = fw ? 0 : 1;
+		nlex = nrex = 0;
+		{
+			const int lim = fw ? off : len - sl - off;
+			if(lim > 0) nlex = (int)extend_one<OFF>(ix.fw, rng[0], rng[1], s, len, strand, fw ? off - 1 : len - off - sl - 1, -1, lim);
+		}
+		{
+			const int lim = fw ? len - sl - off : off;
+			if(lim > 0 && ix.bw.ebwt != nullptr) nrex = (int)extend_one<OFF>(ix.bw, rng[2], rng[3], s, len, strand, fw ? sl + off : len - off, +1, lim);
+		}
+	}
+	__device__ int ungapped(int read, bool fw, int64_t tidx, int64_t refoff, int64_t tlen, int64_t minsc, bt2g_ungapped_result &r) const {
+		bt2g_ungapped_problem p; p.read_idx = (uint32_t)read; p.fw = fw ? 1u : 0u; p.tidx = (uint64_t)tidx; p.refoff = refoff; p.reflen = (uint64_t)tlen;
+		p.minsc = (int32_t)minsc; p.ohang = 0;
+		ungapped_one<OFF>(ix, sc, codes(read), quals(read), rdlen(read), p, r, nullptr, 0);
+		return r.status;
+	}
+	__device__ int refChar(int64_t tidx, int64_t off) const { return ref_base<OFF>(ix, (uint64_t)tidx, off); }
+};
+
+// genRandSeed (pat.cpp:45-82) for every read; names: rows of nameStride bytes (NUL-terminated) or nullptr = "r<unit index>"
+__global__ void k_xe_seeds(const uint8_t *seq, const uint8_t *qual, const uint64_t *roff, uint64_t nReads, const char *names, uint32_t nameStride,
+                           int paired, uint32_t seed, uint32_t *out) {
+	const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(i >= nReads) return;
+	const uint8_t *c = seq + roff[i], *q = qual + roff[i];
+	const int len = (int)(roff[i + 1] - roff[i]);
+	uint32_t rseed = (seed + 101u) * 59u * 61u * 67u * 71u * 73u * 79u * 83u;
+	for(int k = 0; k < len; k++) rseed ^= (uint32_t)c[k] << ((k & 15) << 1);
+	for(int k = 0; k < len; k++) rseed ^= (uint32_t)q[k] << ((k & 3) << 3);
+	if(names) {
+		const char *nm = names + i * (uint64_t)nameStride;
+		for(uint32_t k = 0; k < nameStride && nm[k]; k++) { if(nm[k] == '/') break; rseed ^= (uint32_t)(unsigned char)nm[k] << ((k & 3) << 3); }
+	} else {
+		char buf[24]; int n = 0;
+		uint64_t v = paired ? i >> 1 : i;
+		char tmp[20]; int t = 0;
+		do { tmp[t++] = (char)('0' + v % 10); v /= 10; } while(v);
+		buf[n++] = 'r';
+		while(t) buf[n++] = tmp[--t];
+		for(int k = 0; k < n; k++) rseed ^= (uint32_t)(unsigned char)buf[k] << ((k & 3) << 3);
+	}
+	out[i] = rseed;
+}
+
+__global__ void k_xe_reset(XUnit *units, uint8_t *status, uint64_t nUnits, int paired) {
+	const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(i >= nUnits) return;
+	x_unit_reset(units[i], (uint32_t)i, paired != 0);
+	status[i] = 0;
+}
+
+// status: 0 running, 1 finished, 2 fallback (to be re-run by the coroutine engine)
+template <typename OFF>
+__global__ void __launch_bounds__(64) k_xe_step(DevIndex<OFF> ix, bt2g_scoring sc, XParams P, XDev d) {
+	const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(i >= d.nUnits || d.status[i]) return;
+	XUnit &u = d.units[i];
+	DevSvc<OFF> svc(ix, sc, d);
+	const int r = x_step(P, u, svc);
+	switch(r) {
+	case XR_DP: case XR_DP_MATE: {
+		const bool mate = r == XR_DP_MATE;
+		const uint32_t slot = atomicAdd(mate ? &d.q->nDpM : &d.q->nDpA, 1u);
+		(mate ? d.M : d.A).probs[slot] = u.rqProb;
+		u.dpSlot = (int32_t)slot;
+		const unsigned long long cells = (unsigned long long)svc.rdlen((int)u.rqProb.read_idx) * (unsigned long long)(u.rqProb.refr - u.rqProb.refl + 1);
+		atomicAdd(mate ? &d.q->cellsM : &d.q->cellsA, cells);
+		break; }
+	case XR_ONE_MM: {
+		const uint32_t slot = atomicAdd(&d.q->nMm, 1u);
+		d.mmSel[slot] = (uint32_t)u.rqRead; d.mmMinsc[slot] = u.rqMinsc; d.mmMask[slot] = (uint8_t)((u.rqNofw ? 0 : 1) | (u.rqNorc ? 0 : 2));
+		u.dpSlot = (int32_t)slot;
+		break; }
+	case XR_SEED:
+		d.seedActive[u.rqRead] = 1; d.seedInterval[u.rqRead] = u.rqInterval; d.seedOffset[u.rqRead] = u.rqOffset;
+		atomicAdd(&d.q->nSeed, 1u);
+		break;
+	case XR_DONE: {
+		d.status[i] = 1;
+		atomicAdd(&d.q->nDone, 1u);
+		const uint64_t r0 = u.paired ? 2 * i : i; const int nr = u.paired ? 2 : 1;
+		for(int k = 0; k < nr; k++) x_fill_result(u, k, svc.codes((int)(r0 + k)), d.res[r0 + k], d.resOps + (r0 + k) * (uint64_t)d.resMaxOps, d.resMaxOps);
+		if(u.paired) { bt2g_pair_result pr; pr.pair_type = u.pairType; pr.kind = u.pairKind; pr.source = 0; pr.score_sum = (int32_t)u.scoreSum; pr.fraglen = u.fraglen; d.pairs[i] = pr; }
+		break; }
+	default:
+		d.status[i] = 2;
+		atomicAdd(&d.q->nFallback, 1u);
+		break;
+	}
+}
+
+struct DpWork {                       // workspace of one DP queue (anchor rectangles / mate rectangles)
+	DpOut o{}; uint8_t *codes = nullptr; int32_t *lastH = nullptr; uint64_t *rawKeys = nullptr;
+	int maxCol = 0, packed = 0, maxRaw = 0; uint64_t codeStride = 0, chunk = 0, numSlots = 0;
+};
+
+} // namespace
+
+struct bt2g_xengine {
+	bt2g_ctx *ctx = nullptr;
+	bt2g_policy_params pp{};
+	bt2g_scoring sc{};
+	XParams P{}; XTables T;
+	uint64_t maxUnits = 0, maxReads = 0, maxBases = 0; int maxLen = 0; uint32_t maxOps = 0;
+	std::vector<void *> allocs;
+	int32_t *dTabs = nullptr;
+	XDev d{};
+	DpWork A, M;
+	uint64_t *packed = nullptr; uint32_t *nmask = nullptr; unsigned long long *nextTask = nullptr;
+	uint8_t *dSeq = nullptr, *dQual = nullptr; uint64_t *dOff = nullptr; char *dNames = nullptr; uint32_t nameStrideCap = 0;
+	XQueues *hq = nullptr;             // pinned
+	uint8_t *hStatus = nullptr;        // pinned
+	int sms = 148;
+	uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // waves, fallbacks, anchor DPs, mate DPs, anchor cells, mate cells, 1-mm requests, seed requests
+	float lastMs = 0.f;
+};
+
+namespace {
+
+template <typename T> int xalloc(bt2g_xengine *e, T *&ptr, uint64_t count) {
+	void *v = nullptr;
+	const cudaError_t err = cudaMalloc(&v, (count ? count : 1) * sizeof(T));
+	if(err != cudaSuccess) { e->ctx->err = std::string("xengine cudaMalloc: ") + cudaGetErrorString(err); return -2; }
+	e->allocs.push_back(v);
+	ptr = (T *)v;
+	return 0;
+}
+
+int setupDp(bt2g_xengine *e, DpWork &w, int maxCol, uint64_t cap, int maxCands, int maxAlns) {
+	const bt2g_scoring &sc = e->sc;
+	int64_t mn = 0;
+	for(int l = 1; l <= e->maxLen; l++) if(e->T.minsc[l] < mn) mn = e->T.minsc[l];
+	w.maxCol = maxCol + 1;
+	w.packed = sc.local ? 0 : dp_kernel_mode(sc, mn, e->maxLen, e->ctx->dpModeCap);
+	w.codeStride = dp_code_stride(w.maxCol, e->maxLen, w.packed);
+	w.numSlots = (uint64_t)e->sms * 24;
+	int rc = 0;
+	if(w.packed == 3) { w.chunk = dp_chunk_problems(w.codeStride, cap); rc |= xalloc(e, w.codes, w.chunk * w.codeStride); }
+	else rc |= xalloc(e, w.codes, w.numSlots * w.codeStride * (w.packed ? 2 : 1));
+	rc |= xalloc(e, w.lastH, w.numSlots * (uint64_t)w.maxCol);
+	w.maxRaw = maxCands * 4 < 1024 ? 1024 : maxCands * 4;
+	if(sc.local) rc |= xalloc(e, w.rawKeys, w.numSlots * (uint64_t)w.maxRaw);
+	w.o.maxCands = maxCands; w.o.maxAlns = maxAlns; w.o.maxOps = e->maxLen + 80;
+	rc |= xalloc(e, w.o.probs, cap); rc |= xalloc(e, w.o.summ, cap); rc |= xalloc(e, w.o.cands, cap * (uint64_t)maxCands);
+	rc |= xalloc(e, w.o.alns, cap * (uint64_t)maxAlns); rc |= xalloc(e, w.o.ops, cap * (uint64_t)maxAlns * w.o.maxOps);
+	return rc;
+}
+
+template <typename OFF>
+int launchDp(bt2g_xengine *e, const DpWork &w, uint64_t n, cudaStream_t st) {
+	if(n == 0) return 0;
+	DpLaunch L;
+	L.seq = e->d.seq; L.qual = e->d.qual; L.roff = e->d.roff; L.probs = w.o.probs; L.n = n; L.nDev = nullptr;
+	L.numSlots = w.numSlots; L.codes = w.codes; L.lastH = w.lastH; L.rawKeys = w.rawKeys; L.maxRaw = w.rawKeys ? w.maxRaw : 0;
+	L.codeStride = w.codeStride; L.maxCol = w.maxCol; L.maxCands = w.o.maxCands; L.maxAlns = w.o.maxAlns; L.maxOps = w.o.maxOps;
+	L.chunk = w.chunk; L.packed = w.packed;
+	L.summ = w.o.summ; L.cands = w.o.cands; L.alns = w.o.alns; L.ops = w.o.ops;
+	const DevIndex<OFF> ix = bt2g_dev_index<OFF>(e->ctx);
+	return e->sc.local ? launch_dp_local<OFF>(ix, e->sc, L, e->maxLen, st) : launch_dp_e2e<OFF>(ix, e->sc, L, e->maxLen, st);
+}
+
+// the waves of one batch whose reads are in device memory (e->d.seq / qual / roff set)
+template <typename OFF>
+int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t nameStride, cudaStream_t st) {
+	bt2g_ctx *ctx = e->ctx;
+	const bool paired = e->P.paired != 0;
+	const uint64_t nUnits = paired ? nReads / 2 : nReads;
+	const DevIndex<OFF> ix = bt2g_dev_index<OFF>(ctx);
+	XDev &d = e->d;
+	d.nUnits = nUnits;
+	const unsigned T = 128;
+	auto grid = [&](uint64_t m, unsigned t) { return (unsigned)((m + t - 1) / t); };
+	for(int k = 0; k < 8; k++) e->stats[k] = 0;
+	// admission: read seeds, unit reset, 2-bit packing, exactSweep of every read
+	k_xe_seeds<<<grid(nReads, T), T, 0, st>>>(d.seq, d.qual, d.roff, nReads, dNames, nameStride, paired ? 1 : 0, e->P.seed, const_cast<uint32_t *>(d.seeds));
+	k_xe_reset<<<grid(nUnits, T), T, 0, st>>>(d.units, d.status, nUnits, paired ? 1 : 0);
+	launch_pack_reads(d.seq, d.roff, nReads, e->maxLen, e->packed, e->nmask, st);
+	launch_exact_sweep2<OFF>(ix, d.roff, nReads, 0, 0, const_cast<uint8_t *>(d.mine), const_cast<uint64_t *>(d.ee), e->packed, e->nmask, e->nextTask, e->sms, st, nullptr, 0);
+	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(d.seedActive, 0, nReads, st));
+	BT2G_CUDA_TRY(ctx, cudaGetLastError());
+	uint64_t done = 0;
+	for(uint64_t wave = 0;; wave++) {
+		BT2G_CUDA_TRY(ctx, cudaMemsetAsync(d.q, 0, sizeof(XQueues), st));
+		k_xe_step<OFF><<<grid(nUnits, 64), 64, 0, st>>>(ix, e->sc, e->P, d);
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(e->hq, d.q, sizeof(XQueues), cudaMemcpyDeviceToHost, st));
+		BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		const XQueues q = *e->hq;
+		e->stats[0]++; e->stats[1] += q.nFallback; e->stats[2] += q.nDpA; e->stats[3] += q.nDpM; e->stats[4] += q.cellsA; e->stats[5] += q.cellsM;
+		e->stats[6] += q.nMm; e->stats[7] += q.nSeed;
+		done += q.nDone + q.nFallback;
+		if(done >= nUnits) break;
+		if(q.nDpA + q.nDpM + q.nMm + q.nSeed == 0) { ctx->err = "xengine: units neither finished nor waiting"; return -5; }
+		if(q.nMm) launch_one_mm_sel<OFF>(ix, d.seq, d.qual, d.roff, q.nMm, d.mmSel, d.mmMinsc, d.mmMask, e->sc, XE_MM_MAXHITS, const_cast<bt2g_mm_hit *>(d.mmHits), const_cast<int32_t *>(d.mmCounts), st);
+		if(q.nSeed) {
+			launch_seed_search_active<OFF>(ix, d.roff, nReads, e->P.seedLen, d.maxSeeds, d.seedInterval, d.seedOffset, d.seedActive, const_cast<uint64_t *>(d.ranges),
+			                               const_cast<int32_t *>(d.nseeds), e->packed, e->nmask, e->nextTask, e->sms, st);
+			BT2G_CUDA_TRY(ctx, cudaMemsetAsync(d.seedActive, 0, nReads, st));
+		}
+		if(launchDp<OFF>(e, e->A, q.nDpA, st) || launchDp<OFF>(e, e->M, q.nDpM, st)) { ctx->err = "xengine: DP launch rejected"; return -1; }
+		BT2G_CUDA_TRY(ctx, cudaGetLastError());
+	}
+	return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int bt2g_xengine_create(bt2g_ctx *ctx, const bt2g_policy_params *pp, uint64_t maxUnits, uint32_t maxLen, bt2g_xengine **out) {
+	if(!ctx || !pp || !out || maxUnits == 0 || maxLen == 0) return -1;
+	*out = nullptr;
+	if(!ctx->loaded) { ctx->err = "no index loaded"; return -1; }
+	if(!ctx->info.has_bw || !ctx->info.has_ref) { ctx->err = "xengine: needs the mirror index and the packed reference"; return -1; }
+	if(maxLen > XE_MAX_LEN) { ctx->err = "xengine: reads longer than 512 are not supported"; return -1; }
+	if(pp->all_hits || pp->khits > 1) { ctx->err = "xengine: -k / -a are served by bt2g_policy_align_k"; return -1; }
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	bt2g_xengine *e = new(std::nothrow) bt2g_xengine();
+	if(!e) return -4;
+	e->ctx = ctx; e->pp = *pp; e->maxLen = (int)maxLen; e->maxUnits = maxUnits;
+	e->maxReads = pp->paired ? 2 * maxUnits : maxUnits; e->maxBases = e->maxReads * (uint64_t)maxLen;
+	e->maxOps = maxLen + 80;
+	cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	// the kernels score with the scheme the policy reasons about (one source: the policy parameters)
+	scoringFromParams(pp, &e->sc);
+	ctx->scoring = e->sc;
+	buildParams(pp, ctx->info.off_size, (int)maxLen, e->P, e->T);
+	int rc = 0;
+	const uint64_t nR = e->maxReads, nU = maxUnits;
+	rc |= xalloc(e, e->dTabs, 4ull * (maxLen + 1));
+	XDev &d = e->d;
+	rc |= xalloc(e, e->dSeq, e->maxBases); rc |= xalloc(e, e->dQual, e->maxBases); rc |= xalloc(e, e->dOff, nR + 1);
+	uint32_t *seeds; uint8_t *mine; uint64_t *ee;
+	rc |= xalloc(e, seeds, nR); rc |= xalloc(e, mine, nR * 2); rc |= xalloc(e, ee, nR * 4);
+	d.seeds = seeds; d.mine = mine; d.ee = ee;
+	bt2g_mm_hit *mmHits; int32_t *mmCounts;
+	rc |= xalloc(e, mmHits, nU * 4 * XE_MM_MAXHITS); rc |= xalloc(e, mmCounts, nU * 4);
+	d.mmHits = mmHits; d.mmCounts = mmCounts;
+	rc |= xalloc(e, d.mmSel, nU); rc |= xalloc(e, d.mmMinsc, nU); rc |= xalloc(e, d.mmMask, nU);
+	{
+		int minIval = 1 << 30;
+		for(int l = 1; l <= (int)maxLen; l++) { minIval = std::min(minIval, std::min(e->T.ivalOne[l], e->T.ivalBoth[l])); }
+		int ms = 1 + ((int)maxLen - std::min<int>(pp->seed_len, (int)maxLen)) / std::max(1, minIval) + 1;
+		if(ms > XE_MAX_SEEDS) ms = XE_MAX_SEEDS + 1;          // reads with more seeds fall back
+		d.maxSeeds = ms;
+	}
+	uint64_t *ranges; int32_t *nseeds;
+	rc |= xalloc(e, ranges, nR * 2ull * d.maxSeeds * 4); rc |= xalloc(e, nseeds, nR);
+	d.ranges = ranges; d.nseeds = nseeds;
+	rc |= xalloc(e, d.seedInterval, nR); rc |= xalloc(e, d.seedOffset, nR); rc |= xalloc(e, d.seedActive, nR);
+	rc |= xalloc(e, e->packed, (e->maxBases >> 5) + nR + 2); rc |= xalloc(e, e->nmask, (e->maxBases >> 5) + nR + 2); rc |= xalloc(e, e->nextTask, 1);
+	rc |= xalloc(e, d.q, 1); rc |= xalloc(e, d.units, nU); rc |= xalloc(e, d.status, nU);
+	rc |= xalloc(e, d.res, nR); rc |= xalloc(e, d.resOps, nR * (uint64_t)e->maxOps); rc |= xalloc(e, d.pairs, nU);
+	d.resMaxOps = e->maxOps;
+	if(!rc) {
+		// anchor rectangles: rdlen + 4 * min(maxgap, 15) columns; mate rectangles: the fragment window plus the mate and its gaps
+		const int maxColA = (int)maxLen + 4 * 15 + 4;
+		int gapMax = 15;
+		for(int l = 1; l <= (int)maxLen; l++) { gapMax = std::max(gapMax, std::max(e->P.maxReadGaps(e->T.minsc[l], l), e->P.maxRefGaps(e->T.minsc[l], l))); }
+		if(gapMax > 512) gapMax = 512;
+		const uint64_t maxfrag = std::max<uint64_t>(pp->pe.maxfrag, maxLen);
+		int maxColM = (int)std::min<uint64_t>(maxfrag + 2ull * maxLen + 2ull * gapMax + 16, 8000);
+		const int maxCands = e->sc.local ? 2048 : 256, maxAlns = 8;
+		rc |= setupDp(e, e->A, maxColA, nU, maxCands, maxAlns);
+		if(pp->paired) rc |= setupDp(e, e->M, maxColM, nU, maxCands, maxAlns);
+		else e->M = e->A;
+		d.A = e->A.o; d.M = e->M.o;
+	}
+	cudaError_t err = cudaSuccess;
+	if(!rc) {
+		std::vector<int32_t> tabs(4ull * (maxLen + 1));
+		for(uint32_t l = 0; l <= maxLen; l++) { tabs[l] = e->T.minsc[l]; tabs[(maxLen + 1) + l] = e->T.nceilRaw[l]; tabs[2 * (maxLen + 1) + l] = e->T.ivalOne[l]; tabs[3 * (maxLen + 1) + l] = e->T.ivalBoth[l]; }
+		err = cudaMemcpy(e->dTabs, tabs.data(), tabs.size() * 4, cudaMemcpyHostToDevice);
+		e->P.minscTab = e->dTabs; e->P.nceilRawTab = e->dTabs + (maxLen + 1); e->P.ivalOneTab = e->dTabs + 2 * (maxLen + 1); e->P.ivalBothTab = e->dTabs + 3 * (maxLen + 1);
+		if(err == cudaSuccess) err = cudaHostAlloc((void **)&e->hq, sizeof(XQueues), cudaHostAllocDefault);
+		if(err == cudaSuccess) err = cudaHostAlloc((void **)&e->hStatus, nU, cudaHostAllocDefault);
+	}
+	if(rc || err != cudaSuccess) {
+		if(err != cudaSuccess) ctx->err = std::string("xengine setup: ") + cudaGetErrorString(err);
+		bt2g_xengine_destroy(e);
+		return -2;
+	}
+	*out = e;
+	return 0;
+}
+
+void bt2g_xengine_destroy(bt2g_xengine *e) {
+	if(!e) return;
+	cudaSetDevice(e->ctx->device);
+	for(void *v : e->allocs) cudaFree(v);
+	if(e->hq) cudaFreeHost(e->hq);
+	if(e->hStatus) cudaFreeHost(e->hStatus);
+	delete e;
+}
+
+// reads already in device memory; results stay on the device (bt2g_xengine_results_dev).  Units that fall back are re-run
+// by the coroutine engine over this library's entry points and patched into the device result arrays.
+int bt2g_xengine_run_dev(bt2g_xengine *e, const uint8_t *dSeq, const uint8_t *dQual, const uint64_t *dOff, uint64_t nReads,
+                         const char *dNames, uint32_t nameStride, void *stream, uint64_t *stats) {
+	if(!e || !dSeq || !dQual || !dOff) return -1;
+	bt2g_ctx *ctx = e->ctx;
+	if(nReads > e->maxReads || (e->P.paired && (nReads & 1))) { ctx->err = "xengine: batch larger than the engine was created for"; return -1; }
+	if(nReads == 0) return 0;
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+	ctx->scoring = e->sc;
+	e->d.seq = dSeq; e->d.qual = dQual; e->d.roff = dOff;
+	const int rc = ctx->info.off_size == 4 ? runBatch<uint32_t>(e, nReads, dNames, nameStride, st) : runBatch<uint64_t>(e, nReads, dNames, nameStride, st);
+	if(rc) return rc;
+	if(e->stats[1]) {
+		// fallback units: their reads come back to the host, the coroutine engine answers them through the C ABI
+		const bool paired = e->P.paired != 0;
+		const uint64_t nUnits = paired ? nReads / 2 : nReads, per = paired ? 2 : 1;
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(e->hStatus, e->d.status, nUnits, cudaMemcpyDeviceToHost, st));
+		std::vector<uint64_t> off(nReads + 1);
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(off.data(), dOff, (nReads + 1) * 8, cudaMemcpyDeviceToHost, st));
+		BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		std::vector<uint64_t> ids;
+		for(uint64_t i = 0; i < nUnits; i++) if(e->hStatus[i] == 2) ids.push_back(i);
+		std::vector<uint8_t> seq, qual; std::vector<uint64_t> soff{0}; std::vector<char> names; std::vector<const char *> nptr;
+		for(uint64_t id : ids) for(uint64_t k = 0; k < per; k++) {
+			const uint64_t r = id * per + k, a = off[r], b = off[r + 1];
+			const size_t o = seq.size();
+			seq.resize(o + (b - a)); qual.resize(o + (b - a));
+			BT2G_CUDA_TRY(ctx, cudaMemcpy(seq.data() + o, dSeq + a, b - a, cudaMemcpyDeviceToHost));
+			BT2G_CUDA_TRY(ctx, cudaMemcpy(qual.data() + o, dQual + a, b - a, cudaMemcpyDeviceToHost));
+			soff.push_back(seq.size());
+		}
+		const uint32_t ns = dNames ? nameStride : 24;
+		names.assign(ids.size() * per * (size_t)ns, 0);
+		for(size_t j = 0; j < ids.size() * per; j++) {
+			const uint64_t r = ids[j / per] * per + (j % per);
+			if(dNames) { BT2G_CUDA_TRY(ctx, cudaMemcpy(names.data() + j * ns, dNames + r * (uint64_t)nameStride, nameStride, cudaMemcpyDeviceToHost)); names[j * ns + ns - 1] = 0; }
+			else snprintf(names.data() + j * ns, ns, "r%llu", (unsigned long long)(paired ? r >> 1 : r));
+		}
+		for(size_t j = 0; j < ids.size() * per; j++) nptr.push_back(names.data() + j * ns);
+		bt2g_reads sub; sub.n_reads = ids.size() * per; sub.seq = seq.data(); sub.qual = qual.data(); sub.off = soff.data();
+		std::vector<bt2g_read_result> res(sub.n_reads); std::vector<uint8_t> ops(sub.n_reads * (size_t)e->maxOps); std::vector<bt2g_pair_result> prs(ids.size());
+		bt2g_policy_backend be; bt2g_policy_backend_gpu(ctx, &be);
+		bt2g_policy_params pp = e->pp; pp.host_threads = 8;
+		const int rc2 = bt2g_policy_align(&be, &pp, &sub, nptr.data(), res.data(), ops.data(), e->maxOps, paired ? prs.data() : nullptr, nullptr);
+		if(rc2 < 0) { ctx->err = "xengine: fallback engine failed"; return rc2; }
+		for(size_t j = 0; j < ids.size(); j++) {
+			const uint64_t r0 = ids[j] * per;
+			BT2G_CUDA_TRY(ctx, cudaMemcpy(e->d.res + r0, res.data() + j * per, per * sizeof(bt2g_read_result), cudaMemcpyHostToDevice));
+			BT2G_CUDA_TRY(ctx, cudaMemcpy(e->d.resOps + r0 * (uint64_t)e->maxOps, ops.data() + j * per * (size_t)e->maxOps, per * (size_t)e->maxOps, cudaMemcpyHostToDevice));
+			if(paired) BT2G_CUDA_TRY(ctx, cudaMemcpy(e->d.pairs + ids[j], prs.data() + j, sizeof(bt2g_pair_result), cudaMemcpyHostToDevice));
+		}
+	}
+	if(stats) for(int k = 0; k < 8; k++) stats[k] = e->stats[k];
+	return 0;
+}
+
+int bt2g_xengine_results_dev(bt2g_xengine *e, bt2g_read_result **res, uint8_t **ops, uint32_t *maxOps, bt2g_pair_result **pairs) {
+	if(!e) return -1;
+	if(res) *res = e->d.res;
+	if(ops) *ops = e->d.resOps;
+	if(maxOps) *maxOps = e->maxOps;
+	if(pairs) *pairs = e->d.pairs;
+	return 0;
+}
+
+// host buffers in, host results out: res[n_reads], ops[n_reads * max_ops] (max_ops >= the engine's own stride is not required:
+// rows are copied with the smaller of the two strides), pairs[n_reads / 2] when paired
+int bt2g_xengine_align(bt2g_xengine *e, const bt2g_reads *reads, const char *names, uint32_t nameStride, bt2g_read_result *res, uint8_t *ops,
+                       uint32_t maxOps, bt2g_pair_result *pairs, uint64_t *stats) {
+	if(!e || !reads || !reads->qual || !res || !ops) return -1;
+	bt2g_ctx *ctx = e->ctx;
+	const uint64_t n = reads->n_reads;
+	if(n > e->maxReads || reads->off[n] > e->maxBases) { ctx->err = "xengine: batch larger than the engine was created for"; return -1; }
+	if(e->P.paired && !pairs) return -1;
+	if(n == 0) return 0;
+	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const uint64_t nb = reads->off[n];
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(e->dSeq, reads->seq, nb, cudaMemcpyHostToDevice, st));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(e->dQual, reads->qual, nb, cudaMemcpyHostToDevice, st));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(e->dOff, reads->off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+	char *dn = nullptr;
+	if(names) {
+		if((uint64_t)nameStride * n > (uint64_t)e->nameStrideCap * e->maxReads || !e->dNames) {
+			if(xalloc(e, e->dNames, (uint64_t)nameStride * e->maxReads)) return -2;
+			e->nameStrideCap = nameStride;
+		}
+		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(e->dNames, names, (uint64_t)nameStride * n, cudaMemcpyHostToDevice, st));
+		dn = e->dNames;
+	}
+	const int rc = bt2g_xengine_run_dev(e, e->dSeq, e->dQual, e->dOff, n, dn, nameStride, st, stats);
+	if(rc) return rc;
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(res, e->d.res, n * sizeof(bt2g_read_result), cudaMemcpyDeviceToHost, st));
+	if(maxOps == e->maxOps) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(ops, e->d.resOps, n * (uint64_t)maxOps, cudaMemcpyDeviceToHost, st));
+	else BT2G_CUDA_TRY(ctx, cudaMemcpy2DAsync(ops, maxOps, e->d.resOps, e->maxOps, maxOps < e->maxOps ? maxOps : e->maxOps, n, cudaMemcpyDeviceToHost, st));
+	if(pairs && e->P.paired) BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(pairs, e->d.pairs, (n / 2) * sizeof(bt2g_pair_result), cudaMemcpyDeviceToHost, st));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	return 0;
+}
+
+} // extern "C"

@@ -23,6 +23,7 @@
 #ifndef XE_HD
 #define XE_HD __host__ __device__
 #endif
+#define XE_HH __host__ __device__      // always both: the parameter arithmetic is also used by the host-side set-up
 
 namespace xe {
 
@@ -58,22 +59,22 @@ struct XParams {
 	bt2g_pe_policy pe;
 	int32_t maxLen;                                     // tables below hold maxLen + 1 entries
 	const int32_t *minscTab, *nceilRawTab, *ivalOneTab, *ivalBothTab;   // SimpleFunc values per read length (host-evaluated doubles)
-	XE_HD int64_t perfect(int len) const { return (int64_t)len * matchBonus; }
-	XE_HD int64_t minScore(int len) const { return minscTab[len]; }
-	XE_HD int nCeilRaw(int len) const { return nceilRawTab[len]; }
-	XE_HD int nCeil(int len) const { const int r = nceilRawTab[len]; return r < len ? r : len; }
-	XE_HD int seedInterval(int len, bool both) const { return both ? ivalBothTab[len] : ivalOneTab[len]; }
-	XE_HD int maxReadGaps(int64_t minsc, int len) const {       // Scoring::maxReadGaps (scoring.cpp:42-66)
+	XE_HH int64_t perfect(int len) const { return (int64_t)len * matchBonus; }
+	XE_HH int64_t minScore(int len) const { return minscTab[len]; }
+	XE_HH int nCeilRaw(int len) const { return nceilRawTab[len]; }
+	XE_HH int nCeil(int len) const { const int r = nceilRawTab[len]; return r < len ? r : len; }
+	XE_HH int seedInterval(int len, bool both) const { return both ? ivalBothTab[len] : ivalOneTab[len]; }
+	XE_HH int maxReadGaps(int64_t minsc, int len) const {       // Scoring::maxReadGaps (scoring.cpp:42-66)
 		int64_t sc = perfect(len); bool first = true; int num = 0;
 		while(sc >= minsc) { sc -= first ? rdgConst + rdgLin : rdgLin; first = false; num++; }
 		return num - 1;
 	}
-	XE_HD int maxRefGaps(int64_t minsc, int len) const {        // Scoring::maxRefGaps (scoring.cpp:73-98)
+	XE_HH int maxRefGaps(int64_t minsc, int len) const {        // Scoring::maxRefGaps (scoring.cpp:73-98)
 		int64_t sc = perfect(len); bool first = true; int num = 0;
 		while(sc >= minsc) { sc -= matchBonus; sc -= first ? rfgConst + rfgLin : rfgLin; first = false; num++; }
 		return num - 1;
 	}
-	XE_HD int mmPenalty(int q) const { const int ii = q < 0 ? 0 : (q > 40 ? 40 : q); const float frac = (float)ii / 40.0f; return mmpMin + (int)(frac * (float)(mmpMax - mmpMin)); }
+	XE_HH int mmPenalty(int q) const { const int ii = q < 0 ? 0 : (q > 40 ? 40 : q); const float frac = (float)ii / 40.0f; return mmpMin + (int)(frac * (float)(mmpMax - mmpMin)); }
 };
 
 // ---------------------------------------------------------------------------------------------- small pieces
@@ -303,7 +304,7 @@ XE_HD inline bool x_seen_present(const XMate &c, int64_t tidx, bool fw, int64_t 
 // by walking both alignments row by row.
 struct XCellIt {                                     // per read row: reference columns [left, right)
 	const XAln *a; const XEdit *ed; int k, i, n; int64_t left, right, diff;
-	XE_HD void init(const XAln *al) { a = al; ed = al->edits(); k = 0; i = al->trimLeft(); n = i + al->ext(); left = al->refoff; fetch(); }
+	XE_HD void init(const XAln *al) { a = al; ed = al->edits(); k = 0; i = al->trimLeft(); n = i + al->ext(); left = al->refoff; right = left + 1; diff = 1; fetch(); }
 	XE_HD bool valid() const { return i < n; }
 	XE_HD void fetch() {
 		if(i >= n) return;
@@ -484,7 +485,7 @@ XE_HD inline int64_t x_tightened(const XUnit &u, int64_t bestPairScore) {
 // Svc supplies the read batch, the answers of the batched requests and the inline primitives:
 //   const uint8_t *codes(int read), *quals(int read); int rdlen(int read); uint32_t randSeed(int read)
 //   void sweep(int read, int mined[2], uint64_t tb[4])                                   (exactSweep, computed at admission)
-//   int mmCount(int read, int task); const bt2g_mm_hit *mmHits(int read, int task)       (answer of XR_ONE_MM)
+//   int mmCount(int slot, int task); const bt2g_mm_hit *mmHits(int slot, int task); int mmMax()   (answer of XR_ONE_MM)
 //   int nSeeds(int read); const uint64_t *seedRange(int read, int strand, int i)         (answer of XR_SEED: topf,botf,topb,botb)
 //   const bt2g_dp_summary *dpSumm(int slot, bool mate); const bt2g_dp_cand *dpCands(..); const bt2g_dp_aln *dpAlns(..);
 //   const uint8_t *dpOps(int slot, bool mate, int k); int dpMaxAlns()                   (answer of XR_DP / XR_DP_MATE)
@@ -806,8 +807,9 @@ template <typename Svc>
 XE_HD void XEngine<Svc>::loadMm1(XMate &c, int64_t *neltOut) {
 	c.nmm1 = 0;
 	for(int task = 0; task < 4; task++) {
-		const int n = svc.mmCount(c.idx, task);
-		const bt2g_mm_hit *h = svc.mmHits(c.idx, task);
+		const int n = svc.mmCount(u.dpSlot, task);
+		const bt2g_mm_hit *h = svc.mmHits(u.dpSlot, task);
+		if(n > svc.mmMax()) { u.fallback = 1; return; }
 		for(int j = 0; j < n; j++) {
 			if(c.nmm1 >= XE_MM1) { u.fallback = 1; return; }
 			XEEHit &e = c.mm1[c.nmm1++];
@@ -888,12 +890,14 @@ XE_HD int XEngine<Svc>::stepExtPaired() {
 						if(u.fallback) return XR_FALLBACK;
 					}
 					if(u.state == 0) {
-						const bool found = x_frame_seed(u.refoff, rdlen, u.tlen, u.readGaps, u.refGaps, 15, rect);
-						x_seen_add(u, c, u.tidx, u.fw != 0, u.refoff, 1);
-						if(!found) continue;
-						x_seen_add(u, c, u.tidx, u.fw != 0, rect.reflPre + rect.corel, rect.corer - rect.corel + 1);
-						if(u.fallback) return XR_FALLBACK;
-						setDpReq(c, u.fw != 0, u.tidx, rect, c.minsc, rdlen);
+						{
+							const bool found = x_frame_seed(u.refoff, rdlen, u.tlen, u.readGaps, u.refGaps, 15, rect);
+							x_seen_add(u, c, u.tidx, u.fw != 0, u.refoff, 1);
+							if(!found) continue;
+							x_seen_add(u, c, u.tidx, u.fw != 0, rect.reflPre + rect.corel, rect.corer - rect.corel + 1);
+							if(u.fallback) return XR_FALLBACK;
+							setDpReq(c, u.fw != 0, u.tidx, rect, c.minsc, rdlen);
+						}
 						XE_WAIT(u.pcExt, 1, XR_DP);
 						u.nDps++; u.nDpFail++;
 						if(!loadAnchorDp(c)) { if(u.fallback) return XR_FALLBACK; continue; }
@@ -918,17 +922,17 @@ XE_HD int XEngine<Svc>::stepExtPaired() {
 								                        (uint64_t)(anchor1 ? ordlen : rdlen), oleft, oll, olr, orl, orr, ofw);
 								if(fm) fm = x_frame_mate(!oleft, oll, olr, orl, orr, ordlen, u.tlen, ordgaps, orfgaps, 15, rect);
 								u.foundMate = fm;
-								if(fm) {
-									setDpReq(o, ofw, u.tidx, rect, u.ominscCur, ordlen);
-									XE_WAIT(u.pcExt, 2, XR_DP_MATE);
-									u.nMateDps++;
-									{
-										const bt2g_dp_summary *s = svc.dpSumm(u.dpSlot, true);
-										if(s->flags) { u.fallback = 1; return XR_FALLBACK; }
-										u.foundMate = s->found != 0;
-										u.mateCursor = 0; u.mateAlnK = 0;
-										if(u.foundMate) u.odpU8 = dpU8(s->best, u.ominscCur, o);
-									}
+								if(fm) setDpReq(o, ofw, u.tidx, rect, u.ominscCur, ordlen);
+							}
+							if(u.foundMate) {
+								XE_WAIT(u.pcExt, 2, XR_DP_MATE);
+								u.nMateDps++;
+								{
+									const bt2g_dp_summary *s = svc.dpSumm(u.dpSlot, true);
+									if(s->flags) { u.fallback = 1; return XR_FALLBACK; }
+									u.foundMate = s->found != 0;
+									u.mateCursor = 0; u.mateAlnK = 0;
+									if(u.foundMate) u.odpU8 = dpU8(s->best, u.ominscCur, o);
 								}
 							}
 							u.didAnchor = 0; u.brk = 0;
@@ -1069,12 +1073,14 @@ XE_HD int XEngine<Svc>::stepExtUnpaired() {
 						if(u.fallback) return XR_FALLBACK;
 					}
 					if(u.state == 0) {
-						const bool found = x_frame_seed(u.refoff, rdlen, u.tlen, u.readGaps, u.refGaps, 15, rect);
-						x_seen_add(u, c, u.tidx, u.fw != 0, u.refoff, 1);
-						if(!found) continue;
-						x_seen_add(u, c, u.tidx, u.fw != 0, rect.reflPre + rect.corel, rect.corer - rect.corel + 1);
-						if(u.fallback) return XR_FALLBACK;
-						setDpReq(c, u.fw != 0, u.tidx, rect, c.minsc, rdlen);
+						{
+							const bool found = x_frame_seed(u.refoff, rdlen, u.tlen, u.readGaps, u.refGaps, 15, rect);
+							x_seen_add(u, c, u.tidx, u.fw != 0, u.refoff, 1);
+							if(!found) continue;
+							x_seen_add(u, c, u.tidx, u.fw != 0, rect.reflPre + rect.corel, rect.corer - rect.corel + 1);
+							if(u.fallback) return XR_FALLBACK;
+							setDpReq(c, u.fw != 0, u.tidx, rect, c.minsc, rdlen);
+						}
 						XE_WAIT(u.pcExt, 1, XR_DP);
 						u.nDps++;
 						if(!loadAnchorDp(c)) {
@@ -1114,6 +1120,7 @@ template <typename Svc>
 XE_HD int XEngine<Svc>::stepPair() {
 	switch(u.pc) {
 	case 0: {
+		{
 		const int i1 = (int)(2 * u.id), ls[2] = {svc.rdlen(i1), svc.rdlen(i1 + 1)};
 		for(int k = 0; k < 2; k++) {
 			XMate &c = u.m[k];
@@ -1161,6 +1168,7 @@ XE_HD int XEngine<Svc>::stepPair() {
 			if(tb[3] > tb[2]) { XEEHit &e = c.ee[c.nee++]; e.top = tb[2]; e.bot = tb[3]; e.fw = 0; e.score = (int32_t)c.perfect; e.hasEdit = 0; e.pos = 0; e.chr = e.qchr = 0; e.pad[0] = e.pad[1] = 0; }
 		}
 		if(u.nelt[0] > 0 && u.nelt[1] > 0 && u.nelt[0] > u.nelt[1]) { u.matemap[0] = 1; u.matemap[1] = 0; } else { u.matemap[0] = 0; u.matemap[1] = 1; }
+		}
 		for(u.mi = 0; u.mi < 2; u.mi++) {
 			{
 				const int mate = u.matemap[u.mi]; XMate &c = u.m[mate];
@@ -1353,6 +1361,7 @@ XE_HD int XEngine<Svc>::stepRead() {
 	XMate &c = u.m[0];
 	switch(u.pc) {
 	case 0: {
+		{
 		const int idx = (int)u.id, len = svc.rdlen(idx);
 		u.pairType = 0; u.pairKind = 5; u.scoreSum = 0; u.fraglen = 0;
 		for(int k = 0; k < 2; k++) { u.resAligned[k] = 0; u.resHasXs[k] = 0; u.resMapq[k] = 0; u.resXs[k] = 0; u.resAln[k] = 0xffff; }
@@ -1383,6 +1392,7 @@ XE_HD int XEngine<Svc>::stepRead() {
 			if(tb[1] > tb[0]) { XEEHit &e = c.ee[c.nee++]; e.top = tb[0]; e.bot = tb[1]; e.fw = 1; e.score = (int32_t)c.perfect; e.hasEdit = 0; e.pos = 0; e.chr = e.qchr = 0; e.pad[0] = e.pad[1] = 0; }
 			if(tb[3] > tb[2]) { XEEHit &e = c.ee[c.nee++]; e.top = tb[2]; e.bot = tb[3]; e.fw = 0; e.score = (int32_t)c.perfect; e.hasEdit = 0; e.pos = 0; e.chr = e.qchr = 0; e.pad[0] = e.pad[1] = 0; }
 		}
+		}
 		if(u.nelt[0] > 0) {
 			u.xUseSh = 0; u.xUseEe = 1;
 			XE_CALL_EXT(1, stepExtUnpaired);
@@ -1392,9 +1402,9 @@ XE_HD int XEngine<Svc>::stepRead() {
 			if(!u.rdone && c.minsc == c.perfect) u.rdone = 1;
 		}
 		if(!u.rdone) {
-			const bool yfw = u.mined[0][0] <= 1 && !P.nofw, yrc = u.mined[0][1] <= 1 && !P.norc;
-			if(yfw || yrc) {
-				u.rqRead = c.idx; u.rqMinsc = (int32_t)c.minsc; u.rqNofw = !yfw; u.rqNorc = !yrc;
+			u.rqNofw = !(u.mined[0][0] <= 1 && !P.nofw); u.rqNorc = !(u.mined[0][1] <= 1 && !P.norc);
+			if(!u.rqNofw || !u.rqNorc) {
+				u.rqRead = c.idx; u.rqMinsc = (int32_t)c.minsc;
 				XE_WAIT(u.pc, 2, XR_ONE_MM);
 				loadMm1(c, nullptr);
 				if(u.fallback) return XR_FALLBACK;

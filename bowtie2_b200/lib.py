@@ -949,7 +949,7 @@ class IndexFile:
 
 
 # ---- the exact search policy in waves (include/bt2g.h: bt2g_policy_align; csrc/policy_engine.cpp) ----------------------
-EXPORTS += ["bt2g_policy_align", "bt2g_policy_align_k", "bt2g_policy_backend_gpu"]
+EXPORTS += ["bt2g_policy_align", "bt2g_policy_align_k", "bt2g_policy_backend_gpu", "bt2g_xengine_align_host"]
 _CB = C.CFUNCTYPE
 _vp = C.c_void_p
 
@@ -1014,9 +1014,12 @@ def policy_params(preset="sensitive", local=False, paired=False, seed=0, k=None,
     return p
 
 
-def policy_align(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads: ReadBatch, names):
-    """include/bt2g.h: bt2g_policy_align -> (results, ops, pairs or None, (waves, backend calls, requests))"""
-    lib.bt2g_policy_align.argtypes = [C.POINTER(_PolicyBackend), C.POINTER(_PolicyParams), C.POINTER(_Reads), _vp, _vp, _vp, C.c_uint32, _vp, _vp]
+def policy_align(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads: ReadBatch, names, entry="bt2g_policy_align"):
+    """include/bt2g.h: bt2g_policy_align -> (results, ops, pairs or None, (waves, backend calls, requests)).
+    entry="bt2g_xengine_align_host": the fixed-memory state machine of csrc/xengine.cuh driven on the host over the same table
+    (stats = units, fallbacks to the coroutine engine, requests)."""
+    fn = getattr(lib, entry)
+    fn.argtypes = [C.POINTER(_PolicyBackend), C.POINTER(_PolicyParams), C.POINTER(_Reads), _vp, _vp, _vp, C.c_uint32, _vp, _vp]
     n = reads.n
     max_ops = int(reads.lengths().max()) + 64 if n else 64
     res = np.zeros(n, dtype=READ_RESULT)
@@ -1030,9 +1033,9 @@ def policy_align(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads:
         keep = (C.c_char_p * n)(*[x.encode() for x in names])
         qn = C.cast(keep, _vp)
     st = reads._struct()
-    rc = lib.bt2g_policy_align(C.byref(backend), C.byref(params), C.byref(st), qn, _ptr(res), _ptr(ops), max_ops, _ptr(pairs), _ptr(stats))
+    rc = fn(C.byref(backend), C.byref(params), C.byref(st), qn, _ptr(res), _ptr(ops), max_ops, _ptr(pairs), _ptr(stats))
     if rc:
-        raise RuntimeError(f"bt2g_policy_align failed ({rc})")
+        raise RuntimeError(f"{entry} failed ({rc})")
     return res, ops, pairs, tuple(int(x) for x in stats)
 
 
@@ -1066,3 +1069,71 @@ def policy_backend_gpu(gpu: "Bt2Gpu") -> "_PolicyBackend":
     gpu._lib.bt2g_policy_backend_gpu.restype = None
     gpu._lib.bt2g_policy_backend_gpu(gpu._h, C.byref(be))
     return be
+
+
+# ---- the exact search policy on the device (include/bt2g.h: bt2g_xengine_*; csrc/xengine.cuh, xengine.cu) ---------------
+EXPORTS += ["bt2g_xengine_create", "bt2g_xengine_destroy", "bt2g_xengine_align", "bt2g_xengine_run_dev", "bt2g_xengine_results_dev"]
+
+XENGINE_STATS = ("waves", "fallback_units", "seed_dps", "mate_dps", "seed_dp_cells", "mate_dp_cells", "one_mm_requests", "seed_requests")
+
+
+def name_rows(names, stride=None) -> np.ndarray:
+    """list of str / NameTable -> uint8 rows [n, stride], NUL-terminated"""
+    if isinstance(names, NameTable):
+        return names.rows
+    enc = [x.encode() for x in names]
+    stride = stride or (max((len(x) for x in enc), default=1) + 1)
+    rows = np.zeros((len(enc), stride), dtype=np.uint8)
+    for i, x in enumerate(enc):
+        rows[i, :len(x)] = np.frombuffer(x, dtype=np.uint8)
+    return rows
+
+
+class XEngine:
+    """bt2g_xengine: the reference's search policy as a device-side state machine in waves (records identical to the reference
+    program's).  params: lib.policy_params(...); max_units: pairs (or reads) per call; max_len: longest read."""
+
+    def __init__(self, gpu: "Bt2Gpu", params: "_PolicyParams", max_units: int, max_len: int):
+        self.gpu, self.params, self.max_units, self.max_len = gpu, params, int(max_units), int(max_len)
+        lib = gpu._lib
+        lib.bt2g_xengine_create.argtypes = [_vp, C.POINTER(_PolicyParams), C.c_uint64, C.c_uint32, C.POINTER(_vp)]
+        lib.bt2g_xengine_destroy.argtypes = [_vp]
+        lib.bt2g_xengine_destroy.restype = None
+        lib.bt2g_xengine_align.argtypes = [_vp, C.POINTER(_Reads), _vp, C.c_uint32, _vp, _vp, C.c_uint32, _vp, _vp]
+        lib.bt2g_xengine_run_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, _vp, C.c_uint32, _vp, _vp]
+        lib.bt2g_xengine_results_dev.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_uint32), C.POINTER(_vp)]
+        h = _vp()
+        gpu._check(lib.bt2g_xengine_create(gpu._h, C.byref(params), self.max_units, self.max_len, C.byref(h)), "bt2g_xengine_create")
+        self._h = h
+        self.paired = bool(params.paired)
+        self.max_ops = self.max_len + 80
+
+    def align(self, reads: ReadBatch, names=None):
+        """host buffers in -> (results, ops [n, max_ops], pairs or None, stats dict)"""
+        n = reads.n
+        res = np.zeros(n, dtype=READ_RESULT)
+        ops = np.zeros((max(n, 1), self.max_ops), dtype=np.uint8)
+        pairs = np.zeros(n // 2, dtype=PAIR_RESULT) if self.paired else None
+        stats = np.zeros(8, dtype=np.uint64)
+        rows = None if names is None else name_rows(names)
+        st = reads._struct()
+        self.gpu._check(self.gpu._lib.bt2g_xengine_align(self._h, C.byref(st), _ptr(rows), 0 if rows is None else rows.shape[1], _ptr(res), _ptr(ops),
+                                                         self.max_ops, _ptr(pairs), _ptr(stats)), "bt2g_xengine_align")
+        return res, ops, pairs, dict(zip(XENGINE_STATS, (int(x) for x in stats)))
+
+    def run_dev(self, d_seq: int, d_qual: int, d_off: int, n_reads: int, d_names: int = 0, name_stride: int = 0, stream: int = 0):
+        """device pointers in (ints); results stay on the device (results_dev); returns the stats dict"""
+        stats = np.zeros(8, dtype=np.uint64)
+        self.gpu._check(self.gpu._lib.bt2g_xengine_run_dev(self._h, d_seq, d_qual, d_off, n_reads, d_names or None, name_stride, stream or None,
+                                                           _ptr(stats)), "bt2g_xengine_run_dev")
+        return dict(zip(XENGINE_STATS, (int(x) for x in stats)))
+
+    def results_dev(self):
+        r, o, p, m = _vp(), _vp(), _vp(), C.c_uint32()
+        self.gpu._lib.bt2g_xengine_results_dev(self._h, C.byref(r), C.byref(o), C.byref(m), C.byref(p))
+        return r.value, o.value, int(m.value), p.value
+
+    def close(self):
+        if self._h:
+            self.gpu._lib.bt2g_xengine_destroy(self._h)
+            self._h = None

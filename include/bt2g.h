@@ -559,6 +559,32 @@ int bt2g_policy_align_k(const bt2g_policy_backend *be, const bt2g_policy_params 
                         uint32_t max_per_read, bt2g_read_result *res, uint8_t *ops, uint32_t max_ops, uint32_t *n_reported,
                         uint64_t *stats);
 
+/* ------------------------------------------------------------- the exact search policy ON THE DEVICE ----- */
+/* The same policy as bt2g_policy_align (results identical to the reference program's), but the per-read state machines run as a
+ * kernel (csrc/xengine.cuh / xengine.cu: one thread per read pair or read, state in HBM) and the batched primitives consume
+ * device-side request queues once per wave: no host round trip per request, the host only reads the queue counters of each wave.
+ * This is the entry point the restated multiseedSearchWorker loop (bt2_search.cpp:3094-4254) calls per block of reads.
+ * Supported: the default reporting mode (-M; no -k / -a), end-to-end and --local, paired and unpaired, reads up to 512 bp.
+ * A unit whose state outgrows its fixed capacity is re-run by bt2g_policy_align over bt2g_policy_backend_gpu (same results).
+ * create installs the scoring scheme of `prm` in the context (bt2g_set_scoring). */
+typedef struct bt2g_xengine bt2g_xengine;
+int  bt2g_xengine_create(bt2g_ctx *ctx, const bt2g_policy_params *prm, uint64_t max_units /* pairs or reads per call */, uint32_t max_len,
+                         bt2g_xengine **out);
+void bt2g_xengine_destroy(bt2g_xengine *e);
+/* host buffers in, host results out (mates interleaved when paired).  names: n_reads rows of name_stride bytes, NUL-terminated
+ * (the per-read RNG seed depends on the name, pat.cpp:45-82), or NULL = "r<pair or read index>".  res[n_reads],
+ * ops[n_reads * max_ops], pairs[n_reads / 2] (paired).  stats (optional, 8 entries): waves, fallback units, seed-extension DPs,
+ * mate-finding DPs, their DP cells (2 entries), 1-mismatch searches, seed searches. */
+int  bt2g_xengine_align(bt2g_xengine *e, const bt2g_reads *reads, const char *names, uint32_t name_stride, bt2g_read_result *res,
+                        uint8_t *ops, uint32_t max_ops, bt2g_pair_result *pairs, uint64_t *stats);
+/* inputs already in HBM (d_names as above or NULL); results stay on the device until fetched */
+int  bt2g_xengine_run_dev(bt2g_xengine *e, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_off, uint64_t n_reads,
+                          const char *d_names, uint32_t name_stride, void *stream, uint64_t *stats);
+int  bt2g_xengine_results_dev(bt2g_xengine *e, bt2g_read_result **res, uint8_t **ops, uint32_t *max_ops, bt2g_pair_result **pairs);
+/* the same state machine driven on the host over an entry-point table (no GPU: the CPU pinning of csrc/xengine.cuh) */
+int  bt2g_xengine_align_host(const bt2g_policy_backend *be, const bt2g_policy_params *prm, const bt2g_reads *reads, const char *const *names,
+                             bt2g_read_result *res, uint8_t *ops, uint32_t max_ops, bt2g_pair_result *pairs, uint64_t *stats);
+
 /* bt2g_fastq_parse on `threads` host threads: the text is cut at record boundaries, the pieces parsed concurrently and
  * concatenated in input order; outputs, limits and error codes as bt2g_fastq_parse */
 int bt2g_fastq_parse_mt(const char *text, uint64_t len, uint64_t max_reads, uint64_t max_bases, uint8_t *seq, uint8_t *qual,

@@ -39,8 +39,9 @@ else:                                         # the C table over the oracle (ora
     be, keep = oracle_policy_table(Oracle(base), LOCAL, 8 if os.environ.get('LARGE') else 4)
 batch = ReadBatch.from_list(reads, quals)
 t0 = time.time()
-res, ops, pairs, stats = policy_align(lib, be, policy_params(preset, local=LOCAL, paired=paired, host_threads=8), batch, names)
-print('compiled engine over the oracle-backed table: %.1f s' % (time.time() - t0), 'waves/calls/requests', stats)
+ENTRY = os.environ.get('ENTRY', 'bt2g_policy_align')      # ENTRY=bt2g_xengine_align_host: the state machine of csrc/xengine.cuh
+res, ops, pairs, stats = policy_align(lib, be, policy_params(preset, local=LOCAL, paired=paired, host_threads=8), batch, names, entry=ENTRY)
+print(ENTRY, 'over the oracle-backed table: %.1f s' % (time.time() - t0), 'stats', stats)
 lines = sam_format(lib, batch, res, ops, [f"chr{k+1}" for k in range(4)], read_names=names, pairs=pairs, threads=8, local=LOCAL).rstrip('\n').split('\n')
 bad = [i for i in range(len(want)) if lines[i] != want[i]]
 print('records identical: %d of %d' % (len(want) - len(bad), len(want)))
