@@ -4,9 +4,17 @@
 Default workload = BASELINE.json configs[2], the configuration the metric is quoted on: synthetic 3 Gbp genome
 (.bt2 index built on the GPU by bowtie2_b200.index_build, byte-identical layout to bowtie2-build-s), 2x150 bp FR
 pairs (fragment ~ N(350,30)), --end-to-end --very-sensitive.  A "read" in Mreads/s is one PAIR, as in the
-reference's own summary ("N reads; of these: N were paired").  A "step" is one pass of the hot path over one batch
-of `--batch` pairs: exactSweep -> multiseed search -> offset resolve -> extension DP + backtrace for both mates,
-then mate framing -> mate-finding DP -> pair selection.  Batches are taken round-robin from a resident set.
+reference's own summary ("N reads; of these: N were paired").
+
+The measured path is the EXACT one (`--pipeline exact`, default): the reference's search policy
+(multiseedSearchWorker + SwDriver::extendSeeds[Paired]) as a device-side state machine in waves (bt2g_xengine_*,
+csrc/xengine.cuh / xengine.cu) over the FM / DP kernels.  A "step" is one batch of `--batch` pairs through it:
+read seeds + exactSweep at admission, then waves of {state machine step -> 1-mismatch search, (re-)seeding,
+seed-extension DP, mate-finding DP} until every pair has reported.  PARITY GATE: before timing, rank 0 runs the
+unmodified reference program on a FASTQ sample of the same pairs (same index files, --seed 0 --reorder) and the
+engine on the same sample; the line carries "parity": {"records", "identical"} (whole SAM records: FLAG, POS,
+MAPQ, CIGAR, mate fields, TLEN, AS/XS/YS/NM/MD/YT ...) and `value` is refused unless every record is identical.
+`--pipeline speculative` is round 1's batch pipeline (not SAM-identical; kept as a diagnostic only).
 `--workload se100` runs configs[1] (10 M x 100 bp unpaired, --sensitive) instead.
 
     python bench.py --gpus N --steps K --warmup W          # our arm (torchrun for N > 1)
@@ -246,215 +254,68 @@ def ref_binary():
     return sse, "bowtie2-align-s (SSE2)"
 
 
-def _ref_cmd(exe, preset, threads, index_base, fq):
+def _ref_cmd(exe, preset, threads, index_base, fq, out="/dev/null", reorder=False):
     inp = ["-1", fq[0], "-2", fq[1]] if isinstance(fq, (tuple, list)) else ["-U", fq]
-    return [exe, *preset, "--seed", "0", "-p", str(threads), "-x", index_base, *inp, "-S", "/dev/null"]
+    return [exe, *preset, "--seed", "0", "-p", str(threads), *(["--reorder"] if reorder else []), "-x", index_base, *inp, "-S", out]
 
 
-def time_reference(index_base, fq_small, fq_big, n_small, n_big, threads, preset):
+def run_reference(index_base, fq, threads, preset, out="/dev/null", reorder=False):
+    """wall seconds of one run of the unmodified reference program (index load included)"""
+    exe, _ = ref_binary()
+    t0 = time.time()
+    subprocess.check_call(_ref_cmd(exe, preset, threads, index_base, fq, out, reorder), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return time.time() - t0
+
+
+def reference_thread_candidates(hw_threads, cpu_quota):
+    """-p values tried for the reference, on the BIG sample: the CPUs this container may actually use (cgroup quota, else
+    every hardware thread), and twice / half that -- the reference does not always scale to every hardware thread."""
+    base = max(1, int(round(cpu_quota))) if cpu_quota else hw_threads
+    base = min(base, hw_threads)
+    c = {base, min(hw_threads, 2 * base)}
+    if not cpu_quota:
+        c.add(max(1, base // 2))
+    return sorted(c, reverse=True)
+
+
+def time_reference(index_base, fq_small, fq_big, n_small, n_big, threads, preset, t_big=None):
     """reads (pairs)/s of the reference on the host cores, with index-load time removed by differencing
     two sample sizes (same command otherwise).  fq_* is a path (unpaired) or a (mate1, mate2) tuple."""
     exe, label = ref_binary()
     if not os.path.exists(exe):
         return None
-
-    def run(fq):
-        t0 = time.time()
-        subprocess.check_call(_ref_cmd(exe, preset, threads, index_base, fq), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        return time.time() - t0
-
-    t_small = run(fq_small)
-    t_big = run(fq_big)
+    t_small = run_reference(index_base, fq_small, threads, preset)
+    if t_big is None:
+        t_big = run_reference(index_base, fq_big, threads, preset)
     dt = max(t_big - t_small, 1e-6)
     return {"reads_per_s": (n_big - n_small) / dt, "t_small": t_small, "t_big": t_big, "binary": label, "threads": threads}
 
 
-def best_thread_count(index_base, fq_small, n_small, cores, preset):
-    """The reference does not always scale to every hardware thread (shared input/output locks);
-    give it the thread count at which it is fastest on this box."""
-    exe, _ = ref_binary()
-    best, best_t = cores, None
-    p = cores
-    cands = []
-    while p >= 8:
-        cands.append(p)
-        p //= 2
-    for p in cands or [cores]:
-        t0 = time.time()
-        subprocess.check_call(_ref_cmd(exe, preset, p, index_base, fq_small), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        dt = time.time() - t0
-        log(f"reference -p {p}: {dt:.2f}s for {n_small} reads")
-        if best_t is None or dt < best_t:
-            best, best_t = p, dt
-    return best
+def device_name_rows(torch, dev, first_id, n_units, mates, stride=16):
+    """read-name rows as the FASTQ sample spells them ("r%09d", both mates of a pair share it), NUL-padded to `stride` bytes:
+    the per-read RNG seed of the reference hashes the name (pat.cpp:45-82), so the engine gets the same names."""
+    ids = torch.arange(first_id, first_id + n_units, device=dev, dtype=torch.int64)
+    rows = torch.zeros(n_units, stride, dtype=torch.uint8, device=dev)
+    rows[:, 0] = ord("r")
+    for k in range(9):
+        rows[:, 9 - k] = ((ids // 10 ** k) % 10 + ord("0")).to(torch.uint8)
+    if mates == 2:
+        rows = rows.repeat_interleave(2, dim=0)
+    return rows.contiguous()
 
 
 # ------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pe150", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=1_000_000, help="reads (pairs for a paired workload) per step")
-    ap.add_argument("--genome-mbp", type=float, default=GENOME_CONTIGS * CONTIG_LEN / 1e6,
-                    help="debug only: smaller genome (any value other than the default is NOT the BASELINE config)")
-    ap.add_argument("--reads", type=int, default=0, help="reads (pairs) resident in HBM (0 = the workload's default)")
-    ap.add_argument("--seed-table", type=int, default=16,
-                    help="k of the extended seed table derived from the index at load time (0 = off; results are identical)")
-    ap.add_argument("--dense-sa", type=int, default=0,
-                    help="rate of the denser SA sample derived from the index at load time (0 = full suffix array, -1 = off)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="reads (pairs) in the CPU baseline sample (0 = auto)")
-    args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    paired, READ_LEN = wl["paired"], wl["read_len"]
-    if args.reads <= 0:
-        args.reads = wl["units"]
-    mates = 2 if paired else 1
-    ref_preset = ("--end-to-end", "--" + wl["preset"])
-
+# round 1's speculative batch pipeline (NOT SAM-identical: diagnostic only)
+# ------------------------------------------------------------------------------------------------
+def run_speculative(S, args):
     import torch
     import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference" and rank != 0:
-        return 0
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    distributed = world > 1 and args.impl == "ours"
-    if distributed:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the single JSON line
-        dist.init_process_group("nccl", device_id=dev)
-
-    from bowtie2_b200 import Bt2Gpu
-    from bowtie2_b200.index_build import build_index
-    from bowtie2_b200.lib import Pipeline, READ_RESULT, PAIR_RESULT, _Reads
-
-    full = abs(args.genome_mbp - GENOME_CONTIGS * CONTIG_LEN / 1e6) < 1e-6 and args.reads >= wl["units"]
-    contig_len = int(args.genome_mbp * 1e6 / GENOME_CONTIGS)
-    unit = "pairs" if paired else "reads"
-    workload = (f"{wl['label']}: synthetic {GENOME_CONTIGS * contig_len / 1e9:.2f} Gbp genome .bt2 index, "
-                f"{args.reads / 1e6:g}M {'2x' if paired else '1x'}{READ_LEN} bp {unit} resident in HBM")
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    try:                                   # container CPU quota, if any (explains where the reference stops scaling)
-        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
-        cpu_quota = None if q == "max" else float(q) / float(per)
-    except Exception:
-        cpu_quota = None
-
-    # ---- setup (untimed): genome, index (built once on rank 0, NCCL-broadcast to the others), reads
-    t0 = time.time()
-    contigs = make_genome_gpu(torch, dev, GENOME_CONTIGS, contig_len)
-    need_files = args.impl == "reference" or (rank == 0 and not args.no_cpu_baseline)
-    built = None
-    if rank == 0 or not distributed:
-        built = build_index(contigs)
-        torch.cuda.synchronize()
-        log(f"rank {rank}: index built in {time.time() - t0:.1f}s (len={built.len})")
-    gpu = Bt2Gpu(local_rank)
-    bcast_s = 0.0
-    if distributed:
-        # single broadcast of every index array from rank 0 (SURVEY.md section 8e) over NCCL / NVLink
-        from bowtie2_b200.dist import broadcast_index
-        torch.cuda.synchronize(); dist.barrier()
-        tb = time.time()
-        desc, tensors = broadcast_index(built, 0, dev)
-        torch.cuda.synchronize(); dist.barrier()
-        bcast_s = time.time() - tb
-        gpu.load_index_device(desc, keep=tensors)
-    else:
-        gpu.load_index_device(built.device_desc(dev), keep=built)
-    info = gpu.info()
-    ktab_s = 0.0
-    if args.seed_table > info["ftab_chars"]:
-        torch.cuda.synchronize(); tk = time.time()
-        gpu.build_seed_table(args.seed_table)
-        ktab_s = time.time() - tk
-        log(f"rank {rank}: {args.seed_table}-mer seed table built in {ktab_s:.2f}s")
-    sa_s = 0.0
-    if 0 <= args.dense_sa < info["off_rate"]:
-        torch.cuda.synchronize(); tk = time.time()
-        gpu.build_dense_sa(args.dense_sa)
-        sa_s = time.time() - tk
-        log(f"rank {rank}: SA sample of rate {args.dense_sa} built in {sa_s:.2f}s")
-    if paired:
-        reads, quals = make_pairs_gpu(torch, dev, contigs, args.reads, READ_LEN, seed=1 + rank)
-    else:
-        reads, quals = make_reads_gpu(torch, dev, contigs, args.reads, READ_LEN, seed=1 + rank)
-    index_base = os.path.join(WORKDIR, "idx")
-    if need_files:
-        os.makedirs(WORKDIR, exist_ok=True)
-        built.write_files(index_base)
-        log(f"index files written to {index_base}.*.bt2")
-    del contigs
-    torch.cuda.synchronize()
-    log(f"rank {rank}: setup {time.time() - t0:.1f}s, index {info['device_bytes'] / 1e9:.2f} GB in HBM")
-
-    B = min(args.batch, args.reads)          # units (pairs / reads) per step
-    nb = args.reads // B
-    BR = B * mates                            # reads per step
-    offs = torch.arange(0, (BR + 1) * READ_LEN, READ_LEN, dtype=torch.int64, device=dev)
-
-    # ---- CPU baseline / reference arm -----------------------------------------------------------
-    cpu_baseline = None
-    if need_files:
-        n_big = args.cpu_sample or int(min(args.reads, 400_000 if paired else 1_000_000))
-        n_small = max(n_big // 10, 1000)
-        r_np = reads[:n_big * mates].cpu().numpy(); q_np = quals[:n_big * mates].cpu().numpy()
-        if paired:
-            fq_big = (os.path.join(WORKDIR, "big_1.fq"), os.path.join(WORKDIR, "big_2.fq"))
-            fq_small = (os.path.join(WORKDIR, "small_1.fq"), os.path.join(WORKDIR, "small_2.fq"))
-            for m in range(2):
-                write_fastq(fq_big[m], r_np[m::2], q_np[m::2])
-                write_fastq(fq_small[m], r_np[m:2 * n_small:2], q_np[m:2 * n_small:2])
-        else:
-            fq_big, fq_small = os.path.join(WORKDIR, "big.fq"), os.path.join(WORKDIR, "small.fq")
-            write_fastq(fq_big, r_np, q_np)
-            write_fastq(fq_small, r_np[:n_small], q_np[:n_small])
-        del r_np, q_np
-        threads = best_thread_count(index_base, fq_small, n_small, cores, ref_preset) if os.path.exists(ref_binary()[0]) else cores
-        sample = (f"{{}} {unit}: difference of a {n_big}- and a {n_small}-{unit[:-1]} run of {{}} {' '.join(ref_preset)} -p {threads} "
-                  f"(fastest thread count of those tried on {cores} hardware threads; index load cancels{{}})")
-        if args.impl == "reference":
-            per = []
-            for s in range(args.warmup + args.steps):
-                r = time_reference(index_base, fq_small, fq_big, n_small, n_big, threads, ref_preset)
-                if r is None:
-                    print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bowtie2-align-s not built"}))
-                    return 0
-                if s >= args.warmup:
-                    per.append(r)
-                if s == 0 and r["t_big"] > 60:      # keep the whole run within a few minutes
-                    per = per or [r]
-                    break
-            rps = float(np.median([p["reads_per_s"] for p in per]))
-            val = rps / 1e6
-            line = {"metric": "Mreads/s", "value": val, "unit": "Mreads/s", "n_gpus": 0, "steps": len(per), "warmup": args.warmup,
-                    "ms_per_step": 1e3 * (n_big - n_small) / rps, "higher_is_better": True, "scaling": "weak",
-                    "vs_baseline": None, "dtype": "u8/i16 (SSE/AVX2 striped DP), u64 popcount FM", "data": "synthetic",
-                    "impl": "reference",
-                    "config": {"workload": workload, "full_size": full, "read_unit": unit[:-1], "preset": " ".join(ref_preset),
-                               "host_threads": cores, "cgroup_cpu_quota": cpu_quota},
-                    "cpu_baseline": {"value": val, "unit": "Mreads/s", "cores": threads, "kind": "reference",
-                                     "sample": sample.format(n_big - n_small, per[0]["binary"], "")},
-                    "e2e": {"value": val, "unit": "Mreads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-            print(json.dumps(line))
-            return 0
-        if rank == 0 and not args.no_cpu_baseline:
-            r = time_reference(index_base, fq_small, fq_big, n_small, n_big, threads, ref_preset)
-            if r is not None:
-                cpu_baseline = {"value": r["reads_per_s"] / 1e6, "unit": "Mreads/s", "cores": threads, "kind": "reference",
-                                "sample": sample.format(n_big - n_small, r["binary"], f"; {r['t_big']:.1f}s and {r['t_small']:.1f}s wall")}
-            log("cpu baseline:", cpu_baseline)
-        shutil.rmtree(WORKDIR, ignore_errors=True)
-
+    from bowtie2_b200.lib import PAIR_RESULT, READ_RESULT, Pipeline, _Reads
+    gpu, dev, paired, mates, B, BR, READ_LEN, nb = S.gpu, S.dev, S.paired, S.mates, S.B, S.BR, S.READ_LEN, S.nb
+    wl, reads, quals, offs, rank, world, local_rank, distributed = S.wl, S.reads, S.quals, S.offs, S.rank, S.world, S.local_rank, S.distributed
+    info, cores, cpu_quota, full, unit, workload, ref_preset, cpu_baseline = S.info, S.cores, S.cpu_quota, S.full, S.unit, S.workload, S.ref_preset, S.cpu_baseline
+    ktab_s, sa_s, bcast_s = S.ktab_s, S.sa_s, S.bcast_s
+    line = None
     # ---- our arm -----------------------------------------------------------------------------------
     pipe = Pipeline(gpu, wl["preset"], max_len=READ_LEN, max_reads=BR, row_cap=16, range_max=8, max_cands=48, max_alns=2,
                     max_probs=4 * B, both_mates=paired)
@@ -611,17 +472,448 @@ def main():
                 "config": {"workload": workload, "full_size": full, "read_unit": unit[:-1], "mates_per_s_M": value * mates,
                            "batch": B, "preset": " ".join(ref_preset),
                            "l2": "inputs larger than L2 (random access over a %.1f GB index; a different batch each step)" % (info["device_bytes"] / 1e9),
-                           "pipeline": pipeline_desc, "seed_table_k": args.seed_table, "seed_table_build_s": ktab_s, "dense_sa_rate": args.dense_sa, "dense_sa_build_s": sa_s, "index_bcast_s": bcast_s, "aligned_frac": found, "pairs": conc,
+                           "pipeline": "speculative", "pipeline_desc": pipeline_desc, "seed_table_k": args.seed_table, "seed_table_build_s": ktab_s, "dense_sa_rate": args.dense_sa, "dense_sa_build_s": sa_s, "index_bcast_s": bcast_s, "aligned_frac": found, "pairs": conc,
                            "host_threads": cores, "cgroup_cpu_quota": cpu_quota, "dp_workspace_overflows": overflow},
                 "clocks": clk, "gpu_launches": pipe.kernel_launches() * args.steps,
                 "e2e": {"value": e2e_val, "unit": "Mreads/s", "h2d_bytes_per_step": 2 * BR * READ_LEN + (BR + 1) * 8,
                         "d2h_bytes_per_step": BR * READ_RESULT.itemsize + BR * pipe.max_ops + (B * PAIR_RESULT.itemsize if paired else 0)},
                 "roofline": roof, "stage_ms": stage_ms, "work_per_step": cnt, "sam_format_host": sam_info, "cpu_baseline": cpu_baseline}
+    return line
+
+
+# ------------------------------------------------------------------------------------------------
+# the exact path: bt2g_xengine_* (the reference's search policy as a device-side state machine in waves)
+# ------------------------------------------------------------------------------------------------
+def sam_records(path):
+    """(records, reference names) of a SAM file: every non-header line, and the @SQ names in order"""
+    recs, names = [], []
+    with open(path) as f:
+        for l in f:
+            if l.startswith("@"):
+                if l.startswith("@SQ"):
+                    names.append(l.split("\t")[1][3:])
+                continue
+            recs.append(l.rstrip("\n"))
+    return recs, names
+
+
+def parity_gate(S, eng, sam_path, n_units, B):
+    """every SAM record of the reference program on the sample vs the engine's (through the host-buffer C ABI + bt2g_sam_format)"""
+    from bowtie2_b200.lib import NameTable, ReadBatch, sam_format
+    want, ref_names = sam_records(sam_path)
+    mates, L = S.mates, S.READ_LEN
+    got = []
+    fallbacks = 0
+    for u0 in range(0, n_units, B):
+        n = min(B, n_units - u0)
+        r = S.reads[u0 * mates:(u0 + n) * mates].cpu().numpy().reshape(-1)
+        q = S.quals[u0 * mates:(u0 + n) * mates].cpu().numpy().reshape(-1)
+        rows = S.names[u0 * mates:(u0 + n) * mates].cpu().numpy()
+        batch = ReadBatch(r, np.arange(0, (n * mates + 1) * L, L, dtype=np.uint64), q)
+        res, ops, pairs, st = eng.align(batch, NameTable(rows))
+        fallbacks += st["fallback_units"]
+        txt = sam_format(S.gpu._lib, batch, res, ops, ref_names, read_names=NameTable(rows), pairs=pairs, threads=S.fmt_threads)
+        got.extend(txt.rstrip("\n").split("\n"))
+    same = sum(1 for a, b in zip(got, want) if a == b)
+    out = {"records": len(want), "identical": same if len(got) == len(want) else min(same, len(want) - 1), "units": n_units,
+           "fallback_units": fallbacks,
+           "against": "the unmodified reference program (oracle/_ref, --seed 0 --reorder) on the same index files and FASTQ sample; whole SAM records"}
+    if out["identical"] != out["records"]:
+        bad = next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), None)
+        if bad is not None:
+            log("first differing record:\n  ours:", got[bad][:400], "\n  ref: ", want[bad][:400])
+        log(f"parity: {len(got)} records of ours vs {len(want)} of the reference")
+    return out
+
+
+def run_exact(S, args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from bowtie2_b200.lib import PAIR_RESULT, READ_RESULT, XEngine, _Reads, policy_params
+    gpu, dev, paired, mates, B, BR, L = S.gpu, S.dev, S.paired, S.mates, S.B, S.BR, S.READ_LEN
+    prm = policy_params(S.wl["preset"], local=False, paired=paired, seed=0, host_threads=S.fmt_threads)
+    # E engines, each with its own stream and host thread, take the E parts of every batch: one engine's long tail of waves
+    # (a few thousand repeat-rich pairs) and its per-wave host round trips overlap with the other engines' full waves
+    E = max(1, min(args.engines, B))
+    sub = (B + E - 1) // E                                   # units per engine and step
+    parts = [(j * sub, min(B, (j + 1) * sub)) for j in range(E)]
+    parts = [(a, b) for a, b in parts if b > a]
+    E = len(parts)
+    engines = [XEngine(gpu, prm, sub, L) for _ in range(E)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(E)]
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    log(f"rank {S.rank}: {E} engine(s) of {sub} {S.unit} created; HBM in use {(total_b - free_b) / 1e9:.1f} of {total_b / 1e9:.1f} GB")
+    NS = S.names.shape[1]
+
+    # ---- parity gate (rank 0, needs the reference's SAM of the sample)
+    parity = None
+    if S.parity_sam:
+        t0 = time.time()
+        parity = parity_gate(S, engines[0], S.parity_sam, S.parity_units, sub)
+        log(f"parity gate: {parity['identical']} of {parity['records']} records identical ({time.time() - t0:.1f}s)")
+        try:
+            os.remove(S.parity_sam)
+        except OSError:
+            pass
+    nb = S.nb
+    offs_all = S.offs
+
+    def run_workers(fn, n_steps, first):
+        """fn(j, i) for engine j over steps first..first+n_steps-1, one host thread per engine; returns after all have finished"""
+        errs = []
+
+        def work(j):
+            try:
+                torch.cuda.set_device(dev)
+                for i in range(first, first + n_steps):
+                    fn(j, i)
+            except Exception as e:                      # surfaced below: a failed engine must fail the bench
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(j,)) for j in range(E)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    stage_acc, stat_acc, launches = {}, {}, [0]
+    lock = threading.Lock()
+
+    def step_dev(j, i, record=False):
+        k = i % nb
+        a, b = parts[j]
+        lo, hi = (k * B + a) * mates, (k * B + b) * mates
+        r, q, nm = S.reads[lo:hi], S.quals[lo:hi], S.names[lo:hi]
+        st = engines[j].run_dev(r.data_ptr(), q.data_ptr(), offs_all.data_ptr(), hi - lo, nm.data_ptr(), NS, stream=streams[j].cuda_stream)
+        if record:
+            sm = engines[j].stage_ms()                 # (host-side floats the engine filled from its own CUDA events)
+            with lock:
+                for kk, v in st.items():
+                    stat_acc[kk] = stat_acc.get(kk, 0) + v
+                for kk, v in sm.items():
+                    stage_acc[kk] = stage_acc.get(kk, 0.0) + v
+                launches[0] += engines[j].launches()
+
+    run_workers(step_dev, args.warmup, 0)
+    torch.cuda.synchronize()
+    if S.distributed:
+        dist.barrier()
+    clocks = ClockSampler(S.local_rank)
+    if S.rank == 0:
+        clocks.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(E)]
+    torch.cuda.synchronize()
+    ev0.record(streams[0])
+    torch.cuda.synchronize()                          # every engine's first kernel is ordered after ev0
+    run_workers(lambda j, i: step_dev(j, i, True), args.steps, args.warmup)
+    for j in range(E):
+        ev1[j].record(streams[j])
+    torch.cuda.synchronize()
+    ms = max(ev0.elapsed_time(e) for e in ev1)         # first start -> last engine finished, on the device clock
+    stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
+    work = {k: v / args.steps for k, v in stat_acc.items()}
+    if E > 1:
+        work["waves"] = work.get("waves", 0) / E       # waves per engine and step
+
+    # ---- e2e: host buffers through the C ABI (H2D of reads, qualities, offsets, names + D2H of result structs, edit ops, pair records)
+    nbuf = min(2, nb)
+    subR = sub * mates
+    hseq = [[torch.empty(subR * L, dtype=torch.uint8).pin_memory() for _ in range(nbuf)] for _ in range(E)]
+    hqual = [[torch.empty(subR * L, dtype=torch.uint8).pin_memory() for _ in range(nbuf)] for _ in range(E)]
+    hname = [[torch.empty(subR * NS, dtype=torch.uint8).pin_memory() for _ in range(nbuf)] for _ in range(E)]
+    for j, (a, b) in enumerate(parts):
+        for k in range(nbuf):
+            lo, hi = (k * B + a) * mates, (k * B + b) * mates
+            n = (hi - lo)
+            hseq[j][k][:n * L].copy_(S.reads[lo:hi].reshape(-1)); hqual[j][k][:n * L].copy_(S.quals[lo:hi].reshape(-1))
+            hname[j][k][:n * NS].copy_(S.names[lo:hi].reshape(-1))
+    hoff = np.arange(0, (subR + 1) * L, L, dtype=np.uint64)
+    hres = [torch.empty(subR * READ_RESULT.itemsize, dtype=torch.uint8).pin_memory() for _ in range(E)]
+    hops = [torch.empty(subR * engines[0].max_ops, dtype=torch.uint8).pin_memory() for _ in range(E)]
+    hpairs = [torch.empty(max(sub, 1) * PAIR_RESULT.itemsize, dtype=torch.uint8).pin_memory() for _ in range(E)]
+    hstats = [np.zeros(8, dtype=np.uint64) for _ in range(E)]
+
+    def step_host(j, i):
+        k = i % nbuf
+        a, b = parts[j]
+        st_ = _Reads((b - a) * mates, hseq[j][k].data_ptr(), hqual[j][k].data_ptr(), hoff.ctypes.data)
+        gpu._check(gpu._lib.bt2g_xengine_align(engines[j]._h, C.byref(st_), hname[j][k].data_ptr(), NS, hres[j].data_ptr(), hops[j].data_ptr(),
+                                               engines[j].max_ops, hpairs[j].data_ptr() if paired else None, hstats[j].ctypes.data), "bt2g_xengine_align")
+
+    run_workers(step_host, min(args.warmup, 2), 0)
+    if S.distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_e2e0 = time.perf_counter()
+    run_workers(step_host, args.steps, 0)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t_e2e0
+    res_np = np.frombuffer(hres[0].numpy().tobytes(), dtype=READ_RESULT)[:(parts[0][1] - parts[0][0]) * mates]
+    found = float((res_np["found"] & 0xff != 0).mean())
+    conc = None
+    if paired:
+        pr = np.frombuffer(hpairs[0].numpy().tobytes(), dtype=PAIR_RESULT)[:parts[0][1] - parts[0][0]]
+        conc = {"concordant_frac": float((pr["pair_type"] == 1).mean())}
+    clk = clocks.stop() if S.rank == 0 else None
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if S.distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    total_units = args.steps * B * S.world
+    value = total_units / (ms_max / 1e3) / 1e6
+    e2e_val = total_units / (e2e_ms_max / 1e3) / 1e6
+    if S.rank != 0:
+        return None
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dp_stage = {"seed_dp": work.get("seed_dp_cells", 0), "mate_dp": work.get("mate_dp_cells", 0)}
+    dom = max(("seed_dp", "mate_dp", "state_machine", "admission", "seed_search", "one_mm"), key=lambda k: stage_ms.get(k, 0.0))
+    dp_cells = dp_stage["seed_dp"] + dp_stage["mate_dp"]
+    dp_ms = stage_ms.get("seed_dp", 0.0) + stage_ms.get("mate_dp", 0.0)
+    roof = {"bound": "hbm", "kernel": dom, "kernel_ms": stage_ms.get(dom), "peak": peak, "unit": "GB/s", "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
+    if dom in dp_stage:
+        # algorithmic bytes of a DP stage: one workspace byte per cell update (DESIGN.md section 3); the stage is integer-ALU (DPX)
+        # bound, so cell updates per second are reported beside it
+        roof["algorithmic_bytes_per_launch"] = dp_stage[dom]
+        roof["achieved"] = dp_stage[dom] / (stage_ms[dom] / 1e3) / 1e9
+        roof["gcups"] = roof["achieved"]
+    else:
+        roof["algorithmic_bytes_per_launch"] = None
+        roof["achieved"] = 0.0
+    roof["frac"] = roof["achieved"] / peak
+    roof["dp_gcups_all"] = dp_cells / (dp_ms / 1e3) / 1e9 if dp_ms > 0 else None
+    line = {"metric": "Mreads/s", "value": value, "unit": "Mreads/s", "n_gpus": S.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 popcount (FM rank) + s16x2 DPX (DP)", "data": "synthetic",
+            "config": {"workload": S.workload, "full_size": S.full, "read_unit": S.unit[:-1], "mates_per_s_M": value * mates,
+                       "batch": B, "engines": E, "preset": " ".join(S.ref_preset),
+                       "l2": "inputs larger than L2 (random access over a %.1f GB index; a different batch each step)" % (S.info["device_bytes"] / 1e9),
+                       "pipeline": "exact",
+                       "pipeline_desc": "the reference's search policy (multiseedSearchWorker + SwDriver::extendSeeds[Paired], per-read RNG included) as a "
+                                        "device-side state machine in waves over the FM / DP kernels (bt2g_xengine_*); SAM identical to the reference program; "
+                                        f"every batch is cut into {E} parts run by {E} engines on their own streams and host threads",
+                       "seed_table_k": args.seed_table, "seed_table_build_s": S.ktab_s, "dense_sa_rate": args.dense_sa, "dense_sa_build_s": S.sa_s,
+                       "index_bcast_s": S.bcast_s, "aligned_frac": found, "pairs": conc, "host_threads": S.cores, "cgroup_cpu_quota": S.cpu_quota},
+            "parity": parity, "clocks": clk, "gpu_launches": launches[0],
+            "e2e": {"value": e2e_val, "unit": "Mreads/s", "h2d_bytes_per_step": 2 * BR * L + (BR + E) * 8 + BR * NS,
+                    "d2h_bytes_per_step": BR * READ_RESULT.itemsize + BR * engines[0].max_ops + (B * PAIR_RESULT.itemsize if paired else 0),
+                    "path": "bt2g_xengine_align: pinned host reads / qualities / names in, result structs + edit ops + pair records out"},
+            "roofline": roof, "stage_ms": stage_ms,
+            "stage_ms_note": "device time per stage and step, summed over the engines (they run concurrently: the sum can exceed ms_per_step)",
+            "work_per_step": work, "cpu_baseline": S.cpu_baseline}
+    if parity is not None and parity["identical"] != parity["records"]:
+        line["refused"] = {"value": value, "e2e": e2e_val, "why": "parity gate: SAM records differ from the reference program's"}
+        line["value"] = None
+        line["e2e"]["value"] = None
+    for e in engines:
+        e.close()
+    return line
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pipeline", default="exact", choices=["exact", "speculative"])
+    ap.add_argument("--workload", default="pe150", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=1_000_000, help="reads (pairs for a paired workload) per step")
+    ap.add_argument("--engines", type=int, default=2, help="exact pipeline: engines (streams + host threads) that share every batch")
+    ap.add_argument("--genome-mbp", type=float, default=GENOME_CONTIGS * CONTIG_LEN / 1e6,
+                    help="debug only: smaller genome (any value other than the default is NOT the BASELINE config)")
+    ap.add_argument("--reads", type=int, default=0, help="reads (pairs) resident in HBM (0 = the workload's default)")
+    ap.add_argument("--seed-table", type=int, default=16,
+                    help="k of the extended seed table derived from the index at load time (0 = off; results are identical)")
+    ap.add_argument("--dense-sa", type=int, default=0,
+                    help="rate of the denser SA sample derived from the index at load time (0 = full suffix array, -1 = off)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference runs (no cpu_baseline, no parity gate)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads (pairs) in the CPU baseline / parity sample (0 = auto)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    paired, READ_LEN = wl["paired"], wl["read_len"]
+    if args.reads <= 0:
+        args.reads = wl["units"]
+    mates = 2 if paired else 1
+    ref_preset = ("--end-to-end", "--" + wl["preset"])
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1 and args.impl == "ours"
+    if distributed:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the single JSON line
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bowtie2_b200 import Bt2Gpu
+    from bowtie2_b200.index_build import build_index
+
+    class S:                                   # what the arms share
+        pass
+    S.wl, S.paired, S.READ_LEN, S.mates, S.ref_preset = wl, paired, READ_LEN, mates, ref_preset
+    S.rank, S.world, S.local_rank, S.dev, S.distributed = rank, world, local_rank, dev, distributed
+    full = abs(args.genome_mbp - GENOME_CONTIGS * CONTIG_LEN / 1e6) < 1e-6 and args.reads >= wl["units"]
+    contig_len = int(args.genome_mbp * 1e6 / GENOME_CONTIGS)
+    unit = "pairs" if paired else "reads"
+    workload = (f"{wl['label']}: synthetic {GENOME_CONTIGS * contig_len / 1e9:.2f} Gbp genome .bt2 index, "
+                f"{args.reads / 1e6:g}M {'2x' if paired else '1x'}{READ_LEN} bp {unit} resident in HBM")
+    hw_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:                                   # container CPU quota, if any (explains where the reference stops scaling)
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        cpu_quota = None if q == "max" else float(q) / float(per)
+    except Exception:
+        cpu_quota = None
+    S.full, S.unit, S.workload, S.cores, S.cpu_quota = full, unit, workload, hw_threads, cpu_quota
+    S.fmt_threads = max(1, min(hw_threads, int(cpu_quota) if cpu_quota else 16))
+
+    # ---- setup (untimed): genome, index (built once on rank 0, NCCL-broadcast to the others), reads
+    t0 = time.time()
+    contigs = make_genome_gpu(torch, dev, GENOME_CONTIGS, contig_len)
+    need_files = args.impl == "reference" or (rank == 0 and not args.no_cpu_baseline)
+    built = None
+    if rank == 0 or not distributed:
+        built = build_index(contigs)
+        torch.cuda.synchronize()
+        log(f"rank {rank}: index built in {time.time() - t0:.1f}s (len={built.len})")
+    index_base = os.path.join(WORKDIR, "idx")
+    if need_files:
+        os.makedirs(WORKDIR, exist_ok=True)
+        built.write_files(index_base)
+        log(f"index files written to {index_base}.*.bt2")
+    if paired:
+        reads, quals = make_pairs_gpu(torch, dev, contigs, args.reads, READ_LEN, seed=1 + rank)
+    else:
+        reads, quals = make_reads_gpu(torch, dev, contigs, args.reads, READ_LEN, seed=1 + rank)
+    del contigs
+    S.reads, S.quals = reads, quals
+    S.B = B = min(args.batch, args.reads)          # units (pairs / reads) per step
+    S.nb = args.reads // B
+    S.BR = BR = B * mates                            # reads per step
+    S.offs = torch.arange(0, (BR + 1) * READ_LEN, READ_LEN, dtype=torch.int64, device=dev)
+
+    # ---- CPU baseline / reference arm: the unmodified reference program on the same index files and a FASTQ sample ------------
+    S.cpu_baseline, S.parity_sam, S.parity_units = None, None, 0
+    if need_files and os.path.exists(ref_binary()[0]):
+        n_big = args.cpu_sample or int(min(args.reads, 400_000 if paired else 1_000_000))
+        n_small = max(n_big // 10, 1000)
+        r_np = reads[:n_big * mates].cpu().numpy(); q_np = quals[:n_big * mates].cpu().numpy()
+        if paired:
+            fq_big = (os.path.join(WORKDIR, "big_1.fq"), os.path.join(WORKDIR, "big_2.fq"))
+            fq_small = (os.path.join(WORKDIR, "small_1.fq"), os.path.join(WORKDIR, "small_2.fq"))
+            for m in range(2):
+                write_fastq(fq_big[m], r_np[m::2], q_np[m::2])
+                write_fastq(fq_small[m], r_np[m:2 * n_small:2], q_np[m:2 * n_small:2])
+        else:
+            fq_big, fq_small = os.path.join(WORKDIR, "big.fq"), os.path.join(WORKDIR, "small.fq")
+            write_fastq(fq_big, r_np, q_np)
+            write_fastq(fq_small, r_np[:n_small], q_np[:n_small])
+        del r_np, q_np
+        # -p: chosen on the BIG sample among the CPUs this container may use (quota) and twice that
+        t_big, threads = None, hw_threads
+        for p in reference_thread_candidates(hw_threads, cpu_quota):
+            dt = run_reference(index_base, fq_big, p, ref_preset)
+            log(f"reference -p {p}: {dt:.2f}s for {n_big} {unit}")
+            if t_big is None or dt < t_big:
+                t_big, threads = dt, p
+        sample = (f"{{}} {unit}: difference of a {n_big}- and a {n_small}-{unit[:-1]} run of {{}} {' '.join(ref_preset)} -p {threads} "
+                  f"(fastest of -p {reference_thread_candidates(hw_threads, cpu_quota)} on the {n_big}-{unit[:-1]} sample; {hw_threads} hardware threads, "
+                  f"cgroup quota {cpu_quota}; index load cancels{{}})")
+        if args.impl == "reference":
+            per, t_start = [], time.time()
+            for s in range(args.warmup + args.steps):
+                r = time_reference(index_base, fq_small, fq_big, n_small, n_big, threads, ref_preset)
+                if s >= args.warmup or not per:
+                    per.append(r)
+                if time.time() - t_start > 150:      # keep the whole run within a few minutes
+                    break
+            rps = float(np.median([p["reads_per_s"] for p in per]))
+            val = rps / 1e6
+            line = {"metric": "Mreads/s", "value": val, "unit": "Mreads/s", "n_gpus": 0, "steps": len(per), "warmup": args.warmup,
+                    "ms_per_step": 1e3 * (n_big - n_small) / rps, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "u8/i16 (SSE/AVX2 striped DP), u64 popcount FM", "data": "synthetic",
+                    "impl": "reference",
+                    "config": {"workload": workload, "full_size": full, "read_unit": unit[:-1], "preset": " ".join(ref_preset),
+                               "host_threads": hw_threads, "cgroup_cpu_quota": cpu_quota},
+                    "cpu_baseline": {"value": val, "unit": "Mreads/s", "cores": threads, "kind": "reference",
+                                     "sample": sample.format(n_big - n_small, per[0]["binary"], "")},
+                    "e2e": {"value": val, "unit": "Mreads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            print(json.dumps(line))
+            shutil.rmtree(WORKDIR, ignore_errors=True)
+            return 0
+        r = time_reference(index_base, fq_small, fq_big, n_small, n_big, threads, ref_preset, t_big=t_big)
+        S.cpu_baseline = {"value": r["reads_per_s"] / 1e6, "unit": "Mreads/s", "cores": threads, "kind": "reference",
+                          "sample": sample.format(n_big - n_small, r["binary"], f"; {r['t_big']:.1f}s and {r['t_small']:.1f}s wall")}
+        log("cpu baseline:", S.cpu_baseline)
+        if args.pipeline == "exact":
+            S.parity_sam, S.parity_units = WORKDIR.rstrip("/") + ".parity.sam", n_big
+            run_reference(index_base, fq_big, threads, ref_preset, out=S.parity_sam, reorder=True)
+            shutil.rmtree(WORKDIR, ignore_errors=True)
+        else:
+            shutil.rmtree(WORKDIR, ignore_errors=True)
+    elif args.impl == "reference":
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bowtie2-align-s not built"}))
+        return 0
+
+    # ---- our arm: the index in HBM (+ the acceleration structures derived from it) ---------------------------------------------
+    S.gpu = gpu = Bt2Gpu(local_rank)
+    S.bcast_s = 0.0
+    if distributed:
+        # single broadcast of every index array from rank 0 (SURVEY.md section 8e) over NCCL / NVLink
+        from bowtie2_b200.dist import broadcast_index
+        torch.cuda.synchronize(); dist.barrier()
+        tb = time.time()
+        desc, tensors = broadcast_index(built, 0, dev)
+        torch.cuda.synchronize(); dist.barrier()
+        S.bcast_s = time.time() - tb
+        gpu.load_index_device(desc, keep=tensors)
+    else:
+        gpu.load_index_device(built.device_desc(dev), keep=built)
+    S.info = info = gpu.info()
+    S.ktab_s = 0.0
+    if args.seed_table > info["ftab_chars"]:
+        torch.cuda.synchronize(); tk = time.time()
+        gpu.build_seed_table(args.seed_table)
+        S.ktab_s = time.time() - tk
+        log(f"rank {rank}: {args.seed_table}-mer seed table built in {S.ktab_s:.2f}s")
+    S.sa_s = 0.0
+    if 0 <= args.dense_sa < info["off_rate"]:
+        torch.cuda.synchronize(); tk = time.time()
+        gpu.build_dense_sa(args.dense_sa)
+        S.sa_s = time.time() - tk
+        log(f"rank {rank}: SA sample of rate {args.dense_sa} built in {S.sa_s:.2f}s")
+    S.names = device_name_rows(torch, dev, 0, args.reads, mates)
+    torch.cuda.synchronize()
+    log(f"rank {rank}: setup {time.time() - t0:.1f}s, index {info['device_bytes'] / 1e9:.2f} GB in HBM")
+
+    line = run_exact(S, args) if args.pipeline == "exact" else run_speculative(S, args)
+    if rank == 0:
         print(json.dumps(line))
+    shutil.rmtree(WORKDIR, ignore_errors=True) if rank == 0 else None
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return 0 if (line is None or line.get("value") is not None) else 1
 
 
 if __name__ == "__main__":

@@ -196,6 +196,7 @@ DevIndex<OFF> bt2g_dev_index(const bt2g_ctx *ctx) {
 	ix.ktab = (const OFF *)ctx->ktab.ptr; ix.ktabChars = ctx->ktab.ptr ? ctx->ktabChars : 0;
 	if(ctx->denseSa.ptr) { ix.saOffs = (const OFF *)ctx->denseSa.ptr; ix.saRate = ctx->denseRate; }
 	else { ix.saOffs = ix.offs; ix.saRate = ctx->info.off_rate; }
+	ix.extText = ctx->extendText;
 	ix.offRate = ctx->info.off_rate;
 	ix.rstarts = (const OFF *)ctx->arr[8].ptr;
 	ix.nFrag = ctx->info.n_frag;
@@ -613,6 +614,12 @@ int bt2g_set_scoring(bt2g_ctx *ctx, const bt2g_scoring *sc) {
 	if(!ctx || !sc) return -1;
 	if(sc->gapbar < 1) { ctx->err = "gapbar must be >= 1"; return -1; }
 	ctx->scoring = *sc;
+	return 0;
+}
+
+int bt2g_set_extend_mode(bt2g_ctx *ctx, int through_text) {
+	if(!ctx) return -1;
+	ctx->extendText = through_text ? 1 : 0;
 	return 0;
 }
 

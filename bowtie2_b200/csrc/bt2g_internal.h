@@ -48,6 +48,9 @@ struct DevIndex {
 	// SA sample in effect: the index's own offs[] / offRate, or the denser one of bt2g_build_dense_sa
 	const OFF     *saOffs;
 	int            saRate;
+	// SwDriver::extend of a unique seed hit by comparing the read with the packed reference (fm_device.cuh: extend_one_text)
+	// instead of walking the index; 0 = always walk (bt2g_set_extend_mode)
+	int            extText;
 };
 
 struct DevArray {
@@ -69,6 +72,7 @@ struct bt2g_ctx {
 	DevArray denseSa; int denseRate = -1;
 	cudaStream_t stream = nullptr;
 	bt2g_scoring scoring{};
+	int extendText = 1;            // unique seed hits are extended against the packed reference (bt2g_set_extend_mode)
 	int dpModeCap = 3;             // highest end-to-end DP kernel generation the launchers may pick (dp_device.cuh)
 	// scratch buffers (grown on demand)
 	std::vector<DevArray> scratch;

@@ -291,3 +291,41 @@ __device__ __forceinline__ uint32_t extend_one(const DevEbwt<OFF> &e, uint64_t t
 	return n;
 }
 
+// The same for a range of ONE row, without the index: LF from row r yields BWT[r] = T[SA[r] - 1], the character of the joined
+// text that precedes the suffix (in the mirror index: the one that follows the occurrence), so the walk of a unique seed hit is
+// a comparison of the read with the joined text itself -- ix.refBuf, the 2-bit packed reference, holds exactly the joined
+// text (every unambiguous base in order; index = joined offset).  `b` = joined offset of the first text character compared,
+// `tstep` = -1 (left, forward index) / +1 (right, mirror index).  Off either end of the text the row is the "$" row: LF yields
+// no character (c = -1) and does not move, which only a read N survives (bt2_idx.h:2451-2473).
+template <typename OFF>
+__device__ __forceinline__ uint32_t extend_one_text(const DevIndex<OFF> &ix, int64_t b, int tstep, const uint8_t *s, int len,
+                                                    int strand, int i0, int step, int lim) {
+	uint32_t n = 0;
+	const int64_t tlen = (int64_t)ix.fw.len;
+	for(int ii = 0; ii < lim; ii++) {
+		const int rdc = read_char(s, len, strand, i0 + ii * step);
+		int c = -1;
+		if(b >= 0 && b < tlen) { c = (int)((__ldg(ix.refBuf + (b >> 2)) >> ((b & 3) << 1)) & 3); b += tstep; }
+		if(c != rdc && rdc <= 3) break;
+		if(++n == 255) break;
+	}
+	return n;
+}
+// SwDriver::extend, both directions of one seed hit (range rng = topf, botf, topb, botb of the seed at 5' offset `off` of the
+// strand-oriented read): unique hits through the text, the rest through the index
+template <typename OFF>
+__device__ __forceinline__ void extend_hit(const DevIndex<OFF> &ix, const uint64_t rng[4], const uint8_t *s, int len, bool fw, int off, int sl,
+                                           bool left, bool right, uint32_t &nlex, uint32_t &nrex) {
+	const int strand = fw ? 0 : 1;
+	const int limL = fw ? off : len - sl - off, limR = fw ? len - sl - off : off;
+	const int i0L = fw ? off - 1 : len - off - sl - 1, i0R = fw ? sl + off : len - off;
+	nlex = nrex = 0;
+	const bool unique = ix.extText && ix.refBuf != nullptr && rng[1] - rng[0] == 1;
+	int64_t p = 0;
+	if(unique && ((left && limL > 0) || (right && limR > 0))) { unsigned ns = 0; p = (int64_t)get_offset<OFF>(ix, rng[0], ns); }
+	if(left && limL > 0)
+		nlex = unique ? extend_one_text<OFF>(ix, p - 1, -1, s, len, strand, i0L, -1, limL) : extend_one<OFF>(ix.fw, rng[0], rng[1], s, len, strand, i0L, -1, limL);
+	if(right && limR > 0 && ix.bw.ebwt != nullptr)
+		nrex = unique ? extend_one_text<OFF>(ix, p + sl, +1, s, len, strand, i0R, +1, limR) : extend_one<OFF>(ix.bw, rng[2], rng[3], s, len, strand, i0R, +1, limR);
+}
+

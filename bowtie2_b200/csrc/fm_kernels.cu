@@ -247,14 +247,9 @@ __global__ void k_extend(DevIndex<OFF> ix, const uint8_t *seq, const uint64_t *r
 	const int sl = seedLen < len ? seedLen : len;
 	const int off = k * interval[rd] + offset[rd];
 	const bool fw = strand == 0;
-	if(dir == 0) {
-		const int lim = fw ? off : len - sl - off;
-		if(lim > 0) out[t] = (uint8_t)extend_one<OFF>(ix.fw, q[0], q[1], s, len, strand, fw ? off - 1 : len - off - sl - 1, -1, lim);
-	} else {
-		const int lim = fw ? len - sl - off : off;
-		if(lim > 0 && ix.bw.ebwt != nullptr)
-			out[t] = (uint8_t)extend_one<OFF>(ix.bw, q[2], q[3], s, len, strand, fw ? sl + off : len - off, +1, lim);
-	}
+	uint32_t nl = 0, nr = 0;
+	extend_hit<OFF>(ix, q, s, len, fw, off, sl, dir == 0, dir != 0, nl, nr);
+	out[t] = (uint8_t)(dir == 0 ? nl : nr);
 }
 
 template <typename OFF>

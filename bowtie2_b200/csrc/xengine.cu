@@ -9,6 +9,11 @@
 // SwDriver::extendSeedsPaired, aligner_sw_driver.cpp:1582-2637) with the same decisions, RNG draws included, made by up to
 // hundreds of thousands of reads at once; results are the reference program's (tests/test_xengine_gpu.py, bench.py's parity gate).
 #include <new>
+#include <mutex>
+#include <map>
+#include <cstdio>
+#include <cstddef>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -88,17 +93,10 @@ struct DevSvc {
 	}
 	// SwDriver::extend (k_extend, fm_kernels.cu): left with the forward index, right with the mirror index
 	__device__ void extend(int read, bool fw, int rdoff, int seedlen, const uint64_t rng[4], int &nlex, int &nrex) const {
-		const uint8_t *s = codes(read); const int len = rdlen(read);
-		const int sl = seedlen < len ? seedlen : len, off = rdoff, strand = fw ? 0 : 1;
-		nlex = nrex = 0;
-		{
-			const int lim = fw ? off : len - sl - off;
-			if(lim > 0) nlex = (int)extend_one<OFF>(ix.fw, rng[0], rng[1], s, len, strand, fw ? off - 1 : len - off - sl - 1, -1, lim);
-		}
-		{
-			const int lim = fw ? len - sl - off : off;
-			if(lim > 0 && ix.bw.ebwt != nullptr) nrex = (int)extend_one<OFF>(ix.bw, rng[2], rng[3], s, len, strand, fw ? sl + off : len - off, +1, lim);
-		}
+		const int len = rdlen(read);
+		uint32_t nl = 0, nr = 0;
+		extend_hit<OFF>(ix, rng, codes(read), len, fw, rdoff, seedlen < len ? seedlen : len, true, true, nl, nr);
+		nlex = (int)nl; nrex = (int)nr;
 	}
 	__device__ int ungapped(int read, bool fw, int64_t tidx, int64_t refoff, int64_t tlen, int64_t minsc, bt2g_ungapped_result &r) const {
 		bt2g_ungapped_problem p; p.read_idx = (uint32_t)read; p.fw = fw ? 1u : 0u; p.tidx = (uint64_t)tidx; p.refoff = refoff; p.reflen = (uint64_t)tlen;
@@ -142,8 +140,8 @@ __global__ void k_xe_reset(XUnit *units, uint8_t *status, uint64_t nUnits, int p
 }
 
 // status: 0 running, 1 finished, 2 fallback (to be re-run by the coroutine engine)
-template <typename OFF>
-__global__ void __launch_bounds__(64) k_xe_step(DevIndex<OFF> ix, bt2g_scoring sc, XParams P, XDev d) {
+template <typename OFF, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_xe_step(DevIndex<OFF> ix, bt2g_scoring sc, XParams P, XDev d) {
 	const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(i >= d.nUnits || d.status[i]) return;
 	XUnit &u = d.units[i];
@@ -203,8 +201,15 @@ struct bt2g_xengine {
 	XQueues *hq = nullptr;             // pinned
 	uint8_t *hStatus = nullptr;        // pinned
 	int sms = 148;
+	cudaStream_t stream = nullptr;     // the engine's own stream (bt2g_xengine_align; run_dev when the caller passes none)
+	int debug = 0;                     // BT2G_XE_DEBUG: per-wave log on stderr
+	int stepOcc = 4;                   // resident blocks of 128 threads per SM the step kernel is compiled for (4: 128 registers, 8: 64)
 	uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // waves, fallbacks, anchor DPs, mate DPs, anchor cells, mate cells, 1-mm requests, seed requests
-	float lastMs = 0.f;
+	// device time of the last batch per stage (CUDA events on the batch's stream): admission (read seeds, packing, exactSweep),
+	// state machine (k_xe_step), 1-mismatch search, seed search, seed-extension DP, mate-finding DP, host fallback (wall), total
+	float stageMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	uint64_t launches = 0;             // kernels of this library launched by the last batch
+	cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -248,6 +253,7 @@ int launchDp(bt2g_xengine *e, const DpWork &w, uint64_t n, cudaStream_t st) {
 	L.chunk = w.chunk; L.packed = w.packed;
 	L.summ = w.o.summ; L.cands = w.o.cands; L.alns = w.o.alns; L.ops = w.o.ops;
 	const DevIndex<OFF> ix = bt2g_dev_index<OFF>(e->ctx);
+	e->launches += (!e->sc.local && w.packed == 3) ? 2 * ((n + w.chunk - 1) / w.chunk) : 1;
 	return e->sc.local ? launch_dp_local<OFF>(ix, e->sc, L, e->maxLen, st) : launch_dp_e2e<OFF>(ix, e->sc, L, e->maxLen, st);
 }
 
@@ -262,7 +268,11 @@ int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t name
 	d.nUnits = nUnits;
 	const unsigned T = 128;
 	auto grid = [&](uint64_t m, unsigned t) { return (unsigned)((m + t - 1) / t); };
-	for(int k = 0; k < 8; k++) e->stats[k] = 0;
+	for(int k = 0; k < 8; k++) { e->stats[k] = 0; e->stageMs[k] = 0.f; }
+	e->launches = 4;                                   // k_xe_seeds, k_xe_reset, k_pack_reads, k_exact_sweep2
+	cudaEvent_t *ev = e->ev;
+	auto lap = [&](int a, int b, int stage) { float ms = 0.f; if(cudaEventElapsedTime(&ms, ev[a], ev[b]) == cudaSuccess) e->stageMs[stage] += ms; };
+	cudaEventRecord(ev[7], st);
 	// admission: read seeds, unit reset, 2-bit packing, exactSweep of every read
 	k_xe_seeds<<<grid(nReads, T), T, 0, st>>>(d.seq, d.qual, d.roff, nReads, dNames, nameStride, paired ? 1 : 0, e->P.seed, const_cast<uint32_t *>(d.seeds));
 	k_xe_reset<<<grid(nUnits, T), T, 0, st>>>(d.units, d.status, nUnits, paired ? 1 : 0);
@@ -271,26 +281,46 @@ int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t name
 	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(d.seedActive, 0, nReads, st));
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	uint64_t done = 0;
+	cudaEventRecord(ev[0], st);
 	for(uint64_t wave = 0;; wave++) {
 		BT2G_CUDA_TRY(ctx, cudaMemsetAsync(d.q, 0, sizeof(XQueues), st));
-		k_xe_step<OFF><<<grid(nUnits, 64), 64, 0, st>>>(ix, e->sc, e->P, d);
+		if(e->stepOcc >= 8) k_xe_step<OFF, 8><<<grid(nUnits, 128), 128, 0, st>>>(ix, e->sc, e->P, d);
+		else k_xe_step<OFF, 4><<<grid(nUnits, 128), 128, 0, st>>>(ix, e->sc, e->P, d);
+		cudaEventRecord(ev[1], st);
+		e->launches++;
 		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(e->hq, d.q, sizeof(XQueues), cudaMemcpyDeviceToHost, st));
 		BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		// everything recorded before this synchronisation has completed: the primitives of the previous wave and this step
+		if(wave == 0) lap(7, 0, 0); else { lap(2, 3, 2); lap(3, 4, 3); lap(4, 5, 4); lap(5, 0, 5); }
+		lap(0, 1, 1);
 		const XQueues q = *e->hq;
+		if(e->debug) {
+			float ms = 0.f; cudaEventElapsedTime(&ms, ev[0], ev[1]);
+			fprintf(stderr, "[xengine] wave %llu: step %.3f ms; done %u fallback %u | dpA %u dpM %u mm %u seed %u\n", (unsigned long long)wave, ms, q.nDone, q.nFallback,
+			        q.nDpA, q.nDpM, q.nMm, q.nSeed);
+		}
 		e->stats[0]++; e->stats[1] += q.nFallback; e->stats[2] += q.nDpA; e->stats[3] += q.nDpM; e->stats[4] += q.cellsA; e->stats[5] += q.cellsM;
 		e->stats[6] += q.nMm; e->stats[7] += q.nSeed;
+		e->launches += (q.nMm ? 1 : 0) + (q.nSeed ? 1 : 0);
 		done += q.nDone + q.nFallback;
 		if(done >= nUnits) break;
 		if(q.nDpA + q.nDpM + q.nMm + q.nSeed == 0) { ctx->err = "xengine: units neither finished nor waiting"; return -5; }
+		cudaEventRecord(ev[2], st);
 		if(q.nMm) launch_one_mm_sel<OFF>(ix, d.seq, d.qual, d.roff, q.nMm, d.mmSel, d.mmMinsc, d.mmMask, e->sc, XE_MM_MAXHITS, const_cast<bt2g_mm_hit *>(d.mmHits), const_cast<int32_t *>(d.mmCounts), st);
+		cudaEventRecord(ev[3], st);
 		if(q.nSeed) {
 			launch_seed_search_active<OFF>(ix, d.roff, nReads, e->P.seedLen, d.maxSeeds, d.seedInterval, d.seedOffset, d.seedActive, const_cast<uint64_t *>(d.ranges),
 			                               const_cast<int32_t *>(d.nseeds), e->packed, e->nmask, e->nextTask, e->sms, st);
 			BT2G_CUDA_TRY(ctx, cudaMemsetAsync(d.seedActive, 0, nReads, st));
 		}
-		if(launchDp<OFF>(e, e->A, q.nDpA, st) || launchDp<OFF>(e, e->M, q.nDpM, st)) { ctx->err = "xengine: DP launch rejected"; return -1; }
+		cudaEventRecord(ev[4], st);
+		if(launchDp<OFF>(e, e->A, q.nDpA, st)) { ctx->err = "xengine: DP launch rejected"; return -1; }
+		cudaEventRecord(ev[5], st);
+		if(launchDp<OFF>(e, e->M, q.nDpM, st)) { ctx->err = "xengine: DP launch rejected"; return -1; }
+		cudaEventRecord(ev[0], st);
 		BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	}
+	lap(7, 1, 7);
 	return 0;
 }
 
@@ -312,6 +342,8 @@ int bt2g_xengine_create(bt2g_ctx *ctx, const bt2g_policy_params *pp, uint64_t ma
 	e->maxReads = pp->paired ? 2 * maxUnits : maxUnits; e->maxBases = e->maxReads * (uint64_t)maxLen;
 	e->maxOps = maxLen + 80;
 	cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	if(const char *o = getenv("BT2G_XE_OCC")) e->stepOcc = atoi(o);          // experiment knob, read once
+	if(getenv("BT2G_XE_DEBUG")) e->debug = 1;
 	// the kernels score with the scheme the policy reasons about (one source: the policy parameters)
 	scoringFromParams(pp, &e->sc);
 	ctx->scoring = e->sc;
@@ -365,6 +397,8 @@ int bt2g_xengine_create(bt2g_ctx *ctx, const bt2g_policy_params *pp, uint64_t ma
 		e->P.minscTab = e->dTabs; e->P.nceilRawTab = e->dTabs + (maxLen + 1); e->P.ivalOneTab = e->dTabs + 2 * (maxLen + 1); e->P.ivalBothTab = e->dTabs + 3 * (maxLen + 1);
 		if(err == cudaSuccess) err = cudaHostAlloc((void **)&e->hq, sizeof(XQueues), cudaHostAllocDefault);
 		if(err == cudaSuccess) err = cudaHostAlloc((void **)&e->hStatus, nU, cudaHostAllocDefault);
+		for(int k = 0; k < 8 && err == cudaSuccess; k++) err = cudaEventCreate(&e->ev[k]);
+		if(err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
 	}
 	if(rc || err != cudaSuccess) {
 		if(err != cudaSuccess) ctx->err = std::string("xengine setup: ") + cudaGetErrorString(err);
@@ -381,6 +415,8 @@ void bt2g_xengine_destroy(bt2g_xengine *e) {
 	for(void *v : e->allocs) cudaFree(v);
 	if(e->hq) cudaFreeHost(e->hq);
 	if(e->hStatus) cudaFreeHost(e->hStatus);
+	for(int k = 0; k < 8; k++) if(e->ev[k]) cudaEventDestroy(e->ev[k]);
+	if(e->stream) cudaStreamDestroy(e->stream);
 	delete e;
 }
 
@@ -393,13 +429,17 @@ int bt2g_xengine_run_dev(bt2g_xengine *e, const uint8_t *dSeq, const uint8_t *dQ
 	if(nReads > e->maxReads || (e->P.paired && (nReads & 1))) { ctx->err = "xengine: batch larger than the engine was created for"; return -1; }
 	if(nReads == 0) return 0;
 	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+	cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
 	ctx->scoring = e->sc;
 	e->d.seq = dSeq; e->d.qual = dQual; e->d.roff = dOff;
 	const int rc = ctx->info.off_size == 4 ? runBatch<uint32_t>(e, nReads, dNames, nameStride, st) : runBatch<uint64_t>(e, nReads, dNames, nameStride, st);
 	if(rc) return rc;
 	if(e->stats[1]) {
 		// fallback units: their reads come back to the host, the coroutine engine answers them through the C ABI
+		// (the coroutine engine drives the context's own entry points and scratch buffers: one fallback at a time per process)
+		static std::mutex fbMutex;
+		std::lock_guard<std::mutex> fbLock(fbMutex);
+		const auto tFb = std::chrono::steady_clock::now();
 		const bool paired = e->P.paired != 0;
 		const uint64_t nUnits = paired ? nReads / 2 : nReads, per = paired ? 2 : 1;
 		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(e->hStatus, e->d.status, nUnits, cudaMemcpyDeviceToHost, st));
@@ -408,6 +448,13 @@ int bt2g_xengine_run_dev(bt2g_xengine *e, const uint8_t *dSeq, const uint8_t *dQ
 		BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
 		std::vector<uint64_t> ids;
 		for(uint64_t i = 0; i < nUnits; i++) if(e->hStatus[i] == 2) ids.push_back(i);
+		if(getenv("BT2G_XE_DEBUG")) {                     // which capacity stopped the units (source lines of xengine.cuh)
+			std::map<uint32_t, uint64_t> hist;
+			for(uint64_t id : ids) { uint32_t ln = 0; cudaMemcpy(&ln, reinterpret_cast<const char *>(e->d.units + id) + offsetof(XUnit, fbLine), 4, cudaMemcpyDeviceToHost); hist[ln]++; }
+			fprintf(stderr, "[xengine] %zu fallback units of %llu; by xengine.cuh line:", ids.size(), (unsigned long long)nUnits);
+			for(auto &kv : hist) fprintf(stderr, " %u:%llu", kv.first, (unsigned long long)kv.second);
+			fprintf(stderr, "\n");
+		}
 		std::vector<uint8_t> seq, qual; std::vector<uint64_t> soff{0}; std::vector<char> names; std::vector<const char *> nptr;
 		for(uint64_t id : ids) for(uint64_t k = 0; k < per; k++) {
 			const uint64_t r = id * per + k, a = off[r], b = off[r + 1];
@@ -437,8 +484,16 @@ int bt2g_xengine_run_dev(bt2g_xengine *e, const uint8_t *dSeq, const uint8_t *dQ
 			BT2G_CUDA_TRY(ctx, cudaMemcpy(e->d.resOps + r0 * (uint64_t)e->maxOps, ops.data() + j * per * (size_t)e->maxOps, per * (size_t)e->maxOps, cudaMemcpyHostToDevice));
 			if(paired) BT2G_CUDA_TRY(ctx, cudaMemcpy(e->d.pairs + ids[j], prs.data() + j, sizeof(bt2g_pair_result), cudaMemcpyHostToDevice));
 		}
+		e->stageMs[6] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - tFb).count();
 	}
 	if(stats) for(int k = 0; k < 8; k++) stats[k] = e->stats[k];
+	return 0;
+}
+
+int bt2g_xengine_stage_ms(bt2g_xengine *e, float *ms, uint64_t *launches) {
+	if(!e || !ms) return -1;
+	for(int k = 0; k < 8; k++) ms[k] = e->stageMs[k];
+	if(launches) *launches = e->launches;
 	return 0;
 }
 
@@ -462,7 +517,7 @@ int bt2g_xengine_align(bt2g_xengine *e, const bt2g_reads *reads, const char *nam
 	if(e->P.paired && !pairs) return -1;
 	if(n == 0) return 0;
 	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-	cudaStream_t st = ctx->stream;
+	cudaStream_t st = e->stream;                      // engines of one context overlap their copies and waves
 	const uint64_t nb = reads->off[n];
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(e->dSeq, reads->seq, nb, cudaMemcpyHostToDevice, st));
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(e->dQual, reads->qual, nb, cudaMemcpyHostToDevice, st));

@@ -45,9 +45,12 @@ enum { XR_DONE = 0, XR_ONE_MM = 1, XR_SEED = 2, XR_DP = 3, XR_DP_MATE = 4, XR_FA
 #define XE_RANDS      160        // Random1toN states of multi-element entries
 #define XE_SEENPOOL   416        // pooled "seen" draws of the non-swap-list Random1toN states
 #define XE_LIST       64         // alignments per sink list
-#define XE_RED        96         // alignments per redundancy set
+#define XE_RED        176        // alignments per redundancy set (a pair stopping after mhits + 1 = 51 concordant placements adds 2 x 51 to set 0)
 #define XE_ATT        256        // backtrace attempts kept of the anchor DP
 #define XE_HITL       (2 + XE_MM1)
+
+// a unit that outgrows a capacity: remember where (line of this file) and stop at the next check
+#define XE_FB(U) ((U).fbLine = (U).fallback ? (U).fbLine : (uint32_t)__LINE__, (U).fallback = 1)
 
 // ---------------------------------------------------------------------------------------------- parameters
 struct XParams {
@@ -177,7 +180,7 @@ struct XUnit {
 	int32_t pairType, pairKind; int64_t scoreSum, fraglen;
 	uint8_t resAligned[2], resHasXs[2]; int32_t resMapq[2]; int64_t resXs[2]; uint16_t resAln[2];
 	// ---- arena
-	uint32_t arenaTop; uint32_t pad4;
+	uint32_t arenaTop; uint32_t fbLine;                   // fbLine: source line of the capacity that stopped the unit (diagnostics)
 	alignas(8) uint8_t arena[XE_ARENA];
 };
 
@@ -187,7 +190,7 @@ XE_HD inline const XAln *x_aln(const XUnit &u, uint16_t off) { return reinterpre
 // allocate `bytes` (rounded up to 8); returns the offset in 8-byte units, or 0xffff and sets u.fallback
 XE_HD inline uint16_t x_alloc(XUnit &u, uint32_t bytes) {
 	const uint32_t need = (bytes + 7u) & ~7u;
-	if(u.arenaTop + need > XE_ARENA) { u.fallback = 1; return 0xffff; }
+	if(u.arenaTop + need > XE_ARENA) { XE_FB(u); return 0xffff; }
 	const uint16_t off = (uint16_t)(u.arenaTop >> 3);
 	u.arenaTop += need;
 	return off;
@@ -214,7 +217,7 @@ XE_HD inline void x_rand_init(XUnit &u, XRand &r, uint64_t n, bool all) {
 	r.n = (uint32_t)n; r.cur = 0; r.converted = 0; r.swaplist = (n < 128 || all) ? 1 : 0; r.listOff = 0xffff;
 	const uint32_t t = (uint32_t)(0.10f * (float)n);
 	r.thresh = t > 16 ? t : 16;
-	if(n > 60000) { if(r.swaplist) u.fallback = 1; }          // (-a mode on huge ranges: coroutine engine)
+	if(n > 60000) { if(r.swaplist) XE_FB(u); }          // (-a mode on huge ranges: coroutine engine)
 }
 XE_HD inline bool x_rand_done(const XRand &r) { return r.n > 0 && r.cur >= r.n; }
 XE_HD inline uint32_t x_rand_next(XUnit &u, int rix, XRng &rnd) {
@@ -242,7 +245,7 @@ XE_HD inline uint32_t x_rand_next(XUnit &u, int rix, XRng &rnd) {
 		for(int i = 0; i < u.nseenPool; i++) if(u.seenPool[i].owner == (uint16_t)rix && u.seenPool[i].val == rn) { again = true; break; }
 		if(!again) break;
 	}
-	if(u.nseenPool >= XE_SEENPOOL) { u.fallback = 1; r.cur = r.n; return rn; }
+	if(u.nseenPool >= XE_SEENPOOL) { XE_FB(u); r.cur = r.n; return rn; }
 	u.seenPool[u.nseenPool].val = rn; u.seenPool[u.nseenPool].owner = (uint16_t)rix; u.nseenPool++;
 	r.cur++;
 	uint32_t mine = 0;
@@ -250,7 +253,7 @@ XE_HD inline uint32_t x_rand_next(XUnit &u, int rix, XRng &rnd) {
 	if(mine >= r.thresh && r.cur < r.n) {
 		// convert to a swap list of the unseen elements, ascending (random_util.h:118-145)
 		const uint32_t rest = r.n - mine;
-		if(r.n > 65535u) { u.fallback = 1; r.cur = r.n; return rn; }
+		if(r.n > 65535u) { XE_FB(u); r.cur = r.n; return rn; }
 		r.listOff = x_alloc(u, rest * 2u);
 		if(r.listOff == 0xffff) { r.cur = r.n; return rn; }
 		uint16_t *l = x_rlist(u, r);
@@ -269,7 +272,7 @@ XE_HD inline uint32_t x_rand_next(XUnit &u, int rix, XRng &rnd) {
 	return rn;
 }
 XE_HD inline int x_new_rand(XUnit &u, uint64_t n, bool all) {
-	if(u.nrands >= XE_RANDS) { u.fallback = 1; return 0; }
+	if(u.nrands >= XE_RANDS) { XE_FB(u); return 0; }
 	const int rix = u.nrands++;
 	x_rand_init(u, u.rands[rix], n, all);
 	return rix;
@@ -289,7 +292,7 @@ XE_HD inline void x_shuffle_portion(T *v, int begin, int num, XRng &rnd) {
 
 // ---------------------------------------------------------------------------------------------- seenDiags / redundancy
 XE_HD inline void x_seen_add(XUnit &u, XMate &c, int64_t tidx, bool fw, int64_t off, int64_t len) {
-	if(c.nseen >= XE_SEEN_IV) { u.fallback = 1; return; }
+	if(c.nseen >= XE_SEEN_IV) { XE_FB(u); return; }
 	XIv &x = c.seen[c.nseen++];
 	x.a = off; x.len = (int32_t)len; x.tidx = (int32_t)((uint32_t)tidx | (fw ? 0x80000000u : 0u));
 }
@@ -336,7 +339,7 @@ XE_HD inline bool x_red_overlap(const XUnit &u, int set, uint16_t aoff) {
 	return false;
 }
 XE_HD inline void x_red_add(XUnit &u, int set, uint16_t aoff) {
-	if(u.nred[set] >= XE_RED) { u.fallback = 1; return; }
+	if(u.nred[set] >= XE_RED) { XE_FB(u); return; }
 	u.red[set][u.nred[set]++] = aoff;
 }
 
@@ -444,7 +447,7 @@ XE_HD inline bool x_ps_report(XUnit &u, const XParams &P, int a1, int a2) {     
 		u.doneDiscord = 1;
 		if(u.doneConcord && !u.exitConcordM) u.doneUnp[0] = u.doneUnp[1] = 1;
 		x_ps_update_done(u);
-		if(u.nrs12 >= XE_LIST) { u.fallback = 1; return true; }
+		if(u.nrs12 >= XE_LIST) { XE_FB(u); return true; }
 		u.rs1[u.nrs12] = (uint16_t)a1; u.rs2[u.nrs12] = (uint16_t)a2; u.nrs12++;
 		const int64_t sc = (int64_t)x_aln(u, (uint16_t)a1)->score + x_aln(u, (uint16_t)a2)->score;
 		if(sc > u.bestPair) { u.best2Pair = u.bestPair; u.bestPair = sc; } else if(sc > u.best2Pair) u.best2Pair = sc;
@@ -458,13 +461,13 @@ XE_HD inline bool x_ps_report(XUnit &u, const XParams &P, int a1, int a2) {     
 		}
 		if(u.nunp[m] > 1) u.doneDiscord = 1;
 		uint16_t &cnt = m == 0 ? u.nrs1u : u.nrs2u;
-		if(cnt >= XE_LIST) { u.fallback = 1; return true; }
+		if(cnt >= XE_LIST) { XE_FB(u); return true; }
 		(m == 0 ? u.rs1u : u.rs2u)[cnt++] = (uint16_t)a;
 	}
 	return u.psDone != 0;
 }
 XE_HD inline bool x_us_report(XUnit &u, const XParams &P, uint16_t a) {
-	if(u.nus >= XE_LIST) { u.fallback = 1; return true; }
+	if(u.nus >= XE_LIST) { XE_FB(u); return true; }
 	u.usAlns[u.nus++] = a;
 	if(!u.usDone) {
 		if(!P.mmode && (int64_t)u.nus >= u.khits) u.usDone = u.usExitK = 1;
@@ -507,7 +510,7 @@ struct XEngine {
 	XE_HD int64_t shSize(const XMate &c, bool fw, int i) const { const uint64_t *h = svc.seedRange(c.idx, fw ? 0 : 1, i); return h[1] > h[0] ? (int64_t)(h[1] - h[0]) : 0; }
 	XE_HD void fillSeedHits(XMate &c, int interval, int offset, int seedlen) {
 		c.shN = svc.nSeeds(c.idx); c.shInterval = interval; c.shOffset = offset; c.shSeedlen = seedlen; c.shNonz = 0; c.shNelt = 0;
-		if(c.shN > XE_MAX_SEEDS) { u.fallback = 1; c.shN = XE_MAX_SEEDS; }
+		if(c.shN > XE_MAX_SEEDS) { XE_FB(u); c.shN = XE_MAX_SEEDS; }
 		for(int f = 0; f < 2; f++) for(int i = 0; i < c.shN; i++) { const int64_t sz = shSize(c, f == 0, i); if(sz > 0) { c.shNonz++; c.shNelt += sz; } }
 	}
 	XE_HD void rankSeedHits(XMate &c) {                        // SeedResults::rankSeedHits (aligner_seed.h:1019-1080)
@@ -520,16 +523,19 @@ struct XEngine {
 			return;
 		}
 		uint64_t sfw = 0, src = 0;                             // sorted flags per offset index (num <= 64)
+		// range sizes once (thread-local), capped like the comparison below: the selection scans them nonz x 2 x num times
+		uint32_t szs[2][XE_MAX_SEEDS];
+		for(int f = 0; f < 2; f++) for(int i = 0; i < num; i++) { const int64_t z = shSize(c, f == 0, i); szs[f][i] = z > 0xffffffffll ? 0xffffffffu : (uint32_t)z; }
 		while((int64_t)c.nranks < c.shNonz) {
-			int64_t minsz = 0xffffffffll; int minidx = 0; bool minfw = true;
+			uint32_t minsz = 0xffffffffu; int minidx = 0; bool minfw = true;
 			const int rb = u.rnd.boolean();
 			for(int fwi = 0; fwi < 2; fwi++) {
 				const bool fw = fwi == (rb ? 1 : 0);
 				const uint64_t srt = fw ? sfw : src;
+				const uint32_t *sz = szs[fw ? 0 : 1];
 				int i = (int)(u.rnd.u32() % (uint32_t)num);
 				for(int t = 0; t < num; t++) {
-					const int64_t sz = shSize(c, fw, i);
-					if(sz > 0 && !((srt >> i) & 1) && sz < minsz) { minsz = sz; minidx = i; minfw = fw; }
+					if(sz[i] > 0 && !((srt >> i) & 1) && sz[i] < minsz) { minsz = sz[i]; minidx = i; minfw = fw; }
 					if(++i == num) i = 0;
 				}
 			}
@@ -540,11 +546,11 @@ struct XEngine {
 
 	// ---- eeSaTups (aligner_sw_driver.cpp:66-290)
 	XE_HD void addEnt(uint64_t topf, int64_t size, int rdoff, int seedlen, bool fw, int ee, bool needRand) {
-		if(u.nents >= XE_ENTS) { u.fallback = 1; return; }
+		if(u.nents >= XE_ENTS) { XE_FB(u); return; }
 		XEnt &e = u.ents[u.nents++];
 		e.topf = topf; e.size = (int32_t)size; e.rdoff = (int16_t)rdoff; e.seedlen = (int16_t)seedlen; e.fw = fw; e.ee = (int8_t)ee; e.done1 = 0; e.mateStreak = 0;
 		e.rix = 0xff;
-		if(needRand && size > 1) { e.rix = (uint8_t)x_new_rand(u, (uint64_t)size, P.all != 0); if(XE_RANDS > 255 || e.rix == 0xff) u.fallback = 1; }
+		if(needRand && size > 1) { e.rix = (uint8_t)x_new_rand(u, (uint64_t)size, P.all != 0); if(XE_RANDS > 255 || e.rix == 0xff) XE_FB(u); }
 	}
 	XE_HD void eeAdd(int hi, int64_t &nelt, int64_t maxelt, bool &done) {
 		const XEEHit &hit = u.hitl[hi];
@@ -615,7 +621,7 @@ struct XEngine {
 			bool skip = false;
 			for(int x = 0; x < c.nexr[st]; x++) { const XExr &e = c.exr[st][x]; if(e.p5 <= rdoff && e.p5 + e.len >= rdoff + seedlen && sz <= e.size) { skip = true; break; } }
 			if(skip) { nelt -= sz; continue; }
-			if(u.nsats >= XE_SATS) { u.fallback = 1; break; }
+			if(u.nsats >= XE_SATS) { XE_FB(u); break; }
 			XSat &sp = u.sats[u.nsats++];
 			sp.topf = h[0]; sp.topb = h[2]; sp.size = sz; sp.fw = fw; sp.offidx = (uint8_t)offidx; sp.rdoff = (int16_t)rdoff; sp.seedlen = (int16_t)seedlen;
 			sp.rix = 0xff; sp.elim = 0; sp.mass = 0.0;
@@ -623,7 +629,7 @@ struct XEngine {
 			svc.extend(c.idx, fw, rdoff, seedlen, h, nlex, nrex);
 			sp.nlex = (uint8_t)nlex; sp.nrex = (uint8_t)nrex;
 			if(nlex > 0 || nrex > 0) {
-				if(c.nexr[st] >= XE_EXR) { u.fallback = 1; }
+				if(c.nexr[st] >= XE_EXR) { XE_FB(u); }
 				else { XExr &e = c.exr[st][c.nexr[st]++]; e.p5 = rdoff - (fw ? nlex : nrex); e.len = seedlen + nlex + nrex; e.size = sz; }
 			}
 		}
@@ -698,7 +704,7 @@ struct XEngine {
 	XE_HD bool loadAnchorDp(const XMate &c) {
 		const bt2g_dp_summary *s = svc.dpSumm(u.dpSlot, false);
 		u.natt = 0; u.attCursor = 0;
-		if(s->flags) { u.fallback = 1; return false; }
+		if(s->flags) { XE_FB(u); return false; }
 		if(!s->found) return false;
 		const bt2g_dp_cand *cands = svc.dpCands(u.dpSlot, false);
 		const bt2g_dp_aln *alns = svc.dpAlns(u.dpSlot, false);
@@ -706,11 +712,11 @@ struct XEngine {
 		for(int ci = 0; ci < s->ncand; ci++) {
 			const int f = cands[ci].fate;
 			if(f != BT2G_CAND_SUCCEEDED && f != BT2G_CAND_FAILED) continue;
-			if(u.natt >= XE_ATT) { u.fallback = 1; return false; }
+			if(u.natt >= XE_ATT) { XE_FB(u); return false; }
 			u.attScore[u.natt] = (int16_t)cands[ci].score;
 			uint16_t ao = 0xffff;
 			if(f == BT2G_CAND_SUCCEEDED) {
-				if(k >= svc.dpMaxAlns()) { u.fallback = 1; return false; }
+				if(k >= svc.dpMaxAlns()) { XE_FB(u); return false; }
 				ao = x_aln_from_dp(u, u.rqProb, alns[k], svc.dpOps(u.dpSlot, false, k), svc.codes(c.idx), c.rdlen);
 				if(ao == 0xffff) return false;
 				k++;
@@ -745,7 +751,7 @@ struct XEngine {
 			if(cands[ci].score < minsc) continue;
 			reseed(u.odpU8 != 0);
 			if(ok) {
-				if(k >= svc.dpMaxAlns()) { u.fallback = 1; return false; }
+				if(k >= svc.dpMaxAlns()) { XE_FB(u); return false; }
 				out = x_aln_from_dp(u, u.rqProb, alns[k], svc.dpOps(u.dpSlot, true, k), svc.codes(o.idx), o.rdlen);
 				return out != 0xffff;
 			}
@@ -809,9 +815,9 @@ XE_HD void XEngine<Svc>::loadMm1(XMate &c, int64_t *neltOut) {
 	for(int task = 0; task < 4; task++) {
 		const int n = svc.mmCount(u.dpSlot, task);
 		const bt2g_mm_hit *h = svc.mmHits(u.dpSlot, task);
-		if(n > svc.mmMax()) { u.fallback = 1; return; }
+		if(n > svc.mmMax()) { XE_FB(u); return; }
 		for(int j = 0; j < n; j++) {
-			if(c.nmm1 >= XE_MM1) { u.fallback = 1; return; }
+			if(c.nmm1 >= XE_MM1) { XE_FB(u); return; }
 			XEEHit &e = c.mm1[c.nmm1++];
 			e.top = h[j].top; e.bot = h[j].bot; e.fw = task < 2; e.score = h[j].score; e.hasEdit = 1; e.pos = (int16_t)h[j].pos;
 			e.chr = (uint8_t)x_dna(h[j].chr); e.qchr = (uint8_t)x_dna(h[j].qchr); e.pad[0] = e.pad[1] = 0;
@@ -929,7 +935,7 @@ XE_HD int XEngine<Svc>::stepExtPaired() {
 								u.nMateDps++;
 								{
 									const bt2g_dp_summary *s = svc.dpSumm(u.dpSlot, true);
-									if(s->flags) { u.fallback = 1; return XR_FALLBACK; }
+									if(s->flags) { XE_FB(u); return XR_FALLBACK; }
 									u.foundMate = s->found != 0;
 									u.mateCursor = 0; u.mateAlnK = 0;
 									if(u.foundMate) u.odpU8 = dpU8(s->best, u.ominscCur, o);
@@ -1007,7 +1013,7 @@ XE_HD int XEngine<Svc>::stepExtPaired() {
 		u.xRet = EXHAUSTED;
 		return XR_DONE;
 	}
-	u.fallback = 1;
+	XE_FB(u);
 	return XR_FALLBACK;
 }
 
@@ -1107,7 +1113,7 @@ XE_HD int XEngine<Svc>::stepExtUnpaired() {
 		u.xRet = EXHAUSTED;
 		return XR_DONE;
 	}
-	u.fallback = 1;
+	XE_FB(u);
 	return XR_FALLBACK;
 }
 
@@ -1125,7 +1131,7 @@ XE_HD int XEngine<Svc>::stepPair() {
 		for(int k = 0; k < 2; k++) {
 			XMate &c = u.m[k];
 			c.idx = i1 + k; c.rdlen = ls[k];
-			if(ls[k] > P.maxLen) { u.fallback = 1; return XR_FALLBACK; }
+			if(ls[k] > P.maxLen) { XE_FB(u); return XR_FALLBACK; }
 			c.minsc = ls[k] ? P.minScore(ls[k]) : 0; c.perfect = P.perfect(ls[k]); c.nceil = ls[k] ? P.nCeil(ls[k]) : 0;
 			const uint8_t *cd = svc.codes(c.idx);
 			int nn = 0; for(int i = 0; i < ls[k]; i++) nn += cd[i] > 3;
@@ -1276,7 +1282,7 @@ XE_HD int XEngine<Svc>::stepPair() {
 		return XR_DONE;
 	}
 	}
-	u.fallback = 1;
+	XE_FB(u);
 	return XR_FALLBACK;
 }
 
@@ -1365,7 +1371,7 @@ XE_HD int XEngine<Svc>::stepRead() {
 		const int idx = (int)u.id, len = svc.rdlen(idx);
 		u.pairType = 0; u.pairKind = 5; u.scoreSum = 0; u.fraglen = 0;
 		for(int k = 0; k < 2; k++) { u.resAligned[k] = 0; u.resHasXs[k] = 0; u.resMapq[k] = 0; u.resXs[k] = 0; u.resAln[k] = 0xffff; }
-		if(len > P.maxLen) { u.fallback = 1; return XR_FALLBACK; }
+		if(len > P.maxLen) { XE_FB(u); return XR_FALLBACK; }
 		c.idx = idx; c.rdlen = len;
 		{
 			const uint8_t *cd = svc.codes(idx);
@@ -1445,7 +1451,7 @@ XE_HD int XEngine<Svc>::stepRead() {
 		return XR_DONE;
 	}
 	}
-	u.fallback = 1;
+	XE_FB(u);
 	return XR_FALLBACK;
 }
 

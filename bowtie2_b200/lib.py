@@ -273,7 +273,7 @@ DP_CAND = np.dtype([("score", "<i4"), ("row", "<i4"), ("col", "<i4"), ("fate", "
 DP_ALN = np.dtype([("cand_idx", "<i4"), ("score", "<i4"), ("ns", "<i4"), ("gaps", "<i4"), ("refns", "<i4"),
                    ("row0", "<i4"), ("col0", "<i4"), ("trim_beg", "<i4"), ("trim_end", "<i4"), ("nops", "<i4")])
 
-EXPORTS += ["bt2g_scoring_default", "bt2g_set_scoring", "bt2g_set_dp_mode", "bt2g_dp_extend"]
+EXPORTS += ["bt2g_scoring_default", "bt2g_set_scoring", "bt2g_set_dp_mode", "bt2g_set_extend_mode", "bt2g_dp_extend"]
 
 OP_MATCH, OP_MM, OP_REFGAP, OP_READGAP = 0, 1, 2, 3
 EDIT_READ_GAP, EDIT_REF_GAP, EDIT_MM = 1, 2, 3      # edit.h:34-39
@@ -340,7 +340,14 @@ def _dp_extend(self, reads: ReadBatch, probs: np.ndarray, max_cands=128, max_aln
 
 Bt2Gpu.set_scoring = _set_scoring
 Bt2Gpu.set_scoring_policy = _set_scoring_policy
+def _set_extend_mode(self, through_text: bool):
+    """bt2g_set_extend_mode: unique seed hits extended against the packed reference (default) or by walking the index"""
+    self._lib.bt2g_set_extend_mode.argtypes = [C.c_void_p, C.c_int]
+    self._check(self._lib.bt2g_set_extend_mode(self._h, int(bool(through_text))), "bt2g_set_extend_mode")
+
+
 Bt2Gpu.set_dp_mode = _set_dp_mode
+Bt2Gpu.set_extend_mode = _set_extend_mode
 Bt2Gpu.dp_extend = _dp_extend
 
 
@@ -1072,8 +1079,10 @@ def policy_backend_gpu(gpu: "Bt2Gpu") -> "_PolicyBackend":
 
 
 # ---- the exact search policy on the device (include/bt2g.h: bt2g_xengine_*; csrc/xengine.cuh, xengine.cu) ---------------
-EXPORTS += ["bt2g_xengine_create", "bt2g_xengine_destroy", "bt2g_xengine_align", "bt2g_xengine_run_dev", "bt2g_xengine_results_dev"]
+EXPORTS += ["bt2g_xengine_create", "bt2g_xengine_destroy", "bt2g_xengine_align", "bt2g_xengine_run_dev", "bt2g_xengine_results_dev",
+            "bt2g_xengine_stage_ms"]
 
+XENGINE_STAGES = ("admission", "state_machine", "one_mm", "seed_search", "seed_dp", "mate_dp", "host_fallback", "total")
 XENGINE_STATS = ("waves", "fallback_units", "seed_dps", "mate_dps", "seed_dp_cells", "mate_dp_cells", "one_mm_requests", "seed_requests")
 
 
@@ -1127,6 +1136,19 @@ class XEngine:
         self.gpu._check(self.gpu._lib.bt2g_xengine_run_dev(self._h, d_seq, d_qual, d_off, n_reads, d_names or None, name_stride, stream or None,
                                                            _ptr(stats)), "bt2g_xengine_run_dev")
         return dict(zip(XENGINE_STATS, (int(x) for x in stats)))
+
+    def stage_ms(self):
+        """device milliseconds of the last batch per stage (bt2g_xengine_stage_ms)"""
+        ms = np.zeros(8, dtype=np.float32)
+        n = C.c_uint64(0)
+        self.gpu._lib.bt2g_xengine_stage_ms.argtypes = [_vp, _vp, C.POINTER(C.c_uint64)]
+        self.gpu._check(self.gpu._lib.bt2g_xengine_stage_ms(self._h, _ptr(ms), C.byref(n)), "bt2g_xengine_stage_ms")
+        self._launches = int(n.value)
+        return dict(zip(XENGINE_STAGES, (float(x) for x in ms)))
+
+    def launches(self):
+        """kernels launched by the last batch (valid after stage_ms())"""
+        return getattr(self, "_launches", 0)
 
     def results_dev(self):
         r, o, p, m = _vp(), _vp(), _vp(), C.c_uint32()

@@ -199,6 +199,11 @@ int  bt2g_set_scoring(bt2g_ctx *ctx, const bt2g_scoring *sc);
  * A per-context setting: no process-global state. */
 int  bt2g_set_dp_mode(bt2g_ctx *ctx, int cap);
 
+/* SwDriver::extend (aligner_sw_driver.cpp:299-484) of a seed hit whose range is ONE row: 1 (default) = compare the read with the
+ * 2-bit packed reference at the hit's joined-text offset (the characters LF would yield are the text's own), 0 = walk the index
+ * as the reference does.  Results are identical (tests/test_fm_gpu.py); ranges of several rows always walk the index. */
+int  bt2g_set_extend_mode(bt2g_ctx *ctx, int through_text);
+
 /* One DP problem = one SwAligner::initRef + align + nextAlignment* session as issued by
  * SwDriver::extendSeeds (aligner_sw_driver.cpp:1272-1376).  The rectangle comes from
  * DynProgFramer::frameSeedExtensionRect (dp_framer.cpp:81-129; DPRect, dp_framer.h:59). */
@@ -581,6 +586,10 @@ int  bt2g_xengine_align(bt2g_xengine *e, const bt2g_reads *reads, const char *na
 int  bt2g_xengine_run_dev(bt2g_xengine *e, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_off, uint64_t n_reads,
                           const char *d_names, uint32_t name_stride, void *stream, uint64_t *stats);
 int  bt2g_xengine_results_dev(bt2g_xengine *e, bt2g_read_result **res, uint8_t **ops, uint32_t *max_ops, bt2g_pair_result **pairs);
+/* device time of the last batch per stage, milliseconds (CUDA events on the batch's stream), 8 entries: admission (read seeds,
+ * 2-bit packing, exactSweep), state machine steps, 1-mismatch searches, seed searches, seed-extension DP, mate-finding DP,
+ * host fallback (wall clock), whole batch; *launches (optional) = kernels of this library launched by that batch */
+int  bt2g_xengine_stage_ms(bt2g_xengine *e, float *ms, uint64_t *launches);
 /* the same state machine driven on the host over an entry-point table (no GPU: the CPU pinning of csrc/xengine.cuh) */
 int  bt2g_xengine_align_host(const bt2g_policy_backend *be, const bt2g_policy_params *prm, const bt2g_reads *reads, const char *const *names,
                              bt2g_read_result *res, uint8_t *ops, uint32_t max_ops, bt2g_pair_result *pairs, uint64_t *stats);

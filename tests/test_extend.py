@@ -36,12 +36,24 @@ def test_extend_oracle_vs_reference(synth_index, synth_genome):
 @pytest.mark.gpu
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize("which", ["small", "large"])
-def test_extend_gpu_vs_oracle(which, gpu, synth_index, synth_index_large, synth_genome):
+@pytest.mark.parametrize("through_text", [True, False])
+def test_extend_gpu_vs_oracle(which, through_text, gpu, synth_index, synth_index_large, synth_genome):
+    """both extension paths of the library (unique hits compared with the packed reference = default; index walk) against the
+    oracle; incl. reads cut from the two ends of the joined text (the "$" row) and reads ending in Ns there"""
     from bowtie2_b200.lib import ReadBatch
     base = synth_index if which == "small" else synth_index_large
     gpu.load_index_files(base)
+    gpu.set_extend_mode(through_text)
     O = Oracle(base)
     reads, L, ival = _cases(synth_genome)
+    first = np.array([c for c in synth_genome[0] if c < 4][:90], dtype=np.uint8)
+    last = np.array([c for c in synth_genome[-1] if c < 4][-90:], dtype=np.uint8)
+    for e in (first, last):
+        reads.append(e.copy())
+        for cut in (30, 55):
+            x = e.copy(); x[:cut] = 4; reads.append(x)          # Ns run over the text's start
+            y = e.copy(); y[-cut:] = 4; reads.append(y)         # ... and over its end
+        reads.append((3 - e[::-1]).astype(np.uint8))            # reverse complement
     batch = ReadBatch.from_list(reads)
     ranges, ns = gpu.seed_search(batch, L, ival, 0, 32)
     ext = gpu.extend_exact(batch, L, ival, 0, 32, ranges)
@@ -57,3 +69,4 @@ def test_extend_gpu_vs_oracle(which, gpu, synth_index, synth_index_large, synth_
                 assert tuple(int(x) for x in ext[i, strand, k]) == want, (i, strand, k)
                 nchk += 1
     assert nchk > 500
+    gpu.set_extend_mode(True)
