@@ -904,6 +904,7 @@ def main():
         log(f"rank {rank}: SA sample of rate {args.dense_sa} built in {S.sa_s:.2f}s")
     S.names = device_name_rows(torch, dev, 0, args.reads, mates)
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()                 # the genome / index-builder temporaries torch still caches: the engines allocate with cudaMalloc
     log(f"rank {rank}: setup {time.time() - t0:.1f}s, index {info['device_bytes'] / 1e9:.2f} GB in HBM")
 
     line = run_exact(S, args) if args.pipeline == "exact" else run_speculative(S, args)

@@ -24,6 +24,10 @@ struct DevEbwt {
 	int            ftabChars;
 };
 
+// engine-internal hit encoding: a BW "row" with this bit set is already the joined-text offset of the hit (1-mismatch search of
+// a unique occurrence, fm_onemm.cu: one_mm_text); never crosses the C ABI
+#define BT2G_ROW_IS_OFFSET (1ull << 63)
+
 template <typename OFF>
 struct DevIndex {
 	DevEbwt<OFF>   fw, bw;

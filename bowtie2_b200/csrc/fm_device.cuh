@@ -311,11 +311,99 @@ __device__ __forceinline__ uint32_t extend_one_text(const DevIndex<OFF> &ix, int
 	}
 	return n;
 }
+// ---- the same comparison 32 characters at a time, over the 2-bit packed read (k_pack_reads: word w of a read holds its bases
+// 32w..32w+31, base i at bits 2(i & 31); N mask with the same word structure) and the 2-bit packed joined text.
+__device__ __forceinline__ uint64_t swap_rev_pairs(uint64_t x) {       // reverse the order of the 32 2-bit groups of x
+	const uint64_t y = __brevll(x);
+	return ((y & 0x5555555555555555ull) << 1) | ((y >> 1) & 0x5555555555555555ull);
+}
+__device__ __forceinline__ uint64_t spread_bits(uint32_t m) {            // bit j -> bit 2j
+	uint64_t x = m;
+	x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+	x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+	x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+	x = (x | (x << 2)) & 0x3333333333333333ull;
+	x = (x | (x << 1)) & 0x5555555555555555ull;
+	return x;
+}
+// 32 characters of a packed sequence in WALK order (character j of the walk at bits 2j): ascending from p (p, p+1, ...) or
+// descending from p (p, p-1, ...); `ok` gets one bit per walk position that lies inside [0, n).  Words are fetched through
+// `word(k)` (k >= 0) so that the read (two arrays) and the text (one byte array) share the code.
+template <typename F>
+__device__ __forceinline__ uint64_t walk_window(F word, int64_t p, bool asc, int64_t n, uint32_t &ok) {
+	int64_t q = asc ? p : p - 31;                      // ascending window [q, q + 32)
+	int lshift = 0;                                    // groups the window is moved up by when it starts before 0
+	if(q < 0) { lshift = (int)(-q); q = 0; }
+	uint64_t a = 0;
+	if(lshift < 32 && q < n) {
+		const int64_t w = q >> 5; const int sh = (int)(q & 31);
+		a = word(w) >> (2 * sh);
+		if(sh && ((w + 1) << 5) < n) a |= word(w + 1) << (64 - 2 * sh);
+		if(lshift) a <<= 2 * lshift;
+	}
+	// validity of ascending position k of the (unshifted) window [p or p-31 ...): inside [0, n)
+	const int64_t q0 = asc ? p : p - 31;
+	uint32_t v = 0xffffffffu;
+	if(q0 < 0) v = q0 <= -32 ? 0u : (v << (int)(-q0));
+	if(q0 + 32 > n) { const int64_t keep = n - q0; v = keep <= 0 ? 0u : (keep >= 32 ? v : (v & ((1u << (int)keep) - 1u))); }
+	if(asc) { ok = v; return a; }
+	ok = __brev(v);
+	return swap_rev_pairs(a);
+}
+// extend_one_text, word-parallel.  pk / nm: the read's packed words and N-mask words (word 0 = bases 0..31).
+template <typename OFF>
+__device__ __forceinline__ uint32_t extend_one_text_packed(const DevIndex<OFF> &ix, int64_t b, int tstep, const uint64_t *pk, const uint32_t *nm, int len,
+                                                           int strand, int i0, int step, int lim) {
+	const int64_t tlen = (int64_t)ix.fw.len;
+	const uint64_t *tw = reinterpret_cast<const uint64_t *>(ix.refBuf);
+	auto tword = [&](int64_t k) -> uint64_t { return __ldg(tw + k); };
+	auto rword = [&](int64_t k) -> uint64_t { return pk[k]; };
+	// raw read position and direction of the walk: strand 1 reads the reverse complement
+	int64_t rp = strand == 0 ? i0 : len - 1 - i0;
+	const bool rasc = strand == 0 ? step > 0 : step < 0;
+	const uint64_t comp = strand == 0 ? 0ull : ~0ull;
+	int n = 0;
+	if(lim > 255) lim = 255;
+	while(n < lim) {
+		uint32_t okR, okT, okN;
+		const uint64_t R = walk_window(rword, rp, rasc, (int64_t)len, okR) ^ comp;
+		const uint64_t T = walk_window(tword, b, tstep > 0, tlen, okT);
+		// N mask of the read in walk order (one bit per character)
+		uint32_t nmk;
+		{
+			int64_t q = rasc ? rp : rp - 31; int lshift = 0;
+			if(q < 0) { lshift = (int)(-q); q = 0; }
+			uint32_t a = 0;
+			if(lshift < 32 && q < len) {
+				const int64_t w = q >> 5; const int sh = (int)(q & 31);
+				a = nm[w] >> sh;
+				if(sh && ((w + 1) << 5) < len) a |= nm[w + 1] << (32 - sh);
+				if(lshift) a <<= lshift;
+			}
+			nmk = rasc ? a : __brev(a);
+			okN = 0;
+		}
+		(void)okN;
+		const uint64_t X = R ^ T;
+		const uint64_t neq = (X | (X >> 1)) & 0x5555555555555555ull;
+		// a walk position stops the extension when the read character is not N and (the text has no character there or differs)
+		const uint64_t stop = (neq | spread_bits(~okT)) & ~spread_bits(nmk);
+		const int chunk = lim - n < 32 ? lim - n : 32;
+		int first = stop ? (__ffsll((long long)stop) - 1) >> 1 : 32;
+		if(first < chunk) { n += first; break; }
+		n += chunk;
+		rp += rasc ? 32 : -32;
+		b += tstep > 0 ? 32 : -32;
+		(void)okR;
+	}
+	return (uint32_t)n;
+}
+
 // SwDriver::extend, both directions of one seed hit (range rng = topf, botf, topb, botb of the seed at 5' offset `off` of the
 // strand-oriented read): unique hits through the text, the rest through the index
 template <typename OFF>
 __device__ __forceinline__ void extend_hit(const DevIndex<OFF> &ix, const uint64_t rng[4], const uint8_t *s, int len, bool fw, int off, int sl,
-                                           bool left, bool right, uint32_t &nlex, uint32_t &nrex) {
+                                           bool left, bool right, uint32_t &nlex, uint32_t &nrex, const uint64_t *pk = nullptr, const uint32_t *nm = nullptr) {
 	const int strand = fw ? 0 : 1;
 	const int limL = fw ? off : len - sl - off, limR = fw ? len - sl - off : off;
 	const int i0L = fw ? off - 1 : len - off - sl - 1, i0R = fw ? sl + off : len - off;
@@ -324,8 +412,10 @@ __device__ __forceinline__ void extend_hit(const DevIndex<OFF> &ix, const uint64
 	int64_t p = 0;
 	if(unique && ((left && limL > 0) || (right && limR > 0))) { unsigned ns = 0; p = (int64_t)get_offset<OFF>(ix, rng[0], ns); }
 	if(left && limL > 0)
-		nlex = unique ? extend_one_text<OFF>(ix, p - 1, -1, s, len, strand, i0L, -1, limL) : extend_one<OFF>(ix.fw, rng[0], rng[1], s, len, strand, i0L, -1, limL);
+		nlex = !unique ? extend_one<OFF>(ix.fw, rng[0], rng[1], s, len, strand, i0L, -1, limL)
+		     : (pk ? extend_one_text_packed<OFF>(ix, p - 1, -1, pk, nm, len, strand, i0L, -1, limL) : extend_one_text<OFF>(ix, p - 1, -1, s, len, strand, i0L, -1, limL));
 	if(right && limR > 0 && ix.bw.ebwt != nullptr)
-		nrex = unique ? extend_one_text<OFF>(ix, p + sl, +1, s, len, strand, i0R, +1, limR) : extend_one<OFF>(ix.bw, rng[2], rng[3], s, len, strand, i0R, +1, limR);
+		nrex = !unique ? extend_one<OFF>(ix.bw, rng[2], rng[3], s, len, strand, i0R, +1, limR)
+		     : (pk ? extend_one_text_packed<OFF>(ix, p + sl, +1, pk, nm, len, strand, i0R, +1, limR) : extend_one_text<OFF>(ix, p + sl, +1, s, len, strand, i0R, +1, limR));
 }
 

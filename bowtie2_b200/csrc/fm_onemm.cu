@@ -36,7 +36,72 @@ __device__ __forceinline__ void bi_step(const DevEbwt<OFF> &e, uint64_t top, uin
 	for(int j = 0; j < 4; j++) { tp[j] = acc; acc += b[j] - t[j]; bp[j] = acc; }
 }
 
-template <typename OFF>
+// TEXT: once the range is ONE row the search continues in the joined text itself (ix.refBuf, the 2-bit packed reference = the
+// joined text): every further LF step of a single row yields the text character next to the occurrence, so the rest of the read
+// is compared with the text at the occurrence's joined offset (one SA lookup), and a hit is returned as that offset with
+// BT2G_ROW_IS_OFFSET set in `top` (bot = top + 1) instead of its forward-index row -- the engine resolves rows to offsets anyway
+// (csrc/xengine.cu: DevSvc::resolve).  The ABI entry point bt2g_one_mm keeps TEXT = false (rows).
+template <typename OFF, bool TEXT>
+__device__ __forceinline__ bool one_mm_text(const DevIndex<OFF> &ix, const OneMmCtx &c, uint64_t rowFw, int dep, int nea, int ns, int nceil,
+                                            const bt2g_scoring &sc, int minsc, int maxHits, bt2g_mm_hit *out, int &nh) {
+	const int len = c.len;
+	const int64_t tlen = (int64_t)ix.fw.len;
+	unsigned nside = 0;
+	const int64_t P = (int64_t)get_offset<OFF>(ix, rowFw, nside);       // joined offset where the dep matched characters start
+	// text position consumed by step d: leftwards from the occurrence in the forward-index pass, rightwards in the mirror pass
+	const int64_t base = c.ebwtfw ? P + dep : P;
+	auto tidx = [&](int d) -> int64_t { return c.ebwtfw ? base - 1 - d : base + d; };
+	auto tchr = [&](int64_t b) -> int { return (int)((__ldg(ix.refBuf + (b >> 2)) >> ((b & 3) << 1)) & 3); };
+	for(; dep < nea; dep++) {                                           // near half: exact
+		const int64_t b = tidx(dep);
+		if(b < 0 || b >= tlen || tchr(b) != c.chr(len - dep - 1)) return true;
+	}
+	for(; dep < len; dep++) {                                           // far half: one substitution allowed
+		const int rdc = c.chr(len - dep - 1);
+		const int quc = c.qual(len - dep - 1);
+		if(rdc > 3 && nceil == 0) break;
+		const int64_t b = tidx(dep);
+		if(b < 0 || b >= tlen) break;                                   // the "$" row
+		const int tc = tchr(b);
+		if((ns == 0 || rdc > 3) && tc != rdc) {
+			int depm = dep + 1;
+			for(; depm < len; depm++) {
+				const int rdcm = c.chr(len - depm - 1);
+				if(rdcm > 3) break;
+				const int64_t bm = tidx(depm);
+				if(bm < 0 || bm >= tlen || tchr(bm) != rdcm) break;
+			}
+			if(depm == len) {
+				int off5p = dep;
+				if(c.fw == c.ebwtfw) off5p = len - off5p - 1;
+				int qq = quc - 33; qq = qq < 0 ? 0 : (qq > 63 ? 63 : qq);
+				const int pen = rdc > 3 ? -(int)sc.npen[qq] : -(int)sc.mmpen[qq];
+				const int score = (len - 1) * sc.match_bonus + pen;
+				bool valid = true;
+				if(sc.local) {
+					int lf = 0, lb = 0;
+					for(int i = 0; i < len && valid; i++) {
+						if(i == dep) { if(lf + pen <= 0) valid = false; lf += pen; } else lf += sc.match_bonus;
+						if(len - i - 1 == dep) { if(lb + pen <= 0) valid = false; lb += pen; } else lb += sc.match_bonus;
+					}
+				}
+				if(valid && score >= minsc) {
+					if(nh < maxHits) {
+						bt2g_mm_hit &h = out[nh];
+						h.top = BT2G_ROW_IS_OFFSET | (uint64_t)(c.ebwtfw ? base - len : base); h.bot = h.top + 1;
+						h.pos = off5p; h.chr = tc; h.qchr = rdc; h.score = score;
+					}
+					nh++;
+				}
+			}
+		}
+		if(rdc > 3 || tc != rdc) break;
+		if(dep == len - 1) break;
+	}
+	return true;
+}
+
+template <typename OFF, bool TEXT>
 __global__ void k_one_mm(DevIndex<OFF> ix, const uint8_t *seq, const uint8_t *qual, const uint64_t *roff, uint64_t nReads,
                          const int32_t *minsc, const uint8_t *strandMask, bt2g_scoring sc, int maxHits,
                          bt2g_mm_hit *hits, int32_t *counts, const uint32_t *sel, const uint32_t *nDev) {
@@ -83,8 +148,12 @@ __global__ void k_one_mm(DevIndex<OFF> ix, const uint8_t *seq, const uint8_t *qu
 		dep = 1;
 	}
 	uint64_t tt[4], bb[4], tp[4], bp[4];
+	int nh = 0;
+	bt2g_mm_hit *out = hits + t * (uint64_t)maxHits;
+	const bool text = TEXT && ix.refBuf != nullptr;
 	// near half: exact
 	for(; dep < nea; dep++) {
+		if(text && bot - top == 1) { one_mm_text<OFF, TEXT>(ix, c, c.ebwtfw ? top : topp, dep, nea, ns, nceil, sc, minsc[slot], maxHits, out, nh); counts[t] = nh; return; }
 		const int rdc = c.chr(len - dep - 1);
 		bi_step<OFF>(e, top, bot, topp, tt, bb, tp, bp);
 		const uint64_t nt = rdc == 0 ? tt[0] : (rdc == 1 ? tt[1] : (rdc == 2 ? tt[2] : tt[3]));
@@ -95,9 +164,8 @@ __global__ void k_one_mm(DevIndex<OFF> ix, const uint8_t *seq, const uint8_t *qu
 		top = nt; bot = nb;
 	}
 	// far half: one substitution allowed
-	int nh = 0;
-	bt2g_mm_hit *out = hits + t * (uint64_t)maxHits;
 	for(; dep < len; dep++) {
+		if(text && bot - top == 1) { one_mm_text<OFF, TEXT>(ix, c, c.ebwtfw ? top : topp, dep, nea, ns, nceil, sc, minsc[slot], maxHits, out, nh); break; }
 		const int rdc = c.chr(len - dep - 1);
 		const int quc = c.qual(len - dep - 1);
 		if(rdc > 3 && nceil == 0) break;
@@ -163,17 +231,19 @@ void launch_one_mm(const DevIndex<OFF> &ix, const uint8_t *seq, const uint8_t *q
                    const int32_t *minsc, const uint8_t *strandMask, const bt2g_scoring &sc, int maxHits, bt2g_mm_hit *hits,
                    int32_t *counts, cudaStream_t st) {
 	const uint64_t n = nReads * 4;
-	if(n) k_one_mm<OFF><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ix, seq, qual, roff, nReads, minsc, strandMask, sc, maxHits, hits, counts, nullptr, nullptr);
+	if(n) k_one_mm<OFF, false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ix, seq, qual, roff, nReads, minsc, strandMask, sc, maxHits, hits, counts, nullptr, nullptr);
 }
 // request-queue form: nSlots requests, slot s = read sel[s]
 template <typename OFF>
 void launch_one_mm_sel(const DevIndex<OFF> &ix, const uint8_t *seq, const uint8_t *qual, const uint64_t *roff, uint64_t nSlots, const uint32_t *sel,
                        const int32_t *minsc, const uint8_t *strandMask, const bt2g_scoring &sc, int maxHits, bt2g_mm_hit *hits,
-                       int32_t *counts, cudaStream_t st) {
+                       int32_t *counts, cudaStream_t st, bool text) {
 	const uint64_t n = nSlots * 4;
-	if(n) k_one_mm<OFF><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ix, seq, qual, roff, nSlots, minsc, strandMask, sc, maxHits, hits, counts, sel, nullptr);
+	if(!n) return;
+	if(text) k_one_mm<OFF, true><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ix, seq, qual, roff, nSlots, minsc, strandMask, sc, maxHits, hits, counts, sel, nullptr);
+	else k_one_mm<OFF, false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ix, seq, qual, roff, nSlots, minsc, strandMask, sc, maxHits, hits, counts, sel, nullptr);
 }
-template void launch_one_mm_sel<uint32_t>(const DevIndex<uint32_t> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const uint32_t *, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t);
-template void launch_one_mm_sel<uint64_t>(const DevIndex<uint64_t> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const uint32_t *, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t);
+template void launch_one_mm_sel<uint32_t>(const DevIndex<uint32_t> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const uint32_t *, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t, bool);
+template void launch_one_mm_sel<uint64_t>(const DevIndex<uint64_t> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const uint32_t *, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t, bool);
 template void launch_one_mm<uint32_t>(const DevIndex<uint32_t> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t);
 template void launch_one_mm<uint64_t>(const DevIndex<uint64_t> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t);

@@ -466,9 +466,15 @@ template <typename OFF>
 __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const uint64_t *packed, const uint32_t *nmask,
                                                       const uint64_t *roff, uint64_t nReads, int nofw, int norc,
                                                       uint8_t *mine, uint64_t *ee, unsigned long long *next, unsigned long long *cnt,
-                                                      int eeOnly) {
-	// eeOnly (the pipeline): only the exact end-to-end range is wanted, so the search stops at the first failed
+                                                      int flags) {
+	// flags bit 0, eeOnly (the pipeline): only the exact end-to-end range is wanted, so the search stops at the first failed
 	// extension (mine = 1 then means "at least one edit") and may start from the extended seed table.
+	// flags bit 1, text (the exact engine): once the range is ONE row the sweep continues in the joined text (ix.refBuf): a
+	// single row's LF steps yield the text characters to the left of the occurrence, so the rest of the stretch is compared
+	// with the text at the occurrence's joined offset; an end-to-end range found that way is returned as that offset with
+	// BT2G_ROW_IS_OFFSET set (the engine resolves rows to offsets anyway; csrc/xengine.cu: DevSvc::resolve).
+	const int eeOnly = flags & 1;
+	const bool text = (flags & 2) != 0 && ix.refBuf != nullptr;
 	constexpr uint32_t BL = SideGeom<OFF>::BWT_LEN;
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
@@ -573,7 +579,24 @@ __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const ui
 					stepNow = false;                    // the reference `continue`s: re-init from the new depth
 				} else doInit = false;
 			}
-			if(stepNow && !done && dep < len) {
+			if(stepNow && !done && dep < len && text && bot - top == 1) {
+				unsigned ns2 = 0;
+				int64_t b = (int64_t)get_offset<OFF>(ix, top, ns2) - 1;
+				nside += ns2;
+				bool mism = false;
+				while(dep < len) {
+					const int c = chr(len - dep - 1);
+					if(c > 3 || b < 0 || (int)((__ldg(ix.refBuf + (b >> 2)) >> ((b & 3) << 1)) & 3) != c) { mism = true; break; }
+					b--; dep++;
+				}
+				if(mism) {
+					top = bot = 0;
+					nedit++;
+					if(nedit >= mineMax || eeOnly) done = true;
+					doInit = true;
+					dep++;
+				} else { top = BT2G_ROW_IS_OFFSET | (uint64_t)(b + 1); bot = top + 1; }
+			} else if(stepNow && !done && dep < len) {
 				const int c = chr(len - dep - 1);
 				if(c > 3) { top = bot = 0; }
 				else {
@@ -609,13 +632,13 @@ __global__ void __launch_bounds__(256) k_exact_sweep2(DevIndex<OFF> ix, const ui
 template <typename OFF>
 void launch_exact_sweep2(const DevIndex<OFF> &ix, const uint64_t *roff, uint64_t nReads, int nofw, int norc,
                          uint8_t *mine, uint64_t *ee, const uint64_t *packed, const uint32_t *nmask, unsigned long long *next,
-                         int numSMs, cudaStream_t st, unsigned long long *cnt, int eeOnly) {
+                         int numSMs, cudaStream_t st, unsigned long long *cnt, int flags) {
 	if(nReads == 0) return;
 	cudaMemsetAsync(next, 0, sizeof(unsigned long long), st);
 	int perSM = 4;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_exact_sweep2<OFF>, 256, 0);
 	if(perSM < 1) perSM = 1;
-	k_exact_sweep2<OFF><<<(unsigned)(numSMs * perSM), 256, 0, st>>>(ix, packed, nmask, roff, nReads, nofw, norc, mine, ee, next, cnt, eeOnly);
+	k_exact_sweep2<OFF><<<(unsigned)(numSMs * perSM), 256, 0, st>>>(ix, packed, nmask, roff, nReads, nofw, norc, mine, ee, next, cnt, flags);
 }
 template void launch_exact_sweep2<uint32_t>(const DevIndex<uint32_t> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *, int);
 template void launch_exact_sweep2<uint64_t>(const DevIndex<uint64_t> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *, int);

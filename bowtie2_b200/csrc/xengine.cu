@@ -27,7 +27,7 @@ template <typename OFF> int launch_dp_e2e(const DevIndex<OFF> &, const bt2g_scor
 template <typename OFF> int launch_dp_local(const DevIndex<OFF> &, const bt2g_scoring &, const DpLaunch &, int, cudaStream_t);
 template <typename OFF> void launch_exact_sweep2(const DevIndex<OFF> &, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t, unsigned long long *, int);
 void launch_pack_reads(const uint8_t *, const uint64_t *, uint64_t, int, uint64_t *, uint32_t *, cudaStream_t);
-template <typename OFF> void launch_one_mm_sel(const DevIndex<OFF> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const uint32_t *, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t);
+template <typename OFF> void launch_one_mm_sel(const DevIndex<OFF> &, const uint8_t *, const uint8_t *, const uint64_t *, uint64_t, const uint32_t *, const int32_t *, const uint8_t *, const bt2g_scoring &, int, bt2g_mm_hit *, int32_t *, cudaStream_t, bool);
 template <typename OFF> void launch_seed_search_active(const DevIndex<OFF> &, const uint64_t *, uint64_t, int, int, const int32_t *, const int32_t *, const uint8_t *, uint64_t *, int32_t *, const uint64_t *, const uint32_t *, unsigned long long *, int, cudaStream_t);
 
 extern "C" int bt2g_policy_align(const bt2g_policy_backend *, const bt2g_policy_params *, const bt2g_reads *, const char *const *,
@@ -39,7 +39,7 @@ using namespace xe;
 #define XE_MM_MAXHITS 16
 
 struct XQueues {                     // per wave, reset before k_xe_step
-	uint32_t nDpA, nDpM, nMm, nSeed, nDone, nFallback, pad0, pad1;
+	uint32_t nDpA, nDpM, nMm, nSeed, nDone, nFallback, nActive, pad1;
 	unsigned long long cellsA, cellsM;
 };
 
@@ -48,6 +48,7 @@ struct DpOut { bt2g_dp_problem *probs; bt2g_dp_summary *summ; bt2g_dp_cand *cand
 struct XDev {                        // everything the step kernel needs (passed by value)
 	const uint8_t *seq, *qual; const uint64_t *roff;
 	const uint32_t *seeds;
+	const uint64_t *packed; const uint32_t *nmask;         // the reads 2 bits per base + N masks (k_pack_reads)
 	const uint8_t *mine; const uint64_t *ee;
 	const bt2g_mm_hit *mmHits; const int32_t *mmCounts;
 	uint32_t *mmSel; int32_t *mmMinsc; uint8_t *mmMask;
@@ -85,7 +86,8 @@ struct DevSvc {
 	// GroupWalk2S::advanceElement == Ebwt::getOffset, then Ebwt::joinedToTextOff (k_resolve2, fm_seed2.cu)
 	__device__ bool resolve(uint64_t row, int qlen, bool reject, int64_t &tidx, int64_t &toff, int64_t &tlen) const {
 		unsigned nside = 0;
-		const uint64_t off = get_offset<OFF>(ix, row, nside);
+		// (a 1-mismatch hit of a unique occurrence arrives as its joined offset: fm_onemm.cu)
+		const uint64_t off = (row & BT2G_ROW_IS_OFFSET) ? (row & ~BT2G_ROW_IS_OFFSET) : get_offset<OFF>(ix, row, nside);
 		uint64_t ti, to, tl; bool st;
 		const bool ok = joined_to_text<OFF>(ix, (uint64_t)qlen, off, reject, ti, to, tl, st);
 		tidx = (int64_t)ti; toff = (int64_t)to; tlen = (int64_t)tl;
@@ -95,7 +97,8 @@ struct DevSvc {
 	__device__ void extend(int read, bool fw, int rdoff, int seedlen, const uint64_t rng[4], int &nlex, int &nrex) const {
 		const int len = rdlen(read);
 		uint32_t nl = 0, nr = 0;
-		extend_hit<OFF>(ix, rng, codes(read), len, fw, rdoff, seedlen < len ? seedlen : len, true, true, nl, nr);
+		const uint64_t wb = (d.roff[read] >> 5) + (uint64_t)read;
+		extend_hit<OFF>(ix, rng, codes(read), len, fw, rdoff, seedlen < len ? seedlen : len, true, true, nl, nr, d.packed + wb, d.nmask + wb);
 		nlex = (int)nl; nrex = (int)nr;
 	}
 	__device__ int ungapped(int read, bool fw, int64_t tidx, int64_t refoff, int64_t tlen, int64_t minsc, bt2g_ungapped_result &r) const {
@@ -139,43 +142,75 @@ __global__ void k_xe_reset(XUnit *units, uint8_t *status, uint64_t nUnits, int p
 	status[i] = 0;
 }
 
-// status: 0 running, 1 finished, 2 fallback (to be re-run by the coroutine engine)
+// counter += 1 for every calling lane, one atomic per group of lanes that arrive together on the same counter
+__device__ __forceinline__ uint32_t agg_inc(uint32_t *ctr) {
+	const unsigned act = __activemask();
+	const unsigned peers = __match_any_sync(act, (unsigned long long)ctr);
+	const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+	uint32_t base = 0;
+	if(lane == leader) base = atomicAdd(ctr, (uint32_t)__popc(peers));
+	base = __shfl_sync(peers, base, leader);
+	return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
+
+// status: 0 running, 1 finished, 2 fallback (to be re-run by the coroutine engine).
+// The wave runs over the ACTIVE list (activeIn, nAct entries; nullptr = every unit, the first wave): units that wait for an
+// answer append themselves to activeOut, so later waves launch as many threads as there are unfinished units -- the long tail
+// of a batch (a few thousand repeat-rich pairs going through dozens of DP rounds) then occupies a few warps, not the GPU.
 template <typename OFF, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_xe_step(DevIndex<OFF> ix, bt2g_scoring sc, XParams P, XDev d) {
-	const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	if(i >= d.nUnits || d.status[i]) return;
-	XUnit &u = d.units[i];
-	DevSvc<OFF> svc(ix, sc, d);
-	const int r = x_step(P, u, svc);
-	switch(r) {
-	case XR_DP: case XR_DP_MATE: {
-		const bool mate = r == XR_DP_MATE;
-		const uint32_t slot = atomicAdd(mate ? &d.q->nDpM : &d.q->nDpA, 1u);
-		(mate ? d.M : d.A).probs[slot] = u.rqProb;
-		u.dpSlot = (int32_t)slot;
-		const unsigned long long cells = (unsigned long long)svc.rdlen((int)u.rqProb.read_idx) * (unsigned long long)(u.rqProb.refr - u.rqProb.refl + 1);
-		atomicAdd(mate ? &d.q->cellsM : &d.q->cellsA, cells);
-		break; }
-	case XR_ONE_MM: {
-		const uint32_t slot = atomicAdd(&d.q->nMm, 1u);
-		d.mmSel[slot] = (uint32_t)u.rqRead; d.mmMinsc[slot] = u.rqMinsc; d.mmMask[slot] = (uint8_t)((u.rqNofw ? 0 : 1) | (u.rqNorc ? 0 : 2));
-		u.dpSlot = (int32_t)slot;
-		break; }
-	case XR_SEED:
-		d.seedActive[u.rqRead] = 1; d.seedInterval[u.rqRead] = u.rqInterval; d.seedOffset[u.rqRead] = u.rqOffset;
-		atomicAdd(&d.q->nSeed, 1u);
-		break;
-	case XR_DONE: {
-		d.status[i] = 1;
-		atomicAdd(&d.q->nDone, 1u);
-		const uint64_t r0 = u.paired ? 2 * i : i; const int nr = u.paired ? 2 : 1;
-		for(int k = 0; k < nr; k++) x_fill_result(u, k, svc.codes((int)(r0 + k)), d.res[r0 + k], d.resOps + (r0 + k) * (uint64_t)d.resMaxOps, d.resMaxOps);
-		if(u.paired) { bt2g_pair_result pr; pr.pair_type = u.pairType; pr.kind = u.pairKind; pr.source = 0; pr.score_sum = (int32_t)u.scoreSum; pr.fraglen = u.fraglen; d.pairs[i] = pr; }
-		break; }
-	default:
-		d.status[i] = 2;
-		atomicAdd(&d.q->nFallback, 1u);
-		break;
+__global__ void __launch_bounds__(128, MINB) k_xe_step(DevIndex<OFF> ix, bt2g_scoring sc, XParams P, XDev d, const uint32_t *activeIn, uint32_t *activeOut,
+                                                       uint32_t nAct) {
+	const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	const bool valid = t < nAct;
+	const uint64_t i = valid ? (activeIn ? activeIn[t] : t) : 0;
+	int r = XR_DONE;
+	if(valid) {
+		XUnit &u = d.units[i];
+		DevSvc<OFF> svc(ix, sc, d);
+		r = x_step(P, u, svc);
+		switch(r) {
+		case XR_DP: case XR_DP_MATE: {
+			const bool mate = r == XR_DP_MATE;
+			const uint32_t slot = agg_inc(mate ? &d.q->nDpM : &d.q->nDpA);
+			(mate ? d.M : d.A).probs[slot] = u.rqProb;
+			u.dpSlot = (int32_t)slot;
+			const unsigned long long cells = (unsigned long long)svc.rdlen((int)u.rqProb.read_idx) * (unsigned long long)(u.rqProb.refr - u.rqProb.refl + 1);
+			atomicAdd(mate ? &d.q->cellsM : &d.q->cellsA, cells);
+			break; }
+		case XR_ONE_MM: {
+			const uint32_t slot = agg_inc(&d.q->nMm);
+			d.mmSel[slot] = (uint32_t)u.rqRead; d.mmMinsc[slot] = u.rqMinsc; d.mmMask[slot] = (uint8_t)((u.rqNofw ? 0 : 1) | (u.rqNorc ? 0 : 2));
+			u.dpSlot = (int32_t)slot;
+			break; }
+		case XR_SEED:
+			d.seedActive[u.rqRead] = 1; d.seedInterval[u.rqRead] = u.rqInterval; d.seedOffset[u.rqRead] = u.rqOffset;
+			agg_inc(&d.q->nSeed);
+			break;
+		case XR_DONE: {
+			d.status[i] = 1;
+			agg_inc(&d.q->nDone);
+			const uint64_t r0 = u.paired ? 2 * i : i; const int nr = u.paired ? 2 : 1;
+			for(int k = 0; k < nr; k++) x_fill_result(u, k, svc.codes((int)(r0 + k)), d.res[r0 + k], d.resOps + (r0 + k) * (uint64_t)d.resMaxOps, d.resMaxOps);
+			if(u.paired) { bt2g_pair_result pr; pr.pair_type = u.pairType; pr.kind = u.pairKind; pr.source = 0; pr.score_sum = (int32_t)u.scoreSum; pr.fraglen = u.fraglen; d.pairs[i] = pr; }
+			break; }
+		default:
+			d.status[i] = 2;
+			agg_inc(&d.q->nFallback);
+			break;
+		}
+	}
+	// the units of this warp that wait for an answer, appended as ONE run in their order (the active list stays a sequence of
+	// ascending runs: neighbouring threads keep working on neighbouring units -- their 44 KB states share TLB entries); no
+	// block-wide barrier: a warp retires as soon as its own slowest unit has stepped
+	__syncwarp();
+	const bool cont = valid && (r == XR_DP || r == XR_DP_MATE || r == XR_ONE_MM || r == XR_SEED);
+	const unsigned m = __ballot_sync(0xffffffffu, cont);
+	if(m) {
+		const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+		uint32_t base = 0;
+		if(lane == leader) base = atomicAdd(&d.q->nActive, (uint32_t)__popc(m));
+		base = __shfl_sync(0xffffffffu, base, leader);
+		if(cont) activeOut[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
 	}
 }
 
@@ -197,6 +232,7 @@ struct bt2g_xengine {
 	XDev d{};
 	DpWork A, M;
 	uint64_t *packed = nullptr; uint32_t *nmask = nullptr; unsigned long long *nextTask = nullptr;
+	uint32_t *active[2] = {nullptr, nullptr};          // unit indices of the current / the next wave
 	uint8_t *dSeq = nullptr, *dQual = nullptr; uint64_t *dOff = nullptr; char *dNames = nullptr; uint32_t nameStrideCap = 0;
 	XQueues *hq = nullptr;             // pinned
 	uint8_t *hStatus = nullptr;        // pinned
@@ -266,6 +302,7 @@ int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t name
 	const DevIndex<OFF> ix = bt2g_dev_index<OFF>(ctx);
 	XDev &d = e->d;
 	d.nUnits = nUnits;
+	d.packed = e->packed; d.nmask = e->nmask;
 	const unsigned T = 128;
 	auto grid = [&](uint64_t m, unsigned t) { return (unsigned)((m + t - 1) / t); };
 	for(int k = 0; k < 8; k++) { e->stats[k] = 0; e->stageMs[k] = 0.f; }
@@ -277,15 +314,22 @@ int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t name
 	k_xe_seeds<<<grid(nReads, T), T, 0, st>>>(d.seq, d.qual, d.roff, nReads, dNames, nameStride, paired ? 1 : 0, e->P.seed, const_cast<uint32_t *>(d.seeds));
 	k_xe_reset<<<grid(nUnits, T), T, 0, st>>>(d.units, d.status, nUnits, paired ? 1 : 0);
 	launch_pack_reads(d.seq, d.roff, nReads, e->maxLen, e->packed, e->nmask, st);
-	launch_exact_sweep2<OFF>(ix, d.roff, nReads, 0, 0, const_cast<uint8_t *>(d.mine), const_cast<uint64_t *>(d.ee), e->packed, e->nmask, e->nextTask, e->sms, st, nullptr, 0);
+	launch_exact_sweep2<OFF>(ix, d.roff, nReads, 0, 0, const_cast<uint8_t *>(d.mine), const_cast<uint64_t *>(d.ee), e->packed, e->nmask, e->nextTask, e->sms, st, nullptr,
+	                         ix.extText ? 2 : 0 /* unique ranges continue in the text */);
 	BT2G_CUDA_TRY(ctx, cudaMemsetAsync(d.seedActive, 0, nReads, st));
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	uint64_t done = 0;
+	uint32_t nActive = 0;
 	cudaEventRecord(ev[0], st);
 	for(uint64_t wave = 0;; wave++) {
 		BT2G_CUDA_TRY(ctx, cudaMemsetAsync(d.q, 0, sizeof(XQueues), st));
-		if(e->stepOcc >= 8) k_xe_step<OFF, 8><<<grid(nUnits, 128), 128, 0, st>>>(ix, e->sc, e->P, d);
-		else k_xe_step<OFF, 4><<<grid(nUnits, 128), 128, 0, st>>>(ix, e->sc, e->P, d);
+		{
+			const uint32_t nAct = wave == 0 ? (uint32_t)nUnits : nActive;
+			const uint32_t *in = wave == 0 ? nullptr : e->active[wave & 1];
+			uint32_t *out = e->active[(wave + 1) & 1];
+			if(e->stepOcc >= 8) k_xe_step<OFF, 8><<<grid(nAct, 128), 128, 0, st>>>(ix, e->sc, e->P, d, in, out, nAct);
+			else k_xe_step<OFF, 4><<<grid(nAct, 128), 128, 0, st>>>(ix, e->sc, e->P, d, in, out, nAct);
+		}
 		cudaEventRecord(ev[1], st);
 		e->launches++;
 		BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(e->hq, d.q, sizeof(XQueues), cudaMemcpyDeviceToHost, st));
@@ -303,10 +347,12 @@ int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t name
 		e->stats[6] += q.nMm; e->stats[7] += q.nSeed;
 		e->launches += (q.nMm ? 1 : 0) + (q.nSeed ? 1 : 0);
 		done += q.nDone + q.nFallback;
+		nActive = q.nActive;
 		if(done >= nUnits) break;
 		if(q.nDpA + q.nDpM + q.nMm + q.nSeed == 0) { ctx->err = "xengine: units neither finished nor waiting"; return -5; }
 		cudaEventRecord(ev[2], st);
-		if(q.nMm) launch_one_mm_sel<OFF>(ix, d.seq, d.qual, d.roff, q.nMm, d.mmSel, d.mmMinsc, d.mmMask, e->sc, XE_MM_MAXHITS, const_cast<bt2g_mm_hit *>(d.mmHits), const_cast<int32_t *>(d.mmCounts), st);
+		if(q.nMm) launch_one_mm_sel<OFF>(ix, d.seq, d.qual, d.roff, q.nMm, d.mmSel, d.mmMinsc, d.mmMask, e->sc, XE_MM_MAXHITS, const_cast<bt2g_mm_hit *>(d.mmHits), const_cast<int32_t *>(d.mmCounts), st,
+		                                      ix.extText != 0);
 		cudaEventRecord(ev[3], st);
 		if(q.nSeed) {
 			launch_seed_search_active<OFF>(ix, d.roff, nReads, e->P.seedLen, d.maxSeeds, d.seedInterval, d.seedOffset, d.seedActive, const_cast<uint64_t *>(d.ranges),
@@ -373,6 +419,7 @@ int bt2g_xengine_create(bt2g_ctx *ctx, const bt2g_policy_params *pp, uint64_t ma
 	rc |= xalloc(e, d.seedInterval, nR); rc |= xalloc(e, d.seedOffset, nR); rc |= xalloc(e, d.seedActive, nR);
 	rc |= xalloc(e, e->packed, (e->maxBases >> 5) + nR + 2); rc |= xalloc(e, e->nmask, (e->maxBases >> 5) + nR + 2); rc |= xalloc(e, e->nextTask, 1);
 	rc |= xalloc(e, d.q, 1); rc |= xalloc(e, d.units, nU); rc |= xalloc(e, d.status, nU);
+	rc |= xalloc(e, e->active[0], nU); rc |= xalloc(e, e->active[1], nU);
 	rc |= xalloc(e, d.res, nR); rc |= xalloc(e, d.resOps, nR * (uint64_t)e->maxOps); rc |= xalloc(e, d.pairs, nU);
 	d.resMaxOps = e->maxOps;
 	if(!rc) {

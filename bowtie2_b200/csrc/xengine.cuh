@@ -534,8 +534,9 @@ struct XEngine {
 				const uint64_t srt = fw ? sfw : src;
 				const uint32_t *sz = szs[fw ? 0 : 1];
 				int i = (int)(u.rnd.u32() % (uint32_t)num);
+				if(minsz == 1u) continue;                       // (nothing is smaller than a range of one row; the draw above is still made)
 				for(int t = 0; t < num; t++) {
-					if(sz[i] > 0 && !((srt >> i) & 1) && sz[i] < minsz) { minsz = sz[i]; minidx = i; minfw = fw; }
+					if(sz[i] > 0 && !((srt >> i) & 1) && sz[i] < minsz) { minsz = sz[i]; minidx = i; minfw = fw; if(minsz == 1u) break; }
 					if(++i == num) i = 0;
 				}
 			}
