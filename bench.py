@@ -541,7 +541,8 @@ def run_exact(S, args):
     parts = [(a, b) for a, b in parts if b > a]
     E = len(parts)
     engines = [XEngine(gpu, prm, sub, L) for _ in range(E)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(E)]
+    # the engines' own streams (normal + high priority for the small waves of a batch's tail); events are recorded on them
+    streams = [torch.cuda.ExternalStream(e.streams()[0], device=dev) for e in engines]
     free_b, total_b = torch.cuda.mem_get_info(dev)
     log(f"rank {S.rank}: {E} engine(s) of {sub} {S.unit} created; HBM in use {(total_b - free_b) / 1e9:.1f} of {total_b / 1e9:.1f} GB")
     NS = S.names.shape[1]
@@ -586,7 +587,7 @@ def run_exact(S, args):
         a, b = parts[j]
         lo, hi = (k * B + a) * mates, (k * B + b) * mates
         r, q, nm = S.reads[lo:hi], S.quals[lo:hi], S.names[lo:hi]
-        st = engines[j].run_dev(r.data_ptr(), q.data_ptr(), offs_all.data_ptr(), hi - lo, nm.data_ptr(), NS, stream=streams[j].cuda_stream)
+        st = engines[j].run_dev(r.data_ptr(), q.data_ptr(), offs_all.data_ptr(), hi - lo, nm.data_ptr(), NS, stream=0)
         if record:
             sm = engines[j].stage_ms()                 # (host-side floats the engine filled from its own CUDA events)
             with lock:

@@ -38,8 +38,7 @@ static inline uint64_t dp_code_stride(int maxCol, int maxLen, int mode) {
 }
 
 // mode 3 workspace: as many problems per chunk as fit a byte budget (default 6 GiB; BT2G_DP_CHUNK_MB overrides)
-static inline uint64_t dp_chunk_problems(uint64_t codeStride, uint64_t nMax) {
-	uint64_t budget = 6ull << 30;
+static inline uint64_t dp_chunk_problems(uint64_t codeStride, uint64_t nMax, uint64_t budget = 6ull << 30) {
 	if(const char *e = getenv("BT2G_DP_CHUNK_MB")) { uint64_t v = strtoull(e, nullptr, 10); if(v) budget = v << 20; }
 	uint64_t c = budget / (codeStride ? codeStride : 1);
 	if(c < 1024) c = 1024;
@@ -63,6 +62,8 @@ struct DpLaunch {
 	int             maxCands, maxAlns, maxOps;
 	uint64_t        chunk = 0;    // mode 3: problems per fill/tail chunk
 	int             packed = 0;   // e2e: two problems per warp as s16x2 pairs (codes workspace: 2 * codeStride per slot)
+	uint32_t        zeroP = 0;    // always 0: a zero the compiler cannot see through, so that it stays in ONE register (a literal 0 as
+	                              // the third operand of VIADDMNMX is re-materialised with a PRMT before every use: 13 per step)
 	bt2g_dp_summary *summ;
 	bt2g_dp_cand    *cands;
 	bt2g_dp_aln     *alns;

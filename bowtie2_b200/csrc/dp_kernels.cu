@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 	// OFFDOM (match bonus 0, the end-to-end default): every increment is <= 0, so clamping each intermediate value
 	// at floor commutes with the recurrences (clamp(x) + s clamps to the same value as clamp(x + s) for s <= 0) and the
 	// whole fill can run in the stored domain H - floor with 0 as its lower clamp: the H register IS the byte to store.
-	const uint32_t FLOORP = OFFDOM ? 0u : dpx_both(DPX_FLOOR);
+	const uint32_t FLOORP = OFFDOM ? L.zeroP : dpx_both(DPX_FLOOR);
 	const uint32_t bonusP = dpx_both(bonus), nrdeP = dpx_both(-rdgape);
 
 	for(uint64_t pw = slot; pw < nPairs; pw += nSlots) {

@@ -17,7 +17,8 @@ __device__ __forceinline__ void ungapped_one(const DevIndex<OFF> &ix, const bt2g
 	if(leftNs + rightNs > nceil) return;
 	auto rdc = [&](int i) -> int { int c = p.fw ? rs[i] : rs[len - 1 - i]; return p.fw ? c : (c > 3 ? 4 : 3 - c); };
 	auto qv = [&](int i) -> int { int q = (int)(p.fw ? rq[i] : rq[len - 1 - i]) - 33; return q < 0 ? 0 : (q > 63 ? 63 : q); };
-	auto rfc = [&](int i) -> int { return ref_base<OFF>(ix, p.tidx, p.refoff + i); };      // off-end positions read as N
+	RefCursor<OFF> cur;
+	auto rfc = [&](int i) -> int { return cur.get(ix, p.tidx, p.refoff + i); };      // off-end positions read as N
 	auto cellsc = [&](int c, int f, int q) -> int { return (c > 3 || f > 3) ? -(int)sc.npen[q] : (c == f ? sc.match_bonus : -(int)sc.mmpen[q]); };
 	int64_t score = 0;
 	int ns = 0, rowi = 0, rowf = len - 1, rc = 1;

@@ -222,6 +222,30 @@ __device__ __forceinline__ int ref_base(const DevIndex<OFF> &ix, uint64_t tidx, 
 	return (ix.refBuf[b >> 2] >> ((b & 3) << 1)) & 3;
 }
 
+// ref_base for runs of nearby positions: remembers the unambiguous stretch that held the last position, so that consecutive
+// look-ups (ungapped alignment, edit lists) cost one packed-byte load instead of a binary search over the records each
+template <typename OFF>
+struct RefCursor {
+	uint64_t tidx = ~0ull, b0 = 0;
+	int64_t s = 0, e = 0;                                // positions [s, e) of reference tidx lie at packed offsets b0 ...
+	__device__ __forceinline__ int get(const DevIndex<OFF> &ix, uint64_t t, int64_t toff) {
+		if(t == tidx && toff >= s && toff < e) { const uint64_t b = b0 + (uint64_t)(toff - s); return (__ldg(ix.refBuf + (b >> 2)) >> ((b & 3) << 1)) & 3; }
+		if(toff < 0 || (uint64_t)toff >= ix.refLens[t]) return 4;
+		uint64_t lo = ix.refRecOffs[t], hi = ix.refRecOffs[t + 1];
+		while(hi - lo > 1) {
+			const uint64_t mid = lo + ((hi - lo) >> 1);
+			if(ix.recCumOff[mid] <= (uint64_t)toff) lo = mid; else hi = mid;
+		}
+		const uint64_t start = ix.recCumOff[lo] + (uint64_t)ix.recOff[lo];
+		if((uint64_t)toff < start) return 4;
+		const uint64_t k = (uint64_t)toff - start;
+		if(k >= (uint64_t)ix.recLen[lo]) return 4;
+		tidx = t; s = (int64_t)start; e = (int64_t)(start + (uint64_t)ix.recLen[lo]); b0 = ix.recCumUnamb[lo];
+		const uint64_t b = b0 + k;
+		return (__ldg(ix.refBuf + (b >> 2)) >> ((b & 3) << 1)) & 3;
+	}
+};
+
 // A whole reference window [refl, refl+ncol) into out[] (one warp; lane k fills columns k, k+32, ...).
 // Fast path: the window lies inside one unambiguous stretch, found once per window instead of once
 // per column; otherwise every column goes through ref_base (N runs, reference ends).

@@ -107,7 +107,8 @@ struct DevSvc {
 		ungapped_one<OFF>(ix, sc, codes(read), quals(read), rdlen(read), p, r, nullptr, 0);
 		return r.status;
 	}
-	__device__ int refChar(int64_t tidx, int64_t off) const { return ref_base<OFF>(ix, (uint64_t)tidx, off); }
+	mutable RefCursor<OFF> refCur;
+	__device__ int refChar(int64_t tidx, int64_t off) const { return refCur.get(ix, (uint64_t)tidx, off); }
 };
 
 // genRandSeed (pat.cpp:45-82) for every read; names: rows of nameStride bytes (NUL-terminated) or nullptr = "r<unit index>"
@@ -159,9 +160,12 @@ __device__ __forceinline__ uint32_t agg_inc(uint32_t *ctr) {
 // of a batch (a few thousand repeat-rich pairs going through dozens of DP rounds) then occupies a few warps, not the GPU.
 template <typename OFF, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_xe_step(DevIndex<OFF> ix, bt2g_scoring sc, XParams P, XDev d, const uint32_t *activeIn, uint32_t *activeOut,
-                                                       uint32_t nAct) {
-	const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	const bool valid = t < nAct;
+                                                       uint32_t nAct, int spread) {
+	// spread = s: one unit per 2^s threads (the others idle).  The state machines of a warp's lanes diverge and serialise, so when
+	// a wave has few units (the tail of a batch) one unit per warp finishes sooner than 32.
+	const uint64_t tt = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	const uint64_t t = tt >> spread;
+	const bool valid = t < nAct && (tt & ((1u << spread) - 1u)) == 0;
 	const uint64_t i = valid ? (activeIn ? activeIn[t] : t) : 0;
 	int r = XR_DONE;
 	if(valid) {
@@ -238,7 +242,11 @@ struct bt2g_xengine {
 	uint8_t *hStatus = nullptr;        // pinned
 	int sms = 148;
 	cudaStream_t stream = nullptr;     // the engine's own stream (bt2g_xengine_align; run_dev when the caller passes none)
+	cudaStream_t streamHi = nullptr;   // high-priority twin: the small waves of a batch's tail run here, so that their few blocks are
+	                                   // scheduled ahead of the pending blocks of another engine's full waves
+	bool ownStreams = false;           // this batch runs on the engine's streams (the caller passed none)
 	int debug = 0;                     // BT2G_XE_DEBUG: per-wave log on stderr
+	int bigSpread = 0;                 // log2 of the threads per unit in the full waves (BT2G_XE_SPREAD; experiment knob)
 	int stepOcc = 4;                   // resident blocks of 128 threads per SM the step kernel is compiled for (4: 128 registers, 8: 64)
 	uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // waves, fallbacks, anchor DPs, mate DPs, anchor cells, mate cells, 1-mm requests, seed requests
 	// device time of the last batch per stage (CUDA events on the batch's stream): admission (read seeds, packing, exactSweep),
@@ -268,7 +276,8 @@ int setupDp(bt2g_xengine *e, DpWork &w, int maxCol, uint64_t cap, int maxCands, 
 	w.codeStride = dp_code_stride(w.maxCol, e->maxLen, w.packed);
 	w.numSlots = (uint64_t)e->sms * 24;
 	int rc = 0;
-	if(w.packed == 3) { w.chunk = dp_chunk_problems(w.codeStride, cap); rc |= xalloc(e, w.codes, w.chunk * w.codeStride); }
+	// (3 GiB of H-byte workspace per queue: a chunk still holds tens of thousands of problems, and several engines fit one GPU)
+	if(w.packed == 3) { w.chunk = dp_chunk_problems(w.codeStride, cap, 3ull << 30); rc |= xalloc(e, w.codes, w.chunk * w.codeStride); }
 	else rc |= xalloc(e, w.codes, w.numSlots * w.codeStride * (w.packed ? 2 : 1));
 	rc |= xalloc(e, w.lastH, w.numSlots * (uint64_t)w.maxCol);
 	w.maxRaw = maxCands * 4 < 1024 ? 1024 : maxCands * 4;
@@ -295,7 +304,8 @@ int launchDp(bt2g_xengine *e, const DpWork &w, uint64_t n, cudaStream_t st) {
 
 // the waves of one batch whose reads are in device memory (e->d.seq / qual / roff set)
 template <typename OFF>
-int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t nameStride, cudaStream_t st) {
+int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t nameStride, cudaStream_t st0) {
+	cudaStream_t st = st0;
 	bt2g_ctx *ctx = e->ctx;
 	const bool paired = e->P.paired != 0;
 	const uint64_t nUnits = paired ? nReads / 2 : nReads;
@@ -327,8 +337,11 @@ int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t name
 			const uint32_t nAct = wave == 0 ? (uint32_t)nUnits : nActive;
 			const uint32_t *in = wave == 0 ? nullptr : e->active[wave & 1];
 			uint32_t *out = e->active[(wave + 1) & 1];
-			if(e->stepOcc >= 8) k_xe_step<OFF, 8><<<grid(nAct, 128), 128, 0, st>>>(ix, e->sc, e->P, d, in, out, nAct);
-			else k_xe_step<OFF, 4><<<grid(nAct, 128), 128, 0, st>>>(ix, e->sc, e->P, d, in, out, nAct);
+			const int spread = (uint64_t)nAct * 32 <= (uint64_t)e->sms * 2048 * 4 ? 5 : e->bigSpread;       // few units: one per warp
+			const uint64_t nThr = (uint64_t)nAct << spread;
+			if(e->stepOcc >= 8) k_xe_step<OFF, 8><<<grid(nThr, 128), 128, 0, st>>>(ix, e->sc, e->P, d, in, out, nAct, spread);
+			else if(e->stepOcc >= 6) k_xe_step<OFF, 6><<<grid(nThr, 128), 128, 0, st>>>(ix, e->sc, e->P, d, in, out, nAct, spread);
+			else k_xe_step<OFF, 4><<<grid(nThr, 128), 128, 0, st>>>(ix, e->sc, e->P, d, in, out, nAct, spread);
 		}
 		cudaEventRecord(ev[1], st);
 		e->launches++;
@@ -349,6 +362,9 @@ int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t name
 		done += q.nDone + q.nFallback;
 		nActive = q.nActive;
 		if(done >= nUnits) break;
+		// everything launched so far has completed (the synchronisation above): the primitives of this wave and the next step may
+		// run on another stream -- the high-priority one when few units are left
+		if(e->ownStreams) st = (uint64_t)nActive * 32 <= (uint64_t)e->sms * 2048 * 4 ? e->streamHi : e->stream;
 		if(q.nDpA + q.nDpM + q.nMm + q.nSeed == 0) { ctx->err = "xengine: units neither finished nor waiting"; return -5; }
 		cudaEventRecord(ev[2], st);
 		if(q.nMm) launch_one_mm_sel<OFF>(ix, d.seq, d.qual, d.roff, q.nMm, d.mmSel, d.mmMinsc, d.mmMask, e->sc, XE_MM_MAXHITS, const_cast<bt2g_mm_hit *>(d.mmHits), const_cast<int32_t *>(d.mmCounts), st,
@@ -390,6 +406,7 @@ int bt2g_xengine_create(bt2g_ctx *ctx, const bt2g_policy_params *pp, uint64_t ma
 	cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, ctx->device);
 	if(const char *o = getenv("BT2G_XE_OCC")) e->stepOcc = atoi(o);          // experiment knob, read once
 	if(getenv("BT2G_XE_DEBUG")) e->debug = 1;
+	if(const char *o = getenv("BT2G_XE_SPREAD")) { e->bigSpread = atoi(o); if(e->bigSpread < 0 || e->bigSpread > 5) e->bigSpread = 0; }
 	// the kernels score with the scheme the policy reasons about (one source: the policy parameters)
 	scoringFromParams(pp, &e->sc);
 	ctx->scoring = e->sc;
@@ -446,6 +463,7 @@ int bt2g_xengine_create(bt2g_ctx *ctx, const bt2g_policy_params *pp, uint64_t ma
 		if(err == cudaSuccess) err = cudaHostAlloc((void **)&e->hStatus, nU, cudaHostAllocDefault);
 		for(int k = 0; k < 8 && err == cudaSuccess; k++) err = cudaEventCreate(&e->ev[k]);
 		if(err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+		if(err == cudaSuccess) { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); err = cudaStreamCreateWithPriority(&e->streamHi, cudaStreamNonBlocking, hi); }
 	}
 	if(rc || err != cudaSuccess) {
 		if(err != cudaSuccess) ctx->err = std::string("xengine setup: ") + cudaGetErrorString(err);
@@ -464,6 +482,7 @@ void bt2g_xengine_destroy(bt2g_xengine *e) {
 	if(e->hStatus) cudaFreeHost(e->hStatus);
 	for(int k = 0; k < 8; k++) if(e->ev[k]) cudaEventDestroy(e->ev[k]);
 	if(e->stream) cudaStreamDestroy(e->stream);
+	if(e->streamHi) cudaStreamDestroy(e->streamHi);
 	delete e;
 }
 
@@ -477,6 +496,7 @@ int bt2g_xengine_run_dev(bt2g_xengine *e, const uint8_t *dSeq, const uint8_t *dQ
 	if(nReads == 0) return 0;
 	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+	e->ownStreams = stream == nullptr;
 	ctx->scoring = e->sc;
 	e->d.seq = dSeq; e->d.qual = dQual; e->d.roff = dOff;
 	const int rc = ctx->info.off_size == 4 ? runBatch<uint32_t>(e, nReads, dNames, nameStride, st) : runBatch<uint64_t>(e, nReads, dNames, nameStride, st);
@@ -534,6 +554,13 @@ int bt2g_xengine_run_dev(bt2g_xengine *e, const uint8_t *dSeq, const uint8_t *dQ
 		e->stageMs[6] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - tFb).count();
 	}
 	if(stats) for(int k = 0; k < 8; k++) stats[k] = e->stats[k];
+	return 0;
+}
+
+int bt2g_xengine_streams(bt2g_xengine *e, void **stream, void **stream_hi) {
+	if(!e) return -1;
+	if(stream) *stream = (void *)e->stream;
+	if(stream_hi) *stream_hi = (void *)e->streamHi;
 	return 0;
 }
 

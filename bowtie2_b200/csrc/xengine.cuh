@@ -151,6 +151,7 @@ struct XUnit {
 	uint8_t usDone, usExitM, usExitK, pad2; int64_t usBest, usBest2; uint16_t nus; uint16_t usAlns[XE_LIST];
 	// redundancy sets: 0 = red, 1 / 2 = redMate[0 / 1]
 	uint16_t nred[3]; uint16_t red[3][XE_RED];
+	uint32_t redKey[3][XE_RED];                           // coarse locus of each entry (x_red_key): the scan skips far-away entries without touching them
 	int64_t nIters, nDps, nUgs, nMateDps, streakCur;
 	// ---- pairSteps / readSteps locals
 	int32_t interval[2], nrounds[2], matemap[2], mi, roundi, nroundsAll; int64_t nelt[2]; int32_t mined[2][2];
@@ -333,13 +334,25 @@ XE_HD inline bool x_alns_share_cell(const XAln *a, const XAln *b) {
 }
 // NOTE on positions: XEdit.pos is relative to the first aligned read character in left-to-right order (= Edit.pos after
 // invertEdits), rows i run over trimLeft .. trimLeft + ext - 1 as in RedundantAlns::add.
+// coarse locus of an alignment: 12 bits of (reference, strand), 20 bits of refoff / 2048.  Two alignments that share a cell lie on the
+// same reference and strand within 1200 positions of each other (x_alns_share_cell), i.e. in the same or neighbouring buckets.
+XE_HD inline uint32_t x_red_key(const XAln *a) {
+	return (((uint32_t)a->tidx * 2u + (uint32_t)(a->fw != 0)) << 20) | ((uint32_t)((uint64_t)a->refoff >> 11) & 0xfffffu);
+}
 XE_HD inline bool x_red_overlap(const XUnit &u, int set, uint16_t aoff) {
 	const XAln *a = x_aln(u, aoff);
-	for(int i = 0; i < u.nred[set]; i++) if(x_alns_share_cell(a, x_aln(u, u.red[set][i]))) return true;
+	const uint32_t ka = x_red_key(a);
+	for(int i = 0; i < u.nred[set]; i++) {
+		const uint32_t kb = u.redKey[set][i];
+		if((ka ^ kb) >> 20) continue;                                   // another reference or strand (or a hash neighbour: checked below)
+		if(((kb - ka + 1u) & 0xfffffu) > 2u) continue;                  // buckets further apart than one
+		if(x_alns_share_cell(a, x_aln(u, u.red[set][i]))) return true;
+	}
 	return false;
 }
 XE_HD inline void x_red_add(XUnit &u, int set, uint16_t aoff) {
 	if(u.nred[set] >= XE_RED) { XE_FB(u); return; }
+	u.redKey[set][u.nred[set]] = x_red_key(x_aln(u, aoff));
 	u.red[set][u.nred[set]++] = aoff;
 }
 
@@ -380,9 +393,9 @@ XE_HD inline bool x_frame_mate(bool anchorLeft, int64_t ll, int64_t lr, int64_t 
 // device op string (include/bt2g.h: bt2g_dp_aln) -> arena record with left-to-right edits (lib.py: ops_to_edits without the
 // final inversion for reverse-strand reads)
 XE_HD inline uint16_t x_aln_from_dp(XUnit &u, const bt2g_dp_problem &prob, const bt2g_dp_aln &al, const uint8_t *ops, const uint8_t *codes, int rdlen) {
-	int ned = 0;
-	for(int k = 0; k < al.nops; k++) ned += (ops[k] & 3) != BT2G_OP_MATCH;
-	const uint16_t off = x_new_aln(u, ned);
+	// one pass: the record is allocated for the largest edit list the op string can hold (every op an edit) and the unused
+	// tail of that allocation -- the arena's newest -- is given back
+	const uint16_t off = x_new_aln(u, al.nops);
 	if(off == 0xffff) return off;
 	XAln *a = x_aln(u, off);
 	const bool fw = prob.fw != 0;
@@ -400,6 +413,8 @@ XE_HD inline uint16_t x_aln_from_dp(XUnit &u, const bt2g_dp_problem &prob, const
 		else if(typ == BT2G_OP_REFGAP) { e.chr = '-'; e.qchr = (uint8_t)x_dna(x_rdchar(codes, rdlen, fw, row)); e.type = 2; row++; }
 		else { e.chr = (uint8_t)x_dna(refc); e.qchr = '-'; e.type = 1; }
 	}
+	a->nedits = (int16_t)n;
+	u.arenaTop = ((uint32_t)off << 3) + (((uint32_t)(sizeof(XAln) + (size_t)n * sizeof(XEdit)) + 7u) & ~7u);
 	return off;
 }
 // exact / 1-mismatch end-to-end hit at a resolved offset (SwDriver::extendSeeds eeMode, aligner_sw_driver.cpp:1172-1186)

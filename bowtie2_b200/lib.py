@@ -1080,7 +1080,7 @@ def policy_backend_gpu(gpu: "Bt2Gpu") -> "_PolicyBackend":
 
 # ---- the exact search policy on the device (include/bt2g.h: bt2g_xengine_*; csrc/xengine.cuh, xengine.cu) ---------------
 EXPORTS += ["bt2g_xengine_create", "bt2g_xengine_destroy", "bt2g_xengine_align", "bt2g_xengine_run_dev", "bt2g_xengine_results_dev",
-            "bt2g_xengine_stage_ms"]
+            "bt2g_xengine_stage_ms", "bt2g_xengine_streams"]
 
 XENGINE_STAGES = ("admission", "state_machine", "one_mm", "seed_search", "seed_dp", "mate_dp", "host_fallback", "total")
 XENGINE_STATS = ("waves", "fallback_units", "seed_dps", "mate_dps", "seed_dp_cells", "mate_dp_cells", "one_mm_requests", "seed_requests")
@@ -1136,6 +1136,13 @@ class XEngine:
         self.gpu._check(self.gpu._lib.bt2g_xengine_run_dev(self._h, d_seq, d_qual, d_off, n_reads, d_names or None, name_stride, stream or None,
                                                            _ptr(stats)), "bt2g_xengine_run_dev")
         return dict(zip(XENGINE_STATS, (int(x) for x in stats)))
+
+    def streams(self):
+        """(stream, high-priority stream) of the engine as integers (cudaStream_t)"""
+        a, b = _vp(), _vp()
+        self.gpu._lib.bt2g_xengine_streams.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp)]
+        self.gpu._check(self.gpu._lib.bt2g_xengine_streams(self._h, C.byref(a), C.byref(b)), "bt2g_xengine_streams")
+        return a.value, b.value
 
     def stage_ms(self):
         """device milliseconds of the last batch per stage (bt2g_xengine_stage_ms)"""

@@ -586,6 +586,10 @@ int  bt2g_xengine_align(bt2g_xengine *e, const bt2g_reads *reads, const char *na
 int  bt2g_xengine_run_dev(bt2g_xengine *e, const uint8_t *d_seq, const uint8_t *d_qual, const uint64_t *d_off, uint64_t n_reads,
                           const char *d_names, uint32_t name_stride, void *stream, uint64_t *stats);
 int  bt2g_xengine_results_dev(bt2g_xengine *e, bt2g_read_result **res, uint8_t **ops, uint32_t *max_ops, bt2g_pair_result **pairs);
+/* An engine owns two CUDA streams (cudaStream_t): its waves run on *stream, the small waves of a batch's tail on *stream_hi (high
+ * priority, so that several engines of one context interleave: one engine's tail is not queued behind another's full waves).  They
+ * are used when bt2g_xengine_run_dev is given stream = NULL, and always by bt2g_xengine_align.  Every call returns with both idle. */
+int  bt2g_xengine_streams(bt2g_xengine *e, void **stream, void **stream_hi);
 /* device time of the last batch per stage, milliseconds (CUDA events on the batch's stream), 8 entries: admission (read seeds,
  * 2-bit packing, exactSweep), state machine steps, 1-mismatch searches, seed searches, seed-extension DP, mate-finding DP,
  * host fallback (wall clock), whole batch; *launches (optional) = kernels of this library launched by that batch */
