@@ -676,23 +676,33 @@ def run_exact(S, args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    dp_stage = {"seed_dp": work.get("seed_dp_cells", 0), "mate_dp": work.get("mate_dp_cells", 0)}
-    dom = max(("seed_dp", "mate_dp", "state_machine", "admission", "seed_search", "one_mm"), key=lambda k: stage_ms.get(k, 0.0))
-    dp_cells = dp_stage["seed_dp"] + dp_stage["mate_dp"]
-    dp_ms = stage_ms.get("seed_dp", 0.0) + stage_ms.get("mate_dp", 0.0)
-    roof = {"bound": "hbm", "kernel": dom, "kernel_ms": stage_ms.get(dom), "peak": peak, "unit": "GB/s", "traffic": None,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
-    if dom in dp_stage:
-        # algorithmic bytes of a DP stage: one workspace byte per cell update; the stage is integer-ALU (DPX)
-        # bound, so cell updates per second are reported beside it
-        roof["algorithmic_bytes_per_launch"] = dp_stage[dom]
-        roof["achieved"] = dp_stage[dom] / (stage_ms[dom] / 1e3) / 1e9
-        roof["gcups"] = roof["achieved"]
-    else:
-        roof["algorithmic_bytes_per_launch"] = None
-        roof["achieved"] = 0.0
+    # ---- roofline of the dominant hot-path kernel: the DP fill (k_dp_fill_h), timed live by the engine's own CUDA events between
+    # the fill and the tail launches of every chunk.  Algorithmic bytes: ONE byte per DP cell (the H byte the fill writes for the
+    # backtrace) -- the kernel is bound by that write stream, not by its DPX arithmetic (profiles/README.md).
+    dp_cells = work.get("seed_dp_cells", 0) + work.get("mate_dp_cells", 0)
+    fill_ms, tail_ms = stage_ms.get("dp_fill", 0.0), stage_ms.get("dp_tail", 0.0)
+    dpx_peak, ncu = None, {}
+    try:
+        for l in open(os.path.join(ROOT, "profiles", "r02_dpx_issue_rates.json")):
+            r = json.loads(l)
+            if r.get("op", "").startswith("VIADDMNMX.S16x2"):
+                dpx_peak = r["thread_instr_per_s"]
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_dp_fill_summary.json")))
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": "k_dp_fill_h (seed-extension + mate-finding rectangles)", "kernel_ms": fill_ms, "peak": peak, "unit": "GB/s",
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+            "algorithmic_bytes_per_launch": dp_cells, "achieved": dp_cells / (fill_ms / 1e3) / 1e9 if fill_ms > 0 else 0.0,
+            "traffic": ncu.get("dram_bytes_per_cell", None) and ncu["dram_bytes_per_cell"] * dp_cells,
+            "traffic_source": ncu.get("source"),
+            "gcups_fill": dp_cells / (fill_ms / 1e3) / 1e9 if fill_ms > 0 else None,
+            "gcups_fill_and_tail": dp_cells / ((fill_ms + tail_ms) / 1e3) / 1e9 if fill_ms + tail_ms > 0 else None,
+            "dpx": {"thread_instr_per_cell": 3.0, "achieved_thread_instr_per_s": 3.0 * dp_cells / (fill_ms / 1e3) if fill_ms > 0 else None,
+                    "peak_thread_instr_per_s": dpx_peak, "peak_source": "profiles/r02_dpx_issue_rates.json (tools/dpx_bench.cu on this pool's B200)",
+                    "frac": (3.0 * dp_cells / (fill_ms / 1e3) / dpx_peak) if (dpx_peak and fill_ms > 0) else None},
+            "share_of_step": {k: stage_ms.get(k, 0.0) / max(stage_ms.get("total", 1e-9), 1e-9) for k in
+                              ("dp_fill", "dp_tail", "state_machine", "admission", "one_mm", "seed_search")}}
     roof["frac"] = roof["achieved"] / peak
-    roof["dp_gcups_all"] = dp_cells / (dp_ms / 1e3) / 1e9 if dp_ms > 0 else None
     line = {"metric": "Mreads/s", "value": value, "unit": "Mreads/s", "n_gpus": S.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 popcount (FM rank) + s16x2 DPX (DP)", "data": "synthetic",

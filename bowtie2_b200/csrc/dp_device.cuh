@@ -62,6 +62,9 @@ struct DpLaunch {
 	int             maxCands, maxAlns, maxOps;
 	uint64_t        chunk = 0;    // mode 3: problems per fill/tail chunk
 	int             packed = 0;   // e2e: two problems per warp as s16x2 pairs (codes workspace: 2 * codeStride per slot)
+	cudaEvent_t    *tev = nullptr;  // optional timing marks (mode 3): one before the first fill, then one after every fill and every tail
+	int             tevCap = 0;
+	int            *tevN = nullptr;
 	uint32_t        zeroP = 0;    // always 0: a zero the compiler cannot see through, so that it stays in ONE register (a literal 0 as
 	                              // the third operand of VIADDMNMX is re-materialised with a PRMT before every use: 13 per step)
 	bt2g_dp_summary *summ;

@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(128) k_dp_e2e_x2(DevIndex<OFF> ix, bt2g_scorin
 // Fill of the H-byte kernel (two problems per warp, s16x2; see the description below).
 // H-byte kernels take any R (rows per lane) and store RP = R rounded up to 4 bytes per lane and step
 #define DP_RP(R) ((((R) + 3) / 4) * 4)
-#define DP_QPROF_BYTES(R) ((size_t)(5 * (R) * 32 * 2))                      // fill kernel: query profile of one problem
+#define DP_QPROF_BYTES(R) ((size_t)(5 * (R) * 32 * 4))                      // fill kernel: query profile of one problem (32-bit entries)
 #define DP_PROF_BYTES(R) ((size_t)(3 * 32 * (R) + 15) & ~(size_t)15)      // per-row profile of the tail kernel: 3 bytes x 32 R rows
 // Workspace layout of one problem with S = maxCol + 32 step slots: R / 4 word planes [S][32] x 4 B holding rows
 // 4g..4g+3 of each lane, then one byte plane [S][32] per remaining row, so that every store of a warp is one
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(128, R == 4 ? 6 : 4) k_dp_e2e_h(DevIndex<OFF> 
 // workspace (pure DPX compute, high occupancy), k_dp_tail_h then runs candidates + backtraces with one warp per
 // problem (latency-bound on workspace reads, hidden by far more resident warps than the fused kernel can hold).
 template <typename OFF, int R, bool OFFDOM>
-__global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L, uint64_t chunkStart, uint64_t chunkMax) {
+__global__ void __launch_bounds__(128, R <= 5 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_h(DevIndex<OFF> ix, bt2g_scoring sc, DpLaunch L, uint64_t chunkStart, uint64_t chunkMax) {
 	extern __shared__ uint8_t smem[];
 	const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint64_t slot = blockIdx.x * (uint64_t)(blockDim.x >> 5) + warpInBlock;
@@ -759,9 +759,13 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 	// (buildQueryProfileEnd2EndSseU8, aligner_swsse_ee_u8.cpp:75-142): the substitution score of a cell is then two
 	// shared-memory loads and one IMAD instead of five ALU-pipe instructions -- the ALU pipe is what bounds this kernel
 	const size_t perProb = ((size_t)L.maxCol + 15) & ~(size_t)15;
-	uint8_t *sm0 = smem + (size_t)warpInBlock * (2 * perProb + 2 * DP_QPROF_BYTES(R));
+	uint8_t *sm0 = smem + (size_t)warpInBlock * (2 * perProb + DP_QPROF_BYTES(R));
 	uint8_t *refw[2] = {sm0, sm0 + perProb}; uint8_t *hb[2];
-	uint16_t *qprof[2] = {reinterpret_cast<uint16_t *>(sm0 + 2 * perProb), reinterpret_cast<uint16_t *>(sm0 + 2 * perProb + DP_QPROF_BYTES(R))};
+	// one 32-bit word per entry, [refc][row-in-lane][lane]: lane k always hits bank k whatever its reference character, so the
+	// look-ups are conflict-free (16-bit entries put two lanes in one word: 45 % extra wavefronts in the ncu capture).  A word holds
+	// problem A's score in its low half and problem B's in its high half; the packed pair of a cell is a bit-select of the words
+	// its two reference characters pick
+	uint32_t *qprof = reinterpret_cast<uint32_t *>(sm0 + 2 * perProb);
 	const int rdgapo = sc.rdgap_const + sc.rdgap_linear, rdgape = sc.rdgap_linear;
 	const int rfgapo = sc.rfgap_const + sc.rfgap_linear, rfgape = sc.rfgap_linear;
 	const int bonus = sc.match_bonus;
@@ -832,7 +836,11 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 				// profile entries of this row: score against reference A, C, G, T and N
 #pragma unroll
 				for(int rf = 0; rf < 5; rf++)
-					qprof[x][(rf * R + r) * 32 + lane] = (uint16_t)(int16_t)(rf > 3 ? np : (c == rf ? bonus : mm));
+					{
+						const uint32_t v = (uint32_t)(uint16_t)(int16_t)(rf > 3 ? np : (c == rf ? bonus : mm));
+						uint32_t &q = qprof[(rf * R + r) * 32 + lane];
+						q = x == 0 ? v : (q | (v << 16));
+					}
 				v[x][3] = bar ? -DPX_BIG : -rfgapo; v[x][4] = bar ? -DPX_BIG : -rfgape; v[x][5] = bar ? -DPX_BIG : -rdgapo;
 			}
 			nrfoP[r] = dpx_pack(v[0][3], v[1][3]); nrfeP[r] = dpx_pack(v[0][4], v[1][4]); nrdoP[r] = dpx_pack(v[0][5], v[1][5]);
@@ -859,7 +867,7 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 			if(lane == 0) { inH = FLOORP; inF = FLOORP; }
 			const int j = t - lane;
 			if(j >= 0 && j < ncolMax && lane <= lastLaneMax) {
-				const uint16_t *qa = qprof[0] + (int)refw[0][j] * (R * 32) + lane, *qb = qprof[1] + (int)refw[1][j] * (R * 32) + lane;
+				const uint32_t *qa = qprof + (int)refw[0][j] * (R * 32) + lane, *qb = qprof + (int)refw[1][j] * (R * 32) + lane;
 				// H[i0-1][j-1]: row -1 is the free start row of end-to-end mode (vhilsw, :853,923-927)
 				uint32_t diag = (lane == 0) ? (OFFDOM ? nfloorP : 0u) : prevInH;
 				uint32_t upH = inH, upF = inF;
@@ -870,7 +878,7 @@ __global__ void __launch_bounds__(128, R <= 4 ? 8 : (R <= 6 ? 6 : 4)) k_dp_fill_
 				for(int r = 0; r < R; r++) {
 					// F[i][j] = max(F[i-1][j]-rfgape, H[i-1][j]-rfgapo)
 					const uint32_t F = __viaddmax_s16x2(upF, nrfeP[r], __viaddmax_s16x2(upH, nrfoP[r], FLOORP));
-					const uint32_t sP = (uint32_t)qb[r * 32] * 65536u + (uint32_t)qa[r * 32];
+					const uint32_t sP = (qa[r * 32] & 0x0000ffffu) | (qb[r * 32] & 0xffff0000u);
 					const uint32_t Hd = __viaddmax_s16x2(diag, sP, FLOORP);
 					const uint32_t E = Earr[r];
 					const uint32_t H = __vimax3_s16x2(Hd, E, F);
@@ -1212,7 +1220,7 @@ static void launch_dp_e2e_r(const DevIndex<OFF> &ix, const bt2g_scoring &sc, con
 	if(L.packed == 3) {
 		// split: chunks of L.chunk problems through fill then tail (workspace = L.chunk * codeStride bytes)
 		int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		const size_t smF = (size_t)warpsPerBlock * (2 * (((size_t)L.maxCol + 15) & ~(size_t)15) + 2 * DP_QPROF_BYTES(R));
+		const size_t smF = (size_t)warpsPerBlock * (2 * (((size_t)L.maxCol + 15) & ~(size_t)15) + DP_QPROF_BYTES(R));
 		const size_t smT = (size_t)8 * (dp_smem_per_warp(L.maxCol) + DP_PROF_BYTES(R));
 		auto kfill = sc.match_bonus == 0 ? k_dp_fill_h<OFF, R, true> : k_dp_fill_h<OFF, R, false>;
 		if(smF > 48 * 1024) cudaFuncSetAttribute(kfill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smF);
@@ -1220,9 +1228,13 @@ static void launch_dp_e2e_r(const DevIndex<OFF> &ix, const bt2g_scoring &sc, con
 		int nbF = 1, nbT = 1;
 		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbF, kfill, warpsPerBlock * 32, smF) != cudaSuccess || nbF < 1) nbF = 1;
 		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbT, k_dp_tail_h<OFF, R>, 256, smT) != cudaSuccess || nbT < 1) nbT = 1;
+		auto mark = [&]() { if(L.tev && L.tevN && *L.tevN < L.tevCap) cudaEventRecord(L.tev[(*L.tevN)++], st); };
+		mark();
 		for(uint64_t c0 = 0; c0 < L.n; c0 += L.chunk) {
 			kfill<<<(unsigned)(nbF * sms), warpsPerBlock * 32, smF, st>>>(ix, sc, L, c0, L.chunk);
+			mark();
 			k_dp_tail_h<OFF, R><<<(unsigned)(nbT * sms), 256, smT, st>>>(ix, sc, L, c0, L.chunk);
+			mark();
 		}
 	} else if(L.packed == 2) {
 		const size_t smem = (size_t)warpsPerBlock * 2 * dp_smem_per_warp(L.maxCol);

@@ -37,6 +37,7 @@ namespace {
 using namespace xe;
 
 #define XE_MM_MAXHITS 16
+#define XE_TEV 96                    // timing marks per DP queue and wave (fill / tail split; chunks beyond that go unsplit)
 
 struct XQueues {                     // per wave, reset before k_xe_step
 	uint32_t nDpA, nDpM, nMm, nSeed, nDone, nFallback, nActive, pad1;
@@ -251,7 +252,8 @@ struct bt2g_xengine {
 	uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // waves, fallbacks, anchor DPs, mate DPs, anchor cells, mate cells, 1-mm requests, seed requests
 	// device time of the last batch per stage (CUDA events on the batch's stream): admission (read seeds, packing, exactSweep),
 	// state machine (k_xe_step), 1-mismatch search, seed search, seed-extension DP, mate-finding DP, host fallback (wall), total
-	float stageMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	float stageMs[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [8], [9]: DP fill / DP tail kernels of both queues (split of [4] + [5])
+	cudaEvent_t tev[2][XE_TEV]; int tevN[2] = {0, 0};
 	uint64_t launches = 0;             // kernels of this library launched by the last batch
 	cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -296,6 +298,7 @@ int launchDp(bt2g_xengine *e, const DpWork &w, uint64_t n, cudaStream_t st) {
 	L.numSlots = w.numSlots; L.codes = w.codes; L.lastH = w.lastH; L.rawKeys = w.rawKeys; L.maxRaw = w.rawKeys ? w.maxRaw : 0;
 	L.codeStride = w.codeStride; L.maxCol = w.maxCol; L.maxCands = w.o.maxCands; L.maxAlns = w.o.maxAlns; L.maxOps = w.o.maxOps;
 	L.chunk = w.chunk; L.packed = w.packed;
+	{ const int qi = &w == &e->M ? 1 : 0; e->tevN[qi] = 0; L.tev = e->tev[qi]; L.tevCap = XE_TEV; L.tevN = &e->tevN[qi]; }
 	L.summ = w.o.summ; L.cands = w.o.cands; L.alns = w.o.alns; L.ops = w.o.ops;
 	const DevIndex<OFF> ix = bt2g_dev_index<OFF>(e->ctx);
 	e->launches += (!e->sc.local && w.packed == 3) ? 2 * ((n + w.chunk - 1) / w.chunk) : 1;
@@ -315,7 +318,9 @@ int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t name
 	d.packed = e->packed; d.nmask = e->nmask;
 	const unsigned T = 128;
 	auto grid = [&](uint64_t m, unsigned t) { return (unsigned)((m + t - 1) / t); };
-	for(int k = 0; k < 8; k++) { e->stats[k] = 0; e->stageMs[k] = 0.f; }
+	for(int k = 0; k < 8; k++) e->stats[k] = 0;
+	for(int k = 0; k < 12; k++) e->stageMs[k] = 0.f;
+	e->tevN[0] = e->tevN[1] = 0;
 	e->launches = 4;                                   // k_xe_seeds, k_xe_reset, k_pack_reads, k_exact_sweep2
 	cudaEvent_t *ev = e->ev;
 	auto lap = [&](int a, int b, int stage) { float ms = 0.f; if(cudaEventElapsedTime(&ms, ev[a], ev[b]) == cudaSuccess) e->stageMs[stage] += ms; };
@@ -349,6 +354,10 @@ int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t name
 		BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(st));
 		// everything recorded before this synchronisation has completed: the primitives of the previous wave and this step
 		if(wave == 0) lap(7, 0, 0); else { lap(2, 3, 2); lap(3, 4, 3); lap(4, 5, 4); lap(5, 0, 5); }
+		for(int qi = 0; qi < 2; qi++) {                   // fill / tail split of the DP launches of the previous wave
+			for(int k = 0; k + 1 < e->tevN[qi]; k++) { float ms = 0.f; if(cudaEventElapsedTime(&ms, e->tev[qi][k], e->tev[qi][k + 1]) == cudaSuccess) e->stageMs[8 + (k & 1)] += ms; }
+			e->tevN[qi] = 0;
+		}
 		lap(0, 1, 1);
 		const XQueues q = *e->hq;
 		if(e->debug) {
@@ -462,6 +471,7 @@ int bt2g_xengine_create(bt2g_ctx *ctx, const bt2g_policy_params *pp, uint64_t ma
 		if(err == cudaSuccess) err = cudaHostAlloc((void **)&e->hq, sizeof(XQueues), cudaHostAllocDefault);
 		if(err == cudaSuccess) err = cudaHostAlloc((void **)&e->hStatus, nU, cudaHostAllocDefault);
 		for(int k = 0; k < 8 && err == cudaSuccess; k++) err = cudaEventCreate(&e->ev[k]);
+		for(int k = 0; k < 2 * XE_TEV && err == cudaSuccess; k++) err = cudaEventCreate(&e->tev[k / XE_TEV][k % XE_TEV]);
 		if(err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
 		if(err == cudaSuccess) { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); err = cudaStreamCreateWithPriority(&e->streamHi, cudaStreamNonBlocking, hi); }
 	}
@@ -481,6 +491,7 @@ void bt2g_xengine_destroy(bt2g_xengine *e) {
 	if(e->hq) cudaFreeHost(e->hq);
 	if(e->hStatus) cudaFreeHost(e->hStatus);
 	for(int k = 0; k < 8; k++) if(e->ev[k]) cudaEventDestroy(e->ev[k]);
+	for(int k = 0; k < 2 * XE_TEV; k++) if(e->tev[k / XE_TEV][k % XE_TEV]) cudaEventDestroy(e->tev[k / XE_TEV][k % XE_TEV]);
 	if(e->stream) cudaStreamDestroy(e->stream);
 	if(e->streamHi) cudaStreamDestroy(e->streamHi);
 	delete e;
@@ -566,7 +577,7 @@ int bt2g_xengine_streams(bt2g_xengine *e, void **stream, void **stream_hi) {
 
 int bt2g_xengine_stage_ms(bt2g_xengine *e, float *ms, uint64_t *launches) {
 	if(!e || !ms) return -1;
-	for(int k = 0; k < 8; k++) ms[k] = e->stageMs[k];
+	for(int k = 0; k < 10; k++) ms[k] = e->stageMs[k];
 	if(launches) *launches = e->launches;
 	return 0;
 }

@@ -36,7 +36,7 @@ enum { XR_DONE = 0, XR_ONE_MM = 1, XR_SEED = 2, XR_DP = 3, XR_DP_MATE = 4, XR_FA
 
 #define XE_MAX_LEN    512
 #define XE_ARENA      12288      // bytes
-#define XE_SEEN_IV    96         // seenDiags intervals per mate
+#define XE_SEEN_IV    224        // seenDiags intervals per mate (two per framed DP)
 #define XE_EXR        8          // seedExRange entries per mate and strand
 #define XE_MM1        24         // 1-mismatch end-to-end hits kept per mate
 #define XE_MAX_SEEDS  64         // seed offsets per strand

@@ -1082,7 +1082,7 @@ def policy_backend_gpu(gpu: "Bt2Gpu") -> "_PolicyBackend":
 EXPORTS += ["bt2g_xengine_create", "bt2g_xengine_destroy", "bt2g_xengine_align", "bt2g_xengine_run_dev", "bt2g_xengine_results_dev",
             "bt2g_xengine_stage_ms", "bt2g_xengine_streams"]
 
-XENGINE_STAGES = ("admission", "state_machine", "one_mm", "seed_search", "seed_dp", "mate_dp", "host_fallback", "total")
+XENGINE_STAGES = ("admission", "state_machine", "one_mm", "seed_search", "seed_dp", "mate_dp", "host_fallback", "total", "dp_fill", "dp_tail")
 XENGINE_STATS = ("waves", "fallback_units", "seed_dps", "mate_dps", "seed_dp_cells", "mate_dp_cells", "one_mm_requests", "seed_requests")
 
 
@@ -1146,7 +1146,7 @@ class XEngine:
 
     def stage_ms(self):
         """device milliseconds of the last batch per stage (bt2g_xengine_stage_ms)"""
-        ms = np.zeros(8, dtype=np.float32)
+        ms = np.zeros(10, dtype=np.float32)
         n = C.c_uint64(0)
         self.gpu._lib.bt2g_xengine_stage_ms.argtypes = [_vp, _vp, C.POINTER(C.c_uint64)]
         self.gpu._check(self.gpu._lib.bt2g_xengine_stage_ms(self._h, _ptr(ms), C.byref(n)), "bt2g_xengine_stage_ms")

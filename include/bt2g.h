@@ -590,9 +590,10 @@ int  bt2g_xengine_results_dev(bt2g_xengine *e, bt2g_read_result **res, uint8_t *
  * priority, so that several engines of one context interleave: one engine's tail is not queued behind another's full waves).  They
  * are used when bt2g_xengine_run_dev is given stream = NULL, and always by bt2g_xengine_align.  Every call returns with both idle. */
 int  bt2g_xengine_streams(bt2g_xengine *e, void **stream, void **stream_hi);
-/* device time of the last batch per stage, milliseconds (CUDA events on the batch's stream), 8 entries: admission (read seeds,
+/* device time of the last batch per stage, milliseconds (CUDA events on the batch's stream), 10 entries: admission (read seeds,
  * 2-bit packing, exactSweep), state machine steps, 1-mismatch searches, seed searches, seed-extension DP, mate-finding DP,
- * host fallback (wall clock), whole batch; *launches (optional) = kernels of this library launched by that batch */
+ * host fallback (wall clock), whole batch, and the split of the two DP entries into their fill kernels and their tail
+ * (candidates + backtrace) kernels; *launches (optional) = kernels of this library launched by that batch */
 int  bt2g_xengine_stage_ms(bt2g_xengine *e, float *ms, uint64_t *launches);
 /* the same state machine driven on the host over an entry-point table (no GPU: the CPU pinning of csrc/xengine.cuh) */
 int  bt2g_xengine_align_host(const bt2g_policy_backend *be, const bt2g_policy_params *prm, const bt2g_reads *reads, const char *const *names,
