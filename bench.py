@@ -176,6 +176,14 @@ def make_pairs_gpu(torch, dev, contigs, n_pairs, read_len, seed=1, sub_rate=0.00
     return reads, quals
 
 
+def fastq_text(reads_np, quals_np, first_id=0) -> bytes:
+    """the same records as write_fastq, as bytes in memory"""
+    import tempfile
+    with tempfile.NamedTemporaryFile(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as f:
+        write_fastq(f.name, reads_np, quals_np, first_id)
+        return open(f.name, "rb").read()
+
+
 def write_fastq(path, reads_np, quals_np, first_id=0):
     """fixed-width FASTQ records written as one uint8 matrix (fast)."""
     n, L = reads_np.shape
@@ -660,6 +668,42 @@ def run_exact(S, args):
         conc = {"concordant_frac": float((pr["pair_type"] == 1).mean())}
     clk = clocks.stop() if S.rank == 0 else None
 
+    # ---- text to text (rank 0, informational): FASTQ bytes in host memory -> SAM bytes in host memory, the host stages (parse,
+    # format) overlapped with the engines on threads (bowtie2_b200/stream.py); bounded by the host cores this container may use
+    e2e_text = None
+    if S.rank == 0 and not args.no_text_e2e:
+        try:
+            from bowtie2_b200.stream import TextAligner
+            n_items = max(2, min(2 * E, nb * E))
+            items = []
+            for k in range(n_items):
+                a, b = parts[k % E]
+                lo, hi = ((k // E) * B + a) * mates, ((k // E) * B + b) * mates
+                r_np, q_np = S.reads[lo:hi].cpu().numpy(), S.quals[lo:hi].cpu().numpy()
+                first = (k // E) * B + a
+                items.append((fastq_text(r_np[0::mates], q_np[0::mates], first), fastq_text(r_np[1::2], q_np[1::2], first) if paired else None))
+            ref_names = [f"chr{k + 1}" for k in range(GENOME_CONTIGS)]
+            pthr = max(1, S.fmt_threads // 4)
+            ta = TextAligner(engines, ref_names, paired, parse_threads=pthr, format_threads=max(1, S.fmt_threads - pthr - E), name_stride=NS)
+            reps = max(1, (args.steps * E + n_items - 1) // n_items)
+            sam_bytes = [0]
+
+            def sink(txt):
+                sam_bytes[0] += len(txt)
+            ta.run(iter(items[:E]), sink)                # warm-up
+            sam_bytes[0] = 0
+            t0 = time.perf_counter()
+            recs = ta.run((items[k % n_items] for k in range(reps * n_items)), sink)
+            dt = time.perf_counter() - t0
+            units = recs // mates
+            e2e_text = {"value": units / dt / 1e6, "unit": "Mreads/s", "units": units, "seconds": dt,
+                        "fastq_bytes": sum(len(a) + (len(b) if b else 0) for a, b in items) * reps, "sam_bytes": sam_bytes[0],
+                        "host_threads_parse": pthr, "host_threads_format": max(1, S.fmt_threads - pthr - E),
+                        "path": "FASTQ text (host memory) -> bt2g_fastq_parse_mt -> bt2g_xengine_align -> bt2g_sam_format -> SAM text (host memory); "
+                                "stages overlapped on host threads (bowtie2_b200/stream.py)"}
+        except Exception as e:                      # informational: never breaks the bench line
+            e2e_text = {"error": repr(e)[:300]}
+
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if S.distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -721,7 +765,7 @@ def run_exact(S, args):
                     "path": "bt2g_xengine_align: pinned host reads / qualities / names in, result structs + edit ops + pair records out"},
             "roofline": roof, "stage_ms": stage_ms,
             "stage_ms_note": "device time per stage and step, summed over the engines (they run concurrently: the sum can exceed ms_per_step)",
-            "work_per_step": work, "cpu_baseline": S.cpu_baseline}
+            "work_per_step": work, "e2e_text": e2e_text, "cpu_baseline": S.cpu_baseline}
     if parity is not None and parity["identical"] != parity["records"]:
         line["refused"] = {"value": value, "e2e": e2e_val, "why": "parity gate: SAM records differ from the reference program's"}
         line["value"] = None
@@ -750,6 +794,7 @@ def main():
     ap.add_argument("--dense-sa", type=int, default=0,
                     help="rate of the denser SA sample derived from the index at load time (0 = full suffix array, -1 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference runs (no cpu_baseline, no parity gate)")
+    ap.add_argument("--no-text-e2e", action="store_true", help="skip the informational FASTQ-text -> SAM-text measurement")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads (pairs) in the CPU baseline / parity sample (0 = auto)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -1,0 +1,109 @@
+"""FASTQ text in -> SAM text out around the device engine, with the host stages overlapped on threads:
+
+    parse (bt2g_fastq_parse_mt; mates interleaved)  ||  align (bt2g_xengine_align, one host thread per engine)  ||  format (bt2g_sam_format)
+
+Every stage is one call into libbt2g.so per batch (ctypes releases the GIL), so the threads run concurrently; batches leave in
+input order.  This is the batch loop of multiseedSearchWorker (bt2_search.cpp:3253-4254) with its reader
+(PatternSourcePerThread, pat.cpp) and its sink (AlnSinkSam, aln_sink.cpp:1889) -- host plumbing: nothing here computes
+alignments."""
+import queue
+import threading
+
+import numpy as np
+
+from .lib import NameTable, ReadBatch, XEngine, fastq_parse, load_library, sam_format
+
+
+def interleave_uniform(b1: ReadBatch, b2: ReadBatch, n1: NameTable, n2: NameTable):
+    """mate 1 of pair i -> read 2i, mate 2 -> read 2i + 1; fast path for batches whose reads all have one length per file"""
+    n = b1.n
+    if n != b2.n:
+        raise ValueError(f"mate files differ in length within a batch ({b1.n} vs {b2.n} records)")
+    l1, l2 = b1.lengths(), b2.lengths()
+    if n and (l1 == l1[0]).all() and (l2 == l2[0]).all() and l1[0] == l2[0]:
+        L = int(l1[0])
+        seq = np.empty((n, 2, L), dtype=np.uint8)
+        qual = np.empty((n, 2, L), dtype=np.uint8)
+        seq[:, 0], seq[:, 1] = b1.seq[:n * L].reshape(n, L), b2.seq[:n * L].reshape(n, L)
+        qual[:, 0], qual[:, 1] = b1.qual[:n * L].reshape(n, L), b2.qual[:n * L].reshape(n, L)
+        batch = ReadBatch(seq.reshape(-1), np.arange(0, (2 * n + 1) * L, L, dtype=np.uint64), qual.reshape(-1))
+    else:
+        from .align import interleave
+        batch = interleave(b1, b2)
+    rows = np.empty((2 * n, n1.rows.shape[1]), dtype=np.uint8)
+    rows[0::2], rows[1::2] = n1.rows, n2.rows
+    return batch, NameTable(rows)
+
+
+class TextAligner:
+    """engines: list of XEngine (all created with the same parameters); ref_names: @SQ names in index order"""
+
+    def __init__(self, engines, ref_names, paired, local=False, parse_threads=4, format_threads=8, name_stride=32, depth=2):
+        self.engines, self.ref_names, self.paired, self.local = list(engines), list(ref_names), paired, local
+        self.parse_threads, self.format_threads, self.name_stride, self.depth = parse_threads, format_threads, name_stride, depth
+        self.lib = load_library()
+
+    def _parse(self, item):
+        t1, t2 = item
+        b1, n1, used1 = fastq_parse(self.lib, t1, name_stride=self.name_stride, threads=self.parse_threads)
+        if not self.paired:
+            return b1, n1
+        b2, n2, used2 = fastq_parse(self.lib, t2, name_stride=self.name_stride, threads=self.parse_threads)
+        return interleave_uniform(b1, b2, n1, n2)
+
+    def run(self, items, sink):
+        """items: iterable of (mate-1 FASTQ text, mate-2 FASTQ text or None), each at most one engine batch; sink(sam_bytes) is
+        called once per item, in input order.  Returns the number of records written."""
+        q_parsed, q_done = queue.Queue(self.depth), queue.Queue()
+        errs, total = [], [0]
+        END = object()
+
+        def parser():
+            try:
+                for k, item in enumerate(items):
+                    q_parsed.put((k, *self._parse(item)))
+            except Exception as e:
+                errs.append(e)
+            for _ in self.engines:
+                q_parsed.put(END)
+
+        def aligner(eng):
+            try:
+                while True:
+                    w = q_parsed.get()
+                    if w is END:
+                        break
+                    k, batch, names = w
+                    res, ops, pairs, _ = eng.align(batch, names)
+                    q_done.put((k, batch, names, res, ops, pairs))
+            except Exception as e:
+                errs.append(e)
+            q_done.put(END)
+
+        def formatter():
+            try:
+                pending, nxt, ended = {}, 0, 0
+                while ended < len(self.engines):
+                    w = q_done.get()
+                    if w is END:
+                        ended += 1
+                        continue
+                    pending[w[0]] = w[1:]
+                    while nxt in pending:
+                        batch, names, res, ops, pairs = pending.pop(nxt)
+                        txt = sam_format(self.lib, batch, res, ops, self.ref_names, read_names=names, pairs=pairs, threads=self.format_threads,
+                                         local=self.local, as_bytes=True)
+                        sink(txt)
+                        total[0] += batch.n
+                        nxt += 1
+            except Exception as e:
+                errs.append(e)
+
+        th = [threading.Thread(target=parser)] + [threading.Thread(target=aligner, args=(e,)) for e in self.engines] + [threading.Thread(target=formatter)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        return total[0]
