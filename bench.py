@@ -45,6 +45,11 @@ WORKLOADS = {
                   label="BASELINE.json configs[2]: 2x150 bp paired, --end-to-end --very-sensitive"),
     "se100": dict(paired=False, read_len=100, preset="sensitive", units=10_000_000,
                   label="BASELINE.json configs[1]: 1x100 bp unpaired, --end-to-end --sensitive"),
+    # configs[4]'s index format and preset on ONE GPU: a large (.bt2l, 64-bit offsets) index.  4.5 Gbp instead of 6 Gbp: the
+    # genome must exceed 4 Gbp for the format to be needed, and the torch suffix sort of the bench's index BUILDER (tooling, not
+    # the product) needs more than 180 GB at 6 Gbp
+    "pe150l": dict(paired=True, read_len=150, preset="sensitive", units=4_000_000, large=True, genome_mbp=4500.0, seed_table=15,
+                   label="BASELINE.json configs[4] on one GPU: .bt2l large index, 2x150 bp paired, --end-to-end --sensitive"),
 }
 WORKDIR = os.environ.get("BT2G_BENCH_DIR", "/dev/shm/bt2g_bench")
 
@@ -253,7 +258,12 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the unmodified reference binary on the host cores
 # ------------------------------------------------------------------------------------------------
+LARGE_INDEX = False              # set by main() for a .bt2l workload: the reference's large-index binary
+
+
 def ref_binary():
+    if LARGE_INDEX:
+        return os.path.join(ROOT, "oracle", "_ref", "bowtie2-align-l"), "bowtie2-align-l (SSE2)"
     flags = open("/proc/cpuinfo").read() if os.path.exists("/proc/cpuinfo") else ""
     v256 = os.path.join(ROOT, "oracle", "_ref", "bowtie2-align-s-v256")
     sse = os.path.join(ROOT, "oracle", "_ref", "bowtie2-align-s")
@@ -731,7 +741,7 @@ def run_exact(S, args):
             r = json.loads(l)
             if r.get("op", "").startswith("VIADDMNMX.S16x2"):
                 dpx_peak = r["thread_instr_per_s"]
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_dp_fill_summary.json")))
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_launch_summary.json")))
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": "k_dp_fill_h (seed-extension + mate-finding rectangles)", "kernel_ms": fill_ms, "peak": peak, "unit": "GB/s",
@@ -786,10 +796,10 @@ def main():
     ap.add_argument("--workload", default="pe150", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=1_000_000, help="reads (pairs for a paired workload) per step")
     ap.add_argument("--engines", type=int, default=2, help="exact pipeline: engines (streams + host threads) that share every batch")
-    ap.add_argument("--genome-mbp", type=float, default=GENOME_CONTIGS * CONTIG_LEN / 1e6,
-                    help="debug only: smaller genome (any value other than the default is NOT the BASELINE config)")
+    ap.add_argument("--genome-mbp", type=float, default=0.0,
+                    help="debug only: another genome size (0 = the workload's: 3000; any other value is NOT the BASELINE config)")
     ap.add_argument("--reads", type=int, default=0, help="reads (pairs) resident in HBM (0 = the workload's default)")
-    ap.add_argument("--seed-table", type=int, default=16,
+    ap.add_argument("--seed-table", type=int, default=-1,
                     help="k of the extended seed table derived from the index at load time (0 = off; results are identical)")
     ap.add_argument("--dense-sa", type=int, default=0,
                     help="rate of the denser SA sample derived from the index at load time (0 = full suffix array, -1 = off)")
@@ -801,6 +811,13 @@ def main():
     paired, READ_LEN = wl["paired"], wl["read_len"]
     if args.reads <= 0:
         args.reads = wl["units"]
+    wl_mbp = wl.get("genome_mbp", GENOME_CONTIGS * CONTIG_LEN / 1e6)
+    if args.genome_mbp <= 0:
+        args.genome_mbp = wl_mbp
+    if args.seed_table < 0:
+        args.seed_table = wl.get("seed_table", 16)
+    global LARGE_INDEX
+    LARGE_INDEX = bool(wl.get("large"))
     mates = 2 if paired else 1
     ref_preset = ("--end-to-end", "--" + wl["preset"])
 
@@ -829,10 +846,10 @@ def main():
         pass
     S.wl, S.paired, S.READ_LEN, S.mates, S.ref_preset = wl, paired, READ_LEN, mates, ref_preset
     S.rank, S.world, S.local_rank, S.dev, S.distributed = rank, world, local_rank, dev, distributed
-    full = abs(args.genome_mbp - GENOME_CONTIGS * CONTIG_LEN / 1e6) < 1e-6 and args.reads >= wl["units"]
+    full = abs(args.genome_mbp - wl_mbp) < 1e-6 and args.reads >= wl["units"]
     contig_len = int(args.genome_mbp * 1e6 / GENOME_CONTIGS)
     unit = "pairs" if paired else "reads"
-    workload = (f"{wl['label']}: synthetic {GENOME_CONTIGS * contig_len / 1e9:.2f} Gbp genome .bt2 index, "
+    workload = (f"{wl['label']}: synthetic {GENOME_CONTIGS * contig_len / 1e9:.2f} Gbp genome {'.bt2l' if LARGE_INDEX else '.bt2'} index, "
                 f"{args.reads / 1e6:g}M {'2x' if paired else '1x'}{READ_LEN} bp {unit} resident in HBM")
     hw_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:                                   # container CPU quota, if any (explains where the reference stops scaling)
@@ -849,14 +866,14 @@ def main():
     need_files = args.impl == "reference" or (rank == 0 and not args.no_cpu_baseline)
     built = None
     if rank == 0 or not distributed:
-        built = build_index(contigs)
+        built = build_index(contigs, off_size=8 if LARGE_INDEX else 4)
         torch.cuda.synchronize()
         log(f"rank {rank}: index built in {time.time() - t0:.1f}s (len={built.len})")
     index_base = os.path.join(WORKDIR, "idx")
     if need_files:
         os.makedirs(WORKDIR, exist_ok=True)
         built.write_files(index_base)
-        log(f"index files written to {index_base}.*.bt2")
+        log(f"index files written to {index_base}.*.{'bt2l' if LARGE_INDEX else 'bt2'}")
     if paired:
         reads, quals = make_pairs_gpu(torch, dev, contigs, args.reads, READ_LEN, seed=1 + rank)
     else:

@@ -107,6 +107,21 @@ def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1, opti
         if multi:
             # unpaired -k N / -a (bt2g_policy_align_k): one record per reported alignment, the read repeated; -a is capped per read
             cap = int(options["k"]) if options.get("k") is not None else ALL_HITS_CAP
+            # the multi-hit arrays are dense (n x cap result rows + n x cap op rows): cut the batch so that they stay under ~4 GiB
+            row_bytes = 56 + int(batch.lengths().max() if batch.n else 0) + 64
+            max_n = max(1, (4 << 30) // (cap * row_bytes))
+            if batch.n > max_n:
+                outs = []
+                o = batch.off.astype(np.int64)
+                nm = list(names)
+                for a in range(0, batch.n, max_n):
+                    b = min(batch.n, a + max_n)
+                    sub = ReadBatch(batch.seq[o[a]:o[b]], (batch.off[a:b + 1] - batch.off[a]).astype(np.uint64), batch.qual[o[a]:o[b]])
+                    outs.append(_exact_batch(gpu, sub, nm[a:b], paired, preset, local, seed, threads, options))
+                rb = ReadBatch.from_list([x for t in outs for x in [t[0].seq[int(t[0].off[i]):int(t[0].off[i + 1])] for i in range(t[0].n)]],
+                                         [x for t in outs for x in [t[0].qual[int(t[0].off[i]):int(t[0].off[i + 1])] for i in range(t[0].n)]])
+                return rb, [x for t in outs for x in t[1]], np.concatenate([t[2] for t in outs]), np.concatenate([t[3] for t in outs]), \
+                    np.concatenate([t[4] for t in outs])
             res_k, ops_k, cnt, truncated, stats = policy_align_k(gpu._lib, be, prm, batch, names, cap)
             if truncated:
                 sys.stderr.write(f"Warning: -a: reads with more than {cap} alignments were cut to {cap} records\n")

@@ -1320,7 +1320,8 @@ static void fillResult(const Result &r, const uint8_t *codes, bt2g_read_result &
 	out.score2 = INT32_MIN;
 	if(!r.aligned) return;
 	const Aln &a = r.aln;
-	const int nops = alnToOps(a, codes, ops, maxOps);
+	int nops = alnToOps(a, codes, ops, maxOps);
+	if((uint32_t)nops > maxOps) nops = (int)maxOps;            // (rows are maxOps wide: never report more ops than were written)
 	out.found = (a.edits.empty() && a.ext() == a.rdlen) ? 2 : 1;
 	out.score = (int32_t)a.score; if(r.hasXs) out.score2 = (int32_t)r.xs;
 	out.fw = a.fw; out.tidx = (uint64_t)a.tidx; out.refoff = a.refoff; out.nops = nops;

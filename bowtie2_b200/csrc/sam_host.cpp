@@ -93,7 +93,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		long long refExtent = 0;
 		int nmm = 0, ngo = 0, ngx = 0, nedits = 0;
 		if(aligned) {
-			const int nops = (r.found & 0xff) == 2 ? 0 : r.nops;
+			const int nops = (r.found & 0xff) == 2 ? 0 : (r.nops > (int)maxOps ? (int)maxOps : r.nops);   // never read past the ops row
 			const uint8_t *op = ops ? ops + i * (uint64_t)maxOps : nullptr;
 			bool gapless = true;
 			if((r.found & 0xff) != 2) {
@@ -211,7 +211,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 				long long mExt = 0;
 				const int mlen = (int)(reads->off[(i ^ 1ull) + 1] - reads->off[i ^ 1ull]);
 				if((m->found & 0xff) == 2) mExt = mlen;
-				else if(ops) { const uint8_t *mo = ops + (i ^ 1ull) * (uint64_t)maxOps; for(int k = 0; k < m->nops; k++) mExt += (mo[k] & 3) != BT2G_OP_REFGAP; }
+				else if(ops) { const uint8_t *mo = ops + (i ^ 1ull) * (uint64_t)maxOps; for(int k = 0; k < m->nops && k < (int)maxOps; k++) mExt += (mo[k] & 3) != BT2G_OP_REFGAP; }
 				long long st1 = m->refoff - m->trim_left, en1 = m->refoff + mExt - 1 + m->trim_right;
 				bool up;
 				const bool mfw = m->fw != 0, mate1 = (i & 1) == 0;
@@ -354,7 +354,10 @@ static int fastqParseCore(const char *text, uint64_t len, uint64_t maxReads, uin
 		if(full) { nb = b0; cur = recStart; break; }              // out of room: stop before this record
 		if(cur >= len) { nb = b0; cur = recStart; break; }        // truncated record: leave it for the next call
 		while(cur < len && text[cur] != '\n' && text[cur] != '\r') cur++;   // the '+' line
-		while(cur < len && (text[cur] == '\n' || text[cur] == '\r')) cur++;
+		// exactly ONE line terminator: an empty quality line (an empty read, which the reference reports as unaligned, YF:Z:LN)
+		// must not be skipped
+		if(cur < len && text[cur] == '\r') cur++;
+		if(cur < len && text[cur] == '\n') cur++;
 		const uint64_t nbases = nb - b0;
 		uint64_t nq = 0;
 		while(cur < len && text[cur] != '\n' && text[cur] != '\r') {

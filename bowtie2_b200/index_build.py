@@ -145,7 +145,10 @@ def suffix_array(s: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         gstart = torch.ones_like(grp, dtype=torch.bool)
         gstart[1:] = grp[1:] != grp[:-1]
         gd = torch.cumsum(gstart.to(torch.int64), 0) - 1      # dense group id
-        comp = (gd << 32) | k2
+        shift = max(32, int(n + 1).bit_length())               # ranks need more than 32 bits on a genome beyond 4 Gbp (.bt2l)
+        if int(gd[-1]) >> (63 - shift):
+            raise ValueError("suffix sort: too many tied suffix groups for a 63-bit composite key")
+        comp = (gd << shift) | k2
         comp_s, perm = torch.sort(comp)
         pos_s = pos[perm]
         sa[act] = pos_s

@@ -118,3 +118,36 @@ def test_device_engine_equals_the_reference_program(tmp_path, paired, local, lar
         assert stats["fallback_units"] * 10 <= n, stats
     assert stats["seed_dps"] > 100
     g.close()
+
+
+def test_text_stream_over_device_engines(request):
+    """FASTQ text -> SAM text (bowtie2_b200/stream.py) over TWO device engines sharing one context (own streams, own host threads):
+    the golden lambda pairs, cut into uneven batches, must come out as the reference program's SAM, in input order"""
+    from conftest import GOLDEN
+    from bowtie2_b200.lib import XEngine, policy_params
+    from bowtie2_b200.stream import TextAligner
+    g = _gpu()
+    g.load_index_files(request.getfixturevalue("lambda_index"))
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "lambda_P_sensitive.sam")) if not l.startswith("@")]
+    n = len(golden) // 2
+
+    def recs(path):
+        lines = open(path, "rb").read().split(b"\n")
+        return [b"\n".join(lines[4 * i:4 * i + 4]) + b"\n" for i in range(n)]
+    r1, r2 = recs(os.path.join(GOLDEN, "lambda_reads_1.fq")), recs(os.path.join(GOLDEN, "lambda_reads_2.fq"))
+    cuts = [0, 700, 1000, 1900, n] if n > 1900 else [0, n // 3, n]
+    cuts = sorted(set(min(c, n) for c in cuts))
+    items = [(b"".join(r1[a:b]), b"".join(r2[a:b])) for a, b in zip(cuts[:-1], cuts[1:])]
+    prm = policy_params("sensitive", paired=True)
+    engines = [XEngine(g, prm, max(b - a for a, b in zip(cuts[:-1], cuts[1:])), 256) for _ in range(2)]
+    try:
+        ta = TextAligner(engines, ["gi|9626243|ref|NC_001416.1|"], paired=True, parse_threads=2, format_threads=2, name_stride=64)
+        chunks = []
+        written = ta.run(iter(items), chunks.append)
+    finally:
+        for e in engines:
+            e.close()
+    lines = b"".join(chunks).decode().rstrip("\n").split("\n")
+    bad = [i for i in range(len(golden)) if lines[i] != golden[i]]
+    assert written == 2 * n and not bad, (written, len(bad), lines[bad[0]] if bad else None)
+    g.close()
