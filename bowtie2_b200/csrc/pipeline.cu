@@ -317,11 +317,16 @@ __global__ void k_pick_pairs(uint64_t nPairs, const uint64_t *roff, bt2g_read_re
 	bt2g_pair_result out;
 	out.pair_type = (f1 && f2) ? 2 : ((f1 || f2) ? 3 : 0); out.kind = 5; out.source = 0; out.score_sum = 0; out.fraglen = 0;
 	int bestSum = INT32_MIN, bestSrc = -1, bestKind = 5, bestAln = 0;
+	// the runner-up concordant sum (for the pair's MAPQ, unique.h:205-222: a repeat with several equally good concordant
+	// placements must not report 42): every other concordant (anchor, mate alignment) combination seen here, and each mate's
+	// own runner-up alignment paired with the other mate's best
+	int secSum = INT32_MIN;
+	auto offer = [&](int sum) { if(sum > bestSum) { secSum = bestSum; bestSum = sum; return true; } if(sum > secSum) secSum = sum; return false; };
 	const int e1 = f1 ? pe_ref_extent(a1, resOps + r1 * (size_t)maxOps, len1) : 0;
 	const int e2 = f2 ? pe_ref_extent(a2, resOps + r2 * (size_t)maxOps, len2) : 0;
 	if(f1 && f2 && a1.tidx == a2.tidx) {
 		const int k = pe_classify(pp, a1.refoff, (uint64_t)e1, a1.fw != 0, a2.refoff, (uint64_t)e2, a2.fw != 0);
-		if(k != 5) { bestSum = a1.score + a2.score; bestSrc = 0; bestKind = k; }
+		if(k != 5) { offer(a1.score + a2.score); bestSrc = 0; bestKind = k; }
 	}
 	unsigned long long cells = 0;
 	// anchor = mate 1 (source 1: mate 2 from the mate DP), anchor = mate 2 (source 2)
@@ -347,7 +352,7 @@ __global__ void k_pick_pairs(uint64_t nPairs, const uint64_t *roff, bt2g_read_re
 			                          : pe_classify(pp, moff, (uint64_t)em, q.fw != 0, an.refoff, (uint64_t)ea, an.fw != 0);
 			if(kind == 5) continue;
 			const int sum = an.score + al.score;
-			if(sum > bestSum) { bestSum = sum; bestSrc = src; bestKind = kind; bestAln = k; }
+			if(offer(sum)) { bestSrc = src; bestKind = kind; bestAln = k; }
 		}
 	}
 	if(bestSrc > 0) {
@@ -374,7 +379,12 @@ __global__ void k_pick_pairs(uint64_t nPairs, const uint64_t *roff, bt2g_read_re
 		out.fraglen = (h1 > h2 ? h1 : h2) - lo;
 		// MAPQ of a concordant pair: both mates from the pair's sums (unique.h:205-222)
 		const int l1 = len1 > maxLen ? maxLen : len1, l2 = len2 > maxLen ? maxLen : len2;
-		const int mq = mapq_v2(bestSum, false, 0, (long long)minscByLen[l1] + minscByLen[l2], (long long)(len1 + len2) * matchBonus, monotone != 0);
+		if(f1 && a1.score2 > INT32_MIN / 2 && (long long)a1.score2 + a2.score > secSum) secSum = a1.score2 + a2.score;
+		if(f2 && a2.score2 > INT32_MIN / 2 && (long long)a1.score + a2.score2 > secSum) secSum = a1.score + a2.score2;
+		if(secSum > bestSum) secSum = bestSum;
+		const long long minPair = (long long)minscByLen[l1] + minscByLen[l2];
+		const bool hasSec = secSum > INT32_MIN / 2 && secSum >= minPair;
+		const int mq = mapq_v2(bestSum, hasSec, hasSec ? secSum : 0, minPair, (long long)(len1 + len2) * matchBonus, monotone != 0);
 		res[r1].mapq = mq; res[r2].mapq = mq;
 	}
 	pairs[pr] = out;

@@ -601,6 +601,8 @@ int bt2g_xengine_align(bt2g_xengine *e, const bt2g_reads *reads, const char *nam
 	if(n > e->maxReads || reads->off[n] > e->maxBases) { ctx->err = "xengine: batch larger than the engine was created for"; return -1; }
 	if(e->P.paired && !pairs) return -1;
 	if(n == 0) return 0;
+	for(uint64_t i = 0; i < n; i++)
+		if(reads->off[i + 1] - reads->off[i] > (uint64_t)e->maxLen) { ctx->err = "xengine: a read is longer than the max_len the engine was created for"; return -1; }
 	BT2G_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	cudaStream_t st = e->stream;                      // engines of one context overlap their copies and waves
 	const uint64_t nb = reads->off[n];

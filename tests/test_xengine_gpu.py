@@ -139,7 +139,7 @@ def test_text_stream_over_device_engines(request):
     cuts = sorted(set(min(c, n) for c in cuts))
     items = [(b"".join(r1[a:b]), b"".join(r2[a:b])) for a, b in zip(cuts[:-1], cuts[1:])]
     prm = policy_params("sensitive", paired=True)
-    engines = [XEngine(g, prm, max(b - a for a, b in zip(cuts[:-1], cuts[1:])), 256) for _ in range(2)]
+    engines = [XEngine(g, prm, max(b - a for a, b in zip(cuts[:-1], cuts[1:])), 512) for _ in range(2)]
     try:
         ta = TextAligner(engines, ["gi|9626243|ref|NC_001416.1|"], paired=True, parse_threads=2, format_threads=2, name_stride=64)
         chunks = []
