@@ -45,6 +45,11 @@ WORKLOADS = {
                   label="BASELINE.json configs[2]: 2x150 bp paired, --end-to-end --very-sensitive"),
     "se100": dict(paired=False, read_len=100, preset="sensitive", units=10_000_000,
                   label="BASELINE.json configs[1]: 1x100 bp unpaired, --end-to-end --sensitive"),
+    # configs[3]: --local on 300 bp reads (the i16 territory of the reference's local SSE kernel); the engine's local DP is the
+    # round-1 kernel (one problem per warp, not the H-byte design) and local candidate lists overflow the unit capacities more
+    # often (host fallback): measured for completeness, not tuned
+    "loc300": dict(paired=False, read_len=300, preset="very-sensitive", local=True, units=1_000_000, batch=250_000,
+                   label="BASELINE.json configs[3]: 1x300 bp unpaired, --local --very-sensitive-local"),
     # configs[4]'s index format and preset on ONE GPU: a large (.bt2l, 64-bit offsets) index.  4.5 Gbp instead of 6 Gbp: the
     # genome must exceed 4 Gbp for the format to be needed, and the torch suffix sort of the bench's index BUILDER (tooling, not
     # the product) needs more than 180 GB at 6 Gbp
@@ -530,7 +535,8 @@ def parity_gate(S, eng, sam_path, n_units, B):
         batch = ReadBatch(r, np.arange(0, (n * mates + 1) * L, L, dtype=np.uint64), q)
         res, ops, pairs, st = eng.align(batch, NameTable(rows))
         fallbacks += st["fallback_units"]
-        txt = sam_format(S.gpu._lib, batch, res, ops, ref_names, read_names=NameTable(rows), pairs=pairs, threads=S.fmt_threads)
+        txt = sam_format(S.gpu._lib, batch, res, ops, ref_names, read_names=NameTable(rows), pairs=pairs, threads=S.fmt_threads,
+                         local=bool(S.wl.get("local")))
         got.extend(txt.rstrip("\n").split("\n"))
     same = sum(1 for a, b in zip(got, want) if a == b)
     out = {"records": len(want), "identical": same if len(got) == len(want) else min(same, len(want) - 1), "units": n_units,
@@ -550,7 +556,8 @@ def run_exact(S, args):
     import torch.distributed as dist
     from bowtie2_b200.lib import PAIR_RESULT, READ_RESULT, XEngine, _Reads, policy_params
     gpu, dev, paired, mates, B, BR, L = S.gpu, S.dev, S.paired, S.mates, S.B, S.BR, S.READ_LEN
-    prm = policy_params(S.wl["preset"], local=False, paired=paired, seed=0, host_threads=S.fmt_threads)
+    local = bool(S.wl.get("local"))
+    prm = policy_params(S.wl["preset"], local=local, paired=paired, seed=0, host_threads=S.fmt_threads)
     # E engines, each with its own stream and host thread, take the E parts of every batch: one engine's long tail of waves
     # (a few thousand repeat-rich pairs) and its per-wave host round trips overlap with the other engines' full waves
     E = max(1, min(args.engines, B))
@@ -694,7 +701,7 @@ def run_exact(S, args):
                 items.append((fastq_text(r_np[0::mates], q_np[0::mates], first), fastq_text(r_np[1::2], q_np[1::2], first) if paired else None))
             ref_names = [f"chr{k + 1}" for k in range(GENOME_CONTIGS)]
             pthr = max(1, S.fmt_threads // 4)
-            ta = TextAligner(engines, ref_names, paired, parse_threads=pthr, format_threads=max(1, S.fmt_threads - pthr - E), name_stride=NS)
+            ta = TextAligner(engines, ref_names, paired, local=local, parse_threads=pthr, format_threads=max(1, S.fmt_threads - pthr - E), name_stride=NS)
             reps = max(1, (args.steps * E + n_items - 1) // n_items)
             sam_bytes = [0]
 
@@ -759,7 +766,7 @@ def run_exact(S, args):
     roof["frac"] = roof["achieved"] / peak
     line = {"metric": "Mreads/s", "value": value, "unit": "Mreads/s", "n_gpus": S.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64 popcount (FM rank) + s16x2 DPX (DP)", "data": "synthetic",
+            "dtype": "u64 popcount (FM rank) + " + ("i32 (local DP)" if local else "s16x2 DPX (DP)"), "data": "synthetic",
             "config": {"workload": S.workload, "full_size": S.full, "read_unit": S.unit[:-1], "mates_per_s_M": value * mates,
                        "batch": B, "engines": E, "preset": " ".join(S.ref_preset),
                        "l2": "inputs larger than L2 (random access over a %.1f GB index; a different batch each step)" % (S.info["device_bytes"] / 1e9),
@@ -819,7 +826,9 @@ def main():
     global LARGE_INDEX
     LARGE_INDEX = bool(wl.get("large"))
     mates = 2 if paired else 1
-    ref_preset = ("--end-to-end", "--" + wl["preset"])
+    ref_preset = ("--local", "--" + wl["preset"] + "-local") if wl.get("local") else ("--end-to-end", "--" + wl["preset"])
+    if wl.get("batch") and args.batch == 1_000_000:
+        args.batch = wl["batch"]
 
     import torch
     import torch.distributed as dist
