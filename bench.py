@@ -793,6 +793,94 @@ def run_exact(S, args):
 
 
 # ------------------------------------------------------------------------------------------------
+# SURVEY 8e topology: one reader deals blocks of reads to the ranks, one ordered writer collects the results (--topology dealer)
+# ------------------------------------------------------------------------------------------------
+class _DevView:
+    """device memory owned by the engine as a torch tensor (zero copy)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def run_dealer(S, args):
+    import torch
+    import torch.distributed as dist
+    from bowtie2_b200.dist import deal_blocks
+    from bowtie2_b200.lib import PAIR_RESULT, READ_RESULT, XEngine, policy_params
+    gpu, dev, paired, mates, L = S.gpu, S.dev, S.paired, S.mates, S.READ_LEN
+    blk = min(S.B, 500_000)                                   # units per dealt block
+    per_rank = max(1, args.steps * (S.B // blk))
+    n_blocks = per_rank * S.world
+    prm = policy_params(S.wl["preset"], local=bool(S.wl.get("local")), paired=paired, seed=0, host_threads=S.fmt_threads)
+    eng = XEngine(gpu, prm, blk, L)
+    NS = S.names.shape[1]
+    nR = blk * mates
+    offs = S.offs[:nR + 1]
+    block_spec = [((nR, L), torch.uint8), ((nR, L), torch.uint8), ((nR, NS), torch.uint8)]
+    result_spec = [((nR * READ_RESULT.itemsize,), torch.uint8), ((nR * eng.max_ops,), torch.uint8), ((max(blk, 1) * PAIR_RESULT.itemsize,), torch.uint8)]
+    resident = S.reads.shape[0] // nR                         # blocks of reads resident on the dealer, cycled
+
+    def get_block(k):
+        j = k % resident
+        return S.reads[j * nR:(j + 1) * nR], S.quals[j * nR:(j + 1) * nR], S.names[j * nR:(j + 1) * nR]
+
+    def align(t):
+        r, q, nm = t
+        eng.run_dev(r.data_ptr(), q.data_ptr(), offs.data_ptr(), nR, nm.data_ptr(), NS, stream=0)
+        pr, po, mo, pp = eng.results_dev()
+        out = [torch.as_tensor(_DevView(pr, nR * READ_RESULT.itemsize), device=dev), torch.as_tensor(_DevView(po, nR * mo), device=dev)]
+        out.append(torch.as_tensor(_DevView(pp, blk * PAIR_RESULT.itemsize), device=dev) if paired else torch.zeros(result_spec[2][0], dtype=torch.uint8, device=dev))
+        return tuple(out)
+
+    # the ordered writer (rank 0): results leave for pinned host memory block by block; blocks are released in input order
+    host = [torch.empty(s, dtype=d).pin_memory() for s, d in result_spec] if S.rank == 0 else None
+    state = {"next": 0, "done": set(), "bytes": 0}
+
+    def put_result(k, res):
+        for h, t in zip(host, res):
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        state["bytes"] += sum(h.numel() for h in host)
+        state["done"].add(k)
+        while state["next"] in state["done"]:                 # (a writer would emit block `next` here)
+            state["done"].remove(state["next"]); state["next"] += 1
+
+    # warm-up: one block per rank, then the timed deal
+    sync = lambda: torch.cuda.current_stream().synchronize()      # a received block is complete before the engine's own streams read it
+    deal_blocks(S.world, block_spec, result_spec, get_block, align, put_result if S.rank == 0 else None, dev, sync=sync)
+    state.update(next=0, done=set(), bytes=0)
+    torch.cuda.synchronize()
+    if S.distributed:
+        dist.barrier()
+    clocks = ClockSampler(S.local_rank)
+    if S.rank == 0:
+        clocks.start()
+    t0 = time.perf_counter()
+    deal_blocks(n_blocks, block_spec, result_spec, get_block, align, put_result if S.rank == 0 else None, dev, sync=sync)
+    torch.cuda.synchronize()
+    if S.distributed:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    clk = clocks.stop() if S.rank == 0 else None
+    eng.close()
+    if S.rank != 0:
+        return None
+    assert state["next"] == n_blocks
+    value = n_blocks * blk / dt / 1e6
+    return {"metric": "Mreads/s", "value": value, "unit": "Mreads/s", "n_gpus": S.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 popcount (FM rank) + s16x2 DPX (DP)", "data": "synthetic",
+            "config": {"workload": S.workload, "full_size": S.full, "read_unit": S.unit[:-1], "block": blk, "blocks": n_blocks,
+                       "topology": "dealer: rank 0 holds the reads and deals blocks round-robin over NCCL send / recv, every rank aligns its blocks with one "
+                                   "engine, the results return to rank 0 and leave in block order for pinned host memory (SURVEY 8e: one reader, one ordered writer)",
+                       "pipeline": "exact", "preset": " ".join(S.ref_preset)},
+            "clocks": clk, "gpu_launches": None,
+            "e2e": {"value": value, "unit": "Mreads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": state["bytes"] // max(args.steps, 1),
+                    "path": "device-resident reads on the dealer -> NCCL -> engines -> NCCL -> pinned host results on the dealer"},
+            "roofline": None, "cpu_baseline": S.cpu_baseline}
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -802,6 +890,8 @@ def main():
     ap.add_argument("--pipeline", default="exact", choices=["exact", "speculative"])
     ap.add_argument("--workload", default="pe150", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=1_000_000, help="reads (pairs for a paired workload) per step")
+    ap.add_argument("--topology", default="shard", choices=["shard", "dealer"],
+                    help="shard (default): every rank aligns its own resident reads; dealer: rank 0 deals blocks to the ranks and collects the results in order")
     ap.add_argument("--engines", type=int, default=2, help="exact pipeline: engines (streams + host threads) that share every batch")
     ap.add_argument("--genome-mbp", type=float, default=0.0,
                     help="debug only: another genome size (0 = the workload's: 3000; any other value is NOT the BASELINE config)")
@@ -989,7 +1079,10 @@ def main():
     torch.cuda.empty_cache()                 # the genome / index-builder temporaries torch still caches: the engines allocate with cudaMalloc
     log(f"rank {rank}: setup {time.time() - t0:.1f}s, index {info['device_bytes'] / 1e9:.2f} GB in HBM")
 
-    line = run_exact(S, args) if args.pipeline == "exact" else run_speculative(S, args)
+    if args.topology == "dealer":
+        line = run_dealer(S, args)
+    else:
+        line = run_exact(S, args) if args.pipeline == "exact" else run_speculative(S, args)
     if rank == 0:
         print(json.dumps(line))
     shutil.rmtree(WORKDIR, ignore_errors=True) if rank == 0 else None

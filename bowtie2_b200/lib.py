@@ -1120,9 +1120,9 @@ class XEngine:
     def align(self, reads: ReadBatch, names=None):
         """host buffers in -> (results, ops [n, max_ops], pairs or None, stats dict)"""
         n = reads.n
-        res = np.zeros(n, dtype=READ_RESULT)
-        ops = np.zeros((max(n, 1), self.max_ops), dtype=np.uint8)
-        pairs = np.zeros(n // 2, dtype=PAIR_RESULT) if self.paired else None
+        res = np.empty(n, dtype=READ_RESULT)                     # (every row is overwritten by the copy back from the device)
+        ops = np.empty((max(n, 1), self.max_ops), dtype=np.uint8)
+        pairs = np.empty(n // 2, dtype=PAIR_RESULT) if self.paired else None
         stats = np.zeros(8, dtype=np.uint64)
         rows = None if names is None else name_rows(names)
         st = reads._struct()
