@@ -458,7 +458,7 @@ int bt2g_xengine_create(bt2g_ctx *ctx, const bt2g_policy_params *pp, uint64_t ma
 		int maxColM = (int)std::min<uint64_t>(maxfrag + 2ull * maxLen + 2ull * gapMax + 16, 8000);
 		// (local mode: a 300 bp read has thousands of candidate cells and tens of distinct successful backtraces per rectangle;
 		// a problem that overflows either list sends its unit to the host fallback)
-		const int maxCands = e->sc.local ? 4096 : 256, maxAlns = e->sc.local ? 32 : 8;
+		const int maxCands = e->sc.local ? 16384 : 256, maxAlns = e->sc.local ? 32 : 8;
 		rc |= setupDp(e, e->A, maxColA, nU, maxCands, maxAlns);
 		if(pp->paired) rc |= setupDp(e, e->M, maxColM, nU, maxCands, maxAlns);
 		else e->M = e->A;
