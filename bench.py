@@ -585,13 +585,20 @@ def run_exact(S, args):
     nb = S.nb
     offs_all = S.offs
 
-    def run_workers(fn, n_steps, first):
-        """fn(j, i) for engine j over steps first..first+n_steps-1, one host thread per engine; returns after all have finished"""
+    stagger = [0.0] * E                                     # seconds engine j waits before its first step of a timed run
+
+    def run_workers(fn, n_steps, first, staggered=False):
+        """fn(j, i) for engine j over steps first..first+n_steps-1, one host thread per engine; returns after all have finished.
+        staggered: engine j starts stagger[j] seconds late (inside the timed region), so that the engines -- which all take the
+        same time per batch and would otherwise stay in lockstep, full waves against full waves -- run one engine's sparse tail
+        under another's full waves, as worker threads with their natural jitter would"""
         errs = []
 
         def work(j):
             try:
                 torch.cuda.set_device(dev)
+                if staggered and stagger[j] > 0:
+                    time.sleep(stagger[j])
                 for i in range(first, first + n_steps):
                     fn(j, i)
             except Exception as e:                      # surfaced below: a failed engine must fail the bench
@@ -624,6 +631,12 @@ def run_exact(S, args):
 
     run_workers(step_dev, args.warmup, 0)
     torch.cuda.synchronize()
+    if E > 1 and args.stagger:
+        tw = time.perf_counter()
+        run_workers(step_dev, 1, 0)                          # one more untimed step: the engines' batch time
+        tb = time.perf_counter() - tw
+        for j in range(E):
+            stagger[j] = tb * j / E
     if S.distributed:
         dist.barrier()
     clocks = ClockSampler(S.local_rank)
@@ -634,7 +647,7 @@ def run_exact(S, args):
     torch.cuda.synchronize()
     ev0.record(streams[0])
     torch.cuda.synchronize()                          # every engine's first kernel is ordered after ev0
-    run_workers(lambda j, i: step_dev(j, i, True), args.steps, args.warmup)
+    run_workers(lambda j, i: step_dev(j, i, True), args.steps, args.warmup, staggered=True)
     for j in range(E):
         ev1[j].record(streams[j])
     torch.cuda.synchronize()
@@ -674,7 +687,7 @@ def run_exact(S, args):
         dist.barrier()
     torch.cuda.synchronize()
     t_e2e0 = time.perf_counter()
-    run_workers(step_host, args.steps, 0)
+    run_workers(step_host, args.steps, 0, staggered=True)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t_e2e0
     res_np = np.frombuffer(hres[0].numpy().tobytes(), dtype=READ_RESULT)[:(parts[0][1] - parts[0][0]) * mates]
@@ -768,7 +781,7 @@ def run_exact(S, args):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 popcount (FM rank) + " + ("i32 (local DP)" if local else "s16x2 DPX (DP)"), "data": "synthetic",
             "config": {"workload": S.workload, "full_size": S.full, "read_unit": S.unit[:-1], "mates_per_s_M": value * mates,
-                       "batch": B, "engines": E, "preset": " ".join(S.ref_preset),
+                       "batch": B, "engines": E, "engine_stagger_s": stagger, "preset": " ".join(S.ref_preset),
                        "l2": "inputs larger than L2 (random access over a %.1f GB index; a different batch each step)" % (S.info["device_bytes"] / 1e9),
                        "pipeline": "exact",
                        "pipeline_desc": "the reference's search policy (multiseedSearchWorker + SwDriver::extendSeeds[Paired], per-read RNG included) as a "
@@ -892,6 +905,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1_000_000, help="reads (pairs for a paired workload) per step")
     ap.add_argument("--topology", default="shard", choices=["shard", "dealer"],
                     help="shard (default): every rank aligns its own resident reads; dealer: rank 0 deals blocks to the ranks and collects the results in order")
+    ap.add_argument("--no-stagger", dest="stagger", action="store_false",
+                    help="start the engines of a timed run together instead of 1/E of a batch time apart")
     ap.add_argument("--engines", type=int, default=2, help="exact pipeline: engines (streams + host threads) that share every batch")
     ap.add_argument("--genome-mbp", type=float, default=0.0,
                     help="debug only: another genome size (0 = the workload's: 3000; any other value is NOT the BASELINE config)")
