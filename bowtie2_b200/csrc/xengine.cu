@@ -254,6 +254,7 @@ struct bt2g_xengine {
 	// state machine (k_xe_step), 1-mismatch search, seed search, seed-extension DP, mate-finding DP, host fallback (wall), total
 	float stageMs[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [8], [9]: DP fill / DP tail kernels of both queues (split of [4] + [5])
 	cudaEvent_t tev[2][XE_TEV]; int tevN[2] = {0, 0};
+	cudaEvent_t evJoin = nullptr; int dpSideBySide = 1;   // BT2G_XE_DP_SERIAL=1 turns the side-by-side DP launches of small waves off
 	uint64_t launches = 0;             // kernels of this library launched by the last batch
 	cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -385,9 +386,14 @@ int runBatch(bt2g_xengine *e, uint64_t nReads, const char *dNames, uint32_t name
 			BT2G_CUDA_TRY(ctx, cudaMemsetAsync(d.seedActive, 0, nReads, st));
 		}
 		cudaEventRecord(ev[4], st);
+		// small waves (the tail of a batch): the two DP queues hold a few thousand problems each, so their fill / tail launches run
+		// side by side on the engine's two streams instead of one after the other (everything before this point has completed)
+		const bool sideBySide = e->ownStreams && e->dpSideBySide && q.nDpA && q.nDpM && (uint64_t)(q.nDpA + q.nDpM) * 16 <= (uint64_t)e->sms * 2048;
+		cudaStream_t stM = sideBySide ? (st == e->stream ? e->streamHi : e->stream) : st;
 		if(launchDp<OFF>(e, e->A, q.nDpA, st)) { ctx->err = "xengine: DP launch rejected"; return -1; }
 		cudaEventRecord(ev[5], st);
-		if(launchDp<OFF>(e, e->M, q.nDpM, st)) { ctx->err = "xengine: DP launch rejected"; return -1; }
+		if(launchDp<OFF>(e, e->M, q.nDpM, stM)) { ctx->err = "xengine: DP launch rejected"; return -1; }
+		if(sideBySide) { cudaEventRecord(e->evJoin, stM); cudaStreamWaitEvent(st, e->evJoin, 0); }
 		cudaEventRecord(ev[0], st);
 		BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	}
@@ -415,6 +421,7 @@ int bt2g_xengine_create(bt2g_ctx *ctx, const bt2g_policy_params *pp, uint64_t ma
 	cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, ctx->device);
 	if(const char *o = getenv("BT2G_XE_OCC")) e->stepOcc = atoi(o);          // experiment knob, read once
 	if(getenv("BT2G_XE_DEBUG")) e->debug = 1;
+	if(const char *o = getenv("BT2G_XE_DP_SERIAL")) e->dpSideBySide = atoi(o) ? 0 : 1;
 	if(const char *o = getenv("BT2G_XE_SPREAD")) { e->bigSpread = atoi(o); if(e->bigSpread < 0 || e->bigSpread > 5) e->bigSpread = 0; }
 	// the kernels score with the scheme the policy reasons about (one source: the policy parameters)
 	scoringFromParams(pp, &e->sc);
@@ -474,6 +481,7 @@ int bt2g_xengine_create(bt2g_ctx *ctx, const bt2g_policy_params *pp, uint64_t ma
 		if(err == cudaSuccess) err = cudaHostAlloc((void **)&e->hStatus, nU, cudaHostAllocDefault);
 		for(int k = 0; k < 8 && err == cudaSuccess; k++) err = cudaEventCreate(&e->ev[k]);
 		for(int k = 0; k < 2 * XE_TEV && err == cudaSuccess; k++) err = cudaEventCreate(&e->tev[k / XE_TEV][k % XE_TEV]);
+		if(err == cudaSuccess) err = cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming);
 		if(err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
 		if(err == cudaSuccess) { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); err = cudaStreamCreateWithPriority(&e->streamHi, cudaStreamNonBlocking, hi); }
 	}
@@ -494,6 +502,7 @@ void bt2g_xengine_destroy(bt2g_xengine *e) {
 	if(e->hStatus) cudaFreeHost(e->hStatus);
 	for(int k = 0; k < 8; k++) if(e->ev[k]) cudaEventDestroy(e->ev[k]);
 	for(int k = 0; k < 2 * XE_TEV; k++) if(e->tev[k / XE_TEV][k % XE_TEV]) cudaEventDestroy(e->tev[k / XE_TEV][k % XE_TEV]);
+	if(e->evJoin) cudaEventDestroy(e->evJoin);
 	if(e->stream) cudaStreamDestroy(e->stream);
 	if(e->streamHi) cudaStreamDestroy(e->streamHi);
 	delete e;
