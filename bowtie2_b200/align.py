@@ -89,9 +89,6 @@ def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1, opti
     this library: every read's state machine advances together, each primitive runs as one batched call per wave"""
     from .lib import policy_align, policy_align_k, policy_backend_gpu, policy_params
     multi = bool(options and (options.get("k") is not None or options.get("all_hits")))
-    if multi and paired:
-        # the compiled engine reports the primary pair; the secondary records of paired -k / -a exist in policy_engine.py only
-        raise NotImplementedError("paired -k / -a output needs the secondary records: use bowtie2_b200.policy_engine (PairedPolicyEngine(..., k=...))")
     if hasattr(gpu, "policy_backend_table"):                    # a stand-in device (tests): its own table
         be, keep = gpu.policy_backend_table()
     else:
@@ -104,6 +101,27 @@ def _exact_batch(gpu, batch, names, paired, preset, local, seed, threads=1, opti
         gpu.set_scoring(local=local)
     try:
         prm = policy_params(preset, local=local, paired=paired, seed=seed, host_threads=threads, **(options or {}))
+        if multi and paired:
+            # paired -k N / -a (bt2g_policy_align_pairs_k): entries of two rows per pair (the primaries, then the further concordant pairs
+            # or the mates' further alignments beside the opposite primary); rows that are mate context only are skipped by the formatter
+            from .lib import policy_align_pairs_k
+            cap = int(options["k"]) * 2 + 2 if options.get("k") is not None else 256
+            res_k, ops_k, pairs_k, cnt, truncated, stats = policy_align_pairs_k(gpu._lib, be, prm, batch, names, cap)
+            if truncated:
+                sys.stderr.write(f"Warning: -a: pairs with more than {cap} report entries were cut to {cap}\n")
+            per = np.maximum(cnt.astype(np.int64), 1)
+            pidx = np.repeat(np.arange(batch.n // 2), per)
+            sub = np.arange(len(pidx)) - np.repeat(np.cumsum(per) - per, per)
+            o = batch.off.astype(np.int64)
+            nm = list(names)
+            seqs, quals, nms = [], [], []
+            for i in pidx:
+                for r in (2 * i, 2 * i + 1):
+                    seqs.append(batch.seq[o[r]:o[r + 1]]); quals.append(batch.qual[o[r]:o[r + 1]]); nms.append(nm[r])
+            res_f = np.ascontiguousarray(res_k[pidx, sub]).reshape(-1)
+            ops_f = np.ascontiguousarray(ops_k[pidx, sub]).reshape(len(pidx) * 2, -1)
+            return ReadBatch.from_list(seqs, quals), nms, res_f, ops_f, np.ascontiguousarray(pairs_k[pidx, sub]), \
+                (np.ascontiguousarray(res_k[:, 0]).reshape(-1), np.ascontiguousarray(pairs_k[:, 0]))
         if multi:
             # unpaired -k N / -a (bt2g_policy_align_k): one record per reported alignment, the read repeated; -a is capped per read
             cap = int(options["k"]) if options.get("k") is not None else ALL_HITS_CAP
@@ -191,6 +209,11 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
                                 both_mates=paired)
                 if paired:
                     pipe.enable_pairs()
+            if exact and paired and policy_options and (policy_options.get("k") is not None or policy_options.get("all_hits")):
+                batch_k, names_k, res, ops, pairs_e, (prim_res, prim_pairs) = _exact_batch(gpu, batch, names, paired, preset, local, seed, threads, policy_options)
+                out.write(sam_format(lib, batch_k, res, ops, sam_names, read_names=names_k, pairs=pairs_e, threads=threads, local=local, as_bytes=True))
+                align_counts_add(lib, counts, prim_res, prim_pairs)
+                continue
             if exact and not paired and policy_options and (policy_options.get("k") is not None or policy_options.get("all_hits")):
                 batch_k, names_k, res, ops, primary = _exact_batch(gpu, batch, names, paired, preset, local, seed, threads, policy_options)
                 out.write(sam_format(lib, batch_k, res, ops, sam_names, read_names=names_k, threads=threads, local=local, as_bytes=True))

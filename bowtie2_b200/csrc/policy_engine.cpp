@@ -316,6 +316,7 @@ struct PairedSink {
 	int64_t khits, mhits; bool mmode;
 	std::vector<Aln> rs1, rs2, rs1u, rs2u;
 	bool doneConcord = false, doneDiscord = false, doneUnp[2] = {false, false}, exitConcordM = false, exitConcordK = false, done = false;
+	bool exitUnpK[2] = {false, false};
 	int64_t nconcord = 0, nunp[2] = {0, 0}, bestPair = MIN_I64, best2Pair = MIN_I64;
 	void updateDone() { done = doneUnp[0] && doneUnp[1] && doneDiscord && doneConcord; }
 	bool report(const Aln *a1, const Aln *a2) {
@@ -334,7 +335,7 @@ struct PairedSink {
 			const Aln &a = a1 ? *a1 : *a2;
 			nunp[m]++;
 			if(!doneUnp[m]) {
-				if(!mmode && nunp[m] >= khits) { doneUnp[m] = true; updateDone(); }
+				if(!mmode && nunp[m] >= khits) { doneUnp[m] = true; exitUnpK[m] = true; updateDone(); }
 				else if(mmode && nunp[m] > mhits) { doneUnp[m] = true; updateDone(); }
 			}
 			if(nunp[m] > 1) doneDiscord = true;
@@ -351,7 +352,8 @@ struct PairedSink {
 };
 
 struct Result { bool aligned = false; Aln aln; bool hasXs = false; int64_t xs = 0; int mapq = 0; std::vector<Aln> secondary; };
-struct PairOut { int pairType = 0; Result m[2]; int kind = 5; int64_t scoreSum = 0, fraglen = 0; };
+// secPairs (-k / -a): the further selected concordant pairs in report order; Result::secondary of a mate: its further unpaired alignments
+struct PairOut { int pairType = 0; Result m[2]; int kind = 5; int64_t scoreSum = 0, fraglen = 0; std::vector<std::pair<Aln, Aln>> secPairs; };
 
 struct Engine {
 	const Params &P; Pending *slot;
@@ -1042,6 +1044,10 @@ PairOut Engine::finishPair() {
 			const int64_t s2 = a2.refoff - a2.trimLeft(), e2 = a2.refoff + a2.refExtent() + (a2.rdlen - a2.ext() - a2.trimLeft());
 			po.fraglen = std::max(e1, e2) - std::min(s1, s2);
 		}
+		{   // ReportingState::getReport (aln_sink.cpp:300-330): after a -k short circuit khits pairs, else min(found, khits)
+			const int64_t num = psink.exitConcordK ? P.khits : std::min<int64_t>(psink.nconcord, P.khits);
+			for(int64_t j = 1; j < num && j < (int64_t)buf.size(); j++) po.secPairs.push_back({psink.rs1[buf[j].second], psink.rs2[buf[j].second]});
+		}
 		return po;
 	}
 	if(!psink.doneDiscord && psink.nunp[0] == 1 && psink.nunp[1] == 1) {
@@ -1059,6 +1065,10 @@ PairOut Engine::finishPair() {
 		Result &r = po.m[k]; r.aligned = true; r.aln = rsu[buf[0].second];
 		r.hasXs = buf.size() > 1; r.xs = r.hasXs ? rsu[buf[1].second].score : 0;
 		r.mapq = (int)mapq(r.aln.score, r.hasXs, r.xs, mn[k], m[k].perfect);
+		{
+			const int64_t num = psink.exitUnpK[k] ? P.khits : std::min<int64_t>((int64_t)rsu.size(), P.khits);
+			for(int64_t j = 1; j < num && j < (int64_t)buf.size(); j++) r.secondary.push_back(rsu[buf[j].second]);
+		}
 		nal++;
 	}
 	po.pairType = nal == 2 ? 2 : (nal == 1 ? 3 : 0);
@@ -1360,9 +1370,40 @@ static int policyAlign(const bt2g_policy_backend *be, const bt2g_policy_params *
 	auto finish = [&](Unit &u) {
 		if(P.paired) {
 			PairOut po = std::move(u.tp->h.promise().value);
-			pairs[u.id] = bt2g_pair_result{}; pairs[u.id].pair_type = po.pairType; pairs[u.id].kind = po.kind;
-			pairs[u.id].score_sum = (int32_t)po.scoreSum; pairs[u.id].fraglen = po.fraglen;
-			for(int k = 0; k < 2; k++) fillResult(po.m[k], S.codes((int)(2 * u.id + k)), res[2 * u.id + k], ops + (2 * u.id + k) * (size_t)maxOps, maxOps);
+			// entry e of pair i: rows 2 * (i * maxPerRead + e) + {0, 1} and pairs[i * maxPerRead + e].  Entry 0 carries the primaries of both
+			// mates; further entries (-k / -a, AlnSink::reportHits, aln_sink.h:640-735): the other concordant pairs, or every record of mate 1
+			// and then of mate 2, each beside the opposite mate's primary as its mate.  found bit 8 = secondary (FLAG 256, MAPQ 255),
+			// bit 9 = present only as its mate's mate: bt2g_sam_format does not print it
+			const size_t e0 = u.id * (size_t)maxPerRead;
+			size_t n = 0;
+			auto entry = [&](const Result &r1, const Result &r2, int mark1, int mark2) {
+				if(n >= maxPerRead) { truncated = truncated || maxPerRead > 1; return; }
+				const size_t e = e0 + n;
+				pairs[e] = bt2g_pair_result{}; pairs[e].pair_type = po.pairType; pairs[e].kind = po.kind;
+				pairs[e].score_sum = (int32_t)po.scoreSum; pairs[e].fraglen = po.fraglen;
+				const Result *rr[2] = {&r1, &r2}; const int mk[2] = {mark1, mark2};
+				for(int k = 0; k < 2; k++) {
+					fillResult(*rr[k], S.codes((int)(2 * u.id + k)), res[2 * e + k], ops + (2 * e + k) * (size_t)maxOps, maxOps);
+					res[2 * e + k].found |= mk[k];
+				}
+				n++;
+			};
+			auto secOf = [&](const Result &prim, const Aln &a) { Result s2; s2.aligned = true; s2.aln = a; s2.hasXs = prim.hasXs; s2.xs = prim.xs; s2.mapq = 255; return s2; };
+			const Result &m0 = po.m[0], &m1 = po.m[1];
+			if(po.pairType == 1) {
+				entry(m0, m1, 0, 0);
+				for(auto &pr2 : po.secPairs) entry(secOf(m0, pr2.first), secOf(m1, pr2.second), 0x100, 0x100);
+			} else if(m0.secondary.empty() && m1.secondary.empty()) {
+				entry(m0, m1, 0, 0);
+			} else {
+				// unpaired alignments of a pair: ALL of mate 1's records, then all of mate 2's, an unaligned mate's record last
+				// (AlnSinkWrap::finishRead reports rs1u, then rs2u, then the unaligned mates: aln_sink.cpp:930-1010)
+				if(m0.aligned) { entry(m0, m1, 0, 0x200); for(const Aln &a : m0.secondary) entry(secOf(m0, a), m1, 0x100, 0x200); }
+				if(m1.aligned) { entry(m0, m1, 0x200, 0); for(const Aln &a : m1.secondary) entry(m0, secOf(m1, a), 0x200, 0x100); }
+				if(!m0.aligned) entry(m0, m1, 0, 0x200);
+				if(!m1.aligned) entry(m0, m1, 0x200, 0);
+			}
+			if(nReported) nReported[u.id] = (uint32_t)n;
 		} else {
 			// one row per reported alignment: the primary, then the secondaries (found bit 8 -> FLAG 256, MAPQ 255, the read's XS:i)
 			Result &r = u.tr->h.promise().value;
@@ -1421,6 +1462,15 @@ static int policyAlign(const bt2g_policy_backend *be, const bt2g_policy_params *
 extern "C" int bt2g_policy_align(const bt2g_policy_backend *be, const bt2g_policy_params *pp, const bt2g_reads *reads, const char *const *names,
                                  bt2g_read_result *res, uint8_t *ops, uint32_t maxOps, bt2g_pair_result *pairs, uint64_t *stats) {
 	return policyAlign(be, pp, reads, names, res, ops, maxOps, pairs, stats, 1, nullptr);
+}
+
+// paired -k N / -a: up to maxPerPair entries per pair (see `finish` above); res / ops hold 2 * n_pairs * maxPerPair rows, pairs
+// n_pairs * maxPerPair records, nEntries[n_pairs] the entries used.  Returns 1 when some pair had more entries than maxPerPair.
+extern "C" int bt2g_policy_align_pairs_k(const bt2g_policy_backend *be, const bt2g_policy_params *pp, const bt2g_reads *reads, const char *const *names,
+                                         uint32_t maxPerPair, bt2g_read_result *res, uint8_t *ops, uint32_t maxOps, bt2g_pair_result *pairs,
+                                         uint32_t *nEntries, uint64_t *stats) {
+	if(!pp || !pp->paired || maxPerPair == 0 || !nEntries) return -1;
+	return policyAlign(be, pp, reads, names, res, ops, maxOps, pairs, stats, maxPerPair, nEntries);
 }
 
 extern "C" int bt2g_policy_align_k(const bt2g_policy_backend *be, const bt2g_policy_params *pp, const bt2g_reads *reads, const char *const *names,

@@ -270,6 +270,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		if(opt->rg_optflag && opt->rg_optflag[0]) { line += '\t'; line += opt->rg_optflag; }     // RG:Z:<id> (sam.cpp:384-387)
 		line += '\n';
 		if(noUnal && !aligned) continue;                              // --no-unal (AlnSinkSam::appendMate, aln_sink.cpp:1905)
+		if(r.found & 0x200) continue;                                 // present only as its mate's mate (paired -k / -a entries)
 		// a pair with only mate 2 aligned is printed aligned mate first (AlnSinkWrap::finishRead reports the
 		// unpaired alignment of mate 2, then the unaligned mate 1, aln_sink.cpp:930-1010)
 		if(paired && (i & 1) == 0 && !aligned && mateAligned) { held = line; continue; }

@@ -956,7 +956,7 @@ class IndexFile:
 
 
 # ---- the exact search policy in waves (include/bt2g.h: bt2g_policy_align; csrc/policy_engine.cpp) ----------------------
-EXPORTS += ["bt2g_policy_align", "bt2g_policy_align_k", "bt2g_policy_backend_gpu", "bt2g_xengine_align_host"]
+EXPORTS += ["bt2g_policy_align", "bt2g_policy_align_k", "bt2g_policy_align_pairs_k", "bt2g_policy_backend_gpu", "bt2g_xengine_align_host"]
 _CB = C.CFUNCTYPE
 _vp = C.c_void_p
 
@@ -1044,6 +1044,32 @@ def policy_align(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads:
     if rc:
         raise RuntimeError(f"{entry} failed ({rc})")
     return res, ops, pairs, tuple(int(x) for x in stats)
+
+
+def policy_align_pairs_k(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads: ReadBatch, names, max_per_pair: int):
+    """include/bt2g.h: bt2g_policy_align_pairs_k (paired -k / -a) -> (results [n_pairs, max_per_pair, 2], ops [n_pairs, max_per_pair, 2,
+    max_ops], pair records [n_pairs, max_per_pair], n_entries [n_pairs], truncated, stats)"""
+    lib.bt2g_policy_align_pairs_k.argtypes = [C.POINTER(_PolicyBackend), C.POINTER(_PolicyParams), C.POINTER(_Reads), _vp, C.c_uint32, _vp, _vp, C.c_uint32,
+                                              _vp, _vp, _vp]
+    npairs = reads.n // 2
+    max_ops = int(reads.lengths().max()) + 64 if reads.n else 64
+    res = np.zeros((max(npairs, 1), max_per_pair, 2), dtype=READ_RESULT)
+    ops = np.zeros((max(npairs, 1), max_per_pair, 2, max_ops), dtype=np.uint8)
+    pairs = np.zeros((max(npairs, 1), max_per_pair), dtype=PAIR_RESULT)
+    cnt = np.zeros(max(npairs, 1), dtype=np.uint32)
+    stats = np.zeros(3, dtype=np.uint64)
+    if isinstance(names, NameTable):
+        keep = names.pointers()
+        qn = C.cast(keep.ctypes.data, _vp)
+    else:
+        keep = (C.c_char_p * reads.n)(*[x.encode() for x in names])
+        qn = C.cast(keep, _vp)
+    st = reads._struct()
+    rc = lib.bt2g_policy_align_pairs_k(C.byref(backend), C.byref(params), C.byref(st), qn, int(max_per_pair), _ptr(res), _ptr(ops), max_ops, _ptr(pairs),
+                                       _ptr(cnt), _ptr(stats))
+    if rc < 0:
+        raise RuntimeError(f"bt2g_policy_align_pairs_k failed ({rc})")
+    return res[:npairs], ops[:npairs], pairs[:npairs], cnt[:npairs], rc == 1, tuple(int(x) for x in stats)
 
 
 def policy_align_k(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads: ReadBatch, names, max_per_read: int):

@@ -563,6 +563,15 @@ int bt2g_policy_align(const bt2g_policy_backend *be, const bt2g_policy_params *p
 int bt2g_policy_align_k(const bt2g_policy_backend *be, const bt2g_policy_params *prm, const bt2g_reads *reads, const char *const *names,
                         uint32_t max_per_read, bt2g_read_result *res, uint8_t *ops, uint32_t max_ops, uint32_t *n_reported,
                         uint64_t *stats);
+/* paired -k N / -a: up to max_per_pair ENTRIES per pair.  Entry e of pair i = rows 2 * (i * max_per_pair + e) + {0, 1} of res / ops
+ * and pairs[i * max_per_pair + e]: entry 0 carries the primaries of both mates; the further entries are the other concordant pairs
+ * in the reference's report order, or -- when the pair did not align concordantly and a mate has further alignments -- every record
+ * of mate 1 and then of mate 2, each beside the opposite mate's primary (AlnSinkWrap::finishRead, aln_sink.cpp:930-1010).  bt2g_read_result.found bit 8 marks a secondary
+ * (FLAG 256, MAPQ 255), bit 9 a row that is present only as its mate's mate (bt2g_sam_format skips it).  n_entries[n_pairs].
+ * Returns 1 when a pair had more entries than max_per_pair. */
+int bt2g_policy_align_pairs_k(const bt2g_policy_backend *be, const bt2g_policy_params *prm, const bt2g_reads *reads, const char *const *names,
+                              uint32_t max_per_pair, bt2g_read_result *res, uint8_t *ops, uint32_t max_ops, bt2g_pair_result *pairs,
+                              uint32_t *n_entries, uint64_t *stats);
 
 /* ------------------------------------------------------------- the exact search policy ON THE DEVICE ----- */
 /* The same policy as bt2g_policy_align (results identical to the reference program's), but the per-read state machines run as a

@@ -128,3 +128,26 @@ def test_exact_mode_k_hits_whole_files_over_a_fake_device(tmp_path, rep_index):
     assert got == want, next((a, b) for a, b in zip(got, want) if a != b)
     assert sum(int(l.split("\t")[1]) & 256 != 0 for l in want) > 50
     assert summ.getvalue() == p.stderr
+
+
+def test_exact_mode_paired_k_hits_whole_files_over_a_fake_device(tmp_path, rep_index):
+    """align_files(exact=True, policy_options={"k": 3}) on PAIRS of the repeat-rich fixture (bt2g_policy_align_pairs_k): every record of
+    -k 3 -- secondary pairs and the mates' secondary alignments included -- identical to the reference program's"""
+    import io
+    import subprocess
+    from fake_gpu import FakeGpu
+    from oracle_lib import Oracle, have_reference, ref_bin
+    if not have_reference():
+        pytest.skip("oracle/_ref not built")
+    for m in (1, 2):
+        with open(os.path.join(GOLDEN, f"rep_reads_{m}.fq")) as f, open(tmp_path / f"a{m}.fq", "w") as g:
+            g.writelines(f.readlines()[:4 * 200])
+    p = subprocess.run([ref_bin("bowtie2-align-s"), "--sensitive", "--seed", "0", "-p", "1", "-k", "3", "-x", rep_index,
+                        "-1", str(tmp_path / "a1.fq"), "-2", str(tmp_path / "a2.fq")], capture_output=True, text=True, check=True)
+    want = [l for l in p.stdout.split("\n") if l and not l.startswith("@")]
+    out, summ = str(tmp_path / "o.sam"), io.StringIO()
+    align_files(rep_index, out, str(tmp_path / "a1.fq"), str(tmp_path / "a2.fq"), exact=True, batch_reads=128, summary=summ,
+                gpu=FakeGpu(Oracle(rep_index)), policy_options={"k": 3})
+    got = [l.rstrip("\n") for l in open(out) if not l.startswith("@")]
+    assert len(got) == len(want) and got == want, next(((a, b) for a, b in zip(got, want) if a != b), (len(got), len(want)))
+    assert sum(int(l.split("\t")[1]) & 256 != 0 for l in want) > 50

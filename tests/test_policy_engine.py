@@ -498,8 +498,8 @@ def test_k_and_all_modes_unpaired(tmp_path, args, kw):
 
 def _multi_sam_pairs(outs, reads, quals, names, ref_names, local=False):
     """records of pairs that carry secondary alignments, in the reference's order (AlnSink::reportHits, aln_sink.h:640-735):
-    concordant pairs one after the other; otherwise both primaries, then mate 1's secondaries, then mate 2's (each printed
-    with the opposite mate's primary as its mate).  Every record comes from a formatter pair entry; `keep` picks its lines."""
+    concordant pairs one after the other; otherwise every record of mate 1, then every record of mate 2 (each printed
+    with the opposite mate's primary as its mate), an unaligned mate's record last.  Every record comes from a formatter pair entry; `keep` picks its lines."""
     from bowtie2_b200.lib import PAIR_RESULT
     from bowtie2_b200.policy_engine import ReadResult
     R, Q, N, ent, keep = [], [], [], [], []
@@ -513,15 +513,26 @@ def _multi_sam_pairs(outs, reads, quals, names, ref_names, local=False):
             keep.append(lines)
         a1 = m1.aln if m1.aligned else None
         a2 = m2.aln if m2.aligned else None
-        add(a1, a2, False, False, (0, 1))
         if pr.pair_type == 1:
+            add(a1, a2, False, False, (0, 1))
             for (b1, b2) in pr.secondary_pairs or []:
                 add(b1, b2, True, True, (0, 1))
+        elif not (m1.secondary or m2.secondary):
+            add(a1, a2, False, False, (0, 1))
         else:
-            for b1 in (m1.secondary or []):
-                add(b1, a2, True, False, (0,))
-            for b2 in (m2.secondary or []):
-                add(a1, b2, False, True, (1,))
+            # every record of mate 1, then every record of mate 2, an unaligned mate's record last (AlnSinkWrap::finishRead)
+            if a1 is not None:
+                add(a1, a2, False, False, (0,))
+                for b1 in (m1.secondary or []):
+                    add(b1, a2, True, False, (0,))
+            if a2 is not None:
+                add(a1, a2, False, False, (1,))
+                for b2 in (m2.secondary or []):
+                    add(a1, b2, False, True, (1,))
+            if a1 is None:
+                add(a1, a2, False, False, (0,))
+            if a2 is None:
+                add(a1, a2, False, False, (1,))
     n = len(R)
     if n == 0:
         return []

@@ -194,3 +194,39 @@ def test_k_and_all_modes_unpaired_compiled(tmp_path, args, kw, cap):
     # a cap below the number of alignments drops the extra ones and says so
     res2, ops2, cnt2, truncated2, _ = policy_align_k(load_library(), be, prm, ReadBatch.from_list(reads, quals), names, 2)
     assert truncated2 and int(cnt2.max()) == 2 and np.array_equal(res2[:, 0], res[:, 0])
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args,kw,cap", [(["-k", "3"], dict(k=3), 3), (["-a"], dict(all_hits=True), 64)])
+def test_paired_k_and_all_modes_equal_the_reference_program(tmp_path, args, kw, cap):
+    """bt2g_policy_align_pairs_k: every record of paired -k N / -a -- the primaries, the further concordant pairs, the mates' further
+    unpaired alignments beside the opposite mate's primary -- formatted by bt2g_sam_format straight from the entry rows (bit 9 of
+    `found` = mate context only, not printed): identical to the reference program's SAM"""
+    from bowtie2_b200.lib import policy_align_pairs_k
+    from test_policy_engine import _synth_index
+    genome, base = _synth_index(tmp_path)
+    n = 150
+    reads, quals, _ = synth.make_pairs(genome, n, 100, seed=32, sub_rate=0.02, indel_rate=0.003, hard_frac=0.2, hard_period=12,
+                                       ins_mean=300, ins_sd=90)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    synth.write_fastq(f1, reads[0::2], quals[0::2])
+    synth.write_fastq(f2, reads[1::2], quals[1::2])
+    out = subprocess.check_output([ref_bin("bowtie2-align-s"), "--sensitive", "--seed", "0", "-p", "1", "-x", base, "-1", f1, "-2", f2] + args,
+                                  stderr=subprocess.DEVNULL).decode()
+    want = [l for l in out.split("\n") if l and not l.startswith("@")]
+    names = [f"r{i // 2}" for i in range(2 * n)]
+    be, keep, fake = _table(base)
+    prm = policy_params("sensitive", paired=True, k=kw.get("k"), all_hits=kw.get("all_hits", False))
+    res, ops, pairs, cnt, truncated, stats = policy_align_pairs_k(load_library(), be, prm, ReadBatch.from_list(reads, quals), names, cap)
+    assert not truncated and int(cnt.max()) > 1
+    # flatten the used entries: the pair's reads repeated per entry
+    R, Q, N, rr, oo, pp = [], [], [], [], [], []
+    for i in range(n):
+        for e in range(int(cnt[i])):
+            R += [reads[2 * i], reads[2 * i + 1]]; Q += [quals[2 * i], quals[2 * i + 1]]; N += [names[2 * i], names[2 * i + 1]]
+            rr.append(res[i, e]); oo.append(ops[i, e]); pp.append(pairs[i, e])
+    lines = sam_format(load_library(), ReadBatch.from_list(R, Q), np.concatenate(rr), np.concatenate(oo), ["chr1", "chr2", "chr3"], read_names=N,
+                       pairs=np.array(pp, dtype=PAIR_RESULT)).rstrip("\n").split("\n")
+    diff = [(a, b) for a, b in zip(lines, want) if a != b]
+    assert len(lines) == len(want) and not diff, (len(lines), len(want), diff[:1])
+    assert sum(int(l.split("\t")[1]) & 256 != 0 for l in want) > 20
