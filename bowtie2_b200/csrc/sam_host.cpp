@@ -329,12 +329,44 @@ static int fastqParseCore(const char *text, uint64_t len, uint64_t maxReads, uin
 	uint64_t cur = 0, n = 0, nb = 0;
 	off[0] = 0;
 	*nReads = 0; *consumed = 0;
+	// base codes of the sequence characters (alphabet.cpp asc2dna): letters -> 0..4, '.' -> 4, anything else 0xff (not a sequence character)
+	static const struct Lut { uint8_t v[256]; Lut() { for(int c = 0; c < 256; c++) { const int u = c & ~0x20; v[c] = ((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z')) ? (uint8_t)(u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : 4) : (c == '.' ? 4 : 0xff); } } } lut;
 	while(cur < len && n < maxReads) {
 		while(cur < len && (text[cur] == '\n' || text[cur] == '\r')) cur++;
 		if(cur >= len) break;
 		const uint64_t recStart = cur;
 		if(recStarts) recStarts[n] = recStart;
 		if(text[cur] != '@') return -4;                           // not a FASTQ record
+		{
+			// fast path for the usual record: four '\n'-terminated lines, one sequence line of sequence characters only, as many
+			// qualities; everything else (\r line ends, wrapped sequences, odd characters, truncation, limits) takes the general code below
+			const char *p = text + cur, *end = text + len;
+			const char *nl1 = (const char *)memchr(p, '\n', (size_t)(end - p));
+			const char *nl2 = nl1 ? (const char *)memchr(nl1 + 1, '\n', (size_t)(end - nl1 - 1)) : nullptr;
+			if(nl2 && nl2 + 1 < end && nl2[1] == '+' && nl1[-1] != '\r' && nl2 > nl1 + 1 && nl2[-1] != '\r') {
+				const char *nl3 = (const char *)memchr(nl2 + 1, '\n', (size_t)(end - nl2 - 1));
+				const char *nl4 = nl3 ? (const char *)memchr(nl3 + 1, '\n', (size_t)(end - nl3 - 1)) : nullptr;
+				const uint64_t L = (uint64_t)(nl2 - nl1 - 1);
+				if(nl4 && (uint64_t)(nl4 - nl3 - 1) == L && nb + L <= maxBases && nl4[-1] != '\r' && nl3[-1] != '\r' && !memchr(nl3 + 1, ' ', (size_t)L)) {
+					const unsigned char *sq = (const unsigned char *)nl1 + 1;
+					uint8_t *d = seq + nb;
+					uint8_t bad = 0;
+					for(uint64_t k = 0; k < L; k++) { const uint8_t v = lut.v[sq[k]]; d[k] = v; bad |= v; }
+					if(!(bad & 0x80)) {
+						memcpy(qual + nb, nl3 + 1, (size_t)L);
+						if(names && nameStride) {
+							uint64_t l = (uint64_t)(nl1 - p - 1);
+							if(l >= nameStride) l = nameStride - 1;
+							memcpy(names + n * (uint64_t)nameStride, p + 1, l);
+							names[n * (uint64_t)nameStride + l] = 0;
+						}
+						nb += L; n++; off[n] = nb;
+						cur = (uint64_t)(nl4 + 1 - text);
+						continue;
+					}
+				}
+			}
+		}
 		cur++;
 		const uint64_t nameBeg = cur;
 		while(cur < len && text[cur] != '\n' && text[cur] != '\r') cur++;
