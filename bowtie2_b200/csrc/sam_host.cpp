@@ -98,7 +98,10 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 			bool gapless = true;
 			if((r.found & 0xff) != 2) {
 				if(!op) return -1;
-				for(int k = 0; k < nops; k++) if((op[k] & 3) >= BT2G_OP_REFGAP) { gapless = false; break; }
+				// (8 ops per step: bit 1 of an op's type is set exactly for the two gap kinds)
+				int k = 0;
+				for(; k + 8 <= nops; k += 8) { uint64_t w; memcpy(&w, op + k, 8); if(w & 0x0202020202020202ull) { gapless = false; break; } }
+				for(; gapless && k < nops; k++) if((op[k] & 3) >= BT2G_OP_REFGAP) { gapless = false; break; }
 			}
 			if(gapless) {
 				// no gaps: nothing to left-align; CIGAR is one M run and MD:Z a scan of the mismatches
@@ -118,6 +121,9 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 				if(r.trim_right > 0) { appendInt(cigar, r.trim_right); cigar += 'S'; }
 				int run = 0; bool mmLast = false, first = true;
 				for(int k = nops - 1; k >= 0; k--) {
+					// a stretch of matches (type 0 in both low bits), eight ops at a time
+					while(k >= 7) { uint64_t w; memcpy(&w, op + k - 7, 8); if(w & 0x0303030303030303ull) break; run += 8; k -= 8; }
+					if(k < 0) break;
 					if((op[k] & 3) == BT2G_OP_MM) {
 						if(run > 0) { appendInt(mdz, run); first = false; mmLast = false; run = 0; }
 						if(mmLast || first) mdz += '0';
