@@ -628,6 +628,7 @@ def run_exact(S, args):
                 for kk, v in sm.items():
                     stage_acc[kk] = stage_acc.get(kk, 0.0) + v
                 launches[0] += engines[j].launches()
+        return st
 
     run_workers(step_dev, args.warmup, 0)
     torch.cuda.synchronize()
@@ -656,6 +657,16 @@ def run_exact(S, args):
     work = {k: v / args.steps for k, v in stat_acc.items()}
     if E > 1:
         work["waves"] = work.get("waves", 0) / E       # waves per engine and step
+    # one more (untimed) part of a batch through engine 0 ALONE: the DP fill kernel's launch durations without another engine's
+    # kernels sharing the GPU -- the kernel's own roofline point (the timed region's sum over concurrent engines is a lower bound)
+    alone = None
+    if E > 1:
+        st1 = step_dev(0, 0)
+        sm1 = engines[0].stage_ms()
+        cells1 = st1.get("seed_dp_cells", 0) + st1.get("mate_dp_cells", 0)
+        if sm1.get("dp_fill", 0) > 0:
+            alone = {"units": parts[0][1] - parts[0][0], "dp_cells": cells1, "fill_ms": sm1["dp_fill"], "tail_ms": sm1.get("dp_tail"),
+                     "achieved": cells1 / (sm1["dp_fill"] / 1e3) / 1e9}
 
     # ---- e2e: host buffers through the C ABI (H2D of reads, qualities, offsets, names + D2H of result structs, edit ops, pair records)
     nbuf = min(2, nb)
@@ -770,7 +781,10 @@ def run_exact(S, args):
             "traffic": ncu.get("dram_bytes_per_cell", None) and ncu["dram_bytes_per_cell"] * dp_cells,
             "traffic_source": ncu.get("source"),
             "kernel_ms_note": "sum of the fill launches' CUDA-event times over the engines; with several engines their kernels time-share the GPU, so the "
-                              "sum exceeds the fill's share of the wall clock and `achieved` is a lower bound (one engine: 1.47 TB/s, frac 0.22)",
+                              "sum exceeds the fill's share of the wall clock and `achieved` is a lower bound; `one_engine_alone` is the same kernel on the "
+                              "same data with no other engine running (one untimed part of a batch after the timed region)",
+            "one_engine_alone": alone and dict(alone, frac=alone["achieved"] / peak, unit="GB/s",
+                                               dpx_frac=(3.0 * alone["dp_cells"] / (alone["fill_ms"] / 1e3) / dpx_peak) if dpx_peak else None),
             "gcups_fill": dp_cells / (fill_ms / 1e3) / 1e9 if fill_ms > 0 else None,
             "gcups_fill_and_tail": dp_cells / ((fill_ms + tail_ms) / 1e3) / 1e9 if fill_ms + tail_ms > 0 else None,
             "dpx": {"thread_instr_per_cell": 3.0, "achieved_thread_instr_per_s": 3.0 * dp_cells / (fill_ms / 1e3) if fill_ms > 0 else None,
