@@ -452,7 +452,7 @@ def test_compiled_engine_on_the_regression_corpus(tmp_path):
     from oracle_lib import oracle_policy_table
     from test_policy_engine_cpp import _python_results
     lib = load_library()
-    n_run = 0
+    n_run = n_sm = 0
     for ci, case in enumerate(_cases()):
         if ci % 2 or not _usable(case):                        # every other case: keeps the CPU suite short
             continue
@@ -502,4 +502,14 @@ def test_compiled_engine_on_the_regression_corpus(tmp_path):
         if paired:
             assert np.array_equal(pairs["pair_type"], want_pairs["pair_type"]), (ci, case.get("name"))
         n_run += 1
-    assert n_run >= 55, n_run
+        # ... and through the device engine's state machine compiled for the host (csrc/xengine.cuh via bt2g_xengine_align_host), for the
+        # reporting mode it serves (-M; -k / -a go through the coroutine engine): the same records
+        if ekw.get("k") is None and not ekw.get("all_hits", False) and max(len(r) for r in R) <= 512:
+            res2, ops2, pairs2, _ = policy_align(lib, be, prm, ReadBatch.from_list(R, Q), N, entry="bt2g_xengine_align_host")
+            for f in ("found", "score", "score2", "fw", "tidx", "refoff", "nops", "trim_left", "trim_right", "mapq", "pad"):
+                assert np.array_equal(res2[f], res[f]), (ci, case.get("name"), "state machine", f, res2[f], res[f])
+            assert np.array_equal(ops2, ops), (ci, case.get("name"), "state machine")
+            if paired:
+                assert np.array_equal(pairs2["pair_type"], pairs["pair_type"]), (ci, case.get("name"), "state machine")
+            n_sm += 1
+    assert n_run >= 55 and n_sm >= 25, (n_run, n_sm)
