@@ -444,6 +444,80 @@ def test_reference_corpus_read_formats(tmp_path):
     assert n_run >= 60, (n_run, skipped, why)
 
 
+def _prepare(tmp_path, case):
+    """(R, Q, N, paired, local, sc, pe, ekw, index base) of a corpus case for the compiled engines, or None when its options are the caller's"""
+    toks, kw, sc, pe_kw, local = _options(case)
+    if any(k.startswith("_") for k in kw) or isinstance(sc.score_min_func, _BwaSwLike):
+        return None                                        # trimming / skipping is the caller's; --bwa-sw-like's threshold is not in bt2g_policy_params
+    paired = "mate1s" in case
+    if paired and ("mate1fw" in case or "mate2fw" in case) and "pol" not in pe_kw:
+        m1, m2 = case.get("mate1fw", 1), case.get("mate2fw", 0)
+        if m1 == m2:
+            pe_kw["pol"] = 1
+        elif not m1:
+            pe_kw["pol"] = 4
+    base = _index_for(tmp_path, case["ref"])
+    if not paired:
+        seqs = case["reads"]
+        quals = [(case.get("quals") or [None] * len(seqs))[k] or "I" * len(s) for k, s in enumerate(seqs)]
+        names = [(case.get("names") or [None] * len(seqs))[k] or f"r{k}" for k in range(len(seqs))]
+        R = [_codes(s) for s in seqs]
+        Q = [np.frombuffer(q.encode(), dtype=np.uint8) for q in quals]
+        N = names
+    else:
+        s1, s2 = case["mate1s"], case["mate2s"]
+        q1 = [(case.get("qual1s") or [None] * len(s1))[k] or "I" * len(s) for k, s in enumerate(s1)]
+        q2 = [(case.get("qual2s") or [None] * len(s2))[k] or "I" * len(s) for k, s in enumerate(s2)]
+        names = [(case.get("names") or [None] * len(s1))[k] or f"r{k}" for k in range(len(s1))]
+        R = [x for p in zip((_codes(s) for s in s1), (_codes(s) for s in s2)) for x in p]
+        Q = [np.frombuffer(x.encode(), dtype=np.uint8) for p in zip(q1, q2) for x in p]
+        N = [x for k in range(len(s1)) for x in (names[k] + "/1", names[k] + "/2")]
+    if any(len(r) == 0 for r in R):
+        return None
+    ekw = dict(kw)
+    ekw.setdefault("seed", 0)
+    pe = policy.PairedEndPolicy(local=local, **pe_kw)
+    return R, Q, N, paired, local, sc, pe, ekw, base
+
+
+def _params(policy_params, paired, local, sc, pe, ekw):
+    return policy_params("sensitive", local=local, paired=paired, seed=ekw.get("seed", 0), k=ekw.get("k"), all_hits=ekw.get("all_hits", False),
+                         mhits=ekw.get("mhits", 50), nofw=ekw.get("nofw", False), norc=ekw.get("norc", False),
+                         discord=ekw.get("discord", True), mixed=ekw.get("mixed", True), pe=pe, sc=sc, seed_len=ekw.get("seed_len"),
+                         seed_rounds=ekw.get("seed_rounds"), dp_fail_streak=ekw.get("dp_fail_streak"), ival=ekw.get("ival"))
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
+def test_state_machine_on_the_regression_corpus(tmp_path):
+    """EVERY usable corpus case within the device engine's reporting mode (-M) through csrc/xengine.cuh compiled for the host
+    (bt2g_xengine_align_host) and through the coroutine engine (bt2g_policy_align), both over the C oracle table: identical result
+    arrays -- odd scoring schemes, seed options, pairing options, tiny references and reads included"""
+    from bowtie2_b200.lib import ReadBatch, load_library, policy_align, policy_params
+    from oracle_lib import oracle_policy_table
+    lib = load_library()
+    n_sm = 0
+    for ci, case in enumerate(_cases()):
+        if not _usable(case):
+            continue
+        prep = _prepare(tmp_path, case)
+        if prep is None:
+            continue
+        R, Q, N, paired, local, sc, pe, ekw, base = prep
+        if ekw.get("k") is not None or ekw.get("all_hits", False) or max(len(r) for r in R) > 512:
+            continue
+        be, keep = oracle_policy_table(Oracle(base), local, 4, sc)
+        prm = _params(policy_params, paired, local, sc, pe, ekw)
+        res, ops, pairs, _ = policy_align(lib, be, prm, ReadBatch.from_list(R, Q), N)
+        res2, ops2, pairs2, _ = policy_align(lib, be, prm, ReadBatch.from_list(R, Q), N, entry="bt2g_xengine_align_host")
+        for f in ("found", "score", "score2", "fw", "tidx", "refoff", "nops", "trim_left", "trim_right", "mapq", "pad"):
+            assert np.array_equal(res2[f], res[f]), (ci, case.get("name"), f, res2[f], res[f])
+        assert np.array_equal(ops2, ops), (ci, case.get("name"))
+        if paired:
+            assert np.array_equal(pairs2["pair_type"], pairs["pair_type"]), (ci, case.get("name"))
+        n_sm += 1
+    assert n_sm >= 50, n_sm
+
+
 @pytest.mark.skipif(not have_reference(), reason="oracle/_ref not built")
 def test_compiled_engine_on_the_regression_corpus(tmp_path):
     """the same corpus through csrc/policy_engine.cpp (over the C oracle table): the primary alignment of every read / pair equals
