@@ -740,7 +740,7 @@ def run_exact(S, args):
             e2e_text = {"value": units / dt / 1e6, "unit": "Mreads/s", "units": units, "seconds": dt,
                         "fastq_bytes": sum(len(a) + (len(b) if b else 0) for a, b in items) * reps, "sam_bytes": sam_bytes[0],
                         "host_threads_parse": pthr, "host_threads_format": max(1, S.fmt_threads - pthr - E),
-                        "path": "FASTQ text (host memory) -> bt2g_fastq_parse_mt -> bt2g_xengine_align -> bt2g_sam_format -> SAM text (host memory); "
+                        "path": "FASTQ text (host memory) -> bt2g_fastq_parse_pairs_mt / bt2g_fastq_parse_mt -> bt2g_xengine_align -> bt2g_sam_format -> SAM text (host memory, reused buffers); "
                                 "stages overlapped on host threads (bowtie2_b200/stream.py)"}
         except Exception as e:                      # informational: never breaks the bench line
             e2e_text = {"error": repr(e)[:300]}

@@ -13,9 +13,74 @@
 #include <vector>
 #include <thread>
 #include <memory>
+#include <mutex>
+#include <atomic>
 #include "../../include/bt2g.h"
 
 namespace {
+
+// Scratch blocks that outlive a call: a batch's text is hundreds of megabytes, and memory fresh from the allocator costs a page
+// fault per 4 KB (and an munmap with its TLB shootdown when it is freed, felt by every other host thread of the process).  Blocks
+// go back to the pool instead; the pool keeps at most POOL_BYTES.
+struct Block {
+	std::unique_ptr<uint8_t[]> p; size_t cap = 0;
+	uint8_t *get() const { return p.get(); }
+};
+class BlockPool {
+	static constexpr size_t POOL_BYTES = 6ull << 30, POOL_BLOCKS = 96;
+	std::mutex m; std::vector<Block> idle; size_t held = 0;
+public:
+	Block take(size_t n) {
+		{
+			std::lock_guard<std::mutex> g(m);
+			size_t best = idle.size();
+			for(size_t k = 0; k < idle.size(); k++) if(idle[k].cap >= n && (best == idle.size() || idle[k].cap < idle[best].cap)) best = k;
+			if(best != idle.size() && idle[best].cap <= 4 * n + (1u << 20)) {          // (not a huge block for a small request)
+				Block b = std::move(idle[best]);
+				idle.erase(idle.begin() + (long)best);
+				held -= b.cap;
+				return b;
+			}
+		}
+		Block b; b.cap = (n + (1u << 16)) & ~(size_t)0xffff; b.p.reset(new uint8_t[b.cap]);   // uninitialised
+		return b;
+	}
+	void give(Block &&b) {
+		if(!b.p) return;
+		std::lock_guard<std::mutex> g(m);
+		if(held + b.cap > POOL_BYTES || idle.size() >= POOL_BLOCKS) return;          // freed
+		held += b.cap;
+		idle.push_back(std::move(b));
+	}
+};
+BlockPool &pool() { static BlockPool p; return p; }
+
+// text under construction in a pooled block
+struct OutBuf {
+	Block blk; size_t n = 0;
+	~OutBuf() { pool().give(std::move(blk)); }
+	char *room(size_t extra) {                                   // at least `extra` writable bytes at the returned cursor
+		if(n + extra > blk.cap) {
+			Block nb = pool().take(std::max(n + extra, blk.cap + blk.cap / 2));
+			if(n) memcpy(nb.get(), blk.get(), n);
+			pool().give(std::move(blk));
+			blk = std::move(nb);
+		}
+		return (char *)blk.get() + n;
+	}
+};
+
+inline char *putInt(char *p, long long v) {
+	unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+	if(v < 0) *p++ = '-';
+	if(u < 10) { *p++ = (char)('0' + u); return p; }
+	char b[24]; int k = 24;
+	do { b[--k] = (char)('0' + u % 10); u /= 10; } while(u);
+	memcpy(p, b + k, (size_t)(24 - k));
+	return p + (24 - k);
+}
+inline char *putStr(char *p, const char *s) { const size_t l = strlen(s); memcpy(p, s, l); return p + l; }
+#define PUT_LIT(p, lit) (memcpy((p), (lit), sizeof(lit) - 1), (p) + (sizeof(lit) - 1))
 
 struct Stacked {
 	std::vector<char> ref, rel, rd;          // reference char / relation (= X I D) / read char per alignment column
@@ -52,13 +117,25 @@ void appendInt(std::string &o, long long v) {
 } // namespace
 
 static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const bt2g_read_result *res, const uint8_t *ops,
-                       uint32_t maxOps, const bt2g_pair_result *pairs, uint64_t i0, uint64_t i1, std::string &o) {
+                       uint32_t maxOps, const bt2g_pair_result *pairs, uint64_t i0, uint64_t i1, OutBuf &dst) {
+	// (a local buffer object: the callers' OutBufs sit side by side in one vector, and a cursor updated per record there would
+	// bounce its cache line between the formatting threads)
+	OutBuf o;
+	std::swap(o.blk, dst.blk);
+	struct Back { OutBuf &o, &dst; ~Back() { std::swap(o.blk, dst.blk); dst.n = o.n; o.n = 0; } } back{o, dst};
 	static const char dna[] = "ACGTN";
 	static const char comp[] = "TGCAN";
+	// code -> character, any code above 4 reads as N
+	static const struct Chars { char fw[256], rc[256]; Chars() { for(int c = 0; c < 256; c++) { fw[c] = "ACGTN"[c > 4 ? 4 : c]; rc[c] = "TGCAN"[c > 4 ? 4 : c]; } } } chars;
 	const bool paired = pairs != nullptr;
 	const bool xeq = (opt->flags & BT2G_SAM_XEQ) != 0, noUnal = (opt->flags & BT2G_SAM_NO_UNAL) != 0;
-	o.reserve((size_t)(i1 - i0) * 400);
-	std::string cigar, mdz, line, held;
+	o.n = 0;
+	if(i1 > i0) o.room((size_t)(reads->off[i1] - reads->off[i0]) * 2 + (size_t)(i1 - i0) * 160);      // SEQ + QUAL + the usual fields
+	size_t maxRef = 1;                                                 // longest RNAME ("*" when there is none)
+	for(uint64_t t = 0; opt->ref_names && t < opt->n_refs; t++) if(opt->ref_names[t]) { const size_t l = strlen(opt->ref_names[t]); if(l > maxRef) maxRef = l; }
+	const size_t rgLen = (opt->rg_optflag && opt->rg_optflag[0]) ? strlen(opt->rg_optflag) + 1 : 0;
+	std::string cigar, mdz;
+	std::vector<char> held; size_t heldN = 0;
 	Stacked st;                                                        // buffers reused from record to record
 	for(uint64_t i = i0; i < i1; i++) {
 		const bt2g_read_result &r = res[i];
@@ -188,36 +265,54 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 			for(size_t k = 0; k < ln; k++) refExtent += st.rel[k] != 'I';
 			}
 		}
-		// ---- the record
-		line.clear();
-		if(opt->read_names && opt->read_names[i]) {
+		// ---- the record, written in place: one capacity check, then plain stores
+		if(noUnal && !aligned) continue;                              // --no-unal (AlnSinkSam::appendMate, aln_sink.cpp:1905)
+		if(r.found & 0x200) continue;                                 // present only as its mate's mate (paired -k / -a entries)
+		const char *nm = (opt->read_names && opt->read_names[i]) ? opt->read_names[i] : nullptr;
+		size_t nml = 0;
+		if(nm) {
 			// QNAME = the name up to the first whitespace (sam.h printReadName), without a /1 or /2 mate suffix
-			const char *nm = opt->read_names[i];
-			size_t l = 0;
-			while(nm[l] && nm[l] != ' ' && nm[l] != '\t') l++;
-			if(paired && l >= 2 && nm[l - 2] == '/' && (nm[l - 1] == '1' || nm[l - 1] == '2')) l -= 2;
-			line.append(nm, l);
+			while(nm[nml] && nm[nml] != ' ' && nm[nml] != '\t') nml++;
+			if(paired && nml >= 2 && nm[nml - 2] == '/' && (nm[nml - 1] == '1' || nm[nml - 1] == '2')) nml -= 2;
 		}
-		else { line += 'r'; appendInt(line, (long long)(paired ? (i >> 1) : i)); }
-		line += '\t'; appendInt(line, flag); line += '\t';
+		const size_t bound = nml + 2 * maxRef + cigar.size() + mdz.size() + 2 * (size_t)len + rgLen + 512;
+		// a pair with only mate 2 aligned is printed aligned mate first (AlnSinkWrap::finishRead reports the
+		// unpaired alignment of mate 2, then the unaligned mate 1, aln_sink.cpp:930-1010): mate 1's record waits
+		const bool hold = paired && (i & 1) == 0 && !aligned && mateAligned;
+		if(hold && held.size() < bound) held.resize(bound);
+		char *const rec = hold ? held.data() : o.room(bound + heldN);
+		char *p = rec;
+		if(nm) { memcpy(p, nm, nml); p += nml; }
+		else { *p++ = 'r'; p = putInt(p, (long long)(paired ? (i >> 1) : i)); }
+		*p++ = '\t'; p = putInt(p, flag); *p++ = '\t';
 		auto refName = [&](uint64_t t) -> const char * { return (opt->ref_names && t < opt->n_refs && opt->ref_names[t]) ? opt->ref_names[t] : "*"; };
-		if(aligned) { line += refName(r.tidx); line += '\t'; appendInt(line, r.refoff + 1); line += '\t'; appendInt(line, r.mapq); line += '\t'; line += cigar; }
-		else if(paired && mateAligned) { line += refName(m->tidx); line += '\t'; appendInt(line, m->refoff + 1); line += "\t0\t*"; }   // unaligned mate takes its mate's coordinates
-		else line += "*\t0\t0\t*";
-		line += '\t';
+		if(aligned) {
+			p = putStr(p, refName(r.tidx)); *p++ = '\t'; p = putInt(p, r.refoff + 1); *p++ = '\t'; p = putInt(p, r.mapq); *p++ = '\t';
+			memcpy(p, cigar.data(), cigar.size()); p += cigar.size();
+		}
+		else if(paired && mateAligned) { p = putStr(p, refName(m->tidx)); *p++ = '\t'; p = putInt(p, m->refoff + 1); p = PUT_LIT(p, "\t0\t*"); }   // unaligned mate takes its mate's coordinates
+		else p = PUT_LIT(p, "*\t0\t0\t*");
+		*p++ = '\t';
 		// RNEXT PNEXT TLEN
 		if(paired && mateAligned) {
-			if(aligned && m->tidx == r.tidx) line += '='; else if(!aligned) line += '='; else line += refName(m->tidx);
-			line += '\t'; appendInt(line, m->refoff + 1); line += '\t';
+			if(aligned && m->tidx == r.tidx) *p++ = '='; else if(!aligned) *p++ = '='; else p = putStr(p, refName(m->tidx));
+			*p++ = '\t'; p = putInt(p, m->refoff + 1); *p++ = '\t';
 			long long tlen = 0;
 			if(aligned && asPair && m->tidx == r.tidx) {
 				// AlnRes::setFragmentLength (aligner_result.h:1311-1343); extents include soft-trimmed ends
 				long long st0 = r.refoff - r.trim_left, en0 = r.refoff + refExtent - 1 + r.trim_right;
-				// the mate's extent needs its own ops
+				// the mate's extent needs its own ops: every op but a reference gap (type 2 = bit 1 set, bit 0 clear) consumes a reference character
 				long long mExt = 0;
 				const int mlen = (int)(reads->off[(i ^ 1ull) + 1] - reads->off[i ^ 1ull]);
 				if((m->found & 0xff) == 2) mExt = mlen;
-				else if(ops) { const uint8_t *mo = ops + (i ^ 1ull) * (uint64_t)maxOps; for(int k = 0; k < m->nops && k < (int)maxOps; k++) mExt += (mo[k] & 3) != BT2G_OP_REFGAP; }
+				else if(ops) {
+					const uint8_t *mo = ops + (i ^ 1ull) * (uint64_t)maxOps;
+					const int mn = m->nops < (int)maxOps ? m->nops : (int)maxOps;
+					int k = 0, gaps = 0;
+					for(; k + 8 <= mn; k += 8) { uint64_t w; memcpy(&w, mo + k, 8); gaps += __builtin_popcountll((w >> 1) & ~w & 0x0101010101010101ull); }
+					for(; k < mn; k++) gaps += (mo[k] & 3) == BT2G_OP_REFGAP;
+					mExt = (mn > 0 ? mn : 0) - gaps;
+				}
 				long long st1 = m->refoff - m->trim_left, en1 = m->refoff + mExt - 1 + m->trim_right;
 				bool up;
 				const bool mfw = m->fw != 0, mate1 = (i & 1) == 0;
@@ -226,42 +321,47 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 				tlen = 1 + (en0 > en1 ? en0 : en1) - (st0 < st1 ? st0 : st1);
 				if(!up) tlen = -tlen;
 			}
-			appendInt(line, tlen);
-		} else if(paired && aligned) { line += "=\t"; appendInt(line, r.refoff + 1); line += "\t0"; }       // mate unaligned: points at this mate
-		else line += "*\t0\t0";
-		line += '\t';
+			p = putInt(p, tlen);
+		} else if(paired && aligned) { p = PUT_LIT(p, "=\t"); p = putInt(p, r.refoff + 1); p = PUT_LIT(p, "\t0"); }       // mate unaligned: points at this mate
+		else p = PUT_LIT(p, "*\t0\t0");
+		*p++ = '\t';
 		// SEQ QUAL (reverse-complemented / reversed for the reverse strand)
 		const bool rev = aligned && !fw;
-		if(len == 0) line += "*\t*";                               // an empty (fully trimmed) read
+		if(len == 0) p = PUT_LIT(p, "*\t*");                         // an empty (fully trimmed) read
 		else {
-			const size_t at = line.size();
-			line.resize(at + (size_t)len + 1 + (qual ? (size_t)len : 1));
-			char *d = &line[at];
-			if(rev) for(int k = 0; k < len; k++) { const int c = seq[len - 1 - k]; d[k] = comp[c > 4 ? 4 : c]; }
-			else    for(int k = 0; k < len; k++) { const int c = seq[k]; d[k] = dna[c > 4 ? 4 : c]; }
+			char *d = p;
+			if(rev) for(int k = 0; k < len; k++) d[k] = chars.rc[seq[len - 1 - k]];
+			else    for(int k = 0; k < len; k++) d[k] = chars.fw[seq[k]];
 			d[len] = '\t';
 			char *e = d + len + 1;
-			if(!qual) e[0] = '*';
-			else if(rev) for(int k = 0; k < len; k++) e[k] = (char)qual[len - 1 - k];
-			else memcpy(e, qual, (size_t)len);
+			if(!qual) { e[0] = '*'; p = e + 1; }
+			else {
+				if(rev) {
+					int k = 0;
+					for(; k + 8 <= len; k += 8) { uint64_t w; memcpy(&w, qual + len - 8 - k, 8); w = __builtin_bswap64(w); memcpy(e + k, &w, 8); }
+					for(; k < len; k++) e[k] = (char)qual[len - 1 - k];
+				}
+				else memcpy(e, qual, (size_t)len);
+				p = e + len;
+			}
 		}
 		// optional fields
 		if(aligned) {
-			line += "\tAS:i:"; appendInt(line, r.score);
+			p = PUT_LIT(p, "\tAS:i:"); p = putInt(p, r.score);
 			// XS:i of a paired read is the best unchosen PAIRED score of this mate (sam.cpp:146-158): never set for
 			// mates reported as unpaired alignments
-			if(r.score2 != INT32_MIN && (!paired || concordant)) { line += "\tXS:i:"; appendInt(line, r.score2); }
-			line += "\tXN:i:"; appendInt(line, r.pad);
-			line += "\tXM:i:"; appendInt(line, nmm);
-			line += "\tXO:i:"; appendInt(line, ngo);
-			line += "\tXG:i:"; appendInt(line, ngx);
-			line += "\tNM:i:"; appendInt(line, nedits);
-			line += "\tMD:Z:"; line += mdz;
+			if(r.score2 != INT32_MIN && (!paired || concordant)) { p = PUT_LIT(p, "\tXS:i:"); p = putInt(p, r.score2); }
+			p = PUT_LIT(p, "\tXN:i:"); p = putInt(p, r.pad);
+			p = PUT_LIT(p, "\tXM:i:"); p = putInt(p, nmm);
+			p = PUT_LIT(p, "\tXO:i:"); p = putInt(p, ngo);
+			p = PUT_LIT(p, "\tXG:i:"); p = putInt(p, ngx);
+			p = PUT_LIT(p, "\tNM:i:"); p = putInt(p, nedits);
+			p = PUT_LIT(p, "\tMD:Z:"); memcpy(p, mdz.data(), mdz.size()); p += mdz.size();
 			// YS:i only for mates reported as a pair (summ.paired(), sam.cpp:250)
-			if(paired && mateAligned && asPair) { line += "\tYS:i:"; appendInt(line, m->score); }
+			if(paired && mateAligned && asPair) { p = PUT_LIT(p, "\tYS:i:"); p = putInt(p, m->score); }
 		}
-		line += "\tYT:Z:";
-		line += !paired ? "UU" : (concordant ? "CP" : (discordant ? "DP" : "UP"));
+		p = PUT_LIT(p, "\tYT:Z:");
+		{ const char *yt = !paired ? "UU" : (concordant ? "CP" : (discordant ? "DP" : "UP")); p[0] = yt[0]; p[1] = yt[1]; p += 2; }
 		if(!aligned) {
 			// YF:Z: why the read was filtered out (sam.cpp:331-345; filters at bt2_search.cpp:3405-3431)
 			int ns = 0;
@@ -269,19 +369,15 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 			const double nc = (opt->nceil_const == 0.0 && opt->nceil_linear == 0.0) ? 0.0 : opt->nceil_const;
 			const double nl = (opt->nceil_const == 0.0 && opt->nceil_linear == 0.0) ? (double)0.15f : opt->nceil_linear;
 			int nceil = (int)(nc + nl * (double)len); if(nceil > len) nceil = len;
-			if(len < 2) line += "\tYF:Z:LN";
-			else if(ns > nceil) line += "\tYF:Z:NS";
-			else if(len <= opt->sc_filter_maxlen) line += "\tYF:Z:SC";      // perfect score below the minimum (scoreFilter)
+			if(len < 2) p = PUT_LIT(p, "\tYF:Z:LN");
+			else if(ns > nceil) p = PUT_LIT(p, "\tYF:Z:NS");
+			else if(len <= opt->sc_filter_maxlen) p = PUT_LIT(p, "\tYF:Z:SC");      // perfect score below the minimum (scoreFilter)
 		}
-		if(opt->rg_optflag && opt->rg_optflag[0]) { line += '\t'; line += opt->rg_optflag; }     // RG:Z:<id> (sam.cpp:384-387)
-		line += '\n';
-		if(noUnal && !aligned) continue;                              // --no-unal (AlnSinkSam::appendMate, aln_sink.cpp:1905)
-		if(r.found & 0x200) continue;                                 // present only as its mate's mate (paired -k / -a entries)
-		// a pair with only mate 2 aligned is printed aligned mate first (AlnSinkWrap::finishRead reports the
-		// unpaired alignment of mate 2, then the unaligned mate 1, aln_sink.cpp:930-1010)
-		if(paired && (i & 1) == 0 && !aligned && mateAligned) { held = line; continue; }
-		o += line;
-		if(!held.empty()) { o += held; held.clear(); }
+		if(rgLen) { *p++ = '\t'; memcpy(p, opt->rg_optflag, rgLen - 1); p += rgLen - 1; }     // RG:Z:<id> (sam.cpp:384-387)
+		*p++ = '\n';
+		if(hold) { heldN = (size_t)(p - rec); continue; }
+		if(heldN) { memcpy(p, held.data(), heldN); p += heldN; heldN = 0; }
+		o.n += (size_t)(p - rec);
 	}
 	return 0;
 }
@@ -296,7 +392,7 @@ extern "C" int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads
 	int T = opt->threads > 0 ? opt->threads : 1;
 	const uint64_t units = paired ? n / 2 : n;
 	if((uint64_t)T > units) T = units ? (int)units : 1;
-	std::vector<std::string> parts((size_t)T);
+	std::vector<OutBuf> parts((size_t)T);
 	std::vector<int> rcs((size_t)T, 0);
 	auto work = [&](int t) {
 		const uint64_t u0 = units * (uint64_t)t / T, u1 = units * (uint64_t)(t + 1) / T;
@@ -309,15 +405,15 @@ extern "C" int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads
 		for(auto &x : th) x.join();
 	}
 	uint64_t total = 0;
-	for(int t = 0; t < T; t++) { if(rcs[t]) return rcs[t]; total += parts[t].size(); }
+	for(int t = 0; t < T; t++) { if(rcs[t]) return rcs[t]; total += parts[t].n; }
 	*written = total;
 	if(!out || total > cap) return -3;                             // buffer too small: *written holds the size needed
 	std::vector<uint64_t> at((size_t)T + 1, 0);
-	for(int t = 0; t < T; t++) at[t + 1] = at[t] + parts[t].size();
-	if(T == 1) memcpy(out, parts[0].data(), parts[0].size());
+	for(int t = 0; t < T; t++) at[t + 1] = at[t] + parts[t].n;
+	if(T == 1) { if(parts[0].n) memcpy(out, parts[0].blk.get(), parts[0].n); }
 	else {
 		std::vector<std::thread> th;
-		for(int t = 0; t < T; t++) th.emplace_back([&, t]() { memcpy(out + at[t], parts[t].data(), parts[t].size()); });
+		for(int t = 0; t < T; t++) th.emplace_back([&, t]() { if(parts[t].n) memcpy(out + at[t], parts[t].blk.get(), parts[t].n); });
 		for(auto &x : th) x.join();
 	}
 	return 0;
@@ -364,7 +460,7 @@ static int fastqParseCore(const char *text, uint64_t len, uint64_t maxReads, uin
 							uint64_t l = (uint64_t)(nl1 - p - 1);
 							if(l >= nameStride) l = nameStride - 1;
 							memcpy(names + n * (uint64_t)nameStride, p + 1, l);
-							names[n * (uint64_t)nameStride + l] = 0;
+							memset(names + n * (uint64_t)nameStride + l, 0, nameStride - l);   // the whole row is defined
 						}
 						nb += L; n++; off[n] = nb;
 						cur = (uint64_t)(nl4 + 1 - text);
@@ -414,7 +510,7 @@ static int fastqParseCore(const char *text, uint64_t len, uint64_t maxReads, uin
 			uint64_t l = nameEnd - nameBeg;
 			if(l >= nameStride) l = nameStride - 1;
 			memcpy(names + n * (uint64_t)nameStride, text + nameBeg, l);
-			names[n * (uint64_t)nameStride + l] = 0;
+			memset(names + n * (uint64_t)nameStride + l, 0, nameStride - l);
 		}
 		n++;
 		off[n] = nb;
@@ -431,20 +527,21 @@ extern "C" int bt2g_fastq_parse(const char *text, uint64_t len, uint64_t maxRead
 }
 
 // Multi-threaded variant: the text is cut at record boundaries (a line starting with '@' whose second-next line starts with
-// '+'), the pieces are parsed concurrently into private buffers and concatenated in order.  Same outputs and error codes as
-// bt2g_fastq_parse for 4-line FASTQ (multi-line sequences fall back to the serial parser).
-extern "C" int bt2g_fastq_parse_mt(const char *text, uint64_t len, uint64_t maxReads, uint64_t maxBases, uint8_t *seq, uint8_t *qual,
-                                   uint64_t *off, char *names, uint32_t nameStride, uint64_t *nReads, uint64_t *consumed, int threads) {
-	if(threads <= 1 || len < (1u << 20))
-		return fastqParseCore(text, len, maxReads, maxBases, seq, qual, off, names, nameStride, nReads, consumed, nullptr);
-	if(!text || !seq || !qual || !off || !nReads || !consumed) return -1;
-	// ---- cut points
-	auto lineEnd = [&](uint64_t p) { while(p < len && text[p] != '\n') p++; return p < len ? p + 1 : len; };
-	std::vector<uint64_t> cuts{0};
-	for(int k = 1; k < threads; k++) {
-		uint64_t p = len / (uint64_t)threads * (uint64_t)k;
+// '+'), the pieces are parsed concurrently into pooled scratch and copied to their places concurrently.  Same outputs and error
+// codes as bt2g_fastq_parse for 4-line FASTQ (multi-line sequences fall back to the serial parser).
+namespace {
+struct Piece {
+	Block blk; uint8_t *seq = nullptr, *qual = nullptr; uint64_t *off = nullptr, *starts = nullptr; char *names = nullptr;
+	uint64_t t0 = 0, tl = 0, n = 0, used = 0, base = 0, take = 0; int rc = 0;
+};
+// cut points of a FASTQ text for `pieces` concurrent parsers (a line starting with '@' whose second-next line starts with '+')
+void cutFastq(const char *text, uint64_t len, int pieces, std::vector<uint64_t> &cuts) {
+	auto lineEnd = [&](uint64_t p) { const char *q = (const char *)memchr(text + p, '\n', (size_t)(len - p)); return q ? (uint64_t)(q - text) + 1 : len; };
+	cuts.assign(1, 0);
+	if(len >= (1u << 20)) for(int k = 1; k < pieces; k++) {
+		uint64_t p = len / (uint64_t)pieces * (uint64_t)k;
 		if(p <= cuts.back()) continue;
-		p = lineEnd(p);                                            // first full line after the target
+		p = lineEnd(p);
 		bool found = false;
 		for(int tries = 0; tries < 8 && p < len; tries++) {
 			if(text[p] == '@') {
@@ -456,44 +553,166 @@ extern "C" int bt2g_fastq_parse_mt(const char *text, uint64_t len, uint64_t maxR
 		if(found && p > cuts.back()) cuts.push_back(p);
 	}
 	cuts.push_back(len);
+}
+void parsePiece(Piece &q, const char *text, uint32_t nameStride, bool wantNames) {
+	uint64_t nl = 0;
+	for(const char *p = text + q.t0, *e = p + q.tl; (p = (const char *)memchr(p, '\n', (size_t)(e - p))) != nullptr; p++) nl++;
+	const uint64_t cap = nl / 4 + 2;                               // >= records: each has at least four lines
+	const uint64_t data = (q.tl + 15) & ~15ull, idx = (cap + 1) * 8;
+	q.blk = pool().take((size_t)(2 * data + 2 * idx + (wantNames ? cap * (uint64_t)nameStride : 0) + 64));
+	q.seq = q.blk.get(); q.qual = q.seq + data;
+	q.off = (uint64_t *)(q.qual + data); q.starts = q.off + cap + 1;
+	q.names = wantNames ? (char *)(q.starts + cap + 1) : nullptr;
+	q.rc = fastqParseCore(text + q.t0, q.tl, cap, q.tl, q.seq, q.qual, q.off, q.names, nameStride, &q.n, &q.used, q.starts);
+}
+} // namespace
+
+extern "C" int bt2g_fastq_parse_mt(const char *text, uint64_t len, uint64_t maxReads, uint64_t maxBases, uint8_t *seq, uint8_t *qual,
+                                   uint64_t *off, char *names, uint32_t nameStride, uint64_t *nReads, uint64_t *consumed, int threads) {
+	if(threads <= 1 || len < (1u << 20))
+		return fastqParseCore(text, len, maxReads, maxBases, seq, qual, off, names, nameStride, nReads, consumed, nullptr);
+	if(!text || !seq || !qual || !off || !nReads || !consumed) return -1;
+	std::vector<uint64_t> cuts;
+	cutFastq(text, len, threads, cuts);
 	const size_t nc = cuts.size() - 1;
 	if(nc < 2) return fastqParseCore(text, len, maxReads, maxBases, seq, qual, off, names, nameStride, nReads, consumed, nullptr);
-	// private buffers are left uninitialised (new[]): zero-filling them would cost more than the parse
-	struct Piece { std::unique_ptr<uint8_t[]> seq, qual; std::unique_ptr<uint64_t[]> off, starts; std::unique_ptr<char[]> names;
-	               uint64_t n = 0, used = 0; int rc = 0; };
+	const bool wantNames = names && nameStride;
 	std::vector<Piece> pc(nc);
-	std::vector<std::thread> th;
-	for(size_t k = 0; k < nc; k++) th.emplace_back([&, k]() {
-		Piece &q = pc[k];
-		const uint64_t l = cuts[k + 1] - cuts[k];
-		uint64_t nl = 0;
-		for(const char *p = text + cuts[k], *e = p + l; (p = (const char *)memchr(p, '\n', (size_t)(e - p))) != nullptr; p++) nl++;
-		const uint64_t cap = nl / 4 + 2;                           // >= records: each has at least four lines
-		q.seq.reset(new uint8_t[l]); q.qual.reset(new uint8_t[l]); q.off.reset(new uint64_t[cap + 1]); q.starts.reset(new uint64_t[cap + 1]);
-		if(names && nameStride) q.names.reset(new char[cap * (uint64_t)nameStride]());      // zeroed rows (copied whole)
-		q.rc = fastqParseCore(text + cuts[k], l, cap, l, q.seq.get(), q.qual.get(), q.off.get(), q.names.get(),
-		                      nameStride, &q.n, &q.used, q.starts.get());
-	});
-	for(auto &t : th) t.join();
-	// ---- concatenate while the limits allow; a piece that did not end on its boundary (a truncated last record) ends the parse
+	struct GiveBack { std::vector<Piece> &pc; ~GiveBack() { for(auto &q : pc) pool().give(std::move(q.blk)); } } giveBack{pc};
+	{
+		std::vector<std::thread> th;
+		for(size_t k = 0; k < nc; k++) { pc[k].t0 = cuts[k]; pc[k].tl = cuts[k + 1] - cuts[k]; th.emplace_back([&, k]() { parsePiece(pc[k], text, nameStride, wantNames); }); }
+		for(auto &t : th) t.join();
+	}
+	// ---- what each piece contributes while the limits allow; a piece that did not end on its boundary (a truncated last record) ends the parse
 	uint64_t n = 0, nb = 0, cur = 0;
+	std::vector<uint64_t> nb0(nc, 0);
 	off[0] = 0;
+	*nReads = 0; *consumed = 0;
 	for(size_t k = 0; k < nc; k++) {
 		Piece &q = pc[k];
-		if(q.rc) { if(n == 0 || true) { *nReads = 0; *consumed = 0; return q.rc; } }
+		if(q.rc) return q.rc;
 		uint64_t take = q.n;
 		if(n + take > maxReads) take = maxReads - n;
 		while(take > 0 && nb + q.off[take] > maxBases) take--;
-		const uint64_t bases = q.off[take];
-		memcpy(seq + nb, q.seq.get(), bases);
-		memcpy(qual + nb, q.qual.get(), bases);
-		for(uint64_t i = 1; i <= take; i++) off[n + i] = nb + q.off[i];
-		if(names && nameStride && take) memcpy(names + n * (uint64_t)nameStride, q.names.get(), take * (uint64_t)nameStride);
-		n += take; nb += bases;
-		cur = cuts[k] + (take == q.n ? q.used : q.starts[take]);
-		if(take < q.n || cuts[k] + q.used < cuts[k + 1]) break;   // limit reached, or a truncated record at the end of the piece
+		q.base = n; q.take = take; nb0[k] = nb;
+		n += take; nb += q.off[take];
+		cur = q.t0 + (take == q.n ? q.used : q.starts[take]);
+		if(take < q.n || q.used < q.tl) break;                     // limit reached, or a truncated record at the end of the piece
+	}
+	{
+		std::vector<std::thread> th;
+		for(size_t k = 0; k < nc; k++) if(pc[k].take) th.emplace_back([&, k]() {
+			const Piece &q = pc[k];
+			const uint64_t bases = q.off[q.take];
+			memcpy(seq + nb0[k], q.seq, (size_t)bases);
+			memcpy(qual + nb0[k], q.qual, (size_t)bases);
+			for(uint64_t i = 1; i <= q.take; i++) off[q.base + i] = nb0[k] + q.off[i];
+			if(wantNames) for(uint64_t j = 0; j < q.take; j++) {
+				const char *src = q.names + j * (uint64_t)nameStride;
+				char *dst = names + (q.base + j) * (uint64_t)nameStride;
+				const size_t nl = strnlen(src, nameStride - 1);
+				memcpy(dst, src, nl);
+				memset(dst + nl, 0, nameStride - nl);
+			}
+		});
+		for(auto &t : th) t.join();
 	}
 	*nReads = n; *consumed = cur;
+	return 0;
+}
+
+// ---- two mate files -> one interleaved batch ------------------------------------------------------------------------
+// DualPatternComposer::nextBatch (pat.cpp:222-300) hands the aligner mate 1 and mate 2 of pair i together; here pair i
+// becomes reads 2i and 2i + 1 of the batch, the layout every paired entry point of this library takes.  Both texts are cut at
+// record boundaries and their pieces parsed concurrently (fastqParseCore, into pooled scratch); the records then go straight to
+// their interleaved places, one copy task per piece.
+extern "C" int bt2g_fastq_parse_pairs_mt(const char *text1, uint64_t len1, const char *text2, uint64_t len2, uint64_t maxPairs, uint64_t maxBases,
+                                         uint8_t *seq, uint8_t *qual, uint64_t *off, char *names, uint32_t nameStride, uint64_t *nPairs,
+                                         uint64_t *consumed1, uint64_t *consumed2, int threads) {
+	if(!text1 || !text2 || !seq || !qual || !off || !nPairs || !consumed1 || !consumed2) return -1;
+	const int T = threads > 1 ? threads : 1;
+	const bool wantNames = names && nameStride;
+	const char *text[2] = {text1, text2};
+	const uint64_t len[2] = {len1, len2};
+	std::vector<uint64_t> cuts[2];
+	std::vector<Piece> pc[2];
+	std::vector<std::pair<int, size_t>> tasks;
+	for(int f = 0; f < 2; f++) {
+		cutFastq(text[f], len[f], T > 1 ? (T + 1) / 2 : 1, cuts[f]);
+		pc[f].resize(cuts[f].size() - 1);
+		for(size_t k = 0; k < pc[f].size(); k++) { pc[f][k].t0 = cuts[f][k]; pc[f][k].tl = cuts[f][k + 1] - cuts[f][k]; tasks.emplace_back(f, k); }
+	}
+	auto runTasks = [&](auto &&fn) {
+		std::atomic<size_t> next{0};
+		auto loop = [&]() { for(size_t t; (t = next.fetch_add(1)) < tasks.size();) fn(tasks[t].first, tasks[t].second); };
+		const int nt = (int)std::min<size_t>((size_t)T, tasks.size());
+		if(nt <= 1) { loop(); return; }
+		std::vector<std::thread> th;
+		for(int t = 1; t < nt; t++) th.emplace_back(loop);
+		loop();
+		for(auto &x : th) x.join();
+	};
+	struct GiveBack { std::vector<Piece> *pc; ~GiveBack() { for(int f = 0; f < 2; f++) for(auto &q : pc[f]) pool().give(std::move(q.blk)); } } giveBack{pc};
+	runTasks([&](int f, size_t k) { parsePiece(pc[f][k], text[f], nameStride, wantNames); });
+	// ---- records usable from each file, in order: a piece that did not end on its boundary (a truncated last record) ends them
+	uint64_t avail[2] = {0, 0}; size_t usedPieces[2] = {0, 0};
+	*nPairs = 0; *consumed1 = 0; *consumed2 = 0;
+	off[0] = 0;
+	for(int f = 0; f < 2; f++)
+		for(size_t k = 0; k < pc[f].size(); k++) {
+			Piece &q = pc[f][k];
+			if(q.rc) return q.rc;
+			q.base = avail[f]; avail[f] += q.n; usedPieces[f] = k + 1;
+			if(q.used < q.tl) break;
+		}
+	uint64_t n = std::min(std::min(avail[0], avail[1]), maxPairs);
+	// ---- offsets of the interleaved batch (serial: two additions per pair); the base limit may shorten it
+	{
+		size_t k[2] = {0, 0}; uint64_t nb = 0, i = 0;
+		for(; i < n; i++) {
+			uint64_t l[2];
+			for(int f = 0; f < 2; f++) {
+				while(i >= pc[f][k[f]].base + pc[f][k[f]].n) k[f]++;
+				const Piece &q = pc[f][k[f]];
+				const uint64_t j = i - q.base;
+				l[f] = q.off[j + 1] - q.off[j];
+			}
+			if(nb + l[0] + l[1] > maxBases) break;
+			off[2 * i + 1] = nb + l[0]; nb += l[0] + l[1]; off[2 * i + 2] = nb;
+		}
+		n = i;
+	}
+	for(int f = 0; f < 2; f++)
+		for(size_t k = 0; k < usedPieces[f]; k++) { Piece &q = pc[f][k]; q.take = n > q.base ? std::min(q.n, n - q.base) : 0; }
+	// ---- every piece's records to their places
+	runTasks([&](int f, size_t k) {
+		const Piece &q = pc[f][k];
+		for(uint64_t j = 0; j < q.take; j++) {
+			const uint64_t r = 2 * (q.base + j) + (uint64_t)f, l = q.off[j + 1] - q.off[j];
+			memcpy(seq + off[r], q.seq + q.off[j], (size_t)l);
+			memcpy(qual + off[r], q.qual + q.off[j], (size_t)l);
+			if(wantNames) {
+				const char *src = q.names + j * (uint64_t)nameStride;
+				char *dst = names + r * (uint64_t)nameStride;
+				const size_t nl = strnlen(src, nameStride - 1);
+				memcpy(dst, src, nl);
+				memset(dst + nl, 0, nameStride - nl);                // whole row defined: the scratch it came from is not
+			}
+		}
+	});
+	// ---- first unparsed byte of each text
+	uint64_t *consumed[2] = {consumed1, consumed2};
+	for(int f = 0; f < 2; f++) {
+		uint64_t c = 0;
+		for(size_t k = 0; k < usedPieces[f]; k++) {
+			const Piece &q = pc[f][k];
+			if(q.take == q.n) c = q.t0 + q.used;
+			else { c = q.t0 + q.starts[q.take]; break; }
+		}
+		*consumed[f] = c;
+	}
+	*nPairs = n;
 	return 0;
 }
 

@@ -713,9 +713,27 @@ def sc_filter_maxlen(local: bool) -> int:
     return n
 
 
+class HostBuffers:
+    """named host arrays kept from call to call.  A batch's buffers are hundreds of megabytes; memory fresh from the allocator costs a
+    page fault per 4 KB and an munmap when it is dropped, so the streaming path (stream.py) reuses one set per batch in flight."""
+
+    def __init__(self):
+        self._a = {}
+
+    def get(self, key, shape, dtype):
+        shape = tuple(int(x) for x in (shape if isinstance(shape, tuple) else (shape,)))
+        n = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        b = self._a.get(key)
+        if b is None or b.nbytes < n:
+            b = self._a[key] = np.empty(n + (n >> 3) + 64, dtype=np.uint8)
+        return b[:n].view(dtype).reshape(shape)
+
+
 def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_names=None, pairs=None, threads: int = 1,
-               local: bool = False, xeq: bool = False, no_unal: bool = False, rg_id: str = None, as_bytes: bool = False):
-    """SAM text for pipeline results (one record per read).  `lib` is the loaded libbt2g (load_library())."""
+               local: bool = False, xeq: bool = False, no_unal: bool = False, rg_id: str = None, as_bytes=False, out: HostBuffers = None):
+    """SAM text for pipeline results (one record per read).  `lib` is the loaded libbt2g (load_library()).
+    as_bytes: False -> str, True -> bytes, "view" -> a memoryview of the output buffer (no copy; with `out` given the buffer is reused
+    by the next call, so the view must be consumed before it)."""
     lib.bt2g_sam_format.argtypes = [C.POINTER(_SamOpts), C.POINTER(_Reads), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     rn = (C.c_char_p * len(ref_names))(*[x.encode() for x in ref_names])
@@ -737,15 +755,18 @@ def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_name
     # one formatting pass in the common case: a buffer sized from the batch (SEQ + QUAL + ~220 bytes of fields per record);
     # the call reports the size it needs (-3) when that estimate is short
     cap = int(reads.off[-1]) * 2 + reads.n * 260 + 4096 if reads.n else 4096
-    out = np.empty(cap, dtype=np.uint8)
-    rc = lib.bt2g_sam_format(C.byref(opt), C.byref(st), _ptr(res), _ptr(ops), max_ops, _ptr(pairs), _ptr(out), cap, C.byref(need))
+    alloc = (lambda c: out.get("sam", (c,), np.uint8)) if out is not None else (lambda c: np.empty(c, dtype=np.uint8))
+    buf = alloc(cap)
+    rc = lib.bt2g_sam_format(C.byref(opt), C.byref(st), _ptr(res), _ptr(ops), max_ops, _ptr(pairs), _ptr(buf), cap, C.byref(need))
     if rc == -3:
         cap = int(need.value)
-        out = np.empty(cap, dtype=np.uint8)
-        rc = lib.bt2g_sam_format(C.byref(opt), C.byref(st), _ptr(res), _ptr(ops), max_ops, _ptr(pairs), _ptr(out), cap, C.byref(need))
+        buf = alloc(cap)
+        rc = lib.bt2g_sam_format(C.byref(opt), C.byref(st), _ptr(res), _ptr(ops), max_ops, _ptr(pairs), _ptr(buf), cap, C.byref(need))
     if rc:
         raise RuntimeError(f"bt2g_sam_format failed ({rc})")
-    data = out[:int(need.value)]
+    data = buf[:int(need.value)]
+    if as_bytes == "view":
+        return memoryview(data)
     return data.tobytes() if as_bytes else data.tobytes().decode()
 
 
@@ -782,30 +803,68 @@ class NameTable:
         return (self.rows.ctypes.data + stride * np.arange(n, dtype=np.uint64)).astype(np.uint64)
 
 
-def fastq_parse(lib, text: bytes, max_reads: int = 1 << 30, name_stride: int = 64, threads: int = 1):
-    """include/bt2g.h: bt2g_fastq_parse[_mt] -> (ReadBatch, names (NameTable), bytes consumed)."""
+def fastq_parse(lib, text: bytes, max_reads: int = 1 << 30, name_stride: int = 64, threads: int = 1, out: HostBuffers = None):
+    """include/bt2g.h: bt2g_fastq_parse[_mt] -> (ReadBatch, names (NameTable), bytes consumed).  With `out` the arrays live in
+    reused buffers: they are valid until the next call with the same `out`."""
     args = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
             C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.bt2g_fastq_parse.argtypes = args
     lib.bt2g_fastq_parse_mt.argtypes = args + [C.c_int]
     cap_reads = min(max_reads, text.count(b"\n") // 4 + 1)
-    seq = np.empty(len(text), dtype=np.uint8)
-    qual = np.empty(len(text), dtype=np.uint8)
-    off = np.empty(cap_reads + 1, dtype=np.uint64)
+    cap_bases = len(text)                                   # (never reached: the untouched tail costs no memory)
+    alloc = out.get if out is not None else (lambda key, shape, dtype: np.empty(shape, dtype=dtype))
+    seq = alloc("seq", (cap_bases,), np.uint8)
+    qual = alloc("qual", (cap_bases,), np.uint8)
+    off = alloc("off", (cap_reads + 1,), np.uint64)
     off[0] = 0
-    names = np.zeros((cap_reads, name_stride), dtype=np.uint8)
+    names = alloc("names", (cap_reads, name_stride), np.uint8)   # (the parser defines every byte of the rows it fills)
     n, used = C.c_uint64(0), C.c_uint64(0)
     if threads > 1:
-        rc = lib.bt2g_fastq_parse_mt(text, len(text), cap_reads, len(text), _ptr(seq), _ptr(qual), _ptr(off), _ptr(names), name_stride,
+        rc = lib.bt2g_fastq_parse_mt(text, len(text), cap_reads, cap_bases, _ptr(seq), _ptr(qual), _ptr(off), _ptr(names), name_stride,
                                      C.byref(n), C.byref(used), int(threads))
     else:
-        rc = lib.bt2g_fastq_parse(text, len(text), cap_reads, len(text), _ptr(seq), _ptr(qual), _ptr(off), _ptr(names), name_stride,
+        rc = lib.bt2g_fastq_parse(text, len(text), cap_reads, cap_bases, _ptr(seq), _ptr(qual), _ptr(off), _ptr(names), name_stride,
                                   C.byref(n), C.byref(used))
     if rc:
         raise RuntimeError(f"bt2g_fastq_parse failed ({rc})")
     n = int(n.value)
     nb = int(off[n])
     return ReadBatch(seq[:nb], off[:n + 1], qual[:nb]), NameTable(names[:n]), int(used.value)
+
+
+EXPORTS += ["bt2g_fastq_parse_pairs_mt"]
+
+
+def fastq_parse_pairs(lib, text1: bytes, text2: bytes, name_stride: int = 64, threads: int = 1, out: HostBuffers = None, max_pairs: int = None):
+    """include/bt2g.h: bt2g_fastq_parse_pairs_mt -> (ReadBatch with mate 1 of pair i as read 2i and mate 2 as read 2i + 1, names
+    (NameTable, same order), bytes consumed of text1, of text2).  With `out` the arrays live in reused buffers."""
+    lib.bt2g_fastq_parse_pairs_mt.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                              C.POINTER(C.c_uint64), C.c_int]
+    alloc = out.get if out is not None else (lambda key, shape, dtype: np.empty(shape, dtype=dtype))
+    cap_bases = len(text1) + len(text2)                     # (never reached: the untouched tail costs no memory)
+    # records: the last batch's count is the first guess (batches of a run look alike); an exact line count when that was short
+    guess = getattr(out, "pairs_hint", None) if out is not None else None
+    cap_pairs = max_pairs if max_pairs is not None else (int(guess * 1.05) + 16 if guess else min(text1.count(b"\n"), text2.count(b"\n")) // 4 + 1)
+    while True:
+        seq = alloc("seq", (cap_bases,), np.uint8)
+        qual = alloc("qual", (cap_bases,), np.uint8)
+        off = alloc("off", (2 * cap_pairs + 1,), np.uint64)
+        names = alloc("names", (2 * cap_pairs, name_stride), np.uint8)
+        n, u1, u2 = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        rc = lib.bt2g_fastq_parse_pairs_mt(text1, len(text1), text2, len(text2), cap_pairs, cap_bases, _ptr(seq), _ptr(qual), _ptr(off), _ptr(names),
+                                           name_stride, C.byref(n), C.byref(u1), C.byref(u2), int(threads))
+        if rc:
+            raise RuntimeError(f"bt2g_fastq_parse_pairs_mt failed ({rc})")
+        n = int(n.value)
+        if max_pairs is None and guess and n == cap_pairs and (u1.value < len(text1) or u2.value < len(text2)):
+            guess, cap_pairs = None, min(text1.count(b"\n"), text2.count(b"\n")) // 4 + 1     # the guess was short: parse again
+            continue
+        break
+    if out is not None:
+        out.pairs_hint = n
+    nb = int(off[2 * n])
+    return ReadBatch(seq[:nb], off[:2 * n + 1], qual[:nb]), NameTable(names[:2 * n]), int(u1.value), int(u2.value)
 
 EXPORTS += ["bt2g_mapq", "bt2g_frame_mate_host", "bt2g_pe_classify_host"]
 
@@ -1143,12 +1202,14 @@ class XEngine:
         self.paired = bool(params.paired)
         self.max_ops = self.max_len + 80
 
-    def align(self, reads: ReadBatch, names=None):
-        """host buffers in -> (results, ops [n, max_ops], pairs or None, stats dict)"""
+    def align(self, reads: ReadBatch, names=None, out: "HostBuffers" = None):
+        """host buffers in -> (results, ops [n, max_ops], pairs or None, stats dict); with `out` the result arrays live in reused
+        buffers (valid until the next call with the same `out`)"""
         n = reads.n
-        res = np.empty(n, dtype=READ_RESULT)                     # (every row is overwritten by the copy back from the device)
-        ops = np.empty((max(n, 1), self.max_ops), dtype=np.uint8)
-        pairs = np.empty(n // 2, dtype=PAIR_RESULT) if self.paired else None
+        alloc = out.get if out is not None else (lambda key, shape, dtype: np.empty(shape, dtype=dtype))
+        res = alloc("res", (n,), READ_RESULT)                    # (every row is overwritten by the copy back from the device)
+        ops = alloc("ops", (max(n, 1), self.max_ops), np.uint8)
+        pairs = alloc("pairs", (n // 2,), PAIR_RESULT) if self.paired else None
         stats = np.zeros(8, dtype=np.uint64)
         rows = None if names is None else name_rows(names)
         st = reads._struct()

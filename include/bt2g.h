@@ -613,6 +613,17 @@ int  bt2g_xengine_align_host(const bt2g_policy_backend *be, const bt2g_policy_pa
 int bt2g_fastq_parse_mt(const char *text, uint64_t len, uint64_t max_reads, uint64_t max_bases, uint8_t *seq, uint8_t *qual,
                         uint64_t *off, char *names, uint32_t name_stride, uint64_t *n_reads, uint64_t *consumed, int threads);
 
+/* The two mate files of paired input into ONE interleaved batch: mate 1 of pair i is read 2i, mate 2 read 2i + 1 (the layout of every
+ * paired entry point here; DualPatternComposer::nextBatch, pat.cpp:222-300, hands the reference's aligner the two mates together).
+ * Both texts are parsed concurrently on `threads` host threads and the records written straight to their interleaved places.
+ * Stops after max_pairs pairs, max_bases bases (both mates), or when either text runs out of whole records; *consumed1 / *consumed2 =
+ * offset of the first unparsed byte of each text (the caller feeds the rest with its next block; the reference's "fewer reads in
+ * file specified with -1 / -2" is the caller's call at end of input).  seq / qual: max_bases bytes; off: 2 * max_pairs + 1;
+ * names: 2 * max_pairs rows of name_stride bytes, every byte defined (may be NULL).  Error codes as bt2g_fastq_parse. */
+int bt2g_fastq_parse_pairs_mt(const char *text1, uint64_t len1, const char *text2, uint64_t len2, uint64_t max_pairs, uint64_t max_bases,
+                              uint8_t *seq, uint8_t *qual, uint64_t *off, char *names, uint32_t name_stride, uint64_t *n_pairs,
+                              uint64_t *consumed1, uint64_t *consumed2, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -459,3 +459,94 @@ def test_fastq_parse_multithreaded_equals_serial():
     bad = text[:len(text) // 2] + b"@x\nACGT\n+\nII\n" + text[len(text) // 2:]
     with pytest.raises(RuntimeError):
         fastq_parse(lib, bad, threads=4)
+
+
+def _synthetic_fastq(n, seed, tag, lo=30, hi=150):
+    rng = np.random.default_rng(seed)
+    parts = []
+    for i in range(n):
+        ln = int(rng.integers(lo, hi))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), ln, p=[0.245, 0.245, 0.245, 0.245, 0.02]))
+        q = bytearray(rng.integers(33, 74, ln).astype(np.uint8).tobytes())
+        if i % 7 == 0:
+            q[0] = ord("@")                                  # a quality string that looks like a header
+        parts.append(b"@pair%d/%s a comment\n%s\n+\n%s\n" % (i, tag, seq, bytes(q)))
+    return parts
+
+
+def test_fastq_parse_pairs_equals_two_parses_interleaved():
+    """bt2g_fastq_parse_pairs_mt (the two mate texts straight into one interleaved batch) against bt2g_fastq_parse of each text +
+    the numpy interleave: same arrays whatever the thread count; reused output buffers carry nothing over; the pair limit, a
+    shorter mate file and a truncated tail stop both texts at record boundaries of the same pair"""
+    from bowtie2_b200.align import interleave, interleave_names
+    from bowtie2_b200.lib import HostBuffers, fastq_parse, fastq_parse_pairs
+    lib = load_library()
+    n = 26000
+    p1, p2 = _synthetic_fastq(n, 5, b"1"), _synthetic_fastq(n, 6, b"2", lo=20, hi=260)
+    t1, t2 = b"".join(p1), b"".join(p2)
+    assert len(t1) > (1 << 21) and len(t2) > (1 << 21)
+    b1, n1, _ = fastq_parse(lib, t1)
+    b2, n2, _ = fastq_parse(lib, t2)
+    want, want_names = interleave(b1, b2), interleave_names(n1, n2)
+    out = HostBuffers()
+    for th in (1, 2, 5, 8, 16):
+        got, names, u1, u2 = fastq_parse_pairs(lib, t1, t2, threads=th, out=out if th != 2 else None)
+        assert u1 == len(t1) and u2 == len(t2) and got.n == 2 * n
+        assert np.array_equal(got.off, want.off) and np.array_equal(got.seq, want.seq) and np.array_equal(got.qual, want.qual)
+        assert np.array_equal(names.rows, want_names.rows)
+    # the same buffers again with a smaller input (and a short first guess of the record count on the way back up)
+    k = 1500
+    s1, s2 = b"".join(p1[:k]), b"".join(p2[:k])
+    got, names, u1, u2 = fastq_parse_pairs(lib, s1, s2, threads=4, out=out)
+    assert got.n == 2 * k and u1 == len(s1) and u2 == len(s2)
+    assert np.array_equal(got.seq, want.seq[:int(want.off[2 * k])]) and np.array_equal(names.rows, want_names.rows[:2 * k])
+    got, names, u1, u2 = fastq_parse_pairs(lib, t1, t2, threads=4, out=out)
+    assert got.n == 2 * n and u1 == len(t1) and np.array_equal(got.qual, want.qual) and np.array_equal(names.rows, want_names.rows)
+    # pair limit: both texts stop in front of the same pair, the rest parses to the rest
+    lim = 12345
+    a, an, u1, u2 = fastq_parse_pairs(lib, t1, t2, threads=6, max_pairs=lim)
+    assert a.n == 2 * lim and u1 == len(b"".join(p1[:lim])) and u2 == len(b"".join(p2[:lim]))
+    b, bn, v1, v2 = fastq_parse_pairs(lib, t1[u1:], t2[u2:], threads=3)
+    assert b.n == 2 * (n - lim) and np.array_equal(np.concatenate([a.seq, b.seq]), want.seq)
+    assert np.array_equal(np.concatenate([an.rows, bn.rows]), want_names.rows)
+    # mate file 2 is shorter / its tail is cut inside a record: whole pairs only, mate 1's cursor waits at the unpaired record
+    short2 = b"".join(p2[:n - 3])
+    c, _, u1, u2 = fastq_parse_pairs(lib, t1, short2, threads=4)
+    assert c.n == 2 * (n - 3) and u2 == len(short2) and u1 == len(b"".join(p1[:n - 3]))
+    c, _, u1, u2 = fastq_parse_pairs(lib, t1, t2[:len(t2) - 9], threads=8)
+    assert c.n == 2 * (n - 1) and u1 == len(b"".join(p1[:n - 1])) and u2 == len(b"".join(p2[:n - 1]))
+    assert np.array_equal(c.seq, want.seq[:int(want.off[2 * (n - 1)])])
+    # nothing at all, and small texts (one piece per file)
+    e, en, u1, u2 = fastq_parse_pairs(lib, b"", b"", threads=4)
+    assert e.n == 0 and u1 == 0 and u2 == 0 and len(en) == 0
+    f, fn, _, _ = fastq_parse_pairs(lib, b"@x/1\nacgtN.\n+\nIIIIII\n", b"@x/2\r\nTT\r\n+\r\nII\r\n", threads=4)
+    assert f.n == 2 and f.seq.tolist() == [0, 1, 2, 3, 4, 4, 3, 3] and f.off.tolist() == [0, 6, 8] and list(fn) == ["x/1", "x/2"]
+    # errors surface from either text
+    with pytest.raises(RuntimeError):
+        fastq_parse_pairs(lib, t1, t2[:len(t2) // 2] + b"@x\nACGT\n+\nII\n" + t2[len(t2) // 2:], threads=4)
+    with pytest.raises(RuntimeError):
+        fastq_parse_pairs(lib, b">x\nACGT\n", b"@x\nACGT\n+\nIIII\n")
+
+
+def test_sam_format_threads_views_and_reused_buffers(rep_index):
+    """bt2g_sam_format: the same text from 1 and from several host threads, as bytes and as a view of a reused output buffer, also
+    after the buffer held a longer text (the repeat-rich pairs: every pair kind, held mate-1 records included)"""
+    from bowtie2_b200.lib import HostBuffers
+    golden, names, reads, quals = _load_rep(True)
+    res, ops, pairs, good, order = _rebuild(golden, names, reads, quals, Oracle(rep_index), True)
+    lib = load_library()
+    b = ReadBatch.from_list(reads, quals)
+    one = sam_format(lib, b, res, ops, REP_NAMES, read_names=names, pairs=pairs, threads=1, as_bytes=True)
+    assert one.decode() == sam_format(lib, b, res, ops, REP_NAMES, read_names=names, pairs=pairs, threads=1)
+    out = HostBuffers()
+    for th in (2, 3, 7):
+        v = sam_format(lib, b, res, ops, REP_NAMES, read_names=names, pairs=pairs, threads=th, as_bytes="view", out=out)
+        assert isinstance(v, memoryview) and bytes(v) == one
+    k = 200
+    part = ReadBatch.from_list(reads[:k], quals[:k])
+    v = sam_format(lib, part, res[:k], ops[:k], REP_NAMES, read_names=names[:k], pairs=pairs[:k // 2], threads=2, as_bytes="view", out=out)
+    assert bytes(v) == b"".join(x + b"\n" for x in one.split(b"\n")[:k])
+    # --no-unal and a read group through the in-place writer
+    w1 = sam_format(lib, b, res, ops, REP_NAMES, read_names=names, pairs=pairs, threads=1, no_unal=True, rg_id="grp")
+    w4 = sam_format(lib, b, res, ops, REP_NAMES, read_names=names, pairs=pairs, threads=4, no_unal=True, rg_id="grp")
+    assert w1 == w4 and all(l.endswith("\tRG:Z:grp") and not int(l.split("\t")[1]) & 4 for l in w1.rstrip("\n").split("\n"))

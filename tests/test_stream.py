@@ -48,7 +48,7 @@ def test_fastq_text_to_sam_text_paired(n_engines, cut, lambda_index):
     engines = [_HostEngine(be, policy_params("sensitive", paired=True)) for _ in range(n_engines)]
     ta = TextAligner(engines, ["gi|9626243|ref|NC_001416.1|"], paired=True, parse_threads=2, format_threads=2, name_stride=64)
     chunks = []
-    written = ta.run(iter(items), chunks.append)
+    written = ta.run(iter(items), lambda v: chunks.append(bytes(v)))   # (the view is valid only inside the sink)
     lines = b"".join(chunks).decode().rstrip("\n").split("\n")
     assert written == 2 * n and lines == golden[:2 * n]
 
@@ -62,5 +62,5 @@ def test_fastq_text_to_sam_text_unpaired(lambda_index):
     ta = TextAligner([_HostEngine(be, policy_params("sensitive")) for _ in range(2)], ["gi|9626243|ref|NC_001416.1|"], paired=False,
                      parse_threads=1, format_threads=1, name_stride=64)
     chunks = []
-    ta.run(iter(items), chunks.append)
+    ta.run(iter(items), lambda v: chunks.append(bytes(v)))
     assert b"".join(chunks).decode().rstrip("\n").split("\n") == golden[:n]

@@ -143,7 +143,7 @@ def test_text_stream_over_device_engines(request):
     try:
         ta = TextAligner(engines, ["gi|9626243|ref|NC_001416.1|"], paired=True, parse_threads=2, format_threads=2, name_stride=64)
         chunks = []
-        written = ta.run(iter(items), chunks.append)
+        written = ta.run(iter(items), lambda v: chunks.append(bytes(v)))     # (the view is valid only inside the sink)
     finally:
         for e in engines:
             e.close()
