@@ -731,7 +731,7 @@ def run_exact(S, args):
 
             def sink(txt):
                 sam_bytes[0] += len(txt)
-            ta.run(iter(items[:E]), sink)                # warm-up
+            ta.run((items[k % n_items] for k in range(len(ta._slots))), sink)   # warm-up: every buffer set of the stream is touched once
             sam_bytes[0] = 0
             t0 = time.perf_counter()
             recs = ta.run((items[k % n_items] for k in range(reps * n_items)), sink)
