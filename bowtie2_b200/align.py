@@ -188,6 +188,9 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
     counts = np.zeros(1, dtype=ALIGN_COUNTS)
     pipe, pipe_len = None, 0
     sam_names = [n.split()[0] if n.split() else n for n in ref_names]
+    # --no-discordant / --no-mixed reach the record formatter and the summary too (pair_type 2 alone cannot tell a discordant pair)
+    no_disc = bool(exact and policy_options and policy_options.get("discord") is False)
+    no_mixed = bool(exact and policy_options and policy_options.get("mixed") is False)
     with open(out_path, "wb") as out:
         out.write(sam_header(lib, ref_names, ref_lens, pg_cl).encode())
         while True:
@@ -211,8 +214,9 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
                     pipe.enable_pairs()
             if exact and paired and policy_options and (policy_options.get("k") is not None or policy_options.get("all_hits")):
                 batch_k, names_k, res, ops, pairs_e, (prim_res, prim_pairs) = _exact_batch(gpu, batch, names, paired, preset, local, seed, threads, policy_options)
-                out.write(sam_format(lib, batch_k, res, ops, sam_names, read_names=names_k, pairs=pairs_e, threads=threads, local=local, as_bytes=True))
-                align_counts_add(lib, counts, prim_res, prim_pairs)
+                out.write(sam_format(lib, batch_k, res, ops, sam_names, read_names=names_k, pairs=pairs_e, threads=threads, local=local, as_bytes=True,
+                                     no_discordant=no_disc))
+                align_counts_add(lib, counts, prim_res, prim_pairs, no_discordant=no_disc)
                 continue
             if exact and not paired and policy_options and (policy_options.get("k") is not None or policy_options.get("all_hits")):
                 batch_k, names_k, res, ops, primary = _exact_batch(gpu, batch, names, paired, preset, local, seed, threads, policy_options)
@@ -225,15 +229,16 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
                 res, ops, pairs = pipe.run_paired_host(batch)
             else:
                 (res, ops), pairs = pipe.run_host(batch), None
-            out.write(sam_format(lib, batch, res, ops, sam_names, read_names=names, pairs=pairs, threads=threads, local=local, as_bytes=True))
-            align_counts_add(lib, counts, res, pairs)
+            out.write(sam_format(lib, batch, res, ops, sam_names, read_names=names, pairs=pairs, threads=threads, local=local, as_bytes=True,
+                                 no_discordant=no_disc))
+            align_counts_add(lib, counts, res, pairs, no_discordant=no_disc)
     if pipe is not None:
         pipe.close()
     s1.close()
     if s2 is not None:
         s2.close()
     if summary is not None:
-        summary.write(align_summary(lib, counts))
+        summary.write(align_summary(lib, counts, discord=not no_disc, mixed=not no_mixed))
     if own:
         gpu.close()
     return counts

@@ -129,6 +129,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 	static const struct Chars { char fw[256], rc[256]; Chars() { for(int c = 0; c < 256; c++) { fw[c] = "ACGTN"[c > 4 ? 4 : c]; rc[c] = "TGCAN"[c > 4 ? 4 : c]; } } } chars;
 	const bool paired = pairs != nullptr;
 	const bool xeq = (opt->flags & BT2G_SAM_XEQ) != 0, noUnal = (opt->flags & BT2G_SAM_NO_UNAL) != 0;
+	const bool noDiscord = (opt->flags & BT2G_SAM_NO_DISCORDANT) != 0;
 	o.n = 0;
 	if(i1 > i0) o.room((size_t)(reads->off[i1] - reads->off[i0]) * 2 + (size_t)(i1 - i0) * 160);      // SEQ + QUAL + the usual fields
 	size_t maxRef = 1;                                                 // longest RNAME ("*" when there is none)
@@ -151,7 +152,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		const bool concordant = pr && pr->pair_type == 1;
 		// discordant = no concordant pair and exactly one alignment for each mate (AlnSinkWrap::getReport,
 		// aln_sink.cpp:240-256); with more, the mates are reported as unpaired alignments of a paired read
-		const bool discordant = pr && pr->pair_type == 2 && r.score2 == INT32_MIN && m->score2 == INT32_MIN;
+		const bool discordant = pr && !noDiscord && pr->pair_type == 2 && r.score2 == INT32_MIN && m->score2 == INT32_MIN;
 		const bool asPair = concordant || discordant;
 		int flag = (r.found & 0x100) ? 256 : 0;                   // caller-marked secondary alignment (-k / -a records)
 		if(paired) {
@@ -772,7 +773,12 @@ extern "C" int bt2g_sam_header_rg(const char *const *names, const uint64_t *lens
 // ---- alignment summary (ReportingMetrics updates of AlnSinkWrap::finishRead, aln_sink.cpp:708-1046;
 //      text of AlnSink::printAlSumm, aln_sink.cpp:349-528) ---------------------------------------------
 extern "C" int bt2g_align_counts_add(bt2g_align_counts *c, const bt2g_read_result *res, uint64_t nReads, const bt2g_pair_result *pairs) {
+	return bt2g_align_counts_add_ex(c, res, nReads, pairs, 0);
+}
+
+extern "C" int bt2g_align_counts_add_ex(bt2g_align_counts *c, const bt2g_read_result *res, uint64_t nReads, const bt2g_pair_result *pairs, uint32_t flags) {
 	if(!c || (nReads && !res)) return -1;
+	const bool noDiscord = (flags & BT2G_SAM_NO_DISCORDANT) != 0;
 	auto aligned = [](const bt2g_read_result &r) { return (r.found & 0xff) != 0; };
 	auto multi = [](const bt2g_read_result &r) { return r.score2 != INT32_MIN; };
 	if(!pairs) {
@@ -796,7 +802,7 @@ extern "C" int bt2g_align_counts_add(bt2g_align_counts *c, const bt2g_read_resul
 			continue;
 		}
 		c->nconcord_0++;
-		if(pr.pair_type == 2 && !multi(a) && !multi(b)) { c->ndiscord++; continue; }
+		if(!noDiscord && pr.pair_type == 2 && !multi(a) && !multi(b)) { c->ndiscord++; continue; }
 		for(const bt2g_read_result *m : {&a, &b}) {
 			if(!aligned(*m)) c->nunp_0_0++;
 			else if(multi(*m)) c->nunp_0_gt1++;

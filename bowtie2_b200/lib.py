@@ -730,10 +730,11 @@ class HostBuffers:
 
 
 def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_names=None, pairs=None, threads: int = 1,
-               local: bool = False, xeq: bool = False, no_unal: bool = False, rg_id: str = None, as_bytes=False, out: HostBuffers = None):
+               local: bool = False, xeq: bool = False, no_unal: bool = False, rg_id: str = None, as_bytes=False, out: HostBuffers = None,
+               no_discordant: bool = False):
     """SAM text for pipeline results (one record per read).  `lib` is the loaded libbt2g (load_library()).
     as_bytes: False -> str, True -> bytes, "view" -> a memoryview of the output buffer (no copy; with `out` given the buffer is reused
-    by the next call, so the view must be consumed before it)."""
+    by the next call, so the view must be consumed before it).  no_discordant: the run's --no-discordant (BT2G_SAM_NO_DISCORDANT)."""
     lib.bt2g_sam_format.argtypes = [C.POINTER(_SamOpts), C.POINTER(_Reads), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     rn = (C.c_char_p * len(ref_names))(*[x.encode() for x in ref_names])
@@ -743,7 +744,7 @@ def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_name
     else:
         qn = (C.c_char_p * reads.n)(*[x.encode() for x in read_names]) if read_names is not None else None
     opt = _SamOpts(rn, len(ref_names), qn, int(threads), sc_filter_maxlen(True) if local else 0, 0.0, 0.0,
-                   (1 if xeq else 0) | (2 if no_unal else 0), 0, ("RG:Z:" + rg_id).encode() if rg_id else None)
+                   (1 if xeq else 0) | (2 if no_unal else 0) | (4 if no_discordant else 0), 0, ("RG:Z:" + rg_id).encode() if rg_id else None)
     res = np.ascontiguousarray(res, dtype=READ_RESULT)
     max_ops = 0 if ops is None else ops.shape[1]
     if ops is not None:
@@ -869,7 +870,7 @@ def fastq_parse_pairs(lib, text1: bytes, text2: bytes, name_stride: int = 64, th
 EXPORTS += ["bt2g_mapq", "bt2g_frame_mate_host", "bt2g_pe_classify_host"]
 
 
-EXPORTS += ["bt2g_sam_header", "bt2g_sam_header_rg", "bt2g_align_counts_add", "bt2g_align_summary", "bt2g_index_file_open", "bt2g_index_file_desc",
+EXPORTS += ["bt2g_sam_header", "bt2g_sam_header_rg", "bt2g_align_counts_add", "bt2g_align_counts_add_ex", "bt2g_align_summary", "bt2g_index_file_open", "bt2g_index_file_desc",
             "bt2g_index_file_n_refs", "bt2g_index_file_ref_names", "bt2g_index_file_ref_lens", "bt2g_index_file_close",
             "bt2g_load_index_files_ex"]
 
@@ -906,15 +907,15 @@ ALIGN_COUNTS = np.dtype([(k, np.uint64) for k in ("nread", "npaired", "nunpaired
                                                   "ndiscord", "nunp_0_0", "nunp_0_uni1", "nunp_0_gt1", "nunp_0", "nunp_uni1", "nunp_gt1")])
 
 
-def align_counts_add(lib, counts, res, pairs=None):
-    """include/bt2g.h: bt2g_align_counts_add; `counts` is a 1-element ALIGN_COUNTS array (None starts a new one)."""
+def align_counts_add(lib, counts, res, pairs=None, no_discordant: bool = False):
+    """include/bt2g.h: bt2g_align_counts_add[_ex]; `counts` is a 1-element ALIGN_COUNTS array (None starts a new one)."""
     if counts is None:
         counts = np.zeros(1, dtype=ALIGN_COUNTS)
-    lib.bt2g_align_counts_add.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.bt2g_align_counts_add_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
     res = np.ascontiguousarray(res, dtype=READ_RESULT)
     if pairs is not None:
         pairs = np.ascontiguousarray(pairs, dtype=PAIR_RESULT)
-    rc = lib.bt2g_align_counts_add(_ptr(counts), _ptr(res), len(res), _ptr(pairs))
+    rc = lib.bt2g_align_counts_add_ex(_ptr(counts), _ptr(res), len(res), _ptr(pairs), 4 if no_discordant else 0)
     if rc:
         raise RuntimeError(f"bt2g_align_counts_add failed ({rc})")
     return counts

@@ -43,9 +43,10 @@ class TextAligner:
     of a batch is handed to the sink as a memoryview of one reused output buffer: the sink must consume it (write it) before it
     returns.  No per-batch allocation is left on the steady-state path."""
 
-    def __init__(self, engines, ref_names, paired, local=False, parse_threads=4, format_threads=8, name_stride=32, depth=2):
+    def __init__(self, engines, ref_names, paired, local=False, parse_threads=4, format_threads=8, name_stride=32, depth=2, no_discordant=False):
         self.engines, self.ref_names, self.paired, self.local = list(engines), list(ref_names), paired, local
         self.parse_threads, self.format_threads, self.name_stride, self.depth = parse_threads, format_threads, name_stride, depth
+        self.no_discordant = no_discordant                       # the engines' --no-discordant, for the record formatter
         self.lib = load_library()
         self._slots = [HostBuffers() for _ in range(depth + len(self.engines) + 1)]
         # (engine stand-ins of the CPU tests may not take reusable result buffers)
@@ -112,7 +113,7 @@ class TextAligner:
                     while nxt in pending:
                         slot, batch, names, res, ops, pairs = pending.pop(nxt)
                         txt = sam_format(self.lib, batch, res, ops, self.ref_names, read_names=names, pairs=pairs, threads=self.format_threads,
-                                         local=self.local, as_bytes="view", out=self._out)
+                                         local=self.local, as_bytes="view", out=self._out, no_discordant=self.no_discordant)
                         sink(txt)
                         total[0] += batch.n
                         nxt += 1

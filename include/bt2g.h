@@ -451,6 +451,10 @@ typedef struct {
 } bt2g_sam_opts;
 #define BT2G_SAM_XEQ     1u
 #define BT2G_SAM_NO_UNAL 2u
+/* --no-discordant: a pair whose mates both aligned exactly once without a concordant pair (pair_type 2) is NOT a discordant pair
+ * (ReportingParams::discord, aln_sink.h:305-307; ReportingState::nextRead starts with doneDiscord_ set, aln_sink.cpp:38): its mates are reported as unpaired
+ * alignments of a paired read (YT:Z:UP, no YS:i, TLEN 0).  pair_type 2 alone cannot tell: the caller passes the option. */
+#define BT2G_SAM_NO_DISCORDANT 4u
 int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads, const bt2g_read_result *res, const uint8_t *ops,
                     uint32_t max_ops, const bt2g_pair_result *pairs, char *out, uint64_t cap, uint64_t *written);
 
@@ -492,6 +496,8 @@ typedef struct {
 	uint64_t nunp_0, nunp_uni1, nunp_gt1;             /* unpaired reads */
 } bt2g_align_counts;
 int bt2g_align_counts_add(bt2g_align_counts *c, const bt2g_read_result *res, uint64_t n_reads, const bt2g_pair_result *pairs);
+/* the same with formatter flags: BT2G_SAM_NO_DISCORDANT counts such pairs' mates under the unpaired tallies */
+int bt2g_align_counts_add_ex(bt2g_align_counts *c, const bt2g_read_result *res, uint64_t n_reads, const bt2g_pair_result *pairs, uint32_t flags);
 int bt2g_align_summary(const bt2g_align_counts *c, int discord, int mixed, char *out, uint64_t cap, uint64_t *written);
 
 /* ---------------------------------------------------------------------- index files on the host ----- */

@@ -1,0 +1,134 @@
+"""Parity fuzz on the CPU: the device engine's state machine (csrc/xengine.cuh, the code k_xe_step runs) driven on the host over the
+oracle-backed entry-point table (bt2g_xengine_align_host), against the UNMODIFIED reference program (oracle/_ref/bowtie2-align-s) on
+fresh synthetic genomes and reads: presets x end-to-end / local x unpaired / paired x read lengths x error rates x the policy options
+the engines take (--nofw/--norc, -L, -D, -R, -i, --ff/--rf, -I/-X, --dovetail, --no-contain, --no-overlap, --no-mixed,
+--no-discordant).  Every SAM record must be identical.
+
+Test infrastructure (uses oracle/): `python tests/parity_fuzz.py SEED CASES` prints one line per case and a JSON summary;
+tests/test_parity_fuzz.py runs a few fixed seeds."""
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+REF = os.path.join(ROOT, "oracle", "_ref", "bowtie2-align-s")
+
+
+def draw_case(rng):
+    """one random configuration: genome, reads, preset and options (as keyword arguments of lib.policy_params + the reference's flags)"""
+    from bowtie2_b200 import policy
+    c = {"genome_seed": int(rng.integers(1, 1 << 30)), "n_contigs": int(rng.integers(1, 4)), "contig_len": int(rng.integers(8000, 30000)),
+         "repeat_frac": float(rng.choice([0.02, 0.1, 0.3])), "repeat_len": int(rng.integers(100, 600)), "repeat_copies": int(rng.integers(3, 20)),
+         "n_gap": int(rng.integers(0, 60)), "local": bool(rng.integers(0, 2)), "paired": bool(rng.integers(0, 2)),
+         "preset": str(rng.choice(["very-fast", "fast", "sensitive", "very-sensitive"])), "read_len": int(rng.choice([30, 50, 75, 100, 150, 250])),
+         "sub_rate": float(rng.choice([0.002, 0.01, 0.03, 0.06])), "indel_rate": float(rng.choice([0.0, 0.001, 0.005])),
+         "ins_mean": float(rng.choice([250, 350, 450])), "hard_frac": float(rng.choice([0.0, 0.1]))}
+    kw, flags = {}, []
+    if rng.random() < 0.25:
+        if rng.random() < 0.5:
+            kw["nofw"] = True; flags.append("--nofw")
+        else:
+            kw["norc"] = True; flags.append("--norc")
+    if rng.random() < 0.3:
+        kw["seed_len"] = int(rng.choice([10, 16, 20, 25, 32])); flags += ["-L", str(kw["seed_len"])]
+    if rng.random() < 0.3:
+        kw["dp_fail_streak"] = int(rng.choice([1, 5, 30])); flags += ["-D", str(kw["dp_fail_streak"])]
+    if rng.random() < 0.3:
+        kw["seed_rounds"] = int(rng.choice([0, 1, 4])); flags += ["-R", str(kw["seed_rounds"])]
+    if rng.random() < 0.3:
+        a, b = float(rng.choice([1, 0.5])), float(rng.choice([0.5, 1.15, 2.5]))
+        kw["ival"] = policy.SimpleFunc(policy.SIMPLE_FUNC_SQRT, a, b); flags += ["-i", f"S,{a},{b}"]
+    if c["paired"]:
+        pe = policy.PairedEndPolicy(local=c["local"])
+        if rng.random() < 0.3:
+            pe.pol = int(rng.choice([policy.PE_POLICY_FF, policy.PE_POLICY_RF])); flags.append("--ff" if pe.pol == policy.PE_POLICY_FF else "--rf")
+        if rng.random() < 0.4:
+            pe.maxfrag = int(rng.choice([200, 300, 400, 800])); flags += ["-X", str(pe.maxfrag)]
+        if rng.random() < 0.3:
+            pe.minfrag = int(rng.choice([100, 250, 340])); flags += ["-I", str(pe.minfrag)]
+        if rng.random() < 0.2:
+            pe.dovetail_ok = True; flags.append("--dovetail")
+        if rng.random() < 0.2:
+            pe.contain_ok = False; flags.append("--no-contain")
+        if rng.random() < 0.2:
+            pe.olap_ok = False; flags.append("--no-overlap")
+        kw["pe"] = pe
+        if rng.random() < 0.25:
+            kw["mixed"] = False; flags.append("--no-mixed")
+        if rng.random() < 0.25:
+            kw["discord"] = False; flags.append("--no-discordant")
+    c["kw"], c["flags"] = kw, flags
+    return c
+
+
+def run_case(c, work, n_unpaired=300, n_pairs=200):
+    """-> (records, differing, first difference or None, engine stats, description)"""
+    import conftest
+    from bowtie2_b200 import synth
+    from bowtie2_b200.lib import ReadBatch, load_library, policy_align, policy_params, sam_format
+    from test_policy_engine_cpp import _table
+    lib = load_library()
+    os.makedirs(work, exist_ok=True)
+    contigs = synth.make_genome(n_contigs=c["n_contigs"], contig_len=c["contig_len"], seed=c["genome_seed"], repeat_frac=c["repeat_frac"],
+                                repeat_len=c["repeat_len"], repeat_copies=c["repeat_copies"], n_gap=c["n_gap"])
+    fa, base = os.path.join(work, "g.fa"), os.path.join(work, "g")
+    synth.write_fasta(fa, contigs)
+    conftest._build_index("bowtie2-build-s", fa, base)
+    ref_names = [f"chr{k + 1}" for k in range(len(contigs))]
+    local, paired, L = c["local"], c["paired"], c["read_len"]
+    if paired:
+        reads, quals, _ = synth.make_pairs(contigs, n_pairs, L, seed=c["genome_seed"] + 1, sub_rate=c["sub_rate"], indel_rate=c["indel_rate"],
+                                           ins_mean=c["ins_mean"], hard_frac=c["hard_frac"])
+        f1, f2 = os.path.join(work, "r1.fq"), os.path.join(work, "r2.fq")
+        synth.write_fastq(f1, reads[0::2], quals[0::2], prefix="p"); synth.write_fastq(f2, reads[1::2], quals[1::2], prefix="p")
+        names, inp = [f"p{i // 2}" for i in range(2 * n_pairs)], ["-1", f1, "-2", f2]
+    else:
+        reads, quals, _ = synth.make_reads(contigs, n_unpaired, L, seed=c["genome_seed"] + 1, sub_rate=c["sub_rate"], indel_rate=c["indel_rate"], random_frac=0.03)
+        f1 = os.path.join(work, "r.fq")
+        synth.write_fastq(f1, reads, quals)
+        names, inp = [f"r{i}" for i in range(n_unpaired)], ["-U", f1]
+    pflag = "--" + c["preset"] + ("-local" if local else "")
+    sam = os.path.join(work, "ref.sam")
+    subprocess.check_call([REF, pflag] + (["--local"] if local else []) + c["flags"] + ["--seed", "0", "-p", "1", "--reorder", "-x", base] + inp + ["-S", sam],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    golden = [l.rstrip("\n") for l in open(sam) if not l.startswith("@")]
+    be, keep, fake = _table(base, local)
+    batch = ReadBatch.from_list(reads, quals)
+    res, ops, pairs, st = policy_align(lib, be, policy_params(c["preset"], local=local, paired=paired, **c["kw"]), batch, names, entry="bt2g_xengine_align_host")
+    lines = sam_format(lib, batch, res, ops, ref_names, read_names=names, pairs=pairs, local=local,
+                       no_discordant=(c["kw"].get("discord") is False)).rstrip("\n").split("\n")
+    diff = [i for i, (a, b) in enumerate(zip(lines, golden)) if a != b]
+    nbad = len(diff) + abs(len(lines) - len(golden))
+    first = (lines[diff[0]], golden[diff[0]]) if diff else None
+    desc = f"{pflag} {' '.join(c['flags'])} paired={paired} L={L} sub={c['sub_rate']} indel={c['indel_rate']} contigs={len(contigs)}"
+    return len(golden), nbad, first, st, desc
+
+
+def main():
+    seed, cases = int(sys.argv[1]) if len(sys.argv) > 1 else 1, int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    work = sys.argv[3] if len(sys.argv) > 3 else "/tmp/bt2g_parity_fuzz"
+    rng = np.random.default_rng(seed)
+    tot = bad = units = fallbacks = 0
+    t0 = time.time()
+    for k in range(cases):
+        c = draw_case(rng)
+        n, nb, first, st, desc = run_case(c, work)
+        tot += n; bad += nb; units += st[0]; fallbacks += st[1]
+        print(f"case {k}: {desc}: {n} records, {nb} differing", flush=True)
+        if first:
+            print("  GOT ", first[0][:300]); print("  WANT", first[1][:300])
+    print(json.dumps({"seed": seed, "cases": cases, "records": tot, "differing": bad, "units": units, "host_fallbacks": fallbacks,
+                      "seconds": round(time.time() - t0, 1), "engine": "bt2g_xengine_align_host (csrc/xengine.cuh on the CPU, oracle-backed table)",
+                      "reference": "oracle/_ref/bowtie2-align-s --seed 0 --reorder -p 1"}))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
