@@ -151,3 +151,42 @@ def test_exact_mode_paired_k_hits_whole_files_over_a_fake_device(tmp_path, rep_i
     got = [l.rstrip("\n") for l in open(out) if not l.startswith("@")]
     assert len(got) == len(want) and got == want, next(((a, b) for a, b in zip(got, want) if a != b), (len(got), len(want)))
     assert sum(int(l.split("\t")[1]) & 256 != 0 for l in want) > 50
+
+
+@pytest.mark.parametrize("flags,options", [(["--no-discordant"], {"discord": False}), (["--no-mixed"], {"mixed": False}),
+                                           (["--no-discordant", "--no-mixed"], {"discord": False, "mixed": False})])
+def test_exact_mode_no_discordant_no_mixed_whole_files(tmp_path, rep_index, flags, options):
+    """align_files(exact=True, policy_options={"discord": False} / {"mixed": False}) on pairs of the repeat-rich fixture: records AND
+    the alignment summary identical to the reference program's (--no-discordant has to reach the record formatter and the counts:
+    a pair whose mates each aligned once is then two unpaired alignments, YT:Z:UP)"""
+    import io
+    import subprocess
+    from fake_gpu import FakeGpu
+    from oracle_lib import Oracle, have_reference, ref_bin
+    if not have_reference():
+        pytest.skip("oracle/_ref not built")
+    for m in (1, 2):
+        with open(os.path.join(GOLDEN, f"rep_reads_{m}.fq")) as f, open(tmp_path / f"a{m}.fq", "w") as g:
+            g.writelines(f.readlines()[:4 * 300])
+    p = subprocess.run([ref_bin("bowtie2-align-s"), "--sensitive", "--seed", "0", "-p", "1", *flags, "-x", rep_index,
+                        "-1", str(tmp_path / "a1.fq"), "-2", str(tmp_path / "a2.fq")], capture_output=True, text=True, check=True)
+    want = [l for l in p.stdout.split("\n") if l and not l.startswith("@")]
+    plain = subprocess.run([ref_bin("bowtie2-align-s"), "--sensitive", "--seed", "0", "-p", "1", "-x", rep_index,
+                            "-1", str(tmp_path / "a1.fq"), "-2", str(tmp_path / "a2.fq")], capture_output=True, text=True, check=True)
+    assert plain.stdout != p.stdout                                  # (the options matter on this sample)
+    out, summ = str(tmp_path / "o.sam"), io.StringIO()
+    align_files(rep_index, out, str(tmp_path / "a1.fq"), str(tmp_path / "a2.fq"), exact=True, batch_reads=128, summary=summ,
+                gpu=FakeGpu(Oracle(rep_index)), policy_options=options)
+    got = [l.rstrip("\n") for l in open(out) if not l.startswith("@")]
+    assert len(got) == len(want) and got == want, next(((a, b) for a, b in zip(got, want) if a != b), (len(got), len(want)))
+    # the summary: every line but the documented split of the concordant pairs into "exactly 1" / ">1" (DESIGN.md section 7: the
+    # engines keep one pair per read); those two lines must add up to the same number
+    def split(text):
+        conc, rest = 0, []
+        for l in text.split("\n"):
+            if "aligned concordantly exactly 1 time" in l or "aligned concordantly >1 times" in l:
+                conc += int(l.split()[0])
+            else:
+                rest.append(l)
+        return conc, rest
+    assert split(summ.getvalue()) == split(p.stderr), (summ.getvalue(), p.stderr)
