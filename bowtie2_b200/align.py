@@ -191,6 +191,7 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
     # --no-discordant / --no-mixed reach the record formatter and the summary too (pair_type 2 alone cannot tell a discordant pair)
     no_disc = bool(exact and policy_options and policy_options.get("discord") is False)
     no_mixed = bool(exact and policy_options and policy_options.get("mixed") is False)
+    sc_opt = policy_options.get("sc") if exact and policy_options else None       # --ma / --score-min / --n-ceil decide the YF:Z: tags
     with open(out_path, "wb") as out:
         out.write(sam_header(lib, ref_names, ref_lens, pg_cl).encode())
         while True:
@@ -215,12 +216,12 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
             if exact and paired and policy_options and (policy_options.get("k") is not None or policy_options.get("all_hits")):
                 batch_k, names_k, res, ops, pairs_e, (prim_res, prim_pairs) = _exact_batch(gpu, batch, names, paired, preset, local, seed, threads, policy_options)
                 out.write(sam_format(lib, batch_k, res, ops, sam_names, read_names=names_k, pairs=pairs_e, threads=threads, local=local, as_bytes=True,
-                                     no_discordant=no_disc))
+                                     no_discordant=no_disc, sc=sc_opt))
                 align_counts_add(lib, counts, prim_res, prim_pairs, no_discordant=no_disc)
                 continue
             if exact and not paired and policy_options and (policy_options.get("k") is not None or policy_options.get("all_hits")):
                 batch_k, names_k, res, ops, primary = _exact_batch(gpu, batch, names, paired, preset, local, seed, threads, policy_options)
-                out.write(sam_format(lib, batch_k, res, ops, sam_names, read_names=names_k, threads=threads, local=local, as_bytes=True))
+                out.write(sam_format(lib, batch_k, res, ops, sam_names, read_names=names_k, threads=threads, local=local, as_bytes=True, sc=sc_opt))
                 align_counts_add(lib, counts, primary, None)
                 continue
             if exact:
@@ -230,7 +231,7 @@ def align_files(index_base: str, out_path: str, reads1: str, reads2: str = None,
             else:
                 (res, ops), pairs = pipe.run_host(batch), None
             out.write(sam_format(lib, batch, res, ops, sam_names, read_names=names, pairs=pairs, threads=threads, local=local, as_bytes=True,
-                                 no_discordant=no_disc))
+                                 no_discordant=no_disc, sc=sc_opt))
             align_counts_add(lib, counts, res, pairs, no_discordant=no_disc)
     if pipe is not None:
         pipe.close()

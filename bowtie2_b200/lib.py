@@ -702,10 +702,10 @@ class _SamOpts(C.Structure):
                 ("flags", C.c_uint32), ("reserved2", C.c_uint32), ("rg_optflag", C.c_char_p)]
 
 
-def sc_filter_maxlen(local: bool) -> int:
-    """longest read whose perfect score stays below the minimum score (0 in end-to-end mode)"""
+def sc_filter_maxlen(local: bool, sc=None) -> int:
+    """longest read whose perfect score stays below the minimum score (0 in end-to-end mode); sc: a policy.Scoring (--ma / --score-min)"""
     from . import policy
-    sc = policy.Scoring.default(local)
+    sc = sc or policy.Scoring.default(local)
     n = 0
     for ln in range(2, 200):
         if sc.perfect_score(ln) < sc.score_min().fi(ln):
@@ -731,10 +731,11 @@ class HostBuffers:
 
 def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_names=None, pairs=None, threads: int = 1,
                local: bool = False, xeq: bool = False, no_unal: bool = False, rg_id: str = None, as_bytes=False, out: HostBuffers = None,
-               no_discordant: bool = False):
+               no_discordant: bool = False, sc=None):
     """SAM text for pipeline results (one record per read).  `lib` is the loaded libbt2g (load_library()).
     as_bytes: False -> str, True -> bytes, "view" -> a memoryview of the output buffer (no copy; with `out` given the buffer is reused
-    by the next call, so the view must be consumed before it).  no_discordant: the run's --no-discordant (BT2G_SAM_NO_DISCORDANT)."""
+    by the next call, so the view must be consumed before it).  no_discordant: the run's --no-discordant (BT2G_SAM_NO_DISCORDANT).
+    sc: the run's policy.Scoring when it is not the default one (--ma / --score-min / --n-ceil decide the YF:Z: filter tags of unaligned reads)."""
     lib.bt2g_sam_format.argtypes = [C.POINTER(_SamOpts), C.POINTER(_Reads), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                     C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     rn = (C.c_char_p * len(ref_names))(*[x.encode() for x in ref_names])
@@ -743,7 +744,8 @@ def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_name
         qn = C.cast(ptrs.ctypes.data, C.POINTER(C.c_char_p))
     else:
         qn = (C.c_char_p * reads.n)(*[x.encode() for x in read_names]) if read_names is not None else None
-    opt = _SamOpts(rn, len(ref_names), qn, int(threads), sc_filter_maxlen(True) if local else 0, 0.0, 0.0,
+    nce = sc.n_ceil_func() if sc is not None and sc.n_ceil_over is not None else None
+    opt = _SamOpts(rn, len(ref_names), qn, int(threads), sc_filter_maxlen(True, sc) if local else 0, float(nce.C) if nce else 0.0, float(nce.L) if nce else 0.0,
                    (1 if xeq else 0) | (2 if no_unal else 0) | (4 if no_discordant else 0), 0, ("RG:Z:" + rg_id).encode() if rg_id else None)
     res = np.ascontiguousarray(res, dtype=READ_RESULT)
     max_ops = 0 if ops is None else ops.shape[1]

@@ -2,7 +2,7 @@
 oracle-backed entry-point table (bt2g_xengine_align_host), against the UNMODIFIED reference program (oracle/_ref/bowtie2-align-s) on
 fresh synthetic genomes and reads: presets x end-to-end / local x unpaired / paired x read lengths x error rates x the policy options
 the engines take (--nofw/--norc, -L, -D, -R, -i, --ff/--rf, -I/-X, --dovetail, --no-contain, --no-overlap, --no-mixed,
---no-discordant).  Every SAM record must be identical.
+--no-discordant, --mp, --np, --rdg, --rfg, --ma, --score-min, --n-ceil).  Every SAM record must be identical.
 
 Test infrastructure (uses oracle/): `python tests/parity_fuzz.py SEED CASES` prints one line per case and a JSON summary;
 tests/test_parity_fuzz.py runs a few fixed seeds."""
@@ -64,8 +64,38 @@ def draw_case(rng):
             kw["mixed"] = False; flags.append("--no-mixed")
         if rng.random() < 0.25:
             kw["discord"] = False; flags.append("--no-discordant")
+    # scoring options (drawn last: the draws above keep their sequence)
+    if rng.random() < 0.4:
+        sc = policy.Scoring.default(c["local"])
+        if rng.random() < 0.5:
+            mx = int(rng.choice([3, 4, 6, 8])); mn = min(int(rng.choice([1, 2, 3])), mx)
+            sc.mmp_max, sc.mmp_min = mx, mn; flags += ["--mp", f"{mx},{mn}"]
+        if rng.random() < 0.3:
+            sc.n_pen = int(rng.choice([0, 1, 3])); flags += ["--np", str(sc.n_pen)]
+        if rng.random() < 0.4:
+            sc.rdgap_const, sc.rdgap_linear = int(rng.choice([3, 5, 8])), int(rng.choice([1, 3, 4])); flags += ["--rdg", f"{sc.rdgap_const},{sc.rdgap_linear}"]
+        if rng.random() < 0.4:
+            sc.rfgap_const, sc.rfgap_linear = int(rng.choice([3, 5, 8])), int(rng.choice([1, 3, 4])); flags += ["--rfg", f"{sc.rfgap_const},{sc.rfgap_linear}"]
+        if c["local"] and rng.random() < 0.4:
+            sc.match_bonus = int(rng.choice([1, 3])); flags += ["--ma", str(sc.match_bonus)]
+        if rng.random() < 0.4:
+            if c["local"]:
+                a, b = float(rng.choice([1, 10, 20])), float(rng.choice([5.4, 8, 12]))
+                sc.score_min_func = policy.SimpleFunc(policy.SIMPLE_FUNC_LOG, a, b); flags += ["--score-min", f"G,{a},{b}"]
+            else:
+                a, b = float(rng.choice([0, -0.6, -3])), float(rng.choice([-0.3, -0.6, -1.0]))
+                sc.score_min_func = policy.SimpleFunc(policy.SIMPLE_FUNC_LINEAR, a, b); flags += ["--score-min", f"L,{a},{b}"]
+        if rng.random() < 0.3:
+            a, b = float(rng.choice([0, 2])), float(rng.choice([0.05, 0.15, 0.5]))
+            sc.n_ceil_over = policy.SimpleFunc(policy.SIMPLE_FUNC_LINEAR, a, b); flags += ["--n-ceil", f"L,{a},{b}"]
+        kw["sc"] = sc
     c["kw"], c["flags"] = kw, flags
     return c
+
+
+def _format_options(c, local):
+    """what the record formatter has to know of the scoring options: the N ceiling (YF:Z:NS) and the shortest alignable read (YF:Z:SC)"""
+    return {"sc": c["kw"]["sc"]} if "sc" in c["kw"] else {}
 
 
 def run_case(c, work, n_unpaired=300, n_pairs=200):
@@ -73,7 +103,6 @@ def run_case(c, work, n_unpaired=300, n_pairs=200):
     import conftest
     from bowtie2_b200 import synth
     from bowtie2_b200.lib import ReadBatch, load_library, policy_align, policy_params, sam_format
-    from test_policy_engine_cpp import _table
     lib = load_library()
     os.makedirs(work, exist_ok=True)
     contigs = synth.make_genome(n_contigs=c["n_contigs"], contig_len=c["contig_len"], seed=c["genome_seed"], repeat_frac=c["repeat_frac"],
@@ -99,11 +128,12 @@ def run_case(c, work, n_unpaired=300, n_pairs=200):
     subprocess.check_call([REF, pflag] + (["--local"] if local else []) + c["flags"] + ["--seed", "0", "-p", "1", "--reorder", "-x", base] + inp + ["-S", sam],
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     golden = [l.rstrip("\n") for l in open(sam) if not l.startswith("@")]
-    be, keep, fake = _table(base, local)
+    from oracle_lib import Oracle, oracle_policy_table
+    be, keep = oracle_policy_table(Oracle(base), local, 4, c["kw"].get("sc"))        # the C oracle behind the entry-point table
     batch = ReadBatch.from_list(reads, quals)
     res, ops, pairs, st = policy_align(lib, be, policy_params(c["preset"], local=local, paired=paired, **c["kw"]), batch, names, entry="bt2g_xengine_align_host")
     lines = sam_format(lib, batch, res, ops, ref_names, read_names=names, pairs=pairs, local=local,
-                       no_discordant=(c["kw"].get("discord") is False)).rstrip("\n").split("\n")
+                       no_discordant=(c["kw"].get("discord") is False), **_format_options(c, local)).rstrip("\n").split("\n")
     diff = [i for i, (a, b) in enumerate(zip(lines, golden)) if a != b]
     nbad = len(diff) + abs(len(lines) - len(golden))
     first = (lines[diff[0]], golden[diff[0]]) if diff else None
@@ -121,7 +151,7 @@ def main():
         c = draw_case(rng)
         n, nb, first, st, desc = run_case(c, work)
         tot += n; bad += nb; units += st[0]; fallbacks += st[1]
-        print(f"case {k}: {desc}: {n} records, {nb} differing", flush=True)
+        print(f"case {k}: {desc}: {n} records, {nb} differing; {st[0]} units, {st[1]} finished by the coroutine engine", flush=True)
         if first:
             print("  GOT ", first[0][:300]); print("  WANT", first[1][:300])
     print(json.dumps({"seed": seed, "cases": cases, "records": tot, "differing": bad, "units": units, "host_fallbacks": fallbacks,
