@@ -1273,12 +1273,26 @@ struct Scheduler {
 				rc |= be.dp_extend(be.ctx, b.get(), probs.data(), n, maxCands, maxAlns, maxOps, summ.data(), cands.data(), alns.data(), ops.data()); nCalls++;
 				for(size_t k = 0; k < n; k++) {
 					Req *r = rq[c0 + k];
-					if(summ[k].flags) {                                   // rare: more alignments / candidates than the batch buffers hold
+					if(summ[k].flags) {                                   // rare: more alignments / candidates / edit ops than the batch buffers hold
+						// alone, with buffers grown until everything fits (cheap gaps and a high match bonus give alignments with far more
+						// ops than rows; repeats give hundreds of candidates worth a backtrace)
 						Batch b1; b1.add(reads, r->read); bt2g_dp_problem p1 = r->prob; p1.read_idx = 0;
-						const int32_t mc = 65536, ma = 128, mo = rdlen(r->read) + 80;
-						std::vector<bt2g_dp_summary> s1(1); std::vector<bt2g_dp_cand> c1(mc); std::vector<bt2g_dp_aln> a1(ma); std::vector<uint8_t> o1((size_t)ma * mo);
-						rc |= be.dp_extend(be.ctx, b1.get(), &p1, 1, mc, ma, mo, s1.data(), c1.data(), a1.data(), o1.data()); nCalls++;
-						if(s1[0].flags) rc |= 1;
+						int32_t mc = 65536, ma = 128, mo = rdlen(r->read) + 80;
+						std::vector<bt2g_dp_summary> s1(1); std::vector<bt2g_dp_cand> c1; std::vector<bt2g_dp_aln> a1; std::vector<uint8_t> o1;
+						for(int attempt = 0; attempt < 6; attempt++) {
+							c1.assign((size_t)mc, bt2g_dp_cand{}); a1.assign((size_t)ma, bt2g_dp_aln{}); o1.assign((size_t)ma * mo, 0);
+							rc |= be.dp_extend(be.ctx, b1.get(), &p1, 1, mc, ma, mo, s1.data(), c1.data(), a1.data(), o1.data()); nCalls++;
+							const uint32_t fl = s1[0].flags;
+							if(!fl) break;
+							if(fl & BT2G_DP_FLAG_CAND_OVERFLOW) mc = std::max(2 * mc, s1[0].ncand + 1);
+							if(fl & BT2G_DP_FLAG_ALN_OVERFLOW) ma = std::max(2 * ma, s1[0].naln + 1);
+							if(fl & BT2G_DP_FLAG_OPS_OVERFLOW) {
+								int need = 2 * mo;
+								for(int q = 0; q < s1[0].naln && q < (int)a1.size(); q++) need = std::max(need, a1[q].nops + 16);
+								mo = need;
+							}
+						}
+						if(s1[0].flags) { rc |= 1; if(getenv("BT2G_PE_DEBUG")) fprintf(stderr, "dp retry overflow: flags=%d ncand=%d naln=%d len=%d\n", s1[0].flags, s1[0].ncand, s1[0].naln, rdlen(r->read)); }
 						fillDp(r, s1[0], c1.data(), a1.data(), o1.data(), mo);
 					} else fillDp(r, summ[k], cands.data() + k * (size_t)maxCands, alns.data() + k * (size_t)maxAlns, ops.data() + k * (size_t)maxAlns * maxOps, maxOps);
 				}

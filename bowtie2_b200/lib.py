@@ -1056,6 +1056,8 @@ def policy_params(preset="sensitive", local=False, paired=False, seed=0, k=None,
                   discord=True, mixed=True, pe=None, sc=None, max_inflight=0, host_threads=1, seed_len=None, seed_rounds=None,
                   dp_fail_streak=None, ival=None):
     from . import policy
+    if mhits < 1:
+        raise ValueError("-M must be at least 1 (the reference asserts mhits > 0, bt2_search.cpp:1775)")
     pre = policy.preset(preset, local)
     if seed_len is not None:
         pre.seed_len = seed_len                    # -L

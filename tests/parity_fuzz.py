@@ -2,7 +2,7 @@
 oracle-backed entry-point table (bt2g_xengine_align_host), against the UNMODIFIED reference program (oracle/_ref/bowtie2-align-s) on
 fresh synthetic genomes and reads: presets x end-to-end / local x unpaired / paired x read lengths x error rates x the policy options
 the engines take (--nofw/--norc, -L, -D, -R, -i, --ff/--rf, -I/-X, --dovetail, --no-contain, --no-overlap, --no-mixed,
---no-discordant, --mp, --np, --rdg, --rfg, --ma, --score-min, --n-ceil).  Every SAM record must be identical.
+--no-discordant, --mp, --np, --rdg, --rfg, --ma, --score-min, --n-ceil, --seed, -M; .bt2 and .bt2l indexes).  Every SAM record must be identical.
 
 Test infrastructure (uses oracle/): `python tests/parity_fuzz.py SEED CASES` prints one line per case and a JSON summary;
 tests/test_parity_fuzz.py runs a few fixed seeds."""
@@ -21,9 +21,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 REF = os.path.join(ROOT, "oracle", "_ref", "bowtie2-align-s")
 
 
-def draw_case(rng):
-    """one random configuration: genome, reads, preset and options (as keyword arguments of lib.policy_params + the reference's flags)"""
+def draw_case(seed, k):
+    """configuration k of run `seed`: genome, reads, preset and options (as keyword arguments of lib.policy_params + the reference's
+    flags).  Every group of choices has its own generator, so that a new group does not move the cases of the existing seeds."""
     from bowtie2_b200 import policy
+    rng = np.random.default_rng([seed, k, 0])
     c = {"genome_seed": int(rng.integers(1, 1 << 30)), "n_contigs": int(rng.integers(1, 4)), "contig_len": int(rng.integers(8000, 30000)),
          "repeat_frac": float(rng.choice([0.02, 0.1, 0.3])), "repeat_len": int(rng.integers(100, 600)), "repeat_copies": int(rng.integers(3, 20)),
          "n_gap": int(rng.integers(0, 60)), "local": bool(rng.integers(0, 2)), "paired": bool(rng.integers(0, 2)),
@@ -64,7 +66,7 @@ def draw_case(rng):
             kw["mixed"] = False; flags.append("--no-mixed")
         if rng.random() < 0.25:
             kw["discord"] = False; flags.append("--no-discordant")
-    # scoring options (drawn last: the draws above keep their sequence)
+    rng = np.random.default_rng([seed, k, 1])                      # scoring options
     if rng.random() < 0.4:
         sc = policy.Scoring.default(c["local"])
         if rng.random() < 0.5:
@@ -89,6 +91,11 @@ def draw_case(rng):
             a, b = float(rng.choice([0, 2])), float(rng.choice([0.05, 0.15, 0.5]))
             sc.n_ceil_over = policy.SimpleFunc(policy.SIMPLE_FUNC_LINEAR, a, b); flags += ["--n-ceil", f"L,{a},{b}"]
         kw["sc"] = sc
+    c["large"] = bool(np.random.default_rng([seed, k, 2]).random() < 0.25)          # a .bt2l index (64-bit offsets, 128-byte sides, 64-bit RNG draws) and bowtie2-align-l
+    rng = np.random.default_rng([seed, k, 3])                      # the run's RNG seed and -M
+    c["run_seed"] = int(rng.choice([0, 0, 1, 7, 12345]))
+    if rng.random() < 0.25:
+        kw["mhits"] = int(rng.choice([1, 3, 20, 100])); flags += ["-M", str(kw["mhits"])]     # (-M 0 is not an input: bt2_search.cpp:1775 asserts mhits > 0)
     c["kw"], c["flags"] = kw, flags
     return c
 
@@ -109,7 +116,11 @@ def run_case(c, work, n_unpaired=300, n_pairs=200):
                                 repeat_len=c["repeat_len"], repeat_copies=c["repeat_copies"], n_gap=c["n_gap"])
     fa, base = os.path.join(work, "g.fa"), os.path.join(work, "g")
     synth.write_fasta(fa, contigs)
-    conftest._build_index("bowtie2-build-s", fa, base)
+    large = c.get("large", False)
+    for f in os.listdir(work):                                     # (a stale index of the other kind would be opened first)
+        if f.startswith("g.") and (f.endswith(".bt2") or f.endswith(".bt2l")):
+            os.remove(os.path.join(work, f))
+    conftest._build_index("bowtie2-build-l" if large else "bowtie2-build-s", fa, base)
     ref_names = [f"chr{k + 1}" for k in range(len(contigs))]
     local, paired, L = c["local"], c["paired"], c["read_len"]
     if paired:
@@ -125,30 +136,29 @@ def run_case(c, work, n_unpaired=300, n_pairs=200):
         names, inp = [f"r{i}" for i in range(n_unpaired)], ["-U", f1]
     pflag = "--" + c["preset"] + ("-local" if local else "")
     sam = os.path.join(work, "ref.sam")
-    subprocess.check_call([REF, pflag] + (["--local"] if local else []) + c["flags"] + ["--seed", "0", "-p", "1", "--reorder", "-x", base] + inp + ["-S", sam],
+    subprocess.check_call([REF[:-1] + "l" if large else REF, pflag] + (["--local"] if local else []) + c["flags"] + ["--seed", str(c.get("run_seed", 0)), "-p", "1", "--reorder", "-x", base] + inp + ["-S", sam],
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     golden = [l.rstrip("\n") for l in open(sam) if not l.startswith("@")]
     from oracle_lib import Oracle, oracle_policy_table
-    be, keep = oracle_policy_table(Oracle(base), local, 4, c["kw"].get("sc"))        # the C oracle behind the entry-point table
+    be, keep = oracle_policy_table(Oracle(base), local, 8 if large else 4, c["kw"].get("sc"))        # the C oracle behind the entry-point table
     batch = ReadBatch.from_list(reads, quals)
-    res, ops, pairs, st = policy_align(lib, be, policy_params(c["preset"], local=local, paired=paired, **c["kw"]), batch, names, entry="bt2g_xengine_align_host")
+    res, ops, pairs, st = policy_align(lib, be, policy_params(c["preset"], local=local, paired=paired, seed=c.get("run_seed", 0), **c["kw"]), batch, names, entry="bt2g_xengine_align_host")
     lines = sam_format(lib, batch, res, ops, ref_names, read_names=names, pairs=pairs, local=local,
                        no_discordant=(c["kw"].get("discord") is False), **_format_options(c, local)).rstrip("\n").split("\n")
     diff = [i for i, (a, b) in enumerate(zip(lines, golden)) if a != b]
     nbad = len(diff) + abs(len(lines) - len(golden))
     first = (lines[diff[0]], golden[diff[0]]) if diff else None
-    desc = f"{pflag} {' '.join(c['flags'])} paired={paired} L={L} sub={c['sub_rate']} indel={c['indel_rate']} contigs={len(contigs)}"
+    desc = f"{'.bt2l ' if large else ''}{pflag} --seed {c.get('run_seed', 0)} {' '.join(c['flags'])} paired={paired} L={L} sub={c['sub_rate']} indel={c['indel_rate']} contigs={len(contigs)}"
     return len(golden), nbad, first, st, desc
 
 
 def main():
     seed, cases = int(sys.argv[1]) if len(sys.argv) > 1 else 1, int(sys.argv[2]) if len(sys.argv) > 2 else 20
     work = sys.argv[3] if len(sys.argv) > 3 else "/tmp/bt2g_parity_fuzz"
-    rng = np.random.default_rng(seed)
     tot = bad = units = fallbacks = 0
     t0 = time.time()
     for k in range(cases):
-        c = draw_case(rng)
+        c = draw_case(seed, k)
         n, nb, first, st, desc = run_case(c, work)
         tot += n; bad += nb; units += st[0]; fallbacks += st[1]
         print(f"case {k}: {desc}: {n} records, {nb} differing; {st[0]} units, {st[1]} finished by the coroutine engine", flush=True)
