@@ -96,8 +96,37 @@ def draw_case(seed, k):
     c["run_seed"] = int(rng.choice([0, 0, 1, 7, 12345]))
     if rng.random() < 0.25:
         kw["mhits"] = int(rng.choice([1, 3, 20, 100])); flags += ["-M", str(kw["mhits"])]     # (-M 0 is not an input: bt2_search.cpp:1775 asserts mhits > 0)
+    rng = np.random.default_rng([seed, k, 4])                      # odd reads: ragged lengths (down to 0), Ns, reads across contig ends
+    c["ragged"] = bool(rng.random() < 0.3)
+    c["n_rate"] = float(rng.choice([0.0, 0.0, 0.02, 0.1]))
+    c["straddle"] = bool(rng.random() < 0.3)
+    c["read_seed"] = int(rng.integers(1, 1 << 30))
     c["kw"], c["flags"] = kw, flags
     return c
+
+
+def _odd_reads(c, contigs, reads, quals):
+    """in place: the case's ragged lengths / Ns / contig-straddling reads (same treatment whatever the pairing)"""
+    rng = np.random.default_rng(c.get("read_seed", 1))
+    L = c["read_len"]
+    joined = np.concatenate(contigs) if contigs else np.zeros(0, np.uint8)
+    ends = np.cumsum([len(g) for g in contigs])[:-1]
+    for i in range(len(reads)):
+        r, q = reads[i].copy(), quals[i].copy()
+        if c.get("straddle") and len(ends) and rng.random() < 0.08:
+            e = int(rng.choice(ends)); a = max(0, e - int(rng.integers(1, L)))
+            w = joined[a:a + L].copy()
+            if len(w) == L:
+                w = np.minimum(w, 4)
+                r = (w if rng.random() < 0.5 else np.where(w[::-1] > 3, 4, 3 - np.minimum(w[::-1], 3))).astype(np.uint8)
+        if c.get("n_rate", 0.0) > 0:
+            r[rng.random(len(r)) < c["n_rate"]] = 4
+        if c.get("ragged") and rng.random() < 0.5:
+            n = int(rng.integers(0, len(r) + 1)) if rng.random() < 0.3 else int(rng.integers(max(1, len(r) // 2), len(r) + 1))
+            if c["paired"] and (i & 1) and n == 0:
+                n = 1          # an EMPTY mate 2 makes the reference treat the pair as an unpaired read (bt2_search.cpp:3326): a known difference, DESIGN.md section 7
+            r, q = r[:n], q[:n]
+        reads[i], quals[i] = np.ascontiguousarray(r, dtype=np.uint8), np.ascontiguousarray(q, dtype=np.uint8)
 
 
 def _format_options(c, local):
@@ -126,11 +155,13 @@ def run_case(c, work, n_unpaired=300, n_pairs=200):
     if paired:
         reads, quals, _ = synth.make_pairs(contigs, n_pairs, L, seed=c["genome_seed"] + 1, sub_rate=c["sub_rate"], indel_rate=c["indel_rate"],
                                            ins_mean=c["ins_mean"], hard_frac=c["hard_frac"])
+        _odd_reads(c, contigs, reads, quals)
         f1, f2 = os.path.join(work, "r1.fq"), os.path.join(work, "r2.fq")
         synth.write_fastq(f1, reads[0::2], quals[0::2], prefix="p"); synth.write_fastq(f2, reads[1::2], quals[1::2], prefix="p")
         names, inp = [f"p{i // 2}" for i in range(2 * n_pairs)], ["-1", f1, "-2", f2]
     else:
         reads, quals, _ = synth.make_reads(contigs, n_unpaired, L, seed=c["genome_seed"] + 1, sub_rate=c["sub_rate"], indel_rate=c["indel_rate"], random_frac=0.03)
+        _odd_reads(c, contigs, reads, quals)
         f1 = os.path.join(work, "r.fq")
         synth.write_fastq(f1, reads, quals)
         names, inp = [f"r{i}" for i in range(n_unpaired)], ["-U", f1]
@@ -148,7 +179,8 @@ def run_case(c, work, n_unpaired=300, n_pairs=200):
     diff = [i for i, (a, b) in enumerate(zip(lines, golden)) if a != b]
     nbad = len(diff) + abs(len(lines) - len(golden))
     first = (lines[diff[0]], golden[diff[0]]) if diff else None
-    desc = f"{'.bt2l ' if large else ''}{pflag} --seed {c.get('run_seed', 0)} {' '.join(c['flags'])} paired={paired} L={L} sub={c['sub_rate']} indel={c['indel_rate']} contigs={len(contigs)}"
+    odd = "".join([" ragged" if c.get("ragged") else "", f" Ns={c['n_rate']}" if c.get("n_rate") else "", " straddle" if c.get("straddle") else ""])
+    desc = f"{'.bt2l ' if large else ''}{pflag} --seed {c.get('run_seed', 0)} {' '.join(c['flags'])} paired={paired} L={L} sub={c['sub_rate']} indel={c['indel_rate']} contigs={len(contigs)}{odd}"
     return len(golden), nbad, first, st, desc
 
 
