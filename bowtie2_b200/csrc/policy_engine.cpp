@@ -1345,7 +1345,8 @@ static void fillResult(const Result &r, const uint8_t *codes, bt2g_read_result &
 	if(!r.aligned) return;
 	const Aln &a = r.aln;
 	int nops = alnToOps(a, codes, ops, maxOps);
-	if((uint32_t)nops > maxOps) nops = (int)maxOps;            // (rows are maxOps wide: never report more ops than were written)
+	// (rows are maxOps wide; nops keeps the true count, as the device engine's x_fill_result does: a reader clamps, and
+	// bt2g_sam_format reports such records -- their op string lost its tail, the caller's max_ops was too small)
 	out.found = (a.edits.empty() && a.ext() == a.rdlen) ? 2 : 1;
 	out.score = (int32_t)a.score; if(r.hasXs) out.score2 = (int32_t)r.xs;
 	out.fw = a.fw; out.tidx = (uint64_t)a.tidx; out.refoff = a.refoff; out.nops = nops;

@@ -137,6 +137,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 	const size_t rgLen = (opt->rg_optflag && opt->rg_optflag[0]) ? strlen(opt->rg_optflag) + 1 : 0;
 	std::string cigar, mdz;
 	std::vector<char> held; size_t heldN = 0;
+	uint64_t nTrunc = 0;
 	Stacked st;                                                        // buffers reused from record to record
 	for(uint64_t i = i0; i < i1; i++) {
 		const bt2g_read_result &r = res[i];
@@ -172,6 +173,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		int nmm = 0, ngo = 0, ngx = 0, nedits = 0;
 		if(aligned) {
 			const int nops = (r.found & 0xff) == 2 ? 0 : (r.nops > (int)maxOps ? (int)maxOps : r.nops);   // never read past the ops row
+			if((r.found & 0xff) != 2 && r.nops > (int)maxOps) nTrunc++;                                   // (its CIGAR / MD:Z lost their head)
 			const uint8_t *op = ops ? ops + i * (uint64_t)maxOps : nullptr;
 			bool gapless = true;
 			if((r.found & 0xff) != 2) {
@@ -279,7 +281,8 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		const size_t bound = nml + 2 * maxRef + cigar.size() + mdz.size() + 2 * (size_t)len + rgLen + 512;
 		// a pair with only mate 2 aligned is printed aligned mate first (AlnSinkWrap::finishRead reports the
 		// unpaired alignment of mate 2, then the unaligned mate 1, aln_sink.cpp:930-1010): mate 1's record waits
-		const bool hold = paired && (i & 1) == 0 && !aligned && mateAligned;
+		// (not when mate 2's row is there only as mate context, paired -k / -a entries: nothing of this pair follows to wait for)
+		const bool hold = paired && (i & 1) == 0 && !aligned && mateAligned && !(m->found & 0x200);
 		if(hold && held.size() < bound) held.resize(bound);
 		char *const rec = hold ? held.data() : o.room(bound + heldN);
 		char *p = rec;
@@ -380,7 +383,7 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 		if(heldN) { memcpy(p, held.data(), heldN); p += heldN; heldN = 0; }
 		o.n += (size_t)(p - rec);
 	}
-	return 0;
+	return nTrunc ? 1 : 0;
 }
 
 extern "C" int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads, const bt2g_read_result *res, const uint8_t *ops,
@@ -406,7 +409,8 @@ extern "C" int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads
 		for(auto &x : th) x.join();
 	}
 	uint64_t total = 0;
-	for(int t = 0; t < T; t++) { if(rcs[t]) return rcs[t]; total += parts[t].n; }
+	bool truncated = false;
+	for(int t = 0; t < T; t++) { if(rcs[t] < 0) return rcs[t]; truncated = truncated || rcs[t] > 0; total += parts[t].n; }
 	*written = total;
 	if(!out || total > cap) return -3;                             // buffer too small: *written holds the size needed
 	std::vector<uint64_t> at((size_t)T + 1, 0);
@@ -417,7 +421,7 @@ extern "C" int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads
 		for(int t = 0; t < T; t++) th.emplace_back([&, t]() { if(parts[t].n) memcpy(out + at[t], parts[t].blk.get(), parts[t].n); });
 		for(auto &x : th) x.join();
 	}
-	return 0;
+	return truncated ? 1 : 0;                                      // 1: a record had more edit ops than max_ops (text complete, that CIGAR is not)
 }
 
 // ---- FASTQ text -> bt2g_reads buffers (host) ----------------------------------------------------------------

@@ -765,8 +765,11 @@ def sam_format(lib, reads: ReadBatch, res: np.ndarray, ops, ref_names, read_name
         cap = int(need.value)
         buf = alloc(cap)
         rc = lib.bt2g_sam_format(C.byref(opt), C.byref(st), _ptr(res), _ptr(ops), max_ops, _ptr(pairs), _ptr(buf), cap, C.byref(need))
-    if rc:
+    if rc < 0:
         raise RuntimeError(f"bt2g_sam_format failed ({rc})")
+    if rc == 1:
+        import warnings
+        warnings.warn("bt2g_sam_format: an alignment had more edit ops than max_ops; its CIGAR / MD:Z are incomplete (align with a larger max_ops)")
     data = buf[:int(need.value)]
     if as_bytes == "view":
         return memoryview(data)
@@ -1085,14 +1088,14 @@ def policy_params(preset="sensitive", local=False, paired=False, seed=0, k=None,
     return p
 
 
-def policy_align(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads: ReadBatch, names, entry="bt2g_policy_align"):
+def policy_align(lib, backend: "_PolicyBackend", params: "_PolicyParams", reads: ReadBatch, names, entry="bt2g_policy_align", max_ops=None):
     """include/bt2g.h: bt2g_policy_align -> (results, ops, pairs or None, (waves, backend calls, requests)).
     entry="bt2g_xengine_align_host": the fixed-memory state machine of csrc/xengine.cuh driven on the host over the same table
     (stats = units, fallbacks to the coroutine engine, requests)."""
     fn = getattr(lib, entry)
     fn.argtypes = [C.POINTER(_PolicyBackend), C.POINTER(_PolicyParams), C.POINTER(_Reads), _vp, _vp, _vp, C.c_uint32, _vp, _vp]
     n = reads.n
-    max_ops = int(reads.lengths().max()) + 64 if n else 64
+    max_ops = max_ops or (int(reads.lengths().max()) + 64 if n else 64)      # (more for scoring schemes with very cheap gaps)
     res = np.zeros(n, dtype=READ_RESULT)
     ops = np.zeros((max(n, 1), max_ops), dtype=np.uint8)
     pairs = np.zeros(n // 2, dtype=PAIR_RESULT) if params.paired else None

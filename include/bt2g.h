@@ -435,7 +435,10 @@ int  bt2g_pipeline_stage_ms(bt2g_pipeline *p, float *out8);
  * (aligner_result.cpp:520-880), optional fields in the order of SamConfig::printAlignedOptFlags
  * (sam.cpp:121-330): AS XS XN XM XO XG NM MD YS YT.  `ops` / `max_ops` as returned by
  * bt2g_pipeline_run_*_host; `pairs` NULL for unpaired reads.  Returns 0, or -3 with *written = bytes
- * needed when `cap` is too small. */
+ * needed when `cap` is too small, or 1 when the text is complete but some alignment had more edit ops than
+ * `max_ops` (bt2g_read_result.nops > max_ops: the engine could not store the whole op string, so that record's
+ * CIGAR / MD:Z miss their beginning -- align again with a larger max_ops; only scoring schemes with very cheap gaps
+ * produce alignments with more than read length + 64 ops). */
 typedef struct {
 	const char *const *ref_names;   /* [n_refs] reference names as they should appear in RNAME */
 	uint64_t           n_refs;

@@ -553,7 +553,7 @@ int bt2o_one_mm(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *cod
 	int nh = 0, ns = 0;
 	for(int i = 0; i < len; i++) ns += codes[i] > 3;
 	if(ns > 1 || len < 2 || !ix->has_bw) return 0;
-	const int nceil = (int)(0.0 + (double)0.15f * (double)len);
+	const int nceil = (int)(sc->nceil_const + sc->nceil_linear * (double)len);
 	uint8_t *pat[2][2];                          /* [fw?0:1][ebwtfw?0:1] = patFw, patFwRev, patRc, patRcRev */
 	uint8_t *qu[2];                              /* qual, qualRev */
 	for(int a = 0; a < 2; a++) for(int b = 0; b < 2; b++) pat[a][b] = (uint8_t *)malloc((size_t)len);
@@ -724,6 +724,7 @@ void bt2o_scoring_default(bt2o_scoring *sc, int local) {
 	sc->mmp_max = 6; sc->mmp_min = 2; sc->n_pen = 1;
 	sc->rdgap_const = 5; sc->rdgap_linear = 3; sc->rfgap_const = 5; sc->rfgap_linear = 3;
 	sc->gapbar = 4; sc->local = local;
+	sc->nceil_const = 0.0; sc->nceil_linear = (double)0.15f;
 }
 
 /* Scoring::score(rdc, refm, q) (scoring.h:241-251) with refc a code 0..4 instead of a mask */
@@ -737,7 +738,7 @@ static int cell_score(const bt2o_scoring *sc, int rdc, int refc, int q) {
  * editmask[i] = 1 where row i (strand orientation) carries an edit.  Returns 0 / -1 / 1. */
 int bt2o_ungapped(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, const uint8_t *quals, int len, int fw,
                   uint64_t tidx, int64_t off, int64_t tlen, int ohang, int64_t minsc, int64_t *out6, uint8_t *editmask) {
-	const int nceil = (int)(0.0 + (double)0.15f * (double)len);
+	const int nceil = (int)(sc->nceil_const + sc->nceil_linear * (double)len);
 	int ns = 0;
 	const int64_t rfi = off, rff = off + len;
 	int64_t leftNs = 0, rightNs = 0;

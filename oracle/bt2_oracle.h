@@ -73,6 +73,7 @@ void     bt2o_extend(const bt2o_index *ix, const uint8_t *codes, int len, int fw
 typedef struct {
 	int match_bonus, mmp_max, mmp_min, n_pen;
 	int rdgap_const, rdgap_linear, rfgap_const, rfgap_linear, gapbar, local;
+	double nceil_const, nceil_linear;            /* --n-ceil (Scoring::nCeil, scoring.h:61-63: 0, 0.15f): oneMmSearch and ungappedAlign evaluate it themselves */
 } bt2o_scoring;
 void bt2o_scoring_default(bt2o_scoring *sc, int local);
 int  bt2o_one_mm(const bt2o_index *ix, const bt2o_scoring *sc, const uint8_t *codes, const uint8_t *quals, int len,

@@ -227,4 +227,8 @@ void bt2o_policy_table_scoring(void *tv, int match_bonus, int mmp_max, int mmp_m
 	t->sc.match_bonus = match_bonus; t->sc.mmp_max = mmp_max; t->sc.mmp_min = mmp_min; t->sc.n_pen = n_pen;
 	t->sc.rdgap_const = rdgap_const; t->sc.rdgap_linear = rdgap_linear; t->sc.rfgap_const = rfgap_const; t->sc.rfgap_linear = rfgap_linear;
 }
+void bt2o_policy_table_nceil(void *tv, double nceil_const, double nceil_linear) {
+	table_ctx *t = (table_ctx *)tv;
+	t->sc.nceil_const = nceil_const; t->sc.nceil_linear = nceil_linear;
+}
 void bt2o_policy_table_free(void *t) { free(t); }

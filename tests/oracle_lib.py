@@ -174,7 +174,7 @@ def ref_dp(R, local, codes, quals, fw, tidx, tlen, rect, minsc, rndseed=1234, ma
 
 class _OScoring(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("match_bonus", "mmp_max", "mmp_min", "n_pen", "rdgap_const", "rdgap_linear",
-                                       "rfgap_const", "rfgap_linear", "gapbar", "local")]
+                                       "rfgap_const", "rfgap_linear", "gapbar", "local")] + [("nceil_const", C.c_double), ("nceil_linear", C.c_double)]
 
 
 SCORING_OVERRIDE = None      # a bowtie2_b200.policy.Scoring: non-default penalties for the oracle calls that follow
@@ -189,6 +189,8 @@ def oracle_scoring(O, local):
         sc.match_bonus, sc.mmp_max, sc.mmp_min, sc.n_pen = p.match_bonus, p.mmp_max, p.mmp_min, p.n_pen
         sc.rdgap_const, sc.rdgap_linear, sc.rfgap_const, sc.rfgap_linear, sc.gapbar = (p.rdgap_const, p.rdgap_linear, p.rfgap_const,
                                                                                         p.rfgap_linear, p.gapbar)
+        if p.n_ceil_over is not None:
+            sc.nceil_const, sc.nceil_linear = float(p.n_ceil_over.C), float(p.n_ceil_over.L)
     return sc
 
 
@@ -319,4 +321,8 @@ def oracle_policy_table(O, local=False, off_size=4, scoring=None):
         O.lib.bt2o_policy_table_scoring.restype = None
         O.lib.bt2o_policy_table_scoring(h, scoring.match_bonus, scoring.mmp_max, scoring.mmp_min, scoring.n_pen, scoring.rdgap_const,
                                         scoring.rdgap_linear, scoring.rfgap_const, scoring.rfgap_linear)
+        if scoring.n_ceil_over is not None:
+            O.lib.bt2o_policy_table_nceil.argtypes = [vp, C.c_double, C.c_double]
+            O.lib.bt2o_policy_table_nceil.restype = None
+            O.lib.bt2o_policy_table_nceil(h, float(scoring.n_ceil_over.C), float(scoring.n_ceil_over.L))
     return be, (O, h)

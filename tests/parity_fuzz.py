@@ -96,6 +96,15 @@ def draw_case(seed, k):
     c["run_seed"] = int(rng.choice([0, 0, 1, 7, 12345]))
     if rng.random() < 0.25:
         kw["mhits"] = int(rng.choice([1, 3, 20, 100])); flags += ["-M", str(kw["mhits"])]     # (-M 0 is not an input: bt2_search.cpp:1775 asserts mhits > 0)
+    rng = np.random.default_rng([seed, k, 5])                      # -k N / -a: every reported alignment (the coroutine engine: bt2g_policy_align[_pairs]_k)
+    u = rng.random()
+    if u < 0.25:
+        if "mhits" in kw:
+            del kw["mhits"]; i = flags.index("-M"); del flags[i:i + 2]      # (-M, -k and -a are mutually exclusive)
+        if u < 0.18:
+            kw["k"] = int(rng.choice([2, 3, 10])); flags += ["-k", str(kw["k"])]
+        else:
+            kw["all_hits"] = True; flags.append("-a")
     rng = np.random.default_rng([seed, k, 4])                      # odd reads: ragged lengths (down to 0), Ns, reads across contig ends
     c["ragged"] = bool(rng.random() < 0.3)
     c["n_rate"] = float(rng.choice([0.0, 0.0, 0.02, 0.1]))
@@ -123,6 +132,8 @@ def _odd_reads(c, contigs, reads, quals):
             r[rng.random(len(r)) < c["n_rate"]] = 4
         if c.get("ragged") and rng.random() < 0.5:
             n = int(rng.integers(0, len(r) + 1)) if rng.random() < 0.3 else int(rng.integers(max(1, len(r) // 2), len(r) + 1))
+            if c["kw"].get("k") is not None or c["kw"].get("all_hits"):
+                n = max(n, min(20, len(r)))      # (-a on a 2 bp read reports more alignments than align.py's per-read cap keeps)
             if c["paired"] and (i & 1) and n == 0:
                 n = 1          # an EMPTY mate 2 makes the reference treat the pair as an unpaired read (bt2_search.cpp:3326): a known difference, DESIGN.md section 7
             r, q = r[:n], q[:n]
@@ -171,11 +182,37 @@ def run_case(c, work, n_unpaired=300, n_pairs=200):
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     golden = [l.rstrip("\n") for l in open(sam) if not l.startswith("@")]
     from oracle_lib import Oracle, oracle_policy_table
-    be, keep = oracle_policy_table(Oracle(base), local, 8 if large else 4, c["kw"].get("sc"))        # the C oracle behind the entry-point table
+    fmt = dict(local=local, no_discordant=(c["kw"].get("discord") is False), **_format_options(c, local))
     batch = ReadBatch.from_list(reads, quals)
-    res, ops, pairs, st = policy_align(lib, be, policy_params(c["preset"], local=local, paired=paired, seed=c.get("run_seed", 0), **c["kw"]), batch, names, entry="bt2g_xengine_align_host")
-    lines = sam_format(lib, batch, res, ops, ref_names, read_names=names, pairs=pairs, local=local,
-                       no_discordant=(c["kw"].get("discord") is False), **_format_options(c, local)).rstrip("\n").split("\n")
+    if c["kw"].get("k") is not None or c["kw"].get("all_hits"):
+        # every reported alignment: align.py's own expansion of bt2g_policy_align_k / bt2g_policy_align_pairs_k over the C oracle's table
+        from bowtie2_b200.align import _exact_batch
+
+        class _OracleDevice:
+            _lib = lib
+
+            def __init__(self):
+                self.O, self.sc = Oracle(base), c["kw"].get("sc")
+
+            def set_scoring_policy(self, sc, loc):
+                self.sc = sc if "sc" in c["kw"] else None
+
+            def policy_backend_table(self):
+                return oracle_policy_table(self.O, local, 8 if large else 4, self.sc)
+        out = _exact_batch(_OracleDevice(), batch, names, paired, c["preset"], local, c.get("run_seed", 0), 1, dict(c["kw"]))
+        st = (batch.n // (2 if paired else 1), 0, 0)
+        if paired:
+            batch_k, names_k, res, ops, pairs_e, _ = out
+            lines = sam_format(lib, batch_k, res, ops, ref_names, read_names=names_k, pairs=pairs_e, **fmt).rstrip("\n").split("\n")
+        else:
+            batch_k, names_k, res, ops, _ = out
+            lines = sam_format(lib, batch_k, res, ops, ref_names, read_names=names_k, **fmt).rstrip("\n").split("\n")
+    else:
+        be, keep = oracle_policy_table(Oracle(base), local, 8 if large else 4, c["kw"].get("sc"))        # the C oracle behind the entry-point table
+        res, ops, pairs, st = policy_align(lib, be, policy_params(c["preset"], local=local, paired=paired, seed=c.get("run_seed", 0), **c["kw"]), batch, names,
+                                           entry="bt2g_xengine_align_host", max_ops=4 * L + 64)   # (room for the op strings of cheap-gap scoring schemes)
+        lines = sam_format(lib, batch, res, ops, ref_names, read_names=names, pairs=pairs, **fmt).rstrip("\n").split("\n")
+    run_case.last = (lines, golden)                                # (for a closer look at a failing case)
     diff = [i for i, (a, b) in enumerate(zip(lines, golden)) if a != b]
     nbad = len(diff) + abs(len(lines) - len(golden))
     first = (lines[diff[0]], golden[diff[0]]) if diff else None

@@ -1,22 +1,36 @@
-"""A few fixed seeds of tests/parity_fuzz.py in the CPU suite: random genome / reads / preset / option sets through the device engine's
-state machine on the host, every SAM record identical to the unmodified reference program's (oracle/_ref)."""
+"""A few fixed cases of tests/parity_fuzz.py in the CPU suite: random genome / reads / preset / option sets through the device engine's
+state machine on the host (and, for -k / -a, through the coroutine engine), every SAM record identical to the unmodified reference
+program's (oracle/_ref)."""
 import os
 
 import pytest
 
 import parity_fuzz
 
+CASES = [
+    (11, list(range(16))),
+    # 100/2: --no-discordant on pairs whose mates each aligned once without a concordant pair (records that read YT:Z:DP unless the
+    # formatter is told about the option, BT2G_SAM_NO_DISCORDANT)
+    (100, list(range(8))),
+    # 101/11, 44, 55: paired -k with an unaligned mate 1 beside a multiply aligned mate 2 (the unaligned record is the pair's LAST one);
+    # 101/13: cheap gaps and a high match bonus -- an alignment with more edit ops than read length + 64
+    (101, [11, 13, 44, 55]),
+    # 64/182: an alignment with more ops than the coroutine engine's first retry buffers held; 92/180: 2-5 bp reads with one N under --n-ceil
+    (64, [182]), (92, [180]),
+]
+
 
 @pytest.mark.skipif(not os.path.exists(parity_fuzz.REF), reason="oracle/_ref is not built")
-@pytest.mark.parametrize("seed", [11, 100])
-def test_random_configurations_identical_to_reference(seed, tmp_path):
+@pytest.mark.parametrize("seed,cases", CASES)
+def test_random_configurations_identical_to_reference(seed, cases, tmp_path):
     seen = set()
-    for k in range(16 if seed == 11 else 8):
+    for k in cases:
         c = parity_fuzz.draw_case(seed, k)
-        n, bad, first, st, desc = parity_fuzz.run_case(c, str(tmp_path), n_unpaired=150, n_pairs=100)
+        small = len(cases) > 4
+        n, bad, first, st, desc = parity_fuzz.run_case(c, str(tmp_path), n_unpaired=150 if small else 300, n_pairs=100 if small else 200)
         assert bad == 0, (k, desc, first)
         seen.update(c["flags"])
     if seed == 100:
         assert {"--no-discordant", "--mp", "--score-min", "--n-ceil"}.issubset(seen)
-    # (seed 100, case 2: --no-discordant, with scoring options, on pairs whose mates each aligned once without a concordant pair -- records that read YT:Z:DP
-    # unless the formatter is told about the option, BT2G_SAM_NO_DISCORDANT)
+    if seed == 101:
+        assert "-k" in seen
