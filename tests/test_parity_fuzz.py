@@ -15,8 +15,10 @@ CASES = [
     # 101/11, 44, 55: paired -k with an unaligned mate 1 beside a multiply aligned mate 2 (the unaligned record is the pair's LAST one);
     # 101/13: cheap gaps and a high match bonus -- an alignment with more edit ops than read length + 64
     (101, [11, 13, 44, 55]),
-    # 64/182: an alignment with more ops than the coroutine engine's first retry buffers held; 92/180: 2-5 bp reads with one N under --n-ceil
-    (64, [182]), (92, [180]),
+    # 92/180: 2-5 bp reads with one N under --n-ceil
+    (92, [180]),
+    # (not in the suite, 100 s of oracle DP: `python tests/parity_fuzz.py`'s case 64/182, an alignment with more ops than the coroutine
+    # engine's first retry buffers held -- parity_fuzz.run_case(parity_fuzz.draw_case(64, 182), workdir))
 ]
 
 
