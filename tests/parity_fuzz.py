@@ -212,6 +212,13 @@ def run_case(c, work, n_unpaired=300, n_pairs=200):
         res, ops, pairs, st = policy_align(lib, be, policy_params(c["preset"], local=local, paired=paired, seed=c.get("run_seed", 0), **c["kw"]), batch, names,
                                            entry="bt2g_xengine_align_host", max_ops=4 * L + 64)   # (room for the op strings of cheap-gap scoring schemes)
         lines = sam_format(lib, batch, res, ops, ref_names, read_names=names, pairs=pairs, **fmt).rstrip("\n").split("\n")
+        if os.environ.get("BT2G_FUZZ_BOTH"):
+            # the coroutine engine (csrc/policy_engine.cpp, the fallback of the state machine and align_files' engine) on the same case
+            res2, ops2, pairs2, _ = policy_align(lib, be, policy_params(c["preset"], local=local, paired=paired, seed=c.get("run_seed", 0), **c["kw"]), batch, names,
+                                                 max_ops=4 * L + 64)
+            lines2 = sam_format(lib, batch, res2, ops2, ref_names, read_names=names, pairs=pairs2, **fmt).rstrip("\n").split("\n")
+            if lines2 != lines:
+                lines = lines2 if lines == golden else lines           # (report whichever differs from the reference)
     run_case.last = (lines, golden)                                # (for a closer look at a failing case)
     diff = [i for i, (a, b) in enumerate(zip(lines, golden)) if a != b]
     nbad = len(diff) + abs(len(lines) - len(golden))
