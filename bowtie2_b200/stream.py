@@ -43,10 +43,10 @@ class TextAligner:
     of a batch is handed to the sink as a memoryview of one reused output buffer: the sink must consume it (write it) before it
     returns.  No per-batch allocation is left on the steady-state path."""
 
-    def __init__(self, engines, ref_names, paired, local=False, parse_threads=4, format_threads=8, name_stride=32, depth=2, no_discordant=False):
+    def __init__(self, engines, ref_names, paired, local=False, parse_threads=4, format_threads=8, name_stride=32, depth=2, no_discordant=False, sc=None):
         self.engines, self.ref_names, self.paired, self.local = list(engines), list(ref_names), paired, local
         self.parse_threads, self.format_threads, self.name_stride, self.depth = parse_threads, format_threads, name_stride, depth
-        self.no_discordant = no_discordant                       # the engines' --no-discordant, for the record formatter
+        self.no_discordant, self.sc = no_discordant, sc          # the run's --no-discordant / scoring scheme, for the record formatter
         self.lib = load_library()
         self._slots = [HostBuffers() for _ in range(depth + len(self.engines) + 1)]
         # (engine stand-ins of the CPU tests may not take reusable result buffers)
@@ -65,10 +65,11 @@ class TextAligner:
             raise ValueError(f"mate files differ in length within a batch ({batch.n // 2} whole pairs; {len(t1) - used1} and {len(t2) - used2} bytes left over)")
         return batch, names
 
-    def run(self, items, sink):
-        """items: iterable of (mate-1 FASTQ text, mate-2 FASTQ text or None), each at most one engine batch; sink(view) is called once
-        per item, in input order, with the SAM text as a memoryview that is valid until the sink returns.  Returns the number of
-        records written."""
+    def run(self, items, sink, on_batch=None):
+        """items: iterable of (mate-1 FASTQ text, mate-2 FASTQ text or None), each at most one engine batch -- or a FastqFiles object
+        (whole files, cut into batches here); sink(view) is called once per batch, in input order, with the SAM text as a memoryview
+        that is valid until the sink returns; on_batch(res, pairs), if given, sees every batch's result arrays before the sink (the
+        alignment summary's counts).  Returns the number of reads written."""
         q_free, q_parsed, q_done = queue.Queue(), queue.Queue(), queue.Queue()
         for slot in self._slots:
             q_free.put(slot)
@@ -77,11 +78,24 @@ class TextAligner:
 
         def parser():
             try:
-                for k, item in enumerate(items):
-                    slot = q_free.get()                          # (back-pressure: at most len(slots) batches in flight)
-                    if errs:
-                        break
-                    q_parsed.put((k, slot, *self._parse(item, slot)))
+                if isinstance(items, FastqFiles):
+                    k = 0
+                    while True:
+                        slot = q_free.get()                      # (back-pressure: at most len(slots) batches in flight)
+                        if errs:
+                            break
+                        got = items.next_batch(self.lib, slot, self.name_stride, self.parse_threads)
+                        if got is None:
+                            q_free.put(slot)
+                            break
+                        q_parsed.put((k, slot, *got))
+                        k += 1
+                else:
+                    for k, item in enumerate(items):
+                        slot = q_free.get()
+                        if errs:
+                            break
+                        q_parsed.put((k, slot, *self._parse(item, slot)))
             except Exception as e:
                 errs.append(e)
             for _ in self.engines:
@@ -113,7 +127,9 @@ class TextAligner:
                     while nxt in pending:
                         slot, batch, names, res, ops, pairs = pending.pop(nxt)
                         txt = sam_format(self.lib, batch, res, ops, self.ref_names, read_names=names, pairs=pairs, threads=self.format_threads,
-                                         local=self.local, as_bytes="view", out=self._out, no_discordant=self.no_discordant)
+                                         local=self.local, as_bytes="view", out=self._out, no_discordant=self.no_discordant, sc=self.sc)
+                        if on_batch is not None:
+                            on_batch(res, pairs)
                         sink(txt)
                         total[0] += batch.n
                         nxt += 1
@@ -132,3 +148,117 @@ class TextAligner:
         if errs:
             raise errs[0]
         return total[0]
+
+
+class FastqFiles:
+    """One FASTQ file (unpaired) or the two mate files of paired input (plain or .gz), handed out as engine batches of at most `units`
+    reads / pairs: the reader of PatternComposer (pat.cpp) for FASTQ.  The mate files are read in step (bt2g_fastq_parse_pairs_mt
+    returns how far it got in each text; the rest waits for the next block), so they need not have lines of equal length."""
+
+    def __init__(self, path1, path2=None, units=500_000, chunk_bytes=64 << 20):
+        import gzip
+        op = lambda p: gzip.open(p, "rb") if p.endswith(".gz") else open(p, "rb")
+        self.f = [op(path1)] + ([op(path2)] if path2 else [])
+        self.buf = [b"" for _ in self.f]
+        self.eof = [False for _ in self.f]
+        self.units, self.chunk = int(units), int(chunk_bytes)
+
+    def _fill(self, k, need_lines):
+        while not self.eof[k] and self.buf[k].count(b"\n") < need_lines:
+            more = self.f[k].read(self.chunk)
+            if not more:
+                self.eof[k] = True
+                if self.buf[k] and not self.buf[k].endswith(b"\n"):
+                    self.buf[k] += b"\n"                         # a last record without a final newline
+                break
+            self.buf[k] = self.buf[k] + more if self.buf[k] else more
+
+    def next_batch(self, lib, slot, name_stride, threads):
+        """-> (ReadBatch, NameTable) of the next batch (mates interleaved), or None at the end of the input"""
+        for k in range(len(self.f)):
+            self._fill(k, 4 * self.units + 4)
+        if len(self.f) == 1:
+            if not self.buf[0].strip():
+                return None
+            batch, names, used = fastq_parse(lib, self.buf[0], max_reads=self.units, name_stride=name_stride, threads=threads, out=slot)
+            if batch.n == 0:
+                raise RuntimeError("truncated FASTQ record at the end of the input")
+            self.buf[0] = self.buf[0][used:]
+            self._check_names(names, name_stride)
+            return batch, names
+        e1, e2 = not self.buf[0].strip(), not self.buf[1].strip()
+        if e1 and e2:
+            return None
+        if e1 or e2:
+            # DualPatternComposer::nextBatch (pat.cpp:256-290)
+            raise RuntimeError("Error, fewer reads in file specified with -%d than in file specified with -%d" % ((1, 2) if e1 else (2, 1)))
+        batch, names, u1, u2 = fastq_parse_pairs(lib, self.buf[0], self.buf[1], name_stride=name_stride, threads=threads, out=slot, max_pairs=self.units)
+        if batch.n == 0:
+            raise RuntimeError("truncated FASTQ record at the end of the input")
+        self.buf[0], self.buf[1] = self.buf[0][u1:], self.buf[1][u2:]
+        self._check_names(names, name_stride)
+        return batch, names
+
+    @staticmethod
+    def _check_names(names, name_stride):
+        # the parser keeps name_stride - 1 bytes of a header line: a row filled to its last byte may have lost its tail (the name feeds
+        # the read's random seed and the QNAME, so that is an error)
+        if len(names) and names.rows[:, name_stride - 2].any():
+            raise ValueError(f"a read name is longer than {name_stride - 2} bytes: pass a larger name_stride")
+
+    def close(self):
+        for f in self.f:
+            f.close()
+
+
+def align_files_stream(index_base, out_path, reads1, reads2=None, preset="sensitive", local=False, device=0, engines=2, batch_units=500_000,
+                       max_read_len=320, name_stride=128, threads=8, seed=0, seed_table=0, dense_sa=-1, offrate=-1, pg_cl=None, summary=None, policy_options=None,
+                       gpu=None, make_engine=None):
+    """bowtie2 -x index_base (-U reads1 | -1 reads1 -2 reads2) -S out_path through the device engine (bt2g_xengine_*: records identical
+    to the reference program's) with the host stages overlapped (TextAligner): file blocks are parsed, aligned by `engines` engines on
+    their own streams and host threads, formatted and written in input order.  The primary alignment per read / pair is reported
+    (-M mode; -k / -a are align.align_files(exact=True)'s).  policy_options: keyword arguments of lib.policy_params (nofw, norc, mixed,
+    discord, pe, sc, mhits, seed_len ...).  name_stride: bytes kept per read name (a longer header line is an error, not a silent cut).
+    Returns the ALIGN_COUNTS record; `summary` (a text stream) receives the alignment summary.
+    gpu / make_engine: an open Bt2Gpu with the index loaded / a factory (params, max_units, max_len) -> engine, for callers that keep
+    them (and for the CPU tests' stand-ins)."""
+    from .lib import ALIGN_COUNTS, Bt2Gpu, IndexFile, XEngine, align_counts_add, align_summary, policy_params, sam_header
+    opts = dict(policy_options or {})
+    if opts.get("k") is not None or opts.get("all_hits"):
+        raise ValueError("-k / -a are not in the device engine's reporting mode: use align.align_files(exact=True)")
+    paired = reads2 is not None
+    own = gpu is None
+    image = IndexFile(index_base, offrate)
+    ref_names, ref_lens = image.ref_names, image.ref_lens
+    if own:
+        gpu = Bt2Gpu(device)                                     # raises without a GPU: nothing below runs on the CPU
+        gpu.load_index_host(image)
+        if seed_table:
+            gpu.build_seed_table(seed_table)
+        if dense_sa >= 0:
+            gpu.build_dense_sa(dense_sa)
+    image.close()
+    lib = load_library()
+    prm = policy_params(preset, local=local, paired=paired, seed=seed, host_threads=threads, **opts)
+    make_engine = make_engine or (lambda p, n, l: XEngine(gpu, p, n, l))
+    engs = [make_engine(prm, batch_units, max_read_len) for _ in range(max(1, engines))]
+    no_disc, no_mixed = opts.get("discord") is False, opts.get("mixed") is False
+    counts = np.zeros(1, dtype=ALIGN_COUNTS)
+    src = FastqFiles(reads1, reads2, units=batch_units)
+    pthr = max(1, threads // 4)
+    ta = TextAligner(engs, [n.split()[0] if n.split() else n for n in ref_names], paired, local=local, parse_threads=pthr,
+                     format_threads=max(1, threads - pthr), name_stride=name_stride, no_discordant=no_disc, sc=opts.get("sc"))
+    try:
+        with open(out_path, "wb") as out:
+            out.write(sam_header(lib, ref_names, ref_lens, pg_cl).encode())
+            ta.run(src, out.write, on_batch=lambda res, pairs: align_counts_add(lib, counts, res, pairs, no_discordant=no_disc))
+    finally:
+        src.close()
+        for e in engs:
+            if hasattr(e, "close"):
+                e.close()
+        if own:
+            gpu.close()
+    if summary is not None:
+        summary.write(align_summary(lib, counts, discord=not no_disc, mixed=not no_mixed))
+    return counts

@@ -64,3 +64,54 @@ def test_fastq_text_to_sam_text_unpaired(lambda_index):
     chunks = []
     ta.run(iter(items), lambda v: chunks.append(bytes(v)))
     assert b"".join(chunks).decode().rstrip("\n").split("\n") == golden[:n]
+
+
+@pytest.mark.parametrize("paired,gz", [(True, False), (True, True), (False, False)])
+def test_whole_files_through_the_stream(tmp_path, lambda_index, paired, gz):
+    """stream.align_files_stream: FASTQ FILES (plain / .gz, mate files read in step, ragged batch cuts) -> SAM file + alignment summary
+    around two engines; header, records and summary equal the reference program's golden outputs"""
+    import gzip
+    import io
+    import shutil
+    from bowtie2_b200.stream import align_files_stream
+    fix = "lambda_P_sensitive" if paired else "lambda_U_sensitive"
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, fix + ".sam")) if not l.startswith("@")]
+    files = []
+    for m in ((1, 2) if paired else (1,)):
+        src = os.path.join(GOLDEN, f"lambda_reads_{m}.fq")
+        n_rec = len(golden) // (2 if paired else 1)
+        lines = open(src, "rb").readlines()[:4 * n_rec]
+        dst = str(tmp_path / f"r{m}.fq") + (".gz" if gz else "")
+        with (gzip.open(dst, "wb") if gz else open(dst, "wb")) as f:
+            f.writelines(lines)
+        files.append(dst)
+    be, keep, fake = _table(lambda_index)
+    made = []
+
+    def make_engine(prm, max_units, max_len):
+        assert max_units == 333 and max_len == 600
+        made.append(_HostEngine(be, prm))
+        return made[-1]
+    out, summ = str(tmp_path / "o.sam"), io.StringIO()
+    counts = align_files_stream(lambda_index, out, files[0], files[1] if paired else None, preset="sensitive", engines=2, batch_units=333,
+                                max_read_len=600, threads=3, summary=summ, gpu=object(), make_engine=make_engine)
+    got = [l.rstrip("\n") for l in open(out)]
+    assert [l for l in got if l.startswith("@")][:2] == ["@HD\tVN:1.5\tSO:unsorted\tGO:query", "@SQ\tSN:gi|9626243|ref|NC_001416.1|\tLN:48502"]
+    assert [l for l in got if not l.startswith("@")] == golden and len(made) == 2
+    assert summ.getvalue() == open(os.path.join(GOLDEN, fix + ".summary.txt")).read()
+    assert int(counts["nread"][0]) == len(golden) // (2 if paired else 1)
+
+
+def test_stream_files_errors(tmp_path, lambda_index):
+    """a mate file that ends early and a read name longer than the name rows are errors, not silent cuts"""
+    from bowtie2_b200.stream import align_files_stream
+    l1 = open(os.path.join(GOLDEN, "lambda_reads_1.fq"), "rb").readlines()[:400]
+    l2 = open(os.path.join(GOLDEN, "lambda_reads_2.fq"), "rb").readlines()[:360]
+    (tmp_path / "a1.fq").write_bytes(b"".join(l1)); (tmp_path / "a2.fq").write_bytes(b"".join(l2))
+    be, keep, fake = _table(lambda_index)
+    mk = lambda prm, n, l: _HostEngine(be, prm)
+    with pytest.raises(RuntimeError, match="fewer reads in file specified with -2"):
+        align_files_stream(lambda_index, str(tmp_path / "o.sam"), str(tmp_path / "a1.fq"), str(tmp_path / "a2.fq"), batch_units=64, gpu=object(), make_engine=mk)
+    (tmp_path / "b.fq").write_bytes(b"@" + b"x" * 200 + b"\nACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIII\n")
+    with pytest.raises(ValueError, match="name_stride"):
+        align_files_stream(lambda_index, str(tmp_path / "o.sam"), str(tmp_path / "b.fq"), batch_units=64, gpu=object(), make_engine=mk)
