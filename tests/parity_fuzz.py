@@ -179,7 +179,7 @@ def run_case(c, work, n_unpaired=300, n_pairs=200):
     pflag = "--" + c["preset"] + ("-local" if local else "")
     sam = os.path.join(work, "ref.sam")
     subprocess.check_call([REF[:-1] + "l" if large else REF, pflag] + (["--local"] if local else []) + c["flags"] + ["--seed", str(c.get("run_seed", 0)), "-p", "1", "--reorder", "-x", base] + inp + ["-S", sam],
-                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                          stdout=subprocess.DEVNULL, stderr=open(os.path.join(work, "ref.err"), "w"))
     golden = [l.rstrip("\n") for l in open(sam) if not l.startswith("@")]
     from oracle_lib import Oracle, oracle_policy_table
     fmt = dict(local=local, no_discordant=(c["kw"].get("discord") is False), **_format_options(c, local))
@@ -212,6 +212,39 @@ def run_case(c, work, n_unpaired=300, n_pairs=200):
         res, ops, pairs, st = policy_align(lib, be, policy_params(c["preset"], local=local, paired=paired, seed=c.get("run_seed", 0), **c["kw"]), batch, names,
                                            entry="bt2g_xengine_align_host", max_ops=4 * L + 64)   # (room for the op strings of cheap-gap scoring schemes)
         lines = sam_format(lib, batch, res, ops, ref_names, read_names=names, pairs=pairs, **fmt).rstrip("\n").split("\n")
+        if os.environ.get("BT2G_FUZZ_FILES"):
+            # the same case as FILES: stream.align_files_stream (FastqFiles -> bt2g_fastq_parse[_pairs]_mt -> engine -> bt2g_sam_format -> SAM file
+            # + alignment summary) around the state machine; records and summary against the reference program's
+            import io
+            from bowtie2_b200.stream import align_files_stream
+
+            class _Eng:
+                def __init__(self, prm):
+                    self.prm = prm
+
+                def align(self, b, nm):
+                    return policy_align(lib, be, self.prm, b, nm, entry="bt2g_xengine_align_host", max_ops=4 * L + 64)
+            summ = io.StringIO()
+            outp = os.path.join(work, "ours.sam")
+            align_files_stream(base, outp, inp[1], inp[3] if paired else None, preset=c["preset"], local=local, engines=1, batch_units=int(c["genome_seed"] % 90) + 37,
+                               max_read_len=4 * L, threads=2, seed=c.get("run_seed", 0), summary=summ, policy_options=dict(c["kw"]), gpu=object(),
+                               make_engine=lambda prm, n, l: _Eng(prm))
+            flines = [l.rstrip("\n") for l in open(outp) if not l.startswith("@")]
+
+            def split(text):                       # every line but the documented "exactly 1" / ">1" split of the concordant pairs
+                conc, rest = 0, []
+                for l in text.split("\n"):
+                    if "aligned concordantly exactly 1 time" in l or "aligned concordantly >1 times" in l:
+                        conc += int(l.split()[0])
+                    else:
+                        rest.append(l)
+                return conc, rest
+            ref_summary = "".join(l for l in open(os.path.join(work, "ref.err")) if not l.startswith("Warning"))
+            if flines != lines:
+                lines = flines if lines == golden else lines
+            elif split(summ.getvalue()) != split(ref_summary):
+                lines = lines + ["SUMMARY DIFFERS: " + repr(summ.getvalue())]
+                golden = golden + ["SUMMARY DIFFERS: " + repr(ref_summary)]
         if os.environ.get("BT2G_FUZZ_BOTH"):
             # the coroutine engine (csrc/policy_engine.cpp, the fallback of the state machine and align_files' engine) on the same case
             res2, ops2, pairs2, _ = policy_align(lib, be, policy_params(c["preset"], local=local, paired=paired, seed=c.get("run_seed", 0), **c["kw"]), batch, names,
