@@ -219,7 +219,8 @@ static int formatRange(const bt2g_sam_opts *opt, const bt2g_reads *reads, const 
 			} else {
 			st.ref.clear(); st.rel.clear(); st.rd.clear();
 			// read characters in reference orientation
-			auto rdch = [&](int row) -> char { return fw ? dna[seq[row] > 4 ? 4 : seq[row]] : comp[seq[len - 1 - row] > 4 ? 4 : seq[len - 1 - row]]; };
+			// (rows past the read -- a result row that does not belong to this read -- read as N instead of reading past the batch)
+			auto rdch = [&](int row) -> char { if(row < 0 || row >= len) return 'N'; return fw ? dna[seq[row] > 4 ? 4 : seq[row]] : comp[seq[len - 1 - row] > 4 ? 4 : seq[len - 1 - row]]; };
 			int row = r.trim_left;
 			if((r.found & 0xff) == 2) {
 				for(int k = 0; k < len; k++) { st.ref.push_back(rdch(k)); st.rel.push_back('='); st.rd.push_back(rdch(k)); }
@@ -412,7 +413,7 @@ extern "C" int bt2g_sam_format(const bt2g_sam_opts *opt, const bt2g_reads *reads
 	bool truncated = false;
 	for(int t = 0; t < T; t++) { if(rcs[t] < 0) return rcs[t]; truncated = truncated || rcs[t] > 0; total += parts[t].n; }
 	*written = total;
-	if(!out || total > cap) return -3;                             // buffer too small: *written holds the size needed
+	if(total > cap || (!out && total)) return -3;                  // buffer too small: *written holds the size needed
 	std::vector<uint64_t> at((size_t)T + 1, 0);
 	for(int t = 0; t < T; t++) at[t + 1] = at[t] + parts[t].n;
 	if(T == 1) { if(parts[0].n) memcpy(out, parts[0].blk.get(), parts[0].n); }
@@ -469,6 +470,7 @@ static int fastqParseCore(const char *text, uint64_t len, uint64_t maxReads, uin
 						}
 						nb += L; n++; off[n] = nb;
 						cur = (uint64_t)(nl4 + 1 - text);
+						while(cur < len && (text[cur] == '\n' || text[cur] == '\r')) cur++;     // blank lines between records (as the general path below)
 						continue;
 					}
 				}
