@@ -43,8 +43,13 @@ class TextAligner:
     of a batch is handed to the sink as a memoryview of one reused output buffer: the sink must consume it (write it) before it
     returns.  No per-batch allocation is left on the steady-state path."""
 
-    def __init__(self, engines, ref_names, paired, local=False, parse_threads=4, format_threads=8, name_stride=32, depth=2, no_discordant=False, sc=None):
+    def __init__(self, engines, ref_names, paired, local=False, parse_threads=4, format_threads=8, name_stride=32, depth=2, no_discordant=False, sc=None, make_solo_engine=None):
+        """make_solo_engine: () -> an UNPAIRED engine (same preset and options), created on first use.  A pair whose mate 2 is empty is an
+        unpaired read for the reference (`paired = !read_b().empty()`, bt2_search.cpp:3326: mate 1 goes through the unpaired policy and
+        leaves ONE record, YT:Z:UU, counted with the unpaired reads); with the factory those pairs are aligned and written that way,
+        without it they stay pairs (two records, mate 2 unaligned with YF:Z:LN)."""
         self.engines, self.ref_names, self.paired, self.local = list(engines), list(ref_names), paired, local
+        self.make_solo_engine, self._solo, self._solo_lock = make_solo_engine, None, threading.Lock()
         self.parse_threads, self.format_threads, self.name_stride, self.depth = parse_threads, format_threads, name_stride, depth
         self.no_discordant, self.sc = no_discordant, sc          # the run's --no-discordant / scoring scheme, for the record formatter
         self.lib = load_library()
@@ -65,11 +70,60 @@ class TextAligner:
             raise ValueError(f"mate files differ in length within a batch ({batch.n // 2} whole pairs; {len(t1) - used1} and {len(t2) - used2} bytes left over)")
         return batch, names
 
+    def _align_solos(self, batch, names):
+        """the pairs of a batch whose mate 2 is empty, their mate 1 aligned as unpaired reads: None, or (pair indexes, ReadBatch, names,
+        results, ops)"""
+        ln = batch.lengths()
+        idx = np.nonzero(ln[1::2] == 0)[0]
+        if len(idx) == 0:
+            return None
+        o = batch.off.astype(np.int64)
+        sb = ReadBatch.from_list([batch.seq[o[2 * i]:o[2 * i + 1]] for i in idx], [batch.qual[o[2 * i]:o[2 * i + 1]] for i in idx])
+        sn = NameTable(np.ascontiguousarray(names.rows[2 * idx])) if isinstance(names, NameTable) else [names[2 * int(i)] for i in idx]
+        with self._solo_lock:                                    # (one unpaired engine, shared by the aligner threads: such pairs are rare)
+            if self._solo is None:
+                self._solo = self.make_solo_engine()
+            cap = int(getattr(self._solo, "max_units", 1 << 30))
+            parts = []
+            for a in range(0, sb.n, cap):
+                b = min(sb.n, a + cap)
+                so = sb.off.astype(np.int64)
+                part = ReadBatch(sb.seq[so[a]:so[b]], (sb.off[a:b + 1] - sb.off[a]).astype(np.uint64), sb.qual[so[a]:so[b]])
+                r, op, _, _ = self._solo.align(part, sn[a:b])
+                parts.append((np.array(r, copy=True), np.array(op, copy=True)))
+        width = max(p[1].shape[1] for p in parts)
+        ops = np.zeros((sb.n, width), dtype=np.uint8)
+        at = 0
+        for r, op in parts:
+            ops[at:at + len(r), :op.shape[1]] = op
+            at += len(r)
+        return idx, sb, sn, np.concatenate([p[0] for p in parts]), ops
+
+    @staticmethod
+    def _segments(batch, names, res, ops, pairs, solo):
+        """the batch as runs of ordinary pairs with the solo reads between them, in input order: (ReadBatch, names, res, ops, pairs or None)"""
+        idx, sb, sn, sres, sops = solo
+        o = batch.off.astype(np.int64)
+
+        def pairs_run(a, b):                                     # pairs [a, b)
+            return (ReadBatch(batch.seq[o[2 * a]:o[2 * b]], (batch.off[2 * a:2 * b + 1] - batch.off[2 * a]).astype(np.uint64), batch.qual[o[2 * a]:o[2 * b]]),
+                    names[2 * a:2 * b], res[2 * a:2 * b], ops[2 * a:2 * b], pairs[a:b])
+        so = sb.off.astype(np.int64)
+        prev = 0
+        for j, p in enumerate(int(x) for x in idx):
+            if p > prev:
+                yield pairs_run(prev, p)
+            yield (ReadBatch(sb.seq[so[j]:so[j + 1]], (sb.off[j:j + 2] - sb.off[j]).astype(np.uint64), sb.qual[so[j]:so[j + 1]]), sn[j:j + 1],
+                   sres[j:j + 1], sops[j:j + 1], None)
+            prev = p + 1
+        if prev < batch.n // 2:
+            yield pairs_run(prev, batch.n // 2)
+
     def run(self, items, sink, on_batch=None):
         """items: iterable of (mate-1 FASTQ text, mate-2 FASTQ text or None), each at most one engine batch -- or a FastqFiles object
-        (whole files, cut into batches here); sink(view) is called once per batch, in input order, with the SAM text as a memoryview
-        that is valid until the sink returns; on_batch(res, pairs), if given, sees every batch's result arrays before the sink (the
-        alignment summary's counts).  Returns the number of reads written."""
+        (whole files, cut into batches here); sink(view) is called once per batch (more often for a batch with solo reads, see
+        make_solo_engine), in input order, with the SAM text as a memoryview that is valid until the sink returns; on_batch(res, pairs),
+        if given, sees the result arrays behind every sink call first (the alignment summary's counts).  Returns the number of reads written."""
         q_free, q_parsed, q_done = queue.Queue(), queue.Queue(), queue.Queue()
         for slot in self._slots:
             q_free.put(slot)
@@ -109,7 +163,8 @@ class TextAligner:
                         break
                     k, slot, batch, names = w
                     res, ops, pairs, _ = eng.align(batch, names, out=slot) if reuse else eng.align(batch, names)
-                    q_done.put((k, slot, batch, names, res, ops, pairs))
+                    solo = self._align_solos(batch, names) if self.paired and self.make_solo_engine is not None else None
+                    q_done.put((k, slot, batch, names, res, ops, pairs, solo))
             except Exception as e:
                 errs.append(e)
                 q_free.put(HostBuffers())                        # never leave the parser waiting
@@ -125,15 +180,16 @@ class TextAligner:
                         continue
                     pending[w[0]] = w[1:]
                     while nxt in pending:
-                        slot, batch, names, res, ops, pairs = pending.pop(nxt)
-                        txt = sam_format(self.lib, batch, res, ops, self.ref_names, read_names=names, pairs=pairs, threads=self.format_threads,
-                                         local=self.local, as_bytes="view", out=self._out, no_discordant=self.no_discordant, sc=self.sc)
-                        if on_batch is not None:
-                            on_batch(res, pairs)
-                        sink(txt)
+                        slot, batch, names, res, ops, pairs, solo = pending.pop(nxt)
+                        for b_, n_, r_, o_, p_ in ([(batch, names, res, ops, pairs)] if solo is None else self._segments(batch, names, res, ops, pairs, solo)):
+                            txt = sam_format(self.lib, b_, r_, o_, self.ref_names, read_names=n_, pairs=p_, threads=self.format_threads,
+                                             local=self.local, as_bytes="view", out=self._out, no_discordant=self.no_discordant, sc=self.sc)
+                            if on_batch is not None:
+                                on_batch(r_, p_)
+                            sink(txt)
                         total[0] += batch.n
                         nxt += 1
-                        del batch, names, res, ops, pairs
+                        del batch, names, res, ops, pairs, solo
                         q_free.put(slot)
             except Exception as e:
                 errs.append(e)
@@ -243,18 +299,21 @@ def align_files_stream(index_base, out_path, reads1, reads2=None, preset="sensit
     make_engine = make_engine or (lambda p, n, l: XEngine(gpu, p, n, l))
     engs = [make_engine(prm, batch_units, max_read_len) for _ in range(max(1, engines))]
     no_disc, no_mixed = opts.get("discord") is False, opts.get("mixed") is False
+    solo_opts = {k: v for k, v in opts.items() if k not in ("pe", "mixed", "discord")}      # the unpaired policy of the same run
     counts = np.zeros(1, dtype=ALIGN_COUNTS)
     src = FastqFiles(reads1, reads2, units=batch_units)
     pthr = max(1, threads // 4)
     ta = TextAligner(engs, [n.split()[0] if n.split() else n for n in ref_names], paired, local=local, parse_threads=pthr,
-                     format_threads=max(1, threads - pthr), name_stride=name_stride, no_discordant=no_disc, sc=opts.get("sc"))
+                     format_threads=max(1, threads - pthr), name_stride=name_stride, no_discordant=no_disc, sc=opts.get("sc"),
+                     make_solo_engine=(lambda: make_engine(policy_params(preset, local=local, paired=False, seed=seed, host_threads=threads, **solo_opts),
+                                                           min(batch_units, 4096), max_read_len)) if paired else None)
     try:
         with open(out_path, "wb") as out:
             out.write(sam_header(lib, ref_names, ref_lens, pg_cl).encode())
             ta.run(src, out.write, on_batch=lambda res, pairs: align_counts_add(lib, counts, res, pairs, no_discordant=no_disc))
     finally:
         src.close()
-        for e in engs:
+        for e in engs + ([ta._solo] if ta._solo is not None else []):
             if hasattr(e, "close"):
                 e.close()
         if own:

@@ -23,9 +23,10 @@ CASES = [
 
 
 @pytest.mark.skipif(not os.path.exists(parity_fuzz.REF), reason="oracle/_ref is not built")
-@pytest.mark.parametrize("seed,cases", CASES + [(131, [3, 60, 74, 75])])
+@pytest.mark.parametrize("seed,cases", CASES + [(131, [3, 60, 74, 75]), (151, [10, 34])])
 def test_random_configurations_identical_to_reference(seed, cases, tmp_path, monkeypatch):
-    if seed == 131:
+    if seed in (131, 151):
+        # (151/10, 34: pairs with an EMPTY mate 2 -- an unpaired read for the reference, the stream's solo engine)
         # as FILES too: stream.align_files_stream (reader, parser, engine, formatter, ordered writer, alignment summary) on the same cases --
         # ragged reads down to empty ones, empty mate 1, .bt2l, pairing options
         monkeypatch.setenv("BT2G_FUZZ_FILES", "1")
