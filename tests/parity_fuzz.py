@@ -250,7 +250,7 @@ def run_case(c, work, n_unpaired=300, n_pairs=200):
             res2, ops2, pairs2, _ = policy_align(lib, be, policy_params(c["preset"], local=local, paired=paired, seed=c.get("run_seed", 0), **c["kw"]), batch, names,
                                                  max_ops=4 * L + 64)
             lines2 = sam_format(lib, batch, res2, ops2, ref_names, read_names=names, pairs=pairs2, **fmt).rstrip("\n").split("\n")
-            if lines2 != lines:
+            if lines2 != lines and len(lines2) == len(lines):          # (not comparable when the file path wrote solo reads: empty mate 2)
                 lines = lines2 if lines == golden else lines           # (report whichever differs from the reference)
     run_case.last = (lines, golden)                                # (for a closer look at a failing case)
     diff = [i for i, (a, b) in enumerate(zip(lines, golden)) if a != b]
