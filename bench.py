@@ -724,7 +724,7 @@ def run_exact(S, args):
                 first = (k // E) * B + a
                 items.append((fastq_text(r_np[0::mates], q_np[0::mates], first), fastq_text(r_np[1::2], q_np[1::2], first) if paired else None))
             ref_names = [f"chr{k + 1}" for k in range(GENOME_CONTIGS)]
-            pthr = max(1, S.fmt_threads // 4)
+            pthr = max(1, S.fmt_threads * 3 // 8)        # (parse is the heavier host stage per thread: tools/host_text_bench.py)
             ta = TextAligner(engines, ref_names, paired, local=local, parse_threads=pthr, format_threads=max(1, S.fmt_threads - pthr - E), name_stride=NS)
             reps = max(1, (args.steps * E + n_items - 1) // n_items)
             sam_bytes = [0]
