@@ -8,6 +8,7 @@
 
 // launchers from fm_kernels.cu
 template <typename OFF> void launch_rank4(const DevEbwt<OFF> &, const uint64_t *, uint64_t, uint64_t *, cudaStream_t);
+template <typename OFF> void launch_maplf_range(const DevEbwt<OFF> &, const uint64_t *, const uint64_t *, const uint64_t *, uint64_t, uint64_t *, uint64_t *, uint8_t *, cudaStream_t);
 template <typename OFF> void launch_maplf1(const DevEbwt<OFF> &, const uint64_t *, const uint8_t *, uint64_t, uint64_t *, cudaStream_t);
 template <typename OFF> void launch_ftab(const DevEbwt<OFF> &, const uint64_t *, uint64_t, uint64_t *, cudaStream_t);
 template <typename OFF> void launch_exact_sweep(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, cudaStream_t, unsigned long long * = nullptr);
@@ -308,6 +309,33 @@ int bt2g_maplf1(bt2g_ctx *ctx, int mirror, const uint64_t *rows, const uint8_t *
 	              launch_maplf1<uint64_t>(devEbwt<uint64_t>(ctx, mirror), dr.as<uint64_t>(), dc.as<uint8_t>(), n, dout.as<uint64_t>(), ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaGetLastError());
 	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int bt2g_maplf_range(bt2g_ctx *ctx, int mirror, const uint64_t *tops, const uint64_t *nums, uint64_t n, uint64_t *upto, uint64_t *in, uint8_t *chars) {
+	REQUIRE_LOADED(ctx);
+	if(mirror && !ctx->info.has_bw) { ctx->err = "mirror index not loaded"; return -1; }
+	if(n == 0) return 0;
+	const uint64_t bwtLen = ctx->info.len + 1;
+	std::vector<uint64_t> rowOff(n + 1, 0);
+	for(uint64_t i = 0; i < n; i++) {
+		if(nums[i] == 0 || tops[i] >= bwtLen || nums[i] > bwtLen - tops[i]) { ctx->err = "bt2g_maplf_range: a range is empty or leaves the BWT"; return -1; }
+		rowOff[i + 1] = rowOff[i] + nums[i];
+	}
+	const uint64_t rows = rowOff[n];
+	DBuf dt, dn, dro, du, di, dc;
+	BT2G_CUDA_TRY(ctx, dt.alloc(n * 8)); BT2G_CUDA_TRY(ctx, dn.alloc(n * 8)); BT2G_CUDA_TRY(ctx, dro.alloc((n + 1) * 8));
+	BT2G_CUDA_TRY(ctx, du.alloc(n * 32)); BT2G_CUDA_TRY(ctx, di.alloc(n * 32)); BT2G_CUDA_TRY(ctx, dc.alloc(rows));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(dt.p, tops, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(dn.p, nums, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(dro.p, rowOff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	DISPATCH(ctx, launch_maplf_range<uint32_t>(devEbwt<uint32_t>(ctx, mirror), dt.as<uint64_t>(), dn.as<uint64_t>(), dro.as<uint64_t>(), n, du.as<uint64_t>(), di.as<uint64_t>(), dc.as<uint8_t>(), ctx->stream),
+	              launch_maplf_range<uint64_t>(devEbwt<uint64_t>(ctx, mirror), dt.as<uint64_t>(), dn.as<uint64_t>(), dro.as<uint64_t>(), n, du.as<uint64_t>(), di.as<uint64_t>(), dc.as<uint8_t>(), ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaGetLastError());
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(upto, du.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(in, di.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+	BT2G_CUDA_TRY(ctx, cudaMemcpyAsync(chars, dc.p, rows, cudaMemcpyDeviceToHost, ctx->stream));
 	BT2G_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	return 0;
 }

@@ -276,6 +276,55 @@ __global__ void k_get_stretch(DevIndex<OFF> ix, const uint64_t *tidx, const int6
 // ----------------------------------------------------------------------------------------
 static inline unsigned gridFor(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
+// Ebwt::mapLFRange (bt2_idx.h:2268-2305) = countBt2SideRange (:1804-1865) + countBt2SideRange2 (:2177-2239): the GroupWalk step
+// of a range that is still several rows wide (group_walk.h:897).  One warp per range.  Lane 0 takes the four ranks at `top`
+// (one side fetch, as rank4).  The rows are then walked side by side: the first WORDS lanes pull the side's BWT words with one
+// coalesced load, every lane decodes the characters of its rows out of the word it gets by shuffle, writes them (32 consecutive
+// bytes per warp store) and tallies them; the tallies are reduced over the warp.  The reference's four bool lists are
+// masks[c][j] == (chars[j] == c); like the reference (:2209) the "$" row counts as an A in `in`, and not in `upto`.
+template <typename OFF>
+__global__ void k_maplf_range(DevEbwt<OFF> e, const uint64_t *tops, const uint64_t *nums, const uint64_t *rowOff, uint64_t n,
+                              uint64_t *upto, uint64_t *in, uint8_t *chars) {
+	constexpr uint32_t BL = SideGeom<OFF>::BWT_LEN, WORDS = SideGeom<OFF>::WORDS, SIDE_SZ = SideGeom<OFF>::SIDE_SZ;
+	const uint32_t lane = threadIdx.x & 31;
+	const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+	if(w >= n) return;
+	const uint64_t top = tops[w], num = nums[w];
+	uint8_t *out = chars + rowOff[w];
+	if(lane == 0) {
+		uint64_t r[4];
+		rank4<OFF>(e, top, r);
+		upto[4 * w + 0] = r[0]; upto[4 * w + 1] = r[1]; upto[4 * w + 2] = r[2]; upto[4 * w + 3] = r[3];
+	}
+	uint64_t nA = 0, nC = 0, nG = 0, nT = 0, done = 0;
+	uint64_t sideNum = top / BL;
+	uint32_t charOff = (uint32_t)(top - sideNum * BL);
+	while(done < num) {
+		const uint64_t left = num - done;
+		const uint32_t take = left < (uint64_t)(BL - charOff) ? (uint32_t)left : BL - charOff;
+		uint64_t word = 0;
+		if(lane < WORDS) word = __ldg((const unsigned long long *)(e.ebwt + sideNum * SIDE_SZ) + lane);
+		for(uint32_t base = 0; base < take; base += 32) {
+			const uint32_t k = base + lane, pos = charOff + k;
+			const uint32_t src = (pos >> 5) < WORDS ? (pos >> 5) : WORDS - 1;
+			const uint64_t ww = __shfl_sync(0xffffffffu, word, src);
+			if(k < take) {
+				const uint32_t c = (uint32_t)(ww >> ((pos & 31) * 2)) & 3;
+				out[done + k] = (uint8_t)c;
+				nA += c == 0; nC += c == 1; nG += c == 2; nT += c == 3;
+			}
+		}
+		done += take;
+		sideNum++; charOff = 0;                          // SideLocus::nextSide (:1857)
+	}
+#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) {
+		nA += __shfl_xor_sync(0xffffffffu, nA, d); nC += __shfl_xor_sync(0xffffffffu, nC, d);
+		nG += __shfl_xor_sync(0xffffffffu, nG, d); nT += __shfl_xor_sync(0xffffffffu, nT, d);
+	}
+	if(lane == 0) { in[4 * w + 0] = nA; in[4 * w + 1] = nC; in[4 * w + 2] = nG; in[4 * w + 3] = nT; }
+}
+
 template <typename OFF>
 void launch_rank4(const DevEbwt<OFF> &e, const uint64_t *rows, uint64_t n, uint64_t *out, cudaStream_t st) {
 	if(n) k_rank4<OFF><<<gridFor(n, 256), 256, 0, st>>>(e, rows, n, out);
@@ -283,6 +332,11 @@ void launch_rank4(const DevEbwt<OFF> &e, const uint64_t *rows, uint64_t n, uint6
 template <typename OFF>
 void launch_maplf1(const DevEbwt<OFF> &e, const uint64_t *rows, const uint8_t *chars, uint64_t n, uint64_t *out, cudaStream_t st) {
 	if(n) k_maplf1<OFF><<<gridFor(n, 256), 256, 0, st>>>(e, rows, chars, n, out);
+}
+template <typename OFF>
+void launch_maplf_range(const DevEbwt<OFF> &e, const uint64_t *tops, const uint64_t *nums, const uint64_t *rowOff, uint64_t n,
+                        uint64_t *upto, uint64_t *in, uint8_t *chars, cudaStream_t st) {
+	if(n) k_maplf_range<OFF><<<gridFor(n * 32, 256), 256, 0, st>>>(e, tops, nums, rowOff, n, upto, in, chars);
 }
 template <typename OFF>
 void launch_ftab(const DevEbwt<OFF> &e, const uint64_t *idx, uint64_t n, uint64_t *out, cudaStream_t st) {
@@ -315,6 +369,7 @@ void launch_get_stretch(const DevIndex<OFF> &ix, const uint64_t *tidx, const int
 #define INSTANTIATE(OFF)                                                                                          \
 	template void launch_rank4<OFF>(const DevEbwt<OFF> &, const uint64_t *, uint64_t, uint64_t *, cudaStream_t);  \
 	template void launch_maplf1<OFF>(const DevEbwt<OFF> &, const uint64_t *, const uint8_t *, uint64_t, uint64_t *, cudaStream_t); \
+	template void launch_maplf_range<OFF>(const DevEbwt<OFF> &, const uint64_t *, const uint64_t *, const uint64_t *, uint64_t, uint64_t *, uint64_t *, uint8_t *, cudaStream_t); \
 	template void launch_ftab<OFF>(const DevEbwt<OFF> &, const uint64_t *, uint64_t, uint64_t *, cudaStream_t);   \
 	template void launch_exact_sweep<OFF>(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, uint8_t *, uint64_t *, cudaStream_t, unsigned long long *); \
 	template void launch_seed_search<OFF>(const DevIndex<OFF> &, const uint8_t *, const uint64_t *, uint64_t, int, int, int, int, const int32_t *, const int32_t *, uint64_t *, int32_t *, cudaStream_t, unsigned long long *); \

@@ -64,7 +64,7 @@ EXPORTS = [
     "bt2g_create", "bt2g_destroy", "bt2g_last_error", "bt2g_abi_version",
     "bt2g_load_index_files", "bt2g_load_index_host", "bt2g_load_index_device",
     "bt2g_index_info_get", "bt2g_index_array",
-    "bt2g_rank4", "bt2g_maplf1", "bt2g_ftab_lohi",
+    "bt2g_rank4", "bt2g_maplf1", "bt2g_maplf_range", "bt2g_ftab_lohi",
     "bt2g_exact_sweep", "bt2g_seed_search", "bt2g_resolve", "bt2g_get_stretch",
 ]
 
@@ -92,6 +92,7 @@ def load_library() -> C.CDLL:
     lib.bt2g_index_array.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
     lib.bt2g_rank4.argtypes = [vp, i32, vp, u64, vp]
     lib.bt2g_maplf1.argtypes = [vp, i32, vp, vp, u64, vp]
+    lib.bt2g_maplf_range.argtypes = [vp, i32, vp, vp, u64, vp, vp, vp]
     lib.bt2g_ftab_lohi.argtypes = [vp, i32, vp, u64, vp]
     lib.bt2g_exact_sweep.argtypes = [vp, C.POINTER(_Reads), i32, i32, vp, vp]
     lib.bt2g_seed_search.argtypes = [vp, C.POINTER(_Reads), C.POINTER(_SeedPlan), vp, vp]
@@ -214,6 +215,17 @@ class Bt2Gpu:
         out = np.empty(len(rows), dtype=np.uint64)
         self._check(self._lib.bt2g_maplf1(self._h, int(mirror), _ptr(rows), _ptr(chars), len(rows), _ptr(out)), "bt2g_maplf1")
         return out
+
+    def maplf_range(self, tops, nums, mirror: bool = False):
+        """Ebwt::mapLFRange (bt2_idx.h:2268) for every [top, top+num): (upto[n,4], in[n,4], chars: one BWT character per
+        row, the ranges back to back)."""
+        tops, nums = _c(tops, np.uint64), _c(nums, np.uint64)
+        upto = np.empty((len(tops), 4), dtype=np.uint64)
+        inn = np.empty((len(tops), 4), dtype=np.uint64)
+        chars = np.empty(int(nums.sum()), dtype=np.uint8)
+        self._check(self._lib.bt2g_maplf_range(self._h, int(mirror), _ptr(tops), _ptr(nums), len(tops), _ptr(upto), _ptr(inn), _ptr(chars)),
+                    "bt2g_maplf_range")
+        return upto, inn, chars
 
     def ftab_lohi(self, idx, mirror: bool = False) -> np.ndarray:
         idx = _c(idx, np.uint64)

@@ -107,6 +107,13 @@ typedef struct {
 int bt2g_rank4(bt2g_ctx *ctx, int mirror, const uint64_t *rows, uint64_t n, uint64_t *out);
 /* Ebwt::mapLF1(row, l, c) (bt2_idx.h:2420-2443): next row, or UINT64_MAX. */
 int bt2g_maplf1(bt2g_ctx *ctx, int mirror, const uint64_t *rows, const uint8_t *chars, uint64_t n, uint64_t *out);
+/* Ebwt::mapLFRange(ltop, lbot, num, cntsUpto, cntsIn, masks) (bt2_idx.h:2268-2305; countBt2SideRange :1804-1865,
+ * countBt2SideRange2 :2177-2239), called per GroupWalk step (group_walk.h:897), for n ranges [tops[i], tops[i]+nums[i]):
+ * upto[4*i+c] = rank of c at tops[i] ("$" adjusted), in[4*i+c] = rows of the range whose BWT character is c (the "$" row
+ * tallied as an A, as the reference does), chars = the BWT character of every row, the ranges back to back (range i starts
+ * at nums[0]+...+nums[i-1]); the reference's masks[c][j] is chars[j] == c.  -1 for an empty range or one that leaves the BWT. */
+int bt2g_maplf_range(bt2g_ctx *ctx, int mirror, const uint64_t *tops, const uint64_t *nums, uint64_t n,
+                     uint64_t *upto, uint64_t *in, uint8_t *chars);
 /* Ebwt::ftabLoHi(i, top, bot) (bt2_idx.h:1476-1485). out[2*i]=top, out[2*i+1]=bot. */
 int bt2g_ftab_lohi(bt2g_ctx *ctx, int mirror, const uint64_t *idx, uint64_t n, uint64_t *out);
 

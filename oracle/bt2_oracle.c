@@ -255,6 +255,21 @@ uint64_t bt2o_maplf1(const bt2o_index *ix, int mirror, uint64_t row, int c) {
 	return bt2o_rank1(ix, mirror, row, c);
 }
 
+/* mapLFRange (bt2_idx.h:2268-2305) = countBt2SideRange (:1804-1865) + countBt2SideRange2 (:2177-2239), the
+ * GroupWalk step for a range that is still several rows wide (group_walk.h:897).  upto[c] = rank of c at `top`
+ * (as countBt2SideEx: the "$" stored as an A is not counted); in[c] = rows of [top, top+num) whose BWT character
+ * is c -- the "$" row, if inside, IS tallied as an A there (:2209) -- and chars[j] is that character (the
+ * reference's four bool lists masks[c][j] == (chars[j] == c)). */
+void bt2o_maplf_range(const bt2o_index *ix, int mirror, uint64_t top, uint64_t num, uint64_t upto[4], uint64_t in[4], uint8_t *chars) {
+	bt2o_rank4(ix, mirror, top, upto);
+	in[0] = in[1] = in[2] = in[3] = 0;
+	for(uint64_t j = 0; j < num; j++) {
+		int c = bt2o_rowL(ix, mirror, top + j);   /* nextSide (:1857) == the row's own side */
+		in[c]++;
+		chars[j] = (uint8_t)c;
+	}
+}
+
 /* ftabHi / ftabLo / ftabLoHi (bt2_idx.h:1428-1554): entries > len are indirections */
 static uint64_t ftab_hi(const bt2o_ebwt *e, uint64_t i) {
 	uint64_t v = e->ftab[i];

@@ -53,6 +53,7 @@ void     bt2o_rank4(const bt2o_index *ix, int mirror, uint64_t row, uint64_t out
 uint64_t bt2o_rank1(const bt2o_index *ix, int mirror, uint64_t row, int c);
 int      bt2o_rowL(const bt2o_index *ix, int mirror, uint64_t row);
 uint64_t bt2o_maplf1(const bt2o_index *ix, int mirror, uint64_t row, int c);
+void     bt2o_maplf_range(const bt2o_index *ix, int mirror, uint64_t top, uint64_t num, uint64_t upto[4], uint64_t in[4], uint8_t *chars);
 void     bt2o_ftab_lohi(const bt2o_index *ix, int mirror, uint64_t i, uint64_t *top, uint64_t *bot);
 uint64_t bt2o_get_offset(const bt2o_index *ix, uint64_t row);
 int      bt2o_joined_to_text(const bt2o_index *ix, uint64_t qlen, uint64_t off, int reject_straddle,

@@ -161,6 +161,24 @@ uint64_t ref_maplf1(void* vh, int mirror, uint64_t row, int c) {
 	return r == (TIndexOffU)OFF_MASK ? ~(uint64_t)0 : (uint64_t)r;
 }
 
+// Ebwt::mapLFRange(ltop, lbot, num, cntsUpto, cntsIn, masks) (bt2_idx.h:2268), called as GWState::advance does
+// (group_walk.h:897); the four bool lists come back as one character per row
+void ref_maplf_range(void* vh, int mirror, uint64_t top, uint64_t num, uint64_t* upto, uint64_t* in, uint8_t* chars) {
+	RefHandle* h = (RefHandle*)vh;
+	const Ebwt& e = mirror ? *h->bw : *h->fw;
+	SideLocus tloc, bloc;
+	SideLocus::initFromTopBot((TIndexOffU)top, (TIndexOffU)(top + num), e.eh(), e.ebwt(), tloc, bloc);
+	TIndexOffU u[4] = {0, 0, 0, 0}, n[4] = {0, 0, 0, 0};
+	EList<bool> masks[4];
+	e.mapLFRange(tloc, bloc, (TIndexOffU)num, u, n, masks);
+	for(int c = 0; c < 4; c++) { upto[c] = u[c]; in[c] = n[c]; }
+	for(uint64_t j = 0; j < num; j++) {
+		int cc = 255;
+		for(int c = 0; c < 4; c++) if(masks[c][j]) cc = (cc == 255) ? c : 254;   // exactly one list may hold row j
+		chars[j] = (uint8_t)cc;
+	}
+}
+
 // Ebwt::ftabLoHi(i, top, bot) (bt2_idx.h:1476)
 void ref_ftab_lohi(void* vh, int mirror, uint64_t i, uint64_t* top, uint64_t* bot) {
 	RefHandle* h = (RefHandle*)vh;

@@ -45,6 +45,7 @@ class _Base:
         g("rank1").restype = u64; g("rank1").argtypes = [vp, ci, u64, ci]
         g("rowL").restype = ci; g("rowL").argtypes = [vp, ci, u64]
         g("maplf1").restype = u64; g("maplf1").argtypes = [vp, ci, u64, ci]
+        g("maplf_range").argtypes = [vp, ci, u64, u64, pu64, pu64, vp]; g("maplf_range").restype = None
         g("ftab_lohi").argtypes = [vp, ci, u64, pu64, pu64]; g("ftab_lohi").restype = None
         g("get_offset").restype = u64; g("get_offset").argtypes = [vp, u64]
         g("get_stretch").argtypes = [vp, u64, C.c_int64, C.c_int64, vp]
@@ -69,6 +70,20 @@ class _Base:
 
     def maplf1(self, rows, chars, mirror=False):
         return np.array([self._g("maplf1")(self.h, int(mirror), int(r), int(c)) for r, c in zip(rows, chars)], dtype=np.uint64)
+
+    def maplf_range(self, tops, nums, mirror=False):
+        """Ebwt::mapLFRange for every [top, top+num): (upto[n,4], in[n,4], chars (one per row, ranges back to back))."""
+        upto = np.empty((len(tops), 4), dtype=np.uint64)
+        inn = np.empty((len(tops), 4), dtype=np.uint64)
+        chars = np.empty(int(np.sum(np.asarray(nums, dtype=np.uint64))), dtype=np.uint8)
+        u, n_, o = (u64 * 4)(), (u64 * 4)(), 0
+        for i, (t, n) in enumerate(zip(tops, nums)):
+            buf = np.empty(int(n), dtype=np.uint8)
+            self._g("maplf_range")(self.h, int(mirror), int(t), int(n), u, n_, buf.ctypes.data_as(vp))
+            upto[i], inn[i] = list(u), list(n_)
+            chars[o:o + int(n)] = buf
+            o += int(n)
+        return upto, inn, chars
 
     def ftab_lohi(self, idx, mirror=False):
         out = np.empty((len(idx), 2), dtype=np.uint64)

@@ -44,6 +44,34 @@ def test_rank_lf_ftab(loaded):
         assert np.array_equal(gpu.ftab_lohi(idx, m), O.ftab_lohi(idx, m))
 
 
+def test_maplf_range(loaded):
+    """Ebwt::mapLFRange (bt2_idx.h:2268; GroupWalk's step over a range, group_walk.h:897): counts up to the top row, counts
+    inside the range and the BWT character of every row, against the oracle (pinned to the reference's own mapLFRange in
+    tests/test_oracle.py) and against the identity the reference asserts (:2281-2292) on this library's own rank4."""
+    from test_oracle import maplf_range_cases
+    gpu, O, _ = loaded
+    n = O.scalars()["bwt_len"]
+    side = gpu.info()["side_bwt_len"]
+    rng = np.random.default_rng(15)
+    for m in (False, True):
+        zo = O.scalars(m)["z_off"]
+        tops, nums = maplf_range_cases(rng, n, zo, side, k=2000)
+        upto, inn, chars = gpu.maplf_range(tops, nums, m)
+        wu, wi, wc = O.maplf_range(tops, nums, m)
+        assert np.array_equal(upto, wu) and np.array_equal(inn, wi) and np.array_equal(chars, wc)
+        assert np.array_equal(inn.sum(axis=1), nums)
+        inside = tops + nums < n                              # (rank4 takes rows of the BWT)
+        bots = gpu.rank4((tops + nums)[inside], m)
+        has_z = ((tops <= zo) & (zo < tops + nums))[inside].astype(np.uint64)
+        want = bots - upto[inside]
+        want[:, 0] += has_z                                   # the "$" row is an A inside a range, and no A for a rank
+        assert np.array_equal(inn[inside], want)
+    with pytest.raises(RuntimeError):
+        gpu.maplf_range([n - 1], [2])
+    with pytest.raises(RuntimeError):
+        gpu.maplf_range([0], [0])
+
+
 def test_resolve(loaded):
     gpu, O, _ = loaded
     sc = O.scalars()

@@ -14,6 +14,19 @@ def seed_interval(ln, const=1.0, coeff=1.15):
     return max(1, int(const + coeff * np.sqrt(ln)))
 
 
+def maplf_range_cases(rng, n, zo, side_len, k=300):
+    """[top, top+num) ranges for Ebwt::mapLFRange: random narrow ranges (what GroupWalk holds), ranges over one and several
+    side ends, one row, the rows around the "$" row (the reference tallies it as an A inside a range), the last rows."""
+    tops = [int(t) for t in rng.integers(0, n - 1, k)]
+    nums = [int(x) for x in rng.integers(1, 40, k)]
+    edge = [(0, 1), (0, side_len), (side_len - 1, 2), (side_len - 3, 2 * side_len + 7), (n - 1, 1), (max(0, n - 50), min(50, n)),
+            (zo, 1), (max(zo, 5) - 5, 11), (min(zo + 1, n - 1), 1), (side_len * (zo // side_len), side_len), (3, min(n - 3, 5 * side_len + 1))]
+    for t, m in edge:
+        tops.append(t); nums.append(m)
+    nums = [max(1, min(m, n - t)) for t, m in zip(tops, nums)]
+    return np.array(tops, dtype=np.uint64), np.array(nums, dtype=np.uint64)
+
+
 def test_oracle_matches_golden_fm(lambda_index, golden_fm):
     g = golden_fm
     O = Oracle(lambda_index)
@@ -60,6 +73,9 @@ def test_oracle_matches_live_reference(which, synth_index, synth_index_large, sy
         assert np.array_equal(O.maplf1(rows, ch, m), R.maplf1(rows, ch, m))
         idx = rng.integers(0, so["ftab_len"] - 1, 1000)
         assert np.array_equal(O.ftab_lohi(idx, m), R.ftab_lohi(idx, m))
+        tops, nums = maplf_range_cases(rng, n, zo, so["side_bwt_sz"] * 4)
+        for got, want in zip(O.maplf_range(tops, nums, m), R.maplf_range(tops, nums, m)):
+            assert np.array_equal(got, want)
     rows = rng.integers(0, n, 1000)
     offs = O.get_offset(rows)
     assert np.array_equal(offs, R.get_offset(rows))
