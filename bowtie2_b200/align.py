@@ -323,9 +323,6 @@ def parse_reads(text: str, fmt: str, first_id: int = 0, fasta_cont=None):
             elif name is not None:
                 cur.append(line.strip())
         for nm, s in recs:
-            for off in range(0, len(s) - k + 1):
-                if off % step == 0 or True:
-                    pass
             # FastaContinuousPatternSource: every window of k characters whose end offset is a multiple of the interval
             for end in range(k, len(s) + 1):
                 off = end - k
