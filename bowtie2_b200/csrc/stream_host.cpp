@@ -1,0 +1,223 @@
+// stream_host.cpp -- FASTQ text in -> SAM text out around the engines, the whole batch loop in C++ (host code, no GPU work here).
+//
+// The batch loop of multiseedSearchWorker (bt2_search.cpp:3253-4254) with its reader (PatternComposer / PatternSourcePerThread,
+// pat.cpp:222-300, :1050+) and its sink (AlnSinkWrap::finishRead -> AlnSinkSam::appendMate, aln_sink.cpp:643, :1889; the ordered
+// output of --reorder, OutputQueue, outq.cpp) as four overlapped stages on host threads:
+//
+//     reader callback + parse (bt2g_fastq_parse_pairs_mt / bt2g_fastq_parse_mt)  ->  E aligner threads, one per engine
+//     (bt2g_xengine_align: H2D, the device waves, D2H)  ->  format (bt2g_sam_format) + alignment counts + writer callback, in input order
+//
+// Every block in flight owns one slot of reused host buffers (parsed reads, names, results, edit ops); the SAM text of a block is
+// written into one reused buffer and handed to the writer before the next block is formatted.  bowtie2_b200/stream.py is the same
+// loop on Python threads (it also routes the pairs with an empty mate 2 through an unpaired engine; this entry point refuses them).
+#include "../../include/bt2g.h"
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct Slot {
+	std::vector<uint8_t> seq, qual, ops;
+	std::vector<uint64_t> off;
+	std::vector<char> names;
+	std::vector<const char *> namePtrs;
+	std::vector<bt2g_read_result> res;
+	std::vector<bt2g_pair_result> pairs;
+	uint64_t nReads = 0;
+};
+
+struct Item { uint64_t k; int slot; };
+
+// blocking queue; after abort() or close() + drained, pop() returns false
+template <typename T>
+struct Chan {
+	std::mutex m;
+	std::condition_variable cv;
+	std::deque<T> q;
+	bool closed = false;
+	const std::atomic<bool> *failed = nullptr;
+	void push(const T &v) { { std::lock_guard<std::mutex> l(m); q.push_back(v); } cv.notify_one(); }
+	void close() { { std::lock_guard<std::mutex> l(m); closed = true; } cv.notify_all(); }
+	bool pop(T &v) {
+		std::unique_lock<std::mutex> l(m);
+		cv.wait(l, [&] { return !q.empty() || closed || failed->load(); });
+		if(failed->load() || q.empty()) return false;
+		v = q.front(); q.pop_front();
+		return true;
+	}
+};
+
+struct Run {
+	bt2g_stream_align_fn align;
+	void *const *engines;
+	int nEngines;
+	bt2g_stream_params sp;
+	const bt2g_sam_opts *opt;
+	const bt2g_stream_io *io;
+	bt2g_align_counts *counts;
+	std::vector<Slot> slots;
+	Chan<int> freeSlots;
+	Chan<Item> parsed, done;
+	std::atomic<bool> failed{false};
+	std::atomic<int> alignersLeft{0};
+	std::mutex errM;
+	int rc = 0;
+	std::string err;
+	bool cutOps = false;
+	uint64_t nReads = 0;
+
+	void fail(int code, const std::string &what) {
+		{
+			std::lock_guard<std::mutex> l(errM);
+			if(rc == 0) { rc = code; err = what; }
+		}
+		failed.store(true);
+		freeSlots.close(); parsed.close(); done.close();
+	}
+
+	void reader() {
+		const int mates = sp.paired ? 2 : 1;
+		for(uint64_t k = 0;; k++) {
+			int si;
+			if(!freeSlots.pop(si)) break;                        // (back-pressure: at most slots.size() blocks in flight)
+			const char *t1 = nullptr, *t2 = nullptr;
+			uint64_t l1 = 0, l2 = 0;
+			int r = io->next_block(io->user, &t1, &l1, &t2, &l2);
+			if(r < 0) { fail(-20, "the reader callback failed (" + std::to_string(r) + ")"); break; }
+			if(r == 0) break;
+			Slot &s = slots[si];
+			const uint64_t maxReads = sp.max_units * mates, maxBases = l1 + l2 + 1;
+			if(s.seq.size() < maxBases) { s.seq.resize(maxBases); s.qual.resize(maxBases); }
+			if(s.off.size() < maxReads + 1) { s.off.resize(maxReads + 1); s.names.resize(maxReads * (uint64_t)sp.name_stride); }
+			uint64_t n = 0, c1 = 0, c2 = 0;
+			int prc;
+			if(sp.paired) {
+				if(t2 == nullptr) { fail(-21, "paired run: the reader gave no mate-2 text"); break; }
+				prc = bt2g_fastq_parse_pairs_mt(t1, l1, t2, l2, sp.max_units, maxBases, s.seq.data(), s.qual.data(), s.off.data(), s.names.data(),
+				                                sp.name_stride, &n, &c1, &c2, sp.parse_threads);
+				n *= 2;
+			} else {
+				prc = bt2g_fastq_parse_mt(t1, l1, maxReads, maxBases, s.seq.data(), s.qual.data(), s.off.data(), s.names.data(), sp.name_stride, &n, &c1,
+				                          sp.parse_threads);
+				c2 = l2;
+			}
+			if(prc != 0) { fail(prc, "FASTQ parse failed in block " + std::to_string(k)); break; }
+			if(c1 != l1 || c2 != l2) {
+				fail(-22, "block " + std::to_string(k) + " does not hold whole records (or more than max_units, or mate files of different length): " +
+				              std::to_string(l1 - c1) + " and " + std::to_string(l2 - c2) + " bytes left over");
+				break;
+			}
+			if(sp.paired) {
+				bool solo = false;
+				for(uint64_t i = 0; i + 1 < n && !solo; i += 2) solo = s.off[i + 2] == s.off[i + 1];
+				if(solo) {
+					fail(-23, "a pair with an empty mate 2 is an unpaired read for the reference (bt2_search.cpp:3326): not handled by this entry point");
+					break;
+				}
+			}
+			for(uint64_t i = 0; i < n; i++) {
+				if(s.off[i + 1] - s.off[i] > sp.max_len) { fail(-24, "a read is longer than the engines' max_len"); return; }
+			}
+			s.nReads = n;
+			if(s.res.size() < n) {
+				s.res.resize(n); s.ops.resize(n * (uint64_t)sp.max_ops); s.pairs.resize(n / 2 + 1); s.namePtrs.resize(n);
+			}
+			for(uint64_t i = 0; i < n; i++) s.namePtrs[i] = s.names.data() + i * (uint64_t)sp.name_stride;
+			parsed.push(Item{k, si});
+		}
+		parsed.close();
+	}
+
+	void aligner(int j) {
+		Item it;
+		while(parsed.pop(it)) {
+			Slot &s = slots[it.slot];
+			bt2g_reads rd;
+			rd.n_reads = s.nReads; rd.seq = s.seq.data(); rd.qual = s.qual.data(); rd.off = s.off.data();
+			int r = s.nReads == 0 ? 0 : align(engines[j], &rd, s.names.data(), sp.name_stride, s.res.data(), s.ops.data(), sp.max_ops,
+			                                 sp.paired ? s.pairs.data() : nullptr, nullptr);
+			if(r != 0) { fail(r, "engine " + std::to_string(j) + " failed on block " + std::to_string(it.k)); break; }
+			done.push(it);
+		}
+		if(alignersLeft.fetch_sub(1) == 1) done.close();
+	}
+
+	void writer() {
+		std::map<uint64_t, int> pending;
+		std::vector<char> out;
+		uint64_t next = 0;
+		Item it;
+		while(done.pop(it)) {
+			pending[it.k] = it.slot;
+			for(auto p = pending.find(next); p != pending.end(); p = pending.find(next)) {
+				const int si = p->second;
+				pending.erase(p);
+				Slot &s = slots[si];
+				if(s.nReads) {
+					bt2g_reads rd;
+					rd.n_reads = s.nReads; rd.seq = s.seq.data(); rd.qual = s.qual.data(); rd.off = s.off.data();
+					bt2g_sam_opts o = *opt;
+					o.read_names = s.namePtrs.data();
+					o.threads = sp.format_threads;
+					// one formatting pass in the common case (SEQ + QUAL + ~260 bytes of fields per record); -3 reports the size needed
+					uint64_t cap = s.off[s.nReads] * 2 + s.nReads * 260 + 4096, need = 0;
+					if(out.size() < cap) out.resize(cap);
+					const bt2g_pair_result *pr = sp.paired ? s.pairs.data() : nullptr;
+					int r = bt2g_sam_format(&o, &rd, s.res.data(), s.ops.data(), sp.max_ops, pr, out.data(), out.size(), &need);
+					if(r == -3) {
+						out.resize(need);
+						r = bt2g_sam_format(&o, &rd, s.res.data(), s.ops.data(), sp.max_ops, pr, out.data(), out.size(), &need);
+					}
+					if(r < 0) { fail(r, "bt2g_sam_format failed on block " + std::to_string(next)); return; }
+					if(r == 1) cutOps = true;
+					if(counts) bt2g_align_counts_add_ex(counts, s.res.data(), s.nReads, pr, sp.count_flags);
+					int w = io->write(io->user, out.data(), need);
+					if(w != 0) { fail(-25, "the writer callback failed (" + std::to_string(w) + ")"); return; }
+					nReads += s.nReads;
+				}
+				next++;
+				freeSlots.push(si);
+			}
+		}
+	}
+};
+
+} // namespace
+
+extern "C" int bt2g_stream_run(bt2g_stream_align_fn align, void *const *engines, int32_t n_engines, const bt2g_stream_params *sp,
+                               const bt2g_sam_opts *opt, const bt2g_stream_io *io, bt2g_align_counts *counts, uint64_t *n_reads,
+                               char *err, uint32_t err_cap) {
+	if(err && err_cap) err[0] = 0;
+	if(!align || !engines || n_engines < 1 || !sp || !opt || !io || !io->next_block || !io->write || sp->max_units == 0 || sp->name_stride == 0) {
+		if(err && err_cap) snprintf(err, err_cap, "bt2g_stream_run: bad arguments");
+		return -1;
+	}
+	Run R;
+	R.align = align; R.engines = engines; R.nEngines = n_engines; R.sp = *sp; R.opt = opt; R.io = io; R.counts = counts;
+	if(R.sp.parse_threads < 1) R.sp.parse_threads = 1;
+	if(R.sp.format_threads < 1) R.sp.format_threads = 1;
+	const int depth = sp->depth > 0 ? sp->depth : 2;
+	R.slots.resize((size_t)(depth + n_engines + 1));
+	R.freeSlots.failed = R.parsed.failed = R.done.failed = &R.failed;
+	for(size_t i = 0; i < R.slots.size(); i++) R.freeSlots.push((int)i);
+	R.alignersLeft.store(n_engines);
+	std::vector<std::thread> th;
+	th.emplace_back([&] { R.reader(); });
+	for(int j = 0; j < n_engines; j++) th.emplace_back([&R, j] { R.aligner(j); });
+	th.emplace_back([&] { R.writer(); });
+	for(auto &t : th) t.join();
+	if(n_reads) *n_reads = R.nReads;
+	if(R.rc != 0) {
+		if(err && err_cap) snprintf(err, err_cap, "%s", R.err.c_str());
+		return R.rc;
+	}
+	return R.cutOps ? 1 : 0;
+}

@@ -1273,3 +1273,105 @@ class XEngine:
         if self._h:
             self.gpu._lib.bt2g_xengine_destroy(self._h)
             self._h = None
+
+
+# ---- the whole batch loop in C++ (csrc/stream_host.cpp) --------------------------------------------------------------------
+EXPORTS += ["bt2g_stream_run"]
+
+_STREAM_ALIGN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(_Reads), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p)
+_STREAM_NEXT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64))
+_STREAM_WRITE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
+
+
+class _StreamIO(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("next_block", _STREAM_NEXT), ("write", _STREAM_WRITE)]
+
+
+class _StreamParams(C.Structure):
+    _fields_ = [("paired", C.c_int32), ("parse_threads", C.c_int32), ("format_threads", C.c_int32), ("depth", C.c_int32), ("max_units", C.c_uint64),
+                ("max_len", C.c_uint32), ("max_ops", C.c_uint32), ("name_stride", C.c_uint32), ("count_flags", C.c_uint32)]
+
+
+def stream_run(lib, engines, blocks, sink, ref_names, paired: bool, max_units: int, max_len: int, max_ops: int, name_stride: int = 64,
+               parse_threads: int = 2, format_threads: int = 2, depth: int = 2, local: bool = False, no_discordant: bool = False, sc=None,
+               align=None, want_counts: bool = False):
+    """include/bt2g.h: bt2g_stream_run -- FASTQ text blocks in, SAM text out, reader / engines / ordered writer overlapped in C++.
+    engines: XEngine objects (their bt2g_xengine_align is the aligner), or, with `align` given, any list: align(j, ReadBatch, NameTable)
+    -> (res, ops, pairs or None) is called for engine j from that engine's thread (the CPU tests' stand-ins).
+    blocks: iterable of (mate-1 text, mate-2 text or None) as bytes, whole records, at most max_units reads (pairs) each.
+    sink(bytes) gets the records of one block, in input order.  Returns (reads written, rc, counts or None); raises on a stage error."""
+    lib.bt2g_stream_run.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(_StreamParams), C.POINTER(_SamOpts), C.POINTER(_StreamIO),
+                                    C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p, C.c_uint32]
+    it = iter(blocks)
+    hold, errs = [None], []
+
+    def next_block(_u, t1, l1, t2, l2):
+        try:
+            b = next(it, None)
+            if b is None:
+                return 0
+            hold[0] = b                                          # (the texts stay alive until the next call)
+            t1[0], l1[0] = C.cast(C.c_char_p(b[0]), C.c_void_p).value, len(b[0])
+            if b[1] is not None:
+                t2[0], l2[0] = C.cast(C.c_char_p(b[1]), C.c_void_p).value, len(b[1])
+            else:
+                t2[0], l2[0] = None, 0
+            return 1
+        except Exception as e:                                   # (no exception may cross the C frames)
+            errs.append(e)
+            return -1
+
+    def write(_u, p, n):
+        try:
+            sink(C.string_at(p, n))
+            return 0
+        except Exception as e:
+            errs.append(e)
+            return -1
+
+    if align is not None:
+        def cb(eng, reads, names, stride, res, ops, mo, pairs, _stats):
+            try:
+                r = reads.contents
+                n = int(r.n_reads)
+                off = np.ctypeslib.as_array(C.cast(r.off, C.POINTER(C.c_uint64)), (n + 1,)).copy()
+                nb = int(off[-1])
+                seq = np.ctypeslib.as_array(C.cast(r.seq, C.POINTER(C.c_uint8)), (max(nb, 1),))[:nb].copy()
+                qual = np.ctypeslib.as_array(C.cast(r.qual, C.POINTER(C.c_uint8)), (max(nb, 1),))[:nb].copy()
+                rows = np.ctypeslib.as_array(C.cast(names, C.POINTER(C.c_uint8)), (n * stride,)).reshape(n, stride).copy()
+                rr, oo, pp = align(int(eng or 0), ReadBatch(seq, off, qual), NameTable(rows))
+                rr = np.ascontiguousarray(rr, dtype=READ_RESULT)
+                C.memmove(res, rr.ctypes.data, n * READ_RESULT.itemsize)
+                dst = np.ctypeslib.as_array(C.cast(ops, C.POINTER(C.c_uint8)), (n * mo,)).reshape(n, mo)
+                w = min(mo, oo.shape[1])
+                dst[:, :w] = oo[:n, :w]
+                if pp is not None and pairs:
+                    pp = np.ascontiguousarray(pp, dtype=PAIR_RESULT)
+                    C.memmove(pairs, pp.ctypes.data, (n // 2) * PAIR_RESULT.itemsize)
+                return 0
+            except Exception as e:
+                errs.append(e)
+                return -30
+        fn = _STREAM_ALIGN(cb)
+        fn_ptr = C.cast(fn, C.c_void_p)
+        handles = (C.c_void_p * len(engines))(*[j if j else None for j in range(len(engines))])
+    else:
+        fn = None
+        fn_ptr = C.cast(lib.bt2g_xengine_align, C.c_void_p)
+        handles = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    rn = (C.c_char_p * len(ref_names))(*[x.encode() for x in ref_names])
+    nce = sc.n_ceil_func() if sc is not None and sc.n_ceil_over is not None else None
+    opt = _SamOpts(rn, len(ref_names), None, int(format_threads), sc_filter_maxlen(True, sc) if local else 0, float(nce.C) if nce else 0.0,
+                   float(nce.L) if nce else 0.0, 4 if no_discordant else 0, 0, None)
+    sp = _StreamParams(int(paired), int(parse_threads), int(format_threads), int(depth), int(max_units), int(max_len), int(max_ops), int(name_stride),
+                       4 if no_discordant else 0)
+    io = _StreamIO(None, _STREAM_NEXT(next_block), _STREAM_WRITE(write))
+    counts = np.zeros(1, dtype=ALIGN_COUNTS) if want_counts else None
+    n_reads = C.c_uint64(0)
+    err = C.create_string_buffer(512)
+    rc = lib.bt2g_stream_run(fn_ptr, handles, len(engines), C.byref(sp), C.byref(opt), C.byref(io), _ptr(counts), C.byref(n_reads), err, 512)
+    if errs:
+        raise errs[0]
+    if rc < 0:
+        raise RuntimeError(f"bt2g_stream_run failed ({rc}): {err.value.decode()}")
+    return int(n_reads.value), rc, counts

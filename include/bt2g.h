@@ -640,6 +640,38 @@ int bt2g_fastq_parse_pairs_mt(const char *text1, uint64_t len1, const char *text
                               uint8_t *seq, uint8_t *qual, uint64_t *off, char *names, uint32_t name_stride, uint64_t *n_pairs,
                               uint64_t *consumed1, uint64_t *consumed2, int threads);
 
+/* ------------------------------------------------------------- FASTQ text in -> SAM text out, the whole batch loop ----- */
+/* The loop of multiseedSearchWorker (bt2_search.cpp:3253-4254) around the engines with its reader (PatternComposer::nextBatch,
+ * pat.cpp:222-300; FastqPatternSource::parse :1130) and its ordered sink (AlnSinkWrap::finishRead aln_sink.cpp:643 ->
+ * AlnSinkSam::appendMate :1889; OutputQueue of --reorder, outq.cpp) as overlapped host stages in C++ (csrc/stream_host.cpp):
+ * the reader thread calls next_block and parses (parse_threads), one thread per engine calls `align`, the writer thread formats
+ * (format_threads), adds the block to the alignment counts and calls write -- blocks leave in input order, each block in flight
+ * owns one set of reused host buffers (depth + n_engines + 1 sets).
+ *   align: bt2g_xengine_align itself (cast; engines[j] = a bt2g_xengine*), or any function of that shape.
+ *   next_block: 1 = a block of WHOLE records (at most max_units reads or pairs; paired: the same number of records in both texts,
+ *     *text2 / *len2 ignored otherwise), 0 = end of input, < 0 = error; the texts must stay valid until the next call of next_block.
+ *   write: the SAM records of one block (no header: bt2g_sam_header), valid until write returns; 0 = ok.
+ * opt: as for bt2g_sam_format (read_names and threads are set per block here).  count_flags: as bt2g_align_counts_add_ex.
+ * Returns 0, 1 (complete, but some alignment had more edit ops than max_ops: see bt2g_sam_format), or the first error of a stage
+ * (parser codes -4..-7, engine codes, -20 reader, -22 block does not hold whole records, -23 a pair with an empty mate 2 -- the
+ * reference aligns its mate 1 as an unpaired read, bt2_search.cpp:3326, which needs an unpaired engine: bowtie2_b200/stream.py
+ * does that --, -24 read longer than max_len, -25 writer) with its text in err. */
+typedef int (*bt2g_stream_align_fn)(void *engine, const bt2g_reads *reads, const char *names, uint32_t name_stride, bt2g_read_result *res,
+                                    uint8_t *ops, uint32_t max_ops, bt2g_pair_result *pairs, uint64_t *stats);
+typedef struct {
+	void *user;
+	int (*next_block)(void *user, const char **text1, uint64_t *len1, const char **text2, uint64_t *len2);
+	int (*write)(void *user, const char *sam, uint64_t len);
+} bt2g_stream_io;
+typedef struct {
+	int32_t  paired, parse_threads, format_threads, depth /* parsed blocks waiting for an engine; 0 = 2 */;
+	uint64_t max_units;          /* reads (pairs) per block = the engines' capacity */
+	uint32_t max_len, max_ops, name_stride, count_flags;
+} bt2g_stream_params;
+int bt2g_stream_run(bt2g_stream_align_fn align, void *const *engines, int32_t n_engines, const bt2g_stream_params *sp,
+                    const bt2g_sam_opts *opt, const bt2g_stream_io *io, bt2g_align_counts *counts, uint64_t *n_reads,
+                    char *err, uint32_t err_cap);
+
 #ifdef __cplusplus
 }
 #endif

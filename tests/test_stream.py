@@ -115,3 +115,75 @@ def test_stream_files_errors(tmp_path, lambda_index):
     (tmp_path / "b.fq").write_bytes(b"@" + b"x" * 200 + b"\nACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIII\n")
     with pytest.raises(ValueError, match="name_stride"):
         align_files_stream(lambda_index, str(tmp_path / "o.sam"), str(tmp_path / "b.fq"), batch_units=64, gpu=object(), make_engine=mk)
+
+
+# ---- the same loop in C++ (csrc/stream_host.cpp: bt2g_stream_run) -----------------------------------------------------------
+def _host_align(be_by_engine, params):
+    lib = load_library()
+
+    def align(j, batch, names):
+        with _ORACLE_LOCK:
+            res, ops, pairs, _ = policy_align(lib, be_by_engine[j], params, batch, names, entry="bt2g_xengine_align_host")
+        return res, ops, pairs
+    return align
+
+
+@pytest.mark.parametrize("n_engines,cut", [(1, 100), (2, 37), (3, 64)])
+def test_cxx_stream_paired(n_engines, cut, lambda_index):
+    """bt2g_stream_run: reader callback + parse, one thread per engine, ordered formatter + writer callback; the SAM text and the
+    alignment counts equal the reference program's whatever the block cut and the number of engines"""
+    from bowtie2_b200.lib import align_summary, stream_run
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "lambda_P_sensitive.sam")) if not l.startswith("@")]
+    n = 200
+    l1, l2 = _records(os.path.join(GOLDEN, "lambda_reads_1.fq"), n), _records(os.path.join(GOLDEN, "lambda_reads_2.fq"), n)
+    blocks = [(b"".join(l1[4 * a:4 * min(a + cut, n)]), b"".join(l2[4 * a:4 * min(a + cut, n)])) for a in range(0, n, cut)]
+    be, keep, fake = _table(lambda_index)
+    lib = load_library()
+    chunks = []
+    written, rc, counts = stream_run(lib, list(range(n_engines)), blocks, chunks.append, ["gi|9626243|ref|NC_001416.1|"], paired=True, max_units=cut,
+                                     max_len=1024, max_ops=1024 + 64, name_stride=64, align=_host_align([be] * n_engines, policy_params("sensitive", paired=True)),
+                                     want_counts=True)
+    lines = b"".join(chunks).decode().rstrip("\n").split("\n")
+    assert written == 2 * n and rc == 0 and lines == golden[:2 * n]
+    # the counts of the same records through the Python-side helper
+    from bowtie2_b200.lib import ReadBatch, align_counts_add
+    from conftest import read_fastq_codes
+    n1, r1, q1 = read_fastq_codes(os.path.join(GOLDEN, "lambda_reads_1.fq"), n)
+    n2, r2, q2 = read_fastq_codes(os.path.join(GOLDEN, "lambda_reads_2.fq"), n)
+    il = lambda a, b: [x for p in zip(a, b) for x in p]
+    res, ops, pairs, _ = policy_align(lib, be, policy_params("sensitive", paired=True), ReadBatch.from_list(il(r1, r2), il(q1, q2)), il(n1, n2),
+                                      entry="bt2g_xengine_align_host")
+    assert align_summary(lib, counts) == align_summary(lib, align_counts_add(lib, None, res, pairs))
+
+
+def test_cxx_stream_unpaired_and_errors(lambda_index):
+    from bowtie2_b200.lib import stream_run
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "lambda_U_sensitive.sam")) if not l.startswith("@")]
+    n = 300
+    l1 = _records(os.path.join(GOLDEN, "lambda_reads_1.fq"), n)
+    blocks = [(b"".join(l1[4 * a:4 * min(a + 128, n)]), None) for a in range(0, n, 128)]
+    be, keep, fake = _table(lambda_index)
+    lib = load_library()
+    kw = dict(paired=False, max_units=128, max_len=1024, max_ops=1088, name_stride=64, parse_threads=1, format_threads=1,
+              align=_host_align([be, be], policy_params("sensitive")))
+    chunks = []
+    written, rc, _ = stream_run(lib, [0, 1], blocks, chunks.append, ["gi|9626243|ref|NC_001416.1|"], **kw)
+    assert written == n and rc == 0 and b"".join(chunks).decode().rstrip("\n").split("\n") == golden[:n]
+    # no input: no records, no error
+    assert stream_run(lib, [0, 1], [], chunks.append, ["gi|9626243|ref|NC_001416.1|"], **kw)[:2] == (0, 0)
+    # a block that ends inside a record, a block larger than the engines' capacity, a read longer than max_len, a failing sink
+    with pytest.raises(RuntimeError, match="whole records"):
+        stream_run(lib, [0], [(b"".join(l1[:7]), None)], chunks.append, ["x"], **kw)
+    with pytest.raises(RuntimeError, match="whole records"):
+        stream_run(lib, [0], [(b"".join(l1[:4 * 129]), None)], chunks.append, ["x"], **kw)
+    with pytest.raises(RuntimeError, match="max_len"):
+        stream_run(lib, [0], blocks, chunks.append, ["x"], **{**kw, "max_len": 20})
+
+    def bad_sink(_):
+        raise OSError("disk full")
+    with pytest.raises(OSError):
+        stream_run(lib, [0, 1], blocks, bad_sink, ["gi|9626243|ref|NC_001416.1|"], **kw)
+    # a pair with an empty mate 2 is refused (the reference aligns its mate 1 as an unpaired read: stream.TextAligner does that)
+    pe = dict(kw, paired=True, align=_host_align([be], policy_params("sensitive", paired=True)))
+    with pytest.raises(RuntimeError, match="empty mate 2"):
+        stream_run(lib, [0], [(b"@a\nACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIII\n", b"@a\n\n+\n\n")], chunks.append, ["x"], **pe)
