@@ -134,3 +134,23 @@ def test_search_policy_engines_under_sanitizers(tmp_path):
     exe = _build_engines(tmp_path)
     ran = sum(_engines_case(exe, seed, k, tmp_path) for seed, k in ((114, 3), (114, 8), (101, 13), (31, 5), (31, 12), (64, 7), (43, 2), (44, 64)))
     assert ran >= 5
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="no g++")
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("san", ["address,undefined", "thread"])
+def test_cxx_stream_under_sanitizers(tmp_path, san):
+    """bt2g_stream_run (csrc/stream_host.cpp) with synthetic engines that finish out of order: the SAM text equals the blocks formatted one
+    after the other, a failing engine / reader / writer ends the run with its code and without a hang; under ASan + UBSan, and under TSan
+    (reader, E engine threads and the writer share the slot queues)."""
+    csrc = os.path.join(ROOT, "bowtie2_b200", "csrc")
+    exe = str(tmp_path / "run_stream")
+    cmd = ["g++", "-O1", "-g", "-fsanitize=" + san, "-fno-omit-frame-pointer", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", exe,
+           os.path.join(ROOT, "tests", "sanitize", "run_stream.cpp"), os.path.join(csrc, "stream_host.cpp"), os.path.join(csrc, "sam_host.cpp"), "-lpthread"]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode and ("asan" in p.stderr or "tsan" in p.stderr or "sanitize" in p.stderr):
+        pytest.skip("no sanitizer runtime for g++ here")
+    assert p.returncode == 0, p.stderr[-2000:]
+    for seed in (1, 2):
+        r = subprocess.run([exe, str(seed), "60"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "0 inconsistencies" in r.stdout, (r.stdout[-600:], r.stderr[-3000:])
