@@ -83,8 +83,60 @@ struct Run {
 		freeSlots.close(); parsed.close(); done.close();
 	}
 
-	void reader() {
+	// parse one block into slot si; n = reads parsed, c1 / c2 = bytes used of each text.  false = failed (fail() called).
+	bool parseBlock(uint64_t k, int si, const char *t1, uint64_t l1, const char *t2, uint64_t l2, uint64_t &n, uint64_t &c1, uint64_t &c2) {
 		const int mates = sp.paired ? 2 : 1;
+		Slot &s = slots[si];
+		const uint64_t maxReads = sp.max_units * mates, maxBases = l1 + l2 + 1;
+		if(s.seq.size() < maxBases) { s.seq.resize(maxBases); s.qual.resize(maxBases); }
+		if(s.off.size() < maxReads + 1) { s.off.resize(maxReads + 1); s.names.resize(maxReads * (uint64_t)sp.name_stride); }
+		n = c1 = c2 = 0;
+		int prc;
+		if(sp.paired) {
+			prc = bt2g_fastq_parse_pairs_mt(t1, l1, t2, l2, sp.max_units, maxBases, s.seq.data(), s.qual.data(), s.off.data(), s.names.data(),
+			                                sp.name_stride, &n, &c1, &c2, sp.parse_threads);
+			n *= 2;
+		} else {
+			prc = bt2g_fastq_parse_mt(t1, l1, maxReads, maxBases, s.seq.data(), s.qual.data(), s.off.data(), s.names.data(), sp.name_stride, &n, &c1,
+			                          sp.parse_threads);
+			c2 = l2;
+		}
+		if(prc != 0) { fail(prc, "FASTQ parse failed in block " + std::to_string(k)); return false; }
+		s.nReads = n;
+		return true;
+	}
+
+	// the checks on a parsed block and its hand-over to the engines
+	bool submit(uint64_t k, int si) {
+		Slot &s = slots[si];
+		const uint64_t n = s.nReads;
+		if(sp.paired) {
+			bool solo = false;
+			for(uint64_t i = 0; i + 1 < n && !solo; i += 2) solo = s.off[i + 2] == s.off[i + 1];
+			if(solo) {
+				fail(-23, "a pair with an empty mate 2 is an unpaired read for the reference (bt2_search.cpp:3326): not handled by this entry point");
+				return false;
+			}
+		}
+		for(uint64_t i = 0; i < n; i++) {
+			if(s.off[i + 1] - s.off[i] > sp.max_len) { fail(-24, "a read is longer than the engines' max_len"); return false; }
+			// the parser keeps name_stride - 1 bytes of a header line: a row filled to its last byte may have lost its tail (the name feeds
+			// the read's random seed and the QNAME, so that is an error, not a silent cut)
+			if(sp.name_stride >= 2 && s.names[i * (uint64_t)sp.name_stride + sp.name_stride - 2] != 0) {
+				fail(-27, "a read name is longer than name_stride - 2 bytes");
+				return false;
+			}
+		}
+		if(s.res.size() < n) {
+			s.res.resize(n); s.ops.resize(n * (uint64_t)sp.max_ops); s.pairs.resize(n / 2 + 1); s.namePtrs.resize(n);
+		}
+		for(uint64_t i = 0; i < n; i++) s.namePtrs[i] = s.names.data() + i * (uint64_t)sp.name_stride;
+		parsed.push(Item{k, si});
+		return true;
+	}
+
+	// blocks of whole records from next_block
+	void readerBlocks() {
 		for(uint64_t k = 0;; k++) {
 			int si;
 			if(!freeSlots.pop(si)) break;                        // (back-pressure: at most slots.size() blocks in flight)
@@ -93,48 +145,71 @@ struct Run {
 			int r = io->next_block(io->user, &t1, &l1, &t2, &l2);
 			if(r < 0) { fail(-20, "the reader callback failed (" + std::to_string(r) + ")"); break; }
 			if(r == 0) break;
-			Slot &s = slots[si];
-			const uint64_t maxReads = sp.max_units * mates, maxBases = l1 + l2 + 1;
-			if(s.seq.size() < maxBases) { s.seq.resize(maxBases); s.qual.resize(maxBases); }
-			if(s.off.size() < maxReads + 1) { s.off.resize(maxReads + 1); s.names.resize(maxReads * (uint64_t)sp.name_stride); }
-			uint64_t n = 0, c1 = 0, c2 = 0;
-			int prc;
-			if(sp.paired) {
-				if(t2 == nullptr) { fail(-21, "paired run: the reader gave no mate-2 text"); break; }
-				prc = bt2g_fastq_parse_pairs_mt(t1, l1, t2, l2, sp.max_units, maxBases, s.seq.data(), s.qual.data(), s.off.data(), s.names.data(),
-				                                sp.name_stride, &n, &c1, &c2, sp.parse_threads);
-				n *= 2;
-			} else {
-				prc = bt2g_fastq_parse_mt(t1, l1, maxReads, maxBases, s.seq.data(), s.qual.data(), s.off.data(), s.names.data(), sp.name_stride, &n, &c1,
-				                          sp.parse_threads);
-				c2 = l2;
-			}
-			if(prc != 0) { fail(prc, "FASTQ parse failed in block " + std::to_string(k)); break; }
+			if(sp.paired && t2 == nullptr) { fail(-21, "paired run: the reader gave no mate-2 text"); break; }
+			uint64_t n, c1, c2;
+			if(!parseBlock(k, si, t1, l1, t2, l2, n, c1, c2)) break;
 			if(c1 != l1 || c2 != l2) {
 				fail(-22, "block " + std::to_string(k) + " does not hold whole records (or more than max_units, or mate files of different length): " +
 				              std::to_string(l1 - c1) + " and " + std::to_string(l2 - c2) + " bytes left over");
 				break;
 			}
-			if(sp.paired) {
-				bool solo = false;
-				for(uint64_t i = 0; i + 1 < n && !solo; i += 2) solo = s.off[i + 2] == s.off[i + 1];
-				if(solo) {
-					fail(-23, "a pair with an empty mate 2 is an unpaired read for the reference (bt2_search.cpp:3326): not handled by this entry point");
-					break;
-				}
-			}
-			for(uint64_t i = 0; i < n; i++) {
-				if(s.off[i + 1] - s.off[i] > sp.max_len) { fail(-24, "a read is longer than the engines' max_len"); return; }
-			}
-			s.nReads = n;
-			if(s.res.size() < n) {
-				s.res.resize(n); s.ops.resize(n * (uint64_t)sp.max_ops); s.pairs.resize(n / 2 + 1); s.namePtrs.resize(n);
-			}
-			for(uint64_t i = 0; i < n; i++) s.namePtrs[i] = s.names.data() + i * (uint64_t)sp.name_stride;
-			parsed.push(Item{k, si});
+			if(!submit(k, si)) break;
 		}
 		parsed.close();
 	}
+
+	static bool blank(const std::vector<char> &b, uint64_t have) {
+		for(uint64_t i = 0; i < have; i++) if(b[i] != '\n' && b[i] != '\r' && b[i] != ' ' && b[i] != '\t') return false;
+		return true;
+	}
+
+	// a byte stream per mate file from `read` (fread / gzread behind it): this thread keeps one text buffer per file, parses up to max_units
+	// records from their fronts and moves what is left (the next records, a record cut by the chunk end) to the front for the next block --
+	// the mate files are read in step by RECORD, so their lines need not have equal lengths (DualPatternComposer::nextBatch, pat.cpp:222-300)
+	void readerStream() {
+		const int nf = sp.paired ? 2 : 1;
+		std::vector<char> buf[2];
+		uint64_t have[2] = {0, 0}, chunk = sp.chunk_bytes ? sp.chunk_bytes : (32ull << 20);
+		bool eof[2] = {false, false};
+		uint64_t k = 0;
+		int si = -1;
+		for(;;) {
+			if(si < 0 && !freeSlots.pop(si)) break;
+			for(int f = 0; f < nf; f++) {
+				while(!eof[f] && have[f] < chunk) {
+					if(buf[f].size() < chunk + 1) buf[f].resize(chunk + 1);
+					int64_t r = io->read(io->user, f, buf[f].data() + have[f], chunk - have[f]);
+					if(r < 0 || (uint64_t)r > chunk - have[f]) { fail(-20, "the read callback failed (" + std::to_string(r) + ")"); parsed.close(); return; }
+					if(r == 0) {
+						eof[f] = true;
+						if(have[f] && buf[f][have[f] - 1] != '\n') buf[f][have[f]++] = '\n';      // a last record without a final newline
+					}
+					have[f] += (uint64_t)r;
+				}
+			}
+			const bool done1 = eof[0] && blank(buf[0], have[0]), done2 = nf == 2 ? (eof[1] && blank(buf[1], have[1])) : true;
+			if(done1 && done2) break;                                // end of the input
+			if(nf == 2 && (done1 || done2)) {
+				// DualPatternComposer::nextBatch (pat.cpp:256-290)
+				fail(-26, std::string("Error, fewer reads in file specified with -") + (done1 ? "1" : "2") + " than in file specified with -" + (done1 ? "2" : "1"));
+				break;
+			}
+			uint64_t n, c1, c2;
+			if(!parseBlock(k, si, buf[0].data(), have[0], nf == 2 ? buf[1].data() : nullptr, nf == 2 ? have[1] : 0, n, c1, c2)) break;
+			if(n == 0) {
+				if(eof[0] && (nf == 1 || eof[1])) { fail(-22, "truncated FASTQ record at the end of the input"); break; }
+				chunk *= 2;                                          // a record longer than the chunk: read more
+				continue;
+			}
+			if(!submit(k, si)) break;
+			k++; si = -1;
+			memmove(buf[0].data(), buf[0].data() + c1, have[0] - c1); have[0] -= c1;
+			if(nf == 2) { memmove(buf[1].data(), buf[1].data() + c2, have[1] - c2); have[1] -= c2; }
+		}
+		parsed.close();
+	}
+
+	void reader() { if(io->read) readerStream(); else readerBlocks(); }
 
 	void aligner(int j) {
 		Item it;
@@ -196,7 +271,7 @@ extern "C" int bt2g_stream_run(bt2g_stream_align_fn align, void *const *engines,
                                const bt2g_sam_opts *opt, const bt2g_stream_io *io, bt2g_align_counts *counts, uint64_t *n_reads,
                                char *err, uint32_t err_cap) {
 	if(err && err_cap) err[0] = 0;
-	if(!align || !engines || n_engines < 1 || !sp || !opt || !io || !io->next_block || !io->write || sp->max_units == 0 || sp->name_stride == 0) {
+	if(!align || !engines || n_engines < 1 || !sp || !opt || !io || (!io->next_block && !io->read) || !io->write || sp->max_units == 0 || sp->name_stride == 0) {
 		if(err && err_cap) snprintf(err, err_cap, "bt2g_stream_run: bad arguments");
 		return -1;
 	}

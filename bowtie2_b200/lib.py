@@ -1281,29 +1281,40 @@ EXPORTS += ["bt2g_stream_run"]
 _STREAM_ALIGN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(_Reads), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p)
 _STREAM_NEXT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64))
 _STREAM_WRITE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
+_STREAM_READ = C.CFUNCTYPE(C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64)
 
 
 class _StreamIO(C.Structure):
-    _fields_ = [("user", C.c_void_p), ("next_block", _STREAM_NEXT), ("write", _STREAM_WRITE)]
+    _fields_ = [("user", C.c_void_p), ("next_block", _STREAM_NEXT), ("write", _STREAM_WRITE), ("read", _STREAM_READ)]
 
 
 class _StreamParams(C.Structure):
     _fields_ = [("paired", C.c_int32), ("parse_threads", C.c_int32), ("format_threads", C.c_int32), ("depth", C.c_int32), ("max_units", C.c_uint64),
-                ("max_len", C.c_uint32), ("max_ops", C.c_uint32), ("name_stride", C.c_uint32), ("count_flags", C.c_uint32)]
+                ("max_len", C.c_uint32), ("max_ops", C.c_uint32), ("name_stride", C.c_uint32), ("count_flags", C.c_uint32), ("chunk_bytes", C.c_uint64)]
 
 
 def stream_run(lib, engines, blocks, sink, ref_names, paired: bool, max_units: int, max_len: int, max_ops: int, name_stride: int = 64,
                parse_threads: int = 2, format_threads: int = 2, depth: int = 2, local: bool = False, no_discordant: bool = False, sc=None,
-               align=None, want_counts: bool = False):
+               align=None, want_counts: bool = False, files=None, chunk_bytes: int = 0):
     """include/bt2g.h: bt2g_stream_run -- FASTQ text blocks in, SAM text out, reader / engines / ordered writer overlapped in C++.
     engines: XEngine objects (their bt2g_xengine_align is the aligner), or, with `align` given, any list: align(j, ReadBatch, NameTable)
     -> (res, ops, pairs or None) is called for engine j from that engine's thread (the CPU tests' stand-ins).
-    blocks: iterable of (mate-1 text, mate-2 text or None) as bytes, whole records, at most max_units reads (pairs) each.
+    blocks: iterable of (mate-1 text, mate-2 text or None) as bytes, whole records, at most max_units reads (pairs) each -- or None with
+    files = [binary file object of mate 1 (, of mate 2)] (anything with readinto: open(..., "rb"), gzip.open): the library's reader cuts the
+    blocks itself, chunk_bytes of text per file at a time (the `read` callback of bt2g_stream_io).
     sink(bytes) gets the records of one block, in input order.  Returns (reads written, rc, counts or None); raises on a stage error."""
     lib.bt2g_stream_run.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(_StreamParams), C.POINTER(_SamOpts), C.POINTER(_StreamIO),
                                     C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p, C.c_uint32]
-    it = iter(blocks)
+    it = iter(blocks if blocks is not None else [])
     hold, errs = [None], []
+
+    def read(_u, mate, dst, cap):
+        try:
+            view = (C.c_char * cap).from_address(dst)
+            return files[mate].readinto(view) or 0
+        except Exception as e:
+            errs.append(e)
+            return -1
 
     def next_block(_u, t1, l1, t2, l2):
         try:
@@ -1364,8 +1375,8 @@ def stream_run(lib, engines, blocks, sink, ref_names, paired: bool, max_units: i
     opt = _SamOpts(rn, len(ref_names), None, int(format_threads), sc_filter_maxlen(True, sc) if local else 0, float(nce.C) if nce else 0.0,
                    float(nce.L) if nce else 0.0, 4 if no_discordant else 0, 0, None)
     sp = _StreamParams(int(paired), int(parse_threads), int(format_threads), int(depth), int(max_units), int(max_len), int(max_ops), int(name_stride),
-                       4 if no_discordant else 0)
-    io = _StreamIO(None, _STREAM_NEXT(next_block), _STREAM_WRITE(write))
+                       4 if no_discordant else 0, int(chunk_bytes))
+    io = _StreamIO(None, _STREAM_NEXT(next_block), _STREAM_WRITE(write), _STREAM_READ(read) if files is not None else _STREAM_READ())
     counts = np.zeros(1, dtype=ALIGN_COUNTS) if want_counts else None
     n_reads = C.c_uint64(0)
     err = C.create_string_buffer(512)

@@ -662,11 +662,18 @@ typedef struct {
 	void *user;
 	int (*next_block)(void *user, const char **text1, uint64_t *len1, const char **text2, uint64_t *len2);
 	int (*write)(void *user, const char *sam, uint64_t len);
+	/* Instead of next_block (used when not NULL): the mate files as byte streams -- read(user, mate 0 | 1, dst, cap) copies up to cap bytes of
+	 * that file to dst and returns their number, 0 at the end of the file, < 0 on error (fread / gzread behind it).  The reader keeps one
+	 * text buffer per file, takes up to max_units records from their fronts per block and carries the rest: the files are read in step by
+	 * RECORD (DualPatternComposer::nextBatch, pat.cpp:222-300), a last record needs no final newline, "fewer reads in file specified with
+	 * -1 / -2" is error -26, input that ends inside a record -22, a read name longer than name_stride - 2 bytes -27. */
+	int64_t (*read)(void *user, int mate, char *dst, uint64_t cap);
 } bt2g_stream_io;
 typedef struct {
 	int32_t  paired, parse_threads, format_threads, depth /* parsed blocks waiting for an engine; 0 = 2 */;
 	uint64_t max_units;          /* reads (pairs) per block = the engines' capacity */
 	uint32_t max_len, max_ops, name_stride, count_flags;
+	uint64_t chunk_bytes;        /* read callback: bytes of text kept per file (0 = 32 MiB; grows when a record does not fit) */
 } bt2g_stream_params;
 int bt2g_stream_run(bt2g_stream_align_fn align, void *const *engines, int32_t n_engines, const bt2g_stream_params *sp,
                     const bt2g_sam_opts *opt, const bt2g_stream_io *io, bt2g_align_counts *counts, uint64_t *n_reads,

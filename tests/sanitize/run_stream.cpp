@@ -33,6 +33,7 @@ struct IO {
 	size_t next = 0;
 	std::string out;
 	int failRead = -1, failWrite = -1, writes = 0;
+	void *bytes = nullptr;
 };
 static int nextBlock(void *u, const char **t1, uint64_t *l1, const char **t2, uint64_t *l2) {
 	IO *io = (IO *)u;
@@ -41,6 +42,16 @@ static int nextBlock(void *u, const char **t1, uint64_t *l1, const char **t2, ui
 	const auto &b = (*io->blocks)[io->next++];
 	*t1 = b.first.data(); *l1 = b.first.size(); *t2 = b.second.data(); *l2 = b.second.size();
 	return 1;
+}
+// the same blocks as two byte streams (the read callback), handed out in random-sized pieces
+struct Bytes { std::string text[2]; size_t at[2] = {0, 0}; std::mt19937_64 *rng; IO *io; };
+static int64_t readBytes(void *u, int mate, char *dst, uint64_t cap) {
+	Bytes *b = (Bytes *)((IO *)u)->bytes;
+	size_t left = b->text[mate].size() - b->at[mate];
+	size_t n = std::min<size_t>(std::min<size_t>(left, cap), 1 + (*b->rng)() % 5000);
+	memcpy(dst, b->text[mate].data() + b->at[mate], n);
+	b->at[mate] += n;
+	return (int64_t)n;
 }
 static int writeOut(void *u, const char *s, uint64_t n) {
 	IO *io = (IO *)u;
@@ -53,7 +64,7 @@ int main(int argc, char **argv) {
 	std::mt19937_64 rng(argc > 1 ? atoi(argv[1]) : 1);
 	int iters = argc > 2 ? atoi(argv[2]) : 40;
 	auto rnd = [&](uint64_t n) { return n ? rng() % n : 0; };
-	long bad = 0;
+	long bad = 0, streamed = 0;
 	const char *refNames[1] = {"chr1"};
 	for(int it = 0; it < iters; it++) {
 		const bool paired = rnd(2);
@@ -121,11 +132,22 @@ int main(int argc, char **argv) {
 		io.blocks = &blocks;
 		if(mode == 3) io.failRead = (int)rnd(nblocks + 1);
 		if(mode == 4) io.failWrite = (int)rnd(nblocks + 1);
-		bt2g_stream_io sio{&io, nextBlock, writeOut};
+		bt2g_stream_io sio{&io, nextBlock, writeOut, nullptr};
+		Bytes bytes;
+		const bool asBytes = mode <= 1 && rnd(2);              // clean runs: half of them through the read callback (the library cuts the blocks)
+		if(asBytes) {
+			streamed++;
+			for(auto &bl : blocks) { bytes.text[0] += bl.first; bytes.text[1] += bl.second; }
+			if(rnd(2) && !bytes.text[0].empty()) bytes.text[0].pop_back();              // a last record without a final newline
+			if(rnd(3) == 0) bytes.text[paired ? 1 : 0] += "\n\n";                          // blank lines at the end
+			bytes.rng = &rng; io.bytes = &bytes;
+			sio.next_block = nullptr; sio.read = readBytes;
+		}
 		bt2g_stream_params sp;
 		memset(&sp, 0, sizeof(sp));
 		sp.paired = paired; sp.parse_threads = 1 + (int)rnd(4); sp.format_threads = 1 + (int)rnd(4); sp.depth = (int)rnd(4);
 		sp.max_units = maxUnits; sp.max_len = maxLen; sp.max_ops = maxOps; sp.name_stride = stride;
+		sp.chunk_bytes = asBytes ? 50 + rnd(200000) : 0;        // (small chunks: records cut by the chunk end, chunks that grow)
 		bt2g_align_counts cnt;
 		memset(&cnt, 0, sizeof(cnt));
 		uint64_t nReads = 0;
@@ -138,6 +160,6 @@ int main(int argc, char **argv) {
 		if(ok && rc != 0) ok = want.compare(0, io.out.size(), io.out) == 0;   // what was written before the failure is a prefix, in order
 		if(!ok) { printf("iteration %d: mode %d rc %d (%s): %zu bytes written, %zu expected\n", it, mode, rc, err, io.out.size(), want.size()); bad++; }
 	}
-	printf("%d iterations, %ld inconsistencies\n", iters, bad);
+	printf("%d iterations (%ld through the read callback), %ld inconsistencies\n", iters, streamed, bad);
 	return bad ? 1 : 0;
 }

@@ -187,3 +187,55 @@ def test_cxx_stream_unpaired_and_errors(lambda_index):
     pe = dict(kw, paired=True, align=_host_align([be], policy_params("sensitive", paired=True)))
     with pytest.raises(RuntimeError, match="empty mate 2"):
         stream_run(lib, [0], [(b"@a\nACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIII\n", b"@a\n\n+\n\n")], chunks.append, ["x"], **pe)
+
+
+@pytest.mark.parametrize("paired,gz,chunk", [(True, False, 5000), (True, True, 700), (False, False, 0)])
+def test_cxx_stream_whole_files(tmp_path, lambda_index, paired, gz, chunk):
+    """bt2g_stream_run with the read callback: the mate FILES (plain / .gz) as byte streams, the library's reader cuts the blocks (records
+    cut by the chunk end, chunks smaller than a record, mate files read in step by record); records and alignment summary equal the
+    reference program's golden outputs"""
+    import gzip
+    from bowtie2_b200.lib import align_summary, stream_run
+    fix = "lambda_P_sensitive" if paired else "lambda_U_sensitive"
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, fix + ".sam")) if not l.startswith("@")]
+    files = []
+    for m in ((1, 2) if paired else (1,)):
+        n_rec = len(golden) // (2 if paired else 1)
+        lines = open(os.path.join(GOLDEN, f"lambda_reads_{m}.fq"), "rb").readlines()[:4 * n_rec]
+        lines[-1] = lines[-1].rstrip(b"\n")                      # (no final newline)
+        dst = str(tmp_path / f"r{m}.fq") + (".gz" if gz else "")
+        with (gzip.open(dst, "wb") if gz else open(dst, "wb")) as f:
+            f.writelines(lines)
+        files.append(gzip.open(dst, "rb") if gz else open(dst, "rb"))
+    be, keep, fake = _table(lambda_index)
+    lib = load_library()
+    chunks = []
+    written, rc, counts = stream_run(lib, [0, 1], None, chunks.append, ["gi|9626243|ref|NC_001416.1|"], paired=paired, max_units=333, max_len=1024,
+                                     max_ops=1088, name_stride=128, align=_host_align([be, be], policy_params("sensitive", paired=paired)), want_counts=True,
+                                     files=files, chunk_bytes=chunk)
+    for f in files:
+        f.close()
+    assert rc == 0 and written == len(golden) and b"".join(chunks).decode().rstrip("\n").split("\n") == golden
+    assert align_summary(lib, counts) == open(os.path.join(GOLDEN, fix + ".summary.txt")).read()
+
+
+def test_cxx_stream_file_errors(tmp_path, lambda_index):
+    """a mate file that ends early, input that ends inside a record and a read name longer than the name rows are errors, not silent cuts"""
+    import io
+    from bowtie2_b200.lib import stream_run
+    l1 = open(os.path.join(GOLDEN, "lambda_reads_1.fq"), "rb").readlines()[:400]
+    l2 = open(os.path.join(GOLDEN, "lambda_reads_2.fq"), "rb").readlines()[:360]
+    be, keep, fake = _table(lambda_index)
+    lib = load_library()
+    kw = dict(max_units=64, max_len=1024, max_ops=1088, name_stride=64, chunk_bytes=3000)
+    pe = dict(kw, paired=True, align=_host_align([be], policy_params("sensitive", paired=True)))
+    se = dict(kw, paired=False, align=_host_align([be], policy_params("sensitive")))
+    with pytest.raises(RuntimeError, match="fewer reads in file specified with -2"):
+        stream_run(lib, [0], None, lambda b: None, ["x"], files=[io.BytesIO(b"".join(l1)), io.BytesIO(b"".join(l2))], **pe)
+    with pytest.raises(RuntimeError, match="truncated FASTQ record"):
+        stream_run(lib, [0], None, lambda b: None, ["x"], files=[io.BytesIO(b"".join(l1[:42]))], **se)
+    with pytest.raises(RuntimeError, match="name_stride"):
+        stream_run(lib, [0], None, lambda b: None, ["x"], files=[io.BytesIO(b"@" + b"x" * 200 + b"\nACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIII\n")], **se)
+    # empty input
+    assert stream_run(lib, [0], None, lambda b: None, ["x"], files=[io.BytesIO(b"")], **se)[:2] == (0, 0)
+    assert stream_run(lib, [0], None, lambda b: None, ["x"], files=[io.BytesIO(b"\n"), io.BytesIO(b"")], **pe)[:2] == (0, 0)
