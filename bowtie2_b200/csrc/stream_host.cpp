@@ -9,8 +9,10 @@
 //
 // Every block in flight owns one slot of reused host buffers (parsed reads, names, results, edit ops); the SAM text of a block is
 // written into one reused buffer and handed to the writer before the next block is formatted.  bowtie2_b200/stream.py is the same
-// loop on Python threads (it also routes the pairs with an empty mate 2 through an unpaired engine; this entry point refuses them).
+// loop on Python threads.  Pairs with an empty mate 2 go through an unpaired engine of the same run (bt2g_stream_params.solo_engine), as the
+// reference aligns their mate 1 with the unpaired policy (bt2_search.cpp:3326).
 #include "../../include/bt2g.h"
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdio>
@@ -32,6 +34,12 @@ struct Slot {
 	std::vector<bt2g_read_result> res;
 	std::vector<bt2g_pair_result> pairs;
 	uint64_t nReads = 0;
+	// pairs of this block whose mate 2 is empty, and their mate 1s as a batch of unpaired reads with its results
+	std::vector<uint64_t> soloIdx, soloOff;
+	std::vector<uint8_t> soloSeq, soloQual, soloOps;
+	std::vector<char> soloNames;
+	std::vector<const char *> soloNamePtrs;
+	std::vector<bt2g_read_result> soloRes;
 };
 
 struct Item { uint64_t k; int slot; };
@@ -110,11 +118,11 @@ struct Run {
 	bool submit(uint64_t k, int si) {
 		Slot &s = slots[si];
 		const uint64_t n = s.nReads;
+		s.soloIdx.clear();
 		if(sp.paired) {
-			bool solo = false;
-			for(uint64_t i = 0; i + 1 < n && !solo; i += 2) solo = s.off[i + 2] == s.off[i + 1];
-			if(solo) {
-				fail(-23, "a pair with an empty mate 2 is an unpaired read for the reference (bt2_search.cpp:3326): not handled by this entry point");
+			for(uint64_t i = 0; i + 1 < n; i += 2) if(s.off[i + 2] == s.off[i + 1]) s.soloIdx.push_back(i / 2);
+			if(!s.soloIdx.empty() && !sp.solo_engine) {
+				fail(-23, "a pair with an empty mate 2 is an unpaired read for the reference (bt2_search.cpp:3326): the run needs a solo_engine");
 				return false;
 			}
 		}
@@ -211,6 +219,38 @@ struct Run {
 
 	void reader() { if(io->read) readerStream(); else readerBlocks(); }
 
+	// `paired = !read_b().empty()` (bt2_search.cpp:3326): mate 1 of a pair whose mate 2 is empty goes through the UNPAIRED policy and leaves
+	// one record.  One unpaired engine, shared by the aligner threads (such pairs are rare).
+	std::mutex soloM;
+	bool alignSolos(Slot &s, uint64_t k) {
+		const uint64_t m = s.soloIdx.size(), stride = sp.name_stride;
+		s.soloOff.assign(m + 1, 0);
+		for(uint64_t j = 0; j < m; j++) { const uint64_t i = 2 * s.soloIdx[j]; s.soloOff[j + 1] = s.soloOff[j] + (s.off[i + 1] - s.off[i]); }
+		s.soloSeq.resize(s.soloOff[m] + 1); s.soloQual.resize(s.soloOff[m] + 1); s.soloNames.resize(m * stride); s.soloNamePtrs.resize(m);
+		s.soloRes.resize(m); s.soloOps.assign(m * (uint64_t)sp.max_ops, 0);
+		for(uint64_t j = 0; j < m; j++) {
+			const uint64_t i = 2 * s.soloIdx[j], l = s.off[i + 1] - s.off[i];
+			memcpy(s.soloSeq.data() + s.soloOff[j], s.seq.data() + s.off[i], l);
+			memcpy(s.soloQual.data() + s.soloOff[j], s.qual.data() + s.off[i], l);
+			memcpy(s.soloNames.data() + j * stride, s.names.data() + i * stride, stride);
+			s.soloNamePtrs[j] = s.soloNames.data() + j * stride;
+		}
+		const uint64_t cap = sp.solo_max_units ? sp.solo_max_units : sp.max_units;
+		std::vector<uint64_t> off;
+		std::lock_guard<std::mutex> l(soloM);
+		for(uint64_t a = 0; a < m; a += cap) {
+			const uint64_t b = std::min(m, a + cap);
+			off.assign(s.soloOff.begin() + a, s.soloOff.begin() + b + 1);
+			for(auto &o : off) o -= s.soloOff[a];                    // (a batch of its own: offsets from 0)
+			bt2g_reads rd;
+			rd.n_reads = b - a; rd.seq = s.soloSeq.data() + s.soloOff[a]; rd.qual = s.soloQual.data() + s.soloOff[a]; rd.off = off.data();
+			int r = align(sp.solo_engine, &rd, s.soloNames.data() + a * stride, sp.name_stride, s.soloRes.data() + a, s.soloOps.data() + a * (uint64_t)sp.max_ops,
+			              sp.max_ops, nullptr, nullptr);
+			if(r != 0) { fail(r, "the solo engine failed on block " + std::to_string(k)); return false; }
+		}
+		return true;
+	}
+
 	void aligner(int j) {
 		Item it;
 		while(parsed.pop(it)) {
@@ -220,9 +260,32 @@ struct Run {
 			int r = s.nReads == 0 ? 0 : align(engines[j], &rd, s.names.data(), sp.name_stride, s.res.data(), s.ops.data(), sp.max_ops,
 			                                 sp.paired ? s.pairs.data() : nullptr, nullptr);
 			if(r != 0) { fail(r, "engine " + std::to_string(j) + " failed on block " + std::to_string(it.k)); break; }
+			if(!s.soloIdx.empty() && !alignSolos(s, it.k)) break;
 			done.push(it);
 		}
 		if(alignersLeft.fetch_sub(1) == 1) done.close();
+	}
+
+	// format one run of reads, add it to the counts, hand it to the writer callback
+	bool emit(std::vector<char> &out, const bt2g_reads &rd, const char *const *names, const bt2g_read_result *res, const uint8_t *ops,
+	          const bt2g_pair_result *pr, uint64_t block) {
+		bt2g_sam_opts o = *opt;
+		o.read_names = names;
+		o.threads = sp.format_threads;
+		// one formatting pass in the common case (SEQ + QUAL + ~260 bytes of fields per record); -3 reports the size needed
+		uint64_t cap = (rd.off[rd.n_reads] - rd.off[0]) * 2 + rd.n_reads * 260 + 4096, need = 0;
+		if(out.size() < cap) out.resize(cap);
+		int r = bt2g_sam_format(&o, &rd, res, ops, sp.max_ops, pr, out.data(), out.size(), &need);
+		if(r == -3) {
+			out.resize(need);
+			r = bt2g_sam_format(&o, &rd, res, ops, sp.max_ops, pr, out.data(), out.size(), &need);
+		}
+		if(r < 0) { fail(r, "bt2g_sam_format failed on block " + std::to_string(block)); return false; }
+		if(r == 1) cutOps = true;
+		if(counts) bt2g_align_counts_add_ex(counts, res, rd.n_reads, pr, sp.count_flags);
+		int w = io->write(io->user, out.data(), need);
+		if(w != 0) { fail(-25, "the writer callback failed (" + std::to_string(w) + ")"); return false; }
+		return true;
 	}
 
 	void writer() {
@@ -237,26 +300,25 @@ struct Run {
 				pending.erase(p);
 				Slot &s = slots[si];
 				if(s.nReads) {
-					bt2g_reads rd;
-					rd.n_reads = s.nReads; rd.seq = s.seq.data(); rd.qual = s.qual.data(); rd.off = s.off.data();
-					bt2g_sam_opts o = *opt;
-					o.read_names = s.namePtrs.data();
-					o.threads = sp.format_threads;
-					// one formatting pass in the common case (SEQ + QUAL + ~260 bytes of fields per record); -3 reports the size needed
-					uint64_t cap = s.off[s.nReads] * 2 + s.nReads * 260 + 4096, need = 0;
-					if(out.size() < cap) out.resize(cap);
-					const bt2g_pair_result *pr = sp.paired ? s.pairs.data() : nullptr;
-					int r = bt2g_sam_format(&o, &rd, s.res.data(), s.ops.data(), sp.max_ops, pr, out.data(), out.size(), &need);
-					if(r == -3) {
-						out.resize(need);
-						r = bt2g_sam_format(&o, &rd, s.res.data(), s.ops.data(), sp.max_ops, pr, out.data(), out.size(), &need);
+					// the block as runs of ordinary pairs with the solo reads between them, in input order (one run = the block without solos)
+					const uint64_t units = sp.paired ? s.nReads / 2 : s.nReads, per = sp.paired ? 2 : 1, nSolo = s.soloIdx.size();
+					uint64_t prev = 0;
+					for(uint64_t j = 0; j <= nSolo; j++) {
+						const uint64_t end = j < nSolo ? s.soloIdx[j] : units;
+						if(end > prev) {
+							bt2g_reads rd;
+							rd.n_reads = (end - prev) * per; rd.seq = s.seq.data(); rd.qual = s.qual.data(); rd.off = s.off.data() + prev * per;
+							if(!emit(out, rd, s.namePtrs.data() + prev * per, s.res.data() + prev * per, s.ops.data() + prev * per * (uint64_t)sp.max_ops,
+							         sp.paired ? s.pairs.data() + prev : nullptr, next)) return;
+						}
+						if(j < nSolo) {
+							bt2g_reads rd;
+							rd.n_reads = 1; rd.seq = s.soloSeq.data(); rd.qual = s.soloQual.data(); rd.off = s.soloOff.data() + j;
+							if(!emit(out, rd, s.soloNamePtrs.data() + j, s.soloRes.data() + j, s.soloOps.data() + j * (uint64_t)sp.max_ops, nullptr, next)) return;
+							prev = end + 1;
+						}
 					}
-					if(r < 0) { fail(r, "bt2g_sam_format failed on block " + std::to_string(next)); return; }
-					if(r == 1) cutOps = true;
-					if(counts) bt2g_align_counts_add_ex(counts, s.res.data(), s.nReads, pr, sp.count_flags);
-					int w = io->write(io->user, out.data(), need);
-					if(w != 0) { fail(-25, "the writer callback failed (" + std::to_string(w) + ")"); return; }
-					nReads += s.nReads;
+					nReads += s.nReads - nSolo;                      // (a solo pair leaves one record)
 				}
 				next++;
 				freeSlots.push(si);

@@ -1290,19 +1290,23 @@ class _StreamIO(C.Structure):
 
 class _StreamParams(C.Structure):
     _fields_ = [("paired", C.c_int32), ("parse_threads", C.c_int32), ("format_threads", C.c_int32), ("depth", C.c_int32), ("max_units", C.c_uint64),
-                ("max_len", C.c_uint32), ("max_ops", C.c_uint32), ("name_stride", C.c_uint32), ("count_flags", C.c_uint32), ("chunk_bytes", C.c_uint64)]
+                ("max_len", C.c_uint32), ("max_ops", C.c_uint32), ("name_stride", C.c_uint32), ("count_flags", C.c_uint32), ("chunk_bytes", C.c_uint64),
+                ("solo_engine", C.c_void_p), ("solo_max_units", C.c_uint64)]
 
 
 def stream_run(lib, engines, blocks, sink, ref_names, paired: bool, max_units: int, max_len: int, max_ops: int, name_stride: int = 64,
                parse_threads: int = 2, format_threads: int = 2, depth: int = 2, local: bool = False, no_discordant: bool = False, sc=None,
-               align=None, want_counts: bool = False, files=None, chunk_bytes: int = 0):
+               align=None, want_counts: bool = False, files=None, chunk_bytes: int = 0, solo=None, solo_max_units: int = 0):
     """include/bt2g.h: bt2g_stream_run -- FASTQ text blocks in, SAM text out, reader / engines / ordered writer overlapped in C++.
     engines: XEngine objects (their bt2g_xengine_align is the aligner), or, with `align` given, any list: align(j, ReadBatch, NameTable)
     -> (res, ops, pairs or None) is called for engine j from that engine's thread (the CPU tests' stand-ins).
     blocks: iterable of (mate-1 text, mate-2 text or None) as bytes, whole records, at most max_units reads (pairs) each -- or None with
     files = [binary file object of mate 1 (, of mate 2)] (anything with readinto: open(..., "rb"), gzip.open): the library's reader cuts the
     blocks itself, chunk_bytes of text per file at a time (the `read` callback of bt2g_stream_io).
-    sink(bytes) gets the records of one block, in input order.  Returns (reads written, rc, counts or None); raises on a stage error."""
+    solo: an UNPAIRED XEngine of the same run for the pairs whose mate 2 is empty (the reference aligns their mate 1 as an unpaired read);
+    with `align` given, solo=True makes the library call align(len(engines), ...) for them.
+    sink(bytes) gets the records of one block (of a run of a block with solo reads), in input order.  Returns (records written, rc, counts
+    or None); raises on a stage error."""
     lib.bt2g_stream_run.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(_StreamParams), C.POINTER(_SamOpts), C.POINTER(_StreamIO),
                                     C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p, C.c_uint32]
     it = iter(blocks if blocks is not None else [])
@@ -1375,7 +1379,7 @@ def stream_run(lib, engines, blocks, sink, ref_names, paired: bool, max_units: i
     opt = _SamOpts(rn, len(ref_names), None, int(format_threads), sc_filter_maxlen(True, sc) if local else 0, float(nce.C) if nce else 0.0,
                    float(nce.L) if nce else 0.0, 4 if no_discordant else 0, 0, None)
     sp = _StreamParams(int(paired), int(parse_threads), int(format_threads), int(depth), int(max_units), int(max_len), int(max_ops), int(name_stride),
-                       4 if no_discordant else 0, int(chunk_bytes))
+                       4 if no_discordant else 0, int(chunk_bytes), (len(engines) if align is not None else solo._h) if solo else None, int(solo_max_units))
     io = _StreamIO(None, _STREAM_NEXT(next_block), _STREAM_WRITE(write), _STREAM_READ(read) if files is not None else _STREAM_READ())
     counts = np.zeros(1, dtype=ALIGN_COUNTS) if want_counts else None
     n_reads = C.c_uint64(0)

@@ -650,12 +650,11 @@ int bt2g_fastq_parse_pairs_mt(const char *text1, uint64_t len1, const char *text
  *   align: bt2g_xengine_align itself (cast; engines[j] = a bt2g_xengine*), or any function of that shape.
  *   next_block: 1 = a block of WHOLE records (at most max_units reads or pairs; paired: the same number of records in both texts,
  *     *text2 / *len2 ignored otherwise), 0 = end of input, < 0 = error; the texts must stay valid until the next call of next_block.
- *   write: the SAM records of one block (no header: bt2g_sam_header), valid until write returns; 0 = ok.
+ *   write: SAM records (no header: bt2g_sam_header), valid until write returns; 0 = ok.  One call per block -- more for a block with solo
+ *     reads (see solo_engine) --, blocks in input order.
  * opt: as for bt2g_sam_format (read_names and threads are set per block here).  count_flags: as bt2g_align_counts_add_ex.
  * Returns 0, 1 (complete, but some alignment had more edit ops than max_ops: see bt2g_sam_format), or the first error of a stage
- * (parser codes -4..-7, engine codes, -20 reader, -22 block does not hold whole records, -23 a pair with an empty mate 2 -- the
- * reference aligns its mate 1 as an unpaired read, bt2_search.cpp:3326, which needs an unpaired engine: bowtie2_b200/stream.py
- * does that --, -24 read longer than max_len, -25 writer) with its text in err. */
+ * (parser codes -4..-7, engine codes, -20 reader, -22 block does not hold whole records, -23 a pair with an empty mate 2 and no solo_engine, -24 read longer than max_len, -25 writer) with its text in err. */
 typedef int (*bt2g_stream_align_fn)(void *engine, const bt2g_reads *reads, const char *names, uint32_t name_stride, bt2g_read_result *res,
                                     uint8_t *ops, uint32_t max_ops, bt2g_pair_result *pairs, uint64_t *stats);
 typedef struct {
@@ -674,6 +673,11 @@ typedef struct {
 	uint64_t max_units;          /* reads (pairs) per block = the engines' capacity */
 	uint32_t max_len, max_ops, name_stride, count_flags;
 	uint64_t chunk_bytes;        /* read callback: bytes of text kept per file (0 = 32 MiB; grows when a record does not fit) */
+	void    *solo_engine;        /* an UNPAIRED engine of the same run (same preset and options), or NULL.  A pair whose mate 2 is empty is an
+	                              * unpaired read for the reference (`paired = !read_b().empty()`, bt2_search.cpp:3326): its mate 1 goes through the
+	                              * unpaired policy and leaves ONE record (YT:Z:UU), counted with the unpaired reads.  With a solo engine those
+	                              * pairs are aligned and written that way (in place, input order kept); without one they are error -23. */
+	uint64_t solo_max_units;     /* capacity of the solo engine (0 = max_units) */
 } bt2g_stream_params;
 int bt2g_stream_run(bt2g_stream_align_fn align, void *const *engines, int32_t n_engines, const bt2g_stream_params *sp,
                     const bt2g_sam_opts *opt, const bt2g_stream_io *io, bt2g_align_counts *counts, uint64_t *n_reads,

@@ -239,3 +239,55 @@ def test_cxx_stream_file_errors(tmp_path, lambda_index):
     # empty input
     assert stream_run(lib, [0], None, lambda b: None, ["x"], files=[io.BytesIO(b"")], **se)[:2] == (0, 0)
     assert stream_run(lib, [0], None, lambda b: None, ["x"], files=[io.BytesIO(b"\n"), io.BytesIO(b"")], **pe)[:2] == (0, 0)
+
+
+def test_cxx_stream_pairs_with_an_empty_mate_2(lambda_index):
+    """a pair whose mate 2 is empty is an unpaired read for the reference (bt2_search.cpp:3326): with a solo engine bt2g_stream_run writes
+    its mate 1 as one unpaired record in place; same text and same counts as stream.TextAligner (whose handling of these pairs the file-level
+    fuzz compares with the reference program), and the ordinary pairs around them equal the golden records"""
+    from bowtie2_b200.lib import align_counts_add, align_summary, stream_run
+    golden = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "lambda_P_sensitive.sam")) if not l.startswith("@")]
+    n = 120
+    l1, l2 = _records(os.path.join(GOLDEN, "lambda_reads_1.fq"), n), _records(os.path.join(GOLDEN, "lambda_reads_2.fq"), n)
+    solos = {0, 17, 18, 63, 119}                                 # first, adjacent, at a block end, last
+    for i in solos:
+        l2[4 * i + 1], l2[4 * i + 3] = b"\n", b"\n"
+    cut = 64
+    blocks = [(b"".join(l1[4 * a:4 * min(a + cut, n)]), b"".join(l2[4 * a:4 * min(a + cut, n)])) for a in range(0, n, cut)]
+    be, keep, fake = _table(lambda_index)
+    lib = load_library()
+    pp, up = policy_params("sensitive", paired=True), policy_params("sensitive")
+
+    def align(j, batch, names):                                  # engines 0, 1: paired; 2: the solo engine
+        with _ORACLE_LOCK:
+            res, ops, pairs, _ = policy_align(lib, be, up if j == 2 else pp, batch, names, entry="bt2g_xengine_align_host")
+        return res, ops, pairs
+    chunks = []
+    written, rc, counts = stream_run(lib, [0, 1], blocks, chunks.append, ["gi|9626243|ref|NC_001416.1|"], paired=True, max_units=cut, max_len=1024,
+                                     max_ops=1088, name_stride=64, align=align, want_counts=True, solo=True, solo_max_units=2)
+    got = b"".join(chunks).decode().rstrip("\n").split("\n")
+    assert rc == 0 and written == 2 * n - len(solos) == len(got)
+    # the Python-thread twin on the same blocks
+    ta = TextAligner([_HostEngine(be, pp), _HostEngine(be, pp)], ["gi|9626243|ref|NC_001416.1|"], paired=True, parse_threads=2, format_threads=2, name_stride=64,
+                     make_solo_engine=lambda: _HostEngine(be, up))
+    want_chunks, cnt = [], [None]
+
+    def on_batch(res, pairs):
+        cnt[0] = align_counts_add(lib, cnt[0], res, pairs)
+    ta.run(iter(blocks), lambda v: want_chunks.append(bytes(v)), on_batch=on_batch)
+    want = b"".join(want_chunks).decode().rstrip("\n").split("\n")
+    assert got == want
+    assert align_summary(lib, counts) == align_summary(lib, cnt[0])
+    # the ordinary pairs are the golden records; a solo leaves one record, flagged as an unpaired read
+    gi = 0
+    for i in range(n):
+        if i in solos:
+            rec = got[gi].split("\t")
+            assert int(rec[1]) & 1 == 0 and "YT:Z:UU" in rec
+            gi += 1
+        else:
+            assert got[gi:gi + 2] == golden[2 * i:2 * i + 2]
+            gi += 2
+    # without a solo engine such a pair is refused
+    with pytest.raises(RuntimeError, match="empty mate 2"):
+        stream_run(lib, [0], blocks, chunks.append, ["x"], paired=True, max_units=cut, max_len=1024, max_ops=1088, name_stride=64, align=align)
