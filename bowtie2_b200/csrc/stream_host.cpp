@@ -16,9 +16,11 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -26,13 +28,32 @@
 
 namespace {
 
+// a reusable buffer WITHOUT value-initialisation (a std::vector would zero-fill hundreds of MB per slot before the parser / the engine
+// overwrites them); need() may drop the contents, grow() keeps them
+template <typename T>
+struct Raw {
+	T *p = nullptr;
+	size_t cap = 0;
+	Raw() = default;
+	Raw(const Raw &) = delete;
+	Raw &operator=(const Raw &) = delete;
+	~Raw() { free(p); }
+	T *data() { return p; }
+	const T *data() const { return p; }
+	T &operator[](size_t i) { return p[i]; }
+	const T &operator[](size_t i) const { return p[i]; }
+	size_t size() const { return cap; }
+	bool need(size_t n) { if(n > cap) { free(p); p = (T *)malloc(n * sizeof(T)); cap = p ? n : 0; } return p != nullptr || n == 0; }
+	bool grow(size_t n) { if(n > cap) { T *q = (T *)realloc(p, n * sizeof(T)); if(!q) return false; p = q; cap = n; } return true; }
+};
+
 struct Slot {
-	std::vector<uint8_t> seq, qual, ops;
-	std::vector<uint64_t> off;
-	std::vector<char> names;
-	std::vector<const char *> namePtrs;
-	std::vector<bt2g_read_result> res;
-	std::vector<bt2g_pair_result> pairs;
+	Raw<uint8_t> seq, qual, ops;
+	Raw<uint64_t> off;
+	Raw<char> names;
+	Raw<const char *> namePtrs;
+	Raw<bt2g_read_result> res;
+	Raw<bt2g_pair_result> pairs;
 	uint64_t nReads = 0;
 	// pairs of this block whose mate 2 is empty, and their mate 1s as a batch of unpaired reads with its results
 	std::vector<uint64_t> soloIdx, soloOff;
@@ -71,7 +92,8 @@ struct Run {
 	const bt2g_sam_opts *opt;
 	const bt2g_stream_io *io;
 	bt2g_align_counts *counts;
-	std::vector<Slot> slots;
+	std::unique_ptr<Slot[]> slots;
+	size_t nSlots = 0;
 	Chan<int> freeSlots;
 	Chan<Item> parsed, done;
 	std::atomic<bool> failed{false};
@@ -96,8 +118,9 @@ struct Run {
 		const int mates = sp.paired ? 2 : 1;
 		Slot &s = slots[si];
 		const uint64_t maxReads = sp.max_units * mates, maxBases = l1 + l2 + 1;
-		if(s.seq.size() < maxBases) { s.seq.resize(maxBases); s.qual.resize(maxBases); }
-		if(s.off.size() < maxReads + 1) { s.off.resize(maxReads + 1); s.names.resize(maxReads * (uint64_t)sp.name_stride); }
+		if(!s.seq.need(maxBases) || !s.qual.need(maxBases) || !s.off.need(maxReads + 1) || !s.names.need(maxReads * (uint64_t)sp.name_stride)) {
+			fail(-12, "out of host memory"); return false;
+		}
 		n = c1 = c2 = 0;
 		int prc;
 		if(sp.paired) {
@@ -135,9 +158,7 @@ struct Run {
 				return false;
 			}
 		}
-		if(s.res.size() < n) {
-			s.res.resize(n); s.ops.resize(n * (uint64_t)sp.max_ops); s.pairs.resize(n / 2 + 1); s.namePtrs.resize(n);
-		}
+		if(!s.res.need(n) || !s.ops.need(n * (uint64_t)sp.max_ops) || !s.pairs.need(n / 2 + 1) || !s.namePtrs.need(n)) { fail(-12, "out of host memory"); return false; }
 		for(uint64_t i = 0; i < n; i++) s.namePtrs[i] = s.names.data() + i * (uint64_t)sp.name_stride;
 		parsed.push(Item{k, si});
 		return true;
@@ -166,7 +187,7 @@ struct Run {
 		parsed.close();
 	}
 
-	static bool blank(const std::vector<char> &b, uint64_t have) {
+	static bool blank(const Raw<char> &b, uint64_t have) {
 		for(uint64_t i = 0; i < have; i++) if(b[i] != '\n' && b[i] != '\r' && b[i] != ' ' && b[i] != '\t') return false;
 		return true;
 	}
@@ -176,7 +197,7 @@ struct Run {
 	// the mate files are read in step by RECORD, so their lines need not have equal lengths (DualPatternComposer::nextBatch, pat.cpp:222-300)
 	void readerStream() {
 		const int nf = sp.paired ? 2 : 1;
-		std::vector<char> buf[2];
+		Raw<char> buf[2];
 		uint64_t have[2] = {0, 0}, chunk = sp.chunk_bytes ? sp.chunk_bytes : (32ull << 20);
 		bool eof[2] = {false, false};
 		uint64_t k = 0;
@@ -185,7 +206,7 @@ struct Run {
 			if(si < 0 && !freeSlots.pop(si)) break;
 			for(int f = 0; f < nf; f++) {
 				while(!eof[f] && have[f] < chunk) {
-					if(buf[f].size() < chunk + 1) buf[f].resize(chunk + 1);
+					if(!buf[f].grow(chunk + 1)) { fail(-12, "out of host memory"); parsed.close(); return; }
 					int64_t r = io->read(io->user, f, buf[f].data() + have[f], chunk - have[f]);
 					if(r < 0 || (uint64_t)r > chunk - have[f]) { fail(-20, "the read callback failed (" + std::to_string(r) + ")"); parsed.close(); return; }
 					if(r == 0) {
@@ -211,6 +232,10 @@ struct Run {
 			}
 			if(!submit(k, si)) break;
 			k++; si = -1;
+			// the text kept per file follows the records: a little more than max_units records, so that the blocks are full and little text is
+			// left to move to the front
+			const uint64_t units = sp.paired ? n / 2 : n, want = (std::max(c1, c2) / units + 1) * sp.max_units;
+			chunk = want + want / 16 + 4096;
 			memmove(buf[0].data(), buf[0].data() + c1, have[0] - c1); have[0] -= c1;
 			if(nf == 2) { memmove(buf[1].data(), buf[1].data() + c2, have[1] - c2); have[1] -= c2; }
 		}
@@ -267,17 +292,17 @@ struct Run {
 	}
 
 	// format one run of reads, add it to the counts, hand it to the writer callback
-	bool emit(std::vector<char> &out, const bt2g_reads &rd, const char *const *names, const bt2g_read_result *res, const uint8_t *ops,
+	bool emit(Raw<char> &out, const bt2g_reads &rd, const char *const *names, const bt2g_read_result *res, const uint8_t *ops,
 	          const bt2g_pair_result *pr, uint64_t block) {
 		bt2g_sam_opts o = *opt;
 		o.read_names = names;
 		o.threads = sp.format_threads;
 		// one formatting pass in the common case (SEQ + QUAL + ~260 bytes of fields per record); -3 reports the size needed
 		uint64_t cap = (rd.off[rd.n_reads] - rd.off[0]) * 2 + rd.n_reads * 260 + 4096, need = 0;
-		if(out.size() < cap) out.resize(cap);
+		if(!out.need(cap)) { fail(-12, "out of host memory"); return false; }
 		int r = bt2g_sam_format(&o, &rd, res, ops, sp.max_ops, pr, out.data(), out.size(), &need);
 		if(r == -3) {
-			out.resize(need);
+			if(!out.need(need)) { fail(-12, "out of host memory"); return false; }
 			r = bt2g_sam_format(&o, &rd, res, ops, sp.max_ops, pr, out.data(), out.size(), &need);
 		}
 		if(r < 0) { fail(r, "bt2g_sam_format failed on block " + std::to_string(block)); return false; }
@@ -290,7 +315,7 @@ struct Run {
 
 	void writer() {
 		std::map<uint64_t, int> pending;
-		std::vector<char> out;
+		Raw<char> out;
 		uint64_t next = 0;
 		Item it;
 		while(done.pop(it)) {
@@ -342,9 +367,10 @@ extern "C" int bt2g_stream_run(bt2g_stream_align_fn align, void *const *engines,
 	if(R.sp.parse_threads < 1) R.sp.parse_threads = 1;
 	if(R.sp.format_threads < 1) R.sp.format_threads = 1;
 	const int depth = sp->depth > 0 ? sp->depth : 2;
-	R.slots.resize((size_t)(depth + n_engines + 1));
+	R.nSlots = (size_t)(depth + n_engines + 1);
+	R.slots = std::make_unique<Slot[]>(R.nSlots);
 	R.freeSlots.failed = R.parsed.failed = R.done.failed = &R.failed;
-	for(size_t i = 0; i < R.slots.size(); i++) R.freeSlots.push((int)i);
+	for(size_t i = 0; i < R.nSlots; i++) R.freeSlots.push((int)i);
 	R.alignersLeft.store(n_engines);
 	std::vector<std::thread> th;
 	th.emplace_back([&] { R.reader(); });

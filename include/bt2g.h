@@ -672,7 +672,7 @@ typedef struct {
 	int32_t  paired, parse_threads, format_threads, depth /* parsed blocks waiting for an engine; 0 = 2 */;
 	uint64_t max_units;          /* reads (pairs) per block = the engines' capacity */
 	uint32_t max_len, max_ops, name_stride, count_flags;
-	uint64_t chunk_bytes;        /* read callback: bytes of text kept per file (0 = 32 MiB; grows when a record does not fit) */
+	uint64_t chunk_bytes;        /* read callback: bytes of text kept per file at the start (0 = 32 MiB); grows to a little more than max_units records */
 	void    *solo_engine;        /* an UNPAIRED engine of the same run (same preset and options), or NULL.  A pair whose mate 2 is empty is an
 	                              * unpaired read for the reference (`paired = !read_b().empty()`, bt2_search.cpp:3326): its mate 1 goes through the
 	                              * unpaired policy and leaves ONE record (YT:Z:UU), counted with the unpaired reads.  With a solo engine those
