@@ -64,13 +64,14 @@ int main(int argc, char **argv) {
 	std::mt19937_64 rng(argc > 1 ? atoi(argv[1]) : 1);
 	int iters = argc > 2 ? atoi(argv[2]) : 40;
 	auto rnd = [&](uint64_t n) { return n ? rng() % n : 0; };
-	long bad = 0, streamed = 0;
+	long bad = 0, streamed = 0, solos = 0;
 	const char *refNames[1] = {"chr1"};
 	for(int it = 0; it < iters; it++) {
 		const bool paired = rnd(2);
 		const int nblocks = (int)rnd(9), E = 1 + (int)rnd(4);
 		const uint64_t maxUnits = 1 + rnd(300);
 		const uint32_t stride = 16 + (uint32_t)rnd(40), maxLen = 200, maxOps = 264;
+		const bool withSolos = paired && rnd(3) == 0;             // some pairs have an empty mate 2: they go through the solo engine
 		std::vector<std::pair<std::string, std::string>> blocks;
 		uint64_t id = 0;
 		for(int b = 0; b < nblocks; b++) {
@@ -79,6 +80,7 @@ int main(int argc, char **argv) {
 			for(uint64_t i = 0; i < n; i++, id++)
 				for(int f = 0; f < (paired ? 2 : 1); f++) {
 					int L = 1 + (int)rnd(maxLen);
+					if(withSolos && f == 1 && rnd(7) == 0) L = 0;
 					t[f] += "@read" + std::to_string(id) + "/" + std::to_string(f + 1) + "\n";
 					for(int k = 0; k < L; k++) t[f] += "ACGTN"[rnd(5)];
 					t[f] += "\n+\n";
@@ -92,7 +94,7 @@ int main(int argc, char **argv) {
 		memset(&opt, 0, sizeof(opt));
 		opt.ref_names = refNames; opt.n_refs = 1;
 		std::string want;
-		uint64_t wantReads = 0;
+		uint64_t wantReads = 0, soloCount = 0;
 		for(auto &b : blocks) {
 			const uint64_t cap = b.first.size() + b.second.size() + 1, mr = maxUnits * (paired ? 2 : 1);
 			std::vector<uint8_t> seq(cap), qual(cap);
@@ -117,6 +119,21 @@ int main(int argc, char **argv) {
 			o.read_names = np.data();
 			std::vector<char> out(off[n] * 2 + n * 400 + 4096);
 			uint64_t need = 0;
+			if(withSolos) {
+				// pair by pair: an ordinary pair as two records, a pair with an empty mate 2 as ONE unpaired record of its mate 1
+				for(uint64_t i = 0; i < n; i += 2) {
+					const bool solo = off[i + 2] == off[i + 1];
+					bt2g_reads one{solo ? 1ull : 2ull, seq.data(), qual.data(), off.data() + i};
+					o.read_names = np.data() + i;
+					rc = bt2g_sam_format(&o, &one, res.data(), ops.data(), maxOps, solo ? nullptr : pr.data(), out.data(), out.size(), &need);
+					if(rc) break;
+					want.append(out.data(), need);
+					wantReads += solo ? 1 : 2;
+					soloCount += solo;
+				}
+				if(rc) { printf("iteration %d: reference format failed %d\n", it, rc); bad++; break; }
+				continue;
+			}
 			rc = bt2g_sam_format(&o, &rd, res.data(), ops.data(), maxOps, paired ? pr.data() : nullptr, out.data(), out.size(), &need);
 			if(rc) { printf("iteration %d: reference format failed %d\n", it, rc); bad++; break; }
 			want.append(out.data(), need);
@@ -147,6 +164,8 @@ int main(int argc, char **argv) {
 		memset(&sp, 0, sizeof(sp));
 		sp.paired = paired; sp.parse_threads = 1 + (int)rnd(4); sp.format_threads = 1 + (int)rnd(4); sp.depth = (int)rnd(4);
 		sp.max_units = maxUnits; sp.max_len = maxLen; sp.max_ops = maxOps; sp.name_stride = stride;
+		Eng soloEng{99, -1, &calls};
+		if(withSolos) { sp.solo_engine = &soloEng; sp.solo_max_units = 1 + rnd(5); }
 		sp.chunk_bytes = asBytes ? 50 + rnd(200000) : 0;        // (small chunks: records cut by the chunk end, chunks that grow)
 		bt2g_align_counts cnt;
 		memset(&cnt, 0, sizeof(cnt));
@@ -154,12 +173,13 @@ int main(int argc, char **argv) {
 		char err[256];
 		int rc = bt2g_stream_run(fakeAlign, handles.data(), E, &sp, &opt, &sio, &cnt, &nReads, err, sizeof(err));
 		bool ok;
-		if(mode <= 1) ok = rc == 0 && io.out == want && nReads == wantReads && cnt.nread == wantReads / (paired ? 2 : 1);
+		solos += (long)soloCount;
+		if(mode <= 1) ok = rc == 0 && io.out == want && nReads == wantReads && cnt.nread == (withSolos ? (wantReads + soloCount) / 2 : wantReads / (paired ? 2 : 1));
 		else if(rc == 0) ok = io.out == want;               // the failure point was never reached (fewer non-empty blocks)
 		else ok = (mode == 2 && rc == -77) || (mode == 3 && rc == -20) || (mode == 4 && rc == -25);
 		if(ok && rc != 0) ok = want.compare(0, io.out.size(), io.out) == 0;   // what was written before the failure is a prefix, in order
 		if(!ok) { printf("iteration %d: mode %d rc %d (%s): %zu bytes written, %zu expected\n", it, mode, rc, err, io.out.size(), want.size()); bad++; }
 	}
-	printf("%d iterations (%ld through the read callback), %ld inconsistencies\n", iters, streamed, bad);
+	printf("%d iterations (%ld through the read callback, %ld solo reads), %ld inconsistencies\n", iters, streamed, solos, bad);
 	return bad ? 1 : 0;
 }
