@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun session (round 2: the exact engine is the measured path).
-# usage: tools/gpu_session.sh <tag> [tests|smoke|bench|benchse|benchloc|benchl|benchref|launches|ncustep|ncudp|dpx|builder ...]
+# usage: tools/gpu_session.sh <tag> [tests|smoke|bench|benchse|benchloc|benchl|benchref|launches|ncustep|ncudp|dpx|streamcxx|builder ...]
 set -u
 TAG=${1:-rXX}; shift || true
 WHAT=${*:-tests bench}
@@ -22,6 +22,7 @@ ncustep)  # (a 51 GB seed table cannot be saved / restored for kernel replay: sm
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:^k_xe_step --launch-skip 4 -c 2 -f -o $OUT/${TAG}_k_xe_step python bench.py $SMALL > $OUT/${TAG}_ncu_step.log 2>&1; echo "ncu step exit $?" ;;
 ncudp)    timeout 600 ncu --set full --clock-control none --import-source on -k regex:^k_dp_ --launch-skip 8 -c 2 -f -o $OUT/${TAG}_k_dp python bench.py $SMALL > $OUT/${TAG}_ncu_dp.log 2>&1; echo "ncu dp exit $?" ;;
 dpx)      ./tools/dpx_bench > $OUT/${TAG}_dpx.json; cat $OUT/${TAG}_dpx.json ;;
+streamcxx) timeout 300 python tools/check_stream_cxx_gpu.py > $OUT/${TAG}_stream_cxx.log 2>&1; echo "stream cxx exit $?"; tail -3 $OUT/${TAG}_stream_cxx.log ;;
 builder)  timeout 600 python tools/check_builder_identity.py > $OUT/${TAG}_builder.log 2>&1; echo "builder exit $?"; tail -1 $OUT/${TAG}_builder.log ;;
 esac
 done
