@@ -14,15 +14,51 @@ from conftest import GOLDEN, read_fastq_codes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(tmp_path, name):
-    exe = str(tmp_path / name)
-    cmd = ["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", exe,
-           os.path.join(ROOT, "tests", "sanitize", name + ".cpp"), os.path.join(ROOT, "bowtie2_b200", "csrc", "sam_host.cpp"), "-lpthread"]
-    p = subprocess.run(cmd, capture_output=True, text=True)
-    if p.returncode and ("asan" in p.stderr or "sanitize" in p.stderr):
+# Every instrumented binary of this file is compiled when the first test asks for one, all at the same time (g++ -fsanitize spends ~10 - 30 s
+# on each: side by side they cost the suite one compile, not five); a test then waits for its own.
+_BUILDS, _DONE = {}, {}
+
+
+def _start_builds():
+    if _BUILDS:
+        return
+    import tempfile
+    from oracle_lib import ref_bin
+    d = tempfile.mkdtemp(prefix="bt2g_sanitize_")
+    csrc, san_dir, inc = os.path.join(ROOT, "bowtie2_b200", "csrc"), os.path.join(ROOT, "tests", "sanitize"), os.path.join(ROOT, "include")
+    base = ["g++", "-O1", "-g", "-fno-omit-frame-pointer", "-I", inc]
+    specs = {
+        "fuzz_parse": base + ["-fsanitize=address,undefined", "-std=c++17", os.path.join(san_dir, "fuzz_parse.cpp"), os.path.join(csrc, "sam_host.cpp"), "-lpthread"],
+        "fuzz_format": base + ["-fsanitize=address,undefined", "-std=c++17", os.path.join(san_dir, "fuzz_format.cpp"), os.path.join(csrc, "sam_host.cpp"), "-lpthread"],
+        "run_engines": base + ["-fsanitize=address,undefined", "-std=c++20", "-ffp-contract=off", os.path.join(san_dir, "run_engines.cpp"),
+                               os.path.join(csrc, "xengine_host.cpp"), os.path.join(csrc, "policy_engine.cpp"), ref_bin("libbt2oracle.so"),
+                               "-Wl,-rpath," + os.path.dirname(ref_bin("libbt2oracle.so")), "-lpthread",
+                               "-Wl,--unresolved-symbols=ignore-all"],   # (bt2g_policy_backend_gpu names the device entry points; nothing here calls it)
+    }
+    for san in ("address,undefined", "thread"):
+        specs["run_stream:" + san] = base + ["-fsanitize=" + san, "-std=c++17", os.path.join(san_dir, "run_stream.cpp"), os.path.join(csrc, "stream_host.cpp"),
+                                             os.path.join(csrc, "sam_host.cpp"), "-lpthread"]
+    for k, (name, cmd) in enumerate(specs.items()):
+        exe = os.path.join(d, f"bin{k}")
+        _BUILDS[name] = (subprocess.Popen(cmd + ["-o", exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True), exe)
+
+
+def _built(name):
+    """path of the instrumented binary `name` (skips without a sanitizer runtime)"""
+    _start_builds()
+    if name not in _DONE:
+        p, exe = _BUILDS[name]
+        _, err = p.communicate()
+        _DONE[name] = (p.returncode, err, exe)
+    rc, err, exe = _DONE[name]
+    if rc and ("asan" in err or "tsan" in err or "sanitize" in err):
         pytest.skip("no sanitizer runtime for g++ here")
-    assert p.returncode == 0, p.stderr[-2000:]
+    assert rc == 0, err[-3000:]
     return exe
+
+
+def _build(tmp_path, name):
+    return _built(name)
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="no g++")
@@ -64,18 +100,7 @@ def test_sam_formatter_under_sanitizers(tmp_path, lambda_index):
 
 
 def _build_engines(tmp_path):
-    from oracle_lib import ref_bin
-    exe = str(tmp_path / "run_engines")
-    csrc = os.path.join(ROOT, "bowtie2_b200", "csrc")
-    cmd = ["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-std=c++20", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"),
-           "-o", exe, os.path.join(ROOT, "tests", "sanitize", "run_engines.cpp"), os.path.join(csrc, "xengine_host.cpp"), os.path.join(csrc, "policy_engine.cpp"),
-           ref_bin("libbt2oracle.so"), "-Wl,-rpath," + os.path.dirname(ref_bin("libbt2oracle.so")), "-lpthread",
-           "-Wl,--unresolved-symbols=ignore-all"]          # (bt2g_policy_backend_gpu names the device entry points; nothing here calls it)
-    p = subprocess.run(cmd, capture_output=True, text=True)
-    if p.returncode and ("asan" in p.stderr or "sanitize" in p.stderr):
-        pytest.skip("no sanitizer runtime for g++ here")
-    assert p.returncode == 0, p.stderr[-3000:]
-    return exe
+    return _built("run_engines")
 
 
 def _engines_case(exe, seed, k, tmp_path, n_unpaired=120, n_pairs=60):
@@ -143,14 +168,7 @@ def test_cxx_stream_under_sanitizers(tmp_path, san):
     """bt2g_stream_run (csrc/stream_host.cpp) with synthetic engines that finish out of order: the SAM text equals the blocks formatted one
     after the other, a failing engine / reader / writer ends the run with its code and without a hang; under ASan + UBSan, and under TSan
     (reader, E engine threads and the writer share the slot queues)."""
-    csrc = os.path.join(ROOT, "bowtie2_b200", "csrc")
-    exe = str(tmp_path / "run_stream")
-    cmd = ["g++", "-O1", "-g", "-fsanitize=" + san, "-fno-omit-frame-pointer", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", exe,
-           os.path.join(ROOT, "tests", "sanitize", "run_stream.cpp"), os.path.join(csrc, "stream_host.cpp"), os.path.join(csrc, "sam_host.cpp"), "-lpthread"]
-    p = subprocess.run(cmd, capture_output=True, text=True)
-    if p.returncode and ("asan" in p.stderr or "tsan" in p.stderr or "sanitize" in p.stderr):
-        pytest.skip("no sanitizer runtime for g++ here")
-    assert p.returncode == 0, p.stderr[-2000:]
+    exe = _built("run_stream:" + san)
     for seed in (1, 2):
         r = subprocess.run([exe, str(seed), "60"], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "0 inconsistencies" in r.stdout, (r.stdout[-600:], r.stderr[-3000:])
